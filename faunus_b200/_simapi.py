@@ -1,0 +1,210 @@
+"""ctypes binding of the host-level simulation C ABI (``<prefix>_sim_*`` / ``<prefix>_widom_*``).
+
+The same ABI is exported with prefix ``fbh`` by ``libfaunus_b200.so`` (B200 adaptor terms) and with
+prefix ``fo`` by the oracle library (tests / CPU baseline only); this module is the generic binder.
+See ``faunus_b200/csrc/host/sim_capi.hpp``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Optional, Sequence
+
+import numpy as np
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+c_long_p = C.POINTER(C.c_long)
+
+
+def _dp(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(c_double_p) if a is not None else None
+
+
+def _ip(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(c_int_p) if a is not None else None
+
+
+class SimLibrary:
+    """Function table of one shared library exporting the simulation ABI under ``prefix``."""
+
+    def __init__(self, lib: C.CDLL, prefix: str):
+        self.lib = lib
+        self.prefix = prefix
+        f = self._fn
+        f("last_error", C.c_char_p, [])
+        f("sim_create", C.c_void_p, [C.c_char_p])
+        f("sim_destroy", None, [C.c_void_p])
+        f("sim_restore", C.c_int, [C.c_void_p, C.c_char_p])
+        f("sim_sweep", C.c_int, [C.c_void_p, C.c_int])
+        f("sim_moves_per_sweep", C.c_int, [C.c_void_p])
+        f("sim_system_energy", C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, c_int_p])
+        f("sim_energy", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  c_int_p, C.c_int, c_double_p])
+        f("sim_trial_set", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, C.c_int,
+                                     c_double_p, c_double_p, c_double_p])
+        f("sim_trial_commit", C.c_int, [C.c_void_p, C.c_int])
+        f("sim_drift", C.c_double, [C.c_void_p])
+        f("sim_initial_energy", C.c_double, [C.c_void_p])
+        f("sim_sum_energy_changes", C.c_double, [C.c_void_p])
+        f("sim_trace_enable", None, [C.c_void_p, C.c_int])
+        f("sim_trace_size", C.c_long, [C.c_void_p])
+        f("sim_trace_get", C.c_long, [C.c_void_p, C.c_long, C.c_long, c_double_p, c_double_p,
+                                      c_double_p, c_int_p, c_int_p])
+        f("sim_num_particles", C.c_int, [C.c_void_p])
+        f("sim_num_groups", C.c_int, [C.c_void_p])
+        f("sim_get_particles", C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int_p])
+        f("sim_get_groups", C.c_int, [C.c_void_p, C.c_int, c_int_p, c_double_p])
+        f("sim_state_json", C.c_int, [C.c_void_p, C.c_char_p, C.c_int])
+        f("sim_info_json", C.c_int, [C.c_void_p, C.c_char_p, C.c_int])
+        f("widom_create", C.c_int, [C.c_void_p, C.c_char_p])
+        f("widom_sample", C.c_int, [C.c_void_p, C.c_int, C.c_int])
+        f("widom_result", C.c_int, [C.c_void_p, C.c_int, c_double_p, c_long_p, c_double_p, C.c_int])
+
+    def _fn(self, name, restype, argtypes):
+        fn = getattr(self.lib, f"{self.prefix}_{name}")
+        fn.restype = restype
+        fn.argtypes = argtypes
+        setattr(self, name, fn)
+
+    def error(self) -> str:
+        return self.last_error().decode("utf-8", "replace")
+
+
+class Simulation:
+    """One Metropolis MC simulation (accepted + trial state) driven through the C ABI."""
+
+    def __init__(self, api: SimLibrary, config: dict | str):
+        self.api = api
+        text = config if isinstance(config, str) else json.dumps(config)
+        self.handle = api.sim_create(text.encode())
+        if not self.handle:
+            raise RuntimeError(f"{api.prefix}_sim_create: {api.error()}")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.api.sim_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{self.api.prefix}_{what}: {self.api.error()}")
+
+    # -- state ------------------------------------------------------------------------------
+    def restore(self, state: dict | str):
+        text = state if isinstance(state, str) else json.dumps(state)
+        self._check(self.api.sim_restore(self.handle, text.encode()), "sim_restore")
+
+    @property
+    def num_particles(self) -> int:
+        return self.api.sim_num_particles(self.handle)
+
+    def particles(self, which: int = 0):
+        n = self.num_particles
+        xyzq = np.zeros((n, 4))
+        ids = np.zeros(n, dtype=np.int32)
+        self.api.sim_get_particles(self.handle, which, _dp(xyzq), _ip(ids))
+        return xyzq, ids
+
+    def groups(self, which: int = 0):
+        g = self.api.sim_num_groups(self.handle)
+        rec = np.zeros((g, 4), dtype=np.int32)
+        cm = np.zeros((g, 3))
+        self.api.sim_get_groups(self.handle, which, _ip(rec), _dp(cm))
+        return rec, cm
+
+    def state_json(self) -> dict:
+        n = self.api.sim_state_json(self.handle, None, 0)
+        buf = C.create_string_buffer(n)
+        self.api.sim_state_json(self.handle, buf, n)
+        return json.loads(buf.value.decode())
+
+    def info(self) -> dict:
+        n = self.api.sim_info_json(self.handle, None, 0)
+        buf = C.create_string_buffer(n)
+        self.api.sim_info_json(self.handle, buf, n)
+        return json.loads(buf.value.decode())
+
+    # -- energies ---------------------------------------------------------------------------
+    def system_energy(self):
+        total = C.c_double()
+        terms = np.zeros(16)
+        n = C.c_int()
+        self._check(self.api.sim_system_energy(self.handle, C.byref(total), _dp(terms), 16, C.byref(n)),
+                    "sim_system_energy")
+        return total.value, terms[: n.value].copy()
+
+    def energy(self, which: int = 0, everything: bool = False, volume_change: bool = False,
+               group: int = -1, all: bool = False, internal: bool = False,
+               indices: Sequence[int] = ()) -> float:
+        idx = np.asarray(indices, dtype=np.int32)
+        out = C.c_double()
+        self._check(self.api.sim_energy(self.handle, which, int(everything), int(volume_change), group,
+                                        int(all), int(internal), _ip(idx), len(idx), C.byref(out)),
+                    "sim_energy")
+        return out.value
+
+    def trial_set(self, group: int, indices: Sequence[int], xyz, all: bool = False,
+                  internal: bool = True):
+        idx = np.asarray(indices, dtype=np.int32)
+        pos = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1)
+        u_new, u_old = C.c_double(), C.c_double()
+        self._check(self.api.sim_trial_set(self.handle, group, int(all), int(internal), _ip(idx), len(idx),
+                                           _dp(pos), C.byref(u_new), C.byref(u_old)), "sim_trial_set")
+        return u_new.value, u_old.value
+
+    def trial_commit(self, accept: bool):
+        self._check(self.api.sim_trial_commit(self.handle, int(accept)), "sim_trial_commit")
+
+    # -- Monte Carlo ------------------------------------------------------------------------
+    def sweep(self, n: int = 1):
+        self._check(self.api.sim_sweep(self.handle, n), "sim_sweep")
+
+    @property
+    def moves_per_sweep(self) -> int:
+        return self.api.sim_moves_per_sweep(self.handle)
+
+    def drift(self) -> float:
+        return self.api.sim_drift(self.handle)
+
+    @property
+    def initial_energy(self) -> float:
+        return self.api.sim_initial_energy(self.handle)
+
+    @property
+    def sum_energy_changes(self) -> float:
+        return self.api.sim_sum_energy_changes(self.handle)
+
+    def trace_enable(self, on: bool = True):
+        self.api.sim_trace_enable(self.handle, int(on))
+
+    def trace(self):
+        n = self.api.sim_trace_size(self.handle)
+        du, un, uo = np.zeros(n), np.zeros(n), np.zeros(n)
+        acc = np.zeros(n, dtype=np.int32)
+        mid = np.zeros(n, dtype=np.int32)
+        self.api.sim_trace_get(self.handle, 0, n, _dp(du), _dp(un), _dp(uo), _ip(acc), _ip(mid))
+        return {"du": du, "u_new": un, "u_old": uo, "accepted": acc, "move_id": mid}
+
+    # -- Widom ------------------------------------------------------------------------------
+    def widom_create(self, config: dict) -> int:
+        wid = self.api.widom_create(self.handle, json.dumps(config).encode())
+        if wid < 0:
+            raise RuntimeError(f"{self.api.prefix}_widom_create: {self.api.error()}")
+        return wid
+
+    def widom_sample(self, wid: int, nsamples: int = 1):
+        self._check(self.api.widom_sample(self.handle, wid, nsamples), "widom_sample")
+
+    def widom_result(self, wid: int, max_du: int = 1 << 20):
+        s = C.c_double()
+        cnt = C.c_long()
+        du = np.zeros(max_du)
+        n = self.api.widom_result(self.handle, wid, C.byref(s), C.byref(cnt), _dp(du), max_du)
+        return {"sum_exp": s.value, "count": cnt.value, "last_du": du[: min(n, max_du)].copy()}

@@ -1,0 +1,318 @@
+// The Metropolis engine around the energy boundary: two complete states (accepted, trial), one
+// trial move = mutate trial Space → Change → updateState → u_new, u_old → accept/reject → sync.
+// Mirrors src/montecarlo.cpp:17-34 (metropolisCriterion), :43-71 (init), :85-99 (drift),
+// :139-187 (performMove), :193-209 (getEnergyChange), :220-227 (sweep), :244-254 (State),
+// src/analysis.cpp:807-823 + 1227-1312 (Widom insertion, sequential reference order).
+#pragma once
+#include "moves.hpp"
+
+namespace fb {
+
+struct State
+{
+    std::unique_ptr<Space> spc;
+    std::unique_ptr<Hamiltonian> pot;
+    void sync(const State& other, const Change& change)
+    {
+        spc->sync(*other.spc, change);
+        pot->sync(other.pot.get(), change);
+    }
+};
+
+/** One record per performed move for trace parity checks */
+struct TraceRecord
+{
+    double du = 0;      //!< energy change new − old after the NaN/inf policy (before bias)
+    double u_new = 0;   //!< trial Hamiltonian energy for the change
+    double u_old = 0;   //!< accepted Hamiltonian energy for the change
+    int accepted = 0;
+    int move_id = 0;
+};
+
+class MetropolisMonteCarlo
+{
+  public:
+    Randoms rng;
+    std::shared_ptr<Topology> topology;
+    State state;       //!< accepted
+    State trial_state; //!< trial
+    std::unique_ptr<MoveCollection> moves;
+    double initial_energy = 0.0;
+    double sum_of_energy_changes = 0.0;
+    unsigned int number_of_sweeps = 0;
+    bool record_trace = false;
+    std::vector<TraceRecord> trace;
+
+  private:
+    /** src/montecarlo.cpp:17-34; the uniform is ALWAYS drawn */
+    bool metropolisCriterion(double energy_change)
+    {
+        if (std::isnan(energy_change)) {
+            throw std::runtime_error("Metropolis error: energy cannot be NaN");
+        }
+        const double u = rng.slump();
+        if (std::isinf(energy_change) && energy_change < 0.0) {
+            return true;
+        }
+        if (-energy_change > pc::max_exp_argument) {
+            return true;
+        }
+        return u <= std::exp(-energy_change);
+    }
+
+  public:
+    /** src/montecarlo.cpp:193-209 */
+    static double getEnergyChange(double new_energy, double old_energy)
+    {
+        if (std::isnan(old_energy) && !std::isnan(new_energy)) {
+            return pc::neg_infty;
+        }
+        if (std::isnan(new_energy)) {
+            return pc::infty;
+        }
+        if (new_energy > 0.0 && std::isinf(new_energy)) {
+            return pc::infty;
+        }
+        const double energy_change = new_energy - old_energy;
+        if (std::isnan(energy_change)) {
+            return 0.0;
+        }
+        return energy_change;
+    }
+
+    /**
+     * @param j full input document (temperature, geometry, atomlist, moleculelist,
+     *          insertmolecules | groups+particles, energy, moves, random)
+     */
+    MetropolisMonteCarlo(const Json& j, const TermFactory& factory, ReplicaComm* comm = nullptr)
+    {
+        pc::temperature = j.at("temperature").number(); // src/faunus.cpp:106
+        topology = topologyFromJson(j);
+        auto make_state = [&](State& s) { // src/montecarlo.cpp:244-248
+            s.spc = std::make_unique<Space>();
+            s.spc->topology = topology;
+            spaceFromJson(j, *s.spc, rng.global);
+            s.pot = std::make_unique<Hamiltonian>(*s.spc, j.at("energy"), factory);
+        };
+        make_state(state);
+        make_state(trial_state);
+        static const Json no_moves = Json::array();
+        const Json* jm = j.find("moves");
+        moves = std::make_unique<MoveCollection>(jm ? *jm : no_moves, *trial_state.spc, rng, comm);
+        init();
+    }
+
+    /** src/montecarlo.cpp:43-71 */
+    void init()
+    {
+        sum_of_energy_changes = 0.0;
+        Change change;
+        change.everything = true;
+        state.pot->state = EnergyTerm::MonteCarloState::ACCEPTED;
+        trial_state.pot->state = EnergyTerm::MonteCarloState::TRIAL;
+        state.pot->init();
+        const double energy = state.pot->energy(change);
+        initial_energy = energy;
+        trial_state.sync(state, change);
+        trial_state.pot->init();
+        const double trial_energy = trial_state.pot->energy(change);
+        if (std::isfinite(energy) && std::isfinite(trial_energy)) {
+            if (std::fabs((energy - trial_energy) / energy) > 1e-6) {
+                throw std::runtime_error("error aligning energies - this could be a bug...");
+            }
+        }
+    }
+
+    /** Load a reference `state.json` into both Spaces and re-init; src/montecarlo.cpp:118-137 */
+    void restore(const Json& j)
+    {
+        state.spc->loadState(j);
+        trial_state.spc->loadState(j);
+        init();
+    }
+
+    /** src/montecarlo.cpp:85-99 */
+    double relativeEnergyDrift()
+    {
+        Change change;
+        change.everything = true;
+        const double energy = state.pot->energy(change);
+        const double du = energy - initial_energy;
+        if (std::isfinite(du)) {
+            if (std::fabs(du) <= pc::epsilon_dbl) {
+                return 0.0;
+            }
+            return (energy - (initial_energy + sum_of_energy_changes)) /
+                   (std::fabs(initial_energy) > pc::epsilon_dbl ? initial_energy : energy);
+        }
+        return std::nan("");
+    }
+
+    /** src/montecarlo.cpp:139-187 */
+    void performMove(Move& move, int move_id = 0)
+    {
+        Change change;
+        move.move(change);
+        if (change) {
+            trial_state.pot->updateState(change);
+            const double new_energy = trial_state.pot->energy(change);
+            const double old_energy = state.pot->energy(change);
+            double energy_change = getEnergyChange(new_energy, old_energy);
+            const double energy_bias = move.bias(change, old_energy, new_energy);
+            const double total_trial_energy = energy_change + energy_bias;
+            TraceRecord rec;
+            rec.du = energy_change;
+            rec.u_new = new_energy;
+            rec.u_old = old_energy;
+            rec.move_id = move_id;
+            if (metropolisCriterion(total_trial_energy)) {
+                state.sync(trial_state, change);
+                move.accept(change);
+                rec.accepted = 1;
+            }
+            else {
+                trial_state.sync(state, change);
+                move.reject(change);
+                energy_change = 0.0;
+            }
+            sum_of_energy_changes += energy_change;
+            if (record_trace) {
+                trace.push_back(rec);
+            }
+        }
+        else {
+            rng.slump(); // keep the generator in sync, src/montecarlo.cpp:182-186
+        }
+    }
+
+    /** src/montecarlo.cpp:220-227 */
+    void sweep()
+    {
+        number_of_sweeps++;
+        const auto& all = moves->all();
+        auto id_of = [&](Move& m) {
+            for (size_t i = 0; i < all.size(); ++i) {
+                if (all[i].get() == &m) {
+                    return static_cast<int>(i);
+                }
+            }
+            return -1;
+        };
+        moves->forEachStochasticMove([&](Move& m) { performMove(m, id_of(m)); });
+        moves->forEachIntervalMove(number_of_sweeps, [&](Move& m) { performMove(m, id_of(m)); });
+    }
+
+    double systemEnergy(std::vector<double>* per_term = nullptr)
+    {
+        Change change;
+        change.everything = true;
+        const double u = state.pot->energy(change);
+        if (per_term) {
+            *per_term = state.pot->latestEnergies();
+        }
+        return u;
+    }
+};
+
+/**
+ * Widom particle insertion, sequential reference order: activate the first inactive group of the
+ * molecule, `ninsert` times {random insertion → ΔU = pot.energy(change) → Σ exp(−ΔU)}, deactivate.
+ * src/analysis.cpp:1227-1312 and :807-823. The Hamiltonian is the ACCEPTED one and `updateState`
+ * is never called (so an Ewald reciprocal term does not see the ghost — reference behaviour).
+ */
+class WidomInsertion
+{
+  protected:
+    Space& spc;
+    Hamiltonian& pot;
+    Random& random; //!< global generator (inserter)
+    RandomInserter inserter;
+    int molid = -1;
+    int number_of_insertions = 0;
+    bool absolute_z_coords = false;
+
+  public:
+    double sum_exp = 0;           //!< Σ exp(−ΔU)  (Average::value_sum)
+    unsigned long count = 0;      //!< number of collected insertions
+    std::vector<double> last_du;  //!< ΔU of the most recent sample() call, in insertion order
+
+    WidomInsertion(const Json& j, Space& spc, Hamiltonian& pot, Random& global_random)
+        : spc(spc)
+        , pot(pot)
+        , random(global_random)
+    {
+        number_of_insertions = j.at("ninsert").integer();
+        absolute_z_coords = j.value("absz", false);
+        molid = spc.topology->moleculeId(j.at("molecule").string());
+        // a fresh default RandomInserter (not the molecule's own), src/analysis.cpp:1293-1310
+        if (const auto* d = j.find("dir")) {
+            inserter.dir = pointFromJson(*d);
+        }
+    }
+    virtual ~WidomInsertion() = default;
+
+    /** @return false if no ghost group is available */
+    bool selectGhostGroup(Change& change) const
+    {
+        change.clear();
+        const auto inactive = spc.findMolecules(molid, Space::Selection::INACTIVE);
+        if (inactive.empty()) {
+            return false;
+        }
+        const auto& group = spc.groups[inactive.front()];
+        if (group.empty() && group.capacity() > 0) {
+            auto& gc = change.groups.emplace_back();
+            gc.group_index = inactive.front();
+            gc.all = true;
+            gc.internal = group.isAtomic();
+            return true;
+        }
+        return false;
+    }
+
+    void updateGroup(Group& group, const ParticleVector& particles)
+    {
+        std::copy(particles.begin(), particles.end(), spc.particles.begin() + group.begin);
+        if (absolute_z_coords) {
+            for (size_t i = 0; i < group.size(); ++i) {
+                auto& p = spc.at(group, i).pos;
+                p.z = std::fabs(p.z);
+            }
+        }
+        if (group.isMolecular()) {
+            group.mass_center = spc.massCenter(group, -spc.at(group, 0).pos);
+        }
+    }
+
+    void collect(double energy_change)
+    {
+        if (-energy_change > pc::max_exp_argument) {
+            return; // skipped sample, src/analysis.cpp:809-815
+        }
+        sum_exp += std::exp(-energy_change);
+        count++;
+    }
+
+    virtual void sample()
+    {
+        Change change;
+        last_du.clear();
+        if (!selectGhostGroup(change)) {
+            return;
+        }
+        auto& group = spc.groups.at(change.groups.at(0).group_index);
+        group.resize(group.capacity());
+        for (int cnt = 0; cnt < number_of_insertions; ++cnt) {
+            const auto particles = inserter(spc, spc.topology->molecules[molid], random);
+            updateGroup(group, particles);
+            const double du = pot.energy(change);
+            last_du.push_back(du);
+            collect(du);
+        }
+        group.resize(0);
+    }
+
+    double excessChemicalPotential() const { return -std::log(sum_exp / static_cast<double>(count)); }
+};
+
+} // namespace fb

@@ -1,0 +1,339 @@
+// Host-level C ABI over the MC engine (`MetropolisMonteCarlo`, `WidomInsertion`) used by the Python
+// harness (ctypes), tests and bench. The same driver code is instantiated twice with different
+// energy-term factories: `fbh_*` in libfaunus_b200.so (B200 adaptor terms) and `fo_*` in the oracle
+// library (CPU restatement). Nothing here throws across the ABI: functions return a negative code
+// and `<prefix>_last_error()` holds the message.
+#pragma once
+#include "montecarlo.hpp"
+#include <cstring>
+
+namespace fb::capi {
+
+inline thread_local std::string last_error;
+
+template <class F> int guarded(F&& f)
+{
+    try {
+        f();
+        return 0;
+    }
+    catch (const std::exception& e) {
+        last_error = e.what();
+        return -1;
+    }
+    catch (...) {
+        last_error = "unknown exception";
+        return -1;
+    }
+}
+
+struct Sim
+{
+    std::unique_ptr<MetropolisMonteCarlo> mc;
+    std::vector<std::unique_ptr<WidomInsertion>> widoms;
+    Change pending; //!< change of the manual trial-move protocol
+};
+
+using WidomFactory =
+    std::function<std::unique_ptr<WidomInsertion>(const Json&, MetropolisMonteCarlo&)>;
+
+inline std::unique_ptr<WidomInsertion> defaultWidom(const Json& j, MetropolisMonteCarlo& mc)
+{
+    return std::make_unique<WidomInsertion>(j, *mc.state.spc, *mc.state.pot, mc.rng.global);
+}
+
+inline Sim* create(const char* json_text, const TermFactory& factory, ReplicaComm* comm = nullptr)
+{
+    Sim* sim = nullptr;
+    const int rc = guarded([&] {
+        const Json j = Json::parse(json_text);
+        auto s = std::make_unique<Sim>();
+        s->mc = std::make_unique<MetropolisMonteCarlo>(j, factory, comm);
+        sim = s.release();
+    });
+    return rc == 0 ? sim : nullptr;
+}
+
+inline int copyOut(const std::string& s, char* buf, int len)
+{
+    if (buf == nullptr || len <= 0) {
+        return static_cast<int>(s.size()) + 1;
+    }
+    const int n = std::min<int>(len - 1, static_cast<int>(s.size()));
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+    return static_cast<int>(s.size()) + 1;
+}
+
+/** Build a Change from a flat description (tests drive energy(change) directly with it) */
+inline Change makeChange(int everything, int volume_change, int group_index, int all, int internal,
+                         const int* indices, int n_indices)
+{
+    Change c;
+    c.everything = everything != 0;
+    c.volume_change = volume_change != 0;
+    if (group_index >= 0) {
+        auto& gc = c.groups.emplace_back();
+        gc.group_index = static_cast<size_t>(group_index);
+        gc.all = all != 0;
+        gc.internal = internal != 0;
+        for (int i = 0; i < n_indices; ++i) {
+            gc.relative_atom_indices.push_back(static_cast<size_t>(indices[i]));
+        }
+    }
+    return c;
+}
+
+inline State& pick(Sim& s, int which)
+{
+    return which == 0 ? s.mc->state : s.mc->trial_state;
+}
+
+} // namespace fb::capi
+
+/**
+ * Expands to the extern "C" entry points `<P>_sim_*` / `<P>_widom_*`.
+ * FACTORY: expression yielding a `const fb::TermFactory&`; WIDOM: a `fb::capi::WidomFactory`.
+ */
+#define FB_DEFINE_SIM_CAPI(P, FACTORY, WIDOM)                                                                 \
+    extern "C" {                                                                                              \
+    __attribute__((visibility("default"))) const char* P##_last_error()                                      \
+    {                                                                                                         \
+        return fb::capi::last_error.c_str();                                                                 \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) void* P##_sim_create(const char* json_text)                       \
+    {                                                                                                         \
+        return fb::capi::create(json_text, FACTORY);                                                         \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) void P##_sim_destroy(void* h)                                     \
+    {                                                                                                         \
+        delete static_cast<fb::capi::Sim*>(h);                                                               \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_restore(void* h, const char* state_json)              \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] { s->mc->restore(fb::Json::parse(state_json)); });                      \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_sweep(void* h, int n)                                 \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] {                                                                       \
+            for (int i = 0; i < n; ++i) {                                                                    \
+                s->mc->sweep();                                                                              \
+            }                                                                                                \
+        });                                                                                                  \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_moves_per_sweep(void* h)                              \
+    {                                                                                                         \
+        return static_cast<int>(static_cast<fb::capi::Sim*>(h)->mc->moves->movesPerSweep());                 \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_system_energy(void* h, double* total, double* terms,  \
+                                                                     int max_terms, int* n_terms)            \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] {                                                                       \
+            std::vector<double> per;                                                                         \
+            *total = s->mc->systemEnergy(&per);                                                              \
+            if (n_terms) {                                                                                   \
+                *n_terms = static_cast<int>(per.size());                                                     \
+            }                                                                                                \
+            for (int i = 0; terms && i < max_terms && i < static_cast<int>(per.size()); ++i) {               \
+                terms[i] = per[i];                                                                           \
+            }                                                                                                \
+        });                                                                                                  \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_energy(void* h, int which, int everything,            \
+                                                              int volume_change, int group_index, int all,   \
+                                                              int internal, const int* indices,              \
+                                                              int n_indices, double* energy)                 \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] {                                                                       \
+            const auto c = fb::capi::makeChange(everything, volume_change, group_index, all, internal,       \
+                                                indices, n_indices);                                         \
+            *energy = fb::capi::pick(*s, which).pot->energy(c);                                              \
+        });                                                                                                  \
+    }                                                                                                         \
+    /* manual trial move: displace atoms of one group in the TRIAL space, then the reference's call          \
+       protocol updateState → trial.energy → accepted.energy (montecarlo.cpp:151-155) */                     \
+    __attribute__((visibility("default"))) int P##_sim_trial_set(void* h, int group_index, int all,          \
+                                                                 int internal, const int* indices,           \
+                                                                 int n_indices, const double* xyz,           \
+                                                                 double* u_new, double* u_old)               \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] {                                                                       \
+            auto& spc = *s->mc->trial_state.spc;                                                             \
+            auto& g = spc.groups.at(group_index);                                                            \
+            for (int i = 0; i < n_indices; ++i) {                                                            \
+                auto& p = spc.at(g, indices[i]);                                                             \
+                p.pos = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};                                        \
+            }                                                                                                \
+            if (g.isMolecular()) {                                                                           \
+                g.mass_center = spc.massCenter(g, -g.mass_center);                                           \
+            }                                                                                                \
+            s->pending = fb::capi::makeChange(0, 0, group_index, all, internal, all ? nullptr : indices,     \
+                                              all ? 0 : n_indices);                                          \
+            s->mc->trial_state.pot->updateState(s->pending);                                                 \
+            *u_new = s->mc->trial_state.pot->energy(s->pending);                                             \
+            *u_old = s->mc->state.pot->energy(s->pending);                                                   \
+        });                                                                                                  \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_trial_commit(void* h, int accept)                     \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] {                                                                       \
+            if (accept) {                                                                                    \
+                s->mc->state.sync(s->mc->trial_state, s->pending);                                           \
+            }                                                                                                \
+            else {                                                                                           \
+                s->mc->trial_state.sync(s->mc->state, s->pending);                                           \
+            }                                                                                                \
+        });                                                                                                  \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) double P##_sim_drift(void* h)                                     \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        double d = std::nan("");                                                                             \
+        fb::capi::guarded([&] { d = s->mc->relativeEnergyDrift(); });                                        \
+        return d;                                                                                            \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) double P##_sim_initial_energy(void* h)                            \
+    {                                                                                                         \
+        return static_cast<fb::capi::Sim*>(h)->mc->initial_energy;                                           \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) double P##_sim_sum_energy_changes(void* h)                        \
+    {                                                                                                         \
+        return static_cast<fb::capi::Sim*>(h)->mc->sum_of_energy_changes;                                    \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) void P##_sim_trace_enable(void* h, int on)                        \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        s->mc->record_trace = on != 0;                                                                       \
+        s->mc->trace.clear();                                                                                \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) long P##_sim_trace_size(void* h)                                  \
+    {                                                                                                         \
+        return static_cast<long>(static_cast<fb::capi::Sim*>(h)->mc->trace.size());                          \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) long P##_sim_trace_get(void* h, long offset, long n, double* du,  \
+                                                                  double* u_new, double* u_old,              \
+                                                                  int* accepted, int* move_id)               \
+    {                                                                                                         \
+        const auto& t = static_cast<fb::capi::Sim*>(h)->mc->trace;                                           \
+        long k = 0;                                                                                          \
+        for (long i = offset; i < static_cast<long>(t.size()) && k < n; ++i, ++k) {                          \
+            if (du) du[k] = t[i].du;                                                                         \
+            if (u_new) u_new[k] = t[i].u_new;                                                                \
+            if (u_old) u_old[k] = t[i].u_old;                                                                \
+            if (accepted) accepted[k] = t[i].accepted;                                                       \
+            if (move_id) move_id[k] = t[i].move_id;                                                          \
+        }                                                                                                    \
+        return k;                                                                                            \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_num_particles(void* h)                                \
+    {                                                                                                         \
+        return static_cast<int>(static_cast<fb::capi::Sim*>(h)->mc->state.spc->particles.size());            \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_num_groups(void* h)                                   \
+    {                                                                                                         \
+        return static_cast<int>(static_cast<fb::capi::Sim*>(h)->mc->state.spc->groups.size());               \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_get_particles(void* h, int which, double* xyzq,       \
+                                                                     int* ids)                               \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        const auto& spc = *fb::capi::pick(*s, which).spc;                                                    \
+        for (size_t i = 0; i < spc.particles.size(); ++i) {                                                  \
+            const auto& p = spc.particles[i];                                                                \
+            xyzq[4 * i] = p.pos.x;                                                                           \
+            xyzq[4 * i + 1] = p.pos.y;                                                                       \
+            xyzq[4 * i + 2] = p.pos.z;                                                                       \
+            xyzq[4 * i + 3] = p.charge;                                                                      \
+            if (ids) ids[i] = p.id;                                                                          \
+        }                                                                                                    \
+        return static_cast<int>(spc.particles.size());                                                       \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_get_groups(void* h, int which, int* begin_size_cap_id,\
+                                                                  double* cm)                                \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        const auto& spc = *fb::capi::pick(*s, which).spc;                                                    \
+        for (size_t i = 0; i < spc.groups.size(); ++i) {                                                     \
+            const auto& g = spc.groups[i];                                                                   \
+            begin_size_cap_id[4 * i] = static_cast<int>(g.begin);                                            \
+            begin_size_cap_id[4 * i + 1] = static_cast<int>(g.size());                                       \
+            begin_size_cap_id[4 * i + 2] = static_cast<int>(g.capacity());                                   \
+            begin_size_cap_id[4 * i + 3] = g.id;                                                             \
+            if (cm) {                                                                                        \
+                cm[3 * i] = g.mass_center.x;                                                                 \
+                cm[3 * i + 1] = g.mass_center.y;                                                             \
+                cm[3 * i + 2] = g.mass_center.z;                                                             \
+            }                                                                                                \
+        }                                                                                                    \
+        return static_cast<int>(spc.groups.size());                                                          \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_state_json(void* h, char* buf, int len)               \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::copyOut(s->mc->state.spc->toJson().dump(), buf, len);                               \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_info_json(void* h, char* buf, int len)                \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        fb::Json j = fb::Json::object();                                                                     \
+        fb::Json je;                                                                                         \
+        s->mc->state.pot->to_json(je);                                                                       \
+        j["energy"] = je;                                                                                    \
+        fb::Json jm = fb::Json::array();                                                                     \
+        for (const auto& m : s->mc->moves->all()) {                                                          \
+            fb::Json inner = fb::Json::object();                                                             \
+            m->to_json(inner);                                                                               \
+            fb::Json w = fb::Json::object();                                                                 \
+            w[m->name] = inner;                                                                              \
+            jm.push_back(w);                                                                                 \
+        }                                                                                                    \
+        j["moves"] = jm;                                                                                     \
+        fb::Json jt = fb::Json::array();                                                                     \
+        for (const auto& t : s->mc->state.pot->terms()) {                                                    \
+            fb::Json w = fb::Json::object();                                                                 \
+            w["name"] = t->name;                                                                             \
+            w["seconds"] = t->seconds;                                                                       \
+            jt.push_back(w);                                                                                 \
+        }                                                                                                    \
+        j["term_seconds"] = jt;                                                                              \
+        return fb::capi::copyOut(j.dump(), buf, len);                                                        \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_widom_create(void* h, const char* json_text)              \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        int id = -1;                                                                                         \
+        fb::capi::guarded([&] {                                                                              \
+            s->widoms.push_back((WIDOM)(fb::Json::parse(json_text), *s->mc));                                \
+            id = static_cast<int>(s->widoms.size()) - 1;                                                     \
+        });                                                                                                  \
+        return id;                                                                                           \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_widom_sample(void* h, int id, int nsamples)               \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] {                                                                       \
+            for (int i = 0; i < nsamples; ++i) {                                                             \
+                s->widoms.at(id)->sample();                                                                  \
+            }                                                                                                \
+        });                                                                                                  \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_widom_result(void* h, int id, double* sum_exp,            \
+                                                                long* count, double* last_du, int max_du)    \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        const auto& w = *s->widoms.at(id);                                                                   \
+        *sum_exp = w.sum_exp;                                                                                \
+        *count = static_cast<long>(w.count);                                                                 \
+        const int n = static_cast<int>(w.last_du.size());                                                    \
+        for (int i = 0; last_du && i < n && i < max_du; ++i) {                                               \
+            last_du[i] = w.last_du[i];                                                                       \
+        }                                                                                                    \
+        return n;                                                                                            \
+    }                                                                                                         \
+    }

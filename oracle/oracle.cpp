@@ -1,0 +1,243 @@
+// ORACLE — test infrastructure, not product code. Builds liboracle: the CPU restatement of the
+// reference's energy path behind the same MC driver the product uses, exported as `fo_*`.
+// Only tests/, __graft_entry__.smoke() and bench.py's CPU baseline / reference arm may load it.
+//
+// Term construction order follows the reference: for a `nonbonded*` entry the pair potential's
+// self energy is pushed BEFORE the nonbonded term (src/energy.h:462-477) and an Ewald reciprocal
+// term is appended when coulomb.type == "ewald" (src/energy.cpp:1134-1160, 1185-1198); name → class
+// map: src/energy.cpp:1280-1327.
+#include "../faunus_b200/csrc/host/sim_capi.hpp"
+#include "ewald.hpp"
+#include "nonbonded.hpp"
+
+namespace oracle {
+
+template <class TPot> bool addNonbonded(Hamiltonian& h, Space& spc, const Json& cfg)
+{
+    auto term = std::make_shared<Nonbonded<TPot>>(cfg, spc);
+    if (auto self = term->pairPotential().selfEnergy()) {
+        h.push_back(std::make_shared<ParticleSelfEnergy>(spc, self));
+    }
+    h.push_back(term);
+    return true;
+}
+
+/** src/energy.cpp:1134-1160 */
+inline void addEwald(Hamiltonian& h, Space& spc, const Json& j)
+{
+    const Json* coulomb = nullptr;
+    if (const auto* def = j.find("default")) {
+        for (const auto& i : def->items()) {
+            if (const auto* c = i.find("coulomb")) {
+                coulomb = c;
+                break;
+            }
+        }
+    }
+    else if (const auto* c = j.find("coulomb")) {
+        coulomb = c;
+    }
+    if (coulomb && coulomb->value("type", "") == "ewald") {
+        h.push_back(std::make_shared<Ewald>(*coulomb, spc));
+    }
+}
+
+inline bool termFactory(Hamiltonian& h, Space& spc, const std::string& name, const Json& cfg)
+{
+    bool ok = false;
+    if (name == "nonbonded_coulomblj" || name == "nonbonded_newcoulomblj") {
+        ok = addNonbonded<CoulombLJ>(h, spc, cfg);
+    }
+    else if (name == "nonbonded_coulombwca") {
+        ok = addNonbonded<CoulombWCA>(h, spc, cfg);
+    }
+    else if (name == "nonbonded_pm" || name == "nonbonded_coulombhs") {
+        ok = addNonbonded<PrimitiveModel>(h, spc, cfg);
+    }
+    else if (name == "nonbonded_pmwca") {
+        ok = addNonbonded<PrimitiveModelWCA>(h, spc, cfg);
+    }
+    else if (name == "nonbonded" || name == "nonbonded_exact") {
+        ok = addNonbonded<FunctorPotential>(h, spc, cfg);
+    }
+    else if (name == "nonbonded_splined") {
+        ok = addNonbonded<SplinedPotential>(h, spc, cfg);
+    }
+    if (ok) {
+        addEwald(h, spc, cfg);
+    }
+    return ok;
+}
+
+static const TermFactory factory = termFactory;
+
+} // namespace oracle
+
+FB_DEFINE_SIM_CAPI(fo, oracle::factory, fb::capi::defaultWidom)
+
+#define FO_API extern "C" __attribute__((visibility("default")))
+
+/** Andrea spline of a named test function; pins src/tabulate.h:313-365 */
+FO_API int fo_andrea_test(double utol, double ftol, double xmin, double xmax, double* knots, int max_knots,
+                          double* coeffs, int max_coeffs, int* n_coeffs)
+{
+    oracle::Andrea spline;
+    spline.setTolerance(utol, ftol);
+    const auto d = spline.generate([](double x) { return 0.5 * x * std::sin(x) + 2; }, xmin, xmax);
+    for (size_t i = 0; i < d.r2.size() && static_cast<int>(i) < max_knots; ++i) {
+        knots[i] = d.r2[i];
+    }
+    for (size_t i = 0; i < d.c.size() && static_cast<int>(i) < max_coeffs; ++i) {
+        coeffs[i] = d.c[i];
+    }
+    *n_coeffs = static_cast<int>(d.c.size());
+    return static_cast<int>(d.r2.size());
+}
+
+FO_API double fo_andrea_test_eval(double utol, double ftol, double xmin, double xmax, double x)
+{
+    oracle::Andrea spline;
+    spline.setTolerance(utol, ftol);
+    const auto d = spline.generate([](double t) { return 0.5 * t * std::sin(t) + 2; }, xmin, xmax);
+    return oracle::Andrea::eval(d, x);
+}
+
+/** Splined Coulomb S(q) table for a `coulomb` JSON block at temperature T; returns #knots */
+FO_API int fo_coulomb_table(const char* coulomb_json, double temperature, double* knots, double* coeffs,
+                            int max_knots, double* lB, double* cutoff, double* kappa, double* self_prefactor)
+{
+    int n = -1;
+    fb::capi::guarded([&] {
+        fb::pc::temperature = temperature;
+        oracle::NewCoulombGalore pot;
+        fb::Topology topo;
+        pot.from_json(fb::Json::parse(coulomb_json), topo);
+        n = static_cast<int>(pot.table.r2.size());
+        for (int i = 0; i < n && i < max_knots; ++i) {
+            knots[i] = pot.table.r2[i];
+        }
+        for (int i = 0; i < 6 * (n - 1) && i < 6 * (max_knots - 1); ++i) {
+            coeffs[i] = pot.table.c[i];
+        }
+        *lB = pot.bjerrum_length;
+        *cutoff = pot.scheme.cutoff;
+        *kappa = pot.scheme.kappa;
+        *self_prefactor = pot.scheme.self_prefactor;
+    });
+    return n;
+}
+
+/** Pair energy u(a,b,r) of an `energy`-entry style potential for two atom types (functor tests) */
+FO_API int fo_pair_energy(const char* input_json, const char* nonbonded_name, int id_a, int id_b, const double* r,
+                          int n, double* u)
+{
+    return fb::capi::guarded([&] {
+        const auto j = fb::Json::parse(input_json);
+        fb::pc::temperature = j.at("temperature").number();
+        auto topo = fb::topologyFromJson(j);
+        fb::Space spc;
+        spc.topology = topo;
+        spc.geometry = fb::Geometry::fromJson(fb::Json::parse(R"({"type":"cuboid","length":1e9})"));
+        fb::Particle a = topo->makeParticle(id_a);
+        fb::Particle b = topo->makeParticle(id_b);
+        const fb::Json* cfg = nullptr;
+        for (const auto& e : j.at("energy").items()) {
+            if (e.single().first == nonbonded_name) {
+                cfg = &e.single().second;
+            }
+        }
+        if (!cfg) {
+            throw std::runtime_error("energy entry not found");
+        }
+        const std::string name = nonbonded_name;
+        auto run = [&](auto pot) {
+            pot.from_json(*cfg, *topo);
+            for (int i = 0; i < n; ++i) {
+                u[i] = pot(a, b, r[i] * r[i]);
+            }
+        };
+        if (name == "nonbonded_coulomblj") {
+            run(oracle::CoulombLJ());
+        }
+        else if (name == "nonbonded_coulombwca") {
+            run(oracle::CoulombWCA());
+        }
+        else if (name == "nonbonded_pm") {
+            run(oracle::PrimitiveModel());
+        }
+        else if (name == "nonbonded_pmwca") {
+            run(oracle::PrimitiveModelWCA());
+        }
+        else if (name == "nonbonded") {
+            run(oracle::FunctorPotential());
+        }
+        else if (name == "nonbonded_splined") {
+            run(oracle::SplinedPotential());
+        }
+        else {
+            throw std::runtime_error("unknown nonbonded name");
+        }
+    });
+}
+
+/**
+ * Known-answer harness for the Ewald policies (src/energy.cpp:74-99, 249-305): particles xyzq in a
+ * cubic box, returns K and {self, surface, reciprocal} energies.
+ */
+FO_API int fo_ewald_kat(const char* ewald_json, double temperature, double box, const double* xyzq, int n,
+                        double* self_surface_reciprocal, double* lB)
+{
+    int K = -1;
+    fb::capi::guarded([&] {
+        fb::pc::temperature = temperature;
+        auto topo = std::make_shared<fb::Topology>();
+        fb::AtomData atom;
+        atom.name = "A";
+        atom.id = 0;
+        topo->atoms.push_back(atom);
+        fb::MoleculeData mol;
+        mol.name = "M";
+        mol.id = 0;
+        mol.atomic = true;
+        mol.atoms = {0};
+        topo->molecules.push_back(mol);
+        fb::Space spc;
+        spc.topology = topo;
+        spc.geometry = fb::Geometry::fromJson(
+            fb::Json::parse("{\"type\":\"cuboid\",\"length\":" + std::to_string(box) + "}"));
+        fb::ParticleVector pv;
+        for (int i = 0; i < n; ++i) {
+            fb::Particle p;
+            p.id = 0;
+            p.pos = {xyzq[4 * i], xyzq[4 * i + 1], xyzq[4 * i + 2]};
+            p.charge = xyzq[4 * i + 3];
+            pv.push_back(p);
+        }
+        spc.addGroup(0, pv);
+        oracle::EwaldData data(fb::Json::parse(ewald_json));
+        oracle::ewald::updateBox(data, spc.geometry.getLength());
+        oracle::ewald::updateComplex(data, spc);
+        fb::Change c;
+        c.everything = true;
+        self_surface_reciprocal[0] = oracle::ewald::selfEnergy(data, c, spc);
+        self_surface_reciprocal[1] = oracle::ewald::surfaceEnergy(data, c, spc);
+        self_surface_reciprocal[2] = oracle::ewald::reciprocalEnergy(data);
+        *lB = data.bjerrum_length;
+        K = static_cast<int>(data.k_vectors.size());
+    });
+    return K;
+}
+
+FO_API void fo_set_parallel_ewald_init(int on)
+{
+    oracle::ewald::parallel_full_update = on != 0;
+}
+
+FO_API int fo_openmp_threads()
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
