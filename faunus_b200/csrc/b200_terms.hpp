@@ -1,0 +1,600 @@
+// B200 adaptor terms: `Energy::EnergyTerm` subclasses that stand where the reference's
+// `Energy::Nonbonded<…>`, `Energy::Ewald` and `ParticleSelfEnergy` stand in the Hamiltonian and
+// forward energy(Change) / updateState / sync / init to the CUDA library through its C ABI
+// (include/faunus_b200.h). No CPU fallback: if the device library cannot create a context the
+// constructor throws.
+//
+// Protocol (src/montecarlo.cpp:151-175): trial.updateState(c) → trial.energy(c) → accepted.energy(c)
+// → accepted.sync(trial) | trial.sync(accepted). The two Hamiltonians (accepted, trial) share ONE
+// device context with two mirror slots; `updateState` pushes only the particles listed in the
+// Change into the trial slot; `trial.energy` evaluates new and old in one fused launch and the
+// following `accepted.energy` picks up the cached old value; `sync` is a device-to-device copy of
+// the changed particles. Callers that skip updateState/sync (Widom, SystemEnergy) are served by
+// re-uploading the changed group from the Space the term is bound to.
+#pragma once
+#include "../../include/faunus_b200.h"
+#include "host/energyterm.hpp"
+#include "host/montecarlo.hpp"
+#include "host/potential_tables.hpp"
+#include <map>
+
+namespace fb {
+
+inline void fbCheck(int rc, fb_ctx* ctx, const char* what)
+{
+    if (rc != FB_OK) {
+        throw std::runtime_error(std::string(what) + ": " + fb_last_error(ctx));
+    }
+}
+
+/** Flat view of a Change for the C ABI (keeps the index storage alive) */
+struct FlatChange
+{
+    fb_change change{};
+    std::vector<fb_group_change> groups;
+    std::vector<std::vector<int>> indices;
+    explicit FlatChange(const Change& c)
+    {
+        change.everything = c.everything;
+        change.volume_change = c.volume_change;
+        indices.resize(c.groups.size());
+        for (size_t i = 0; i < c.groups.size(); ++i) {
+            const auto& g = c.groups[i];
+            indices[i].assign(g.relative_atom_indices.begin(), g.relative_atom_indices.end());
+            fb_group_change f{};
+            f.group_index = static_cast<int>(g.group_index);
+            f.all = g.all;
+            f.internal = g.internal;
+            f.n_atoms = static_cast<int>(indices[i].size());
+            f.atoms = indices[i].data();
+            groups.push_back(f);
+        }
+        change.n_groups = static_cast<int>(groups.size());
+        change.groups = groups.data();
+    }
+    /** content signature used to pair trial.energy with the following accepted.energy */
+    std::string signature() const
+    {
+        std::string s = std::to_string(change.everything) + ":" + std::to_string(change.volume_change);
+        for (size_t i = 0; i < groups.size(); ++i) {
+            s += "|" + std::to_string(groups[i].group_index) + "," + std::to_string(groups[i].all) + "," +
+                 std::to_string(groups[i].internal);
+            for (int a : indices[i]) {
+                s += "," + std::to_string(a);
+            }
+        }
+        return s;
+    }
+};
+
+inline fb_group groupRecord(const Group& g)
+{
+    fb_group r{};
+    r.begin = static_cast<int>(g.begin);
+    r.size = static_cast<int>(g.size());
+    r.capacity = static_cast<int>(g.capacity());
+    r.molid = g.id;
+    r.cm[0] = g.mass_center.x;
+    r.cm[1] = g.mass_center.y;
+    r.cm[2] = g.mass_center.z;
+    return r;
+}
+
+/**
+ * One device context shared by the accepted and trial instances of a non-bonded term (and its Ewald
+ * sibling). Created by the first instance, joined by the second (registry keyed on the topology
+ * the two States share, in construction order: accepted → slot 0, trial → slot 1).
+ */
+class DeviceContext
+{
+  public:
+    fb_ctx* ctx = nullptr;
+    PairTables tables;
+    int attached = 0;
+    // fused ΔU cache: filled by the trial term, consumed by the accepted term
+    bool cache_valid = false;
+    std::string cache_signature;
+    double cached_old_energy = 0;
+    // Ewald bookkeeping shared by the two EwaldB200 instances
+    bool ewald_cache_valid = false;
+
+    DeviceContext(const std::string& name, const Json& cfg, const Space& spc, int device)
+    {
+        const Topology& topo = *spc.topology;
+        tables = buildPairTables(name, cfg, topo);
+        fb_config fc{};
+        fc.device = device;
+        const auto& L = spc.geometry.getLength();
+        for (int i = 0; i < 3; ++i) {
+            fc.box[i] = L[i];
+            fc.periodic[i] = spc.geometry.isPeriodic(i);
+        }
+        fc.n_atom_types = static_cast<int>(topo.atoms.size());
+        fc.n_molecule_types = static_cast<int>(topo.molecules.size());
+        std::vector<int> molflags, molnatoms;
+        std::vector<const unsigned char*> exclusions;
+        for (const auto& m : topo.molecules) {
+            molflags.push_back((m.atomic ? FB_MOL_ATOMIC : 0) | (m.rigid ? FB_MOL_RIGID : 0) |
+                               (m.compressible ? FB_MOL_COMPRESSIBLE : 0));
+            molnatoms.push_back(static_cast<int>(m.atoms.size()));
+            exclusions.push_back(m.excluded.empty() ? nullptr : m.excluded.data());
+        }
+        fc.molecule_flags = molflags.data();
+        fc.molecule_natoms = molnatoms.data();
+        fc.exclusions = exclusions.data();
+        fc.g2g_cutoff_squared = tables.g2g_cutoff_squared.data();
+        fc.kind = tables.kind;
+        auto opt = [](const auto& v) { return v.empty() ? nullptr : v.data(); };
+        fc.pair_flags = (tables.kind == potkind::FUNCTOR || tables.kind == potkind::SPLINED) ? tables.flags.data()
+                                                                                            : nullptr;
+        fc.lj_sigma2 = opt(tables.lj_s2);
+        fc.lj_eps4 = opt(tables.lj_e4);
+        fc.wca_sigma2 = opt(tables.wca_s2);
+        fc.wca_eps4 = opt(tables.wca_e4);
+        fc.hs_sigma2 = opt(tables.hs_s2);
+        if (tables.has_coulomb) {
+            fc.coulomb_bjerrum_length = tables.coulomb.bjerrum_length;
+            fc.coulomb_cutoff = tables.coulomb.cutoff;
+            fc.coulomb_kappa = tables.coulomb.kappa;
+            fc.coulomb_n_knots = static_cast<int>(tables.coulomb.S.knots.size());
+            fc.coulomb_knots = tables.coulomb.S.knots.data();
+            fc.coulomb_coeffs = tables.coulomb.S.coeffs.data();
+        }
+        fc.plain_bjerrum_length = tables.plain_bjerrum_length;
+        if (tables.kind == potkind::SPLINED) {
+            fc.spline_offset = tables.sp_offset.data();
+            fc.spline_knots = tables.sp_knots.data();
+            fc.spline_coeffs = tables.sp_coeffs.data();
+            fc.spline_rmin2 = tables.sp_rmin2.data();
+            fc.spline_rmax2 = tables.sp_rmax2.data();
+            fc.spline_hardsphere = tables.sp_hs.data();
+        }
+        const int rc = fb_create(&fc, &ctx);
+        if (rc != FB_OK) {
+            throw std::runtime_error(std::string("fb_create: ") + fb_last_error(nullptr));
+        }
+    }
+    ~DeviceContext() { fb_destroy(ctx); }
+    DeviceContext(const DeviceContext&) = delete;
+    DeviceContext& operator=(const DeviceContext&) = delete;
+
+    /** full upload of a Space into a slot */
+    void uploadSpace(int slot, const Space& spc)
+    {
+        const size_t n = spc.particles.size();
+        std::vector<double> xyzq(4 * n);
+        std::vector<int> ids(n);
+        for (size_t i = 0; i < n; ++i) {
+            const auto& p = spc.particles[i];
+            xyzq[4 * i] = p.pos.x;
+            xyzq[4 * i + 1] = p.pos.y;
+            xyzq[4 * i + 2] = p.pos.z;
+            xyzq[4 * i + 3] = p.charge;
+            ids[i] = p.id;
+        }
+        std::vector<fb_group> groups;
+        for (const auto& g : spc.groups) {
+            groups.push_back(groupRecord(g));
+        }
+        const auto& L = spc.geometry.getLength();
+        const double box[3] = {L.x, L.y, L.z};
+        fbCheck(fb_set_box(ctx, slot, box), ctx, "fb_set_box");
+        fbCheck(fb_upload_space(ctx, slot, xyzq.data(), ids.data(), groups.data(), static_cast<int>(n),
+                                static_cast<int>(groups.size())),
+                ctx, "fb_upload_space");
+        cache_valid = false;
+    }
+
+    /** push the groups/particles a partial Change lists from `spc` into `slot` */
+    void uploadChange(int slot, const Space& spc, const Change& change)
+    {
+        for (const auto& gc : change.groups) {
+            const auto& g = spc.groups.at(gc.group_index);
+            const fb_group rec = groupRecord(g);
+            std::vector<int> rel;
+            if (gc.all || gc.relative_atom_indices.empty()) {
+                rel.resize(g.capacity()); // whole group incl. inactive tail (Space::sync copies it too)
+                std::iota(rel.begin(), rel.end(), 0);
+            }
+            else {
+                rel.assign(gc.relative_atom_indices.begin(), gc.relative_atom_indices.end());
+            }
+            std::vector<double> xyzq(4 * rel.size());
+            std::vector<int> ids(rel.size());
+            for (size_t i = 0; i < rel.size(); ++i) {
+                const auto& p = spc.at(g, rel[i]);
+                xyzq[4 * i] = p.pos.x;
+                xyzq[4 * i + 1] = p.pos.y;
+                xyzq[4 * i + 2] = p.pos.z;
+                xyzq[4 * i + 3] = p.charge;
+                ids[i] = p.id;
+            }
+            fbCheck(fb_update_group(ctx, slot, static_cast<int>(gc.group_index), &rec, static_cast<int>(rel.size()),
+                                    rel.data(), xyzq.data(), ids.data()),
+                    ctx, "fb_update_group");
+        }
+        cache_valid = false;
+    }
+};
+
+/** process-wide registry pairing the accepted and trial instances (see DeviceContext) */
+inline std::map<std::pair<const Topology*, std::string>, std::weak_ptr<DeviceContext>>& deviceRegistry()
+{
+    static std::map<std::pair<const Topology*, std::string>, std::weak_ptr<DeviceContext>> registry;
+    return registry;
+}
+
+inline int& defaultDevice()
+{
+    static int device = 0;
+    return device;
+}
+
+/** Replaces Energy::Nonbonded<PairEnergy<…>, GroupPairing<…>> (src/energy.h:1512-1598) */
+class NonbondedB200 : public EnergyTerm
+{
+    const Space& spc;
+    std::shared_ptr<DeviceContext> dev;
+    int slot = 0;             //!< 0 accepted, 1 trial (construction order)
+    bool state_pushed = false; //!< updateState() already pushed the pending change into our slot
+    std::string pushed_signature;
+
+  public:
+    NonbondedB200(const std::string& key, const Json& j, Space& spc)
+        : spc(spc)
+    {
+        name = "nonbonded";
+        const auto reg_key = std::make_pair(spc.topology.get(), key + j.dump());
+        auto& registry = deviceRegistry();
+        auto it = registry.find(reg_key);
+        if (it != registry.end()) {
+            dev = it->second.lock();
+        }
+        if (!dev || dev->attached >= 2) {
+            dev = std::make_shared<DeviceContext>(key, j, spc, defaultDevice());
+            registry[reg_key] = dev;
+        }
+        slot = dev->attached++;
+        dev->uploadSpace(slot, spc);
+    }
+    ~NonbondedB200() override
+    {
+        if (dev) {
+            dev->attached--;
+        }
+    }
+    const std::shared_ptr<DeviceContext>& device() const { return dev; }
+    int deviceSlot() const { return slot; }
+
+    void init() override { dev->uploadSpace(slot, spc); }
+
+    /** trial Space was mutated by a move: push what the Change lists into our slot */
+    void updateState(const Change& change) override
+    {
+        if (!change) {
+            return;
+        }
+        if (change.everything || change.volume_change) {
+            dev->uploadSpace(slot, spc);
+        }
+        else {
+            dev->uploadChange(slot, spc, change);
+        }
+        state_pushed = true;
+        pushed_signature = FlatChange(change).signature();
+    }
+
+    double energy(const Change& change) override
+    {
+        if (!change) {
+            return 0.0;
+        }
+        if (change.matter_change) {
+            throw std::runtime_error("matter_change (speciation) is outside the B200 hot-path scope");
+        }
+        FlatChange flat(change);
+        const std::string sig = flat.signature();
+        const bool partial = !change.everything && !change.volume_change;
+        // accepted instance right after the trial instance evaluated the same change: cached old energy
+        if (partial && dev->cache_valid && state != MonteCarloState::TRIAL && dev->cache_signature == sig) {
+            dev->cache_valid = false;
+            return dev->cached_old_energy;
+        }
+        const bool pushed = state_pushed && pushed_signature == sig;
+        state_pushed = false;
+        if (!pushed) { // caller mutated our Space without updateState (Widom, SystemEnergy, tests)
+            if (partial) {
+                dev->uploadChange(slot, spc, change);
+            }
+            else {
+                dev->uploadSpace(slot, spc);
+            }
+        }
+        double u = 0.0;
+        if (partial && pushed && state == MonteCarloState::TRIAL && dev->attached == 2) {
+            double u_old = 0.0;
+            fbCheck(fb_nonbonded_delta(dev->ctx, slot, 1 - slot, &flat.change, &u, &u_old), dev->ctx,
+                    "fb_nonbonded_delta");
+            dev->cache_valid = true;
+            dev->cache_signature = sig;
+            dev->cached_old_energy = u_old;
+        }
+        else {
+            fbCheck(fb_nonbonded_energy(dev->ctx, slot, &flat.change, &u), dev->ctx, "fb_nonbonded_energy");
+        }
+        return u;
+    }
+
+    /** our slot := other's slot for the changed particles (device-to-device) */
+    void sync(EnergyTerm* other_term, const Change& change) override
+    {
+        auto* other = dynamic_cast<NonbondedB200*>(other_term);
+        if (!other || other->dev != dev) {
+            throw std::runtime_error("sync error");
+        }
+        FlatChange flat(change);
+        fbCheck(fb_sync(dev->ctx, slot, other->slot, &flat.change), dev->ctx, "fb_sync");
+        dev->cache_valid = false;
+        state_pushed = false;
+    }
+
+    void to_json(Json& j) const override
+    {
+        j["device"] = "B200 sm_100a";
+        j["kind"] = dev->tables.kind;
+        j["launches"] = static_cast<size_t>(fb_launch_count(dev->ctx));
+    }
+};
+
+/** Replaces Energy::Ewald (src/energy.cpp:539-658); shares the context of its non-bonded sibling */
+class EwaldB200 : public EnergyTerm
+{
+    const Space& spc;
+    std::shared_ptr<DeviceContext> dev;
+    std::shared_ptr<NonbondedB200> sibling;
+    int slot;
+    bool have_old = false; //!< `old_groups` set (after the first sync from the accepted instance)
+
+    void fullUpdate()
+    {
+        int K = 0;
+        fbCheck(fb_ewald_update_box(dev->ctx, slot, &K), dev->ctx, "fb_ewald_update_box");
+        fbCheck(fb_ewald_update_full(dev->ctx, slot), dev->ctx, "fb_ewald_update_full");
+    }
+
+  public:
+    EwaldB200(const Json& j, const Space& spc, std::shared_ptr<NonbondedB200> nonbonded)
+        : spc(spc)
+        , dev(nonbonded->device())
+        , sibling(std::move(nonbonded))
+        , slot(sibling->deviceSlot())
+    {
+        name = "ewald";
+        fb_ewald_config cfg{};
+        cfg.alpha = j.at("alpha").number();
+        cfg.n_cutoff = j.contains("kcutoff") ? j.at("kcutoff").number() : j.at("ncutoff").number();
+        cfg.kappa = j.value("kappa", 0.0);
+        cfg.surface_dielectric_constant = j.value("epss", 0.0);
+        cfg.bjerrum_length = pc::bjerrumLength(j.at("epsr").number());
+        cfg.spherical_sum = j.value("spherical_sum", true);
+        const std::string scheme = j.value("ipbc", false) ? "IPBC" : j.value("ewaldscheme", "PBC");
+        if (scheme == "PBC") {
+            cfg.policy = 0;
+        }
+        else if (scheme == "PBCEigen") {
+            cfg.policy = 1;
+        }
+        else if (scheme == "IPBC" || scheme == "IPBCEigen") {
+            cfg.policy = 2;
+        }
+        else {
+            throw std::runtime_error("invalid `ewaldpolicy`");
+        }
+        fbCheck(fb_ewald_configure(dev->ctx, &cfg), dev->ctx, "fb_ewald_configure");
+        init();
+    }
+
+    /** the mirror was uploaded by the sibling's init(); rebuild k-vectors and Q(k) */
+    void init() override { fullUpdate(); }
+
+    void updateState(const Change& change) override
+    {
+        if (!change) {
+            return;
+        }
+        // the sibling non-bonded term (earlier in the Hamiltonian) has already pushed the change
+        if (!change.groups.empty() && have_old && !change.everything && !change.volume_change) {
+            FlatChange flat(change);
+            fbCheck(fb_ewald_update_partial(dev->ctx, slot, 1 - slot, &flat.change), dev->ctx,
+                    "fb_ewald_update_partial");
+        }
+        else {
+            fullUpdate();
+        }
+    }
+
+    double energy(const Change& change) override
+    {
+        if (!change) {
+            return 0.0;
+        }
+        FlatChange flat(change);
+        double u = 0.0;
+        fbCheck(fb_ewald_energy(dev->ctx, slot, &flat.change, &u), dev->ctx, "fb_ewald_energy");
+        return u;
+    }
+
+    void sync(EnergyTerm* other_term, const Change& change) override
+    {
+        auto* other = dynamic_cast<EwaldB200*>(other_term);
+        if (!other || other->dev != dev) {
+            throw std::runtime_error("sync error");
+        }
+        if (!have_old && other->state == MonteCarloState::ACCEPTED) {
+            have_old = true;
+        }
+        FlatChange flat(change);
+        fbCheck(fb_ewald_sync(dev->ctx, slot, other->slot, &flat.change), dev->ctx, "fb_ewald_sync");
+    }
+
+    void to_json(Json& j) const override
+    {
+        j["device"] = "B200 sm_100a";
+    }
+};
+
+/**
+ * ParticleSelfEnergy (src/externalpotential.cpp:94-126, 514-537) with the Coulomb scheme's
+ * per-particle self energy lB·prefactor·q²/Rc (src/potentials.cpp:1599-1604). O(changed particles)
+ * scalar work on the host; full sums are O(N) and only run with everything/volume changes.
+ */
+class ParticleSelfEnergyB200 : public EnergyTerm
+{
+    const Space& spc;
+    double prefactor; //!< lB · self_prefactor / cutoff
+
+    double groupEnergy(const Group& g) const
+    {
+        double e = 0;
+        for (size_t i = 0; i < g.size(); ++i) {
+            const double q = spc.at(g, i).charge;
+            e += prefactor * q * q;
+        }
+        return e;
+    }
+
+  public:
+    ParticleSelfEnergyB200(const Space& spc, const CoulombTable& c)
+        : spc(spc)
+        , prefactor(c.bjerrum_length * c.self_prefactor / c.cutoff)
+    {
+        name = "particle-self-energy";
+    }
+    double energy(const Change& change) override
+    {
+        double e = 0;
+        if (change.volume_change || change.everything || change.matter_change) {
+            for (const auto& g : spc.groups) {
+                e += groupEnergy(g);
+            }
+            return e;
+        }
+        for (const auto& gc : change.groups) {
+            const auto& g = spc.groups.at(gc.group_index);
+            if (gc.all) {
+                e += groupEnergy(g);
+            }
+            else {
+                for (auto i : gc.relative_atom_indices) {
+                    const double q = spc.at(g, i).charge;
+                    e += prefactor * q * q;
+                }
+            }
+        }
+        return e;
+    }
+};
+
+/** Hamiltonian term factory for the product build (order: self energy, nonbonded, ewald) */
+inline bool b200TermFactory(Hamiltonian& h, Space& spc, const std::string& name, const Json& cfg)
+{
+    if (!isNonbondedName(name)) {
+        return false;
+    }
+    auto nonbonded = std::make_shared<NonbondedB200>(name, cfg, spc);
+    const auto& tables = nonbonded->device()->tables;
+    if (tables.has_coulomb) { // CoulombGalore always defines a self energy functor (possibly zero)
+        h.push_back(std::make_shared<ParticleSelfEnergyB200>(spc, tables.coulomb));
+    }
+    h.push_back(nonbonded);
+    if (tables.ewald_json != nullptr) {
+        h.push_back(std::make_shared<EwaldB200>(*tables.ewald_json, spc, nonbonded));
+    }
+    return true;
+}
+
+/**
+ * Batched Widom insertion: all `ninsert` ghosts of one sample event are generated on the host in the
+ * reference's RNG order (they never depend on energies), evaluated in ONE launch, and exp(−ΔU) is
+ * accumulated on the host in the reference's sequential order (bit-compatible `Average`).
+ * Replaces the loop of src/analysis.cpp:1255-1262; scalar terms (self energy, container overlap)
+ * come from the host Hamiltonian terms.
+ */
+class WidomB200 : public WidomInsertion
+{
+    std::shared_ptr<NonbondedB200> nonbonded;
+    std::vector<std::shared_ptr<EnergyTerm>> other_terms;
+
+  public:
+    WidomB200(const Json& j, MetropolisMonteCarlo& mc)
+        : WidomInsertion(j, *mc.state.spc, *mc.state.pot, mc.rng.global)
+    {
+        const auto nb = mc.state.pot->find<NonbondedB200>();
+        if (nb.size() != 1) {
+            throw std::runtime_error("batched Widom needs exactly one B200 non-bonded term");
+        }
+        nonbonded = nb.front();
+        for (const auto& t : mc.state.pot->terms()) {
+            if (t != nonbonded && !std::dynamic_pointer_cast<EwaldB200>(t)) {
+                other_terms.push_back(t);
+            }
+        }
+    }
+
+    void sample() override
+    {
+        Change change;
+        last_du.clear();
+        if (!selectGhostGroup(change)) {
+            return;
+        }
+        const size_t gi = change.groups.at(0).group_index;
+        auto& group = spc.groups.at(gi);
+        const auto& mol = spc.topology->molecules[molid];
+        const int n_g = static_cast<int>(group.capacity());
+        const int B = number_of_insertions;
+        std::vector<double> xyzq(static_cast<size_t>(B) * n_g * 4), cm(static_cast<size_t>(B) * 3), host_terms(B, 0.0);
+        std::vector<int> ids(n_g);
+        group.resize(group.capacity());
+        // Ewald terms see a Q(k) without the ghost (Widom never calls updateState):
+        // their energy is the same for every insertion and is evaluated once.
+        double ewald_energy = 0.0;
+        for (const auto& t : pot.find<EwaldB200>()) {
+            ewald_energy += t->energy(change);
+        }
+        for (int b = 0; b < B; ++b) {
+            const auto particles = inserter(spc, mol, random);
+            updateGroup(group, particles);
+            for (int a = 0; a < n_g; ++a) {
+                const auto& p = spc.at(group, a);
+                const size_t o = (static_cast<size_t>(b) * n_g + a) * 4;
+                xyzq[o] = p.pos.x;
+                xyzq[o + 1] = p.pos.y;
+                xyzq[o + 2] = p.pos.z;
+                xyzq[o + 3] = p.charge;
+                ids[a] = p.id;
+            }
+            cm[3 * b] = group.mass_center.x;
+            cm[3 * b + 1] = group.mass_center.y;
+            cm[3 * b + 2] = group.mass_center.z;
+            for (const auto& t : other_terms) { // scalar host terms, in Hamiltonian order semantics
+                t->state = pot.state;
+                host_terms[b] += t->energy(change);
+            }
+        }
+        group.resize(0);
+        std::vector<double> du(B);
+        auto& dev = *nonbonded->device();
+        fbCheck(fb_widom_batch(dev.ctx, nonbonded->deviceSlot(), static_cast<int>(gi), n_g, B, xyzq.data(),
+                               ids.data(), group.isMolecular() ? cm.data() : nullptr,
+                               change.groups[0].internal ? 1 : 0, du.data()),
+                dev.ctx, "fb_widom_batch");
+        for (int b = 0; b < B; ++b) {
+            const double total = host_terms[b] + du[b] + ewald_energy;
+            last_du.push_back(total);
+            collect(total);
+        }
+    }
+};
+
+} // namespace fb

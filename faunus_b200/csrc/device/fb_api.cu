@@ -1,0 +1,1375 @@
+// Host side of the C ABI declared in include/faunus_b200.h: context, device-resident Space mirror
+// (two slots), lowering of `Change` records to launch descriptors, kernel launches.
+// One CUDA stream per context; results come back through mapped pinned memory.
+#include "../../../include/faunus_b200.h"
+#include "fb_kernels.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace fbdev;
+
+#define FB_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaError
+{
+    std::string msg;
+};
+
+#define CUDA_CHECK(expr)                                                                                      \
+    do {                                                                                                      \
+        cudaError_t err__ = (expr);                                                                           \
+        if (err__ != cudaSuccess) {                                                                           \
+            throw CudaError{std::string(#expr) + ": " + cudaGetErrorString(err__)};                          \
+        }                                                                                                     \
+    } while (0)
+
+template <class T> struct DeviceBuffer
+{
+    T* ptr = nullptr;
+    size_t count = 0;
+    void alloc(size_t n)
+    {
+        release();
+        if (n > 0) {
+            CUDA_CHECK(cudaMalloc(&ptr, n * sizeof(T)));
+        }
+        count = n;
+    }
+    void ensure(size_t n)
+    {
+        if (n > count) {
+            alloc(n + n / 4);
+        }
+    }
+    void upload(const T* src, size_t n, cudaStream_t s)
+    {
+        ensure(n);
+        if (n > 0) {
+            CUDA_CHECK(cudaMemcpyAsync(ptr, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+        }
+    }
+    void uploadVector(const std::vector<T>& v, cudaStream_t s) { upload(v.data(), v.size(), s); }
+    void release()
+    {
+        if (ptr) {
+            cudaFree(ptr);
+            ptr = nullptr;
+        }
+        count = 0;
+    }
+    ~DeviceBuffer() { release(); }
+};
+
+template <class T> struct PinnedBuffer
+{
+    T* ptr = nullptr;
+    size_t count = 0;
+    void ensure(size_t n)
+    {
+        if (n > count) {
+            if (ptr) {
+                cudaFreeHost(ptr);
+                ptr = nullptr;
+            }
+            CUDA_CHECK(cudaHostAlloc(&ptr, (n + n / 4) * sizeof(T), cudaHostAllocDefault));
+            count = n + n / 4;
+        }
+    }
+    ~PinnedBuffer()
+    {
+        if (ptr) {
+            cudaFreeHost(ptr);
+        }
+    }
+};
+
+struct Slot
+{
+    DeviceBuffer<double4> posq;
+    DeviceBuffer<int> atom_id;
+    DeviceBuffer<int> gid;
+    DeviceBuffer<double4> gcm;
+    DeviceBuffer<int> gsize;
+    double box[3] = {0, 0, 0};
+    std::vector<fb_group> groups; //!< host shadow of the group table
+    bool uploaded = false;
+    // Ewald
+    DeviceBuffer<double4> kA;
+    DeviceBuffer<double2> Q;
+    int K = 0;
+    double ewald_box[3] = {0, 0, 0};
+    bool rec_valid = false; //!< rec_sum holds Σ A_k |Q_k|² of the current Q
+    double rec_sum = 0;
+};
+
+} // namespace
+
+struct fb_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    unsigned long long launches = 0;
+
+    int n_slots = 0;
+    int n_groups = 0;
+    int periodic[3] = {1, 1, 1};
+    Slot slot[2];
+    DeviceBuffer<int> gbegin, gcap, ginfo;
+    std::vector<int> molecule_flags;
+
+    // potential tables
+    PotParams P{};
+    DeviceBuffer<unsigned> d_flags;
+    DeviceBuffer<double> d_lj_s2, d_lj_e4, d_wca_s2, d_wca_e4, d_hs_s2, d_knots, d_coef, d_g2g;
+    DeviceBuffer<int> d_lut, d_sp_offset, d_excl_offset, d_excl_natoms;
+    DeviceBuffer<double> d_sp_knots, d_sp_coef, d_sp_rmin2, d_sp_rmax2;
+    DeviceBuffer<unsigned char> d_sp_hs, d_excl;
+
+    // reductions and results
+    DeviceBuffer<double> partials;
+    DeviceBuffer<unsigned> ticket;
+    double* h_result = nullptr; //!< mapped pinned, 8 doubles
+    double* d_result = nullptr; //!< device alias of h_result
+
+    // staging
+    PinnedBuffer<int> h_list;
+    DeviceBuffer<int> d_list;
+    PinnedBuffer<int> h_upd_slot, h_upd_id;
+    PinnedBuffer<double4> h_upd_posq;
+    DeviceBuffer<int> d_upd_slot, d_upd_id;
+    DeviceBuffer<double4> d_upd_posq;
+    DeviceBuffer<double4> d_ghost, d_ghost_cm;
+    DeviceBuffer<int> d_ghost_id;
+    DeviceBuffer<double> d_widom_partial, d_widom_du;
+    PinnedBuffer<double> h_widom_du;
+    PinnedBuffer<double4> h_ghost;
+    DeviceBuffer<double> d_state;
+    PinnedBuffer<double> h_state;
+
+    // Ewald
+    bool ewald_configured = false;
+    fb_ewald_config ewald{};
+
+    // timing
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0;
+
+    int max_blocks = 148 * 4;
+};
+
+namespace {
+
+constexpr int kMaxPartialBlocks = 4096;
+
+SlotView makeView(fb_ctx* c, int s)
+{
+    Slot& sl = c->slot[s];
+    SlotView v{};
+    v.posq = sl.posq.ptr;
+    v.atom_id = sl.atom_id.ptr;
+    v.gid = sl.gid.ptr;
+    v.gcm = sl.gcm.ptr;
+    v.gsize = sl.gsize.ptr;
+    v.gbegin = c->gbegin.ptr;
+    v.gcap = c->gcap.ptr;
+    v.ginfo = c->ginfo.ptr;
+    for (int i = 0; i < 3; ++i) {
+        v.len[i] = sl.box[i];
+        v.half[i] = 0.5 * sl.box[i];
+        v.len_or_zero[i] = c->periodic[i] ? sl.box[i] : 0.0;
+    }
+    v.n_slots = c->n_slots;
+    v.n_groups = c->n_groups;
+    return v;
+}
+
+EwaldView makeEwaldView(fb_ctx* c, int s)
+{
+    EwaldView e{};
+    e.kA = c->slot[s].kA.ptr;
+    e.Q = c->slot[s].Q.ptr;
+    e.K = c->slot[s].K;
+    e.policy = c->ewald.policy;
+    return e;
+}
+
+void checkSlot(fb_ctx* c, int s, bool need_upload = true)
+{
+    if (s < 0 || s > 1) {
+        throw CudaError{"slot must be 0 (accepted) or 1 (trial)"};
+    }
+    if (need_upload && !c->slot[s].uploaded) {
+        throw CudaError{"slot has no uploaded Space (call fb_upload_space first)"};
+    }
+}
+
+void beginTiming(fb_ctx* c)
+{
+    if (c->timing) {
+        CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+    }
+}
+
+/** Wait for the stream; collects kernel time when timing is on */
+void finish(fb_ctx* c)
+{
+    if (c->timing) {
+        CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->timing) {
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->last_ms = ms;
+    }
+}
+
+void launched(fb_ctx* c, const char* what)
+{
+    c->launches++;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        throw CudaError{std::string(what) + " launch: " + cudaGetErrorString(err)};
+    }
+}
+
+template <class F> int guarded(fb_ctx* c, F&& f)
+{
+    try {
+        if (c == nullptr) {
+            return FB_ERR_INVALID;
+        }
+        CUDA_CHECK(cudaSetDevice(c->device));
+        f();
+        return FB_OK;
+    }
+    catch (const CudaError& e) {
+        c->last_error = e.msg;
+        return (e.msg.find("cuda") == 0) ? FB_ERR_CUDA : FB_ERR_INVALID;
+    }
+    catch (const std::exception& e) {
+        c->last_error = e.what();
+        return FB_ERR_INVALID;
+    }
+}
+
+/**
+ * Lower a partial Change to the moved-atom list (GroupPairing::accumulate dispatch,
+ * src/energy.h:1447-1475 and accumulateGroup :1347-1377): one group → by the number of indices
+ * (1, none = all, subset); several groups → all active atoms of each, no internal pairs.
+ * `for_ewald` follows PolicyIonIon::updateComplex (src/energy.cpp:228-235): `all` → iota(max size).
+ */
+MovedDesc lowerChange(fb_ctx* c, int slot_a, int slot_b, const fb_change* change, bool for_ewald)
+{
+    if (change->n_groups <= 0) {
+        throw CudaError{"change lists no groups"};
+    }
+    if (change->n_groups > kMaxMovedGroups) {
+        throw CudaError{"too many changed groups in one Change (max 16)"};
+    }
+    MovedDesc md{};
+    md.n_groups = change->n_groups;
+    std::vector<int> slots, gpos;
+    const auto& ga = c->slot[slot_a].groups;
+    const auto& gb = c->slot[slot_b].groups;
+    const bool multi = change->n_groups > 1 && !for_ewald;
+    md.all_moved = 1;
+    for (int t = 0; t < change->n_groups; ++t) {
+        const fb_group_change& gc = change->groups[t];
+        if (gc.group_index < 0 || gc.group_index >= c->n_groups) {
+            throw CudaError{"group index out of range"};
+        }
+        md.groups[t] = gc.group_index;
+        const fb_group& g = ga[gc.group_index];
+        bool take_all;
+        int count;
+        if (for_ewald) {
+            take_all = gc.all != 0 && c->ewald.policy != 2;
+            count = std::max(g.size, gb[gc.group_index].size);
+        }
+        else {
+            take_all = multi || gc.n_atoms == 0;
+            count = g.size;
+        }
+        if (take_all) {
+            for (int i = 0; i < count; ++i) {
+                slots.push_back(g.begin + i);
+                gpos.push_back(t);
+            }
+        }
+        else {
+            md.all_moved = 0;
+            for (int i = 0; i < gc.n_atoms; ++i) {
+                if (gc.atoms[i] < 0 || gc.atoms[i] >= g.capacity) {
+                    throw CudaError{"relative atom index out of range"};
+                }
+                slots.push_back(g.begin + gc.atoms[i]);
+                gpos.push_back(t);
+            }
+        }
+    }
+    md.internal = (!multi && change->groups[0].internal) ? 1 : 0;
+    md.n_moved = static_cast<int>(slots.size());
+    if (md.n_moved <= kInlineMoved) {
+        md.list = nullptr;
+        for (int i = 0; i < md.n_moved; ++i) {
+            md.inline_slot[i] = slots[i];
+            md.inline_gpos[i] = gpos[i];
+        }
+    }
+    else {
+        CUDA_CHECK(cudaStreamSynchronize(c->stream)); // staging buffer reuse
+        c->h_list.ensure(2 * slots.size());
+        std::copy(slots.begin(), slots.end(), c->h_list.ptr);
+        std::copy(gpos.begin(), gpos.end(), c->h_list.ptr + slots.size());
+        c->d_list.upload(c->h_list.ptr, 2 * slots.size(), c->stream);
+        md.list = c->d_list.ptr;
+    }
+    return md;
+}
+
+int gridFor(fb_ctx* c, int n, int block)
+{
+    return std::max(1, std::min((n + block - 1) / block, c->max_blocks));
+}
+
+template <bool FUSED> void launchMoved(fb_ctx* c, const SlotView& A, const SlotView& B, const MovedDesc& md)
+{
+    const int grid = gridFor(c, c->n_slots, kBlock);
+#define FB_CASE(K)                                                                                            \
+    case K:                                                                                                   \
+        movedEnergyKernel<K, FUSED><<<grid, kBlock, 0, c->stream>>>(A, B, c->P, md, c->partials.ptr,          \
+                                                                   c->ticket.ptr, c->d_result);               \
+        break;
+    switch (c->P.kind) {
+        FB_CASE(POT_COULOMB_LJ)
+        FB_CASE(POT_COULOMB_WCA)
+        FB_CASE(POT_PM)
+        FB_CASE(POT_PMWCA)
+        FB_CASE(POT_FUNCTOR)
+        FB_CASE(POT_SPLINED)
+    default:
+        throw CudaError{"unknown potential kind"};
+    }
+#undef FB_CASE
+    launched(c, "movedEnergyKernel");
+}
+
+void launchFull(fb_ctx* c, const SlotView& V, int volume_predicate)
+{
+    const int nt = (c->n_slots + kTile - 1) / kTile;
+    const size_t npart = static_cast<size_t>(nt) * (nt + 1) / 2;
+    c->partials.ensure(std::max<size_t>(npart, 4 * kMaxPartialBlocks));
+    dim3 grid(nt, nt);
+#define FB_CASE(K)                                                                                            \
+    case K:                                                                                                   \
+        fullEnergyKernel<K><<<grid, kTile, 0, c->stream>>>(V, c->P, volume_predicate, c->partials.ptr);       \
+        break;
+    switch (c->P.kind) {
+        FB_CASE(POT_COULOMB_LJ)
+        FB_CASE(POT_COULOMB_WCA)
+        FB_CASE(POT_PM)
+        FB_CASE(POT_PMWCA)
+        FB_CASE(POT_FUNCTOR)
+        FB_CASE(POT_SPLINED)
+    default:
+        throw CudaError{"unknown potential kind"};
+    }
+#undef FB_CASE
+    launched(c, "fullEnergyKernel");
+    orderedSumKernel<<<1, 1024, 0, c->stream>>>(c->partials.ptr, npart, 1, c->d_result);
+    launched(c, "orderedSumKernel");
+}
+
+/** PolicyIonIon::updateBox / PolicyIonIonIPBC::updateBox, src/energy.cpp:133-186, 356-412 */
+void generateKVectors(const fb_ewald_config& cfg, const double box[3], std::vector<double4>& kA)
+{
+    kA.clear();
+    const bool ipbc = cfg.policy == 2;
+    const int ncc = static_cast<int>(std::ceil(cfg.n_cutoff));
+    const double pi = 3.141592653589793238462643383279502884;
+    const double lmax = std::max(box[0], std::max(box[1], box[2]));
+    const double check_k2_zero = 0.1 * std::pow(2 * pi / lmax, 2);
+    const long k_vector_size = static_cast<long>(2 * ncc + 1) * (2 * ncc + 1) * (2 * ncc + 1) - 1;
+    if (k_vector_size == 0) {
+        kA.push_back(make_double4(1, 0, 0, 0));
+        return;
+    }
+    const double nc2 = cfg.n_cutoff * cfg.n_cutoff;
+    const double kappa2 = cfg.kappa * cfg.kappa;
+    const int start_value = ipbc ? 0 : 1;
+    for (int nx = 0; nx <= ncc; nx++) {
+        const double dnx2 = static_cast<double>(nx * nx);
+        const double xfactor = (nx > 0) ? 2.0 : 1.0;
+        for (int ny = -ncc * start_value; ny <= ncc; ny++) {
+            const double dny2 = static_cast<double>(ny * ny);
+            const double yfactor = (ny > 0) ? 2.0 : 1.0;
+            for (int nz = -ncc * start_value; nz <= ncc; nz++) {
+                double factor = xfactor;
+                if (ipbc) {
+                    factor = xfactor * yfactor;
+                    if (nz > 0) {
+                        factor *= 2;
+                    }
+                }
+                const double kx = 2 * pi * nx / box[0];
+                const double ky = 2 * pi * ny / box[1];
+                const double kz = 2 * pi * nz / box[2];
+                const double k2 = kx * kx + ky * ky + kz * kz + kappa2;
+                if (k2 < check_k2_zero) {
+                    continue;
+                }
+                if (cfg.spherical_sum) {
+                    const double dnz2 = static_cast<double>(nz * nz);
+                    if ((dnx2 + dny2 + dnz2) / nc2 > 1) {
+                        continue;
+                    }
+                }
+                kA.push_back(make_double4(kx, ky, kz, factor * std::exp(-k2 / (4 * cfg.alpha * cfg.alpha)) / k2));
+            }
+        }
+    }
+}
+
+template <class T> void copyTable(DeviceBuffer<T>& dst, const T* src, size_t n, cudaStream_t s, const T** out)
+{
+    if (src == nullptr) {
+        *out = nullptr;
+        return;
+    }
+    dst.upload(src, n, s);
+    *out = dst.ptr;
+}
+
+} // namespace
+
+// =================================================================================================
+// life cycle
+// =================================================================================================
+FB_API int fb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+FB_API const char* fb_last_error(const fb_ctx* ctx)
+{
+    return ctx ? ctx->last_error.c_str() : g_create_error.c_str();
+}
+
+FB_API int fb_create(const fb_config* cfg, fb_ctx** out)
+{
+    if (cfg == nullptr || out == nullptr) {
+        g_create_error = "null argument";
+        return FB_ERR_INVALID;
+    }
+    *out = nullptr;
+    fb_ctx* c = nullptr;
+    try {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            g_create_error = "no CUDA device: libfaunus_b200 has no CPU fallback";
+            return FB_ERR_CUDA;
+        }
+        if (cfg->device < 0 || cfg->device >= ndev) {
+            g_create_error = "device ordinal out of range";
+            return FB_ERR_INVALID;
+        }
+        if (cfg->n_atom_types <= 0 || cfg->n_molecule_types <= 0) {
+            g_create_error = "need at least one atom type and one molecule type";
+            return FB_ERR_INVALID;
+        }
+        c = new fb_ctx();
+        c->device = cfg->device;
+        CUDA_CHECK(cudaSetDevice(c->device));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreate(&c->ev0));
+        CUDA_CHECK(cudaEventCreate(&c->ev1));
+        cudaDeviceProp prop{};
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, c->device));
+        c->max_blocks = std::min(prop.multiProcessorCount * 4, kMaxPartialBlocks);
+        CUDA_CHECK(cudaHostAlloc(&c->h_result, 8 * sizeof(double), cudaHostAllocMapped));
+        CUDA_CHECK(cudaHostGetDevicePointer(&c->d_result, c->h_result, 0));
+        c->partials.alloc(4 * kMaxPartialBlocks);
+        c->ticket.alloc(1);
+        CUDA_CHECK(cudaMemsetAsync(c->ticket.ptr, 0, sizeof(unsigned), c->stream));
+
+        for (int i = 0; i < 3; ++i) {
+            c->periodic[i] = cfg->periodic[i];
+            c->slot[0].box[i] = c->slot[1].box[i] = cfg->box[i];
+        }
+        const size_t T2 = static_cast<size_t>(cfg->n_atom_types) * cfg->n_atom_types;
+        const size_t M = static_cast<size_t>(cfg->n_molecule_types);
+        PotParams& P = c->P;
+        P.kind = cfg->kind;
+        P.n_types = cfg->n_atom_types;
+        P.n_mol = cfg->n_molecule_types;
+        cudaStream_t s = c->stream;
+        copyTable(c->d_flags, reinterpret_cast<const unsigned*>(cfg->pair_flags), T2, s, &P.flags);
+        copyTable(c->d_lj_s2, cfg->lj_sigma2, T2, s, &P.lj_s2);
+        copyTable(c->d_lj_e4, cfg->lj_eps4, T2, s, &P.lj_e4);
+        copyTable(c->d_wca_s2, cfg->wca_sigma2, T2, s, &P.wca_s2);
+        copyTable(c->d_wca_e4, cfg->wca_eps4, T2, s, &P.wca_e4);
+        copyTable(c->d_hs_s2, cfg->hs_sigma2, T2, s, &P.hs_s2);
+        P.lB = cfg->coulomb_bjerrum_length;
+        P.Rc = cfg->coulomb_cutoff;
+        P.invRc = cfg->coulomb_cutoff > 0 ? 1.0 / cfg->coulomb_cutoff : 0.0;
+        P.kappa = cfg->coulomb_kappa;
+        P.lB_plain = cfg->plain_bjerrum_length;
+        P.nk = cfg->coulomb_n_knots;
+        const bool needs_spline_coulomb =
+            cfg->kind == FB_POT_COULOMB_LJ || cfg->kind == FB_POT_COULOMB_WCA ||
+            (cfg->pair_flags && std::any_of(cfg->pair_flags, cfg->pair_flags + T2,
+                                            [](uint32_t f) { return f & FB_TERM_COULOMB_SPLINED; }));
+        if (needs_spline_coulomb) {
+            if (cfg->coulomb_n_knots < 2 || !cfg->coulomb_knots || !cfg->coulomb_coeffs) {
+                throw CudaError{"splined Coulomb requires the S(q) table"};
+            }
+            const int nk = cfg->coulomb_n_knots;
+            copyTable(c->d_knots, cfg->coulomb_knots, static_cast<size_t>(nk), s, &P.knots);
+            // pad the coefficient table with one block so that index nk-1 is addressable
+            std::vector<double> coef(cfg->coulomb_coeffs, cfg->coulomb_coeffs + 6 * (nk - 1));
+            coef.resize(6 * nk, 0.0);
+            c->d_coef.uploadVector(coef, s);
+            P.coef = c->d_coef.ptr;
+            // bucket start index: (#knots < b/nlut) − 1, clamped to 0
+            const int nlut = 256;
+            std::vector<int> lut(nlut);
+            for (int b = 0; b < nlut; ++b) {
+                const double x = static_cast<double>(b) / nlut;
+                int cnt = 0;
+                while (cnt < nk && cfg->coulomb_knots[cnt] < x) {
+                    ++cnt;
+                }
+                lut[b] = std::max(0, cnt - 1);
+            }
+            c->d_lut.uploadVector(lut, s);
+            P.lut = c->d_lut.ptr;
+            P.nlut = nlut;
+        }
+        const bool functor_like = cfg->kind == FB_POT_FUNCTOR || cfg->kind == FB_POT_SPLINED;
+        if (functor_like && cfg->pair_flags == nullptr) {
+            throw CudaError{"functor / splined potentials require pair_flags"};
+        }
+        auto need = [&](const void* p, const char* what) {
+            if (p == nullptr) {
+                throw CudaError{std::string("missing table: ") + what};
+            }
+        };
+        if (cfg->kind == FB_POT_COULOMB_LJ) {
+            need(cfg->lj_sigma2, "lj_sigma2");
+            need(cfg->lj_eps4, "lj_eps4");
+        }
+        if (cfg->kind == FB_POT_COULOMB_WCA || cfg->kind == FB_POT_PMWCA) {
+            need(cfg->wca_sigma2, "wca_sigma2");
+            need(cfg->wca_eps4, "wca_eps4");
+        }
+        if (cfg->kind == FB_POT_PM) {
+            need(cfg->hs_sigma2, "hs_sigma2");
+        }
+        if (functor_like) {
+            for (size_t t = 0; t < T2; ++t) {
+                const uint32_t f = cfg->pair_flags[t];
+                if ((f & FB_TERM_LJ) && (!cfg->lj_sigma2 || !cfg->lj_eps4)) {
+                    throw CudaError{"pair_flags request LJ without tables"};
+                }
+                if ((f & FB_TERM_WCA) && (!cfg->wca_sigma2 || !cfg->wca_eps4)) {
+                    throw CudaError{"pair_flags request WCA without tables"};
+                }
+                if ((f & FB_TERM_HARDSPHERE) && !cfg->hs_sigma2) {
+                    throw CudaError{"pair_flags request hard spheres without table"};
+                }
+            }
+        }
+        if (cfg->kind == FB_POT_SPLINED) {
+            need(cfg->spline_offset, "spline_offset");
+            need(cfg->spline_knots, "spline_knots");
+            need(cfg->spline_coeffs, "spline_coeffs");
+            const int total = cfg->spline_offset[T2];
+            copyTable(c->d_sp_offset, cfg->spline_offset, T2 + 1, s, &P.sp_offset);
+            copyTable(c->d_sp_knots, cfg->spline_knots, static_cast<size_t>(total), s, &P.sp_knots);
+            // re-block coefficients per knot index: interval k of pair p lives at 6*(offset[p]+k)
+            std::vector<double> coef(6 * static_cast<size_t>(total), 0.0);
+            size_t src = 0;
+            for (size_t p = 0; p < T2; ++p) {
+                const int first = cfg->spline_offset[p];
+                const int nk = cfg->spline_offset[p + 1] - first;
+                for (int k = 0; k + 1 < nk; ++k) {
+                    for (int i = 0; i < 6; ++i) {
+                        coef[6 * (static_cast<size_t>(first) + k) + i] = cfg->spline_coeffs[src++];
+                    }
+                }
+            }
+            c->d_sp_coef.uploadVector(coef, s);
+            P.sp_coef = c->d_sp_coef.ptr;
+            copyTable(c->d_sp_rmin2, cfg->spline_rmin2, T2, s, &P.sp_rmin2);
+            copyTable(c->d_sp_rmax2, cfg->spline_rmax2, T2, s, &P.sp_rmax2);
+            copyTable(c->d_sp_hs, cfg->spline_hardsphere, T2, s, &P.sp_hs);
+        }
+        // molecules
+        need(cfg->molecule_flags, "molecule_flags");
+        c->molecule_flags.assign(cfg->molecule_flags, cfg->molecule_flags + M);
+        std::vector<double> g2g(M * M, DBL_MAX);
+        if (cfg->g2g_cutoff_squared) {
+            g2g.assign(cfg->g2g_cutoff_squared, cfg->g2g_cutoff_squared + M * M);
+        }
+        c->d_g2g.uploadVector(g2g, s);
+        P.g2g_cut2 = c->d_g2g.ptr;
+        std::vector<int> excl_offset(M, -1), excl_natoms(M, 0);
+        std::vector<unsigned char> excl;
+        for (size_t m = 0; m < M; ++m) {
+            const int n = cfg->molecule_natoms ? cfg->molecule_natoms[m] : 0;
+            excl_natoms[m] = n;
+            if (cfg->exclusions && cfg->exclusions[m] && n > 0) {
+                excl_offset[m] = static_cast<int>(excl.size());
+                excl.insert(excl.end(), cfg->exclusions[m], cfg->exclusions[m] + static_cast<size_t>(n) * n);
+            }
+        }
+        if (excl.empty()) {
+            excl.push_back(0);
+        }
+        c->d_excl_offset.uploadVector(excl_offset, s);
+        c->d_excl_natoms.uploadVector(excl_natoms, s);
+        c->d_excl.uploadVector(excl, s);
+        P.excl_offset = c->d_excl_offset.ptr;
+        P.excl_natoms = c->d_excl_natoms.ptr;
+        P.excl = c->d_excl.ptr;
+        P.any_molecular = 1; // refined at upload time
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        *out = c;
+        return FB_OK;
+    }
+    catch (const CudaError& e) {
+        g_create_error = e.msg;
+        delete c;
+        return FB_ERR_CUDA;
+    }
+    catch (const std::exception& e) {
+        g_create_error = e.what();
+        delete c;
+        return FB_ERR_INVALID;
+    }
+}
+
+FB_API void fb_destroy(fb_ctx* c)
+{
+    if (c == nullptr) {
+        return;
+    }
+    cudaSetDevice(c->device);
+    if (c->stream) {
+        cudaStreamSynchronize(c->stream);
+    }
+    if (c->h_result) {
+        cudaFreeHost(c->h_result);
+    }
+    if (c->ev0) {
+        cudaEventDestroy(c->ev0);
+    }
+    if (c->ev1) {
+        cudaEventDestroy(c->ev1);
+    }
+    cudaStream_t s = c->stream;
+    delete c;
+    if (s) {
+        cudaStreamDestroy(s);
+    }
+}
+
+FB_API unsigned long long fb_launch_count(const fb_ctx* c)
+{
+    return c ? c->launches : 0;
+}
+
+FB_API void* fb_stream(const fb_ctx* c)
+{
+    return c ? static_cast<void*>(c->stream) : nullptr;
+}
+
+FB_API int fb_enable_timing(fb_ctx* c, int on)
+{
+    if (!c) {
+        return FB_ERR_INVALID;
+    }
+    c->timing = on != 0;
+    return FB_OK;
+}
+
+FB_API double fb_last_kernel_ms(const fb_ctx* c)
+{
+    return c ? c->last_ms : 0.0;
+}
+
+// =================================================================================================
+// Space mirror
+// =================================================================================================
+FB_API int fb_upload_space(fb_ctx* c, int s, const double* xyzq, const int* atom_id, const fb_group* groups,
+                           int n_particles, int n_groups)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s, false);
+        if (n_particles <= 0 || n_groups <= 0 || !xyzq || !atom_id || !groups) {
+            throw CudaError{"empty space"};
+        }
+        if (c->n_slots != 0 && (c->n_slots != n_particles || c->n_groups != n_groups)) {
+            throw CudaError{"particle / group count differs from the first upload"};
+        }
+        int expect = 0;
+        bool any_molecular = false;
+        for (int g = 0; g < n_groups; ++g) {
+            if (groups[g].begin != expect || groups[g].size > groups[g].capacity || groups[g].size < 0) {
+                throw CudaError{"groups must tile the particle array"};
+            }
+            if (groups[g].molid < 0 || groups[g].molid >= c->P.n_mol) {
+                throw CudaError{"molecule id out of range"};
+            }
+            expect += groups[g].capacity;
+            any_molecular |= !(c->molecule_flags[groups[g].molid] & FB_MOL_ATOMIC);
+        }
+        if (expect != n_particles) {
+            throw CudaError{"groups must tile the particle array"};
+        }
+        for (int i = 0; i < n_particles; ++i) {
+            if (atom_id[i] < 0 || atom_id[i] >= c->P.n_types) {
+                throw CudaError{"atom id out of range"};
+            }
+        }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->n_slots = n_particles;
+        c->n_groups = n_groups;
+        c->P.any_molecular = any_molecular ? 1 : 0;
+        Slot& sl = c->slot[s];
+        sl.groups.assign(groups, groups + n_groups);
+        std::vector<int> gbegin(n_groups), gcap(n_groups), ginfo(n_groups), gsize(n_groups);
+        std::vector<double4> gcm(n_groups);
+        for (int g = 0; g < n_groups; ++g) {
+            gbegin[g] = groups[g].begin;
+            gcap[g] = groups[g].capacity;
+            gsize[g] = groups[g].size;
+            ginfo[g] = (groups[g].molid << 8) | c->molecule_flags[groups[g].molid];
+            gcm[g] = make_double4(groups[g].cm[0], groups[g].cm[1], groups[g].cm[2], 0.0);
+        }
+        c->gbegin.uploadVector(gbegin, c->stream);
+        c->gcap.uploadVector(gcap, c->stream);
+        c->ginfo.uploadVector(ginfo, c->stream);
+        sl.gsize.uploadVector(gsize, c->stream);
+        sl.gcm.uploadVector(gcm, c->stream);
+        sl.posq.upload(reinterpret_cast<const double4*>(xyzq), n_particles, c->stream);
+        sl.atom_id.upload(atom_id, n_particles, c->stream);
+        sl.gid.ensure(n_particles);
+        sl.uploaded = true;
+        buildGidKernel<<<n_groups, 128, 0, c->stream>>>(makeView(c, s));
+        launched(c, "buildGidKernel");
+        CUDA_CHECK(cudaStreamSynchronize(c->stream)); // host vectors above go out of scope
+        sl.rec_valid = false;
+    });
+}
+
+FB_API int fb_update_group(fb_ctx* c, int s, int group_index, const fb_group* record, int n_atoms,
+                           const int* rel_index, const double* xyzq, const int* atom_id)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s);
+        if (group_index < 0 || group_index >= c->n_groups || !record) {
+            throw CudaError{"group index out of range"};
+        }
+        Slot& sl = c->slot[s];
+        fb_group& g = sl.groups[group_index];
+        if (record->begin != g.begin || record->capacity != g.capacity || record->molid != g.molid ||
+            record->size < 0 || record->size > g.capacity) {
+            throw CudaError{"group record does not match the uploaded layout"};
+        }
+        if (n_atoms < 0 || n_atoms > g.capacity || (n_atoms > 0 && (!xyzq || !atom_id))) {
+            throw CudaError{"bad particle update"};
+        }
+        g = *record;
+        InlineUpdate upd{};
+        int n_staged = 0;
+        auto slot_of = [&](int i) {
+            const int rel = rel_index ? rel_index[i] : i;
+            if (rel < 0 || rel >= g.capacity) {
+                throw CudaError{"relative atom index out of range"};
+            }
+            return g.begin + rel;
+        };
+        if (n_atoms <= kInlineUpdate) {
+            upd.n = n_atoms;
+            for (int i = 0; i < n_atoms; ++i) {
+                upd.slot[i] = slot_of(i);
+                upd.id[i] = atom_id[i];
+                upd.posq[i] = make_double4(xyzq[4 * i], xyzq[4 * i + 1], xyzq[4 * i + 2], xyzq[4 * i + 3]);
+            }
+        }
+        else {
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            n_staged = n_atoms;
+            c->h_upd_slot.ensure(n_atoms);
+            c->h_upd_id.ensure(n_atoms);
+            c->h_upd_posq.ensure(n_atoms);
+            for (int i = 0; i < n_atoms; ++i) {
+                c->h_upd_slot.ptr[i] = slot_of(i);
+                c->h_upd_id.ptr[i] = atom_id[i];
+                c->h_upd_posq.ptr[i] =
+                    make_double4(xyzq[4 * i], xyzq[4 * i + 1], xyzq[4 * i + 2], xyzq[4 * i + 3]);
+            }
+            c->d_upd_slot.upload(c->h_upd_slot.ptr, n_atoms, c->stream);
+            c->d_upd_id.upload(c->h_upd_id.ptr, n_atoms, c->stream);
+            c->d_upd_posq.upload(c->h_upd_posq.ptr, n_atoms, c->stream);
+        }
+        const int work = std::max(g.capacity, n_atoms);
+        const int grid = std::max(1, std::min((work + 255) / 256, 64));
+        updateGroupKernel<<<grid, 256, 0, c->stream>>>(
+            makeView(c, s), group_index, g.begin, g.capacity, g.size,
+            make_double4(g.cm[0], g.cm[1], g.cm[2], 0.0), upd, n_staged, c->d_upd_slot.ptr, c->d_upd_id.ptr,
+            c->d_upd_posq.ptr);
+        launched(c, "updateGroupKernel");
+        sl.rec_valid = sl.rec_valid; // Q is unaffected until fb_ewald_update_*
+    });
+}
+
+FB_API int fb_set_box(fb_ctx* c, int s, const double box[3])
+{
+    return guarded(c, [&] {
+        checkSlot(c, s, false);
+        for (int i = 0; i < 3; ++i) {
+            c->slot[s].box[i] = box[i];
+        }
+    });
+}
+
+FB_API int fb_sync(fb_ctx* c, int dst, int src, const fb_change* change)
+{
+    return guarded(c, [&] {
+        checkSlot(c, dst, false);
+        checkSlot(c, src);
+        if (dst == src || !change) {
+            throw CudaError{"bad sync arguments"};
+        }
+        Slot& d = c->slot[dst];
+        Slot& sr = c->slot[src];
+        if (change->everything || change->volume_change) {
+            for (int i = 0; i < 3; ++i) {
+                d.box[i] = sr.box[i];
+            }
+        }
+        if (change->everything || !d.uploaded) {
+            const size_t n = c->n_slots;
+            const size_t g = c->n_groups;
+            d.posq.ensure(n);
+            d.atom_id.ensure(n);
+            d.gid.ensure(n);
+            d.gcm.ensure(g);
+            d.gsize.ensure(g);
+            CUDA_CHECK(cudaMemcpyAsync(d.posq.ptr, sr.posq.ptr, n * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_CHECK(cudaMemcpyAsync(d.atom_id.ptr, sr.atom_id.ptr, n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_CHECK(cudaMemcpyAsync(d.gid.ptr, sr.gid.ptr, n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_CHECK(cudaMemcpyAsync(d.gcm.ptr, sr.gcm.ptr, g * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_CHECK(cudaMemcpyAsync(d.gsize.ptr, sr.gsize.ptr, g * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+            d.groups = sr.groups;
+            d.uploaded = true;
+            return;
+        }
+        if (change->n_groups == 0) {
+            return;
+        }
+        if (change->n_groups > kMaxMovedGroups) {
+            throw CudaError{"too many changed groups in one Change (max 16)"};
+        }
+        SyncDesc sd{};
+        sd.n_groups = change->n_groups;
+        std::vector<int> slots;
+        for (int t = 0; t < change->n_groups; ++t) {
+            const fb_group_change& gc = change->groups[t];
+            if (gc.group_index < 0 || gc.group_index >= c->n_groups) {
+                throw CudaError{"group index out of range"};
+            }
+            sd.group[t] = gc.group_index;
+            sd.whole[t] = gc.all ? 1 : 0;
+            const fb_group& g = sr.groups[gc.group_index];
+            if (!gc.all) {
+                for (int i = 0; i < gc.n_atoms; ++i) {
+                    if (gc.atoms[i] < 0 || gc.atoms[i] >= g.capacity) {
+                        throw CudaError{"relative atom index out of range"};
+                    }
+                    slots.push_back(g.begin + gc.atoms[i]);
+                }
+            }
+            d.groups[gc.group_index] = g;
+        }
+        sd.n_slots = static_cast<int>(slots.size());
+        int work = sd.n_slots;
+        for (int t = 0; t < sd.n_groups; ++t) {
+            work = std::max(work, sr.groups[sd.group[t]].capacity);
+        }
+        if (sd.n_slots <= kInlineMoved) {
+            sd.slots = nullptr;
+            std::copy(slots.begin(), slots.end(), sd.inline_slots);
+        }
+        else {
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            c->h_list.ensure(slots.size());
+            std::copy(slots.begin(), slots.end(), c->h_list.ptr);
+            c->d_list.upload(c->h_list.ptr, slots.size(), c->stream);
+            sd.slots = c->d_list.ptr;
+        }
+        const int grid = std::max(1, std::min((work + 255) / 256, 64));
+        syncGroupsKernel<<<grid, 256, 0, c->stream>>>(makeView(c, dst), makeView(c, src), sd);
+        launched(c, "syncGroupsKernel");
+    });
+}
+
+FB_API int fb_download_space(fb_ctx* c, int s, double* xyzq, int* atom_id, fb_group* groups)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s);
+        Slot& sl = c->slot[s];
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (xyzq) {
+            CUDA_CHECK(cudaMemcpy(xyzq, sl.posq.ptr, c->n_slots * sizeof(double4), cudaMemcpyDeviceToHost));
+        }
+        if (atom_id) {
+            CUDA_CHECK(cudaMemcpy(atom_id, sl.atom_id.ptr, c->n_slots * sizeof(int), cudaMemcpyDeviceToHost));
+        }
+        if (groups) {
+            std::vector<double4> gcm(c->n_groups);
+            std::vector<int> gsize(c->n_groups);
+            CUDA_CHECK(cudaMemcpy(gcm.data(), sl.gcm.ptr, c->n_groups * sizeof(double4), cudaMemcpyDeviceToHost));
+            CUDA_CHECK(cudaMemcpy(gsize.data(), sl.gsize.ptr, c->n_groups * sizeof(int), cudaMemcpyDeviceToHost));
+            for (int g = 0; g < c->n_groups; ++g) {
+                groups[g] = sl.groups[g];
+                groups[g].size = gsize[g];
+                groups[g].cm[0] = gcm[g].x;
+                groups[g].cm[1] = gcm[g].y;
+                groups[g].cm[2] = gcm[g].z;
+            }
+        }
+    });
+}
+
+// =================================================================================================
+// non-bonded energy
+// =================================================================================================
+FB_API int fb_nonbonded_energy(fb_ctx* c, int s, const fb_change* change, double* energy)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s);
+        if (!change || !energy) {
+            throw CudaError{"null argument"};
+        }
+        beginTiming(c);
+        if (change->everything || change->volume_change) {
+            launchFull(c, makeView(c, s), (!change->everything && change->volume_change) ? 1 : 0);
+        }
+        else {
+            if (change->n_groups == 0) {
+                *energy = 0.0;
+                return;
+            }
+            const MovedDesc md = lowerChange(c, s, s, change, false);
+            if (md.n_moved == 0) {
+                *energy = 0.0;
+                return;
+            }
+            const SlotView V = makeView(c, s);
+            launchMoved<false>(c, V, V, md);
+        }
+        finish(c);
+        *energy = c->h_result[0];
+    });
+}
+
+FB_API int fb_nonbonded_delta(fb_ctx* c, int s_new, int s_old, const fb_change* change, double* u_new,
+                              double* u_old)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s_new);
+        checkSlot(c, s_old);
+        if (!change || !u_new || !u_old || s_new == s_old) {
+            throw CudaError{"bad arguments"};
+        }
+        beginTiming(c);
+        if (change->everything || change->volume_change) {
+            const int pred = (!change->everything && change->volume_change) ? 1 : 0;
+            launchFull(c, makeView(c, s_new), pred);
+            finish(c);
+            *u_new = c->h_result[0];
+            launchFull(c, makeView(c, s_old), pred);
+            finish(c);
+            *u_old = c->h_result[0];
+            return;
+        }
+        if (change->n_groups == 0) {
+            *u_new = *u_old = 0.0;
+            return;
+        }
+        const MovedDesc md = lowerChange(c, s_new, s_old, change, false);
+        if (md.n_moved == 0) {
+            *u_new = *u_old = 0.0;
+            return;
+        }
+        launchMoved<true>(c, makeView(c, s_new), makeView(c, s_old), md);
+        finish(c);
+        *u_new = c->h_result[0];
+        *u_old = c->h_result[1];
+    });
+}
+
+// =================================================================================================
+// Ewald
+// =================================================================================================
+FB_API int fb_ewald_configure(fb_ctx* c, const fb_ewald_config* cfg)
+{
+    return guarded(c, [&] {
+        if (!cfg || cfg->alpha <= 0 || cfg->policy < 0 || cfg->policy > 2) {
+            throw CudaError{"bad Ewald configuration"};
+        }
+        c->ewald = *cfg;
+        c->ewald_configured = true;
+    });
+}
+
+FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s, false);
+        if (!c->ewald_configured) {
+            throw CudaError{"Ewald not configured"};
+        }
+        Slot& sl = c->slot[s];
+        std::vector<double4> kA;
+        generateKVectors(c->ewald, sl.box, kA);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        sl.kA.upload(kA.data(), kA.size(), c->stream);
+        sl.Q.ensure(kA.size());
+        sl.K = static_cast<int>(kA.size());
+        for (int i = 0; i < 3; ++i) {
+            sl.ewald_box[i] = sl.box[i];
+        }
+        sl.rec_valid = false;
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (n_kvectors) {
+            *n_kvectors = sl.K;
+        }
+    });
+}
+
+FB_API int fb_ewald_update_full(fb_ctx* c, int s)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s);
+        Slot& sl = c->slot[s];
+        if (sl.K <= 0) {
+            throw CudaError{"no k-vectors (call fb_ewald_update_box first)"};
+        }
+        const int grid = (sl.K + kEwaldBlock - 1) / kEwaldBlock;
+        ewaldFullKernel<<<grid, kEwaldBlock, 0, c->stream>>>(makeView(c, s), makeEwaldView(c, s));
+        launched(c, "ewaldFullKernel");
+        sl.rec_valid = false;
+    });
+}
+
+FB_API int fb_ewald_update_partial(fb_ctx* c, int s_new, int s_old, const fb_change* change)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s_new);
+        checkSlot(c, s_old);
+        if (!change || s_new == s_old) {
+            throw CudaError{"bad arguments"};
+        }
+        Slot& sn = c->slot[s_new];
+        Slot& so = c->slot[s_old];
+        if (sn.K <= 0 || sn.K != so.K) {
+            throw CudaError{"k-vector sets of the two slots differ; use a full update"};
+        }
+        const MovedDesc md = lowerChange(c, s_new, s_old, change, true);
+        const int grid = (sn.K + kBlock - 1) / kBlock;
+        if (grid > kMaxPartialBlocks * 4) {
+            c->partials.ensure(static_cast<size_t>(grid));
+        }
+        beginTiming(c);
+        ewaldPartialKernel<<<grid, kBlock, 0, c->stream>>>(makeView(c, s_new), makeView(c, s_old),
+                                                           makeEwaldView(c, s_new), makeEwaldView(c, s_old), md,
+                                                           c->partials.ptr, c->ticket.ptr, c->d_result + 4);
+        launched(c, "ewaldPartialKernel");
+        finish(c);
+        sn.rec_sum = c->h_result[4];
+        sn.rec_valid = true;
+    });
+}
+
+FB_API int fb_ewald_energy(fb_ctx* c, int s, const fb_change* change, double* energy)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s);
+        if (!energy) {
+            throw CudaError{"null argument"};
+        }
+        const bool empty = !change || (!change->everything && !change->volume_change && change->n_groups == 0);
+        if (empty) {
+            *energy = 0.0;
+            return;
+        }
+        Slot& sl = c->slot[s];
+        if (sl.K <= 0) {
+            throw CudaError{"no k-vectors"};
+        }
+        const double pi = 3.141592653589793238462643383279502884;
+        const double volume = sl.ewald_box[0] * sl.ewald_box[1] * sl.ewald_box[2];
+        beginTiming(c);
+        bool pending = false;
+        if (!sl.rec_valid) {
+            const int grid = (sl.K + kBlock - 1) / kBlock;
+            c->partials.ensure(static_cast<size_t>(grid));
+            ewaldEnergyKernel<<<grid, kBlock, 0, c->stream>>>(makeEwaldView(c, s), c->partials.ptr, c->ticket.ptr,
+                                                             c->d_result + 4);
+            launched(c, "ewaldEnergyKernel");
+            pending = true;
+        }
+        const bool surface = c->ewald.surface_dielectric_constant >= 1.0;
+        if (surface) {
+            const int grid = gridFor(c, c->n_slots, kBlock);
+            dipoleKernel<<<grid, kBlock, 0, c->stream>>>(makeView(c, s), c->partials.ptr, c->ticket.ptr,
+                                                        c->d_result + 5);
+            launched(c, "dipoleKernel");
+            pending = true;
+        }
+        if (pending) {
+            finish(c);
+        }
+        if (!sl.rec_valid) {
+            sl.rec_sum = c->h_result[4];
+            sl.rec_valid = true;
+        }
+        double u = 2 * pi * sl.rec_sum * c->ewald.bjerrum_length / volume;
+        if (surface) {
+            const double qr2 = c->h_result[5] * c->h_result[5] + c->h_result[6] * c->h_result[6] +
+                               c->h_result[7] * c->h_result[7];
+            u += 2.0 * pi / ((2.0 * c->ewald.surface_dielectric_constant + 1.0) * volume) * qr2 *
+                 c->ewald.bjerrum_length;
+        }
+        *energy = u;
+    });
+}
+
+FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
+{
+    return guarded(c, [&] {
+        checkSlot(c, dst, false);
+        checkSlot(c, src, false);
+        if (dst == src || !change) {
+            throw CudaError{"bad sync arguments"};
+        }
+        Slot& d = c->slot[dst];
+        Slot& s = c->slot[src];
+        if (s.K <= 0) {
+            throw CudaError{"source slot has no k-vectors"};
+        }
+        if (change->everything || change->volume_change || d.K != s.K) {
+            d.kA.ensure(s.K);
+            CUDA_CHECK(cudaMemcpyAsync(d.kA.ptr, s.kA.ptr, s.K * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
+            d.K = s.K;
+            for (int i = 0; i < 3; ++i) {
+                d.ewald_box[i] = s.ewald_box[i];
+            }
+        }
+        d.Q.ensure(s.K);
+        CUDA_CHECK(cudaMemcpyAsync(d.Q.ptr, s.Q.ptr, s.K * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
+        d.rec_valid = s.rec_valid;
+        d.rec_sum = s.rec_sum;
+    });
+}
+
+FB_API int fb_ewald_download(fb_ctx* c, int s, double* q_re_im, double* kvectors, double* aks)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s, false);
+        Slot& sl = c->slot[s];
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (q_re_im) {
+            CUDA_CHECK(cudaMemcpy(q_re_im, sl.Q.ptr, sl.K * sizeof(double2), cudaMemcpyDeviceToHost));
+        }
+        if (kvectors || aks) {
+            std::vector<double4> kA(sl.K);
+            CUDA_CHECK(cudaMemcpy(kA.data(), sl.kA.ptr, sl.K * sizeof(double4), cudaMemcpyDeviceToHost));
+            for (int k = 0; k < sl.K; ++k) {
+                if (kvectors) {
+                    kvectors[3 * k] = kA[k].x;
+                    kvectors[3 * k + 1] = kA[k].y;
+                    kvectors[3 * k + 2] = kA[k].z;
+                }
+                if (aks) {
+                    aks[k] = kA[k].w;
+                }
+            }
+        }
+    });
+}
+
+// =================================================================================================
+// Widom
+// =================================================================================================
+FB_API int fb_widom_batch(fb_ctx* c, int s, int ghost_group, int n_ghost_atoms, int n_insertions,
+                          const double* ghost_xyzq, const int* ghost_atom_id, const double* ghost_cm, int internal,
+                          double* du)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s);
+        if (ghost_group < 0 || ghost_group >= c->n_groups || n_insertions <= 0 || !ghost_xyzq ||
+            !ghost_atom_id || !du) {
+            throw CudaError{"bad Widom arguments"};
+        }
+        if (n_ghost_atoms <= 0 || n_ghost_atoms > kWidomMaxAtoms) {
+            throw CudaError{"Widom ghosts of 1..8 atoms are supported"};
+        }
+        for (int a = 0; a < n_ghost_atoms; ++a) {
+            if (ghost_atom_id[a] < 0 || ghost_atom_id[a] >= c->P.n_types) {
+                throw CudaError{"ghost atom id out of range"};
+            }
+        }
+        const size_t natoms = static_cast<size_t>(n_insertions) * n_ghost_atoms;
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->d_ghost.upload(reinterpret_cast<const double4*>(ghost_xyzq), natoms, c->stream);
+        c->d_ghost_id.upload(ghost_atom_id, n_ghost_atoms, c->stream);
+        const double4* d_cm = nullptr;
+        const bool molecular = !(c->molecule_flags[c->slot[s].groups[ghost_group].molid] & FB_MOL_ATOMIC);
+        if (molecular) {
+            if (!ghost_cm) {
+                throw CudaError{"molecular ghosts need mass centres"};
+            }
+            c->h_ghost.ensure(n_insertions);
+            for (int b = 0; b < n_insertions; ++b) {
+                c->h_ghost.ptr[b] = make_double4(ghost_cm[3 * b], ghost_cm[3 * b + 1], ghost_cm[3 * b + 2], 0);
+            }
+            c->d_ghost_cm.upload(c->h_ghost.ptr, n_insertions, c->stream);
+            d_cm = c->d_ghost_cm.ptr;
+        }
+        const int bx = (n_insertions + kWidomBlock - 1) / kWidomBlock;
+        const int max_split = (c->n_slots + kWidomChunk - 1) / kWidomChunk;
+        int n_split = std::max(1, std::min(max_split, (c->max_blocks * 2 + bx - 1) / bx));
+        int j_per_split = (c->n_slots + n_split - 1) / n_split;
+        j_per_split = ((j_per_split + kWidomChunk - 1) / kWidomChunk) * kWidomChunk;
+        n_split = (c->n_slots + j_per_split - 1) / j_per_split;
+        c->d_widom_partial.ensure(static_cast<size_t>(n_split) * n_insertions);
+        c->d_widom_du.ensure(n_insertions);
+        c->h_widom_du.ensure(n_insertions);
+        const SlotView V = makeView(c, s);
+        dim3 grid(bx, n_split);
+        beginTiming(c);
+#define FB_CASE(K)                                                                                            \
+    case K:                                                                                                   \
+        widomKernel<K><<<grid, kWidomBlock, 0, c->stream>>>(V, c->P, ghost_group, n_ghost_atoms, n_insertions, \
+                                                            c->d_ghost.ptr, c->d_ghost_id.ptr, d_cm,          \
+                                                            j_per_split, c->d_widom_partial.ptr);             \
+        launched(c, "widomKernel");                                                                           \
+        widomFinishKernel<K><<<(n_insertions + 127) / 128, 128, 0, c->stream>>>(                              \
+            V, c->P, ghost_group, n_ghost_atoms, n_insertions, n_split, c->d_ghost.ptr, c->d_ghost_id.ptr,    \
+            internal, c->d_widom_partial.ptr, c->d_widom_du.ptr);                                             \
+        launched(c, "widomFinishKernel");                                                                     \
+        break;
+        switch (c->P.kind) {
+            FB_CASE(POT_COULOMB_LJ)
+            FB_CASE(POT_COULOMB_WCA)
+            FB_CASE(POT_PM)
+            FB_CASE(POT_PMWCA)
+            FB_CASE(POT_FUNCTOR)
+            FB_CASE(POT_SPLINED)
+        default:
+            throw CudaError{"unknown potential kind"};
+        }
+#undef FB_CASE
+        CUDA_CHECK(cudaMemcpyAsync(c->h_widom_du.ptr, c->d_widom_du.ptr, n_insertions * sizeof(double),
+                                   cudaMemcpyDeviceToHost, c->stream));
+        finish(c);
+        std::memcpy(du, c->h_widom_du.ptr, n_insertions * sizeof(double));
+    });
+}
+
+// =================================================================================================
+// replica exchange packing
+// =================================================================================================
+FB_API size_t fb_state_doubles(const fb_ctx* c)
+{
+    return c ? 3 + static_cast<size_t>(c->n_groups) + 5 * static_cast<size_t>(c->n_slots) : 0;
+}
+
+FB_API int fb_export_state(fb_ctx* c, int s, double* device_buffer)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s);
+        if (!device_buffer) {
+            throw CudaError{"null buffer"};
+        }
+        packStateKernel<<<gridFor(c, c->n_slots, 256), 256, 0, c->stream>>>(makeView(c, s), device_buffer);
+        launched(c, "packStateKernel");
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+FB_API int fb_import_state(fb_ctx* c, int s, const double* device_buffer)
+{
+    return guarded(c, [&] {
+        checkSlot(c, s);
+        if (!device_buffer) {
+            throw CudaError{"null buffer"};
+        }
+        Slot& sl = c->slot[s];
+        std::vector<double> head(3 + c->n_groups);
+        CUDA_CHECK(cudaMemcpyAsync(head.data(), device_buffer, head.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                                   c->stream));
+        unpackStateKernel<<<gridFor(c, c->n_slots, 256), 256, 0, c->stream>>>(makeView(c, s), device_buffer);
+        launched(c, "unpackStateKernel");
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 3; ++i) {
+            sl.box[i] = head[i];
+        }
+        for (int g = 0; g < c->n_groups; ++g) {
+            sl.groups[g].size = static_cast<int>(head[3 + g]);
+        }
+        buildGidKernel<<<c->n_groups, 128, 0, c->stream>>>(makeView(c, s));
+        launched(c, "buildGidKernel");
+        sl.rec_valid = false;
+    });
+}
+
+FB_API int fb_export_state_host(fb_ctx* c, int s, double* host_buffer)
+{
+    return guarded(c, [&] {
+        const size_t n = fb_state_doubles(c);
+        c->d_state.ensure(n);
+        const int rc = fb_export_state(c, s, c->d_state.ptr);
+        if (rc != FB_OK) {
+            throw CudaError{c->last_error};
+        }
+        CUDA_CHECK(cudaMemcpy(host_buffer, c->d_state.ptr, n * sizeof(double), cudaMemcpyDeviceToHost));
+    });
+}
+
+FB_API int fb_import_state_host(fb_ctx* c, int s, const double* host_buffer)
+{
+    return guarded(c, [&] {
+        const size_t n = fb_state_doubles(c);
+        c->d_state.ensure(n);
+        CUDA_CHECK(cudaMemcpy(c->d_state.ptr, host_buffer, n * sizeof(double), cudaMemcpyHostToDevice));
+        const int rc = fb_import_state(c, s, c->d_state.ptr);
+        if (rc != FB_OK) {
+            throw CudaError{c->last_error};
+        }
+    });
+}

@@ -1,0 +1,1000 @@
+// Device code of libfaunus_b200: FP64 pair-potential functors, the moved-set ΔU kernel, the tiled
+// full-energy kernel, the batched Widom kernel, the k-parallel Ewald kernels and the mirror
+// maintenance kernels. sm_100a; no tensor cores (nothing here is a dense contraction); all
+// reductions are fixed-shape (warp shuffle → block → ordered final pass) so results do not depend
+// on block scheduling.
+//
+// Semantics restated from the reference (mlund/faunus):
+//   min-image r² ............ src/geometry.h:460-470 (single fold: d=|a-b|; d -= L·[d > L/2])
+//   pair functors ........... src/potentials.h:42-49 (LJ), 151-160 (WCA), 203-207 (HS), 472-476
+//                             (plain Coulomb), 591-598 (CoulombGalore: r = sqrt(r²)+eps, zero for
+//                             r ≥ Rc), src/tabulate.h:184-196 (Andrea eval)
+//   which pairs ............. src/energy.h:856-914 (groupInternal), 979-1027 (group2group),
+//                             1155-1226 (group2all), 1241-1278 (groups2all), 1290-1325 (all),
+//                             761-768 (GroupCutoff::cut)
+//   Ewald ................... src/energy.cpp:191-247 (Q(k) full / partial), 524-531 (energy)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace fbdev {
+
+constexpr int kMovedChunk = 64;     //!< moved atoms staged in shared memory per pass
+constexpr int kInlineMoved = 12;    //!< moved-atom indices carried in kernel parameters
+constexpr int kMaxMovedGroups = 16; //!< changed groups per launch
+constexpr int kBlock = 256;
+constexpr int kTile = 256;          //!< i/j tile edge of the full-energy kernel
+constexpr int kInlineUpdate = 8;    //!< particles per fb_update_group carried in kernel parameters
+
+enum : int
+{
+    MOL_ATOMIC = 1,
+    MOL_RIGID = 2,
+    MOL_COMPRESSIBLE = 4
+};
+enum : unsigned
+{
+    TERM_COULOMB_SPLINED = 1,
+    TERM_COULOMB_PLAIN = 2,
+    TERM_LJ = 4,
+    TERM_WCA = 8,
+    TERM_HS = 16
+};
+enum : int
+{
+    POT_COULOMB_LJ = 0,
+    POT_COULOMB_WCA = 1,
+    POT_PM = 2,
+    POT_PMWCA = 3,
+    POT_FUNCTOR = 4,
+    POT_SPLINED = 5
+};
+
+/** One slot of the device-resident Space mirror (structure of arrays) */
+struct SlotView
+{
+    double4* posq;       //!< [n_slots] x, y, z, charge
+    int* atom_id;        //!< [n_slots] atom type
+    int* gid;            //!< [n_slots] group index g if active, -1-g if inactive
+    double4* gcm;        //!< [n_groups] mass centre (w unused)
+    int* gsize;          //!< [n_groups] active particles
+    const int* gbegin;   //!< [n_groups] first slot (shared by both slots)
+    const int* gcap;     //!< [n_groups] capacity
+    const int* ginfo;    //!< [n_groups] molid << 8 | MOL_* flags
+    double len[3];       //!< box lengths
+    double half[3];      //!< box half lengths
+    double len_or_zero[3]; //!< length if periodic else 0
+    int n_slots;
+    int n_groups;
+};
+
+/** Pair potential tables (device pointers) and scalars */
+struct PotParams
+{
+    int kind;
+    int n_types;
+    const unsigned* flags;
+    const double* lj_s2;
+    const double* lj_e4;
+    const double* wca_s2;
+    const double* wca_e4;
+    const double* hs_s2;
+    // splined Coulomb
+    double lB, Rc, invRc, kappa;
+    int nk;
+    const double* knots;
+    const double* coef;
+    const int* lut;
+    int nlut;
+    double lB_plain;
+    // per-pair r² splines
+    const int* sp_offset;
+    const double* sp_knots;
+    const double* sp_coef;
+    const double* sp_rmin2;
+    const double* sp_rmax2;
+    const unsigned char* sp_hs;
+    // groups / molecules
+    const double* g2g_cut2; //!< [n_mol²]
+    int n_mol;
+    const int* excl_offset;    //!< [n_mol] offset into excl, -1 if none
+    const int* excl_natoms;    //!< [n_mol]
+    const unsigned char* excl; //!< concatenated natoms² matrices
+    int any_molecular;         //!< 0 if every group is atomic (skips cutoff / exclusion logic)
+};
+
+struct MovedDesc
+{
+    int n_moved;
+    int n_groups;
+    int groups[kMaxMovedGroups];
+    int internal;  //!< single moved group only
+    int all_moved; //!< every active atom of the moved group(s) is in the list
+    const int* list; //!< [2*n_moved] slots then group positions; nullptr → inline arrays
+    int inline_slot[kInlineMoved];
+    int inline_gpos[kInlineMoved];
+};
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double minImageR2(const SlotView& v, double ax, double ay, double az, double bx,
+                                             double by, double bz)
+{
+    double dx = fabs(ax - bx);
+    double dy = fabs(ay - by);
+    double dz = fabs(az - bz);
+    dx -= (dx > v.half[0]) ? v.len_or_zero[0] : 0.0;
+    dy -= (dy > v.half[1]) ? v.len_or_zero[1] : 0.0;
+    dz -= (dz > v.half[2]) ? v.len_or_zero[2] : 0.0;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+/** Andrea spline: pos = (#knots < x) − 1 via a uniform-bucket start index + forward scan */
+__device__ __forceinline__ double andreaEval(const double* __restrict__ knots, const double* __restrict__ coef,
+                                             int first, int nk, const int* __restrict__ lut, int nlut,
+                                             double lut_scale, double x)
+{
+    int pos = 0;
+    if (lut != nullptr) {
+        int b = static_cast<int>(x * lut_scale);
+        b = b < 0 ? 0 : (b >= nlut ? nlut - 1 : b);
+        pos = __ldg(lut + b);
+    }
+    while (pos + 2 < nk && __ldg(knots + first + pos + 1) < x) {
+        ++pos;
+    }
+    const double dz = x - __ldg(knots + first + pos);
+    const double* c = coef + 6 * (first + pos);
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 5; i > 0; --i) {
+        sum = dz * (sum + __ldg(c + i));
+    }
+    return sum + __ldg(c);
+}
+
+__device__ __forceinline__ double coulombSplined(const PotParams& P, double qq, double r2)
+{
+    const double r = sqrt(r2) + 2.220446049250313e-16;
+    if (r < P.Rc) {
+        const double S = andreaEval(P.knots, P.coef, 0, P.nk, P.lut, P.nlut, static_cast<double>(P.nlut),
+                                    r * P.invRc);
+        double u = qq / r * S;
+        if (P.kappa > 0.0) {
+            u *= exp(-P.kappa * r);
+        }
+        return P.lB * u;
+    }
+    return 0.0;
+}
+
+__device__ __forceinline__ double lennardJones(const double* s2, const double* e4, int t, double r2)
+{
+    double x = __ldg(s2 + t) / r2;
+    x = x * x * x;
+    return __ldg(e4 + t) * (x * x - x);
+}
+
+__device__ __forceinline__ double wca(const double* s2, const double* e4, int t, double r2)
+{
+    double x = __ldg(s2 + t);
+    if (r2 > x * 1.2599210498948732) {
+        return 0.0;
+    }
+    x = x / r2;
+    x = x * x * x;
+    return __ldg(e4 + t) * (x * x - x + 0.25);
+}
+
+__device__ __forceinline__ double hardSphere(const double* s2, int t, double r2)
+{
+    return r2 < __ldg(s2 + t) ? __longlong_as_double(0x7ff0000000000000LL) : 0.0;
+}
+
+__device__ __forceinline__ double termSum(const PotParams& P, unsigned flags, int t, double qq, double r2)
+{
+    double u = 0.0;
+    if (flags & TERM_COULOMB_SPLINED) {
+        u += coulombSplined(P, qq, r2);
+    }
+    if (flags & TERM_COULOMB_PLAIN) {
+        u += P.lB_plain * qq / sqrt(r2);
+    }
+    if (flags & TERM_LJ) {
+        u += lennardJones(P.lj_s2, P.lj_e4, t, r2);
+    }
+    if (flags & TERM_WCA) {
+        u += wca(P.wca_s2, P.wca_e4, t, r2);
+    }
+    if (flags & TERM_HS) {
+        u += hardSphere(P.hs_s2, t, r2);
+    }
+    return u;
+}
+
+/** u(a, b, r²) for the compile-time potential flavour (first + second, src/potentials_base.h:234-240) */
+template <int KIND>
+__device__ __forceinline__ double pairEnergy(const PotParams& P, int ida, int idb, double qa, double qb, double r2)
+{
+    const int t = ida * P.n_types + idb;
+    const double qq = qa * qb;
+    if constexpr (KIND == POT_COULOMB_LJ) {
+        return coulombSplined(P, qq, r2) + lennardJones(P.lj_s2, P.lj_e4, t, r2);
+    }
+    else if constexpr (KIND == POT_COULOMB_WCA) {
+        return coulombSplined(P, qq, r2) + wca(P.wca_s2, P.wca_e4, t, r2);
+    }
+    else if constexpr (KIND == POT_PM) {
+        return P.lB_plain * qq / sqrt(r2) + hardSphere(P.hs_s2, t, r2);
+    }
+    else if constexpr (KIND == POT_PMWCA) {
+        return P.lB_plain * qq / sqrt(r2) + wca(P.wca_s2, P.wca_e4, t, r2);
+    }
+    else if constexpr (KIND == POT_FUNCTOR) {
+        return termSum(P, __ldg(P.flags + t), t, qq, r2);
+    }
+    else { // POT_SPLINED, src/potentials.h:807-823
+        if (r2 >= __ldg(P.sp_rmax2 + t)) {
+            return 0.0;
+        }
+        if (r2 > __ldg(P.sp_rmin2 + t)) {
+            const int first = __ldg(P.sp_offset + t);
+            const int nk = __ldg(P.sp_offset + t + 1) - first;
+            // coefficient blocks are stored per knot index (one unused block per table end)
+            return andreaEval(P.sp_knots, P.sp_coef, first, nk, nullptr, 0, 0.0, r2);
+        }
+        if (__ldg(P.sp_hs + t)) {
+            return __longlong_as_double(0x7ff0000000000000LL);
+        }
+        return termSum(P, __ldg(P.flags + t), t, qq, r2);
+    }
+}
+
+__device__ __forceinline__ bool pairExcluded(const PotParams& P, int molid, int i, int j)
+{
+    const int off = __ldg(P.excl_offset + molid);
+    if (off < 0) {
+        return false;
+    }
+    const int n = __ldg(P.excl_natoms + molid);
+    return __ldg(P.excl + off + i * n + j) != 0;
+}
+
+/** GroupCutoff::cut on one view; both groups must be molecular to be cut */
+__device__ __forceinline__ bool groupCut(const SlotView& v, const PotParams& P, int g1, int info1, int g2, int info2)
+{
+    if ((info1 | info2) & MOL_ATOMIC) {
+        return false;
+    }
+    const double4 a = v.gcm[g1];
+    const double4 b = v.gcm[g2];
+    const double r2 = minImageR2(v, a.x, a.y, a.z, b.x, b.y, b.z);
+    return r2 >= __ldg(P.g2g_cut2 + (info1 >> 8) * P.n_mol + (info2 >> 8));
+}
+
+__device__ __forceinline__ double warpSum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v += __shfl_down_sync(0xffffffffu, v, o);
+    }
+    return v;
+}
+
+/** Fixed-shape block sum; result valid in thread 0 */
+template <int NT> __device__ __forceinline__ double blockSum(double v, double* scratch /*[NT/32]*/)
+{
+    v = warpSum(v);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        scratch[warp] = v;
+    }
+    __syncthreads();
+    double r = 0.0;
+    if (warp == 0) {
+        r = (lane < NT / 32) ? scratch[lane] : 0.0;
+        r = warpSum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+/**
+ * Last-block-done final reduction: every block stores `nval` partials, the block that draws the
+ * last ticket sums all partials in index order (fixed shape) and writes `out[0..nval)`.
+ */
+template <int NT>
+__device__ __forceinline__ void finalReduce(const double* block_values, int nval, double* partials,
+                                            unsigned* ticket, double* out, double* scratch)
+{
+    __shared__ bool is_last;
+    const int nblocks = gridDim.x * gridDim.y;
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) {
+        for (int v = 0; v < nval; ++v) {
+            partials[v * nblocks + bid] = block_values[v];
+        }
+        __threadfence();
+        const unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == static_cast<unsigned>(nblocks - 1));
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int v = 0; v < nval; ++v) {
+            double s = 0.0;
+            for (int i = threadIdx.x; i < nblocks; i += NT) {
+                s += __ldcg(partials + v * nblocks + i);
+            }
+            s = blockSum<NT>(s, scratch);
+            if (threadIdx.x == 0) {
+                out[v] = s;
+            }
+        }
+        if (threadIdx.x == 0) {
+            *ticket = 0u;
+            __threadfence_system();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1/K2: moved set vs the rest (group2all / groupInternal / groups2all), optionally on two slots in
+// one pass over j (new on A, old on B)
+// ------------------------------------------------------------------------------------------------
+template <int KIND, bool FUSED>
+__global__ void __launch_bounds__(kBlock)
+    movedEnergyKernel(SlotView A, SlotView B, PotParams P, MovedDesc md, double* partials, unsigned* ticket,
+                      double* out)
+{
+    __shared__ double4 s_posA[kMovedChunk];
+    __shared__ double4 s_posB[kMovedChunk];
+    __shared__ int s_idA[kMovedChunk];
+    __shared__ int s_idB[kMovedChunk];
+    __shared__ int s_slot[kMovedChunk];
+    __shared__ int s_gpos[kMovedChunk];
+    __shared__ double scratch[kBlock / 32];
+
+    double eA = 0.0;
+    double eB = 0.0;
+    const int stride = gridDim.x * blockDim.x;
+    const bool multi = md.n_groups > 1;
+
+    for (int chunk0 = 0; chunk0 < md.n_moved; chunk0 += kMovedChunk) {
+        const int nm = min(kMovedChunk, md.n_moved - chunk0);
+        __syncthreads();
+        if (threadIdx.x < nm) {
+            const int m = chunk0 + threadIdx.x;
+            const int slot = md.list ? md.list[m] : md.inline_slot[m];
+            const int gpos = md.list ? md.list[md.n_moved + m] : md.inline_gpos[m];
+            s_slot[threadIdx.x] = slot;
+            s_gpos[threadIdx.x] = gpos;
+            s_posA[threadIdx.x] = A.posq[slot];
+            s_idA[threadIdx.x] = A.atom_id[slot];
+            if (FUSED) {
+                s_posB[threadIdx.x] = B.posq[slot];
+                s_idB[threadIdx.x] = B.atom_id[slot];
+            }
+        }
+        __syncthreads();
+
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < A.n_slots; j += stride) {
+            const int g = A.gid[j];
+            if (g < 0) {
+                continue; // inactive particles never interact
+            }
+            int mg = -1; // position of j's group in the moved-group list
+#pragma unroll 1
+            for (int t = 0; t < md.n_groups; ++t) {
+                if (md.groups[t] == g) {
+                    mg = t;
+                }
+            }
+            const double4 pA = A.posq[j];
+            const int idjA = A.atom_id[j];
+            double4 pB = pA;
+            int idjB = idjA;
+            if (FUSED && mg >= 0) {
+                pB = B.posq[j];
+                idjB = B.atom_id[j];
+            }
+            const int info_j = P.any_molecular ? A.ginfo[g] : MOL_ATOMIC;
+
+            // mass-centre cutoff of j's group against every moved group, per view
+            unsigned cutA = 0u;
+            unsigned cutB = 0u;
+            if (P.any_molecular && !(info_j & MOL_ATOMIC)) {
+#pragma unroll 1
+                for (int t = 0; t < md.n_groups; ++t) {
+                    const int gi = md.groups[t];
+                    if (gi == g) {
+                        continue;
+                    }
+                    const int info_i = A.ginfo[gi];
+                    if (groupCut(A, P, g, info_j, gi, info_i)) {
+                        cutA |= 1u << t;
+                    }
+                    if (FUSED && groupCut(B, P, g, info_j, gi, info_i)) {
+                        cutB |= 1u << t;
+                    }
+                }
+            }
+
+            bool j_moved = false;
+            if (mg >= 0) {
+                if (md.all_moved || multi) {
+                    j_moved = true;
+                }
+                else {
+#pragma unroll 1
+                    for (int m = 0; m < md.n_moved; ++m) {
+                        const int slot = md.list ? md.list[m] : md.inline_slot[m];
+                        if (slot == j) {
+                            j_moved = true;
+                        }
+                    }
+                }
+            }
+
+#pragma unroll 1
+            for (int m = 0; m < nm; ++m) {
+                const int si = s_slot[m];
+                const int gp = s_gpos[m];
+                if (mg == gp) { // same group: internal pairs
+                    if (!md.internal || multi || j == si) {
+                        continue;
+                    }
+                    if (j_moved && j < si) {
+                        continue; // moved-moved pairs once
+                    }
+                    if (!(info_j & MOL_ATOMIC)) {
+                        if (info_j & MOL_RIGID) {
+                            continue;
+                        }
+                        const int b = A.gbegin[g];
+                        if (pairExcluded(P, info_j >> 8, si - b, j - b)) {
+                            continue;
+                        }
+                    }
+                }
+                else if (mg >= 0 && mg < gp) {
+                    continue; // both groups moved: pair counted from the earlier group
+                }
+                const double4 a = s_posA[m];
+                if (mg == gp || !((cutA >> gp) & 1u)) {
+                    const double r2 = minImageR2(A, a.x, a.y, a.z, pA.x, pA.y, pA.z);
+                    eA += pairEnergy<KIND>(P, s_idA[m], idjA, a.w, pA.w, r2);
+                }
+                if (FUSED) {
+                    const double4 b4 = s_posB[m];
+                    if (mg == gp || !((cutB >> gp) & 1u)) {
+                        const double r2 = minImageR2(B, b4.x, b4.y, b4.z, pB.x, pB.y, pB.z);
+                        eB += pairEnergy<KIND>(P, s_idB[m], idjB, b4.w, pB.w, r2);
+                    }
+                }
+            }
+        }
+    }
+
+    double vals[2];
+    vals[0] = blockSum<kBlock>(eA, scratch);
+    vals[1] = FUSED ? blockSum<kBlock>(eB, scratch) : 0.0;
+    finalReduce<kBlock>(vals, FUSED ? 2 : 1, partials, ticket, out, scratch);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: full energy Σ_{i<j} (GroupPairingPolicy::all); one block per (i-tile, j-tile ≥ i-tile)
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(kTile)
+    fullEnergyKernel(SlotView V, PotParams P, int volume_predicate, double* partials)
+{
+    const int ti = blockIdx.y;
+    const int tj = blockIdx.x;
+    if (tj < ti) {
+        return;
+    }
+    __shared__ double4 s_pos[kTile];
+    __shared__ int s_id[kTile];
+    __shared__ int s_gid[kTile];
+    __shared__ double scratch[kTile / 32];
+
+    const int j0 = tj * kTile;
+    {
+        const int j = j0 + threadIdx.x;
+        if (j < V.n_slots) {
+            s_pos[threadIdx.x] = V.posq[j];
+            s_id[threadIdx.x] = V.atom_id[j];
+            s_gid[threadIdx.x] = V.gid[j];
+        }
+        else {
+            s_gid[threadIdx.x] = -1;
+        }
+    }
+    __syncthreads();
+
+    const int i = ti * kTile + threadIdx.x;
+    double e = 0.0;
+    const int gi = (i < V.n_slots) ? V.gid[i] : -1;
+    if (gi >= 0) {
+        const double4 pi = V.posq[i];
+        const int idi = V.atom_id[i];
+        const int info_i = P.any_molecular ? V.ginfo[gi] : MOL_ATOMIC;
+        const int begin_i = P.any_molecular ? V.gbegin[gi] : 0;
+        const int jstart = (ti == tj) ? threadIdx.x + 1 : 0;
+        int last_g = -1;
+        bool last_cut = false;
+        for (int jj = jstart; jj < kTile; ++jj) {
+            const int gj = s_gid[jj];
+            if (gj < 0) {
+                continue;
+            }
+            if (P.any_molecular) {
+                if (gj == gi) { // groupInternal, src/energy.h:856-871
+                    if (!(info_i & MOL_ATOMIC)) {
+                        if (info_i & MOL_RIGID) {
+                            continue;
+                        }
+                        if (pairExcluded(P, info_i >> 8, i - begin_i, j0 + jj - begin_i)) {
+                            continue;
+                        }
+                    }
+                    if (volume_predicate && !(info_i & (MOL_ATOMIC | MOL_COMPRESSIBLE))) {
+                        continue; // internal energy of incompressible molecules, energy.h:1454-1459
+                    }
+                }
+                else if (!(info_i & MOL_ATOMIC)) {
+                    if (gj != last_g) {
+                        last_g = gj;
+                        last_cut = groupCut(V, P, gi, info_i, gj, V.ginfo[gj]);
+                    }
+                    if (last_cut) {
+                        continue;
+                    }
+                }
+            }
+            const double4 pj = s_pos[jj];
+            const double r2 = minImageR2(V, pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
+            e += pairEnergy<KIND>(P, idi, s_id[jj], pi.w, pj.w, r2);
+        }
+    }
+    const double s = blockSum<kTile>(e, scratch);
+    if (threadIdx.x == 0) {
+        const int nt = gridDim.x;
+        partials[static_cast<size_t>(ti) * nt - static_cast<size_t>(ti) * (ti - 1) / 2 + (tj - ti)] = s;
+    }
+}
+
+/** Ordered sum of `n` doubles (per column v of `nval` columns with stride `n`) by one block */
+__global__ void __launch_bounds__(1024) orderedSumKernel(const double* values, size_t n, int nval, double* out)
+{
+    __shared__ double scratch[32];
+    for (int v = 0; v < nval; ++v) {
+        double s = 0.0;
+        for (size_t i = threadIdx.x; i < n; i += 1024) {
+            s += values[v * n + i];
+        }
+        s = blockSum<1024>(s, scratch);
+        if (threadIdx.x == 0) {
+            out[v] = s;
+            __threadfence_system();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: batched Widom insertions — thread b owns ghost b, blocks sweep j-chunks staged in smem
+// ------------------------------------------------------------------------------------------------
+constexpr int kWidomBlock = 128;
+constexpr int kWidomChunk = 512;
+constexpr int kWidomMaxAtoms = 8;
+
+template <int KIND>
+__global__ void __launch_bounds__(kWidomBlock)
+    widomKernel(SlotView V, PotParams P, int ghost_group, int n_ghost_atoms, int n_insertions,
+                const double4* ghost_posq, const int* ghost_id, const double4* ghost_cm, int j_per_split,
+                double* partial /*[n_split][n_insertions]*/)
+{
+    __shared__ double4 s_pos[kWidomChunk];
+    __shared__ int s_id[kWidomChunk];
+    __shared__ int s_gid[kWidomChunk];
+
+    const int b = blockIdx.x * kWidomBlock + threadIdx.x;
+    const int split = blockIdx.y;
+    const int jbegin = split * j_per_split;
+    const int jend = min(V.n_slots, jbegin + j_per_split);
+    const bool valid = b < n_insertions;
+
+    double4 gp[kWidomMaxAtoms];
+    int gtype[kWidomMaxAtoms];
+#pragma unroll
+    for (int a = 0; a < kWidomMaxAtoms; ++a) {
+        if (a < n_ghost_atoms) {
+            gp[a] = valid ? ghost_posq[static_cast<size_t>(b) * n_ghost_atoms + a] : make_double4(0, 0, 0, 0);
+            gtype[a] = ghost_id[a];
+        }
+    }
+    const int info_ghost = P.any_molecular ? V.ginfo[ghost_group] : MOL_ATOMIC;
+    double4 cm = make_double4(0, 0, 0, 0);
+    if (!(info_ghost & MOL_ATOMIC) && valid && ghost_cm != nullptr) {
+        cm = ghost_cm[b];
+    }
+
+    double e = 0.0;
+    for (int c0 = jbegin; c0 < jend; c0 += kWidomChunk) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < kWidomChunk; t += kWidomBlock) {
+            const int j = c0 + t;
+            if (j < jend) {
+                s_pos[t] = V.posq[j];
+                s_id[t] = V.atom_id[j];
+                s_gid[t] = V.gid[j];
+            }
+            else {
+                s_gid[t] = -1;
+            }
+        }
+        __syncthreads();
+        if (!valid) {
+            continue;
+        }
+        const int n = min(kWidomChunk, jend - c0);
+        int last_g = -1;
+        bool last_cut = false;
+        for (int t = 0; t < n; ++t) {
+            const int gj = s_gid[t];
+            if (gj < 0 || gj == ghost_group) {
+                continue;
+            }
+            if (P.any_molecular && !(info_ghost & MOL_ATOMIC)) {
+                if (gj != last_g) {
+                    last_g = gj;
+                    const int info_j = V.ginfo[gj];
+                    last_cut = false;
+                    if (!(info_j & MOL_ATOMIC)) {
+                        const double4 c2 = V.gcm[gj];
+                        const double r2 = minImageR2(V, cm.x, cm.y, cm.z, c2.x, c2.y, c2.z);
+                        last_cut = r2 >= __ldg(P.g2g_cut2 + (info_ghost >> 8) * P.n_mol + (info_j >> 8));
+                    }
+                }
+                if (last_cut) {
+                    continue;
+                }
+            }
+            const double4 pj = s_pos[t];
+            const int idj = s_id[t];
+#pragma unroll
+            for (int a = 0; a < kWidomMaxAtoms; ++a) {
+                if (a < n_ghost_atoms) {
+                    const double r2 = minImageR2(V, gp[a].x, gp[a].y, gp[a].z, pj.x, pj.y, pj.z);
+                    e += pairEnergy<KIND>(P, gtype[a], idj, gp[a].w, pj.w, r2);
+                }
+            }
+        }
+    }
+    if (valid) {
+        partial[static_cast<size_t>(split) * n_insertions + b] = e;
+    }
+}
+
+/** du[b] = Σ_split partial + ghost-internal pairs (atomic ghosts with internal flag) */
+template <int KIND>
+__global__ void widomFinishKernel(SlotView V, PotParams P, int ghost_group, int n_ghost_atoms, int n_insertions,
+                                  int n_split, const double4* ghost_posq, const int* ghost_id, int internal,
+                                  const double* partial, double* du)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_insertions) {
+        return;
+    }
+    double e = 0.0;
+    for (int s = 0; s < n_split; ++s) {
+        e += partial[static_cast<size_t>(s) * n_insertions + b];
+    }
+    if (internal) {
+        const int info = P.any_molecular ? V.ginfo[ghost_group] : MOL_ATOMIC;
+        const bool atomic = info & MOL_ATOMIC;
+        if (atomic || !(info & MOL_RIGID)) {
+            const double4* g = ghost_posq + static_cast<size_t>(b) * n_ghost_atoms;
+            for (int i = 0; i < n_ghost_atoms - 1; ++i) {
+                for (int j = i + 1; j < n_ghost_atoms; ++j) {
+                    if (!atomic && pairExcluded(P, info >> 8, i, j)) {
+                        continue;
+                    }
+                    const double r2 = minImageR2(V, g[i].x, g[i].y, g[i].z, g[j].x, g[j].y, g[j].z);
+                    e += pairEnergy<KIND>(P, ghost_id[i], ghost_id[j], g[i].w, g[j].w, r2);
+                }
+            }
+        }
+    }
+    du[b] = e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ewald reciprocal space: one thread per k-vector
+// ------------------------------------------------------------------------------------------------
+struct EwaldView
+{
+    double4* kA; //!< [K] kx, ky, kz, A_k
+    double2* Q;  //!< [K] structure factor
+    int K;
+    int policy; //!< 0 PBC, 1 PBCEigen (quirk on full update), 2 IPBC
+};
+
+__device__ __forceinline__ double2 phase(int policy, const double4& k, const double4& p)
+{
+    if (policy == 2) { // IPBC, src/energy.cpp:422
+        return make_double2(cos(k.x * p.x) * cos(k.y * p.y) * cos(k.z * p.z) * p.w, 0.0);
+    }
+    double s, c;
+    sincos(k.x * p.x + k.y * p.y + k.z * p.z, &s, &c);
+    return make_double2(p.w * c, p.w * s);
+}
+
+constexpr int kEwaldBlock = 128;
+constexpr int kEwaldChunk = 512;
+
+/** Q(k) = Σ_j q_j e^{ik·r_j}, j in storage order (= the reference's group/particle order) */
+__global__ void __launch_bounds__(kEwaldBlock) ewaldFullKernel(SlotView V, EwaldView E)
+{
+    __shared__ double4 s_pos[kEwaldChunk];
+    __shared__ int s_active[kEwaldChunk];
+    const int k = blockIdx.x * kEwaldBlock + threadIdx.x;
+    const bool valid = k < E.K;
+    const double4 kv = valid ? E.kA[k] : make_double4(0, 0, 0, 0);
+    double qr = 0.0, qi = 0.0, qi_unweighted = 0.0;
+    for (int c0 = 0; c0 < V.n_slots; c0 += kEwaldChunk) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < kEwaldChunk; t += kEwaldBlock) {
+            const int j = c0 + t;
+            if (j < V.n_slots) {
+                s_pos[t] = V.posq[j];
+                s_active[t] = V.gid[j] >= 0;
+            }
+            else {
+                s_active[t] = 0;
+            }
+        }
+        __syncthreads();
+        if (!valid) {
+            continue;
+        }
+        const int n = min(kEwaldChunk, V.n_slots - c0);
+        for (int t = 0; t < n; ++t) {
+            if (!s_active[t]) {
+                continue;
+            }
+            const double4 p = s_pos[t];
+            if (E.policy == 2) {
+                qr += cos(kv.x * p.x) * cos(kv.y * p.y) * cos(kv.z * p.z) * p.w;
+            }
+            else {
+                double s, c;
+                sincos(kv.x * p.x + kv.y * p.y + kv.z * p.z, &s, &c);
+                qr += p.w * c;
+                qi += p.w * s;
+                qi_unweighted += s;
+            }
+        }
+    }
+    if (valid) {
+        E.Q[k] = make_double2(qr, E.policy == 1 ? qi_unweighted : qi);
+    }
+}
+
+/**
+ * Partial update + energy: Q_new = Q_old + Σ_moved (new − old); partial Σ A_k |Q_new|² reduced to
+ * out[0]. Moved atoms are read from the two mirrors by slot index.
+ */
+__global__ void __launch_bounds__(kBlock)
+    ewaldPartialKernel(SlotView A, SlotView B, EwaldView Enew, EwaldView Eold, MovedDesc md, double* partials,
+                       unsigned* ticket, double* out)
+{
+    __shared__ double4 s_new[kMovedChunk];
+    __shared__ double4 s_old[kMovedChunk];
+    __shared__ int s_flags[kMovedChunk];
+    __shared__ double scratch[kBlock / 32];
+    const int k = blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = k < Enew.K;
+    double4 kv = make_double4(0, 0, 0, 0);
+    double2 Q = make_double2(0, 0);
+    if (valid) {
+        kv = Enew.kA[k];
+        Q = Eold.Q[k];
+    }
+    for (int chunk0 = 0; chunk0 < md.n_moved; chunk0 += kMovedChunk) {
+        const int nm = min(kMovedChunk, md.n_moved - chunk0);
+        __syncthreads();
+        if (threadIdx.x < nm) {
+            const int m = chunk0 + threadIdx.x;
+            const int slot = md.list ? md.list[m] : md.inline_slot[m];
+            s_new[threadIdx.x] = A.posq[slot];
+            s_old[threadIdx.x] = B.posq[slot];
+            s_flags[threadIdx.x] = (A.gid[slot] >= 0 ? 1 : 0) | (B.gid[slot] >= 0 ? 2 : 0);
+        }
+        __syncthreads();
+        if (valid) {
+            for (int m = 0; m < nm; ++m) {
+                if (s_flags[m] & 1) {
+                    const double2 f = phase(Enew.policy, kv, s_new[m]);
+                    Q.x += f.x;
+                    Q.y += f.y;
+                }
+                if (s_flags[m] & 2) {
+                    const double2 f = phase(Enew.policy, kv, s_old[m]);
+                    Q.x -= f.x;
+                    Q.y -= f.y;
+                }
+            }
+        }
+    }
+    double e = 0.0;
+    if (valid) {
+        Enew.Q[k] = Q;
+        e = kv.w * (Q.x * Q.x + Q.y * Q.y);
+    }
+    double val = blockSum<kBlock>(e, scratch);
+    finalReduce<kBlock>(&val, 1, partials, ticket, out, scratch);
+}
+
+/** Σ_k A_k |Q_k|² */
+__global__ void __launch_bounds__(kBlock)
+    ewaldEnergyKernel(EwaldView E, double* partials, unsigned* ticket, double* out)
+{
+    __shared__ double scratch[kBlock / 32];
+    const int k = blockIdx.x * kBlock + threadIdx.x;
+    double e = 0.0;
+    if (k < E.K) {
+        const double2 Q = E.Q[k];
+        e = E.kA[k].w * (Q.x * Q.x + Q.y * Q.y);
+    }
+    double val = blockSum<kBlock>(e, scratch);
+    finalReduce<kBlock>(&val, 1, partials, ticket, out, scratch);
+}
+
+/** Σ q_j r_j over active particles (surface term, src/energy.cpp:466-482) → out[0..3) */
+__global__ void __launch_bounds__(kBlock)
+    dipoleKernel(SlotView V, double* partials, unsigned* ticket, double* out)
+{
+    __shared__ double scratch[kBlock / 32];
+    double sx = 0, sy = 0, sz = 0;
+    for (int j = blockIdx.x * kBlock + threadIdx.x; j < V.n_slots; j += gridDim.x * kBlock) {
+        if (V.gid[j] >= 0) {
+            const double4 p = V.posq[j];
+            sx += p.w * p.x;
+            sy += p.w * p.y;
+            sz += p.w * p.z;
+        }
+    }
+    double vals[3];
+    vals[0] = blockSum<kBlock>(sx, scratch);
+    vals[1] = blockSum<kBlock>(sy, scratch);
+    vals[2] = blockSum<kBlock>(sz, scratch);
+    finalReduce<kBlock>(vals, 3, partials, ticket, out, scratch);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mirror maintenance
+// ------------------------------------------------------------------------------------------------
+struct InlineUpdate
+{
+    int n;
+    int slot[kInlineUpdate];
+    int id[kInlineUpdate];
+    double4 posq[kInlineUpdate];
+};
+
+/** Apply a group update: group record, activity of its slots, and the listed particles */
+__global__ void updateGroupKernel(SlotView V, int g, int begin, int cap, int size, double4 cm, InlineUpdate upd,
+                                  int n_staged, const int* staged_slot, const int* staged_id,
+                                  const double4* staged_posq)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    if (tid == 0) {
+        V.gcm[g] = cm;
+        V.gsize[g] = size;
+    }
+    for (int t = tid; t < cap; t += stride) {
+        V.gid[begin + t] = (t < size) ? g : -1 - g;
+    }
+    for (int t = tid; t < upd.n; t += stride) {
+        V.posq[upd.slot[t]] = upd.posq[t];
+        V.atom_id[upd.slot[t]] = upd.id[t];
+    }
+    for (int t = tid; t < n_staged; t += stride) {
+        V.posq[staged_slot[t]] = staged_posq[t];
+        V.atom_id[staged_slot[t]] = staged_id[t];
+    }
+}
+
+/** Space::sync for a list of groups: dst := src (whole capacity or listed slots) */
+struct SyncDesc
+{
+    int n_groups;
+    int group[kMaxMovedGroups];
+    int whole[kMaxMovedGroups]; //!< copy the whole capacity range (Change::GroupChange::all)
+    int n_slots;                //!< listed particle slots (subset changes)
+    const int* slots;           //!< device list or nullptr → inline
+    int inline_slots[kInlineMoved];
+};
+
+__global__ void syncGroupsKernel(SlotView dst, SlotView src, SyncDesc d)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    for (int t = 0; t < d.n_groups; ++t) {
+        const int g = d.group[t];
+        const int begin = src.gbegin[g];
+        const int cap = src.gcap[g];
+        const int size = src.gsize[g];
+        if (tid == 0) {
+            dst.gcm[g] = src.gcm[g];
+            dst.gsize[g] = size;
+        }
+        for (int i = tid; i < cap; i += stride) {
+            dst.gid[begin + i] = (i < size) ? g : -1 - g;
+            if (d.whole[t]) {
+                dst.posq[begin + i] = src.posq[begin + i];
+                dst.atom_id[begin + i] = src.atom_id[begin + i];
+            }
+        }
+    }
+    for (int i = tid; i < d.n_slots; i += stride) {
+        const int s = d.slots ? d.slots[i] : d.inline_slots[i];
+        dst.posq[s] = src.posq[s];
+        dst.atom_id[s] = src.atom_id[s];
+    }
+}
+
+/** gid from group tables after a full upload */
+__global__ void buildGidKernel(SlotView V)
+{
+    const int g = blockIdx.x;
+    const int begin = V.gbegin[g];
+    const int cap = V.gcap[g];
+    const int size = V.gsize[g];
+    for (int t = threadIdx.x; t < cap; t += blockDim.x) {
+        V.gid[begin + t] = (t < size) ? g : -1 - g;
+    }
+}
+
+/** Replica exchange packing: [box(3) | sizes(G) | x y z q id (5 per slot)] */
+__global__ void packStateKernel(SlotView V, double* buf)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    if (tid < 3) {
+        buf[tid] = V.len[tid];
+    }
+    for (int g = tid; g < V.n_groups; g += stride) {
+        buf[3 + g] = static_cast<double>(V.gsize[g]);
+    }
+    double* p = buf + 3 + V.n_groups;
+    for (int j = tid; j < V.n_slots; j += stride) {
+        const double4 v = V.posq[j];
+        p[5 * j] = v.x;
+        p[5 * j + 1] = v.y;
+        p[5 * j + 2] = v.z;
+        p[5 * j + 3] = v.w;
+        p[5 * j + 4] = static_cast<double>(V.atom_id[j]);
+    }
+}
+
+__global__ void unpackStateKernel(SlotView V, const double* buf)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    for (int g = tid; g < V.n_groups; g += stride) {
+        V.gsize[g] = static_cast<int>(buf[3 + g]);
+    }
+    const double* p = buf + 3 + V.n_groups;
+    for (int j = tid; j < V.n_slots; j += stride) {
+        V.posq[j] = make_double4(p[5 * j], p[5 * j + 1], p[5 * j + 2], p[5 * j + 3]);
+        V.atom_id[j] = static_cast<int>(p[5 * j + 4]);
+    }
+}
+
+} // namespace fbdev

@@ -1,0 +1,103 @@
+// Host-level entry points of libfaunus_b200.so (`fbh_*`): the MC driver and Widom analysis running on
+// the B200 adaptor terms. See host/sim_capi.hpp for the ABI and b200_terms.hpp for the adaptors.
+#include "b200_terms.hpp"
+#include "host/sim_capi.hpp"
+
+namespace {
+const fb::TermFactory b200_factory = fb::b200TermFactory;
+
+std::unique_ptr<fb::WidomInsertion> makeWidom(const fb::Json& j, fb::MetropolisMonteCarlo& mc)
+{
+    if (j.value("batched", true)) {
+        return std::make_unique<fb::WidomB200>(j, mc);
+    }
+    return fb::capi::defaultWidom(j, mc); // sequential reference order through energy(change)
+}
+} // namespace
+
+FB_DEFINE_SIM_CAPI(fbh, b200_factory, makeWidom)
+
+extern "C" __attribute__((visibility("default"))) void fbh_set_device(int device)
+{
+    fb::defaultDevice() = device;
+}
+
+/** kernels launched so far by the non-bonded/Ewald context of a simulation */
+extern "C" __attribute__((visibility("default"))) unsigned long long fbh_sim_launch_count(void* h)
+{
+    auto* s = static_cast<fb::capi::Sim*>(h);
+    unsigned long long n = 0;
+    for (const auto& t : s->mc->state.pot->find<fb::NonbondedB200>()) {
+        n += fb_launch_count(t->device()->ctx);
+    }
+    return n;
+}
+
+/** S(q) table of a `coulomb` block as built by the product's host-side generator (tests compare it
+ * bit for bit with the oracle's) */
+extern "C" __attribute__((visibility("default"))) int fbh_coulomb_table(const char* coulomb_json, double temperature,
+                                                                        double* knots, double* coeffs, int max_knots,
+                                                                        double* lB, double* cutoff, double* kappa,
+                                                                        double* self_prefactor)
+{
+    int n = -1;
+    fb::capi::guarded([&] {
+        fb::pc::temperature = temperature;
+        const auto t = fb::makeCoulombTable(fb::Json::parse(coulomb_json));
+        n = static_cast<int>(t.S.knots.size());
+        for (int i = 0; i < n && i < max_knots; ++i) {
+            knots[i] = t.S.knots[i];
+        }
+        for (int i = 0; i < 6 * (n - 1) && i < 6 * (max_knots - 1); ++i) {
+            coeffs[i] = t.S.coeffs[i];
+        }
+        *lB = t.bjerrum_length;
+        *cutoff = t.cutoff;
+        *kappa = t.kappa;
+        *self_prefactor = t.self_prefactor;
+    });
+    return n;
+}
+
+/** Host-side pair tables of one `energy` entry as JSON (mixing matrices, flags, spline ranges) */
+extern "C" __attribute__((visibility("default"))) int fbh_pair_tables_json(const char* input_json,
+                                                                           const char* nonbonded_name, char* buf,
+                                                                           int len)
+{
+    int n = -1;
+    fb::capi::guarded([&] {
+        const auto j = fb::Json::parse(input_json);
+        fb::pc::temperature = j.at("temperature").number();
+        const auto topo = fb::topologyFromJson(j);
+        const fb::Json* cfg = nullptr;
+        for (const auto& e : j.at("energy").items()) {
+            if (e.single().first == nonbonded_name) {
+                cfg = &e.single().second;
+            }
+        }
+        if (!cfg) {
+            throw std::runtime_error("energy entry not found");
+        }
+        const auto t = fb::buildPairTables(nonbonded_name, *cfg, *topo);
+        fb::Json out = fb::Json::object();
+        out["kind"] = t.kind;
+        out["n_types"] = t.n_types;
+        std::vector<double> flags(t.flags.begin(), t.flags.end());
+        out["flags"] = fb::Json::fromVector(flags);
+        out["lj_s2"] = fb::Json::fromVector(t.lj_s2);
+        out["lj_e4"] = fb::Json::fromVector(t.lj_e4);
+        out["wca_s2"] = fb::Json::fromVector(t.wca_s2);
+        out["wca_e4"] = fb::Json::fromVector(t.wca_e4);
+        out["hs_s2"] = fb::Json::fromVector(t.hs_s2);
+        out["plain_lB"] = t.plain_bjerrum_length;
+        out["g2g_cutoff_squared"] = fb::Json::fromVector(t.g2g_cutoff_squared);
+        out["sp_rmin2"] = fb::Json::fromVector(t.sp_rmin2);
+        out["sp_rmax2"] = fb::Json::fromVector(t.sp_rmax2);
+        out["sp_knots"] = fb::Json::fromVector(t.sp_knots);
+        out["sp_coeffs"] = fb::Json::fromVector(t.sp_coeffs);
+        std::vector<double> off(t.sp_offset.begin(), t.sp_offset.end());
+        out["sp_offset"] = fb::Json::fromVector(off);
+        n = fb::capi::copyOut(out.dump(), buf, len);
+    });
+    return n;
+}

@@ -1,0 +1,184 @@
+"""ctypes binding of libfaunus_b200.so.
+
+Two layers are exported by the library:
+
+* ``fb_*``  — the device-level C ABI of ``include/faunus_b200.h`` (what an ``EnergyTerm`` adaptor
+  calls): context, Space mirror, non-bonded ΔU, Ewald, Widom batches, replica state packing.
+* ``fbh_*`` — the host-level simulation ABI (C++ MC driver on the B200 adaptor terms), bound by
+  :class:`faunus_b200._simapi.SimLibrary`.
+
+The library is required: importing this module raises if it cannot be loaded, and creating a context
+without a CUDA device fails loudly (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from ._simapi import SimLibrary, Simulation, c_double_p, c_int_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "libfaunus_b200.so")
+
+FB_OK = 0
+POT_COULOMB_LJ, POT_COULOMB_WCA, POT_PM, POT_PMWCA, POT_FUNCTOR, POT_SPLINED = range(6)
+TERM_COULOMB_SPLINED, TERM_COULOMB_PLAIN, TERM_LJ, TERM_WCA, TERM_HARDSPHERE = 1, 2, 4, 8, 16
+MOL_ATOMIC, MOL_RIGID, MOL_COMPRESSIBLE = 1, 2, 4
+
+
+class FbGroup(C.Structure):
+    _fields_ = [("begin", C.c_int), ("size", C.c_int), ("capacity", C.c_int), ("molid", C.c_int),
+                ("cm", C.c_double * 3)]
+
+
+class FbGroupChange(C.Structure):
+    _fields_ = [("group_index", C.c_int), ("all", C.c_int), ("internal", C.c_int), ("n_atoms", C.c_int),
+                ("atoms", c_int_p)]
+
+
+class FbChange(C.Structure):
+    _fields_ = [("everything", C.c_int), ("volume_change", C.c_int), ("n_groups", C.c_int),
+                ("groups", C.POINTER(FbGroupChange))]
+
+
+class FbEwaldConfig(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("n_cutoff", C.c_double), ("kappa", C.c_double),
+                ("surface_dielectric_constant", C.c_double), ("bjerrum_length", C.c_double),
+                ("spherical_sum", C.c_int), ("policy", C.c_int)]
+
+
+c_ubyte_p = C.POINTER(C.c_ubyte)
+c_uint32_p = C.POINTER(C.c_uint32)
+
+
+class FbConfig(C.Structure):
+    _fields_ = [
+        ("device", C.c_int),
+        ("box", C.c_double * 3), ("periodic", C.c_int * 3),
+        ("n_atom_types", C.c_int), ("n_molecule_types", C.c_int),
+        ("molecule_flags", c_int_p), ("molecule_natoms", c_int_p),
+        ("exclusions", C.POINTER(c_ubyte_p)), ("g2g_cutoff_squared", c_double_p),
+        ("kind", C.c_int), ("pair_flags", c_uint32_p),
+        ("lj_sigma2", c_double_p), ("lj_eps4", c_double_p), ("wca_sigma2", c_double_p),
+        ("wca_eps4", c_double_p), ("hs_sigma2", c_double_p),
+        ("coulomb_bjerrum_length", C.c_double), ("coulomb_cutoff", C.c_double), ("coulomb_kappa", C.c_double),
+        ("coulomb_n_knots", C.c_int), ("coulomb_knots", c_double_p), ("coulomb_coeffs", c_double_p),
+        ("plain_bjerrum_length", C.c_double),
+        ("spline_offset", c_int_p), ("spline_knots", c_double_p), ("spline_coeffs", c_double_p),
+        ("spline_rmin2", c_double_p), ("spline_rmax2", c_double_p), ("spline_hardsphere", c_ubyte_p),
+    ]
+
+
+#: every symbol include/faunus_b200.h declares
+C_ABI_SYMBOLS = [
+    "fb_create", "fb_destroy", "fb_last_error", "fb_device_count", "fb_upload_space", "fb_update_group",
+    "fb_set_box", "fb_sync", "fb_download_space", "fb_nonbonded_energy", "fb_nonbonded_delta",
+    "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
+    "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
+    "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_launch_count",
+    "fb_stream", "fb_enable_timing", "fb_last_kernel_ms",
+]
+
+_lib: Optional[C.CDLL] = None
+_simlib: Optional[SimLibrary] = None
+
+
+def load() -> C.CDLL:
+    """Load libfaunus_b200.so (building it first if the sources are newer). Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from .build import build
+        build()
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    sig = {
+        "fb_create": (C.c_int, [C.POINTER(FbConfig), C.POINTER(vp)]),
+        "fb_destroy": (None, [vp]),
+        "fb_last_error": (C.c_char_p, [vp]),
+        "fb_device_count": (C.c_int, []),
+        "fb_upload_space": (C.c_int, [vp, C.c_int, c_double_p, c_int_p, C.POINTER(FbGroup), C.c_int, C.c_int]),
+        "fb_update_group": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(FbGroup), C.c_int, c_int_p, c_double_p,
+                                      c_int_p]),
+        "fb_set_box": (C.c_int, [vp, C.c_int, c_double_p]),
+        "fb_sync": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(FbChange)]),
+        "fb_download_space": (C.c_int, [vp, C.c_int, c_double_p, c_int_p, C.POINTER(FbGroup)]),
+        "fb_nonbonded_energy": (C.c_int, [vp, C.c_int, C.POINTER(FbChange), c_double_p]),
+        "fb_nonbonded_delta": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(FbChange), c_double_p, c_double_p]),
+        "fb_ewald_configure": (C.c_int, [vp, C.POINTER(FbEwaldConfig)]),
+        "fb_ewald_update_box": (C.c_int, [vp, C.c_int, c_int_p]),
+        "fb_ewald_update_full": (C.c_int, [vp, C.c_int]),
+        "fb_ewald_update_partial": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(FbChange)]),
+        "fb_ewald_energy": (C.c_int, [vp, C.c_int, C.POINTER(FbChange), c_double_p]),
+        "fb_ewald_sync": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(FbChange)]),
+        "fb_ewald_download": (C.c_int, [vp, C.c_int, c_double_p, c_double_p, c_double_p]),
+        "fb_widom_batch": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_int_p, c_double_p,
+                                     C.c_int, c_double_p]),
+        "fb_state_doubles": (C.c_size_t, [vp]),
+        "fb_export_state": (C.c_int, [vp, C.c_int, vp]),
+        "fb_import_state": (C.c_int, [vp, C.c_int, vp]),
+        "fb_export_state_host": (C.c_int, [vp, C.c_int, c_double_p]),
+        "fb_import_state_host": (C.c_int, [vp, C.c_int, c_double_p]),
+        "fb_launch_count": (C.c_ulonglong, [vp]),
+        "fb_stream": (vp, [vp]),
+        "fb_enable_timing": (C.c_int, [vp, C.c_int]),
+        "fb_last_kernel_ms": (C.c_double, [vp]),
+        "fbh_set_device": (None, [C.c_int]),
+        "fbh_sim_launch_count": (C.c_ulonglong, [vp]),
+    }
+    for name, (restype, argtypes) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def sim_library() -> SimLibrary:
+    global _simlib
+    if _simlib is None:
+        _simlib = SimLibrary(load(), "fbh")
+    return _simlib
+
+
+def device_count() -> int:
+    return load().fb_device_count()
+
+
+def require_device():
+    if device_count() == 0:
+        raise RuntimeError("faunus_b200: no CUDA device visible; the B200 energy path has no CPU fallback")
+
+
+class B200Simulation(Simulation):
+    """Metropolis MC simulation whose non-bonded/Ewald terms run on the B200 (``fbh_*`` ABI)."""
+
+    def __init__(self, config, device: int = 0):
+        require_device()
+        load().fbh_set_device(device)
+        super().__init__(sim_library(), config)
+
+    @property
+    def launch_count(self) -> int:
+        return int(load().fbh_sim_launch_count(self.handle))
+
+
+def make_change(everything=False, volume_change=False, groups: Sequence[dict] = ()):
+    """Build an :class:`FbChange` (keeps the backing arrays alive on the returned object)."""
+    arr = (FbGroupChange * max(1, len(groups)))()
+    keep = []
+    for i, g in enumerate(groups):
+        idx = np.asarray(g.get("atoms", ()), dtype=np.int32)
+        keep.append(idx)
+        arr[i].group_index = int(g["group"])
+        arr[i].all = int(bool(g.get("all", False)))
+        arr[i].internal = int(bool(g.get("internal", False)))
+        arr[i].n_atoms = len(idx)
+        arr[i].atoms = idx.ctypes.data_as(c_int_p)
+    ch = FbChange(int(everything), int(volume_change), len(groups), arr)
+    ch._keep = (arr, keep)
+    return ch

@@ -1,0 +1,237 @@
+/*
+ * faunus_b200.h — C ABI of the B200 (sm_100a) energy-evaluation library, libfaunus_b200.so.
+ *
+ * These are the entry points a Faunus-side `Energy::EnergyTerm` adaptor binds in place of the
+ * reference's CPU loops (INTEGRATION.md shows the adaptor). Plain pointers and sizes only, no C++
+ * or torch types. All functions return 0 on success or a negative fb_status; the message is
+ * available from fb_last_error(). Nothing throws across this boundary. A context owns all of its
+ * device memory and one CUDA stream; callers own the host buffers they pass. A context is not
+ * thread-safe (the reference drives everything from one host thread).
+ *
+ * State model: a context holds TWO device-resident structure-of-arrays mirrors of `Space`
+ * ("slots"), matching the reference's accepted and trial `State` (src/montecarlo.h:52-64).
+ * Slot 0 mirrors the accepted Space, slot 1 the trial Space. Only changed particles cross PCIe.
+ *
+ * Reference interface each entry point replaces (file:line in mlund/faunus):
+ *   fb_create / fb_destroy ......... Nonbonded<>::Nonbonded + PairEnergy::from_json  src/energy.h:1525-1534, 470-477
+ *                                    (pair-potential tables: src/potentials.cpp:672-703, 956-977, 1628-1699)
+ *   fb_upload_space ................ EnergyTerm::init() with Space contents           src/externalpotential.h:38, src/space.h:92-373
+ *   fb_update_group ................ Space::updateParticles / trial Space mutation    src/space.h:193-217, src/move.cpp:225-240
+ *   fb_set_box ..................... Space::scaleVolume → Chameleon::setVolume        src/space.cpp:249-302
+ *   fb_sync ........................ Space::sync + EnergyTerm::sync                   src/space.cpp:199-240, src/energy.cpp:1254-1268
+ *   fb_nonbonded_energy ............ Nonbonded::energy(Change) → GroupPairing::accumulate  src/energy.h:1561-1577, 1447-1475
+ *   fb_nonbonded_delta ............. the pair of calls trial.energy / accepted.energy  src/montecarlo.cpp:154-155
+ *   fb_ewald_* ..................... Energy::Ewald + PolicyIonIon                      src/energy.cpp:28-59, 133-247, 466-531, 539-658
+ *   fb_widom_batch ................. WidomInsertion::_sample insertion loop            src/analysis.cpp:1243-1265
+ *   fb_export_state/fb_import_state  MPI::ExchangeParticles / exchangeGroupSizes       src/mpicontroller.cpp:192-219, src/move.cpp:860-881
+ */
+#ifndef FAUNUS_B200_H
+#define FAUNUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fb_ctx fb_ctx;
+
+typedef enum
+{
+    FB_OK = 0,
+    FB_ERR_INVALID = -1, /* bad argument / unsupported configuration */
+    FB_ERR_CUDA = -2,    /* CUDA runtime error (no device, launch failure, ...) */
+    FB_ERR_STATE = -3,   /* call order violated (e.g. energy before upload) */
+    FB_ERR_NOMEM = -4
+} fb_status;
+
+/* Pair-potential flavour, one per `nonbonded*` name (src/energy.cpp:1284-1327) */
+typedef enum
+{
+    FB_POT_COULOMB_LJ = 0,  /* nonbonded_coulomblj : splined CoulombGalore + Lennard-Jones   */
+    FB_POT_COULOMB_WCA = 1, /* nonbonded_coulombwca: splined CoulombGalore + WCA             */
+    FB_POT_PM = 2,          /* nonbonded_pm        : plain Coulomb + hard sphere             */
+    FB_POT_PMWCA = 3,       /* nonbonded_pmwca     : plain Coulomb + WCA                     */
+    FB_POT_FUNCTOR = 4,     /* nonbonded           : per-(type,type) sum of terms, see flags */
+    FB_POT_SPLINED = 5      /* nonbonded_splined   : per-(type,type) Andrea table in r^2     */
+} fb_potential_kind;
+
+/* Per type-pair term flags for FB_POT_FUNCTOR / exact part of FB_POT_SPLINED */
+enum
+{
+    FB_TERM_COULOMB_SPLINED = 1, /* lB zz/r S(r/Rc) exp(-kappa r), r < Rc (src/potentials.h:591-598) */
+    FB_TERM_COULOMB_PLAIN = 2,   /* lB zz/sqrt(r2)                         (src/potentials.h:472-476) */
+    FB_TERM_LJ = 4,              /* 4 eps ((s2/r2)^6 - (s2/r2)^3)          (src/potentials.h:42-49)   */
+    FB_TERM_WCA = 8,             /* LJ + 1/4 cut at r2 > s2 2^(1/3)         (src/potentials.h:151-160) */
+    FB_TERM_HARDSPHERE = 16      /* r2 < s2 ? inf : 0                       (src/potentials.h:203-207) */
+};
+
+/* Molecule-kind flags (src/molecule.h:233-236) */
+enum
+{
+    FB_MOL_ATOMIC = 1,
+    FB_MOL_RIGID = 2,
+    FB_MOL_COMPRESSIBLE = 4
+};
+
+typedef struct
+{
+    int device; /* CUDA device ordinal */
+
+    /* geometry: orthogonal cell, per-axis periodicity (cuboid 1,1,1; slit 1,1,0; sphere 0,0,0) */
+    double box[3];
+    int periodic[3];
+
+    /* atom / molecule kinds */
+    int n_atom_types;
+    int n_molecule_types;
+    const int* molecule_flags;              /* [n_molecule_types] FB_MOL_* */
+    const int* molecule_natoms;             /* [n_molecule_types] atoms per molecule (exclusion matrix edge) */
+    const unsigned char* const* exclusions; /* [n_molecule_types] natoms*natoms 0/1 matrix or NULL */
+    const double* g2g_cutoff_squared;       /* [n_molecule_types^2] mass-centre cutoff^2 (DBL_MAX = none) */
+
+    /* pair potential */
+    int kind;                    /* fb_potential_kind */
+    const uint32_t* pair_flags;  /* [n_atom_types^2] FB_TERM_* (FUNCTOR, SPLINED); NULL otherwise */
+    const double* lj_sigma2;     /* [n_atom_types^2] sigma_ij^2   or NULL */
+    const double* lj_eps4;       /* [n_atom_types^2] 4 eps_ij/kT  or NULL */
+    const double* wca_sigma2;    /* idem for WCA */
+    const double* wca_eps4;
+    const double* hs_sigma2;     /* [n_atom_types^2] hard-sphere sigma_ij^2 or NULL */
+
+    /* splined Coulomb (CoulombGalore): u = lB zz / r * S(r/Rc) * exp(-kappa r) for r < Rc */
+    double coulomb_bjerrum_length;
+    double coulomb_cutoff;
+    double coulomb_kappa;
+    int coulomb_n_knots;          /* Andrea table of S(q), q in [0,1] */
+    const double* coulomb_knots;  /* [n_knots] */
+    const double* coulomb_coeffs; /* [6 (n_knots-1)] */
+
+    /* plain Coulomb (FB_POT_PM, FB_POT_PMWCA, FB_TERM_COULOMB_PLAIN) */
+    double plain_bjerrum_length;
+
+    /* per-pair splines in r^2 (FB_POT_SPLINED), concatenated over the n_atom_types^2 pairs */
+    const int* spline_offset;     /* [n_atom_types^2 + 1] first knot of each pair table */
+    const double* spline_knots;   /* [spline_offset[n^2]] */
+    const double* spline_coeffs;  /* 6 per interval, interval k of pair p at 6*(spline_offset[p] - p + k) */
+    const double* spline_rmin2;   /* [n_atom_types^2] */
+    const double* spline_rmax2;   /* [n_atom_types^2] */
+    const unsigned char* spline_hardsphere; /* [n_atom_types^2] infinite below rmin */
+} fb_config;
+
+/* One group record: index range into the particle arrays + mass centre (src/group.h:60-177) */
+typedef struct
+{
+    int begin;    /* first particle slot */
+    int size;     /* active particles */
+    int capacity; /* active + inactive */
+    int molid;    /* molecule type */
+    double cm[3]; /* mass centre (molecular groups) */
+} fb_group;
+
+/* One changed group of a Change record (src/space.h:40-52) */
+typedef struct
+{
+    int group_index;
+    int all;          /* Change::GroupChange::all */
+    int internal;     /* Change::GroupChange::internal */
+    int n_atoms;      /* number of relative_atom_indices (0 with all) */
+    const int* atoms; /* relative_atom_indices */
+} fb_group_change;
+
+/* Change record (src/space.h:29-75); matter_change is outside the hot-path scope */
+typedef struct
+{
+    int everything;
+    int volume_change;
+    int n_groups;
+    const fb_group_change* groups;
+} fb_change;
+
+/* Ewald reciprocal space parameters (EwaldData, src/energy.cpp:28-59) */
+typedef struct
+{
+    double alpha;
+    double n_cutoff;
+    double kappa;
+    double surface_dielectric_constant; /* epss; < 1 means tinfoil */
+    double bjerrum_length;
+    int spherical_sum;
+    int policy; /* 0 = PBC, 1 = PBCEigen (reference full-update quirk), 2 = IPBC */
+} fb_ewald_config;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+int fb_create(const fb_config* config, fb_ctx** ctx);
+void fb_destroy(fb_ctx* ctx);
+const char* fb_last_error(const fb_ctx* ctx); /* ctx may be NULL: error of the last failed fb_create */
+int fb_device_count(void);                    /* number of visible CUDA devices, 0 if none */
+
+/* ---- device-resident Space mirror ------------------------------------------------------- */
+/* full upload of one slot: xyzq[4*n_particles] (x,y,z,charge), atom_id[n_particles] */
+int fb_upload_space(fb_ctx* ctx, int slot, const double* xyzq, const int* atom_id, const fb_group* groups,
+                    int n_particles, int n_groups);
+/* incremental update of one group: its record plus n_atoms particles at relative indices rel_index
+ * (rel_index == NULL: the first n_atoms particles of the group) */
+int fb_update_group(fb_ctx* ctx, int slot, int group_index, const fb_group* record, int n_atoms,
+                    const int* rel_index, const double* xyzq, const int* atom_id);
+int fb_set_box(fb_ctx* ctx, int slot, const double box[3]);
+/* dst slot := src slot for what `change` lists (Space::sync direction); device-to-device */
+int fb_sync(fb_ctx* ctx, int dst_slot, int src_slot, const fb_change* change);
+int fb_download_space(fb_ctx* ctx, int slot, double* xyzq, int* atom_id, fb_group* groups);
+
+/* ---- non-bonded energy -------------------------------------------------------------------- */
+/* energy of the pairs `change` touches, evaluated on one slot (Nonbonded::energy) */
+int fb_nonbonded_energy(fb_ctx* ctx, int slot, const fb_change* change, double* energy);
+/* the same for two slots in ONE pass over the particles: u_new on slot_new, u_old on slot_old */
+int fb_nonbonded_delta(fb_ctx* ctx, int slot_new, int slot_old, const fb_change* change, double* u_new,
+                       double* u_old);
+
+/* ---- Ewald reciprocal space --------------------------------------------------------------- */
+int fb_ewald_configure(fb_ctx* ctx, const fb_ewald_config* config);
+/* k-vectors and A_k for the slot's current box (PolicyIonIon::updateBox); returns K in *n_kvectors */
+int fb_ewald_update_box(fb_ctx* ctx, int slot, int* n_kvectors);
+/* Q(k) = sum_j q_j exp(i k.r_j) over all active particles (updateComplex, full) */
+int fb_ewald_update_full(fb_ctx* ctx, int slot);
+/* Q_new(k) = Q_old(k) + sum_moved [q e^{ik.r}]_new - [q e^{ik.r}]_old (updateComplex, partial) */
+int fb_ewald_update_partial(fb_ctx* ctx, int slot_new, int slot_old, const fb_change* change);
+/* surface + reciprocal energy of a slot (Ewald::energy) */
+int fb_ewald_energy(fb_ctx* ctx, int slot, const fb_change* change, double* energy);
+/* Ewald::sync: Q (and, for everything/volume changes, k-vectors and A_k) dst := src */
+int fb_ewald_sync(fb_ctx* ctx, int dst_slot, int src_slot, const fb_change* change);
+/* debug/tests: copy out K complex numbers (re,im interleaved), k-vectors [3K], A_k [K] (NULL skips) */
+int fb_ewald_download(fb_ctx* ctx, int slot, double* q_re_im, double* kvectors, double* aks);
+
+/* ---- Widom: B independent ghost insertions per launch ------------------------------------- */
+/* ghost_xyzq[B*n_ghost_atoms*4], ghost_atom_id[n_ghost_atoms], ghost_cm[B*3] (molecular ghosts;
+ * NULL for atomic), internal != 0 adds the ghost's own pair energy; du[B] = non-bonded energy of
+ * each ghost with all active particles of `slot` */
+int fb_widom_batch(fb_ctx* ctx, int slot, int ghost_group_index, int n_ghost_atoms, int n_insertions,
+                   const double* ghost_xyzq, const int* ghost_atom_id, const double* ghost_cm, int internal,
+                   double* du);
+
+/* ---- replica exchange (parallel tempering) ------------------------------------------------ */
+/* packed device-side state of a slot: [box(3) | group sizes (G) | x,y,z,q,id per particle (5N)]
+ * as doubles; fb_state_doubles gives the length. The buffers are DEVICE pointers so that the
+ * exchange can go GPU to GPU (NCCL send/recv or peer copy) without touching the host. */
+size_t fb_state_doubles(const fb_ctx* ctx);
+int fb_export_state(fb_ctx* ctx, int slot, double* device_buffer);
+int fb_import_state(fb_ctx* ctx, int slot, const double* device_buffer);
+/* host-side view of the same packing (tests, gloo) */
+int fb_export_state_host(fb_ctx* ctx, int slot, double* host_buffer);
+int fb_import_state_host(fb_ctx* ctx, int slot, const double* host_buffer);
+
+/* ---- instrumentation ----------------------------------------------------------------------- */
+/* number of kernels this context has launched so far */
+unsigned long long fb_launch_count(const fb_ctx* ctx);
+/* raw CUDA stream (cudaStream_t) of the context, for event timing by the caller */
+void* fb_stream(const fb_ctx* ctx);
+/* device time in milliseconds spent in the kernels launched by the most recent energy call
+ * (cudaEvent pair on the context's stream); enabled with fb_enable_timing */
+int fb_enable_timing(fb_ctx* ctx, int on);
+double fb_last_kernel_ms(const fb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAUNUS_B200_H */

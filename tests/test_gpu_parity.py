@@ -1,0 +1,218 @@
+"""Parity of the B200 path (through the C ABI / adaptor terms) with the oracle on identical inputs.
+Tolerance: 1e-10 relative on energies (FP64, summation order only; BASELINE.json north_star), identical
+accept/reject traces for a fixed seed."""
+import numpy as np
+import pytest
+
+from _oraclelib import oracle_sim
+from conftest import nacl_pair_input, small_electrolyte
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def b200_sim(cfg):
+    from faunus_b200.native import B200Simulation
+    return B200Simulation(cfg)
+
+
+def assert_close(a, b, rtol=RTOL, scale=None):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    assert a.shape == b.shape
+    inf = np.isinf(a) | np.isinf(b)
+    assert np.array_equal(a[inf], b[inf])
+    ref = np.abs(a[~inf]) if scale is None else scale
+    assert np.all(np.abs(a[~inf] - b[~inf]) <= rtol * np.maximum(ref, 1e-300) + 1e-300), \
+        f"max abs diff {np.abs(a[~inf] - b[~inf]).max()} (ref scale {np.max(ref) if np.size(ref) else 0})"
+
+
+def pair_of_sims(cfg):
+    return oracle_sim(cfg), b200_sim(cfg)
+
+
+def electrolyte_variants():
+    ew = {"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 6}
+    return {
+        "coulombwca_ewald": small_electrolyte(coulomb=ew),
+        "coulombwca_ewald_surface": small_electrolyte(coulomb=dict(ew, epss=80.0)),
+        "coulomblj_fanourgakis": small_electrolyte(energy_name="nonbonded_coulomblj",
+                                                   coulomb={"type": "fanourgakis", "epsr": 78.7, "cutoff": 12.0}),
+        "coulombwca_yukawa": small_electrolyte(coulomb={"type": "yukawa", "epsr": 78.7, "debyelength": 9.0}),
+        "coulombwca_qpot": small_electrolyte(coulomb={"type": "qpotential", "epsr": 78.7, "cutoff": 12.0, "order": 3}),
+        "pm": small_electrolyte(energy_name="nonbonded_pm", coulomb={"epsr": 78.7}),
+        "pmwca": small_electrolyte(energy_name="nonbonded_pmwca", coulomb={"epsr": 78.7}),
+    }
+
+
+def functor_variants():
+    base = small_electrolyte(coulomb={"type": "plain", "epsr": 78.7})
+    functor = dict(base)
+    functor["energy"] = [{"nonbonded": {
+        "default": [{"lennardjones": {"mixing": "LB"}}, {"coulomb": {"type": "fanourgakis", "epsr": 78.7, "cutoff": 12}}],
+        "Na Cl": [{"coulomb": {"type": "fanourgakis", "epsr": 78.7, "cutoff": 12}}, {"wca": {"mixing": "LB"}}],
+        "Cl Cl": [{"coulomb": {"type": "fanourgakis", "epsr": 78.7, "cutoff": 12}}, {"hardsphere": {}}]}}]
+    splined = dict(base)
+    splined["energy"] = [{"nonbonded_splined": {
+        "default": [{"lennardjones": {"mixing": "LB"}}, {"coulomb": {"type": "fanourgakis", "epsr": 78.7, "cutoff": 12}}]}}]
+    return {"functor": functor, "splined": splined}
+
+
+ALL_VARIANTS = {**electrolyte_variants(), **functor_variants()}
+
+
+@pytest.mark.parametrize("name", sorted(ALL_VARIANTS))
+def test_system_energy_and_moves(name):
+    """Full energy per term, then 300 single-ion trial moves: u_new/u_old per move and the trace"""
+    cfg = ALL_VARIANTS[name]
+    o, g = pair_of_sims(cfg)
+    eo, to = o.system_energy()
+    eg, tg = g.system_energy()
+    assert len(to) == len(tg)
+    assert_close(to, tg, scale=np.abs(to).max())
+    for s in (o, g):
+        s.trace_enable()
+        s.sweep(300)
+    a, b = o.trace(), g.trace()
+    assert np.array_equal(a["accepted"], b["accepted"])
+    scale = np.abs(a["u_new"][np.isfinite(a["u_new"])]).max()
+    assert_close(a["u_new"], b["u_new"], scale=scale)
+    assert_close(a["u_old"], b["u_old"], scale=scale)
+    assert abs(g.drift()) < 1e-9
+    assert_close(o.system_energy()[1], g.system_energy()[1], scale=np.abs(to).max())
+    assert g.launch_count > 0
+
+
+def test_bulk_example_trace(bulk_input):
+    """examples/bulk state: identical accept/reject sequence over 3 sweeps (6912 moves)"""
+    o, g = pair_of_sims(bulk_input)
+    assert_close(o.system_energy()[1], g.system_energy()[1], scale=7e4)
+    for s in (o, g):
+        s.trace_enable()
+        s.sweep(3)
+    a, b = o.trace(), g.trace()
+    assert len(a["du"]) == 3 * 2304
+    assert np.array_equal(a["accepted"], b["accepted"])
+    assert_close(a["u_new"], b["u_new"], scale=np.abs(a["u_new"]).max())
+    assert abs(g.drift()) < 1e-9
+
+
+def test_minimal_example(minimal_input):
+    o, g = pair_of_sims(minimal_input)
+    assert_close(o.system_energy()[1], g.system_energy()[1], scale=abs(o.system_energy()[0]))
+    for s in (o, g):
+        s.trace_enable()
+        s.sweep(100)
+    assert np.array_equal(o.trace()["accepted"], g.trace()["accepted"])
+
+
+def test_water_example(water_input):
+    """examples/water: rigid SPC/E, mass-centre cutoff, Ewald partial updates for 3-atom moves,
+    volume moves (full updates + box change)"""
+    o, g = pair_of_sims(water_input)
+    eo, to = o.system_energy()
+    eg, tg = g.system_energy()
+    assert len(to) == 4
+    assert_close(to, tg, scale=np.abs(to).max())
+    for s in (o, g):
+        s.trace_enable()
+        s.sweep(3)
+    a, b = o.trace(), g.trace()
+    assert len(a["du"]) > 700
+    assert np.array_equal(a["move_id"], b["move_id"])
+    assert np.array_equal(a["accepted"], b["accepted"])
+    scale = np.abs(to).max()
+    assert_close(a["du"], b["du"], rtol=1e-9, scale=scale)  # ΔU of full energies: cancellation of ~1e4 kT sums
+    assert (a["move_id"] == 1).any(), "no volume move sampled"
+    assert_close(o.system_energy()[1], g.system_energy()[1], scale=scale)
+    xo, _ = o.particles()
+    xg, _ = g.particles()
+    assert np.array_equal(xo, xg)
+
+
+def test_ewald_doctest_values(reference_values):
+    """The reference's Energy::Ewald known answers on the device (src/energy.cpp:665-762)"""
+    ref = reference_values["ewald_doctest"]
+    lB = 560.4557863339663
+    for scheme in ("PBC", "PBCEigen"):
+        g = b200_sim(nacl_pair_input(scheme))
+        terms = g.system_energy()[1]
+        assert terms[2] == pytest.approx((ref["surface_over_lB"] + ref["reciprocal_over_lB"]) * lB, rel=1e-10)
+    for use_all in (True, False):
+        g = b200_sim(nacl_pair_input())
+        before = g.system_energy()[1][2]
+        g.trial_set(0, [0], [[0.1, 0.1, 0.1]], all=use_all, internal=True)
+        g.trial_commit(True)
+        after = g.system_energy()[1][2]
+        assert after == pytest.approx(ref["energy_after_move"], rel=1e-9)
+        assert after - before == pytest.approx(ref["energy_change"], rel=1e-9)
+    g = b200_sim(nacl_pair_input("IPBC"))
+    o = oracle_sim(nacl_pair_input("IPBC"))
+    assert g.system_energy()[1][2] == pytest.approx(o.system_energy()[1][2], rel=1e-10)
+
+
+def test_reject_restores_state():
+    """trial → reject → the next evaluation sees the accepted state again (sync direction)"""
+    cfg = small_electrolyte(coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 6})
+    o, g = pair_of_sims(cfg)
+    rng = np.random.RandomState(3)
+    xyzq, _ = g.particles()
+    for step in range(40):
+        i = int(rng.randint(0, len(xyzq)))
+        new = xyzq[i, :3] + rng.uniform(-2, 2, 3)
+        uo = o.trial_set(0, [i], [new])
+        ug = g.trial_set(0, [i], [new])
+        assert_close(uo, ug, scale=max(abs(uo[0]), 1.0))
+        accept = bool(step % 3 == 0)
+        o.trial_commit(accept)
+        g.trial_commit(accept)
+        if accept:
+            xyzq[i, :3] = new
+    assert_close(o.system_energy()[1], g.system_energy()[1], scale=abs(o.system_energy()[0]))
+
+
+def test_energy_without_update_state():
+    """Callers like SystemEnergy / Widom call energy(change) on the accepted Hamiltonian with no
+    updateState and no sync: the term must be idempotent"""
+    cfg = small_electrolyte(coulomb={"type": "fanourgakis", "epsr": 78.7, "cutoff": 12.0})
+    o, g = pair_of_sims(cfg)
+    for idx in ([5], [1, 7, 20], []):
+        kw = dict(group=0, internal=True, indices=idx, all=not idx)
+        e1 = g.energy(0, **kw)
+        e2 = g.energy(0, **kw)
+        assert e1 == e2
+        assert_close([o.energy(0, **kw)], [e1])
+
+
+def test_widom_batched_matches_sequential():
+    """Batched ghost insertions (one launch) == sequential energy(change) calls == oracle"""
+    cfg = small_electrolyte(coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 6},
+                            ghost_pairs=1)
+    analysis = {"molecule": "ghost", "ninsert": 64}
+    o, g, g_seq = oracle_sim(cfg), b200_sim(cfg), b200_sim(cfg)
+    wo = o.widom_create(analysis)
+    wg = g.widom_create(analysis)
+    ws = g_seq.widom_create(dict(analysis, batched=False))
+    for s, w in ((o, wo), (g, wg), (g_seq, ws)):
+        s.widom_sample(w, 3)
+    ro, rg, rs = o.widom_result(wo), g.widom_result(wg), g_seq.widom_result(ws)
+    assert ro["count"] == rg["count"] == rs["count"] == 3 * 64
+    scale = np.abs(ro["last_du"]).max()
+    assert_close(ro["last_du"], rg["last_du"], scale=scale)
+    assert_close(ro["last_du"], rs["last_du"], scale=scale)
+    assert rg["sum_exp"] == pytest.approx(ro["sum_exp"], rel=1e-9)
+
+
+def test_widom_example(reference_values, widom_input):
+    """examples/widom on the device: hard-sphere μ_ex within the reference's 1 % of 0.13353"""
+    cfg = dict(widom_input)
+    analysis = dict(cfg.pop("analysis")[0]["widom"], ninsert=4096)
+    o, g = pair_of_sims(cfg)
+    wo, wg = o.widom_create(analysis), g.widom_create(analysis)
+    o.widom_sample(wo, 50)
+    g.widom_sample(wg, 50)
+    ro, rg = o.widom_result(wo), g.widom_result(wg)
+    assert np.array_equal(ro["last_du"], rg["last_du"])  # 0 or +inf
+    assert ro["sum_exp"] == rg["sum_exp"]
+    mu = -np.log(rg["sum_exp"] / rg["count"])
+    assert mu == pytest.approx(reference_values["widom"]["mu_excess"], rel=0.01)
