@@ -33,10 +33,26 @@ def with_state(config: dict, state: dict) -> dict:
     return out
 
 
+def lattice_positions(n: int, box: float, jitter: float, seed: int = 5489) -> np.ndarray:
+    """Ions on a randomly filled simple-cubic lattice with uniform jitter (vectorised; N = 1e6 in < 1 s).
+
+    Sites are visited in a random permutation so that the alternating Na/Cl ids are spatially mixed.
+    """
+    rng = np.random.RandomState(seed)
+    m = int(np.ceil(n ** (1.0 / 3.0)))
+    spacing = box / m
+    sites = rng.permutation(m ** 3)[:n]
+    ijk = np.stack(np.unravel_index(sites, (m, m, m)), axis=1).astype(np.float64)
+    pos = (ijk + 0.5) * spacing - 0.5 * box
+    pos += (rng.random_sample((n, 3)) - 0.5) * 2.0 * min(jitter, 0.45 * spacing)
+    return pos
+
+
 def electrolyte_positions(n: int, box: float, min_distance: float, seed: int = 5489) -> np.ndarray:
     """Uniform random ion positions in a cubic box, rejecting overlaps below ``min_distance``.
 
-    Uses a cell grid so that N = 1e6 is generated in seconds. Deterministic for a given seed.
+    Pure-Python rejection sampling with a cell grid; use for small systems (tests).
+    Deterministic for a given seed.
     """
     rng = np.random.RandomState(seed)
     ncell = max(1, int(box / max(min_distance, 1e-9)))
@@ -79,7 +95,7 @@ def primitive_model(n: int = 100_000, molarity: float = 1.0, coulomb: Optional[d
                     energy_name: str = "nonbonded_coulombwca", sigma: float = 4.0, eps: float = 0.2,
                     dp: float = 4.0, temperature: float = 298.15, seed: int = 5489,
                     ghost_pairs: int = 0, min_distance: float = 3.5, summation_policy: str = "serial",
-                    extra_nonbonded: Optional[dict] = None) -> dict:
+                    extra_nonbonded: Optional[dict] = None, placement: str = "auto", moves_per_sweep: int = 1) -> dict:
     """restricted primitive model 1:1 electrolyte, one atomic group.
 
     N ions (alternating Na+/Cl−, as ``atoms: [Na, Cl]`` insertion gives) in a cubic PBC box at
@@ -94,7 +110,12 @@ def primitive_model(n: int = 100_000, molarity: float = 1.0, coulomb: Optional[d
     box = volume ** (1.0 / 3.0)
     if coulomb is None:
         coulomb = {"type": "ewald", "epsr": 78.7, "cutoff": 14.0, "alpha": 0.22, "ncutoff": 30}
-    pos = electrolyte_positions(n, box, min_distance, seed)
+    if placement == "auto":
+        placement = "random" if n <= 5000 else "lattice"
+    if placement == "random":
+        pos = electrolyte_positions(n, box, min_distance, seed)
+    else:
+        pos = lattice_positions(n, box, jitter=2.0, seed=seed)
     particles = [{"id": i % 2, "pos": pos[i].tolist(), "q": 1.0 if i % 2 == 0 else -1.0} for i in range(n)]
     groups = [{"id": 0, "size": n, "cm": [0.0, 0.0, 0.0], "atomic": True, "compressible": False}]
     moleculelist = [{"salt": {"atoms": ["Na", "Cl"], "atomic": True}}]
@@ -128,5 +149,5 @@ def primitive_model(n: int = 100_000, molarity: float = 1.0, coulomb: Optional[d
         "groups": groups,
         "particles": particles,
         "energy": [{energy_name: nonbonded}],
-        "moves": [{"transrot": {"molecule": "salt", "repeat": 1}}],
+        "moves": [{"transrot": {"molecule": "salt", "repeat": moves_per_sweep}}],
     }

@@ -165,6 +165,9 @@ struct fb_ctx
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0;
+    int timing_class = -1;    //!< which accumulator the current event pair feeds
+    double acc_ms[4] = {0, 0, 0, 0};
+    double acc_launches[4] = {0, 0, 0, 0};
 
     int max_blocks = 148 * 4;
 };
@@ -215,9 +218,18 @@ void checkSlot(fb_ctx* c, int s, bool need_upload = true)
     }
 }
 
-void beginTiming(fb_ctx* c)
+enum TimingClass
+{
+    TIME_PAIR = 0,
+    TIME_EWALD = 1,
+    TIME_FULL = 2,
+    TIME_WIDOM = 3
+};
+
+void beginTiming(fb_ctx* c, int timing_class = -1)
 {
     if (c->timing) {
+        c->timing_class = timing_class;
         CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
     }
 }
@@ -233,6 +245,11 @@ void finish(fb_ctx* c)
         float ms = 0;
         CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         c->last_ms = ms;
+        if (c->timing_class >= 0) {
+            c->acc_ms[c->timing_class] += ms;
+            c->acc_launches[c->timing_class] += 1;
+            c->timing_class = -1;
+        }
     }
 }
 
@@ -717,6 +734,55 @@ FB_API double fb_last_kernel_ms(const fb_ctx* c)
     return c ? c->last_ms : 0.0;
 }
 
+FB_API int fb_get_timing(const fb_ctx* c, double out[8])
+{
+    if (!c || !out) {
+        return FB_ERR_INVALID;
+    }
+    for (int i = 0; i < 4; ++i) {
+        out[2 * i] = c->acc_ms[i];
+        out[2 * i + 1] = c->acc_launches[i];
+    }
+    return FB_OK;
+}
+
+FB_API int fb_measure_fp64_peak(int device, double* tflops)
+{
+    if (!tflops || cudaSetDevice(device) != cudaSuccess) {
+        cudaGetLastError();
+        return FB_ERR_CUDA;
+    }
+    cudaDeviceProp prop{};
+    double* d = nullptr;
+    cudaEvent_t e0, e1;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || cudaMalloc(&d, 64) != cudaSuccess) {
+        cudaGetLastError();
+        return FB_ERR_CUDA;
+    }
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = prop.multiProcessorCount * 8;
+    const int iters = 200000;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        dfmaPeakKernel<<<blocks, 256>>>(d, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * iters * 256.0 * blocks;
+        if (rep > 0 && ms > 0) {
+            best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return cudaGetLastError() == cudaSuccess ? FB_OK : FB_ERR_CUDA;
+}
+
 // =================================================================================================
 // Space mirror
 // =================================================================================================
@@ -973,8 +1039,8 @@ FB_API int fb_nonbonded_energy(fb_ctx* c, int s, const fb_change* change, double
         if (!change || !energy) {
             throw CudaError{"null argument"};
         }
-        beginTiming(c);
         if (change->everything || change->volume_change) {
+            beginTiming(c, TIME_FULL);
             launchFull(c, makeView(c, s), (!change->everything && change->volume_change) ? 1 : 0);
         }
         else {
@@ -988,6 +1054,7 @@ FB_API int fb_nonbonded_energy(fb_ctx* c, int s, const fb_change* change, double
                 return;
             }
             const SlotView V = makeView(c, s);
+            beginTiming(c, TIME_PAIR);
             launchMoved<false>(c, V, V, md);
         }
         finish(c);
@@ -1004,12 +1071,13 @@ FB_API int fb_nonbonded_delta(fb_ctx* c, int s_new, int s_old, const fb_change* 
         if (!change || !u_new || !u_old || s_new == s_old) {
             throw CudaError{"bad arguments"};
         }
-        beginTiming(c);
         if (change->everything || change->volume_change) {
             const int pred = (!change->everything && change->volume_change) ? 1 : 0;
+            beginTiming(c, TIME_FULL);
             launchFull(c, makeView(c, s_new), pred);
             finish(c);
             *u_new = c->h_result[0];
+            beginTiming(c, TIME_FULL);
             launchFull(c, makeView(c, s_old), pred);
             finish(c);
             *u_old = c->h_result[0];
@@ -1024,6 +1092,7 @@ FB_API int fb_nonbonded_delta(fb_ctx* c, int s_new, int s_old, const fb_change* 
             *u_new = *u_old = 0.0;
             return;
         }
+        beginTiming(c, TIME_PAIR);
         launchMoved<true>(c, makeView(c, s_new), makeView(c, s_old), md);
         finish(c);
         *u_new = c->h_result[0];
@@ -1103,7 +1172,7 @@ FB_API int fb_ewald_update_partial(fb_ctx* c, int s_new, int s_old, const fb_cha
         if (grid > kMaxPartialBlocks * 4) {
             c->partials.ensure(static_cast<size_t>(grid));
         }
-        beginTiming(c);
+        beginTiming(c, TIME_EWALD);
         ewaldPartialKernel<<<grid, kBlock, 0, c->stream>>>(makeView(c, s_new), makeView(c, s_old),
                                                            makeEwaldView(c, s_new), makeEwaldView(c, s_old), md,
                                                            c->partials.ptr, c->ticket.ptr, c->d_result + 4);
@@ -1271,7 +1340,7 @@ FB_API int fb_widom_batch(fb_ctx* c, int s, int ghost_group, int n_ghost_atoms, 
         c->h_widom_du.ensure(n_insertions);
         const SlotView V = makeView(c, s);
         dim3 grid(bx, n_split);
-        beginTiming(c);
+        beginTiming(c, TIME_WIDOM);
 #define FB_CASE(K)                                                                                            \
     case K:                                                                                                   \
         widomKernel<K><<<grid, kWidomBlock, 0, c->stream>>>(V, c->P, ghost_group, n_ghost_atoms, n_insertions, \

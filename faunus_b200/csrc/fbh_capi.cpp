@@ -101,3 +101,29 @@ extern "C" __attribute__((visibility("default"))) int fbh_pair_tables_json(const
     });
     return n;
 }
+
+/** toggle CUDA-event timing of the hot kernels; read the accumulators (see fb_get_timing) */
+extern "C" __attribute__((visibility("default"))) int fbh_sim_enable_timing(void* h, int on)
+{
+    auto* s = static_cast<fb::capi::Sim*>(h);
+    for (const auto& t : s->mc->state.pot->find<fb::NonbondedB200>()) {
+        fb_enable_timing(t->device()->ctx, on);
+    }
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int fbh_sim_get_timing(void* h, double out[8])
+{
+    auto* s = static_cast<fb::capi::Sim*>(h);
+    for (int i = 0; i < 8; ++i) {
+        out[i] = 0;
+    }
+    for (const auto& t : s->mc->state.pot->find<fb::NonbondedB200>()) {
+        double v[8];
+        fb_get_timing(t->device()->ctx, v);
+        for (int i = 0; i < 8; ++i) {
+            out[i] += v[i];
+        }
+    }
+    return 0;
+}

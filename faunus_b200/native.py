@@ -79,7 +79,7 @@ C_ABI_SYMBOLS = [
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
     "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
     "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_launch_count",
-    "fb_stream", "fb_enable_timing", "fb_last_kernel_ms",
+    "fb_stream", "fb_enable_timing", "fb_last_kernel_ms", "fb_get_timing", "fb_measure_fp64_peak",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -127,6 +127,10 @@ def load() -> C.CDLL:
         "fb_stream": (vp, [vp]),
         "fb_enable_timing": (C.c_int, [vp, C.c_int]),
         "fb_last_kernel_ms": (C.c_double, [vp]),
+        "fb_get_timing": (C.c_int, [vp, c_double_p]),
+        "fb_measure_fp64_peak": (C.c_int, [C.c_int, c_double_p]),
+        "fbh_sim_enable_timing": (C.c_int, [vp, C.c_int]),
+        "fbh_sim_get_timing": (C.c_int, [vp, c_double_p]),
         "fbh_set_device": (None, [C.c_int]),
         "fbh_sim_launch_count": (C.c_ulonglong, [vp]),
     }
@@ -165,6 +169,16 @@ class B200Simulation(Simulation):
     @property
     def launch_count(self) -> int:
         return int(load().fbh_sim_launch_count(self.handle))
+
+    def enable_timing(self, on: bool = True):
+        """CUDA-event timing of every hot-kernel launch (adds ~2 event records per launch)"""
+        load().fbh_sim_enable_timing(self.handle, int(on))
+
+    def device_time_ms(self) -> dict:
+        out = np.zeros(8)
+        load().fbh_sim_get_timing(self.handle, out.ctypes.data_as(c_double_p))
+        return {"pair_ms": out[0], "pair_launches": int(out[1]), "ewald_ms": out[2], "ewald_launches": int(out[3]),
+                "full_ms": out[4], "full_launches": int(out[5]), "widom_ms": out[6], "widom_launches": int(out[7])}
 
 
 def make_change(everything=False, volume_change=False, groups: Sequence[dict] = ()):

@@ -230,6 +230,12 @@ void* fb_stream(const fb_ctx* ctx);
  * (cudaEvent pair on the context's stream); enabled with fb_enable_timing */
 int fb_enable_timing(fb_ctx* ctx, int on);
 double fb_last_kernel_ms(const fb_ctx* ctx);
+/* accumulated since creation (timing enabled): out[0] = ms in the moved-set pair kernel, out[1] = its
+ * launches, out[2] = ms in the Ewald partial-update kernel, out[3] = its launches, out[4] = ms in the
+ * full-energy kernel (+ ordered sum), out[5] = its launches, out[6] = ms in Widom kernels, out[7] = launches */
+int fb_get_timing(const fb_ctx* ctx, double out[8]);
+/* dependent-free DFMA microbenchmark on `device`: sustained FP64 FMA throughput in TFLOP/s */
+int fb_measure_fp64_peak(int device, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_functions():
     text = open(os.path.join(ROOT, "include", "faunus_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(fb_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(fb_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_exported():

@@ -40,7 +40,7 @@ def electrolyte_variants():
                                                    coulomb={"type": "fanourgakis", "epsr": 78.7, "cutoff": 12.0}),
         "coulombwca_yukawa": small_electrolyte(coulomb={"type": "yukawa", "epsr": 78.7, "debyelength": 9.0}),
         "coulombwca_qpot": small_electrolyte(coulomb={"type": "qpotential", "epsr": 78.7, "cutoff": 12.0, "order": 3}),
-        "pm": small_electrolyte(energy_name="nonbonded_pm", coulomb={"epsr": 78.7}),
+        "pm": small_electrolyte(energy_name="nonbonded_pm", coulomb={"epsr": 78.7}, sigma=3.0),
         "pmwca": small_electrolyte(energy_name="nonbonded_pmwca", coulomb={"epsr": 78.7}),
     }
 
@@ -51,7 +51,7 @@ def functor_variants():
     functor["energy"] = [{"nonbonded": {
         "default": [{"lennardjones": {"mixing": "LB"}}, {"coulomb": {"type": "fanourgakis", "epsr": 78.7, "cutoff": 12}}],
         "Na Cl": [{"coulomb": {"type": "fanourgakis", "epsr": 78.7, "cutoff": 12}}, {"wca": {"mixing": "LB"}}],
-        "Cl Cl": [{"coulomb": {"type": "fanourgakis", "epsr": 78.7, "cutoff": 12}}, {"hardsphere": {}}]}}]
+        "Cl Cl": [{"coulomb": {"type": "fanourgakis", "epsr": 78.7, "cutoff": 12}}, {"hardsphere": {"custom": [{"Cl Cl": {"sigma": 3.2}}]}}]}}]
     splined = dict(base)
     splined["energy"] = [{"nonbonded_splined": {
         "default": [{"lennardjones": {"mixing": "LB"}}, {"coulomb": {"type": "fanourgakis", "epsr": 78.7, "cutoff": 12}}]}}]
