@@ -95,8 +95,43 @@ class DeviceContext
     bool cache_valid = false;
     std::string cache_signature;
     double cached_old_energy = 0;
-    // Ewald bookkeeping shared by the two EwaldB200 instances
-    bool ewald_cache_valid = false;
+    // Ewald sibling: present? eligible for the fused fast path (no surface term)? old groups known?
+    bool has_ewald = false;
+    bool ewald_fast_ok = false;
+    bool ewald_have_old = false;
+    // fast path: one staged small trial move (fb_trial_energy / fb_trial_commit)
+    bool fast_enabled = true;
+    bool fast_staged = false;
+    bool fast_evaluated = false;
+    bool fast_sync_for_ewald = false;
+    fb_trial_move fast_move{};
+    uint64_t fast_key = 0;
+    double fast_u_new = 0, fast_u_old = 0, fast_ew_new = 0, fast_ew_old = 0;
+    const Space* spaces[2] = {nullptr, nullptr}; //!< Space of the instance bound to each slot
+
+    /** cheap identity of a single-group Change (group, flags, indices) */
+    static uint64_t changeKey(const Change& c)
+    {
+        if (c.everything || c.volume_change || c.groups.size() != 1) {
+            return 0;
+        }
+        const auto& g = c.groups[0];
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+        mix(g.group_index + 1);
+        mix((g.all ? 2 : 0) | (g.internal ? 1 : 0));
+        for (auto i : g.relative_atom_indices) {
+            mix(i + 7);
+        }
+        return h | 1ull;
+    }
+
+    void evaluateFast()
+    {
+        fbCheck(fb_trial_energy(ctx, &fast_move, &fast_u_new, &fast_u_old, &fast_ew_new, &fast_ew_old), ctx,
+                "fb_trial_energy");
+        fast_evaluated = true;
+    }
 
     DeviceContext(const std::string& name, const Json& cfg, const Space& spc, int device)
     {
@@ -255,6 +290,7 @@ class NonbondedB200 : public EnergyTerm
             registry[reg_key] = dev;
         }
         slot = dev->attached++;
+        dev->spaces[slot] = &spc;
         dev->uploadSpace(slot, spc);
     }
     ~NonbondedB200() override
@@ -268,10 +304,70 @@ class NonbondedB200 : public EnergyTerm
 
     void init() override { dev->uploadSpace(slot, spc); }
 
+    /**
+     * Small move of one group (≤ 8 atoms, no size change) on the trial instance: nothing is pushed;
+     * the particles are staged for the fused single-launch evaluation.
+     */
+    bool stageFastMove(const Change& change)
+    {
+        auto& d = *dev;
+        if (!d.fast_enabled || state != MonteCarloState::TRIAL || d.attached != 2 || slot != 1) {
+            return false;
+        }
+        const uint64_t key = DeviceContext::changeKey(change);
+        if (key == 0 || change.matter_change) {
+            return false;
+        }
+        if (d.has_ewald && !(d.ewald_fast_ok && d.ewald_have_old)) {
+            return false;
+        }
+        const auto& gc = change.groups[0];
+        const auto& g = spc.groups.at(gc.group_index);
+        const auto& g_old = d.spaces[0]->groups.at(gc.group_index);
+        if (g.size() != g_old.size()) {
+            return false;
+        }
+        const bool whole = gc.relative_atom_indices.empty();
+        const size_t n = whole ? g.size() : gc.relative_atom_indices.size();
+        if (n < 1 || n > FB_FAST_ATOMS) {
+            return false;
+        }
+        fb_trial_move& mv = d.fast_move;
+        mv.group_index = static_cast<int>(gc.group_index);
+        mv.n_atoms = static_cast<int>(n);
+        for (size_t i = 0; i < n; ++i) {
+            const size_t rel = whole ? i : gc.relative_atom_indices[i];
+            if (rel >= g.size()) {
+                return false;
+            }
+            const auto& p = spc.at(g, rel);
+            mv.rel_index[i] = static_cast<int>(rel);
+            mv.xyzq[i][0] = p.pos.x;
+            mv.xyzq[i][1] = p.pos.y;
+            mv.xyzq[i][2] = p.pos.z;
+            mv.xyzq[i][3] = p.charge;
+            mv.atom_id[i] = p.id;
+        }
+        mv.cm[0] = g.mass_center.x;
+        mv.cm[1] = g.mass_center.y;
+        mv.cm[2] = g.mass_center.z;
+        mv.internal = gc.internal ? 1 : 0;
+        mv.with_ewald = 0; // set by the Ewald sibling's updateState
+        d.fast_staged = true;
+        d.fast_evaluated = false;
+        d.fast_key = key;
+        d.cache_valid = false;
+        return true;
+    }
+
     /** trial Space was mutated by a move: push what the Change lists into our slot */
     void updateState(const Change& change) override
     {
         if (!change) {
+            return;
+        }
+        dev->fast_staged = false;
+        if (stageFastMove(change)) {
             return;
         }
         if (change.everything || change.volume_change) {
@@ -291,6 +387,22 @@ class NonbondedB200 : public EnergyTerm
         }
         if (change.matter_change) {
             throw std::runtime_error("matter_change (speciation) is outside the B200 hot-path scope");
+        }
+        if (dev->fast_staged && dev->fast_key == DeviceContext::changeKey(change)) {
+            if (state == MonteCarloState::TRIAL) {
+                if (!dev->fast_evaluated) {
+                    dev->evaluateFast();
+                }
+                return dev->fast_u_new;
+            }
+            if (dev->fast_evaluated) {
+                return dev->fast_u_old;
+            }
+        }
+        if (dev->fast_staged && state == MonteCarloState::TRIAL) {
+            // a different change is evaluated on the trial state while a fast move is staged: materialise it
+            dev->fast_staged = false;
+            dev->uploadChange(slot, spc, change);
         }
         FlatChange flat(change);
         const std::string sig = flat.signature();
@@ -332,6 +444,18 @@ class NonbondedB200 : public EnergyTerm
         if (!other || other->dev != dev) {
             throw std::runtime_error("sync error");
         }
+        if (dev->fast_staged && dev->fast_key == DeviceContext::changeKey(change)) {
+            // accepted.sync(trial) = accept, trial.sync(accepted) = reject (src/montecarlo.cpp:167-175)
+            if (!dev->fast_evaluated) {
+                dev->evaluateFast();
+            }
+            fbCheck(fb_trial_commit(dev->ctx, slot == 0 ? 1 : 0), dev->ctx, "fb_trial_commit");
+            dev->fast_staged = false;
+            dev->fast_evaluated = false;
+            dev->fast_sync_for_ewald = dev->has_ewald;
+            return;
+        }
+        dev->fast_staged = false;
         FlatChange flat(change);
         fbCheck(fb_sync(dev->ctx, slot, other->slot, &flat.change), dev->ctx, "fb_sync");
         dev->cache_valid = false;
@@ -391,6 +515,8 @@ class EwaldB200 : public EnergyTerm
             throw std::runtime_error("invalid `ewaldpolicy`");
         }
         fbCheck(fb_ewald_configure(dev->ctx, &cfg), dev->ctx, "fb_ewald_configure");
+        dev->has_ewald = true;
+        dev->ewald_fast_ok = cfg.surface_dielectric_constant < 1.0; // tinfoil: no surface term to track
         init();
     }
 
@@ -400,6 +526,10 @@ class EwaldB200 : public EnergyTerm
     void updateState(const Change& change) override
     {
         if (!change) {
+            return;
+        }
+        if (dev->fast_staged && dev->fast_key == DeviceContext::changeKey(change)) {
+            dev->fast_move.with_ewald = 1; // evaluated by the sibling's fused launch
             return;
         }
         // the sibling non-bonded term (earlier in the Hamiltonian) has already pushed the change
@@ -418,6 +548,10 @@ class EwaldB200 : public EnergyTerm
         if (!change) {
             return 0.0;
         }
+        if (dev->fast_staged && dev->fast_evaluated && dev->fast_move.with_ewald &&
+            dev->fast_key == DeviceContext::changeKey(change)) {
+            return state == MonteCarloState::TRIAL ? dev->fast_ew_new : dev->fast_ew_old;
+        }
         FlatChange flat(change);
         double u = 0.0;
         fbCheck(fb_ewald_energy(dev->ctx, slot, &flat.change, &u), dev->ctx, "fb_ewald_energy");
@@ -432,6 +566,11 @@ class EwaldB200 : public EnergyTerm
         }
         if (!have_old && other->state == MonteCarloState::ACCEPTED) {
             have_old = true;
+            dev->ewald_have_old = true;
+        }
+        if (dev->fast_sync_for_ewald) { // the sibling's fb_trial_commit swapped Q already
+            dev->fast_sync_for_ewald = false;
+            return;
         }
         FlatChange flat(change);
         fbCheck(fb_ewald_sync(dev->ctx, slot, other->slot, &flat.change), dev->ctx, "fb_ewald_sync");

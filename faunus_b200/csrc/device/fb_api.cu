@@ -161,6 +161,15 @@ struct fb_ctx
     bool ewald_configured = false;
     fb_ewald_config ewald{};
 
+    // fast path (fb_trial_energy / fb_trial_commit)
+    Overlay commit{};          //!< accepted move not yet written to the mirrors
+    bool has_commit = false;
+    Overlay trial{};
+    bool trial_active = false;
+    bool trial_with_ewald = false;
+    double trial_rec_sum = 0;
+    double sequence = 0;
+
     // timing
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -206,6 +215,19 @@ EwaldView makeEwaldView(fb_ctx* c, int s)
     e.K = c->slot[s].K;
     e.policy = c->ewald.policy;
     return e;
+}
+
+void launched(fb_ctx* c, const char* what);
+
+/** Write a lazily accepted fast-path move into both mirrors before any other kind of access */
+void flushPending(fb_ctx* c)
+{
+    if (c->has_commit) {
+        applyCommitKernel<<<1, 32, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), c->commit);
+        launched(c, "applyCommitKernel");
+        c->has_commit = false;
+    }
+    c->trial_active = false;
 }
 
 void checkSlot(fb_ctx* c, int s, bool need_upload = true)
@@ -790,6 +812,7 @@ FB_API int fb_upload_space(fb_ctx* c, int s, const double* xyzq, const int* atom
                            int n_particles, int n_groups)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, s, false);
         if (n_particles <= 0 || n_groups <= 0 || !xyzq || !atom_id || !groups) {
             throw CudaError{"empty space"};
@@ -852,6 +875,7 @@ FB_API int fb_update_group(fb_ctx* c, int s, int group_index, const fb_group* re
                            const int* rel_index, const double* xyzq, const int* atom_id)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, s);
         if (group_index < 0 || group_index >= c->n_groups || !record) {
             throw CudaError{"group index out of range"};
@@ -923,6 +947,7 @@ FB_API int fb_set_box(fb_ctx* c, int s, const double box[3])
 FB_API int fb_sync(fb_ctx* c, int dst, int src, const fb_change* change)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, dst, false);
         checkSlot(c, src);
         if (dst == src || !change) {
@@ -1004,6 +1029,7 @@ FB_API int fb_sync(fb_ctx* c, int dst, int src, const fb_change* change)
 FB_API int fb_download_space(fb_ctx* c, int s, double* xyzq, int* atom_id, fb_group* groups)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, s);
         Slot& sl = c->slot[s];
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -1035,6 +1061,7 @@ FB_API int fb_download_space(fb_ctx* c, int s, double* xyzq, int* atom_id, fb_gr
 FB_API int fb_nonbonded_energy(fb_ctx* c, int s, const fb_change* change, double* energy)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, s);
         if (!change || !energy) {
             throw CudaError{"null argument"};
@@ -1066,6 +1093,7 @@ FB_API int fb_nonbonded_delta(fb_ctx* c, int s_new, int s_old, const fb_change* 
                               double* u_old)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, s_new);
         checkSlot(c, s_old);
         if (!change || !u_new || !u_old || s_new == s_old) {
@@ -1097,6 +1125,166 @@ FB_API int fb_nonbonded_delta(fb_ctx* c, int s_new, int s_old, const fb_change* 
         finish(c);
         *u_new = c->h_result[0];
         *u_old = c->h_result[1];
+    });
+}
+
+// =================================================================================================
+// fast path
+// =================================================================================================
+namespace {
+
+void waitSequence(fb_ctx* c, double seq)
+{
+    volatile double* flag = c->h_result + 3;
+    unsigned long spins = 0;
+    while (*flag != seq) {
+        __builtin_ia32_pause();
+        if ((++spins & 0x3FFFFul) == 0) {
+            const cudaError_t q = cudaStreamQuery(c->stream);
+            if (q == cudaSuccess) {
+                if (*flag != seq) {
+                    throw CudaError{"cuda: trial kernel finished without publishing its result"};
+                }
+            }
+            else if (q != cudaErrorNotReady) {
+                throw CudaError{std::string("cuda: trial kernel failed: ") + cudaGetErrorString(q)};
+            }
+        }
+    }
+}
+
+template <int K>
+void launchTrial(fb_ctx* c, int grid, int n_pair_blocks, int internal, const EwaldView& Ecur, const EwaldView& Eout)
+{
+    trialMoveKernel<K><<<grid, kBlock, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), c->P,
+                                                      c->has_commit ? c->commit : Overlay{0, -1, {}, {}, {}, {}},
+                                                      c->trial, internal, Ecur, Eout, n_pair_blocks,
+                                                      c->partials.ptr, c->ticket.ptr, c->d_result, c->sequence);
+}
+
+} // namespace
+
+FB_API int fb_trial_energy(fb_ctx* c, const fb_trial_move* mv, double* u_new, double* u_old, double* ewald_new,
+                           double* ewald_old)
+{
+    return guarded(c, [&] {
+        checkSlot(c, 0);
+        checkSlot(c, 1);
+        if (!mv || !u_new || !u_old) {
+            throw CudaError{"null argument"};
+        }
+        if (mv->group_index < 0 || mv->group_index >= c->n_groups || mv->n_atoms < 1 || mv->n_atoms > kFastAtoms) {
+            throw CudaError{"trial move outside the fast path (1..8 atoms of one group)"};
+        }
+        const fb_group& g = c->slot[0].groups[mv->group_index];
+        Overlay t{};
+        t.n = mv->n_atoms;
+        t.group = mv->group_index;
+        for (int i = 0; i < mv->n_atoms; ++i) {
+            if (mv->rel_index[i] < 0 || mv->rel_index[i] >= g.size) {
+                throw CudaError{"relative atom index out of range (fast path moves active atoms only)"};
+            }
+            if (mv->atom_id[i] < 0 || mv->atom_id[i] >= c->P.n_types) {
+                throw CudaError{"atom id out of range"};
+            }
+            t.slot[i] = g.begin + mv->rel_index[i];
+            t.id[i] = mv->atom_id[i];
+            t.posq[i] = make_double4(mv->xyzq[i][0], mv->xyzq[i][1], mv->xyzq[i][2], mv->xyzq[i][3]);
+        }
+        t.cm = make_double4(mv->cm[0], mv->cm[1], mv->cm[2], 0.0);
+        c->trial = t;
+        c->trial_with_ewald = mv->with_ewald != 0;
+        EwaldView Ecur{}, Eout{};
+        int n_k_blocks = 0;
+        if (mv->with_ewald) {
+            if (!c->ewald_configured || c->slot[0].K <= 0 || c->slot[1].K != c->slot[0].K) {
+                throw CudaError{"Ewald state of the two slots is not aligned for the fast path"};
+            }
+            if (!ewald_new || !ewald_old) {
+                throw CudaError{"null argument"};
+            }
+            if (!c->slot[0].rec_valid) { // Σ A_k|Q_k|² of the accepted state, once
+                Slot& sl = c->slot[0];
+                const int grid = (sl.K + kBlock - 1) / kBlock;
+                c->partials.ensure(static_cast<size_t>(grid));
+                ewaldEnergyKernel<<<grid, kBlock, 0, c->stream>>>(makeEwaldView(c, 0), c->partials.ptr, c->ticket.ptr,
+                                                                 c->d_result + 4);
+                launched(c, "ewaldEnergyKernel");
+                CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                sl.rec_sum = c->h_result[4];
+                sl.rec_valid = true;
+            }
+            Ecur = makeEwaldView(c, 0);
+            Eout = makeEwaldView(c, 1);
+            n_k_blocks = (Ecur.K + kBlock - 1) / kBlock;
+        }
+        const int n_pair_blocks = gridFor(c, c->n_slots, kBlock);
+        const int grid = n_pair_blocks + n_k_blocks;
+        c->partials.ensure(static_cast<size_t>(3) * grid);
+        c->sequence += 1.0;
+        beginTiming(c, TIME_PAIR);
+#define FB_CASE(K)                                                                                            \
+    case K:                                                                                                   \
+        launchTrial<K>(c, grid, n_pair_blocks, mv->internal, Ecur, Eout);                                     \
+        break;
+        switch (c->P.kind) {
+            FB_CASE(POT_COULOMB_LJ)
+            FB_CASE(POT_COULOMB_WCA)
+            FB_CASE(POT_PM)
+            FB_CASE(POT_PMWCA)
+            FB_CASE(POT_FUNCTOR)
+            FB_CASE(POT_SPLINED)
+        default:
+            throw CudaError{"unknown potential kind"};
+        }
+#undef FB_CASE
+        launched(c, "trialMoveKernel");
+        c->has_commit = false; // the launch materialises the pending commit
+        if (c->timing) {
+            finish(c);
+        }
+        else {
+            waitSequence(c, c->sequence);
+        }
+        *u_new = c->h_result[0];
+        *u_old = c->h_result[1];
+        if (mv->with_ewald) {
+            const double pi = 3.141592653589793238462643383279502884;
+            const Slot& sl = c->slot[0];
+            const double pref = 2 * pi * c->ewald.bjerrum_length / (sl.ewald_box[0] * sl.ewald_box[1] * sl.ewald_box[2]);
+            c->trial_rec_sum = c->h_result[2];
+            *ewald_new = pref * c->trial_rec_sum;
+            *ewald_old = pref * sl.rec_sum;
+        }
+        c->trial_active = true;
+    });
+}
+
+FB_API int fb_trial_commit(fb_ctx* c, int accept)
+{
+    return guarded(c, [&] {
+        if (!c->trial_active) {
+            throw CudaError{"no evaluated trial move to commit"};
+        }
+        c->trial_active = false;
+        if (!accept) {
+            return; // nothing was written anywhere
+        }
+        c->commit = c->trial;
+        c->has_commit = true;
+        for (int s = 0; s < 2; ++s) {
+            fb_group& g = c->slot[s].groups[c->trial.group];
+            g.cm[0] = c->trial.cm.x;
+            g.cm[1] = c->trial.cm.y;
+            g.cm[2] = c->trial.cm.z;
+        }
+        if (c->trial_with_ewald) { // Q_out becomes the accepted structure factor: swap the two buffers
+            std::swap(c->slot[0].Q.ptr, c->slot[1].Q.ptr);
+            std::swap(c->slot[0].Q.count, c->slot[1].Q.count);
+            c->slot[0].rec_sum = c->trial_rec_sum;
+            c->slot[0].rec_valid = true;
+            c->slot[1].rec_valid = false;
+        }
     });
 }
 
@@ -1142,6 +1330,7 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
 FB_API int fb_ewald_update_full(fb_ctx* c, int s)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, s);
         Slot& sl = c->slot[s];
         if (sl.K <= 0) {
@@ -1157,6 +1346,7 @@ FB_API int fb_ewald_update_full(fb_ctx* c, int s)
 FB_API int fb_ewald_update_partial(fb_ctx* c, int s_new, int s_old, const fb_change* change)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, s_new);
         checkSlot(c, s_old);
         if (!change || s_new == s_old) {
@@ -1186,6 +1376,7 @@ FB_API int fb_ewald_update_partial(fb_ctx* c, int s_new, int s_old, const fb_cha
 FB_API int fb_ewald_energy(fb_ctx* c, int s, const fb_change* change, double* energy)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, s);
         if (!energy) {
             throw CudaError{"null argument"};
@@ -1240,6 +1431,7 @@ FB_API int fb_ewald_energy(fb_ctx* c, int s, const fb_change* change, double* en
 FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, dst, false);
         checkSlot(c, src, false);
         if (dst == src || !change) {
@@ -1299,6 +1491,7 @@ FB_API int fb_widom_batch(fb_ctx* c, int s, int ghost_group, int n_ghost_atoms, 
                           double* du)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, s);
         if (ghost_group < 0 || ghost_group >= c->n_groups || n_insertions <= 0 || !ghost_xyzq ||
             !ghost_atom_id || !du) {
@@ -1381,6 +1574,7 @@ FB_API size_t fb_state_doubles(const fb_ctx* c)
 FB_API int fb_export_state(fb_ctx* c, int s, double* device_buffer)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, s);
         if (!device_buffer) {
             throw CudaError{"null buffer"};
@@ -1394,6 +1588,7 @@ FB_API int fb_export_state(fb_ctx* c, int s, double* device_buffer)
 FB_API int fb_import_state(fb_ctx* c, int s, const double* device_buffer)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, s);
         if (!device_buffer) {
             throw CudaError{"null buffer"};

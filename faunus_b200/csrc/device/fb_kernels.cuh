@@ -307,7 +307,8 @@ template <int NT> __device__ __forceinline__ double blockSum(double v, double* s
  */
 template <int NT>
 __device__ __forceinline__ void finalReduce(const double* block_values, int nval, double* partials,
-                                            unsigned* ticket, double* out, double* scratch)
+                                            unsigned* ticket, double* out, double* scratch,
+                                            volatile double* publish_ptr = nullptr, double publish_value = 0.0)
 {
     __shared__ bool is_last;
     const int nblocks = gridDim.x * gridDim.y;
@@ -336,6 +337,10 @@ __device__ __forceinline__ void finalReduce(const double* block_values, int nval
         if (threadIdx.x == 0) {
             *ticket = 0u;
             __threadfence_system();
+            if (publish_ptr != nullptr) { // results first, then the sequence number the host polls on
+                *publish_ptr = publish_value;
+                __threadfence_system();
+            }
         }
     }
 }
@@ -994,6 +999,194 @@ __global__ void unpackStateKernel(SlotView V, const double* buf)
     for (int j = tid; j < V.n_slots; j += stride) {
         V.posq[j] = make_double4(p[5 * j], p[5 * j + 1], p[5 * j + 2], p[5 * j + 3]);
         V.atom_id[j] = static_cast<int>(p[5 * j + 4]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: ONE launch per small trial move (≤ 8 atoms of one group, no size change).
+//   * the trial particles travel in the kernel parameters (no mirror update),
+//   * the previously accepted move (`commit`) is written into both mirrors by block 0 and forwarded
+//     to every reader in this launch, so accept needs no launch and reject no device work at all,
+//   * pair blocks sum u_new / u_old over all particles, k-space blocks do the Ewald partial update
+//     Q_out = Q_cur + Σ(new − old) and Σ A_k |Q_out|², one ordered final reduction for all three,
+//   * results land in mapped host memory followed by a sequence number the host polls on.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFastAtoms = 8;
+
+struct Overlay
+{
+    int n;       //!< particles (0 = empty)
+    int group;   //!< group whose mass centre is overridden, -1 if none
+    int slot[kFastAtoms];
+    int id[kFastAtoms];
+    double4 posq[kFastAtoms];
+    double4 cm;
+};
+
+__device__ __forceinline__ double4 loadParticle(const SlotView& v, const Overlay& o, int j, int& id)
+{
+    double4 p = v.posq[j];
+    id = v.atom_id[j];
+#pragma unroll
+    for (int t = 0; t < kFastAtoms; ++t) {
+        if (t < o.n && o.slot[t] == j) {
+            p = o.posq[t];
+            id = o.id[t];
+        }
+    }
+    return p;
+}
+
+__device__ __forceinline__ double4 loadMassCentre(const SlotView& v, const Overlay& o, int g)
+{
+    return (g == o.group) ? o.cm : v.gcm[g];
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kBlock)
+    trialMoveKernel(SlotView M0, SlotView M1, PotParams P, Overlay commit, Overlay trial, int internal,
+                    EwaldView Ecur, EwaldView Eout, int n_pair_blocks, double* partials, unsigned* ticket,
+                    double* out, double sequence)
+{
+    __shared__ double4 s_new[kFastAtoms];
+    __shared__ double4 s_old[kFastAtoms];
+    __shared__ int s_idnew[kFastAtoms];
+    __shared__ int s_idold[kFastAtoms];
+    __shared__ double scratch[kBlock / 32];
+
+    if (threadIdx.x < trial.n) {
+        s_new[threadIdx.x] = trial.posq[threadIdx.x];
+        s_idnew[threadIdx.x] = trial.id[threadIdx.x];
+        int id;
+        s_old[threadIdx.x] = loadParticle(M0, commit, trial.slot[threadIdx.x], id);
+        s_idold[threadIdx.x] = id;
+    }
+    if (blockIdx.x == 0) { // lazily materialise the previously accepted move in both mirrors
+        if (threadIdx.x < commit.n) {
+            const int s = commit.slot[threadIdx.x];
+            M0.posq[s] = commit.posq[threadIdx.x];
+            M0.atom_id[s] = commit.id[threadIdx.x];
+            M1.posq[s] = commit.posq[threadIdx.x];
+            M1.atom_id[s] = commit.id[threadIdx.x];
+        }
+        if (threadIdx.x == 0 && commit.group >= 0) {
+            M0.gcm[commit.group] = commit.cm;
+            M1.gcm[commit.group] = commit.cm;
+        }
+    }
+    __syncthreads();
+
+    double eA = 0.0, eB = 0.0, eK = 0.0;
+    if (static_cast<int>(blockIdx.x) < n_pair_blocks) {
+        const int gT = trial.group;
+        const int info_T = P.any_molecular ? M0.ginfo[gT] : MOL_ATOMIC;
+        const int begin_T = P.any_molecular ? M0.gbegin[gT] : 0;
+        const int stride = n_pair_blocks * blockDim.x;
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M0.n_slots; j += stride) {
+            const int g = M0.gid[j];
+            int idj;
+            const double4 pj = loadParticle(M0, commit, j, idj);
+            if (g < 0) {
+                continue;
+            }
+            bool j_moved = false;
+            bool cut_new = false, cut_old = false;
+            if (g == gT) {
+                if (!internal) {
+                    continue;
+                }
+#pragma unroll
+                for (int t = 0; t < kFastAtoms; ++t) {
+                    if (t < trial.n && trial.slot[t] == j) {
+                        j_moved = true;
+                    }
+                }
+                if (!(info_T & MOL_ATOMIC) && (info_T & MOL_RIGID)) {
+                    continue;
+                }
+            }
+            else if (P.any_molecular && !(info_T & MOL_ATOMIC)) {
+                const int info_j = M0.ginfo[g];
+                if (!(info_j & MOL_ATOMIC)) {
+                    const double c2 = __ldg(P.g2g_cut2 + (info_T >> 8) * P.n_mol + (info_j >> 8));
+                    const double4 cj = loadMassCentre(M0, commit, g);
+                    const double4 co = loadMassCentre(M0, commit, gT);
+                    cut_new = minImageR2(M0, cj.x, cj.y, cj.z, trial.cm.x, trial.cm.y, trial.cm.z) >= c2;
+                    cut_old = minImageR2(M0, cj.x, cj.y, cj.z, co.x, co.y, co.z) >= c2;
+                }
+            }
+#pragma unroll 1
+            for (int m = 0; m < trial.n; ++m) {
+                const int si = trial.slot[m];
+                double4 pj_new = pj;
+                int idj_new = idj;
+                if (g == gT) {
+                    if (j == si || (j_moved && j < si)) {
+                        continue;
+                    }
+                    if (!(info_T & MOL_ATOMIC) && pairExcluded(P, info_T >> 8, si - begin_T, j - begin_T)) {
+                        continue;
+                    }
+                    if (j_moved) { // moved-moved pair: the partner sits at its new position in the trial state
+#pragma unroll
+                        for (int t = 0; t < kFastAtoms; ++t) {
+                            if (t < trial.n && trial.slot[t] == j) {
+                                pj_new = s_new[t];
+                                idj_new = s_idnew[t];
+                            }
+                        }
+                    }
+                }
+                if (!cut_new) {
+                    const double4 a = s_new[m];
+                    const double r2 = minImageR2(M0, a.x, a.y, a.z, pj_new.x, pj_new.y, pj_new.z);
+                    eA += pairEnergy<KIND>(P, s_idnew[m], idj_new, a.w, pj_new.w, r2);
+                }
+                if (!cut_old) {
+                    const double4 b = s_old[m];
+                    const double r2 = minImageR2(M0, b.x, b.y, b.z, pj.x, pj.y, pj.z);
+                    eB += pairEnergy<KIND>(P, s_idold[m], idj, b.w, pj.w, r2);
+                }
+            }
+        }
+    }
+    else {
+        const int k = (blockIdx.x - n_pair_blocks) * kBlock + threadIdx.x;
+        if (k < Ecur.K) {
+            const double4 kv = Ecur.kA[k];
+            double2 Q = Ecur.Q[k];
+            for (int m = 0; m < trial.n; ++m) {
+                const double2 fn = phase(Ecur.policy, kv, s_new[m]);
+                Q.x += fn.x;
+                Q.y += fn.y;
+                const double2 fo = phase(Ecur.policy, kv, s_old[m]);
+                Q.x -= fo.x;
+                Q.y -= fo.y;
+            }
+            Eout.Q[k] = Q;
+            eK = kv.w * (Q.x * Q.x + Q.y * Q.y);
+        }
+    }
+    double vals[3];
+    vals[0] = blockSum<kBlock>(eA, scratch);
+    vals[1] = blockSum<kBlock>(eB, scratch);
+    vals[2] = blockSum<kBlock>(eK, scratch);
+    finalReduce<kBlock>(vals, 3, partials, ticket, out, scratch, out + 3, sequence);
+}
+
+/** Materialise a pending commit without evaluating anything (before non-fast-path calls) */
+__global__ void applyCommitKernel(SlotView M0, SlotView M1, Overlay commit)
+{
+    if (threadIdx.x < commit.n) {
+        const int s = commit.slot[threadIdx.x];
+        M0.posq[s] = commit.posq[threadIdx.x];
+        M0.atom_id[s] = commit.id[threadIdx.x];
+        M1.posq[s] = commit.posq[threadIdx.x];
+        M1.atom_id[s] = commit.id[threadIdx.x];
+    }
+    if (threadIdx.x == 0 && commit.group >= 0) {
+        M0.gcm[commit.group] = commit.cm;
+        M1.gcm[commit.group] = commit.cm;
     }
 }
 

@@ -50,6 +50,12 @@ class FbEwaldConfig(C.Structure):
                 ("spherical_sum", C.c_int), ("policy", C.c_int)]
 
 
+class FbTrialMove(C.Structure):
+    _fields_ = [("group_index", C.c_int), ("n_atoms", C.c_int), ("rel_index", C.c_int * 8),
+                ("xyzq", (C.c_double * 4) * 8), ("atom_id", C.c_int * 8), ("cm", C.c_double * 3),
+                ("internal", C.c_int), ("with_ewald", C.c_int)]
+
+
 c_ubyte_p = C.POINTER(C.c_ubyte)
 c_uint32_p = C.POINTER(C.c_uint32)
 
@@ -76,6 +82,7 @@ class FbConfig(C.Structure):
 C_ABI_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_last_error", "fb_device_count", "fb_upload_space", "fb_update_group",
     "fb_set_box", "fb_sync", "fb_download_space", "fb_nonbonded_energy", "fb_nonbonded_delta",
+    "fb_trial_energy", "fb_trial_commit",
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
     "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
     "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_launch_count",
@@ -109,6 +116,8 @@ def load() -> C.CDLL:
         "fb_download_space": (C.c_int, [vp, C.c_int, c_double_p, c_int_p, C.POINTER(FbGroup)]),
         "fb_nonbonded_energy": (C.c_int, [vp, C.c_int, C.POINTER(FbChange), c_double_p]),
         "fb_nonbonded_delta": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(FbChange), c_double_p, c_double_p]),
+        "fb_trial_energy": (C.c_int, [vp, C.POINTER(FbTrialMove), c_double_p, c_double_p, c_double_p, c_double_p]),
+        "fb_trial_commit": (C.c_int, [vp, C.c_int]),
         "fb_ewald_configure": (C.c_int, [vp, C.POINTER(FbEwaldConfig)]),
         "fb_ewald_update_box": (C.c_int, [vp, C.c_int, c_int_p]),
         "fb_ewald_update_full": (C.c_int, [vp, C.c_int]),

@@ -187,6 +187,31 @@ int fb_nonbonded_energy(fb_ctx* ctx, int slot, const fb_change* change, double* 
 int fb_nonbonded_delta(fb_ctx* ctx, int slot_new, int slot_old, const fb_change* change, double* u_new,
                        double* u_old);
 
+/* ---- fast path: one launch per small trial move -------------------------------------------- */
+/* A trial move of up to FB_FAST_ATOMS particles of one group without size change
+ * (AtomicTranslateRotate, src/move.cpp:267-293; TranslateRotate of small rigid molecules, :1670-1689).
+ * Both slots must mirror the accepted state when fb_trial_energy is called; the trial particles
+ * travel in the kernel parameters. fb_trial_energy = updateState + energy(trial) + energy(accepted)
+ * of the non-bonded term and, with `with_ewald`, of the Ewald term, in ONE kernel launch.
+ * fb_trial_commit = the following sync: accept is applied lazily by the next launch, reject is free. */
+#define FB_FAST_ATOMS 8
+typedef struct
+{
+    int group_index;
+    int n_atoms;                     /* 1..FB_FAST_ATOMS */
+    int rel_index[FB_FAST_ATOMS];    /* relative atom indices within the group */
+    double xyzq[FB_FAST_ATOMS][4];   /* trial position and charge */
+    int atom_id[FB_FAST_ATOMS];
+    double cm[3];                    /* trial mass centre of the group */
+    int internal;                    /* Change::GroupChange::internal */
+    int with_ewald;                  /* include the reciprocal-space partial update + energy */
+} fb_trial_move;
+/* ewald_new / ewald_old: surface-free reciprocal energies 2 pi lB / V * sum_k A_k |Q_k|^2 (NULL allowed
+ * without with_ewald) */
+int fb_trial_energy(fb_ctx* ctx, const fb_trial_move* move, double* u_new, double* u_old, double* ewald_new,
+                    double* ewald_old);
+int fb_trial_commit(fb_ctx* ctx, int accept);
+
 /* ---- Ewald reciprocal space --------------------------------------------------------------- */
 int fb_ewald_configure(fb_ctx* ctx, const fb_ewald_config* config);
 /* k-vectors and A_k for the slot's current box (PolicyIonIon::updateBox); returns K in *n_kvectors */

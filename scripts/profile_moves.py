@@ -1,0 +1,10 @@
+"""Short profiling driver: N=1e5 workload, a few hundred moves (for ncu)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+import faunus_b200.native as native
+moves = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+sim = native.B200Simulation(bench.workload(moves_per_step=moves))
+sim.sweep(2)
+print("done", sim.launch_count)
