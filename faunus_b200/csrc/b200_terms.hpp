@@ -17,6 +17,7 @@
 #include "host/montecarlo.hpp"
 #include "host/potential_tables.hpp"
 #include <map>
+#include <mutex>
 
 namespace fb {
 
@@ -259,10 +260,17 @@ inline std::map<std::pair<const Topology*, std::string>, std::weak_ptr<DeviceCon
     return registry;
 }
 
+/** CUDA device new contexts are created on; per thread (in-process replicas run one thread per GPU) */
 inline int& defaultDevice()
 {
-    static int device = 0;
+    static thread_local int device = 0;
     return device;
+}
+
+inline std::mutex& deviceRegistryMutex()
+{
+    static std::mutex m;
+    return m;
 }
 
 /** Replaces Energy::Nonbonded<PairEnergy<…>, GroupPairing<…>> (src/energy.h:1512-1598) */
@@ -280,6 +288,7 @@ class NonbondedB200 : public EnergyTerm
     {
         name = "nonbonded";
         const auto reg_key = std::make_pair(spc.topology.get(), key + j.dump());
+        std::lock_guard<std::mutex> lock(deviceRegistryMutex());
         auto& registry = deviceRegistry();
         auto it = registry.find(reg_key);
         if (it != registry.end()) {

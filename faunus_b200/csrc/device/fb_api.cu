@@ -1133,20 +1133,44 @@ FB_API int fb_nonbonded_delta(fb_ctx* c, int s_new, int s_old, const fb_change* 
 // =================================================================================================
 namespace {
 
-void waitSequence(fb_ctx* c, double seq)
+constexpr unsigned long long kSentinel = 0xFFF8DEADBEEF5A5Aull; //!< a NaN payload arithmetic never produces
+
+void armResults(fb_ctx* c, int n)
 {
-    volatile double* flag = c->h_result + 3;
+    volatile unsigned long long* r = reinterpret_cast<volatile unsigned long long*>(c->h_result);
+    for (int i = 0; i < n; ++i) {
+        r[i] = kSentinel;
+    }
+    __sync_synchronize();
+}
+
+/** Spin until the kernel has overwritten all `n` armed result slots (mapped pinned memory) */
+void waitResults(fb_ctx* c, int n)
+{
+    volatile unsigned long long* r = reinterpret_cast<volatile unsigned long long*>(c->h_result);
     unsigned long spins = 0;
-    while (*flag != seq) {
+    while (true) {
+        bool done = true;
+        for (int i = 0; i < n; ++i) {
+            done = done && (r[i] != kSentinel);
+        }
+        if (done) {
+            return;
+        }
         __builtin_ia32_pause();
-        if ((++spins & 0x3FFFFul) == 0) {
+        if ((++spins & 0xFFFFFul) == 0) {
             const cudaError_t q = cudaStreamQuery(c->stream);
             if (q == cudaSuccess) {
-                if (*flag != seq) {
+                bool ok = true;
+                for (int i = 0; i < n; ++i) {
+                    ok = ok && (r[i] != kSentinel);
+                }
+                if (!ok) {
                     throw CudaError{"cuda: trial kernel finished without publishing its result"};
                 }
+                return;
             }
-            else if (q != cudaErrorNotReady) {
+            if (q != cudaErrorNotReady) {
                 throw CudaError{std::string("cuda: trial kernel failed: ") + cudaGetErrorString(q)};
             }
         }
@@ -1159,7 +1183,7 @@ void launchTrial(fb_ctx* c, int grid, int n_pair_blocks, int internal, const Ewa
     trialMoveKernel<K><<<grid, kBlock, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), c->P,
                                                       c->has_commit ? c->commit : Overlay{0, -1, {}, {}, {}, {}},
                                                       c->trial, internal, Ecur, Eout, n_pair_blocks,
-                                                      c->partials.ptr, c->ticket.ptr, c->d_result, c->sequence);
+                                                      c->partials.ptr, c->ticket.ptr, c->d_result);
 }
 
 } // namespace
@@ -1218,10 +1242,22 @@ FB_API int fb_trial_energy(fb_ctx* c, const fb_trial_move* mv, double* u_new, do
             Eout = makeEwaldView(c, 1);
             n_k_blocks = (Ecur.K + kBlock - 1) / kBlock;
         }
-        const int n_pair_blocks = gridFor(c, c->n_slots, kBlock);
+        // one resident wave: split the block budget between the pair part and the k-space part by work
+        int n_pair_blocks = (c->n_slots + kBlock - 1) / kBlock;
+        if (n_pair_blocks + n_k_blocks > c->max_blocks) {
+            const double share = static_cast<double>(n_pair_blocks) / (n_pair_blocks + n_k_blocks);
+            int pair_budget = std::max(1, static_cast<int>(share * c->max_blocks));
+            if (n_k_blocks > 0) {
+                pair_budget = std::min(pair_budget, c->max_blocks - 1);
+            }
+            n_pair_blocks = std::min(n_pair_blocks, pair_budget);
+            n_k_blocks = std::min(n_k_blocks, c->max_blocks - n_pair_blocks);
+        }
         const int grid = n_pair_blocks + n_k_blocks;
         c->partials.ensure(static_cast<size_t>(3) * grid);
-        c->sequence += 1.0;
+        if (!c->timing) {
+            armResults(c, 3);
+        }
         beginTiming(c, TIME_PAIR);
 #define FB_CASE(K)                                                                                            \
     case K:                                                                                                   \
@@ -1244,7 +1280,7 @@ FB_API int fb_trial_energy(fb_ctx* c, const fb_trial_move* mv, double* u_new, do
             finish(c);
         }
         else {
-            waitSequence(c, c->sequence);
+            waitResults(c, 3);
         }
         *u_new = c->h_result[0];
         *u_old = c->h_result[1];

@@ -308,7 +308,7 @@ template <int NT> __device__ __forceinline__ double blockSum(double v, double* s
 template <int NT>
 __device__ __forceinline__ void finalReduce(const double* block_values, int nval, double* partials,
                                             unsigned* ticket, double* out, double* scratch,
-                                            volatile double* publish_ptr = nullptr, double publish_value = 0.0)
+                                            bool host_polls_values = false)
 {
     __shared__ bool is_last;
     const int nblocks = gridDim.x * gridDim.y;
@@ -331,14 +331,14 @@ __device__ __forceinline__ void finalReduce(const double* block_values, int nval
             }
             s = blockSum<NT>(s, scratch);
             if (threadIdx.x == 0) {
-                out[v] = s;
+                // host_polls_values: the host pre-fills every slot with a sentinel and waits until all
+                // are overwritten; each 8-byte store is atomic, so no system-scope fence is needed
+                *reinterpret_cast<volatile double*>(out + v) = s;
             }
         }
         if (threadIdx.x == 0) {
             *ticket = 0u;
-            __threadfence_system();
-            if (publish_ptr != nullptr) { // results first, then the sequence number the host polls on
-                *publish_ptr = publish_value;
+            if (!host_polls_values) {
                 __threadfence_system();
             }
         }
@@ -1046,7 +1046,7 @@ template <int KIND>
 __global__ void __launch_bounds__(kBlock)
     trialMoveKernel(SlotView M0, SlotView M1, PotParams P, Overlay commit, Overlay trial, int internal,
                     EwaldView Ecur, EwaldView Eout, int n_pair_blocks, double* partials, unsigned* ticket,
-                    double* out, double sequence)
+                    double* out)
 {
     __shared__ double4 s_new[kFastAtoms];
     __shared__ double4 s_old[kFastAtoms];
@@ -1151,8 +1151,8 @@ __global__ void __launch_bounds__(kBlock)
         }
     }
     else {
-        const int k = (blockIdx.x - n_pair_blocks) * kBlock + threadIdx.x;
-        if (k < Ecur.K) {
+        const int kstride = (gridDim.x - n_pair_blocks) * kBlock;
+        for (int k = (blockIdx.x - n_pair_blocks) * kBlock + threadIdx.x; k < Ecur.K; k += kstride) {
             const double4 kv = Ecur.kA[k];
             double2 Q = Ecur.Q[k];
             for (int m = 0; m < trial.n; ++m) {
@@ -1164,14 +1164,14 @@ __global__ void __launch_bounds__(kBlock)
                 Q.y -= fo.y;
             }
             Eout.Q[k] = Q;
-            eK = kv.w * (Q.x * Q.x + Q.y * Q.y);
+            eK += kv.w * (Q.x * Q.x + Q.y * Q.y);
         }
     }
     double vals[3];
     vals[0] = blockSum<kBlock>(eA, scratch);
     vals[1] = blockSum<kBlock>(eB, scratch);
     vals[2] = blockSum<kBlock>(eK, scratch);
-    finalReduce<kBlock>(vals, 3, partials, ticket, out, scratch, out + 3, sequence);
+    finalReduce<kBlock>(vals, 3, partials, ticket, out, scratch, true);
 }
 
 /** Materialise a pending commit without evaluating anything (before non-fast-path calls) */

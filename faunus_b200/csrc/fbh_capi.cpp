@@ -15,6 +15,13 @@ std::unique_ptr<fb::WidomInsertion> makeWidom(const fb::Json& j, fb::MetropolisM
 }
 } // namespace
 
+/** in-process replicas: replica r runs on GPU r modulo the visible device count */
+static void fbh_replica_setup(int rank)
+{
+    const int n = fb_device_count();
+    fb::defaultDevice() = n > 0 ? rank % n : 0;
+}
+
 FB_DEFINE_SIM_CAPI(fbh, b200_factory, makeWidom)
 
 extern "C" __attribute__((visibility("default"))) void fbh_set_device(int device)
@@ -126,4 +133,12 @@ extern "C" __attribute__((visibility("default"))) int fbh_sim_get_timing(void* h
         }
     }
     return 0;
+}
+
+/** the fb_ctx of the (single) B200 non-bonded term of a simulation, for direct C-ABI calls (benchmarks, tests) */
+extern "C" __attribute__((visibility("default"))) void* fbh_sim_ctx(void* h)
+{
+    auto* s = static_cast<fb::capi::Sim*>(h);
+    const auto terms = s->mc->state.pot->find<fb::NonbondedB200>();
+    return terms.empty() ? nullptr : static_cast<void*>(terms.front()->device()->ctx);
 }

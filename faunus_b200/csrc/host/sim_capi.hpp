@@ -5,7 +5,9 @@
 // and `<prefix>_last_error()` holds the message.
 #pragma once
 #include "montecarlo.hpp"
+#include "replica_comm.hpp"
 #include <cstring>
+#include <thread>
 
 namespace fb::capi {
 
@@ -29,6 +31,7 @@ template <class F> int guarded(F&& f)
 
 struct Sim
 {
+    std::unique_ptr<ReplicaComm> comm; //!< must outlive mc (the temper move holds a reference)
     std::unique_ptr<MetropolisMonteCarlo> mc;
     std::vector<std::unique_ptr<WidomInsertion>> widoms;
     Change pending; //!< change of the manual trial-move protocol
@@ -42,16 +45,79 @@ inline std::unique_ptr<WidomInsertion> defaultWidom(const Json& j, MetropolisMon
     return std::make_unique<WidomInsertion>(j, *mc.state.spc, *mc.state.pot, mc.rng.global);
 }
 
-inline Sim* create(const char* json_text, const TermFactory& factory, ReplicaComm* comm = nullptr)
+inline Sim* create(const char* json_text, const TermFactory& factory, std::unique_ptr<ReplicaComm> comm = nullptr)
 {
     Sim* sim = nullptr;
     const int rc = guarded([&] {
         const Json j = Json::parse(json_text);
         auto s = std::make_unique<Sim>();
-        s->mc = std::make_unique<MetropolisMonteCarlo>(j, factory, comm);
+        s->comm = std::move(comm);
+        s->mc = std::make_unique<MetropolisMonteCarlo>(j, factory, s->comm.get());
         sim = s.release();
     });
     return rc == 0 ? sim : nullptr;
+}
+
+/** Per-replica result of an in-process tempering run */
+struct LocalReplicaResult
+{
+    double energy = 0;
+    double drift = 0;
+    std::vector<double> xyzq;
+    std::string info;
+    std::string error;
+};
+
+/**
+ * All replicas of a parallel-tempering run in ONE process, one thread per replica (LocalComm).
+ * `configs` is a JSON array of per-replica input documents; `setup(rank)` runs in the replica's thread
+ * before its simulation is created (e.g. selects the CUDA device).
+ */
+inline std::vector<LocalReplicaResult> runLocalReplicas(const Json& configs, int sweeps, const TermFactory& factory,
+                                                        const std::function<void(int)>& setup)
+{
+    const int size = static_cast<int>(configs.size());
+    auto exchange = std::make_shared<LocalExchange>(size);
+    std::vector<LocalReplicaResult> results(static_cast<size_t>(size));
+    std::vector<std::thread> threads;
+    for (int r = 0; r < size; ++r) {
+        threads.emplace_back([&, r] {
+            auto comm = std::make_unique<LocalComm>(exchange, r);
+            LocalComm* raw = comm.get();
+            try {
+                if (setup) {
+                    setup(r);
+                }
+                MetropolisMonteCarlo mc(configs.at(r), factory, raw);
+                for (int i = 0; i < sweeps; ++i) {
+                    mc.sweep();
+                }
+                auto& res = results[r];
+                res.energy = mc.systemEnergy();
+                res.drift = mc.relativeEnergyDrift();
+                for (const auto& p : mc.state.spc->particles) {
+                    res.xyzq.insert(res.xyzq.end(), {p.pos.x, p.pos.y, p.pos.z, p.charge});
+                }
+                Json jm = Json::array();
+                for (const auto& m : mc.moves->all()) {
+                    Json inner = Json::object();
+                    m->to_json(inner);
+                    Json w = Json::object();
+                    w[m->name] = inner;
+                    jm.push_back(w);
+                }
+                res.info = jm.dump();
+            }
+            catch (const std::exception& e) {
+                results[r].error = e.what();
+                raw->fail();
+            }
+        });
+    }
+    for (auto& t : threads) {
+        t.join();
+    }
+    return results;
 }
 
 inline int copyOut(const std::string& s, char* buf, int len)
@@ -104,6 +170,37 @@ inline State& pick(Sim& s, int which)
     __attribute__((visibility("default"))) void* P##_sim_create(const char* json_text)                       \
     {                                                                                                         \
         return fb::capi::create(json_text, FACTORY);                                                         \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) void* P##_sim_create_replica(const char* json_text,               \
+                                                                        const fb_replica_callbacks* cb)      \
+    {                                                                                                         \
+        std::unique_ptr<fb::ReplicaComm> comm;                                                               \
+        if (fb::capi::guarded([&] { comm = std::make_unique<fb::CallbackComm>(*cb); }) != 0) {               \
+            return nullptr;                                                                                  \
+        }                                                                                                    \
+        return fb::capi::create(json_text, FACTORY, std::move(comm));                                        \
+    }                                                                                                         \
+    /* in-process tempering: configs = JSON array of inputs; returns JSON array of per-replica results */    \
+    __attribute__((visibility("default"))) int P##_temper_run_local(const char* configs_json, int sweeps,    \
+                                                                    char* buf, int len)                      \
+    {                                                                                                         \
+        int n = -1;                                                                                          \
+        fb::capi::guarded([&] {                                                                              \
+            const auto configs = fb::Json::parse(configs_json);                                              \
+            const auto results = fb::capi::runLocalReplicas(configs, sweeps, FACTORY, P##_replica_setup);    \
+            fb::Json out = fb::Json::array();                                                                \
+            for (const auto& r : results) {                                                                  \
+                fb::Json j = fb::Json::object();                                                             \
+                j["energy"] = r.energy;                                                                      \
+                j["drift"] = r.drift;                                                                        \
+                j["xyzq"] = fb::Json::fromVector(r.xyzq);                                                    \
+                j["moves"] = r.info.empty() ? fb::Json() : fb::Json::parse(r.info);                          \
+                j["error"] = r.error;                                                                        \
+                out.push_back(j);                                                                            \
+            }                                                                                                \
+            n = fb::capi::copyOut(out.dump(), buf, len);                                                     \
+        });                                                                                                  \
+        return n;                                                                                            \
     }                                                                                                         \
     __attribute__((visibility("default"))) void P##_sim_destroy(void* h)                                     \
     {                                                                                                         \

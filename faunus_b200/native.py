@@ -140,6 +140,7 @@ def load() -> C.CDLL:
         "fb_measure_fp64_peak": (C.c_int, [C.c_int, c_double_p]),
         "fbh_sim_enable_timing": (C.c_int, [vp, C.c_int]),
         "fbh_sim_get_timing": (C.c_int, [vp, c_double_p]),
+        "fbh_sim_ctx": (vp, [vp]),
         "fbh_set_device": (None, [C.c_int]),
         "fbh_sim_launch_count": (C.c_ulonglong, [vp]),
     }
@@ -178,6 +179,11 @@ class B200Simulation(Simulation):
     @property
     def launch_count(self) -> int:
         return int(load().fbh_sim_launch_count(self.handle))
+
+    @property
+    def ctx(self):
+        """raw fb_ctx* of the non-bonded/Ewald device context (for direct C-ABI calls)"""
+        return load().fbh_sim_ctx(self.handle)
 
     def enable_timing(self, on: bool = True):
         """CUDA-event timing of every hot-kernel launch (adds ~2 event records per launch)"""

@@ -1,0 +1,104 @@
+"""Parallel tempering across processes: one replica per process / GPU, exchange over torch.distributed.
+
+The C++ ``ParallelTempering`` move (faunus_b200/csrc/host/moves.hpp, restating src/move.cpp:844-968) talks to a
+``ReplicaComm``; this module supplies the callback flavour implemented with ``torch.distributed``
+point-to-point operations: NCCL send/recv between GPUs (NVLink/NVSwitch) when the process group uses the
+``nccl`` backend, gloo on CPU (tests). Messages are the reference's: 8-byte energy and volume
+exchanges, group sizes, and the XYZQI particle buffer (src/mpicontroller.cpp:94-246).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+
+import numpy as np
+
+from ._simapi import SimLibrary, Simulation, c_double_p
+
+_BARRIER = C.CFUNCTYPE(None, C.c_void_p)
+_SENDRECV = C.CFUNCTYPE(None, C.c_void_p, c_double_p, C.c_size_t, C.c_int)
+_GATHER = C.CFUNCTYPE(None, C.c_void_p, C.c_double, c_double_p)
+
+
+class FbReplicaCallbacks(C.Structure):
+    _fields_ = [("rank", C.c_int), ("size", C.c_int), ("user", C.c_void_p), ("barrier", _BARRIER),
+                ("sendrecv_replace", _SENDRECV), ("gather", _GATHER)]
+
+
+class TorchReplicaComm:
+    """Exchange primitives over the default ``torch.distributed`` process group."""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.size = dist.get_rank(), dist.get_world_size()
+        self.device = device if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
+        self.bytes_exchanged = 0
+        self.exchanges = 0
+        self._cb = FbReplicaCallbacks(self.rank, self.size, None, _BARRIER(self._barrier),
+                                      _SENDRECV(self._sendrecv), _GATHER(self._gather))
+
+    @property
+    def callbacks(self) -> FbReplicaCallbacks:
+        return self._cb
+
+    def _barrier(self, _user):
+        if self.device.type == "cuda":
+            self.dist.barrier(device_ids=[self.device.index])
+        else:
+            self.dist.barrier()
+
+    def _sendrecv(self, _user, data, n, partner):
+        torch, dist = self.torch, self.dist
+        host = np.ctypeslib.as_array(data, shape=(n,))
+        send = torch.from_numpy(host.copy()).to(self.device)
+        recv = torch.empty_like(send)
+        ops = [dist.P2POp(dist.isend, send, partner), dist.P2POp(dist.irecv, recv, partner)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        host[:] = recv.cpu().numpy()
+        self.bytes_exchanged += 8 * n
+        self.exchanges += 1
+
+    def _gather(self, _user, value, out):
+        torch, dist = self.torch, self.dist
+        mine = torch.tensor([value], dtype=torch.float64, device=self.device)
+        everyone = [torch.empty_like(mine) for _ in range(self.size)]
+        dist.all_gather(everyone, mine)
+        for i, t in enumerate(everyone):
+            out[i] = float(t.item())
+
+
+class ReplicaSimulation(Simulation):
+    """A simulation whose ``temper`` move exchanges with the other ranks of the process group."""
+
+    def __init__(self, api: SimLibrary, config, comm: TorchReplicaComm):
+        self.comm = comm  # keep the ctypes callbacks alive
+        fn = getattr(api.lib, f"{api.prefix}_sim_create_replica")
+        fn.restype = C.c_void_p
+        fn.argtypes = [C.c_char_p, C.POINTER(FbReplicaCallbacks)]
+        self.api = api
+        text = config if isinstance(config, str) else json.dumps(config)
+        self.handle = fn(text.encode(), C.byref(comm.callbacks))
+        if not self.handle:
+            raise RuntimeError(f"{api.prefix}_sim_create_replica: {api.error()}")
+
+
+def run_local_replicas(api: SimLibrary, configs, sweeps: int):
+    """All replicas in this process, one thread each (``<prefix>_temper_run_local``)."""
+    fn = getattr(api.lib, f"{api.prefix}_temper_run_local")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    text = json.dumps(list(configs)).encode()
+    size = 1 << 16
+    while True:
+        buf = C.create_string_buffer(size)
+        n = fn(text, sweeps, buf, size)
+        if n < 0:
+            raise RuntimeError(f"{api.prefix}_temper_run_local: {api.error()}")
+        if n <= size:
+            return json.loads(buf.value.decode())
+        size = n + 16
+        # results are deterministic, so re-running with a larger buffer returns the same data

@@ -73,6 +73,8 @@ static const TermFactory factory = termFactory;
 
 } // namespace oracle
 
+static void fo_replica_setup(int) {}
+
 FB_DEFINE_SIM_CAPI(fo, oracle::factory, fb::capi::defaultWidom)
 
 #define FO_API extern "C" __attribute__((visibility("default")))
