@@ -34,7 +34,10 @@ sys.path.insert(0, ROOT)
 
 MOVES_PER_STEP = 2000
 N_IONS = 100_000
-FLOP_PER_PAIR = 49          # splined Coulomb + WCA, SURVEY §8(d)
+FLOP_PER_PAIR = 49          # splined Coulomb + WCA, pair within the cutoffs, SURVEY §8(d)
+FLOP_PER_FAR_PAIR = 25      # pair beyond both cutoffs: min-image r² (20) + sqrt, +eps, r<Rc test (3) + WCA cut test (2)
+FLOP_PER_K_MOVE = 40        # per (k-vector, move): 2 factorised phases (24) + δ (4) + A_k(2 Re(conj Q δ)+|δ|²) (12)
+FLOP_PER_K_CROSS = 4        # per (k-vector, ordered pair of moves): A_k Re(conj δ_a δ_m) = 2 FMA
 BYTES_PER_PARTICLE = 36     # x, y, z, q doubles + int32 id
 BYTES_PER_KVECTOR = 64      # k (24) + A_k (8) + Q read (16) + Q write (16), k-vector components read
 
@@ -178,13 +181,13 @@ def b200_arm(args):
     if dist is not None:
         dist.barrier(device_ids=[local])
     cfg = workload(seed=5489 + rank)
-    sim = native.B200Simulation(cfg, device=local)
+    sim = native.B200Simulation(cfg, device=local, window=args.window)
     n = sim.num_particles
     info0 = sim.info()
     kvectors = None
     for term in info0["energy"]:
         if "ewald" in term:
-            kvectors = term["ewald"].get("wavefunctions")
+            kvectors = term["ewald"].get("wavefunctions") or kvectors
     for _ in range(args.warmup):
         sim.sweep(1)
     torch.cuda.synchronize()
@@ -211,19 +214,29 @@ def b200_arm(args):
         elapsed = float(t.item())
     moves = args.steps * MOVES_PER_STEP
     e2e = world * moves / elapsed
-    # second pass over the same number of steps with per-launch CUDA-event timing of the hot kernels
-    # (events on the context's own stream): device-only time, inputs resident in HBM
+    # second pass over the same number of steps with CUDA-event timing of the hot kernels (events on the
+    # context's own stream): device-only time, inputs resident in HBM
     sim.enable_timing(True)
-    stats0 = sim.device_time_ms()
+    w0, s0 = sim.window_time_ms(), sim.device_time_ms()
     for _ in range(args.steps):
         sim.sweep(1)
-    stats1 = sim.device_time_ms()
+    w1, s1 = sim.window_time_ms(), sim.device_time_ms()
     sim.enable_timing(False)
     clocks = sampler.stop()
-    kernel_ms = stats1["pair_ms"] - stats0["pair_ms"]
-    ewald_ms = stats1["ewald_ms"] - stats0["ewald_ms"]
-    pair_launches = stats1["pair_launches"] - stats0["pair_launches"]
-    device_s = (kernel_ms + ewald_ms) / 1e3
+    windowed = sim.window > 0
+    if windowed:
+        pair_ms = w1["pair_ms"] - w0["pair_ms"]
+        ewald_ms = w1["ewald_ms"] - w0["ewald_ms"]
+        other_ms = w1["other_ms"] - w0["other_ms"]
+        n_windows = w1["windows"] - w0["windows"]
+        evaluated = w1["moves"] - w0["moves"]
+    else:
+        pair_ms = s1["pair_ms"] - s0["pair_ms"]
+        ewald_ms = s1["ewald_ms"] - s0["ewald_ms"]
+        other_ms = 0.0
+        n_windows = s1["pair_launches"] - s0["pair_launches"]
+        evaluated = n_windows
+    device_s = (pair_ms + ewald_ms + other_ms) / 1e3
     if dist is not None:
         t = torch.tensor([device_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -239,22 +252,38 @@ def b200_arm(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     roofline = None
-    if kernel_ms > 0 and pair_launches:
-        per_launch_s = kernel_ms / 1e3 / pair_launches
-        alg_bytes = BYTES_PER_PARTICLE * (n - 1)
-        alg_flop = 2 * (n - 1) * FLOP_PER_PAIR
+    if pair_ms > 0 and n_windows:
+        # the pair kernel of the windowed path: every move of a window against all N particles, new + old
+        L = cfg["geometry"]["length"]
+        L = L if isinstance(L, (int, float)) else L[0]
+        in_range = (4.0 / 3.0) * 3.141592653589793 * 28.0 ** 3 / L ** 3
+        flop_pair = FLOP_PER_FAR_PAIR + in_range * (FLOP_PER_PAIR - FLOP_PER_FAR_PAIR)
+        per_launch_s = pair_ms / 1e3 / n_windows
+        moves_per_launch = evaluated / n_windows
+        alg_flop = 2 * moves_per_launch * (n - 1) * flop_pair
+        alg_bytes = BYTES_PER_PARTICLE * n
         fp64_peak = measure_fp64_peak(native, local)
+        nominal = 148 * 64 * 2 * 1.965e9 / 1e12
         roofline = {
-            "kernel": "movedEnergyKernel<COULOMB_WCA, fused new+old>", "bound": "hbm",
-            "achieved": alg_bytes / per_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": alg_bytes / per_launch_s / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
-            "us_per_launch": per_launch_s * 1e6, "algorithmic_bytes_per_launch": alg_bytes,
-            "algorithmic_flop_per_launch": alg_flop,
-            "fp64": {"achieved_tflops": alg_flop / per_launch_s / 1e12, "peak_tflops": fp64_peak,
-                     "frac": (alg_flop / per_launch_s / 1e12 / fp64_peak) if fp64_peak else None,
-                     "peak_source": "DFMA microbenchmark on this GPU (fb_measure_fp64_peak)"},
-            "note": "positions (3.6 MB) are L2-resident; a single-move launch is latency-bound (SURVEY §8d)",
+            "kernel": "batchPairKernel<COULOMB_WCA>" if windowed else "trialMoveKernel<COULOMB_WCA>",
+            "bound": "fp64", "achieved": alg_flop / per_launch_s / 1e12, "peak": fp64_peak or nominal,
+            "unit": "TFLOP/s", "frac": alg_flop / per_launch_s / 1e12 / (fp64_peak or nominal), "traffic": None,
+            "peak_source": "FP64 DFMA microbenchmark on this GPU in this run (fb_measure_fp64_peak); nominal "
+                           f"148 SM x 64 FMA/clk x 1.965 GHz = {nominal:.1f} TFLOP/s" if fp64_peak else "nominal",
+            "us_per_launch": per_launch_s * 1e6, "moves_per_launch": moves_per_launch,
+            "algorithmic_flop_per_launch": alg_flop, "flop_per_pair": flop_pair,
+            "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / per_launch_s / 1e9,
+                    "peak_gbs": hbm_peak, "frac": alg_bytes / per_launch_s / 1e9 / hbm_peak, "peak_source": peak_src},
+            "note": "FP64-pipe bound: 36 B per particle are read once per window and reused by every move of "
+                    "the window (positions are L2-resident); no tensor-core work on this path",
         }
+        if windowed and ewald_ms > 0 and kvectors:
+            ew_flop = moves_per_launch * kvectors * FLOP_PER_K_MOVE + \
+                moves_per_launch * (moves_per_launch - 1) / 2 * kvectors * FLOP_PER_K_CROSS
+            roofline["ewald_kernel"] = {"kernel": "batchEwaldKernel", "bound": "fp64",
+                                        "achieved": ew_flop / (ewald_ms / 1e3 / n_windows) / 1e12,
+                                        "unit": "TFLOP/s", "us_per_launch": ewald_ms / n_windows * 1e3,
+                                        "algorithmic_flop_per_launch": ew_flop}
     cpu = None
     if not args.no_cpu_baseline:
         try:
@@ -264,6 +293,12 @@ def b200_arm(args):
                              f"(reference default), -O3 -ffast-math -march={r['arch']}; Ewald init parallelised"}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "moves/s", "cores": 1, "kind": "port", "sample": f"failed: {e}"}
+    if windowed:  # per window: proposals in (BatchInput), result block out (8 + 3S + 4S² doubles, S = 32)
+        wps = n_windows / args.steps
+        h2d_per_step = int(wps * (8 + 64 * (4 + 4 + 32)))
+        d2h_per_step = int(wps * 8 * (8 + 3 * 32 + 4 * 32 * 32))
+    else:
+        h2d_per_step, d2h_per_step = 36 * MOVES_PER_STEP, 24 * MOVES_PER_STEP
     line = {
         "metric": "MC trial moves/s", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
@@ -272,11 +307,12 @@ def b200_arm(args):
                    "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
                    "l2": "positions 3.6 MB + Q/k tables 3.6 MB are L2-resident by design; every move touches a "
                          "different particle, no flush applied"},
-        "e2e": {"value": e2e, "unit": "moves/s", "h2d_bytes_per_step": 36 * MOVES_PER_STEP,
-                "d2h_bytes_per_step": 24 * MOVES_PER_STEP},
+        "e2e": {"value": e2e, "unit": "moves/s", "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step},
         "gpu_launches": launches,
         "pair_interactions_per_s": e2e * 2 * (n - 1),
-        "device_time_split_ms_per_move": {"pair": kernel_ms / moves, "ewald_partial": ewald_ms / moves},
+        "window": sim.window,
+        "device_time_split_us_per_move": {"pair": 1e3 * pair_ms / moves, "kspace": 1e3 * ewald_ms / moves,
+                                          "commit_phase_finish": 1e3 * other_ms / moves},
         "clocks": clocks,
     }
     if roofline:
@@ -293,6 +329,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--window", type=int, default=None, help="proposals per device pass (0: one move per launch)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -98,6 +98,7 @@ class DeviceContext
     double cached_old_energy = 0;
     // Ewald sibling: present? eligible for the fused fast path (no surface term)? old groups known?
     bool has_ewald = false;
+    int ewald_policy = 0;
     bool ewald_fast_ok = false;
     bool ewald_have_old = false;
     // fast path: one staged small trial move (fb_trial_energy / fb_trial_commit)
@@ -487,11 +488,13 @@ class EwaldB200 : public EnergyTerm
     std::shared_ptr<NonbondedB200> sibling;
     int slot;
     bool have_old = false; //!< `old_groups` set (after the first sync from the accepted instance)
+    int n_kvectors = 0;
 
     void fullUpdate()
     {
         int K = 0;
         fbCheck(fb_ewald_update_box(dev->ctx, slot, &K), dev->ctx, "fb_ewald_update_box");
+        n_kvectors = K;
         fbCheck(fb_ewald_update_full(dev->ctx, slot), dev->ctx, "fb_ewald_update_full");
     }
 
@@ -525,6 +528,7 @@ class EwaldB200 : public EnergyTerm
         }
         fbCheck(fb_ewald_configure(dev->ctx, &cfg), dev->ctx, "fb_ewald_configure");
         dev->has_ewald = true;
+        dev->ewald_policy = cfg.policy;
         dev->ewald_fast_ok = cfg.surface_dielectric_constant < 1.0; // tinfoil: no surface term to track
         init();
     }
@@ -588,6 +592,7 @@ class EwaldB200 : public EnergyTerm
     void to_json(Json& j) const override
     {
         j["device"] = "B200 sm_100a";
+        j["wavefunctions"] = n_kvectors;
     }
 };
 
@@ -660,6 +665,172 @@ inline bool b200TermFactory(Hamiltonian& h, Space& spc, const std::string& name,
     }
     return true;
 }
+
+/**
+ * Windowed evaluation of runs of `transrot` moves on the device (fb_batch_trial / fb_batch_commit):
+ * the engine hands over a window of drawn proposals, one pass evaluates all of them against the
+ * accepted state, and `energies()` assembles for each move — given the decisions on the earlier
+ * ones — what `trial.energy(change)` and `accepted.energy(change)` return in the one-at-a-time
+ * protocol (src/montecarlo.cpp:151-156; Hamiltonian::energy term order and early stop,
+ * src/energy.cpp:1227-1241). Only additions of device results happen on the host.
+ */
+class B200WindowEvaluator : public WindowEvaluator
+{
+    MetropolisMonteCarlo& mc;
+    std::shared_ptr<DeviceContext> dev;
+    bool with_ewald = false;
+    int window_capacity;
+    fb_batch_result res{};
+    std::vector<fb_batch_move> moves;
+    std::vector<double> rec_change; //!< corrected raw reciprocal change Σ_k A_k(…) of each decided move
+    enum class Kind
+    {
+        SELF,
+        NONBONDED,
+        EWALD
+    };
+    std::vector<Kind> kinds; //!< Hamiltonian term order
+
+  public:
+    static constexpr double cancellation_limit = 1e4; //!< kT; larger pair terms in a correction → re-evaluate
+
+    /** nullptr if the Hamiltonian holds anything but self energy / B200 non-bonded / tinfoil Ewald terms */
+    static std::unique_ptr<B200WindowEvaluator> tryCreate(MetropolisMonteCarlo& mc, int capacity)
+    {
+        if (capacity < 1) {
+            return nullptr;
+        }
+        std::vector<Kind> kinds;
+        std::shared_ptr<NonbondedB200> nonbonded;
+        const auto& trial_terms = mc.trial_state.pot->terms();
+        const auto& terms = mc.state.pot->terms();
+        if (terms.size() != trial_terms.size()) {
+            return nullptr;
+        }
+        for (const auto& t : terms) {
+            if (std::dynamic_pointer_cast<ParticleSelfEnergyB200>(t)) {
+                kinds.push_back(Kind::SELF);
+            }
+            else if (auto nb = std::dynamic_pointer_cast<NonbondedB200>(t)) {
+                if (nonbonded) {
+                    return nullptr;
+                }
+                nonbonded = nb;
+                kinds.push_back(Kind::NONBONDED);
+            }
+            else if (std::dynamic_pointer_cast<EwaldB200>(t)) {
+                kinds.push_back(Kind::EWALD);
+            }
+            else {
+                return nullptr;
+            }
+        }
+        if (!nonbonded || nonbonded->device()->attached != 2) {
+            return nullptr;
+        }
+        const auto& d = *nonbonded->device();
+        if (d.has_ewald && (!d.ewald_fast_ok || d.ewald_policy == 2)) {
+            return nullptr; // surface term / IPBC: one move at a time
+        }
+        auto e = std::unique_ptr<B200WindowEvaluator>(new B200WindowEvaluator(mc, std::min(capacity, FB_BATCH_MAX)));
+        e->dev = nonbonded->device();
+        e->with_ewald = d.has_ewald;
+        e->kinds = std::move(kinds);
+        return e;
+    }
+
+    int capacity() const override { return window_capacity; }
+
+    void evaluate(const std::vector<WindowProposal>& window, int n) override
+    {
+        moves.resize(static_cast<size_t>(n));
+        const Space& trial = *mc.trial_state.spc;
+        for (int m = 0; m < n; ++m) {
+            const auto& gc = window[m].change.groups.at(0);
+            const auto& g = trial.groups.at(gc.group_index);
+            const auto& p = trial.at(g, gc.relative_atom_indices.at(0));
+            fb_batch_move& mv = moves[m];
+            mv.group_index = static_cast<int>(gc.group_index);
+            mv.rel_index = static_cast<int>(gc.relative_atom_indices[0]);
+            mv.atom_id = p.id;
+            mv.xyzq[0] = p.pos.x;
+            mv.xyzq[1] = p.pos.y;
+            mv.xyzq[2] = p.pos.z;
+            mv.xyzq[3] = p.charge;
+        }
+        dev->fast_staged = false;
+        dev->cache_valid = false;
+        fbCheck(fb_batch_trial(dev->ctx, n, moves.data(), with_ewald ? 1 : 0, &res), dev->ctx, "fb_batch_trial");
+        rec_change.assign(static_cast<size_t>(n), 0.0);
+    }
+
+    bool energies(int m, const std::vector<unsigned char>& accepted, const WindowProposal& proposal,
+                  double& new_energy, double& old_energy) override
+    {
+        const size_t S = static_cast<size_t>(res.stride);
+        double nb_new = res.u_new[m];
+        double nb_old = res.u_old[m];
+        double rec = with_ewald ? res.rec_delta[m] : 0.0;
+        double rec_running = res.rec_start;
+        for (int a = 0; a < m; ++a) {
+            if (!accepted[a]) {
+                continue;
+            }
+            const size_t am = static_cast<size_t>(a) * S + m;
+            if (!(res.cross_max[am] < cancellation_limit)) {
+                return false;
+            }
+            nb_new += res.cross_new[am];
+            nb_old += res.cross_old[am];
+            if (with_ewald) {
+                rec += 2.0 * res.rec_cross[am];
+                rec_running += rec_change[a];
+            }
+        }
+        rec_change[m] = rec;
+        // Hamiltonian::energy on the trial and on the accepted state
+        const double limit = mc.state.pot->maximumAllowedEnergy();
+        auto total = [&](Hamiltonian& pot, bool is_trial) {
+            double sum = 0.0;
+            const auto& terms = pot.terms();
+            for (size_t i = 0; i < terms.size(); ++i) {
+                double u = 0.0;
+                switch (kinds[i]) {
+                case Kind::SELF:
+                    u = terms[i]->energy(proposal.change);
+                    break;
+                case Kind::NONBONDED:
+                    u = is_trial ? nb_new : nb_old;
+                    break;
+                case Kind::EWALD:
+                    u = res.rec_prefactor * (is_trial ? rec_running + rec : rec_running);
+                    break;
+                }
+                sum += u;
+                if (u >= limit || std::isnan(u)) {
+                    break;
+                }
+            }
+            return sum;
+        };
+        new_energy = total(*mc.trial_state.pot, true);
+        old_energy = total(*mc.state.pot, false);
+        return true;
+    }
+
+    void commit(const std::vector<unsigned char>& accepted) override
+    {
+        fbCheck(fb_batch_commit(dev->ctx, static_cast<int>(accepted.size()), accepted.data()), dev->ctx,
+                "fb_batch_commit");
+    }
+
+  private:
+    B200WindowEvaluator(MetropolisMonteCarlo& mc, int capacity)
+        : mc(mc)
+        , window_capacity(capacity)
+    {
+    }
+};
 
 /**
  * Batched Widom insertion: all `ninsert` ghosts of one sample event are generated on the host in the

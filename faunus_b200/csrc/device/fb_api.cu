@@ -3,12 +3,14 @@
 // One CUDA stream per context; results come back through mapped pinned memory.
 #include "../../../include/faunus_b200.h"
 #include "fb_kernels.cuh"
+#include "fb_batch.cuh"
 
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -105,6 +107,7 @@ struct Slot
     bool uploaded = false;
     // Ewald
     DeviceBuffer<double4> kA;
+    DeviceBuffer<int4> kn; //!< integer triplets (nx, ny, nz) of the k-vectors, same order as kA
     DeviceBuffer<double2> Q;
     int K = 0;
     double ewald_box[3] = {0, 0, 0};
@@ -179,6 +182,34 @@ struct fb_ctx
     double acc_launches[4] = {0, 0, 0, 0};
 
     int max_blocks = 148 * 4;
+    int n_sm = 148;
+
+    // windowed speculative evaluation (fb_batch_trial / fb_batch_commit), see fb_batch.cuh
+    struct Batch
+    {
+        DeviceBuffer<BatchInput> d_in[2];
+        DeviceBuffer<double4> d_pold[2];
+        DeviceBuffer<int> d_idold[2];
+        DeviceBuffer<double2> d_table[2];
+        PinnedBuffer<BatchInput> h_in;
+        DeviceBuffer<double> d_pair_partials, d_r_partials, d_g_partials, d_e_partials, d_result;
+        PinnedBuffer<double> h_result;
+        int parity = 0;
+        int last_n = 0;            //!< moves of the most recent window (0: none evaluated)
+        int last_with_ewald = 0;
+        int last_slots[kBatchMax] = {};
+        CommitList pending{};      //!< accepted moves of the previous window not yet on the device
+        bool has_pending = false;
+        bool pending_with_ewald = false;
+        bool q_dirty = false;      //!< slot 0's Q(k) is ahead of slot 1's
+        bool rec_known = false;    //!< rec_sum is Σ A_k|Q_k|² of slot 0's current Q(k)
+        double rec_sum = 0;
+        PhaseGeometry geo{};
+        cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        double acc_ms[3] = {0, 0, 0}; //!< pair, ewald, other (commit + phase + finish)
+        double windows = 0, moves = 0;
+    } batch;
+    double pair_cut2 = 0; //!< no pair energy beyond this r² (+inf when some term has no cutoff)
 };
 
 namespace {
@@ -220,8 +251,11 @@ EwaldView makeEwaldView(fb_ctx* c, int s)
 void launched(fb_ctx* c, const char* what);
 
 /** Write a lazily accepted fast-path move into both mirrors before any other kind of access */
+void flushBatch(fb_ctx* c);
+
 void flushPending(fb_ctx* c)
 {
+    flushBatch(c);
     if (c->has_commit) {
         applyCommitKernel<<<1, 32, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), c->commit);
         launched(c, "applyCommitKernel");
@@ -433,9 +467,11 @@ void launchFull(fb_ctx* c, const SlotView& V, int volume_predicate)
 }
 
 /** PolicyIonIon::updateBox / PolicyIonIonIPBC::updateBox, src/energy.cpp:133-186, 356-412 */
-void generateKVectors(const fb_ewald_config& cfg, const double box[3], std::vector<double4>& kA)
+void generateKVectors(const fb_ewald_config& cfg, const double box[3], std::vector<double4>& kA,
+                      std::vector<int4>& kn)
 {
     kA.clear();
+    kn.clear();
     const bool ipbc = cfg.policy == 2;
     const int ncc = static_cast<int>(std::ceil(cfg.n_cutoff));
     const double pi = 3.141592653589793238462643383279502884;
@@ -444,6 +480,7 @@ void generateKVectors(const fb_ewald_config& cfg, const double box[3], std::vect
     const long k_vector_size = static_cast<long>(2 * ncc + 1) * (2 * ncc + 1) * (2 * ncc + 1) - 1;
     if (k_vector_size == 0) {
         kA.push_back(make_double4(1, 0, 0, 0));
+        kn.push_back(make_int4(0, 0, 0, 0));
         return;
     }
     const double nc2 = cfg.n_cutoff * cfg.n_cutoff;
@@ -477,6 +514,7 @@ void generateKVectors(const fb_ewald_config& cfg, const double box[3], std::vect
                     }
                 }
                 kA.push_back(make_double4(kx, ky, kz, factor * std::exp(-k2 / (4 * cfg.alpha * cfg.alpha)) / k2));
+                kn.push_back(make_int4(nx, ny, nz, 0));
             }
         }
     }
@@ -544,6 +582,10 @@ FB_API int fb_create(const fb_config* cfg, fb_ctx** out)
         cudaDeviceProp prop{};
         CUDA_CHECK(cudaGetDeviceProperties(&prop, c->device));
         c->max_blocks = std::min(prop.multiProcessorCount * 4, kMaxPartialBlocks);
+        c->n_sm = prop.multiProcessorCount;
+        for (auto& e : c->batch.ev) {
+            CUDA_CHECK(cudaEventCreate(&e));
+        }
         CUDA_CHECK(cudaHostAlloc(&c->h_result, 8 * sizeof(double), cudaHostAllocMapped));
         CUDA_CHECK(cudaHostGetDevicePointer(&c->d_result, c->h_result, 0));
         c->partials.alloc(4 * kMaxPartialBlocks);
@@ -662,6 +704,47 @@ FB_API int fb_create(const fb_config* cfg, fb_ctx** out)
             copyTable(c->d_sp_rmax2, cfg->spline_rmax2, T2, s, &P.sp_rmax2);
             copyTable(c->d_sp_hs, cfg->spline_hardsphere, T2, s, &P.sp_hs);
         }
+        { // r² beyond which every pair energy is exactly zero (pre-filter of the windowed pair kernel)
+            const double inf = std::numeric_limits<double>::infinity();
+            const double wca_factor = 1.2599210498948732;
+            auto table_max = [&](const double* t, double scale) {
+                double m = 0.0;
+                for (size_t i = 0; i < T2; ++i) {
+                    m = std::max(m, t[i] * scale);
+                }
+                return m;
+            };
+            const double rc2 = cfg->coulomb_cutoff * cfg->coulomb_cutoff;
+            double cut = 0.0;
+            switch (cfg->kind) {
+            case FB_POT_COULOMB_WCA:
+                cut = std::max(rc2, table_max(cfg->wca_sigma2, wca_factor));
+                break;
+            case FB_POT_FUNCTOR:
+                for (size_t t = 0; t < T2; ++t) {
+                    const uint32_t f = cfg->pair_flags[t];
+                    if (f & (FB_TERM_LJ | FB_TERM_COULOMB_PLAIN)) {
+                        cut = inf;
+                    }
+                    if (f & FB_TERM_COULOMB_SPLINED) {
+                        cut = std::max(cut, rc2);
+                    }
+                    if (f & FB_TERM_WCA) {
+                        cut = std::max(cut, cfg->wca_sigma2[t] * wca_factor);
+                    }
+                    if (f & FB_TERM_HARDSPHERE) {
+                        cut = std::max(cut, cfg->hs_sigma2[t]);
+                    }
+                }
+                break;
+            case FB_POT_SPLINED:
+                cut = table_max(cfg->spline_rmax2, 1.0);
+                break;
+            default: // Lennard-Jones and plain Coulomb have no cutoff
+                cut = inf;
+            }
+            c->pair_cut2 = cut * (1.0 + 1e-9);
+        }
         // molecules
         need(cfg->molecule_flags, "molecule_flags");
         c->molecule_flags.assign(cfg->molecule_flags, cfg->molecule_flags + M);
@@ -724,6 +807,11 @@ FB_API void fb_destroy(fb_ctx* c)
     }
     if (c->ev1) {
         cudaEventDestroy(c->ev1);
+    }
+    for (auto& e : c->batch.ev) {
+        if (e) {
+            cudaEventDestroy(e);
+        }
     }
     cudaStream_t s = c->stream;
     delete c;
@@ -1192,6 +1280,7 @@ FB_API int fb_trial_energy(fb_ctx* c, const fb_trial_move* mv, double* u_new, do
                            double* ewald_old)
 {
     return guarded(c, [&] {
+        flushBatch(c);
         checkSlot(c, 0);
         checkSlot(c, 1);
         if (!mv || !u_new || !u_old) {
@@ -1346,10 +1435,13 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
             throw CudaError{"Ewald not configured"};
         }
         Slot& sl = c->slot[s];
+        flushBatch(c);
         std::vector<double4> kA;
-        generateKVectors(c->ewald, sl.box, kA);
+        std::vector<int4> kn;
+        generateKVectors(c->ewald, sl.box, kA, kn);
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         sl.kA.upload(kA.data(), kA.size(), c->stream);
+        sl.kn.upload(kn.data(), kn.size(), c->stream);
         sl.Q.ensure(kA.size());
         sl.K = static_cast<int>(kA.size());
         for (int i = 0; i < 3; ++i) {
@@ -1481,6 +1573,8 @@ FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
         if (change->everything || change->volume_change || d.K != s.K) {
             d.kA.ensure(s.K);
             CUDA_CHECK(cudaMemcpyAsync(d.kA.ptr, s.kA.ptr, s.K * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
+            d.kn.ensure(s.K);
+            CUDA_CHECK(cudaMemcpyAsync(d.kn.ptr, s.kn.ptr, s.K * sizeof(int4), cudaMemcpyDeviceToDevice, c->stream));
             d.K = s.K;
             for (int i = 0; i < 3; ++i) {
                 d.ewald_box[i] = s.ewald_box[i];
@@ -1673,3 +1767,5 @@ FB_API int fb_import_state_host(fb_ctx* c, int s, const double* host_buffer)
         }
     });
 }
+
+#include "fb_batch_api.inl"

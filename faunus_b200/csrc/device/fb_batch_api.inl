@@ -1,0 +1,341 @@
+// fb_batch_trial / fb_batch_commit: host side of the windowed speculative evaluation (fb_batch.cuh).
+// Included at the end of fb_api.cu (same translation unit: fb_ctx, guarded(), CUDA_CHECK, ...).
+
+namespace {
+
+BatchBuffers batchBuffers(fb_ctx* c, int which)
+{
+    BatchBuffers b{};
+    b.in = c->batch.d_in[which].ptr;
+    b.pold = c->batch.d_pold[which].ptr;
+    b.idold = c->batch.d_idold[which].ptr;
+    b.table = c->batch.d_table[which].ptr;
+    return b;
+}
+
+void batchAllocate(fb_ctx* c)
+{
+    auto& b = c->batch;
+    for (int i = 0; i < 2; ++i) {
+        b.d_in[i].ensure(1);
+        b.d_pold[i].ensure(kBatchMax);
+        b.d_idold[i].ensure(kBatchMax);
+    }
+    b.h_in.ensure(1);
+}
+
+/** (re)size the phase tables for the current k-vector cutoff */
+void batchEwaldGeometry(fb_ctx* c)
+{
+    auto& b = c->batch;
+    const int ncc = static_cast<int>(std::ceil(c->ewald.n_cutoff));
+    b.geo.ncc = ncc;
+    b.geo.table_stride = (ncc + 1) + 2 * (2 * ncc + 1);
+    for (int i = 0; i < 3; ++i) {
+        b.geo.len[i] = c->slot[0].ewald_box[i];
+    }
+    for (int i = 0; i < 2; ++i) {
+        b.d_table[i].ensure(static_cast<size_t>(2 * kBatchMax) * b.geo.table_stride);
+    }
+}
+
+int commitGrid(fb_ctx* c, bool with_ewald)
+{
+    if (!with_ewald) {
+        return 1;
+    }
+    return std::max(1, std::min((c->slot[0].K + kBlock - 1) / kBlock, 2 * c->n_sm));
+}
+
+/** launch the commit kernel for the pending accepted moves (and/or to obtain Σ A_k|Q_k|²) */
+void launchBatchCommit(fb_ctx* c, bool with_ewald, int* n_blocks_out)
+{
+    auto& b = c->batch;
+    const int grid = commitGrid(c, with_ewald);
+    if (with_ewald) {
+        b.d_e_partials.ensure(static_cast<size_t>(grid));
+    }
+    CommitList list = b.has_pending ? b.pending : CommitList{};
+    batchCommitKernel<<<grid, kBlock, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), makeEwaldView(c, 0),
+                                                      c->slot[0].kn.ptr, batchBuffers(c, b.parity), b.geo, list,
+                                                      with_ewald ? 1 : 0, b.d_e_partials.ptr);
+    launched(c, "batchCommitKernel");
+    b.has_pending = false;
+    if (n_blocks_out) {
+        *n_blocks_out = with_ewald ? grid : 0;
+    }
+}
+
+template <int KIND>
+void launchBatchPairFinish(fb_ctx* c, const BatchBuffers& cur, int stride, int n_pair_blocks, int n_ewald_blocks,
+                           int n_commit_blocks, bool with_ewald, bool timing)
+{
+    auto& b = c->batch;
+    const SlotView M0 = makeView(c, 0);
+    batchPairKernel<KIND><<<n_pair_blocks, kBlock, 0, c->stream>>>(M0, c->P, cur, c->pair_cut2, stride,
+                                                                  b.d_pair_partials.ptr);
+    launched(c, "batchPairKernel");
+    if (timing) {
+        CUDA_CHECK(cudaEventRecord(b.ev[2], c->stream));
+    }
+    if (with_ewald) {
+        const EwaldView E = makeEwaldView(c, 0);
+        const int4* kn = c->slot[0].kn.ptr;
+        const int kt = kBatchDeltaElems / stride;
+        const int n_tiles = (E.K + kt - 1) / kt;
+        const int tiles_per_block = (n_tiles + n_ewald_blocks - 1) / n_ewald_blocks;
+        switch (stride) {
+        case 16:
+            batchEwaldKernel<4><<<n_ewald_blocks, kBlock, 0, c->stream>>>(E, kn, cur, b.geo, tiles_per_block,
+                                                                         b.d_r_partials.ptr, b.d_g_partials.ptr);
+            break;
+        case 32:
+            batchEwaldKernel<8><<<n_ewald_blocks, kBlock, 0, c->stream>>>(E, kn, cur, b.geo, tiles_per_block,
+                                                                         b.d_r_partials.ptr, b.d_g_partials.ptr);
+            break;
+        default:
+            batchEwaldKernel<16><<<n_ewald_blocks, kBlock, 0, c->stream>>>(E, kn, cur, b.geo, tiles_per_block,
+                                                                          b.d_r_partials.ptr, b.d_g_partials.ptr);
+        }
+        launched(c, "batchEwaldKernel");
+    }
+    if (timing) {
+        CUDA_CHECK(cudaEventRecord(b.ev[3], c->stream));
+    }
+    const int finish_grid = std::max(1, (stride * stride + kBlock - 1) / kBlock);
+    batchFinishKernel<KIND><<<finish_grid, kBlock, 0, c->stream>>>(
+        M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, with_ewald ? n_ewald_blocks : 0,
+        b.d_r_partials.ptr, b.d_g_partials.ptr, n_commit_blocks, b.d_e_partials.ptr, b.d_result.ptr);
+    launched(c, "batchFinishKernel");
+}
+
+/** Leave windowed mode: put pending accepted moves on the device and re-align the trial slot's Q(k) */
+void flushBatch(fb_ctx* c)
+{
+    auto& b = c->batch;
+    if (b.has_pending) {
+        launchBatchCommit(c, b.pending_with_ewald, nullptr);
+        b.rec_known = false;
+    }
+    if (b.q_dirty) {
+        Slot& s0 = c->slot[0];
+        Slot& s1 = c->slot[1];
+        if (s1.K == s0.K && s0.K > 0) {
+            CUDA_CHECK(cudaMemcpyAsync(s1.Q.ptr, s0.Q.ptr, s0.K * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
+        }
+        s0.rec_valid = false;
+        s1.rec_valid = false;
+        b.q_dirty = false;
+    }
+    b.last_n = 0;
+    b.rec_known = false;
+}
+
+} // namespace
+
+FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, int with_ewald, fb_batch_result* out)
+{
+    return guarded(c, [&] {
+        checkSlot(c, 0);
+        checkSlot(c, 1);
+        if (!moves || !out || n_moves < 1 || n_moves > kBatchMax) {
+            throw CudaError{"fb_batch_trial: 1..64 moves per window"};
+        }
+        auto& b = c->batch;
+        if (c->has_commit) { // an accepted fast-path move is still only on the host
+            applyCommitKernel<<<1, 32, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), c->commit);
+            launched(c, "applyCommitKernel");
+            c->has_commit = false;
+        }
+        c->trial_active = false;
+        if (with_ewald) {
+            if (!c->ewald_configured || c->slot[0].K <= 0) {
+                throw CudaError{"fb_batch_trial: Ewald is not initialised on the accepted slot"};
+            }
+            if (c->ewald.policy == 2) {
+                throw CudaError{"fb_batch_trial: IPBC is not supported by the windowed path"};
+            }
+            if (b.has_pending && !b.pending_with_ewald) {
+                throw CudaError{"fb_batch_trial: windows with and without Ewald cannot be mixed"};
+            }
+        }
+        batchAllocate(c);
+        // the moved atoms: distinct, active, members of atomic groups
+        BatchInput& in = *b.h_in.ptr;
+        in.n = n_moves;
+        in.with_ewald = with_ewald ? 1 : 0;
+        for (int m = 0; m < n_moves; ++m) {
+            const fb_batch_move& mv = moves[m];
+            if (mv.group_index < 0 || mv.group_index >= c->n_groups) {
+                throw CudaError{"fb_batch_trial: group index out of range"};
+            }
+            const fb_group& g = c->slot[0].groups[mv.group_index];
+            if (!(c->molecule_flags[g.molid] & FB_MOL_ATOMIC)) {
+                throw CudaError{"fb_batch_trial: windowed moves are single atoms of atomic groups"};
+            }
+            if (mv.rel_index < 0 || mv.rel_index >= g.size) {
+                throw CudaError{"fb_batch_trial: relative atom index out of range"};
+            }
+            if (mv.atom_id < 0 || mv.atom_id >= c->P.n_types) {
+                throw CudaError{"fb_batch_trial: atom id out of range"};
+            }
+            in.slot[m] = g.begin + mv.rel_index;
+            in.id[m] = mv.atom_id;
+            in.pnew[m] = make_double4(mv.xyzq[0], mv.xyzq[1], mv.xyzq[2], mv.xyzq[3]);
+            for (int a = 0; a < m; ++a) {
+                if (in.slot[a] == in.slot[m]) {
+                    throw CudaError{"fb_batch_trial: the moves of one window must touch distinct atoms"};
+                }
+            }
+        }
+        const int stride = n_moves <= 16 ? 16 : (n_moves <= 32 ? 32 : 64);
+        const bool timing = c->timing;
+        if (timing) {
+            CUDA_CHECK(cudaEventRecord(b.ev[0], c->stream));
+        }
+        // 1. previous window's accepted moves (still described by the buffers of parity `b.parity`)
+        int n_commit_blocks = 0;
+        if (with_ewald) {
+            batchEwaldGeometry(c);
+        }
+        const bool need_rec = with_ewald && !b.rec_known;
+        if (b.has_pending || need_rec) {
+            const bool commit_ewald = with_ewald || (b.has_pending && b.pending_with_ewald);
+            launchBatchCommit(c, commit_ewald, &n_commit_blocks);
+        }
+        // 2. this window
+        b.parity ^= 1;
+        const BatchBuffers cur = batchBuffers(c, b.parity);
+        CUDA_CHECK(cudaMemcpyAsync(cur.in, b.h_in.ptr, sizeof(BatchInput), cudaMemcpyHostToDevice, c->stream));
+        const int phase_grid =
+            with_ewald ? std::max(1, (2 * n_moves * b.geo.table_stride + kBlock - 1) / kBlock) : 1;
+        batchPhaseKernel<<<phase_grid, kBlock, 0, c->stream>>>(makeView(c, 0), cur, b.geo);
+        launched(c, "batchPhaseKernel");
+        if (timing) {
+            CUDA_CHECK(cudaEventRecord(b.ev[1], c->stream));
+        }
+        const int n_pair_blocks = (c->n_slots + kBatchTile - 1) / kBatchTile;
+        b.d_pair_partials.ensure(static_cast<size_t>(n_pair_blocks) * 2 * kBatchMax);
+        int n_ewald_blocks = 0;
+        if (with_ewald) {
+            const int kt = kBatchDeltaElems / stride;
+            const int n_tiles = (c->slot[0].K + kt - 1) / kt;
+            n_ewald_blocks = std::max(1, std::min(n_tiles, 2 * c->n_sm));
+            b.d_r_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax);
+            b.d_g_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax * kBatchMax);
+        }
+        const size_t n_result = batchResultDoubles(stride);
+        b.d_result.ensure(batchResultDoubles(kBatchMax));
+        b.h_result.ensure(batchResultDoubles(kBatchMax));
+#define FB_CASE(K)                                                                                            \
+    case K:                                                                                                   \
+        launchBatchPairFinish<K>(c, cur, stride, n_pair_blocks, n_ewald_blocks, n_commit_blocks,              \
+                                 with_ewald != 0, timing);                                                    \
+        break;
+        switch (c->P.kind) {
+            FB_CASE(POT_COULOMB_LJ)
+            FB_CASE(POT_COULOMB_WCA)
+            FB_CASE(POT_PM)
+            FB_CASE(POT_PMWCA)
+            FB_CASE(POT_FUNCTOR)
+            FB_CASE(POT_SPLINED)
+        default:
+            throw CudaError{"unknown potential kind"};
+        }
+#undef FB_CASE
+        if (timing) {
+            CUDA_CHECK(cudaEventRecord(b.ev[4], c->stream));
+        }
+        CUDA_CHECK(cudaMemcpyAsync(b.h_result.ptr, b.d_result.ptr, n_result * sizeof(double), cudaMemcpyDeviceToHost,
+                                   c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (timing) {
+            float t01 = 0, t12 = 0, t23 = 0, t34 = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&t01, b.ev[0], b.ev[1]));
+            CUDA_CHECK(cudaEventElapsedTime(&t12, b.ev[1], b.ev[2]));
+            CUDA_CHECK(cudaEventElapsedTime(&t23, b.ev[2], b.ev[3]));
+            CUDA_CHECK(cudaEventElapsedTime(&t34, b.ev[3], b.ev[4]));
+            b.acc_ms[0] += t12;
+            b.acc_ms[1] += t23;
+            b.acc_ms[2] += t01 + t34;
+        }
+        b.windows += 1;
+        b.moves += n_moves;
+        const double* r = b.h_result.ptr;
+        if (with_ewald) {
+            if (n_commit_blocks > 0) {
+                b.rec_sum = r[0];
+                b.rec_known = true;
+            }
+        }
+        b.last_n = n_moves;
+        b.last_with_ewald = with_ewald ? 1 : 0;
+        const size_t S = static_cast<size_t>(stride);
+        out->n_moves = n_moves;
+        out->stride = stride;
+        out->u_new = r + 8;
+        out->u_old = r + 8 + S;
+        out->rec_delta = r + 8 + 2 * S;
+        out->cross_new = r + 8 + 3 * S;
+        out->cross_old = r + 8 + 3 * S + S * S;
+        out->cross_max = r + 8 + 3 * S + 2 * S * S;
+        out->rec_cross = r + 8 + 3 * S + 3 * S * S;
+        out->rec_start = 0.0;
+        out->rec_prefactor = 0.0;
+        if (with_ewald) {
+            const double pi = 3.141592653589793238462643383279502884;
+            const Slot& sl = c->slot[0];
+            out->rec_prefactor = 2 * pi * c->ewald.bjerrum_length / (sl.ewald_box[0] * sl.ewald_box[1] * sl.ewald_box[2]);
+            out->rec_start = b.rec_sum;
+        }
+    });
+}
+
+FB_API int fb_batch_commit(fb_ctx* c, int n_decided, const unsigned char* accepted)
+{
+    return guarded(c, [&] {
+        auto& b = c->batch;
+        if (b.last_n <= 0) {
+            throw CudaError{"fb_batch_commit: no evaluated window"};
+        }
+        if (n_decided < 0 || n_decided > b.last_n || (n_decided > 0 && !accepted)) {
+            throw CudaError{"fb_batch_commit: bad arguments"};
+        }
+        if (b.has_pending) {
+            throw CudaError{"fb_batch_commit: the window was already committed"};
+        }
+        CommitList list{};
+        for (int m = 0; m < n_decided; ++m) {
+            if (accepted[m]) {
+                list.index[list.n++] = m;
+            }
+        }
+        b.last_n = 0;
+        if (list.n == 0) {
+            return;
+        }
+        b.pending = list;
+        b.has_pending = true;
+        b.pending_with_ewald = b.last_with_ewald != 0;
+        if (b.pending_with_ewald) {
+            b.q_dirty = true;
+            b.rec_known = false;
+            c->slot[0].rec_valid = false;
+            c->slot[1].rec_valid = false;
+        }
+    });
+}
+
+FB_API int fb_get_batch_timing(const fb_ctx* c, double out[8])
+{
+    if (!c || !out) {
+        return FB_ERR_INVALID;
+    }
+    out[0] = c->batch.acc_ms[0];
+    out[1] = c->batch.acc_ms[1];
+    out[2] = c->batch.acc_ms[2];
+    out[3] = c->batch.windows;
+    out[4] = c->batch.moves;
+    out[5] = out[6] = out[7] = 0.0;
+    return FB_OK;
+}

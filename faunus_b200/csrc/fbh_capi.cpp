@@ -142,3 +142,36 @@ extern "C" __attribute__((visibility("default"))) void* fbh_sim_ctx(void* h)
     const auto terms = s->mc->state.pot->find<fb::NonbondedB200>();
     return terms.empty() ? nullptr : static_cast<void*>(terms.front()->device()->ctx);
 }
+
+/**
+ * Windowed evaluation of `transrot` runs (fb_batch_trial): capacity 0 switches it off (one move at a
+ * time through updateState/energy/sync). Returns the capacity in effect (0 if the Hamiltonian is not
+ * eligible: only self-energy, B200 non-bonded and tinfoil PBC Ewald terms can be windowed).
+ */
+extern "C" __attribute__((visibility("default"))) int fbh_sim_set_window(void* h, int capacity)
+{
+    auto* s = static_cast<fb::capi::Sim*>(h);
+    int result = 0;
+    fb::capi::guarded([&] {
+        s->mc->window_evaluator = fb::B200WindowEvaluator::tryCreate(*s->mc, capacity);
+        result = s->mc->window_evaluator ? s->mc->window_evaluator->capacity() : 0;
+    });
+    return result;
+}
+
+/** out[0..2] = ms in pair / k-space / other kernels of the windowed path, out[3] = windows, out[4] = moves */
+extern "C" __attribute__((visibility("default"))) int fbh_sim_get_window_timing(void* h, double out[8])
+{
+    auto* s = static_cast<fb::capi::Sim*>(h);
+    for (int i = 0; i < 8; ++i) {
+        out[i] = 0;
+    }
+    for (const auto& t : s->mc->state.pot->find<fb::NonbondedB200>()) {
+        double v[8];
+        fb_get_batch_timing(t->device()->ctx, v);
+        for (int i = 0; i < 8; ++i) {
+            out[i] += v[i];
+        }
+    }
+    return 0;
+}

@@ -226,6 +226,7 @@ class Hamiltonian : public EnergyTerm
     size_t size() const { return energy_terms.size(); }
     const std::vector<std::shared_ptr<EnergyTerm>>& terms() const { return energy_terms; }
     const std::vector<double>& latestEnergies() const { return latest_energies; }
+    double maximumAllowedEnergy() const { return maximum_allowed_energy; }
 
     template <class T> std::vector<std::shared_ptr<T>> find() const
     {

@@ -29,6 +29,43 @@ struct TraceRecord
     int move_id = 0;
 };
 
+/** One drawn, not yet decided trial move of the windowed path */
+struct WindowProposal
+{
+    AtomicTranslateRotate* move = nullptr;
+    int move_id = 0;
+    AtomicTranslateRotate::Draw draw;
+    Change change;                  //!< filled when the draw is applied to the trial Space
+    bool applied = false;
+    double uniform = 0;             //!< the Metropolis uniform of this move (drawn in reference order)
+    double displacement_squared = 0;
+};
+
+/**
+ * Evaluates a window of consecutive single-atom trial moves at once. The proposals of `transrot` and
+ * the Metropolis uniform consume the generator independently of any energy (src/move.cpp:267-293,
+ * src/montecarlo.cpp:17-34), so the engine can draw a run of moves ahead, have all of them evaluated
+ * against the current accepted state in one pass, and then decide them strictly in order; the
+ * evaluator supplies the energies of move m GIVEN the decisions taken on the earlier moves of the
+ * window. The accept/reject sequence is the one of the one-at-a-time loop (src/montecarlo.cpp:139-187).
+ */
+class WindowEvaluator
+{
+  public:
+    virtual ~WindowEvaluator() = default;
+    virtual int capacity() const = 0;
+    /** evaluate proposals [0, n) of `window` (all applied to the trial Space, distinct atoms) */
+    virtual void evaluate(const std::vector<WindowProposal>& window, int n) = 0;
+    /**
+     * Hamiltonian energies of proposal m in the trial / accepted state, given which of the proposals
+     * before m were accepted. Returns false if m has to be evaluated again in a fresh window.
+     */
+    virtual bool energies(int m, const std::vector<unsigned char>& accepted, const WindowProposal& proposal,
+                          double& new_energy, double& old_energy) = 0;
+    /** the first `accepted.size()` proposals are decided; the rest will be submitted again */
+    virtual void commit(const std::vector<unsigned char>& accepted) = 0;
+};
+
 class MetropolisMonteCarlo
 {
   public:
@@ -42,6 +79,9 @@ class MetropolisMonteCarlo
     unsigned int number_of_sweeps = 0;
     bool record_trace = false;
     std::vector<TraceRecord> trace;
+    std::unique_ptr<WindowEvaluator> window_evaluator; //!< set by the B200 build; nullptr = one move at a time
+    unsigned long windows_evaluated = 0;
+    unsigned long window_moves_evaluated = 0;
 
   private:
     /** src/montecarlo.cpp:17-34; the uniform is ALWAYS drawn */
@@ -185,6 +225,143 @@ class MetropolisMonteCarlo
         }
     }
 
+    /** metropolisCriterion with the uniform drawn earlier (same rule, src/montecarlo.cpp:17-34) */
+    static bool metropolisDecision(double energy_change, double uniform)
+    {
+        if (std::isnan(energy_change)) {
+            throw std::runtime_error("Metropolis error: energy cannot be NaN");
+        }
+        if (std::isinf(energy_change) && energy_change < 0.0) {
+            return true;
+        }
+        if (-energy_change > pc::max_exp_argument) {
+            return true;
+        }
+        return uniform <= std::exp(-energy_change);
+    }
+
+  private:
+    std::vector<WindowProposal> window; //!< drawn, undecided proposals in move order
+
+    void applyProposal(WindowProposal& p)
+    {
+        p.move->moveFromDraw(p.draw, p.change);
+        p.displacement_squared = p.move->latestDisplacementSquared();
+        p.applied = true;
+    }
+
+    /** evaluate the first `n` queued proposals (all applied) and decide as many as possible, in order */
+    void decideWindow(int n)
+    {
+        window_evaluator->evaluate(window, n);
+        windows_evaluated++;
+        window_moves_evaluated += static_cast<unsigned long>(n);
+        std::vector<unsigned char> accepted;
+        for (int m = 0; m < n; ++m) {
+            auto& p = window[m];
+            double new_energy = 0, old_energy = 0;
+            if (!window_evaluator->energies(m, accepted, p, new_energy, old_energy)) {
+                break;
+            }
+            double energy_change = getEnergyChange(new_energy, old_energy);
+            TraceRecord rec;
+            rec.du = energy_change;
+            rec.u_new = new_energy;
+            rec.u_old = old_energy;
+            rec.move_id = p.move_id;
+            p.move->setLatestDisplacementSquared(p.displacement_squared);
+            if (metropolisDecision(energy_change, p.uniform)) {
+                state.spc->sync(*trial_state.spc, p.change);
+                p.move->accept(p.change);
+                rec.accepted = 1;
+            }
+            else {
+                trial_state.spc->sync(*state.spc, p.change);
+                p.move->reject(p.change);
+                energy_change = 0.0;
+            }
+            accepted.push_back(static_cast<unsigned char>(rec.accepted));
+            sum_of_energy_changes += energy_change;
+            if (record_trace) {
+                trace.push_back(rec);
+            }
+        }
+        if (accepted.empty()) {
+            throw std::runtime_error("windowed evaluation made no progress");
+        }
+        window_evaluator->commit(accepted);
+        // undecided proposals stay queued: their trial positions are in the trial Space (distinct atoms)
+        window.erase(window.begin(), window.begin() + static_cast<long>(accepted.size()));
+    }
+
+    int readyProposals() const
+    {
+        int r = 0;
+        while (r < static_cast<int>(window.size()) && window[r].applied) {
+            r++;
+        }
+        return r;
+    }
+
+    /** The stochastic part of a sweep with runs of `transrot` moves evaluated window by window */
+    template <class IdOf> void sweepStochasticWindowed(IdOf&& id_of)
+    {
+        const int capacity = window_evaluator->capacity();
+        unsigned int remaining = moves->movesPerSweep();
+        Move* deferred = nullptr; // a move of another kind: runs once the queue is empty
+        while (remaining > 0 || !window.empty() || deferred != nullptr) {
+            bool blocked = !window.empty() && !window.back().applied;
+            while (!blocked && deferred == nullptr && remaining > 0 && static_cast<int>(window.size()) < capacity) {
+                remaining--;
+                Move* selected = moves->sampleStochasticMove();
+                if (selected == nullptr) {
+                    continue;
+                }
+                auto* transrot = dynamic_cast<AtomicTranslateRotate*>(selected);
+                if (transrot == nullptr || !transrot->targetsAtomicGroups()) {
+                    deferred = selected;
+                    break;
+                }
+                WindowProposal p;
+                p.move = transrot;
+                p.move_id = id_of(*selected);
+                p.draw = transrot->draw();
+                if (!(p.draw.valid && (p.draw.dp > 0.0 || p.draw.dprot > 0.0))) {
+                    Change none; // empty Change: count the attempt, keep the generator in step (montecarlo.cpp:182-186)
+                    transrot->moveFromDraw(p.draw, none);
+                    rng.slump();
+                    continue;
+                }
+                p.uniform = rng.slump();
+                for (const auto& q : window) {
+                    blocked = blocked || (q.draw.group_index == p.draw.group_index &&
+                                          q.draw.atom_index == p.draw.atom_index);
+                }
+                if (!blocked) {
+                    applyProposal(p);
+                }
+                // else: its start position is only known once the earlier move on this atom is decided
+                window.push_back(std::move(p));
+            }
+            if (blocked || deferred != nullptr || remaining == 0) { // drain the queue
+                while (readyProposals() > 0) {
+                    decideWindow(readyProposals());
+                }
+                if (!window.empty()) {
+                    applyProposal(window.front());
+                }
+                if (deferred != nullptr) {
+                    performMove(*deferred, id_of(*deferred));
+                    deferred = nullptr;
+                }
+            }
+            else if (!window.empty()) { // full window
+                decideWindow(readyProposals());
+            }
+        }
+    }
+
+  public:
     /** src/montecarlo.cpp:220-227 */
     void sweep()
     {
@@ -198,7 +375,12 @@ class MetropolisMonteCarlo
             }
             return -1;
         };
-        moves->forEachStochasticMove([&](Move& m) { performMove(m, id_of(m)); });
+        if (window_evaluator) {
+            sweepStochasticWindowed(id_of);
+        }
+        else {
+            moves->forEachStochasticMove([&](Move& m) { performMove(m, id_of(m)); });
+        }
         moves->forEachIntervalMove(number_of_sweeps, [&](Move& m) { performMove(m, id_of(m)); });
     }
 

@@ -137,47 +137,87 @@ class AtomicTranslateRotate : public Move
         j["msd"] = msd_cnt ? msd_sum / msd_cnt : 0.0;
     }
 
-    void _move(Change& change) override
+  public:
+    /** The random part of one proposal: everything `_move` draws, nothing that depends on positions */
+    struct Draw
     {
+        bool valid = false; //!< a particle was picked
+        size_t group_index = 0;
+        size_t atom_index = 0;
+        double dp = 0, dprot = 0;
+        double scalar = 0;
+        Point unit{0, 0, 0};
+    };
+
+    /** consumes the generator exactly as the reference's `_move` does (src/move.cpp:267-293, 328-346) */
+    Draw draw()
+    {
+        Draw d;
         const auto selection =
             spc.topology->molecules[molid].atomic ? Space::Selection::ALL : Space::Selection::ACTIVE;
         const auto mollist = spc.findMolecules(molid, selection);
         if (mollist.empty()) {
-            latest_displacement_squared = 0.0;
-            return;
+            return d;
         }
-        const auto group_index = mollist[rng.slump.sampleIndex(static_cast<int>(mollist.size()))];
-        auto& group = spc.groups[group_index];
+        d.group_index = mollist[rng.slump.sampleIndex(static_cast<int>(mollist.size()))];
+        const auto& group = spc.groups[d.group_index];
         if (group.empty()) {
-            latest_displacement_squared = 0.0;
+            return d;
+        }
+        d.atom_index = static_cast<size_t>(rng.slump.sampleIndex(static_cast<int>(group.size())));
+        d.valid = true;
+        const auto& atom = spc.traits(spc.at(group, d.atom_index));
+        d.dp = atom.dp.value_or(default_dp);
+        d.dprot = atom.dprot.value_or(default_dprot);
+        if (d.dp > 0.0) { // src/move.cpp:225-240
+            d.scalar = rng.slump(); // GCC order: scalar first, then the unit vector
+            d.unit = randomUnitVector(rng.slump, directions);
+        }
+        if (d.dprot > 0.0) { // isotropic particles: draws are consumed, nothing rotates
+            (void)randomUnitVector(rng.slump);
+            (void)(d.dprot * (rng.slump() - 0.5));
+        }
+        return d;
+    }
+
+    /** displace the picked particle in the trial Space and describe it in `change` */
+    void apply(const Draw& d, Change& change)
+    {
+        latest_displacement_squared = 0.0;
+        if (!d.valid) {
             return;
         }
-        const auto atom_index = static_cast<size_t>(rng.slump.sampleIndex(static_cast<int>(group.size())));
-        cdata.group_index = group_index;
-        cdata.relative_atom_indices[0] = atom_index;
-        auto& particle = spc.at(group, atom_index);
-        const auto& atom = spc.traits(particle);
-        const double dp = atom.dp.value_or(default_dp);
-        const double dprot = atom.dprot.value_or(default_dprot);
-        if (dp > 0.0) { // src/move.cpp:225-240
+        auto& group = spc.groups[d.group_index];
+        cdata.group_index = d.group_index;
+        cdata.relative_atom_indices[0] = d.atom_index;
+        auto& particle = spc.at(group, d.atom_index);
+        if (d.dp > 0.0) {
             const Point old_position = particle.pos;
-            const double scalar = rng.slump(); // GCC order: scalar first, then the unit vector
-            const Point unit = randomUnitVector(rng.slump, directions);
-            particle.pos += unit * dp * scalar;
+            particle.pos += d.unit * d.dp * d.scalar;
             spc.geometry.boundary(particle.pos);
             latest_displacement_squared = spc.geometry.sqdist(old_position, particle.pos);
             if (group.isMolecular()) {
                 group.mass_center = spc.massCenter(group, -group.mass_center);
             }
         }
-        if (dprot > 0.0) { // isotropic particles: draws are consumed, nothing rotates
-            (void)randomUnitVector(rng.slump);
-            (void)(dprot * (rng.slump() - 0.5));
-        }
-        if (dp > 0.0 || dprot > 0.0) {
+        if (d.dp > 0.0 || d.dprot > 0.0) {
             change.groups.push_back(cdata);
         }
     }
+
+    /** windowed path: count the attempt and apply a proposal drawn earlier */
+    void moveFromDraw(const Draw& d, Change& change)
+    {
+        number_of_attempted_moves++;
+        change.clear();
+        apply(d, change);
+    }
+    bool targetsAtomicGroups() const { return spc.topology->molecules[molid].atomic; }
+    double latestDisplacementSquared() const { return latest_displacement_squared; }
+    void setLatestDisplacementSquared(double d2) { latest_displacement_squared = d2; }
+
+  private:
+    void _move(Change& change) override { apply(draw(), change); }
     void _accept(Change&) override
     {
         msd_sum += latest_displacement_squared;
@@ -559,6 +599,15 @@ class MoveCollection
                 perform(*selected);
             }
         }
+    }
+    /** one iteration of forEachStochasticMove: the move to perform, or nullptr if the probe was not stochastic */
+    Move* sampleStochasticMove()
+    {
+        Move* probe = sample();
+        if (probe != nullptr && probe->isStochastic()) {
+            return sample();
+        }
+        return nullptr;
     }
     template <class F> void forEachIntervalMove(unsigned int sweep_number, F&& perform)
     {

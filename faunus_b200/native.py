@@ -50,6 +50,17 @@ class FbEwaldConfig(C.Structure):
                 ("spherical_sum", C.c_int), ("policy", C.c_int)]
 
 
+class FbBatchMove(C.Structure):
+    _fields_ = [("group_index", C.c_int), ("rel_index", C.c_int), ("atom_id", C.c_int), ("xyzq", C.c_double * 4)]
+
+
+class FbBatchResult(C.Structure):
+    _fields_ = [("n_moves", C.c_int), ("stride", C.c_int), ("u_new", c_double_p), ("u_old", c_double_p),
+                ("rec_delta", c_double_p), ("cross_new", c_double_p), ("cross_old", c_double_p),
+                ("cross_max", c_double_p), ("rec_cross", c_double_p), ("rec_start", C.c_double),
+                ("rec_prefactor", C.c_double)]
+
+
 class FbTrialMove(C.Structure):
     _fields_ = [("group_index", C.c_int), ("n_atoms", C.c_int), ("rel_index", C.c_int * 8),
                 ("xyzq", (C.c_double * 4) * 8), ("atom_id", C.c_int * 8), ("cm", C.c_double * 3),
@@ -82,7 +93,7 @@ class FbConfig(C.Structure):
 C_ABI_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_last_error", "fb_device_count", "fb_upload_space", "fb_update_group",
     "fb_set_box", "fb_sync", "fb_download_space", "fb_nonbonded_energy", "fb_nonbonded_delta",
-    "fb_trial_energy", "fb_trial_commit",
+    "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_commit", "fb_get_batch_timing",
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
     "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
     "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_launch_count",
@@ -118,6 +129,9 @@ def load() -> C.CDLL:
         "fb_nonbonded_delta": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(FbChange), c_double_p, c_double_p]),
         "fb_trial_energy": (C.c_int, [vp, C.POINTER(FbTrialMove), c_double_p, c_double_p, c_double_p, c_double_p]),
         "fb_trial_commit": (C.c_int, [vp, C.c_int]),
+        "fb_batch_trial": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchMove), C.c_int, C.POINTER(FbBatchResult)]),
+        "fb_batch_commit": (C.c_int, [vp, C.c_int, c_ubyte_p]),
+        "fb_get_batch_timing": (C.c_int, [vp, c_double_p]),
         "fb_ewald_configure": (C.c_int, [vp, C.POINTER(FbEwaldConfig)]),
         "fb_ewald_update_box": (C.c_int, [vp, C.c_int, c_int_p]),
         "fb_ewald_update_full": (C.c_int, [vp, C.c_int]),
@@ -143,6 +157,8 @@ def load() -> C.CDLL:
         "fbh_sim_ctx": (vp, [vp]),
         "fbh_set_device": (None, [C.c_int]),
         "fbh_sim_launch_count": (C.c_ulonglong, [vp]),
+        "fbh_sim_set_window": (C.c_int, [vp, C.c_int]),
+        "fbh_sim_get_window_timing": (C.c_int, [vp, c_double_p]),
     }
     for name, (restype, argtypes) in sig.items():
         fn = getattr(lib, name)
@@ -171,10 +187,26 @@ def require_device():
 class B200Simulation(Simulation):
     """Metropolis MC simulation whose non-bonded/Ewald terms run on the B200 (``fbh_*`` ABI)."""
 
-    def __init__(self, config, device: int = 0):
+    #: proposals evaluated per device pass for runs of `transrot` moves (0: one move at a time)
+    DEFAULT_WINDOW = int(os.environ.get("FAUNUS_B200_WINDOW", "32"))
+
+    def __init__(self, config, device: int = 0, window: Optional[int] = None):
         require_device()
         load().fbh_set_device(device)
         super().__init__(sim_library(), config)
+        self.window = self.set_window(self.DEFAULT_WINDOW if window is None else window)
+
+    def set_window(self, capacity: int) -> int:
+        """Windowed evaluation of single-atom move runs (fb_batch_trial); returns the capacity in effect
+        (0 when switched off or when the Hamiltonian is not eligible)."""
+        self.window = int(load().fbh_sim_set_window(self.handle, int(capacity)))
+        return self.window
+
+    def window_time_ms(self) -> dict:
+        out = np.zeros(8)
+        load().fbh_sim_get_window_timing(self.handle, out.ctypes.data_as(c_double_p))
+        return {"pair_ms": out[0], "ewald_ms": out[1], "other_ms": out[2], "windows": int(out[3]),
+                "moves": int(out[4])}
 
     @property
     def launch_count(self) -> int:

@@ -22,6 +22,8 @@
  *   fb_nonbonded_energy ............ Nonbonded::energy(Change) → GroupPairing::accumulate  src/energy.h:1561-1577, 1447-1475
  *   fb_nonbonded_delta ............. the pair of calls trial.energy / accepted.energy  src/montecarlo.cpp:154-155
  *   fb_ewald_* ..................... Energy::Ewald + PolicyIonIon                      src/energy.cpp:28-59, 133-247, 466-531, 539-658
+ *   fb_batch_trial / fb_batch_commit a window of consecutive MetropolisMonteCarlo::performMove calls
+ *                                    (updateState + energy(trial) + energy(accepted) + sync each)     src/montecarlo.cpp:139-187
  *   fb_widom_batch ................. WidomInsertion::_sample insertion loop            src/analysis.cpp:1243-1265
  *   fb_export_state/fb_import_state  MPI::ExchangeParticles / exchangeGroupSizes       src/mpicontroller.cpp:192-219, src/move.cpp:860-881
  */
@@ -211,6 +213,54 @@ typedef struct
 int fb_trial_energy(fb_ctx* ctx, const fb_trial_move* move, double* u_new, double* u_old, double* ewald_new,
                     double* ewald_old);
 int fb_trial_commit(fb_ctx* ctx, int accept);
+
+/* ---- windowed path: a run of consecutive single-atom trial moves in one pass ------------------ */
+/* The proposals of `transrot` (AtomicTranslateRotate, src/move.cpp:267-293) do not depend on energies,
+ * so the caller can draw a window of up to FB_BATCH_MAX consecutive moves on DISTINCT atoms of atomic
+ * groups ahead of time. fb_batch_trial evaluates all of them against the window-start state (both
+ * slots must mirror the accepted state) and returns, besides the per-move energies, the exact
+ * corrections that apply when an EARLIER move of the window has been accepted:
+ *
+ *   u_new(m | accepted set A) = u_new[m] + sum_{a in A, a < m} cross_new[a * stride + m]
+ *   u_old(m | A)              = u_old[m] + sum_{a in A, a < m} cross_old[a * stride + m]
+ *   dU_rec(m | A)             = rec_prefactor * (rec_delta[m] + 2 sum_{a in A, a < m} rec_cross[a * stride + m])
+ *
+ * (nonbonded energy of the moved atom with all other active particles, src/energy.h:1182-1195 + 885-914;
+ * reciprocal Ewald energy change of the partial update, src/energy.cpp:219-247 + 524-531.) The caller
+ * decides the moves in order (Metropolis on the host, reference RNG order) and reports the outcome with
+ * fb_batch_commit; undecided moves (n_decided < n_moves) are simply dropped and may be re-submitted.
+ * cross_max[a * stride + m] is the largest |pair energy| entering cross_new/old: if it is huge or
+ * infinite the caller should stop the window at move m and re-evaluate it in the next one
+ * (cancellation). The result arrays live in pinned memory owned by the context and stay valid until
+ * the next fb_batch_trial. */
+#define FB_BATCH_MAX 64
+typedef struct
+{
+    int group_index;
+    int rel_index;  /* relative atom index within the group */
+    int atom_id;    /* atom type at the trial position */
+    double xyzq[4]; /* trial position and charge */
+} fb_batch_move;
+typedef struct
+{
+    int n_moves;
+    int stride;              /* row length of the [a][m] matrices (16, 32 or 64) */
+    const double* u_new;     /* [n_moves] */
+    const double* u_old;     /* [n_moves] */
+    const double* rec_delta; /* [n_moves] sum_k A_k (2 Re(conj Q_k d_k) + |d_k|^2), 0 without Ewald */
+    const double* cross_new; /* [stride * stride], entries a < m */
+    const double* cross_old;
+    const double* cross_max;
+    const double* rec_cross; /* sum_k A_k Re(conj d_a,k d_m,k) */
+    double rec_start;        /* sum_k A_k |Q_k|^2 of the window-start state */
+    double rec_prefactor;    /* 2 pi lB / V */
+} fb_batch_result;
+int fb_batch_trial(fb_ctx* ctx, int n_moves, const fb_batch_move* moves, int with_ewald, fb_batch_result* result);
+/* accepted[m] != 0 for the accepted ones among the first n_decided moves of the last window */
+int fb_batch_commit(fb_ctx* ctx, int n_decided, const unsigned char* accepted);
+/* timing enabled: out[0..2] = ms in the pair / k-space / other (commit, phase tables, final sums) kernels of
+ * the windowed path, out[3] = windows, out[4] = moves evaluated */
+int fb_get_batch_timing(const fb_ctx* ctx, double out[8]);
 
 /* ---- Ewald reciprocal space --------------------------------------------------------------- */
 int fb_ewald_configure(fb_ctx* ctx, const fb_ewald_config* config);

@@ -12,9 +12,9 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-10
 
 
-def b200_sim(cfg):
+def b200_sim(cfg, window=None):
     from faunus_b200.native import B200Simulation
-    return B200Simulation(cfg)
+    return B200Simulation(cfg, window=window)
 
 
 def assert_close(a, b, rtol=RTOL, scale=None):
@@ -27,8 +27,8 @@ def assert_close(a, b, rtol=RTOL, scale=None):
         f"max abs diff {np.abs(a[~inf] - b[~inf]).max()} (ref scale {np.max(ref) if np.size(ref) else 0})"
 
 
-def pair_of_sims(cfg):
-    return oracle_sim(cfg), b200_sim(cfg)
+def pair_of_sims(cfg, window=None):
+    return oracle_sim(cfg), b200_sim(cfg, window)
 
 
 def electrolyte_variants():
@@ -61,11 +61,18 @@ def functor_variants():
 ALL_VARIANTS = {**electrolyte_variants(), **functor_variants()}
 
 
+#: 0 = one move per launch (updateState/energy/sync protocol); > 0 = windowed evaluation (fb_batch_trial)
+WINDOWS = [0, 32]
+
+
+@pytest.mark.parametrize("window", WINDOWS)
 @pytest.mark.parametrize("name", sorted(ALL_VARIANTS))
-def test_system_energy_and_moves(name):
+def test_system_energy_and_moves(name, window):
     """Full energy per term, then 300 single-ion trial moves: u_new/u_old per move and the trace"""
     cfg = ALL_VARIANTS[name]
-    o, g = pair_of_sims(cfg)
+    o, g = pair_of_sims(cfg, window)
+    if window and "surface" not in name:
+        assert g.window == window
     eo, to = o.system_energy()
     eg, tg = g.system_energy()
     assert len(to) == len(tg)
@@ -83,9 +90,10 @@ def test_system_energy_and_moves(name):
     assert g.launch_count > 0
 
 
-def test_bulk_example_trace(bulk_input):
+@pytest.mark.parametrize("window", [0, 7, 64])
+def test_bulk_example_trace(bulk_input, window):
     """examples/bulk state: identical accept/reject sequence over 3 sweeps (6912 moves)"""
-    o, g = pair_of_sims(bulk_input)
+    o, g = pair_of_sims(bulk_input, window)
     assert_close(o.system_energy()[1], g.system_energy()[1], scale=7e4)
     for s in (o, g):
         s.trace_enable()
@@ -97,8 +105,9 @@ def test_bulk_example_trace(bulk_input):
     assert abs(g.drift()) < 1e-9
 
 
-def test_minimal_example(minimal_input):
-    o, g = pair_of_sims(minimal_input)
+@pytest.mark.parametrize("window", [0, 16])
+def test_minimal_example(minimal_input, window):
+    o, g = pair_of_sims(minimal_input, window)
     assert_close(o.system_energy()[1], g.system_energy()[1], scale=abs(o.system_energy()[0]))
     for s in (o, g):
         s.trace_enable()
@@ -216,3 +225,73 @@ def test_widom_example(reference_values, widom_input):
     assert ro["sum_exp"] == rg["sum_exp"]
     mu = -np.log(rg["sum_exp"] / rg["count"])
     assert mu == pytest.approx(reference_values["widom"]["mu_excess"], rel=0.01)
+
+
+def test_window_matches_single_moves():
+    """fb_batch_trial through the raw C ABI: window energies + corrections reproduce one-at-a-time
+    fb_trial_energy / fb_trial_commit on the same proposals (Ewald electrolyte, every 2nd move accepted)"""
+    import ctypes as C
+    import faunus_b200.native as native
+    lib = native.load()
+    cfg = small_electrolyte(n=600, coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 6})
+    ga, gb = b200_sim(cfg, 0), b200_sim(cfg, 0)
+    xyzq, ids = ga.particles()
+    rng = np.random.RandomState(11)
+    n = 40
+    picks = rng.choice(len(xyzq), n, replace=False)
+    newpos = xyzq[picks, :3] + rng.uniform(-1.5, 1.5, (n, 3))
+    accept = [(m % 2 == 0) for m in range(n)]
+    # reference: one move at a time on context A
+    ref = []
+    mv = native.FbTrialMove()
+    for m in range(n):
+        mv.group_index, mv.n_atoms, mv.internal, mv.with_ewald = 0, 1, 1, 1
+        mv.rel_index[0], mv.atom_id[0] = int(picks[m]), int(ids[picks[m]])
+        for d in range(3):
+            mv.xyzq[0][d] = newpos[m, d]
+        mv.xyzq[0][3] = xyzq[picks[m], 3]
+        out = [C.c_double() for _ in range(4)]
+        assert lib.fb_trial_energy(ga.ctx, C.byref(mv), *[C.byref(x) for x in out]) == 0, lib.fb_last_error(ga.ctx)
+        ref.append([x.value for x in out])
+        assert lib.fb_trial_commit(ga.ctx, int(accept[m])) == 0
+    ref = np.array(ref)
+    # window on context B
+    moves = (native.FbBatchMove * n)()
+    for m in range(n):
+        moves[m].group_index, moves[m].rel_index, moves[m].atom_id = 0, int(picks[m]), int(ids[picks[m]])
+        for d in range(3):
+            moves[m].xyzq[d] = newpos[m, d]
+        moves[m].xyzq[3] = xyzq[picks[m], 3]
+    res = native.FbBatchResult()
+    assert lib.fb_batch_trial(gb.ctx, n, moves, 1, C.byref(res)) == 0, lib.fb_last_error(gb.ctx)
+    S = res.stride
+    assert S == 64 and res.n_moves == n
+    arr = lambda p, k: np.ctypeslib.as_array(p, shape=(k,)).copy()
+    u_new, u_old, rec = arr(res.u_new, S), arr(res.u_old, S), arr(res.rec_delta, S)
+    cn, co, g = (arr(p, S * S).reshape(S, S) for p in (res.cross_new, res.cross_old, res.rec_cross))
+    run = res.rec_start
+    scale = np.abs(ref[:, :2]).max()
+    for m in range(n):
+        acc = [a for a in range(m) if accept[a]]
+        un = u_new[m] + sum(cn[a, m] for a in acc)
+        uo = u_old[m] + sum(co[a, m] for a in acc)
+        dr = rec[m] + 2 * sum(g[a, m] for a in acc)
+        assert abs(un - ref[m, 0]) <= RTOL * scale
+        assert abs(uo - ref[m, 1]) <= RTOL * scale
+        assert abs(res.rec_prefactor * run - ref[m, 3]) <= RTOL * abs(ref[m, 3])
+        assert abs(res.rec_prefactor * (run + dr) - ref[m, 2]) <= RTOL * abs(ref[m, 2])
+        if accept[m]:
+            run += dr
+    flags = (C.c_ubyte * n)(*[int(a) for a in accept])
+    assert lib.fb_batch_commit(gb.ctx, n, flags) == 0
+    # both contexts now hold the same state: full energies agree, and a second window starts from it
+    # (the Simulation's host Space was bypassed; compare the device mirrors directly)
+    xa = np.zeros((len(xyzq), 4)); xb = np.zeros((len(xyzq), 4))
+    ia = np.zeros(len(xyzq), dtype=np.int32); ib = np.zeros(len(xyzq), dtype=np.int32)
+    for ctx, x, i in ((ga.ctx, xa, ia), (gb.ctx, xb, ib)):
+        assert lib.fb_download_space(ctx, 0, x.ctypes.data_as(native.c_double_p), i.ctypes.data_as(native.c_int_p), None) == 0
+    assert np.array_equal(xa, xb) and np.array_equal(ia, ib)
+    qa, qb = np.zeros(8000), np.zeros(8000)  # K < 4000 here; Q(k) after the commits: same to rounding
+    assert lib.fb_ewald_download(ga.ctx, 0, qa.ctypes.data_as(native.c_double_p), None, None) == 0
+    assert lib.fb_ewald_download(gb.ctx, 0, qb.ctypes.data_as(native.c_double_p), None, None) == 0
+    assert np.allclose(qa, qb, rtol=0, atol=1e-10 * np.abs(qa).max())
