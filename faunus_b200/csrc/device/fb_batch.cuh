@@ -25,9 +25,12 @@
 namespace fbdev {
 
 constexpr int kBatchMax = 64;    //!< moves per window
-constexpr int kBatchTile = 256;  //!< particles staged per block of the pair kernel
 constexpr int kBatchDeltaElems = 2048; //!< double2 elements of the δ tile in shared memory (32 KB + padding)
-static_assert(kBatchTile == kBlock, "the pair kernel stages one particle per thread");
+/** k-vectors per tile of the k-space kernel for a window stride of 16 / 32 / 64 moves */
+__host__ __device__ constexpr int batchTileK(int stride)
+{
+    return kBatchDeltaElems / stride < 64 ? kBatchDeltaElems / stride : 64;
+}
 
 /** Host → device description of one window (copied as one block) */
 struct BatchInput
@@ -85,34 +88,42 @@ __global__ void __launch_bounds__(kBlock)
                       PhaseGeometry geo, CommitList commit, int with_ewald, double* __restrict__ e_partials)
 {
     __shared__ double scratch[kBlock / 32];
-    if (blockIdx.x == 0 && threadIdx.x < commit.n) {
+    __shared__ double s_qn[kBatchMax], s_qo[kBatchMax];
+    __shared__ int s_table[kBatchMax]; //!< first table entry of the accepted move's new position
+    if (threadIdx.x < commit.n) {
         const int m = commit.index[threadIdx.x];
-        const int s = prev.in->slot[m];
         const double4 p = prev.in->pnew[m];
-        const int id = prev.in->id[m];
-        M0.posq[s] = p;
-        M0.atom_id[s] = id;
-        M1.posq[s] = p;
-        M1.atom_id[s] = id;
+        s_qn[threadIdx.x] = p.w;
+        s_qo[threadIdx.x] = prev.pold[m].w;
+        s_table[threadIdx.x] = 2 * m * geo.table_stride;
+        if (blockIdx.x == 0) {
+            const int s = prev.in->slot[m];
+            const int id = prev.in->id[m];
+            M0.posq[s] = p;
+            M0.atom_id[s] = id;
+            M1.posq[s] = p;
+            M1.atom_id[s] = id;
+        }
     }
     if (!with_ewald) {
         return;
     }
+    __syncthreads();
+    const int ncommit = commit.n;
+    const double2* __restrict__ table = prev.table;
     double e = 0.0;
     for (int k = blockIdx.x * kBlock + threadIdx.x; k < E.K; k += gridDim.x * kBlock) {
         const int4 n = __ldg(kn + k);
         double2 Q = E.Q[k];
-        for (int a = 0; a < commit.n; ++a) {
-            const int m = commit.index[a];
-            const double2 en = tablePhase(prev.table + static_cast<size_t>(2 * m) * geo.table_stride, geo, n.x, n.y, n.z);
-            const double2 eo =
-                tablePhase(prev.table + static_cast<size_t>(2 * m + 1) * geo.table_stride, geo, n.x, n.y, n.z);
-            const double qn = prev.in->pnew[m].w;
-            const double qo = prev.pold[m].w;
-            Q.x += qn * en.x - qo * eo.x;
-            Q.y += qn * en.y - qo * eo.y;
+#pragma unroll 4
+        for (int a = 0; a < ncommit; ++a) {
+            const double2* t = table + s_table[a];
+            const double2 en = tablePhase(t, geo, n.x, n.y, n.z);
+            const double2 eo = tablePhase(t + geo.table_stride, geo, n.x, n.y, n.z);
+            Q.x += s_qn[a] * en.x - s_qo[a] * eo.x;
+            Q.y += s_qn[a] * en.y - s_qo[a] * eo.y;
         }
-        if (commit.n > 0) {
+        if (ncommit > 0) {
             E.Q[k] = Q;
         }
         e += E.kA[k].w * (Q.x * Q.x + Q.y * Q.y);
@@ -126,14 +137,46 @@ __global__ void __launch_bounds__(kBlock)
 // ------------------------------------------------------------------------------------------------
 // window set-up: old positions from the (committed) mirror and the per-axis phase tables
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) batchPhaseKernel(SlotView M0, BatchBuffers cur, PhaseGeometry geo)
+/** position and type of `slot` at window start: the previous window's accepted trial if it moved this atom */
+__device__ __forceinline__ double4 committedParticle(const SlotView& M0, const BatchBuffers& prev,
+                                                     const CommitList& commit, int slot, int& id)
+{
+    double4 p = M0.posq[slot];
+    id = M0.atom_id[slot];
+    for (int a = 0; a < commit.n; ++a) {
+        const int m = commit.index[a];
+        if (prev.in->slot[m] == slot) {
+            p = prev.in->pnew[m];
+            id = prev.in->id[m];
+        }
+    }
+    return p;
+}
+
+/**
+ * Block 0 also writes the previous window's accepted positions into both mirrors; every read of a
+ * possibly committed slot in THIS kernel goes through committedParticle, so there is no race. The
+ * kernels that follow in the stream see the committed mirror.
+ */
+__global__ void __launch_bounds__(kBlock)
+    batchPhaseKernel(SlotView M0, SlotView M1, BatchBuffers cur, BatchBuffers prev, CommitList commit, PhaseGeometry geo)
 {
     const int n = cur.in->n;
     const int tid = blockIdx.x * kBlock + threadIdx.x;
     if (tid < n) {
-        const int s = cur.in->slot[tid];
-        cur.pold[tid] = M0.posq[s];
-        cur.idold[tid] = M0.atom_id[s];
+        int id;
+        cur.pold[tid] = committedParticle(M0, prev, commit, cur.in->slot[tid], id);
+        cur.idold[tid] = id;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < commit.n) {
+        const int m = commit.index[threadIdx.x];
+        const int s = prev.in->slot[m];
+        const double4 p = prev.in->pnew[m];
+        const int id = prev.in->id[m];
+        M0.posq[s] = p;
+        M0.atom_id[s] = id;
+        M1.posq[s] = p;
+        M1.atom_id[s] = id;
     }
     if (!cur.in->with_ewald) {
         return;
@@ -143,7 +186,8 @@ __global__ void __launch_bounds__(kBlock) batchPhaseKernel(SlotView M0, BatchBuf
         const int variant = t / geo.table_stride;
         const int e = t - variant * geo.table_stride;
         const int m = variant >> 1;
-        const double4 p = (variant & 1) ? M0.posq[cur.in->slot[m]] : cur.in->pnew[m];
+        int unused_id;
+        const double4 p = (variant & 1) ? committedParticle(M0, prev, commit, cur.in->slot[m], unused_id) : cur.in->pnew[m];
         int axis, nn;
         if (e <= geo.ncc) {
             axis = 0;
@@ -167,96 +211,174 @@ __global__ void __launch_bounds__(kBlock) batchPhaseKernel(SlotView M0, BatchBuf
 }
 
 // ------------------------------------------------------------------------------------------------
-// pair part: thread ↔ (move variant, j sub-range); blocks sweep tiles of particles staged in shared
-// memory (broadcast reads). Inactive particles are staged with NaN coordinates, so r² compares false.
+// pair part: lane ↔ particle j (two per thread, held in registers for the whole window), the block
+// walks the 2n move variants (warp-uniform data from shared memory). Pairs beyond `cut2` contribute
+// exactly zero, so a variant is reduced across the warp only when some lane found a pair in range.
+// The minimum-image fold of an axis is skipped for variants whose position is at least the cutoff away
+// from both cell faces on that axis (then no pair in range folds, and an unfolded r² ≥ the folded one
+// keeps every other pair out of range) — positions are inside the cell (Geometry::boundary).
+// Inactive particles are staged with NaN coordinates, so their r² compares false.
 // ------------------------------------------------------------------------------------------------
+constexpr int kPairThreads = 128;
+constexpr int kPairPerThread = 2;
+constexpr int kPairChunk = kPairThreads * kPairPerThread; //!< particles per block
+constexpr int kPairVariantsPerBlock = 32;                 //!< variant range of one block (grid.y covers the window)
+
 template <int KIND>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kPairThreads)
     batchPairKernel(SlotView M0, PotParams P, BatchBuffers cur, double cut2, int stride,
                     double* __restrict__ partials /*[gridDim.x][2·stride]*/)
 {
-    __shared__ double4 s_pos[kBatchTile];
-    __shared__ int s_id[kBatchTile];
-    __shared__ double s_red[kBlock];
+    __shared__ double4 s_var[2 * kBatchMax];
+    __shared__ int s_vid[2 * kBatchMax];
+    __shared__ int s_vslot[2 * kBatchMax];
+    __shared__ int s_vfold[2 * kBatchMax];
+    __shared__ double s_acc[kPairThreads / 32][2 * kBatchMax];
 
     const int n = cur.in->n;
-    const int nv = 2 * n;                 // variants
-    const int nsub = kBlock / nv;         // j sub-ranges per tile (≥ 2 for n ≤ 64)
-    const int v = threadIdx.x % nv;
-    const int sub = threadIdx.x / nv;
-    const bool worker = sub < nsub;
-    const int m = v >> 1;
-
-    double4 me = make_double4(0, 0, 0, 0);
-    int my_id = 0;
-    int my_slot = -1;
-    if (worker) {
-        my_slot = cur.in->slot[m];
-        if (v & 1) {
-            me = cur.pold[m];
-            my_id = cur.idold[m];
-        }
-        else {
-            me = cur.in->pnew[m];
-            my_id = cur.in->id[m];
-        }
-    }
+    const int nv = 2 * n;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const double hx = M0.half[0], hy = M0.half[1], hz = M0.half[2];
     const double lx = M0.len_or_zero[0], ly = M0.len_or_zero[1], lz = M0.len_or_zero[2];
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
 
-    double e0 = 0.0, e1 = 0.0;
-    const int j0 = blockIdx.x * kBatchTile;
-    {
-        const int j = j0 + threadIdx.x;
-        if (j < M0.n_slots) {
-            double4 p = M0.posq[j];
-            if (M0.gid[j] < 0) {
-                p.x = nan;
-            }
-            s_pos[threadIdx.x] = p;
-            s_id[threadIdx.x] = M0.atom_id[j];
+    for (int v = threadIdx.x; v < nv; v += kPairThreads) {
+        const int m = v >> 1;
+        double4 a;
+        int id;
+        if (v & 1) {
+            a = cur.pold[m];
+            id = cur.idold[m];
         }
         else {
-            s_pos[threadIdx.x] = make_double4(nan, 0, 0, 0);
-            s_id[threadIdx.x] = 0;
+            a = cur.in->pnew[m];
+            id = cur.in->id[m];
         }
+        s_var[v] = a;
+        s_vid[v] = id;
+        s_vslot[v] = cur.in->slot[m];
+        // fold needed on an axis unless the variant keeps the cutoff distance from both faces
+        const double rc = sqrt(cut2); // +inf when some term has no cutoff
+        int fold = 0;
+        fold |= (lx > 0.0 && !(fabs(a.x) + rc < hx)) ? 1 : 0;
+        fold |= (ly > 0.0 && !(fabs(a.y) + rc < hy)) ? 2 : 0;
+        fold |= (lz > 0.0 && !(fabs(a.z) + rc < hz)) ? 4 : 0;
+        s_vfold[v] = fold;
     }
-    __syncthreads();
-    if (worker) {
-        const int per = (kBatchTile + nsub - 1) / nsub;
-        const int jb = sub * per;
-        const int je = min(kBatchTile, jb + per);
-        auto one = [&](int jj, double& acc) {
-            const double4 pj = s_pos[jj];
-            double dx = fabs(me.x - pj.x);
-            double dy = fabs(me.y - pj.y);
-            double dz = fabs(me.z - pj.z);
-            dx -= (dx > hx) ? lx : 0.0;
-            dy -= (dy > hy) ? ly : 0.0;
-            dz -= (dz > hz) ? lz : 0.0;
-            const double r2 = dx * dx + dy * dy + dz * dz;
-            if (r2 < cut2 && (j0 + jj) != my_slot) {
-                acc += pairEnergy<KIND>(P, my_id, s_id[jj], me.w, pj.w, r2);
+    for (int v = threadIdx.x; v < (kPairThreads / 32) * 2 * kBatchMax; v += kPairThreads) {
+        (&s_acc[0][0])[v] = 0.0;
+    }
+
+    // this thread's particles: j0 = base + tid, j1 = base + 128 + tid (coalesced)
+    const int base = blockIdx.x * kPairChunk;
+    double4 p[kPairPerThread];
+    int pid[kPairPerThread];
+    int pj[kPairPerThread];
+#pragma unroll
+    for (int t = 0; t < kPairPerThread; ++t) {
+        const int j = base + t * kPairThreads + threadIdx.x;
+        pj[t] = j;
+        pid[t] = 0;
+        p[t] = make_double4(nan, 0, 0, 0);
+        if (j < M0.n_slots) {
+            p[t] = M0.posq[j];
+            pid[t] = M0.atom_id[j];
+            if (M0.gid[j] < 0) {
+                p[t].x = nan;
             }
-        };
-        int jj = jb;
-        for (; jj + 1 < je; jj += 2) { // two independent chains
-            one(jj, e0);
-            one(jj + 1, e1);
-        }
-        if (jj < je) {
-            one(jj, e0);
         }
     }
-    s_red[threadIdx.x] = worker ? (e0 + e1) : 0.0;
     __syncthreads();
-    if (static_cast<int>(threadIdx.x) < nv) {
-        double s = 0.0;
-        for (int t = 0; t < nsub; ++t) {
-            s += s_red[t * nv + threadIdx.x];
+
+    // two variants per iteration (four independent r² chains per lane); blockIdx.y selects the variant range
+    const int v_begin = blockIdx.y * kPairVariantsPerBlock;
+    const int v_end = min(nv, v_begin + kPairVariantsPerBlock);
+    for (int v0 = v_begin; v0 < v_end; v0 += 2) {
+        double4 a[2];
+        int fold[2];
+        double r2[2][kPairPerThread];
+        bool any_in = false;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int v = min(v0 + u, v_end - 1);
+            a[u] = s_var[v];
+            fold[u] = s_vfold[v];
         }
-        partials[static_cast<size_t>(blockIdx.x) * (2 * stride) + threadIdx.x] = s;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            double dx[kPairPerThread], dy[kPairPerThread], dz[kPairPerThread];
+#pragma unroll
+            for (int t = 0; t < kPairPerThread; ++t) {
+                dx[t] = a[u].x - p[t].x;
+                dy[t] = a[u].y - p[t].y;
+                dz[t] = a[u].z - p[t].z;
+            }
+            if (fold[u] & 1) {
+#pragma unroll
+                for (int t = 0; t < kPairPerThread; ++t) {
+                    const double ad = fabs(dx[t]);
+                    dx[t] = (ad > hx) ? ad - lx : dx[t];
+                }
+            }
+            if (fold[u] & 2) {
+#pragma unroll
+                for (int t = 0; t < kPairPerThread; ++t) {
+                    const double ad = fabs(dy[t]);
+                    dy[t] = (ad > hy) ? ad - ly : dy[t];
+                }
+            }
+            if (fold[u] & 4) {
+#pragma unroll
+                for (int t = 0; t < kPairPerThread; ++t) {
+                    const double ad = fabs(dz[t]);
+                    dz[t] = (ad > hz) ? ad - lz : dz[t];
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < kPairPerThread; ++t) {
+                r2[u][t] = dx[t] * dx[t] + dy[t] * dy[t] + dz[t] * dz[t];
+                any_in = any_in || (r2[u][t] < cut2);
+            }
+        }
+        if (__any_sync(0xffffffffu, any_in)) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int v = v0 + u;
+                bool in_u = false;
+#pragma unroll
+                for (int t = 0; t < kPairPerThread; ++t) {
+                    in_u = in_u || (r2[u][t] < cut2);
+                }
+                if (v < v_end && __any_sync(0xffffffffu, in_u)) {
+                    double e = 0.0;
+                    const int vid = s_vid[v];
+                    const int vslot = s_vslot[v];
+#pragma unroll
+                    for (int t = 0; t < kPairPerThread; ++t) {
+                        if (r2[u][t] < cut2 && pj[t] != vslot) {
+                            e += pairEnergy<KIND>(P, vid, pid[t], a[u].w, p[t].w, r2[u][t]);
+                        }
+                    }
+                    e = warpSum(e);
+                    if (lane == 0) {
+                        s_acc[warp][v] = e;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int v_store_end = (blockIdx.y + 1 == gridDim.y) ? 2 * stride : v_begin + kPairVariantsPerBlock;
+    for (int v = v_begin + threadIdx.x; v < v_store_end; v += kPairThreads) {
+        double s = 0.0;
+        if (v < nv) {
+#pragma unroll
+            for (int w = 0; w < kPairThreads / 32; ++w) {
+                s += s_acc[w][v];
+            }
+        }
+        partials[static_cast<size_t>(blockIdx.x) * (2 * stride) + v] = s;
     }
 }
 
@@ -266,20 +388,36 @@ __global__ void __launch_bounds__(kBlock)
 // BT = stride / 4 ∈ {4, 8, 16}.
 // ------------------------------------------------------------------------------------------------
 template <int BT>
-__global__ void __launch_bounds__(kBlock)
-    batchEwaldKernel(EwaldView E, const int4* __restrict__ kn, BatchBuffers cur, PhaseGeometry geo, int tiles_per_block,
-                     double* __restrict__ r_partials /*[gridDim.x][stride]*/,
-                     double* __restrict__ g_partials /*[gridDim.x][stride²]*/)
+__global__ void __launch_bounds__(kBlock, 2)
+    batchEwaldKernel(EwaldView E, const int4* __restrict__ kn, BatchBuffers cur, BatchBuffers prev, CommitList commit,
+                     PhaseGeometry geo, int n_tiles, double* __restrict__ r_partials /*[gridDim.x][stride]*/,
+                     double* __restrict__ g_partials /*[gridDim.x][stride²]*/,
+                     double* __restrict__ e_partials /*[gridDim.x]*/)
 {
     constexpr int STRIDE = BT * 4;
-    constexpr int KT = kBatchDeltaElems / STRIDE;   // k-vectors per tile: 128, 64, 32
+    constexpr int KT = batchTileK(STRIDE);          // k-vectors per tile: 64, 64, 32
     constexpr int NTILE = BT * BT;                  // 4×4 output tiles
     constexpr int KG = kBlock / NTILE;              // k sub-groups: 16, 4, 1
     constexpr int MPW = STRIDE / (kBlock / 32);     // moves per warp: 2, 4, 8
-    constexpr int KPL = KT / 32;                    // k-vectors per lane: 4, 2, 1
+    constexpr int KPL = KT / 32;                    // k-vectors per lane: 2, 2, 1
 
     constexpr int LD = KT + 1;                      // padded leading dimension of s_delta[m][k]
-    __shared__ double2 s_delta[STRIDE * LD];
+    constexpr int NW = kBlock / 32;
+    constexpr int DELTA_ELEMS = STRIDE * LD > kBatchDeltaElems ? STRIDE * LD : kBatchDeltaElems; // ≥ 32 KB for s_g
+    __shared__ double2 s_delta[DELTA_ELEMS];
+    __shared__ double2 s_dq[NW][KT];                // per-warp share of the committed ΔQ(k) of a tile
+    __shared__ double s_cqn[kBatchMax], s_cqo[kBatchMax];
+    __shared__ int s_ctable[kBatchMax];
+
+    // accepted moves of the previous window: their δ is added to Q(k) here, tile by tile
+    const int ncommit = commit.n;
+    if (static_cast<int>(threadIdx.x) < ncommit) {
+        const int m = commit.index[threadIdx.x];
+        s_cqn[threadIdx.x] = prev.in->pnew[m].w;
+        s_cqo[threadIdx.x] = prev.pold[m].w;
+        s_ctable[threadIdx.x] = 2 * m * geo.table_stride;
+    }
+    double eacc = 0.0; // Σ A_k |Q_k|² of the window-start state (warp 0)
 
     const int n = cur.in->n;
     const int lane = threadIdx.x & 31;
@@ -312,13 +450,30 @@ __global__ void __launch_bounds__(kBlock)
         qo[i] = (m < n) ? cur.pold[m].w : 0.0;
     }
 
-    const int first_tile = blockIdx.x * tiles_per_block;
-    for (int tile = first_tile; tile < first_tile + tiles_per_block; ++tile) {
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int k0 = tile * KT;
-        if (k0 >= E.K) {
-            break;
+        __syncthreads(); // previous tile's phase 2 is done with s_delta (and everybody with s_dq)
+        double2 qkeep[KPL];
+        if (ncommit > 0) {
+#pragma unroll
+            for (int kk = 0; kk < KPL; ++kk) {
+                const int kl = lane + 32 * kk;
+                const int k = k0 + kl;
+                double2 dq = make_double2(0, 0);
+                if (k < E.K) {
+                    const int4 nn = __ldg(kn + k);
+                    for (int a = warp; a < ncommit; a += NW) {
+                        const double2* t = prev.table + s_ctable[a];
+                        const double2 en = tablePhase(t, geo, nn.x, nn.y, nn.z);
+                        const double2 eo = tablePhase(t + geo.table_stride, geo, nn.x, nn.y, nn.z);
+                        dq.x += s_cqn[a] * en.x - s_cqo[a] * eo.x;
+                        dq.y += s_cqn[a] * en.y - s_cqo[a] * eo.y;
+                    }
+                }
+                s_dq[warp][kl] = dq;
+            }
+            __syncthreads();
         }
-        __syncthreads(); // previous tile's phase 2 is done with s_delta
 #pragma unroll
         for (int kk = 0; kk < KPL; ++kk) {
             const int kl = lane + 32 * kk;
@@ -331,7 +486,18 @@ __global__ void __launch_bounds__(kBlock)
                 nn = __ldg(kn + k);
                 Q = E.Q[k];
                 A = E.kA[k].w;
+                if (ncommit > 0) { // every warp adds the shares in the same order → the same Q(k) everywhere
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        Q.x += s_dq[w][kl].x;
+                        Q.y += s_dq[w][kl].y;
+                    }
+                }
+                if (warp == 0) {
+                    eacc += A * (Q.x * Q.x + Q.y * Q.y);
+                }
             }
+            qkeep[kk] = Q;
             const double sqrtA = sqrt(A);
 #pragma unroll
             for (int i = 0; i < MPW; ++i) {
@@ -350,6 +516,15 @@ __global__ void __launch_bounds__(kBlock)
             }
         }
         __syncthreads();
+        if (ncommit > 0 && warp == 0) { // every warp has read the old Q(k) of this tile by now
+#pragma unroll
+            for (int kk = 0; kk < KPL; ++kk) {
+                const int k = k0 + lane + 32 * kk;
+                if (k < E.K) {
+                    E.Q[k] = qkeep[kk];
+                }
+            }
+        }
         if (kg < KG) {
 #pragma unroll 4
             for (int kl = kg; kl < KT; kl += KG) {
@@ -362,7 +537,7 @@ __global__ void __launch_bounds__(kBlock)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = i; j < 4; ++j) { // a = ta + BT·i < m = tm + BT·j needs i ≤ j
                         gacc[i][j] = fma(da[i].x, dm[j].x, fma(da[i].y, dm[j].y, gacc[i][j]));
                     }
                 }
@@ -370,6 +545,12 @@ __global__ void __launch_bounds__(kBlock)
         }
     }
 
+    if (warp == 0) {
+        const double es = warpSum(eacc);
+        if (lane == 0) {
+            e_partials[blockIdx.x] = es;
+        }
+    }
     // R[m]: warp-level sums (each warp owns its moves)
 #pragma unroll
     for (int i = 0; i < MPW; ++i) {
@@ -380,24 +561,24 @@ __global__ void __launch_bounds__(kBlock)
     }
     // G: reduce the k sub-groups through shared memory (fixed order), then one store per element
     __syncthreads();
-    double* s_g = reinterpret_cast<double*>(s_delta); // [KG][NTILE][16] = 4096 doubles = 32 KB
+    double* s_g = reinterpret_cast<double*>(s_delta); // [16][kBlock] = 4096 doubles = 32 KB, thread-fastest
     if (kg < KG) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                s_g[(kg * NTILE + tile_id) * 16 + i * 4 + j] = gacc[i][j];
+                s_g[(i * 4 + j) * kBlock + threadIdx.x] = gacc[i][j];
             }
         }
     }
     __syncthreads();
     for (int o = threadIdx.x; o < NTILE * 16; o += kBlock) {
+        const int t = o % NTILE;
+        const int ij = o / NTILE;
         double s = 0.0;
         for (int g = 0; g < KG; ++g) {
-            s += s_g[g * NTILE * 16 + o];
+            s += s_g[ij * kBlock + g * NTILE + t];
         }
-        const int t = o / 16;
-        const int ij = o % 16;
         const int a = (t / BT) + BT * (ij / 4);
         const int m = (t % BT) + BT * (ij % 4);
         g_partials[static_cast<size_t>(blockIdx.x) * (STRIDE * STRIDE) + a * STRIDE + m] = s;
@@ -416,6 +597,17 @@ __host__ __device__ inline size_t batchResultDoubles(int stride)
     return 8 + 3 * static_cast<size_t>(stride) + 4 * static_cast<size_t>(stride) * stride;
 }
 
+/** Σ over `rows` of column `col` of a row-major [rows][ld] array by one warp (fixed order); valid in lane 0 */
+__device__ __forceinline__ double warpColumnSum(const double* __restrict__ a, int rows, size_t ld, int col, int lane)
+{
+    double s = 0.0;
+    for (int b = lane; b < rows; b += 32) {
+        s += a[static_cast<size_t>(b) * ld + col];
+    }
+    return warpSum(s);
+}
+
+/** one warp per output: 2S pair sums, S reciprocal sums, S² cross entries, 1 reciprocal start sum */
 template <int KIND>
 __global__ void __launch_bounds__(kBlock)
     batchFinishKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, int n_pair_blocks,
@@ -426,74 +618,80 @@ __global__ void __launch_bounds__(kBlock)
     const int n = cur.in->n;
     const int with_ewald = cur.in->with_ewald;
     const int S = stride;
-    const int tid = blockIdx.x * kBlock + threadIdx.x;
-    const int nthreads = gridDim.x * kBlock;
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     double* u = result + 8;
     double* cross = result + 8 + 3 * S;
-    if (tid == 0) {
-        double e = 0.0;
-        if (with_ewald) {
-            for (int b = 0; b < n_commit_blocks; ++b) {
-                e += e_partials[b];
-            }
-        }
-        result[0] = e;
-        result[1] = static_cast<double>(n);
-    }
-    // pair sums: 2S columns (variant order new/old interleaved → split)
-    for (int t = tid; t < 2 * S; t += nthreads) {
+    if (w < 2 * S) { // pair sums: variant order new/old interleaved → split
         double s = 0.0;
-        if (t < 2 * n) {
-            for (int b = 0; b < n_pair_blocks; ++b) {
-                s += pair_partials[static_cast<size_t>(b) * (2 * S) + t];
-            }
+        if (w < 2 * n) {
+            s = warpColumnSum(pair_partials, n_pair_blocks, 2 * static_cast<size_t>(S), w, lane);
         }
-        u[(t & 1) * S + (t >> 1)] = s;
+        if (lane == 0) {
+            u[(w & 1) * S + (w >> 1)] = s;
+        }
     }
-    for (int t = tid; t < S; t += nthreads) {
+    else if (w < 3 * S) {
+        const int m = w - 2 * S;
         double s = 0.0;
-        if (with_ewald && t < n) {
-            for (int b = 0; b < n_ewald_blocks; ++b) {
-                s += r_partials[static_cast<size_t>(b) * S + t];
-            }
+        if (with_ewald && m < n) {
+            s = warpColumnSum(r_partials, n_ewald_blocks, static_cast<size_t>(S), m, lane);
         }
-        u[2 * S + t] = s;
+        if (lane == 0) {
+            u[2 * S + m] = s;
+        }
     }
-    for (int t = tid; t < S * S; t += nthreads) {
+    else if (w < 3 * S + S * S) {
+        const int t = w - 3 * S;
         const int a = t / S;
         const int m = t % S;
         double g = 0.0;
         double cn = 0.0, co = 0.0, cmax = 0.0;
         if (a < m && m < n) {
             if (with_ewald) {
-                for (int b = 0; b < n_ewald_blocks; ++b) {
-                    g += g_partials[static_cast<size_t>(b) * (S * S) + t];
+                g = warpColumnSum(g_partials, n_ewald_blocks, static_cast<size_t>(S) * S, t, lane);
+            }
+            if (lane == 0) { // how the energies of move m change when the earlier move a has been accepted
+                const double4 na = cur.in->pnew[a];
+                const double4 oa = cur.pold[a];
+                const int ida_n = cur.in->id[a];
+                const int ida_o = cur.idold[a];
+                const double4 nm = cur.in->pnew[m];
+                const double4 om = cur.pold[m];
+                const int idm_n = cur.in->id[m];
+                const int idm_o = cur.idold[m];
+                const double t1 =
+                    pairEnergy<KIND>(P, idm_n, ida_n, nm.w, na.w, minImageR2(M0, nm.x, nm.y, nm.z, na.x, na.y, na.z));
+                const double t2 =
+                    pairEnergy<KIND>(P, idm_n, ida_o, nm.w, oa.w, minImageR2(M0, nm.x, nm.y, nm.z, oa.x, oa.y, oa.z));
+                const double t3 =
+                    pairEnergy<KIND>(P, idm_o, ida_n, om.w, na.w, minImageR2(M0, om.x, om.y, om.z, na.x, na.y, na.z));
+                const double t4 =
+                    pairEnergy<KIND>(P, idm_o, ida_o, om.w, oa.w, minImageR2(M0, om.x, om.y, om.z, oa.x, oa.y, oa.z));
+                cn = t1 - t2;
+                co = t3 - t4;
+                cmax = fmax(fmax(fabs(t1), fabs(t2)), fmax(fabs(t3), fabs(t4)));
+                if (t1 != t1 || t2 != t2 || t3 != t3 || t4 != t4) {
+                    cmax = __longlong_as_double(0x7ff0000000000000LL);
                 }
             }
-            // how the energies of move m change when the earlier move a has been accepted
-            const double4 na = cur.in->pnew[a];
-            const double4 oa = cur.pold[a];
-            const int ida_n = cur.in->id[a];
-            const int ida_o = cur.idold[a];
-            const double4 nm = cur.in->pnew[m];
-            const double4 om = cur.pold[m];
-            const int idm_n = cur.in->id[m];
-            const int idm_o = cur.idold[m];
-            const double t1 = pairEnergy<KIND>(P, idm_n, ida_n, nm.w, na.w, minImageR2(M0, nm.x, nm.y, nm.z, na.x, na.y, na.z));
-            const double t2 = pairEnergy<KIND>(P, idm_n, ida_o, nm.w, oa.w, minImageR2(M0, nm.x, nm.y, nm.z, oa.x, oa.y, oa.z));
-            const double t3 = pairEnergy<KIND>(P, idm_o, ida_n, om.w, na.w, minImageR2(M0, om.x, om.y, om.z, na.x, na.y, na.z));
-            const double t4 = pairEnergy<KIND>(P, idm_o, ida_o, om.w, oa.w, minImageR2(M0, om.x, om.y, om.z, oa.x, oa.y, oa.z));
-            cn = t1 - t2;
-            co = t3 - t4;
-            cmax = fmax(fmax(fabs(t1), fabs(t2)), fmax(fabs(t3), fabs(t4)));
-            if (t1 != t1 || t2 != t2 || t3 != t3 || t4 != t4) {
-                cmax = __longlong_as_double(0x7ff0000000000000LL);
-            }
         }
-        cross[t] = cn;
-        cross[S * S + t] = co;
-        cross[2 * S * S + t] = cmax;
-        cross[3 * S * S + t] = g;
+        if (lane == 0) {
+            cross[t] = cn;
+            cross[S * S + t] = co;
+            cross[2 * S * S + t] = cmax;
+            cross[3 * S * S + t] = g;
+        }
+    }
+    else if (w == 3 * S + S * S) {
+        double e = 0.0;
+        if (with_ewald && n_commit_blocks > 0) {
+            e = warpColumnSum(e_partials, n_commit_blocks, 1, 0, lane);
+        }
+        if (lane == 0) {
+            result[0] = e;
+            result[1] = static_cast<double>(n);
+        }
     }
 }
 

@@ -67,12 +67,14 @@ void launchBatchCommit(fb_ctx* c, bool with_ewald, int* n_blocks_out)
 }
 
 template <int KIND>
-void launchBatchPairFinish(fb_ctx* c, const BatchBuffers& cur, int stride, int n_pair_blocks, int n_ewald_blocks,
-                           int n_commit_blocks, bool with_ewald, bool timing)
+void launchBatchPairFinish(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, const CommitList& commit,
+                           int stride, int n_pair_blocks, int n_ewald_blocks, bool with_ewald, bool timing)
 {
     auto& b = c->batch;
     const SlotView M0 = makeView(c, 0);
-    batchPairKernel<KIND><<<n_pair_blocks, kBlock, 0, c->stream>>>(M0, c->P, cur, c->pair_cut2, stride,
+    const int n_now = b.h_in.ptr->n;
+    const dim3 pair_grid(n_pair_blocks, (2 * n_now + kPairVariantsPerBlock - 1) / kPairVariantsPerBlock);
+    batchPairKernel<KIND><<<pair_grid, kPairThreads, 0, c->stream>>>(M0, c->P, cur, c->pair_cut2, stride,
                                                                   b.d_pair_partials.ptr);
     launched(c, "batchPairKernel");
     if (timing) {
@@ -81,31 +83,30 @@ void launchBatchPairFinish(fb_ctx* c, const BatchBuffers& cur, int stride, int n
     if (with_ewald) {
         const EwaldView E = makeEwaldView(c, 0);
         const int4* kn = c->slot[0].kn.ptr;
-        const int kt = kBatchDeltaElems / stride;
+        const int kt = batchTileK(stride);
         const int n_tiles = (E.K + kt - 1) / kt;
-        const int tiles_per_block = (n_tiles + n_ewald_blocks - 1) / n_ewald_blocks;
         switch (stride) {
         case 16:
-            batchEwaldKernel<4><<<n_ewald_blocks, kBlock, 0, c->stream>>>(E, kn, cur, b.geo, tiles_per_block,
-                                                                         b.d_r_partials.ptr, b.d_g_partials.ptr);
+            batchEwaldKernel<4><<<n_ewald_blocks, kBlock, 0, c->stream>>>(E, kn, cur, prev, commit, b.geo, n_tiles,
+                                                                         b.d_r_partials.ptr, b.d_g_partials.ptr, b.d_e_partials.ptr);
             break;
         case 32:
-            batchEwaldKernel<8><<<n_ewald_blocks, kBlock, 0, c->stream>>>(E, kn, cur, b.geo, tiles_per_block,
-                                                                         b.d_r_partials.ptr, b.d_g_partials.ptr);
+            batchEwaldKernel<8><<<n_ewald_blocks, kBlock, 0, c->stream>>>(E, kn, cur, prev, commit, b.geo, n_tiles,
+                                                                         b.d_r_partials.ptr, b.d_g_partials.ptr, b.d_e_partials.ptr);
             break;
         default:
-            batchEwaldKernel<16><<<n_ewald_blocks, kBlock, 0, c->stream>>>(E, kn, cur, b.geo, tiles_per_block,
-                                                                          b.d_r_partials.ptr, b.d_g_partials.ptr);
+            batchEwaldKernel<16><<<n_ewald_blocks, kBlock, 0, c->stream>>>(E, kn, cur, prev, commit, b.geo, n_tiles,
+                                                                          b.d_r_partials.ptr, b.d_g_partials.ptr, b.d_e_partials.ptr);
         }
         launched(c, "batchEwaldKernel");
     }
     if (timing) {
         CUDA_CHECK(cudaEventRecord(b.ev[3], c->stream));
     }
-    const int finish_grid = std::max(1, (stride * stride + kBlock - 1) / kBlock);
+    const int finish_grid = (3 * stride + stride * stride + 1 + kBlock / 32 - 1) / (kBlock / 32); // one warp per output
     batchFinishKernel<KIND><<<finish_grid, kBlock, 0, c->stream>>>(
         M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, with_ewald ? n_ewald_blocks : 0,
-        b.d_r_partials.ptr, b.d_g_partials.ptr, n_commit_blocks, b.d_e_partials.ptr, b.d_result.ptr);
+        b.d_r_partials.ptr, b.d_g_partials.ptr, with_ewald ? n_ewald_blocks : 0, b.d_e_partials.ptr, b.d_result.ptr);
     launched(c, "batchFinishKernel");
 }
 
@@ -193,34 +194,35 @@ FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, in
         if (timing) {
             CUDA_CHECK(cudaEventRecord(b.ev[0], c->stream));
         }
-        // 1. previous window's accepted moves (still described by the buffers of parity `b.parity`)
-        int n_commit_blocks = 0;
+        // the previous window's accepted moves (described by the buffers of parity `b.parity`): positions are
+        // written by the phase kernel, their δ is added to Q(k) inside the k-space kernel
         if (with_ewald) {
             batchEwaldGeometry(c);
         }
-        const bool need_rec = with_ewald && !b.rec_known;
-        if (b.has_pending || need_rec) {
-            const bool commit_ewald = with_ewald || (b.has_pending && b.pending_with_ewald);
-            launchBatchCommit(c, commit_ewald, &n_commit_blocks);
+        if (b.has_pending && b.pending_with_ewald && !with_ewald) {
+            launchBatchCommit(c, true, nullptr); // Q(k) has to follow although this window has no k-space part
         }
-        // 2. this window
+        const CommitList commit = b.has_pending ? b.pending : CommitList{};
+        b.has_pending = false;
+        const BatchBuffers prev = batchBuffers(c, b.parity);
         b.parity ^= 1;
         const BatchBuffers cur = batchBuffers(c, b.parity);
         CUDA_CHECK(cudaMemcpyAsync(cur.in, b.h_in.ptr, sizeof(BatchInput), cudaMemcpyHostToDevice, c->stream));
         const int phase_grid =
             with_ewald ? std::max(1, (2 * n_moves * b.geo.table_stride + kBlock - 1) / kBlock) : 1;
-        batchPhaseKernel<<<phase_grid, kBlock, 0, c->stream>>>(makeView(c, 0), cur, b.geo);
+        batchPhaseKernel<<<phase_grid, kBlock, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), cur, prev, commit, b.geo);
         launched(c, "batchPhaseKernel");
         if (timing) {
             CUDA_CHECK(cudaEventRecord(b.ev[1], c->stream));
         }
-        const int n_pair_blocks = (c->n_slots + kBatchTile - 1) / kBatchTile;
+        const int n_pair_blocks = (c->n_slots + kPairChunk - 1) / kPairChunk;
         b.d_pair_partials.ensure(static_cast<size_t>(n_pair_blocks) * 2 * kBatchMax);
         int n_ewald_blocks = 0;
         if (with_ewald) {
-            const int kt = kBatchDeltaElems / stride;
+            const int kt = batchTileK(stride);
             const int n_tiles = (c->slot[0].K + kt - 1) / kt;
             n_ewald_blocks = std::max(1, std::min(n_tiles, 2 * c->n_sm));
+            b.d_e_partials.ensure(static_cast<size_t>(2 * c->n_sm));
             b.d_r_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax);
             b.d_g_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax * kBatchMax);
         }
@@ -229,8 +231,8 @@ FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, in
         b.h_result.ensure(batchResultDoubles(kBatchMax));
 #define FB_CASE(K)                                                                                            \
     case K:                                                                                                   \
-        launchBatchPairFinish<K>(c, cur, stride, n_pair_blocks, n_ewald_blocks, n_commit_blocks,              \
-                                 with_ewald != 0, timing);                                                    \
+        launchBatchPairFinish<K>(c, cur, prev, commit, stride, n_pair_blocks, n_ewald_blocks, with_ewald != 0, \
+                                 timing);                                                                     \
         break;
         switch (c->P.kind) {
             FB_CASE(POT_COULOMB_LJ)
@@ -263,10 +265,8 @@ FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, in
         b.moves += n_moves;
         const double* r = b.h_result.ptr;
         if (with_ewald) {
-            if (n_commit_blocks > 0) {
-                b.rec_sum = r[0];
-                b.rec_known = true;
-            }
+            b.rec_sum = r[0];
+            b.rec_known = true;
         }
         b.last_n = n_moves;
         b.last_with_ewald = with_ewald ? 1 : 0;
