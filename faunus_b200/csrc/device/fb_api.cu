@@ -108,6 +108,10 @@ struct Slot
     // Ewald
     DeviceBuffer<double4> kA;
     DeviceBuffer<int4> kn; //!< integer triplets (nx, ny, nz) of the k-vectors, same order as kA
+    DeviceBuffer<double> ksq; //!< sqrt(A_k)
+    DeviceBuffer<int> cell_start; //!< [n_cells + 1] first k of each 4×4×4 cell of integer triplets (storage order)
+    int n_cells = 0;
+    std::vector<int> perm; //!< storage index → index in the reference's k-vector order
     DeviceBuffer<double2> Q;
     int K = 0;
     double ewald_box[3] = {0, 0, 0};
@@ -193,6 +197,7 @@ struct fb_ctx
         DeviceBuffer<double2> d_table[2];
         PinnedBuffer<BatchInput> h_in;
         DeviceBuffer<double> d_pair_partials, d_r_partials, d_g_partials, d_e_partials, d_result;
+        DeviceBuffer<double2> d_delta; //!< sqrt(A_k) δ_m,k of the current window, [tile][move][k]
         PinnedBuffer<double> h_result;
         int parity = 0;
         int last_n = 0;            //!< moves of the most recent window (0: none evaluated)
@@ -203,10 +208,14 @@ struct fb_ctx
         bool pending_with_ewald = false;
         bool q_dirty = false;      //!< slot 0's Q(k) is ahead of slot 1's
         bool rec_known = false;    //!< rec_sum is Σ A_k|Q_k|² of slot 0's current Q(k)
+        bool last_rec_fresh = false; //!< the last window recomputed that sum on the device
         double rec_sum = 0;
         PhaseGeometry geo{};
         cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        cudaStream_t pair_stream = nullptr; //!< the pair kernel runs beside the k-space kernels
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
         double acc_ms[3] = {0, 0, 0}; //!< pair, ewald, other (commit + phase + finish)
+        double acc_total_ms = 0;      //!< first to last kernel of every window (all modes)
         double windows = 0, moves = 0;
     } batch;
     double pair_cut2 = 0; //!< no pair energy beyond this r² (+inf when some term has no cutoff)
@@ -586,6 +595,9 @@ FB_API int fb_create(const fb_config* cfg, fb_ctx** out)
         for (auto& e : c->batch.ev) {
             CUDA_CHECK(cudaEventCreate(&e));
         }
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->batch.pair_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->batch.ev_fork, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->batch.ev_join, cudaEventDisableTiming));
         CUDA_CHECK(cudaHostAlloc(&c->h_result, 8 * sizeof(double), cudaHostAllocMapped));
         CUDA_CHECK(cudaHostGetDevicePointer(&c->d_result, c->h_result, 0));
         c->partials.alloc(4 * kMaxPartialBlocks);
@@ -812,6 +824,16 @@ FB_API void fb_destroy(fb_ctx* c)
         if (e) {
             cudaEventDestroy(e);
         }
+    }
+    if (c->batch.ev_fork) {
+        cudaEventDestroy(c->batch.ev_fork);
+    }
+    if (c->batch.ev_join) {
+        cudaEventDestroy(c->batch.ev_join);
+    }
+    if (c->batch.pair_stream) {
+        cudaStreamSynchronize(c->batch.pair_stream);
+        cudaStreamDestroy(c->batch.pair_stream);
     }
     cudaStream_t s = c->stream;
     delete c;
@@ -1439,9 +1461,43 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
         std::vector<double4> kA;
         std::vector<int4> kn;
         generateKVectors(c->ewald, sl.box, kA, kn);
+        { // store cell by cell (see fb_batch.cuh); the reference order is kept in `perm` for downloads
+            const int ncc = static_cast<int>(std::ceil(c->ewald.n_cutoff));
+            const long nc = (2 * ncc) / 4 + 1;
+            auto cell_of = [&](const int4& n) {
+                return (static_cast<long>(n.x >> 2) * nc + ((n.y + ncc) >> 2)) * nc + ((n.z + ncc) >> 2);
+            };
+            std::vector<int> perm(kA.size());
+            for (size_t i = 0; i < perm.size(); ++i) {
+                perm[i] = static_cast<int>(i);
+            }
+            std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cell_of(kn[a]) < cell_of(kn[b]); });
+            std::vector<double4> kA2(kA.size());
+            std::vector<int4> kn2(kn.size());
+            std::vector<int> cell_start;
+            for (size_t i = 0; i < perm.size(); ++i) {
+                kA2[i] = kA[perm[i]];
+                kn2[i] = kn[perm[i]];
+                if (i == 0 || cell_of(kn2[i]) != cell_of(kn2[i - 1])) {
+                    cell_start.push_back(static_cast<int>(i));
+                }
+            }
+            cell_start.push_back(static_cast<int>(perm.size()));
+            kA.swap(kA2);
+            kn.swap(kn2);
+            sl.perm.swap(perm);
+            sl.n_cells = static_cast<int>(cell_start.size()) - 1;
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            sl.cell_start.upload(cell_start.data(), cell_start.size(), c->stream);
+        }
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         sl.kA.upload(kA.data(), kA.size(), c->stream);
         sl.kn.upload(kn.data(), kn.size(), c->stream);
+        std::vector<double> ksq(kA.size());
+        for (size_t i = 0; i < kA.size(); ++i) {
+            ksq[i] = std::sqrt(kA[i].w);
+        }
+        sl.ksq.upload(ksq.data(), ksq.size(), c->stream);
         sl.Q.ensure(kA.size());
         sl.K = static_cast<int>(kA.size());
         for (int i = 0; i < 3; ++i) {
@@ -1575,6 +1631,13 @@ FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
             CUDA_CHECK(cudaMemcpyAsync(d.kA.ptr, s.kA.ptr, s.K * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
             d.kn.ensure(s.K);
             CUDA_CHECK(cudaMemcpyAsync(d.kn.ptr, s.kn.ptr, s.K * sizeof(int4), cudaMemcpyDeviceToDevice, c->stream));
+            d.ksq.ensure(s.K);
+            CUDA_CHECK(cudaMemcpyAsync(d.ksq.ptr, s.ksq.ptr, s.K * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            d.cell_start.ensure(s.n_cells + 1);
+            CUDA_CHECK(cudaMemcpyAsync(d.cell_start.ptr, s.cell_start.ptr, (s.n_cells + 1) * sizeof(int),
+                                       cudaMemcpyDeviceToDevice, c->stream));
+            d.n_cells = s.n_cells;
+            d.perm = s.perm;
             d.K = s.K;
             for (int i = 0; i < 3; ++i) {
                 d.ewald_box[i] = s.ewald_box[i];
@@ -1590,23 +1653,32 @@ FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
 FB_API int fb_ewald_download(fb_ctx* c, int s, double* q_re_im, double* kvectors, double* aks)
 {
     return guarded(c, [&] {
+        flushPending(c);
         checkSlot(c, s, false);
         Slot& sl = c->slot[s];
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        // the device stores the k-vectors cell by cell; hand them out in the reference's order
         if (q_re_im) {
-            CUDA_CHECK(cudaMemcpy(q_re_im, sl.Q.ptr, sl.K * sizeof(double2), cudaMemcpyDeviceToHost));
+            std::vector<double2> Q(sl.K);
+            CUDA_CHECK(cudaMemcpy(Q.data(), sl.Q.ptr, sl.K * sizeof(double2), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < sl.K; ++i) {
+                const int k = sl.perm.empty() ? i : sl.perm[i];
+                q_re_im[2 * k] = Q[i].x;
+                q_re_im[2 * k + 1] = Q[i].y;
+            }
         }
         if (kvectors || aks) {
             std::vector<double4> kA(sl.K);
             CUDA_CHECK(cudaMemcpy(kA.data(), sl.kA.ptr, sl.K * sizeof(double4), cudaMemcpyDeviceToHost));
-            for (int k = 0; k < sl.K; ++k) {
+            for (int i = 0; i < sl.K; ++i) {
+                const int k = sl.perm.empty() ? i : sl.perm[i];
                 if (kvectors) {
-                    kvectors[3 * k] = kA[k].x;
-                    kvectors[3 * k + 1] = kA[k].y;
-                    kvectors[3 * k + 2] = kA[k].z;
+                    kvectors[3 * k] = kA[i].x;
+                    kvectors[3 * k + 1] = kA[i].y;
+                    kvectors[3 * k + 2] = kA[i].z;
                 }
                 if (aks) {
-                    aks[k] = kA[k].w;
+                    aks[k] = kA[i].w;
                 }
             }
         }

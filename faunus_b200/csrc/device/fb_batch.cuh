@@ -138,19 +138,21 @@ __global__ void __launch_bounds__(kBlock)
 // window set-up: old positions from the (committed) mirror and the per-axis phase tables
 // ------------------------------------------------------------------------------------------------
 /** position and type of `slot` at window start: the previous window's accepted trial if it moved this atom */
-__device__ __forceinline__ double4 committedParticle(const SlotView& M0, const BatchBuffers& prev,
-                                                     const CommitList& commit, int slot, int& id)
+__device__ __forceinline__ double4 committedParticle(const SlotView& M0, const BatchBuffers& prev, int ncommit,
+                                                     const int* s_cslot, const int* s_cindex, int slot, int& id)
 {
-    double4 p = M0.posq[slot];
-    id = M0.atom_id[slot];
-    for (int a = 0; a < commit.n; ++a) {
-        const int m = commit.index[a];
-        if (prev.in->slot[m] == slot) {
-            p = prev.in->pnew[m];
-            id = prev.in->id[m];
+    int hit = -1;
+    for (int a = 0; a < ncommit; ++a) {
+        if (s_cslot[a] == slot) {
+            hit = s_cindex[a];
         }
     }
-    return p;
+    if (hit >= 0) {
+        id = prev.in->id[hit];
+        return prev.in->pnew[hit];
+    }
+    id = M0.atom_id[slot];
+    return M0.posq[slot];
 }
 
 /**
@@ -161,11 +163,17 @@ __device__ __forceinline__ double4 committedParticle(const SlotView& M0, const B
 __global__ void __launch_bounds__(kBlock)
     batchPhaseKernel(SlotView M0, SlotView M1, BatchBuffers cur, BatchBuffers prev, CommitList commit, PhaseGeometry geo)
 {
+    __shared__ int s_cslot[kBatchMax], s_cindex[kBatchMax];
+    if (static_cast<int>(threadIdx.x) < commit.n) {
+        s_cindex[threadIdx.x] = commit.index[threadIdx.x];
+        s_cslot[threadIdx.x] = prev.in->slot[commit.index[threadIdx.x]];
+    }
     const int n = cur.in->n;
+    __syncthreads();
     const int tid = blockIdx.x * kBlock + threadIdx.x;
     if (tid < n) {
         int id;
-        cur.pold[tid] = committedParticle(M0, prev, commit, cur.in->slot[tid], id);
+        cur.pold[tid] = committedParticle(M0, prev, commit.n, s_cslot, s_cindex, cur.in->slot[tid], id);
         cur.idold[tid] = id;
     }
     if (blockIdx.x == 0 && threadIdx.x < commit.n) {
@@ -187,7 +195,8 @@ __global__ void __launch_bounds__(kBlock)
         const int e = t - variant * geo.table_stride;
         const int m = variant >> 1;
         int unused_id;
-        const double4 p = (variant & 1) ? committedParticle(M0, prev, commit, cur.in->slot[m], unused_id) : cur.in->pnew[m];
+        const double4 p = (variant & 1) ? committedParticle(M0, prev, commit.n, s_cslot, s_cindex, cur.in->slot[m], unused_id)
+                                        : cur.in->pnew[m];
         int axis, nn;
         if (e <= geo.ncc) {
             axis = 0;
@@ -224,11 +233,19 @@ constexpr int kPairPerThread = 2;
 constexpr int kPairChunk = kPairThreads * kPairPerThread; //!< particles per block
 constexpr int kPairVariantsPerBlock = 32;                 //!< variant range of one block (grid.y covers the window)
 
-template <int KIND>
+constexpr int kPairQueue = 256; //!< in-range candidates a warp collects before it evaluates them
+
+template <int KIND, bool DENSE>
 __global__ void __launch_bounds__(kPairThreads)
     batchPairKernel(SlotView M0, PotParams P, BatchBuffers cur, double cut2, int stride,
                     double* __restrict__ partials /*[gridDim.x][2·stride]*/)
 {
+    // DENSE: some term has no cutoff, every pair is evaluated in place. Otherwise the few pairs in range are
+    // queued per warp (ballot order: deterministic) and evaluated afterwards with all lanes busy.
+    __shared__ double4 s_pos[DENSE ? 1 : kPairChunk];
+    __shared__ int s_id[DENSE ? 1 : kPairChunk];
+    __shared__ double s_qr[DENSE ? 1 : kPairThreads / 32][DENSE ? 1 : kPairQueue];
+    __shared__ unsigned short s_qe[DENSE ? 1 : kPairThreads / 32][DENSE ? 1 : kPairQueue];
     __shared__ double4 s_var[2 * kBatchMax];
     __shared__ int s_vid[2 * kBatchMax];
     __shared__ int s_vslot[2 * kBatchMax];
@@ -288,8 +305,35 @@ __global__ void __launch_bounds__(kPairThreads)
                 p[t].x = nan;
             }
         }
+        if (!DENSE) {
+            s_pos[t * kPairThreads + threadIdx.x] = p[t];
+            s_id[t * kPairThreads + threadIdx.x] = pid[t];
+        }
     }
     __syncthreads();
+
+    int queued = 0; // warp-uniform
+    // evaluate the queued candidates of this warp: lane ↔ entry, then lane ↔ variant for the ordered sums
+    auto flush = [&]() {
+        for (int e = lane; e < queued; e += 32) {
+            const unsigned ent = s_qe[warp][e];
+            const int v = ent & 0xffu;
+            const int jl = ent >> 8;
+            const double4 a = s_var[v];
+            s_qr[warp][e] = pairEnergy<KIND>(P, s_vid[v], s_id[jl], a.w, s_pos[jl].w, s_qr[warp][e]);
+        }
+        __syncwarp();
+        const int myv = blockIdx.y * kPairVariantsPerBlock + lane;
+        double acc = 0.0;
+        for (int e = 0; e < queued; ++e) {
+            if (static_cast<int>(s_qe[warp][e] & 0xffu) == myv) {
+                acc += s_qr[warp][e];
+            }
+        }
+        s_acc[warp][myv] += acc;
+        __syncwarp();
+        queued = 0;
+    };
 
     // two variants per iteration (four independent r² chains per lane); blockIdx.y selects the variant range
     const int v_begin = blockIdx.y * kPairVariantsPerBlock;
@@ -341,7 +385,34 @@ __global__ void __launch_bounds__(kPairThreads)
                 any_in = any_in || (r2[u][t] < cut2);
             }
         }
-        if (__any_sync(0xffffffffu, any_in)) {
+        if (!DENSE) {
+            if (__any_sync(0xffffffffu, any_in)) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int v = v0 + u;
+                    if (v >= v_end) {
+                        continue;
+                    }
+                    const int vslot = s_vslot[v];
+#pragma unroll
+                    for (int t = 0; t < kPairPerThread; ++t) {
+                        const bool in = r2[u][t] < cut2 && pj[t] != vslot;
+                        const unsigned mask = __ballot_sync(0xffffffffu, in);
+                        if (in) {
+                            const int at = queued + __popc(mask & ((1u << lane) - 1u));
+                            s_qe[warp][at] = static_cast<unsigned short>(v | ((t * kPairThreads + threadIdx.x) << 8));
+                            s_qr[warp][at] = r2[u][t];
+                        }
+                        queued += __popc(mask);
+                    }
+                }
+                __syncwarp();
+                if (queued > kPairQueue - 2 * kPairPerThread * 32) {
+                    flush();
+                }
+            }
+        }
+        else if (__any_sync(0xffffffffu, any_in)) {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int v = v0 + u;
@@ -368,6 +439,9 @@ __global__ void __launch_bounds__(kPairThreads)
             }
         }
     }
+    if (!DENSE) {
+        flush();
+    }
     __syncthreads();
     const int v_store_end = (blockIdx.y + 1 == gridDim.y) ? 2 * stride : v_begin + kPairVariantsPerBlock;
     for (int v = v_begin + threadIdx.x; v < v_store_end; v += kPairThreads) {
@@ -383,55 +457,238 @@ __global__ void __launch_bounds__(kPairThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k-space part. Per tile of KT k-vectors: (1) lane ↔ k, warp ↔ moves: δ_m,k → R[m] accumulators and
-// s_delta[k][m] = sqrt(A_k) δ_m,k; (2) thread ↔ 4×4 tile of G (and a k sub-group): rank-KT update.
+// k-space part, three kernels over tiles of kTileK k-vectors (every one with thousands of warps, the
+// intermediate δ array stays in L2):
+//   batchCommitQKernel  Q(k) += Σ_accepted δ of the previous window; Σ_k A_k|Q_k|² partial per tile
+//   batchDeltaKernel    lane ↔ k, warp ↔ moves: δ_m,k → R[m] partial per tile, sqrt(A_k) δ_m,k → scratch
+//   batchGramKernel     thread ↔ 4×4 entries of G (and a k sub-group): rank-kTileK updates from the scratch
 // BT = stride / 4 ∈ {4, 8, 16}.
 // ------------------------------------------------------------------------------------------------
-template <int BT>
-__global__ void __launch_bounds__(kBlock, 2)
-    batchEwaldKernel(EwaldView E, const int4* __restrict__ kn, BatchBuffers cur, BatchBuffers prev, CommitList commit,
-                     PhaseGeometry geo, int n_tiles, double* __restrict__ r_partials /*[gridDim.x][stride]*/,
-                     double* __restrict__ g_partials /*[gridDim.x][stride²]*/,
-                     double* __restrict__ e_partials /*[gridDim.x]*/)
+constexpr int kTileK = 64; //!< k-vectors per tile (two per lane)
+
+/**
+ * The k-vectors are stored cell by cell: a cell is the 4×4×4 block of integer triplets with the same
+ * (nx >> 2, (ny + ncc) >> 2, (nz + ncc) >> 2), ≤ 64 k-vectors that need only 12 phase-table entries per
+ * position. One block per cell stages those entries in shared memory once.
+ */
+constexpr int kCellEntries = 12;
+
+struct CellBase
 {
-    constexpr int STRIDE = BT * 4;
-    constexpr int KT = batchTileK(STRIDE);          // k-vectors per tile: 64, 64, 32
-    constexpr int NTILE = BT * BT;                  // 4×4 output tiles
-    constexpr int KG = kBlock / NTILE;              // k sub-groups: 16, 4, 1
-    constexpr int MPW = STRIDE / (kBlock / 32);     // moves per warp: 2, 4, 8
-    constexpr int KPL = KT / 32;                    // k-vectors per lane: 2, 2, 1
+    int nx, ny, nz; //!< smallest triplet component of the cell
+};
 
-    constexpr int LD = KT + 1;                      // padded leading dimension of s_delta[m][k]
+__device__ __forceinline__ CellBase cellBase(const int4& first, int ncc)
+{
+    CellBase b;
+    b.nx = first.x & ~3;
+    b.ny = ((first.y + ncc) & ~3) - ncc;
+    b.nz = ((first.z + ncc) & ~3) - ncc;
+    return b;
+}
+
+/** s_tab[v][0..4) = e^{i kx x}, [4..8) = e^{i ky y}, [8..12) = e^{i kz z} of the cell's triplet range */
+__device__ __forceinline__ void stageCellTables(double2 (*s_tab)[kCellEntries], const double2* __restrict__ table,
+                                                const int* table_of_variant, int n_variants, const CellBase& base,
+                                                const PhaseGeometry& geo)
+{
+    for (int e = threadIdx.x; e < n_variants * kCellEntries; e += blockDim.x) {
+        const int v = e / kCellEntries;
+        const int t = e % kCellEntries;
+        const int i = t & 3;
+        int offset;
+        if (t < 4) {
+            offset = min(base.nx + i, geo.ncc);
+        }
+        else if (t < 8) {
+            offset = (geo.ncc + 1) + min(base.ny + i, geo.ncc) + geo.ncc;
+        }
+        else {
+            offset = (geo.ncc + 1) + (2 * geo.ncc + 1) + min(base.nz + i, geo.ncc) + geo.ncc;
+        }
+        const int first = table_of_variant ? table_of_variant[v] : v * geo.table_stride;
+        s_tab[v][t] = __ldg(table + first + offset);
+    }
+}
+
+__device__ __forceinline__ double2 cellPhase(const double2* t, int li, int lj, int ll)
+{
+    return cmul(cmul(t[li], t[4 + lj]), t[8 + ll]);
+}
+
+/** grid = cells; block = 256: warp w takes the accepted moves a ≡ w (mod 8) for the cell's k-vectors */
+__global__ void __launch_bounds__(kBlock)
+    batchCommitQKernel(EwaldView E, const int4* __restrict__ kn, const int* __restrict__ cell_start, BatchBuffers prev,
+                       CommitList commit, PhaseGeometry geo, double* __restrict__ e_partials /*[gridDim.x]*/)
+{
     constexpr int NW = kBlock / 32;
-    constexpr int DELTA_ELEMS = STRIDE * LD > kBatchDeltaElems ? STRIDE * LD : kBatchDeltaElems; // ≥ 32 KB for s_g
-    __shared__ double2 s_delta[DELTA_ELEMS];
-    __shared__ double2 s_dq[NW][KT];                // per-warp share of the committed ΔQ(k) of a tile
+    __shared__ double2 s_tab[2 * kBatchMax][kCellEntries];
+    __shared__ double2 s_dq[NW][kTileK];
     __shared__ double s_cqn[kBatchMax], s_cqo[kBatchMax];
-    __shared__ int s_ctable[kBatchMax];
-
-    // accepted moves of the previous window: their δ is added to Q(k) here, tile by tile
+    __shared__ int s_ctable[2 * kBatchMax];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int ncommit = commit.n;
+    const int p0 = cell_start[blockIdx.x];
+    const int len = cell_start[blockIdx.x + 1] - p0;
     if (static_cast<int>(threadIdx.x) < ncommit) {
         const int m = commit.index[threadIdx.x];
         s_cqn[threadIdx.x] = prev.in->pnew[m].w;
         s_cqo[threadIdx.x] = prev.pold[m].w;
-        s_ctable[threadIdx.x] = 2 * m * geo.table_stride;
+        s_ctable[2 * threadIdx.x] = 2 * m * geo.table_stride;
+        s_ctable[2 * threadIdx.x + 1] = (2 * m + 1) * geo.table_stride;
     }
-    double eacc = 0.0; // Σ A_k |Q_k|² of the window-start state (warp 0)
+    __syncthreads();
+    if (ncommit > 0) {
+        stageCellTables(s_tab, prev.table, s_ctable, 2 * ncommit, cellBase(__ldg(kn + p0), geo.ncc), geo);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        const int kl = lane + 32 * kk;
+        double2 dq = make_double2(0, 0);
+        if (kl < len && ncommit > 0) {
+            const int4 nn = __ldg(kn + p0 + kl);
+            const int li = nn.x & 3, lj = (nn.y + geo.ncc) & 3, ll = (nn.z + geo.ncc) & 3;
+            for (int a = warp; a < ncommit; a += NW) {
+                const double2 en = cellPhase(s_tab[2 * a], li, lj, ll);
+                const double2 eo = cellPhase(s_tab[2 * a + 1], li, lj, ll);
+                dq.x += s_cqn[a] * en.x - s_cqo[a] * eo.x;
+                dq.y += s_cqn[a] * en.y - s_cqo[a] * eo.y;
+            }
+        }
+        s_dq[warp][kl] = dq;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double e = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const int kl = lane + 32 * kk;
+            if (kl < len) {
+                const int k = p0 + kl;
+                double2 Q = E.Q[k];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    Q.x += s_dq[w][kl].x;
+                    Q.y += s_dq[w][kl].y;
+                }
+                if (ncommit > 0) {
+                    E.Q[k] = Q;
+                }
+                e += E.kA[k].w * (Q.x * Q.x + Q.y * Q.y);
+            }
+        }
+        e = warpSum(e);
+        if (lane == 0) {
+            e_partials[blockIdx.x] = e;
+        }
+    }
+}
 
+/**
+ * grid = cells; block = 256 threads: lane ↔ k-vector of the cell (two per lane), warp ↔ moves.
+ * scratch layout: [tile of kTileK consecutive k][m (stride)][k local] double2 — dense tiles of the
+ * cell-ordered k index for the Gram kernel. r_partials [cell][stride].
+ */
+__global__ void __launch_bounds__(kBlock)
+    batchDeltaKernel(EwaldView E, const int4* __restrict__ kn, const double* __restrict__ sqrt_ak,
+                     const int* __restrict__ cell_start, BatchBuffers cur, PhaseGeometry geo, int stride,
+                     double2* __restrict__ scratch, double* __restrict__ r_partials)
+{
+    constexpr int NW = kBlock / 32;
+    __shared__ double2 s_tab[2 * kBatchMax][kCellEntries];
     const int n = cur.in->n;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const int p0 = cell_start[blockIdx.x];
+    const int len = cell_start[blockIdx.x + 1] - p0;
+    stageCellTables(s_tab, cur.table, nullptr, 2 * n, cellBase(__ldg(kn + p0), geo.ncc), geo);
+
+    int li[2], lj[2], ll[2];
+    double2 Q[2];
+    double A[2], sA[2];
+    bool valid[2];
+    size_t out[2];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        const int kl = lane + 32 * kk;
+        const int k = p0 + kl;
+        valid[kk] = kl < len;
+        li[kk] = lj[kk] = ll[kk] = 0;
+        Q[kk] = make_double2(0, 0);
+        A[kk] = 0.0;
+        sA[kk] = 0.0;
+        out[kk] = 0;
+        if (valid[kk]) {
+            const int4 nn = __ldg(kn + k);
+            li[kk] = nn.x & 3;
+            lj[kk] = (nn.y + geo.ncc) & 3;
+            ll[kk] = (nn.z + geo.ncc) & 3;
+            Q[kk] = E.Q[k];
+            A[kk] = E.kA[k].w;
+            sA[kk] = __ldg(sqrt_ak + k);
+            out[kk] = static_cast<size_t>(k / kTileK) * stride * kTileK + (k % kTileK);
+        }
+    }
+    __syncthreads();
+    for (int m = warp; m < stride; m += NW) {
+        double racc = 0.0;
+        double2 d[2] = {make_double2(0, 0), make_double2(0, 0)};
+        if (m < n) {
+            const double qn = cur.in->pnew[m].w;
+            const double qo = cur.pold[m].w;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                if (valid[kk]) {
+                    const double2 en = cellPhase(s_tab[2 * m], li[kk], lj[kk], ll[kk]);
+                    const double2 eo = cellPhase(s_tab[2 * m + 1], li[kk], lj[kk], ll[kk]);
+                    d[kk].x = qn * en.x - qo * eo.x;
+                    d[kk].y = qn * en.y - qo * eo.y;
+                    racc += A[kk] * (2.0 * (Q[kk].x * d[kk].x + Q[kk].y * d[kk].y) + (d[kk].x * d[kk].x + d[kk].y * d[kk].y));
+                }
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            if (valid[kk]) {
+                scratch[out[kk] + static_cast<size_t>(m) * kTileK] = make_double2(sA[kk] * d[kk].x, sA[kk] * d[kk].y);
+            }
+        }
+        racc = warpSum(racc);
+        if (lane == 0) {
+            r_partials[static_cast<size_t>(blockIdx.x) * stride + m] = racc;
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1) { // zero the unused tail of the last dense tile
+        const int tail0 = E.K;
+        const int tail1 = ((E.K + kTileK - 1) / kTileK) * kTileK;
+        for (int e = threadIdx.x; e < (tail1 - tail0) * stride; e += kBlock) {
+            const int k = tail0 + e % (tail1 - tail0);
+            const int m = e / (tail1 - tail0);
+            scratch[static_cast<size_t>(k / kTileK) * stride * kTileK + static_cast<size_t>(m) * kTileK + (k % kTileK)] =
+                make_double2(0, 0);
+        }
+    }
+}
+
+template <int BT>
+__global__ void __launch_bounds__(kBlock, 2)
+    batchGramKernel(const double2* __restrict__ scratch, int n_tiles, double* __restrict__ g_partials /*[gridDim.x][stride²]*/)
+{
+    constexpr int STRIDE = BT * 4;
+    constexpr int NTILE = BT * BT;           // 4×4 output tiles
+    constexpr int KG = kBlock / NTILE;       // k sub-groups: 16, 4, 1
+    constexpr int KH = STRIDE == 64 ? 32 : kTileK; // k-vectors staged at a time (shared memory ≤ 48 KB)
+    constexpr int LD = KH + 1;               // padded leading dimension of s_delta[m][k]
+    constexpr int DELTA_ELEMS = STRIDE * LD > 2048 ? STRIDE * LD : 2048; // ≥ 32 KB: reused for the final reduction
+    __shared__ double2 s_delta[DELTA_ELEMS];
+
     const int tile_id = threadIdx.x % NTILE;
     const int kg = threadIdx.x / NTILE;
-    const int ta = tile_id / BT; // this thread owns G[ta + BT·i][tm + BT·j], i, j < 4 (bank-conflict-free reads)
+    const int ta = tile_id / BT; // this thread owns G[ta + BT·i][tm + BT·j], i ≤ j < 4 (bank-conflict-free reads)
     const int tm = tile_id % BT;
 
-    double racc[MPW];
-#pragma unroll
-    for (int i = 0; i < MPW; ++i) {
-        racc[i] = 0.0;
-    }
     double gacc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -440,135 +697,42 @@ __global__ void __launch_bounds__(kBlock, 2)
             gacc[i][j] = 0.0;
         }
     }
-
-    // per-warp move data
-    double qn[MPW], qo[MPW];
-#pragma unroll
-    for (int i = 0; i < MPW; ++i) {
-        const int m = warp * MPW + i;
-        qn[i] = (m < n) ? cur.in->pnew[m].w : 0.0;
-        qo[i] = (m < n) ? cur.pold[m].w : 0.0;
-    }
-
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int k0 = tile * KT;
-        __syncthreads(); // previous tile's phase 2 is done with s_delta (and everybody with s_dq)
-        double2 qkeep[KPL];
-        if (ncommit > 0) {
-#pragma unroll
-            for (int kk = 0; kk < KPL; ++kk) {
-                const int kl = lane + 32 * kk;
-                const int k = k0 + kl;
-                double2 dq = make_double2(0, 0);
-                if (k < E.K) {
-                    const int4 nn = __ldg(kn + k);
-                    for (int a = warp; a < ncommit; a += NW) {
-                        const double2* t = prev.table + s_ctable[a];
-                        const double2 en = tablePhase(t, geo, nn.x, nn.y, nn.z);
-                        const double2 eo = tablePhase(t + geo.table_stride, geo, nn.x, nn.y, nn.z);
-                        dq.x += s_cqn[a] * en.x - s_cqo[a] * eo.x;
-                        dq.y += s_cqn[a] * en.y - s_cqo[a] * eo.y;
-                    }
-                }
-                s_dq[warp][kl] = dq;
-            }
-            __syncthreads();
-        }
-#pragma unroll
-        for (int kk = 0; kk < KPL; ++kk) {
-            const int kl = lane + 32 * kk;
-            const int k = k0 + kl;
-            const bool valid = k < E.K;
-            int4 nn = make_int4(0, 0, 0, 0);
-            double2 Q = make_double2(0, 0);
-            double A = 0.0;
-            if (valid) {
-                nn = __ldg(kn + k);
-                Q = E.Q[k];
-                A = E.kA[k].w;
-                if (ncommit > 0) { // every warp adds the shares in the same order → the same Q(k) everywhere
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) {
-                        Q.x += s_dq[w][kl].x;
-                        Q.y += s_dq[w][kl].y;
-                    }
-                }
-                if (warp == 0) {
-                    eacc += A * (Q.x * Q.x + Q.y * Q.y);
-                }
-            }
-            qkeep[kk] = Q;
-            const double sqrtA = sqrt(A);
-#pragma unroll
-            for (int i = 0; i < MPW; ++i) {
-                const int m = warp * MPW + i;
-                double2 d = make_double2(0, 0);
-                if (valid && m < n) {
-                    const double2 en =
-                        tablePhase(cur.table + static_cast<size_t>(2 * m) * geo.table_stride, geo, nn.x, nn.y, nn.z);
-                    const double2 eo =
-                        tablePhase(cur.table + static_cast<size_t>(2 * m + 1) * geo.table_stride, geo, nn.x, nn.y, nn.z);
-                    d.x = qn[i] * en.x - qo[i] * eo.x;
-                    d.y = qn[i] * en.y - qo[i] * eo.y;
-                    racc[i] += A * (2.0 * (Q.x * d.x + Q.y * d.y) + (d.x * d.x + d.y * d.y));
-                }
-                s_delta[m * LD + kl] = make_double2(sqrtA * d.x, sqrtA * d.y);
-            }
+    for (int part = blockIdx.x; part < n_tiles * (kTileK / KH); part += gridDim.x) {
+        const int tile = part / (kTileK / KH);
+        const int half = part % (kTileK / KH);
+        const double2* src = scratch + static_cast<size_t>(tile) * STRIDE * kTileK + half * KH;
+        __syncthreads(); // previous part consumed
+        for (int e = threadIdx.x; e < STRIDE * KH; e += kBlock) {
+            const int m = e / KH;
+            const int kl = e % KH;
+            s_delta[m * LD + kl] = src[m * kTileK + kl];
         }
         __syncthreads();
-        if (ncommit > 0 && warp == 0) { // every warp has read the old Q(k) of this tile by now
-#pragma unroll
-            for (int kk = 0; kk < KPL; ++kk) {
-                const int k = k0 + lane + 32 * kk;
-                if (k < E.K) {
-                    E.Q[k] = qkeep[kk];
-                }
-            }
-        }
-        if (kg < KG) {
 #pragma unroll 4
-            for (int kl = kg; kl < KT; kl += KG) {
-                double2 da[4], dm[4];
+        for (int kl = kg; kl < KH; kl += KG) {
+            double2 da[4], dm[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    da[i] = s_delta[(ta + BT * i) * LD + kl];
-                    dm[i] = s_delta[(tm + BT * i) * LD + kl];
-                }
+            for (int i = 0; i < 4; ++i) {
+                da[i] = s_delta[(ta + BT * i) * LD + kl];
+                dm[i] = s_delta[(tm + BT * i) * LD + kl];
+            }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 4; ++i) {
 #pragma unroll
-                    for (int j = i; j < 4; ++j) { // a = ta + BT·i < m = tm + BT·j needs i ≤ j
-                        gacc[i][j] = fma(da[i].x, dm[j].x, fma(da[i].y, dm[j].y, gacc[i][j]));
-                    }
+                for (int j = i; j < 4; ++j) { // a = ta + BT·i < m = tm + BT·j needs i ≤ j
+                    gacc[i][j] = fma(da[i].x, dm[j].x, fma(da[i].y, dm[j].y, gacc[i][j]));
                 }
             }
         }
     }
-
-    if (warp == 0) {
-        const double es = warpSum(eacc);
-        if (lane == 0) {
-            e_partials[blockIdx.x] = es;
-        }
-    }
-    // R[m]: warp-level sums (each warp owns its moves)
-#pragma unroll
-    for (int i = 0; i < MPW; ++i) {
-        const double s = warpSum(racc[i]);
-        if (lane == 0) {
-            r_partials[static_cast<size_t>(blockIdx.x) * STRIDE + warp * MPW + i] = s;
-        }
-    }
-    // G: reduce the k sub-groups through shared memory (fixed order), then one store per element
+    // reduce the k sub-groups through shared memory (fixed order), then one store per element
     __syncthreads();
-    double* s_g = reinterpret_cast<double*>(s_delta); // [16][kBlock] = 4096 doubles = 32 KB, thread-fastest
-    if (kg < KG) {
+    double* s_g = reinterpret_cast<double*>(s_delta); // [16][kBlock] doubles = 32 KB, thread-fastest
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 4; ++i) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                s_g[(i * 4 + j) * kBlock + threadIdx.x] = gacc[i][j];
-            }
+        for (int j = 0; j < 4; ++j) {
+            s_g[(i * 4 + j) * kBlock + threadIdx.x] = gacc[i][j];
         }
     }
     __syncthreads();
@@ -601,8 +765,9 @@ __host__ __device__ inline size_t batchResultDoubles(int stride)
 __device__ __forceinline__ double warpColumnSum(const double* __restrict__ a, int rows, size_t ld, int col, int lane)
 {
     double s = 0.0;
+#pragma unroll 8
     for (int b = lane; b < rows; b += 32) {
-        s += a[static_cast<size_t>(b) * ld + col];
+        s += __ldcg(a + static_cast<size_t>(b) * ld + col);
     }
     return warpSum(s);
 }
@@ -611,9 +776,9 @@ __device__ __forceinline__ double warpColumnSum(const double* __restrict__ a, in
 template <int KIND>
 __global__ void __launch_bounds__(kBlock)
     batchFinishKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, int n_pair_blocks,
-                      const double* __restrict__ pair_partials, int n_ewald_blocks,
-                      const double* __restrict__ r_partials, const double* __restrict__ g_partials,
-                      int n_commit_blocks, const double* __restrict__ e_partials, double* __restrict__ result)
+                      const double* __restrict__ pair_partials, int n_r_rows, const double* __restrict__ r_partials,
+                      int n_g_rows, const double* __restrict__ g_partials, int n_e_rows,
+                      const double* __restrict__ e_partials, double* __restrict__ result)
 {
     const int n = cur.in->n;
     const int with_ewald = cur.in->with_ewald;
@@ -635,7 +800,7 @@ __global__ void __launch_bounds__(kBlock)
         const int m = w - 2 * S;
         double s = 0.0;
         if (with_ewald && m < n) {
-            s = warpColumnSum(r_partials, n_ewald_blocks, static_cast<size_t>(S), m, lane);
+            s = warpColumnSum(r_partials, n_r_rows, static_cast<size_t>(S), m, lane);
         }
         if (lane == 0) {
             u[2 * S + m] = s;
@@ -649,31 +814,29 @@ __global__ void __launch_bounds__(kBlock)
         double cn = 0.0, co = 0.0, cmax = 0.0;
         if (a < m && m < n) {
             if (with_ewald) {
-                g = warpColumnSum(g_partials, n_ewald_blocks, static_cast<size_t>(S) * S, t, lane);
+                g = warpColumnSum(g_partials, n_g_rows, static_cast<size_t>(S) * S, t, lane);
             }
-            if (lane == 0) { // how the energies of move m change when the earlier move a has been accepted
-                const double4 na = cur.in->pnew[a];
-                const double4 oa = cur.pold[a];
-                const int ida_n = cur.in->id[a];
-                const int ida_o = cur.idold[a];
-                const double4 nm = cur.in->pnew[m];
-                const double4 om = cur.pold[m];
-                const int idm_n = cur.in->id[m];
-                const int idm_o = cur.idold[m];
-                const double t1 =
-                    pairEnergy<KIND>(P, idm_n, ida_n, nm.w, na.w, minImageR2(M0, nm.x, nm.y, nm.z, na.x, na.y, na.z));
-                const double t2 =
-                    pairEnergy<KIND>(P, idm_n, ida_o, nm.w, oa.w, minImageR2(M0, nm.x, nm.y, nm.z, oa.x, oa.y, oa.z));
-                const double t3 =
-                    pairEnergy<KIND>(P, idm_o, ida_n, om.w, na.w, minImageR2(M0, om.x, om.y, om.z, na.x, na.y, na.z));
-                const double t4 =
-                    pairEnergy<KIND>(P, idm_o, ida_o, om.w, oa.w, minImageR2(M0, om.x, om.y, om.z, oa.x, oa.y, oa.z));
-                cn = t1 - t2;
-                co = t3 - t4;
-                cmax = fmax(fmax(fabs(t1), fabs(t2)), fmax(fabs(t3), fabs(t4)));
-                if (t1 != t1 || t2 != t2 || t3 != t3 || t4 != t4) {
-                    cmax = __longlong_as_double(0x7ff0000000000000LL);
-                }
+            // how the energies of move m change when the earlier move a has been accepted: lanes 0..3 take
+            // the four pair energies u(new_m|old_m , new_a|old_a)
+            double term = 0.0;
+            if (lane < 4) {
+                const bool m_new = lane < 2;
+                const bool a_new = (lane & 1) == 0;
+                const double4 pm = m_new ? cur.in->pnew[m] : cur.pold[m];
+                const int idm = m_new ? cur.in->id[m] : cur.idold[m];
+                const double4 pa = a_new ? cur.in->pnew[a] : cur.pold[a];
+                const int ida = a_new ? cur.in->id[a] : cur.idold[a];
+                term = pairEnergy<KIND>(P, idm, ida, pm.w, pa.w, minImageR2(M0, pm.x, pm.y, pm.z, pa.x, pa.y, pa.z));
+            }
+            const double t1 = __shfl_sync(0xffffffffu, term, 0);
+            const double t2 = __shfl_sync(0xffffffffu, term, 1);
+            const double t3 = __shfl_sync(0xffffffffu, term, 2);
+            const double t4 = __shfl_sync(0xffffffffu, term, 3);
+            cn = t1 - t2;
+            co = t3 - t4;
+            cmax = fmax(fmax(fabs(t1), fabs(t2)), fmax(fabs(t3), fabs(t4)));
+            if (t1 != t1 || t2 != t2 || t3 != t3 || t4 != t4) {
+                cmax = __longlong_as_double(0x7ff0000000000000LL);
             }
         }
         if (lane == 0) {
@@ -685,8 +848,8 @@ __global__ void __launch_bounds__(kBlock)
     }
     else if (w == 3 * S + S * S) {
         double e = 0.0;
-        if (with_ewald && n_commit_blocks > 0) {
-            e = warpColumnSum(e_partials, n_commit_blocks, 1, 0, lane);
+        if (with_ewald && n_e_rows > 0) {
+            e = warpColumnSum(e_partials, n_e_rows, 1, 0, lane);
         }
         if (lane == 0) {
             result[0] = e;

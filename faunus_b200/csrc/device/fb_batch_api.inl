@@ -66,48 +66,82 @@ void launchBatchCommit(fb_ctx* c, bool with_ewald, int* n_blocks_out)
     }
 }
 
+/** launches of one window after the phase kernel: pair, k-space (commit-Q, δ, Gram), final sums */
 template <int KIND>
 void launchBatchPairFinish(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, const CommitList& commit,
-                           int stride, int n_pair_blocks, int n_ewald_blocks, bool with_ewald, bool timing)
+                           int stride, int n_pair_blocks, bool with_ewald, bool want_rec_sum, bool timing)
 {
     auto& b = c->batch;
     const SlotView M0 = makeView(c, 0);
     const int n_now = b.h_in.ptr->n;
     const dim3 pair_grid(n_pair_blocks, (2 * n_now + kPairVariantsPerBlock - 1) / kPairVariantsPerBlock);
-    batchPairKernel<KIND><<<pair_grid, kPairThreads, 0, c->stream>>>(M0, c->P, cur, c->pair_cut2, stride,
-                                                                  b.d_pair_partials.ptr);
+    // with a k-space part the pair kernel runs on its own stream beside it (serialised when timing per kernel)
+    const bool fork = with_ewald && !timing;
+    cudaStream_t ps = fork ? b.pair_stream : c->stream;
+    if (fork) {
+        CUDA_CHECK(cudaEventRecord(b.ev_fork, c->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(ps, b.ev_fork, 0));
+    }
+    if (std::isinf(c->pair_cut2)) {
+        batchPairKernel<KIND, true><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
+                                                                       b.d_pair_partials.ptr);
+    }
+    else {
+        batchPairKernel<KIND, false><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
+                                                                        b.d_pair_partials.ptr);
+    }
     launched(c, "batchPairKernel");
+    if (fork) {
+        CUDA_CHECK(cudaEventRecord(b.ev_join, ps));
+    }
     if (timing) {
         CUDA_CHECK(cudaEventRecord(b.ev[2], c->stream));
     }
+    int n_tiles = 0, n_cells = 0, n_gram_blocks = 0, n_e_rows = 0;
     if (with_ewald) {
         const EwaldView E = makeEwaldView(c, 0);
         const int4* kn = c->slot[0].kn.ptr;
-        const int kt = batchTileK(stride);
-        const int n_tiles = (E.K + kt - 1) / kt;
+        n_tiles = (E.K + kTileK - 1) / kTileK;
+        n_cells = c->slot[0].n_cells;
+        const int* cell_start = c->slot[0].cell_start.ptr;
+        n_gram_blocks = std::min(n_tiles, 2 * c->n_sm);
+        b.d_e_partials.ensure(static_cast<size_t>(n_cells));
+        b.d_r_partials.ensure(static_cast<size_t>(n_cells) * kBatchMax);
+        b.d_g_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax * kBatchMax);
+        b.d_delta.ensure(static_cast<size_t>(n_tiles) * stride * kTileK);
+        if (commit.n > 0 || want_rec_sum) {
+            batchCommitQKernel<<<n_cells, kBlock, 0, c->stream>>>(E, kn, cell_start, prev, commit, b.geo,
+                                                                  b.d_e_partials.ptr);
+            launched(c, "batchCommitQKernel");
+            n_e_rows = n_cells;
+        }
+        batchDeltaKernel<<<n_cells, kBlock, 0, c->stream>>>(E, kn, c->slot[0].ksq.ptr, cell_start, cur, b.geo, stride,
+                                                            b.d_delta.ptr, b.d_r_partials.ptr);
+        launched(c, "batchDeltaKernel");
         switch (stride) {
         case 16:
-            batchEwaldKernel<4><<<n_ewald_blocks, kBlock, 0, c->stream>>>(E, kn, cur, prev, commit, b.geo, n_tiles,
-                                                                         b.d_r_partials.ptr, b.d_g_partials.ptr, b.d_e_partials.ptr);
+            batchGramKernel<4><<<n_gram_blocks, kBlock, 0, c->stream>>>(b.d_delta.ptr, n_tiles, b.d_g_partials.ptr);
             break;
         case 32:
-            batchEwaldKernel<8><<<n_ewald_blocks, kBlock, 0, c->stream>>>(E, kn, cur, prev, commit, b.geo, n_tiles,
-                                                                         b.d_r_partials.ptr, b.d_g_partials.ptr, b.d_e_partials.ptr);
+            batchGramKernel<8><<<n_gram_blocks, kBlock, 0, c->stream>>>(b.d_delta.ptr, n_tiles, b.d_g_partials.ptr);
             break;
         default:
-            batchEwaldKernel<16><<<n_ewald_blocks, kBlock, 0, c->stream>>>(E, kn, cur, prev, commit, b.geo, n_tiles,
-                                                                          b.d_r_partials.ptr, b.d_g_partials.ptr, b.d_e_partials.ptr);
+            batchGramKernel<16><<<n_gram_blocks, kBlock, 0, c->stream>>>(b.d_delta.ptr, n_tiles, b.d_g_partials.ptr);
         }
-        launched(c, "batchEwaldKernel");
+        launched(c, "batchGramKernel");
     }
     if (timing) {
         CUDA_CHECK(cudaEventRecord(b.ev[3], c->stream));
     }
+    if (fork) {
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream, b.ev_join, 0));
+    }
     const int finish_grid = (3 * stride + stride * stride + 1 + kBlock / 32 - 1) / (kBlock / 32); // one warp per output
     batchFinishKernel<KIND><<<finish_grid, kBlock, 0, c->stream>>>(
-        M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, with_ewald ? n_ewald_blocks : 0,
-        b.d_r_partials.ptr, b.d_g_partials.ptr, with_ewald ? n_ewald_blocks : 0, b.d_e_partials.ptr, b.d_result.ptr);
+        M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, n_cells, b.d_r_partials.ptr, n_gram_blocks,
+        b.d_g_partials.ptr, n_e_rows, b.d_e_partials.ptr, b.d_result.ptr);
     launched(c, "batchFinishKernel");
+    b.last_rec_fresh = n_e_rows > 0;
 }
 
 /** Leave windowed mode: put pending accepted moves on the device and re-align the trial slot's Q(k) */
@@ -191,9 +225,7 @@ FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, in
         }
         const int stride = n_moves <= 16 ? 16 : (n_moves <= 32 ? 32 : 64);
         const bool timing = c->timing;
-        if (timing) {
-            CUDA_CHECK(cudaEventRecord(b.ev[0], c->stream));
-        }
+        CUDA_CHECK(cudaEventRecord(b.ev[0], c->stream));
         // the previous window's accepted moves (described by the buffers of parity `b.parity`): positions are
         // written by the phase kernel, their δ is added to Q(k) inside the k-space kernel
         if (with_ewald) {
@@ -217,22 +249,13 @@ FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, in
         }
         const int n_pair_blocks = (c->n_slots + kPairChunk - 1) / kPairChunk;
         b.d_pair_partials.ensure(static_cast<size_t>(n_pair_blocks) * 2 * kBatchMax);
-        int n_ewald_blocks = 0;
-        if (with_ewald) {
-            const int kt = batchTileK(stride);
-            const int n_tiles = (c->slot[0].K + kt - 1) / kt;
-            n_ewald_blocks = std::max(1, std::min(n_tiles, 2 * c->n_sm));
-            b.d_e_partials.ensure(static_cast<size_t>(2 * c->n_sm));
-            b.d_r_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax);
-            b.d_g_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax * kBatchMax);
-        }
         const size_t n_result = batchResultDoubles(stride);
         b.d_result.ensure(batchResultDoubles(kBatchMax));
         b.h_result.ensure(batchResultDoubles(kBatchMax));
 #define FB_CASE(K)                                                                                            \
     case K:                                                                                                   \
-        launchBatchPairFinish<K>(c, cur, prev, commit, stride, n_pair_blocks, n_ewald_blocks, with_ewald != 0, \
-                                 timing);                                                                     \
+        launchBatchPairFinish<K>(c, cur, prev, commit, stride, n_pair_blocks, with_ewald != 0,                \
+                                 with_ewald != 0 && !b.rec_known, timing);                                    \
         break;
         switch (c->P.kind) {
             FB_CASE(POT_COULOMB_LJ)
@@ -245,12 +268,15 @@ FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, in
             throw CudaError{"unknown potential kind"};
         }
 #undef FB_CASE
-        if (timing) {
-            CUDA_CHECK(cudaEventRecord(b.ev[4], c->stream));
-        }
+        CUDA_CHECK(cudaEventRecord(b.ev[4], c->stream));
         CUDA_CHECK(cudaMemcpyAsync(b.h_result.ptr, b.d_result.ptr, n_result * sizeof(double), cudaMemcpyDeviceToHost,
                                    c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        {
+            float t04 = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&t04, b.ev[0], b.ev[4]));
+            b.acc_total_ms += t04;
+        }
         if (timing) {
             float t01 = 0, t12 = 0, t23 = 0, t34 = 0;
             CUDA_CHECK(cudaEventElapsedTime(&t01, b.ev[0], b.ev[1]));
@@ -264,7 +290,7 @@ FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, in
         b.windows += 1;
         b.moves += n_moves;
         const double* r = b.h_result.ptr;
-        if (with_ewald) {
+        if (with_ewald && b.last_rec_fresh) {
             b.rec_sum = r[0];
             b.rec_known = true;
         }
@@ -336,6 +362,7 @@ FB_API int fb_get_batch_timing(const fb_ctx* c, double out[8])
     out[2] = c->batch.acc_ms[2];
     out[3] = c->batch.windows;
     out[4] = c->batch.moves;
-    out[5] = out[6] = out[7] = 0.0;
+    out[5] = c->batch.acc_total_ms;
+    out[6] = out[7] = 0.0;
     return FB_OK;
 }

@@ -159,7 +159,8 @@ extern "C" __attribute__((visibility("default"))) int fbh_sim_set_window(void* h
     return result;
 }
 
-/** out[0..2] = ms in pair / k-space / other kernels of the windowed path, out[3] = windows, out[4] = moves */
+/** out[0..5] as fb_get_batch_timing; out[6] = host ms inside evaluate (launch + wait), out[7] = host ms of the
+ * whole windowed sweep part (drawing proposals, evaluate, deciding) */
 extern "C" __attribute__((visibility("default"))) int fbh_sim_get_window_timing(void* h, double out[8])
 {
     auto* s = static_cast<fb::capi::Sim*>(h);
@@ -173,5 +174,7 @@ extern "C" __attribute__((visibility("default"))) int fbh_sim_get_window_timing(
             out[i] += v[i];
         }
     }
+    out[6] = 1e3 * s->mc->window_seconds_evaluate;
+    out[7] = 1e3 * s->mc->window_seconds_total;
     return 0;
 }

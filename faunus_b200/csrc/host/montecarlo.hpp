@@ -5,6 +5,7 @@
 // src/analysis.cpp:807-823 + 1227-1312 (Widom insertion, sequential reference order).
 #pragma once
 #include "moves.hpp"
+#include <chrono>
 
 namespace fb {
 
@@ -82,6 +83,9 @@ class MetropolisMonteCarlo
     std::unique_ptr<WindowEvaluator> window_evaluator; //!< set by the B200 build; nullptr = one move at a time
     unsigned long windows_evaluated = 0;
     unsigned long window_moves_evaluated = 0;
+    double window_seconds_evaluate = 0; //!< host wall time inside WindowEvaluator::evaluate (launch + wait)
+    double window_seconds_decide = 0;   //!< ... deciding moves and syncing the Spaces
+    double window_seconds_total = 0;    //!< ... in the windowed part of sweeps (proposal drawing is the remainder)
 
   private:
     /** src/montecarlo.cpp:17-34; the uniform is ALWAYS drawn */
@@ -253,7 +257,10 @@ class MetropolisMonteCarlo
     /** evaluate the first `n` queued proposals (all applied) and decide as many as possible, in order */
     void decideWindow(int n)
     {
+        const auto t_begin = std::chrono::steady_clock::now();
         window_evaluator->evaluate(window, n);
+        const auto t_evaluated = std::chrono::steady_clock::now();
+        window_seconds_evaluate += std::chrono::duration<double>(t_evaluated - t_begin).count();
         windows_evaluated++;
         window_moves_evaluated += static_cast<unsigned long>(n);
         std::vector<unsigned char> accepted;
@@ -292,6 +299,7 @@ class MetropolisMonteCarlo
         window_evaluator->commit(accepted);
         // undecided proposals stay queued: their trial positions are in the trial Space (distinct atoms)
         window.erase(window.begin(), window.begin() + static_cast<long>(accepted.size()));
+        window_seconds_decide += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_evaluated).count();
     }
 
     int readyProposals() const
@@ -376,7 +384,9 @@ class MetropolisMonteCarlo
             return -1;
         };
         if (window_evaluator) {
+            const auto t0 = std::chrono::steady_clock::now();
             sweepStochasticWindowed(id_of);
+            window_seconds_total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
         else {
             moves->forEachStochasticMove([&](Move& m) { performMove(m, id_of(m)); });

@@ -206,7 +206,7 @@ class B200Simulation(Simulation):
         out = np.zeros(8)
         load().fbh_sim_get_window_timing(self.handle, out.ctypes.data_as(c_double_p))
         return {"pair_ms": out[0], "ewald_ms": out[1], "other_ms": out[2], "windows": int(out[3]),
-                "moves": int(out[4])}
+                "moves": int(out[4]), "total_ms": out[5], "host_evaluate_ms": out[6], "host_sweep_ms": out[7]}
 
     @property
     def launch_count(self) -> int:

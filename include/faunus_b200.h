@@ -259,7 +259,8 @@ int fb_batch_trial(fb_ctx* ctx, int n_moves, const fb_batch_move* moves, int wit
 /* accepted[m] != 0 for the accepted ones among the first n_decided moves of the last window */
 int fb_batch_commit(fb_ctx* ctx, int n_decided, const unsigned char* accepted);
 /* timing enabled: out[0..2] = ms in the pair / k-space / other (commit, phase tables, final sums) kernels of
- * the windowed path, out[3] = windows, out[4] = moves evaluated */
+ * the windowed path (kernels serialised while timing), out[3] = windows, out[4] = moves evaluated,
+ * out[5] = ms from the first to the last kernel of every window (always accumulated) */
 int fb_get_batch_timing(const fb_ctx* ctx, double out[8]);
 
 /* ---- Ewald reciprocal space --------------------------------------------------------------- */
