@@ -172,6 +172,72 @@ def measure_fp64_peak(native, device):
     return out.value if lib.fb_measure_fp64_peak(device, C.byref(out)) == 0 else None
 
 
+def sharded_extras(args, native, torch, dist, rank, world, local):
+    """Work that shards over GPUs, same S1 state on every rank (same seed): Widom ion-pair
+    insertions split by index range, full-system energy split by tile rows (pair part) and k-vector slabs
+    (reciprocal part). Device-event time, max over ranks; strong scaling (total work fixed)."""
+    from faunus_b200.config import primitive_model
+    from faunus_b200.replica import reduce_in_rank_order, torch_all_gather
+    import math
+    # Widom: the reference's Ewald term returns the TOTAL reciprocal energy for any non-empty change and never
+    # sees the ghost (SURVEY §3.4), which makes exp(-dU) underflow; the insertion workload therefore uses the
+    # cutoff scheme (Fanourgakis) on the same ion configuration. The system energy uses the Ewald S1 workload.
+    cfg_widom = primitive_model(n=N_IONS, molarity=1.0, seed=5489, moves_per_sweep=10, ghost_pairs=1,
+                                coulomb={"type": "fanourgakis", "epsr": 78.7, "cutoff": 28.0})
+    sim = native.B200Simulation(cfg_widom, device=local)
+    n_insert = 32768
+    wid = sim.widom_create({"molecule": "ghost", "ninsert": n_insert})
+    gather = torch_all_gather() if world > 1 else None
+
+    def timed(fn, reps):
+        fn()  # warm-up
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier(device_ids=[local])
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    sim.enable_timing(True)
+    t0 = sim.device_time_ms()
+    dt_widom = timed(lambda: sim.widom_sample_sharded(wid, rank, world, gather), 3)
+    t1 = sim.device_time_ms()
+    widom_kernel_ms = (t1["widom_ms"] - t0["widom_ms"]) / max(1, t1["widom_launches"] - t0["widom_launches"])
+    res = sim.widom_result(wid)
+    sim.close()
+    sim = native.B200Simulation(workload(moves_per_step=10), device=local)
+    shares = {}
+
+    def energy():
+        nb, rec = sim.system_energy_shard(rank, world)
+        tot = reduce_in_rank_order([nb, rec]) if world > 1 else [nb, rec]
+        shares["nonbonded"], shares["reciprocal"] = float(tot[0]), float(tot[1])
+
+    dt_energy = timed(energy, 2)
+    n_active = N_IONS
+    out = {
+        "scaling": "strong", "n_gpus": world,
+        "widom": {"insertions_per_s": n_insert / dt_widom, "insertions_per_sample": n_insert, "ghost_atoms": 2,
+                  "ms_per_sample_e2e": 1e3 * dt_widom, "kernel_ms_this_rank": widom_kernel_ms,
+                  "pair_interactions_per_s": n_insert * 2 * n_active / dt_widom,
+                  "mu_excess_kT": -math.log(res["sum_exp"] / res["count"]) if res["count"] and res["sum_exp"] > 0 else None,
+                  "workload": "S1 ion configuration, nonbonded_coulombwca with Fanourgakis Rc=28, Na+Cl ghost pair",
+                  "note": "ghost generation (host, reference RNG order) and the all-gather of the slices are inside e2e"},
+        "system_energy": {"ms": 1e3 * dt_energy, "nonbonded_kT": shares.get("nonbonded"),
+                          "reciprocal_kT": shares.get("reciprocal"),
+                          "pairs": N_IONS * (N_IONS - 1) // 2, "n_times_k": N_IONS * 57950},
+    }
+    sim.close()
+    return out
+
+
 def b200_arm(args):
     rank, world, local, dist = dist_setup(args.gpus, "nccl")
     import torch
@@ -246,6 +312,10 @@ def b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         device_s = float(t.item())
     value = world * moves / device_s if device_s > 0 else e2e
+    sim.close()
+    extras = None
+    if not args.no_extras:
+        extras = sharded_extras(args, native, torch, dist, rank, world, local)
     if rank != 0:
         return
     peaks = {}
@@ -324,6 +394,8 @@ def b200_arm(args):
                                           "commit_phase_finish": 1e3 * other_ms / moves},
         "clocks": clocks,
     }
+    if extras:
+        line["sharded"] = extras
     if roofline:
         line["roofline"] = roofline
     if cpu:
@@ -338,6 +410,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sharded Widom / system-energy measurements")
     ap.add_argument("--window", type=int, default=None, help="proposals per device pass (0: one move per launch)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -60,6 +60,9 @@ class SimLibrary:
         f("widom_create", C.c_int, [C.c_void_p, C.c_char_p])
         f("widom_sample", C.c_int, [C.c_void_p, C.c_int, C.c_int])
         f("widom_result", C.c_int, [C.c_void_p, C.c_int, c_double_p, c_long_p, c_double_p, C.c_int])
+        f("widom_prepare", C.c_int, [C.c_void_p, C.c_int])
+        f("widom_evaluate_slice", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p])
+        f("widom_collect", C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int])
 
     def _fn(self, name, restype, argtypes):
         fn = getattr(self.lib, f"{self.prefix}_{name}")
@@ -201,6 +204,29 @@ class Simulation:
 
     def widom_sample(self, wid: int, nsamples: int = 1):
         self._check(self.api.widom_sample(self.handle, wid, nsamples), "widom_sample")
+
+    def widom_sample_sharded(self, wid: int, rank: int, size: int, all_gather=None) -> int:
+        """One Widom sample event with the insertions split over `size` ranks. Every rank calls
+        this with simulations in the same state (same seed): the ghosts are generated identically everywhere,
+        this rank evaluates its slice, ``all_gather(local, counts) -> np.ndarray`` returns the ΔU of all ranks
+        concatenated in rank order, and every rank collects all of them in insertion order — so the running
+        averages are bit-identical to an unsharded run."""
+        n = self.api.widom_prepare(self.handle, wid)
+        if n < 0:
+            raise RuntimeError(f"{self.api.prefix}_widom_prepare: {self.api.error()}")
+        if n == 0:
+            return 0
+        bounds = [n * r // size for r in range(size + 1)]
+        first, count = bounds[rank], bounds[rank + 1] - bounds[rank]
+        local = np.zeros(max(count, 1))
+        self._check(self.api.widom_evaluate_slice(self.handle, wid, first, count, _dp(local)), "widom_evaluate_slice")
+        local = local[:count]
+        everyone = local if size == 1 else all_gather(local, [bounds[r + 1] - bounds[r] for r in range(size)])
+        everyone = np.ascontiguousarray(everyone, dtype=np.float64)
+        if len(everyone) != n:
+            raise RuntimeError("all_gather returned the wrong number of insertion energies")
+        self._check(self.api.widom_collect(self.handle, wid, _dp(everyone), n), "widom_collect")
+        return n
 
     def widom_result(self, wid: int, max_du: int = 1 << 20):
         s = C.c_double()

@@ -860,20 +860,20 @@ class WidomB200 : public WidomInsertion
         }
     }
 
-    void sample() override
+    /** ΔU of insertions [first, first + count) of the prepared event: ONE launch for the whole slice */
+    void evaluateSlice(int first, int count, double* du_total) override
     {
-        Change change;
-        last_du.clear();
-        if (!selectGhostGroup(change)) {
+        checkSlice(first, count);
+        if (count == 0) {
             return;
         }
+        const Change& change = prepared.change;
         const size_t gi = change.groups.at(0).group_index;
         auto& group = spc.groups.at(gi);
-        const auto& mol = spc.topology->molecules[molid];
         const int n_g = static_cast<int>(group.capacity());
-        const int B = number_of_insertions;
-        std::vector<double> xyzq(static_cast<size_t>(B) * n_g * 4), cm(static_cast<size_t>(B) * 3), host_terms(B, 0.0);
-        std::vector<int> ids(n_g);
+        std::vector<double> xyzq(static_cast<size_t>(count) * n_g * 4), cm(static_cast<size_t>(count) * 3);
+        std::vector<double> host_terms(static_cast<size_t>(count), 0.0), du(static_cast<size_t>(count));
+        std::vector<int> ids(static_cast<size_t>(n_g));
         group.resize(group.capacity());
         // Ewald terms see a Q(k) without the ghost (Widom never calls updateState):
         // their energy is the same for every insertion and is evaluated once.
@@ -881,9 +881,8 @@ class WidomB200 : public WidomInsertion
         for (const auto& t : pot.find<EwaldB200>()) {
             ewald_energy += t->energy(change);
         }
-        for (int b = 0; b < B; ++b) {
-            const auto particles = inserter(spc, mol, random);
-            updateGroup(group, particles);
+        for (int b = 0; b < count; ++b) {
+            updateGroup(group, prepared.ghosts[first + b]);
             for (int a = 0; a < n_g; ++a) {
                 const auto& p = spc.at(group, a);
                 const size_t o = (static_cast<size_t>(b) * n_g + a) * 4;
@@ -901,17 +900,15 @@ class WidomB200 : public WidomInsertion
                 host_terms[b] += t->energy(change);
             }
         }
+        const bool molecular = group.isMolecular();
         group.resize(0);
-        std::vector<double> du(B);
         auto& dev = *nonbonded->device();
-        fbCheck(fb_widom_batch(dev.ctx, nonbonded->deviceSlot(), static_cast<int>(gi), n_g, B, xyzq.data(),
-                               ids.data(), group.isMolecular() ? cm.data() : nullptr,
-                               change.groups[0].internal ? 1 : 0, du.data()),
+        fbCheck(fb_widom_batch(dev.ctx, nonbonded->deviceSlot(), static_cast<int>(gi), n_g, count, xyzq.data(),
+                               ids.data(), molecular ? cm.data() : nullptr, change.groups[0].internal ? 1 : 0,
+                               du.data()),
                 dev.ctx, "fb_widom_batch");
-        for (int b = 0; b < B; ++b) {
-            const double total = host_terms[b] + du[b] + ewald_energy;
-            last_du.push_back(total);
-            collect(total);
+        for (int b = 0; b < count; ++b) {
+            du_total[b] = host_terms[b] + du[b] + ewald_energy;
         }
     }
 };

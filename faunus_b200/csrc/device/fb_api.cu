@@ -449,7 +449,7 @@ template <bool FUSED> void launchMoved(fb_ctx* c, const SlotView& A, const SlotV
     launched(c, "movedEnergyKernel");
 }
 
-void launchFull(fb_ctx* c, const SlotView& V, int volume_predicate)
+void launchFull(fb_ctx* c, const SlotView& V, int volume_predicate, int shard = 0, int n_shards = 1)
 {
     const int nt = (c->n_slots + kTile - 1) / kTile;
     const size_t npart = static_cast<size_t>(nt) * (nt + 1) / 2;
@@ -457,7 +457,8 @@ void launchFull(fb_ctx* c, const SlotView& V, int volume_predicate)
     dim3 grid(nt, nt);
 #define FB_CASE(K)                                                                                            \
     case K:                                                                                                   \
-        fullEnergyKernel<K><<<grid, kTile, 0, c->stream>>>(V, c->P, volume_predicate, c->partials.ptr);       \
+        fullEnergyKernel<K><<<grid, kTile, 0, c->stream>>>(V, c->P, volume_predicate, shard, n_shards,        \
+                                                           c->partials.ptr);                                  \
         break;
     switch (c->P.kind) {
         FB_CASE(POT_COULOMB_LJ)
@@ -1235,6 +1236,43 @@ FB_API int fb_nonbonded_delta(fb_ctx* c, int s_new, int s_old, const fb_change* 
         finish(c);
         *u_new = c->h_result[0];
         *u_old = c->h_result[1];
+    });
+}
+
+/** share `shard` of `n_shards` of the full-system non-bonded and reciprocal energies (multi-GPU system energy) */
+FB_API int fb_system_energy_shard(fb_ctx* c, int s, int shard, int n_shards, double* nonbonded, double* reciprocal)
+{
+    return guarded(c, [&] {
+        flushPending(c);
+        checkSlot(c, s);
+        if (!nonbonded || !reciprocal || n_shards < 1 || shard < 0 || shard >= n_shards) {
+            throw CudaError{"bad shard arguments"};
+        }
+        beginTiming(c, TIME_FULL);
+        launchFull(c, makeView(c, s), 0, shard, n_shards);
+        finish(c);
+        *nonbonded = c->h_result[0];
+        *reciprocal = 0.0;
+        Slot& sl = c->slot[s];
+        if (c->ewald_configured && sl.K > 0) {
+            const int k_begin = static_cast<int>(static_cast<long long>(sl.K) * shard / n_shards);
+            const int k_end = static_cast<int>(static_cast<long long>(sl.K) * (shard + 1) / n_shards);
+            double sum = 0.0;
+            if (k_end > k_begin) {
+                const int grid = (k_end - k_begin + kEwaldBlock - 1) / kEwaldBlock;
+                c->partials.ensure(static_cast<size_t>(grid));
+                ewaldSlabEnergyKernel<<<grid, kEwaldBlock, 0, c->stream>>>(makeView(c, s), makeEwaldView(c, s), k_begin,
+                                                                          k_end, c->partials.ptr);
+                launched(c, "ewaldSlabEnergyKernel");
+                orderedSumKernel<<<1, 1024, 0, c->stream>>>(c->partials.ptr, static_cast<size_t>(grid), 1, c->d_result);
+                launched(c, "orderedSumKernel");
+                CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                sum = c->h_result[0];
+            }
+            const double pi = 3.141592653589793238462643383279502884;
+            const double volume = sl.ewald_box[0] * sl.ewald_box[1] * sl.ewald_box[2];
+            *reciprocal = 2 * pi * sum * c->ewald.bjerrum_length / volume;
+        }
     });
 }
 

@@ -494,11 +494,18 @@ __global__ void __launch_bounds__(kBlock)
 // ------------------------------------------------------------------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(kTile)
-    fullEnergyKernel(SlotView V, PotParams P, int volume_predicate, double* partials)
+    fullEnergyKernel(SlotView V, PotParams P, int volume_predicate, int shard, int n_shards, double* partials)
 {
     const int ti = blockIdx.y;
     const int tj = blockIdx.x;
     if (tj < ti) {
+        return;
+    }
+    if (ti % n_shards != shard) { // another rank's tile row (multi-GPU full energy): contributes zero here
+        if (threadIdx.x == 0) {
+            const int nt = gridDim.x;
+            partials[static_cast<size_t>(ti) * nt - static_cast<size_t>(ti) * (ti - 1) / 2 + (tj - ti)] = 0.0;
+        }
         return;
     }
     __shared__ double4 s_pos[kTile];
@@ -786,6 +793,63 @@ __global__ void __launch_bounds__(kEwaldBlock) ewaldFullKernel(SlotView V, Ewald
     }
     if (valid) {
         E.Q[k] = make_double2(qr, E.policy == 1 ? qi_unweighted : qi);
+    }
+}
+
+/**
+ * Reciprocal energy share of the k-vector slab [k_begin, k_end): Q(k) is rebuilt from the positions
+ * (as ewaldFullKernel does) and Σ A_k |Q_k|² of the slab is reduced to per-block partials. Nothing
+ * is stored in the slot's Q(k) (multi-GPU system energy, SURVEY §8e: k-vectors partitioned over GPUs).
+ */
+__global__ void __launch_bounds__(kEwaldBlock)
+    ewaldSlabEnergyKernel(SlotView V, EwaldView E, int k_begin, int k_end, double* partials)
+{
+    __shared__ double4 s_pos[kEwaldChunk];
+    __shared__ int s_active[kEwaldChunk];
+    __shared__ double scratch[kEwaldBlock / 32];
+    const int k = k_begin + blockIdx.x * kEwaldBlock + threadIdx.x;
+    const bool valid = k < k_end;
+    const double4 kv = valid ? E.kA[k] : make_double4(0, 0, 0, 0);
+    double qr = 0.0, qi = 0.0, qi_unweighted = 0.0;
+    for (int c0 = 0; c0 < V.n_slots; c0 += kEwaldChunk) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < kEwaldChunk; t += kEwaldBlock) {
+            const int j = c0 + t;
+            if (j < V.n_slots) {
+                s_pos[t] = V.posq[j];
+                s_active[t] = V.gid[j] >= 0;
+            }
+            else {
+                s_active[t] = 0;
+            }
+        }
+        __syncthreads();
+        if (!valid) {
+            continue;
+        }
+        const int n = min(kEwaldChunk, V.n_slots - c0);
+        for (int t = 0; t < n; ++t) {
+            if (!s_active[t]) {
+                continue;
+            }
+            const double4 p = s_pos[t];
+            if (E.policy == 2) {
+                qr += cos(kv.x * p.x) * cos(kv.y * p.y) * cos(kv.z * p.z) * p.w;
+            }
+            else {
+                double s, c;
+                sincos(kv.x * p.x + kv.y * p.y + kv.z * p.z, &s, &c);
+                qr += p.w * c;
+                qi += p.w * s;
+                qi_unweighted += s;
+            }
+        }
+    }
+    const double im = E.policy == 1 ? qi_unweighted : qi;
+    const double e = valid ? kv.w * (qr * qr + im * im) : 0.0;
+    const double sum = blockSum<kEwaldBlock>(e, scratch);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = sum;
     }
 }
 

@@ -178,3 +178,23 @@ extern "C" __attribute__((visibility("default"))) int fbh_sim_get_window_timing(
     out[7] = 1e3 * s->mc->window_seconds_total;
     return 0;
 }
+
+/**
+ * This rank's share of the full-system non-bonded and reciprocal Ewald energy of the accepted state
+ * (tile rows / k-vector slab `shard` of `n_shards`); the shares of all ranks add up to the terms
+ * `systemEnergy` reports. out[0] = non-bonded, out[1] = reciprocal (0 without Ewald).
+ */
+extern "C" __attribute__((visibility("default"))) int fbh_system_energy_shard(void* h, int shard, int n_shards,
+                                                                              double out[2])
+{
+    auto* s = static_cast<fb::capi::Sim*>(h);
+    return fb::capi::guarded([&] {
+        const auto terms = s->mc->state.pot->find<fb::NonbondedB200>();
+        if (terms.size() != 1) {
+            throw std::runtime_error("exactly one B200 non-bonded term expected");
+        }
+        auto& t = *terms.front();
+        fb::fbCheck(fb_system_energy_shard(t.device()->ctx, t.deviceSlot(), shard, n_shards, &out[0], &out[1]),
+                    t.device()->ctx, "fb_system_energy_shard");
+    });
+}

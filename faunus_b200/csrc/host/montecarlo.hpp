@@ -485,25 +485,80 @@ class WidomInsertion
         count++;
     }
 
-    virtual void sample()
+    // One sample event in three steps so that the insertions can be split over ranks: the ghosts
+    // never depend on energies, so generating all of them first consumes the generator exactly as the
+    // reference's insert → energy → insert → … loop does (src/analysis.cpp:1255-1262).
+    struct PreparedEvent
     {
+        bool valid = false;
         Change change;
+        std::vector<ParticleVector> ghosts;
+    } prepared;
+
+    /** generate the ghosts of one sample event; false if no ghost group is available */
+    virtual bool prepare()
+    {
+        prepared = PreparedEvent();
         last_du.clear();
-        if (!selectGhostGroup(change)) {
-            return;
+        if (!selectGhostGroup(prepared.change)) {
+            return false;
         }
-        auto& group = spc.groups.at(change.groups.at(0).group_index);
-        group.resize(group.capacity());
+        const auto& mol = spc.topology->molecules[molid];
         for (int cnt = 0; cnt < number_of_insertions; ++cnt) {
-            const auto particles = inserter(spc, spc.topology->molecules[molid], random);
-            updateGroup(group, particles);
-            const double du = pot.energy(change);
-            last_du.push_back(du);
-            collect(du);
+            prepared.ghosts.push_back(inserter(spc, mol, random));
+        }
+        prepared.valid = true;
+        return true;
+    }
+
+    int preparedInsertions() const { return prepared.valid ? static_cast<int>(prepared.ghosts.size()) : 0; }
+
+    /** ΔU of insertions [first, first + count) of the prepared event */
+    virtual void evaluateSlice(int first, int count, double* du)
+    {
+        checkSlice(first, count);
+        auto& group = spc.groups.at(prepared.change.groups.at(0).group_index);
+        group.resize(group.capacity());
+        for (int b = 0; b < count; ++b) {
+            updateGroup(group, prepared.ghosts[first + b]);
+            du[b] = pot.energy(prepared.change);
         }
         group.resize(0);
     }
 
+    /** accumulate exp(−ΔU) of ALL insertions of the event, in insertion order */
+    void collectAll(const double* du, int n)
+    {
+        if (!prepared.valid || n != static_cast<int>(prepared.ghosts.size())) {
+            throw std::runtime_error("Widom: wrong number of insertion energies");
+        }
+        for (int b = 0; b < n; ++b) {
+            last_du.push_back(du[b]);
+            collect(du[b]);
+        }
+        prepared.valid = false;
+    }
+
+    void sample()
+    {
+        if (!prepare()) {
+            return;
+        }
+        const int n = preparedInsertions();
+        std::vector<double> du(static_cast<size_t>(n));
+        evaluateSlice(0, n, du.data());
+        collectAll(du.data(), n);
+    }
+
+  protected:
+    void checkSlice(int first, int count) const
+    {
+        if (!prepared.valid || first < 0 || count < 0 || first + count > static_cast<int>(prepared.ghosts.size())) {
+            throw std::runtime_error("Widom slice out of range");
+        }
+    }
+
+  public:
     double excessChemicalPotential() const { return -std::log(sum_exp / static_cast<double>(count)); }
 };
 

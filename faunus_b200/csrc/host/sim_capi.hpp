@@ -420,6 +420,28 @@ inline State& pick(Sim& s, int which)
             }                                                                                                \
         });                                                                                                  \
     }                                                                                                         \
+    /* one sample event sharded over ranks: prepare (same ghosts on every rank) → evaluate a slice → collect all */ \
+    __attribute__((visibility("default"))) int P##_widom_prepare(void* h, int id)                            \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        int n = -1;                                                                                          \
+        fb::capi::guarded([&] {                                                                              \
+            auto& w = *s->widoms.at(id);                                                                     \
+            n = w.prepare() ? w.preparedInsertions() : 0;                                                    \
+        });                                                                                                  \
+        return n;                                                                                            \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_widom_evaluate_slice(void* h, int id, int first,          \
+                                                                        int count, double* du)               \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] { s->widoms.at(id)->evaluateSlice(first, count, du); });                \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_widom_collect(void* h, int id, const double* du, int n)   \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] { s->widoms.at(id)->collectAll(du, n); });                              \
+    }                                                                                                         \
     __attribute__((visibility("default"))) int P##_widom_result(void* h, int id, double* sum_exp,            \
                                                                 long* count, double* last_du, int max_du)    \
     {                                                                                                         \

@@ -93,7 +93,7 @@ class FbConfig(C.Structure):
 C_ABI_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_last_error", "fb_device_count", "fb_upload_space", "fb_update_group",
     "fb_set_box", "fb_sync", "fb_download_space", "fb_nonbonded_energy", "fb_nonbonded_delta",
-    "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_commit", "fb_get_batch_timing",
+    "fb_system_energy_shard", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_commit", "fb_get_batch_timing",
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
     "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
     "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_launch_count",
@@ -129,6 +129,7 @@ def load() -> C.CDLL:
         "fb_nonbonded_delta": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(FbChange), c_double_p, c_double_p]),
         "fb_trial_energy": (C.c_int, [vp, C.POINTER(FbTrialMove), c_double_p, c_double_p, c_double_p, c_double_p]),
         "fb_trial_commit": (C.c_int, [vp, C.c_int]),
+        "fb_system_energy_shard": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p]),
         "fb_batch_trial": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchMove), C.c_int, C.POINTER(FbBatchResult)]),
         "fb_batch_commit": (C.c_int, [vp, C.c_int, c_ubyte_p]),
         "fb_get_batch_timing": (C.c_int, [vp, c_double_p]),
@@ -158,6 +159,7 @@ def load() -> C.CDLL:
         "fbh_set_device": (None, [C.c_int]),
         "fbh_sim_launch_count": (C.c_ulonglong, [vp]),
         "fbh_sim_set_window": (C.c_int, [vp, C.c_int]),
+        "fbh_system_energy_shard": (C.c_int, [vp, C.c_int, C.c_int, c_double_p]),
         "fbh_sim_get_window_timing": (C.c_int, [vp, c_double_p]),
     }
     for name, (restype, argtypes) in sig.items():
@@ -201,6 +203,14 @@ class B200Simulation(Simulation):
         (0 when switched off or when the Hamiltonian is not eligible)."""
         self.window = int(load().fbh_sim_set_window(self.handle, int(capacity)))
         return self.window
+
+    # ---- work sharded over the ranks of a process group (SURVEY §8e); see also Simulation.widom_sample_sharded
+    def system_energy_shard(self, rank: int, size: int):
+        """(non-bonded, reciprocal) share of this rank of the full-system energy"""
+        out = np.zeros(2)
+        self._check(load().fbh_system_energy_shard(self.handle, rank, size, out.ctypes.data_as(c_double_p)),
+                    "system_energy_shard")
+        return float(out[0]), float(out[1])
 
     def window_time_ms(self) -> dict:
         out = np.zeros(8)

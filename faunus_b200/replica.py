@@ -102,3 +102,37 @@ def run_local_replicas(api: SimLibrary, configs, sweeps: int):
             return json.loads(buf.value.decode())
         size = n + 16
         # results are deterministic, so re-running with a larger buffer returns the same data
+
+
+def torch_all_gather(device=None):
+    """``all_gather(local, counts)`` for :meth:`Simulation.widom_sample_sharded` over the default process group
+    (NCCL between GPUs, gloo on CPU): ragged slices are padded to the longest one."""
+    import torch
+    import torch.distributed as dist
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+    def gather(local: np.ndarray, counts):
+        width = max(counts)
+        mine = torch.zeros(width, dtype=torch.float64, device=device)
+        mine[: len(local)] = torch.from_numpy(np.ascontiguousarray(local)).to(device)
+        everyone = [torch.empty_like(mine) for _ in counts]
+        dist.all_gather(everyone, mine)
+        return np.concatenate([t[:c].cpu().numpy() for t, c in zip(everyone, counts)])
+
+    return gather
+
+
+def reduce_in_rank_order(values, device=None):
+    """Sum of per-rank partial energies in rank order on every rank (deterministic)."""
+    import torch
+    import torch.distributed as dist
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(values), dtype=torch.float64, device=device)
+    everyone = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(everyone, mine)
+    total = np.zeros(len(mine))
+    for t in everyone:
+        total += t.cpu().numpy()
+    return total

@@ -189,6 +189,13 @@ int fb_nonbonded_energy(fb_ctx* ctx, int slot, const fb_change* change, double* 
 int fb_nonbonded_delta(fb_ctx* ctx, int slot_new, int slot_old, const fb_change* change, double* u_new,
                        double* u_old);
 
+/* share `shard` of `n_shards` of the full-system energy of a slot, for one evaluation spread over several
+ * GPUs that hold the same Space (GroupPairingPolicy::all, src/energy.h:1290-1326: tile rows are dealt
+ * round robin; PolicyIonIon::updateComplex + reciprocalEnergy, src/energy.cpp:191-206, 524-531: a slab of
+ * k-vectors, Q(k) rebuilt from the positions and not stored). The shares of all shards add up to
+ * fb_nonbonded_energy(everything) and to the reciprocal part of fb_ewald_energy. */
+int fb_system_energy_shard(fb_ctx* ctx, int slot, int shard, int n_shards, double* nonbonded, double* reciprocal);
+
 /* ---- fast path: one launch per small trial move -------------------------------------------- */
 /* A trial move of up to FB_FAST_ATOMS particles of one group without size change
  * (AtomicTranslateRotate, src/move.cpp:267-293; TranslateRotate of small rigid molecules, :1670-1689).
