@@ -417,6 +417,12 @@ def main():
         reference_arm(args)
     else:
         b200_arm(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        pass
 
 
 if __name__ == "__main__":

@@ -4,6 +4,7 @@
 #include "../../../include/faunus_b200.h"
 #include "fb_kernels.cuh"
 #include "fb_batch.cuh"
+#include "fb_stream.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -209,6 +210,7 @@ struct fb_ctx
         bool q_dirty = false;      //!< slot 0's Q(k) is ahead of slot 1's
         bool rec_known = false;    //!< rec_sum is Σ A_k|Q_k|² of slot 0's current Q(k)
         bool last_rec_fresh = false; //!< the last window recomputed that sum on the device
+        bool kspace_configured[3] = {false, false, false}; //!< dynamic shared memory opt-in done (stride 16/32/64)
         double rec_sum = 0;
         PhaseGeometry geo{};
         cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -449,8 +451,46 @@ template <bool FUSED> void launchMoved(fb_ctx* c, const SlotView& A, const SlotV
     launched(c, "movedEnergyKernel");
 }
 
+template <int KIND> void launchFullStream(fb_ctx* c, const SlotView& V, dim3 grid, int shard, int n_shards)
+{
+    if (std::isinf(c->pair_cut2)) {
+        fullStreamKernel<KIND, true><<<grid, kStreamThreads, 0, c->stream>>>(V, c->P, c->pair_cut2, 0, shard, n_shards,
+                                                                             c->partials.ptr);
+    }
+    else {
+        fullStreamKernel<KIND, false><<<grid, kStreamThreads, 0, c->stream>>>(V, c->P, c->pair_cut2, 0, shard,
+                                                                              n_shards, c->partials.ptr);
+    }
+}
+
 void launchFull(fb_ctx* c, const SlotView& V, int volume_predicate, int shard = 0, int n_shards = 1)
 {
+    if (!c->P.any_molecular) { // all groups atomic: no mass-centre cutoffs, exclusions or rigid bodies to honour
+        const int n_itiles = (c->n_slots + kStreamVariants - 1) / kStreamVariants;
+        const int gy = std::max(1, std::min(16, (4 * c->n_sm) / std::max(1, n_itiles)));
+        const dim3 grid(n_itiles, gy);
+        const size_t npart = static_cast<size_t>(n_itiles) * gy;
+        c->partials.ensure(std::max<size_t>(npart, 4 * kMaxPartialBlocks));
+#define FB_CASE(K)                                                                                            \
+    case K:                                                                                                   \
+        launchFullStream<K>(c, V, grid, shard, n_shards);                                                     \
+        break;
+        switch (c->P.kind) {
+            FB_CASE(POT_COULOMB_LJ)
+            FB_CASE(POT_COULOMB_WCA)
+            FB_CASE(POT_PM)
+            FB_CASE(POT_PMWCA)
+            FB_CASE(POT_FUNCTOR)
+            FB_CASE(POT_SPLINED)
+        default:
+            throw CudaError{"unknown potential kind"};
+        }
+#undef FB_CASE
+        launched(c, "fullStreamKernel");
+        orderedSumKernel<<<1, 1024, 0, c->stream>>>(c->partials.ptr, npart, 1, c->d_result);
+        launched(c, "orderedSumKernel");
+        return;
+    }
     const int nt = (c->n_slots + kTile - 1) / kTile;
     const size_t npart = static_cast<size_t>(nt) * (nt + 1) / 2;
     c->partials.ensure(std::max<size_t>(npart, 4 * kMaxPartialBlocks));
@@ -1761,6 +1801,50 @@ FB_API int fb_widom_batch(fb_ctx* c, int s, int ghost_group, int n_ghost_atoms, 
             }
             c->d_ghost_cm.upload(c->h_ghost.ptr, n_insertions, c->stream);
             d_cm = c->d_ghost_cm.ptr;
+        }
+        if (!molecular) { // atomic ghosts: the streaming kernel (fb_stream.cuh)
+            const int n_variants = n_insertions * n_ghost_atoms;
+            c->d_widom_partial.ensure(static_cast<size_t>(n_variants));
+            c->d_widom_du.ensure(n_insertions);
+            c->h_widom_du.ensure(n_insertions);
+            const SlotView V = makeView(c, s);
+            const int grid = (n_variants + kStreamVariants - 1) / kStreamVariants;
+            const bool dense = std::isinf(c->pair_cut2);
+            beginTiming(c, TIME_WIDOM);
+#define FB_CASE(K)                                                                                            \
+    case K:                                                                                                   \
+        if (dense) {                                                                                          \
+            widomStreamKernel<K, true><<<grid, kStreamThreads, 0, c->stream>>>(                               \
+                V, c->P, ghost_group, n_ghost_atoms, n_variants, c->d_ghost.ptr, c->d_ghost_id.ptr, c->pair_cut2, \
+                c->d_widom_partial.ptr);                                                                      \
+        }                                                                                                     \
+        else {                                                                                                \
+            widomStreamKernel<K, false><<<grid, kStreamThreads, 0, c->stream>>>(                              \
+                V, c->P, ghost_group, n_ghost_atoms, n_variants, c->d_ghost.ptr, c->d_ghost_id.ptr, c->pair_cut2, \
+                c->d_widom_partial.ptr);                                                                      \
+        }                                                                                                     \
+        launched(c, "widomStreamKernel");                                                                     \
+        widomStreamFinishKernel<K><<<(n_insertions + 127) / 128, 128, 0, c->stream>>>(                        \
+            V, c->P, n_ghost_atoms, n_insertions, c->d_ghost.ptr, c->d_ghost_id.ptr, internal,                \
+            c->d_widom_partial.ptr, c->d_widom_du.ptr);                                                       \
+        launched(c, "widomStreamFinishKernel");                                                               \
+        break;
+            switch (c->P.kind) {
+                FB_CASE(POT_COULOMB_LJ)
+                FB_CASE(POT_COULOMB_WCA)
+                FB_CASE(POT_PM)
+                FB_CASE(POT_PMWCA)
+                FB_CASE(POT_FUNCTOR)
+                FB_CASE(POT_SPLINED)
+            default:
+                throw CudaError{"unknown potential kind"};
+            }
+#undef FB_CASE
+            CUDA_CHECK(cudaMemcpyAsync(c->h_widom_du.ptr, c->d_widom_du.ptr, n_insertions * sizeof(double),
+                                       cudaMemcpyDeviceToHost, c->stream));
+            finish(c);
+            std::memcpy(du, c->h_widom_du.ptr, n_insertions * sizeof(double));
+            return;
         }
         const int bx = (n_insertions + kWidomBlock - 1) / kWidomBlock;
         const int max_split = (c->n_slots + kWidomChunk - 1) / kWidomChunk;

@@ -750,6 +750,232 @@ __global__ void __launch_bounds__(kBlock, 2)
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same three steps in ONE persistent kernel: block b walks the cells b, b + grid, … and keeps the
+// per-move and per-pair sums in registers, so nothing but the final partials leaves the SM:
+//   per cell: stage the 12 table entries of every position (accepted moves of the previous window and the
+//   2B positions of this one) → ΔQ of the commits (warps split the commits) → Q(k) updated in place →
+//   δ_m,k for the warp's moves into shared memory, R[m] in registers → rank-update of G from shared memory.
+// Dynamic shared memory (≈ 92 kB): two blocks per SM.
+// ------------------------------------------------------------------------------------------------
+template <int BT> struct KspaceSmem
+{
+    static constexpr int STRIDE = BT * 4;
+    static constexpr int KH = STRIDE == 64 ? 32 : kTileK; //!< k-vectors per pass
+    static constexpr int LD = KH + 1;
+    static constexpr int DELTA_ELEMS = STRIDE * LD > 2048 ? STRIDE * LD : 2048;
+    static constexpr size_t bytes()
+    {
+        return sizeof(double2) * (2 * 2 * kBatchMax * kCellEntries + DELTA_ELEMS + (kBlock / 32) * KH) +
+               sizeof(double) * 2 * kBatchMax + sizeof(int) * 2 * kBatchMax;
+    }
+};
+
+template <int BT>
+__global__ void __launch_bounds__(kBlock, 2)
+    batchKspaceKernel(EwaldView E, const int4* __restrict__ kn, const double* __restrict__ sqrt_ak,
+                      const int* __restrict__ cell_start, int n_cells, BatchBuffers cur, BatchBuffers prev,
+                      CommitList commit, PhaseGeometry geo, double* __restrict__ r_partials /*[grid][stride]*/,
+                      double* __restrict__ g_partials /*[grid][stride²]*/, double* __restrict__ e_partials /*[grid]*/)
+{
+    using L = KspaceSmem<BT>;
+    constexpr int STRIDE = L::STRIDE;
+    constexpr int KH = L::KH;
+    constexpr int LD = L::LD;
+    constexpr int NW = kBlock / 32;
+    constexpr int KPL = KH / 32;               // k-vectors per lane and pass
+    constexpr int MPW = STRIDE / NW;           // moves per warp: 2, 4, 8
+    constexpr int NTILE = BT * BT;
+    constexpr int KG = kBlock / NTILE;         // k sub-groups of the Gram update: 16, 4, 1
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2(*s_tab_new)[kCellEntries] = reinterpret_cast<double2(*)[kCellEntries]>(smem_raw);
+    double2(*s_tab_com)[kCellEntries] = s_tab_new + 2 * kBatchMax;
+    double2* s_delta = reinterpret_cast<double2*>(s_tab_com + 2 * kBatchMax);
+    double2(*s_dq)[KH] = reinterpret_cast<double2(*)[KH]>(s_delta + L::DELTA_ELEMS);
+    double* s_cqn = reinterpret_cast<double*>(s_dq + NW);
+    double* s_cqo = s_cqn + kBatchMax;
+    int* s_ctable = reinterpret_cast<int*>(s_cqo + kBatchMax);
+
+    const int n = cur.in->n;
+    const int ncommit = commit.n;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int tile_id = threadIdx.x % NTILE;
+    const int kg = threadIdx.x / NTILE;
+    const int ta = tile_id / BT; // this thread owns G[ta + BT·i][tm + BT·j], i ≤ j
+    const int tm = tile_id % BT;
+
+    if (static_cast<int>(threadIdx.x) < ncommit) {
+        const int m = commit.index[threadIdx.x];
+        s_cqn[threadIdx.x] = prev.in->pnew[m].w;
+        s_cqo[threadIdx.x] = prev.pold[m].w;
+        s_ctable[2 * threadIdx.x] = 2 * m * geo.table_stride;
+        s_ctable[2 * threadIdx.x + 1] = (2 * m + 1) * geo.table_stride;
+    }
+    double qn[MPW], qo[MPW], racc[MPW];
+#pragma unroll
+    for (int i = 0; i < MPW; ++i) {
+        const int m = warp * MPW + i;
+        qn[i] = (m < n) ? cur.in->pnew[m].w : 0.0;
+        qo[i] = (m < n) ? cur.pold[m].w : 0.0;
+        racc[i] = 0.0;
+    }
+    double gacc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            gacc[i][j] = 0.0;
+        }
+    }
+    double eacc = 0.0;
+
+    for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        const int p0 = __ldg(cell_start + cell);
+        const int len = __ldg(cell_start + cell + 1) - p0;
+        __syncthreads(); // the previous cell is done with the tables and tiles (and s_ctable is written)
+        {
+            const CellBase base = cellBase(__ldg(kn + p0), geo.ncc);
+            stageCellTables(s_tab_new, cur.table, nullptr, 2 * n, base, geo);
+            if (ncommit > 0) {
+                stageCellTables(s_tab_com, prev.table, s_ctable, 2 * ncommit, base, geo);
+            }
+        }
+        __syncthreads();
+        for (int pass0 = 0; pass0 < len; pass0 += KH) {
+            int li[KPL], lj[KPL], ll[KPL];
+            double2 Q[KPL];
+            double A[KPL], sA[KPL];
+            bool valid[KPL];
+#pragma unroll
+            for (int kk = 0; kk < KPL; ++kk) {
+                const int kl = pass0 + lane + 32 * kk;
+                valid[kk] = kl < len;
+                li[kk] = lj[kk] = ll[kk] = 0;
+                Q[kk] = make_double2(0, 0);
+                A[kk] = 0.0;
+                sA[kk] = 0.0;
+                if (valid[kk]) {
+                    const int k = p0 + kl;
+                    const int4 nn = __ldg(kn + k);
+                    li[kk] = nn.x & 3;
+                    lj[kk] = (nn.y + geo.ncc) & 3;
+                    ll[kk] = (nn.z + geo.ncc) & 3;
+                    Q[kk] = E.Q[k];
+                    A[kk] = E.kA[k].w;
+                    sA[kk] = __ldg(sqrt_ak + k);
+                }
+            }
+            if (ncommit > 0) {
+#pragma unroll
+                for (int kk = 0; kk < KPL; ++kk) {
+                    double2 dq = make_double2(0, 0);
+                    if (valid[kk]) {
+                        for (int a = warp; a < ncommit; a += NW) {
+                            const double2 en = cellPhase(s_tab_com[2 * a], li[kk], lj[kk], ll[kk]);
+                            const double2 eo = cellPhase(s_tab_com[2 * a + 1], li[kk], lj[kk], ll[kk]);
+                            dq.x += s_cqn[a] * en.x - s_cqo[a] * eo.x;
+                            dq.y += s_cqn[a] * en.y - s_cqo[a] * eo.y;
+                        }
+                    }
+                    s_dq[warp][lane + 32 * kk] = dq;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < KPL; ++kk) {
+                    if (valid[kk]) { // every warp adds the shares in the same order → the same Q(k) everywhere
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) {
+                            Q[kk].x += s_dq[w][lane + 32 * kk].x;
+                            Q[kk].y += s_dq[w][lane + 32 * kk].y;
+                        }
+                        if (warp == 0) {
+                            E.Q[p0 + pass0 + lane + 32 * kk] = Q[kk]; // only warps of this block touch this k
+                        }
+                    }
+                }
+            }
+            if (warp == 0) {
+#pragma unroll
+                for (int kk = 0; kk < KPL; ++kk) {
+                    eacc += A[kk] * (Q[kk].x * Q[kk].x + Q[kk].y * Q[kk].y);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MPW; ++i) {
+                const int m = warp * MPW + i;
+#pragma unroll
+                for (int kk = 0; kk < KPL; ++kk) {
+                    double2 d = make_double2(0, 0);
+                    if (valid[kk] && m < n) {
+                        const double2 en = cellPhase(s_tab_new[2 * m], li[kk], lj[kk], ll[kk]);
+                        const double2 eo = cellPhase(s_tab_new[2 * m + 1], li[kk], lj[kk], ll[kk]);
+                        d.x = qn[i] * en.x - qo[i] * eo.x;
+                        d.y = qn[i] * en.y - qo[i] * eo.y;
+                        racc[i] += A[kk] * (2.0 * (Q[kk].x * d.x + Q[kk].y * d.y) + (d.x * d.x + d.y * d.y));
+                    }
+                    s_delta[m * LD + lane + 32 * kk] = make_double2(sA[kk] * d.x, sA[kk] * d.y);
+                }
+            }
+            __syncthreads();
+            const int kend = min(KH, len - pass0);
+#pragma unroll 2
+            for (int kl = kg; kl < kend; kl += KG) {
+                double2 da[4], dm[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    da[i] = s_delta[(ta + BT * i) * LD + kl];
+                    dm[i] = s_delta[(tm + BT * i) * LD + kl];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int j = i; j < 4; ++j) {
+                        gacc[i][j] = fma(da[i].x, dm[j].x, fma(da[i].y, dm[j].y, gacc[i][j]));
+                    }
+                }
+            }
+            __syncthreads(); // s_delta and s_dq are free again
+        }
+    }
+
+    if (warp == 0) {
+        const double es = warpSum(eacc);
+        if (lane == 0) {
+            e_partials[blockIdx.x] = es;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MPW; ++i) {
+        const double rs = warpSum(racc[i]);
+        if (lane == 0) {
+            r_partials[static_cast<size_t>(blockIdx.x) * STRIDE + warp * MPW + i] = rs;
+        }
+    }
+    __syncthreads();
+    double* s_g = reinterpret_cast<double*>(s_delta); // [16][kBlock] doubles = 32 KB, thread-fastest
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s_g[(i * 4 + j) * kBlock + threadIdx.x] = gacc[i][j];
+        }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < NTILE * 16; o += kBlock) {
+        const int t = o % NTILE;
+        const int ij = o / NTILE;
+        double sum = 0.0;
+        for (int g = 0; g < KG; ++g) {
+            sum += s_g[ij * kBlock + g * NTILE + t];
+        }
+        const int a = (t / BT) + BT * (ij / 4);
+        const int m = (t % BT) + BT * (ij % 4);
+        g_partials[static_cast<size_t>(blockIdx.x) * (STRIDE * STRIDE) + a * STRIDE + m] = sum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // final ordered sums + the pair cross terms
 // result layout (doubles), S = stride:
 //   [0] Σ_k A_k|Q_k|² at window start   [1] n

@@ -101,34 +101,40 @@ void launchBatchPairFinish(fb_ctx* c, const BatchBuffers& cur, const BatchBuffer
     if (with_ewald) {
         const EwaldView E = makeEwaldView(c, 0);
         const int4* kn = c->slot[0].kn.ptr;
-        n_tiles = (E.K + kTileK - 1) / kTileK;
         n_cells = c->slot[0].n_cells;
         const int* cell_start = c->slot[0].cell_start.ptr;
-        n_gram_blocks = std::min(n_tiles, 2 * c->n_sm);
-        b.d_e_partials.ensure(static_cast<size_t>(n_cells));
-        b.d_r_partials.ensure(static_cast<size_t>(n_cells) * kBatchMax);
+        const double* ksq = c->slot[0].ksq.ptr;
+        n_gram_blocks = std::max(1, std::min(n_cells, 2 * c->n_sm));
+        b.d_e_partials.ensure(static_cast<size_t>(2 * c->n_sm));
+        b.d_r_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax);
         b.d_g_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax * kBatchMax);
-        b.d_delta.ensure(static_cast<size_t>(n_tiles) * stride * kTileK);
-        if (commit.n > 0 || want_rec_sum) {
-            batchCommitQKernel<<<n_cells, kBlock, 0, c->stream>>>(E, kn, cell_start, prev, commit, b.geo,
-                                                                  b.d_e_partials.ptr);
-            launched(c, "batchCommitQKernel");
-            n_e_rows = n_cells;
-        }
-        batchDeltaKernel<<<n_cells, kBlock, 0, c->stream>>>(E, kn, c->slot[0].ksq.ptr, cell_start, cur, b.geo, stride,
-                                                            b.d_delta.ptr, b.d_r_partials.ptr);
-        launched(c, "batchDeltaKernel");
+        (void)want_rec_sum; // the persistent kernel always produces the reciprocal sum
+        n_e_rows = n_gram_blocks;
+        n_tiles = n_gram_blocks; // rows of the R partials
+#define FB_KSPACE(BT)                                                                                         \
+    {                                                                                                         \
+        bool& configured = b.kspace_configured[BT == 4 ? 0 : (BT == 8 ? 1 : 2)];                              \
+        if (!configured) { /* per device: a context lives on one device */                                   \
+            CUDA_CHECK(cudaFuncSetAttribute(batchKspaceKernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            static_cast<int>(KspaceSmem<BT>::bytes())));                      \
+            configured = true;                                                                                \
+        }                                                                                                     \
+        batchKspaceKernel<BT><<<n_gram_blocks, kBlock, KspaceSmem<BT>::bytes(), c->stream>>>(                 \
+            E, kn, ksq, cell_start, n_cells, cur, prev, commit, b.geo, b.d_r_partials.ptr, b.d_g_partials.ptr, \
+            b.d_e_partials.ptr);                                                                              \
+    }
         switch (stride) {
         case 16:
-            batchGramKernel<4><<<n_gram_blocks, kBlock, 0, c->stream>>>(b.d_delta.ptr, n_tiles, b.d_g_partials.ptr);
+            FB_KSPACE(4)
             break;
         case 32:
-            batchGramKernel<8><<<n_gram_blocks, kBlock, 0, c->stream>>>(b.d_delta.ptr, n_tiles, b.d_g_partials.ptr);
+            FB_KSPACE(8)
             break;
         default:
-            batchGramKernel<16><<<n_gram_blocks, kBlock, 0, c->stream>>>(b.d_delta.ptr, n_tiles, b.d_g_partials.ptr);
+            FB_KSPACE(16)
         }
-        launched(c, "batchGramKernel");
+#undef FB_KSPACE
+        launched(c, "batchKspaceKernel");
     }
     if (timing) {
         CUDA_CHECK(cudaEventRecord(b.ev[3], c->stream));
@@ -138,7 +144,7 @@ void launchBatchPairFinish(fb_ctx* c, const BatchBuffers& cur, const BatchBuffer
     }
     const int finish_grid = (3 * stride + stride * stride + 1 + kBlock / 32 - 1) / (kBlock / 32); // one warp per output
     batchFinishKernel<KIND><<<finish_grid, kBlock, 0, c->stream>>>(
-        M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, n_cells, b.d_r_partials.ptr, n_gram_blocks,
+        M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, n_tiles, b.d_r_partials.ptr, n_gram_blocks,
         b.d_g_partials.ptr, n_e_rows, b.d_e_partials.ptr, b.d_result.ptr);
     launched(c, "batchFinishKernel");
     b.last_rec_fresh = n_e_rows > 0;

@@ -1,0 +1,406 @@
+// Streaming pair kernels for the two compute-bound passes (sm_100a, FP64 CUDA cores):
+//   widomStreamKernel   B ghost insertions × all particles      (WidomInsertion::_sample, src/analysis.cpp:1255-1262)
+//   fullStreamKernel    Σ_{i<j} over an all-atomic system       (GroupPairingPolicy::all, src/energy.h:1290-1326)
+// Same inner loop as batchPairKernel (fb_batch.cuh): lane ↔ particle j held in registers (two per
+// thread), the block walks "variants" (ghost atoms / particles i) staged in shared memory, two per
+// iteration; the minimum-image fold of an axis is skipped for variants at least the cutoff away from
+// both cell faces; the few pairs inside the cutoff are queued per warp in ballot order (deterministic)
+// and evaluated afterwards with all lanes busy. With a potential that has no cutoff (DENSE) every pair
+// is evaluated in place.
+#pragma once
+#include "fb_batch.cuh"
+
+namespace fbdev {
+
+constexpr int kStreamThreads = 128;
+constexpr int kStreamChunk = 2 * kStreamThreads; //!< particles j per block iteration (two per thread)
+constexpr int kStreamVariants = 64;              //!< variants per block
+constexpr int kStreamQueue = 384;                //!< queued in-range candidates per warp
+
+struct StreamFold
+{
+    double hx, hy, hz, lx, ly, lz;
+};
+
+__device__ __forceinline__ int foldFlags(const SlotView& V, const double4& a, double cut2)
+{
+    const double rc = sqrt(cut2); // +inf when some term has no cutoff
+    int fold = 0;
+    fold |= (V.len_or_zero[0] > 0.0 && !(fabs(a.x) + rc < V.half[0])) ? 1 : 0;
+    fold |= (V.len_or_zero[1] > 0.0 && !(fabs(a.y) + rc < V.half[1])) ? 2 : 0;
+    fold |= (V.len_or_zero[2] > 0.0 && !(fabs(a.z) + rc < V.half[2])) ? 4 : 0;
+    return fold;
+}
+
+/** r² of variant `a` with the thread's two particles; fold only where the flags ask for it */
+__device__ __forceinline__ void streamR2(const double4& a, int fold, const double4 (&p)[2], const StreamFold& f,
+                                         double (&r2)[2])
+{
+    double dx[2], dy[2], dz[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        dx[t] = a.x - p[t].x;
+        dy[t] = a.y - p[t].y;
+        dz[t] = a.z - p[t].z;
+    }
+    if (fold & 1) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const double ad = fabs(dx[t]);
+            dx[t] = (ad > f.hx) ? ad - f.lx : dx[t];
+        }
+    }
+    if (fold & 2) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const double ad = fabs(dy[t]);
+            dy[t] = (ad > f.hy) ? ad - f.ly : dy[t];
+        }
+    }
+    if (fold & 4) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const double ad = fabs(dz[t]);
+            dz[t] = (ad > f.hz) ? ad - f.lz : dz[t];
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        r2[t] = dx[t] * dx[t] + dy[t] * dy[t] + dz[t] * dz[t];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Widom: variant v = b · n_ghost_atoms + a (ghost atom a of insertion b). Block = 64 consecutive
+// variants, loops over ALL particles. out[v] = energy of that ghost atom with every active particle
+// outside the ghost group. Atomic ghost groups only (no mass-centre cutoff applies to them).
+// ------------------------------------------------------------------------------------------------
+template <int KIND, bool DENSE>
+__global__ void __launch_bounds__(kStreamThreads)
+    widomStreamKernel(SlotView V, PotParams P, int ghost_group, int n_ghost_atoms, int n_variants,
+                      const double4* __restrict__ ghost_posq, const int* __restrict__ ghost_id, double cut2,
+                      double* __restrict__ out /*[n_variants]*/)
+{
+    constexpr int NW = kStreamThreads / 32;
+    __shared__ double4 s_var[kStreamVariants];
+    __shared__ int s_vid[kStreamVariants];
+    __shared__ int s_vfold[kStreamVariants];
+    __shared__ double s_acc[NW][kStreamVariants];
+    __shared__ double s_qr[DENSE ? 1 : NW][DENSE ? 1 : kStreamQueue];
+    __shared__ unsigned s_qe[DENSE ? 1 : NW][DENSE ? 1 : kStreamQueue];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int v0 = blockIdx.x * kStreamVariants;
+    const int nv = min(kStreamVariants, n_variants - v0);
+    const StreamFold f{V.half[0], V.half[1], V.half[2], V.len_or_zero[0], V.len_or_zero[1], V.len_or_zero[2]};
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+
+    for (int v = threadIdx.x; v < kStreamVariants; v += kStreamThreads) {
+        double4 a = make_double4(nan, 0, 0, 0);
+        int id = 0;
+        if (v < nv) {
+            a = ghost_posq[v0 + v];
+            id = ghost_id[(v0 + v) % n_ghost_atoms];
+        }
+        s_var[v] = a;
+        s_vid[v] = id;
+        s_vfold[v] = v < nv ? foldFlags(V, a, cut2) : 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            s_acc[w][v] = 0.0;
+        }
+    }
+    __syncthreads();
+
+    int queued = 0; // warp-uniform
+    auto flush = [&]() {
+        for (int e = lane; e < queued; e += 32) {
+            const unsigned ent = s_qe[warp][e];
+            const int v = ent & 0xffu;
+            const int j = ent >> 8;
+            const double4 a = s_var[v];
+            s_qr[warp][e] = pairEnergy<KIND>(P, s_vid[v], V.atom_id[j], a.w, V.posq[j].w, s_qr[warp][e]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < kStreamVariants / 32; ++h) {
+            const int myv = lane + 32 * h;
+            double acc = 0.0;
+            for (int e = 0; e < queued; ++e) {
+                if (static_cast<int>(s_qe[warp][e] & 0xffu) == myv) {
+                    acc += s_qr[warp][e];
+                }
+            }
+            s_acc[warp][myv] += acc;
+        }
+        __syncwarp();
+        queued = 0;
+    };
+
+    for (int base = 0; base < V.n_slots; base += kStreamChunk) {
+        double4 p[2];
+        int pid[2], pj[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int j = base + t * kStreamThreads + threadIdx.x;
+            pj[t] = j;
+            pid[t] = 0;
+            p[t] = make_double4(nan, 0, 0, 0);
+            if (j < V.n_slots) {
+                const int g = V.gid[j];
+                if (g >= 0 && g != ghost_group) {
+                    p[t] = V.posq[j];
+                    pid[t] = V.atom_id[j];
+                }
+            }
+        }
+        for (int vv = 0; vv < nv; vv += 2) {
+            double4 a[2];
+            int fold[2];
+            double r2[2][2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int v = min(vv + u, nv - 1);
+                a[u] = s_var[v];
+                fold[u] = s_vfold[v];
+            }
+            bool any_in = false;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                streamR2(a[u], fold[u], p, f, r2[u]);
+                any_in = any_in || (r2[u][0] < cut2) || (r2[u][1] < cut2);
+            }
+            if (!__any_sync(0xffffffffu, any_in)) {
+                continue;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int v = vv + u;
+                if (v >= nv) {
+                    continue;
+                }
+                if (DENSE) {
+                    double e = 0.0;
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        if (r2[u][t] < cut2) {
+                            e += pairEnergy<KIND>(P, s_vid[v], pid[t], a[u].w, p[t].w, r2[u][t]);
+                        }
+                    }
+                    e = warpSum(e);
+                    if (lane == 0) {
+                        s_acc[warp][v] += e;
+                    }
+                }
+                else {
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const bool in = r2[u][t] < cut2;
+                        const unsigned mask = __ballot_sync(0xffffffffu, in);
+                        if (in) {
+                            const int at = queued + __popc(mask & ((1u << lane) - 1u));
+                            s_qe[warp][at] = static_cast<unsigned>(v) | (static_cast<unsigned>(pj[t]) << 8);
+                            s_qr[warp][at] = r2[u][t];
+                        }
+                        queued += __popc(mask);
+                    }
+                }
+            }
+            if (!DENSE) {
+                __syncwarp();
+                if (queued > kStreamQueue - 128) {
+                    flush();
+                }
+            }
+        }
+    }
+    if (!DENSE) {
+        flush();
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < nv; v += kStreamThreads) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            s += s_acc[w][v];
+        }
+        out[v0 + v] = s;
+    }
+}
+
+/** du[b] = Σ_a out[b·n_g + a] + ghost-internal pairs (atomic ghosts with the internal flag) */
+template <int KIND>
+__global__ void widomStreamFinishKernel(SlotView V, PotParams P, int n_ghost_atoms, int n_insertions,
+                                        const double4* __restrict__ ghost_posq, const int* __restrict__ ghost_id,
+                                        int internal, const double* __restrict__ per_variant, double* __restrict__ du)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_insertions) {
+        return;
+    }
+    double e = 0.0;
+    for (int a = 0; a < n_ghost_atoms; ++a) {
+        e += per_variant[static_cast<size_t>(b) * n_ghost_atoms + a];
+    }
+    if (internal) {
+        const double4* g = ghost_posq + static_cast<size_t>(b) * n_ghost_atoms;
+        for (int i = 0; i < n_ghost_atoms - 1; ++i) {
+            for (int j = i + 1; j < n_ghost_atoms; ++j) {
+                const double r2 = minImageR2(V, g[i].x, g[i].y, g[i].z, g[j].x, g[j].y, g[j].z);
+                e += pairEnergy<KIND>(P, ghost_id[i], ghost_id[j], g[i].w, g[j].w, r2);
+            }
+        }
+    }
+    du[b] = e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Full energy of an all-atomic system: block (bi, bj ≥ bi·…) — variants are the particles i of tile bi
+// (64 per block row), the block walks the particles j > i. grid.x = i-tiles of 64; every block loops over
+// the j-chunks from its own tile on; shard/n_shards deal the i-tiles round robin (multi-GPU).
+// partials[blockIdx.x] = Σ over the block's pairs.
+// ------------------------------------------------------------------------------------------------
+template <int KIND, bool DENSE>
+__global__ void __launch_bounds__(kStreamThreads)
+    fullStreamKernel(SlotView V, PotParams P, double cut2, int j_split, int shard, int n_shards,
+                     double* __restrict__ partials /*[gridDim.x · gridDim.y]*/)
+{
+    constexpr int NW = kStreamThreads / 32;
+    __shared__ double4 s_var[kStreamVariants];
+    __shared__ int s_vid[kStreamVariants];
+    __shared__ int s_vfold[kStreamVariants];
+    __shared__ double s_qr[DENSE ? 1 : NW][DENSE ? 1 : kStreamQueue];
+    __shared__ unsigned s_qe[DENSE ? 1 : NW][DENSE ? 1 : kStreamQueue];
+    __shared__ double s_sum[NW];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int i0 = blockIdx.x * kStreamVariants;
+    const StreamFold f{V.half[0], V.half[1], V.half[2], V.len_or_zero[0], V.len_or_zero[1], V.len_or_zero[2]};
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const size_t out_index = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
+    if (static_cast<int>(blockIdx.x) % n_shards != shard) {
+        if (threadIdx.x == 0) {
+            partials[out_index] = 0.0;
+        }
+        return;
+    }
+    for (int v = threadIdx.x; v < kStreamVariants; v += kStreamThreads) {
+        const int i = i0 + v;
+        double4 a = make_double4(nan, 0, 0, 0);
+        int id = 0;
+        if (i < V.n_slots && V.gid[i] >= 0) {
+            a = V.posq[i];
+            id = V.atom_id[i];
+        }
+        s_var[v] = a;
+        s_vid[v] = id;
+        s_vfold[v] = (a.x == a.x) ? foldFlags(V, a, cut2) : 0;
+    }
+    __syncthreads();
+
+    double esum = 0.0;
+    int queued = 0;
+    auto flush = [&]() {
+        for (int e = lane; e < queued; e += 32) {
+            const unsigned ent = s_qe[warp][e];
+            const int v = ent & 0xffu;
+            const int j = ent >> 8;
+            const double4 a = s_var[v];
+            esum += pairEnergy<KIND>(P, s_vid[v], V.atom_id[j], a.w, V.posq[j].w, s_qr[warp][e]);
+        }
+        __syncwarp();
+        queued = 0;
+    };
+
+    // j-chunks from the one containing i0 on; blockIdx.y takes every gridDim.y-th chunk
+    const int first_chunk = i0 / kStreamChunk;
+    const int n_chunks = (V.n_slots + kStreamChunk - 1) / kStreamChunk;
+    (void)j_split;
+    for (int chunk = first_chunk + blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
+        const int base = chunk * kStreamChunk;
+        double4 p[2];
+        int pid[2], pj[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int j = base + t * kStreamThreads + threadIdx.x;
+            pj[t] = j;
+            pid[t] = 0;
+            p[t] = make_double4(nan, 0, 0, 0);
+            if (j < V.n_slots && V.gid[j] >= 0) {
+                p[t] = V.posq[j];
+                pid[t] = V.atom_id[j];
+            }
+        }
+        const bool diagonal = base < i0 + kStreamVariants; // some j of this chunk are ≤ some i of the tile
+        for (int vv = 0; vv < kStreamVariants; vv += 2) {
+            double4 a[2];
+            int fold[2];
+            double r2[2][2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                a[u] = s_var[vv + u];
+                fold[u] = s_vfold[vv + u];
+            }
+            bool in[2][2];
+            bool any_in = false;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                streamR2(a[u], fold[u], p, f, r2[u]);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    in[u][t] = r2[u][t] < cut2 && (!diagonal || pj[t] > i0 + vv + u);
+                    any_in = any_in || in[u][t];
+                }
+            }
+            if (!__any_sync(0xffffffffu, any_in)) {
+                continue;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (DENSE) {
+                        if (in[u][t]) {
+                            esum += pairEnergy<KIND>(P, s_vid[vv + u], pid[t], a[u].w, p[t].w, r2[u][t]);
+                        }
+                    }
+                    else {
+                        const unsigned mask = __ballot_sync(0xffffffffu, in[u][t]);
+                        if (in[u][t]) {
+                            const int at = queued + __popc(mask & ((1u << lane) - 1u));
+                            s_qe[warp][at] = static_cast<unsigned>(vv + u) | (static_cast<unsigned>(pj[t]) << 8);
+                            s_qr[warp][at] = r2[u][t];
+                        }
+                        queued += __popc(mask);
+                    }
+                }
+            }
+            if (!DENSE) {
+                __syncwarp();
+                if (queued > kStreamQueue - 128) {
+                    flush();
+                }
+            }
+        }
+    }
+    if (!DENSE) {
+        flush();
+    }
+    esum = warpSum(esum);
+    if (lane == 0) {
+        s_sum[warp] = esum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            s += s_sum[w];
+        }
+        partials[out_index] = s;
+    }
+}
+
+} // namespace fbdev

@@ -338,3 +338,23 @@ def test_widom_sharded_matches_unsharded():
     wc = c.widom_create(analysis)
     assert c.widom_sample_sharded(wc, 0, 1) == 101
     assert c.widom_result(wc)["sum_exp"] == rr["sum_exp"]
+
+
+def test_tempering_replicas_on_device():
+    """Hamiltonian parallel tempering (examples/temper semantics, src/move.cpp:844-968) with the replicas'
+    energies on the B200 terms: same exchanges and final states as the oracle replicas"""
+    import faunus_b200.native as native
+    from faunus_b200.replica import run_local_replicas
+    from _oraclelib import oracle_api
+    from test_tempering_cpu import electrolyte_replicas
+    cfgs = electrolyte_replicas(2)
+    want = run_local_replicas(oracle_api(), cfgs, sweeps=20)
+    got = run_local_replicas(native.sim_library(), cfgs, sweeps=20)
+    assert all(r["error"] == "" for r in got)
+    for w, g in zip(want, got):
+        assert np.array_equal(np.array(w["xyzq"]), np.array(g["xyzq"]))   # identical trajectories
+        assert g["energy"] == pytest.approx(w["energy"], rel=1e-10)
+        assert abs(g["drift"]) < 1e-9
+        tw = [m["temper"] for m in w["moves"] if "temper" in m][0]
+        tg = [m["temper"] for m in g["moves"] if "temper" in m][0]
+        assert tw["exchange"] == tg["exchange"]
