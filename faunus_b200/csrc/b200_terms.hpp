@@ -741,7 +741,7 @@ class B200WindowEvaluator : public WindowEvaluator
 
     int capacity() const override { return window_capacity; }
 
-    void evaluate(const std::vector<WindowProposal>& window, int n) override
+    void submit(const std::vector<WindowProposal>& window, int n) override
     {
         moves.resize(static_cast<size_t>(n));
         const Space& trial = *mc.trial_state.spc;
@@ -760,9 +760,11 @@ class B200WindowEvaluator : public WindowEvaluator
         }
         dev->fast_staged = false;
         dev->cache_valid = false;
-        fbCheck(fb_batch_trial(dev->ctx, n, moves.data(), with_ewald ? 1 : 0, &res), dev->ctx, "fb_batch_trial");
+        fbCheck(fb_batch_submit(dev->ctx, n, moves.data(), with_ewald ? 1 : 0), dev->ctx, "fb_batch_submit");
         rec_change.assign(static_cast<size_t>(n), 0.0);
     }
+
+    void wait() override { fbCheck(fb_batch_wait(dev->ctx, &res), dev->ctx, "fb_batch_wait"); }
 
     bool energies(int m, const std::vector<unsigned char>& accepted, const WindowProposal& proposal,
                   double& new_energy, double& old_energy) override

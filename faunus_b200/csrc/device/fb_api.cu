@@ -210,6 +210,9 @@ struct fb_ctx
         bool q_dirty = false;      //!< slot 0's Q(k) is ahead of slot 1's
         bool rec_known = false;    //!< rec_sum is Σ A_k|Q_k|² of slot 0's current Q(k)
         bool last_rec_fresh = false; //!< the last window recomputed that sum on the device
+        bool in_flight = false;      //!< fb_batch_submit done, fb_batch_wait pending
+        int flight_n = 0, flight_stride = 0, flight_with_ewald = 0;
+        bool flight_timing = false;
         bool kspace_configured[3] = {false, false, false}; //!< dynamic shared memory opt-in done (stride 16/32/64)
         double rec_sum = 0;
         PhaseGeometry geo{};

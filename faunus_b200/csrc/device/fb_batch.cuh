@@ -137,46 +137,14 @@ __global__ void __launch_bounds__(kBlock)
 // ------------------------------------------------------------------------------------------------
 // window set-up: old positions from the (committed) mirror and the per-axis phase tables
 // ------------------------------------------------------------------------------------------------
-/** position and type of `slot` at window start: the previous window's accepted trial if it moved this atom */
-__device__ __forceinline__ double4 committedParticle(const SlotView& M0, const BatchBuffers& prev, int ncommit,
-                                                     const int* s_cslot, const int* s_cindex, int slot, int& id)
-{
-    int hit = -1;
-    for (int a = 0; a < ncommit; ++a) {
-        if (s_cslot[a] == slot) {
-            hit = s_cindex[a];
-        }
-    }
-    if (hit >= 0) {
-        id = prev.in->id[hit];
-        return prev.in->pnew[hit];
-    }
-    id = M0.atom_id[slot];
-    return M0.posq[slot];
-}
-
 /**
- * Block 0 also writes the previous window's accepted positions into both mirrors; every read of a
- * possibly committed slot in THIS kernel goes through committedParticle, so there is no race. The
- * kernels that follow in the stream see the committed mirror.
+ * Window set-up, one block: the previous window's accepted trial positions go into both mirrors, then the
+ * old positions of this window's atoms are gathered from the (now committed) mirror.
  */
-__global__ void __launch_bounds__(kBlock)
-    batchPhaseKernel(SlotView M0, SlotView M1, BatchBuffers cur, BatchBuffers prev, CommitList commit, PhaseGeometry geo)
+__global__ void __launch_bounds__(2 * kBatchMax)
+    batchPrepKernel(SlotView M0, SlotView M1, BatchBuffers cur, BatchBuffers prev, CommitList commit)
 {
-    __shared__ int s_cslot[kBatchMax], s_cindex[kBatchMax];
     if (static_cast<int>(threadIdx.x) < commit.n) {
-        s_cindex[threadIdx.x] = commit.index[threadIdx.x];
-        s_cslot[threadIdx.x] = prev.in->slot[commit.index[threadIdx.x]];
-    }
-    const int n = cur.in->n;
-    __syncthreads();
-    const int tid = blockIdx.x * kBlock + threadIdx.x;
-    if (tid < n) {
-        int id;
-        cur.pold[tid] = committedParticle(M0, prev, commit.n, s_cslot, s_cindex, cur.in->slot[tid], id);
-        cur.idold[tid] = id;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < commit.n) {
         const int m = commit.index[threadIdx.x];
         const int s = prev.in->slot[m];
         const double4 p = prev.in->pnew[m];
@@ -186,17 +154,25 @@ __global__ void __launch_bounds__(kBlock)
         M1.posq[s] = p;
         M1.atom_id[s] = id;
     }
-    if (!cur.in->with_ewald) {
-        return;
+    __syncthreads(); // global writes of this block are visible to its own threads after the barrier
+    if (static_cast<int>(threadIdx.x) < cur.in->n) {
+        const int s = cur.in->slot[threadIdx.x];
+        cur.pold[threadIdx.x] = M0.posq[s];
+        cur.idold[threadIdx.x] = M0.atom_id[s];
     }
+}
+
+/** per-axis phase tables e^{i 2π n x / L} of the 2n positions of the window (after batchPrepKernel) */
+__global__ void __launch_bounds__(kBlock) batchPhaseKernel(BatchBuffers cur, PhaseGeometry geo)
+{
+    const int n = cur.in->n;
+    const int tid = blockIdx.x * kBlock + threadIdx.x;
     const int total = 2 * n * geo.table_stride;
     for (int t = tid; t < total; t += gridDim.x * kBlock) {
         const int variant = t / geo.table_stride;
         const int e = t - variant * geo.table_stride;
         const int m = variant >> 1;
-        int unused_id;
-        const double4 p = (variant & 1) ? committedParticle(M0, prev, commit.n, s_cslot, s_cindex, cur.in->slot[m], unused_id)
-                                        : cur.in->pnew[m];
+        const double4 p = (variant & 1) ? cur.pold[m] : cur.in->pnew[m];
         int axis, nn;
         if (e <= geo.ncc) {
             axis = 0;
@@ -757,16 +733,42 @@ __global__ void __launch_bounds__(kBlock, 2)
 //   δ_m,k for the warp's moves into shared memory, R[m] in registers → rank-update of G from shared memory.
 // Dynamic shared memory (≈ 92 kB): two blocks per SM.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cpAsync16(void* smem, const void* gmem)
+{
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cpAsync8(void* smem, const void* gmem)
+{
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+/** Everything one cell needs, staged by cp.async (LDGSTS) while the previous cell is being processed */
+template <int STRIDE> struct CellStage
+{
+    double2 tab_new[2 * STRIDE][kCellEntries];
+    double2 tab_com[2 * STRIDE][kCellEntries];
+    int4 kn[kTileK];
+    double2 Q[kTileK];
+    double A[kTileK];
+    double sA[kTileK];
+};
+
 template <int BT> struct KspaceSmem
 {
     static constexpr int STRIDE = BT * 4;
     static constexpr int KH = STRIDE == 64 ? 32 : kTileK; //!< k-vectors per pass
     static constexpr int LD = KH + 1;
     static constexpr int DELTA_ELEMS = STRIDE * LD > 2048 ? STRIDE * LD : 2048;
+    static constexpr int NBUF = STRIDE == 64 ? 1 : 2; //!< double-buffered staging where two blocks per SM still fit
+    static constexpr int MAX_CELLS = 32;              //!< cells per block held in the list (more: extra rounds)
     static constexpr size_t bytes()
     {
-        return sizeof(double2) * (2 * 2 * kBatchMax * kCellEntries + DELTA_ELEMS + (kBlock / 32) * KH) +
-               sizeof(double) * 2 * kBatchMax + sizeof(int) * 2 * kBatchMax;
+        return sizeof(CellStage<STRIDE>) * NBUF + sizeof(double2) * (DELTA_ELEMS + (kBlock / 32) * KH) +
+               sizeof(double) * 2 * kBatchMax + sizeof(int) * 2 * kBatchMax + sizeof(int4) * 2 * MAX_CELLS;
     }
 };
 
@@ -781,23 +783,25 @@ __global__ void __launch_bounds__(kBlock, 2)
     constexpr int STRIDE = L::STRIDE;
     constexpr int KH = L::KH;
     constexpr int LD = L::LD;
+    constexpr int NBUF = L::NBUF;
     constexpr int NW = kBlock / 32;
     constexpr int KPL = KH / 32;               // k-vectors per lane and pass
     constexpr int MPW = STRIDE / NW;           // moves per warp: 2, 4, 8
     constexpr int NTILE = BT * BT;
     constexpr int KG = kBlock / NTILE;         // k sub-groups of the Gram update: 16, 4, 1
+    using Stage = CellStage<STRIDE>;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2(*s_tab_new)[kCellEntries] = reinterpret_cast<double2(*)[kCellEntries]>(smem_raw);
-    double2(*s_tab_com)[kCellEntries] = s_tab_new + 2 * kBatchMax;
-    double2* s_delta = reinterpret_cast<double2*>(s_tab_com + 2 * kBatchMax);
+    Stage* stage = reinterpret_cast<Stage*>(smem_raw);
+    double2* s_delta = reinterpret_cast<double2*>(stage + NBUF);
     double2(*s_dq)[KH] = reinterpret_cast<double2(*)[KH]>(s_delta + L::DELTA_ELEMS);
     double* s_cqn = reinterpret_cast<double*>(s_dq + NW);
     double* s_cqo = s_cqn + kBatchMax;
     int* s_ctable = reinterpret_cast<int*>(s_cqo + kBatchMax);
+    int4* s_cell = reinterpret_cast<int4*>(s_ctable + 2 * kBatchMax); // {p0, len, –, –} and {nx0, ny0, nz0, –}
 
     const int n = cur.in->n;
-    const int ncommit = commit.n;
+    const int ncommit = min(commit.n, STRIDE);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int tile_id = threadIdx.x % NTILE;
@@ -805,6 +809,8 @@ __global__ void __launch_bounds__(kBlock, 2)
     const int ta = tile_id / BT; // this thread owns G[ta + BT·i][tm + BT·j], i ≤ j
     const int tm = tile_id % BT;
 
+    // the cells of this block: b, b + grid, …
+    const int my_cells = (n_cells - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     if (static_cast<int>(threadIdx.x) < ncommit) {
         const int m = commit.index[threadIdx.x];
         s_cqn[threadIdx.x] = prev.in->pnew[m].w;
@@ -812,6 +818,59 @@ __global__ void __launch_bounds__(kBlock, 2)
         s_ctable[2 * threadIdx.x] = 2 * m * geo.table_stride;
         s_ctable[2 * threadIdx.x + 1] = (2 * m + 1) * geo.table_stride;
     }
+    auto loadCellList = [&](int first) { // entries [first, first + MAX_CELLS) of this block's cell sequence
+        if (static_cast<int>(threadIdx.x) < L::MAX_CELLS && first + static_cast<int>(threadIdx.x) < my_cells) {
+            const int cell = blockIdx.x + (first + threadIdx.x) * gridDim.x;
+            const int p0 = __ldg(cell_start + cell);
+            const int len = __ldg(cell_start + cell + 1) - p0;
+            const CellBase base = cellBase(__ldg(kn + p0), geo.ncc);
+            s_cell[2 * threadIdx.x] = make_int4(p0, len, 0, 0);
+            s_cell[2 * threadIdx.x + 1] = make_int4(base.nx, base.ny, base.nz, 0);
+        }
+    };
+    loadCellList(0);
+    __syncthreads();
+
+    // asynchronous staging of cell number `c` (in this block's sequence) into buffer `buf`
+    auto issue = [&](int c, int buf) {
+        const int4 info = s_cell[2 * (c % L::MAX_CELLS)];
+        const int4 bs = s_cell[2 * (c % L::MAX_CELLS) + 1];
+        Stage& st = stage[buf];
+        const int n_new = 2 * n * kCellEntries;
+        const int n_all = n_new + 2 * ncommit * kCellEntries;
+        for (int e = threadIdx.x; e < n_all; e += kBlock) {
+            const bool is_new = e < n_new;
+            const int ee = is_new ? e : e - n_new;
+            const int v = ee / kCellEntries;
+            const int t = ee - v * kCellEntries;
+            const int i = t & 3;
+            int offset;
+            if (t < 4) {
+                offset = min(bs.x + i, geo.ncc);
+            }
+            else if (t < 8) {
+                offset = (geo.ncc + 1) + min(bs.y + i, geo.ncc) + geo.ncc;
+            }
+            else {
+                offset = (geo.ncc + 1) + (2 * geo.ncc + 1) + min(bs.z + i, geo.ncc) + geo.ncc;
+            }
+            if (is_new) {
+                cpAsync16(&st.tab_new[v][t], cur.table + v * geo.table_stride + offset);
+            }
+            else {
+                cpAsync16(&st.tab_com[v][t], prev.table + s_ctable[v] + offset);
+            }
+        }
+        if (static_cast<int>(threadIdx.x) < info.y) {
+            const int k = info.x + threadIdx.x;
+            cpAsync16(&st.kn[threadIdx.x], kn + k);
+            cpAsync16(&st.Q[threadIdx.x], E.Q + k);
+            cpAsync8(&st.A[threadIdx.x], &E.kA[k].w);
+            cpAsync8(&st.sA[threadIdx.x], sqrt_ak + k);
+        }
+        cpAsyncCommit();
+    };
+
     double qn[MPW], qo[MPW], racc[MPW];
 #pragma unroll
     for (int i = 0; i < MPW; ++i) {
@@ -830,18 +889,25 @@ __global__ void __launch_bounds__(kBlock, 2)
     }
     double eacc = 0.0;
 
-    for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
-        const int p0 = __ldg(cell_start + cell);
-        const int len = __ldg(cell_start + cell + 1) - p0;
-        __syncthreads(); // the previous cell is done with the tables and tiles (and s_ctable is written)
-        {
-            const CellBase base = cellBase(__ldg(kn + p0), geo.ncc);
-            stageCellTables(s_tab_new, cur.table, nullptr, 2 * n, base, geo);
-            if (ncommit > 0) {
-                stageCellTables(s_tab_com, prev.table, s_ctable, 2 * ncommit, base, geo);
-            }
+    if (my_cells > 0) {
+        issue(0, 0);
+    }
+    for (int c = 0; c < my_cells; ++c) {
+        const int buf = NBUF == 2 ? (c & 1) : 0;
+        const int4 info = s_cell[2 * (c % L::MAX_CELLS)];
+        const int p0 = info.x;
+        const int len = info.y;
+        cpAsyncWaitAll();
+        __syncthreads(); // cell c is staged for everybody; everybody is done with cell c − 1
+        if ((c + 1) % L::MAX_CELLS == 0 && c + 1 < my_cells) { // refill the cell list (rare: > 32 cells per block)
+            __syncthreads();
+            loadCellList(c + 1);
+            __syncthreads();
         }
-        __syncthreads();
+        if (NBUF == 2 && c + 1 < my_cells) {
+            issue(c + 1, buf ^ 1); // lands while this cell is processed
+        }
+        const Stage& st = stage[buf];
         for (int pass0 = 0; pass0 < len; pass0 += KH) {
             int li[KPL], lj[KPL], ll[KPL];
             double2 Q[KPL];
@@ -856,14 +922,13 @@ __global__ void __launch_bounds__(kBlock, 2)
                 A[kk] = 0.0;
                 sA[kk] = 0.0;
                 if (valid[kk]) {
-                    const int k = p0 + kl;
-                    const int4 nn = __ldg(kn + k);
+                    const int4 nn = st.kn[kl];
                     li[kk] = nn.x & 3;
                     lj[kk] = (nn.y + geo.ncc) & 3;
                     ll[kk] = (nn.z + geo.ncc) & 3;
-                    Q[kk] = E.Q[k];
-                    A[kk] = E.kA[k].w;
-                    sA[kk] = __ldg(sqrt_ak + k);
+                    Q[kk] = st.Q[kl];
+                    A[kk] = st.A[kl];
+                    sA[kk] = st.sA[kl];
                 }
             }
             if (ncommit > 0) {
@@ -872,8 +937,8 @@ __global__ void __launch_bounds__(kBlock, 2)
                     double2 dq = make_double2(0, 0);
                     if (valid[kk]) {
                         for (int a = warp; a < ncommit; a += NW) {
-                            const double2 en = cellPhase(s_tab_com[2 * a], li[kk], lj[kk], ll[kk]);
-                            const double2 eo = cellPhase(s_tab_com[2 * a + 1], li[kk], lj[kk], ll[kk]);
+                            const double2 en = cellPhase(st.tab_com[2 * a], li[kk], lj[kk], ll[kk]);
+                            const double2 eo = cellPhase(st.tab_com[2 * a + 1], li[kk], lj[kk], ll[kk]);
                             dq.x += s_cqn[a] * en.x - s_cqo[a] * eo.x;
                             dq.y += s_cqn[a] * en.y - s_cqo[a] * eo.y;
                         }
@@ -890,7 +955,7 @@ __global__ void __launch_bounds__(kBlock, 2)
                             Q[kk].y += s_dq[w][lane + 32 * kk].y;
                         }
                         if (warp == 0) {
-                            E.Q[p0 + pass0 + lane + 32 * kk] = Q[kk]; // only warps of this block touch this k
+                            E.Q[p0 + pass0 + lane + 32 * kk] = Q[kk]; // only this block touches the cell's k-vectors
                         }
                     }
                 }
@@ -908,8 +973,8 @@ __global__ void __launch_bounds__(kBlock, 2)
                 for (int kk = 0; kk < KPL; ++kk) {
                     double2 d = make_double2(0, 0);
                     if (valid[kk] && m < n) {
-                        const double2 en = cellPhase(s_tab_new[2 * m], li[kk], lj[kk], ll[kk]);
-                        const double2 eo = cellPhase(s_tab_new[2 * m + 1], li[kk], lj[kk], ll[kk]);
+                        const double2 en = cellPhase(st.tab_new[2 * m], li[kk], lj[kk], ll[kk]);
+                        const double2 eo = cellPhase(st.tab_new[2 * m + 1], li[kk], lj[kk], ll[kk]);
                         d.x = qn[i] * en.x - qo[i] * eo.x;
                         d.y = qn[i] * en.y - qo[i] * eo.y;
                         racc[i] += A[kk] * (2.0 * (Q[kk].x * d.x + Q[kk].y * d.y) + (d.x * d.x + d.y * d.y));
@@ -936,6 +1001,9 @@ __global__ void __launch_bounds__(kBlock, 2)
                 }
             }
             __syncthreads(); // s_delta and s_dq are free again
+        }
+        if (NBUF == 1 && c + 1 < my_cells) {
+            issue(c + 1, 0); // single buffer: after the cell is done (waited for at the top of the loop)
         }
     }
 
@@ -998,22 +1066,19 @@ __device__ __forceinline__ double warpColumnSum(const double* __restrict__ a, in
     return warpSum(s);
 }
 
-/** one warp per output: 2S pair sums, S reciprocal sums, S² cross entries, 1 reciprocal start sum */
+/** pair side, one warp per output: 2S pair sums and the S² cross entries (4 pair energies each, a < m) */
 template <int KIND>
 __global__ void __launch_bounds__(kBlock)
-    batchFinishKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, int n_pair_blocks,
-                      const double* __restrict__ pair_partials, int n_r_rows, const double* __restrict__ r_partials,
-                      int n_g_rows, const double* __restrict__ g_partials, int n_e_rows,
-                      const double* __restrict__ e_partials, double* __restrict__ result)
+    batchPairFinishKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, int n_pair_blocks,
+                          const double* __restrict__ pair_partials, double* __restrict__ result)
 {
     const int n = cur.in->n;
-    const int with_ewald = cur.in->with_ewald;
     const int S = stride;
     const int lane = threadIdx.x & 31;
     const int w = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     double* u = result + 8;
     double* cross = result + 8 + 3 * S;
-    if (w < 2 * S) { // pair sums: variant order new/old interleaved → split
+    if (w < 2 * S) { // variant order new/old interleaved → split
         double s = 0.0;
         if (w < 2 * n) {
             s = warpColumnSum(pair_partials, n_pair_blocks, 2 * static_cast<size_t>(S), w, lane);
@@ -1022,26 +1087,12 @@ __global__ void __launch_bounds__(kBlock)
             u[(w & 1) * S + (w >> 1)] = s;
         }
     }
-    else if (w < 3 * S) {
-        const int m = w - 2 * S;
-        double s = 0.0;
-        if (with_ewald && m < n) {
-            s = warpColumnSum(r_partials, n_r_rows, static_cast<size_t>(S), m, lane);
-        }
-        if (lane == 0) {
-            u[2 * S + m] = s;
-        }
-    }
-    else if (w < 3 * S + S * S) {
-        const int t = w - 3 * S;
+    else if (w < 2 * S + S * S) {
+        const int t = w - 2 * S;
         const int a = t / S;
         const int m = t % S;
-        double g = 0.0;
         double cn = 0.0, co = 0.0, cmax = 0.0;
         if (a < m && m < n) {
-            if (with_ewald) {
-                g = warpColumnSum(g_partials, n_g_rows, static_cast<size_t>(S) * S, t, lane);
-            }
             // how the energies of move m change when the earlier move a has been accepted: lanes 0..3 take
             // the four pair energies u(new_m|old_m , new_a|old_a)
             double term = 0.0;
@@ -1069,13 +1120,47 @@ __global__ void __launch_bounds__(kBlock)
             cross[t] = cn;
             cross[S * S + t] = co;
             cross[2 * S * S + t] = cmax;
+        }
+    }
+}
+
+/** k-space side, one warp per output: S reciprocal sums R, S² Gram entries G (a < m), the start sum */
+__global__ void __launch_bounds__(kBlock)
+    batchKspaceFinishKernel(BatchBuffers cur, int stride, int with_ewald, int n_rows, const double* __restrict__ r_partials,
+                            const double* __restrict__ g_partials, const double* __restrict__ e_partials,
+                            double* __restrict__ result)
+{
+    const int n = cur.in->n;
+    const int S = stride;
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    double* u = result + 8;
+    double* cross = result + 8 + 3 * S;
+    if (w < S) {
+        double s = 0.0;
+        if (with_ewald && w < n) {
+            s = warpColumnSum(r_partials, n_rows, static_cast<size_t>(S), w, lane);
+        }
+        if (lane == 0) {
+            u[2 * S + w] = s;
+        }
+    }
+    else if (w < S + S * S) {
+        const int t = w - S;
+        const int a = t / S;
+        const int m = t % S;
+        double g = 0.0;
+        if (with_ewald && a < m && m < n) {
+            g = warpColumnSum(g_partials, n_rows, static_cast<size_t>(S) * S, t, lane);
+        }
+        if (lane == 0) {
             cross[3 * S * S + t] = g;
         }
     }
-    else if (w == 3 * S + S * S) {
+    else if (w == S + S * S) {
         double e = 0.0;
-        if (with_ewald && n_e_rows > 0) {
-            e = warpColumnSum(e_partials, n_e_rows, 1, 0, lane);
+        if (with_ewald && n_rows > 0) {
+            e = warpColumnSum(e_partials, n_rows, 1, 0, lane);
         }
         if (lane == 0) {
             result[0] = e;

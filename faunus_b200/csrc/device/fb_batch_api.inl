@@ -66,22 +66,32 @@ void launchBatchCommit(fb_ctx* c, bool with_ewald, int* n_blocks_out)
     }
 }
 
-/** launches of one window after the phase kernel: pair, k-space (commit-Q, δ, Gram), final sums */
+/**
+ * Launches of one window. Main stream: prep → phase tables → k-space → k-space sums; pair stream (forked
+ * after prep, joined before the copy-out): pair kernel → pair sums + cross terms. Serialised on the
+ * main stream when per-kernel timing is on.
+ */
 template <int KIND>
-void launchBatchPairFinish(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, const CommitList& commit,
-                           int stride, int n_pair_blocks, bool with_ewald, bool want_rec_sum, bool timing)
+void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, const CommitList& commit, int n_moves,
+                  int stride, bool with_ewald, bool timing)
 {
     auto& b = c->batch;
     const SlotView M0 = makeView(c, 0);
-    const int n_now = b.h_in.ptr->n;
-    const dim3 pair_grid(n_pair_blocks, (2 * n_now + kPairVariantsPerBlock - 1) / kPairVariantsPerBlock);
-    // with a k-space part the pair kernel runs on its own stream beside it (serialised when timing per kernel)
+    batchPrepKernel<<<1, 2 * kBatchMax, 0, c->stream>>>(M0, makeView(c, 1), cur, prev, commit);
+    launched(c, "batchPrepKernel");
     const bool fork = with_ewald && !timing;
     cudaStream_t ps = fork ? b.pair_stream : c->stream;
     if (fork) {
         CUDA_CHECK(cudaEventRecord(b.ev_fork, c->stream));
         CUDA_CHECK(cudaStreamWaitEvent(ps, b.ev_fork, 0));
     }
+    if (timing) {
+        CUDA_CHECK(cudaEventRecord(b.ev[1], c->stream));
+    }
+    // ---- pair side
+    const int n_pair_blocks = (c->n_slots + kPairChunk - 1) / kPairChunk;
+    b.d_pair_partials.ensure(static_cast<size_t>(n_pair_blocks) * 2 * kBatchMax);
+    const dim3 pair_grid(n_pair_blocks, (2 * n_moves + kPairVariantsPerBlock - 1) / kPairVariantsPerBlock);
     if (std::isinf(c->pair_cut2)) {
         batchPairKernel<KIND, true><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
                                                                        b.d_pair_partials.ptr);
@@ -91,26 +101,31 @@ void launchBatchPairFinish(fb_ctx* c, const BatchBuffers& cur, const BatchBuffer
                                                                         b.d_pair_partials.ptr);
     }
     launched(c, "batchPairKernel");
+    const int pair_finish_grid = (2 * stride + stride * stride + kBlock / 32 - 1) / (kBlock / 32); // one warp per output
+    batchPairFinishKernel<KIND><<<pair_finish_grid, kBlock, 0, ps>>>(M0, c->P, cur, stride, n_pair_blocks,
+                                                                     b.d_pair_partials.ptr, b.d_result.ptr);
+    launched(c, "batchPairFinishKernel");
     if (fork) {
         CUDA_CHECK(cudaEventRecord(b.ev_join, ps));
     }
     if (timing) {
         CUDA_CHECK(cudaEventRecord(b.ev[2], c->stream));
     }
-    int n_tiles = 0, n_cells = 0, n_gram_blocks = 0, n_e_rows = 0;
+    // ---- k-space side
+    int n_rows = 0;
     if (with_ewald) {
+        const int phase_grid = std::max(1, (2 * n_moves * b.geo.table_stride + kBlock - 1) / kBlock);
+        batchPhaseKernel<<<phase_grid, kBlock, 0, c->stream>>>(cur, b.geo);
+        launched(c, "batchPhaseKernel");
         const EwaldView E = makeEwaldView(c, 0);
         const int4* kn = c->slot[0].kn.ptr;
-        n_cells = c->slot[0].n_cells;
+        const int n_cells = c->slot[0].n_cells;
         const int* cell_start = c->slot[0].cell_start.ptr;
         const double* ksq = c->slot[0].ksq.ptr;
-        n_gram_blocks = std::max(1, std::min(n_cells, 2 * c->n_sm));
+        n_rows = std::max(1, std::min(n_cells, 2 * c->n_sm));
         b.d_e_partials.ensure(static_cast<size_t>(2 * c->n_sm));
         b.d_r_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax);
         b.d_g_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax * kBatchMax);
-        (void)want_rec_sum; // the persistent kernel always produces the reciprocal sum
-        n_e_rows = n_gram_blocks;
-        n_tiles = n_gram_blocks; // rows of the R partials
 #define FB_KSPACE(BT)                                                                                         \
     {                                                                                                         \
         bool& configured = b.kspace_configured[BT == 4 ? 0 : (BT == 8 ? 1 : 2)];                              \
@@ -119,7 +134,7 @@ void launchBatchPairFinish(fb_ctx* c, const BatchBuffers& cur, const BatchBuffer
                                             static_cast<int>(KspaceSmem<BT>::bytes())));                      \
             configured = true;                                                                                \
         }                                                                                                     \
-        batchKspaceKernel<BT><<<n_gram_blocks, kBlock, KspaceSmem<BT>::bytes(), c->stream>>>(                 \
+        batchKspaceKernel<BT><<<n_rows, kBlock, KspaceSmem<BT>::bytes(), c->stream>>>(                        \
             E, kn, ksq, cell_start, n_cells, cur, prev, commit, b.geo, b.d_r_partials.ptr, b.d_g_partials.ptr, \
             b.d_e_partials.ptr);                                                                              \
     }
@@ -139,21 +154,25 @@ void launchBatchPairFinish(fb_ctx* c, const BatchBuffers& cur, const BatchBuffer
     if (timing) {
         CUDA_CHECK(cudaEventRecord(b.ev[3], c->stream));
     }
+    const int k_finish_grid = (stride + stride * stride + 1 + kBlock / 32 - 1) / (kBlock / 32);
+    batchKspaceFinishKernel<<<k_finish_grid, kBlock, 0, c->stream>>>(cur, stride, with_ewald ? 1 : 0, n_rows,
+                                                                     b.d_r_partials.ptr, b.d_g_partials.ptr,
+                                                                     b.d_e_partials.ptr, b.d_result.ptr);
+    launched(c, "batchKspaceFinishKernel");
     if (fork) {
         CUDA_CHECK(cudaStreamWaitEvent(c->stream, b.ev_join, 0));
     }
-    const int finish_grid = (3 * stride + stride * stride + 1 + kBlock / 32 - 1) / (kBlock / 32); // one warp per output
-    batchFinishKernel<KIND><<<finish_grid, kBlock, 0, c->stream>>>(
-        M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, n_tiles, b.d_r_partials.ptr, n_gram_blocks,
-        b.d_g_partials.ptr, n_e_rows, b.d_e_partials.ptr, b.d_result.ptr);
-    launched(c, "batchFinishKernel");
-    b.last_rec_fresh = n_e_rows > 0;
+    b.last_rec_fresh = with_ewald;
 }
 
 /** Leave windowed mode: put pending accepted moves on the device and re-align the trial slot's Q(k) */
 void flushBatch(fb_ctx* c)
 {
     auto& b = c->batch;
+    if (b.in_flight) { // a submitted window nobody waited for: drop its results
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        b.in_flight = false;
+    }
     if (b.has_pending) {
         launchBatchCommit(c, b.pending_with_ewald, nullptr);
         b.rec_known = false;
@@ -174,15 +193,18 @@ void flushBatch(fb_ctx* c)
 
 } // namespace
 
-FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, int with_ewald, fb_batch_result* out)
+FB_API int fb_batch_submit(fb_ctx* c, int n_moves, const fb_batch_move* moves, int with_ewald)
 {
     return guarded(c, [&] {
         checkSlot(c, 0);
         checkSlot(c, 1);
-        if (!moves || !out || n_moves < 1 || n_moves > kBatchMax) {
+        if (!moves || n_moves < 1 || n_moves > kBatchMax) {
             throw CudaError{"fb_batch_trial: 1..64 moves per window"};
         }
         auto& b = c->batch;
+        if (b.in_flight) {
+            throw CudaError{"fb_batch_submit: the previous window has not been waited for"};
+        }
         if (c->has_commit) { // an accepted fast-path move is still only on the host
             applyCommitKernel<<<1, 32, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), c->commit);
             launched(c, "applyCommitKernel");
@@ -237,8 +259,9 @@ FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, in
         if (with_ewald) {
             batchEwaldGeometry(c);
         }
-        if (b.has_pending && b.pending_with_ewald && !with_ewald) {
-            launchBatchCommit(c, true, nullptr); // Q(k) has to follow although this window has no k-space part
+        if (b.has_pending && b.pending_with_ewald && (!with_ewald || b.pending.n > stride)) {
+            // Q(k) has to follow although this window has no k-space part / has no room for that many commits
+            launchBatchCommit(c, true, nullptr);
         }
         const CommitList commit = b.has_pending ? b.pending : CommitList{};
         b.has_pending = false;
@@ -246,22 +269,12 @@ FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, in
         b.parity ^= 1;
         const BatchBuffers cur = batchBuffers(c, b.parity);
         CUDA_CHECK(cudaMemcpyAsync(cur.in, b.h_in.ptr, sizeof(BatchInput), cudaMemcpyHostToDevice, c->stream));
-        const int phase_grid =
-            with_ewald ? std::max(1, (2 * n_moves * b.geo.table_stride + kBlock - 1) / kBlock) : 1;
-        batchPhaseKernel<<<phase_grid, kBlock, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), cur, prev, commit, b.geo);
-        launched(c, "batchPhaseKernel");
-        if (timing) {
-            CUDA_CHECK(cudaEventRecord(b.ev[1], c->stream));
-        }
-        const int n_pair_blocks = (c->n_slots + kPairChunk - 1) / kPairChunk;
-        b.d_pair_partials.ensure(static_cast<size_t>(n_pair_blocks) * 2 * kBatchMax);
         const size_t n_result = batchResultDoubles(stride);
         b.d_result.ensure(batchResultDoubles(kBatchMax));
         b.h_result.ensure(batchResultDoubles(kBatchMax));
 #define FB_CASE(K)                                                                                            \
     case K:                                                                                                   \
-        launchBatchPairFinish<K>(c, cur, prev, commit, stride, n_pair_blocks, with_ewald != 0,                \
-                                 with_ewald != 0 && !b.rec_known, timing);                                    \
+        launchWindow<K>(c, cur, prev, commit, n_moves, stride, with_ewald != 0, timing);                      \
         break;
         switch (c->P.kind) {
             FB_CASE(POT_COULOMB_LJ)
@@ -277,6 +290,26 @@ FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, in
         CUDA_CHECK(cudaEventRecord(b.ev[4], c->stream));
         CUDA_CHECK(cudaMemcpyAsync(b.h_result.ptr, b.d_result.ptr, n_result * sizeof(double), cudaMemcpyDeviceToHost,
                                    c->stream));
+        b.in_flight = true;
+        b.flight_n = n_moves;
+        b.flight_stride = stride;
+        b.flight_with_ewald = with_ewald ? 1 : 0;
+        b.flight_timing = timing;
+    });
+}
+
+FB_API int fb_batch_wait(fb_ctx* c, fb_batch_result* out)
+{
+    return guarded(c, [&] {
+        auto& b = c->batch;
+        if (!out || !b.in_flight) {
+            throw CudaError{"fb_batch_wait: no submitted window"};
+        }
+        const int n_moves = b.flight_n;
+        const int stride = b.flight_stride;
+        const int with_ewald = b.flight_with_ewald;
+        const bool timing = b.flight_timing;
+        b.in_flight = false;
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         {
             float t04 = 0;
@@ -321,6 +354,12 @@ FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, in
             out->rec_start = b.rec_sum;
         }
     });
+}
+
+FB_API int fb_batch_trial(fb_ctx* c, int n_moves, const fb_batch_move* moves, int with_ewald, fb_batch_result* out)
+{
+    const int rc = fb_batch_submit(c, n_moves, moves, with_ewald);
+    return rc != FB_OK ? rc : fb_batch_wait(c, out);
 }
 
 FB_API int fb_batch_commit(fb_ctx* c, int n_decided, const unsigned char* accepted)

@@ -6,6 +6,7 @@
 #pragma once
 #include "moves.hpp"
 #include <chrono>
+#include <functional>
 
 namespace fb {
 
@@ -55,8 +56,10 @@ class WindowEvaluator
   public:
     virtual ~WindowEvaluator() = default;
     virtual int capacity() const = 0;
-    /** evaluate proposals [0, n) of `window` (all applied to the trial Space, distinct atoms) */
-    virtual void evaluate(const std::vector<WindowProposal>& window, int n) = 0;
+    /** start evaluating proposals [0, n) of `window` (all applied to the trial Space, distinct atoms) … */
+    virtual void submit(const std::vector<WindowProposal>& window, int n) = 0;
+    /** … and wait for the results; the engine draws the next proposals in between */
+    virtual void wait() = 0;
     /**
      * Hamiltonian energies of proposal m in the trial / accepted state, given which of the proposals
      * before m were accepted. Returns false if m has to be evaluated again in a fresh window.
@@ -258,9 +261,13 @@ class MetropolisMonteCarlo
     void decideWindow(int n)
     {
         const auto t_begin = std::chrono::steady_clock::now();
-        window_evaluator->evaluate(window, n);
+        window_evaluator->submit(window, n);
+        const auto t_submitted = std::chrono::steady_clock::now();
+        fillWindow(n + window_evaluator->capacity()); // the next window's proposals, while the device works
+        const auto t_filled = std::chrono::steady_clock::now();
+        window_evaluator->wait();
         const auto t_evaluated = std::chrono::steady_clock::now();
-        window_seconds_evaluate += std::chrono::duration<double>(t_evaluated - t_begin).count();
+        window_seconds_evaluate += std::chrono::duration<double>((t_submitted - t_begin) + (t_evaluated - t_filled)).count();
         windows_evaluated++;
         window_moves_evaluated += static_cast<unsigned long>(n);
         std::vector<unsigned char> accepted;
@@ -311,60 +318,75 @@ class MetropolisMonteCarlo
         return r;
     }
 
+    unsigned int sweep_remaining = 0;     //!< stochastic moves of the current sweep not yet drawn
+    Move* sweep_deferred = nullptr;       //!< a move of another kind: runs once the queue is empty
+    std::function<int(Move&)> sweep_id_of;
+
+    bool windowBlocked() const { return !window.empty() && !window.back().applied; }
+
+    /** draw proposals (in move order, generator order of performMove) until the queue holds `max_size` */
+    void fillWindow(int max_size)
+    {
+        bool blocked = windowBlocked();
+        while (!blocked && sweep_deferred == nullptr && sweep_remaining > 0 &&
+               static_cast<int>(window.size()) < max_size) {
+            sweep_remaining--;
+            Move* selected = moves->sampleStochasticMove();
+            if (selected == nullptr) {
+                continue;
+            }
+            auto* transrot = dynamic_cast<AtomicTranslateRotate*>(selected);
+            if (transrot == nullptr || !transrot->targetsAtomicGroups()) {
+                sweep_deferred = selected;
+                break;
+            }
+            WindowProposal p;
+            p.move = transrot;
+            p.move_id = sweep_id_of(*selected);
+            p.draw = transrot->draw();
+            if (!(p.draw.valid && (p.draw.dp > 0.0 || p.draw.dprot > 0.0))) {
+                Change none; // empty Change: count the attempt, keep the generator in step (montecarlo.cpp:182-186)
+                transrot->moveFromDraw(p.draw, none);
+                rng.slump();
+                continue;
+            }
+            p.uniform = rng.slump();
+            for (const auto& q : window) {
+                blocked = blocked || (q.draw.group_index == p.draw.group_index &&
+                                      q.draw.atom_index == p.draw.atom_index);
+            }
+            if (!blocked) {
+                applyProposal(p);
+            }
+            // else: its start position is only known once the earlier move on this atom is decided
+            window.push_back(std::move(p));
+        }
+    }
+
     /** The stochastic part of a sweep with runs of `transrot` moves evaluated window by window */
     template <class IdOf> void sweepStochasticWindowed(IdOf&& id_of)
     {
         const int capacity = window_evaluator->capacity();
-        unsigned int remaining = moves->movesPerSweep();
-        Move* deferred = nullptr; // a move of another kind: runs once the queue is empty
-        while (remaining > 0 || !window.empty() || deferred != nullptr) {
-            bool blocked = !window.empty() && !window.back().applied;
-            while (!blocked && deferred == nullptr && remaining > 0 && static_cast<int>(window.size()) < capacity) {
-                remaining--;
-                Move* selected = moves->sampleStochasticMove();
-                if (selected == nullptr) {
-                    continue;
-                }
-                auto* transrot = dynamic_cast<AtomicTranslateRotate*>(selected);
-                if (transrot == nullptr || !transrot->targetsAtomicGroups()) {
-                    deferred = selected;
-                    break;
-                }
-                WindowProposal p;
-                p.move = transrot;
-                p.move_id = id_of(*selected);
-                p.draw = transrot->draw();
-                if (!(p.draw.valid && (p.draw.dp > 0.0 || p.draw.dprot > 0.0))) {
-                    Change none; // empty Change: count the attempt, keep the generator in step (montecarlo.cpp:182-186)
-                    transrot->moveFromDraw(p.draw, none);
-                    rng.slump();
-                    continue;
-                }
-                p.uniform = rng.slump();
-                for (const auto& q : window) {
-                    blocked = blocked || (q.draw.group_index == p.draw.group_index &&
-                                          q.draw.atom_index == p.draw.atom_index);
-                }
-                if (!blocked) {
-                    applyProposal(p);
-                }
-                // else: its start position is only known once the earlier move on this atom is decided
-                window.push_back(std::move(p));
-            }
-            if (blocked || deferred != nullptr || remaining == 0) { // drain the queue
+        sweep_remaining = moves->movesPerSweep();
+        sweep_deferred = nullptr;
+        sweep_id_of = id_of;
+        while (sweep_remaining > 0 || !window.empty() || sweep_deferred != nullptr) {
+            fillWindow(capacity);
+            if (windowBlocked() || sweep_deferred != nullptr || sweep_remaining == 0) { // drain the queue
                 while (readyProposals() > 0) {
-                    decideWindow(readyProposals());
+                    decideWindow(std::min(readyProposals(), capacity));
                 }
-                if (!window.empty()) {
+                if (!window.empty()) { // the blocked proposal: its atom is decided now
                     applyProposal(window.front());
                 }
-                if (deferred != nullptr) {
-                    performMove(*deferred, id_of(*deferred));
-                    deferred = nullptr;
+                if (sweep_deferred != nullptr) {
+                    Move* m = sweep_deferred;
+                    sweep_deferred = nullptr;
+                    performMove(*m, sweep_id_of(*m));
                 }
             }
             else if (!window.empty()) { // full window
-                decideWindow(readyProposals());
+                decideWindow(std::min(readyProposals(), capacity));
             }
         }
     }

@@ -93,7 +93,7 @@ class FbConfig(C.Structure):
 C_ABI_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_last_error", "fb_device_count", "fb_upload_space", "fb_update_group",
     "fb_set_box", "fb_sync", "fb_download_space", "fb_nonbonded_energy", "fb_nonbonded_delta",
-    "fb_system_energy_shard", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_commit", "fb_get_batch_timing",
+    "fb_system_energy_shard", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_wait", "fb_batch_commit", "fb_get_batch_timing",
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
     "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
     "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_launch_count",
@@ -131,6 +131,8 @@ def load() -> C.CDLL:
         "fb_trial_commit": (C.c_int, [vp, C.c_int]),
         "fb_system_energy_shard": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p]),
         "fb_batch_trial": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchMove), C.c_int, C.POINTER(FbBatchResult)]),
+        "fb_batch_submit": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchMove), C.c_int]),
+        "fb_batch_wait": (C.c_int, [vp, C.POINTER(FbBatchResult)]),
         "fb_batch_commit": (C.c_int, [vp, C.c_int, c_ubyte_p]),
         "fb_get_batch_timing": (C.c_int, [vp, c_double_p]),
         "fb_ewald_configure": (C.c_int, [vp, C.POINTER(FbEwaldConfig)]),

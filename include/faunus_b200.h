@@ -263,6 +263,10 @@ typedef struct
     double rec_prefactor;    /* 2 pi lB / V */
 } fb_batch_result;
 int fb_batch_trial(fb_ctx* ctx, int n_moves, const fb_batch_move* moves, int with_ewald, fb_batch_result* result);
+/* the same in two halves, so that the caller can draw the next proposals while the device works:
+ * fb_batch_submit queues the launches and returns, fb_batch_wait blocks for the results */
+int fb_batch_submit(fb_ctx* ctx, int n_moves, const fb_batch_move* moves, int with_ewald);
+int fb_batch_wait(fb_ctx* ctx, fb_batch_result* result);
 /* accepted[m] != 0 for the accepted ones among the first n_decided moves of the last window */
 int fb_batch_commit(fb_ctx* ctx, int n_decided, const unsigned char* accepted);
 /* timing enabled: out[0..2] = ms in the pair / k-space / other (commit, phase tables, final sums) kernels of
