@@ -126,13 +126,13 @@ __global__ void __launch_bounds__(kStreamThreads)
 #pragma unroll
         for (int h = 0; h < kStreamVariants / 32; ++h) {
             const int myv = lane + 32 * h;
-            double acc = 0.0;
+            double acc = s_acc[warp][myv]; // one running sum per variant: independent of when the queue is flushed
             for (int e = 0; e < queued; ++e) {
                 if (static_cast<int>(s_qe[warp][e] & 0xffu) == myv) {
                     acc += s_qr[warp][e];
                 }
             }
-            s_acc[warp][myv] += acc;
+            s_acc[warp][myv] = acc;
         }
         __syncwarp();
         queued = 0;
