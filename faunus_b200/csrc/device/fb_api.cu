@@ -5,6 +5,7 @@
 #include "fb_kernels.cuh"
 #include "fb_batch.cuh"
 #include "fb_stream.cuh"
+#include "fb_cells.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -214,6 +215,16 @@ struct fb_ctx
         int flight_n = 0, flight_stride = 0, flight_with_ewald = 0;
         bool flight_timing = false;
         bool kspace_configured[3] = {false, false, false}; //!< dynamic shared memory opt-in done (stride 16/32/64)
+        // device cell list of slot 0 for the pair part of a window (fb_cells.cuh)
+        int cell_min_particles = 200000; //!< use the cell list from this many particle slots on (< 0: never)
+        bool cells_valid = false;
+        bool cells_used = false;        //!< the window in flight went through the cell list
+        int cell_cap = 0;
+        bool cell_cap_forced = false;
+        int cell_dims[3] = {0, 0, 0};
+        DeviceBuffer<int> d_cell_count, d_cell_bucket, d_cell_overflow;
+        std::vector<fb_batch_move> last_moves; //!< proposals of the window in flight (for a brute-force re-run)
+        bool force_brute = false;
         double rec_sum = 0;
         PhaseGeometry geo{};
         cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -1088,7 +1088,8 @@ __device__ __forceinline__ double warpColumnSum(const double* __restrict__ a, in
 template <int KIND>
 __global__ void __launch_bounds__(kBlock)
     batchPairFinishKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, int n_pair_blocks,
-                          const double* __restrict__ pair_partials, double* __restrict__ result)
+                          const double* __restrict__ pair_partials, int sums_done, const int* __restrict__ cell_overflow,
+                          double* __restrict__ result)
 {
     const int n = cur.in->n;
     const int S = stride;
@@ -1096,12 +1097,15 @@ __global__ void __launch_bounds__(kBlock)
     const int w = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     double* u = result + 8;
     double* cross = result + 8 + 3 * S;
+    if (w == 0 && lane == 0) { // the cell list ran out of bucket space: the caller re-runs the window brute force
+        result[2] = (cell_overflow != nullptr && *cell_overflow != 0) ? 1.0 : 0.0;
+    }
     if (w < 2 * S) { // variant order new/old interleaved → split
         double s = 0.0;
-        if (w < 2 * n) {
+        if (w < 2 * n && !sums_done) {
             s = warpColumnSum(pair_partials, n_pair_blocks, 2 * static_cast<size_t>(S), w, lane);
         }
-        if (lane == 0) {
+        if (lane == 0 && !(sums_done && w < 2 * n)) { // with the cell list the sums are already in place
             u[(w & 1) * S + (w >> 1)] = s;
         }
     }

@@ -66,6 +66,67 @@ void launchBatchCommit(fb_ctx* c, bool with_ewald, int* n_blocks_out)
     }
 }
 
+/** can the pair part of a window go through the device cell list? (re)computes the grid geometry */
+bool cellGridFor(fb_ctx* c, CellGrid& g)
+{
+    auto& b = c->batch;
+    if (b.force_brute || b.cell_min_particles < 0 || c->n_slots < b.cell_min_particles || c->P.any_molecular ||
+        std::isinf(c->pair_cut2) || !(c->pair_cut2 > 0)) {
+        return false;
+    }
+    const double rc = std::sqrt(c->pair_cut2);
+    long n_cells = 1;
+    for (int i = 0; i < 3; ++i) {
+        if (!c->periodic[i]) {
+            return false;
+        }
+        const double len = c->slot[0].box[i];
+        const int n = static_cast<int>(std::floor(len / rc)); // cell edge = box / floor(box / cutoff) ≥ cutoff
+        if (n < 3) {
+            return false;
+        }
+        g.n[i] = std::min(n, 64);
+        g.inv_edge[i] = g.n[i] / len;
+        g.half[i] = 0.5 * len;
+        n_cells *= g.n[i];
+    }
+    const bool same = b.cell_dims[0] == g.n[0] && b.cell_dims[1] == g.n[1] && b.cell_dims[2] == g.n[2];
+    if (!same) {
+        b.cells_valid = false;
+        if (!b.cell_cap_forced) {
+            b.cell_cap = 0;
+        }
+        for (int i = 0; i < 3; ++i) {
+            b.cell_dims[i] = g.n[i];
+        }
+    }
+    if (b.cell_cap == 0) {
+        const double mean = static_cast<double>(c->n_slots) / static_cast<double>(n_cells);
+        b.cell_cap = std::max(16, static_cast<int>(2.0 * mean) + 16);
+    }
+    b.d_cell_count.ensure(static_cast<size_t>(n_cells));
+    b.d_cell_bucket.ensure(static_cast<size_t>(n_cells) * b.cell_cap);
+    b.d_cell_overflow.ensure(1);
+    g.cap = b.cell_cap;
+    g.count = b.d_cell_count.ptr;
+    g.bucket = b.d_cell_bucket.ptr;
+    g.overflow = b.d_cell_overflow.ptr;
+    return true;
+}
+
+/** build the cell list of slot 0 from scratch on `stream` (positions must be final for this window) */
+void buildCellList(fb_ctx* c, const CellGrid& g, cudaStream_t stream)
+{
+    const long n_cells = static_cast<long>(g.n[0]) * g.n[1] * g.n[2];
+    CUDA_CHECK(cudaMemsetAsync(g.count, 0, n_cells * sizeof(int), stream));
+    CUDA_CHECK(cudaMemsetAsync(g.overflow, 0, sizeof(int), stream));
+    cellAppendKernel<<<(c->n_slots + 255) / 256, 256, 0, stream>>>(makeView(c, 0), g);
+    launched(c, "cellAppendKernel");
+    cellSortKernel<<<static_cast<int>((n_cells + 127) / 128), 128, 0, stream>>>(g, static_cast<int>(n_cells));
+    launched(c, "cellSortKernel");
+    c->batch.cells_valid = true;
+}
+
 /**
  * Launches of one window. Main stream: prep → phase tables → k-space → k-space sums; pair stream (forked
  * after prep, joined before the copy-out): pair kernel → pair sums + cross terms. Serialised on the
@@ -90,20 +151,37 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
     }
     // ---- pair side
     const int n_pair_blocks = (c->n_slots + kPairChunk - 1) / kPairChunk;
-    b.d_pair_partials.ensure(static_cast<size_t>(n_pair_blocks) * 2 * kBatchMax);
-    const dim3 pair_grid(n_pair_blocks, (2 * n_moves + kPairVariantsPerBlock - 1) / kPairVariantsPerBlock);
-    if (std::isinf(c->pair_cut2)) {
-        batchPairKernel<KIND, true><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
-                                                                       b.d_pair_partials.ptr);
+    CellGrid grid{};
+    b.cells_used = cellGridFor(c, grid);
+    if (b.cells_used) { // large N: 27 neighbour cells per position instead of all particles
+        if (!b.cells_valid) {
+            buildCellList(c, grid, ps);
+        }
+        else if (commit.n > 0) {
+            cellCommitKernel<<<1, 2 * kBatchMax, 0, ps>>>(grid, prev, commit);
+            launched(c, "cellCommitKernel");
+        }
+        batchPairCellKernel<KIND><<<2 * n_moves, kCellThreads, 0, ps>>>(M0, c->P, grid, cur, c->pair_cut2, stride,
+                                                                        b.d_result.ptr);
+        launched(c, "batchPairCellKernel");
     }
     else {
-        batchPairKernel<KIND, false><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
-                                                                        b.d_pair_partials.ptr);
+        b.d_pair_partials.ensure(static_cast<size_t>(n_pair_blocks) * 2 * kBatchMax);
+        const dim3 pair_grid(n_pair_blocks, (2 * n_moves + kPairVariantsPerBlock - 1) / kPairVariantsPerBlock);
+        if (std::isinf(c->pair_cut2)) {
+            batchPairKernel<KIND, true><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
+                                                                           b.d_pair_partials.ptr);
+        }
+        else {
+            batchPairKernel<KIND, false><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
+                                                                            b.d_pair_partials.ptr);
+        }
+        launched(c, "batchPairKernel");
     }
-    launched(c, "batchPairKernel");
     const int pair_finish_grid = (2 * stride + stride * stride + kBlock / 32 - 1) / (kBlock / 32); // one warp per output
-    batchPairFinishKernel<KIND><<<pair_finish_grid, kBlock, 0, ps>>>(M0, c->P, cur, stride, n_pair_blocks,
-                                                                     b.d_pair_partials.ptr, b.d_result.ptr);
+    batchPairFinishKernel<KIND><<<pair_finish_grid, kBlock, 0, ps>>>(
+        M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, b.cells_used ? 1 : 0,
+        b.cells_used ? b.d_cell_overflow.ptr : nullptr, b.d_result.ptr);
     launched(c, "batchPairFinishKernel");
     if (fork) {
         CUDA_CHECK(cudaEventRecord(b.ev_join, ps));
@@ -189,6 +267,7 @@ void flushBatch(fb_ctx* c)
     }
     b.last_n = 0;
     b.rec_known = false;
+    b.cells_valid = false; // whatever follows may move particles behind the cell list's back
 }
 
 } // namespace
@@ -209,8 +288,10 @@ FB_API int fb_batch_submit(fb_ctx* c, int n_moves, const fb_batch_move* moves, i
             applyCommitKernel<<<1, 32, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), c->commit);
             launched(c, "applyCommitKernel");
             c->has_commit = false;
+            b.cells_valid = false;
         }
         c->trial_active = false;
+        b.last_moves.assign(moves, moves + n_moves);
         if (with_ewald) {
             if (!c->ewald_configured || c->slot[0].K <= 0) {
                 throw CudaError{"fb_batch_trial: Ewald is not initialised on the accepted slot"};
@@ -262,6 +343,7 @@ FB_API int fb_batch_submit(fb_ctx* c, int n_moves, const fb_batch_move* moves, i
         if (b.has_pending && b.pending_with_ewald && (!with_ewald || b.pending.n > stride)) {
             // Q(k) has to follow although this window has no k-space part / has no room for that many commits
             launchBatchCommit(c, true, nullptr);
+            b.cells_valid = false; // these moves bypass the incremental cell update
         }
         const CommitList commit = b.has_pending ? b.pending : CommitList{};
         b.has_pending = false;
@@ -329,6 +411,22 @@ FB_API int fb_batch_wait(fb_ctx* c, fb_batch_result* out)
         b.windows += 1;
         b.moves += n_moves;
         const double* r = b.h_result.ptr;
+        if (b.cells_used && r[2] != 0.0) { // a bucket ran full: this window's pair sums are incomplete
+            b.cells_valid = false;
+            b.cell_cap *= 2;
+            b.force_brute = true; // the commits of this window are already on the device: plain re-evaluation
+            const std::vector<fb_batch_move> again = b.last_moves;
+            const int rc = fb_batch_submit(c, n_moves, again.data(), with_ewald);
+            b.force_brute = false;
+            if (rc != FB_OK) {
+                throw CudaError{c->last_error};
+            }
+            const int rc2 = fb_batch_wait(c, out);
+            if (rc2 != FB_OK) {
+                throw CudaError{c->last_error};
+            }
+            return;
+        }
         if (with_ewald && b.last_rec_fresh) {
             b.rec_sum = r[0];
             b.rec_known = true;
@@ -395,6 +493,28 @@ FB_API int fb_batch_commit(fb_ctx* c, int n_decided, const unsigned char* accept
             c->slot[1].rec_valid = false;
         }
     });
+}
+
+FB_API int fb_configure_cells(fb_ctx* c, int min_particles)
+{
+    if (!c) {
+        return FB_ERR_INVALID;
+    }
+    c->batch.cell_min_particles = min_particles;
+    c->batch.cells_valid = false;
+    return FB_OK;
+}
+
+/** test hook: start from this bucket capacity (the library doubles it whenever a bucket runs full) */
+FB_API int fb_debug_set_cell_capacity(fb_ctx* c, int capacity)
+{
+    if (!c || capacity < 1) {
+        return FB_ERR_INVALID;
+    }
+    c->batch.cell_cap = capacity;
+    c->batch.cell_cap_forced = true;
+    c->batch.cells_valid = false;
+    return FB_OK;
 }
 
 FB_API int fb_get_batch_timing(const fb_ctx* c, double out[8])

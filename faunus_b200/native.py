@@ -93,7 +93,7 @@ class FbConfig(C.Structure):
 C_ABI_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_last_error", "fb_device_count", "fb_upload_space", "fb_update_group",
     "fb_set_box", "fb_sync", "fb_download_space", "fb_nonbonded_energy", "fb_nonbonded_delta",
-    "fb_system_energy_shard", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_wait", "fb_batch_commit", "fb_get_batch_timing",
+    "fb_system_energy_shard", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_wait", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing",
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
     "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
     "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_launch_count",
@@ -134,6 +134,8 @@ def load() -> C.CDLL:
         "fb_batch_submit": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchMove), C.c_int]),
         "fb_batch_wait": (C.c_int, [vp, C.POINTER(FbBatchResult)]),
         "fb_batch_commit": (C.c_int, [vp, C.c_int, c_ubyte_p]),
+        "fb_configure_cells": (C.c_int, [vp, C.c_int]),
+        "fb_debug_set_cell_capacity": (C.c_int, [vp, C.c_int]),
         "fb_get_batch_timing": (C.c_int, [vp, c_double_p]),
         "fb_ewald_configure": (C.c_int, [vp, C.POINTER(FbEwaldConfig)]),
         "fb_ewald_update_box": (C.c_int, [vp, C.c_int, c_int_p]),
@@ -213,6 +215,10 @@ class B200Simulation(Simulation):
         self._check(load().fbh_system_energy_shard(self.handle, rank, size, out.ctypes.data_as(c_double_p)),
                     "system_energy_shard")
         return float(out[0]), float(out[1])
+
+    def configure_cells(self, min_particles: int):
+        """Device cell list for the pair part of windows: from `min_particles` slots on (0 always, < 0 never)."""
+        self._check(load().fb_configure_cells(self.ctx, int(min_particles)), "fb_configure_cells")
 
     def window_time_ms(self) -> dict:
         out = np.zeros(8)

@@ -269,6 +269,15 @@ int fb_batch_submit(fb_ctx* ctx, int n_moves, const fb_batch_move* moves, int wi
 int fb_batch_wait(fb_ctx* ctx, fb_batch_result* result);
 /* accepted[m] != 0 for the accepted ones among the first n_decided moves of the last window */
 int fb_batch_commit(fb_ctx* ctx, int n_decided, const unsigned char* accepted);
+/* The pair part of a window goes through a device cell list (cell edge = box / floor(box / cutoff), 27
+ * neighbour cells per position; src/celllistimpl.h:223-236 for the geometry convention) when the system is
+ * all-atomic, every pair term has a cutoff, the cell is periodic in x, y, z with at least 3 cells per axis
+ * and there are at least `min_particles` particle slots (default 200000 — below that the brute-force pass over
+ * the L2-resident positions is as fast; 0: whenever eligible; < 0: never).
+ * The reference itself is brute force (src/energy.h:1182-1195); sums differ in order only. */
+int fb_configure_cells(fb_ctx* ctx, int min_particles);
+/* test hook: initial bucket capacity of the cell list (doubled by the library whenever a bucket runs full) */
+int fb_debug_set_cell_capacity(fb_ctx* ctx, int capacity);
 /* timing enabled: out[0..2] = ms in the pair / k-space / other (commit, phase tables, final sums) kernels of
  * the windowed path (kernels serialised while timing), out[3] = windows, out[4] = moves evaluated,
  * out[5] = ms from the first to the last kernel of every window (always accumulated) */

@@ -54,6 +54,21 @@ def test_s1_windowed_equals_single_moves():
     assert np.abs(ea - eb).max() <= 1e-10 * np.abs(ea).max()
 
 
+def test_s1_cell_list_equals_brute_force():
+    """N = 1e5: windows through the device cell list (forced; the default starts at 200 000 particles) vs brute force"""
+    a, b = sim(s1(600), window=32), sim(s1(600), window=32)
+    a.configure_cells(0)
+    b.configure_cells(-1)
+    for s in (a, b):
+        s.trace_enable()
+        s.sweep(1)
+    ta, tb = a.trace(), b.trace()
+    assert np.array_equal(ta["accepted"], tb["accepted"])
+    scale = np.abs(ta["u_new"]).max()
+    assert np.abs(ta["u_new"] - tb["u_new"]).max() <= 1e-10 * scale
+    assert abs(a.drift()) < 1e-9
+
+
 def test_s1_shards_add_up():
     g = sim(s1(10))
     _, terms = g.system_energy()

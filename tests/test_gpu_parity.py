@@ -358,3 +358,27 @@ def test_tempering_replicas_on_device():
         tw = [m["temper"] for m in w["moves"] if "temper" in m][0]
         tg = [m["temper"] for m in g["moves"] if "temper" in m][0]
         assert tw["exchange"] == tg["exchange"]
+
+
+@pytest.mark.parametrize("capacity", [None, 2])
+def test_window_cell_list(capacity):
+    """pair part of the windows through the device cell list (forced on a small system): same trace as the
+    oracle's brute-force sums; capacity 2 makes buckets run full, which must fall back and grow"""
+    import faunus_b200.native as native
+    cfg = small_electrolyte(n=500, moves_per_sweep=200,
+                            coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 6})
+    o, g = pair_of_sims(cfg, 32)
+    g.configure_cells(0)
+    if capacity:
+        assert native.load().fb_debug_set_cell_capacity(g.ctx, capacity) == 0
+    launches0 = g.launch_count
+    for s in (o, g):
+        s.trace_enable()
+        s.sweep(3)
+    a, b = o.trace(), g.trace()
+    assert np.array_equal(a["accepted"], b["accepted"])
+    scale = np.abs(a["u_new"][np.isfinite(a["u_new"])]).max()
+    assert_close(a["u_new"], b["u_new"], scale=scale)
+    assert_close(a["u_old"], b["u_old"], scale=scale)
+    assert abs(g.drift()) < 1e-9
+    assert g.launch_count > launches0
