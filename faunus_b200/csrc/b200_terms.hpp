@@ -757,6 +757,13 @@ class B200WindowEvaluator : public WindowEvaluator
             mv.xyzq[1] = p.pos.y;
             mv.xyzq[2] = p.pos.z;
             mv.xyzq[3] = p.charge;
+            const Space& accepted = *mc.state.spc; // the caller owns the Space: old positions travel with the window
+            const auto& q = accepted.at(accepted.groups.at(gc.group_index), gc.relative_atom_indices[0]);
+            mv.old_atom_id = q.id;
+            mv.old_xyzq[0] = q.pos.x;
+            mv.old_xyzq[1] = q.pos.y;
+            mv.old_xyzq[2] = q.pos.z;
+            mv.old_xyzq[3] = q.charge;
         }
         dev->fast_staged = false;
         dev->cache_valid = false;

@@ -194,8 +194,6 @@ struct fb_ctx
     struct Batch
     {
         DeviceBuffer<BatchInput> d_in[2];
-        DeviceBuffer<double4> d_pold[2];
-        DeviceBuffer<int> d_idold[2];
         DeviceBuffer<double2> d_table[2];
         PinnedBuffer<BatchInput> h_in;
         DeviceBuffer<double> d_pair_partials, d_r_partials, d_g_partials, d_e_partials, d_result;

@@ -40,13 +40,15 @@ struct BatchInput
     int slot[kBatchMax];
     int id[kBatchMax];
     double4 pnew[kBatchMax];
+    int idold[kBatchMax];    //!< the atoms as they are in the accepted state (supplied by the caller, who owns
+    double4 pold[kBatchMax]; //!< the Space: no gather from the mirror on the critical path)
 };
 
 /** Device-resident working set of one window */
 struct BatchBuffers
 {
     BatchInput* in;
-    double4* pold;   //!< [kBatchMax] positions at window start (gathered from the mirror)
+    double4* pold;   //!< [kBatchMax] positions at window start (points into *in)
     int* idold;      //!< [kBatchMax]
     double2* table;  //!< [2·kBatchMax][table_stride] phase factors, variant 2m = new, 2m+1 = old
 };
@@ -155,12 +157,8 @@ __global__ void __launch_bounds__(kBlock)
 // ------------------------------------------------------------------------------------------------
 // window set-up: old positions from the (committed) mirror and the per-axis phase tables
 // ------------------------------------------------------------------------------------------------
-/**
- * Window set-up, one block: the previous window's accepted trial positions go into both mirrors, then the
- * old positions of this window's atoms are gathered from the (now committed) mirror.
- */
-__global__ void __launch_bounds__(2 * kBatchMax)
-    batchPrepKernel(SlotView M0, SlotView M1, BatchBuffers cur, BatchBuffers prev, CommitList commit)
+/** the previous window's accepted trial positions go into both mirrors (pair stream, before the pair kernel) */
+__global__ void __launch_bounds__(kBatchMax) batchPrepKernel(SlotView M0, SlotView M1, BatchBuffers prev, CommitList commit)
 {
     if (static_cast<int>(threadIdx.x) < commit.n) {
         const int m = commit.index[threadIdx.x];
@@ -172,15 +170,9 @@ __global__ void __launch_bounds__(2 * kBatchMax)
         M1.posq[s] = p;
         M1.atom_id[s] = id;
     }
-    __syncthreads(); // global writes of this block are visible to its own threads after the barrier
-    if (static_cast<int>(threadIdx.x) < cur.in->n) {
-        const int s = cur.in->slot[threadIdx.x];
-        cur.pold[threadIdx.x] = M0.posq[s];
-        cur.idold[threadIdx.x] = M0.atom_id[s];
-    }
 }
 
-/** per-axis phase tables e^{i 2π n x / L} of the 2n positions of the window (after batchPrepKernel) */
+/** per-axis phase tables e^{i 2π n x / L} of the 2n positions of the window */
 __global__ void __launch_bounds__(kBlock) batchPhaseKernel(BatchBuffers cur, PhaseGeometry geo)
 {
     const int n = cur.in->n;

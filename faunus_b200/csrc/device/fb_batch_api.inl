@@ -7,8 +7,8 @@ BatchBuffers batchBuffers(fb_ctx* c, int which)
 {
     BatchBuffers b{};
     b.in = c->batch.d_in[which].ptr;
-    b.pold = c->batch.d_pold[which].ptr;
-    b.idold = c->batch.d_idold[which].ptr;
+    b.pold = b.in ? b.in->pold : nullptr;   // host-side address arithmetic on a device pointer
+    b.idold = b.in ? b.in->idold : nullptr;
     b.table = c->batch.d_table[which].ptr;
     return b;
 }
@@ -18,8 +18,6 @@ void batchAllocate(fb_ctx* c)
     auto& b = c->batch;
     for (int i = 0; i < 2; ++i) {
         b.d_in[i].ensure(1);
-        b.d_pold[i].ensure(kBatchMax);
-        b.d_idold[i].ensure(kBatchMax);
     }
     b.h_in.ensure(1);
 }
@@ -138,13 +136,15 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
 {
     auto& b = c->batch;
     const SlotView M0 = makeView(c, 0);
-    batchPrepKernel<<<1, 2 * kBatchMax, 0, c->stream>>>(M0, makeView(c, 1), cur, prev, commit);
-    launched(c, "batchPrepKernel");
     const bool fork = with_ewald && !timing;
     cudaStream_t ps = fork ? b.pair_stream : c->stream;
     if (fork) {
-        CUDA_CHECK(cudaEventRecord(b.ev_fork, c->stream));
+        CUDA_CHECK(cudaEventRecord(b.ev_fork, c->stream)); // after the H2D copy of the window description
         CUDA_CHECK(cudaStreamWaitEvent(ps, b.ev_fork, 0));
+    }
+    if (commit.n > 0) {
+        batchPrepKernel<<<1, kBatchMax, 0, ps>>>(M0, makeView(c, 1), prev, commit);
+        launched(c, "batchPrepKernel");
     }
     if (timing) {
         CUDA_CHECK(cudaEventRecord(b.ev[1], c->stream));
@@ -326,6 +326,11 @@ FB_API int fb_batch_submit(fb_ctx* c, int n_moves, const fb_batch_move* moves, i
             in.slot[m] = g.begin + mv.rel_index;
             in.id[m] = mv.atom_id;
             in.pnew[m] = make_double4(mv.xyzq[0], mv.xyzq[1], mv.xyzq[2], mv.xyzq[3]);
+            in.pold[m] = make_double4(mv.old_xyzq[0], mv.old_xyzq[1], mv.old_xyzq[2], mv.old_xyzq[3]);
+            in.idold[m] = mv.old_atom_id;
+            if (mv.old_atom_id < 0 || mv.old_atom_id >= c->P.n_types) {
+                throw CudaError{"fb_batch_trial: atom id out of range"};
+            }
             for (int a = 0; a < m; ++a) {
                 if (in.slot[a] == in.slot[m]) {
                     throw CudaError{"fb_batch_trial: the moves of one window must touch distinct atoms"};

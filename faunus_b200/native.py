@@ -51,7 +51,8 @@ class FbEwaldConfig(C.Structure):
 
 
 class FbBatchMove(C.Structure):
-    _fields_ = [("group_index", C.c_int), ("rel_index", C.c_int), ("atom_id", C.c_int), ("xyzq", C.c_double * 4)]
+    _fields_ = [("group_index", C.c_int), ("rel_index", C.c_int), ("atom_id", C.c_int), ("xyzq", C.c_double * 4),
+                ("old_atom_id", C.c_int), ("old_xyzq", C.c_double * 4)]
 
 
 class FbBatchResult(C.Structure):

@@ -245,8 +245,10 @@ typedef struct
 {
     int group_index;
     int rel_index;  /* relative atom index within the group */
-    int atom_id;    /* atom type at the trial position */
-    double xyzq[4]; /* trial position and charge */
+    int atom_id;        /* atom type at the trial position */
+    double xyzq[4];     /* trial position and charge */
+    int old_atom_id;    /* the atom as it is in the accepted Space (what both slots hold for it) */
+    double old_xyzq[4];
 } fb_batch_move;
 typedef struct
 {

@@ -48,8 +48,11 @@ def main(path):
             v = r[idx[m]]
             try:
                 f = float(v)
-                if units[idx[m]] in ("byte", "Mbyte") and "dram" in m:
-                    f = f if units[idx[m]] == "Mbyte" else f / 1e6
+                unit = units[idx[m]]
+                if "dram" in m:
+                    f *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(unit, 1.0)
+                if m == "gpu__time_duration.sum":
+                    f *= {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6, "ns": 1e-3, "us": 1.0, "ms": 1e3}.get(unit, 1.0)
                 v = f"{f:.4g}"
             except ValueError:
                 pass

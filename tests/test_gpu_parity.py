@@ -262,6 +262,9 @@ def test_window_matches_single_moves():
         for d in range(3):
             moves[m].xyzq[d] = newpos[m, d]
         moves[m].xyzq[3] = xyzq[picks[m], 3]
+        moves[m].old_atom_id = int(ids[picks[m]])
+        for d in range(4):
+            moves[m].old_xyzq[d] = xyzq[picks[m], d]
     res = native.FbBatchResult()
     assert lib.fb_batch_trial(gb.ctx, n, moves, 1, C.byref(res)) == 0, lib.fb_last_error(gb.ctx)
     S = res.stride
