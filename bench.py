@@ -125,7 +125,9 @@ def cpu_reference_run(steps: int, warmup: int, moves_per_step: int, policy: str)
     so, arch = build_oracle_native()
     lib = C.CDLL(so)
     lib.fo_set_parallel_ewald_init.argtypes = [C.c_int]
+    lib.fo_set_openmp_threads.argtypes = [C.c_int]
     lib.fo_openmp_threads.restype = C.c_int
+    lib.fo_set_openmp_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1 to its workers
     lib.fo_set_parallel_ewald_init(1)  # one-off N·K init over all cores; per-move path stays as in the reference
     threads = lib.fo_openmp_threads() if policy == "openmp" else 1
     sim = Simulation(SimLibrary(lib, "fo"), workload(moves_per_step, summation_policy=policy))
@@ -140,8 +142,8 @@ def cpu_reference_run(steps: int, warmup: int, moves_per_step: int, policy: str)
 
 
 def reference_arm(args):
-    rank, world, _, dist = dist_setup(args.gpus, "gloo")
-    if rank != 0:
+    # CPU only: under torchrun rank 0 alone runs and prints, the other ranks exit without work (no rendezvous)
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     moves = 25  # bounded sample per step: ~4 ms/move → 0.1 s/step
     res = cpu_reference_run(args.steps, min(args.warmup, 3), moves, "openmp")

@@ -195,7 +195,7 @@ class B200Simulation(Simulation):
     """Metropolis MC simulation whose non-bonded/Ewald terms run on the B200 (``fbh_*`` ABI)."""
 
     #: proposals evaluated per device pass for runs of `transrot` moves (0: one move at a time)
-    DEFAULT_WINDOW = int(os.environ.get("FAUNUS_B200_WINDOW", "32"))
+    DEFAULT_WINDOW = int(os.environ.get("FAUNUS_B200_WINDOW", "64"))
 
     def __init__(self, config, device: int = 0, window: Optional[int] = None):
         require_device()

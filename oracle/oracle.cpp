@@ -235,6 +235,18 @@ FO_API void fo_set_parallel_ewald_init(int on)
     oracle::ewald::parallel_full_update = on != 0;
 }
 
+/** torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline sets its thread count explicitly */
+FO_API void fo_set_openmp_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) {
+        omp_set_num_threads(n);
+    }
+#else
+    (void)n;
+#endif
+}
+
 FO_API int fo_openmp_threads()
 {
 #ifdef _OPENMP
