@@ -528,6 +528,27 @@ void launchFull(fb_ctx* c, const SlotView& V, int volume_predicate, int shard = 
     launched(c, "orderedSumKernel");
 }
 
+/** Q(k) of the k-cells [cell_begin, cell_end) of a slot from its positions (ewaldFullCellKernel) */
+void launchFullQ(fb_ctx* c, int s, int cell_begin, int cell_end, bool store_q, double* e_partials)
+{
+    Slot& sl = c->slot[s];
+    PhaseGeometry geo{};
+    geo.ncc = static_cast<int>(std::ceil(c->ewald.n_cutoff));
+    geo.table_stride = 0;
+    for (int i = 0; i < 3; ++i) {
+        geo.len[i] = sl.ewald_box[i];
+    }
+    static thread_local int configured_device = -1;
+    if (configured_device != c->device) {
+        CUDA_CHECK(cudaFuncSetAttribute(ewaldFullCellKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(sizeof(FullQSmem))));
+        configured_device = c->device;
+    }
+    ewaldFullCellKernel<<<cell_end - cell_begin, kBlock, sizeof(FullQSmem), c->stream>>>(
+        makeView(c, s), makeEwaldView(c, s), sl.kn.ptr, sl.cell_start.ptr, cell_begin, geo, store_q ? 1 : 0, e_partials);
+    launched(c, "ewaldFullCellKernel");
+}
+
 /** PolicyIonIon::updateBox / PolicyIonIonIPBC::updateBox, src/energy.cpp:133-186, 356-412 */
 void generateKVectors(const fb_ewald_config& cfg, const double box[3], std::vector<double4>& kA,
                       std::vector<int4>& kn)
@@ -1307,19 +1328,34 @@ FB_API int fb_system_energy_shard(fb_ctx* c, int s, int shard, int n_shards, dou
         *reciprocal = 0.0;
         Slot& sl = c->slot[s];
         if (c->ewald_configured && sl.K > 0) {
-            const int k_begin = static_cast<int>(static_cast<long long>(sl.K) * shard / n_shards);
-            const int k_end = static_cast<int>(static_cast<long long>(sl.K) * (shard + 1) / n_shards);
             double sum = 0.0;
-            if (k_end > k_begin) {
-                const int grid = (k_end - k_begin + kEwaldBlock - 1) / kEwaldBlock;
-                c->partials.ensure(static_cast<size_t>(grid));
-                ewaldSlabEnergyKernel<<<grid, kEwaldBlock, 0, c->stream>>>(makeView(c, s), makeEwaldView(c, s), k_begin,
-                                                                          k_end, c->partials.ptr);
-                launched(c, "ewaldSlabEnergyKernel");
-                orderedSumKernel<<<1, 1024, 0, c->stream>>>(c->partials.ptr, static_cast<size_t>(grid), 1, c->d_result);
-                launched(c, "orderedSumKernel");
-                CUDA_CHECK(cudaStreamSynchronize(c->stream));
-                sum = c->h_result[0];
+            if (c->ewald.policy != 2 && sl.n_cells > 0) { // a slab of k-cells
+                const int cell_begin = static_cast<int>(static_cast<long long>(sl.n_cells) * shard / n_shards);
+                const int cell_end = static_cast<int>(static_cast<long long>(sl.n_cells) * (shard + 1) / n_shards);
+                if (cell_end > cell_begin) {
+                    const int grid = cell_end - cell_begin;
+                    c->partials.ensure(static_cast<size_t>(grid));
+                    launchFullQ(c, s, cell_begin, cell_end, false, c->partials.ptr);
+                    orderedSumKernel<<<1, 1024, 0, c->stream>>>(c->partials.ptr, static_cast<size_t>(grid), 1, c->d_result);
+                    launched(c, "orderedSumKernel");
+                    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                    sum = c->h_result[0];
+                }
+            }
+            else {
+                const int k_begin = static_cast<int>(static_cast<long long>(sl.K) * shard / n_shards);
+                const int k_end = static_cast<int>(static_cast<long long>(sl.K) * (shard + 1) / n_shards);
+                if (k_end > k_begin) {
+                    const int grid = (k_end - k_begin + kEwaldBlock - 1) / kEwaldBlock;
+                    c->partials.ensure(static_cast<size_t>(grid));
+                    ewaldSlabEnergyKernel<<<grid, kEwaldBlock, 0, c->stream>>>(makeView(c, s), makeEwaldView(c, s),
+                                                                              k_begin, k_end, c->partials.ptr);
+                    launched(c, "ewaldSlabEnergyKernel");
+                    orderedSumKernel<<<1, 1024, 0, c->stream>>>(c->partials.ptr, static_cast<size_t>(grid), 1, c->d_result);
+                    launched(c, "orderedSumKernel");
+                    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                    sum = c->h_result[0];
+                }
             }
             const double pi = 3.141592653589793238462643383279502884;
             const double volume = sl.ewald_box[0] * sl.ewald_box[1] * sl.ewald_box[2];
@@ -1610,9 +1646,14 @@ FB_API int fb_ewald_update_full(fb_ctx* c, int s)
         if (sl.K <= 0) {
             throw CudaError{"no k-vectors (call fb_ewald_update_box first)"};
         }
-        const int grid = (sl.K + kEwaldBlock - 1) / kEwaldBlock;
-        ewaldFullKernel<<<grid, kEwaldBlock, 0, c->stream>>>(makeView(c, s), makeEwaldView(c, s));
-        launched(c, "ewaldFullKernel");
+        if (c->ewald.policy != 2 && sl.n_cells > 0) { // PBC / PBCEigen: factorised phases, one block per k-cell
+            launchFullQ(c, s, 0, sl.n_cells, true, nullptr);
+        }
+        else {
+            const int grid = (sl.K + kEwaldBlock - 1) / kEwaldBlock;
+            ewaldFullKernel<<<grid, kEwaldBlock, 0, c->stream>>>(makeView(c, s), makeEwaldView(c, s));
+            launched(c, "ewaldFullKernel");
+        }
         sl.rec_valid = false;
     });
 }

@@ -402,4 +402,130 @@ __global__ void __launch_bounds__(kStreamThreads)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Full rebuild of Q(k) (PolicyIonIon::updateComplex, src/energy.cpp:191-206; PBCEigen quirk :208-217) with
+// factorised phases: one block per 4×4×4 cell of k-vectors, particles in chunks of 256.
+//   phase A  thread ↔ particle: 2 sincos per axis (cell base 2π b x/L and step 2π x/L), the other three
+//            entries of each axis by complex products, then the 16 x·y products → shared memory
+//   phase B  thread ↔ (k of the cell, quarter of the chunk): one complex product and two FMAs per
+//            (k, particle) instead of a sincos
+// Σ_k A_k |Q_k|² of the cell is optionally reduced to e_partials (sharded system energy: no store of Q).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFullQChunk = 256;
+
+struct FullQSmem
+{
+    double2 exy[kFullQChunk][16];
+    double2 ez[kFullQChunk][4];
+    double wre[kFullQChunk]; //!< weight of the real part (charge, 0 if inactive)
+    double wim[kFullQChunk]; //!< weight of the imaginary part (charge; PBCEigen: 1 if active)
+    double2 red[4][kTileK];
+};
+
+__global__ void __launch_bounds__(kBlock, 2)
+    ewaldFullCellKernel(SlotView V, EwaldView E, const int4* __restrict__ kn, const int* __restrict__ cell_start,
+                        int cell_begin, PhaseGeometry geo, int store_q, double* __restrict__ e_partials)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FullQSmem& sm = *reinterpret_cast<FullQSmem*>(smem_raw);
+    const int cell = cell_begin + blockIdx.x;
+    const int p0 = cell_start[cell];
+    const int len = cell_start[cell + 1] - p0;
+    const CellBase base = cellBase(__ldg(kn + p0), geo.ncc);
+    const double two_pi = 2.0 * 3.141592653589793238462643383279502884;
+    const double kb[3] = {two_pi * static_cast<double>(base.nx) / geo.len[0], two_pi * static_cast<double>(base.ny) / geo.len[1],
+                          two_pi * static_cast<double>(base.nz) / geo.len[2]};
+    const double k1[3] = {two_pi / geo.len[0], two_pi / geo.len[1], two_pi / geo.len[2]};
+
+    const int kl = threadIdx.x & (kTileK - 1);
+    const int quarter = threadIdx.x / kTileK;
+    int li = 0, lj = 0, ll = 0;
+    const bool kvalid = kl < len;
+    if (kvalid) {
+        const int4 nn = __ldg(kn + p0 + kl);
+        li = nn.x & 3;
+        lj = (nn.y + geo.ncc) & 3;
+        ll = (nn.z + geo.ncc) & 3;
+    }
+    const int ixy = li * 4 + lj;
+    double qre = 0.0, qim = 0.0;
+
+    for (int c0 = 0; c0 < V.n_slots; c0 += kFullQChunk) {
+        __syncthreads(); // previous chunk consumed
+        {
+            const int j = c0 + threadIdx.x;
+            double4 p = make_double4(0, 0, 0, 0);
+            bool active = false;
+            if (j < V.n_slots) {
+                p = V.posq[j];
+                active = V.gid[j] >= 0;
+            }
+            double2 e[3][4];
+            const double x[3] = {p.x, p.y, p.z};
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                double s, c;
+                sincos(kb[ax] * x[ax], &s, &c);
+                e[ax][0] = make_double2(c, s);
+                sincos(k1[ax] * x[ax], &s, &c);
+                const double2 step = make_double2(c, s);
+#pragma unroll
+                for (int i = 1; i < 4; ++i) {
+                    e[ax][i] = cmul(e[ax][i - 1], step);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    sm.exy[threadIdx.x][i * 4 + jj] = cmul(e[0][i], e[1][jj]);
+                }
+                sm.ez[threadIdx.x][i] = e[2][i];
+            }
+            sm.wre[threadIdx.x] = active ? p.w : 0.0;
+            sm.wim[threadIdx.x] = active ? (E.policy == 1 ? 1.0 : p.w) : 0.0;
+        }
+        __syncthreads();
+        if (kvalid) {
+            const int n = min(kFullQChunk, V.n_slots - c0);
+#pragma unroll 4
+            for (int t = quarter; t < n; t += 4) {
+                const double2 ph = cmul(sm.exy[t][ixy], sm.ez[t][ll]);
+                qre = fma(sm.wre[t], ph.x, qre);
+                qim = fma(sm.wim[t], ph.y, qim);
+            }
+        }
+    }
+    __syncthreads();
+    sm.red[quarter][kl] = make_double2(qre, qim);
+    __syncthreads();
+    double e = 0.0;
+    if (quarter == 0 && kvalid) {
+        double2 Q = make_double2(0, 0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            Q.x += sm.red[q][kl].x;
+            Q.y += sm.red[q][kl].y;
+        }
+        if (store_q) {
+            E.Q[p0 + kl] = Q;
+        }
+        e = E.kA[p0 + kl].w * (Q.x * Q.x + Q.y * Q.y);
+    }
+    __syncthreads();
+    if (e_partials != nullptr) {
+        __shared__ double s_e[2];
+        if (threadIdx.x < 64) {
+            const double s = warpSum(e);
+            if ((threadIdx.x & 31) == 0) {
+                s_e[threadIdx.x >> 5] = s;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            e_partials[blockIdx.x] = s_e[0] + s_e[1];
+        }
+    }
+}
+
 } // namespace fbdev
