@@ -237,6 +237,48 @@ def sharded_extras(args, native, torch, dist, rank, world, local):
                           "pairs": N_IONS * (N_IONS - 1) // 2, "n_times_k": N_IONS * 57950},
     }
     sim.close()
+    if world > 1:
+        out["temper"] = temper_extras(native, torch, dist, rank, world, local)
+    return out
+
+
+def temper_extras(native, torch, dist, rank, world, local):
+    """Hamiltonian parallel tempering: one replica per GPU, replicas differ in eps_r; the
+    `temper` move of every sweep exchanges volume, group sizes, the XYZQI particle buffer and the energy change
+    with the partner rank through torch.distributed (NCCL send/recv between the GPUs)."""
+    from faunus_b200.config import primitive_model
+    from faunus_b200.replica import ReplicaSimulation, TorchReplicaComm
+    n, moves, sweeps = 20000, 200, 12
+    cfg = primitive_model(n=n, molarity=1.0, seed=5489, moves_per_sweep=moves,
+                          coulomb={"type": "ewald", "epsr": 78.7 * (1.0 + 0.01 * rank), "cutoff": 14.0, "alpha": 0.22,
+                                   "ncutoff": 12, "ewaldscheme": "PBC"})
+    cfg["moves"].append({"temper": {"format": "xyzqi"}})
+    native.load().fbh_set_device(local)
+    comm = TorchReplicaComm()
+    sim = ReplicaSimulation(native.sim_library(), cfg, comm)
+    native.load().fbh_sim_set_window(sim.handle, 64)
+    sim.sweep(2)
+    torch.cuda.synchronize()
+    dist.barrier(device_ids=[local])
+    b0, x0 = comm.bytes_exchanged, comm.exchanges
+    t0 = time.perf_counter()
+    sim.sweep(sweeps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    info = sim.info()
+    temper = [m["temper"] for m in info["moves"] if "temper" in m][0]
+    drift = sim.drift()
+    out = {"replicas": world, "particles_per_replica": n, "sweeps_per_s": sweeps / dt,
+           "moves_per_s_all_replicas": world * sweeps * moves / dt,
+           "exchange_attempts_per_s_this_rank": sum(s["attempts"] for s in temper["exchange"].values()) / dt,
+           "bytes_exchanged_per_sweep_this_rank": (comm.bytes_exchanged - b0) / sweeps,
+           "messages_per_sweep_this_rank": (comm.exchanges - x0) / sweeps,
+           "exchange_statistics_rank0": temper["exchange"], "relative_drift_rank0": drift,
+           "backend": dist.get_backend()}
+    sim.close()
     return out
 
 

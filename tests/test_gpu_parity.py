@@ -105,6 +105,25 @@ def test_bulk_example_trace(bulk_input, window):
     assert abs(g.drift()) < 1e-9
 
 
+def test_bulk_example_trace_1e5_moves(bulk_input):
+    """BASELINE.json north star: with the same seed the accept/reject sequence over 10^5 moves is identical
+    on the bundled example (examples/bulk: N = 2304, Fanourgakis + LJ; 44 sweeps = 101 376 moves, windowed)"""
+    o, g = pair_of_sims(bulk_input, 64)
+    for s in (o, g):
+        s.trace_enable()
+        s.sweep(44)
+    a, b = o.trace(), g.trace()
+    assert len(a["du"]) == 44 * 2304 > 100_000
+    assert np.array_equal(a["accepted"], b["accepted"])
+    finite = np.isfinite(a["du"])
+    assert np.array_equal(finite, np.isfinite(b["du"]))
+    assert np.abs(a["du"][finite] - b["du"][finite]).max() <= 1e-10 * np.abs(a["u_new"][np.isfinite(a["u_new"])]).max()
+    xo, _ = o.particles()
+    xg, _ = g.particles()
+    assert np.array_equal(xo, xg)
+    assert abs(g.drift()) < 1e-9
+
+
 @pytest.mark.parametrize("window", [0, 16])
 def test_minimal_example(minimal_input, window):
     o, g = pair_of_sims(minimal_input, window)
