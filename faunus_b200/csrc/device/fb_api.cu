@@ -197,7 +197,6 @@ struct fb_ctx
         DeviceBuffer<double2> d_table[2];
         PinnedBuffer<BatchInput> h_in;
         DeviceBuffer<double> d_pair_partials, d_r_partials, d_g_partials, d_e_partials, d_result;
-        DeviceBuffer<double2> d_delta; //!< sqrt(A_k) δ_m,k of the current window, [tile][move][k]
         PinnedBuffer<double> h_result;
         int parity = 0;
         int last_n = 0;            //!< moves of the most recent window (0: none evaluated)

@@ -6,16 +6,17 @@
 // the reciprocal energy before/after the partial Q(k) update (src/energy.cpp:219-247, 524-531).
 // A window of B such moves on DISTINCT atoms is evaluated here against the window-start state S0:
 //
-//   pair     u_new[m], u_old[m]     = Σ_{j≠p_m} u(trial_m | old_m , r_j(S0))           batchPairKernel
-//   cross    C_new[a][m], C_old[a][m] = u(x_m, new_a) − u(x_m, old_a)                   batchFinishKernel
-//   k-space  R[m]  = Σ_k A_k (2 Re(conj(Q_k) δ_m,k) + |δ_m,k|²)                        batchEwaldKernel
+//   pair     u_new[m], u_old[m]     = Σ_{j≠p_m} u(trial_m | old_m , r_j(S0))           batchPairKernel / batchPairCellKernel
+//   cross    C_new[a][m], C_old[a][m] = u(x_m, new_a) − u(x_m, old_a)                   batchPairFinishKernel
+//   k-space  R[m]  = Σ_k A_k (2 Re(conj(Q_k) δ_m,k) + |δ_m,k|²)                        batchKspaceKernel
 //            G[a][m] = Σ_k A_k Re(conj(δ_a,k) δ_m,k),  δ_m,k = q (e^{ik·new_m} − e^{ik·old_m})
 //
 // so that the energies of move m in the state where the accepted moves a < m have been applied are
 //   u_x[m] + Σ_{a accepted} C_x[a][m]          and     ΔU_rec = pref (R[m] + 2 Σ_{a accepted} G[a][m]),
 // exact identities — only the summation order differs from the one-move-at-a-time evaluation. The
 // caller walks the window in order, decides each move, and tells the next launch which were accepted
-// (batchCommitKernel writes their positions into both mirrors and adds their δ to Q(k)).
+// (batchPrepKernel writes their positions into both mirrors, batchKspaceKernel adds their δ to Q(k);
+// batchCommitKernel does both when windowed evaluation is left).
 //
 // e^{ik·r} is factorised into per-axis phase tables e^{i 2π n x/L} (k = 2π n/L on an orthogonal box),
 // built once per window by batchPhaseKernel: 2 complex products per (k, position) instead of a sincos.
@@ -25,12 +26,6 @@
 namespace fbdev {
 
 constexpr int kBatchMax = 64;    //!< moves per window
-constexpr int kBatchDeltaElems = 2048; //!< double2 elements of the δ tile in shared memory (32 KB + padding)
-/** k-vectors per tile of the k-space kernel for a window stride of 16 / 32 / 64 moves */
-__host__ __device__ constexpr int batchTileK(int stride)
-{
-    return kBatchDeltaElems / stride < 64 ? kBatchDeltaElems / stride : 64;
-}
 
 /** Host → device description of one window (copied as one block) */
 struct BatchInput
@@ -443,12 +438,7 @@ __global__ void __launch_bounds__(kPairThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k-space part, three kernels over tiles of kTileK k-vectors (every one with thousands of warps, the
-// intermediate δ array stays in L2):
-//   batchCommitQKernel  Q(k) += Σ_accepted δ of the previous window; Σ_k A_k|Q_k|² partial per tile
-//   batchDeltaKernel    lane ↔ k, warp ↔ moves: δ_m,k → R[m] partial per tile, sqrt(A_k) δ_m,k → scratch
-//   batchGramKernel     thread ↔ 4×4 entries of G (and a k sub-group): rank-kTileK updates from the scratch
-// BT = stride / 4 ∈ {4, 8, 16}.
+// k-space part (BT = stride / 4 ∈ {4, 8, 16}); cells of ≤ kTileK k-vectors, two per lane.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTileK = 64; //!< k-vectors per tile (two per lane)
 
@@ -502,242 +492,9 @@ __device__ __forceinline__ double2 cellPhase(const double2* t, int li, int lj, i
     return cmul(cmul(t[li], t[4 + lj]), t[8 + ll]);
 }
 
-/** grid = cells; block = 256: warp w takes the accepted moves a ≡ w (mod 8) for the cell's k-vectors */
-__global__ void __launch_bounds__(kBlock)
-    batchCommitQKernel(EwaldView E, const int4* __restrict__ kn, const int* __restrict__ cell_start, BatchBuffers prev,
-                       CommitList commit, PhaseGeometry geo, double* __restrict__ e_partials /*[gridDim.x]*/)
-{
-    constexpr int NW = kBlock / 32;
-    __shared__ double2 s_tab[2 * kBatchMax][kCellEntries];
-    __shared__ double2 s_dq[NW][kTileK];
-    __shared__ double s_cqn[kBatchMax], s_cqo[kBatchMax];
-    __shared__ int s_ctable[2 * kBatchMax];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int ncommit = commit.n;
-    const int p0 = cell_start[blockIdx.x];
-    const int len = cell_start[blockIdx.x + 1] - p0;
-    if (static_cast<int>(threadIdx.x) < ncommit) {
-        const int m = commit.index[threadIdx.x];
-        s_cqn[threadIdx.x] = prev.in->pnew[m].w;
-        s_cqo[threadIdx.x] = prev.pold[m].w;
-        s_ctable[2 * threadIdx.x] = 2 * m * geo.table_stride;
-        s_ctable[2 * threadIdx.x + 1] = (2 * m + 1) * geo.table_stride;
-    }
-    __syncthreads();
-    if (ncommit > 0) {
-        stageCellTables(s_tab, prev.table, s_ctable, 2 * ncommit, cellBase(__ldg(kn + p0), geo.ncc), geo);
-        __syncthreads();
-    }
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-        const int kl = lane + 32 * kk;
-        double2 dq = make_double2(0, 0);
-        if (kl < len && ncommit > 0) {
-            const int4 nn = __ldg(kn + p0 + kl);
-            const int li = nn.x & 3, lj = (nn.y + geo.ncc) & 3, ll = (nn.z + geo.ncc) & 3;
-            for (int a = warp; a < ncommit; a += NW) {
-                const double2 en = cellPhase(s_tab[2 * a], li, lj, ll);
-                const double2 eo = cellPhase(s_tab[2 * a + 1], li, lj, ll);
-                dq.x += s_cqn[a] * en.x - s_cqo[a] * eo.x;
-                dq.y += s_cqn[a] * en.y - s_cqo[a] * eo.y;
-            }
-        }
-        s_dq[warp][kl] = dq;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        double e = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-            const int kl = lane + 32 * kk;
-            if (kl < len) {
-                const int k = p0 + kl;
-                double2 Q = E.Q[k];
-#pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    Q.x += s_dq[w][kl].x;
-                    Q.y += s_dq[w][kl].y;
-                }
-                if (ncommit > 0) {
-                    E.Q[k] = Q;
-                }
-                e += E.kA[k].w * (Q.x * Q.x + Q.y * Q.y);
-            }
-        }
-        e = warpSum(e);
-        if (lane == 0) {
-            e_partials[blockIdx.x] = e;
-        }
-    }
-}
-
-/**
- * grid = cells; block = 256 threads: lane ↔ k-vector of the cell (two per lane), warp ↔ moves.
- * scratch layout: [tile of kTileK consecutive k][m (stride)][k local] double2 — dense tiles of the
- * cell-ordered k index for the Gram kernel. r_partials [cell][stride].
- */
-__global__ void __launch_bounds__(kBlock)
-    batchDeltaKernel(EwaldView E, const int4* __restrict__ kn, const double* __restrict__ sqrt_ak,
-                     const int* __restrict__ cell_start, BatchBuffers cur, PhaseGeometry geo, int stride,
-                     double2* __restrict__ scratch, double* __restrict__ r_partials)
-{
-    constexpr int NW = kBlock / 32;
-    __shared__ double2 s_tab[2 * kBatchMax][kCellEntries];
-    const int n = cur.in->n;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int p0 = cell_start[blockIdx.x];
-    const int len = cell_start[blockIdx.x + 1] - p0;
-    stageCellTables(s_tab, cur.table, nullptr, 2 * n, cellBase(__ldg(kn + p0), geo.ncc), geo);
-
-    int li[2], lj[2], ll[2];
-    double2 Q[2];
-    double A[2], sA[2];
-    bool valid[2];
-    size_t out[2];
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-        const int kl = lane + 32 * kk;
-        const int k = p0 + kl;
-        valid[kk] = kl < len;
-        li[kk] = lj[kk] = ll[kk] = 0;
-        Q[kk] = make_double2(0, 0);
-        A[kk] = 0.0;
-        sA[kk] = 0.0;
-        out[kk] = 0;
-        if (valid[kk]) {
-            const int4 nn = __ldg(kn + k);
-            li[kk] = nn.x & 3;
-            lj[kk] = (nn.y + geo.ncc) & 3;
-            ll[kk] = (nn.z + geo.ncc) & 3;
-            Q[kk] = E.Q[k];
-            A[kk] = E.kA[k].w;
-            sA[kk] = __ldg(sqrt_ak + k);
-            out[kk] = static_cast<size_t>(k / kTileK) * stride * kTileK + (k % kTileK);
-        }
-    }
-    __syncthreads();
-    for (int m = warp; m < stride; m += NW) {
-        double racc = 0.0;
-        double2 d[2] = {make_double2(0, 0), make_double2(0, 0)};
-        if (m < n) {
-            const double qn = cur.in->pnew[m].w;
-            const double qo = cur.pold[m].w;
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                if (valid[kk]) {
-                    const double2 en = cellPhase(s_tab[2 * m], li[kk], lj[kk], ll[kk]);
-                    const double2 eo = cellPhase(s_tab[2 * m + 1], li[kk], lj[kk], ll[kk]);
-                    d[kk].x = qn * en.x - qo * eo.x;
-                    d[kk].y = qn * en.y - qo * eo.y;
-                    racc += A[kk] * (2.0 * (Q[kk].x * d[kk].x + Q[kk].y * d[kk].y) + (d[kk].x * d[kk].x + d[kk].y * d[kk].y));
-                }
-            }
-        }
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-            if (valid[kk]) {
-                scratch[out[kk] + static_cast<size_t>(m) * kTileK] = make_double2(sA[kk] * d[kk].x, sA[kk] * d[kk].y);
-            }
-        }
-        racc = warpSum(racc);
-        if (lane == 0) {
-            r_partials[static_cast<size_t>(blockIdx.x) * stride + m] = racc;
-        }
-    }
-    if (blockIdx.x == gridDim.x - 1) { // zero the unused tail of the last dense tile
-        const int tail0 = E.K;
-        const int tail1 = ((E.K + kTileK - 1) / kTileK) * kTileK;
-        for (int e = threadIdx.x; e < (tail1 - tail0) * stride; e += kBlock) {
-            const int k = tail0 + e % (tail1 - tail0);
-            const int m = e / (tail1 - tail0);
-            scratch[static_cast<size_t>(k / kTileK) * stride * kTileK + static_cast<size_t>(m) * kTileK + (k % kTileK)] =
-                make_double2(0, 0);
-        }
-    }
-}
-
-template <int BT>
-__global__ void __launch_bounds__(kBlock, 2)
-    batchGramKernel(const double2* __restrict__ scratch, int n_tiles, double* __restrict__ g_partials /*[gridDim.x][stride²]*/)
-{
-    constexpr int STRIDE = BT * 4;
-    constexpr int NTILE = BT * BT;           // 4×4 output tiles
-    constexpr int KG = kBlock / NTILE;       // k sub-groups: 16, 4, 1
-    constexpr int KH = STRIDE == 64 ? 32 : kTileK; // k-vectors staged at a time (shared memory ≤ 48 KB)
-    constexpr int LD = KH + 1;               // padded leading dimension of s_delta[m][k]
-    constexpr int DELTA_ELEMS = STRIDE * LD > 2048 ? STRIDE * LD : 2048; // ≥ 32 KB: reused for the final reduction
-    __shared__ double2 s_delta[DELTA_ELEMS];
-
-    const int tile_id = threadIdx.x % NTILE;
-    const int kg = threadIdx.x / NTILE;
-    const int ta = tile_id / BT; // this thread owns G[ta + BT·i][tm + BT·j], i ≤ j < 4 (bank-conflict-free reads)
-    const int tm = tile_id % BT;
-
-    double gacc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            gacc[i][j] = 0.0;
-        }
-    }
-    for (int part = blockIdx.x; part < n_tiles * (kTileK / KH); part += gridDim.x) {
-        const int tile = part / (kTileK / KH);
-        const int half = part % (kTileK / KH);
-        const double2* src = scratch + static_cast<size_t>(tile) * STRIDE * kTileK + half * KH;
-        __syncthreads(); // previous part consumed
-        for (int e = threadIdx.x; e < STRIDE * KH; e += kBlock) {
-            const int m = e / KH;
-            const int kl = e % KH;
-            s_delta[m * LD + kl] = src[m * kTileK + kl];
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int kl = kg; kl < KH; kl += KG) {
-            double2 da[4], dm[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                da[i] = s_delta[(ta + BT * i) * LD + kl];
-                dm[i] = s_delta[(tm + BT * i) * LD + kl];
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                for (int j = i; j < 4; ++j) { // a = ta + BT·i < m = tm + BT·j needs i ≤ j
-                    gacc[i][j] = fma(da[i].x, dm[j].x, fma(da[i].y, dm[j].y, gacc[i][j]));
-                }
-            }
-        }
-    }
-    // reduce the k sub-groups through shared memory (fixed order), then one store per element
-    __syncthreads();
-    double* s_g = reinterpret_cast<double*>(s_delta); // [16][kBlock] doubles = 32 KB, thread-fastest
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            s_g[(i * 4 + j) * kBlock + threadIdx.x] = gacc[i][j];
-        }
-    }
-    __syncthreads();
-    for (int o = threadIdx.x; o < NTILE * 16; o += kBlock) {
-        const int t = o % NTILE;
-        const int ij = o / NTILE;
-        double s = 0.0;
-        for (int g = 0; g < KG; ++g) {
-            s += s_g[ij * kBlock + g * NTILE + t];
-        }
-        const int a = (t / BT) + BT * (ij / 4);
-        const int m = (t % BT) + BT * (ij % 4);
-        g_partials[static_cast<size_t>(blockIdx.x) * (STRIDE * STRIDE) + a * STRIDE + m] = s;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// The same three steps in ONE persistent kernel: block b walks the cells b, b + grid, … and keeps the
-// per-move and per-pair sums in registers, so nothing but the final partials leaves the SM:
+// ONE persistent kernel: block b walks the cells b, b + grid, … and keeps the per-move and per-pair sums in
+// registers, so nothing but the final partials leaves the SM:
 //   per cell: stage the 12 table entries of every position (accepted moves of the previous window and the
 //   2B positions of this one) → ΔQ of the commits (warps split the commits) → Q(k) updated in place →
 //   δ_m,k for the warp's moves into shared memory, R[m] in registers → rank-update of G from shared memory.
