@@ -67,7 +67,7 @@ class ClockSampler:
                 ["nvidia-smi", f"--id={self.index}",
                  "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"],
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -257,7 +257,7 @@ def temper_extras(native, torch, dist, rank, world, local):
     comm = TorchReplicaComm()
     sim = ReplicaSimulation(native.sim_library(), cfg, comm)
     native.load().fbh_sim_set_window(sim.handle, 64)
-    sim.sweep(2)
+    sim.sweep(8)  # both odd/even partner pairings occur: NCCL sets up its peer connections lazily
     torch.cuda.synchronize()
     dist.barrier(device_ids=[local])
     b0, x0 = comm.bytes_exchanged, comm.exchanges
@@ -305,14 +305,14 @@ def b200_arm(args):
         flush_buffer.fill_(1)
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)  # samples every 50 ms from the warm-up on (same load) until the timing pass ends
+    sampler.start()
     for _ in range(args.warmup):
         flush_l2()
         sim.sweep(1)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier(device_ids=[local])
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = sim.launch_count
     wt0 = sim.window_time_ms()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
