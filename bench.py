@@ -77,17 +77,20 @@ class ClockSampler:
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 6:
-                self.samples.append(parts)
+                self.samples.append((time.perf_counter(), parts))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """median SM clock / reasons of the samples that arrived in [t_begin, t_end] (the window under load)"""
         if self.proc:
             self.proc.terminate()
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        window = [p for t, p in self.samples if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end)]
+        sm = sorted(int(s[0]) for s in window if s[0].isdigit())
+        mx = [int(s[1]) for s in window if s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[2 + i].lower() == "active"})
+        reasons = sorted({names[i] for s in window for i in range(4) if s[2 + i].lower() == "active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm),
+                "window": "warm-up + timed steps + per-kernel timing pass (same workload), nvidia-smi every 50 ms"}
 
 
 def dist_setup(n_gpus: int, backend: str):
@@ -290,6 +293,8 @@ def b200_arm(args):
     torch.cuda.set_device(local)
     if dist is not None:
         dist.barrier(device_ids=[local])
+    sampler = ClockSampler(local)  # nvidia-smi needs ~1 s to start: launched before the simulation is set up
+    sampler.start()
     cfg = workload(seed=5489 + rank)
     sim = native.B200Simulation(cfg, device=local, window=args.window)
     n = sim.num_particles
@@ -305,8 +310,7 @@ def b200_arm(args):
         flush_buffer.fill_(1)
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)  # samples every 50 ms from the warm-up on (same load) until the timing pass ends
-    sampler.start()
+    t_load_begin = time.perf_counter()
     for _ in range(args.warmup):
         flush_l2()
         sim.sweep(1)
@@ -343,7 +347,7 @@ def b200_arm(args):
         sim.sweep(1)
     w1, s1 = sim.window_time_ms(), sim.device_time_ms()
     sim.enable_timing(False)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_load_begin, time.perf_counter())
     windowed = sim.window > 0
     if windowed:
         pair_ms = w1["pair_ms"] - w0["pair_ms"]

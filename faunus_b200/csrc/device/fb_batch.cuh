@@ -84,6 +84,19 @@ __device__ __forceinline__ bool anyBelow(double a, double b, double c, double d,
     return p != 0;
 }
 
+/**
+ * Position (x, y, z) and fold flags of variant `v` from shared memory through 32-bit shared addresses that
+ * the caller computes ONCE: with ordinary indexing nvcc re-derives the shared window base (S2UR
+ * SR_CgaCtaId + 6 uniform instructions) in every iteration of the pair loops.
+ */
+__device__ __forceinline__ void loadVariant(unsigned var_addr, unsigned fold_addr, int v, double4& a, int& fold)
+{
+    const unsigned at = var_addr + static_cast<unsigned>(v) * 32u;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a.x), "=d"(a.y) : "r"(at));
+    asm("ld.shared.f64 %0, [%1+16];" : "=d"(a.z) : "r"(at));
+    asm("ld.shared.s32 %0, [%1];" : "=r"(fold) : "r"(fold_addr + static_cast<unsigned>(v) * 4u));
+}
+
 /** e^{ik·r} for k = 2π(nx, ny, nz)/L from the phase table of one position */
 __device__ __forceinline__ double2 tablePhase(const double2* __restrict__ t, const PhaseGeometry& g, int nx, int ny,
                                               int nz)
@@ -317,6 +330,8 @@ __global__ void __launch_bounds__(kPairThreads)
     };
 
     // two variants per iteration (four independent r² chains per lane); blockIdx.y selects the variant range
+    const unsigned var_addr = static_cast<unsigned>(__cvta_generic_to_shared(&s_var[0]));
+    const unsigned fold_addr = static_cast<unsigned>(__cvta_generic_to_shared(&s_vfold[0]));
     const int v_begin = blockIdx.y * kPairVariantsPerBlock;
     const int v_end = min(nv, v_begin + kPairVariantsPerBlock);
     for (int v0 = v_begin; v0 < v_end; v0 += 2) {
@@ -325,9 +340,7 @@ __global__ void __launch_bounds__(kPairThreads)
         double r2[2][kPairPerThread];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const int v = min(v0 + u, v_end - 1);
-            a[u] = s_var[v];
-            fold[u] = s_vfold[v];
+            loadVariant(var_addr, fold_addr, min(v0 + u, v_end - 1), a[u], fold[u]);
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -409,7 +422,7 @@ __global__ void __launch_bounds__(kPairThreads)
 #pragma unroll
                     for (int t = 0; t < kPairPerThread; ++t) {
                         if (r2[u][t] < cut2 && pj[t] != vslot) {
-                            e += pairEnergy<KIND>(P, vid, pid[t], a[u].w, p[t].w, r2[u][t]);
+                            e += pairEnergy<KIND>(P, vid, pid[t], s_var[v].w, p[t].w, r2[u][t]);
                         }
                     }
                     e = warpSum(e);

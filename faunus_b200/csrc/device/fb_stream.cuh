@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(kStreamThreads)
         queued = 0;
     };
 
+    const unsigned var_addr = static_cast<unsigned>(__cvta_generic_to_shared(&s_var[0]));
+    const unsigned fold_addr = static_cast<unsigned>(__cvta_generic_to_shared(&s_vfold[0]));
     for (int base = 0; base < V.n_slots; base += kStreamChunk) {
         double4 p[2];
         int pid[2], pj[2];
@@ -161,9 +163,7 @@ __global__ void __launch_bounds__(kStreamThreads)
             double r2[2][2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const int v = min(vv + u, nv - 1);
-                a[u] = s_var[v];
-                fold[u] = s_vfold[v];
+                loadVariant(var_addr, fold_addr, min(vv + u, nv - 1), a[u], fold[u]);
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kStreamThreads)
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
                         if (r2[u][t] < cut2) {
-                            e += pairEnergy<KIND>(P, s_vid[v], pid[t], a[u].w, p[t].w, r2[u][t]);
+                            e += pairEnergy<KIND>(P, s_vid[v], pid[t], s_var[v].w, p[t].w, r2[u][t]);
                         }
                     }
                     e = warpSum(e);
@@ -312,6 +312,8 @@ __global__ void __launch_bounds__(kStreamThreads)
         queued = 0;
     };
 
+    const unsigned var_addr = static_cast<unsigned>(__cvta_generic_to_shared(&s_var[0]));
+    const unsigned fold_addr = static_cast<unsigned>(__cvta_generic_to_shared(&s_vfold[0]));
     // j-chunks from the one containing i0 on; blockIdx.y takes every gridDim.y-th chunk
     const int first_chunk = i0 / kStreamChunk;
     const int n_chunks = (V.n_slots + kStreamChunk - 1) / kStreamChunk;
@@ -338,8 +340,7 @@ __global__ void __launch_bounds__(kStreamThreads)
             double r2[2][2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                a[u] = s_var[vv + u];
-                fold[u] = s_vfold[vv + u];
+                loadVariant(var_addr, fold_addr, vv + u, a[u], fold[u]);
             }
             bool in[2][2];
 #pragma unroll
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(kStreamThreads)
                 for (int t = 0; t < 2; ++t) {
                     if (DENSE) {
                         if (in[u][t]) {
-                            esum += pairEnergy<KIND>(P, s_vid[vv + u], pid[t], a[u].w, p[t].w, r2[u][t]);
+                            esum += pairEnergy<KIND>(P, s_vid[vv + u], pid[t], s_var[vv + u].w, p[t].w, r2[u][t]);
                         }
                     }
                     else {

@@ -40,6 +40,11 @@ def electrolyte_variants():
                                                    coulomb={"type": "fanourgakis", "epsr": 78.7, "cutoff": 12.0}),
         "coulombwca_yukawa": small_electrolyte(coulomb={"type": "yukawa", "epsr": 78.7, "debyelength": 9.0}),
         "coulombwca_qpot": small_electrolyte(coulomb={"type": "qpotential", "epsr": 78.7, "cutoff": 12.0, "order": 3}),
+        "coulombwca_wolf": small_electrolyte(coulomb={"type": "wolf", "epsr": 78.7, "cutoff": 12.0, "alpha": 0.2}),
+        "coulombwca_zerodipole": small_electrolyte(coulomb={"type": "zerodipole", "epsr": 78.7, "cutoff": 12.0, "alpha": 0.2}),
+        "coulombwca_reactionfield": small_electrolyte(coulomb={"type": "reactionfield", "epsr": 78.7, "epsrf": 40.0,
+                                                                "cutoff": 12.0}),
+        "coulombwca_poisson": small_electrolyte(coulomb={"type": "poisson", "epsr": 78.7, "cutoff": 12.0, "C": 4, "D": 3}),
         "pm": small_electrolyte(energy_name="nonbonded_pm", coulomb={"epsr": 78.7}, sigma=3.0),
         "pmwca": small_electrolyte(energy_name="nonbonded_pmwca", coulomb={"epsr": 78.7}),
     }
