@@ -541,7 +541,7 @@ template <int BT> struct KspaceSmem
 {
     static constexpr int STRIDE = BT * 4;
     static constexpr int KH = STRIDE == 64 ? 32 : kTileK; //!< k-vectors per pass
-    static constexpr int LD = KH + 1;
+    static constexpr int LD = KH + 2; //!< row stride ≡ 32 B (mod 128 B): the DMMA fragment loads are conflict-free
     static constexpr int DELTA_ELEMS = STRIDE * LD > 2048 ? STRIDE * LD : 2048;
     static constexpr int NBUF = STRIDE == 64 ? 1 : 2; //!< double-buffered staging where two blocks per SM still fit
     static constexpr int MAX_CELLS = 32;              //!< cells per block held in the list (more: extra rounds)
@@ -567,8 +567,13 @@ __global__ void __launch_bounds__(kBlock, 2)
     constexpr int NW = kBlock / 32;
     constexpr int KPL = KH / 32;               // k-vectors per lane and pass
     constexpr int MPW = STRIDE / NW;           // moves per warp: 2, 4, 8
-    constexpr int NTILE = BT * BT;
-    constexpr int KG = kBlock / NTILE;         // k sub-groups of the Gram update: 16, 4, 1
+    // Gram update on the FP64 tensor path (mma.sync m8n8k4): 8×8 tiles of G, only the tiles on or above the
+    // diagonal; the 8 warps form KGW k-groups of WPG warps, the tiles of a group are dealt round robin.
+    constexpr int T = STRIDE / 8;              // tiles per dimension: 2, 4, 8
+    constexpr int NT = T * (T + 1) / 2;        // upper-triangular tiles: 3, 10, 36
+    constexpr int KGW = STRIDE == 64 ? 1 : (STRIDE == 32 ? 2 : 8);
+    constexpr int WPG = NW / KGW;              // warps per k-group: 8, 4, 1
+    constexpr int MAXT = (NT + WPG - 1) / WPG; // tiles per warp: 5, 3, 3
     using Stage = CellStage<STRIDE>;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -584,10 +589,25 @@ __global__ void __launch_bounds__(kBlock, 2)
     const int ncommit = min(commit.n, STRIDE);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int tile_id = threadIdx.x % NTILE;
-    const int kg = threadIdx.x / NTILE;
-    const int ta = tile_id / BT; // this thread owns G[ta + BT·i][tm + BT·j], i ≤ j
-    const int tm = tile_id % BT;
+    const int kgroup = warp / WPG;
+    const int wig = warp % WPG;                // warp in its k-group
+    const int frag_g = lane >> 2;              // DMMA fragment coordinates of this lane
+    const int frag_t = lane & 3;
+    int tile_a[MAXT], tile_m[MAXT];            // this warp's tiles (ta ≤ tm), −1: none
+#pragma unroll
+    for (int q = 0; q < MAXT; ++q) {
+        int idx = wig + q * WPG;
+        tile_a[q] = tile_m[q] = -1;
+        if (idx < NT) {
+            int ta = 0;
+            while (idx >= T - ta) {
+                idx -= T - ta;
+                ++ta;
+            }
+            tile_a[q] = ta;
+            tile_m[q] = ta + idx;
+        }
+    }
 
     // the cells of this block: b, b + grid, …
     const int my_cells = (n_cells - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -659,13 +679,10 @@ __global__ void __launch_bounds__(kBlock, 2)
         qo[i] = (m < n) ? cur.pold[m].w : 0.0;
         racc[i] = 0.0;
     }
-    double gacc[4][4];
+    double gacc[MAXT][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            gacc[i][j] = 0.0;
-        }
+    for (int q = 0; q < MAXT; ++q) {
+        gacc[q][0] = gacc[q][1] = 0.0;
     }
     double eacc = 0.0;
 
@@ -763,20 +780,19 @@ __global__ void __launch_bounds__(kBlock, 2)
                 }
             }
             __syncthreads();
-            const int kend = min(KH, len - pass0);
-#pragma unroll 2
-            for (int kl = kg; kl < kend; kl += KG) {
-                double2 da[4], dm[4];
+            // rank update of G: A[a][kk] = B[kk][m] = √A_k δ (re, im of two k-vectors per step of 4)
+            const int ksteps = (min(KH, len - pass0) + 1) / 2;
+            const double* sd = reinterpret_cast<const double*>(s_delta);
+            for (int step = kgroup; step < ksteps; step += KGW) {
+                const int col = 4 * step + frag_t; // double index inside a row: 2·k + (re | im)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    da[i] = s_delta[(ta + BT * i) * LD + kl];
-                    dm[i] = s_delta[(tm + BT * i) * LD + kl];
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                    for (int j = i; j < 4; ++j) {
-                        gacc[i][j] = fma(da[i].x, dm[j].x, fma(da[i].y, dm[j].y, gacc[i][j]));
+                for (int q = 0; q < MAXT; ++q) {
+                    if (tile_a[q] >= 0) {
+                        const double fa = sd[(tile_a[q] * 8 + frag_g) * (2 * LD) + col];
+                        const double fb = sd[(tile_m[q] * 8 + frag_g) * (2 * LD) + col];
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                     : "+d"(gacc[q][0]), "+d"(gacc[q][1])
+                                     : "d"(fa), "d"(fb));
                     }
                 }
             }
@@ -800,26 +816,29 @@ __global__ void __launch_bounds__(kBlock, 2)
             r_partials[static_cast<size_t>(blockIdx.x) * STRIDE + warp * MPW + i] = rs;
         }
     }
+    // G: add the k-groups in fixed order through shared memory; lane (g, t) of a tile holds G[8ta + g][8tm + 2t + {0, 1}]
     __syncthreads();
-    double* s_g = reinterpret_cast<double*>(s_delta); // [16][kBlock] doubles = 32 KB, thread-fastest
+    double* s_g = reinterpret_cast<double*>(s_delta); // [KGW][STRIDE²] doubles (≤ 32 KB)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            s_g[(i * 4 + j) * kBlock + threadIdx.x] = gacc[i][j];
+    for (int q = 0; q < MAXT; ++q) {
+        if (tile_a[q] >= 0) {
+            const int a = tile_a[q] * 8 + frag_g;
+            const int m = tile_m[q] * 8 + 2 * frag_t;
+            s_g[kgroup * STRIDE * STRIDE + a * STRIDE + m] = gacc[q][0];
+            s_g[kgroup * STRIDE * STRIDE + a * STRIDE + m + 1] = gacc[q][1];
         }
     }
     __syncthreads();
-    for (int o = threadIdx.x; o < NTILE * 16; o += kBlock) {
-        const int t = o % NTILE;
-        const int ij = o / NTILE;
+    for (int o = threadIdx.x; o < STRIDE * STRIDE; o += kBlock) {
+        const int a = o / STRIDE;
+        const int m = o % STRIDE;
         double sum = 0.0;
-        for (int g = 0; g < KG; ++g) {
-            sum += s_g[ij * kBlock + g * NTILE + t];
+        if (a / 8 <= m / 8) { // a tile on or above the diagonal was computed
+            for (int g = 0; g < KGW; ++g) {
+                sum += s_g[g * STRIDE * STRIDE + o];
+            }
         }
-        const int a = (t / BT) + BT * (ij / 4);
-        const int m = (t % BT) + BT * (ij % 4);
-        g_partials[static_cast<size_t>(blockIdx.x) * (STRIDE * STRIDE) + a * STRIDE + m] = sum;
+        g_partials[static_cast<size_t>(blockIdx.x) * (STRIDE * STRIDE) + o] = sum;
     }
 }
 
