@@ -785,7 +785,7 @@ class B200WindowEvaluator : public WindowEvaluator
             if (!accepted[a]) {
                 continue;
             }
-            const size_t am = static_cast<size_t>(a) * S + m;
+            const size_t am = static_cast<size_t>(m) * S + a; // row m: contiguous over the earlier moves
             if (!(res.cross_max[am] < cancellation_limit)) {
                 return false;
             }

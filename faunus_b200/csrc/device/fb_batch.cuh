@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(kBlock, 2)
 // result layout (doubles), S = stride:
 //   [0] Σ_k A_k|Q_k|² at window start   [1] n
 //   [8 + 0·S ..) u_new   [8 + 1·S ..) u_old   [8 + 2·S ..) R
-//   [8 + 3·S + 0·S² ..) C_new[a][m]   [+1·S²) C_old   [+2·S²) C_max   [+3·S²) G
+//   [8 + 3·S + 0·S² ..) C_new   [+1·S²) C_old   [+2·S²) C_max   [+3·S²) G      each stored [m][a], a < m
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t batchResultDoubles(int stride)
 {
@@ -920,9 +920,10 @@ __global__ void __launch_bounds__(kBlock)
             }
         }
         if (lane == 0) {
-            cross[t] = cn;
-            cross[S * S + t] = co;
-            cross[2 * S * S + t] = cmax;
+            const int tt = m * S + a; // stored [m][a]: the caller reads one row per move
+            cross[tt] = cn;
+            cross[S * S + tt] = co;
+            cross[2 * S * S + tt] = cmax;
         }
     }
 }
@@ -957,7 +958,7 @@ __global__ void __launch_bounds__(kBlock)
             g = warpColumnSum(g_partials, n_rows, static_cast<size_t>(S) * S, t, lane);
         }
         if (lane == 0) {
-            cross[3 * S * S + t] = g;
+            cross[3 * S * S + m * S + a] = g; // stored [m][a]
         }
     }
     else if (w == S + S * S) {

@@ -228,15 +228,15 @@ int fb_trial_commit(fb_ctx* ctx, int accept);
  * slots must mirror the accepted state) and returns, besides the per-move energies, the exact
  * corrections that apply when an EARLIER move of the window has been accepted:
  *
- *   u_new(m | accepted set A) = u_new[m] + sum_{a in A, a < m} cross_new[a * stride + m]
- *   u_old(m | A)              = u_old[m] + sum_{a in A, a < m} cross_old[a * stride + m]
- *   dU_rec(m | A)             = rec_prefactor * (rec_delta[m] + 2 sum_{a in A, a < m} rec_cross[a * stride + m])
+ *   u_new(m | accepted set A) = u_new[m] + sum_{a in A, a < m} cross_new[m * stride + a]
+ *   u_old(m | A)              = u_old[m] + sum_{a in A, a < m} cross_old[m * stride + a]
+ *   dU_rec(m | A)             = rec_prefactor * (rec_delta[m] + 2 sum_{a in A, a < m} rec_cross[m * stride + a])
  *
  * (nonbonded energy of the moved atom with all other active particles, src/energy.h:1182-1195 + 885-914;
  * reciprocal Ewald energy change of the partial update, src/energy.cpp:219-247 + 524-531.) The caller
  * decides the moves in order (Metropolis on the host, reference RNG order) and reports the outcome with
  * fb_batch_commit; undecided moves (n_decided < n_moves) are simply dropped and may be re-submitted.
- * cross_max[a * stride + m] is the largest |pair energy| entering cross_new/old: if it is huge or
+ * cross_max[m * stride + a] is the largest |pair energy| entering cross_new/old: if it is huge or
  * infinite the caller should stop the window at move m and re-evaluate it in the next one
  * (cancellation). The result arrays live in pinned memory owned by the context and stay valid until
  * the next fb_batch_trial. */
@@ -253,11 +253,11 @@ typedef struct
 typedef struct
 {
     int n_moves;
-    int stride;              /* row length of the [a][m] matrices (16, 32 or 64) */
+    int stride;              /* row length of the [m][a] matrices (16, 32 or 64): one row per move m */
     const double* u_new;     /* [n_moves] */
     const double* u_old;     /* [n_moves] */
     const double* rec_delta; /* [n_moves] sum_k A_k (2 Re(conj Q_k d_k) + |d_k|^2), 0 without Ewald */
-    const double* cross_new; /* [stride * stride], entries a < m */
+    const double* cross_new; /* [stride * stride], row m holds the entries of the earlier moves a < m */
     const double* cross_old;
     const double* cross_max;
     const double* rec_cross; /* sum_k A_k Re(conj d_a,k d_m,k) */

@@ -300,9 +300,9 @@ def test_window_matches_single_moves():
     scale = np.abs(ref[:, :2]).max()
     for m in range(n):
         acc = [a for a in range(m) if accept[a]]
-        un = u_new[m] + sum(cn[a, m] for a in acc)
-        uo = u_old[m] + sum(co[a, m] for a in acc)
-        dr = rec[m] + 2 * sum(g[a, m] for a in acc)
+        un = u_new[m] + sum(cn[m, a] for a in acc)   # matrices are stored [m][a]
+        uo = u_old[m] + sum(co[m, a] for a in acc)
+        dr = rec[m] + 2 * sum(g[m, a] for a in acc)
         assert abs(un - ref[m, 0]) <= RTOL * scale
         assert abs(uo - ref[m, 1]) <= RTOL * scale
         assert abs(res.rec_prefactor * run - ref[m, 3]) <= RTOL * abs(ref[m, 3])
