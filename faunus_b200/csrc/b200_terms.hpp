@@ -694,7 +694,8 @@ class B200WindowEvaluator : public WindowEvaluator
   public:
     static constexpr double cancellation_limit = 1e4; //!< kT; larger pair terms in a correction → re-evaluate
 
-    /** nullptr if the Hamiltonian holds anything but self energy / B200 non-bonded / tinfoil Ewald terms */
+    /** nullptr if the Hamiltonian holds anything but per-atom host terms (self energy, isobaric, container
+     * overlap), one B200 non-bonded term and a tinfoil PBC Ewald term */
     static std::unique_ptr<B200WindowEvaluator> tryCreate(MetropolisMonteCarlo& mc, int capacity)
     {
         if (capacity < 1) {
@@ -708,7 +709,10 @@ class B200WindowEvaluator : public WindowEvaluator
             return nullptr;
         }
         for (const auto& t : terms) {
-            if (std::dynamic_pointer_cast<ParticleSelfEnergyB200>(t)) {
+            // host terms that only look at the atoms the Change lists (or at nothing for a particle move): their
+            // energy(change) stays valid while OTHER proposals are pending in the trial Space
+            if (std::dynamic_pointer_cast<ParticleSelfEnergyB200>(t) || std::dynamic_pointer_cast<Isobaric>(t) ||
+                std::dynamic_pointer_cast<ContainerOverlap>(t)) {
                 kinds.push_back(Kind::SELF);
             }
             else if (auto nb = std::dynamic_pointer_cast<NonbondedB200>(t)) {
@@ -806,6 +810,7 @@ class B200WindowEvaluator : public WindowEvaluator
                 double u = 0.0;
                 switch (kinds[i]) {
                 case Kind::SELF:
+                    terms[i]->state = pot.state;
                     u = terms[i]->energy(proposal.change);
                     break;
                 case Kind::NONBONDED:

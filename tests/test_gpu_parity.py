@@ -409,3 +409,29 @@ def test_window_cell_list(capacity):
     assert_close(a["u_old"], b["u_old"], scale=scale)
     assert abs(g.drift()) < 1e-9
     assert g.launch_count > launches0
+
+
+def test_window_with_volume_moves():
+    """NPT electrolyte: runs of windowed `transrot` moves interleaved with `volume` moves (everything changes:
+    box, k-vectors, Q(k), cell list) — the queue is drained, the other move runs one at a time, windows resume"""
+    cfg = small_electrolyte(n=300, moves_per_sweep=60,
+                            coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 5})
+    cfg["energy"] = [{"isobaric": {"P/mM": 2000.0}}] + cfg["energy"]
+    cfg["moves"].append({"volume": {"dV": 0.03, "repeat": 6}})
+    o = oracle_sim(cfg)
+    g = b200_sim(cfg, 16)
+    assert g.window == 16   # the isobaric term is a per-atom host term: windows stay eligible
+    g.configure_cells(0)
+    for s in (o, g):
+        s.trace_enable()
+        s.sweep(6)
+    a, b = o.trace(), g.trace()
+    assert (a["move_id"] == 1).sum() > 5, "no volume moves sampled"
+    assert np.array_equal(a["move_id"], b["move_id"])
+    assert np.array_equal(a["accepted"], b["accepted"])
+    scale = np.abs(o.system_energy()[1]).max()
+    assert_close(a["du"], b["du"], rtol=1e-9, scale=scale)   # volume moves: differences of full energies
+    assert_close(o.system_energy()[1], g.system_energy()[1], scale=scale)
+    xo, _ = o.particles()
+    xg, _ = g.particles()
+    assert np.array_equal(xo, xg)
