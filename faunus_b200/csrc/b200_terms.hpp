@@ -682,6 +682,10 @@ class B200WindowEvaluator : public WindowEvaluator
     int window_capacity;
     fb_batch_result res{};
     std::vector<fb_batch_move> moves;
+    std::vector<fb_batch_group_move> group_moves;
+    bool group_mode = false;         //!< the window in flight holds rigid-molecule moves
+    std::vector<int> first_atom;     //!< group mode: atoms [first_atom[m], first_atom[m + 1]) belong to move m
+    int largest_molecule = 0;        //!< atoms in the largest molecular group
     std::vector<double> rec_change; //!< corrected raw reciprocal change Σ_k A_k(…) of each decided move
     enum class Kind
     {
@@ -740,13 +744,92 @@ class B200WindowEvaluator : public WindowEvaluator
         e->dev = nonbonded->device();
         e->with_ewald = d.has_ewald;
         e->kinds = std::move(kinds);
+        for (const auto& g : mc.state.spc->groups) {
+            if (g.isMolecular()) {
+                e->largest_molecule = std::max(e->largest_molecule, static_cast<int>(g.capacity()));
+            }
+        }
         return e;
     }
 
     int capacity() const override { return window_capacity; }
 
+    bool supports(WindowProposal::Kind kind) const override
+    {
+        return kind == WindowProposal::Kind::ATOM || (largest_molecule >= 1 && largest_molecule <= FB_FAST_ATOMS);
+    }
+
+    /** group mode: a window holds at most FB_BATCH_MAX ATOMS */
+    int fit(const std::vector<WindowProposal>& window, int ready) const override
+    {
+        int n = std::min(ready, window_capacity);
+        if (n > 0 && window.front().kind == WindowProposal::Kind::GROUP) {
+            const Space& trial = *mc.trial_state.spc;
+            int atoms = 0;
+            int m = 0;
+            for (; m < n; ++m) {
+                atoms += static_cast<int>(trial.groups.at(window[m].change.groups.at(0).group_index).size());
+                if (atoms > FB_BATCH_MAX) {
+                    break;
+                }
+            }
+            n = std::max(1, m);
+        }
+        return n;
+    }
+
+    void submitGroups(const std::vector<WindowProposal>& window, int n)
+    {
+        group_moves.resize(static_cast<size_t>(n));
+        first_atom.assign(static_cast<size_t>(n) + 1, 0);
+        const Space& trial = *mc.trial_state.spc;
+        const Space& accepted = *mc.state.spc;
+        for (int m = 0; m < n; ++m) {
+            const auto& gc = window[m].change.groups.at(0);
+            const auto& g = trial.groups.at(gc.group_index);
+            const auto& g_old = accepted.groups.at(gc.group_index);
+            fb_batch_group_move& mv = group_moves[m];
+            if (static_cast<int>(g.size()) > FB_FAST_ATOMS || g.size() != g_old.size() || !gc.all || gc.internal) {
+                throw std::runtime_error("windowed moltransrot: unexpected change record");
+            }
+            mv.group_index = static_cast<int>(gc.group_index);
+            mv.n_atoms = static_cast<int>(g.size());
+            first_atom[m + 1] = first_atom[m] + mv.n_atoms;
+            for (int i = 0; i < mv.n_atoms; ++i) {
+                const auto& p = trial.at(g, i);
+                const auto& q = accepted.at(g_old, i);
+                mv.atom_id[i] = p.id;
+                mv.xyzq[i][0] = p.pos.x;
+                mv.xyzq[i][1] = p.pos.y;
+                mv.xyzq[i][2] = p.pos.z;
+                mv.xyzq[i][3] = p.charge;
+                mv.old_atom_id[i] = q.id;
+                mv.old_xyzq[i][0] = q.pos.x;
+                mv.old_xyzq[i][1] = q.pos.y;
+                mv.old_xyzq[i][2] = q.pos.z;
+                mv.old_xyzq[i][3] = q.charge;
+            }
+            mv.cm[0] = g.mass_center.x;
+            mv.cm[1] = g.mass_center.y;
+            mv.cm[2] = g.mass_center.z;
+            mv.old_cm[0] = g_old.mass_center.x;
+            mv.old_cm[1] = g_old.mass_center.y;
+            mv.old_cm[2] = g_old.mass_center.z;
+        }
+        dev->fast_staged = false;
+        dev->cache_valid = false;
+        fbCheck(fb_batch_submit_groups(dev->ctx, n, group_moves.data(), with_ewald ? 1 : 0), dev->ctx,
+                "fb_batch_submit_groups");
+        rec_change.assign(static_cast<size_t>(n), 0.0);
+    }
+
     void submit(const std::vector<WindowProposal>& window, int n) override
     {
+        group_mode = n > 0 && window.front().kind == WindowProposal::Kind::GROUP;
+        if (group_mode) {
+            submitGroups(window, n);
+            return;
+        }
         moves.resize(static_cast<size_t>(n));
         const Space& trial = *mc.trial_state.spc;
         for (int m = 0; m < n; ++m) {
@@ -783,7 +866,18 @@ class B200WindowEvaluator : public WindowEvaluator
         const size_t S = static_cast<size_t>(res.stride);
         double nb_new = res.u_new[m];
         double nb_old = res.u_old[m];
-        double rec = with_ewald ? res.rec_delta[m] : 0.0;
+        double rec = 0.0;
+        if (with_ewald && group_mode) { // the molecule's δ is the sum of its atoms' δ (fb_batch_submit_groups)
+            for (int j = first_atom[m]; j < first_atom[m + 1]; ++j) {
+                rec += res.rec_delta[j];
+                for (int i = first_atom[m]; i < j; ++i) {
+                    rec += 2.0 * res.rec_cross[static_cast<size_t>(j) * S + i];
+                }
+            }
+        }
+        else if (with_ewald) {
+            rec = res.rec_delta[m];
+        }
         double rec_running = res.rec_start;
         for (int a = 0; a < m; ++a) {
             if (!accepted[a]) {
@@ -796,7 +890,18 @@ class B200WindowEvaluator : public WindowEvaluator
             nb_new += res.cross_new[am];
             nb_old += res.cross_old[am];
             if (with_ewald) {
-                rec += 2.0 * res.rec_cross[am];
+                if (group_mode) {
+                    double cross = 0.0;
+                    for (int j = first_atom[m]; j < first_atom[m + 1]; ++j) {
+                        for (int i = first_atom[a]; i < first_atom[a + 1]; ++i) {
+                            cross += res.rec_cross[static_cast<size_t>(j) * S + i];
+                        }
+                    }
+                    rec += 2.0 * cross;
+                }
+                else {
+                    rec += 2.0 * res.rec_cross[am];
+                }
                 rec_running += rec_change[a];
             }
         }

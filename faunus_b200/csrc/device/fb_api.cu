@@ -202,14 +202,17 @@ struct fb_ctx
         int last_n = 0;            //!< moves of the most recent window (0: none evaluated)
         int last_with_ewald = 0;
         int last_slots[kBatchMax] = {};
-        CommitList pending{};      //!< accepted moves of the previous window not yet on the device
+        CommitList pending{};      //!< accepted moves (atoms) of the previous window not yet on the device
+        CommitList pending_moves{}; //!< group mode: the accepted moves (for the mass centres)
+        int last_groups = 0;       //!< group mode: moves of the most recent window (0: atomic mode)
+        int last_first[kBatchMax] = {}, last_natoms[kBatchMax] = {};
         bool has_pending = false;
         bool pending_with_ewald = false;
         bool q_dirty = false;      //!< slot 0's Q(k) is ahead of slot 1's
         bool rec_known = false;    //!< rec_sum is Σ A_k|Q_k|² of slot 0's current Q(k)
         bool last_rec_fresh = false; //!< the last window recomputed that sum on the device
         bool in_flight = false;      //!< fb_batch_submit done, fb_batch_wait pending
-        int flight_n = 0, flight_stride = 0, flight_with_ewald = 0;
+        int flight_n = 0, flight_stride = 0, flight_with_ewald = 0, flight_atoms = 0, flight_groups = 0;
         bool flight_timing = false;
         bool kspace_configured[3] = {false, false, false}; //!< dynamic shared memory opt-in done (stride 16/32/64)
         // device cell list of slot 0 for the pair part of a window (fb_cells.cuh)

@@ -37,6 +37,14 @@ struct BatchInput
     double4 pnew[kBatchMax];
     int idold[kBatchMax];    //!< the atoms as they are in the accepted state (supplied by the caller, who owns
     double4 pold[kBatchMax]; //!< the Space: no gather from the mirror on the critical path)
+    // group mode (rigid-molecule moves, `moltransrot`): the n atoms above belong to n_groups moved groups, the
+    // atoms of a move are contiguous; n_groups == 0: every atom is a move of its own (`transrot`)
+    int n_groups;
+    int move_first[kBatchMax];
+    int move_natoms[kBatchMax];
+    int move_group[kBatchMax];
+    double4 cm_new[kBatchMax];
+    double4 cm_old[kBatchMax];
 };
 
 /** Device-resident working set of one window */
@@ -165,8 +173,12 @@ __global__ void __launch_bounds__(kBlock)
 // ------------------------------------------------------------------------------------------------
 // window set-up: old positions from the (committed) mirror and the per-axis phase tables
 // ------------------------------------------------------------------------------------------------
-/** the previous window's accepted trial positions go into both mirrors (pair stream, before the pair kernel) */
-__global__ void __launch_bounds__(kBatchMax) batchPrepKernel(SlotView M0, SlotView M1, BatchBuffers prev, CommitList commit)
+/**
+ * The previous window's accepted trial positions go into both mirrors (pair stream, before the pair kernel);
+ * in group mode also the mass centres of the accepted groups (`moves` lists move indices).
+ */
+__global__ void __launch_bounds__(kBatchMax)
+    batchPrepKernel(SlotView M0, SlotView M1, BatchBuffers prev, CommitList commit, CommitList moves)
 {
     if (static_cast<int>(threadIdx.x) < commit.n) {
         const int m = commit.index[threadIdx.x];
@@ -177,6 +189,12 @@ __global__ void __launch_bounds__(kBatchMax) batchPrepKernel(SlotView M0, SlotVi
         M0.atom_id[s] = id;
         M1.posq[s] = p;
         M1.atom_id[s] = id;
+    }
+    if (static_cast<int>(threadIdx.x) < moves.n) {
+        const int g = moves.index[threadIdx.x];
+        const int group = prev.in->move_group[g];
+        M0.gcm[group] = prev.in->cm_new[g];
+        M1.gcm[group] = prev.in->cm_new[g];
     }
 }
 
@@ -447,6 +465,137 @@ __global__ void __launch_bounds__(kPairThreads)
             }
         }
         partials[static_cast<size_t>(blockIdx.x) * (2 * stride) + v] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// group mode: rigid-molecule moves (TranslateRotate, src/move.cpp:1670-1689: Change {group, all, internal =
+// false}). Energy of the moved group with every other group (group2all → group2group with the mass-centre
+// cutoff, src/energy.h:1155-1163, 979-989, 761-768). One block per (move, new | old); threads ↔ other groups.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGroupMoveAtoms = 8;
+
+template <int KIND>
+__global__ void __launch_bounds__(kBlock)
+    batchPairGroupKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, double* __restrict__ result)
+{
+    __shared__ double4 s_atom[kGroupMoveAtoms];
+    __shared__ int s_id[kGroupMoveAtoms];
+    __shared__ double scratch[kBlock / 32];
+    const int g = blockIdx.x >> 1;
+    const bool is_old = blockIdx.x & 1;
+    const int first = cur.in->move_first[g];
+    const int na = cur.in->move_natoms[g];
+    const int my_group = cur.in->move_group[g];
+    if (static_cast<int>(threadIdx.x) < na) {
+        s_atom[threadIdx.x] = is_old ? cur.pold[first + threadIdx.x] : cur.in->pnew[first + threadIdx.x];
+        s_id[threadIdx.x] = is_old ? cur.idold[first + threadIdx.x] : cur.in->id[first + threadIdx.x];
+    }
+    const double4 cm = is_old ? cur.in->cm_old[g] : cur.in->cm_new[g];
+    const int my_info = M0.ginfo[my_group];
+    __syncthreads();
+    double e = 0.0;
+    for (int gg = threadIdx.x; gg < M0.n_groups; gg += kBlock) {
+        const int size = M0.gsize[gg];
+        if (gg == my_group || size == 0) {
+            continue;
+        }
+        const int info = M0.ginfo[gg];
+        if (!((info | my_info) & MOL_ATOMIC)) { // GroupCutoff::cut: both molecular
+            const double4 c2 = M0.gcm[gg];
+            const double r2 = minImageR2(M0, cm.x, cm.y, cm.z, c2.x, c2.y, c2.z);
+            if (r2 >= __ldg(P.g2g_cut2 + (my_info >> 8) * P.n_mol + (info >> 8))) {
+                continue;
+            }
+        }
+        const int begin = M0.gbegin[gg];
+        for (int j = begin; j < begin + size; ++j) {
+            const double4 pj = M0.posq[j];
+            const int idj = M0.atom_id[j];
+            for (int i = 0; i < na; ++i) {
+                const double4 a = s_atom[i];
+                e += pairEnergy<KIND>(P, s_id[i], idj, a.w, pj.w, minImageR2(M0, a.x, a.y, a.z, pj.x, pj.y, pj.z));
+            }
+        }
+    }
+    const double sum = blockSum<kBlock>(e, scratch);
+    if (threadIdx.x == 0) {
+        result[8 + (is_old ? stride : 0) + g] = sum;
+    }
+}
+
+/** group-group energy U(m_x, a_y) of two moved groups (x, y ∈ {new, old}) with the mass-centre cutoff; one warp */
+template <int KIND>
+__device__ __forceinline__ double groupPairEnergy(const SlotView& M0, const PotParams& P, const BatchBuffers& cur, int m,
+                                                  bool m_new, int a, bool a_new, int lane)
+{
+    const int info_m = M0.ginfo[cur.in->move_group[m]];
+    const int info_a = M0.ginfo[cur.in->move_group[a]];
+    if (!((info_m | info_a) & MOL_ATOMIC)) {
+        const double4 cm = m_new ? cur.in->cm_new[m] : cur.in->cm_old[m];
+        const double4 ca = a_new ? cur.in->cm_new[a] : cur.in->cm_old[a];
+        if (minImageR2(M0, cm.x, cm.y, cm.z, ca.x, ca.y, ca.z) >= __ldg(P.g2g_cut2 + (info_m >> 8) * P.n_mol + (info_a >> 8))) {
+            return 0.0;
+        }
+    }
+    const int nm = cur.in->move_natoms[m], na = cur.in->move_natoms[a];
+    const int fm = cur.in->move_first[m], fa = cur.in->move_first[a];
+    double e = 0.0;
+    for (int t = lane; t < nm * na; t += 32) {
+        const int i = fm + t / na;
+        const int j = fa + t % na;
+        const double4 pi = m_new ? cur.in->pnew[i] : cur.pold[i];
+        const int idi = m_new ? cur.in->id[i] : cur.idold[i];
+        const double4 pj = a_new ? cur.in->pnew[j] : cur.pold[j];
+        const int idj = a_new ? cur.in->id[j] : cur.idold[j];
+        e += pairEnergy<KIND>(P, idi, idj, pi.w, pj.w, minImageR2(M0, pi.x, pi.y, pi.z, pj.x, pj.y, pj.z));
+    }
+    return warpSum(e); // valid in lane 0
+}
+
+/** group mode: cross terms between the moves of a window, one warp per (a, m); zero padding of the pair sums */
+template <int KIND>
+__global__ void __launch_bounds__(kBlock)
+    batchPairGroupFinishKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, double* __restrict__ result)
+{
+    const int ng = cur.in->n_groups;
+    const int S = stride;
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    double* u = result + 8;
+    double* cross = result + 8 + 3 * S;
+    if (w == 0 && lane == 0) {
+        result[2] = 0.0;
+    }
+    if (w < 2 * S) {
+        const int m = w % S;
+        if (m >= ng && lane == 0) {
+            u[(w / S) * S + m] = 0.0;
+        }
+    }
+    else if (w < 2 * S + S * S) {
+        const int t = w - 2 * S;
+        const int a = t / S;
+        const int m = t % S;
+        double cn = 0.0, co = 0.0, cmax = 0.0;
+        if (a < m && m < ng) {
+            const double t1 = groupPairEnergy<KIND>(M0, P, cur, m, true, a, true, lane);
+            const double t2 = groupPairEnergy<KIND>(M0, P, cur, m, true, a, false, lane);
+            const double t3 = groupPairEnergy<KIND>(M0, P, cur, m, false, a, true, lane);
+            const double t4 = groupPairEnergy<KIND>(M0, P, cur, m, false, a, false, lane);
+            cn = t1 - t2;
+            co = t3 - t4;
+            cmax = fmax(fmax(fabs(t1), fabs(t2)), fmax(fabs(t3), fabs(t4)));
+            if (t1 != t1 || t2 != t2 || t3 != t3 || t4 != t4) {
+                cmax = __longlong_as_double(0x7ff0000000000000LL);
+            }
+        }
+        if (lane == 0) {
+            const int tt = m * S + a; // stored [m][a]
+            cross[tt] = cn;
+            cross[S * S + tt] = co;
+            cross[2 * S * S + tt] = cmax;
+        }
     }
 }
 

@@ -58,6 +58,12 @@ void launchBatchCommit(fb_ctx* c, bool with_ewald, int* n_blocks_out)
                                                       c->slot[0].kn.ptr, batchBuffers(c, b.parity), b.geo, list,
                                                       with_ewald ? 1 : 0, b.d_e_partials.ptr);
     launched(c, "batchCommitKernel");
+    if (b.pending_moves.n > 0) { // group mode: mass centres of the accepted groups
+        batchPrepKernel<<<1, kBatchMax, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), batchBuffers(c, b.parity),
+                                                        CommitList{}, b.pending_moves);
+        launched(c, "batchPrepKernel");
+        b.pending_moves = CommitList{};
+    }
     b.has_pending = false;
     if (n_blocks_out) {
         *n_blocks_out = with_ewald ? grid : 0;
@@ -131,8 +137,8 @@ void buildCellList(fb_ctx* c, const CellGrid& g, cudaStream_t stream)
  * main stream when per-kernel timing is on.
  */
 template <int KIND>
-void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, const CommitList& commit, int n_moves,
-                  int stride, bool with_ewald, bool timing)
+void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, const CommitList& commit,
+                  const CommitList& commit_moves, int n_moves, int n_groups, int stride, bool with_ewald, bool timing)
 {
     auto& b = c->batch;
     const SlotView M0 = makeView(c, 0);
@@ -142,8 +148,8 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
         CUDA_CHECK(cudaEventRecord(b.ev_fork, c->stream)); // after the H2D copy of the window description
         CUDA_CHECK(cudaStreamWaitEvent(ps, b.ev_fork, 0));
     }
-    if (commit.n > 0) {
-        batchPrepKernel<<<1, kBatchMax, 0, ps>>>(M0, makeView(c, 1), prev, commit);
+    if (commit.n > 0 || commit_moves.n > 0) {
+        batchPrepKernel<<<1, kBatchMax, 0, ps>>>(M0, makeView(c, 1), prev, commit, commit_moves);
         launched(c, "batchPrepKernel");
     }
     if (timing) {
@@ -151,38 +157,47 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
     }
     // ---- pair side
     const int n_pair_blocks = (c->n_slots + kPairChunk - 1) / kPairChunk;
+    const int pair_finish_grid = (2 * stride + stride * stride + kBlock / 32 - 1) / (kBlock / 32); // one warp per output
     CellGrid grid{};
-    b.cells_used = cellGridFor(c, grid);
-    if (b.cells_used) { // large N: 27 neighbour cells per position instead of all particles
-        if (!b.cells_valid) {
-            buildCellList(c, grid, ps);
-        }
-        else if (commit.n > 0) {
-            cellCommitKernel<<<1, 2 * kBatchMax, 0, ps>>>(grid, prev, commit);
-            launched(c, "cellCommitKernel");
-        }
-        batchPairCellKernel<KIND><<<2 * n_moves, kCellThreads, 0, ps>>>(M0, c->P, grid, cur, c->pair_cut2, stride,
-                                                                        b.d_result.ptr);
-        launched(c, "batchPairCellKernel");
+    b.cells_used = false;
+    if (n_groups > 0) { // rigid-molecule moves: one block per (move, new | old), threads over the other groups
+        batchPairGroupKernel<KIND><<<2 * n_groups, kBlock, 0, ps>>>(M0, c->P, cur, stride, b.d_result.ptr);
+        launched(c, "batchPairGroupKernel");
+        batchPairGroupFinishKernel<KIND><<<pair_finish_grid, kBlock, 0, ps>>>(M0, c->P, cur, stride, b.d_result.ptr);
+        launched(c, "batchPairGroupFinishKernel");
     }
     else {
-        b.d_pair_partials.ensure(static_cast<size_t>(n_pair_blocks) * 2 * kBatchMax);
-        const dim3 pair_grid(n_pair_blocks, (2 * n_moves + kPairVariantsPerBlock - 1) / kPairVariantsPerBlock);
-        if (std::isinf(c->pair_cut2)) {
-            batchPairKernel<KIND, true><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
-                                                                           b.d_pair_partials.ptr);
+        b.cells_used = cellGridFor(c, grid);
+        if (b.cells_used) { // large N: 27 neighbour cells per position instead of all particles
+            if (!b.cells_valid) {
+                buildCellList(c, grid, ps);
+            }
+            else if (commit.n > 0) {
+                cellCommitKernel<<<1, 2 * kBatchMax, 0, ps>>>(grid, prev, commit);
+                launched(c, "cellCommitKernel");
+            }
+            batchPairCellKernel<KIND><<<2 * n_moves, kCellThreads, 0, ps>>>(M0, c->P, grid, cur, c->pair_cut2, stride,
+                                                                            b.d_result.ptr);
+            launched(c, "batchPairCellKernel");
         }
         else {
-            batchPairKernel<KIND, false><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
-                                                                            b.d_pair_partials.ptr);
+            b.d_pair_partials.ensure(static_cast<size_t>(n_pair_blocks) * 2 * kBatchMax);
+            const dim3 pair_grid(n_pair_blocks, (2 * n_moves + kPairVariantsPerBlock - 1) / kPairVariantsPerBlock);
+            if (std::isinf(c->pair_cut2)) {
+                batchPairKernel<KIND, true><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
+                                                                               b.d_pair_partials.ptr);
+            }
+            else {
+                batchPairKernel<KIND, false><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
+                                                                                b.d_pair_partials.ptr);
+            }
+            launched(c, "batchPairKernel");
         }
-        launched(c, "batchPairKernel");
+        batchPairFinishKernel<KIND><<<pair_finish_grid, kBlock, 0, ps>>>(
+            M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, b.cells_used ? 1 : 0,
+            b.cells_used ? b.d_cell_overflow.ptr : nullptr, b.d_result.ptr);
+        launched(c, "batchPairFinishKernel");
     }
-    const int pair_finish_grid = (2 * stride + stride * stride + kBlock / 32 - 1) / (kBlock / 32); // one warp per output
-    batchPairFinishKernel<KIND><<<pair_finish_grid, kBlock, 0, ps>>>(
-        M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, b.cells_used ? 1 : 0,
-        b.cells_used ? b.d_cell_overflow.ptr : nullptr, b.d_result.ptr);
-    launched(c, "batchPairFinishKernel");
     if (fork) {
         CUDA_CHECK(cudaEventRecord(b.ev_join, ps));
     }
@@ -272,41 +287,109 @@ void flushBatch(fb_ctx* c)
 
 } // namespace
 
+namespace {
+
+/** common head of the two submit flavours */
+void beginWindow(fb_ctx* c, int with_ewald)
+{
+    checkSlot(c, 0);
+    checkSlot(c, 1);
+    auto& b = c->batch;
+    if (b.in_flight) {
+        throw CudaError{"fb_batch_submit: the previous window has not been waited for"};
+    }
+    if (c->has_commit) { // an accepted fast-path move is still only on the host
+        applyCommitKernel<<<1, 32, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), c->commit);
+        launched(c, "applyCommitKernel");
+        c->has_commit = false;
+        b.cells_valid = false;
+    }
+    c->trial_active = false;
+    if (with_ewald) {
+        if (!c->ewald_configured || c->slot[0].K <= 0) {
+            throw CudaError{"fb_batch_trial: Ewald is not initialised on the accepted slot"};
+        }
+        if (c->ewald.policy == 2) {
+            throw CudaError{"fb_batch_trial: IPBC is not supported by the windowed path"};
+        }
+        if (b.has_pending && !b.pending_with_ewald) {
+            throw CudaError{"fb_batch_trial: windows with and without Ewald cannot be mixed"};
+        }
+    }
+    batchAllocate(c);
+}
+
+/** launches for the window described by b.h_in (n atoms; n_groups > 0: group mode) */
+void launchPreparedWindow(fb_ctx* c, int n_atoms, int n_groups, int with_ewald)
+{
+    auto& b = c->batch;
+    const int stride = n_atoms <= 16 ? 16 : (n_atoms <= 32 ? 32 : 64);
+    const bool timing = c->timing;
+    CUDA_CHECK(cudaEventRecord(b.ev[0], c->stream));
+    // the previous window's accepted moves (described by the buffers of parity `b.parity`): positions are
+    // written by the prep kernel, their δ is added to Q(k) inside the k-space kernel
+    if (with_ewald) {
+        batchEwaldGeometry(c);
+    }
+    if (b.has_pending && b.pending_with_ewald && (!with_ewald || b.pending.n > stride)) {
+        // Q(k) has to follow although this window has no k-space part / has no room for that many commits
+        launchBatchCommit(c, true, nullptr);
+        b.cells_valid = false; // these moves bypass the incremental cell update
+    }
+    const bool pending = b.has_pending;
+    const CommitList commit = pending ? b.pending : CommitList{};
+    const CommitList commit_moves = b.pending_moves;
+    b.has_pending = false;
+    b.pending_moves = CommitList{};
+    const BatchBuffers prev = batchBuffers(c, b.parity);
+    b.parity ^= 1;
+    const BatchBuffers cur = batchBuffers(c, b.parity);
+    CUDA_CHECK(cudaMemcpyAsync(cur.in, b.h_in.ptr, sizeof(BatchInput), cudaMemcpyHostToDevice, c->stream));
+    const size_t n_result = batchResultDoubles(stride);
+    b.d_result.ensure(batchResultDoubles(kBatchMax));
+    b.h_result.ensure(batchResultDoubles(kBatchMax));
+#define FB_CASE(K)                                                                                            \
+    case K:                                                                                                   \
+        launchWindow<K>(c, cur, prev, commit, commit_moves, n_atoms, n_groups, stride, with_ewald != 0, timing); \
+        break;
+    switch (c->P.kind) {
+        FB_CASE(POT_COULOMB_LJ)
+        FB_CASE(POT_COULOMB_WCA)
+        FB_CASE(POT_PM)
+        FB_CASE(POT_PMWCA)
+        FB_CASE(POT_FUNCTOR)
+        FB_CASE(POT_SPLINED)
+    default:
+        throw CudaError{"unknown potential kind"};
+    }
+#undef FB_CASE
+    CUDA_CHECK(cudaEventRecord(b.ev[4], c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(b.h_result.ptr, b.d_result.ptr, n_result * sizeof(double), cudaMemcpyDeviceToHost,
+                               c->stream));
+    b.in_flight = true;
+    b.flight_n = n_groups > 0 ? n_groups : n_atoms;
+    b.flight_atoms = n_atoms;
+    b.flight_groups = n_groups;
+    b.flight_stride = stride;
+    b.flight_with_ewald = with_ewald ? 1 : 0;
+    b.flight_timing = timing;
+}
+
+} // namespace
+
 FB_API int fb_batch_submit(fb_ctx* c, int n_moves, const fb_batch_move* moves, int with_ewald)
 {
     return guarded(c, [&] {
-        checkSlot(c, 0);
-        checkSlot(c, 1);
         if (!moves || n_moves < 1 || n_moves > kBatchMax) {
             throw CudaError{"fb_batch_trial: 1..64 moves per window"};
         }
+        beginWindow(c, with_ewald);
         auto& b = c->batch;
-        if (b.in_flight) {
-            throw CudaError{"fb_batch_submit: the previous window has not been waited for"};
-        }
-        if (c->has_commit) { // an accepted fast-path move is still only on the host
-            applyCommitKernel<<<1, 32, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), c->commit);
-            launched(c, "applyCommitKernel");
-            c->has_commit = false;
-            b.cells_valid = false;
-        }
-        c->trial_active = false;
         b.last_moves.assign(moves, moves + n_moves);
-        if (with_ewald) {
-            if (!c->ewald_configured || c->slot[0].K <= 0) {
-                throw CudaError{"fb_batch_trial: Ewald is not initialised on the accepted slot"};
-            }
-            if (c->ewald.policy == 2) {
-                throw CudaError{"fb_batch_trial: IPBC is not supported by the windowed path"};
-            }
-            if (b.has_pending && !b.pending_with_ewald) {
-                throw CudaError{"fb_batch_trial: windows with and without Ewald cannot be mixed"};
-            }
-        }
-        batchAllocate(c);
         // the moved atoms: distinct, active, members of atomic groups
         BatchInput& in = *b.h_in.ptr;
         in.n = n_moves;
+        in.n_groups = 0;
         in.with_ewald = with_ewald ? 1 : 0;
         for (int m = 0; m < n_moves; ++m) {
             const fb_batch_move& mv = moves[m];
@@ -320,7 +403,7 @@ FB_API int fb_batch_submit(fb_ctx* c, int n_moves, const fb_batch_move* moves, i
             if (mv.rel_index < 0 || mv.rel_index >= g.size) {
                 throw CudaError{"fb_batch_trial: relative atom index out of range"};
             }
-            if (mv.atom_id < 0 || mv.atom_id >= c->P.n_types) {
+            if (mv.atom_id < 0 || mv.atom_id >= c->P.n_types || mv.old_atom_id < 0 || mv.old_atom_id >= c->P.n_types) {
                 throw CudaError{"fb_batch_trial: atom id out of range"};
             }
             in.slot[m] = g.begin + mv.rel_index;
@@ -328,60 +411,72 @@ FB_API int fb_batch_submit(fb_ctx* c, int n_moves, const fb_batch_move* moves, i
             in.pnew[m] = make_double4(mv.xyzq[0], mv.xyzq[1], mv.xyzq[2], mv.xyzq[3]);
             in.pold[m] = make_double4(mv.old_xyzq[0], mv.old_xyzq[1], mv.old_xyzq[2], mv.old_xyzq[3]);
             in.idold[m] = mv.old_atom_id;
-            if (mv.old_atom_id < 0 || mv.old_atom_id >= c->P.n_types) {
-                throw CudaError{"fb_batch_trial: atom id out of range"};
-            }
             for (int a = 0; a < m; ++a) {
                 if (in.slot[a] == in.slot[m]) {
                     throw CudaError{"fb_batch_trial: the moves of one window must touch distinct atoms"};
                 }
             }
         }
-        const int stride = n_moves <= 16 ? 16 : (n_moves <= 32 ? 32 : 64);
-        const bool timing = c->timing;
-        CUDA_CHECK(cudaEventRecord(b.ev[0], c->stream));
-        // the previous window's accepted moves (described by the buffers of parity `b.parity`): positions are
-        // written by the phase kernel, their δ is added to Q(k) inside the k-space kernel
-        if (with_ewald) {
-            batchEwaldGeometry(c);
+        launchPreparedWindow(c, n_moves, 0, with_ewald);
+    });
+}
+
+FB_API int fb_batch_submit_groups(fb_ctx* c, int n_moves, const fb_batch_group_move* moves, int with_ewald)
+{
+    return guarded(c, [&] {
+        if (!moves || n_moves < 1 || n_moves > kBatchMax) {
+            throw CudaError{"fb_batch_submit_groups: 1..64 moves per window"};
         }
-        if (b.has_pending && b.pending_with_ewald && (!with_ewald || b.pending.n > stride)) {
-            // Q(k) has to follow although this window has no k-space part / has no room for that many commits
-            launchBatchCommit(c, true, nullptr);
-            b.cells_valid = false; // these moves bypass the incremental cell update
+        beginWindow(c, with_ewald);
+        auto& b = c->batch;
+        b.last_moves.clear(); // no cell list in group mode, hence no brute-force re-run
+        BatchInput& in = *b.h_in.ptr;
+        in.with_ewald = with_ewald ? 1 : 0;
+        in.n_groups = n_moves;
+        int n_atoms = 0;
+        for (int m = 0; m < n_moves; ++m) {
+            const fb_batch_group_move& mv = moves[m];
+            if (mv.group_index < 0 || mv.group_index >= c->n_groups) {
+                throw CudaError{"fb_batch_submit_groups: group index out of range"};
+            }
+            const fb_group& g = c->slot[0].groups[mv.group_index];
+            if (c->molecule_flags[g.molid] & FB_MOL_ATOMIC) {
+                throw CudaError{"fb_batch_submit_groups: whole-group moves are for molecular groups"};
+            }
+            if (mv.n_atoms != g.size || mv.n_atoms < 1 || mv.n_atoms > FB_FAST_ATOMS) {
+                throw CudaError{"fb_batch_submit_groups: all (1..8) active atoms of the group must be given"};
+            }
+            if (n_atoms + mv.n_atoms > kBatchMax) {
+                throw CudaError{"fb_batch_submit_groups: more than 64 atoms in one window"};
+            }
+            for (int a = 0; a < m; ++a) {
+                if (in.move_group[a] == mv.group_index) {
+                    throw CudaError{"fb_batch_submit_groups: the moves of one window must touch distinct groups"};
+                }
+            }
+            in.move_first[m] = n_atoms;
+            in.move_natoms[m] = mv.n_atoms;
+            in.move_group[m] = mv.group_index;
+            in.cm_new[m] = make_double4(mv.cm[0], mv.cm[1], mv.cm[2], 0.0);
+            in.cm_old[m] = make_double4(mv.old_cm[0], mv.old_cm[1], mv.old_cm[2], 0.0);
+            for (int i = 0; i < mv.n_atoms; ++i, ++n_atoms) {
+                if (mv.atom_id[i] < 0 || mv.atom_id[i] >= c->P.n_types || mv.old_atom_id[i] < 0 ||
+                    mv.old_atom_id[i] >= c->P.n_types) {
+                    throw CudaError{"fb_batch_submit_groups: atom id out of range"};
+                }
+                in.slot[n_atoms] = g.begin + i;
+                in.id[n_atoms] = mv.atom_id[i];
+                in.idold[n_atoms] = mv.old_atom_id[i];
+                in.pnew[n_atoms] = make_double4(mv.xyzq[i][0], mv.xyzq[i][1], mv.xyzq[i][2], mv.xyzq[i][3]);
+                in.pold[n_atoms] = make_double4(mv.old_xyzq[i][0], mv.old_xyzq[i][1], mv.old_xyzq[i][2], mv.old_xyzq[i][3]);
+            }
         }
-        const CommitList commit = b.has_pending ? b.pending : CommitList{};
-        b.has_pending = false;
-        const BatchBuffers prev = batchBuffers(c, b.parity);
-        b.parity ^= 1;
-        const BatchBuffers cur = batchBuffers(c, b.parity);
-        CUDA_CHECK(cudaMemcpyAsync(cur.in, b.h_in.ptr, sizeof(BatchInput), cudaMemcpyHostToDevice, c->stream));
-        const size_t n_result = batchResultDoubles(stride);
-        b.d_result.ensure(batchResultDoubles(kBatchMax));
-        b.h_result.ensure(batchResultDoubles(kBatchMax));
-#define FB_CASE(K)                                                                                            \
-    case K:                                                                                                   \
-        launchWindow<K>(c, cur, prev, commit, n_moves, stride, with_ewald != 0, timing);                      \
-        break;
-        switch (c->P.kind) {
-            FB_CASE(POT_COULOMB_LJ)
-            FB_CASE(POT_COULOMB_WCA)
-            FB_CASE(POT_PM)
-            FB_CASE(POT_PMWCA)
-            FB_CASE(POT_FUNCTOR)
-            FB_CASE(POT_SPLINED)
-        default:
-            throw CudaError{"unknown potential kind"};
+        in.n = n_atoms;
+        for (int m = 0; m < n_moves; ++m) {
+            b.last_first[m] = in.move_first[m];
+            b.last_natoms[m] = in.move_natoms[m];
         }
-#undef FB_CASE
-        CUDA_CHECK(cudaEventRecord(b.ev[4], c->stream));
-        CUDA_CHECK(cudaMemcpyAsync(b.h_result.ptr, b.d_result.ptr, n_result * sizeof(double), cudaMemcpyDeviceToHost,
-                                   c->stream));
-        b.in_flight = true;
-        b.flight_n = n_moves;
-        b.flight_stride = stride;
-        b.flight_with_ewald = with_ewald ? 1 : 0;
-        b.flight_timing = timing;
+        launchPreparedWindow(c, n_atoms, n_moves, with_ewald);
     });
 }
 
@@ -416,7 +511,7 @@ FB_API int fb_batch_wait(fb_ctx* c, fb_batch_result* out)
         b.windows += 1;
         b.moves += n_moves;
         const double* r = b.h_result.ptr;
-        if (b.cells_used && r[2] != 0.0) { // a bucket ran full: this window's pair sums are incomplete
+        if (b.cells_used && b.flight_groups == 0 && r[2] != 0.0) { // a bucket ran full: this window's pair sums are incomplete
             b.cells_valid = false;
             b.cell_cap *= 2;
             b.force_brute = true; // the commits of this window are already on the device: plain re-evaluation
@@ -437,8 +532,10 @@ FB_API int fb_batch_wait(fb_ctx* c, fb_batch_result* out)
             b.rec_known = true;
         }
         b.last_n = n_moves;
+        b.last_groups = b.flight_groups;
         b.last_with_ewald = with_ewald ? 1 : 0;
         const size_t S = static_cast<size_t>(stride);
+        out->n_atoms = b.flight_atoms;
         out->n_moves = n_moves;
         out->stride = stride;
         out->u_new = r + 8;
@@ -479,8 +576,18 @@ FB_API int fb_batch_commit(fb_ctx* c, int n_decided, const unsigned char* accept
             throw CudaError{"fb_batch_commit: the window was already committed"};
         }
         CommitList list{};
+        CommitList moves{};
         for (int m = 0; m < n_decided; ++m) {
-            if (accepted[m]) {
+            if (!accepted[m]) {
+                continue;
+            }
+            if (b.last_groups > 0) { // group mode: every atom of the accepted group, and its mass centre
+                moves.index[moves.n++] = m;
+                for (int i = 0; i < b.last_natoms[m]; ++i) {
+                    list.index[list.n++] = b.last_first[m] + i;
+                }
+            }
+            else {
                 list.index[list.n++] = m;
             }
         }
@@ -489,6 +596,7 @@ FB_API int fb_batch_commit(fb_ctx* c, int n_decided, const unsigned char* accept
             return;
         }
         b.pending = list;
+        b.pending_moves = moves;
         b.has_pending = true;
         b.pending_with_ewald = b.last_with_ewald != 0;
         if (b.pending_with_ewald) {

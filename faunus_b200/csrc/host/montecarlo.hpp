@@ -34,9 +34,21 @@ struct TraceRecord
 /** One drawn, not yet decided trial move of the windowed path */
 struct WindowProposal
 {
-    AtomicTranslateRotate* move = nullptr;
+    /** single atom of an atomic group (`transrot`) or a whole rigid molecule (`moltransrot`); a window is of one kind */
+    enum class Kind
+    {
+        ATOM,
+        GROUP
+    };
+    Kind kind = Kind::ATOM;
+    Move* base = nullptr;                  //!< the move, whatever its kind (statistics)
+    AtomicTranslateRotate* move = nullptr; //!< Kind::ATOM
+    TranslateRotate* group_move = nullptr; //!< Kind::GROUP
     int move_id = 0;
     AtomicTranslateRotate::Draw draw;
+    TranslateRotate::Draw group_draw;
+    size_t key_group = 0;                  //!< what the proposal touches: two proposals on the same
+    long key_atom = -1;                    //!< (group, atom) cannot be pending at the same time
     Change change;                  //!< filled when the draw is applied to the trial Space
     bool applied = false;
     double uniform = 0;             //!< the Metropolis uniform of this move (drawn in reference order)
@@ -56,6 +68,10 @@ class WindowEvaluator
   public:
     virtual ~WindowEvaluator() = default;
     virtual int capacity() const = 0;
+    /** how many of the first `ready` proposals of `window` fit into one evaluation */
+    virtual int fit(const std::vector<WindowProposal>& /*window*/, int ready) const { return std::min(ready, capacity()); }
+    /** can proposals of this kind be evaluated at all? */
+    virtual bool supports(WindowProposal::Kind kind) const { return kind == WindowProposal::Kind::ATOM; }
     /** start evaluating proposals [0, n) of `window` (all applied to the trial Space, distinct atoms) … */
     virtual void submit(const std::vector<WindowProposal>& window, int n) = 0;
     /** … and wait for the results; the engine draws the next proposals in between */
@@ -252,8 +268,13 @@ class MetropolisMonteCarlo
 
     void applyProposal(WindowProposal& p)
     {
-        p.move->moveFromDraw(p.draw, p.change);
-        p.displacement_squared = p.move->latestDisplacementSquared();
+        if (p.kind == WindowProposal::Kind::GROUP) {
+            p.group_move->moveFromDraw(p.group_draw, p.change);
+        }
+        else {
+            p.move->moveFromDraw(p.draw, p.change);
+            p.displacement_squared = p.move->latestDisplacementSquared();
+        }
         p.applied = true;
     }
 
@@ -283,15 +304,17 @@ class MetropolisMonteCarlo
             rec.u_new = new_energy;
             rec.u_old = old_energy;
             rec.move_id = p.move_id;
-            p.move->setLatestDisplacementSquared(p.displacement_squared);
+            if (p.move != nullptr) {
+                p.move->setLatestDisplacementSquared(p.displacement_squared);
+            }
             if (metropolisDecision(energy_change, p.uniform)) {
                 state.spc->sync(*trial_state.spc, p.change);
-                p.move->accept(p.change);
+                p.base->accept(p.change);
                 rec.accepted = 1;
             }
             else {
                 trial_state.spc->sync(*state.spc, p.change);
-                p.move->reject(p.change);
+                p.base->reject(p.change);
                 energy_change = 0.0;
             }
             accepted.push_back(static_cast<unsigned char>(rec.accepted));
@@ -324,42 +347,88 @@ class MetropolisMonteCarlo
 
     bool windowBlocked() const { return !window.empty() && !window.back().applied; }
 
+    /** the kind of window `selected` can go into, if any */
+    bool windowKind(Move* selected, WindowProposal::Kind& kind) const
+    {
+        if (auto* transrot = dynamic_cast<AtomicTranslateRotate*>(selected)) {
+            kind = WindowProposal::Kind::ATOM;
+            return transrot->targetsAtomicGroups() && window_evaluator->supports(kind);
+        }
+        if (dynamic_cast<TranslateRotate*>(selected) != nullptr) {
+            kind = WindowProposal::Kind::GROUP;
+            return window_evaluator->supports(kind);
+        }
+        return false;
+    }
+
+    /**
+     * Draw the proposal of `selected` (generator order of performMove: proposal, then the Metropolis uniform) and
+     * queue it; applied to the trial Space unless an earlier queued proposal touches the same atom / molecule.
+     */
+    void enqueue(Move* selected, WindowProposal::Kind kind)
+    {
+        WindowProposal p;
+        p.kind = kind;
+        p.base = selected;
+        p.move_id = sweep_id_of(*selected);
+        bool moves_something = false;
+        if (kind == WindowProposal::Kind::GROUP) {
+            p.group_move = static_cast<TranslateRotate*>(selected);
+            p.group_draw = p.group_move->draw();
+            p.key_group = p.group_draw.group_index;
+            moves_something = p.group_draw.valid && ((p.group_draw.translate && p.group_draw.scalar != 0.0) ||
+                                                     (p.group_draw.rotate && p.group_draw.angle != 0.0));
+            if (!moves_something) {
+                Change none; // empty Change: count the attempt, keep the generator in step (montecarlo.cpp:182-186)
+                p.group_move->moveFromDraw(p.group_draw, none);
+                if (!none.empty()) {
+                    throw std::runtime_error("windowed moltransrot: unexpected non-empty change");
+                }
+            }
+        }
+        else {
+            p.move = static_cast<AtomicTranslateRotate*>(selected);
+            p.draw = p.move->draw();
+            p.key_group = p.draw.group_index;
+            p.key_atom = static_cast<long>(p.draw.atom_index);
+            moves_something = p.draw.valid && (p.draw.dp > 0.0 || p.draw.dprot > 0.0);
+            if (!moves_something) {
+                Change none;
+                p.move->moveFromDraw(p.draw, none);
+            }
+        }
+        if (!moves_something) {
+            rng.slump();
+            return;
+        }
+        p.uniform = rng.slump();
+        bool blocked = false;
+        for (const auto& q : window) {
+            blocked = blocked || (q.key_group == p.key_group && q.key_atom == p.key_atom);
+        }
+        if (!blocked) {
+            applyProposal(p);
+        }
+        // else: its start position is only known once the earlier move on this atom / molecule is decided
+        window.push_back(std::move(p));
+    }
+
     /** draw proposals (in move order, generator order of performMove) until the queue holds `max_size` */
     void fillWindow(int max_size)
     {
-        bool blocked = windowBlocked();
-        while (!blocked && sweep_deferred == nullptr && sweep_remaining > 0 &&
+        while (!windowBlocked() && sweep_deferred == nullptr && sweep_remaining > 0 &&
                static_cast<int>(window.size()) < max_size) {
             sweep_remaining--;
             Move* selected = moves->sampleStochasticMove();
             if (selected == nullptr) {
                 continue;
             }
-            auto* transrot = dynamic_cast<AtomicTranslateRotate*>(selected);
-            if (transrot == nullptr || !transrot->targetsAtomicGroups()) {
-                sweep_deferred = selected;
+            WindowProposal::Kind kind{};
+            if (!windowKind(selected, kind) || (!window.empty() && window.front().kind != kind)) {
+                sweep_deferred = selected; // another kind of move: runs / opens a new window once the queue is empty
                 break;
             }
-            WindowProposal p;
-            p.move = transrot;
-            p.move_id = sweep_id_of(*selected);
-            p.draw = transrot->draw();
-            if (!(p.draw.valid && (p.draw.dp > 0.0 || p.draw.dprot > 0.0))) {
-                Change none; // empty Change: count the attempt, keep the generator in step (montecarlo.cpp:182-186)
-                transrot->moveFromDraw(p.draw, none);
-                rng.slump();
-                continue;
-            }
-            p.uniform = rng.slump();
-            for (const auto& q : window) {
-                blocked = blocked || (q.draw.group_index == p.draw.group_index &&
-                                      q.draw.atom_index == p.draw.atom_index);
-            }
-            if (!blocked) {
-                applyProposal(p);
-            }
-            // else: its start position is only known once the earlier move on this atom is decided
-            window.push_back(std::move(p));
+            enqueue(selected, kind);
         }
     }
 
@@ -374,7 +443,7 @@ class MetropolisMonteCarlo
             fillWindow(capacity);
             if (windowBlocked() || sweep_deferred != nullptr || sweep_remaining == 0) { // drain the queue
                 while (readyProposals() > 0) {
-                    decideWindow(std::min(readyProposals(), capacity));
+                    decideWindow(window_evaluator->fit(window, readyProposals()));
                 }
                 if (!window.empty()) { // the blocked proposal: its atom is decided now
                     applyProposal(window.front());
@@ -382,11 +451,17 @@ class MetropolisMonteCarlo
                 if (sweep_deferred != nullptr) {
                     Move* m = sweep_deferred;
                     sweep_deferred = nullptr;
-                    performMove(*m, sweep_id_of(*m));
+                    WindowProposal::Kind kind{};
+                    if (windowKind(m, kind)) { // window.empty(): a blocked proposal is always the last one drawn
+                        enqueue(m, kind);
+                    }
+                    else {
+                        performMove(*m, sweep_id_of(*m));
+                    }
                 }
             }
             else if (!window.empty()) { // full window
-                decideWindow(std::min(readyProposals(), capacity));
+                decideWindow(window_evaluator->fit(window, readyProposals()));
             }
         }
     }

@@ -277,38 +277,69 @@ class TranslateRotate : public Move
         j["dprot"] = rotational_displacement;
     }
 
-    void _move(Change& change) override
+  public:
+    /** The random part of one proposal: everything `_move` draws (src/move.cpp:1619-1689), no positions */
+    struct Draw
     {
+        bool valid = false; //!< a non-empty molecule was picked
+        size_t group_index = 0;
+        bool translate = false;
+        double scalar = 0;
+        Point unit{0, 0, 0};
+        bool rotate = false;
+        Point axis{0, 0, 0};
+        double angle = 0;
+    };
+
+    Draw draw()
+    {
+        Draw d;
         const auto mollist = spc.findMolecules(molid, Space::Selection::ACTIVE);
         if (mollist.empty()) {
-            return;
+            return d;
         }
         // molecule picked with the GLOBAL generator, src/move.cpp:1622
-        const auto group_index = mollist[rng.global.sampleIndex(static_cast<int>(mollist.size()))];
-        auto& group = spc.groups[group_index];
-        if (group.empty()) {
-            return;
+        d.group_index = mollist[rng.global.sampleIndex(static_cast<int>(mollist.size()))];
+        if (spc.groups[d.group_index].empty()) {
+            return d;
         }
-        double displacement_squared = 0.0;
-        double angle_squared = 0.0;
+        d.valid = true;
         if (translational_displacement > 0.0) {
-            const Point old_mass_center = group.mass_center;
-            const double scalar = rng.slump(); // GCC order, see file header
-            const Point unit = randomUnitVector(rng.slump, translational_direction);
-            spc.translate(group, unit * translational_displacement * scalar);
-            displacement_squared = spc.geometry.sqdist(old_mass_center, group.mass_center);
+            d.translate = true;
+            d.scalar = rng.slump(); // GCC order, see file header
+            d.unit = randomUnitVector(rng.slump, translational_direction);
         }
         if (rotational_displacement > pc::epsilon_dbl) {
             const bool fixed = (fixed_rotation_axis.x != 0) || (fixed_rotation_axis.y != 0) ||
                                (fixed_rotation_axis.z != 0);
-            const Point axis = fixed ? fixed_rotation_axis : randomUnitVector(rng.slump);
-            const double angle = rotational_displacement * (rng.slump() - 0.5);
-            spc.rotate(group, Quaternion(angle, axis));
-            angle_squared = angle * angle;
+            d.rotate = true;
+            d.axis = fixed ? fixed_rotation_axis : randomUnitVector(rng.slump);
+            d.angle = rotational_displacement * (rng.slump() - 0.5);
+        }
+        return d;
+    }
+
+    /** move the picked molecule in the trial Space and describe it in `change` */
+    void apply(const Draw& d, Change& change)
+    {
+        if (!d.valid) {
+            return;
+        }
+        auto& group = spc.groups[d.group_index];
+        double displacement_squared = 0.0;
+        double angle_squared = 0.0;
+        if (d.translate) {
+            const Point old_mass_center = group.mass_center;
+            spc.translate(group, d.unit * translational_displacement * d.scalar);
+            displacement_squared = spc.geometry.sqdist(old_mass_center, group.mass_center);
+        }
+        if (d.rotate) {
+            spc.rotate(group, Quaternion(d.angle, d.axis));
+            angle_squared = d.angle * d.angle;
         }
         if (displacement_squared > 0.0 || angle_squared > 0.0) {
             auto& change_data = change.groups.emplace_back();
-            change_data.group_index = group_index;
+            change_data.group_index = d.group_index;
             change_data.all = true;
             change_data.internal = false;
         }
@@ -318,6 +349,17 @@ class TranslateRotate : public Move
             throw std::runtime_error("molecule likely too large for periodic boundaries; increase box size?");
         }
     }
+
+    /** windowed path: count the attempt and apply a proposal drawn earlier */
+    void moveFromDraw(const Draw& d, Change& change)
+    {
+        number_of_attempted_moves++;
+        change.clear();
+        apply(d, change);
+    }
+
+  private:
+    void _move(Change& change) override { apply(draw(), change); }
 
   public:
     TranslateRotate(Space& spc, Randoms& rng)

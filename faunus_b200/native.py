@@ -59,7 +59,13 @@ class FbBatchResult(C.Structure):
     _fields_ = [("n_moves", C.c_int), ("stride", C.c_int), ("u_new", c_double_p), ("u_old", c_double_p),
                 ("rec_delta", c_double_p), ("cross_new", c_double_p), ("cross_old", c_double_p),
                 ("cross_max", c_double_p), ("rec_cross", c_double_p), ("rec_start", C.c_double),
-                ("rec_prefactor", C.c_double)]
+                ("rec_prefactor", C.c_double), ("n_atoms", C.c_int)]
+
+
+class FbBatchGroupMove(C.Structure):
+    _fields_ = [("group_index", C.c_int), ("n_atoms", C.c_int), ("atom_id", C.c_int * 8),
+                ("xyzq", (C.c_double * 4) * 8), ("cm", C.c_double * 3), ("old_atom_id", C.c_int * 8),
+                ("old_xyzq", (C.c_double * 4) * 8), ("old_cm", C.c_double * 3)]
 
 
 class FbTrialMove(C.Structure):
@@ -94,7 +100,7 @@ class FbConfig(C.Structure):
 C_ABI_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_last_error", "fb_device_count", "fb_upload_space", "fb_update_group",
     "fb_set_box", "fb_sync", "fb_download_space", "fb_nonbonded_energy", "fb_nonbonded_delta",
-    "fb_system_energy_shard", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_wait", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing",
+    "fb_system_energy_shard", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_submit_groups", "fb_batch_wait", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing",
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
     "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
     "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_launch_count",
@@ -133,6 +139,7 @@ def load() -> C.CDLL:
         "fb_system_energy_shard": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p]),
         "fb_batch_trial": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchMove), C.c_int, C.POINTER(FbBatchResult)]),
         "fb_batch_submit": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchMove), C.c_int]),
+        "fb_batch_submit_groups": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchGroupMove), C.c_int]),
         "fb_batch_wait": (C.c_int, [vp, C.POINTER(FbBatchResult)]),
         "fb_batch_commit": (C.c_int, [vp, C.c_int, c_ubyte_p]),
         "fb_configure_cells": (C.c_int, [vp, C.c_int]),

@@ -263,12 +263,34 @@ typedef struct
     const double* rec_cross; /* sum_k A_k Re(conj d_a,k d_m,k) */
     double rec_start;        /* sum_k A_k |Q_k|^2 of the window-start state */
     double rec_prefactor;    /* 2 pi lB / V */
+    int n_atoms;             /* group mode: moved atoms in the window (rec_delta/rec_cross are per ATOM); else n_moves */
 } fb_batch_result;
 int fb_batch_trial(fb_ctx* ctx, int n_moves, const fb_batch_move* moves, int with_ewald, fb_batch_result* result);
 /* the same in two halves, so that the caller can draw the next proposals while the device works:
  * fb_batch_submit queues the launches and returns, fb_batch_wait blocks for the results */
 int fb_batch_submit(fb_ctx* ctx, int n_moves, const fb_batch_move* moves, int with_ewald);
 int fb_batch_wait(fb_ctx* ctx, fb_batch_result* result);
+/* Group mode: a window of rigid-body moves of whole molecular groups (Move::TranslateRotate::_move,
+ * src/move.cpp:1623-1689; Change {group, all = true, internal = false}), at most 8 atoms per group and 64 atoms per
+ * window, distinct groups. u_new/u_old[m] = energy of moved group m with every other group (group2all with the
+ * mass-centre cutoff, src/energy.h:1155-1163, 979-989, 761-768), cross_*[m * stride + a] = the same group-group
+ * differences between the moves of the window. The k-space results stay PER ATOM, atoms numbered in the order
+ * given (move 0's atoms first): for a move holding atoms i..j
+ *   rec_delta(move) = sum_i rec_delta[i] + 2 sum_{i<j in move} rec_cross[j * stride + i],
+ *   rec_cross(m, a) = sum_{i in a, j in m} rec_cross[j * stride + i].
+ * Decide and fb_batch_commit as in atomic mode (accepted[] is per move). */
+typedef struct
+{
+    int group_index;
+    int n_atoms;              /* active size of the group, 1..8 */
+    int atom_id[8];
+    double xyzq[8][4];        /* trial positions and charges */
+    double cm[3];             /* trial mass centre */
+    int old_atom_id[8];
+    double old_xyzq[8][4];    /* the group as it is in the accepted Space */
+    double old_cm[3];
+} fb_batch_group_move;
+int fb_batch_submit_groups(fb_ctx* ctx, int n_moves, const fb_batch_group_move* moves, int with_ewald);
 /* accepted[m] != 0 for the accepted ones among the first n_decided moves of the last window */
 int fb_batch_commit(fb_ctx* ctx, int n_decided, const unsigned char* accepted);
 /* The pair part of a window goes through a device cell list (cell edge = box / floor(box / cutoff), 27

@@ -65,3 +65,34 @@ def nacl_pair_input(ewaldscheme="PBC"):
 def small_electrolyte(n=400, seed=7, **kw):
     from faunus_b200.config import primitive_model
     return primitive_model(n=n, molarity=1.0, seed=seed, **kw)
+
+
+def water_with_salt(water, n_pairs=8, seed=3, coulomb=None, volume_move=False):
+    """examples/water plus an atomic NaCl group: `moltransrot` and `transrot` moves interleave"""
+    import copy
+    import numpy as np
+    cfg = copy.deepcopy(water)
+    rng = np.random.RandomState(seed)
+    box = np.array(cfg["geometry"]["length"], dtype=float)
+    pos = np.array([p["pos"] for p in cfg["particles"]])
+    cfg["atomlist"] += [{"Na": {"q": 1.0, "sigma": 2.6, "eps": 0.3, "dp": 1.2, "mw": 22.99}},
+                        {"Cl": {"q": -1.0, "sigma": 4.0, "eps": 0.3, "dp": 1.2, "mw": 35.45}}]
+    cfg["moleculelist"] += [{"salt": {"atoms": ["Na", "Cl"] * n_pairs, "atomic": True}}]
+    ions = []
+    while len(ions) < 2 * n_pairs:
+        x = (rng.uniform(size=3) - 0.5) * box
+        d = pos - x
+        d -= box * np.round(d / box)
+        if (np.einsum("ij,ij->i", d, d) > 2.4 ** 2).all():
+            pos = np.vstack([pos, x])
+            ions.append({"id": 2 + len(ions) % 2, "pos": x.tolist(), "q": 1.0 if len(ions) % 2 == 0 else -1.0})
+    cfg["groups"].append({"id": 1, "size": 2 * n_pairs, "cm": [0, 0, 0], "atomic": True, "compressible": False})
+    cfg["particles"] += ions
+    cfg["moves"] = [m for m in cfg["moves"] if volume_move or "volume" not in m] + [
+        {"transrot": {"molecule": "salt", "repeat": 40}}]
+    if coulomb is not None:
+        for term in cfg["energy"]:
+            for name, body in term.items():
+                if name.startswith("nonbonded"):
+                    body["coulomb"] = coulomb
+    return cfg

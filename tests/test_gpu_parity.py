@@ -139,10 +139,11 @@ def test_minimal_example(minimal_input, window):
     assert np.array_equal(o.trace()["accepted"], g.trace()["accepted"])
 
 
-def test_water_example(water_input):
+@pytest.mark.parametrize("window", [0, 64])
+def test_water_example(water_input, window):
     """examples/water: rigid SPC/E, mass-centre cutoff, Ewald partial updates for 3-atom moves,
-    volume moves (full updates + box change)"""
-    o, g = pair_of_sims(water_input)
+    volume moves (full updates + box change); one move per launch and windows of rigid-molecule moves"""
+    o, g = pair_of_sims(water_input, window)
     eo, to = o.system_energy()
     eg, tg = g.system_energy()
     assert len(to) == 4
@@ -161,6 +162,37 @@ def test_water_example(water_input):
     xo, _ = o.particles()
     xg, _ = g.particles()
     assert np.array_equal(xo, xg)
+    t = g.window_time_ms()
+    assert (t["windows"] > 20 and t["moves"] > 600) if window else t["windows"] == 0
+
+
+@pytest.mark.parametrize("coulomb", [None, {"type": "fanourgakis", "epsr": 1, "cutoff": 9}])
+@pytest.mark.parametrize("window", [5, 64])
+def test_water_with_salt_windows(water_input, coulomb, window):
+    """rigid-molecule windows and single-atom windows interleave (a window is of one kind), with and without
+    k-space; short windows (5) exercise atom-capacity splits"""
+    from conftest import water_with_salt
+    cfg = water_with_salt(water_input, coulomb=coulomb)
+    o, g = pair_of_sims(cfg, window)
+    to = o.system_energy()[1]
+    scale = np.abs(to).max()
+    assert_close(to, g.system_energy()[1], scale=scale)
+    for s in (o, g):
+        s.trace_enable()
+        s.sweep(4)
+    a, b = o.trace(), g.trace()
+    assert len(a["du"]) > 900 and set(a["move_id"]) == {0, 1}
+    assert np.array_equal(a["move_id"], b["move_id"])
+    assert np.array_equal(a["accepted"], b["accepted"])
+    per_move = np.maximum(np.abs(a["u_new"]), np.abs(a["u_old"]))  # the example starts with overlapping molecules
+    finite = np.isfinite(per_move)
+    assert np.all(np.abs(a["du"] - b["du"])[finite] <= RTOL * per_move[finite])
+    assert 0.05 < a["accepted"].mean() < 0.95
+    assert_close(o.system_energy()[1], g.system_energy()[1], scale=scale)
+    xo, _ = o.particles()
+    xg, _ = g.particles()
+    assert np.array_equal(xo, xg)
+    assert g.window_time_ms()["moves"] > 900
 
 
 def test_ewald_doctest_values(reference_values):
