@@ -687,6 +687,11 @@ class B200WindowEvaluator : public WindowEvaluator
     std::vector<int> first_atom;     //!< group mode: atoms [first_atom[m], first_atom[m + 1]) belong to move m
     int largest_molecule = 0;        //!< atoms in the largest molecular group
     std::vector<double> rec_change; //!< corrected raw reciprocal change Σ_k A_k(…) of each decided move
+    // runs: windows of single-atom moves decided on the device (fb_run_submit), several windows per round trip
+    int run_capacity = 0;            //!< 0: every window is walked on the host
+    bool run_mode = false;           //!< the evaluation in flight is a run
+    std::vector<fb_run_move> run_moves;
+    fb_run_result run_res{};
     enum class Kind
     {
         SELF,
@@ -752,7 +757,16 @@ class B200WindowEvaluator : public WindowEvaluator
         return e;
     }
 
-    int capacity() const override { return window_capacity; }
+    int capacity() const override { return std::max(window_capacity, run_capacity); }
+
+    /** let the device walk the windows of single-atom moves itself, up to `moves` (≤ FB_RUN_MAX) per round trip */
+    void enableRuns(int moves)
+    {
+        run_capacity = (kinds.size() <= FB_RUN_TERMS && window_capacity == FB_BATCH_MAX)
+                           ? std::max(0, std::min(moves, FB_RUN_MAX))
+                           : 0;
+    }
+    int runCapacity() const { return run_capacity; }
 
     bool supports(WindowProposal::Kind kind) const override
     {
@@ -762,6 +776,9 @@ class B200WindowEvaluator : public WindowEvaluator
     /** group mode: a window holds at most FB_BATCH_MAX ATOMS */
     int fit(const std::vector<WindowProposal>& window, int ready) const override
     {
+        if (ready > 0 && run_capacity > 0 && window.front().kind == WindowProposal::Kind::ATOM) {
+            return std::min(ready, run_capacity);
+        }
         int n = std::min(ready, window_capacity);
         if (n > 0 && window.front().kind == WindowProposal::Kind::GROUP) {
             const Space& trial = *mc.trial_state.spc;
@@ -823,9 +840,41 @@ class B200WindowEvaluator : public WindowEvaluator
         rec_change.assign(static_cast<size_t>(n), 0.0);
     }
 
+    /** the proposals of a run travel with their Metropolis uniform and the host terms' energies */
+    void submitRun(const std::vector<WindowProposal>& window, int n)
+    {
+        run_moves.resize(static_cast<size_t>(n));
+        fb_run_config cfg{};
+        cfg.n_terms = static_cast<int>(kinds.size());
+        for (size_t i = 0; i < kinds.size(); ++i) {
+            cfg.term_kind[i] = kinds[i] == Kind::SELF ? FB_TERM_HOST
+                                                     : (kinds[i] == Kind::NONBONDED ? FB_TERM_NONBONDED : FB_TERM_EWALD);
+        }
+        cfg.max_energy = mc.state.pot->maximumAllowedEnergy();
+        cfg.cancellation_limit = cancellation_limit;
+        const auto& trial_terms = mc.trial_state.pot->terms();
+        const auto& terms = mc.state.pot->terms();
+        for (int m = 0; m < n; ++m) {
+            fb_run_move& r = run_moves[m];
+            r.move = moves[m];
+            r.uniform = window[m].uniform;
+            for (size_t i = 0; i < kinds.size(); ++i) {
+                r.host_new[i] = r.host_old[i] = 0.0;
+                if (kinds[i] == Kind::SELF) { // looks at the atoms of the Change only: valid while others are pending
+                    trial_terms[i]->state = mc.trial_state.pot->state;
+                    r.host_new[i] = trial_terms[i]->energy(window[m].change);
+                    terms[i]->state = mc.state.pot->state;
+                    r.host_old[i] = terms[i]->energy(window[m].change);
+                }
+            }
+        }
+        fbCheck(fb_run_submit(dev->ctx, n, run_moves.data(), with_ewald ? 1 : 0, &cfg), dev->ctx, "fb_run_submit");
+    }
+
     void submit(const std::vector<WindowProposal>& window, int n) override
     {
         group_mode = n > 0 && window.front().kind == WindowProposal::Kind::GROUP;
+        run_mode = false;
         if (group_mode) {
             submitGroups(window, n);
             return;
@@ -854,15 +903,35 @@ class B200WindowEvaluator : public WindowEvaluator
         }
         dev->fast_staged = false;
         dev->cache_valid = false;
+        if (run_capacity > 0) {
+            run_mode = true;
+            submitRun(window, n);
+            return;
+        }
         fbCheck(fb_batch_submit(dev->ctx, n, moves.data(), with_ewald ? 1 : 0), dev->ctx, "fb_batch_submit");
         rec_change.assign(static_cast<size_t>(n), 0.0);
     }
 
-    void wait() override { fbCheck(fb_batch_wait(dev->ctx, &res), dev->ctx, "fb_batch_wait"); }
+    void wait() override
+    {
+        if (run_mode) {
+            fbCheck(fb_run_wait(dev->ctx, &run_res), dev->ctx, "fb_run_wait");
+        }
+        else {
+            fbCheck(fb_batch_wait(dev->ctx, &res), dev->ctx, "fb_batch_wait");
+        }
+    }
+
+    int decision(int m) const override { return run_mode ? static_cast<int>(run_res.accepted[m]) : -1; }
 
     bool energies(int m, const std::vector<unsigned char>& accepted, const WindowProposal& proposal,
                   double& new_energy, double& old_energy) override
     {
+        if (run_mode) { // decided on the device, in the same order with the same numbers
+            new_energy = run_res.u_new[m];
+            old_energy = run_res.u_old[m];
+            return m < run_res.n_moves;
+        }
         const size_t S = static_cast<size_t>(res.stride);
         double nb_new = res.u_new[m];
         double nb_old = res.u_old[m];
@@ -939,6 +1008,9 @@ class B200WindowEvaluator : public WindowEvaluator
 
     void commit(const std::vector<unsigned char>& accepted) override
     {
+        if (run_mode) {
+            return; // the device keeps its own books
+        }
         fbCheck(fb_batch_commit(dev->ctx, static_cast<int>(accepted.size()), accepted.data()), dev->ctx,
                 "fb_batch_commit");
     }

@@ -6,6 +6,7 @@
 #include "fb_batch.cuh"
 #include "fb_stream.cuh"
 #include "fb_cells.cuh"
+#include "fb_run.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -224,6 +225,31 @@ struct fb_ctx
         int cell_dims[3] = {0, 0, 0};
         DeviceBuffer<int> d_cell_count, d_cell_bucket, d_cell_overflow;
         std::vector<fb_batch_move> last_moves; //!< proposals of the window in flight (for a brute-force re-run)
+        // runs of windows decided on the device (fb_run.cuh)
+        struct RunBlock
+        {
+            RunHeader header;
+            RunMove moves[kRunMax];
+        };
+        struct RunBack
+        {
+            RunState state;
+            double overflow; //!< result[2] of the last window: a cell bucket ran full
+            RunOutput out[kRunMax];
+        };
+        PinnedBuffer<RunBlock> h_run;
+        DeviceBuffer<RunBlock> d_run;
+        PinnedBuffer<RunBack> h_back;
+        DeviceBuffer<RunBack> d_back;
+        std::vector<int> run_stamp; //!< per particle slot: the run that last touched it (distinctness check)
+        int run_id = 0;
+        bool run_in_flight = false;
+        int run_n = 0, run_stride = 0, run_with_ewald = 0, run_steps_launched = 0;
+        bool run_decide_configured = false;
+        std::vector<unsigned char> run_accepted;
+        std::vector<double> run_u_new, run_u_old;
+        double run_steps = 0, run_count = 0;
+        double round_trips = 0; //!< waits for the device (windows walked on the host + runs)
         bool force_brute = false;
         double rec_sum = 0;
         PhaseGeometry geo{};

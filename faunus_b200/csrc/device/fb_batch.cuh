@@ -27,7 +27,13 @@ namespace fbdev {
 
 constexpr int kBatchMax = 64;    //!< moves per window
 
-/** Host → device description of one window (copied as one block) */
+struct CommitList
+{
+    int n;
+    int index[kBatchMax]; //!< indices into the PREVIOUS window
+};
+
+/** Description of one window: copied from the host as one block, or assembled on the device (fb_run.cuh) */
 struct BatchInput
 {
     int n;
@@ -45,6 +51,10 @@ struct BatchInput
     int move_group[kBatchMax];
     double4 cm_new[kBatchMax];
     double4 cm_old[kBatchMax];
+    // what became of the PREVIOUS window: its accepted atoms (positions → mirrors, δ → Q(k)) and, in group mode,
+    // its accepted moves (mass centres)
+    CommitList commit;
+    CommitList commit_moves;
 };
 
 /** Device-resident working set of one window */
@@ -61,12 +71,6 @@ struct PhaseGeometry
     int ncc;          //!< ceil(n_cutoff): n_x ∈ [0, ncc], n_y, n_z ∈ [−ncc, ncc]
     int table_stride; //!< entries per position: (ncc+1) + 2(2ncc+1)
     double len[3];    //!< box lengths
-};
-
-struct CommitList
-{
-    int n;
-    int index[kBatchMax]; //!< indices into the PREVIOUS window
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b)
@@ -177,9 +181,10 @@ __global__ void __launch_bounds__(kBlock)
  * The previous window's accepted trial positions go into both mirrors (pair stream, before the pair kernel);
  * in group mode also the mass centres of the accepted groups (`moves` lists move indices).
  */
-__global__ void __launch_bounds__(kBatchMax)
-    batchPrepKernel(SlotView M0, SlotView M1, BatchBuffers prev, CommitList commit, CommitList moves)
+__global__ void __launch_bounds__(kBatchMax) batchPrepKernel(SlotView M0, SlotView M1, BatchBuffers cur, BatchBuffers prev)
 {
+    const CommitList& commit = cur.in->commit;
+    const CommitList& moves = cur.in->commit_moves;
     if (static_cast<int>(threadIdx.x) < commit.n) {
         const int m = commit.index[threadIdx.x];
         const int s = prev.in->slot[m];
@@ -190,6 +195,17 @@ __global__ void __launch_bounds__(kBatchMax)
         M1.posq[s] = p;
         M1.atom_id[s] = id;
     }
+    if (static_cast<int>(threadIdx.x) < moves.n) {
+        const int g = moves.index[threadIdx.x];
+        const int group = prev.in->move_group[g];
+        M0.gcm[group] = prev.in->cm_new[g];
+        M1.gcm[group] = prev.in->cm_new[g];
+    }
+}
+
+/** leaving windowed mode (group mode): the mass centres of the accepted groups, list by value */
+__global__ void __launch_bounds__(kBatchMax) batchCommitGroupsKernel(SlotView M0, SlotView M1, BatchBuffers prev, CommitList moves)
+{
     if (static_cast<int>(threadIdx.x) < moves.n) {
         const int g = moves.index[threadIdx.x];
         const int group = prev.in->move_group[g];
@@ -705,7 +721,7 @@ template <int BT>
 __global__ void __launch_bounds__(kBlock, 2)
     batchKspaceKernel(EwaldView E, const int4* __restrict__ kn, const double* __restrict__ sqrt_ak,
                       const int* __restrict__ cell_start, int n_cells, BatchBuffers cur, BatchBuffers prev,
-                      CommitList commit, PhaseGeometry geo, double* __restrict__ r_partials /*[grid][stride]*/,
+                      PhaseGeometry geo, double* __restrict__ r_partials /*[grid][stride]*/,
                       double* __restrict__ g_partials /*[grid][stride²]*/, double* __restrict__ e_partials /*[grid]*/)
 {
     using L = KspaceSmem<BT>;
@@ -735,6 +751,7 @@ __global__ void __launch_bounds__(kBlock, 2)
     int4* s_cell = reinterpret_cast<int4*>(s_ctable + 2 * kBatchMax); // {p0, len, –, –} and {nx0, ny0, nz0, –}
 
     const int n = cur.in->n;
+    const CommitList& commit = cur.in->commit;
     const int ncommit = min(commit.n, STRIDE);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;

@@ -59,9 +59,9 @@ void launchBatchCommit(fb_ctx* c, bool with_ewald, int* n_blocks_out)
                                                       with_ewald ? 1 : 0, b.d_e_partials.ptr);
     launched(c, "batchCommitKernel");
     if (b.pending_moves.n > 0) { // group mode: mass centres of the accepted groups
-        batchPrepKernel<<<1, kBatchMax, 0, c->stream>>>(makeView(c, 0), makeView(c, 1), batchBuffers(c, b.parity),
-                                                        CommitList{}, b.pending_moves);
-        launched(c, "batchPrepKernel");
+        batchCommitGroupsKernel<<<1, kBatchMax, 0, c->stream>>>(makeView(c, 0), makeView(c, 1),
+                                                                batchBuffers(c, b.parity), b.pending_moves);
+        launched(c, "batchCommitGroupsKernel");
         b.pending_moves = CommitList{};
     }
     b.has_pending = false;
@@ -138,8 +138,10 @@ void buildCellList(fb_ctx* c, const CellGrid& g, cudaStream_t stream)
  */
 template <int KIND>
 void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, const CommitList& commit,
-                  const CommitList& commit_moves, int n_moves, int n_groups, int stride, bool with_ewald, bool timing)
+                  const CommitList& commit_moves, int n_moves, int n_groups, int stride, bool with_ewald, bool timing,
+                  bool device_commit = false)
 {
+    // device_commit: the commit list is written on the device (a run), the host does not know whether it is empty
     auto& b = c->batch;
     const SlotView M0 = makeView(c, 0);
     const bool fork = with_ewald && !timing;
@@ -148,8 +150,8 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
         CUDA_CHECK(cudaEventRecord(b.ev_fork, c->stream)); // after the H2D copy of the window description
         CUDA_CHECK(cudaStreamWaitEvent(ps, b.ev_fork, 0));
     }
-    if (commit.n > 0 || commit_moves.n > 0) {
-        batchPrepKernel<<<1, kBatchMax, 0, ps>>>(M0, makeView(c, 1), prev, commit, commit_moves);
+    if (commit.n > 0 || commit_moves.n > 0 || device_commit) {
+        batchPrepKernel<<<1, kBatchMax, 0, ps>>>(M0, makeView(c, 1), cur, prev);
         launched(c, "batchPrepKernel");
     }
     if (timing) {
@@ -172,8 +174,8 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
             if (!b.cells_valid) {
                 buildCellList(c, grid, ps);
             }
-            else if (commit.n > 0) {
-                cellCommitKernel<<<1, 2 * kBatchMax, 0, ps>>>(grid, prev, commit);
+            else if (commit.n > 0 || device_commit) {
+                cellCommitKernel<<<1, 2 * kBatchMax, 0, ps>>>(grid, cur, prev);
                 launched(c, "cellCommitKernel");
             }
             batchPairCellKernel<KIND><<<2 * n_moves, kCellThreads, 0, ps>>>(M0, c->P, grid, cur, c->pair_cut2, stride,
@@ -228,7 +230,7 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
             configured = true;                                                                                \
         }                                                                                                     \
         batchKspaceKernel<BT><<<n_rows, kBlock, KspaceSmem<BT>::bytes(), c->stream>>>(                        \
-            E, kn, ksq, cell_start, n_cells, cur, prev, commit, b.geo, b.d_r_partials.ptr, b.d_g_partials.ptr, \
+            E, kn, ksq, cell_start, n_cells, cur, prev, b.geo, b.d_r_partials.ptr, b.d_g_partials.ptr,       \
             b.d_e_partials.ptr);                                                                              \
     }
         switch (stride) {
@@ -289,13 +291,32 @@ void flushBatch(fb_ctx* c)
 
 namespace {
 
+/** after a synchronize: device time of the window(s) between ev[0] and ev[4] (+ the per-kernel split) */
+void accumulateWindowTiming(fb_ctx* c, bool timing)
+{
+    auto& b = c->batch;
+    float t04 = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&t04, b.ev[0], b.ev[4]));
+    b.acc_total_ms += t04;
+    if (timing) {
+        float t01 = 0, t12 = 0, t23 = 0, t34 = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&t01, b.ev[0], b.ev[1]));
+        CUDA_CHECK(cudaEventElapsedTime(&t12, b.ev[1], b.ev[2]));
+        CUDA_CHECK(cudaEventElapsedTime(&t23, b.ev[2], b.ev[3]));
+        CUDA_CHECK(cudaEventElapsedTime(&t34, b.ev[3], b.ev[4]));
+        b.acc_ms[0] += t12;
+        b.acc_ms[1] += t23;
+        b.acc_ms[2] += t01 + t34;
+    }
+}
+
 /** common head of the two submit flavours */
 void beginWindow(fb_ctx* c, int with_ewald)
 {
     checkSlot(c, 0);
     checkSlot(c, 1);
     auto& b = c->batch;
-    if (b.in_flight) {
+    if (b.in_flight || b.run_in_flight) {
         throw CudaError{"fb_batch_submit: the previous window has not been waited for"};
     }
     if (c->has_commit) { // an accepted fast-path move is still only on the host
@@ -344,6 +365,8 @@ void launchPreparedWindow(fb_ctx* c, int n_atoms, int n_groups, int with_ewald)
     const BatchBuffers prev = batchBuffers(c, b.parity);
     b.parity ^= 1;
     const BatchBuffers cur = batchBuffers(c, b.parity);
+    b.h_in.ptr->commit = commit;
+    b.h_in.ptr->commit_moves = commit_moves;
     CUDA_CHECK(cudaMemcpyAsync(cur.in, b.h_in.ptr, sizeof(BatchInput), cudaMemcpyHostToDevice, c->stream));
     const size_t n_result = batchResultDoubles(stride);
     b.d_result.ensure(batchResultDoubles(kBatchMax));
@@ -480,6 +503,248 @@ FB_API int fb_batch_submit_groups(fb_ctx* c, int n_moves, const fb_batch_group_m
     });
 }
 
+namespace {
+
+/** launches of one window of the run in flight: set-up from the device cursor, the window kernels, the decisions */
+void launchRunStep(fb_ctx* c, bool timing)
+{
+    auto& b = c->batch;
+    const int stride = b.run_stride;
+    const bool with_ewald = b.run_with_ewald != 0;
+    const BatchBuffers prev = batchBuffers(c, b.parity);
+    b.parity ^= 1;
+    const BatchBuffers cur = batchBuffers(c, b.parity);
+    const RunHeader* hdr = &b.d_run.ptr->header;
+    const RunMove* moves = b.d_run.ptr->moves;
+    RunState* st = &b.d_back.ptr->state;
+    runSetupKernel<<<1, kBatchMax, 0, c->stream>>>(hdr, moves, st, cur.in, stride);
+    launched(c, "runSetupKernel");
+#define FB_CASE(K)                                                                                             \
+    case K:                                                                                                    \
+        launchWindow<K>(c, cur, prev, CommitList{}, CommitList{}, stride, 0, stride, with_ewald, timing, true); \
+        break;
+    switch (c->P.kind) {
+        FB_CASE(POT_COULOMB_LJ)
+        FB_CASE(POT_COULOMB_WCA)
+        FB_CASE(POT_PM)
+        FB_CASE(POT_PMWCA)
+        FB_CASE(POT_FUNCTOR)
+        FB_CASE(POT_SPLINED)
+    default:
+        throw CudaError{"unknown potential kind"};
+    }
+#undef FB_CASE
+    const size_t smem = runDecideSmemBytes(stride);
+    if (!b.run_decide_configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(runDecideKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(runDecideSmemBytes(kBatchMax))));
+        b.run_decide_configured = true;
+    }
+    runDecideKernel<<<1, kDecideThreads, smem, c->stream>>>(hdr, moves, st, cur, stride, b.cells_used ? 1 : 0,
+                                                           b.d_result.ptr, b.d_back.ptr->out);
+    launched(c, "runDecideKernel");
+    b.run_steps_launched += 1;
+}
+
+/** queue `steps` windows of the run and the read-back of where it stands */
+void launchRunSteps(fb_ctx* c, int steps)
+{
+    auto& b = c->batch;
+    if (c->timing) { // per-kernel events: one window at a time, kernels serialised
+        for (int s = 0; s < steps; ++s) {
+            CUDA_CHECK(cudaEventRecord(b.ev[0], c->stream));
+            launchRunStep(c, true);
+            CUDA_CHECK(cudaEventRecord(b.ev[4], c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            accumulateWindowTiming(c, true);
+        }
+    }
+    else {
+        CUDA_CHECK(cudaEventRecord(b.ev[0], c->stream));
+        for (int s = 0; s < steps; ++s) {
+            launchRunStep(c, false);
+        }
+        CUDA_CHECK(cudaEventRecord(b.ev[4], c->stream));
+    }
+    // state + overflow flag + the decisions
+    CUDA_CHECK(cudaMemcpyAsync(&b.d_back.ptr->overflow, b.d_result.ptr + 2, sizeof(double), cudaMemcpyDeviceToDevice,
+                               c->stream));
+    const size_t bytes = offsetof(fb_ctx::Batch::RunBack, out) + sizeof(RunOutput) * static_cast<size_t>(b.run_n);
+    CUDA_CHECK(cudaMemcpyAsync(b.h_back.ptr, b.d_back.ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+}
+
+} // namespace
+
+FB_API int fb_run_submit(fb_ctx* c, int n_moves, const fb_run_move* moves, int with_ewald, const fb_run_config* config)
+{
+    return guarded(c, [&] {
+        if (!moves || !config || n_moves < 1 || n_moves > kRunMax) {
+            throw CudaError{"fb_run_submit: 1..1024 moves per run"};
+        }
+        if (config->n_terms < 1 || config->n_terms > kRunTerms) {
+            throw CudaError{"fb_run_submit: 1..6 Hamiltonian terms"};
+        }
+        beginWindow(c, with_ewald);
+        auto& b = c->batch;
+        b.h_run.ensure(1);
+        b.d_run.ensure(1);
+        b.h_back.ensure(1);
+        b.d_back.ensure(1);
+        if (static_cast<int>(b.run_stamp.size()) != c->n_slots) {
+            b.run_stamp.assign(static_cast<size_t>(c->n_slots), 0);
+            b.run_id = 0;
+        }
+        b.run_id += 1;
+        RunHeader& h = b.h_run.ptr->header;
+        h.n_moves = n_moves;
+        h.with_ewald = with_ewald ? 1 : 0;
+        h.n_terms = config->n_terms;
+        h.pad = 0;
+        int n_nonbonded = 0, n_ewald = 0;
+        for (int i = 0; i < kRunTerms; ++i) {
+            h.term_kind[i] = i < config->n_terms ? config->term_kind[i] : RUN_TERM_HOST;
+            if (h.term_kind[i] < RUN_TERM_HOST || h.term_kind[i] > RUN_TERM_EWALD) {
+                throw CudaError{"fb_run_submit: unknown term kind"};
+            }
+            n_nonbonded += h.term_kind[i] == RUN_TERM_NONBONDED;
+            n_ewald += h.term_kind[i] == RUN_TERM_EWALD;
+        }
+        if (n_nonbonded != 1 || n_ewald > 1 || (n_ewald == 1) != (with_ewald != 0)) {
+            throw CudaError{"fb_run_submit: one non-bonded term, and an Ewald term exactly when with_ewald is set"};
+        }
+        h.max_energy = config->max_energy;
+        h.cancellation_limit = config->cancellation_limit;
+        h.rec_prefactor = 0.0;
+        if (with_ewald) {
+            batchEwaldGeometry(c);
+            const double pi = 3.141592653589793238462643383279502884;
+            const Slot& sl = c->slot[0];
+            h.rec_prefactor = 2 * pi * c->ewald.bjerrum_length / (sl.ewald_box[0] * sl.ewald_box[1] * sl.ewald_box[2]);
+        }
+        for (int m = 0; m < n_moves; ++m) {
+            const fb_batch_move& mv = moves[m].move;
+            if (mv.group_index < 0 || mv.group_index >= c->n_groups) {
+                throw CudaError{"fb_run_submit: group index out of range"};
+            }
+            const fb_group& g = c->slot[0].groups[mv.group_index];
+            if (!(c->molecule_flags[g.molid] & FB_MOL_ATOMIC)) {
+                throw CudaError{"fb_run_submit: the moves of a run are single atoms of atomic groups"};
+            }
+            if (mv.rel_index < 0 || mv.rel_index >= g.size) {
+                throw CudaError{"fb_run_submit: relative atom index out of range"};
+            }
+            if (mv.atom_id < 0 || mv.atom_id >= c->P.n_types || mv.old_atom_id < 0 || mv.old_atom_id >= c->P.n_types) {
+                throw CudaError{"fb_run_submit: atom id out of range"};
+            }
+            const int slot = g.begin + mv.rel_index;
+            if (b.run_stamp[slot] == b.run_id) {
+                throw CudaError{"fb_run_submit: the moves of one run must touch distinct atoms"};
+            }
+            b.run_stamp[slot] = b.run_id;
+            RunMove& r = b.h_run.ptr->moves[m];
+            r.slot = slot;
+            r.id = mv.atom_id;
+            r.idold = mv.old_atom_id;
+            r.pad = 0;
+            r.pnew = make_double4(mv.xyzq[0], mv.xyzq[1], mv.xyzq[2], mv.xyzq[3]);
+            r.pold = make_double4(mv.old_xyzq[0], mv.old_xyzq[1], mv.old_xyzq[2], mv.old_xyzq[3]);
+            r.uniform = moves[m].uniform;
+            for (int i = 0; i < kRunTerms; ++i) {
+                r.host_new[i] = moves[m].host_new[i];
+                r.host_old[i] = moves[m].host_old[i];
+            }
+        }
+        // accepted moves of an earlier window / run that are not yet on the device
+        b.run_stride = n_moves <= 16 ? 16 : (n_moves <= 32 ? 32 : 64);
+        if (b.has_pending &&
+            (b.pending_moves.n > 0 || (b.pending_with_ewald && (!with_ewald || b.pending.n > b.run_stride)))) {
+            // rigid-molecule moves (mass centres) / Q(k) has to follow although this run has no k-space part / its
+            // windows have no room for that many commits: apply them now
+            launchBatchCommit(c, b.pending_with_ewald, nullptr);
+            b.cells_valid = false;
+        }
+        const CommitList pending = b.has_pending ? b.pending : CommitList{};
+        b.has_pending = false;
+        b.d_result.ensure(batchResultDoubles(kBatchMax));
+        b.h_result.ensure(batchResultDoubles(kBatchMax));
+        const size_t bytes = offsetof(fb_ctx::Batch::RunBlock, moves) + sizeof(RunMove) * static_cast<size_t>(n_moves);
+        CUDA_CHECK(cudaMemcpyAsync(b.d_run.ptr, b.h_run.ptr, bytes, cudaMemcpyHostToDevice, c->stream));
+        runInitKernel<<<1, kBatchMax, 0, c->stream>>>(&b.d_back.ptr->state, pending);
+        launched(c, "runInitKernel");
+        b.run_n = n_moves;
+        b.run_with_ewald = with_ewald ? 1 : 0;
+        b.run_steps_launched = 0;
+        b.run_in_flight = true;
+        launchRunSteps(c, (n_moves + b.run_stride - 1) / b.run_stride);
+    });
+}
+
+FB_API int fb_run_wait(fb_ctx* c, fb_run_result* out)
+{
+    return guarded(c, [&] {
+        auto& b = c->batch;
+        if (!out || !b.run_in_flight) {
+            throw CudaError{"fb_run_wait: no submitted run"};
+        }
+        for (;;) {
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            if (!c->timing) {
+                accumulateWindowTiming(c, false);
+            }
+            const RunState& st = b.h_back.ptr->state;
+            if (st.cursor >= b.run_n) {
+                break;
+            }
+            if (b.run_steps_launched > 4 * kRunMax) {
+                throw CudaError{"fb_run_wait: the run makes no progress"};
+            }
+            // a window stopped early (cancellation) or a cell bucket ran full: more windows
+            if (b.cells_used && b.h_back.ptr->overflow != 0.0) {
+                b.cells_valid = false;
+                b.cell_cap *= 2;
+            }
+            const int left = b.run_n - st.cursor;
+            launchRunSteps(c, (left + b.run_stride - 1) / b.run_stride);
+        }
+        b.run_in_flight = false;
+        const RunState& st = b.h_back.ptr->state;
+        b.windows += st.steps;
+        b.moves += b.run_n;
+        b.run_steps += st.steps;
+        b.run_count += 1;
+        b.round_trips += 1;
+        b.run_accepted.resize(static_cast<size_t>(b.run_n));
+        b.run_u_new.resize(static_cast<size_t>(b.run_n));
+        b.run_u_old.resize(static_cast<size_t>(b.run_n));
+        bool any = false;
+        for (int m = 0; m < b.run_n; ++m) {
+            const RunOutput& o = b.h_back.ptr->out[m];
+            b.run_accepted[m] = static_cast<unsigned char>(o.accepted != 0);
+            b.run_u_new[m] = o.u_new;
+            b.run_u_old[m] = o.u_old;
+            any = any || o.accepted != 0;
+        }
+        // the accepted moves of the last window are still to be applied (by the next window, run or flush)
+        b.pending = st.commit;
+        b.has_pending = st.commit.n > 0;
+        b.pending_moves = CommitList{};
+        b.pending_with_ewald = b.run_with_ewald != 0;
+        b.last_n = 0;
+        b.last_groups = 0;
+        if (any && b.run_with_ewald) {
+            b.q_dirty = true;
+            c->slot[0].rec_valid = false;
+            c->slot[1].rec_valid = false;
+        }
+        b.rec_known = false;
+        out->n_moves = b.run_n;
+        out->n_windows = st.steps;
+        out->accepted = b.run_accepted.data();
+        out->u_new = b.run_u_new.data();
+        out->u_old = b.run_u_old.data();
+    });
+}
+
 FB_API int fb_batch_wait(fb_ctx* c, fb_batch_result* out)
 {
     return guarded(c, [&] {
@@ -493,22 +758,9 @@ FB_API int fb_batch_wait(fb_ctx* c, fb_batch_result* out)
         const bool timing = b.flight_timing;
         b.in_flight = false;
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        {
-            float t04 = 0;
-            CUDA_CHECK(cudaEventElapsedTime(&t04, b.ev[0], b.ev[4]));
-            b.acc_total_ms += t04;
-        }
-        if (timing) {
-            float t01 = 0, t12 = 0, t23 = 0, t34 = 0;
-            CUDA_CHECK(cudaEventElapsedTime(&t01, b.ev[0], b.ev[1]));
-            CUDA_CHECK(cudaEventElapsedTime(&t12, b.ev[1], b.ev[2]));
-            CUDA_CHECK(cudaEventElapsedTime(&t23, b.ev[2], b.ev[3]));
-            CUDA_CHECK(cudaEventElapsedTime(&t34, b.ev[3], b.ev[4]));
-            b.acc_ms[0] += t12;
-            b.acc_ms[1] += t23;
-            b.acc_ms[2] += t01 + t34;
-        }
+        accumulateWindowTiming(c, timing);
         b.windows += 1;
+        b.round_trips += 1;
         b.moves += n_moves;
         const double* r = b.h_result.ptr;
         if (b.cells_used && b.flight_groups == 0 && r[2] != 0.0) { // a bucket ran full: this window's pair sums are incomplete
@@ -641,6 +893,7 @@ FB_API int fb_get_batch_timing(const fb_ctx* c, double out[8])
     out[3] = c->batch.windows;
     out[4] = c->batch.moves;
     out[5] = c->batch.acc_total_ms;
-    out[6] = out[7] = 0.0;
+    out[6] = c->batch.round_trips;
+    out[7] = c->batch.run_count;
     return FB_OK;
 }

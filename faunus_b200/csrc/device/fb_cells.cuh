@@ -79,8 +79,9 @@ __global__ void cellSortKernel(CellGrid g, int n_cells)
  * re-sorted (tombstones sink to the end and are trimmed) by the first thread that lists it — the result is the
  * sorted set of slots again, whatever the order of the atomics.
  */
-__global__ void __launch_bounds__(2 * kBatchMax) cellCommitKernel(CellGrid g, BatchBuffers prev, CommitList commit)
+__global__ void __launch_bounds__(2 * kBatchMax) cellCommitKernel(CellGrid g, BatchBuffers cur, BatchBuffers prev)
 {
+    const CommitList& commit = cur.in->commit;
     __shared__ int s_cell[2 * kBatchMax]; // [a] old cell, [n + a] new cell; −1: nothing to do
     constexpr int tombstone = 0x7fffffff;
     const int n = commit.n;

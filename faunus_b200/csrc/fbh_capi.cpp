@@ -159,12 +159,30 @@ extern "C" __attribute__((visibility("default"))) int fbh_sim_set_window(void* h
     return result;
 }
 
-/** out[0..5] as fb_get_batch_timing; out[6] = host ms inside evaluate (launch + wait), out[7] = host ms of the
- * whole windowed sweep part (drawing proposals, evaluate, deciding) */
-extern "C" __attribute__((visibility("default"))) int fbh_sim_get_window_timing(void* h, double out[8])
+/**
+ * Runs: the device walks the windows of single-atom moves itself (fb_run_submit), up to `moves` proposals per
+ * host round trip (0: the host walks every window). Needs fbh_sim_set_window(64). Returns the run capacity in effect.
+ */
+extern "C" __attribute__((visibility("default"))) int fbh_sim_set_run(void* h, int moves)
 {
     auto* s = static_cast<fb::capi::Sim*>(h);
-    for (int i = 0; i < 8; ++i) {
+    int result = 0;
+    fb::capi::guarded([&] {
+        auto* e = dynamic_cast<fb::B200WindowEvaluator*>(s->mc->window_evaluator.get());
+        if (e != nullptr) {
+            e->enableRuns(moves);
+            result = e->runCapacity();
+        }
+    });
+    return result;
+}
+
+/** out[0..5] as fb_get_batch_timing; out[6] = host ms inside evaluate (launch + wait), out[7] = host ms of the
+ * whole windowed sweep part (drawing proposals, evaluate, deciding); out[8] = host round trips, out[9] = runs */
+extern "C" __attribute__((visibility("default"))) int fbh_sim_get_window_timing(void* h, double out[10])
+{
+    auto* s = static_cast<fb::capi::Sim*>(h);
+    for (int i = 0; i < 10; ++i) {
         out[i] = 0;
     }
     for (const auto& t : s->mc->state.pot->find<fb::NonbondedB200>()) {
@@ -173,6 +191,8 @@ extern "C" __attribute__((visibility("default"))) int fbh_sim_get_window_timing(
         for (int i = 0; i < 8; ++i) {
             out[i] += v[i];
         }
+        out[8] += v[6];
+        out[9] += v[7];
     }
     out[6] = 1e3 * s->mc->window_seconds_evaluate;
     out[7] = 1e3 * s->mc->window_seconds_total;

@@ -6,7 +6,10 @@
 #pragma once
 #include "moves.hpp"
 #include <chrono>
+#include <algorithm>
 #include <functional>
+#include <unordered_map>
+#include <unordered_set>
 
 namespace fb {
 
@@ -82,6 +85,8 @@ class WindowEvaluator
      */
     virtual bool energies(int m, const std::vector<unsigned char>& accepted, const WindowProposal& proposal,
                           double& new_energy, double& old_energy) = 0;
+    /** the evaluator already decided proposal m (1 accepted, 0 rejected; the caller replays it); −1: caller decides */
+    virtual int decision(int /*m*/) const { return -1; }
     /** the first `accepted.size()` proposals are decided; the rest will be submitted again */
     virtual void commit(const std::vector<unsigned char>& accepted) = 0;
 };
@@ -278,6 +283,39 @@ class MetropolisMonteCarlo
         p.applied = true;
     }
 
+    static uint64_t proposalKey(const WindowProposal& p)
+    {
+        return (static_cast<uint64_t>(p.key_group) << 32) | static_cast<uint64_t>(static_cast<uint32_t>(p.key_atom + 1));
+    }
+
+    /** undecided proposals per touched atom / molecule, and which of them are applied to the trial Space */
+    std::unordered_map<uint64_t, int> pending_keys;
+    std::unordered_set<uint64_t> applied_keys;
+    int unapplied_count = 0;
+
+    /** apply every queued proposal whose atom / molecule has no earlier undecided proposal any more */
+    void applyUnblocked()
+    {
+        if (unapplied_count == 0) {
+            return;
+        }
+        std::vector<uint64_t> seen;
+        for (auto& p : window) {
+            if (p.applied) {
+                continue;
+            }
+            const uint64_t key = proposalKey(p);
+            if (applied_keys.count(key) == 0 && std::find(seen.begin(), seen.end(), key) == seen.end()) {
+                applyProposal(p);
+                applied_keys.insert(key);
+                unapplied_count--;
+            }
+            else {
+                seen.push_back(key);
+            }
+        }
+    }
+
     /** evaluate the first `n` queued proposals (all applied) and decide as many as possible, in order */
     void decideWindow(int n)
     {
@@ -307,7 +345,8 @@ class MetropolisMonteCarlo
             if (p.move != nullptr) {
                 p.move->setLatestDisplacementSquared(p.displacement_squared);
             }
-            if (metropolisDecision(energy_change, p.uniform)) {
+            const int decided = window_evaluator->decision(m);
+            if (decided >= 0 ? decided != 0 : metropolisDecision(energy_change, p.uniform)) {
                 state.spc->sync(*trial_state.spc, p.change);
                 p.base->accept(p.change);
                 rec.accepted = 1;
@@ -328,7 +367,16 @@ class MetropolisMonteCarlo
         }
         window_evaluator->commit(accepted);
         // undecided proposals stay queued: their trial positions are in the trial Space (distinct atoms)
+        for (size_t m = 0; m < accepted.size(); ++m) {
+            const uint64_t key = proposalKey(window[m]);
+            applied_keys.erase(key);
+            auto it = pending_keys.find(key);
+            if (--(it->second) == 0) {
+                pending_keys.erase(it);
+            }
+        }
         window.erase(window.begin(), window.begin() + static_cast<long>(accepted.size()));
+        applyUnblocked();
         window_seconds_decide += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_evaluated).count();
     }
 
@@ -344,8 +392,6 @@ class MetropolisMonteCarlo
     unsigned int sweep_remaining = 0;     //!< stochastic moves of the current sweep not yet drawn
     Move* sweep_deferred = nullptr;       //!< a move of another kind: runs once the queue is empty
     std::function<int(Move&)> sweep_id_of;
-
-    bool windowBlocked() const { return !window.empty() && !window.back().applied; }
 
     /** the kind of window `selected` can go into, if any */
     bool windowKind(Move* selected, WindowProposal::Kind& kind) const
@@ -402,22 +448,23 @@ class MetropolisMonteCarlo
             return;
         }
         p.uniform = rng.slump();
-        bool blocked = false;
-        for (const auto& q : window) {
-            blocked = blocked || (q.key_group == p.key_group && q.key_atom == p.key_atom);
-        }
-        if (!blocked) {
+        const uint64_t key = proposalKey(p);
+        int& pending = pending_keys[key];
+        if (pending == 0) {
             applyProposal(p);
+            applied_keys.insert(key);
         }
-        // else: its start position is only known once the earlier move on this atom / molecule is decided
+        else { // its start position is only known once the earlier moves on this atom / molecule are decided
+            unapplied_count++;
+        }
+        pending++;
         window.push_back(std::move(p));
     }
 
     /** draw proposals (in move order, generator order of performMove) until the queue holds `max_size` */
     void fillWindow(int max_size)
     {
-        while (!windowBlocked() && sweep_deferred == nullptr && sweep_remaining > 0 &&
-               static_cast<int>(window.size()) < max_size) {
+        while (sweep_deferred == nullptr && sweep_remaining > 0 && static_cast<int>(window.size()) < max_size) {
             sweep_remaining--;
             Move* selected = moves->sampleStochasticMove();
             if (selected == nullptr) {
@@ -441,27 +488,21 @@ class MetropolisMonteCarlo
         sweep_id_of = id_of;
         while (sweep_remaining > 0 || !window.empty() || sweep_deferred != nullptr) {
             fillWindow(capacity);
-            if (windowBlocked() || sweep_deferred != nullptr || sweep_remaining == 0) { // drain the queue
-                while (readyProposals() > 0) {
-                    decideWindow(window_evaluator->fit(window, readyProposals()));
-                }
-                if (!window.empty()) { // the blocked proposal: its atom is decided now
-                    applyProposal(window.front());
-                }
-                if (sweep_deferred != nullptr) {
-                    Move* m = sweep_deferred;
-                    sweep_deferred = nullptr;
-                    WindowProposal::Kind kind{};
-                    if (windowKind(m, kind)) { // window.empty(): a blocked proposal is always the last one drawn
-                        enqueue(m, kind);
-                    }
-                    else {
-                        performMove(*m, sweep_id_of(*m));
-                    }
-                }
-            }
-            else if (!window.empty()) { // full window
+            if (!window.empty()) {
+                // the applied head of the queue (its first proposal always is): proposals further back whose atom /
+                // molecule is still undecided wait for their turn
                 decideWindow(window_evaluator->fit(window, readyProposals()));
+            }
+            else if (sweep_deferred != nullptr) {
+                Move* m = sweep_deferred;
+                sweep_deferred = nullptr;
+                WindowProposal::Kind kind{};
+                if (windowKind(m, kind)) {
+                    enqueue(m, kind);
+                }
+                else {
+                    performMove(*m, sweep_id_of(*m));
+                }
             }
         }
     }

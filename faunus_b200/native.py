@@ -68,6 +68,21 @@ class FbBatchGroupMove(C.Structure):
                 ("old_xyzq", (C.c_double * 4) * 8), ("old_cm", C.c_double * 3)]
 
 
+class FbRunMove(C.Structure):
+    _fields_ = [("move", FbBatchMove), ("uniform", C.c_double), ("host_new", C.c_double * 6),
+                ("host_old", C.c_double * 6)]
+
+
+class FbRunConfig(C.Structure):
+    _fields_ = [("n_terms", C.c_int), ("term_kind", C.c_int * 6), ("max_energy", C.c_double),
+                ("cancellation_limit", C.c_double)]
+
+
+class FbRunResult(C.Structure):
+    _fields_ = [("n_moves", C.c_int), ("n_windows", C.c_int), ("accepted", C.POINTER(C.c_ubyte)),
+                ("u_new", c_double_p), ("u_old", c_double_p)]
+
+
 class FbTrialMove(C.Structure):
     _fields_ = [("group_index", C.c_int), ("n_atoms", C.c_int), ("rel_index", C.c_int * 8),
                 ("xyzq", (C.c_double * 4) * 8), ("atom_id", C.c_int * 8), ("cm", C.c_double * 3),
@@ -100,7 +115,7 @@ class FbConfig(C.Structure):
 C_ABI_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_last_error", "fb_device_count", "fb_upload_space", "fb_update_group",
     "fb_set_box", "fb_sync", "fb_download_space", "fb_nonbonded_energy", "fb_nonbonded_delta",
-    "fb_system_energy_shard", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_submit_groups", "fb_batch_wait", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing",
+    "fb_system_energy_shard", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_submit_groups", "fb_batch_wait", "fb_run_submit", "fb_run_wait", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing",
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
     "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
     "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_launch_count",
@@ -140,6 +155,8 @@ def load() -> C.CDLL:
         "fb_batch_trial": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchMove), C.c_int, C.POINTER(FbBatchResult)]),
         "fb_batch_submit": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchMove), C.c_int]),
         "fb_batch_submit_groups": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchGroupMove), C.c_int]),
+        "fb_run_submit": (C.c_int, [vp, C.c_int, C.POINTER(FbRunMove), C.c_int, C.POINTER(FbRunConfig)]),
+        "fb_run_wait": (C.c_int, [vp, C.POINTER(FbRunResult)]),
         "fb_batch_wait": (C.c_int, [vp, C.POINTER(FbBatchResult)]),
         "fb_batch_commit": (C.c_int, [vp, C.c_int, c_ubyte_p]),
         "fb_configure_cells": (C.c_int, [vp, C.c_int]),
@@ -171,6 +188,7 @@ def load() -> C.CDLL:
         "fbh_set_device": (None, [C.c_int]),
         "fbh_sim_launch_count": (C.c_ulonglong, [vp]),
         "fbh_sim_set_window": (C.c_int, [vp, C.c_int]),
+        "fbh_sim_set_run": (C.c_int, [vp, C.c_int]),
         "fbh_system_energy_shard": (C.c_int, [vp, C.c_int, C.c_int, c_double_p]),
         "fbh_sim_get_window_timing": (C.c_int, [vp, c_double_p]),
     }
@@ -204,17 +222,31 @@ class B200Simulation(Simulation):
     #: proposals evaluated per device pass for runs of `transrot` moves (0: one move at a time)
     DEFAULT_WINDOW = int(os.environ.get("FAUNUS_B200_WINDOW", "64"))
 
-    def __init__(self, config, device: int = 0, window: Optional[int] = None):
+    #: single-atom proposals shipped per host round trip when the device walks the windows itself (fb_run_submit;
+    #: 0: every window is walked on the host). Needs the full window of 64.
+    DEFAULT_RUN = int(os.environ.get("FAUNUS_B200_RUN", "512"))
+
+    def __init__(self, config, device: int = 0, window: Optional[int] = None, run: Optional[int] = None):
         require_device()
         load().fbh_set_device(device)
         super().__init__(sim_library(), config)
+        self.run = 0
+        self._run_request = self.DEFAULT_RUN if run is None else int(run)
         self.window = self.set_window(self.DEFAULT_WINDOW if window is None else window)
 
     def set_window(self, capacity: int) -> int:
         """Windowed evaluation of single-atom move runs (fb_batch_trial); returns the capacity in effect
         (0 when switched off or when the Hamiltonian is not eligible)."""
         self.window = int(load().fbh_sim_set_window(self.handle, int(capacity)))
+        self.set_run(self._run_request)
         return self.window
+
+    def set_run(self, moves: int) -> int:
+        """Device-decided runs of windows (fb_run_submit): up to `moves` proposals per round trip; returns the
+        capacity in effect (0 unless the window is 64 and the Hamiltonian has at most 6 terms)."""
+        self._run_request = int(moves)
+        self.run = int(load().fbh_sim_set_run(self.handle, int(moves))) if self.window else 0
+        return self.run
 
     # ---- work sharded over the ranks of a process group (SURVEY §8e); see also Simulation.widom_sample_sharded
     def system_energy_shard(self, rank: int, size: int):
@@ -229,10 +261,11 @@ class B200Simulation(Simulation):
         self._check(load().fb_configure_cells(self.ctx, int(min_particles)), "fb_configure_cells")
 
     def window_time_ms(self) -> dict:
-        out = np.zeros(8)
+        out = np.zeros(10)
         load().fbh_sim_get_window_timing(self.handle, out.ctypes.data_as(c_double_p))
         return {"pair_ms": out[0], "ewald_ms": out[1], "other_ms": out[2], "windows": int(out[3]),
-                "moves": int(out[4]), "total_ms": out[5], "host_evaluate_ms": out[6], "host_sweep_ms": out[7]}
+                "moves": int(out[4]), "total_ms": out[5], "host_evaluate_ms": out[6], "host_sweep_ms": out[7],
+                "round_trips": int(out[8]), "runs": int(out[9])}
 
     @property
     def launch_count(self) -> int:

@@ -291,6 +291,43 @@ typedef struct
     double old_cm[3];
 } fb_batch_group_move;
 int fb_batch_submit_groups(fb_ctx* ctx, int n_moves, const fb_batch_group_move* moves, int with_ewald);
+/* Runs: windows decided on the device (the batched sequential-MC driver). For single-atom moves
+ * everything the in-order walk needs besides the device results is known when the proposals are drawn: the
+ * Metropolis uniform (always drawn, src/montecarlo.cpp:17-34) and the energies of the caller's own Hamiltonian
+ * terms. A run is up to FB_RUN_MAX proposals on DISTINCT atoms; the device evaluates it window by window
+ * (64 moves), walks each window in order — corrected energies, Hamiltonian sum in term order with the reference's
+ * early exit (src/energy.cpp:1227-1247), getEnergyChange (src/montecarlo.cpp:193-209), Metropolis — and feeds the
+ * accepted moves to the next window without a host round trip. fb_run_wait returns the outcome of every move
+ * (all moves of the run are decided when it returns); the caller replays it into its Space. Nothing to commit. */
+#define FB_RUN_MAX 1024
+#define FB_RUN_TERMS 6
+#define FB_TERM_HOST 0      /* evaluated by the caller: host_new / host_old */
+#define FB_TERM_NONBONDED 1 /* the pair energy of the moved atom (this library) */
+#define FB_TERM_EWALD 2     /* reciprocal energy of the system (this library) */
+typedef struct
+{
+    fb_batch_move move;
+    double uniform;                 /* the Metropolis uniform drawn for this move */
+    double host_new[FB_RUN_TERMS];  /* caller-evaluated terms, trial state, Hamiltonian order (other slots unused) */
+    double host_old[FB_RUN_TERMS];  /* ... accepted state */
+} fb_run_move;
+typedef struct
+{
+    int n_terms;                    /* Hamiltonian terms in order, 1..FB_RUN_TERMS */
+    int term_kind[FB_RUN_TERMS];    /* FB_TERM_* */
+    double max_energy;              /* the sum over terms stops after a term >= this or NaN (energy.cpp:1238-1244) */
+    double cancellation_limit;      /* see cross_max above */
+} fb_run_config;
+typedef struct
+{
+    int n_moves;
+    int n_windows;                  /* windows the device needed */
+    const unsigned char* accepted;  /* [n_moves] */
+    const double* u_new;            /* [n_moves] Hamiltonian energy of the move in the trial state at its turn */
+    const double* u_old;            /* [n_moves] ... in the accepted state */
+} fb_run_result;
+int fb_run_submit(fb_ctx* ctx, int n_moves, const fb_run_move* moves, int with_ewald, const fb_run_config* config);
+int fb_run_wait(fb_ctx* ctx, fb_run_result* result);
 /* accepted[m] != 0 for the accepted ones among the first n_decided moves of the last window */
 int fb_batch_commit(fb_ctx* ctx, int n_decided, const unsigned char* accepted);
 /* The pair part of a window goes through a device cell list (cell edge = box / floor(box / cutoff), 27
@@ -304,7 +341,8 @@ int fb_configure_cells(fb_ctx* ctx, int min_particles);
 int fb_debug_set_cell_capacity(fb_ctx* ctx, int capacity);
 /* timing enabled: out[0..2] = ms in the pair / k-space / other (commit, phase tables, final sums) kernels of
  * the windowed path (kernels serialised while timing), out[3] = windows, out[4] = moves evaluated,
- * out[5] = ms from the first to the last kernel of every window (always accumulated) */
+ * out[5] = ms from the first to the last kernel of every window (always accumulated), out[6] = host round trips
+ * (fb_batch_wait + fb_run_wait), out[7] = runs */
 int fb_get_batch_timing(const fb_ctx* ctx, double out[8]);
 
 /* ---- Ewald reciprocal space --------------------------------------------------------------- */

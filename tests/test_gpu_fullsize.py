@@ -21,9 +21,9 @@ def s1(moves_per_sweep, **kw):
     return primitive_model(n=100_000, molarity=1.0, seed=5489, moves_per_sweep=moves_per_sweep, coulomb=EWALD, **kw)
 
 
-def sim(cfg, window=None):
+def sim(cfg, window=None, run=None):
     from faunus_b200.native import B200Simulation
-    return B200Simulation(cfg, window=window)
+    return B200Simulation(cfg, window=window, run=run)
 
 
 def test_s1_drift_invariant_windowed():
@@ -34,6 +34,28 @@ def test_s1_drift_invariant_windowed():
     assert len(tr["du"]) == 6000
     assert 0.05 < tr["accepted"].mean() < 0.95
     assert abs(g.drift()) < 1e-9
+
+
+def test_s1_device_walk_equals_host_walk():
+    """N = 1e5: runs of ~400 proposals (6 windows per round trip) decided on the device == windows walked on the host"""
+    a, b = sim(s1(3000), window=64, run=0), sim(s1(3000), window=64, run=512)
+    for s in (a, b):
+        s.trace_enable()
+        s.sweep(1)
+    ta, tb = a.trace(), b.trace()
+    assert len(ta["du"]) == 3000
+    assert np.array_equal(ta["accepted"], tb["accepted"])
+    # the same corrections in the same order, but the windows are cut differently (proposals on a pending atom
+    # end a run where the host walk had already decided the earlier move): equal to rounding
+    scale = np.abs(ta["u_new"]).max()
+    for key in ("u_new", "u_old"):
+        assert np.abs(ta[key] - tb[key]).max() <= 1e-12 * scale
+    xa, _ = a.particles()
+    xb, _ = b.particles()
+    assert np.array_equal(xa, xb)
+    wa, wb = a.window_time_ms(), b.window_time_ms()
+    assert wb["round_trips"] < wa["round_trips"] / 3
+    assert abs(b.drift()) < 1e-9
 
 
 def test_s1_windowed_equals_single_moves():

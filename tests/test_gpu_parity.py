@@ -12,9 +12,9 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-10
 
 
-def b200_sim(cfg, window=None):
+def b200_sim(cfg, window=None, run=None):
     from faunus_b200.native import B200Simulation
-    return B200Simulation(cfg, window=window)
+    return B200Simulation(cfg, window=window, run=run)
 
 
 def assert_close(a, b, rtol=RTOL, scale=None):
@@ -66,8 +66,9 @@ def functor_variants():
 ALL_VARIANTS = {**electrolyte_variants(), **functor_variants()}
 
 
-#: 0 = one move per launch (updateState/energy/sync protocol); > 0 = windowed evaluation (fb_batch_trial)
-WINDOWS = [0, 32]
+#: 0 = one move per launch (updateState/energy/sync protocol); > 0 = windowed evaluation (fb_batch_trial);
+#: 64 = runs of windows walked on the device (fb_run_submit)
+WINDOWS = [0, 32, 64]
 
 
 @pytest.mark.parametrize("window", WINDOWS)
@@ -78,6 +79,7 @@ def test_system_energy_and_moves(name, window):
     o, g = pair_of_sims(cfg, window)
     if window and "surface" not in name:
         assert g.window == window
+        assert (g.run > 0) == (window == 64)
     eo, to = o.system_energy()
     eg, tg = g.system_energy()
     assert len(to) == len(tg)
@@ -356,6 +358,34 @@ def test_window_matches_single_moves():
     assert np.allclose(qa, qb, rtol=0, atol=1e-10 * np.abs(qa).max())
 
 
+def test_device_walk_equals_host_walk():
+    """runs (the device walks the windows, fb_run_submit) against windows walked on the host (fb_batch_submit):
+    the same additions in the same order, windows cut differently — identical decisions, energies equal to
+    rounding; hard spheres (`pm`: infinite pair
+    energies stop windows early) and Ewald"""
+    for name in ("pm", "coulombwca_ewald"):
+        cfg = dict(ALL_VARIANTS[name])
+        host, dev = b200_sim(cfg, 64, run=0), b200_sim(cfg, 64, run=512)
+        assert host.run == 0 and dev.run == 512
+        for s in (host, dev):
+            s.trace_enable()
+            s.sweep(600)
+        a, b = host.trace(), dev.trace()
+        assert len(a["du"]) > 500
+        assert np.array_equal(a["accepted"], b["accepted"])
+        finite = np.isfinite(a["u_new"])
+        assert np.array_equal(finite, np.isfinite(b["u_new"]))
+        scale = np.abs(a["u_new"][finite]).max()
+        for key in ("u_new", "u_old"):
+            assert np.abs(a[key][finite] - b[key][finite]).max() <= 1e-12 * scale, key
+        xa, _ = host.particles()
+        xb, _ = dev.particles()
+        assert np.array_equal(xa, xb)
+        assert host.system_energy()[0] == pytest.approx(dev.system_energy()[0], rel=1e-12)
+        th, td = host.window_time_ms(), dev.window_time_ms()
+        assert td["moves"] == th["moves"] and td["round_trips"] <= th["round_trips"]
+
+
 def test_system_energy_shards_add_up():
     """fb_system_energy_shard: tile rows / k-vector slabs dealt to 3 'GPUs' add up to the full energies"""
     cfg = small_electrolyte(n=900, coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 6})
@@ -419,14 +449,16 @@ def test_tempering_replicas_on_device():
         assert tw["exchange"] == tg["exchange"]
 
 
+@pytest.mark.parametrize("window", [32, 64])
 @pytest.mark.parametrize("capacity", [None, 2])
-def test_window_cell_list(capacity):
+def test_window_cell_list(capacity, window):
     """pair part of the windows through the device cell list (forced on a small system): same trace as the
-    oracle's brute-force sums; capacity 2 makes buckets run full, which must fall back and grow"""
+    oracle's brute-force sums; capacity 2 makes buckets run full, which must fall back and grow (window 64:
+    inside a device-decided run)"""
     import faunus_b200.native as native
     cfg = small_electrolyte(n=500, moves_per_sweep=200,
                             coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 6})
-    o, g = pair_of_sims(cfg, 32)
+    o, g = pair_of_sims(cfg, window)
     g.configure_cells(0)
     if capacity:
         assert native.load().fb_debug_set_cell_capacity(g.ctx, capacity) == 0
@@ -443,7 +475,8 @@ def test_window_cell_list(capacity):
     assert g.launch_count > launches0
 
 
-def test_window_with_volume_moves():
+@pytest.mark.parametrize("window", [16, 64])
+def test_window_with_volume_moves(window):
     """NPT electrolyte: runs of windowed `transrot` moves interleaved with `volume` moves (everything changes:
     box, k-vectors, Q(k), cell list) — the queue is drained, the other move runs one at a time, windows resume"""
     cfg = small_electrolyte(n=300, moves_per_sweep=60,
@@ -451,8 +484,8 @@ def test_window_with_volume_moves():
     cfg["energy"] = [{"isobaric": {"P/mM": 2000.0}}] + cfg["energy"]
     cfg["moves"].append({"volume": {"dV": 0.03, "repeat": 6}})
     o = oracle_sim(cfg)
-    g = b200_sim(cfg, 16)
-    assert g.window == 16   # the isobaric term is a per-atom host term: windows stay eligible
+    g = b200_sim(cfg, window)
+    assert g.window == window   # the isobaric term is a per-atom host term: windows stay eligible
     g.configure_cells(0)
     for s in (o, g):
         s.trace_enable()
