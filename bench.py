@@ -319,6 +319,7 @@ def b200_arm(args):
         dist.barrier(device_ids=[local])
     launches0 = sim.launch_count
     wt0 = sim.window_time_ms()
+    rs0 = sim.run_stats() if sim.window else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
@@ -330,6 +331,7 @@ def b200_arm(args):
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     wt1 = sim.window_time_ms()
+    rs1 = sim.run_stats() if sim.window else None
     event_s = ev0.elapsed_time(ev1) / 1e3
     launches = sim.launch_count - launches0
     elapsed = max(wall, event_s)
@@ -445,10 +447,21 @@ def b200_arm(args):
                              f"(reference default), -O3 -ffast-math -march={r['arch']}; Ewald init parallelised"}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "moves/s", "cores": 1, "kind": "port", "sample": f"failed: {e}"}
-    if windowed:  # per window: proposals in (BatchInput), result block out (8 + 3S + 4S² doubles, S = 32)
-        wps = n_windows / args.steps
-        h2d_per_step = int(wps * (8 + 64 * (4 + 4 + 32)))
-        d2h_per_step = int(wps * 8 * (8 + 3 * 32 + 4 * 32 * 32))
+    runs = None
+    if windowed:
+        # windows walked on the host: the window description in (sizeof(BatchInput) = 10288 B), the result block out
+        # (8 + 3S + 4S² doubles, S = 64); runs (windows walked on the device): header + 112 B per proposal in,
+        # state + 24 B per decision out
+        r = {k: rs1[k] - rs0[k] for k in rs1}
+        host_windows = (wt1["windows"] - wt0["windows"]) - r["windows"]
+        h2d_per_step = int((host_windows * 10288 + r["runs"] * 32 + r["moves"] * 112) / args.steps)
+        d2h_per_step = int((host_windows * 8 * (8 + 3 * 64 + 4 * 64 * 64) + r["runs"] * 288 + r["moves"] * 24) / args.steps)
+        if r["runs"]:
+            runs = {"runs_per_step": r["runs"] / args.steps, "moves_per_run": r["moves"] / r["runs"],
+                    "windows_per_run": r["windows"] / r["runs"], "walk_rounds_per_window": r["rounds"] / r["windows"],
+                    "host_round_trips_per_step": (wt1["round_trips"] - wt0["round_trips"]) / args.steps,
+                    "note": "proposals on distinct atoms are shipped a run at a time; the device walks each window "
+                            "(fixed-point Metropolis walk) and feeds the next; the host replays the decisions"}
     else:
         h2d_per_step, d2h_per_step = 36 * MOVES_PER_STEP, 24 * MOVES_PER_STEP
     line = {
@@ -463,6 +476,7 @@ def b200_arm(args):
         "gpu_launches": launches,
         "pair_interactions_per_s": e2e * 2 * (n - 1),
         "window": sim.window,
+        "runs": runs,
         "host_split_us_per_move": {
             "evaluate_launch_and_wait": 1e3 * (wt1["host_evaluate_ms"] - wt0["host_evaluate_ms"]) / moves,
             "draw_decide_sync_spaces": 1e3 * ((wt1["host_sweep_ms"] - wt0["host_sweep_ms"]) -

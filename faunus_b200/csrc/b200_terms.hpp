@@ -689,8 +689,11 @@ class B200WindowEvaluator : public WindowEvaluator
     std::vector<double> rec_change; //!< corrected raw reciprocal change Σ_k A_k(…) of each decided move
     // runs: windows of single-atom moves decided on the device (fb_run_submit), several windows per round trip
     int run_capacity = 0;            //!< 0: every window is walked on the host
+    /** a run pays off from two windows on: a single window is walked on the host, which costs one kernel less */
+    int run_threshold = FB_BATCH_MAX;
     bool run_mode = false;           //!< the evaluation in flight is a run
     std::vector<fb_run_move> run_moves;
+    fb_run_config run_config{};
     fb_run_result run_res{};
     enum class Kind
     {
@@ -760,11 +763,22 @@ class B200WindowEvaluator : public WindowEvaluator
     int capacity() const override { return std::max(window_capacity, run_capacity); }
 
     /** let the device walk the windows of single-atom moves itself, up to `moves` (≤ FB_RUN_MAX) per round trip */
-    void enableRuns(int moves)
+    void enableRuns(int moves, int min_moves = FB_BATCH_MAX + 1)
     {
-        run_capacity = (kinds.size() <= FB_RUN_TERMS && window_capacity == FB_BATCH_MAX)
-                           ? std::max(0, std::min(moves, FB_RUN_MAX))
-                           : 0;
+        run_threshold = std::max(0, min_moves - 1);
+        // the device walk adds [the caller's terms …, non-bonded, Ewald] in this order: the Hamiltonian must look so
+        size_t i = 0;
+        while (i < kinds.size() && kinds[i] == Kind::SELF) {
+            ++i;
+        }
+        bool layout_ok = i < kinds.size() && kinds[i] == Kind::NONBONDED;
+        ++i;
+        if (with_ewald) {
+            layout_ok = layout_ok && i < kinds.size() && kinds[i] == Kind::EWALD;
+            ++i;
+        }
+        layout_ok = layout_ok && i == kinds.size();
+        run_capacity = (layout_ok && window_capacity == FB_BATCH_MAX) ? std::max(0, std::min(moves, FB_RUN_MAX)) : 0;
     }
     int runCapacity() const { return run_capacity; }
 
@@ -774,18 +788,18 @@ class B200WindowEvaluator : public WindowEvaluator
     }
 
     /** group mode: a window holds at most FB_BATCH_MAX ATOMS */
-    int fit(const std::vector<WindowProposal>& window, int ready) const override
+    int fit(const std::vector<WindowProposal>& window, int first, int ready) const override
     {
-        if (ready > 0 && run_capacity > 0 && window.front().kind == WindowProposal::Kind::ATOM) {
+        if (ready > run_threshold && run_capacity > 0 && window[first].kind == WindowProposal::Kind::ATOM) {
             return std::min(ready, run_capacity);
         }
         int n = std::min(ready, window_capacity);
-        if (n > 0 && window.front().kind == WindowProposal::Kind::GROUP) {
+        if (n > 0 && window[first].kind == WindowProposal::Kind::GROUP) {
             const Space& trial = *mc.trial_state.spc;
             int atoms = 0;
             int m = 0;
             for (; m < n; ++m) {
-                atoms += static_cast<int>(trial.groups.at(window[m].change.groups.at(0).group_index).size());
+                atoms += static_cast<int>(trial.groups.at(window[first + m].change.groups.at(0).group_index).size());
                 if (atoms > FB_BATCH_MAX) {
                     break;
                 }
@@ -795,8 +809,9 @@ class B200WindowEvaluator : public WindowEvaluator
         return n;
     }
 
-    void submitGroups(const std::vector<WindowProposal>& window, int n)
+    void submitGroups(const std::vector<WindowProposal>& all, int first, int n)
     {
+        const WindowProposal* window = all.data() + first;
         group_moves.resize(static_cast<size_t>(n));
         first_atom.assign(static_cast<size_t>(n) + 1, 0);
         const Space& trial = *mc.trial_state.spc;
@@ -840,47 +855,12 @@ class B200WindowEvaluator : public WindowEvaluator
         rec_change.assign(static_cast<size_t>(n), 0.0);
     }
 
-    /** the proposals of a run travel with their Metropolis uniform and the host terms' energies */
-    void submitRun(const std::vector<WindowProposal>& window, int n)
+    /** single-atom proposals → fb_batch_move records (trial and accepted positions: the caller owns the Space) */
+    void packMoves(const WindowProposal* window, int n)
     {
-        run_moves.resize(static_cast<size_t>(n));
-        fb_run_config cfg{};
-        cfg.n_terms = static_cast<int>(kinds.size());
-        for (size_t i = 0; i < kinds.size(); ++i) {
-            cfg.term_kind[i] = kinds[i] == Kind::SELF ? FB_TERM_HOST
-                                                     : (kinds[i] == Kind::NONBONDED ? FB_TERM_NONBONDED : FB_TERM_EWALD);
-        }
-        cfg.max_energy = mc.state.pot->maximumAllowedEnergy();
-        cfg.cancellation_limit = cancellation_limit;
-        const auto& trial_terms = mc.trial_state.pot->terms();
-        const auto& terms = mc.state.pot->terms();
-        for (int m = 0; m < n; ++m) {
-            fb_run_move& r = run_moves[m];
-            r.move = moves[m];
-            r.uniform = window[m].uniform;
-            for (size_t i = 0; i < kinds.size(); ++i) {
-                r.host_new[i] = r.host_old[i] = 0.0;
-                if (kinds[i] == Kind::SELF) { // looks at the atoms of the Change only: valid while others are pending
-                    trial_terms[i]->state = mc.trial_state.pot->state;
-                    r.host_new[i] = trial_terms[i]->energy(window[m].change);
-                    terms[i]->state = mc.state.pot->state;
-                    r.host_old[i] = terms[i]->energy(window[m].change);
-                }
-            }
-        }
-        fbCheck(fb_run_submit(dev->ctx, n, run_moves.data(), with_ewald ? 1 : 0, &cfg), dev->ctx, "fb_run_submit");
-    }
-
-    void submit(const std::vector<WindowProposal>& window, int n) override
-    {
-        group_mode = n > 0 && window.front().kind == WindowProposal::Kind::GROUP;
-        run_mode = false;
-        if (group_mode) {
-            submitGroups(window, n);
-            return;
-        }
         moves.resize(static_cast<size_t>(n));
         const Space& trial = *mc.trial_state.spc;
+        const Space& accepted = *mc.state.spc;
         for (int m = 0; m < n; ++m) {
             const auto& gc = window[m].change.groups.at(0);
             const auto& g = trial.groups.at(gc.group_index);
@@ -893,7 +873,6 @@ class B200WindowEvaluator : public WindowEvaluator
             mv.xyzq[1] = p.pos.y;
             mv.xyzq[2] = p.pos.z;
             mv.xyzq[3] = p.charge;
-            const Space& accepted = *mc.state.spc; // the caller owns the Space: old positions travel with the window
             const auto& q = accepted.at(accepted.groups.at(gc.group_index), gc.relative_atom_indices[0]);
             mv.old_atom_id = q.id;
             mv.old_xyzq[0] = q.pos.x;
@@ -901,13 +880,78 @@ class B200WindowEvaluator : public WindowEvaluator
             mv.old_xyzq[2] = q.pos.z;
             mv.old_xyzq[3] = q.charge;
         }
+    }
+
+    bool pipelined(const std::vector<WindowProposal>& window, int first) const override
+    {
+        return run_mode && run_capacity > 0 && window[first].kind == WindowProposal::Kind::ATOM;
+    }
+
+    /** the proposals of a run travel with their Metropolis uniform and the host terms' energies */
+    void prepare(const std::vector<WindowProposal>& all, int first, int n) override
+    {
+        const WindowProposal* window = all.data() + first;
+        packMoves(window, n);
+        run_moves.resize(static_cast<size_t>(n));
+        run_config = fb_run_config{};
+        run_config.max_energy = mc.state.pot->maximumAllowedEnergy();
+        run_config.cancellation_limit = cancellation_limit;
+        const auto& trial_terms = mc.trial_state.pot->terms();
+        const auto& terms = mc.state.pot->terms();
+        // Hamiltonian::energy over the caller's own terms, which all precede the device terms (enableRuns): they look
+        // at the atoms of the Change only, so their energies are valid while other proposals are pending
+        auto leading_sum = [&](const std::vector<std::shared_ptr<EnergyTerm>>& list, EnergyTerm::MonteCarloState state,
+                               const Change& change, bool& closed) {
+            double sum = 0.0;
+            closed = false;
+            for (size_t i = 0; i < kinds.size() && kinds[i] == Kind::SELF; ++i) {
+                list[i]->state = state;
+                const double u = list[i]->energy(change);
+                sum += u;
+                if (u >= run_config.max_energy || std::isnan(u)) {
+                    closed = true;
+                    break;
+                }
+            }
+            return sum;
+        };
+        for (int m = 0; m < n; ++m) {
+            fb_run_move& r = run_moves[m];
+            r.move = moves[m];
+            r.uniform = window[m].uniform;
+            bool closed_new = false, closed_old = false;
+            r.host_new = leading_sum(trial_terms, mc.trial_state.pot->state, window[m].change, closed_new);
+            r.host_old = leading_sum(terms, mc.state.pot->state, window[m].change, closed_old);
+            r.flags = (closed_new ? FB_RUN_HOST_NEW_CLOSED : 0) | (closed_old ? FB_RUN_HOST_OLD_CLOSED : 0);
+        }
+    }
+
+    void submitPrepared() override
+    {
         dev->fast_staged = false;
         dev->cache_valid = false;
-        if (run_capacity > 0) {
-            run_mode = true;
-            submitRun(window, n);
+        fbCheck(fb_run_submit(dev->ctx, static_cast<int>(run_moves.size()), run_moves.data(), with_ewald ? 1 : 0,
+                              &run_config),
+                dev->ctx, "fb_run_submit");
+        run_mode = true;
+    }
+
+    void submit(const std::vector<WindowProposal>& window, int first, int n) override
+    {
+        group_mode = n > 0 && window[first].kind == WindowProposal::Kind::GROUP;
+        run_mode = false;
+        if (group_mode) {
+            submitGroups(window, first, n);
             return;
         }
+        if (run_capacity > 0 && n > run_threshold) {
+            prepare(window, first, n);
+            submitPrepared();
+            return;
+        }
+        packMoves(window.data() + first, n);
+        dev->fast_staged = false;
+        dev->cache_valid = false;
         fbCheck(fb_batch_submit(dev->ctx, n, moves.data(), with_ewald ? 1 : 0), dev->ctx, "fb_batch_submit");
         rec_change.assign(static_cast<size_t>(n), 0.0);
     }

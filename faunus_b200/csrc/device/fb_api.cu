@@ -248,7 +248,7 @@ struct fb_ctx
         bool run_decide_configured = false;
         std::vector<unsigned char> run_accepted;
         std::vector<double> run_u_new, run_u_old;
-        double run_steps = 0, run_count = 0;
+        double run_steps = 0, run_count = 0, run_rounds = 0, run_moves = 0;
         double round_trips = 0; //!< waits for the device (windows walked on the host + runs)
         bool force_brute = false;
         double rec_sum = 0;

@@ -505,8 +505,11 @@ FB_API int fb_batch_submit_groups(fb_ctx* c, int n_moves, const fb_batch_group_m
 
 namespace {
 
-/** launches of one window of the run in flight: set-up from the device cursor, the window kernels, the decisions */
-void launchRunStep(fb_ctx* c, bool timing)
+/**
+ * Launches of one window of the run in flight: the window kernels and the walk (which also sets up the next
+ * window); `setup`: the window description is not there yet (continuation after the host looked at the run).
+ */
+void launchRunStep(fb_ctx* c, bool timing, bool setup)
 {
     auto& b = c->batch;
     const int stride = b.run_stride;
@@ -514,11 +517,14 @@ void launchRunStep(fb_ctx* c, bool timing)
     const BatchBuffers prev = batchBuffers(c, b.parity);
     b.parity ^= 1;
     const BatchBuffers cur = batchBuffers(c, b.parity);
+    const BatchBuffers next = batchBuffers(c, b.parity ^ 1);
     const RunHeader* hdr = &b.d_run.ptr->header;
     const RunMove* moves = b.d_run.ptr->moves;
     RunState* st = &b.d_back.ptr->state;
-    runSetupKernel<<<1, kBatchMax, 0, c->stream>>>(hdr, moves, st, cur.in, stride);
-    launched(c, "runSetupKernel");
+    if (setup) {
+        runSetupKernel<<<1, kBatchMax, 0, c->stream>>>(hdr, moves, st, cur.in, stride);
+        launched(c, "runSetupKernel");
+    }
 #define FB_CASE(K)                                                                                             \
     case K:                                                                                                    \
         launchWindow<K>(c, cur, prev, CommitList{}, CommitList{}, stride, 0, stride, with_ewald, timing, true); \
@@ -540,20 +546,22 @@ void launchRunStep(fb_ctx* c, bool timing)
                                         static_cast<int>(runDecideSmemBytes(kBatchMax))));
         b.run_decide_configured = true;
     }
-    runDecideKernel<<<1, kDecideThreads, smem, c->stream>>>(hdr, moves, st, cur, stride, b.cells_used ? 1 : 0,
+    // the walk reads the window it decides (cur) and writes the description of the next one (next == prev's
+    // buffer: the window kernels of this step, the last readers of prev, are done by then)
+    runDecideKernel<<<1, kDecideThreads, smem, c->stream>>>(hdr, moves, st, cur, next.in, stride, b.cells_used ? 1 : 0,
                                                            b.d_result.ptr, b.d_back.ptr->out);
     launched(c, "runDecideKernel");
     b.run_steps_launched += 1;
 }
 
 /** queue `steps` windows of the run and the read-back of where it stands */
-void launchRunSteps(fb_ctx* c, int steps)
+void launchRunSteps(fb_ctx* c, int steps, bool continuation)
 {
     auto& b = c->batch;
     if (c->timing) { // per-kernel events: one window at a time, kernels serialised
         for (int s = 0; s < steps; ++s) {
             CUDA_CHECK(cudaEventRecord(b.ev[0], c->stream));
-            launchRunStep(c, true);
+            launchRunStep(c, true, continuation && s == 0);
             CUDA_CHECK(cudaEventRecord(b.ev[4], c->stream));
             CUDA_CHECK(cudaStreamSynchronize(c->stream));
             accumulateWindowTiming(c, true);
@@ -562,7 +570,7 @@ void launchRunSteps(fb_ctx* c, int steps)
     else {
         CUDA_CHECK(cudaEventRecord(b.ev[0], c->stream));
         for (int s = 0; s < steps; ++s) {
-            launchRunStep(c, false);
+            launchRunStep(c, false, continuation && s == 0);
         }
         CUDA_CHECK(cudaEventRecord(b.ev[4], c->stream));
     }
@@ -581,9 +589,6 @@ FB_API int fb_run_submit(fb_ctx* c, int n_moves, const fb_run_move* moves, int w
         if (!moves || !config || n_moves < 1 || n_moves > kRunMax) {
             throw CudaError{"fb_run_submit: 1..1024 moves per run"};
         }
-        if (config->n_terms < 1 || config->n_terms > kRunTerms) {
-            throw CudaError{"fb_run_submit: 1..6 Hamiltonian terms"};
-        }
         beginWindow(c, with_ewald);
         auto& b = c->batch;
         b.h_run.ensure(1);
@@ -598,20 +603,6 @@ FB_API int fb_run_submit(fb_ctx* c, int n_moves, const fb_run_move* moves, int w
         RunHeader& h = b.h_run.ptr->header;
         h.n_moves = n_moves;
         h.with_ewald = with_ewald ? 1 : 0;
-        h.n_terms = config->n_terms;
-        h.pad = 0;
-        int n_nonbonded = 0, n_ewald = 0;
-        for (int i = 0; i < kRunTerms; ++i) {
-            h.term_kind[i] = i < config->n_terms ? config->term_kind[i] : RUN_TERM_HOST;
-            if (h.term_kind[i] < RUN_TERM_HOST || h.term_kind[i] > RUN_TERM_EWALD) {
-                throw CudaError{"fb_run_submit: unknown term kind"};
-            }
-            n_nonbonded += h.term_kind[i] == RUN_TERM_NONBONDED;
-            n_ewald += h.term_kind[i] == RUN_TERM_EWALD;
-        }
-        if (n_nonbonded != 1 || n_ewald > 1 || (n_ewald == 1) != (with_ewald != 0)) {
-            throw CudaError{"fb_run_submit: one non-bonded term, and an Ewald term exactly when with_ewald is set"};
-        }
         h.max_energy = config->max_energy;
         h.cancellation_limit = config->cancellation_limit;
         h.rec_prefactor = 0.0;
@@ -645,14 +636,13 @@ FB_API int fb_run_submit(fb_ctx* c, int n_moves, const fb_run_move* moves, int w
             r.slot = slot;
             r.id = mv.atom_id;
             r.idold = mv.old_atom_id;
-            r.pad = 0;
+            r.flags = moves[m].flags;
+            r.pad = 0.0;
             r.pnew = make_double4(mv.xyzq[0], mv.xyzq[1], mv.xyzq[2], mv.xyzq[3]);
             r.pold = make_double4(mv.old_xyzq[0], mv.old_xyzq[1], mv.old_xyzq[2], mv.old_xyzq[3]);
             r.uniform = moves[m].uniform;
-            for (int i = 0; i < kRunTerms; ++i) {
-                r.host_new[i] = moves[m].host_new[i];
-                r.host_old[i] = moves[m].host_old[i];
-            }
+            r.host_new = moves[m].host_new;
+            r.host_old = moves[m].host_old;
         }
         // accepted moves of an earlier window / run that are not yet on the device
         b.run_stride = n_moves <= 16 ? 16 : (n_moves <= 32 ? 32 : 64);
@@ -669,13 +659,15 @@ FB_API int fb_run_submit(fb_ctx* c, int n_moves, const fb_run_move* moves, int w
         b.h_result.ensure(batchResultDoubles(kBatchMax));
         const size_t bytes = offsetof(fb_ctx::Batch::RunBlock, moves) + sizeof(RunMove) * static_cast<size_t>(n_moves);
         CUDA_CHECK(cudaMemcpyAsync(b.d_run.ptr, b.h_run.ptr, bytes, cudaMemcpyHostToDevice, c->stream));
-        runInitKernel<<<1, kBatchMax, 0, c->stream>>>(&b.d_back.ptr->state, pending);
+        // the first window goes into the buffer the first step will call `cur`
+        runInitKernel<<<1, kBatchMax, 0, c->stream>>>(&b.d_run.ptr->header, b.d_run.ptr->moves, &b.d_back.ptr->state,
+                                                      pending, batchBuffers(c, b.parity ^ 1).in, b.run_stride);
         launched(c, "runInitKernel");
         b.run_n = n_moves;
         b.run_with_ewald = with_ewald ? 1 : 0;
         b.run_steps_launched = 0;
         b.run_in_flight = true;
-        launchRunSteps(c, (n_moves + b.run_stride - 1) / b.run_stride);
+        launchRunSteps(c, (n_moves + b.run_stride - 1) / b.run_stride, false);
     });
 }
 
@@ -704,13 +696,14 @@ FB_API int fb_run_wait(fb_ctx* c, fb_run_result* out)
                 b.cell_cap *= 2;
             }
             const int left = b.run_n - st.cursor;
-            launchRunSteps(c, (left + b.run_stride - 1) / b.run_stride);
+            launchRunSteps(c, (left + b.run_stride - 1) / b.run_stride, true);
         }
         b.run_in_flight = false;
         const RunState& st = b.h_back.ptr->state;
         b.windows += st.steps;
         b.moves += b.run_n;
         b.run_steps += st.steps;
+        b.run_moves += b.run_n;
         b.run_count += 1;
         b.round_trips += 1;
         b.run_accepted.resize(static_cast<size_t>(b.run_n));
@@ -739,6 +732,8 @@ FB_API int fb_run_wait(fb_ctx* c, fb_run_result* out)
         b.rec_known = false;
         out->n_moves = b.run_n;
         out->n_windows = st.steps;
+        out->n_rounds = st.rounds;
+        b.run_rounds += st.rounds;
         out->accepted = b.run_accepted.data();
         out->u_new = b.run_u_new.data();
         out->u_old = b.run_u_old.data();
@@ -879,6 +874,18 @@ FB_API int fb_debug_set_cell_capacity(fb_ctx* c, int capacity)
     c->batch.cell_cap = capacity;
     c->batch.cell_cap_forced = true;
     c->batch.cells_valid = false;
+    return FB_OK;
+}
+
+FB_API int fb_get_run_stats(const fb_ctx* c, double out[4])
+{
+    if (!c || !out) {
+        return FB_ERR_INVALID;
+    }
+    out[0] = c->batch.run_count;
+    out[1] = c->batch.run_steps;
+    out[2] = c->batch.run_rounds;
+    out[3] = c->batch.run_moves;
     return FB_OK;
 }
 

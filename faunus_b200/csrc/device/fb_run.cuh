@@ -6,12 +6,12 @@
 // is ALWAYS drawn) and the energies of the caller's own Hamiltonian terms for a single-atom move — so the
 // caller can ship a RUN of up to kRunMax proposals on distinct atoms at once. The device then repeats
 //
-//   runSetupKernel   window = the next ≤ stride undecided moves of the run → BatchInput (+ the commit list)
 //   … the kernels of a window, unchanged (pair / cross terms, phase tables, k-space, sums) …
 //   runDecideKernel  the walk of B200WindowEvaluator::energies + MetropolisMonteCarlo::decideWindow:
 //                    corrected energies of move m given the accepted a < m, Hamiltonian sum in term order with
 //                    the reference's early exit (src/energy.cpp:1227-1247), getEnergyChange
-//                    (src/montecarlo.cpp:193-209), Metropolis; accepted moves → the next window's commit list
+//                    (src/montecarlo.cpp:193-209), Metropolis; accepted moves → the next window's commit list;
+//                    then the next window = the next ≤ stride undecided moves of the run → BatchInput
 //
 // without a host round trip, and returns per move {accepted, u_new, u_old} for the host to replay into its
 // Space. A window that meets a cancellation (|pair energy| in a correction ≥ the limit) stops there; the
@@ -22,32 +22,29 @@
 namespace fbdev {
 
 constexpr int kRunMax = 1024; //!< moves per run
-constexpr int kRunTerms = 6;  //!< Hamiltonian terms at most
 
-enum RunTermKind : int
+/** closed: the in-order sum of the caller's terms ended early (a term ≥ max_energy or NaN, src/energy.cpp:1238-1244) */
+enum RunMoveFlags : int
 {
-    RUN_TERM_HOST = 0,      //!< evaluated by the caller, travels with the move
-    RUN_TERM_NONBONDED = 1, //!< pair energy of the moved atom
-    RUN_TERM_EWALD = 2      //!< reciprocal-space energy of the whole system
+    RUN_HOST_NEW_CLOSED = 1,
+    RUN_HOST_OLD_CLOSED = 2
 };
 
 struct RunMove
 {
     double4 pnew;
     double4 pold;
-    int slot, id, idold, pad;
-    double uniform;              //!< the Metropolis uniform of this move
-    double host_new[kRunTerms];  //!< caller-evaluated terms in the trial state, Hamiltonian order (others unused)
-    double host_old[kRunTerms];  //!< … in the accepted state
+    int slot, id, idold, flags;
+    double uniform;   //!< the Metropolis uniform of this move
+    double host_new;  //!< in-order sum of the caller's Hamiltonian terms (they precede the device terms), trial state
+    double host_old;  //!< … accepted state
+    double pad;
 };
 
 struct RunHeader
 {
     int n_moves;
     int with_ewald;
-    int n_terms;
-    int pad;
-    int term_kind[kRunTerms];
     double max_energy;         //!< Hamiltonian::maximumAllowedEnergy: the sum stops after a term ≥ this (or NaN)
     double cancellation_limit; //!< |pair energy| in a correction from which on a move is evaluated afresh
     double rec_prefactor;      //!< 2π lB / V
@@ -59,6 +56,7 @@ struct RunState
     int window_first; //!< first move and size of the window decided last
     int window_n;
     int steps;        //!< windows evaluated for this run
+    int rounds;       //!< rounds of the fixed-point walk, summed over the windows
     CommitList commit; //!< its accepted moves (indices into that window): what the next window has to apply
 };
 
@@ -69,38 +67,21 @@ struct RunOutput
     int step;            //!< which window of the run decided it
 };
 
-/** first launch of a run: where the device stands (the pending accepted moves of whatever came before) */
-__global__ void __launch_bounds__(kBatchMax) runInitKernel(RunState* st, CommitList pending)
+/** the next window of the run, moves [cursor, cursor + stride), with the commit list the window before it left */
+__device__ __forceinline__ void runSetupWindow(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves,
+                                               int cursor, const CommitList& commit, BatchInput* __restrict__ in,
+                                               int stride, int t)
 {
-    if (threadIdx.x == 0) {
-        st->cursor = 0;
-        st->window_first = 0;
-        st->window_n = 0;
-        st->steps = 0;
-        st->commit.n = pending.n;
-    }
-    if (static_cast<int>(threadIdx.x) < pending.n) {
-        st->commit.index[threadIdx.x] = pending.index[threadIdx.x];
-    }
-}
-
-/** the next window of the run: moves [cursor, cursor + stride) */
-__global__ void __launch_bounds__(kBatchMax)
-    runSetupKernel(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves, const RunState* __restrict__ st,
-                   BatchInput* __restrict__ in, int stride)
-{
-    const int cursor = st->cursor;
     const int n = max(0, min(stride, hdr->n_moves - cursor));
-    const int t = threadIdx.x;
     if (t == 0) {
         in->n = n;
         in->with_ewald = hdr->with_ewald;
         in->n_groups = 0;
-        in->commit.n = st->commit.n;
+        in->commit.n = commit.n;
         in->commit_moves.n = 0;
     }
-    if (t < st->commit.n) {
-        in->commit.index[t] = st->commit.index[t];
+    if (t < commit.n) {
+        in->commit.index[t] = commit.index[t];
     }
     if (t < n) {
         const RunMove& mv = moves[cursor + t];
@@ -112,25 +93,65 @@ __global__ void __launch_bounds__(kBatchMax)
     }
 }
 
+/**
+ * First launch of a run: where the device stands (the pending accepted moves of whatever came before) and the
+ * first window. Every later window is set up by the runDecideKernel of the window before it.
+ */
+__global__ void __launch_bounds__(kBatchMax)
+    runInitKernel(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves, RunState* st, CommitList pending,
+                  BatchInput* __restrict__ in, int stride)
+{
+    if (threadIdx.x == 0) {
+        st->cursor = 0;
+        st->window_first = 0;
+        st->window_n = 0;
+        st->steps = 0;
+        st->rounds = 0;
+        st->commit.n = pending.n;
+    }
+    if (static_cast<int>(threadIdx.x) < pending.n) {
+        st->commit.index[threadIdx.x] = pending.index[threadIdx.x];
+    }
+    runSetupWindow(hdr, moves, 0, pending, in, stride, threadIdx.x);
+}
+
+/** a window of a run that is continued after the host looked at it: set up from the cursor on the device */
+__global__ void __launch_bounds__(kBatchMax)
+    runSetupKernel(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves, const RunState* __restrict__ st,
+                   BatchInput* __restrict__ in, int stride)
+{
+    runSetupWindow(hdr, moves, st->cursor, st->commit, in, stride, threadIdx.x);
+}
+
 constexpr int kDecideThreads = 256;
 
 /** dynamic shared memory of runDecideKernel: four S × (S + 1) matrices, TRANSPOSED ([a][m], padded rows) */
 inline size_t runDecideSmemBytes(int stride) { return sizeof(double) * 4 * static_cast<size_t>(stride) * (stride + 1); }
 
+__device__ __forceinline__ void barrier64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
 /**
- * One block. Thread m < n owns move m of the window: its running pair energies and reciprocal change, corrected
- * every time an earlier move a is accepted (additions in the order a = 0, 1, … — the order of the host walk).
- * Step a of the loop: thread a decides its move, everybody else folds the outcome in.
+ * The in-order walk of a window as a fixed-point iteration. One block; all threads stage the correction
+ * matrices in shared memory (transposed: thread m reads column m of row a, conflict-free), then thread m < n
+ * owns move m. Given a GUESS of which moves are accepted (a 64-bit mask, initially none), every thread
+ * evaluates its move exactly as the host walk would — corrections of the accepted a < m added in the order
+ * a = 0, 1, …, Hamiltonian sum in term order with the early exit, getEnergyChange, Metropolis — all moves in
+ * parallel. The decision of move m only depends on the bits below m, so everything up to and including the
+ * first move whose decision contradicts the guess is FINAL; the guess is replaced by the new decisions and the
+ * iteration repeats from there. It ends after (1 + number of decisions that the corrections overturned)
+ * rounds — a handful — instead of n dependent steps, with bit-identical results. A move whose correction
+ * meets a huge pair energy (cancellation) ends the window: it is re-evaluated at the head of the next one.
+ * At the end the next window of the run is set up (`next`).
  */
 __global__ void __launch_bounds__(kDecideThreads)
     runDecideKernel(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves, RunState* __restrict__ st,
-                    BatchBuffers cur, int stride, int cell_list, const double* __restrict__ result,
-                    RunOutput* __restrict__ out)
+                    BatchBuffers cur, BatchInput* __restrict__ next, int stride, int cell_list,
+                    const double* __restrict__ result, RunOutput* __restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char run_smem[];
-    __shared__ int s_accepted[kBatchMax];
-    __shared__ double s_rec_change;
-    __shared__ int s_flag; // 0 rejected, 1 accepted, 2 stop (cancellation)
+    __shared__ CommitList s_commit;
+    __shared__ double s_rec[kBatchMax];
+    __shared__ unsigned s_ballot[3][2]; // per warp: accepted, mismatch with the guess, stop
 
     const int S = stride;
     const int LD = S + 1;
@@ -140,150 +161,182 @@ __global__ void __launch_bounds__(kDecideThreads)
     double* s_g = s_cmax + S * LD;
     const int n = cur.in->n;
     const int cursor = st->cursor;
+    const int step = st->steps;
     const double* u = result + 8;
     const double* cross = result + 8 + 3 * S;
-    // only a < m < n is ever read
-    for (int t = threadIdx.x; t < n * S; t += kDecideThreads) {
-        const int m = t / S;
-        const int a = t - m * S;
-        if (a < m) {
-            s_cn[a * LD + m] = cross[t];
-            s_co[a * LD + m] = cross[S * S + t];
-            s_cmax[a * LD + m] = cross[2 * S * S + t];
-            s_g[a * LD + m] = cross[3 * S * S + t];
-        }
+    const int shift = S == 64 ? 6 : (S == 32 ? 5 : 4);
+    const int total = n * S;
+#pragma unroll 4
+    for (int t = threadIdx.x; t < total; t += kDecideThreads) { // no branch: the loads of several rounds overlap
+        const int m = t >> shift;
+        const int a = t & (S - 1);
+        const double v0 = cross[t], v1 = cross[S * S + t], v2 = cross[2 * S * S + t], v3 = cross[3 * S * S + t];
+        s_cn[a * LD + m] = v0;
+        s_co[a * LD + m] = v1;
+        s_cmax[a * LD + m] = v2;
+        s_g[a * LD + m] = v3;
     }
     const int m = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const bool mine = m < n;
     const bool with_ewald = hdr->with_ewald != 0;
-    double nb_new = 0.0, nb_old = 0.0, rec = 0.0;
-    RunMove mv{};
-    if (mine) {
-        nb_new = u[m];
-        nb_old = u[S + m];
-        rec = with_ewald ? u[2 * S + m] : 0.0;
-        mv = moves[cursor + m];
+    double u_new0 = 0.0, u_old0 = 0.0, rec0 = 0.0, uniform = 0.0, host_new = 0.0, host_old = 0.0;
+    int flags = 0;
+    if (mine && m < kBatchMax) {
+        u_new0 = u[m];
+        u_old0 = u[S + m];
+        rec0 = with_ewald ? u[2 * S + m] : 0.0;
+        const RunMove& mv = moves[cursor + m];
+        uniform = mv.uniform;
+        host_new = mv.host_new;
+        host_old = mv.host_old;
+        flags = mv.flags;
     }
-    double rec_running = result[0]; // Σ_k A_k |Q_k|² of the window-start state (0 without Ewald)
-    bool cancelled = false;         // a correction of this move met a huge pair energy
+    const double rec_start = result[0]; // Σ_k A_k |Q_k|² of the window-start state (0 without Ewald)
     const bool overflow = cell_list && result[2] != 0.0; // a cell bucket ran full: nothing of this window counts
-    const int n_terms = hdr->n_terms;
     const double limit = hdr->max_energy;
     const double cancellation_limit = hdr->cancellation_limit;
     const double pref = hdr->rec_prefactor;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
     __syncthreads();
+    if (threadIdx.x >= kBatchMax) {
+        return; // the walk is the business of the first two warps (named barrier)
+    }
 
-    int n_decided = 0;
-    for (int a = 0; a < n; ++a) {
-        if (m == a) {
-            int flag = 2;
-            if (!cancelled && !overflow) {
-                // Hamiltonian::energy on the trial and on the accepted state (no FMA contraction: the host adds
-                // the same numbers one by one)
-                double total[2];
-#pragma unroll
-                for (int is_old = 0; is_old < 2; ++is_old) {
-                    double sum = 0.0;
-                    for (int i = 0; i < n_terms; ++i) {
-                        double e;
-                        const int kind = hdr->term_kind[i];
-                        if (kind == RUN_TERM_NONBONDED) {
-                            e = is_old ? nb_old : nb_new;
-                        }
-                        else if (kind == RUN_TERM_EWALD) {
-                            e = __dmul_rn(pref, is_old ? rec_running : __dadd_rn(rec_running, rec));
-                        }
-                        else {
-                            e = is_old ? mv.host_old[i] : mv.host_new[i];
-                        }
-                        sum = __dadd_rn(sum, e);
-                        if (e >= limit || e != e) {
-                            break;
-                        }
-                    }
-                    total[is_old] = sum;
-                }
-                const double u_new = total[0], u_old = total[1];
-                // getEnergyChange, src/montecarlo.cpp:193-209
-                double du;
-                if (u_old != u_old && u_new == u_new) {
-                    du = -__longlong_as_double(0x7ff0000000000000LL);
-                }
-                else if (u_new != u_new) {
-                    du = __longlong_as_double(0x7ff0000000000000LL);
-                }
-                else if (u_new > 0.0 && isinf(u_new)) {
-                    du = __longlong_as_double(0x7ff0000000000000LL);
-                }
-                else {
-                    du = __dsub_rn(u_new, u_old);
-                    if (du != du) {
-                        du = 0.0;
-                    }
-                }
-                // metropolisCriterion, src/montecarlo.cpp:17-34
-                bool accept;
-                if (isinf(du) && du < 0.0) {
-                    accept = true;
-                }
-                else if (-du > 709.782712893384) {
-                    accept = true;
-                }
-                else {
-                    accept = mv.uniform <= exp(-du);
-                }
-                flag = accept ? 1 : 0;
-                RunOutput o;
-                o.u_new = u_new;
-                o.u_old = u_old;
-                o.accepted = flag;
-                o.step = st->steps;
-                out[cursor + a] = o;
-                s_rec_change = rec;
-            }
-            s_flag = flag;
-        }
-        __syncthreads();
-        const int flag = s_flag;
-        if (flag == 2) {
-            break;
-        }
-        n_decided = a + 1;
-        if (m == a) {
-            s_accepted[a] = flag;
-        }
-        if (flag == 1) {
-            if (mine && m > a) {
-                const int t = a * LD + m;
-                if (!(s_cmax[t] < cancellation_limit)) {
-                    cancelled = true;
-                }
+    unsigned long long guess = 0ull; // bit a: move a taken as accepted
+    int fixed = 0;                   // decisions [0, fixed) are final
+    int n_decided = n;
+    int decision = 0;                // of this thread's move: 0 rejected, 1 accepted, 2 stop
+    double total_new = 0.0, total_old = 0.0;
+    int rounds = 0;
+    if (overflow) {
+        n_decided = 0;
+        fixed = n;
+    }
+    while (fixed < n) {
+        rounds++;
+        const bool active = mine && m >= fixed;
+        double nb_new = u_new0, nb_old = u_old0, rec = rec0;
+        bool cancelled = false;
+        const unsigned long long below = guess & ((1ull << m) - 1ull);
+        if (active) { // corrections for the accepted earlier moves, in the order of the host walk
+            for (unsigned long long bits = below; bits != 0ull; bits &= bits - 1ull) {
+                const int t = (__ffsll(static_cast<long long>(bits)) - 1) * LD + m;
+                cancelled = cancelled || !(s_cmax[t] < cancellation_limit);
                 nb_new = __dadd_rn(nb_new, s_cn[t]);
                 nb_old = __dadd_rn(nb_old, s_co[t]);
-                if (with_ewald) {
-                    rec = __dadd_rn(rec, __dmul_rn(2.0, s_g[t]));
+                rec = __dadd_rn(rec, __dmul_rn(2.0, s_g[t]));
+            }
+            s_rec[m] = rec;
+        }
+        barrier64();
+        if (active) {
+            double rec_running = rec_start;
+            if (with_ewald) {
+                for (unsigned long long bits = below; bits != 0ull; bits &= bits - 1ull) {
+                    rec_running = __dadd_rn(rec_running, s_rec[__ffsll(static_cast<long long>(bits)) - 1]);
                 }
             }
-            if (with_ewald) {
-                rec_running = __dadd_rn(rec_running, s_rec_change);
+            // Hamiltonian::energy on the trial and on the accepted state: the caller's terms, the non-bonded term,
+            // the Ewald term; the sum stops after a term ≥ limit or NaN (no FMA contraction: the host adds the same
+            // numbers one by one)
+            total_new = host_new;
+            if (!(flags & RUN_HOST_NEW_CLOSED)) {
+                total_new = __dadd_rn(total_new, nb_new);
+                if (with_ewald && !(nb_new >= limit || nb_new != nb_new)) {
+                    total_new = __dadd_rn(total_new, __dmul_rn(pref, __dadd_rn(rec_running, rec)));
+                }
             }
+            total_old = host_old;
+            if (!(flags & RUN_HOST_OLD_CLOSED)) {
+                total_old = __dadd_rn(total_old, nb_old);
+                if (with_ewald && !(nb_old >= limit || nb_old != nb_old)) {
+                    total_old = __dadd_rn(total_old, __dmul_rn(pref, rec_running));
+                }
+            }
+            // getEnergyChange, src/montecarlo.cpp:193-209
+            double du;
+            if (total_old != total_old && total_new == total_new) {
+                du = -inf;
+            }
+            else if (total_new != total_new) {
+                du = inf;
+            }
+            else if (total_new > 0.0 && isinf(total_new)) {
+                du = inf;
+            }
+            else {
+                du = __dsub_rn(total_new, total_old);
+                if (du != du) {
+                    du = 0.0;
+                }
+            }
+            // metropolisCriterion, src/montecarlo.cpp:17-34
+            bool accept;
+            if (isinf(du) && du < 0.0) {
+                accept = true;
+            }
+            else if (-du > 709.782712893384) {
+                accept = true;
+            }
+            else {
+                accept = uniform <= exp(-du);
+            }
+            decision = cancelled ? 2 : (accept ? 1 : 0);
         }
-        __syncthreads(); // s_flag / s_rec_change are rewritten in the next step
+        const bool taken = ((guess >> m) & 1ull) != 0ull;
+        const unsigned b_acc = __ballot_sync(0xffffffffu, mine && decision == 1);
+        const unsigned b_mis = __ballot_sync(0xffffffffu, active && ((decision == 1) != taken));
+        const unsigned b_stop = __ballot_sync(0xffffffffu, active && decision == 2);
+        if (lane == 0) {
+            s_ballot[0][warp] = b_acc;
+            s_ballot[1][warp] = b_mis;
+            s_ballot[2][warp] = b_stop;
+        }
+        barrier64();
+        const unsigned long long accepted = s_ballot[0][0] | (static_cast<unsigned long long>(s_ballot[0][1]) << 32);
+        const unsigned long long mismatch = s_ballot[1][0] | (static_cast<unsigned long long>(s_ballot[1][1]) << 32);
+        const unsigned long long stops = s_ballot[2][0] | (static_cast<unsigned long long>(s_ballot[2][1]) << 32);
+        const int first_mismatch = mismatch ? __ffsll(static_cast<long long>(mismatch)) - 1 : n;
+        const int first_stop = stops ? __ffsll(static_cast<long long>(stops)) - 1 : n;
+        guess = accepted; // final below `fixed` (those threads kept their decision), the new guess above
+        if (first_stop <= first_mismatch && first_stop < n) { // a final stop: the window ends there
+            n_decided = first_stop;
+            fixed = n;
+        }
+        else {
+            fixed = min(n, first_mismatch + 1);
+        }
+        barrier64(); // s_ballot / s_rec are rewritten in the next round
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int k = 0;
-        for (int a = 0; a < n_decided; ++a) {
-            if (s_accepted[a]) {
-                st->commit.index[k++] = a;
-            }
+    const unsigned long long decided_mask = n_decided >= 64 ? ~0ull : ((1ull << n_decided) - 1ull);
+    const unsigned long long accepted = guess & decided_mask;
+    if (mine && m < n_decided) {
+        RunOutput o;
+        o.u_new = total_new;
+        o.u_old = total_old;
+        o.accepted = decision == 1 ? 1 : 0;
+        o.step = step;
+        out[cursor + m] = o;
+        if (decision == 1) {
+            const int k = __popcll(accepted & ((1ull << m) - 1ull));
+            s_commit.index[k] = m;
+            st->commit.index[k] = m;
         }
+    }
+    if (m == 0) {
+        const int k = __popcll(accepted);
+        s_commit.n = k;
         st->commit.n = k;
         st->window_first = cursor;
         st->window_n = n;
         st->cursor = cursor + n_decided;
-        st->steps += 1;
+        st->steps = step + 1;
+        st->rounds += rounds;
     }
+    barrier64();
+    runSetupWindow(hdr, moves, cursor + n_decided, s_commit, next, stride, m);
 }
 
 } // namespace fbdev

@@ -161,16 +161,17 @@ extern "C" __attribute__((visibility("default"))) int fbh_sim_set_window(void* h
 
 /**
  * Runs: the device walks the windows of single-atom moves itself (fb_run_submit), up to `moves` proposals per
- * host round trip (0: the host walks every window). Needs fbh_sim_set_window(64). Returns the run capacity in effect.
+ * host round trip (0: the host walks every window), used when at least `min_moves` proposals are ready (default 65:
+ * a single window is walked on the host). Needs fbh_sim_set_window(64). Returns the run capacity in effect.
  */
-extern "C" __attribute__((visibility("default"))) int fbh_sim_set_run(void* h, int moves)
+extern "C" __attribute__((visibility("default"))) int fbh_sim_set_run(void* h, int moves, int min_moves)
 {
     auto* s = static_cast<fb::capi::Sim*>(h);
     int result = 0;
     fb::capi::guarded([&] {
         auto* e = dynamic_cast<fb::B200WindowEvaluator*>(s->mc->window_evaluator.get());
         if (e != nullptr) {
-            e->enableRuns(moves);
+            e->enableRuns(moves, min_moves);
             result = e->runCapacity();
         }
     });

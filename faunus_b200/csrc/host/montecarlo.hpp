@@ -71,12 +71,24 @@ class WindowEvaluator
   public:
     virtual ~WindowEvaluator() = default;
     virtual int capacity() const = 0;
-    /** how many of the first `ready` proposals of `window` fit into one evaluation */
-    virtual int fit(const std::vector<WindowProposal>& /*window*/, int ready) const { return std::min(ready, capacity()); }
+    /** how many of the `ready` proposals of `window` from `first` on fit into one evaluation */
+    virtual int fit(const std::vector<WindowProposal>& /*window*/, int /*first*/, int ready) const
+    {
+        return std::min(ready, capacity());
+    }
     /** can proposals of this kind be evaluated at all? */
     virtual bool supports(WindowProposal::Kind kind) const { return kind == WindowProposal::Kind::ATOM; }
-    /** start evaluating proposals [0, n) of `window` (all applied to the trial Space, distinct atoms) … */
-    virtual void submit(const std::vector<WindowProposal>& window, int n) = 0;
+    /** start evaluating proposals [first, first + n) of `window` (all applied to the trial Space, distinct atoms) … */
+    virtual void submit(const std::vector<WindowProposal>& window, int first, int n) = 0;
+    /**
+     * Pipelining: an evaluator that decides on its own (decision() ≥ 0) can take the NEXT evaluation while the
+     * results of the one in flight are still out — the queued proposals behind it are on other atoms, so nothing
+     * they need depends on those results. prepare() packs proposals [first, first + n) while the device works,
+     * submitPrepared() hands them over right after wait().
+     */
+    virtual bool pipelined(const std::vector<WindowProposal>& /*window*/, int /*first*/) const { return false; }
+    virtual void prepare(const std::vector<WindowProposal>& /*window*/, int /*first*/, int /*n*/) {}
+    virtual void submitPrepared() {}
     /** … and wait for the results; the engine draws the next proposals in between */
     virtual void wait() = 0;
     /**
@@ -316,19 +328,41 @@ class MetropolisMonteCarlo
         }
     }
 
-    /** evaluate the first `n` queued proposals (all applied) and decide as many as possible, in order */
-    void decideWindow(int n)
+    int in_flight = 0; //!< proposals at the head of the queue whose evaluation is submitted
+
+    /**
+     * Evaluate the applied head of the queue (unless a pipelined evaluation of it is already in flight), draw
+     * ahead and hand the next evaluation over while waiting, then decide / replay as many as possible, in order.
+     */
+    void decideWindow()
     {
         const auto t_begin = std::chrono::steady_clock::now();
-        window_evaluator->submit(window, n);
+        if (in_flight == 0) {
+            in_flight = window_evaluator->fit(window, 0, readyProposals());
+            window_evaluator->submit(window, 0, in_flight);
+            windows_evaluated++;
+            window_moves_evaluated += static_cast<unsigned long>(in_flight);
+        }
+        const int n = in_flight;
         const auto t_submitted = std::chrono::steady_clock::now();
-        fillWindow(n + window_evaluator->capacity()); // the next window's proposals, while the device works
+        fillWindow(n + window_evaluator->capacity()); // the next proposals, while the device works
+        int next_n = 0;
+        if (static_cast<int>(window.size()) > n && window_evaluator->pipelined(window, n)) {
+            const int ready_behind = readyProposals() - n;
+            if (ready_behind > 0) {
+                next_n = window_evaluator->fit(window, n, ready_behind);
+                window_evaluator->prepare(window, n, next_n);
+            }
+        }
         const auto t_filled = std::chrono::steady_clock::now();
         window_evaluator->wait();
+        if (next_n > 0) {
+            window_evaluator->submitPrepared();
+            windows_evaluated++;
+            window_moves_evaluated += static_cast<unsigned long>(next_n);
+        }
         const auto t_evaluated = std::chrono::steady_clock::now();
         window_seconds_evaluate += std::chrono::duration<double>((t_submitted - t_begin) + (t_evaluated - t_filled)).count();
-        windows_evaluated++;
-        window_moves_evaluated += static_cast<unsigned long>(n);
         std::vector<unsigned char> accepted;
         for (int m = 0; m < n; ++m) {
             auto& p = window[m];
@@ -377,6 +411,10 @@ class MetropolisMonteCarlo
         }
         window.erase(window.begin(), window.begin() + static_cast<long>(accepted.size()));
         applyUnblocked();
+        if (next_n > 0 && static_cast<int>(accepted.size()) != n) {
+            throw std::runtime_error("pipelined evaluation left proposals undecided");
+        }
+        in_flight = next_n;
         window_seconds_decide += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_evaluated).count();
     }
 
@@ -491,7 +529,7 @@ class MetropolisMonteCarlo
             if (!window.empty()) {
                 // the applied head of the queue (its first proposal always is): proposals further back whose atom /
                 // molecule is still undecided wait for their turn
-                decideWindow(window_evaluator->fit(window, readyProposals()));
+                decideWindow();
             }
             else if (sweep_deferred != nullptr) {
                 Move* m = sweep_deferred;

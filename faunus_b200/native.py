@@ -69,17 +69,16 @@ class FbBatchGroupMove(C.Structure):
 
 
 class FbRunMove(C.Structure):
-    _fields_ = [("move", FbBatchMove), ("uniform", C.c_double), ("host_new", C.c_double * 6),
-                ("host_old", C.c_double * 6)]
+    _fields_ = [("move", FbBatchMove), ("uniform", C.c_double), ("host_new", C.c_double), ("host_old", C.c_double),
+                ("flags", C.c_int)]
 
 
 class FbRunConfig(C.Structure):
-    _fields_ = [("n_terms", C.c_int), ("term_kind", C.c_int * 6), ("max_energy", C.c_double),
-                ("cancellation_limit", C.c_double)]
+    _fields_ = [("max_energy", C.c_double), ("cancellation_limit", C.c_double)]
 
 
 class FbRunResult(C.Structure):
-    _fields_ = [("n_moves", C.c_int), ("n_windows", C.c_int), ("accepted", C.POINTER(C.c_ubyte)),
+    _fields_ = [("n_moves", C.c_int), ("n_windows", C.c_int), ("n_rounds", C.c_int), ("accepted", C.POINTER(C.c_ubyte)),
                 ("u_new", c_double_p), ("u_old", c_double_p)]
 
 
@@ -115,7 +114,7 @@ class FbConfig(C.Structure):
 C_ABI_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_last_error", "fb_device_count", "fb_upload_space", "fb_update_group",
     "fb_set_box", "fb_sync", "fb_download_space", "fb_nonbonded_energy", "fb_nonbonded_delta",
-    "fb_system_energy_shard", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_submit_groups", "fb_batch_wait", "fb_run_submit", "fb_run_wait", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing",
+    "fb_system_energy_shard", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_submit_groups", "fb_batch_wait", "fb_run_submit", "fb_run_wait", "fb_get_run_stats", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing",
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
     "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
     "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_launch_count",
@@ -157,6 +156,7 @@ def load() -> C.CDLL:
         "fb_batch_submit_groups": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchGroupMove), C.c_int]),
         "fb_run_submit": (C.c_int, [vp, C.c_int, C.POINTER(FbRunMove), C.c_int, C.POINTER(FbRunConfig)]),
         "fb_run_wait": (C.c_int, [vp, C.POINTER(FbRunResult)]),
+        "fb_get_run_stats": (C.c_int, [vp, c_double_p]),
         "fb_batch_wait": (C.c_int, [vp, C.POINTER(FbBatchResult)]),
         "fb_batch_commit": (C.c_int, [vp, C.c_int, c_ubyte_p]),
         "fb_configure_cells": (C.c_int, [vp, C.c_int]),
@@ -188,7 +188,7 @@ def load() -> C.CDLL:
         "fbh_set_device": (None, [C.c_int]),
         "fbh_sim_launch_count": (C.c_ulonglong, [vp]),
         "fbh_sim_set_window": (C.c_int, [vp, C.c_int]),
-        "fbh_sim_set_run": (C.c_int, [vp, C.c_int]),
+        "fbh_sim_set_run": (C.c_int, [vp, C.c_int, C.c_int]),
         "fbh_system_energy_shard": (C.c_int, [vp, C.c_int, C.c_int, c_double_p]),
         "fbh_sim_get_window_timing": (C.c_int, [vp, c_double_p]),
     }
@@ -225,13 +225,17 @@ class B200Simulation(Simulation):
     #: single-atom proposals shipped per host round trip when the device walks the windows itself (fb_run_submit;
     #: 0: every window is walked on the host). Needs the full window of 64.
     DEFAULT_RUN = int(os.environ.get("FAUNUS_B200_RUN", "512"))
+    #: ... used when at least this many proposals are ready (a single window is walked on the host)
+    DEFAULT_RUN_MIN = int(os.environ.get("FAUNUS_B200_RUN_MIN", "65"))
 
-    def __init__(self, config, device: int = 0, window: Optional[int] = None, run: Optional[int] = None):
+    def __init__(self, config, device: int = 0, window: Optional[int] = None, run: Optional[int] = None,
+                 run_min: Optional[int] = None):
         require_device()
         load().fbh_set_device(device)
         super().__init__(sim_library(), config)
         self.run = 0
         self._run_request = self.DEFAULT_RUN if run is None else int(run)
+        self._run_min = self.DEFAULT_RUN_MIN if run_min is None else int(run_min)
         self.window = self.set_window(self.DEFAULT_WINDOW if window is None else window)
 
     def set_window(self, capacity: int) -> int:
@@ -245,7 +249,7 @@ class B200Simulation(Simulation):
         """Device-decided runs of windows (fb_run_submit): up to `moves` proposals per round trip; returns the
         capacity in effect (0 unless the window is 64 and the Hamiltonian has at most 6 terms)."""
         self._run_request = int(moves)
-        self.run = int(load().fbh_sim_set_run(self.handle, int(moves))) if self.window else 0
+        self.run = int(load().fbh_sim_set_run(self.handle, int(moves), self._run_min)) if self.window else 0
         return self.run
 
     # ---- work sharded over the ranks of a process group (SURVEY §8e); see also Simulation.widom_sample_sharded
@@ -266,6 +270,12 @@ class B200Simulation(Simulation):
         return {"pair_ms": out[0], "ewald_ms": out[1], "other_ms": out[2], "windows": int(out[3]),
                 "moves": int(out[4]), "total_ms": out[5], "host_evaluate_ms": out[6], "host_sweep_ms": out[7],
                 "round_trips": int(out[8]), "runs": int(out[9])}
+
+    def run_stats(self) -> dict:
+        """device-decided runs since creation: runs, windows, rounds of the fixed-point walk, moves"""
+        out = np.zeros(4)
+        self._check(load().fb_get_run_stats(self.ctx, out.ctypes.data_as(c_double_p)), "fb_get_run_stats")
+        return {"runs": int(out[0]), "windows": int(out[1]), "rounds": int(out[2]), "moves": int(out[3])}
 
     @property
     def launch_count(self) -> int:

@@ -296,38 +296,42 @@ int fb_batch_submit_groups(fb_ctx* ctx, int n_moves, const fb_batch_group_move* 
  * Metropolis uniform (always drawn, src/montecarlo.cpp:17-34) and the energies of the caller's own Hamiltonian
  * terms. A run is up to FB_RUN_MAX proposals on DISTINCT atoms; the device evaluates it window by window
  * (64 moves), walks each window in order — corrected energies, Hamiltonian sum in term order with the reference's
- * early exit (src/energy.cpp:1227-1247), getEnergyChange (src/montecarlo.cpp:193-209), Metropolis — and feeds the
- * accepted moves to the next window without a host round trip. fb_run_wait returns the outcome of every move
+ * early exit (src/energy.cpp:1227-1247), getEnergyChange (src/montecarlo.cpp:193-209), Metropolis; as a fixed-point
+ * iteration over all moves of the window at once, same results — and feeds the accepted moves to the next window
+ * without a host round trip. fb_run_wait returns the outcome of every move
  * (all moves of the run are decided when it returns); the caller replays it into its Space. Nothing to commit. */
 #define FB_RUN_MAX 1024
-#define FB_RUN_TERMS 6
-#define FB_TERM_HOST 0      /* evaluated by the caller: host_new / host_old */
-#define FB_TERM_NONBONDED 1 /* the pair energy of the moved atom (this library) */
-#define FB_TERM_EWALD 2     /* reciprocal energy of the system (this library) */
+/* The caller's Hamiltonian must be [its own terms ..., the non-bonded term, the Ewald term (with_ewald)]: the walk
+ * adds host_new / host_old (the caller's in-order sum of its own terms), the pair energy and the reciprocal energy
+ * in this order and stops after a term >= max_energy or NaN like Hamiltonian::energy (src/energy.cpp:1238-1244). */
+#define FB_RUN_HOST_NEW_CLOSED 1 /* the caller's own sum already ended early (trial state) */
+#define FB_RUN_HOST_OLD_CLOSED 2 /* ... accepted state */
 typedef struct
 {
     fb_batch_move move;
-    double uniform;                 /* the Metropolis uniform drawn for this move */
-    double host_new[FB_RUN_TERMS];  /* caller-evaluated terms, trial state, Hamiltonian order (other slots unused) */
-    double host_old[FB_RUN_TERMS];  /* ... accepted state */
+    double uniform;   /* the Metropolis uniform drawn for this move */
+    double host_new;  /* in-order sum of the caller's own Hamiltonian terms, trial state */
+    double host_old;  /* ... accepted state */
+    int flags;        /* FB_RUN_HOST_*_CLOSED */
 } fb_run_move;
 typedef struct
 {
-    int n_terms;                    /* Hamiltonian terms in order, 1..FB_RUN_TERMS */
-    int term_kind[FB_RUN_TERMS];    /* FB_TERM_* */
-    double max_energy;              /* the sum over terms stops after a term >= this or NaN (energy.cpp:1238-1244) */
-    double cancellation_limit;      /* see cross_max above */
+    double max_energy;         /* the sum over terms stops after a term >= this or NaN */
+    double cancellation_limit; /* see cross_max above */
 } fb_run_config;
 typedef struct
 {
     int n_moves;
     int n_windows;                  /* windows the device needed */
+    int n_rounds;                   /* rounds of the fixed-point walk, summed over the windows */
     const unsigned char* accepted;  /* [n_moves] */
     const double* u_new;            /* [n_moves] Hamiltonian energy of the move in the trial state at its turn */
     const double* u_old;            /* [n_moves] ... in the accepted state */
 } fb_run_result;
 int fb_run_submit(fb_ctx* ctx, int n_moves, const fb_run_move* moves, int with_ewald, const fb_run_config* config);
 int fb_run_wait(fb_ctx* ctx, fb_run_result* result);
+/* since creation: out[0] = runs, out[1] = windows in runs, out[2] = rounds of the fixed-point walk, out[3] = moves */
+int fb_get_run_stats(const fb_ctx* ctx, double out[4]);
 /* accepted[m] != 0 for the accepted ones among the first n_decided moves of the last window */
 int fb_batch_commit(fb_ctx* ctx, int n_decided, const unsigned char* accepted);
 /* The pair part of a window goes through a device cell list (cell edge = box / floor(box / cutoff), 27

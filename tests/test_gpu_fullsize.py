@@ -21,9 +21,9 @@ def s1(moves_per_sweep, **kw):
     return primitive_model(n=100_000, molarity=1.0, seed=5489, moves_per_sweep=moves_per_sweep, coulomb=EWALD, **kw)
 
 
-def sim(cfg, window=None, run=None):
+def sim(cfg, window=None, run=None, run_min=None):
     from faunus_b200.native import B200Simulation
-    return B200Simulation(cfg, window=window, run=run)
+    return B200Simulation(cfg, window=window, run=run, run_min=run_min)
 
 
 def test_s1_drift_invariant_windowed():

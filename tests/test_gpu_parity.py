@@ -14,7 +14,7 @@ RTOL = 1e-10
 
 def b200_sim(cfg, window=None, run=None):
     from faunus_b200.native import B200Simulation
-    return B200Simulation(cfg, window=window, run=run)
+    return B200Simulation(cfg, window=window, run=run, run_min=1)   # run_min=1: runs even for a single window
 
 
 def assert_close(a, b, rtol=RTOL, scale=None):
@@ -384,6 +384,8 @@ def test_device_walk_equals_host_walk():
         assert host.system_energy()[0] == pytest.approx(dev.system_energy()[0], rel=1e-12)
         th, td = host.window_time_ms(), dev.window_time_ms()
         assert td["moves"] == th["moves"] and td["round_trips"] <= th["round_trips"]
+        stats = dev.run_stats()
+        assert stats["moves"] == td["moves"] and stats["rounds"] >= stats["windows"] > 0
 
 
 def test_system_energy_shards_add_up():
