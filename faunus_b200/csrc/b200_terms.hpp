@@ -794,6 +794,11 @@ class B200WindowEvaluator : public WindowEvaluator
             return std::min(ready, run_capacity);
         }
         int n = std::min(ready, window_capacity);
+        for (int m = 1; m < n; ++m) { // walked on the host: a conditional proposal waits for the window after
+            if (window[first + m].conditional && !window[first + m].applied) {
+                n = m;
+            }
+        }
         if (n > 0 && window[first].kind == WindowProposal::Kind::GROUP) {
             const Space& trial = *mc.trial_state.spc;
             int atoms = 0;
@@ -855,6 +860,23 @@ class B200WindowEvaluator : public WindowEvaluator
         rec_change.assign(static_cast<size_t>(n), 0.0);
     }
 
+    static void fillMove(fb_batch_move& mv, const Change::GroupChange& gc, const Particle& particle, const Point& start,
+                         const Point& trial)
+    {
+        mv.group_index = static_cast<int>(gc.group_index);
+        mv.rel_index = static_cast<int>(gc.relative_atom_indices[0]);
+        mv.atom_id = particle.id;
+        mv.xyzq[0] = trial.x;
+        mv.xyzq[1] = trial.y;
+        mv.xyzq[2] = trial.z;
+        mv.xyzq[3] = particle.charge;
+        mv.old_atom_id = particle.id; // a translation: id and charge stay
+        mv.old_xyzq[0] = start.x;
+        mv.old_xyzq[1] = start.y;
+        mv.old_xyzq[2] = start.z;
+        mv.old_xyzq[3] = particle.charge;
+    }
+
     /** single-atom proposals → fb_batch_move records (trial and accepted positions: the caller owns the Space) */
     void packMoves(const WindowProposal* window, int n)
     {
@@ -866,6 +888,10 @@ class B200WindowEvaluator : public WindowEvaluator
             const auto& g = trial.groups.at(gc.group_index);
             const auto& p = trial.at(g, gc.relative_atom_indices.at(0));
             fb_batch_move& mv = moves[m];
+            if (window[m].conditional && !window[m].applied) { // the variant "the earlier move on this atom is accepted"
+                fillMove(mv, gc, p, window[m].alt_start[0], window[m].alt_new[0]);
+                continue;
+            }
             mv.group_index = static_cast<int>(gc.group_index);
             mv.rel_index = static_cast<int>(gc.relative_atom_indices[0]);
             mv.atom_id = p.id;
@@ -882,10 +908,12 @@ class B200WindowEvaluator : public WindowEvaluator
         }
     }
 
-    bool pipelined(const std::vector<WindowProposal>& window, int first) const override
+    bool pipelined(const std::vector<WindowProposal>& window, int first, int ready) const override
     {
-        return run_mode && run_capacity > 0 && window[first].kind == WindowProposal::Kind::ATOM;
+        return run_mode && run_capacity > 0 && ready > run_threshold && window[first].kind == WindowProposal::Kind::ATOM;
     }
+
+    bool conditionals() const override { return run_capacity > 0; }
 
     /** the proposals of a run travel with their Metropolis uniform and the host terms' energies */
     void prepare(const std::vector<WindowProposal>& all, int first, int n) override
@@ -919,7 +947,46 @@ class B200WindowEvaluator : public WindowEvaluator
             fb_run_move& r = run_moves[m];
             r.move = moves[m];
             r.uniform = window[m].uniform;
+            r.depends_on = -1;
+            r.alt = moves[m];
+            r.alt_host_new = r.alt_host_old = 0.0;
             bool closed_new = false, closed_old = false;
+            if (window[m].conditional && !window[m].applied) {
+                // the proposal it depends on: earlier in the queue — in this run, or in the run in flight, whose
+                // moves are the first `first` proposals of the queue
+                int at = first + m - 1;
+                while (at >= 0 && all[at].serial != window[m].dependency) {
+                    --at;
+                }
+                if (at < 0) {
+                    throw std::runtime_error("windowed evaluation: lost the proposal a conditional one depends on");
+                }
+                r.depends_on = at >= first ? at - first : (FB_RUN_DEP_PREVIOUS | at);
+                const auto& gc = window[m].change.groups.at(0);
+                auto& trial_particle = mc.trial_state.spc->at(mc.trial_state.spc->groups.at(gc.group_index),
+                                                              gc.relative_atom_indices.at(0));
+                auto& particle = mc.state.spc->at(mc.state.spc->groups.at(gc.group_index), gc.relative_atom_indices[0]);
+                fillMove(r.alt, gc, trial_particle, window[m].alt_start[1], window[m].alt_new[1]);
+                // the caller's terms see the Spaces: show them either outcome in turn
+                const Point keep_trial = trial_particle.pos, keep = particle.pos;
+                double host[2][2];
+                bool closed[2][2];
+                for (int v = 0; v < 2; ++v) {
+                    trial_particle.pos = window[m].alt_new[v];
+                    particle.pos = window[m].alt_start[v];
+                    host[v][0] = leading_sum(trial_terms, mc.trial_state.pot->state, window[m].change, closed[v][0]);
+                    host[v][1] = leading_sum(terms, mc.state.pot->state, window[m].change, closed[v][1]);
+                }
+                trial_particle.pos = keep_trial;
+                particle.pos = keep;
+                r.host_new = host[0][0];
+                r.host_old = host[0][1];
+                r.alt_host_new = host[1][0];
+                r.alt_host_old = host[1][1];
+                r.flags = (closed[0][0] ? FB_RUN_HOST_NEW_CLOSED : 0) | (closed[0][1] ? FB_RUN_HOST_OLD_CLOSED : 0) |
+                          (closed[1][0] ? FB_RUN_ALT_HOST_NEW_CLOSED : 0) | (closed[1][1] ? FB_RUN_ALT_HOST_OLD_CLOSED : 0);
+                continue;
+            }
             r.host_new = leading_sum(trial_terms, mc.trial_state.pot->state, window[m].change, closed_new);
             r.host_old = leading_sum(terms, mc.state.pot->state, window[m].change, closed_old);
             r.flags = (closed_new ? FB_RUN_HOST_NEW_CLOSED : 0) | (closed_old ? FB_RUN_HOST_OLD_CLOSED : 0);

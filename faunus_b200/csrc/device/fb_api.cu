@@ -237,14 +237,25 @@ struct fb_ctx
             double overflow; //!< result[2] of the last window: a cell bucket ran full
             RunOutput out[kRunMax];
         };
-        PinnedBuffer<RunBlock> h_run;
-        DeviceBuffer<RunBlock> d_run;
-        PinnedBuffer<RunBack> h_back;
-        DeviceBuffer<RunBack> d_back;
-        std::vector<int> run_stamp; //!< per particle slot: the run that last touched it (distinctness check)
+        /** a run in flight; two of them so that the next one can be queued behind the one the device works on */
+        struct RunSlot
+        {
+            PinnedBuffer<RunBlock> h_run;
+            DeviceBuffer<RunBlock> d_run;
+            PinnedBuffer<RunBack> h_back;
+            DeviceBuffer<RunBack> d_back;
+            cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;
+            int id = 0;            //!< stamp of its proposals in run_stamp
+            int n = 0, stride = 0, with_ewald = 0, steps_launched = 0;
+            int last_parity = 0;   //!< window buffer of the last window launched for it
+            bool chained = false;  //!< queued while its predecessor was still in flight (started by runChainKernel)
+        };
+        RunSlot run[2];
+        int run_head = 0;      //!< slot of the oldest run in flight
+        int runs_in_flight = 0;
+        std::vector<int> run_stamp; //!< per particle slot: the run that last touched it (distinctness check) …
+        std::vector<int> run_last;  //!< … and its latest move there
         int run_id = 0;
-        bool run_in_flight = false;
-        int run_n = 0, run_stride = 0, run_with_ewald = 0, run_steps_launched = 0;
         bool run_decide_configured = false;
         std::vector<unsigned char> run_accepted;
         std::vector<double> run_u_new, run_u_old;
@@ -700,6 +711,11 @@ FB_API int fb_create(const fb_config* cfg, fb_ctx** out)
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->batch.pair_stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&c->batch.ev_fork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&c->batch.ev_join, cudaEventDisableTiming));
+        for (auto& r : c->batch.run) {
+            CUDA_CHECK(cudaEventCreate(&r.ev_begin));
+            CUDA_CHECK(cudaEventCreate(&r.ev_end));
+            CUDA_CHECK(cudaEventCreateWithFlags(&r.ev_done, cudaEventDisableTiming));
+        }
         CUDA_CHECK(cudaHostAlloc(&c->h_result, 8 * sizeof(double), cudaHostAllocMapped));
         CUDA_CHECK(cudaHostGetDevicePointer(&c->d_result, c->h_result, 0));
         c->partials.alloc(4 * kMaxPartialBlocks);
@@ -932,6 +948,13 @@ FB_API void fb_destroy(fb_ctx* c)
     }
     if (c->batch.ev_join) {
         cudaEventDestroy(c->batch.ev_join);
+    }
+    for (auto& r : c->batch.run) {
+        for (cudaEvent_t e : {r.ev_begin, r.ev_end, r.ev_done}) {
+            if (e) {
+                cudaEventDestroy(e);
+            }
+        }
     }
     if (c->batch.pair_stream) {
         cudaStreamSynchronize(c->batch.pair_stream);

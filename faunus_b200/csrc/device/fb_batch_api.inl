@@ -264,9 +264,10 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
 void flushBatch(fb_ctx* c)
 {
     auto& b = c->batch;
-    if (b.in_flight) { // a submitted window nobody waited for: drop its results
+    if (b.in_flight || b.runs_in_flight > 0) { // submitted work nobody waited for: drop its results
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         b.in_flight = false;
+        b.runs_in_flight = 0;
     }
     if (b.has_pending) {
         launchBatchCommit(c, b.pending_with_ewald, nullptr);
@@ -292,11 +293,11 @@ void flushBatch(fb_ctx* c)
 namespace {
 
 /** after a synchronize: device time of the window(s) between ev[0] and ev[4] (+ the per-kernel split) */
-void accumulateWindowTiming(fb_ctx* c, bool timing)
+void accumulateWindowTiming(fb_ctx* c, bool timing, cudaEvent_t begin = nullptr, cudaEvent_t end = nullptr)
 {
     auto& b = c->batch;
     float t04 = 0;
-    CUDA_CHECK(cudaEventElapsedTime(&t04, b.ev[0], b.ev[4]));
+    CUDA_CHECK(cudaEventElapsedTime(&t04, begin ? begin : b.ev[0], end ? end : b.ev[4]));
     b.acc_total_ms += t04;
     if (timing) {
         float t01 = 0, t12 = 0, t23 = 0, t34 = 0;
@@ -310,13 +311,13 @@ void accumulateWindowTiming(fb_ctx* c, bool timing)
     }
 }
 
-/** common head of the two submit flavours */
-void beginWindow(fb_ctx* c, int with_ewald)
+/** common head of the submit flavours; a run may be queued behind ONE run in flight (`chain`) */
+void beginWindow(fb_ctx* c, int with_ewald, bool chain = false)
 {
     checkSlot(c, 0);
     checkSlot(c, 1);
     auto& b = c->batch;
-    if (b.in_flight || b.run_in_flight) {
+    if (b.in_flight || b.runs_in_flight > (chain ? 1 : 0)) {
         throw CudaError{"fb_batch_submit: the previous window has not been waited for"};
     }
     if (c->has_commit) { // an accepted fast-path move is still only on the host
@@ -506,23 +507,24 @@ FB_API int fb_batch_submit_groups(fb_ctx* c, int n_moves, const fb_batch_group_m
 namespace {
 
 /**
- * Launches of one window of the run in flight: the window kernels and the walk (which also sets up the next
- * window); `setup`: the window description is not there yet (continuation after the host looked at the run).
+ * Launches of one window of a run: the window kernels and the walk (which also sets up the next window);
+ * `setup`: the window description is not there yet (continuation after the host looked at the run).
  */
-void launchRunStep(fb_ctx* c, bool timing, bool setup)
+void launchRunStep(fb_ctx* c, fb_ctx::Batch::RunSlot& r, bool timing, bool setup)
 {
     auto& b = c->batch;
-    const int stride = b.run_stride;
-    const bool with_ewald = b.run_with_ewald != 0;
+    const int stride = r.stride;
+    const bool with_ewald = r.with_ewald != 0;
     const BatchBuffers prev = batchBuffers(c, b.parity);
     b.parity ^= 1;
     const BatchBuffers cur = batchBuffers(c, b.parity);
     const BatchBuffers next = batchBuffers(c, b.parity ^ 1);
-    const RunHeader* hdr = &b.d_run.ptr->header;
-    const RunMove* moves = b.d_run.ptr->moves;
-    RunState* st = &b.d_back.ptr->state;
+    const RunHeader* hdr = &r.d_run.ptr->header;
+    const RunMove* moves = r.d_run.ptr->moves;
+    RunState* st = &r.d_back.ptr->state;
+    const RunOutput* prev_out = b.run[&r == &b.run[0] ? 1 : 0].d_back.ptr ? b.run[&r == &b.run[0] ? 1 : 0].d_back.ptr->out : nullptr;
     if (setup) {
-        runSetupKernel<<<1, kBatchMax, 0, c->stream>>>(hdr, moves, st, cur.in, stride);
+        runSetupKernel<<<1, kBatchMax, 0, c->stream>>>(hdr, moves, st, cur.in, stride, r.d_back.ptr->out, prev_out);
         launched(c, "runSetupKernel");
     }
 #define FB_CASE(K)                                                                                             \
@@ -549,36 +551,74 @@ void launchRunStep(fb_ctx* c, bool timing, bool setup)
     // the walk reads the window it decides (cur) and writes the description of the next one (next == prev's
     // buffer: the window kernels of this step, the last readers of prev, are done by then)
     runDecideKernel<<<1, kDecideThreads, smem, c->stream>>>(hdr, moves, st, cur, next.in, stride, b.cells_used ? 1 : 0,
-                                                           b.d_result.ptr, b.d_back.ptr->out);
+                                                           b.d_result.ptr, r.d_back.ptr->out, prev_out);
     launched(c, "runDecideKernel");
-    b.run_steps_launched += 1;
+    r.steps_launched += 1;
+    r.last_parity = b.parity;
 }
 
 /** queue `steps` windows of the run and the read-back of where it stands */
-void launchRunSteps(fb_ctx* c, int steps, bool continuation)
+void launchRunSteps(fb_ctx* c, fb_ctx::Batch::RunSlot& r, int steps, bool continuation)
 {
     auto& b = c->batch;
     if (c->timing) { // per-kernel events: one window at a time, kernels serialised
         for (int s = 0; s < steps; ++s) {
             CUDA_CHECK(cudaEventRecord(b.ev[0], c->stream));
-            launchRunStep(c, true, continuation && s == 0);
+            launchRunStep(c, r, true, continuation && s == 0);
             CUDA_CHECK(cudaEventRecord(b.ev[4], c->stream));
             CUDA_CHECK(cudaStreamSynchronize(c->stream));
             accumulateWindowTiming(c, true);
         }
     }
     else {
-        CUDA_CHECK(cudaEventRecord(b.ev[0], c->stream));
+        CUDA_CHECK(cudaEventRecord(r.ev_begin, c->stream));
         for (int s = 0; s < steps; ++s) {
-            launchRunStep(c, false, continuation && s == 0);
+            launchRunStep(c, r, false, continuation && s == 0);
         }
-        CUDA_CHECK(cudaEventRecord(b.ev[4], c->stream));
+        CUDA_CHECK(cudaEventRecord(r.ev_end, c->stream));
     }
     // state + overflow flag + the decisions
-    CUDA_CHECK(cudaMemcpyAsync(&b.d_back.ptr->overflow, b.d_result.ptr + 2, sizeof(double), cudaMemcpyDeviceToDevice,
+    CUDA_CHECK(cudaMemcpyAsync(&r.d_back.ptr->overflow, b.d_result.ptr + 2, sizeof(double), cudaMemcpyDeviceToDevice,
                                c->stream));
-    const size_t bytes = offsetof(fb_ctx::Batch::RunBack, out) + sizeof(RunOutput) * static_cast<size_t>(b.run_n);
-    CUDA_CHECK(cudaMemcpyAsync(b.h_back.ptr, b.d_back.ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    const size_t bytes = offsetof(fb_ctx::Batch::RunBack, out) + sizeof(RunOutput) * static_cast<size_t>(r.n);
+    CUDA_CHECK(cudaMemcpyAsync(r.h_back.ptr, r.d_back.ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaEventRecord(r.ev_done, c->stream));
+}
+
+/** first launches of a run: its start state (from the host's pending list, or chained to the run before it) */
+void launchRun(fb_ctx* c, fb_ctx::Batch::RunSlot& r, const fb_ctx::Batch::RunSlot* behind, const CommitList& pending)
+{
+    auto& b = c->batch;
+    // the first window goes into the buffer the first step will call `cur`
+    BatchInput* first = batchBuffers(c, b.parity ^ 1).in;
+    auto& other = b.run[&r == &b.run[0] ? 1 : 0];
+    const RunOutput* prev_out = other.d_back.ptr ? other.d_back.ptr->out : nullptr;
+    if (behind != nullptr) {
+        runChainKernel<<<1, kBatchMax, 0, c->stream>>>(&behind->d_run.ptr->header, &behind->d_back.ptr->state,
+                                                       &r.d_run.ptr->header, r.d_run.ptr->moves, &r.d_back.ptr->state,
+                                                       first, r.stride, r.d_back.ptr->out, prev_out);
+        launched(c, "runChainKernel");
+    }
+    else {
+        runInitKernel<<<1, kBatchMax, 0, c->stream>>>(&r.d_run.ptr->header, r.d_run.ptr->moves, &r.d_back.ptr->state,
+                                                      pending, first, r.stride, r.d_back.ptr->out, prev_out);
+        launched(c, "runInitKernel");
+    }
+    r.chained = behind != nullptr;
+    r.steps_launched = 0;
+    // windows the run needs (barring cancellations): a window ends before a proposal that depends on one of its moves
+    int steps = 0;
+    for (int cursor = 0; cursor < r.n; ++steps) {
+        int len = std::min(r.stride, r.n - cursor);
+        for (int t = 1; t < len; ++t) {
+            const int dep = r.h_run.ptr->moves[cursor + t].dep;
+            if (dep >= cursor && !(dep & kRunDepPrevious)) {
+                len = t;
+            }
+        }
+        cursor += len;
+    }
+    launchRunSteps(c, r, steps, false);
 }
 
 } // namespace
@@ -589,18 +629,26 @@ FB_API int fb_run_submit(fb_ctx* c, int n_moves, const fb_run_move* moves, int w
         if (!moves || !config || n_moves < 1 || n_moves > kRunMax) {
             throw CudaError{"fb_run_submit: 1..1024 moves per run"};
         }
-        beginWindow(c, with_ewald);
         auto& b = c->batch;
-        b.h_run.ensure(1);
-        b.d_run.ensure(1);
-        b.h_back.ensure(1);
-        b.d_back.ensure(1);
+        const bool chain = b.runs_in_flight == 1;
+        beginWindow(c, with_ewald, chain);
+        auto& r = b.run[(b.run_head + b.runs_in_flight) % 2];
+        const fb_ctx::Batch::RunSlot* behind = chain ? &b.run[b.run_head] : nullptr;
+        if (chain && behind->with_ewald != (with_ewald ? 1 : 0)) {
+            throw CudaError{"fb_run_submit: runs with and without Ewald cannot be queued behind each other"};
+        }
+        r.h_run.ensure(1);
+        r.d_run.ensure(1);
+        r.h_back.ensure(1);
+        r.d_back.ensure(1);
         if (static_cast<int>(b.run_stamp.size()) != c->n_slots) {
             b.run_stamp.assign(static_cast<size_t>(c->n_slots), 0);
+            b.run_last.assign(static_cast<size_t>(c->n_slots), 0);
             b.run_id = 0;
         }
         b.run_id += 1;
-        RunHeader& h = b.h_run.ptr->header;
+        r.id = b.run_id;
+        RunHeader& h = r.h_run.ptr->header;
         h.n_moves = n_moves;
         h.with_ewald = with_ewald ? 1 : 0;
         h.max_energy = config->max_energy;
@@ -628,46 +676,71 @@ FB_API int fb_run_submit(fb_ctx* c, int n_moves, const fb_run_move* moves, int w
                 throw CudaError{"fb_run_submit: atom id out of range"};
             }
             const int slot = g.begin + mv.rel_index;
-            if (b.run_stamp[slot] == b.run_id) {
-                throw CudaError{"fb_run_submit: the moves of one run must touch distinct atoms"};
+            const int dep = moves[m].depends_on;
+            RunMove& rm = r.h_run.ptr->moves[m];
+            if (dep < 0) { // an ordinary proposal: nobody else in flight touches its atom
+                if (b.run_stamp[slot] == r.id || (chain && b.run_stamp[slot] == behind->id)) {
+                    throw CudaError{"fb_run_submit: the moves of a run (and of the run it is queued behind) must touch "
+                                    "distinct atoms unless they name the move they depend on"};
+                }
             }
-            b.run_stamp[slot] = b.run_id;
-            RunMove& r = b.h_run.ptr->moves[m];
-            r.slot = slot;
-            r.id = mv.atom_id;
-            r.idold = mv.old_atom_id;
-            r.flags = moves[m].flags;
-            r.pad = 0.0;
-            r.pnew = make_double4(mv.xyzq[0], mv.xyzq[1], mv.xyzq[2], mv.xyzq[3]);
-            r.pold = make_double4(mv.old_xyzq[0], mv.old_xyzq[1], mv.old_xyzq[2], mv.old_xyzq[3]);
-            r.uniform = moves[m].uniform;
-            r.host_new = moves[m].host_new;
-            r.host_old = moves[m].host_old;
+            else { // it starts where move `dep` leaves the atom: same atom, earlier, and nobody in between
+                const bool previous = (dep & FB_RUN_DEP_PREVIOUS) != 0;
+                const int index = dep & (FB_RUN_DEP_PREVIOUS - 1);
+                const RunMove* target = nullptr;
+                if (previous) {
+                    target = (chain && index < behind->n) ? &behind->h_run.ptr->moves[index] : nullptr;
+                }
+                else {
+                    target = index < m ? &r.h_run.ptr->moves[index] : nullptr;
+                }
+                if (target == nullptr || target->slot != slot || b.run_stamp[slot] != (previous ? behind->id : r.id) ||
+                    b.run_last[slot] != index) {
+                    throw CudaError{"fb_run_submit: depends_on must name the latest earlier move on the same atom"};
+                }
+                const fb_batch_move& av = moves[m].alt;
+                if (av.atom_id < 0 || av.atom_id >= c->P.n_types || av.old_atom_id < 0 || av.old_atom_id >= c->P.n_types) {
+                    throw CudaError{"fb_run_submit: atom id out of range"};
+                }
+                rm.pnew_alt = make_double4(av.xyzq[0], av.xyzq[1], av.xyzq[2], av.xyzq[3]);
+                rm.pold_alt = make_double4(av.old_xyzq[0], av.old_xyzq[1], av.old_xyzq[2], av.old_xyzq[3]);
+            }
+            b.run_stamp[slot] = r.id;
+            b.run_last[slot] = m;
+            rm.slot = slot;
+            rm.id = mv.atom_id;
+            rm.idold = mv.old_atom_id;
+            rm.flags = moves[m].flags;
+            rm.dep = dep;
+            rm.pad = 0;
+            rm.pnew = make_double4(mv.xyzq[0], mv.xyzq[1], mv.xyzq[2], mv.xyzq[3]);
+            rm.pold = make_double4(mv.old_xyzq[0], mv.old_xyzq[1], mv.old_xyzq[2], mv.old_xyzq[3]);
+            rm.uniform = moves[m].uniform;
+            rm.host_new = moves[m].host_new;
+            rm.host_old = moves[m].host_old;
+            rm.host_new_alt = moves[m].alt_host_new;
+            rm.host_old_alt = moves[m].alt_host_old;
         }
+        r.n = n_moves;
+        r.with_ewald = with_ewald ? 1 : 0;
+        // behind another run the size of the commit list it leaves is not known here: full windows
+        r.stride = (chain || n_moves > 32) ? 64 : (n_moves <= 16 ? 16 : 32);
         // accepted moves of an earlier window / run that are not yet on the device
-        b.run_stride = n_moves <= 16 ? 16 : (n_moves <= 32 ? 32 : 64);
-        if (b.has_pending &&
-            (b.pending_moves.n > 0 || (b.pending_with_ewald && (!with_ewald || b.pending.n > b.run_stride)))) {
+        if (!chain && b.has_pending &&
+            (b.pending_moves.n > 0 || (b.pending_with_ewald && (!with_ewald || b.pending.n > r.stride)))) {
             // rigid-molecule moves (mass centres) / Q(k) has to follow although this run has no k-space part / its
             // windows have no room for that many commits: apply them now
             launchBatchCommit(c, b.pending_with_ewald, nullptr);
             b.cells_valid = false;
         }
-        const CommitList pending = b.has_pending ? b.pending : CommitList{};
+        const CommitList pending = (!chain && b.has_pending) ? b.pending : CommitList{};
         b.has_pending = false;
         b.d_result.ensure(batchResultDoubles(kBatchMax));
         b.h_result.ensure(batchResultDoubles(kBatchMax));
         const size_t bytes = offsetof(fb_ctx::Batch::RunBlock, moves) + sizeof(RunMove) * static_cast<size_t>(n_moves);
-        CUDA_CHECK(cudaMemcpyAsync(b.d_run.ptr, b.h_run.ptr, bytes, cudaMemcpyHostToDevice, c->stream));
-        // the first window goes into the buffer the first step will call `cur`
-        runInitKernel<<<1, kBatchMax, 0, c->stream>>>(&b.d_run.ptr->header, b.d_run.ptr->moves, &b.d_back.ptr->state,
-                                                      pending, batchBuffers(c, b.parity ^ 1).in, b.run_stride);
-        launched(c, "runInitKernel");
-        b.run_n = n_moves;
-        b.run_with_ewald = with_ewald ? 1 : 0;
-        b.run_steps_launched = 0;
-        b.run_in_flight = true;
-        launchRunSteps(c, (n_moves + b.run_stride - 1) / b.run_stride, false);
+        CUDA_CHECK(cudaMemcpyAsync(r.d_run.ptr, r.h_run.ptr, bytes, cudaMemcpyHostToDevice, c->stream));
+        b.runs_in_flight += 1;
+        launchRun(c, r, behind, pending);
     });
 }
 
@@ -675,62 +748,77 @@ FB_API int fb_run_wait(fb_ctx* c, fb_run_result* out)
 {
     return guarded(c, [&] {
         auto& b = c->batch;
-        if (!out || !b.run_in_flight) {
+        if (!out || b.runs_in_flight < 1) {
             throw CudaError{"fb_run_wait: no submitted run"};
         }
+        auto& r = b.run[b.run_head];
+        fb_ctx::Batch::RunSlot* successor = b.runs_in_flight == 2 ? &b.run[b.run_head ^ 1] : nullptr;
+        bool continued = false;
         for (;;) {
-            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            CUDA_CHECK(cudaEventSynchronize(r.ev_done));
             if (!c->timing) {
-                accumulateWindowTiming(c, false);
+                accumulateWindowTiming(c, false, r.ev_begin, r.ev_end);
             }
-            const RunState& st = b.h_back.ptr->state;
-            if (st.cursor >= b.run_n) {
+            const RunState& st = r.h_back.ptr->state;
+            if (st.cursor >= r.n) {
                 break;
             }
-            if (b.run_steps_launched > 4 * kRunMax) {
+            if (r.steps_launched > 4 * kRunMax) {
                 throw CudaError{"fb_run_wait: the run makes no progress"};
             }
-            // a window stopped early (cancellation) or a cell bucket ran full: more windows
-            if (b.cells_used && b.h_back.ptr->overflow != 0.0) {
+            // a window stopped early (cancellation) or a cell bucket ran full: more windows. A run queued behind
+            // this one has halted on the device; its (empty) windows are in the stream before what follows.
+            if (b.cells_used && r.h_back.ptr->overflow != 0.0) {
                 b.cells_valid = false;
                 b.cell_cap *= 2;
             }
-            const int left = b.run_n - st.cursor;
-            launchRunSteps(c, (left + b.run_stride - 1) / b.run_stride, true);
+            if (!continued && successor != nullptr) {
+                b.parity = r.last_parity; // the window buffers as this run left them (its last window is `prev`)
+            }
+            continued = true;
+            const int left = r.n - st.cursor;
+            launchRunSteps(c, r, (left + r.stride - 1) / r.stride, true);
         }
-        b.run_in_flight = false;
-        const RunState& st = b.h_back.ptr->state;
+        const RunState& st = r.h_back.ptr->state;
+        if (successor != nullptr && continued) { // launch the halted run again, from the state this one leaves
+            launchRun(c, *successor, nullptr, st.commit);
+        }
+        b.runs_in_flight -= 1;
+        b.run_head ^= 1;
         b.windows += st.steps;
-        b.moves += b.run_n;
+        b.moves += r.n;
         b.run_steps += st.steps;
-        b.run_moves += b.run_n;
+        b.run_moves += r.n;
         b.run_count += 1;
         b.round_trips += 1;
-        b.run_accepted.resize(static_cast<size_t>(b.run_n));
-        b.run_u_new.resize(static_cast<size_t>(b.run_n));
-        b.run_u_old.resize(static_cast<size_t>(b.run_n));
+        b.run_accepted.resize(static_cast<size_t>(r.n));
+        b.run_u_new.resize(static_cast<size_t>(r.n));
+        b.run_u_old.resize(static_cast<size_t>(r.n));
         bool any = false;
-        for (int m = 0; m < b.run_n; ++m) {
-            const RunOutput& o = b.h_back.ptr->out[m];
+        for (int m = 0; m < r.n; ++m) {
+            const RunOutput& o = r.h_back.ptr->out[m];
             b.run_accepted[m] = static_cast<unsigned char>(o.accepted != 0);
             b.run_u_new[m] = o.u_new;
             b.run_u_old[m] = o.u_old;
             any = any || o.accepted != 0;
         }
-        // the accepted moves of the last window are still to be applied (by the next window, run or flush)
-        b.pending = st.commit;
-        b.has_pending = st.commit.n > 0;
-        b.pending_moves = CommitList{};
-        b.pending_with_ewald = b.run_with_ewald != 0;
+        // the accepted moves of the last window are still to be applied: by the run queued behind this one (on the
+        // device), else by the next window, run or flush
+        if (successor == nullptr) {
+            b.pending = st.commit;
+            b.has_pending = st.commit.n > 0;
+            b.pending_moves = CommitList{};
+            b.pending_with_ewald = r.with_ewald != 0;
+        }
         b.last_n = 0;
         b.last_groups = 0;
-        if (any && b.run_with_ewald) {
+        if (any && r.with_ewald) {
             b.q_dirty = true;
             c->slot[0].rec_valid = false;
             c->slot[1].rec_valid = false;
         }
         b.rec_known = false;
-        out->n_moves = b.run_n;
+        out->n_moves = r.n;
         out->n_windows = st.steps;
         out->n_rounds = st.rounds;
         b.run_rounds += st.rounds;

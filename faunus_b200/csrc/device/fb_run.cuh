@@ -27,18 +27,32 @@ constexpr int kRunMax = 1024; //!< moves per run
 enum RunMoveFlags : int
 {
     RUN_HOST_NEW_CLOSED = 1,
-    RUN_HOST_OLD_CLOSED = 2
+    RUN_HOST_OLD_CLOSED = 2,
+    RUN_ALT_HOST_NEW_CLOSED = 4,
+    RUN_ALT_HOST_OLD_CLOSED = 8
 };
 
+constexpr int kRunDepPrevious = 1 << 30; //!< RunMove::dep refers to the run this one is queued behind
+
+/**
+ * One proposal. A proposal on an atom that an EARLIER, still undecided proposal `dep` already moves comes in two
+ * variants — it starts where that move leaves the atom: (pnew, pold, host_*) if `dep` is accepted, the *_alt
+ * fields if it is rejected. The window set-up picks the variant once `dep` is decided (it never shares a window
+ * with it).
+ */
 struct RunMove
 {
     double4 pnew;
     double4 pold;
+    double4 pnew_alt;
+    double4 pold_alt;
     int slot, id, idold, flags;
     double uniform;   //!< the Metropolis uniform of this move
     double host_new;  //!< in-order sum of the caller's Hamiltonian terms (they precede the device terms), trial state
     double host_old;  //!< … accepted state
-    double pad;
+    double host_new_alt, host_old_alt;
+    int dep;          //!< −1, or the index of the move this one depends on (| kRunDepPrevious: in the previous run)
+    int pad;
 };
 
 struct RunHeader
@@ -57,6 +71,8 @@ struct RunState
     int window_n;
     int steps;        //!< windows evaluated for this run
     int rounds;       //!< rounds of the fixed-point walk, summed over the windows
+    int halted;       //!< queued behind a run that did not finish in its scheduled windows: does nothing, is launched again
+    int pad;
     CommitList commit; //!< its accepted moves (indices into that window): what the next window has to apply
 };
 
@@ -67,12 +83,38 @@ struct RunOutput
     int step;            //!< which window of the run decided it
 };
 
-/** the next window of the run, moves [cursor, cursor + stride), with the commit list the window before it left */
+__device__ __forceinline__ void barrier64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+/** was the move that proposal `mv` depends on accepted? (it is decided: earlier window or earlier run) */
+__device__ __forceinline__ bool runDependencyAccepted(const RunMove& mv, const RunOutput* out, const RunOutput* prev_out)
+{
+    return (mv.dep & kRunDepPrevious) ? prev_out[mv.dep & (kRunDepPrevious - 1)].accepted != 0 : out[mv.dep].accepted != 0;
+}
+
+/**
+ * The next window of the run: moves [cursor, cursor + n), n ≤ stride, cut before the first proposal that depends on
+ * a move of this very window; with the commit list the window before it left. Called by 64 threads (t = 0 … 63).
+ */
 __device__ __forceinline__ void runSetupWindow(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves,
                                                int cursor, const CommitList& commit, BatchInput* __restrict__ in,
-                                               int stride, int t)
+                                               int stride, int t, const RunOutput* out /* written by this very kernel */,
+                                               const RunOutput* prev_out)
 {
-    const int n = max(0, min(stride, hdr->n_moves - cursor));
+    __shared__ int s_window_n;
+    const int n_max = max(0, min(stride, hdr->n_moves - cursor));
+    if (t == 0) {
+        s_window_n = n_max;
+    }
+    barrier64();
+    int dep = -1;
+    if (t < n_max) {
+        dep = moves[cursor + t].dep;
+        if (dep >= cursor && !(dep & kRunDepPrevious)) {
+            atomicMin(&s_window_n, t);
+        }
+    }
+    barrier64();
+    const int n = s_window_n;
     if (t == 0) {
         in->n = n;
         in->with_ewald = hdr->with_ewald;
@@ -85,11 +127,12 @@ __device__ __forceinline__ void runSetupWindow(const RunHeader* __restrict__ hdr
     }
     if (t < n) {
         const RunMove& mv = moves[cursor + t];
+        const bool alt = dep >= 0 && !runDependencyAccepted(mv, out, prev_out);
         in->slot[t] = mv.slot;
         in->id[t] = mv.id;
         in->idold[t] = mv.idold;
-        in->pnew[t] = mv.pnew;
-        in->pold[t] = mv.pold;
+        in->pnew[t] = alt ? mv.pnew_alt : mv.pnew;
+        in->pold[t] = alt ? mv.pold_alt : mv.pold;
     }
 }
 
@@ -99,7 +142,8 @@ __device__ __forceinline__ void runSetupWindow(const RunHeader* __restrict__ hdr
  */
 __global__ void __launch_bounds__(kBatchMax)
     runInitKernel(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves, RunState* st, CommitList pending,
-                  BatchInput* __restrict__ in, int stride)
+                  BatchInput* __restrict__ in, int stride, const RunOutput* __restrict__ out,
+                  const RunOutput* __restrict__ prev_out)
 {
     if (threadIdx.x == 0) {
         st->cursor = 0;
@@ -107,28 +151,62 @@ __global__ void __launch_bounds__(kBatchMax)
         st->window_n = 0;
         st->steps = 0;
         st->rounds = 0;
+        st->halted = 0;
         st->commit.n = pending.n;
     }
     if (static_cast<int>(threadIdx.x) < pending.n) {
         st->commit.index[threadIdx.x] = pending.index[threadIdx.x];
     }
-    runSetupWindow(hdr, moves, 0, pending, in, stride, threadIdx.x);
+    runSetupWindow(hdr, moves, 0, pending, in, stride, threadIdx.x, out, prev_out);
+}
+
+/**
+ * First launch of a run queued BEHIND a run that is still in flight: it starts from what that run left (the
+ * accepted moves of its last window) — unless that run did not get through in the windows scheduled for it (a
+ * cancellation or a full cell bucket cost it extra windows): then this run halts, its windows do nothing, and the
+ * host launches it again once the earlier run is complete.
+ */
+__global__ void __launch_bounds__(kBatchMax)
+    runChainKernel(const RunHeader* __restrict__ prev_hdr, const RunState* __restrict__ prev, const RunHeader* __restrict__ hdr,
+                   const RunMove* __restrict__ moves, RunState* st, BatchInput* __restrict__ in, int stride,
+                   const RunOutput* __restrict__ out, const RunOutput* __restrict__ prev_out)
+{
+    const bool halted = prev->cursor < prev_hdr->n_moves || prev->halted != 0;
+    if (threadIdx.x == 0) {
+        st->cursor = 0;
+        st->window_first = 0;
+        st->window_n = 0;
+        st->steps = 0;
+        st->rounds = 0;
+        st->halted = halted ? 1 : 0;
+        st->commit.n = 0;
+    }
+    if (halted) {
+        if (threadIdx.x == 0) {
+            in->n = 0;
+            in->with_ewald = hdr->with_ewald;
+            in->n_groups = 0;
+            in->commit.n = 0;
+            in->commit_moves.n = 0;
+        }
+        return;
+    }
+    runSetupWindow(hdr, moves, 0, prev->commit, in, stride, threadIdx.x, out, prev_out);
 }
 
 /** a window of a run that is continued after the host looked at it: set up from the cursor on the device */
 __global__ void __launch_bounds__(kBatchMax)
     runSetupKernel(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves, const RunState* __restrict__ st,
-                   BatchInput* __restrict__ in, int stride)
+                   BatchInput* __restrict__ in, int stride, const RunOutput* __restrict__ out,
+                   const RunOutput* __restrict__ prev_out)
 {
-    runSetupWindow(hdr, moves, st->cursor, st->commit, in, stride, threadIdx.x);
+    runSetupWindow(hdr, moves, st->cursor, st->commit, in, stride, threadIdx.x, out, prev_out);
 }
 
 constexpr int kDecideThreads = 256;
 
 /** dynamic shared memory of runDecideKernel: four S × (S + 1) matrices, TRANSPOSED ([a][m], padded rows) */
 inline size_t runDecideSmemBytes(int stride) { return sizeof(double) * 4 * static_cast<size_t>(stride) * (stride + 1); }
-
-__device__ __forceinline__ void barrier64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
 /**
  * The in-order walk of a window as a fixed-point iteration. One block; all threads stage the correction
@@ -146,7 +224,8 @@ __device__ __forceinline__ void barrier64() { asm volatile("bar.sync 1, 64;" :::
 __global__ void __launch_bounds__(kDecideThreads)
     runDecideKernel(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves, RunState* __restrict__ st,
                     BatchBuffers cur, BatchInput* __restrict__ next, int stride, int cell_list,
-                    const double* __restrict__ result, RunOutput* __restrict__ out)
+                    const double* __restrict__ result, RunOutput* __restrict__ out,
+                    const RunOutput* __restrict__ prev_out)
 {
     extern __shared__ __align__(16) unsigned char run_smem[];
     __shared__ CommitList s_commit;
@@ -159,6 +238,16 @@ __global__ void __launch_bounds__(kDecideThreads)
     double* s_co = s_cn + S * LD;
     double* s_cmax = s_co + S * LD;
     double* s_g = s_cmax + S * LD;
+    if (st->halted) { // behind an unfinished run: nothing was evaluated, nothing is decided, nothing follows
+        if (threadIdx.x == 0) {
+            next->n = 0;
+            next->with_ewald = hdr->with_ewald;
+            next->n_groups = 0;
+            next->commit.n = 0;
+            next->commit_moves.n = 0;
+        }
+        return;
+    }
     const int n = cur.in->n;
     const int cursor = st->cursor;
     const int step = st->steps;
@@ -188,10 +277,11 @@ __global__ void __launch_bounds__(kDecideThreads)
         u_old0 = u[S + m];
         rec0 = with_ewald ? u[2 * S + m] : 0.0;
         const RunMove& mv = moves[cursor + m];
+        const bool alt = mv.dep >= 0 && !runDependencyAccepted(mv, out, prev_out); // as the window set-up chose
         uniform = mv.uniform;
-        host_new = mv.host_new;
-        host_old = mv.host_old;
-        flags = mv.flags;
+        host_new = alt ? mv.host_new_alt : mv.host_new;
+        host_old = alt ? mv.host_old_alt : mv.host_old;
+        flags = alt ? (mv.flags >> 2) : mv.flags;
     }
     const double rec_start = result[0]; // Σ_k A_k |Q_k|² of the window-start state (0 without Ewald)
     const bool overflow = cell_list && result[2] != 0.0; // a cell bucket ran full: nothing of this window counts
@@ -336,7 +426,7 @@ __global__ void __launch_bounds__(kDecideThreads)
         st->rounds += rounds;
     }
     barrier64();
-    runSetupWindow(hdr, moves, cursor + n_decided, s_commit, next, stride, m);
+    runSetupWindow(hdr, moves, cursor + n_decided, s_commit, next, stride, m, out, prev_out);
 }
 
 } // namespace fbdev

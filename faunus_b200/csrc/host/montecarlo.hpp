@@ -50,8 +50,17 @@ struct WindowProposal
     int move_id = 0;
     AtomicTranslateRotate::Draw draw;
     TranslateRotate::Draw group_draw;
-    size_t key_group = 0;                  //!< what the proposal touches: two proposals on the same
-    long key_atom = -1;                    //!< (group, atom) cannot be pending at the same time
+    size_t key_group = 0;                  //!< what the proposal touches: a proposal on a (group, atom) that an
+    long key_atom = -1;                    //!< earlier undecided one moves starts where that one leaves it
+    /**
+     * Conditional proposal: ONE earlier undecided proposal (`dependency`, by serial number) moves the same atom. Not
+     * applied to the trial Space yet, but both outcomes are known: start/trial position if that proposal is accepted
+     * ([0]) or rejected ([1]). An evaluator that decides on its own can take it along (WindowEvaluator::conditionals).
+     */
+    bool conditional = false;
+    uint64_t serial = 0;
+    uint64_t dependency = 0;
+    Point alt_start[2], alt_new[2];
     Change change;                  //!< filled when the draw is applied to the trial Space
     bool applied = false;
     double uniform = 0;             //!< the Metropolis uniform of this move (drawn in reference order)
@@ -84,9 +93,14 @@ class WindowEvaluator
      * Pipelining: an evaluator that decides on its own (decision() ≥ 0) can take the NEXT evaluation while the
      * results of the one in flight are still out — the queued proposals behind it are on other atoms, so nothing
      * they need depends on those results. prepare() packs proposals [first, first + n) while the device works,
-     * submitPrepared() hands them over right after wait().
+     * submitPrepared() queues them behind the evaluation in flight; wait() then returns the OLDER evaluation.
      */
-    virtual bool pipelined(const std::vector<WindowProposal>& /*window*/, int /*first*/) const { return false; }
+    virtual bool pipelined(const std::vector<WindowProposal>& /*window*/, int /*first*/, int /*ready*/) const
+    {
+        return false;
+    }
+    /** can conditional proposals be part of an evaluation? */
+    virtual bool conditionals() const { return false; }
     virtual void prepare(const std::vector<WindowProposal>& /*window*/, int /*first*/, int /*n*/) {}
     virtual void submitPrepared() {}
     /** … and wait for the results; the engine draws the next proposals in between */
@@ -304,6 +318,7 @@ class MetropolisMonteCarlo
     std::unordered_map<uint64_t, int> pending_keys;
     std::unordered_set<uint64_t> applied_keys;
     int unapplied_count = 0;
+    uint64_t proposal_serial = 0;
 
     /** apply every queued proposal whose atom / molecule has no earlier undecided proposal any more */
     void applyUnblocked()
@@ -347,20 +362,20 @@ class MetropolisMonteCarlo
         const auto t_submitted = std::chrono::steady_clock::now();
         fillWindow(n + window_evaluator->capacity()); // the next proposals, while the device works
         int next_n = 0;
-        if (static_cast<int>(window.size()) > n && window_evaluator->pipelined(window, n)) {
+        if (static_cast<int>(window.size()) > n) {
             const int ready_behind = readyProposals() - n;
-            if (ready_behind > 0) {
+            if (ready_behind > 0 && window_evaluator->pipelined(window, n, ready_behind)) {
                 next_n = window_evaluator->fit(window, n, ready_behind);
                 window_evaluator->prepare(window, n, next_n);
             }
         }
         const auto t_filled = std::chrono::steady_clock::now();
-        window_evaluator->wait();
-        if (next_n > 0) {
+        if (next_n > 0) { // queued behind the evaluation in flight: the device goes on without waiting for the host
             window_evaluator->submitPrepared();
             windows_evaluated++;
             window_moves_evaluated += static_cast<unsigned long>(next_n);
         }
+        window_evaluator->wait(); // … for the OLDER evaluation
         const auto t_evaluated = std::chrono::steady_clock::now();
         window_seconds_evaluate += std::chrono::duration<double>((t_submitted - t_begin) + (t_evaluated - t_filled)).count();
         std::vector<unsigned char> accepted;
@@ -369,6 +384,11 @@ class MetropolisMonteCarlo
             double new_energy = 0, old_energy = 0;
             if (!window_evaluator->energies(m, accepted, p, new_energy, old_energy)) {
                 break;
+            }
+            if (!p.applied) { // conditional: the proposal it depends on is decided (and replayed) by now
+                applyProposal(p);
+                applied_keys.insert(proposalKey(p));
+                unapplied_count--;
             }
             double energy_change = getEnergyChange(new_energy, old_energy);
             TraceRecord rec;
@@ -418,10 +438,11 @@ class MetropolisMonteCarlo
         window_seconds_decide += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_evaluated).count();
     }
 
+    /** leading proposals that can be evaluated: applied to the trial Space, or conditional (both outcomes known) */
     int readyProposals() const
     {
         int r = 0;
-        while (r < static_cast<int>(window.size()) && window[r].applied) {
+        while (r < static_cast<int>(window.size()) && (window[r].applied || window[r].conditional)) {
             r++;
         }
         return r;
@@ -488,12 +509,33 @@ class MetropolisMonteCarlo
         p.uniform = rng.slump();
         const uint64_t key = proposalKey(p);
         int& pending = pending_keys[key];
+        p.serial = ++proposal_serial;
         if (pending == 0) {
             applyProposal(p);
             applied_keys.insert(key);
         }
         else { // its start position is only known once the earlier moves on this atom / molecule are decided
             unapplied_count++;
+            if (pending == 1 && kind == WindowProposal::Kind::ATOM && window_evaluator->conditionals()) {
+                // one earlier proposal q on this atom: applied (the trial Space holds its trial position, the
+                // accepted Space its start), so both possible starts of this proposal are known
+                for (auto q = window.rbegin(); q != window.rend(); ++q) {
+                    if (proposalKey(*q) == key) {
+                        if (q->applied) {
+                            const auto& trial_group = trial_state.spc->groups.at(p.draw.group_index);
+                            const auto& group = state.spc->groups.at(p.draw.group_index);
+                            p.conditional = true;
+                            p.dependency = q->serial;
+                            p.alt_start[0] = trial_state.spc->at(trial_group, p.draw.atom_index).pos;
+                            p.alt_start[1] = state.spc->at(group, p.draw.atom_index).pos;
+                            p.alt_new[0] = p.move->displaced(p.alt_start[0], p.draw);
+                            p.alt_new[1] = p.move->displaced(p.alt_start[1], p.draw);
+                            p.move->describe(p.draw, p.change);
+                        }
+                        break;
+                    }
+                }
+            }
         }
         pending++;
         window.push_back(std::move(p));

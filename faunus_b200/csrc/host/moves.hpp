@@ -212,6 +212,25 @@ class AtomicTranslateRotate : public Move
         change.clear();
         apply(d, change);
     }
+    /** where `apply` puts a particle that starts at `start` (the very same arithmetic) */
+    Point displaced(const Point& start, const Draw& d) const
+    {
+        Point pos = start;
+        if (d.dp > 0.0) {
+            pos += d.unit * d.dp * d.scalar;
+            spc.geometry.boundary(pos);
+        }
+        return pos;
+    }
+    /** the Change `apply` will describe the proposal with */
+    void describe(const Draw& d, Change& change) const
+    {
+        change.clear();
+        auto record = cdata;
+        record.group_index = d.group_index;
+        record.relative_atom_indices[0] = d.atom_index;
+        change.groups.push_back(record);
+    }
     bool targetsAtomicGroups() const { return spc.topology->molecules[molid].atomic; }
     double latestDisplacementSquared() const { return latest_displacement_squared; }
     void setLatestDisplacementSquared(double d2) { latest_displacement_squared = d2; }

@@ -70,7 +70,8 @@ class FbBatchGroupMove(C.Structure):
 
 class FbRunMove(C.Structure):
     _fields_ = [("move", FbBatchMove), ("uniform", C.c_double), ("host_new", C.c_double), ("host_old", C.c_double),
-                ("flags", C.c_int)]
+                ("flags", C.c_int), ("depends_on", C.c_int), ("alt", FbBatchMove), ("alt_host_new", C.c_double),
+                ("alt_host_old", C.c_double)]
 
 
 class FbRunConfig(C.Structure):

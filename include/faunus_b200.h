@@ -306,13 +306,24 @@ int fb_batch_submit_groups(fb_ctx* ctx, int n_moves, const fb_batch_group_move* 
  * in this order and stops after a term >= max_energy or NaN like Hamiltonian::energy (src/energy.cpp:1238-1244). */
 #define FB_RUN_HOST_NEW_CLOSED 1 /* the caller's own sum already ended early (trial state) */
 #define FB_RUN_HOST_OLD_CLOSED 2 /* ... accepted state */
+#define FB_RUN_ALT_HOST_NEW_CLOSED 4
+#define FB_RUN_ALT_HOST_OLD_CLOSED 8
+#define FB_RUN_DEP_PREVIOUS (1 << 30)
+/* A proposal on an atom that ONE earlier, still undecided proposal already moves may travel too: it starts where
+ * that move leaves the atom, so the caller supplies both variants — `move`, host_new, host_old if the earlier move
+ * (`depends_on`: its index in this run, or FB_RUN_DEP_PREVIOUS | its index in the run this one is queued behind) is
+ * accepted, `alt` (+ alt_host_*) if it is rejected. The device picks the variant once that move is decided and
+ * never puts the two into one window. depends_on = -1: an ordinary proposal. */
 typedef struct
 {
     fb_batch_move move;
     double uniform;   /* the Metropolis uniform drawn for this move */
     double host_new;  /* in-order sum of the caller's own Hamiltonian terms, trial state */
     double host_old;  /* ... accepted state */
-    int flags;        /* FB_RUN_HOST_*_CLOSED */
+    int flags;        /* FB_RUN_*_CLOSED */
+    int depends_on;
+    fb_batch_move alt;
+    double alt_host_new, alt_host_old;
 } fb_run_move;
 typedef struct
 {
