@@ -6,13 +6,15 @@ restricted-primitive-model 1:1 electrolyte, N = 100 000 ions in one atomic group
 L = 436.25 Å, T = 298.15 K, eps_r = 78.7, `nonbonded_coulombwca` with Ewald real space (alpha 0.12,
 cutoff 28 Å) + reciprocal space (ncutoff 30 → K = 56 k k-vectors, policy PBC), single-ion `transrot`
 moves (dp = 4 Å), fixed seed. One "step" = one sweep of MOVES_PER_STEP trial moves through the
-Metropolis engine on the `Energy::EnergyTerm` adaptor terms (updateState → energy(trial) →
-energy(accepted) → sync per move).
+Metropolis engine on the `Energy::EnergyTerm` adaptor terms; runs of `transrot` proposals travel to the
+device a run at a time (fb_run_submit: windows of 64 evaluated speculatively and walked in order on the
+device), everything else through updateState → energy(trial) → energy(accepted) → sync.
 
-  value  : trial moves/s counting only device time of the hot kernels (inputs resident in HBM:
-           CUDA-event time between first and last kernel of each energy evaluation)
-  e2e    : trial moves/s end to end through the reference-facing adaptor (host Space → changed
-           particles H2D per move → kernels → energies D2H per move), wall/CUDA-event bracketed
+  value  : trial moves/s counting only device time (inputs resident in HBM: CUDA-event time from the first
+           to the last kernel of every run / window)
+  e2e    : trial moves/s end to end through the engine (proposals drawn on the host from the host Space →
+           H2D per run → kernels → decisions and energies D2H → replay into the host Spaces),
+           wall/CUDA-event bracketed, L2 flushed between steps
   --impl reference : the same moves by the CPU restatement of the reference path (oracle, built with the
            reference's Release flags + OpenMP) on the host cores, bounded sample.
 
@@ -32,7 +34,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-MOVES_PER_STEP = 2000
+MOVES_PER_STEP = 20000  # a fifth of the reference's own sweep for this system (`repeat: N`)
 N_IONS = 100_000
 FLOP_PER_PAIR = 49          # splined Coulomb + WCA, pair within the cutoffs, SURVEY §8(d)
 FLOP_PER_FAR_PAIR = 25      # pair beyond both cutoffs: min-image r² (20) + sqrt, +eps, r<Rc test (3) + WCA cut test (2)

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kBatchMax)
     runSetupWindow(hdr, moves, st->cursor, st->commit, in, stride, threadIdx.x, out, prev_out);
 }
 
-constexpr int kDecideThreads = 256;
+constexpr int kDecideThreads = 1024; //!< staging is latency bound: every thread has all its 16 loads in flight at once
 
 /** dynamic shared memory of runDecideKernel: four S × (S + 1) matrices, TRANSPOSED ([a][m], padded rows) */
 inline size_t runDecideSmemBytes(int stride) { return sizeof(double) * 4 * static_cast<size_t>(stride) * (stride + 1); }
@@ -238,7 +238,26 @@ __global__ void __launch_bounds__(kDecideThreads)
     double* s_co = s_cn + S * LD;
     double* s_cmax = s_co + S * LD;
     double* s_g = s_cmax + S * LD;
-    if (st->halted) { // behind an unfinished run: nothing was evaluated, nothing is decided, nothing follows
+    const int halted = st->halted;
+    const int n = cur.in->n;
+    const int cursor = st->cursor;
+    const int step = st->steps;
+    const double* u = result + 8;
+    const double* cross = result + 8 + 3 * S;
+    const int shift = S == 64 ? 6 : (S == 32 ? 5 : 4);
+    // all S rows (rows ≥ n are zero padding): the staging does not wait for n, and it has no branch, so that the
+    // loads of all rounds are in flight together
+#pragma unroll 4
+    for (int t = threadIdx.x; t < S * S; t += kDecideThreads) {
+        const int m = t >> shift;
+        const int a = t & (S - 1);
+        const double v0 = cross[t], v1 = cross[S * S + t], v2 = cross[2 * S * S + t], v3 = cross[3 * S * S + t];
+        s_cn[a * LD + m] = v0;
+        s_co[a * LD + m] = v1;
+        s_cmax[a * LD + m] = v2;
+        s_g[a * LD + m] = v3;
+    }
+    if (halted) { // behind an unfinished run: nothing was evaluated, nothing is decided, nothing follows
         if (threadIdx.x == 0) {
             next->n = 0;
             next->with_ewald = hdr->with_ewald;
@@ -248,22 +267,11 @@ __global__ void __launch_bounds__(kDecideThreads)
         }
         return;
     }
-    const int n = cur.in->n;
-    const int cursor = st->cursor;
-    const int step = st->steps;
-    const double* u = result + 8;
-    const double* cross = result + 8 + 3 * S;
-    const int shift = S == 64 ? 6 : (S == 32 ? 5 : 4);
-    const int total = n * S;
-#pragma unroll 4
-    for (int t = threadIdx.x; t < total; t += kDecideThreads) { // no branch: the loads of several rounds overlap
-        const int m = t >> shift;
-        const int a = t & (S - 1);
-        const double v0 = cross[t], v1 = cross[S * S + t], v2 = cross[2 * S * S + t], v3 = cross[3 * S * S + t];
-        s_cn[a * LD + m] = v0;
-        s_co[a * LD + m] = v1;
-        s_cmax[a * LD + m] = v2;
-        s_g[a * LD + m] = v3;
+    if (threadIdx.x < kBatchMax && cursor + n + static_cast<int>(threadIdx.x) < hdr->n_moves) {
+        // the proposals the next window most likely starts with (this window decided completely)
+        const char* ahead = reinterpret_cast<const char*>(moves + cursor + n + threadIdx.x);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead + 128));
     }
     const int m = threadIdx.x;
     const int lane = threadIdx.x & 31;
