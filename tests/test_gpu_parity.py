@@ -388,6 +388,107 @@ def test_device_walk_equals_host_walk():
         assert stats["moves"] == td["moves"] and stats["rounds"] >= stats["windows"] > 0
 
 
+def test_runs_through_the_c_abi():
+    """fb_run_submit / fb_run_wait through the raw C ABI: two runs queued behind each other, with conditional
+    proposals (a second move on an atom whose first move is still undecided, in the same run and across the two
+    runs), against one-move-at-a-time fb_trial_energy / fb_trial_commit with the Metropolis rule applied here."""
+    import ctypes as C
+    import faunus_b200.native as native
+    lib = native.load()
+    cfg = small_electrolyte(n=600, coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 6})
+    ga, gb = b200_sim(cfg, 0), b200_sim(cfg, 0)
+    xyzq, ids = ga.particles()
+    box = np.array(cfg["geometry"]["length"], dtype=float) * np.ones(3)
+    rng = np.random.RandomState(5)
+    n1, n2 = 150, 90
+    n = n1 + n2
+    atoms = rng.choice(len(xyzq), n, replace=False)
+    # repeats: (later move, earlier move) on the same atom — 3 inside run 1 (one of them within one window),
+    # 2 inside run 2, 2 from run 2 back into run 1
+    for later, earlier in ((40, 10), (100, 20), (149, 140), (n1 + 30, n1 + 5), (n1 + 80, n1 + 70), (n1 + 10, 120), (n1 + 60, 60)):
+        atoms[later] = atoms[earlier]
+    disp = rng.uniform(-1.2, 1.2, (n, 3))
+    uniform = rng.uniform(size=n)
+    wrap = lambda x: x - box * np.round(x / box)
+
+    # reference: one move at a time on context A, Hamiltonian = [non-bonded, Ewald]
+    pos = xyzq[:, :3].copy()
+    ref_acc, ref_new, ref_old = [], [], []
+    mv = native.FbTrialMove()
+    for m in range(n):
+        a = int(atoms[m])
+        new = wrap(pos[a] + disp[m])
+        mv.group_index, mv.n_atoms, mv.internal, mv.with_ewald = 0, 1, 1, 1
+        mv.rel_index[0], mv.atom_id[0] = a, int(ids[a])
+        for d in range(3):
+            mv.xyzq[0][d] = new[d]
+        mv.xyzq[0][3] = xyzq[a, 3]
+        out = [C.c_double() for _ in range(4)]
+        assert lib.fb_trial_energy(ga.ctx, C.byref(mv), *[C.byref(x) for x in out]) == 0, lib.fb_last_error(ga.ctx)
+        u_new, u_old, ew_new, ew_old = (x.value for x in out)
+        t_new, t_old = u_new + ew_new, u_old + ew_old
+        accept = bool(uniform[m] <= np.exp(-(t_new - t_old)))
+        assert lib.fb_trial_commit(ga.ctx, int(accept)) == 0
+        if accept:
+            pos[a] = new
+        ref_acc.append(accept); ref_new.append(t_new); ref_old.append(t_old)
+
+    # the same proposals as two runs on context B
+    def fill(rec, a, start, new):
+        rec.group_index, rec.rel_index, rec.atom_id, rec.old_atom_id = 0, a, int(ids[a]), int(ids[a])
+        for d in range(3):
+            rec.xyzq[d], rec.old_xyzq[d] = new[d], start[d]
+        rec.xyzq[3] = rec.old_xyzq[3] = xyzq[a, 3]
+
+    def pack(first, count):
+        block = (native.FbRunMove * count)()
+        for i in range(count):
+            m = first + i
+            a = int(atoms[m])
+            earlier = [k for k in range(m) if atoms[k] == a]
+            r = block[i]
+            r.uniform, r.host_new, r.host_old, r.flags = uniform[m], 0.0, 0.0, 0
+            start = xyzq[a, :3]
+            if not earlier:
+                r.depends_on = -1
+                fill(r.move, a, start, wrap(start + disp[m]))
+            else:
+                (q,) = earlier
+                r.depends_on = q - first if q >= first else (1 << 30) | q
+                q_new = wrap(start + disp[q])
+                fill(r.move, a, q_new, wrap(q_new + disp[m]))   # the earlier move is accepted
+                fill(r.alt, a, start, wrap(start + disp[m]))     # ... rejected
+        return block
+
+    cfg_run = native.FbRunConfig(max_energy=float("inf"), cancellation_limit=1e4)
+    b1, b2 = pack(0, n1), pack(n1, n2)
+    assert lib.fb_run_submit(gb.ctx, n1, b1, 1, C.byref(cfg_run)) == 0, lib.fb_last_error(gb.ctx)
+    assert lib.fb_run_submit(gb.ctx, n2, b2, 1, C.byref(cfg_run)) == 0, lib.fb_last_error(gb.ctx)   # queued behind
+    assert lib.fb_run_submit(gb.ctx, n2, b2, 1, C.byref(cfg_run)) != 0                               # two at most
+    got_acc, got_new, got_old, windows = [], [], [], []
+    for count in (n1, n2):
+        res = native.FbRunResult()
+        assert lib.fb_run_wait(gb.ctx, C.byref(res)) == 0, lib.fb_last_error(gb.ctx)
+        assert res.n_moves == count
+        got_acc += [bool(res.accepted[i]) for i in range(count)]
+        got_new += [res.u_new[i] for i in range(count)]
+        got_old += [res.u_old[i] for i in range(count)]
+        windows.append(res.n_windows)
+    assert windows[0] == 4 and windows[1] >= 2   # 150 moves: 64 + 64 + 21 (cut before move 149, which depends on 140) + 1
+    assert got_acc == ref_acc
+    assert 0.2 < np.mean(ref_acc) < 0.9
+    scale = np.abs(ref_new).max()
+    assert np.abs(np.array(got_new) - ref_new).max() <= RTOL * scale
+    assert np.abs(np.array(got_old) - ref_old).max() <= RTOL * scale
+    # both contexts end in the same state (fb_download_space applies what is still pending)
+    xa, xb = np.zeros((len(xyzq), 4)), np.zeros((len(xyzq), 4))
+    ia, ib = np.zeros(len(xyzq), dtype=np.int32), np.zeros(len(xyzq), dtype=np.int32)
+    for ctx, x, i in ((ga.ctx, xa, ia), (gb.ctx, xb, ib)):
+        assert lib.fb_download_space(ctx, 0, x.ctypes.data_as(native.c_double_p), i.ctypes.data_as(native.c_int_p), None) == 0
+    assert np.array_equal(xa, xb)
+    assert np.array_equal(xa[:, :3], pos)
+
+
 def test_system_energy_shards_add_up():
     """fb_system_energy_shard: tile rows / k-vector slabs dealt to 3 'GPUs' add up to the full energies"""
     cfg = small_electrolyte(n=900, coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 6})
