@@ -195,6 +195,10 @@ struct fb_ctx
     struct Batch
     {
         DeviceBuffer<BatchInput> d_in[2];
+        DeviceBuffer<BatchInput> d_ahead[2];  //!< runs: the window predicted to follow (pair sums one window ahead)
+        DeviceBuffer<double> d_pair_fix;      //!< … and what the accepted moves of the window before change in them
+        DeviceBuffer<int> d_pair_redo;
+        bool prepair = false;                 //!< fb_configure_runs (off: measured +1 % at S1, −12 % on examples/bulk)
         DeviceBuffer<double2> d_table[2];
         PinnedBuffer<BatchInput> h_in;
         DeviceBuffer<double> d_pair_partials, d_r_partials, d_g_partials, d_e_partials, d_result;

@@ -55,6 +55,10 @@ struct BatchInput
     // its accepted moves (mass centres)
     CommitList commit;
     CommitList commit_moves;
+    // runs (fb_run.cuh): first move of the window in its run; pair_ready: the pair sums of exactly this window were
+    // evaluated ahead, against the state BEFORE the commit list above was applied (batchPairFixKernel corrects them)
+    int first;
+    int pair_ready;
 };
 
 /** Device-resident working set of one window */
@@ -181,8 +185,12 @@ __global__ void __launch_bounds__(kBlock)
  * The previous window's accepted trial positions go into both mirrors (pair stream, before the pair kernel);
  * in group mode also the mass centres of the accepted groups (`moves` lists move indices).
  */
-__global__ void __launch_bounds__(kBatchMax) batchPrepKernel(SlotView M0, SlotView M1, BatchBuffers cur, BatchBuffers prev)
+__global__ void __launch_bounds__(kBatchMax)
+    batchPrepKernel(SlotView M0, SlotView M1, BatchBuffers cur, BatchBuffers prev, int* __restrict__ redo = nullptr)
 {
+    if (redo != nullptr && threadIdx.x == 0) {
+        *redo = 0; // raised by batchPairFixKernel, read by the gated pair kernel and the pair sums
+    }
     const CommitList& commit = cur.in->commit;
     const CommitList& moves = cur.in->commit_moves;
     if (static_cast<int>(threadIdx.x) < commit.n) {
@@ -266,8 +274,13 @@ constexpr int kPairQueue = 256; //!< in-range candidates a warp collects before 
 template <int KIND, bool DENSE>
 __global__ void __launch_bounds__(kPairThreads)
     batchPairKernel(SlotView M0, PotParams P, BatchBuffers cur, double cut2, int stride,
-                    double* __restrict__ partials /*[gridDim.x][2·stride]*/)
+                    double* __restrict__ partials /*[gridDim.x][2·stride]*/, const int* __restrict__ redo = nullptr)
 {
+    // redo != nullptr: the sums of this window may have been evaluated ahead (fb_run.cuh); then there is nothing to
+    // do unless the correction met a cancellation (*redo)
+    if (redo != nullptr && cur.in->pair_ready && *redo == 0) {
+        return;
+    }
     // DENSE: some term has no cutoff, every pair is evaluated in place. Otherwise the few pairs in range are
     // queued per warp (ballot order: deterministic) and evaluated afterwards with all lanes busy.
     __shared__ double4 s_pos[DENSE ? 1 : kPairChunk];
@@ -1031,12 +1044,64 @@ __device__ __forceinline__ double warpColumnSum(const double* __restrict__ a, in
     return warpSum(s);
 }
 
+/**
+ * Runs: the pair sums of this window were evaluated one window ahead (batchPairKernel on the predicted window,
+ * overlapping the k-space kernel of the window before), i.e. against the state in which the accepted moves of the
+ * window before — this window's commit list — were not applied yet. One warp per variant v adds up
+ *     fix[v] = Σ_a [ u(x_v, new_a) − u(x_v, old_a) ]      (a: accepted moves of the previous window, in order)
+ * — the same identity as the cross terms inside a window. A pair energy ≥ `limit` (or not finite) in there would
+ * cancel badly: then *redo is raised and the gated batchPairKernel evaluates the window from scratch.
+ */
+template <int KIND>
+__global__ void __launch_bounds__(kBlock)
+    batchPairFixKernel(SlotView M0, PotParams P, BatchBuffers cur, BatchBuffers prev, double limit,
+                       double* __restrict__ fix /*[2·kBatchMax]*/, int* __restrict__ redo)
+{
+    __shared__ double s_delta[kBlock / 32][kBatchMax];
+    if (!cur.in->pair_ready) {
+        return;
+    }
+    const int n = cur.in->n;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int v = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    if (v >= 2 * n) {
+        return;
+    }
+    const int m = v >> 1;
+    const double4 x = (v & 1) ? cur.pold[m] : cur.in->pnew[m];
+    const int id = (v & 1) ? cur.idold[m] : cur.in->id[m];
+    const int nc = cur.in->commit.n;
+    bool bad = false;
+    for (int k = lane; k < nc; k += 32) {
+        const int a = cur.in->commit.index[k];
+        const double4 pn = prev.in->pnew[a];
+        const double4 po = prev.pold[a];
+        const double un = pairEnergy<KIND>(P, id, prev.in->id[a], x.w, pn.w, minImageR2(M0, x.x, x.y, x.z, pn.x, pn.y, pn.z));
+        const double uo = pairEnergy<KIND>(P, id, prev.idold[a], x.w, po.w, minImageR2(M0, x.x, x.y, x.z, po.x, po.y, po.z));
+        bad = bad || !(fabs(un) < limit) || !(fabs(uo) < limit);
+        s_delta[warp][k] = un - uo;
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, bad) && lane == 0) {
+        atomicOr(redo, 1);
+    }
+    if (lane == 0) {
+        double s = 0.0;
+        for (int k = 0; k < nc; ++k) {
+            s += s_delta[warp][k];
+        }
+        fix[v] = s;
+    }
+}
+
 /** pair side, one warp per output: 2S pair sums and the S² cross entries (4 pair energies each, a < m) */
 template <int KIND>
 __global__ void __launch_bounds__(kBlock)
     batchPairFinishKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, int n_pair_blocks,
                           const double* __restrict__ pair_partials, int sums_done, const int* __restrict__ cell_overflow,
-                          double* __restrict__ result)
+                          double* __restrict__ result, const double* __restrict__ fix = nullptr,
+                          const int* __restrict__ redo = nullptr)
 {
     const int n = cur.in->n;
     const int S = stride;
@@ -1051,6 +1116,9 @@ __global__ void __launch_bounds__(kBlock)
         double s = 0.0;
         if (w < 2 * n && !sums_done) {
             s = warpColumnSum(pair_partials, n_pair_blocks, 2 * static_cast<size_t>(S), w, lane);
+            if (fix != nullptr && cur.in->pair_ready && *redo == 0) { // sums taken one window ahead: what the accepted
+                s += fix[w];                                         // moves of the window before changed
+            }
         }
         if (lane == 0 && !(sums_done && w < 2 * n)) { // with the cell list the sums are already in place
             u[(w & 1) * S + (w >> 1)] = s;

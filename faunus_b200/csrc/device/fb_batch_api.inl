@@ -18,7 +18,10 @@ void batchAllocate(fb_ctx* c)
     auto& b = c->batch;
     for (int i = 0; i < 2; ++i) {
         b.d_in[i].ensure(1);
+        b.d_ahead[i].ensure(1);
     }
+    b.d_pair_fix.ensure(2 * kBatchMax);
+    b.d_pair_redo.ensure(1);
     b.h_in.ensure(1);
 }
 
@@ -139,8 +142,10 @@ void buildCellList(fb_ctx* c, const CellGrid& g, cudaStream_t stream)
 template <int KIND>
 void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, const CommitList& commit,
                   const CommitList& commit_moves, int n_moves, int n_groups, int stride, bool with_ewald, bool timing,
-                  bool device_commit = false)
+                  bool device_commit = false, const BatchBuffers* ahead = nullptr, double fix_limit = 0.0)
 {
+    // ahead != nullptr (runs): the pair sums of `cur` may have been taken a window ahead, and those of `ahead` are
+    // taken now, behind this window's own pair work
     // device_commit: the commit list is written on the device (a run), the host does not know whether it is empty
     auto& b = c->batch;
     const SlotView M0 = makeView(c, 0);
@@ -150,8 +155,9 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
         CUDA_CHECK(cudaEventRecord(b.ev_fork, c->stream)); // after the H2D copy of the window description
         CUDA_CHECK(cudaStreamWaitEvent(ps, b.ev_fork, 0));
     }
+    const bool pair_ahead = ahead != nullptr;
     if (commit.n > 0 || commit_moves.n > 0 || device_commit) {
-        batchPrepKernel<<<1, kBatchMax, 0, ps>>>(M0, makeView(c, 1), cur, prev);
+        batchPrepKernel<<<1, kBatchMax, 0, ps>>>(M0, makeView(c, 1), cur, prev, pair_ahead ? b.d_pair_redo.ptr : nullptr);
         launched(c, "batchPrepKernel");
     }
     if (timing) {
@@ -185,23 +191,45 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
         else {
             b.d_pair_partials.ensure(static_cast<size_t>(n_pair_blocks) * 2 * kBatchMax);
             const dim3 pair_grid(n_pair_blocks, (2 * n_moves + kPairVariantsPerBlock - 1) / kPairVariantsPerBlock);
+            const int* redo = pair_ahead ? b.d_pair_redo.ptr : nullptr;
+            if (pair_ahead) { // sums taken a window ahead → corrections for what was accepted since; else: from scratch
+                batchPairFixKernel<KIND><<<(2 * n_moves * 32 + kBlock - 1) / kBlock, kBlock, 0, ps>>>(
+                    M0, c->P, cur, prev, fix_limit, b.d_pair_fix.ptr, b.d_pair_redo.ptr);
+                launched(c, "batchPairFixKernel");
+            }
             if (std::isinf(c->pair_cut2)) {
                 batchPairKernel<KIND, true><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
-                                                                               b.d_pair_partials.ptr);
+                                                                               b.d_pair_partials.ptr, redo);
             }
             else {
                 batchPairKernel<KIND, false><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
-                                                                                b.d_pair_partials.ptr);
+                                                                                b.d_pair_partials.ptr, redo);
             }
             launched(c, "batchPairKernel");
         }
+        const bool fixed = pair_ahead && !b.cells_used;
         batchPairFinishKernel<KIND><<<pair_finish_grid, kBlock, 0, ps>>>(
             M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, b.cells_used ? 1 : 0,
-            b.cells_used ? b.d_cell_overflow.ptr : nullptr, b.d_result.ptr);
+            b.cells_used ? b.d_cell_overflow.ptr : nullptr, b.d_result.ptr, fixed ? b.d_pair_fix.ptr : nullptr,
+            fixed ? b.d_pair_redo.ptr : nullptr);
         launched(c, "batchPairFinishKernel");
     }
     if (fork) {
         CUDA_CHECK(cudaEventRecord(b.ev_join, ps));
+    }
+    if (pair_ahead && !b.cells_used && n_groups == 0) {
+        // the pair sums of the window predicted to follow, against the positions as they are now: behind this
+        // window's own pair work on the pair stream, beside its k-space kernel and its walk
+        const dim3 pair_grid(n_pair_blocks, (2 * n_moves + kPairVariantsPerBlock - 1) / kPairVariantsPerBlock);
+        if (std::isinf(c->pair_cut2)) {
+            batchPairKernel<KIND, true><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, *ahead, c->pair_cut2, stride,
+                                                                           b.d_pair_partials.ptr);
+        }
+        else {
+            batchPairKernel<KIND, false><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, *ahead, c->pair_cut2, stride,
+                                                                            b.d_pair_partials.ptr);
+        }
+        launched(c, "batchPairKernel");
     }
     if (timing) {
         CUDA_CHECK(cudaEventRecord(b.ev[2], c->stream));
@@ -368,6 +396,8 @@ void launchPreparedWindow(fb_ctx* c, int n_atoms, int n_groups, int with_ewald)
     const BatchBuffers cur = batchBuffers(c, b.parity);
     b.h_in.ptr->commit = commit;
     b.h_in.ptr->commit_moves = commit_moves;
+    b.h_in.ptr->first = 0;
+    b.h_in.ptr->pair_ready = 0;
     CUDA_CHECK(cudaMemcpyAsync(cur.in, b.h_in.ptr, sizeof(BatchInput), cudaMemcpyHostToDevice, c->stream));
     const size_t n_result = batchResultDoubles(stride);
     b.d_result.ensure(batchResultDoubles(kBatchMax));
@@ -523,13 +553,23 @@ void launchRunStep(fb_ctx* c, fb_ctx::Batch::RunSlot& r, bool timing, bool setup
     const RunMove* moves = r.d_run.ptr->moves;
     RunState* st = &r.d_back.ptr->state;
     const RunOutput* prev_out = b.run[&r == &b.run[0] ? 1 : 0].d_back.ptr ? b.run[&r == &b.run[0] ? 1 : 0].d_back.ptr->out : nullptr;
+    // the prediction of the window with buffer parity q lives in d_ahead[q]
+    BatchInput* ahead_next = b.d_ahead[b.parity ^ 1].ptr; // of the window after this one
+    BatchInput* ahead_after = b.d_ahead[b.parity].ptr;    // of the one after that (written by this step's walk)
+    BatchBuffers ahead{};
+    ahead.in = ahead_next;
+    ahead.pold = ahead_next->pold; // host-side address arithmetic on a device pointer
+    ahead.idold = ahead_next->idold;
+    const bool prepair = r.h_run.ptr->header.prepair != 0;
     if (setup) {
-        runSetupKernel<<<1, kBatchMax, 0, c->stream>>>(hdr, moves, st, cur.in, stride, r.d_back.ptr->out, prev_out);
+        runSetupKernel<<<1, kBatchMax, 0, c->stream>>>(hdr, moves, st, cur.in, stride, r.d_back.ptr->out, prev_out,
+                                                       ahead_next);
         launched(c, "runSetupKernel");
     }
 #define FB_CASE(K)                                                                                             \
     case K:                                                                                                    \
-        launchWindow<K>(c, cur, prev, CommitList{}, CommitList{}, stride, 0, stride, with_ewald, timing, true); \
+        launchWindow<K>(c, cur, prev, CommitList{}, CommitList{}, stride, 0, stride, with_ewald, timing, true,   \
+                        prepair ? &ahead : nullptr, r.h_run.ptr->header.cancellation_limit);                  \
         break;
     switch (c->P.kind) {
         FB_CASE(POT_COULOMB_LJ)
@@ -551,7 +591,8 @@ void launchRunStep(fb_ctx* c, fb_ctx::Batch::RunSlot& r, bool timing, bool setup
     // the walk reads the window it decides (cur) and writes the description of the next one (next == prev's
     // buffer: the window kernels of this step, the last readers of prev, are done by then)
     runDecideKernel<<<1, kDecideThreads, smem, c->stream>>>(hdr, moves, st, cur, next.in, stride, b.cells_used ? 1 : 0,
-                                                           b.d_result.ptr, r.d_back.ptr->out, prev_out);
+                                                           b.d_result.ptr, r.d_back.ptr->out, prev_out, ahead_next,
+                                                           ahead_after);
     launched(c, "runDecideKernel");
     r.steps_launched += 1;
     r.last_parity = b.parity;
@@ -596,12 +637,14 @@ void launchRun(fb_ctx* c, fb_ctx::Batch::RunSlot& r, const fb_ctx::Batch::RunSlo
     if (behind != nullptr) {
         runChainKernel<<<1, kBatchMax, 0, c->stream>>>(&behind->d_run.ptr->header, &behind->d_back.ptr->state,
                                                        &r.d_run.ptr->header, r.d_run.ptr->moves, &r.d_back.ptr->state,
-                                                       first, r.stride, r.d_back.ptr->out, prev_out);
+                                                       first, r.stride, r.d_back.ptr->out, prev_out,
+                                                       b.d_ahead[b.parity].ptr);
         launched(c, "runChainKernel");
     }
     else {
         runInitKernel<<<1, kBatchMax, 0, c->stream>>>(&r.d_run.ptr->header, r.d_run.ptr->moves, &r.d_back.ptr->state,
-                                                      pending, first, r.stride, r.d_back.ptr->out, prev_out);
+                                                      pending, first, r.stride, r.d_back.ptr->out, prev_out,
+                                                      b.d_ahead[b.parity].ptr);
         launched(c, "runInitKernel");
     }
     r.chained = behind != nullptr;
@@ -653,6 +696,11 @@ FB_API int fb_run_submit(fb_ctx* c, int n_moves, const fb_run_move* moves, int w
         h.with_ewald = with_ewald ? 1 : 0;
         h.max_energy = config->max_energy;
         h.cancellation_limit = config->cancellation_limit;
+        h.pad = 0;
+        {
+            CellGrid grid{};
+            h.prepair = (b.prepair && !c->timing && !cellGridFor(c, grid)) ? 1 : 0;
+        }
         h.rec_prefactor = 0.0;
         if (with_ewald) {
             batchEwaldGeometry(c);
@@ -962,6 +1010,15 @@ FB_API int fb_debug_set_cell_capacity(fb_ctx* c, int capacity)
     c->batch.cell_cap = capacity;
     c->batch.cell_cap_forced = true;
     c->batch.cells_valid = false;
+    return FB_OK;
+}
+
+FB_API int fb_configure_runs(fb_ctx* c, int pair_sums_ahead)
+{
+    if (!c) {
+        return FB_ERR_INVALID;
+    }
+    c->batch.prepair = pair_sums_ahead != 0;
     return FB_OK;
 }
 

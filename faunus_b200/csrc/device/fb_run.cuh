@@ -59,6 +59,8 @@ struct RunHeader
 {
     int n_moves;
     int with_ewald;
+    int prepair; //!< evaluate the pair sums of a window one window ahead (see runSetupWindow)
+    int pad;
     double max_energy;         //!< Hamiltonian::maximumAllowedEnergy: the sum stops after a term ≥ this (or NaN)
     double cancellation_limit; //!< |pair energy| in a correction from which on a move is evaluated afresh
     double rec_prefactor;      //!< 2π lB / V
@@ -94,14 +96,21 @@ __device__ __forceinline__ bool runDependencyAccepted(const RunMove& mv, const R
 /**
  * The next window of the run: moves [cursor, cursor + n), n ≤ stride, cut before the first proposal that depends on
  * a move of this very window; with the commit list the window before it left. Called by 64 threads (t = 0 … 63).
+ *
+ * Pair sums one window ahead: `ahead` (may be null) receives the window that will MOST LIKELY follow this one —
+ * moves [cursor + n, …) — so that its pair sums can be evaluated while this window's k-space kernel runs
+ * (batchPairKernel on `ahead`, then batchPairFixKernel once this window is decided). `guess` (may be null) is what
+ * was predicted for THIS window a step ago: if it is exactly this window, its sums are there (pair_ready).
  */
 __device__ __forceinline__ void runSetupWindow(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves,
                                                int cursor, const CommitList& commit, BatchInput* __restrict__ in,
                                                int stride, int t, const RunOutput* out /* written by this very kernel */,
-                                               const RunOutput* prev_out)
+                                               const RunOutput* prev_out, const BatchInput* guess,
+                                               BatchInput* __restrict__ ahead)
 {
-    __shared__ int s_window_n;
-    const int n_max = max(0, min(stride, hdr->n_moves - cursor));
+    __shared__ int s_window_n, s_ahead_n, s_ahead_ok;
+    const int n_moves = hdr->n_moves;
+    const int n_max = max(0, min(stride, n_moves - cursor));
     if (t == 0) {
         s_window_n = n_max;
     }
@@ -121,6 +130,8 @@ __device__ __forceinline__ void runSetupWindow(const RunHeader* __restrict__ hdr
         in->n_groups = 0;
         in->commit.n = commit.n;
         in->commit_moves.n = 0;
+        in->first = cursor;
+        in->pair_ready = (guess != nullptr && guess->pair_ready && guess->first == cursor && guess->n == n && n > 0) ? 1 : 0;
     }
     if (t < commit.n) {
         in->commit.index[t] = commit.index[t];
@@ -134,6 +145,50 @@ __device__ __forceinline__ void runSetupWindow(const RunHeader* __restrict__ hdr
         in->pnew[t] = alt ? mv.pnew_alt : mv.pnew;
         in->pold[t] = alt ? mv.pold_alt : mv.pold;
     }
+    if (ahead == nullptr) {
+        return;
+    }
+    // the window after this one, if this one decides all its moves; a proposal that depends on a move of THIS window
+    // has no known start yet: no prediction then
+    const int first = cursor + n;
+    const int a_max = hdr->prepair ? max(0, min(stride, n_moves - first)) : 0;
+    if (t == 0) {
+        s_ahead_n = a_max;
+        s_ahead_ok = 1;
+    }
+    barrier64();
+    int adep = -1;
+    if (t < a_max) {
+        adep = moves[first + t].dep;
+        if (adep >= 0 && !(adep & kRunDepPrevious)) {
+            if (adep >= first) {
+                atomicMin(&s_ahead_n, t);
+            }
+            else if (adep >= cursor) {
+                s_ahead_ok = 0;
+            }
+        }
+    }
+    barrier64();
+    const int an = s_ahead_ok ? s_ahead_n : 0;
+    if (t == 0) {
+        ahead->n = an;
+        ahead->with_ewald = hdr->with_ewald;
+        ahead->n_groups = 0;
+        ahead->commit.n = 0;
+        ahead->commit_moves.n = 0;
+        ahead->first = first;
+        ahead->pair_ready = an > 0 ? 1 : 0;
+    }
+    if (t < an) {
+        const RunMove& mv = moves[first + t];
+        const bool alt = adep >= 0 && !runDependencyAccepted(mv, out, prev_out); // decided: before this window
+        ahead->slot[t] = mv.slot;
+        ahead->id[t] = mv.id;
+        ahead->idold[t] = mv.idold;
+        ahead->pnew[t] = alt ? mv.pnew_alt : mv.pnew;
+        ahead->pold[t] = alt ? mv.pold_alt : mv.pold;
+    }
 }
 
 /**
@@ -143,7 +198,7 @@ __device__ __forceinline__ void runSetupWindow(const RunHeader* __restrict__ hdr
 __global__ void __launch_bounds__(kBatchMax)
     runInitKernel(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves, RunState* st, CommitList pending,
                   BatchInput* __restrict__ in, int stride, const RunOutput* __restrict__ out,
-                  const RunOutput* __restrict__ prev_out)
+                  const RunOutput* __restrict__ prev_out, BatchInput* __restrict__ ahead)
 {
     if (threadIdx.x == 0) {
         st->cursor = 0;
@@ -157,7 +212,7 @@ __global__ void __launch_bounds__(kBatchMax)
     if (static_cast<int>(threadIdx.x) < pending.n) {
         st->commit.index[threadIdx.x] = pending.index[threadIdx.x];
     }
-    runSetupWindow(hdr, moves, 0, pending, in, stride, threadIdx.x, out, prev_out);
+    runSetupWindow(hdr, moves, 0, pending, in, stride, threadIdx.x, out, prev_out, nullptr, ahead);
 }
 
 /**
@@ -169,7 +224,8 @@ __global__ void __launch_bounds__(kBatchMax)
 __global__ void __launch_bounds__(kBatchMax)
     runChainKernel(const RunHeader* __restrict__ prev_hdr, const RunState* __restrict__ prev, const RunHeader* __restrict__ hdr,
                    const RunMove* __restrict__ moves, RunState* st, BatchInput* __restrict__ in, int stride,
-                   const RunOutput* __restrict__ out, const RunOutput* __restrict__ prev_out)
+                   const RunOutput* __restrict__ out, const RunOutput* __restrict__ prev_out,
+                   BatchInput* __restrict__ ahead)
 {
     const bool halted = prev->cursor < prev_hdr->n_moves || prev->halted != 0;
     if (threadIdx.x == 0) {
@@ -188,19 +244,22 @@ __global__ void __launch_bounds__(kBatchMax)
             in->n_groups = 0;
             in->commit.n = 0;
             in->commit_moves.n = 0;
+            in->pair_ready = 0;
+            ahead->n = 0;
+            ahead->pair_ready = 0;
         }
         return;
     }
-    runSetupWindow(hdr, moves, 0, prev->commit, in, stride, threadIdx.x, out, prev_out);
+    runSetupWindow(hdr, moves, 0, prev->commit, in, stride, threadIdx.x, out, prev_out, nullptr, ahead);
 }
 
 /** a window of a run that is continued after the host looked at it: set up from the cursor on the device */
 __global__ void __launch_bounds__(kBatchMax)
     runSetupKernel(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves, const RunState* __restrict__ st,
                    BatchInput* __restrict__ in, int stride, const RunOutput* __restrict__ out,
-                   const RunOutput* __restrict__ prev_out)
+                   const RunOutput* __restrict__ prev_out, BatchInput* __restrict__ ahead)
 {
-    runSetupWindow(hdr, moves, st->cursor, st->commit, in, stride, threadIdx.x, out, prev_out);
+    runSetupWindow(hdr, moves, st->cursor, st->commit, in, stride, threadIdx.x, out, prev_out, nullptr, ahead);
 }
 
 constexpr int kDecideThreads = 1024; //!< staging is latency bound: every thread has all its 16 loads in flight at once
@@ -225,7 +284,7 @@ __global__ void __launch_bounds__(kDecideThreads)
     runDecideKernel(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves, RunState* __restrict__ st,
                     BatchBuffers cur, BatchInput* __restrict__ next, int stride, int cell_list,
                     const double* __restrict__ result, RunOutput* __restrict__ out,
-                    const RunOutput* __restrict__ prev_out)
+                    const RunOutput* __restrict__ prev_out, const BatchInput* predicted, BatchInput* __restrict__ ahead)
 {
     extern __shared__ __align__(16) unsigned char run_smem[];
     __shared__ CommitList s_commit;
@@ -264,6 +323,9 @@ __global__ void __launch_bounds__(kDecideThreads)
             next->n_groups = 0;
             next->commit.n = 0;
             next->commit_moves.n = 0;
+            next->pair_ready = 0;
+            ahead->n = 0;
+            ahead->pair_ready = 0;
         }
         return;
     }
@@ -434,7 +496,7 @@ __global__ void __launch_bounds__(kDecideThreads)
         st->rounds += rounds;
     }
     barrier64();
-    runSetupWindow(hdr, moves, cursor + n_decided, s_commit, next, stride, m, out, prev_out);
+    runSetupWindow(hdr, moves, cursor + n_decided, s_commit, next, stride, m, out, prev_out, predicted, ahead);
 }
 
 } // namespace fbdev

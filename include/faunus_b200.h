@@ -341,6 +341,12 @@ typedef struct
 } fb_run_result;
 int fb_run_submit(fb_ctx* ctx, int n_moves, const fb_run_move* moves, int with_ewald, const fb_run_config* config);
 int fb_run_wait(fb_ctx* ctx, fb_run_result* result);
+/* pair_sums_ahead != 0: inside a run the pair sums of a window are evaluated one window ahead (beside the k-space
+ * kernel and the walk of the window before) and corrected for the moves accepted since — the same exact identity
+ * as the cross terms inside a window; 0 (default): every window evaluates its pair sums itself. Off by default: the
+ * k-space kernel owns the register file, so the kernel running ahead only finds room in the gaps, where it delays
+ * the walk (measured: +1 % moves/s at N = 1e5, -12 % at N = 2304). */
+int fb_configure_runs(fb_ctx* ctx, int pair_sums_ahead);
 /* since creation: out[0] = runs, out[1] = windows in runs, out[2] = rounds of the fixed-point walk, out[3] = moves */
 int fb_get_run_stats(const fb_ctx* ctx, double out[4]);
 /* accepted[m] != 0 for the accepted ones among the first n_decided moves of the last window */

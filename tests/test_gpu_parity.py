@@ -388,6 +388,30 @@ def test_device_walk_equals_host_walk():
         assert stats["moves"] == td["moves"] and stats["rounds"] >= stats["windows"] > 0
 
 
+def test_runs_with_pair_sums_ahead(bulk_input):
+    """fb_configure_runs(1): pair sums of a window evaluated one window ahead and corrected for the moves accepted
+    since (batchPairFixKernel; predictions fail at conditional proposals and early stops and fall back) — same
+    trace as the oracle on examples/bulk and on a hard-sphere electrolyte (infinite corrections → redo)"""
+    for cfg, sweeps in ((bulk_input, 3), (ALL_VARIANTS["pm"], 600), (ALL_VARIANTS["coulombwca_ewald"], 600)):
+        o, g = pair_of_sims(cfg, 64)
+        g.configure_runs(True)
+        for s in (o, g):
+            s.trace_enable()
+            s.sweep(sweeps)
+        a, b = o.trace(), g.trace()
+        assert len(a["du"]) > 500
+        assert np.array_equal(a["accepted"], b["accepted"])
+        finite = np.isfinite(a["u_new"])
+        scale = np.abs(a["u_new"][finite]).max()
+        assert_close(a["u_new"], b["u_new"], scale=scale)
+        assert_close(a["u_old"], b["u_old"], scale=scale)
+        xo, _ = o.particles()
+        xg, _ = g.particles()
+        assert np.array_equal(xo, xg)
+        assert abs(g.drift()) < 1e-9
+        assert g.run_stats()["windows"] > 0
+
+
 def test_runs_through_the_c_abi():
     """fb_run_submit / fb_run_wait through the raw C ABI: two runs queued behind each other, with conditional
     proposals (a second move on an atom whose first move is still undecided, in the same run and across the two
