@@ -222,36 +222,43 @@ __global__ void __launch_bounds__(kBatchMax) batchCommitGroupsKernel(SlotView M0
     }
 }
 
-/** per-axis phase tables e^{i 2π n x / L} of the 2n positions of the window */
+/** entry t of the per-axis phase tables e^{i 2π n x / L} of the 2n positions of a window */
+__device__ __forceinline__ void phaseTableEntry(const BatchInput* in, double2* __restrict__ table, const PhaseGeometry& geo,
+                                                int t)
+{
+    const int variant = t / geo.table_stride;
+    const int e = t - variant * geo.table_stride;
+    const int m = variant >> 1;
+    const double4 p = (variant & 1) ? in->pold[m] : in->pnew[m];
+    int axis, nn;
+    if (e <= geo.ncc) {
+        axis = 0;
+        nn = e;
+    }
+    else if (e < (geo.ncc + 1) + (2 * geo.ncc + 1)) {
+        axis = 1;
+        nn = e - (geo.ncc + 1) - geo.ncc;
+    }
+    else {
+        axis = 2;
+        nn = e - (geo.ncc + 1) - (2 * geo.ncc + 1) - geo.ncc;
+    }
+    const double x = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+    // k component exactly as the k-vector table has it: 2π n / L (src/energy.cpp:158-160)
+    const double kc = 2.0 * 3.141592653589793238462643383279502884 * static_cast<double>(nn) / geo.len[axis];
+    double sn, cs;
+    sincos(kc * x, &sn, &cs);
+    table[t] = make_double2(cs, sn);
+}
+
+/** per-axis phase tables of the 2n positions of the window */
 __global__ void __launch_bounds__(kBlock) batchPhaseKernel(BatchBuffers cur, PhaseGeometry geo)
 {
     const int n = cur.in->n;
     const int tid = blockIdx.x * kBlock + threadIdx.x;
     const int total = 2 * n * geo.table_stride;
     for (int t = tid; t < total; t += gridDim.x * kBlock) {
-        const int variant = t / geo.table_stride;
-        const int e = t - variant * geo.table_stride;
-        const int m = variant >> 1;
-        const double4 p = (variant & 1) ? cur.pold[m] : cur.in->pnew[m];
-        int axis, nn;
-        if (e <= geo.ncc) {
-            axis = 0;
-            nn = e;
-        }
-        else if (e < (geo.ncc + 1) + (2 * geo.ncc + 1)) {
-            axis = 1;
-            nn = e - (geo.ncc + 1) - geo.ncc;
-        }
-        else {
-            axis = 2;
-            nn = e - (geo.ncc + 1) - (2 * geo.ncc + 1) - geo.ncc;
-        }
-        const double x = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
-        // k component exactly as the k-vector table has it: 2π n / L (src/energy.cpp:158-160)
-        const double kc = 2.0 * 3.141592653589793238462643383279502884 * static_cast<double>(nn) / geo.len[axis];
-        double sn, cs;
-        sincos(kc * x, &sn, &cs);
-        cur.table[t] = make_double2(cs, sn);
+        phaseTableEntry(cur.in, cur.table, geo, t);
     }
 }
 
@@ -1162,48 +1169,84 @@ __global__ void __launch_bounds__(kBlock)
     }
 }
 
-/** k-space side, one warp per output: S reciprocal sums R, S² Gram entries G (a < m), the start sum */
-__global__ void __launch_bounds__(kBlock)
+/**
+ * k-space side: ordered sums of the per-block partials R[rows][S], G[rows][S²], E[rows] → the result block.
+ * Coalesced: a block takes 32 adjacent columns (lane ↔ column), its 32 warps take the rows w, w + 32, … (all loads
+ * of a warp in flight at once), the 32 partial sums per column are added in warp order. (One warp per column
+ * striding over the rows — the first version — touched a different 32-byte sector with every load: 39 MB of L2
+ * traffic for 9.8 MB of data, 9 µs.)
+ */
+constexpr int kFinishThreads = 1024;
+
+inline int kspaceFinishGrid(int stride) { return stride * stride / 32 + (stride + 31) / 32 + 1; }
+
+__global__ void __launch_bounds__(kFinishThreads)
     batchKspaceFinishKernel(BatchBuffers cur, int stride, int with_ewald, int n_rows, const double* __restrict__ r_partials,
                             const double* __restrict__ g_partials, const double* __restrict__ e_partials,
                             double* __restrict__ result)
 {
+    __shared__ double s_part[kFinishThreads / 32][33];
     const int n = cur.in->n;
     const int S = stride;
     const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const int warp = threadIdx.x >> 5;
+    const int g_blocks = S * S / 32;
+    const int r_blocks = (S + 31) / 32;
+    const int block = blockIdx.x;
+    const double* src;
+    size_t ld;
+    int col;
+    bool wanted; // is this output defined (else it is written as zero)?
+    if (block < g_blocks) {
+        col = block * 32 + lane; // = a·S + m
+        src = g_partials;
+        ld = static_cast<size_t>(S) * S;
+        const int a = col / S, m = col - a * S;
+        wanted = a < m && m < n;
+    }
+    else if (block < g_blocks + r_blocks) {
+        col = (block - g_blocks) * 32 + lane;
+        src = r_partials;
+        ld = static_cast<size_t>(S);
+        wanted = col < n;
+    }
+    else {
+        col = 0;
+        src = e_partials;
+        ld = 1;
+        wanted = lane == 0;
+    }
+    double s = 0.0;
+    if (with_ewald && wanted) {
+#pragma unroll 10
+        for (int row = warp; row < n_rows; row += kFinishThreads / 32) {
+            s += __ldcg(src + static_cast<size_t>(row) * ld + col);
+        }
+    }
+    s_part[warp][lane] = s;
+    __syncthreads();
+    if (warp != 0) {
+        return;
+    }
+    double total = 0.0;
+#pragma unroll
+    for (int w = 0; w < kFinishThreads / 32; ++w) {
+        total += s_part[w][lane];
+    }
     double* u = result + 8;
     double* cross = result + 8 + 3 * S;
-    if (w < S) {
-        double s = 0.0;
-        if (with_ewald && w < n) {
-            s = warpColumnSum(r_partials, n_rows, static_cast<size_t>(S), w, lane);
-        }
-        if (lane == 0) {
-            u[2 * S + w] = s;
+    if (block < g_blocks) {
+        const int a = col / S, m = col - a * S;
+        cross[3 * S * S + m * S + a] = wanted ? total : 0.0; // stored [m][a]
+    }
+    else if (block < g_blocks + r_blocks) {
+        if (col < S) {
+            u[2 * S + col] = wanted ? total : 0.0;
         }
     }
-    else if (w < S + S * S) {
-        const int t = w - S;
-        const int a = t / S;
-        const int m = t % S;
-        double g = 0.0;
-        if (with_ewald && a < m && m < n) {
-            g = warpColumnSum(g_partials, n_rows, static_cast<size_t>(S) * S, t, lane);
-        }
-        if (lane == 0) {
-            cross[3 * S * S + m * S + a] = g; // stored [m][a]
-        }
-    }
-    else if (w == S + S * S) {
-        double e = 0.0;
-        if (with_ewald && n_rows > 0) {
-            e = warpColumnSum(e_partials, n_rows, 1, 0, lane);
-        }
-        if (lane == 0) {
-            result[0] = e;
-            result[1] = static_cast<double>(n);
-        }
+    else if (lane == 0) {
+        result[0] = (with_ewald && n_rows > 0) ? total : 0.0;
+        result[1] = static_cast<double>(n);
     }
 }
 

@@ -277,10 +277,9 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
     if (timing) {
         CUDA_CHECK(cudaEventRecord(b.ev[3], c->stream));
     }
-    const int k_finish_grid = (stride + stride * stride + 1 + kBlock / 32 - 1) / (kBlock / 32);
-    batchKspaceFinishKernel<<<k_finish_grid, kBlock, 0, c->stream>>>(cur, stride, with_ewald ? 1 : 0, n_rows,
-                                                                     b.d_r_partials.ptr, b.d_g_partials.ptr,
-                                                                     b.d_e_partials.ptr, b.d_result.ptr);
+    batchKspaceFinishKernel<<<kspaceFinishGrid(stride), kFinishThreads, 0, c->stream>>>(
+        cur, stride, with_ewald ? 1 : 0, n_rows, b.d_r_partials.ptr, b.d_g_partials.ptr, b.d_e_partials.ptr,
+        b.d_result.ptr);
     launched(c, "batchKspaceFinishKernel");
     if (fork) {
         CUDA_CHECK(cudaStreamWaitEvent(c->stream, b.ev_join, 0));
