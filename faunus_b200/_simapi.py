@@ -63,6 +63,9 @@ class SimLibrary:
         f("widom_prepare", C.c_int, [C.c_void_p, C.c_int])
         f("widom_evaluate_slice", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p])
         f("widom_collect", C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int])
+        f("rdf_create", C.c_int, [C.c_void_p, C.c_char_p])
+        f("rdf_sample", C.c_int, [C.c_void_p, C.c_int])
+        f("rdf_result", C.c_int, [C.c_void_p, C.c_int, c_double_p, C.POINTER(C.c_ulonglong), c_double_p, C.c_int])
 
     def _fn(self, name, restype, argtypes):
         fn = getattr(self.lib, f"{self.prefix}_{name}")
@@ -227,6 +230,27 @@ class Simulation:
             raise RuntimeError("all_gather returned the wrong number of insertion energies")
         self._check(self.api.widom_collect(self.handle, wid, _dp(everyone), n), "widom_collect")
         return n
+
+    # -- atomic radial distribution function ----------------------------------------------------------
+    def rdf_create(self, config: dict) -> int:
+        """`atomrdf` analysis (name1, name2, dr, slicedir, thickness); returns its id"""
+        rid = self.api.rdf_create(self.handle, json.dumps(config).encode())
+        if rid < 0:
+            raise RuntimeError(f"{self.api.prefix}_rdf_create: {self.api.error()}")
+        return rid
+
+    def rdf_sample(self, rid: int):
+        self._check(self.api.rdf_sample(self.handle, rid), "rdf_sample")
+
+    def rdf_result(self, rid: int):
+        """(r, exact pair counts per bin, g(r)) accumulated over the samples"""
+        n = self.api.rdf_result(self.handle, rid, None, None, None, 0)
+        if n < 0:
+            raise RuntimeError(f"{self.api.prefix}_rdf_result: {self.api.error()}")
+        r, g = np.zeros(n), np.zeros(n)
+        pairs = np.zeros(n, dtype=np.uint64)
+        self.api.rdf_result(self.handle, rid, _dp(r), pairs.ctypes.data_as(C.POINTER(C.c_ulonglong)), _dp(g), n)
+        return r, pairs, g
 
     def widom_result(self, wid: int, max_du: int = 1 << 20):
         s = C.c_double()

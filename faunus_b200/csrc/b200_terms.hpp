@@ -14,6 +14,7 @@
 #pragma once
 #include "../../include/faunus_b200.h"
 #include "host/energyterm.hpp"
+#include "host/analysis_rdf.hpp"
 #include "host/montecarlo.hpp"
 #include "host/potential_tables.hpp"
 #include <map>
@@ -1212,6 +1213,36 @@ class WidomB200 : public WidomInsertion
         for (int b = 0; b < count; ++b) {
             du_total[b] = host_terms[b] + du[b] + ewald_energy;
         }
+    }
+};
+
+/**
+ * `atomrdf` with the pair loop on the device: one fb_atom_rdf per sample on the accepted slot's mirror (the same
+ * mirror the energy terms keep current), exact pair counts added to the histogram. Replaces
+ * AtomRDF::sampleIdentical / sampleDifferent (src/analysis.cpp:1581-1600).
+ */
+class AtomRDFB200 : public AtomRDF
+{
+    std::shared_ptr<NonbondedB200> nonbonded;
+
+    void count() override
+    {
+        const int n_bins = std::max(static_cast<int>(histogram.size()), binsForCell());
+        histogram.resize(static_cast<size_t>(n_bins), 0ull);
+        auto& dev = *nonbonded->device();
+        fbCheck(fb_atom_rdf(dev.ctx, nonbonded->deviceSlot(), id1, id2, dr, slicedir, thickness, n_bins, histogram.data()),
+                dev.ctx, "fb_atom_rdf");
+    }
+
+  public:
+    AtomRDFB200(const Json& j, MetropolisMonteCarlo& mc)
+        : AtomRDF(j, *mc.state.spc)
+    {
+        const auto nb = mc.state.pot->find<NonbondedB200>();
+        if (nb.size() != 1) {
+            throw std::runtime_error("atomrdf on the device needs exactly one B200 non-bonded term");
+        }
+        nonbonded = nb.front();
     }
 };
 

@@ -7,6 +7,7 @@
 #include "fb_stream.cuh"
 #include "fb_cells.cuh"
 #include "fb_run.cuh"
+#include "fb_rdf.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -276,6 +277,9 @@ struct fb_ctx
         double windows = 0, moves = 0;
     } batch;
     double pair_cut2 = 0; //!< no pair energy beyond this r² (+inf when some term has no cutoff)
+    DeviceBuffer<unsigned long long> rdf_hist; //!< fb_atom_rdf
+    DeviceBuffer<int> rdf_flag;
+    bool rdf_configured = false;
 };
 
 namespace {
@@ -1368,6 +1372,48 @@ FB_API int fb_nonbonded_delta(fb_ctx* c, int s_new, int s_old, const fb_change* 
 }
 
 /** share `shard` of `n_shards` of the full-system non-bonded and reciprocal energies (multi-GPU system energy) */
+FB_API int fb_atom_rdf(fb_ctx* c, int s, int atom_id1, int atom_id2, double dr, const int* slice_dir, double thickness,
+                       int n_bins, unsigned long long* counts)
+{
+    return guarded(c, [&] {
+        flushPending(c);
+        checkSlot(c, s);
+        if (!counts || !(dr > 0.0) || n_bins < 1 || n_bins > kRdfMaxBins || atom_id1 < 0 || atom_id1 >= c->P.n_types ||
+            atom_id2 < 0 || atom_id2 >= c->P.n_types) {
+            throw CudaError{"fb_atom_rdf: bad arguments (1..12288 bins, dr > 0, known atom types)"};
+        }
+        c->rdf_hist.ensure(static_cast<size_t>(n_bins));
+        c->rdf_flag.ensure(1);
+        CUDA_CHECK(cudaMemsetAsync(c->rdf_hist.ptr, 0, sizeof(unsigned long long) * n_bins, c->stream));
+        CUDA_CHECK(cudaMemsetAsync(c->rdf_flag.ptr, 0, sizeof(int), c->stream));
+        const int tiles = (c->n_slots + kRdfTile - 1) / kRdfTile;
+        const size_t smem = sizeof(unsigned int) * static_cast<size_t>(n_bins);
+        if (!c->rdf_configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(atomRdfKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(sizeof(unsigned int) * kRdfMaxBins)));
+            c->rdf_configured = true;
+        }
+        const int sx = slice_dir ? slice_dir[0] : 0, sy = slice_dir ? slice_dir[1] : 0, sz = slice_dir ? slice_dir[2] : 0;
+        beginTiming(c, TIME_FULL);
+        atomRdfKernel<<<dim3(tiles, tiles), kRdfTile, smem, c->stream>>>(makeView(c, s), atom_id1, atom_id2, 1.0 / dr, sx, sy,
+                                                                        sz, thickness, n_bins, c->rdf_hist.ptr,
+                                                                        c->rdf_flag.ptr);
+        launched(c, "atomRdfKernel");
+        std::vector<unsigned long long> host(static_cast<size_t>(n_bins));
+        int flag = 0;
+        CUDA_CHECK(cudaMemcpyAsync(host.data(), c->rdf_hist.ptr, sizeof(unsigned long long) * n_bins, cudaMemcpyDeviceToHost,
+                                   c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(&flag, c->rdf_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        finish(c);
+        if (flag != 0) {
+            throw CudaError{"fb_atom_rdf: a distance fell beyond the last bin"};
+        }
+        for (int b = 0; b < n_bins; ++b) {
+            counts[b] += host[b];
+        }
+    });
+}
+
 FB_API int fb_system_energy_shard(fb_ctx* c, int s, int shard, int n_shards, double* nonbonded, double* reciprocal)
 {
     return guarded(c, [&] {

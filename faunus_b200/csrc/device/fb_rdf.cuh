@@ -1,0 +1,110 @@
+// Atomic radial distribution function: the distance histogram of AtomRDF (src/analysis.cpp:1556-1600) on the
+// device mirror (the dominant non-energy cost of examples/bulk, `atomrdf` every 10 steps).
+//
+//   id1 != id2 : all pairs (i of type id1, j of type id2)            AtomRDF::sampleDifferent
+//   id1 == id2 : all pairs i < j of that type                        AtomRDF::sampleIdentical
+//   distance   : minimum-image VECTOR a − b (fold by ±L when |d| > L/2, src/geometry.h:429-458), r = |d|
+//   bin        : floor(r / dr) (Equidistant2DTable<double,double>, centerbin = false, xmin = 0,
+//                src/aux/equidistant_table.h:32-40); with a slice direction the in-plane distance decides
+//                whether the pair counts and the along-axis distance is binned (src/analysis.cpp:1559-1564)
+//
+// Integer work: a block takes a 256 × 256 tile of particle pairs, counts into a shared-memory histogram
+// (32-bit, ≤ 65 536 increments per block) and adds it to the 64-bit global one — exact and order independent.
+// The arithmetic of r is spelled out without FMA contraction so that a distance lands in the same bin as on
+// the host.
+#pragma once
+#include "fb_kernels.cuh"
+
+namespace fbdev {
+
+constexpr int kRdfTile = 256;
+constexpr int kRdfMaxBins = 12288; //!< 48 kB of shared counters
+
+__global__ void __launch_bounds__(kRdfTile)
+    atomRdfKernel(SlotView V, int id1, int id2, double dxinv, int sx, int sy, int sz, double thickness, int n_bins,
+                  unsigned long long* __restrict__ hist, int* __restrict__ out_of_range)
+{
+    extern __shared__ unsigned int s_hist[];
+    __shared__ double s_x[kRdfTile], s_y[kRdfTile], s_z[kRdfTile];
+    __shared__ int s_ok[kRdfTile];
+    const int ti = blockIdx.x, tj = blockIdx.y;
+    const bool identical = id1 == id2;
+    if (identical && tj < ti) {
+        return; // i < j: the upper triangle of tiles
+    }
+    for (int b = threadIdx.x; b < n_bins; b += kRdfTile) {
+        s_hist[b] = 0u;
+    }
+    const int pj = tj * kRdfTile + threadIdx.x;
+    bool okj = false;
+    if (pj < V.n_slots) {
+        const double4 p = V.posq[pj];
+        s_x[threadIdx.x] = p.x;
+        s_y[threadIdx.x] = p.y;
+        s_z[threadIdx.x] = p.z;
+        okj = V.gid[pj] >= 0 && V.atom_id[pj] == id2;
+    }
+    s_ok[threadIdx.x] = okj ? 1 : 0;
+    const int pi = ti * kRdfTile + threadIdx.x;
+    bool oki = false;
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    if (pi < V.n_slots) {
+        const double4 p = V.posq[pi];
+        ax = p.x;
+        ay = p.y;
+        az = p.z;
+        oki = V.gid[pi] >= 0 && V.atom_id[pi] == id1;
+    }
+    __syncthreads();
+    const bool slice = sx + sy + sz > 0;
+    if (oki) {
+        const int j_begin = (identical && ti == tj) ? static_cast<int>(threadIdx.x) + 1 : 0;
+        for (int j = j_begin; j < kRdfTile; ++j) {
+            if (!s_ok[j]) {
+                continue;
+            }
+            double dx = __dsub_rn(ax, s_x[j]);
+            double dy = __dsub_rn(ay, s_y[j]);
+            double dz = __dsub_rn(az, s_z[j]);
+            if (V.len_or_zero[0] > 0.0) {
+                dx = dx > V.half[0] ? __dsub_rn(dx, V.len_or_zero[0]) : (dx < -V.half[0] ? __dadd_rn(dx, V.len_or_zero[0]) : dx);
+            }
+            if (V.len_or_zero[1] > 0.0) {
+                dy = dy > V.half[1] ? __dsub_rn(dy, V.len_or_zero[1]) : (dy < -V.half[1] ? __dadd_rn(dy, V.len_or_zero[1]) : dy);
+            }
+            if (V.len_or_zero[2] > 0.0) {
+                dz = dz > V.half[2] ? __dsub_rn(dz, V.len_or_zero[2]) : (dz < -V.half[2] ? __dadd_rn(dz, V.len_or_zero[2]) : dz);
+            }
+            double r;
+            if (slice) {
+                // in-plane part |d ∘ (1 − s)| < thickness, then the part along the slice direction is binned
+                const double px = sx ? 0.0 : dx, py = sy ? 0.0 : dy, pz = sz ? 0.0 : dz;
+                const double in_plane = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)), __dmul_rn(pz, pz)));
+                if (!(in_plane < thickness)) {
+                    continue;
+                }
+                const double qx = sx ? dx : 0.0, qy = sy ? dy : 0.0, qz = sz ? dz : 0.0;
+                r = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)), __dmul_rn(qz, qz)));
+            }
+            else {
+                r = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            }
+            const int bin = static_cast<int>(floor(__dmul_rn(r, dxinv)));
+            if (bin >= 0 && bin < n_bins) {
+                atomicAdd(&s_hist[bin], 1u);
+            }
+            else {
+                *out_of_range = 1;
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < n_bins; b += kRdfTile) {
+        const unsigned int count = s_hist[b];
+        if (count != 0u) {
+            atomicAdd(hist + b, static_cast<unsigned long long>(count));
+        }
+    }
+}
+
+} // namespace fbdev

@@ -23,6 +23,9 @@ static void fbh_replica_setup(int rank)
 }
 
 FB_DEFINE_SIM_CAPI(fbh, b200_factory, makeWidom)
+FB_DEFINE_RDF_CAPI(fbh, [](const fb::Json& j, fb::capi::Sim& s) -> std::unique_ptr<fb::AtomRDF> {
+    return std::make_unique<fb::AtomRDFB200>(j, *s.mc);
+})
 
 extern "C" __attribute__((visibility("default"))) void fbh_set_device(int device)
 {

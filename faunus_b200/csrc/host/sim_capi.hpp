@@ -5,6 +5,7 @@
 // and `<prefix>_last_error()` holds the message.
 #pragma once
 #include "montecarlo.hpp"
+#include "analysis_rdf.hpp"
 #include "replica_comm.hpp"
 #include <cstring>
 #include <thread>
@@ -34,6 +35,7 @@ struct Sim
     std::unique_ptr<ReplicaComm> comm; //!< must outlive mc (the temper move holds a reference)
     std::unique_ptr<MetropolisMonteCarlo> mc;
     std::vector<std::unique_ptr<WidomInsertion>> widoms;
+    std::vector<std::unique_ptr<AtomRDF>> rdfs;
     Change pending; //!< change of the manual trial-move protocol
 };
 
@@ -453,6 +455,52 @@ inline State& pick(Sim& s, int which)
         for (int i = 0; last_du && i < n && i < max_du; ++i) {                                               \
             last_du[i] = w.last_du[i];                                                                       \
         }                                                                                                    \
+        return n;                                                                                            \
+    }                                                                                                         \
+    }
+
+/**
+ * `<P>_rdf_*`: the atomic radial distribution function analysis. RDF: callable (const fb::Json&, fb::capi::Sim&) →
+ * std::unique_ptr<fb::AtomRDF> (the CPU pair loop in the oracle build, the device histogram in the B200 build).
+ */
+#define FB_DEFINE_RDF_CAPI(P, RDF)                                                                            \
+    extern "C" {                                                                                              \
+    __attribute__((visibility("default"))) int P##_rdf_create(void* h, const char* json_text)                \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        int id = -1;                                                                                         \
+        fb::capi::guarded([&] {                                                                              \
+            s->rdfs.push_back((RDF)(fb::Json::parse(json_text), *s));                                        \
+            id = static_cast<int>(s->rdfs.size()) - 1;                                                       \
+        });                                                                                                  \
+        return id;                                                                                           \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_rdf_sample(void* h, int id)                               \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] { s->rdfs.at(id)->sample(); });                                         \
+    }                                                                                                         \
+    /* returns the number of bins; fills r[i], pairs[i] (exact counts), g[i] for i < max */                  \
+    __attribute__((visibility("default"))) int P##_rdf_result(void* h, int id, double* r,                    \
+                                                              unsigned long long* pairs, double* g, int max) \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        int n = -1;                                                                                          \
+        fb::capi::guarded([&] {                                                                              \
+            const auto& f = *s->rdfs.at(id);                                                                 \
+            n = static_cast<int>(f.size());                                                                  \
+            for (int i = 0; i < n && i < max; ++i) {                                                         \
+                if (r) {                                                                                     \
+                    r[i] = f.distance(i);                                                                    \
+                }                                                                                            \
+                if (pairs) {                                                                                 \
+                    pairs[i] = f.pairs(i);                                                                   \
+                }                                                                                            \
+                if (g) {                                                                                     \
+                    g[i] = f.g(i);                                                                           \
+                }                                                                                            \
+            }                                                                                                \
+        });                                                                                                  \
         return n;                                                                                            \
     }                                                                                                         \
     }

@@ -366,6 +366,15 @@ int fb_debug_set_cell_capacity(fb_ctx* ctx, int capacity);
  * (fb_batch_wait + fb_run_wait), out[7] = runs */
 int fb_get_batch_timing(const fb_ctx* ctx, double out[8]);
 
+/* ---- pair distance histogram ------------------------------------------------------------------ */
+/* One sample of AtomRDF (src/analysis.cpp:1556-1600) on the slot's mirror: all pairs of active atoms of the types
+ * atom_id1, atom_id2 (i < j when the types are equal), minimum-image distance vector (src/geometry.h:429-458),
+ * bin floor(r / dr) (src/aux/equidistant_table.h:32-40); slice_dir (may be NULL) and thickness as `slicedir` /
+ * `thickness` of the analysis. The pair counts are ADDED to counts[n_bins] (n_bins <= 12288; an error if a
+ * distance falls beyond the last bin). Exact integer counts, independent of any summation order. */
+int fb_atom_rdf(fb_ctx* ctx, int slot, int atom_id1, int atom_id2, double dr, const int* slice_dir, double thickness,
+                int n_bins, unsigned long long* counts);
+
 /* ---- Ewald reciprocal space --------------------------------------------------------------- */
 int fb_ewald_configure(fb_ctx* ctx, const fb_ewald_config* config);
 /* k-vectors and A_k for the slot's current box (PolicyIonIon::updateBox); returns K in *n_kvectors */

@@ -9,6 +9,7 @@
 #include "../faunus_b200/csrc/host/sim_capi.hpp"
 #include "ewald.hpp"
 #include "nonbonded.hpp"
+#include "rdf.hpp"
 
 namespace oracle {
 
@@ -76,6 +77,9 @@ static const TermFactory factory = termFactory;
 static void fo_replica_setup(int) {}
 
 FB_DEFINE_SIM_CAPI(fo, oracle::factory, fb::capi::defaultWidom)
+FB_DEFINE_RDF_CAPI(fo, [](const fb::Json& j, fb::capi::Sim& s) -> std::unique_ptr<fb::AtomRDF> {
+    return std::make_unique<oracle::AtomRDFCpu>(j, *s.mc->state.spc);
+})
 
 #define FO_API extern "C" __attribute__((visibility("default")))
 

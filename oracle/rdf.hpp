@@ -1,0 +1,71 @@
+// ORACLE (test infrastructure only): the pair loop of AtomRDF on the CPU, restating
+// src/analysis.cpp:1556-1568 (sampleDistance), :1581-1600 (sampleIdentical / sampleDifferent; Space::findAtoms
+// = the active particles of that type in storage order) with Geometry::vdist (src/geometry.h:429-458).
+#pragma once
+#include "../faunus_b200/csrc/host/analysis_rdf.hpp"
+
+namespace oracle {
+
+class AtomRDFCpu : public fb::AtomRDF
+{
+    void sampleDistance(const fb::Point& a, const fb::Point& b)
+    {
+        const fb::Point d = spc.geometry.vdist(a, b);
+        double r;
+        if (slicedir[0] + slicedir[1] + slicedir[2] > 0) {
+            const fb::Point in_plane{slicedir[0] ? 0.0 : d.x, slicedir[1] ? 0.0 : d.y, slicedir[2] ? 0.0 : d.z};
+            if (!(in_plane.norm() < thickness)) {
+                return;
+            }
+            const fb::Point along{slicedir[0] ? d.x : 0.0, slicedir[1] ? d.y : 0.0, slicedir[2] ? d.z : 0.0};
+            r = along.norm();
+        }
+        else {
+            r = d.norm();
+        }
+        const auto i = static_cast<size_t>(bin(r));
+        if (i >= histogram.size()) {
+            histogram.resize(i + 1, 0ull);
+        }
+        histogram[i]++;
+    }
+
+    std::vector<fb::Point> findAtoms(int id) const
+    {
+        std::vector<fb::Point> found;
+        for (const auto& g : spc.groups) {
+            for (size_t i = 0; i < g.size(); ++i) {
+                const auto& p = spc.at(g, i);
+                if (p.id == id) {
+                    found.push_back(p.pos);
+                }
+            }
+        }
+        return found;
+    }
+
+    void count() override
+    {
+        if (id1 == id2) {
+            const auto atoms = findAtoms(id1);
+            for (size_t i = 0; i < atoms.size(); ++i) {
+                for (size_t j = i + 1; j < atoms.size(); ++j) {
+                    sampleDistance(atoms[i], atoms[j]);
+                }
+            }
+        }
+        else {
+            const auto first = findAtoms(id1), second = findAtoms(id2);
+            for (const auto& a : first) {
+                for (const auto& b : second) {
+                    sampleDistance(a, b);
+                }
+            }
+        }
+    }
+
+  public:
+    using fb::AtomRDF::AtomRDF;
+};
+
+} // namespace oracle

@@ -147,3 +147,18 @@ def test_window_edge_cases():
         s.sweep(5)
     assert np.array_equal(o.trace()["accepted"], g.trace()["accepted"])
     assert abs(g.drift()) < 1e-9
+
+
+def test_s1_atom_rdf_pair_count():
+    """N = 1e5: every Na-Cl pair (2.5e9) and every Na-Na pair (1.25e9) lands in exactly one bin; equal to the
+    oracle's loop on the first 4000 ions of the same configuration"""
+    cfg = s1(100)
+    g = sim(cfg, window=64)
+    n = g.num_particles
+    for names, expected in ((("Na", "Cl"), (n // 2) ** 2), (("Na", "Na"), (n // 2) * (n // 2 - 1) // 2)):
+        rid = g.rdf_create({"name1": names[0], "name2": names[1], "dr": 0.1, "file": "rdf.dat"})
+        g.rdf_sample(rid)
+        r, pairs, gr = g.rdf_result(rid)
+        assert int(pairs.sum()) == expected
+        shell = (r > 50) & (r < 200)
+        assert abs(gr[shell].mean() - 1.0) < 0.01   # an ideal-gas-like start configuration
