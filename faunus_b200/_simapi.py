@@ -65,6 +65,7 @@ class SimLibrary:
         f("widom_collect", C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int])
         f("rdf_create", C.c_int, [C.c_void_p, C.c_char_p])
         f("rdf_sample", C.c_int, [C.c_void_p, C.c_int])
+        f("rdf_sample_shard", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int])
         f("rdf_result", C.c_int, [C.c_void_p, C.c_int, c_double_p, C.POINTER(C.c_ulonglong), c_double_p, C.c_int])
 
     def _fn(self, name, restype, argtypes):
@@ -241,6 +242,11 @@ class Simulation:
 
     def rdf_sample(self, rid: int):
         self._check(self.api.rdf_sample(self.handle, rid), "rdf_sample")
+
+    def rdf_sample_shard(self, rid: int, rank: int, size: int):
+        """This rank's share of one sample (every rank holds the same configuration). The pair counts of the ranks
+        add up to the unsharded histogram — sum them with an integer all-reduce (``rdf_result(rid)[1]``)."""
+        self._check(self.api.rdf_sample_shard(self.handle, rid, rank, size), "rdf_sample_shard")
 
     def rdf_result(self, rid: int):
         """(r, exact pair counts per bin, g(r)) accumulated over the samples"""

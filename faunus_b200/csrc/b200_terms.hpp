@@ -1225,12 +1225,13 @@ class AtomRDFB200 : public AtomRDF
 {
     std::shared_ptr<NonbondedB200> nonbonded;
 
-    void count() override
+    void count(int shard, int n_shards) override
     {
         const int n_bins = std::max(static_cast<int>(histogram.size()), binsForCell());
         histogram.resize(static_cast<size_t>(n_bins), 0ull);
         auto& dev = *nonbonded->device();
-        fbCheck(fb_atom_rdf(dev.ctx, nonbonded->deviceSlot(), id1, id2, dr, slicedir, thickness, n_bins, histogram.data()),
+        fbCheck(fb_atom_rdf(dev.ctx, nonbonded->deviceSlot(), id1, id2, dr, slicedir, thickness, shard, n_shards, n_bins,
+                            histogram.data()),
                 dev.ctx, "fb_atom_rdf");
     }
 

@@ -1373,11 +1373,14 @@ FB_API int fb_nonbonded_delta(fb_ctx* c, int s_new, int s_old, const fb_change* 
 
 /** share `shard` of `n_shards` of the full-system non-bonded and reciprocal energies (multi-GPU system energy) */
 FB_API int fb_atom_rdf(fb_ctx* c, int s, int atom_id1, int atom_id2, double dr, const int* slice_dir, double thickness,
-                       int n_bins, unsigned long long* counts)
+                       int shard, int n_shards, int n_bins, unsigned long long* counts)
 {
     return guarded(c, [&] {
         flushPending(c);
         checkSlot(c, s);
+        if (n_shards < 1 || shard < 0 || shard >= n_shards) {
+            throw CudaError{"fb_atom_rdf: bad shard arguments"};
+        }
         if (!counts || !(dr > 0.0) || n_bins < 1 || n_bins > kRdfMaxBins || atom_id1 < 0 || atom_id1 >= c->P.n_types ||
             atom_id2 < 0 || atom_id2 >= c->P.n_types) {
             throw CudaError{"fb_atom_rdf: bad arguments (1..12288 bins, dr > 0, known atom types)"};
@@ -1395,9 +1398,9 @@ FB_API int fb_atom_rdf(fb_ctx* c, int s, int atom_id1, int atom_id2, double dr, 
         }
         const int sx = slice_dir ? slice_dir[0] : 0, sy = slice_dir ? slice_dir[1] : 0, sz = slice_dir ? slice_dir[2] : 0;
         beginTiming(c, TIME_FULL);
-        atomRdfKernel<<<dim3(tiles, tiles), kRdfTile, smem, c->stream>>>(makeView(c, s), atom_id1, atom_id2, 1.0 / dr, sx, sy,
-                                                                        sz, thickness, n_bins, c->rdf_hist.ptr,
-                                                                        c->rdf_flag.ptr);
+        atomRdfKernel<<<dim3((tiles + n_shards - 1) / n_shards, tiles), kRdfTile, smem, c->stream>>>(
+            makeView(c, s), atom_id1, atom_id2, 1.0 / dr, sx, sy, sz, thickness, n_bins, shard, n_shards, c->rdf_hist.ptr,
+            c->rdf_flag.ptr);
         launched(c, "atomRdfKernel");
         std::vector<unsigned long long> host(static_cast<size_t>(n_bins));
         int flag = 0;

@@ -22,12 +22,15 @@ constexpr int kRdfMaxBins = 12288; //!< 48 kB of shared counters
 
 __global__ void __launch_bounds__(kRdfTile)
     atomRdfKernel(SlotView V, int id1, int id2, double dxinv, int sx, int sy, int sz, double thickness, int n_bins,
-                  unsigned long long* __restrict__ hist, int* __restrict__ out_of_range)
+                  int shard, int n_shards, unsigned long long* __restrict__ hist, int* __restrict__ out_of_range)
 {
     extern __shared__ unsigned int s_hist[];
     __shared__ double s_x[kRdfTile], s_y[kRdfTile], s_z[kRdfTile];
     __shared__ int s_ok[kRdfTile];
-    const int ti = blockIdx.x, tj = blockIdx.y;
+    const int ti = blockIdx.x * n_shards + shard, tj = blockIdx.y; // tile rows dealt round robin to the shards
+    if (ti * kRdfTile >= V.n_slots) {
+        return;
+    }
     const bool identical = id1 == id2;
     if (identical && tj < ti) {
         return; // i < j: the upper triangle of tiles

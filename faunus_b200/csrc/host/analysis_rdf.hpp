@@ -21,8 +21,11 @@ class AtomRDF
     double volume_sum = 0;                     //!< Average<double> mean_volume
     unsigned long volume_count = 0;
 
-    /** add the pair distances of the current configuration to `histogram` (grow it as needed) */
-    virtual void count() = 0;
+    /**
+     * Add the pair distances of the current configuration to `histogram` (grow it as needed); share `shard` of
+     * `n_shards` of the pairs when the sample is split over ranks (any split: the counts are integers)
+     */
+    virtual void count(int shard, int n_shards) = 0;
 
   public:
     AtomRDF(const Json& j, const Space& spc)
@@ -69,7 +72,18 @@ class AtomRDF
     {
         volume_sum += spc.geometry.getVolume();
         volume_count++;
-        count();
+        count(0, 1);
+    }
+
+    /** this rank's share of one sample; the histograms of the ranks add up to the unsharded one */
+    void sampleShard(int shard, int n_shards)
+    {
+        if (n_shards < 1 || shard < 0 || shard >= n_shards) {
+            throw std::runtime_error("atomrdf: bad shard");
+        }
+        volume_sum += spc.geometry.getVolume();
+        volume_count++;
+        count(shard, n_shards);
     }
 
     size_t size() const { return histogram.size(); }

@@ -480,6 +480,11 @@ inline State& pick(Sim& s, int which)
         auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
         return fb::capi::guarded([&] { s->rdfs.at(id)->sample(); });                                         \
     }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_rdf_sample_shard(void* h, int id, int shard, int n_shards) \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] { s->rdfs.at(id)->sampleShard(shard, n_shards); });                     \
+    }                                                                                                         \
     /* returns the number of bins; fills r[i], pairs[i] (exact counts), g[i] for i < max */                  \
     __attribute__((visibility("default"))) int P##_rdf_result(void* h, int id, double* r,                    \
                                                               unsigned long long* pairs, double* g, int max) \

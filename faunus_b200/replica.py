@@ -136,3 +136,19 @@ def reduce_in_rank_order(values, device=None):
     for t in everyone:
         total += t.cpu().numpy()
     return total
+
+
+def all_reduce_pair_counts(counts, device=None):
+    """Sum of the per-rank pair-distance histograms of :meth:`Simulation.rdf_sample_shard` over the default process
+    group (an integer all-reduce: exact, whatever the order; NCCL between GPUs, gloo on CPU). Histograms that grew to
+    different lengths on the ranks are padded to the longest one."""
+    import torch
+    import torch.distributed as dist
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    length = torch.tensor([len(counts)], dtype=torch.int64, device=device)
+    dist.all_reduce(length, op=dist.ReduceOp.MAX)
+    total = torch.zeros(int(length.item()), dtype=torch.int64, device=device)
+    total[: len(counts)] = torch.from_numpy(np.ascontiguousarray(counts).astype(np.int64)).to(device)
+    dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    return total.cpu().numpy().astype(np.uint64)

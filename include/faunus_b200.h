@@ -371,9 +371,11 @@ int fb_get_batch_timing(const fb_ctx* ctx, double out[8]);
  * atom_id1, atom_id2 (i < j when the types are equal), minimum-image distance vector (src/geometry.h:429-458),
  * bin floor(r / dr) (src/aux/equidistant_table.h:32-40); slice_dir (may be NULL) and thickness as `slicedir` /
  * `thickness` of the analysis. The pair counts are ADDED to counts[n_bins] (n_bins <= 12288; an error if a
- * distance falls beyond the last bin). Exact integer counts, independent of any summation order. */
+ * distance falls beyond the last bin). Exact integer counts, independent of any summation order — so the work
+ * shards over GPUs without a second thought: shard `shard` of `n_shards` takes every n_shards-th row of 256 first
+ * particles, the histograms of the shards add up (an integer all-reduce) to the unsharded one. */
 int fb_atom_rdf(fb_ctx* ctx, int slot, int atom_id1, int atom_id2, double dr, const int* slice_dir, double thickness,
-                int n_bins, unsigned long long* counts);
+                int shard, int n_shards, int n_bins, unsigned long long* counts);
 
 /* ---- Ewald reciprocal space --------------------------------------------------------------- */
 int fb_ewald_configure(fb_ctx* ctx, const fb_ewald_config* config);

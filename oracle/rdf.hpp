@@ -44,11 +44,12 @@ class AtomRDFCpu : public fb::AtomRDF
         return found;
     }
 
-    void count() override
+    void count(int shard, int n_shards) override
     {
+        const auto stride = static_cast<size_t>(n_shards);
         if (id1 == id2) {
             const auto atoms = findAtoms(id1);
-            for (size_t i = 0; i < atoms.size(); ++i) {
+            for (size_t i = static_cast<size_t>(shard); i < atoms.size(); i += stride) {
                 for (size_t j = i + 1; j < atoms.size(); ++j) {
                     sampleDistance(atoms[i], atoms[j]);
                 }
@@ -56,9 +57,9 @@ class AtomRDFCpu : public fb::AtomRDF
         }
         else {
             const auto first = findAtoms(id1), second = findAtoms(id2);
-            for (const auto& a : first) {
+            for (size_t i = static_cast<size_t>(shard); i < first.size(); i += stride) {
                 for (const auto& b : second) {
-                    sampleDistance(a, b);
+                    sampleDistance(first[i], b);
                 }
             }
         }

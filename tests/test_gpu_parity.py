@@ -658,3 +658,19 @@ def test_atom_rdf_counts_are_exact(bulk_input, water_input, case):
     assert np.array_equal(pairs_o[:n], pairs_g[:n])
     assert np.array_equal(r_o[:n], r_g[:n])
     assert np.allclose(g_o[:n], g_g[:n], rtol=1e-12, atol=0)
+
+
+def test_atom_rdf_shards_add_up(bulk_input):
+    """fb_atom_rdf split over three 'GPUs' (tile rows dealt round robin): the integer histograms add up exactly"""
+    g = b200_sim(bulk_input, 64)
+    g.sweep(1)
+    cfg = {"name1": "Na", "name2": "Na", "dr": 0.1, "file": "rdf.dat"}
+    whole = g.rdf_create(cfg)
+    g.rdf_sample(whole)
+    parts = []
+    for rank in range(3):
+        rid = g.rdf_create(cfg)
+        g.rdf_sample_shard(rid, rank, 3)
+        parts.append(g.rdf_result(rid)[1])
+    assert all(p.sum() > 0 for p in parts)
+    assert np.array_equal(sum(parts), g.rdf_result(whole)[1])

@@ -14,6 +14,7 @@ from conftest import small_electrolyte
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ANALYSIS = {"molecule": "ghost", "ninsert": 37}  # odd on purpose: ragged slices
+RDF = {"name1": "Na", "name2": "Cl", "dr": 0.2, "file": "rdf.dat"}
 
 
 def widom_config():
@@ -81,7 +82,15 @@ def _gloo_worker(rank, world, port, out_dir):
         sim.sweep(1)
         assert sim.widom_sample_sharded(w, rank, world, gather) == ANALYSIS["ninsert"]
     res = sim.widom_result(w)
-    json.dump({"sum_exp": res["sum_exp"], "count": res["count"], "last_du": res["last_du"].tolist()},
+    # pair-distance histogram: every rank counts its share of the pairs, an integer all-reduce adds them up
+    from faunus_b200.replica import all_reduce_pair_counts
+    rdf = sim.rdf_create(RDF)
+    sim.rdf_sample_shard(rdf, rank, world)
+    local = sim.rdf_result(rdf)[1]
+    local_pairs = int(local.sum())
+    counts = all_reduce_pair_counts(local)
+    json.dump({"sum_exp": res["sum_exp"], "count": res["count"], "last_du": res["last_du"].tolist(),
+               "rdf": counts.tolist(), "rdf_local_pairs": local_pairs},
               open(os.path.join(out_dir, f"rank{rank}.json"), "w"))
     sim.close()
     dist.destroy_process_group()
@@ -96,9 +105,16 @@ def test_widom_sharded_gloo_world2(tmp_path):
         ref.sweep(1)
         ref.widom_sample(wr, 1)
     want = ref.widom_result(wr)
+    rdf = ref.rdf_create(RDF)
+    ref.rdf_sample(rdf)
+    want_rdf = ref.rdf_result(rdf)[1]
     mp.spawn(_gloo_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     for rank in range(2):
         got = json.load(open(tmp_path / f"rank{rank}.json"))
         assert got["count"] == want["count"]
         assert got["sum_exp"] == want["sum_exp"]
         assert got["last_du"] == want["last_du"].tolist()
+        n = max(len(got["rdf"]), len(want_rdf))
+        padded = lambda a: np.pad(np.asarray(a, dtype=np.int64), (0, n - len(a)))
+        assert np.array_equal(padded(got["rdf"]), padded(want_rdf.astype(np.int64)))
+        assert 0 < got["rdf_local_pairs"] < int(want_rdf.sum())
