@@ -279,6 +279,8 @@ struct fb_ctx
     double pair_cut2 = 0; //!< no pair energy beyond this r² (+inf when some term has no cutoff)
     DeviceBuffer<unsigned long long> rdf_hist; //!< fb_atom_rdf
     DeviceBuffer<int> rdf_flag;
+    DeviceBuffer<double4> rdf_list[2];
+    DeviceBuffer<int> rdf_n;
     bool rdf_configured = false;
 };
 
@@ -1389,7 +1391,13 @@ FB_API int fb_atom_rdf(fb_ctx* c, int s, int atom_id1, int atom_id2, double dr, 
         c->rdf_flag.ensure(1);
         CUDA_CHECK(cudaMemsetAsync(c->rdf_hist.ptr, 0, sizeof(unsigned long long) * n_bins, c->stream));
         CUDA_CHECK(cudaMemsetAsync(c->rdf_flag.ptr, 0, sizeof(int), c->stream));
-        const int tiles = (c->n_slots + kRdfTile - 1) / kRdfTile;
+        // the particles of the two types, compacted (all threads and all inner iterations of the tiles do work)
+        c->rdf_list[0].ensure(static_cast<size_t>(c->n_slots));
+        c->rdf_list[1].ensure(static_cast<size_t>(c->n_slots));
+        c->rdf_n.ensure(2);
+        CUDA_CHECK(cudaMemsetAsync(c->rdf_n.ptr, 0, 2 * sizeof(int), c->stream));
+        const bool identical = atom_id1 == atom_id2;
+        const int tiles = (c->n_slots + kRdfTile - 1) / kRdfTile; // upper bound: blocks beyond the lists return
         const size_t smem = sizeof(unsigned int) * static_cast<size_t>(n_bins);
         if (!c->rdf_configured) {
             CUDA_CHECK(cudaFuncSetAttribute(atomRdfKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1398,9 +1406,13 @@ FB_API int fb_atom_rdf(fb_ctx* c, int s, int atom_id1, int atom_id2, double dr, 
         }
         const int sx = slice_dir ? slice_dir[0] : 0, sy = slice_dir ? slice_dir[1] : 0, sz = slice_dir ? slice_dir[2] : 0;
         beginTiming(c, TIME_FULL);
+        atomRdfCompactKernel<<<1, kRdfCompactThreads, 0, c->stream>>>(makeView(c, s), atom_id1, atom_id2,
+                                                                      c->rdf_list[0].ptr, c->rdf_list[1].ptr,
+                                                                      c->rdf_n.ptr);
+        launched(c, "atomRdfCompactKernel");
         atomRdfKernel<<<dim3((tiles + n_shards - 1) / n_shards, tiles), kRdfTile, smem, c->stream>>>(
-            makeView(c, s), atom_id1, atom_id2, 1.0 / dr, sx, sy, sz, thickness, n_bins, shard, n_shards, c->rdf_hist.ptr,
-            c->rdf_flag.ptr);
+            makeView(c, s), c->rdf_list[0].ptr, c->rdf_list[1].ptr, c->rdf_n.ptr, identical, 1.0 / dr, sx, sy, sz, thickness,
+            n_bins, shard, n_shards, c->rdf_hist.ptr, c->rdf_flag.ptr);
         launched(c, "atomRdfKernel");
         std::vector<unsigned long long> host(static_cast<size_t>(n_bins));
         int flag = 0;

@@ -8,8 +8,9 @@
 //                src/aux/equidistant_table.h:32-40); with a slice direction the in-plane distance decides
 //                whether the pair counts and the along-axis distance is binned (src/analysis.cpp:1559-1564)
 //
-// Integer work: a block takes a 256 × 256 tile of particle pairs, counts into a shared-memory histogram
-// (32-bit, ≤ 65 536 increments per block) and adds it to the 64-bit global one — exact and order independent.
+// Integer work: the particles of the two types are compacted first (stable), then a block takes a 256 × 256 tile
+// of pairs of the two lists, counts into a shared-memory histogram (32-bit, ≤ 65 536 increments per block) and
+// adds it to the 64-bit global one — exact and order independent.
 // The arithmetic of r is spelled out without FMA contraction so that a distance lands in the same bin as on
 // the host.
 #pragma once
@@ -20,52 +21,117 @@ namespace fbdev {
 constexpr int kRdfTile = 256;
 constexpr int kRdfMaxBins = 12288; //!< 48 kB of shared counters
 
+/**
+ * Positions of the active particles of type id1 (list 0) and id2 (list 1; unused when the types are equal),
+ * compacted IN STORAGE ORDER so that every thread of the histogram kernel has a particle and every inner iteration
+ * a pair. Stable (one block walks the mirror 1024 slots at a time, ballot + scan): the ranks of a sharded sample
+ * must cut the very same lists into tiles.
+ */
+constexpr int kRdfCompactThreads = 1024;
+
+__global__ void __launch_bounds__(kRdfCompactThreads)
+    atomRdfCompactKernel(SlotView V, int id1, int id2, double4* __restrict__ list0, double4* __restrict__ list1,
+                         int* __restrict__ n_list /*[2]*/)
+{
+    __shared__ int s_warp[2][32];
+    __shared__ int s_total[2];
+    __shared__ int s_base[2];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned below = (1u << lane) - 1u;
+    if (threadIdx.x < 2) {
+        s_base[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (int start = 0; start < V.n_slots; start += kRdfCompactThreads) {
+        const int j = start + threadIdx.x;
+        bool f0 = false, f1 = false;
+        double4 p = make_double4(0, 0, 0, 0);
+        if (j < V.n_slots && V.gid[j] >= 0) {
+            const int id = V.atom_id[j];
+            f0 = id == id1;
+            f1 = id == id2 && id1 != id2;
+            p = V.posq[j];
+        }
+        const unsigned b0 = __ballot_sync(0xffffffffu, f0);
+        const unsigned b1 = __ballot_sync(0xffffffffu, f1);
+        if (lane == 0) {
+            s_warp[0][warp] = __popc(b0);
+            s_warp[1][warp] = __popc(b1);
+        }
+        __syncthreads();
+        if (warp < 2) { // warp k scans the 32 warp counts of list k
+            const int count = s_warp[warp][lane];
+            int inclusive = count;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, inclusive, o);
+                if (lane >= o) {
+                    inclusive += up;
+                }
+            }
+            s_warp[warp][lane] = inclusive - count;
+            if (lane == 31) {
+                s_total[warp] = inclusive;
+            }
+        }
+        __syncthreads();
+        if (f0) {
+            list0[s_base[0] + s_warp[0][warp] + __popc(b0 & below)] = p;
+        }
+        if (f1) {
+            list1[s_base[1] + s_warp[1][warp] + __popc(b1 & below)] = p;
+        }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            s_base[threadIdx.x] += s_total[threadIdx.x];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 2) {
+        n_list[threadIdx.x] = s_base[threadIdx.x];
+    }
+}
+
 __global__ void __launch_bounds__(kRdfTile)
-    atomRdfKernel(SlotView V, int id1, int id2, double dxinv, int sx, int sy, int sz, double thickness, int n_bins,
-                  int shard, int n_shards, unsigned long long* __restrict__ hist, int* __restrict__ out_of_range)
+    atomRdfKernel(SlotView V, const double4* __restrict__ list0, const double4* __restrict__ list1,
+                  const int* __restrict__ n_list, bool identical, double dxinv, int sx, int sy, int sz, double thickness,
+                  int n_bins, int shard, int n_shards, unsigned long long* __restrict__ hist, int* __restrict__ out_of_range)
 {
     extern __shared__ unsigned int s_hist[];
     __shared__ double s_x[kRdfTile], s_y[kRdfTile], s_z[kRdfTile];
-    __shared__ int s_ok[kRdfTile];
+    const int n_i = n_list[0];
+    const int n_j = identical ? n_i : n_list[1];
+    const double4* __restrict__ list_j = identical ? list0 : list1;
     const int ti = blockIdx.x * n_shards + shard, tj = blockIdx.y; // tile rows dealt round robin to the shards
-    if (ti * kRdfTile >= V.n_slots) {
-        return;
-    }
-    const bool identical = id1 == id2;
-    if (identical && tj < ti) {
-        return; // i < j: the upper triangle of tiles
+    if (ti * kRdfTile >= n_i || tj * kRdfTile >= n_j || (identical && tj < ti)) {
+        return; // beyond the lists; i < j: the upper triangle of tiles
     }
     for (int b = threadIdx.x; b < n_bins; b += kRdfTile) {
         s_hist[b] = 0u;
     }
     const int pj = tj * kRdfTile + threadIdx.x;
-    bool okj = false;
-    if (pj < V.n_slots) {
-        const double4 p = V.posq[pj];
+    if (pj < n_j) {
+        const double4 p = list_j[pj];
         s_x[threadIdx.x] = p.x;
         s_y[threadIdx.x] = p.y;
         s_z[threadIdx.x] = p.z;
-        okj = V.gid[pj] >= 0 && V.atom_id[pj] == id2;
     }
-    s_ok[threadIdx.x] = okj ? 1 : 0;
+    const int j_end = min(kRdfTile, n_j - tj * kRdfTile);
     const int pi = ti * kRdfTile + threadIdx.x;
-    bool oki = false;
+    const bool oki = pi < n_i;
     double ax = 0.0, ay = 0.0, az = 0.0;
-    if (pi < V.n_slots) {
-        const double4 p = V.posq[pi];
+    if (oki) {
+        const double4 p = list0[pi];
         ax = p.x;
         ay = p.y;
         az = p.z;
-        oki = V.gid[pi] >= 0 && V.atom_id[pi] == id1;
     }
     __syncthreads();
     const bool slice = sx + sy + sz > 0;
     if (oki) {
         const int j_begin = (identical && ti == tj) ? static_cast<int>(threadIdx.x) + 1 : 0;
-        for (int j = j_begin; j < kRdfTile; ++j) {
-            if (!s_ok[j]) {
-                continue;
-            }
+        for (int j = j_begin; j < j_end; ++j) {
             double dx = __dsub_rn(ax, s_x[j]);
             double dy = __dsub_rn(ay, s_y[j]);
             double dz = __dsub_rn(az, s_z[j]);
