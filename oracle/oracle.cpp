@@ -10,6 +10,7 @@
 #include "ewald.hpp"
 #include "nonbonded.hpp"
 #include "rdf.hpp"
+#include "window_shadow.hpp"
 
 namespace oracle {
 
@@ -82,6 +83,33 @@ FB_DEFINE_RDF_CAPI(fo, [](const fb::Json& j, fb::capi::Sim& s) -> std::unique_pt
 })
 
 #define FO_API extern "C" __attribute__((visibility("default")))
+
+/**
+ * Test hook: run the windowed engine of `h` against a CPU stand-in for the device (window_shadow.hpp) built from the
+ * same input `json_text`; `moves` proposals per evaluation. Only for inputs whose moves are all `transrot`.
+ */
+FO_API int fo_sim_set_shadow_window(void* h, const char* json_text, int moves)
+{
+    auto* s = static_cast<fb::capi::Sim*>(h);
+    return fb::capi::guarded([&] {
+        auto shadow = std::make_unique<fb::MetropolisMonteCarlo>(fb::Json::parse(json_text), oracle::factory, nullptr);
+        s->mc->window_evaluator = std::make_unique<oracle::ShadowWindowEvaluator>(*s->mc, std::move(shadow), moves);
+    });
+}
+
+/** out[0] = conditional proposals shipped, out[1] = evaluations queued behind another one, out[2] = evaluations */
+FO_API int fo_sim_shadow_stats(void* h, double out[3])
+{
+    auto* s = static_cast<fb::capi::Sim*>(h);
+    auto* e = dynamic_cast<oracle::ShadowWindowEvaluator*>(s->mc->window_evaluator.get());
+    if (e == nullptr) {
+        return -1;
+    }
+    out[0] = static_cast<double>(e->conditional_proposals);
+    out[1] = static_cast<double>(e->queued_evaluations);
+    out[2] = static_cast<double>(e->evaluations);
+    return 0;
+}
 
 /** Andrea spline of a named test function; pins src/tabulate.h:313-365 */
 FO_API int fo_andrea_test(double utol, double ftol, double xmin, double xmax, double* knots, int max_knots,
