@@ -63,6 +63,9 @@ class SimLibrary:
         f("widom_prepare", C.c_int, [C.c_void_p, C.c_int])
         f("widom_evaluate_slice", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p])
         f("widom_collect", C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int])
+        f("virtualvolume_create", C.c_int, [C.c_void_p, C.c_char_p])
+        f("virtualvolume_sample", C.c_int, [C.c_void_p, C.c_int])
+        f("virtualvolume_result", C.c_int, [C.c_void_p, C.c_int, c_double_p])
         f("rdf_create", C.c_int, [C.c_void_p, C.c_char_p])
         f("rdf_sample", C.c_int, [C.c_void_p, C.c_int])
         f("rdf_sample_shard", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int])
@@ -231,6 +234,22 @@ class Simulation:
             raise RuntimeError("all_gather returned the wrong number of insertion energies")
         self._check(self.api.widom_collect(self.handle, wid, _dp(everyone), n), "widom_collect")
         return n
+
+    # -- virtual volume move (excess pressure) --------------------------------------------------------
+    def virtualvolume_create(self, config: dict) -> int:
+        """`virtualvolume` analysis (dV, scaling); returns its id"""
+        vid = self.api.virtualvolume_create(self.handle, json.dumps(config).encode())
+        if vid < 0:
+            raise RuntimeError(f"{self.api.prefix}_virtualvolume_create: {self.api.error()}")
+        return vid
+
+    def virtualvolume_sample(self, vid: int):
+        self._check(self.api.virtualvolume_sample(self.handle, vid), "virtualvolume_sample")
+
+    def virtualvolume_result(self, vid: int) -> dict:
+        out = np.zeros(4)
+        self._check(self.api.virtualvolume_result(self.handle, vid, _dp(out)), "virtualvolume_result")
+        return {"sum_exp": out[0], "count": int(out[1]), "last_du": out[2], "excess_pressure_kT_per_A3": out[3]}
 
     # -- atomic radial distribution function ----------------------------------------------------------
     def rdf_create(self, config: dict) -> int:

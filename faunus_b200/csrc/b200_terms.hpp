@@ -111,6 +111,12 @@ class DeviceContext
     uint64_t fast_key = 0;
     double fast_u_new = 0, fast_u_old = 0, fast_ew_new = 0, fast_ew_old = 0;
     const Space* spaces[2] = {nullptr, nullptr}; //!< Space of the instance bound to each slot
+    /**
+     * A caller that mutates a Space, asks for energy(everything) and puts the Space back without ever calling
+     * updateState or sync (VirtualVolumeMove, src/analysis.cpp:825-843) leaves the mirror with whatever it was
+     * refreshed from last. Such a refresh marks the slot; whoever touches the mirror next brings it back in step.
+     */
+    bool unsynchronised[2] = {false, false};
 
     /** cheap identity of a single-group Change (group, flags, indices) */
     static uint64_t changeKey(const Change& c)
@@ -221,6 +227,17 @@ class DeviceContext
                                 static_cast<int>(groups.size())),
                 ctx, "fb_upload_space");
         cache_valid = false;
+    }
+
+    /** the mirrors that were last refreshed from an unsynchronised Space := the Spaces as they are now */
+    void resynchronise()
+    {
+        for (int slot = 0; slot < 2; ++slot) {
+            if (unsynchronised[slot] && spaces[slot] != nullptr) {
+                unsynchronised[slot] = false;
+                uploadSpace(slot, *spaces[slot]);
+            }
+        }
     }
 
     /** push the groups/particles a partial Change lists from `spc` into `slot` */
@@ -377,6 +394,7 @@ class NonbondedB200 : public EnergyTerm
         if (!change) {
             return;
         }
+        dev->resynchronise();
         dev->fast_staged = false;
         if (stageFastMove(change)) {
             return;
@@ -399,6 +417,10 @@ class NonbondedB200 : public EnergyTerm
         if (change.matter_change) {
             throw std::runtime_error("matter_change (speciation) is outside the B200 hot-path scope");
         }
+        if (change.everything || change.volume_change) {
+            dev->unsynchronised[slot] = false; // refreshed below (or by updateState just now) anyway
+        }
+        dev->resynchronise();
         if (dev->fast_staged && dev->fast_key == DeviceContext::changeKey(change)) {
             if (state == MonteCarloState::TRIAL) {
                 if (!dev->fast_evaluated) {
@@ -431,6 +453,7 @@ class NonbondedB200 : public EnergyTerm
             }
             else {
                 dev->uploadSpace(slot, spc);
+                dev->unsynchronised[slot] = true; // the caller may put the Space back without telling anybody
             }
         }
         double u = 0.0;
@@ -455,6 +478,7 @@ class NonbondedB200 : public EnergyTerm
         if (!other || other->dev != dev) {
             throw std::runtime_error("sync error");
         }
+        dev->resynchronise();
         if (dev->fast_staged && dev->fast_key == DeviceContext::changeKey(change)) {
             // accepted.sync(trial) = accept, trial.sync(accepted) = reject (src/montecarlo.cpp:167-175)
             if (!dev->fast_evaluated) {
@@ -817,6 +841,7 @@ class B200WindowEvaluator : public WindowEvaluator
 
     void submitGroups(const std::vector<WindowProposal>& all, int first, int n)
     {
+        dev->resynchronise();
         const WindowProposal* window = all.data() + first;
         group_moves.resize(static_cast<size_t>(n));
         first_atom.assign(static_cast<size_t>(n) + 1, 0);
@@ -996,6 +1021,7 @@ class B200WindowEvaluator : public WindowEvaluator
 
     void submitPrepared() override
     {
+        dev->resynchronise();
         dev->fast_staged = false;
         dev->cache_valid = false;
         fbCheck(fb_run_submit(dev->ctx, static_cast<int>(run_moves.size()), run_moves.data(), with_ewald ? 1 : 0,
@@ -1018,6 +1044,7 @@ class B200WindowEvaluator : public WindowEvaluator
             return;
         }
         packMoves(window.data() + first, n);
+        dev->resynchronise();
         dev->fast_staged = false;
         dev->cache_valid = false;
         fbCheck(fb_batch_submit(dev->ctx, n, moves.data(), with_ewald ? 1 : 0), dev->ctx, "fb_batch_submit");
@@ -1170,6 +1197,7 @@ class WidomB200 : public WidomInsertion
         if (count == 0) {
             return;
         }
+        nonbonded->device()->resynchronise();
         const Change& change = prepared.change;
         const size_t gi = change.groups.at(0).group_index;
         auto& group = spc.groups.at(gi);
@@ -1230,6 +1258,7 @@ class AtomRDFB200 : public AtomRDF
         const int n_bins = std::max(static_cast<int>(histogram.size()), binsForCell());
         histogram.resize(static_cast<size_t>(n_bins), 0ull);
         auto& dev = *nonbonded->device();
+        dev.resynchronise();
         fbCheck(fb_atom_rdf(dev.ctx, nonbonded->deviceSlot(), id1, id2, dr, slicedir, thickness, shard, n_shards, n_bins,
                             histogram.data()),
                 dev.ctx, "fb_atom_rdf");

@@ -23,6 +23,7 @@ static void fbh_replica_setup(int rank)
 }
 
 FB_DEFINE_SIM_CAPI(fbh, b200_factory, makeWidom)
+FB_DEFINE_VIRTUALVOLUME_CAPI(fbh)
 FB_DEFINE_RDF_CAPI(fbh, [](const fb::Json& j, fb::capi::Sim& s) -> std::unique_ptr<fb::AtomRDF> {
     return std::make_unique<fb::AtomRDFB200>(j, *s.mc);
 })
@@ -218,6 +219,7 @@ extern "C" __attribute__((visibility("default"))) int fbh_system_energy_shard(vo
             throw std::runtime_error("exactly one B200 non-bonded term expected");
         }
         auto& t = *terms.front();
+        t.device()->resynchronise();
         fb::fbCheck(fb_system_energy_shard(t.device()->ctx, t.deviceSlot(), shard, n_shards, &out[0], &out[1]),
                     t.device()->ctx, "fb_system_energy_shard");
     });

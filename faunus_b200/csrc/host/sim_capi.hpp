@@ -6,6 +6,7 @@
 #pragma once
 #include "montecarlo.hpp"
 #include "analysis_rdf.hpp"
+#include "analysis_virtual.hpp"
 #include "replica_comm.hpp"
 #include <cstring>
 #include <thread>
@@ -36,6 +37,7 @@ struct Sim
     std::unique_ptr<MetropolisMonteCarlo> mc;
     std::vector<std::unique_ptr<WidomInsertion>> widoms;
     std::vector<std::unique_ptr<AtomRDF>> rdfs;
+    std::vector<std::unique_ptr<VirtualVolumeMove>> virtual_volumes;
     Change pending; //!< change of the manual trial-move protocol
 };
 
@@ -456,6 +458,39 @@ inline State& pick(Sim& s, int which)
             last_du[i] = w.last_du[i];                                                                       \
         }                                                                                                    \
         return n;                                                                                            \
+    }                                                                                                         \
+    }
+
+/** `<P>_virtualvolume_*`: the virtual volume move analysis (host code only; energies from the Hamiltonian of `h`) */
+#define FB_DEFINE_VIRTUALVOLUME_CAPI(P)                                                                       \
+    extern "C" {                                                                                              \
+    __attribute__((visibility("default"))) int P##_virtualvolume_create(void* h, const char* json_text)      \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        int id = -1;                                                                                         \
+        fb::capi::guarded([&] {                                                                              \
+            s->virtual_volumes.push_back(std::make_unique<fb::VirtualVolumeMove>(                            \
+                fb::Json::parse(json_text), *s->mc->state.spc, *s->mc->state.pot));                          \
+            id = static_cast<int>(s->virtual_volumes.size()) - 1;                                            \
+        });                                                                                                  \
+        return id;                                                                                           \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_virtualvolume_sample(void* h, int id)                     \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] { s->virtual_volumes.at(id)->sample(); });                              \
+    }                                                                                                         \
+    /* out[0] = Σ exp(−ΔU), out[1] = samples, out[2] = last ΔU, out[3] = excess pressure / kT Å⁻³ */         \
+    __attribute__((visibility("default"))) int P##_virtualvolume_result(void* h, int id, double out[4])      \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] {                                                                       \
+            const auto& v = *s->virtual_volumes.at(id);                                                      \
+            out[0] = v.sum_exp;                                                                              \
+            out[1] = static_cast<double>(v.count);                                                           \
+            out[2] = v.last_energy_change;                                                                   \
+            out[3] = v.count > 0 ? v.excessPressure() : 0.0;                                                 \
+        });                                                                                                  \
     }                                                                                                         \
     }
 

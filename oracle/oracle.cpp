@@ -78,6 +78,7 @@ static const TermFactory factory = termFactory;
 static void fo_replica_setup(int) {}
 
 FB_DEFINE_SIM_CAPI(fo, oracle::factory, fb::capi::defaultWidom)
+FB_DEFINE_VIRTUALVOLUME_CAPI(fo)
 FB_DEFINE_RDF_CAPI(fo, [](const fb::Json& j, fb::capi::Sim& s) -> std::unique_ptr<fb::AtomRDF> {
     return std::make_unique<oracle::AtomRDFCpu>(j, *s.mc->state.spc);
 })

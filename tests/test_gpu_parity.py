@@ -674,3 +674,30 @@ def test_atom_rdf_shards_add_up(bulk_input):
         parts.append(g.rdf_result(rid)[1])
     assert all(p.sum() > 0 for p in parts)
     assert np.array_equal(sum(parts), g.rdf_result(whole)[1])
+
+
+@pytest.mark.parametrize("case", ["bulk", "ewald", "water"])
+def test_virtual_volume_move(bulk_input, water_input, case):
+    """VirtualVolumeMove (src/analysis.cpp:825-843): energy(change = everything + volume) on the accepted
+    Hamiltonian before and after scaling the Space, no updateState, no sync — the adaptor terms refresh their mirror
+    (and, like the reference, the Ewald term keeps the k-vectors of the unscaled cell); then MC goes on as before"""
+    cfg = {"bulk": bulk_input, "water": water_input,
+           "ewald": small_electrolyte(n=400, coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35,
+                                                      "ncutoff": 6})}[case]
+    o, g = pair_of_sims(cfg, 64)
+    vo, vg = o.virtualvolume_create({"dV": 20.0}), g.virtualvolume_create({"dV": 20.0})
+    scale = np.abs(o.system_energy()[1]).max()
+    for _ in range(2):
+        for s, v in ((o, vo), (g, vg)):
+            s.sweep(1)
+            s.virtualvolume_sample(v)
+    ro, rg = o.virtualvolume_result(vo), g.virtualvolume_result(vg)
+    assert ro["count"] == rg["count"]
+    assert abs(ro["last_du"] - rg["last_du"]) <= 1e-9 * scale   # a difference of two full energies
+    if ro["count"]:
+        assert rg["excess_pressure_kT_per_A3"] == pytest.approx(ro["excess_pressure_kT_per_A3"], rel=1e-6, abs=1e-9 * scale)
+    for s in (o, g):   # the analysis left both sides where they were
+        s.trace_enable()
+        s.sweep(1)
+    assert np.array_equal(o.trace()["accepted"], g.trace()["accepted"])
+    assert_close(o.system_energy()[1], g.system_energy()[1], scale=scale)
