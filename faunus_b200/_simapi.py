@@ -66,6 +66,9 @@ class SimLibrary:
         f("virtualvolume_create", C.c_int, [C.c_void_p, C.c_char_p])
         f("virtualvolume_sample", C.c_int, [C.c_void_p, C.c_int])
         f("virtualvolume_result", C.c_int, [C.c_void_p, C.c_int, c_double_p])
+        f("virtualtranslate_create", C.c_int, [C.c_void_p, C.c_char_p])
+        f("virtualtranslate_sample", C.c_int, [C.c_void_p, C.c_int])
+        f("virtualtranslate_result", C.c_int, [C.c_void_p, C.c_int, c_double_p])
         f("rdf_create", C.c_int, [C.c_void_p, C.c_char_p])
         f("rdf_sample", C.c_int, [C.c_void_p, C.c_int])
         f("rdf_sample_shard", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int])
@@ -250,6 +253,21 @@ class Simulation:
         out = np.zeros(4)
         self._check(self.api.virtualvolume_result(self.handle, vid, _dp(out)), "virtualvolume_result")
         return {"sum_exp": out[0], "count": int(out[1]), "last_du": out[2], "excess_pressure_kT_per_A3": out[3]}
+
+    def virtualtranslate_create(self, config: dict) -> int:
+        """`virtualtranslate` analysis (molecule, dL, dir); returns its id"""
+        vid = self.api.virtualtranslate_create(self.handle, json.dumps(config).encode())
+        if vid < 0:
+            raise RuntimeError(f"{self.api.prefix}_virtualtranslate_create: {self.api.error()}")
+        return vid
+
+    def virtualtranslate_sample(self, vid: int):
+        self._check(self.api.virtualtranslate_sample(self.handle, vid), "virtualtranslate_sample")
+
+    def virtualtranslate_result(self, vid: int) -> dict:
+        out = np.zeros(4)
+        self._check(self.api.virtualtranslate_result(self.handle, vid, _dp(out)), "virtualtranslate_result")
+        return {"sum_exp": out[0], "count": int(out[1]), "last_du": out[2], "mean_force_kT_per_A": out[3]}
 
     # -- atomic radial distribution function ----------------------------------------------------------
     def rdf_create(self, config: dict) -> int:

@@ -117,6 +117,7 @@ class DeviceContext
      * refreshed from last. Such a refresh marks the slot; whoever touches the mirror next brings it back in step.
      */
     bool unsynchronised[2] = {false, false};
+    std::vector<size_t> unsynchronised_groups[2]; //!< … the same for single groups (VirtualTranslate, :2847-2860)
 
     /** cheap identity of a single-group Change (group, flags, indices) */
     static uint64_t changeKey(const Change& c)
@@ -235,7 +236,18 @@ class DeviceContext
         for (int slot = 0; slot < 2; ++slot) {
             if (unsynchronised[slot] && spaces[slot] != nullptr) {
                 unsynchronised[slot] = false;
+                unsynchronised_groups[slot].clear();
                 uploadSpace(slot, *spaces[slot]);
+            }
+            if (!unsynchronised_groups[slot].empty() && spaces[slot] != nullptr) {
+                Change refresh;
+                for (const auto g : unsynchronised_groups[slot]) {
+                    auto& record = refresh.groups.emplace_back();
+                    record.group_index = g;
+                    record.all = true;
+                }
+                unsynchronised_groups[slot].clear();
+                uploadChange(slot, *spaces[slot], refresh);
             }
         }
     }
@@ -450,10 +462,13 @@ class NonbondedB200 : public EnergyTerm
         if (!pushed) { // caller mutated our Space without updateState (Widom, SystemEnergy, tests)
             if (partial) {
                 dev->uploadChange(slot, spc, change);
+                for (const auto& gc : change.groups) { // the caller may put the group back without telling anybody
+                    dev->unsynchronised_groups[slot].push_back(gc.group_index);
+                }
             }
             else {
                 dev->uploadSpace(slot, spc);
-                dev->unsynchronised[slot] = true; // the caller may put the Space back without telling anybody
+                dev->unsynchronised[slot] = true; // … or the whole Space
             }
         }
         double u = 0.0;

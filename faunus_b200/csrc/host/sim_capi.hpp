@@ -38,6 +38,7 @@ struct Sim
     std::vector<std::unique_ptr<WidomInsertion>> widoms;
     std::vector<std::unique_ptr<AtomRDF>> rdfs;
     std::vector<std::unique_ptr<VirtualVolumeMove>> virtual_volumes;
+    std::vector<std::unique_ptr<VirtualTranslate>> virtual_translates;
     Change pending; //!< change of the manual trial-move protocol
 };
 
@@ -479,6 +480,34 @@ inline State& pick(Sim& s, int which)
     {                                                                                                         \
         auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
         return fb::capi::guarded([&] { s->virtual_volumes.at(id)->sample(); });                              \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_virtualtranslate_create(void* h, const char* json_text)   \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        int id = -1;                                                                                         \
+        fb::capi::guarded([&] {                                                                              \
+            s->virtual_translates.push_back(std::make_unique<fb::VirtualTranslate>(                          \
+                fb::Json::parse(json_text), *s->mc->state.spc, *s->mc->state.pot, s->mc->rng.global));       \
+            id = static_cast<int>(s->virtual_translates.size()) - 1;                                         \
+        });                                                                                                  \
+        return id;                                                                                           \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_virtualtranslate_sample(void* h, int id)                  \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] { s->virtual_translates.at(id)->sample(); });                           \
+    }                                                                                                         \
+    /* out[0] = Σ exp(−ΔU), out[1] = samples, out[2] = last ΔU, out[3] = mean force / kT Å⁻¹ */              \
+    __attribute__((visibility("default"))) int P##_virtualtranslate_result(void* h, int id, double out[4])   \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] {                                                                       \
+            const auto& v = *s->virtual_translates.at(id);                                                   \
+            out[0] = v.sum_exp;                                                                              \
+            out[1] = static_cast<double>(v.count);                                                           \
+            out[2] = v.last_energy_change;                                                                   \
+            out[3] = v.count > 0 ? v.meanForce() : 0.0;                                                      \
+        });                                                                                                  \
     }                                                                                                         \
     /* out[0] = Σ exp(−ΔU), out[1] = samples, out[2] = last ΔU, out[3] = excess pressure / kT Å⁻³ */         \
     __attribute__((visibility("default"))) int P##_virtualvolume_result(void* h, int id, double out[4])      \

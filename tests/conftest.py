@@ -96,3 +96,16 @@ def water_with_salt(water, n_pairs=8, seed=3, coulomb=None, volume_move=False):
                 if name.startswith("nonbonded"):
                     body["coulomb"] = coulomb
     return cfg
+
+
+def one_water_in_salt(water, n_pairs=40, coulomb=None):
+    """ONE rigid water molecule in an NaCl solution (what `virtualtranslate` wants: exactly one active molecule)"""
+    import copy
+    single = copy.deepcopy(water)
+    single["groups"] = single["groups"][:1]
+    single["particles"] = single["particles"][:3]
+    cfg = water_with_salt(single, n_pairs=n_pairs, coulomb=coulomb)
+    cfg["moves"] = [{"moltransrot": {"molecule": "water", "dp": 0.4, "dprot": 0.4, "repeat": 5}},
+                    {"transrot": {"molecule": "salt", "repeat": 60}}]
+    cfg["energy"] = [t for t in cfg["energy"] if "isobaric" not in t]
+    return cfg

@@ -701,3 +701,31 @@ def test_virtual_volume_move(bulk_input, water_input, case):
         s.sweep(1)
     assert np.array_equal(o.trace()["accepted"], g.trace()["accepted"])
     assert_close(o.system_energy()[1], g.system_energy()[1], scale=scale)
+
+
+@pytest.mark.parametrize("coulomb", [None, {"type": "fanourgakis", "epsr": 1, "cutoff": 9}])
+def test_virtual_translate(water_input, coulomb):
+    """VirtualTranslate (src/analysis.cpp:2794-2860) between sweeps: a group moved, evaluated and moved back
+    without updateState / sync — same ΔU as the oracle, and the mirror is back in step afterwards (identical
+    traces); with and without Ewald (whose Q(k), like the reference's, does not follow the virtual move)"""
+    from conftest import one_water_in_salt
+    cfg = one_water_in_salt(water_input, coulomb=coulomb)
+    o, g = pair_of_sims(cfg, 64)
+    scale = np.abs(o.system_energy()[1]).max()
+    vo, vg = (s.virtualtranslate_create({"molecule": "water", "dL": 0.25, "dir": [0, 0, 1]}) for s in (o, g))
+    for s in (o, g):
+        s.trace_enable()
+    for _ in range(3):
+        for s, v in ((o, vo), (g, vg)):
+            s.sweep(1)
+            s.virtualtranslate_sample(v)
+    ro, rg = o.virtualtranslate_result(vo), g.virtualtranslate_result(vg)
+    assert ro["count"] == rg["count"] == 3
+    assert abs(ro["last_du"] - rg["last_du"]) <= 1e-10 * scale
+    assert rg["sum_exp"] == pytest.approx(ro["sum_exp"], rel=1e-9)
+    a, b = o.trace(), g.trace()
+    assert np.array_equal(a["move_id"], b["move_id"]) and np.array_equal(a["accepted"], b["accepted"])
+    assert_close(o.system_energy()[1], g.system_energy()[1], scale=scale)
+    xo, _ = o.particles()
+    xg, _ = g.particles()
+    assert np.array_equal(xo, xg)

@@ -40,3 +40,33 @@ def test_virtual_volume_energy_change(bulk_input):
     assert sim.virtualvolume_result(idle)["count"] == 0
     with pytest.raises(RuntimeError):
         sim.virtualvolume_create({"dV": 1.0, "scaling": "isochoric"})
+
+
+def test_virtual_translate(water_input):
+    """VirtualTranslate (src/analysis.cpp:2794-2860): ΔU of moving the one molecule by dL along `dir` equals the
+    difference of the full energies of two independently built systems; the Space is put back; the molecule is
+    picked with one draw of the global generator"""
+    from conftest import one_water_in_salt
+    cfg = one_water_in_salt(water_input, coulomb={"type": "fanourgakis", "epsr": 1, "cutoff": 9})
+    sim = oracle_sim(cfg)
+    before = sim.system_energy()[0]
+    x0, _ = sim.particles()
+    vid = sim.virtualtranslate_create({"molecule": "water", "dL": 0.3, "dir": [1, 1, 0]})
+    sim.virtualtranslate_sample(vid)
+    res = sim.virtualtranslate_result(vid)
+    assert res["count"] == 1
+    x1, _ = sim.particles()
+    assert np.allclose(x0, x1, rtol=0, atol=1e-12)
+    moved = copy.deepcopy(cfg)
+    d = 0.3 * np.array([1.0, 1.0, 0.0]) / np.sqrt(2.0)
+    box = np.array(cfg["geometry"]["length"], dtype=float)
+    for p in moved["particles"][:3]:
+        q = np.array(p["pos"]) + d
+        p["pos"] = (q - box * np.round(q / box)).tolist()
+    c = np.array(moved["groups"][0]["cm"]) + d
+    moved["groups"][0]["cm"] = (c - box * np.round(c / box)).tolist()
+    after = oracle_sim(moved).system_energy()[0]
+    assert res["last_du"] == pytest.approx(after - before, rel=1e-9, abs=1e-9 * abs(before))
+    assert res["mean_force_kT_per_A"] == pytest.approx(np.log(res["sum_exp"]) / 0.3, rel=1e-12)
+    with pytest.raises(RuntimeError):
+        sim.virtualtranslate_create({"molecule": "salt", "dL": 0.3})   # atomic molecules are not allowed
