@@ -392,7 +392,10 @@ def b200_arm(args):
     sim.close()
     extras = None
     if not args.no_extras:
-        extras = sharded_extras(args, native, torch, dist, rank, world, local)
+        try:  # the extras must never cost the headline line
+            extras = sharded_extras(args, native, torch, dist, rank, world, local)
+        except Exception as e:  # noqa: BLE001
+            extras = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         return
     peaks = {}
