@@ -1274,6 +1274,11 @@ class AtomRDFB200 : public AtomRDF
         histogram.resize(static_cast<size_t>(n_bins), 0ull);
         auto& dev = *nonbonded->device();
         dev.resynchronise();
+        if (molecular) {
+            fbCheck(fb_molecule_rdf(dev.ctx, nonbonded->deviceSlot(), id1, id2, dr, shard, n_shards, n_bins, histogram.data()),
+                    dev.ctx, "fb_molecule_rdf");
+            return;
+        }
         fbCheck(fb_atom_rdf(dev.ctx, nonbonded->deviceSlot(), id1, id2, dr, slicedir, thickness, shard, n_shards, n_bins,
                             histogram.data()),
                 dev.ctx, "fb_atom_rdf");

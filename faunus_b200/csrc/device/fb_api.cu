@@ -1374,8 +1374,11 @@ FB_API int fb_nonbonded_delta(fb_ctx* c, int s_new, int s_old, const fb_change* 
 }
 
 /** share `shard` of `n_shards` of the full-system non-bonded and reciprocal energies (multi-GPU system energy) */
-FB_API int fb_atom_rdf(fb_ctx* c, int s, int atom_id1, int atom_id2, double dr, const int* slice_dir, double thickness,
-                       int shard, int n_shards, int n_bins, unsigned long long* counts)
+namespace {
+
+/** the pair-distance histogram of atoms of two types, or of the mass centres of molecular groups of two kinds */
+int pairRdf(fb_ctx* c, int s, bool molecular, int atom_id1, int atom_id2, double dr, const int* slice_dir, double thickness,
+            int shard, int n_shards, int n_bins, unsigned long long* counts)
 {
     return guarded(c, [&] {
         flushPending(c);
@@ -1383,21 +1386,26 @@ FB_API int fb_atom_rdf(fb_ctx* c, int s, int atom_id1, int atom_id2, double dr, 
         if (n_shards < 1 || shard < 0 || shard >= n_shards) {
             throw CudaError{"fb_atom_rdf: bad shard arguments"};
         }
-        if (!counts || !(dr > 0.0) || n_bins < 1 || n_bins > kRdfMaxBins || atom_id1 < 0 || atom_id1 >= c->P.n_types ||
-            atom_id2 < 0 || atom_id2 >= c->P.n_types) {
-            throw CudaError{"fb_atom_rdf: bad arguments (1..12288 bins, dr > 0, known atom types)"};
+        const int n_kinds = molecular ? c->P.n_mol : c->P.n_types;
+        if (!counts || !(dr > 0.0) || n_bins < 1 || n_bins > kRdfMaxBins || atom_id1 < 0 || atom_id1 >= n_kinds ||
+            atom_id2 < 0 || atom_id2 >= n_kinds) {
+            throw CudaError{"fb_atom_rdf / fb_molecule_rdf: bad arguments (1..12288 bins, dr > 0, known types)"};
+        }
+        if (molecular && ((c->molecule_flags[atom_id1] | c->molecule_flags[atom_id2]) & FB_MOL_ATOMIC)) {
+            throw CudaError{"fb_molecule_rdf: molecular groups required"};
         }
         c->rdf_hist.ensure(static_cast<size_t>(n_bins));
         c->rdf_flag.ensure(1);
         CUDA_CHECK(cudaMemsetAsync(c->rdf_hist.ptr, 0, sizeof(unsigned long long) * n_bins, c->stream));
         CUDA_CHECK(cudaMemsetAsync(c->rdf_flag.ptr, 0, sizeof(int), c->stream));
         // the particles of the two types, compacted (all threads and all inner iterations of the tiles do work)
-        c->rdf_list[0].ensure(static_cast<size_t>(c->n_slots));
-        c->rdf_list[1].ensure(static_cast<size_t>(c->n_slots));
+        const int n_items = molecular ? c->n_groups : c->n_slots;
+        c->rdf_list[0].ensure(static_cast<size_t>(n_items));
+        c->rdf_list[1].ensure(static_cast<size_t>(n_items));
         c->rdf_n.ensure(2);
         CUDA_CHECK(cudaMemsetAsync(c->rdf_n.ptr, 0, 2 * sizeof(int), c->stream));
         const bool identical = atom_id1 == atom_id2;
-        const int tiles = (c->n_slots + kRdfTile - 1) / kRdfTile; // upper bound: blocks beyond the lists return
+        const int tiles = (n_items + kRdfTile - 1) / kRdfTile; // upper bound: blocks beyond the lists return
         const size_t smem = sizeof(unsigned int) * static_cast<size_t>(n_bins);
         if (!c->rdf_configured) {
             CUDA_CHECK(cudaFuncSetAttribute(atomRdfKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1406,12 +1414,21 @@ FB_API int fb_atom_rdf(fb_ctx* c, int s, int atom_id1, int atom_id2, double dr, 
         }
         const int sx = slice_dir ? slice_dir[0] : 0, sy = slice_dir ? slice_dir[1] : 0, sz = slice_dir ? slice_dir[2] : 0;
         beginTiming(c, TIME_FULL);
-        atomRdfCompactKernel<<<1, kRdfCompactThreads, 0, c->stream>>>(makeView(c, s), atom_id1, atom_id2,
-                                                                      c->rdf_list[0].ptr, c->rdf_list[1].ptr,
-                                                                      c->rdf_n.ptr);
-        launched(c, "atomRdfCompactKernel");
+        if (molecular) {
+            moleculeRdfCompactKernel<<<1, kRdfCompactThreads, 0, c->stream>>>(makeView(c, s), atom_id1, atom_id2,
+                                                                              c->rdf_list[0].ptr, c->rdf_list[1].ptr,
+                                                                              c->rdf_n.ptr);
+            launched(c, "moleculeRdfCompactKernel");
+        }
+        else {
+            atomRdfCompactKernel<<<1, kRdfCompactThreads, 0, c->stream>>>(makeView(c, s), atom_id1, atom_id2,
+                                                                          c->rdf_list[0].ptr, c->rdf_list[1].ptr,
+                                                                          c->rdf_n.ptr);
+            launched(c, "atomRdfCompactKernel");
+        }
         atomRdfKernel<<<dim3((tiles + n_shards - 1) / n_shards, tiles), kRdfTile, smem, c->stream>>>(
-            makeView(c, s), c->rdf_list[0].ptr, c->rdf_list[1].ptr, c->rdf_n.ptr, identical, 1.0 / dr, sx, sy, sz, thickness,
+            makeView(c, s), c->rdf_list[0].ptr, c->rdf_list[1].ptr, c->rdf_n.ptr, identical, molecular, 1.0 / dr, sx, sy, sz,
+            thickness,
             n_bins, shard, n_shards, c->rdf_hist.ptr, c->rdf_flag.ptr);
         launched(c, "atomRdfKernel");
         std::vector<unsigned long long> host(static_cast<size_t>(n_bins));
@@ -1427,6 +1444,20 @@ FB_API int fb_atom_rdf(fb_ctx* c, int s, int atom_id1, int atom_id2, double dr, 
             counts[b] += host[b];
         }
     });
+}
+
+} // namespace
+
+FB_API int fb_atom_rdf(fb_ctx* c, int s, int atom_id1, int atom_id2, double dr, const int* slice_dir, double thickness,
+                       int shard, int n_shards, int n_bins, unsigned long long* counts)
+{
+    return pairRdf(c, s, false, atom_id1, atom_id2, dr, slice_dir, thickness, shard, n_shards, n_bins, counts);
+}
+
+FB_API int fb_molecule_rdf(fb_ctx* c, int s, int molid1, int molid2, double dr, int shard, int n_shards, int n_bins,
+                           unsigned long long* counts)
+{
+    return pairRdf(c, s, true, molid1, molid2, dr, nullptr, 0.0, shard, n_shards, n_bins, counts);
 }
 
 FB_API int fb_system_energy_shard(fb_ctx* c, int s, int shard, int n_shards, double* nonbonded, double* reciprocal)

@@ -93,9 +93,75 @@ __global__ void __launch_bounds__(kRdfCompactThreads)
     }
 }
 
+/** the same for the mass centres of the active molecular groups of kind molid1 / molid2 ("molrdf") */
+__global__ void __launch_bounds__(kRdfCompactThreads)
+    moleculeRdfCompactKernel(SlotView V, int molid1, int molid2, double4* __restrict__ list0, double4* __restrict__ list1,
+                             int* __restrict__ n_list /*[2]*/)
+{
+    __shared__ int s_warp[2][32];
+    __shared__ int s_total[2];
+    __shared__ int s_base[2];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned below = (1u << lane) - 1u;
+    if (threadIdx.x < 2) {
+        s_base[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (int start = 0; start < V.n_groups; start += kRdfCompactThreads) {
+        const int g = start + threadIdx.x;
+        bool f0 = false, f1 = false;
+        double4 p = make_double4(0, 0, 0, 0);
+        if (g < V.n_groups && V.gsize[g] > 0) {
+            const int molid = V.ginfo[g] >> 8;
+            f0 = molid == molid1;
+            f1 = molid == molid2 && molid1 != molid2;
+            p = V.gcm[g];
+        }
+        const unsigned b0 = __ballot_sync(0xffffffffu, f0);
+        const unsigned b1 = __ballot_sync(0xffffffffu, f1);
+        if (lane == 0) {
+            s_warp[0][warp] = __popc(b0);
+            s_warp[1][warp] = __popc(b1);
+        }
+        __syncthreads();
+        if (warp < 2) {
+            const int count = s_warp[warp][lane];
+            int inclusive = count;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, inclusive, o);
+                if (lane >= o) {
+                    inclusive += up;
+                }
+            }
+            s_warp[warp][lane] = inclusive - count;
+            if (lane == 31) {
+                s_total[warp] = inclusive;
+            }
+        }
+        __syncthreads();
+        if (f0) {
+            list0[s_base[0] + s_warp[0][warp] + __popc(b0 & below)] = p;
+        }
+        if (f1) {
+            list1[s_base[1] + s_warp[1][warp] + __popc(b1 & below)] = p;
+        }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            s_base[threadIdx.x] += s_total[threadIdx.x];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 2) {
+        n_list[threadIdx.x] = s_base[threadIdx.x];
+    }
+}
+
 __global__ void __launch_bounds__(kRdfTile)
     atomRdfKernel(SlotView V, const double4* __restrict__ list0, const double4* __restrict__ list1,
-                  const int* __restrict__ n_list, bool identical, double dxinv, int sx, int sy, int sz, double thickness,
+                  const int* __restrict__ n_list, bool identical, bool fold_absolute, double dxinv, int sx, int sy, int sz,
+                  double thickness,
                   int n_bins, int shard, int n_shards, unsigned long long* __restrict__ hist, int* __restrict__ out_of_range)
 {
     extern __shared__ unsigned int s_hist[];
@@ -135,7 +201,15 @@ __global__ void __launch_bounds__(kRdfTile)
             double dx = __dsub_rn(ax, s_x[j]);
             double dy = __dsub_rn(ay, s_y[j]);
             double dz = __dsub_rn(az, s_z[j]);
-            if (V.len_or_zero[0] > 0.0) {
+            if (fold_absolute) { // Geometry::sqdist (src/geometry.h:460-470): |d| − L·[|d| > L/2], as MoleculeRDF uses it
+                dx = fabs(dx);
+                dy = fabs(dy);
+                dz = fabs(dz);
+                dx = dx > V.half[0] ? __dsub_rn(dx, V.len_or_zero[0]) : dx;
+                dy = dy > V.half[1] ? __dsub_rn(dy, V.len_or_zero[1]) : dy;
+                dz = dz > V.half[2] ? __dsub_rn(dz, V.len_or_zero[2]) : dz;
+            }
+            else if (V.len_or_zero[0] > 0.0) {
                 dx = dx > V.half[0] ? __dsub_rn(dx, V.len_or_zero[0]) : (dx < -V.half[0] ? __dadd_rn(dx, V.len_or_zero[0]) : dx);
             }
             if (V.len_or_zero[1] > 0.0) {

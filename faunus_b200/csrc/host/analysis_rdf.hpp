@@ -1,4 +1,4 @@
-// Atomic radial distribution function g(r) ("atomrdf"), restated caller side:
+// Radial distribution functions g(r) of atoms ("atomrdf") and of molecular mass centres ("molrdf"), restated caller side:
 // src/analysis.cpp:712-722 (PairFunction::_from_json), :1570-1579 (AtomRDF::_sample), :724-757 (normalisation),
 // src/aux/equidistant_table.h:32-40 (binning: floor(r / dr), xmin = 0, the table grows on demand).
 // The pair loop itself (AtomRDF::sampleIdentical / sampleDifferent / sampleDistance, :1556-1600) is the part a
@@ -12,6 +12,7 @@ class AtomRDF
 {
   protected:
     const Space& spc;
+    bool molecular = false; //!< "molrdf": mass centres of molecular groups, distance = sqrt(sqdist) (:1642-1648)
     int id1 = 0, id2 = 0;
     double dr = 0.1;
     int dimensions = 3;
@@ -31,8 +32,18 @@ class AtomRDF
     AtomRDF(const Json& j, const Space& spc)
         : spc(spc)
     {
-        id1 = spc.topology->atomId(j.at("name1").string());
-        id2 = spc.topology->atomId(j.at("name2").string());
+        molecular = j.value("type", "atomrdf") == "molrdf";
+        if (molecular) { // MoleculeRDF::MoleculeRDF, src/analysis.cpp:1650-1658
+            id1 = spc.topology->moleculeId(j.at("name1").string());
+            id2 = spc.topology->moleculeId(j.at("name2").string());
+            if (spc.topology->molecules.at(id1).atomic || spc.topology->molecules.at(id2).atomic) {
+                throw std::runtime_error("molrdf: molecular groups required");
+            }
+        }
+        else {
+            id1 = spc.topology->atomId(j.at("name1").string());
+            id2 = spc.topology->atomId(j.at("name2").string());
+        }
         dr = j.value("dr", 0.1);
         dimensions = static_cast<int>(j.value("dim", 3.0));
         if (const auto* s = j.find("slicedir")) {

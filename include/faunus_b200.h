@@ -377,6 +377,11 @@ int fb_get_batch_timing(const fb_ctx* ctx, double out[8]);
 int fb_atom_rdf(fb_ctx* ctx, int slot, int atom_id1, int atom_id2, double dr, const int* slice_dir, double thickness,
                 int shard, int n_shards, int n_bins, unsigned long long* counts);
 
+/* MoleculeRDF (src/analysis.cpp:1607-1658): the same for the mass centres of the active molecular groups of the kinds
+ * molid1, molid2, distance = sqrt(Geometry::sqdist) (src/geometry.h:460-470), no slices. */
+int fb_molecule_rdf(fb_ctx* ctx, int slot, int molid1, int molid2, double dr, int shard, int n_shards, int n_bins,
+                    unsigned long long* counts);
+
 /* ---- Ewald reciprocal space --------------------------------------------------------------- */
 int fb_ewald_configure(fb_ctx* ctx, const fb_ewald_config* config);
 /* k-vectors and A_k for the slot's current box (PolicyIonIon::updateBox); returns K in *n_kvectors */

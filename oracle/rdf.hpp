@@ -44,8 +44,43 @@ class AtomRDFCpu : public fb::AtomRDF
         return found;
     }
 
+    /** MoleculeRDF::sampleDistance, src/analysis.cpp:1642-1648 */
+    void sampleMassCenters(const fb::Point& a, const fb::Point& b)
+    {
+        const auto i = static_cast<size_t>(bin(std::sqrt(spc.geometry.sqdist(a, b))));
+        if (i >= histogram.size()) {
+            histogram.resize(i + 1, 0ull);
+        }
+        histogram[i]++;
+    }
+
+    std::vector<fb::Point> findMassCenters(int molid) const
+    {
+        std::vector<fb::Point> found;
+        for (const auto g : spc.findMolecules(molid, fb::Space::Selection::ACTIVE)) {
+            found.push_back(spc.groups[g].mass_center);
+        }
+        return found;
+    }
+
+    void countMolecules(int shard, int n_shards)
+    {
+        const auto stride = static_cast<size_t>(n_shards);
+        const auto first = findMassCenters(id1);
+        const auto second = id1 == id2 ? first : findMassCenters(id2);
+        for (size_t i = static_cast<size_t>(shard); i < first.size(); i += stride) {
+            for (size_t j = (id1 == id2 ? i + 1 : 0); j < second.size(); ++j) {
+                sampleMassCenters(first[i], second[j]);
+            }
+        }
+    }
+
     void count(int shard, int n_shards) override
     {
+        if (molecular) {
+            countMolecules(shard, n_shards);
+            return;
+        }
         const auto stride = static_cast<size_t>(n_shards);
         if (id1 == id2) {
             const auto atoms = findAtoms(id1);

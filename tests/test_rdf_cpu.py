@@ -51,3 +51,22 @@ def test_oracle_rdf_matches_numpy(bulk_input, names, extra):
     # a second sample accumulates
     sim.rdf_sample(rid)
     assert np.array_equal(sim.rdf_result(rid)[1], 2 * pairs)
+
+
+def test_oracle_molecule_rdf_matches_numpy(water_input):
+    """MoleculeRDF (src/analysis.cpp:1607-1658): mass centres of the water molecules, distance = sqrt(sqdist)"""
+    sim = oracle_sim(water_input)
+    sim.sweep(1)
+    rid = sim.rdf_create({"type": "molrdf", "name1": "water", "name2": "water", "dr": 0.1, "file": "rdf.dat"})
+    sim.rdf_sample(rid)
+    r, pairs, g = sim.rdf_result(rid)
+    _, cm = sim.groups()
+    box = np.array(sim.state_json()["geometry"]["length"], dtype=float) * np.ones(3)   # after a volume move
+    d = np.abs(cm[:, None, :] - cm[None, :, :])
+    d = d - box * (d > box / 2)                                   # Geometry::sqdist, src/geometry.h:460-470
+    dist = np.sqrt((d ** 2).sum(axis=2))[np.triu_indices(len(cm), k=1)]
+    want = np.bincount(np.floor(dist * (1.0 / 0.1)).astype(int))
+    assert np.array_equal(pairs, want.astype(np.uint64))
+    assert pairs.sum() == len(cm) * (len(cm) - 1) // 2
+    with pytest.raises(RuntimeError):
+        oracle_sim(water_input).rdf_create({"type": "molrdf", "name1": "water", "name2": "nosuch", "dr": 0.1, "file": "x"})
