@@ -76,9 +76,11 @@ def test_s1_windowed_equals_single_moves():
     assert np.abs(ea - eb).max() <= 1e-10 * np.abs(ea).max()
 
 
-def test_s1_cell_list_equals_brute_force():
-    """N = 1e5: windows through the device cell list (forced; the default starts at 200 000 particles) vs brute force"""
-    a, b = sim(s1(600), window=32), sim(s1(600), window=32)
+@pytest.mark.parametrize("window", [32, 64])
+def test_s1_cell_list_equals_brute_force(window):
+    """N = 1e5: windows through the device cell list (forced; the default starts at 200 000 particles) vs brute
+    force; window 64: inside runs walked on the device (the cell list is updated from the device-side commit list)"""
+    a, b = sim(s1(600), window=window), sim(s1(600), window=window)
     a.configure_cells(0)
     b.configure_cells(-1)
     for s in (a, b):
