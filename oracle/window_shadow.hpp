@@ -20,6 +20,9 @@ class ShadowWindowEvaluator : public fb::WindowEvaluator
     {
         fb::Change change;
         fb::Point start[2], trial[2]; //!< [0]: plain proposal, or "dependency accepted"; [1]: "dependency rejected"
+        bool group = false;           //!< rigid-molecule move: all atoms and the mass centre travel
+        std::vector<fb::Point> group_start, group_trial;
+        fb::Point cm_start, cm_trial;
         bool conditional = false;
         uint64_t serial = 0, dependency = 0;
         double uniform = 0;
@@ -52,14 +55,29 @@ class ShadowWindowEvaluator : public fb::WindowEvaluator
             const auto& gc = p.change.groups.at(0);
             auto& trial_spc = *shadow->trial_state.spc;
             auto& spc = *shadow->state.spc;
-            auto& particle = trial_spc.at(trial_spc.groups.at(gc.group_index), gc.relative_atom_indices.at(0));
-            const auto& accepted_particle = spc.at(spc.groups.at(gc.group_index), gc.relative_atom_indices[0]);
-            const fb::Point& at = accepted_particle.pos;
-            const fb::Point& want = p.start[variant];
-            if (at.x != want.x || at.y != want.y || at.z != want.z) {
-                throw std::runtime_error("shadow: the start position shipped with a proposal is not where the atom is");
+            auto same = [](const fb::Point& a, const fb::Point& b) { return a.x == b.x && a.y == b.y && a.z == b.z; };
+            if (p.group) {
+                auto& trial_group = trial_spc.groups.at(gc.group_index);
+                const auto& group = spc.groups.at(gc.group_index);
+                if (group.size() != p.group_start.size() || !same(group.mass_center, p.cm_start)) {
+                    throw std::runtime_error("shadow: the molecule shipped with a proposal is not where the molecule is");
+                }
+                for (size_t i = 0; i < group.size(); ++i) {
+                    if (!same(spc.at(group, i).pos, p.group_start[i])) {
+                        throw std::runtime_error("shadow: the molecule shipped with a proposal is not where the molecule is");
+                    }
+                    trial_spc.at(trial_group, i).pos = p.group_trial[i];
+                }
+                trial_group.mass_center = p.cm_trial;
             }
-            particle.pos = p.trial[variant];
+            else {
+                auto& particle = trial_spc.at(trial_spc.groups.at(gc.group_index), gc.relative_atom_indices.at(0));
+                const auto& accepted_particle = spc.at(spc.groups.at(gc.group_index), gc.relative_atom_indices[0]);
+                if (!same(accepted_particle.pos, p.start[variant])) {
+                    throw std::runtime_error("shadow: the start position shipped with a proposal is not where the atom is");
+                }
+                particle.pos = p.trial[variant];
+            }
             shadow->trial_state.pot->updateState(p.change);
             Outcome o;
             o.u_new = shadow->trial_state.pot->energy(p.change);
@@ -89,6 +107,7 @@ class ShadowWindowEvaluator : public fb::WindowEvaluator
     }
 
     int capacity() const override { return moves_per_evaluation; }
+    bool supports(fb::WindowProposal::Kind) const override { return true; } // single atoms and rigid molecules
     bool conditionals() const override { return true; }
     bool pipelined(const std::vector<fb::WindowProposal>&, int, int ready) const override { return ready > 0; }
 
@@ -103,7 +122,19 @@ class ShadowWindowEvaluator : public fb::WindowEvaluator
             p.change = w.change;
             p.serial = w.serial;
             p.uniform = w.uniform;
-            if (w.conditional && !w.applied) {
+            if (w.kind == fb::WindowProposal::Kind::GROUP) {
+                const auto& gc = w.change.groups.at(0);
+                const auto& trial_group = trial.groups.at(gc.group_index);
+                const auto& group = accepted.groups.at(gc.group_index);
+                p.group = true;
+                p.cm_trial = trial_group.mass_center;
+                p.cm_start = group.mass_center;
+                for (size_t i = 0; i < group.size(); ++i) {
+                    p.group_trial.push_back(trial.at(trial_group, i).pos);
+                    p.group_start.push_back(accepted.at(group, i).pos);
+                }
+            }
+            else if (w.conditional && !w.applied) {
                 p.conditional = true;
                 p.dependency = w.dependency;
                 for (int v = 0; v < 2; ++v) {

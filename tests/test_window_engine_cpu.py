@@ -68,3 +68,26 @@ def test_windowed_engine_reproduces_the_plain_run(name, moves):
             assert stats["queued"] > 0, "no evaluation was queued behind another one"
     info_a, info_b = plain.info(), windowed.info()
     assert [m for m in info_a["moves"]] == [m for m in info_b["moves"]]   # attempts, acceptance, msd per move
+
+
+@pytest.mark.parametrize("moves", [5, 64])
+def test_windowed_engine_with_rigid_molecules(water_input, moves):
+    """windows of rigid-molecule moves and of single-atom moves take turns (a window is of one kind; the queue drains
+    when the move sampler changes kind): water + NaCl, cutoff electrostatics, against the plain run"""
+    from conftest import water_with_salt
+    cfg = water_with_salt(water_input, coulomb={"type": "fanourgakis", "epsr": 1, "cutoff": 9})
+    plain, windowed = oracle_sim(cfg), shadowed(cfg, moves)
+    for s in (plain, windowed):
+        s.trace_enable()
+        s.sweep(2)
+    a, b = plain.trace(), windowed.trace()
+    assert len(a["du"]) > 500 and set(a["move_id"]) == {0, 1}
+    assert np.array_equal(a["move_id"], b["move_id"])
+    assert np.array_equal(a["accepted"], b["accepted"])
+    for key in ("u_new", "u_old", "du"):
+        assert np.array_equal(a[key], b[key]), key
+    xa, _ = plain.particles()
+    xb, _ = windowed.particles()
+    assert np.array_equal(xa, xb)
+    assert np.array_equal(plain.groups()[1], windowed.groups()[1])   # mass centres
+    assert shadow_stats(windowed)["evaluations"] > 10
