@@ -412,10 +412,14 @@ def test_runs_with_pair_sums_ahead(bulk_input):
         assert g.run_stats()["windows"] > 0
 
 
-def test_runs_through_the_c_abi():
+@pytest.mark.parametrize("collide", [False, True])
+def test_runs_through_the_c_abi(collide):
     """fb_run_submit / fb_run_wait through the raw C ABI: two runs queued behind each other, with conditional
     proposals (a second move on an atom whose first move is still undecided, in the same run and across the two
-    runs), against one-move-at-a-time fb_trial_energy / fb_trial_commit with the Metropolis rule applied here."""
+    runs), against one-move-at-a-time fb_trial_energy / fb_trial_commit with the Metropolis rule applied here.
+    collide: move 22 lands 0.01 Å from where the (accepted) move 21 has just put another ion — the correction of its
+    energies would cancel 1e28 kT, so the window stops there, the first run needs a window more than scheduled, the
+    run queued behind it halts on the device and is launched again."""
     import ctypes as C
     import faunus_b200.native as native
     lib = native.load()
@@ -424,16 +428,24 @@ def test_runs_through_the_c_abi():
     xyzq, ids = ga.particles()
     box = np.array(cfg["geometry"]["length"], dtype=float) * np.ones(3)
     rng = np.random.RandomState(5)
-    n1, n2 = 150, 90
+    n1, n2 = (128, 90) if collide else (150, 90)
     n = n1 + n2
     atoms = rng.choice(len(xyzq), n, replace=False)
-    # repeats: (later move, earlier move) on the same atom — 3 inside run 1 (one of them within one window),
-    # 2 inside run 2, 2 from run 2 back into run 1
-    for later, earlier in ((40, 10), (100, 20), (149, 140), (n1 + 30, n1 + 5), (n1 + 80, n1 + 70), (n1 + 10, 120), (n1 + 60, 60)):
+    # repeats: (later move, earlier move) on the same atom — inside run 1 (one of them within one window), inside
+    # run 2, and from run 2 back into run 1
+    repeats = [(40, 10), (100, 20), (n1 + 30, n1 + 5), (n1 + 80, n1 + 70), (n1 + 10, 120), (n1 + 60, 60)]
+    if not collide:
+        repeats.append((149, 140))
+    for later, earlier in repeats:
         atoms[later] = atoms[earlier]
     disp = rng.uniform(-1.2, 1.2, (n, 3))
     uniform = rng.uniform(size=n)
     wrap = lambda x: x - box * np.round(x / box)
+    if collide:
+        disp[21] = (1e-3, 0.0, 0.0)   # practically always accepted
+        uniform[21] = 0.5
+        target = wrap(xyzq[atoms[21], :3] + disp[21]) + np.array([0.01, 0.0, 0.0])
+        disp[22] = target - xyzq[atoms[22], :3]
 
     # reference: one move at a time on context A, Hamiltonian = [non-bonded, Ewald]
     pos = xyzq[:, :3].copy()
@@ -498,12 +510,17 @@ def test_runs_through_the_c_abi():
         got_new += [res.u_new[i] for i in range(count)]
         got_old += [res.u_old[i] for i in range(count)]
         windows.append(res.n_windows)
-    assert windows[0] == 4 and windows[1] >= 2   # 150 moves: 64 + 64 + 21 (cut before move 149, which depends on 140) + 1
+    if collide:   # 128 moves: 22 (stopped at the collision) + 64 + 42, one more than the two scheduled
+        assert windows[0] == 3 and ref_acc[21] and not ref_acc[22]
+    else:         # 150 moves: 64 + 64 + 21 (cut before move 149, which depends on 140) + 1
+        assert windows[0] == 4 and windows[1] >= 2
     assert got_acc == ref_acc
     assert 0.2 < np.mean(ref_acc) < 0.9
-    scale = np.abs(ref_new).max()
-    assert np.abs(np.array(got_new) - ref_new).max() <= RTOL * scale
-    assert np.abs(np.array(got_old) - ref_old).max() <= RTOL * scale
+    ordinary = np.abs(ref_new) < 1e6   # the collision itself: 1e28 kT, compared relatively below
+    scale = np.abs(np.array(ref_new)[ordinary]).max()
+    assert np.abs(np.array(got_new) - ref_new)[ordinary].max() <= RTOL * scale
+    assert np.abs(np.array(got_old) - ref_old)[ordinary].max() <= RTOL * scale
+    assert np.allclose(np.array(got_new)[~ordinary], np.array(ref_new)[~ordinary], rtol=1e-9)
     # both contexts end in the same state (fb_download_space applies what is still pending)
     xa, xb = np.zeros((len(xyzq), 4)), np.zeros((len(xyzq), 4))
     ia, ib = np.zeros(len(xyzq), dtype=np.int32), np.zeros(len(xyzq), dtype=np.int32)
