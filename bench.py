@@ -441,7 +441,7 @@ def b200_arm(args):
                 "kernel": "batchKspaceKernel (+ batchPhaseKernel)", "bound": "fp64",
                 "achieved": ew_flop / ew_s / 1e12, "peak": peak, "unit": "TFLOP/s",
                 "frac": ew_flop / ew_s / 1e12 / peak, "us_per_launch": ew_s * 1e6,
-                "traffic": 4.5e6, "traffic_source": "dram__bytes_read+write per launch, profiles/r01d_kspace_summary.csv",
+                "traffic": 4.82e6, "traffic_source": "dram__bytes_read+write per launch, profiles/r01i_run_kernels_summary.csv",
                 "algorithmic_flop_per_launch": ew_flop,
                 "algorithmic_bytes_per_launch": kvectors * 40,
                 "flop_model": "per k-vector: 40 per move + 4 per ordered pair of moves + 26 per committed move + 4",
