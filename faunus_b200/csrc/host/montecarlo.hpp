@@ -321,25 +321,50 @@ class MetropolisMonteCarlo
     uint64_t proposal_serial = 0;
 
     /** apply every queued proposal whose atom / molecule has no earlier undecided proposal any more */
+    /** both outcomes of proposal `p` on an atom that the applied, undecided proposal `q` moves (see WindowProposal) */
+    void makeConditional(WindowProposal& p, const WindowProposal& q)
+    {
+        const auto& trial_group = trial_state.spc->groups.at(p.draw.group_index);
+        const auto& group = state.spc->groups.at(p.draw.group_index);
+        p.conditional = true;
+        p.dependency = q.serial;
+        p.alt_start[0] = trial_state.spc->at(trial_group, p.draw.atom_index).pos; // q accepted: where q puts the atom
+        p.alt_start[1] = state.spc->at(group, p.draw.atom_index).pos;             // q rejected: where the atom is
+        p.alt_new[0] = p.move->displaced(p.alt_start[0], p.draw);
+        p.alt_new[1] = p.move->displaced(p.alt_start[1], p.draw);
+        p.move->describe(p.draw, p.change);
+    }
+
+    /**
+     * After decisions: apply every queued proposal whose atom / molecule has no earlier undecided proposal any more,
+     * and make those conditional that are left with exactly ONE (applied) undecided predecessor.
+     */
     void applyUnblocked()
     {
         if (unapplied_count == 0) {
             return;
         }
-        std::vector<uint64_t> seen;
+        const bool conditionals = window_evaluator->conditionals();
+        std::unordered_map<uint64_t, std::pair<int, const WindowProposal*>> earlier; // key → (undecided so far, the first)
         for (auto& p : window) {
-            if (p.applied) {
-                continue;
-            }
             const uint64_t key = proposalKey(p);
-            if (applied_keys.count(key) == 0 && std::find(seen.begin(), seen.end(), key) == seen.end()) {
-                applyProposal(p);
-                applied_keys.insert(key);
-                unapplied_count--;
+            auto& [count, first] = earlier[key];
+            if (!p.applied) {
+                if (count == 0) {
+                    applyProposal(p);
+                    applied_keys.insert(key);
+                    p.conditional = false;
+                    unapplied_count--;
+                }
+                else if (count == 1 && !p.conditional && conditionals && p.kind == WindowProposal::Kind::ATOM &&
+                         first->applied) {
+                    makeConditional(p, *first);
+                }
             }
-            else {
-                seen.push_back(key);
+            if (count == 0) {
+                first = &p;
             }
+            count++;
         }
     }
 
@@ -522,15 +547,7 @@ class MetropolisMonteCarlo
                 for (auto q = window.rbegin(); q != window.rend(); ++q) {
                     if (proposalKey(*q) == key) {
                         if (q->applied) {
-                            const auto& trial_group = trial_state.spc->groups.at(p.draw.group_index);
-                            const auto& group = state.spc->groups.at(p.draw.group_index);
-                            p.conditional = true;
-                            p.dependency = q->serial;
-                            p.alt_start[0] = trial_state.spc->at(trial_group, p.draw.atom_index).pos;
-                            p.alt_start[1] = state.spc->at(group, p.draw.atom_index).pos;
-                            p.alt_new[0] = p.move->displaced(p.alt_start[0], p.draw);
-                            p.alt_new[1] = p.move->displaced(p.alt_start[1], p.draw);
-                            p.move->describe(p.draw, p.change);
+                            makeConditional(p, *q);
                         }
                         break;
                     }
