@@ -133,17 +133,45 @@ def cpu_reference_run(steps: int, warmup: int, moves_per_step: int, policy: str)
     lib.fo_set_openmp_threads.argtypes = [C.c_int]
     lib.fo_openmp_threads.restype = C.c_int
     lib.fo_set_openmp_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1 to its workers
-    lib.fo_set_parallel_ewald_init(1)  # one-off N·K init over all cores; per-move path stays as in the reference
+    # one-off start-up passes (N·K structure factor, all-pairs energy of the start configuration) over all cores and
+    # computed once for the two identical states; the timed per-move path stays as in the reference
+    lib.fo_set_large_system_mode.argtypes = [C.c_int]
+    lib.fo_set_large_system_mode(1)
     threads = lib.fo_openmp_threads() if policy == "openmp" else 1
     sim = Simulation(SimLibrary(lib, "fo"), workload(moves_per_step, summation_policy=policy))
+    sim.trace_enable()
     for _ in range(warmup):
         sim.sweep(1)
     t0 = time.perf_counter()
     for _ in range(steps):
         sim.sweep(1)
     dt = time.perf_counter() - t0
+    trace = sim.trace()
+    sim.close()
+    lib.fo_set_large_system_mode(0)
     return {"moves_per_s": steps * moves_per_step / dt, "seconds": dt, "threads": threads, "arch": arch,
-            "policy": policy, "moves": steps * moves_per_step}
+            "policy": policy, "moves": steps * moves_per_step, "trace": trace,
+            "sweeps": warmup + steps, "moves_per_sweep": moves_per_step}
+
+
+def parity_against_cpu_sample(native, device, cpu_run):
+    """The trial moves the CPU baseline just timed, again on the device (same workload, same seed, runs walked on the
+    device): identical accept/reject sequence, u_new / u_old within 1e-10 of the largest energy. Raises otherwise."""
+    import numpy as np
+    ref = cpu_run["trace"]
+    sim = native.B200Simulation(workload(cpu_run["moves_per_sweep"]), device=device, run_min=1)
+    sim.trace_enable()
+    sim.sweep(cpu_run["sweeps"])
+    got = sim.trace()
+    sim.close()
+    n = len(ref["du"])
+    if len(got["du"]) != n or not np.array_equal(got["accepted"], ref["accepted"]):
+        raise AssertionError("parity: the accept/reject sequence differs from the CPU port's")
+    scale = max(np.abs(ref["u_new"]).max(), np.abs(ref["u_old"]).max())
+    worst = max(np.abs(got["u_new"] - ref["u_new"]).max(), np.abs(got["u_old"] - ref["u_old"]).max()) / scale
+    if not worst <= 1e-10:
+        raise AssertionError(f"parity: per-move energies differ by {worst:.3e} (relative) from the CPU port's")
+    return {"moves": n, "max_relative_energy_difference": float(worst), "acceptance": float(ref["accepted"].mean())}
 
 
 def reference_arm(args):
@@ -465,14 +493,18 @@ def b200_arm(args):
                                         "pairs_per_s": pairs / (w["kernel_ms_this_rank"] / 1e3),
                                         "ms_per_launch": w["kernel_ms_this_rank"]}
     cpu = None
+    parity = None
     if not args.no_cpu_baseline:
+        r = None
         try:
             r = cpu_reference_run(steps=4, warmup=1, moves_per_step=25, policy="serial")
             cpu = {"value": r["moves_per_s"], "unit": "moves/s", "cores": 1, "kind": "port",
                    "sample": f"{r['moves']} trial moves of the same N=1e5 workload, serial summation "
-                             f"(reference default), -O3 -ffast-math -march={r['arch']}; Ewald init parallelised"}
+                             f"(reference default), -O3 -ffast-math -march={r['arch']}; start-up passes parallelised"}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "moves/s", "cores": 1, "kind": "port", "sample": f"failed: {e}"}
+        if r is not None:  # a parity failure must be loud: no bench line without it
+            parity = parity_against_cpu_sample(native, local, r)
     runs = None
     if windowed:
         # windows walked on the host: the window description in (sizeof(BatchInput) = 10288 B), the result block out
@@ -518,6 +550,9 @@ def b200_arm(args):
         line["roofline"] = roofline
     if cpu:
         line["cpu_baseline"] = cpu
+    if parity:
+        line["parity_checked_moves"] = parity["moves"]
+        line["parity"] = parity
     print(json.dumps(line), flush=True)
 
 

@@ -6,7 +6,7 @@
 //
 // The non-bonded / Ewald / self-energy terms are supplied by a factory: the product build plugs in
 // the B200 adaptor terms (faunus_b200/csrc/b200_terms.hpp), the oracle build its CPU restatement
-// (oracle/terms.hpp). Everything else in this file is caller-side scaffolding.
+// (oracle/nonbonded.hpp, oracle/ewald.hpp; wired up in oracle/oracle.cpp). Everything else in this file is caller-side scaffolding.
 #pragma once
 #include "space.hpp"
 #include <chrono>

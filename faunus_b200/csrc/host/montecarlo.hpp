@@ -217,12 +217,44 @@ class MetropolisMonteCarlo
         }
     }
 
-    /** Load a reference `state.json` into both Spaces and re-init; src/montecarlo.cpp:118-137 */
+    /**
+     * Load a reference `state.json` into both Spaces, restore the two generators if the file carries them
+     * (`random-move` = Move::slump, `random-global` = Faunus::random, each {"seed": "<engine state>"} as
+     * src/random.cpp:10-45 writes them) and re-init; src/montecarlo.cpp:118-137
+     */
     void restore(const Json& j)
     {
+        if (!window.empty()) {
+            throw std::runtime_error("restore: proposals are still in flight (restore between sweeps)");
+        }
         state.spc->loadState(j);
         trial_state.spc->loadState(j);
+        auto restore_generator = [&](const char* key, Random& generator) {
+            if (const Json* node = j.find(key)) {
+                const std::string seed = node->is_object() ? node->value("seed", std::string()) : std::string();
+                if (!seed.empty() && seed != "default" && seed != "fixed") {
+                    generator.setState(seed);
+                }
+            }
+        };
+        restore_generator("random-move", rng.slump);
+        restore_generator("random-global", rng.global);
         init();
+    }
+
+    /** The state file of `savestate` with `saverandom: true`; src/analysis.cpp:656-682 */
+    Json saveState() const
+    {
+        Json j = state.spc->toJson();
+        auto generator = [](const Random& r) {
+            Json g = Json::object();
+            g["seed"] = r.state();
+            g["engine"] = "Mersenne Twister (std::mt19937)";
+            return g;
+        };
+        j["random-move"] = generator(rng.slump);
+        j["random-global"] = generator(rng.global);
+        return j;
     }
 
     /** src/montecarlo.cpp:85-99 */

@@ -9,6 +9,7 @@
 #include "analysis_virtual.hpp"
 #include "replica_comm.hpp"
 #include <cstring>
+#include <mutex>
 #include <thread>
 
 namespace fb::capi {
@@ -93,7 +94,15 @@ inline std::vector<LocalReplicaResult> runLocalReplicas(const Json& configs, int
                 if (setup) {
                     setup(r);
                 }
-                MetropolisMonteCarlo mc(configs.at(r), factory, raw);
+                // the constructor sets the process-global pc::temperature and converts units / builds tables from
+                // it (the reference runs one process per replica): replicas are constructed one at a time
+                static std::mutex construction;
+                std::unique_ptr<MetropolisMonteCarlo> owner;
+                {
+                    std::lock_guard<std::mutex> lock(construction);
+                    owner = std::make_unique<MetropolisMonteCarlo>(configs.at(r), factory, raw);
+                }
+                MetropolisMonteCarlo& mc = *owner;
                 for (int i = 0; i < sweeps; ++i) {
                     mc.sweep();
                 }
@@ -378,7 +387,7 @@ inline State& pick(Sim& s, int which)
     __attribute__((visibility("default"))) int P##_sim_state_json(void* h, char* buf, int len)               \
     {                                                                                                         \
         auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
-        return fb::capi::copyOut(s->mc->state.spc->toJson().dump(), buf, len);                               \
+        return fb::capi::copyOut(s->mc->saveState().dump(), buf, len);                                        \
     }                                                                                                         \
     __attribute__((visibility("default"))) int P##_sim_info_json(void* h, char* buf, int len)                \
     {                                                                                                         \

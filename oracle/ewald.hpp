@@ -94,6 +94,20 @@ namespace ewald {
  */
 inline bool parallel_full_update = false;
 
+/**
+ * The MC driver computes the full structure factor four times at start-up (constructor + init(), for the accepted
+ * and for the trial state, src/montecarlo.cpp:43-71) from IDENTICAL positions. With this flag a full update whose
+ * inputs (k-vectors, policy, every active particle) equal those of the previous full update returns the stored
+ * result — the same numbers, computed once. Large synthetic systems only (tests/test_gpu_fullsize.py, bench.py).
+ */
+inline bool memoize_full_update = false;
+struct FullUpdateMemo
+{
+    std::vector<double> key;
+    std::vector<std::complex<double>> Q;
+};
+inline FullUpdateMemo full_update_memo;
+
 /** src/energy.cpp:133-186 (PBC) and :356-412 (IPBC) */
 inline void updateBox(EwaldData& d, const Point& box)
 {
@@ -153,6 +167,21 @@ inline void updateBox(EwaldData& d, const Point& box)
 inline void updateComplex(EwaldData& d, const Space& spc)
 {
     const long K = static_cast<long>(d.k_vectors.size());
+    std::vector<double> key;
+    if (memoize_full_update) {
+        key = {static_cast<double>(K), static_cast<double>(d.policy), d.box_length.x, d.box_length.y, d.box_length.z,
+               d.n_cutoff, d.alpha, d.kappa};
+        for (const auto& g : spc.groups) {
+            for (size_t i = 0; i < g.size(); ++i) {
+                const auto& particle = spc.at(g, i);
+                key.insert(key.end(), {particle.pos.x, particle.pos.y, particle.pos.z, particle.charge});
+            }
+        }
+        if (key == full_update_memo.key && static_cast<long>(full_update_memo.Q.size()) == K) {
+            d.Q_ion = full_update_memo.Q;
+            return;
+        }
+    }
 #pragma omp parallel for schedule(static) if (parallel_full_update)
     for (long k = 0; k < K; k++) {
         const Point& q = d.k_vectors[k];
@@ -176,6 +205,10 @@ inline void updateComplex(EwaldData& d, const Space& spc)
             Q = {Q.real(), imag_unweighted}; // reference quirk, src/energy.cpp:215-216
         }
         d.Q_ion[k] = Q;
+    }
+    if (memoize_full_update) {
+        full_update_memo.key = std::move(key);
+        full_update_memo.Q = d.Q_ion;
     }
 }
 

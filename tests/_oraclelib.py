@@ -47,6 +47,7 @@ def oracle_lib() -> C.CDLL:
         _lib.fo_ewald_kat.argtypes = [C.c_char_p, C.c_double, C.c_double, c_double_p, C.c_int, c_double_p,
                                       c_double_p]
         _lib.fo_set_parallel_ewald_init.argtypes = [C.c_int]
+        _lib.fo_set_large_system_mode.argtypes = [C.c_int]
         _lib.fo_openmp_threads.restype = C.c_int
     return _lib
 

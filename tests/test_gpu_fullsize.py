@@ -1,5 +1,12 @@
-"""Full-size checks (BASELINE.json sizes) through size-independent properties — the oracle would need
-minutes per move at N = 1e5, so these tests compare the device paths with each other and with invariants:
+"""Full-size checks (BASELINE.json sizes).
+
+The headline configuration S1 (N = 1e5, exactly `bench.workload()`) is compared with the ORACLE move by move
+(`test_s1_matches_oracle`: per-term system energies, u_new / u_old of every trial move, the accept/reject
+sequence and the final positions, for one move per launch, windows walked on the host and runs walked on the
+device), and S2 (N = 1e6, device cell list) with the oracle's brute-force pair sums (`test_s2_pair_part_matches_oracle`).
+The oracle's start-up passes over all pairs / all (k, particle) run in its large-system mode (all host threads,
+identical repeats answered from the stored result, oracle/oracle.cpp `fo_set_large_system_mode`); its per-move
+path is the serial reference restatement. The remaining tests use size-independent properties:
 
   * energy bookkeeping: E_final − (E_init + Σ accepted ΔU) ≈ 0 (the reference's own drift check,
     src/montecarlo.cpp:85-99) after thousands of windowed moves,
@@ -24,6 +31,86 @@ def s1(moves_per_sweep, **kw):
 def sim(cfg, window=None, run=None, run_min=None):
     from faunus_b200.native import B200Simulation
     return B200Simulation(cfg, window=window, run=run, run_min=run_min)
+
+
+@pytest.fixture(scope="module")
+def s1_oracle():
+    """256 trial moves of bench.workload() by the oracle: energies per term before and after, trace, positions"""
+    import bench
+    from _oraclelib import oracle_lib, oracle_sim
+    lib = oracle_lib()
+    lib.fo_set_large_system_mode(1)
+    try:
+        o = oracle_sim(bench.workload(moves_per_step=256))
+        before = o.system_energy()[1]
+        o.trace_enable()
+        o.sweep(1)
+        after = o.system_energy()[1]
+        out = {"before": before, "after": after, "trace": o.trace(), "positions": o.particles()[0], "drift": o.drift()}
+        o.close()
+    finally:
+        lib.fo_set_large_system_mode(0)
+    return out
+
+
+@pytest.mark.parametrize("mode", ["single", "windows", "runs"])
+def test_s1_matches_oracle(s1_oracle, mode):
+    """The headline workload against the oracle (src/montecarlo.cpp:139-187 move by move). Tolerance: 1e-10 relative
+    to the largest energy of the comparison (FP64, summation order only); decisions and positions identical."""
+    import bench
+    kw = {"single": dict(window=0), "windows": dict(window=64, run=0), "runs": dict(window=64, run=512, run_min=1)}[mode]
+    g = sim(bench.workload(moves_per_step=256), **kw)
+    assert g.num_particles == 100_000
+    before = g.system_energy()[1]
+    g.trace_enable()
+    g.sweep(1)
+    after = g.system_energy()[1]
+    o, t = s1_oracle["trace"], g.trace()
+    assert len(t["du"]) == len(o["du"]) == 256
+    if mode == "runs":
+        assert g.run_stats()["windows"] > 0
+    scale = np.abs(s1_oracle["before"]).max()
+    assert np.abs(before - s1_oracle["before"]).max() <= 1e-10 * scale
+    assert np.abs(after - s1_oracle["after"]).max() <= 1e-10 * scale
+    assert np.array_equal(t["accepted"], o["accepted"])
+    move_scale = max(np.abs(o["u_new"]).max(), np.abs(o["u_old"]).max())
+    assert np.abs(t["u_new"] - o["u_new"]).max() <= 1e-10 * move_scale
+    assert np.abs(t["u_old"] - o["u_old"]).max() <= 1e-10 * move_scale
+    assert np.abs(t["du"] - o["du"]).max() <= 1e-10 * move_scale
+    assert np.array_equal(g.particles()[0], s1_oracle["positions"])
+    assert abs(g.drift()) < 1e-9 and abs(s1_oracle["drift"]) < 1e-9
+
+
+def test_s2_pair_part_matches_oracle():
+    """S2 (N = 1e6, L = 939.8 A): 24 trial moves through the device cell list against the oracle's
+    brute-force pair sums, cutoff scheme without k-space. The oracle skips the Σ_{i<j} over all 5e11 pairs of the
+    start configuration (large-system mode 2): only the per-move energies and decisions are compared."""
+    from faunus_b200.config import primitive_model
+    from _oraclelib import oracle_lib, oracle_sim
+    cfg = primitive_model(n=1_000_000, molarity=1.0, seed=5489, moves_per_sweep=24,
+                          coulomb={"type": "fanourgakis", "epsr": 78.7, "cutoff": 28.0})
+    lib = oracle_lib()
+    lib.fo_set_large_system_mode(2)
+    try:
+        o = oracle_sim(cfg)
+        o.trace_enable()
+        o.sweep(1)
+        to, xo = o.trace(), o.particles()[0]
+        o.close()
+    finally:
+        lib.fo_set_large_system_mode(0)
+    g = sim(cfg, window=64)
+    g.trace_enable()
+    g.sweep(1)
+    tg = g.trace()
+    assert len(tg["du"]) == len(to["du"]) == 24
+    assert np.array_equal(tg["accepted"], to["accepted"])
+    # the oracle's trace holds Hamiltonian energies: self-energy term (identical on both sides) + pair sums
+    scale = max(np.abs(to["u_new"]).max(), np.abs(to["u_old"]).max())
+    assert np.abs(tg["u_new"] - to["u_new"]).max() <= 1e-10 * scale
+    assert np.abs(tg["u_old"] - to["u_old"]).max() <= 1e-10 * scale
+    assert np.array_equal(g.particles()[0], xo)
+    assert abs(g.drift()) < 1e-9
 
 
 def test_s1_drift_invariant_windowed():

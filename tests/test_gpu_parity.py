@@ -770,3 +770,29 @@ def test_molecule_rdf_counts_are_exact(water_input):
         g.rdf_sample_shard(rid, rank, 3)
         parts.append(g.rdf_result(rid)[1])
     assert np.array_equal(sum(parts), g.rdf_result(whole)[1])
+
+
+def test_restore_on_the_device(water_input):
+    """`restore` (src/montecarlo.cpp:118-137) of a state file written by the ORACLE after two sweeps — positions,
+    group records and both generators — into a fresh device simulation: the mirror is re-uploaded, Q(k) rebuilt, and
+    the continued run equals the oracle's own continuation (windows and one move per launch)."""
+    from conftest import water_with_salt
+    cfg = water_with_salt(water_input, n_pairs=6)
+    o = oracle_sim(cfg)
+    o.sweep(2)
+    state = o.state_json()
+    o.trace_enable()
+    o.sweep(2)
+    ref = o.trace()
+    for window in (0, 64):
+        g = b200_sim(cfg, window)
+        g.sweep(1)  # the device has moved on before the restore
+        g.restore(state)
+        g.trace_enable()
+        g.sweep(2)
+        got = g.trace()
+        assert np.array_equal(ref["move_id"], got["move_id"]) and np.array_equal(ref["accepted"], got["accepted"])
+        scale = np.abs(ref["u_new"]).max()
+        assert np.abs(ref["u_new"] - got["u_new"]).max() <= 1e-10 * scale
+        assert np.array_equal(o.particles()[0], g.particles()[0])
+        assert abs(g.drift()) < 1e-9

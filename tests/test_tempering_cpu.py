@@ -110,3 +110,29 @@ def test_temper_gloo_matches_local(tmp_path):
         assert got["bytes"] > 0
         temper = [m["temper"] for m in got["info"]["moves"] if "temper" in m][0]
         assert temper["replicas"] == 2
+
+
+def test_temper_local_replicas_at_different_temperatures(tmp_path):
+    """Temperature tempering inside ONE process: the input temperature is a process-global in the reference
+    (`pc::temperature`, src/faunus.cpp:106; one MPI process per replica). The in-process replicas are constructed
+    one at a time so that each builds its Bjerrum length and kJ/mol tables at its OWN temperature: equal, bit for
+    bit, to the run with one process per replica."""
+    import torch.multiprocessing as mp
+    from faunus_b200.replica import run_local_replicas
+    configs = electrolyte_replicas(2)
+    configs[0]["temperature"], configs[1]["temperature"] = 300.0, 345.0
+    for cfg in configs:  # same dielectric constant: the replicas differ in temperature only
+        cfg["energy"][0]["nonbonded_coulombwca"]["coulomb"]["epsr"] = 70.0
+    sweeps = 12
+    for attempt in range(3):  # a construction race would show up as run-to-run differences
+        local = run_local_replicas(oracle_api(), configs, sweeps=sweeps)
+        assert all(r["error"] == "" for r in local)
+        if attempt == 0:
+            first = local
+        else:
+            assert [r["energy"] for r in local] == [r["energy"] for r in first]
+    mp.spawn(_gloo_worker, args=(2, _free_port(), configs, sweeps, str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        got = json.load(open(tmp_path / f"rank{rank}.json"))
+        assert got["energy"] == local[rank]["energy"]
+        assert got["xyzq"] == local[rank]["xyzq"]
