@@ -4,6 +4,7 @@
 #include "../../../include/faunus_b200.h"
 #include "fb_kernels.cuh"
 #include "fb_batch.cuh"
+#include "fb_kspace.cuh"
 #include "fb_stream.cuh"
 #include "fb_cells.cuh"
 #include "fb_run.cuh"
@@ -115,6 +116,11 @@ struct Slot
     DeviceBuffer<double> ksq; //!< sqrt(A_k)
     DeviceBuffer<int> cell_start; //!< [n_cells + 1] first k of each 4×4×4 cell of integer triplets (storage order)
     int n_cells = 0;
+    // work units of the window k-space kernel (fb_kspace.cuh): halves of the cells, 32 k-slots each
+    DeviceBuffer<double2> aks;            //!< [K] {A_k, √A_k}
+    DeviceBuffer<int4> unit_info;         //!< [n_units] {first k of the cell, x, y, z table index of the first slot}
+    DeviceBuffer<unsigned char> unit_map; //!< [n_units][32] slot → index inside the cell's storage range, 255: none
+    int n_units = 0;
     std::vector<int> perm; //!< storage index → index in the reference's k-vector order
     DeviceBuffer<double2> Q;
     int K = 0;
@@ -221,6 +227,7 @@ struct fb_ctx
         int flight_n = 0, flight_stride = 0, flight_with_ewald = 0, flight_atoms = 0, flight_groups = 0;
         bool flight_timing = false;
         bool kspace_configured[3] = {false, false, false}; //!< dynamic shared memory opt-in done (stride 16/32/64)
+        bool kspace_unit_configured = false;
         // device cell list of slot 0 for the pair part of a window (fb_cells.cuh)
         int cell_min_particles = 200000; //!< use the cell list from this many particle slots on (< 0: never)
         bool cells_valid = false;
@@ -1771,6 +1778,54 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
             ksq[i] = std::sqrt(kA[i].w);
         }
         sl.ksq.upload(ksq.data(), ksq.size(), c->stream);
+        { // units of the window k-space kernel: the y-rows {0, 1} and {2, 3} of every cell that hold k-vectors
+            const int ncc = static_cast<int>(std::ceil(c->ewald.n_cutoff));
+            std::vector<double2> aks(kA.size());
+            for (size_t i = 0; i < kA.size(); ++i) {
+                aks[i] = make_double2(kA[i].w, ksq[i]);
+            }
+            std::vector<int4> unit_info;
+            std::vector<unsigned char> unit_map;
+            std::vector<int> cell_start_host;
+            for (size_t i = 0; i < kn.size(); ++i) {
+                if (i == 0 || (kn[i].x >> 2) != (kn[i - 1].x >> 2) || ((kn[i].y + ncc) >> 2) != ((kn[i - 1].y + ncc) >> 2) ||
+                    ((kn[i].z + ncc) >> 2) != ((kn[i - 1].z + ncc) >> 2)) {
+                    cell_start_host.push_back(static_cast<int>(i));
+                }
+            }
+            cell_start_host.push_back(static_cast<int>(kn.size()));
+            for (size_t cell = 0; cell + 1 < cell_start_host.size(); ++cell) {
+                const int p0 = cell_start_host[cell];
+                const int len = cell_start_host[cell + 1] - p0;
+                const int bx = kn[p0].x & ~3;
+                const int by = (kn[p0].y + ncc) & ~3; // table indices (offset by ncc)
+                const int bz = (kn[p0].z + ncc) & ~3;
+                for (int h = 0; h < 2; ++h) {
+                    unsigned char map[32];
+                    std::fill(map, map + 32, static_cast<unsigned char>(255));
+                    bool any = false;
+                    for (int t = 0; t < len; ++t) {
+                        const int4 v = kn[p0 + t];
+                        const int li = v.x - bx, lj = (v.y + ncc) - by, ll = (v.z + ncc) - bz;
+                        if ((lj >> 1) == h) {
+                            map[8 * li + 4 * (lj & 1) + ll] = static_cast<unsigned char>(t);
+                            any = true;
+                        }
+                    }
+                    if (any) {
+                        unit_info.push_back(make_int4(p0, bx, by + 2 * h, bz));
+                        unit_map.insert(unit_map.end(), map, map + 32);
+                    }
+                }
+            }
+            sl.n_units = static_cast<int>(unit_info.size());
+            sl.aks.upload(aks.data(), aks.size(), c->stream);
+            if (sl.n_units > 0) {
+                sl.unit_info.upload(unit_info.data(), unit_info.size(), c->stream);
+                sl.unit_map.upload(unit_map.data(), unit_map.size(), c->stream);
+            }
+            CUDA_CHECK(cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
+        }
         sl.Q.ensure(kA.size());
         sl.K = static_cast<int>(kA.size());
         for (int i = 0; i < 3; ++i) {
@@ -1915,6 +1970,17 @@ FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
             CUDA_CHECK(cudaMemcpyAsync(d.cell_start.ptr, s.cell_start.ptr, (s.n_cells + 1) * sizeof(int),
                                        cudaMemcpyDeviceToDevice, c->stream));
             d.n_cells = s.n_cells;
+            d.aks.ensure(s.K);
+            CUDA_CHECK(cudaMemcpyAsync(d.aks.ptr, s.aks.ptr, s.K * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
+            d.n_units = s.n_units;
+            if (s.n_units > 0) {
+                d.unit_info.ensure(s.n_units);
+                CUDA_CHECK(cudaMemcpyAsync(d.unit_info.ptr, s.unit_info.ptr, s.n_units * sizeof(int4),
+                                           cudaMemcpyDeviceToDevice, c->stream));
+                d.unit_map.ensure(static_cast<size_t>(s.n_units) * 32);
+                CUDA_CHECK(cudaMemcpyAsync(d.unit_map.ptr, s.unit_map.ptr, static_cast<size_t>(s.n_units) * 32,
+                                           cudaMemcpyDeviceToDevice, c->stream));
+            }
             d.perm = s.perm;
             d.K = s.K;
             for (int i = 0; i < 3; ++i) {

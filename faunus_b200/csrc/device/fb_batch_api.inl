@@ -249,6 +249,20 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
         b.d_e_partials.ensure(static_cast<size_t>(2 * c->n_sm));
         b.d_r_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax);
         b.d_g_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax * kBatchMax);
+        static const bool old_kernel = std::getenv("FAUNUS_B200_OLD_KSPACE") != nullptr; // A/B switch while the new kernel is validated
+        if (!old_kernel) {
+            const Slot& sl = c->slot[0];
+            n_rows = std::max(1, std::min(sl.n_units, 2 * c->n_sm));
+            if (!b.kspace_unit_configured) {
+                CUDA_CHECK(cudaFuncSetAttribute(windowKspaceKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                static_cast<int>(sizeof(KspaceUnitSmem))));
+                b.kspace_unit_configured = true;
+            }
+            windowKspaceKernel<<<n_rows, kKsThreads, sizeof(KspaceUnitSmem), c->stream>>>(
+                E, sl.aks.ptr, sl.unit_info.ptr, sl.unit_map.ptr, sl.n_units, cur, prev, b.geo, stride,
+                b.d_r_partials.ptr, b.d_g_partials.ptr, b.d_e_partials.ptr);
+        }
+        else {
 #define FB_KSPACE(BT)                                                                                         \
     {                                                                                                         \
         bool& configured = b.kspace_configured[BT == 4 ? 0 : (BT == 8 ? 1 : 2)];                              \
@@ -272,6 +286,7 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
             FB_KSPACE(16)
         }
 #undef FB_KSPACE
+        }
         launched(c, "batchKspaceKernel");
     }
     if (timing) {
