@@ -120,6 +120,7 @@ struct Slot
     DeviceBuffer<double2> aks;            //!< [K] {A_k, √A_k}
     DeviceBuffer<int4> unit_info;         //!< [n_units] {first k of the cell, x, y, z table index of the first slot}
     DeviceBuffer<unsigned char> unit_map; //!< [n_units][32] slot → index inside the cell's storage range, 255: none
+    DeviceBuffer<double> unit_sa;         //!< [n_units][32] √A_k in slot layout, 0 for empty slots
     int n_units = 0;
     std::vector<int> perm; //!< storage index → index in the reference's k-vector order
     DeviceBuffer<double2> Q;
@@ -209,6 +210,7 @@ struct fb_ctx
         DeviceBuffer<double2> d_table[2];
         PinnedBuffer<BatchInput> h_in;
         DeviceBuffer<double> d_pair_partials, d_r_partials, d_g_partials, d_e_partials, d_result;
+        DeviceBuffer<double2> d_kq; //!< [n_units][32] √A_k·Q_k of the window-start state (windowFrontKernel)
         PinnedBuffer<double> h_result;
         int parity = 0;
         int last_n = 0;            //!< moves of the most recent window (0: none evaluated)
@@ -226,8 +228,7 @@ struct fb_ctx
         bool in_flight = false;      //!< fb_batch_submit done, fb_batch_wait pending
         int flight_n = 0, flight_stride = 0, flight_with_ewald = 0, flight_atoms = 0, flight_groups = 0;
         bool flight_timing = false;
-        bool kspace_configured[3] = {false, false, false}; //!< dynamic shared memory opt-in done (stride 16/32/64)
-        bool kspace_unit_configured = false;
+        bool kspace_unit_configured = false; //!< dynamic shared memory opt-in of windowKspaceKernel done
         // device cell list of slot 0 for the pair part of a window (fb_cells.cuh)
         int cell_min_particles = 200000; //!< use the cell list from this many particle slots on (< 0: never)
         bool cells_valid = false;
@@ -1786,6 +1787,7 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
             }
             std::vector<int4> unit_info;
             std::vector<unsigned char> unit_map;
+            std::vector<double> unit_sa;
             std::vector<int> cell_start_host;
             for (size_t i = 0; i < kn.size(); ++i) {
                 if (i == 0 || (kn[i].x >> 2) != (kn[i - 1].x >> 2) || ((kn[i].y + ncc) >> 2) != ((kn[i - 1].y + ncc) >> 2) ||
@@ -1802,6 +1804,7 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
                 const int bz = (kn[p0].z + ncc) & ~3;
                 for (int h = 0; h < 2; ++h) {
                     unsigned char map[32];
+                    double sa[32] = {};
                     std::fill(map, map + 32, static_cast<unsigned char>(255));
                     bool any = false;
                     for (int t = 0; t < len; ++t) {
@@ -1809,12 +1812,14 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
                         const int li = v.x - bx, lj = (v.y + ncc) - by, ll = (v.z + ncc) - bz;
                         if ((lj >> 1) == h) {
                             map[8 * li + 4 * (lj & 1) + ll] = static_cast<unsigned char>(t);
+                            sa[8 * li + 4 * (lj & 1) + ll] = ksq[p0 + t];
                             any = true;
                         }
                     }
                     if (any) {
                         unit_info.push_back(make_int4(p0, bx, by + 2 * h, bz));
                         unit_map.insert(unit_map.end(), map, map + 32);
+                        unit_sa.insert(unit_sa.end(), sa, sa + 32);
                     }
                 }
             }
@@ -1823,6 +1828,7 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
             if (sl.n_units > 0) {
                 sl.unit_info.upload(unit_info.data(), unit_info.size(), c->stream);
                 sl.unit_map.upload(unit_map.data(), unit_map.size(), c->stream);
+                sl.unit_sa.upload(unit_sa.data(), unit_sa.size(), c->stream);
             }
             CUDA_CHECK(cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
         }
@@ -1979,6 +1985,9 @@ FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
                                            cudaMemcpyDeviceToDevice, c->stream));
                 d.unit_map.ensure(static_cast<size_t>(s.n_units) * 32);
                 CUDA_CHECK(cudaMemcpyAsync(d.unit_map.ptr, s.unit_map.ptr, static_cast<size_t>(s.n_units) * 32,
+                                           cudaMemcpyDeviceToDevice, c->stream));
+                d.unit_sa.ensure(static_cast<size_t>(s.n_units) * 32);
+                CUDA_CHECK(cudaMemcpyAsync(d.unit_sa.ptr, s.unit_sa.ptr, static_cast<size_t>(s.n_units) * 32 * sizeof(double),
                                            cudaMemcpyDeviceToDevice, c->stream));
             }
             d.perm = s.perm;

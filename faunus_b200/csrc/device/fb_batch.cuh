@@ -8,18 +8,18 @@
 //
 //   pair     u_new[m], u_old[m]     = Σ_{j≠p_m} u(trial_m | old_m , r_j(S0))           batchPairKernel / batchPairCellKernel
 //   cross    C_new[a][m], C_old[a][m] = u(x_m, new_a) − u(x_m, old_a)                   batchPairFinishKernel
-//   k-space  R[m]  = Σ_k A_k (2 Re(conj(Q_k) δ_m,k) + |δ_m,k|²)                        batchKspaceKernel
+//   k-space  R[m]  = Σ_k A_k (2 Re(conj(Q_k) δ_m,k) + |δ_m,k|²)                        windowKspaceKernel (fb_kspace.cuh)
 //            G[a][m] = Σ_k A_k Re(conj(δ_a,k) δ_m,k),  δ_m,k = q (e^{ik·new_m} − e^{ik·old_m})
 //
 // so that the energies of move m in the state where the accepted moves a < m have been applied are
 //   u_x[m] + Σ_{a accepted} C_x[a][m]          and     ΔU_rec = pref (R[m] + 2 Σ_{a accepted} G[a][m]),
 // exact identities — only the summation order differs from the one-move-at-a-time evaluation. The
 // caller walks the window in order, decides each move, and tells the next launch which were accepted
-// (batchPrepKernel writes their positions into both mirrors, batchKspaceKernel adds their δ to Q(k);
+// (batchPrepKernel writes their positions into both mirrors, windowFrontKernel adds their δ to Q(k);
 // batchCommitKernel does both when windowed evaluation is left).
 //
 // e^{ik·r} is factorised into per-axis phase tables e^{i 2π n x/L} (k = 2π n/L on an orthogonal box),
-// built once per window by batchPhaseKernel: 2 complex products per (k, position) instead of a sincos.
+// built once per window by windowFrontKernel: complex products per (k, position) instead of a sincos.
 #pragma once
 #include "fb_kernels.cuh"
 
@@ -113,7 +113,7 @@ __device__ __forceinline__ void loadVariant(unsigned var_addr, unsigned fold_add
     asm("ld.shared.s32 %0, [%1];" : "=r"(fold) : "r"(fold_addr + static_cast<unsigned>(v) * 4u));
 }
 
-/** e^{ik·r} for k = 2π(nx, ny, nz)/L from the phase table of one position */
+/** q e^{ik·r} for k = 2π(nx, ny, nz)/L from the phase table of one position (the x entries carry the charge) */
 __device__ __forceinline__ double2 tablePhase(const double2* __restrict__ t, const PhaseGeometry& g, int nx, int ny,
                                               int nz)
 {
@@ -132,13 +132,10 @@ __global__ void __launch_bounds__(kBlock)
                       PhaseGeometry geo, CommitList commit, int with_ewald, double* __restrict__ e_partials)
 {
     __shared__ double scratch[kBlock / 32];
-    __shared__ double s_qn[kBatchMax], s_qo[kBatchMax];
     __shared__ int s_table[kBatchMax]; //!< first table entry of the accepted move's new position
     if (threadIdx.x < commit.n) {
         const int m = commit.index[threadIdx.x];
         const double4 p = prev.in->pnew[m];
-        s_qn[threadIdx.x] = p.w;
-        s_qo[threadIdx.x] = prev.pold[m].w;
         s_table[threadIdx.x] = 2 * m * geo.table_stride;
         if (blockIdx.x == 0) {
             const int s = prev.in->slot[m];
@@ -164,8 +161,8 @@ __global__ void __launch_bounds__(kBlock)
             const double2* t = table + s_table[a];
             const double2 en = tablePhase(t, geo, n.x, n.y, n.z);
             const double2 eo = tablePhase(t + geo.table_stride, geo, n.x, n.y, n.z);
-            Q.x += s_qn[a] * en.x - s_qo[a] * eo.x;
-            Q.y += s_qn[a] * en.y - s_qo[a] * eo.y;
+            Q.x += en.x - eo.x;
+            Q.y += en.y - eo.y;
         }
         if (ncommit > 0) {
             E.Q[k] = Q;
@@ -222,7 +219,11 @@ __global__ void __launch_bounds__(kBatchMax) batchCommitGroupsKernel(SlotView M0
     }
 }
 
-/** entry t of the per-axis phase tables e^{i 2π n x / L} of the 2n positions of a window */
+/**
+ * entry t of the per-axis phase tables e^{i 2π n x / L} of the 2n positions of a window; the x-axis entries carry the
+ * CHARGE of the position (q e^{i k_x x}), so a product of one entry per axis is q e^{ik·r} and nobody downstream
+ * needs the charges
+ */
 __device__ __forceinline__ void phaseTableEntry(const BatchInput* in, double2* __restrict__ table, const PhaseGeometry& geo,
                                                 int t)
 {
@@ -248,18 +249,8 @@ __device__ __forceinline__ void phaseTableEntry(const BatchInput* in, double2* _
     const double kc = 2.0 * 3.141592653589793238462643383279502884 * static_cast<double>(nn) / geo.len[axis];
     double sn, cs;
     sincos(kc * x, &sn, &cs);
-    table[t] = make_double2(cs, sn);
-}
-
-/** per-axis phase tables of the 2n positions of the window */
-__global__ void __launch_bounds__(kBlock) batchPhaseKernel(BatchBuffers cur, PhaseGeometry geo)
-{
-    const int n = cur.in->n;
-    const int tid = blockIdx.x * kBlock + threadIdx.x;
-    const int total = 2 * n * geo.table_stride;
-    for (int t = tid; t < total; t += gridDim.x * kBlock) {
-        phaseTableEntry(cur.in, cur.table, geo, t);
-    }
+    const double q = axis == 0 ? p.w : 1.0;
+    table[t] = make_double2(q * cs, q * sn);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -281,8 +272,28 @@ constexpr int kPairQueue = 256; //!< in-range candidates a warp collects before 
 template <int KIND, bool DENSE>
 __global__ void __launch_bounds__(kPairThreads)
     batchPairKernel(SlotView M0, PotParams P, BatchBuffers cur, double cut2, int stride,
-                    double* __restrict__ partials /*[gridDim.x][2·stride]*/, const int* __restrict__ redo = nullptr)
+                    double* __restrict__ partials /*[gridDim.x][2·stride]*/, const int* __restrict__ redo = nullptr,
+                    SlotView M1 = SlotView{}, BatchBuffers prev = BatchBuffers{}, int apply_commit = 0)
 {
+    // apply_commit: the accepted moves of the previous window are not in the mirrors yet (no batchPrepKernel ran):
+    // every block writes those that fall into ITS particle range, into both mirrors, before it loads the range (the
+    // blocks of the other variant ranges write the same values)
+    if (apply_commit) {
+        const CommitList& commit = cur.in->commit;
+        if (static_cast<int>(threadIdx.x) < commit.n) {
+            const int m = commit.index[threadIdx.x];
+            const int s = prev.in->slot[m];
+            if (s >= static_cast<int>(blockIdx.x) * kPairChunk && s < static_cast<int>(blockIdx.x + 1) * kPairChunk) {
+                const double4 p = prev.in->pnew[m];
+                const int id = prev.in->id[m];
+                M0.posq[s] = p;
+                M0.atom_id[s] = id;
+                M1.posq[s] = p;
+                M1.atom_id[s] = id;
+            }
+        }
+        __syncthreads();
+    }
     // redo != nullptr: the sums of this window may have been evaluated ahead (fb_run.cuh); then there is nothing to
     // do unless the correction met a cancellation (*redo)
     if (redo != nullptr && cur.in->pair_ready && *redo == 0) {
@@ -636,9 +647,9 @@ __global__ void __launch_bounds__(kBlock)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k-space part (BT = stride / 4 ∈ {4, 8, 16}); cells of ≤ kTileK k-vectors, two per lane.
+// k-vector cells (used by the full rebuild of Q(k), fb_stream.cuh; the window kernels are in fb_kspace.cuh)
 // ------------------------------------------------------------------------------------------------
-constexpr int kTileK = 64; //!< k-vectors per tile (two per lane)
+constexpr int kTileK = 64; //!< k-vectors per cell
 
 /**
  * The k-vectors are stored cell by cell: a cell is the 4×4×4 block of integer triplets with the same
@@ -690,14 +701,7 @@ __device__ __forceinline__ double2 cellPhase(const double2* t, int li, int lj, i
     return cmul(cmul(t[li], t[4 + lj]), t[8 + ll]);
 }
 
-// ------------------------------------------------------------------------------------------------
-// ONE persistent kernel: block b walks the cells b, b + grid, … and keeps the per-move and per-pair sums in
-// registers, so nothing but the final partials leaves the SM:
-//   per cell: stage the 12 table entries of every position (accepted moves of the previous window and the
-//   2B positions of this one) → ΔQ of the commits (warps split the commits) → Q(k) updated in place →
-//   δ_m,k for the warp's moves into shared memory, R[m] in registers → rank-update of G from shared memory.
-// Dynamic shared memory (≈ 92 kB): two blocks per SM.
-// ------------------------------------------------------------------------------------------------
+// cp.async (LDGSTS) helpers of the k-space kernels (fb_kspace.cuh)
 __device__ __forceinline__ void cpAsync16(void* smem, const void* gmem)
 {
     const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
@@ -710,323 +714,6 @@ __device__ __forceinline__ void cpAsync8(void* smem, const void* gmem)
 }
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;\n" ::); }
-
-/** Everything one cell needs, staged by cp.async (LDGSTS) while the previous cell is being processed */
-template <int STRIDE> struct CellStage
-{
-    double2 tab_new[2 * STRIDE][kCellEntries];
-    double2 tab_com[2 * STRIDE][kCellEntries];
-    int4 kn[kTileK];
-    double2 Q[kTileK];
-    double A[kTileK];
-    double sA[kTileK];
-};
-
-template <int BT> struct KspaceSmem
-{
-    static constexpr int STRIDE = BT * 4;
-    static constexpr int KH = STRIDE == 64 ? 32 : kTileK; //!< k-vectors per pass
-    static constexpr int LD = KH + 2; //!< row stride ≡ 32 B (mod 128 B): the DMMA fragment loads are conflict-free
-    static constexpr int DELTA_ELEMS = STRIDE * LD > 2048 ? STRIDE * LD : 2048;
-    static constexpr int NBUF = STRIDE == 64 ? 1 : 2; //!< double-buffered staging where two blocks per SM still fit
-    static constexpr int MAX_CELLS = 32;              //!< cells per block held in the list (more: extra rounds)
-    static constexpr size_t bytes()
-    {
-        return sizeof(CellStage<STRIDE>) * NBUF + sizeof(double2) * (DELTA_ELEMS + (kBlock / 32) * KH) +
-               sizeof(double) * 2 * kBatchMax + sizeof(int) * 2 * kBatchMax + sizeof(int4) * 2 * MAX_CELLS;
-    }
-};
-
-template <int BT>
-__global__ void __launch_bounds__(kBlock, 2)
-    batchKspaceKernel(EwaldView E, const int4* __restrict__ kn, const double* __restrict__ sqrt_ak,
-                      const int* __restrict__ cell_start, int n_cells, BatchBuffers cur, BatchBuffers prev,
-                      PhaseGeometry geo, double* __restrict__ r_partials /*[grid][stride]*/,
-                      double* __restrict__ g_partials /*[grid][stride²]*/, double* __restrict__ e_partials /*[grid]*/)
-{
-    using L = KspaceSmem<BT>;
-    constexpr int STRIDE = L::STRIDE;
-    constexpr int KH = L::KH;
-    constexpr int LD = L::LD;
-    constexpr int NBUF = L::NBUF;
-    constexpr int NW = kBlock / 32;
-    constexpr int KPL = KH / 32;               // k-vectors per lane and pass
-    constexpr int MPW = STRIDE / NW;           // moves per warp: 2, 4, 8
-    // Gram update on the FP64 tensor path (mma.sync m8n8k4): 8×8 tiles of G, only the tiles on or above the
-    // diagonal; the 8 warps form KGW k-groups of WPG warps, the tiles of a group are dealt round robin.
-    constexpr int T = STRIDE / 8;              // tiles per dimension: 2, 4, 8
-    constexpr int NT = T * (T + 1) / 2;        // upper-triangular tiles: 3, 10, 36
-    constexpr int KGW = STRIDE == 64 ? 1 : (STRIDE == 32 ? 2 : 8);
-    constexpr int WPG = NW / KGW;              // warps per k-group: 8, 4, 1
-    constexpr int MAXT = (NT + WPG - 1) / WPG; // tiles per warp: 5, 3, 3
-    using Stage = CellStage<STRIDE>;
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Stage* stage = reinterpret_cast<Stage*>(smem_raw);
-    double2* s_delta = reinterpret_cast<double2*>(stage + NBUF);
-    double2(*s_dq)[KH] = reinterpret_cast<double2(*)[KH]>(s_delta + L::DELTA_ELEMS);
-    double* s_cqn = reinterpret_cast<double*>(s_dq + NW);
-    double* s_cqo = s_cqn + kBatchMax;
-    int* s_ctable = reinterpret_cast<int*>(s_cqo + kBatchMax);
-    int4* s_cell = reinterpret_cast<int4*>(s_ctable + 2 * kBatchMax); // {p0, len, –, –} and {nx0, ny0, nz0, –}
-
-    const int n = cur.in->n;
-    const CommitList& commit = cur.in->commit;
-    const int ncommit = min(commit.n, STRIDE);
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int kgroup = warp / WPG;
-    const int wig = warp % WPG;                // warp in its k-group
-    const int frag_g = lane >> 2;              // DMMA fragment coordinates of this lane
-    const int frag_t = lane & 3;
-    int tile_a[MAXT], tile_m[MAXT];            // this warp's tiles (ta ≤ tm), −1: none
-#pragma unroll
-    for (int q = 0; q < MAXT; ++q) {
-        int idx = wig + q * WPG;
-        tile_a[q] = tile_m[q] = -1;
-        if (idx < NT) {
-            int ta = 0;
-            while (idx >= T - ta) {
-                idx -= T - ta;
-                ++ta;
-            }
-            tile_a[q] = ta;
-            tile_m[q] = ta + idx;
-        }
-    }
-
-    // the cells of this block: b, b + grid, …
-    const int my_cells = (n_cells - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    if (static_cast<int>(threadIdx.x) < ncommit) {
-        const int m = commit.index[threadIdx.x];
-        s_cqn[threadIdx.x] = prev.in->pnew[m].w;
-        s_cqo[threadIdx.x] = prev.pold[m].w;
-        s_ctable[2 * threadIdx.x] = 2 * m * geo.table_stride;
-        s_ctable[2 * threadIdx.x + 1] = (2 * m + 1) * geo.table_stride;
-    }
-    auto loadCellList = [&](int first) { // entries [first, first + MAX_CELLS) of this block's cell sequence
-        if (static_cast<int>(threadIdx.x) < L::MAX_CELLS && first + static_cast<int>(threadIdx.x) < my_cells) {
-            const int cell = blockIdx.x + (first + threadIdx.x) * gridDim.x;
-            const int p0 = __ldg(cell_start + cell);
-            const int len = __ldg(cell_start + cell + 1) - p0;
-            const CellBase base = cellBase(__ldg(kn + p0), geo.ncc);
-            s_cell[2 * threadIdx.x] = make_int4(p0, len, 0, 0);
-            s_cell[2 * threadIdx.x + 1] = make_int4(base.nx, base.ny, base.nz, 0);
-        }
-    };
-    loadCellList(0);
-    __syncthreads();
-
-    // asynchronous staging of cell number `c` (in this block's sequence) into buffer `buf`
-    auto issue = [&](int c, int buf) {
-        const int4 info = s_cell[2 * (c % L::MAX_CELLS)];
-        const int4 bs = s_cell[2 * (c % L::MAX_CELLS) + 1];
-        Stage& st = stage[buf];
-        const int n_new = 2 * n * kCellEntries;
-        const int n_all = n_new + 2 * ncommit * kCellEntries;
-        for (int e = threadIdx.x; e < n_all; e += kBlock) {
-            const bool is_new = e < n_new;
-            const int ee = is_new ? e : e - n_new;
-            const int v = ee / kCellEntries;
-            const int t = ee - v * kCellEntries;
-            const int i = t & 3;
-            int offset;
-            if (t < 4) {
-                offset = min(bs.x + i, geo.ncc);
-            }
-            else if (t < 8) {
-                offset = (geo.ncc + 1) + min(bs.y + i, geo.ncc) + geo.ncc;
-            }
-            else {
-                offset = (geo.ncc + 1) + (2 * geo.ncc + 1) + min(bs.z + i, geo.ncc) + geo.ncc;
-            }
-            if (is_new) {
-                cpAsync16(&st.tab_new[v][t], cur.table + v * geo.table_stride + offset);
-            }
-            else {
-                cpAsync16(&st.tab_com[v][t], prev.table + s_ctable[v] + offset);
-            }
-        }
-        if (static_cast<int>(threadIdx.x) < info.y) {
-            const int k = info.x + threadIdx.x;
-            cpAsync16(&st.kn[threadIdx.x], kn + k);
-            cpAsync16(&st.Q[threadIdx.x], E.Q + k);
-            cpAsync8(&st.A[threadIdx.x], &E.kA[k].w);
-            cpAsync8(&st.sA[threadIdx.x], sqrt_ak + k);
-        }
-        cpAsyncCommit();
-    };
-
-    double qn[MPW], qo[MPW], racc[MPW];
-#pragma unroll
-    for (int i = 0; i < MPW; ++i) {
-        const int m = warp * MPW + i;
-        qn[i] = (m < n) ? cur.in->pnew[m].w : 0.0;
-        qo[i] = (m < n) ? cur.pold[m].w : 0.0;
-        racc[i] = 0.0;
-    }
-    double gacc[MAXT][2];
-#pragma unroll
-    for (int q = 0; q < MAXT; ++q) {
-        gacc[q][0] = gacc[q][1] = 0.0;
-    }
-    double eacc = 0.0;
-
-    if (my_cells > 0) {
-        issue(0, 0);
-    }
-    for (int c = 0; c < my_cells; ++c) {
-        const int buf = NBUF == 2 ? (c & 1) : 0;
-        const int4 info = s_cell[2 * (c % L::MAX_CELLS)];
-        const int p0 = info.x;
-        const int len = info.y;
-        cpAsyncWaitAll();
-        __syncthreads(); // cell c is staged for everybody; everybody is done with cell c − 1
-        if ((c + 1) % L::MAX_CELLS == 0 && c + 1 < my_cells) { // refill the cell list (rare: > 32 cells per block)
-            __syncthreads();
-            loadCellList(c + 1);
-            __syncthreads();
-        }
-        if (NBUF == 2 && c + 1 < my_cells) {
-            issue(c + 1, buf ^ 1); // lands while this cell is processed
-        }
-        const Stage& st = stage[buf];
-        for (int pass0 = 0; pass0 < len; pass0 += KH) {
-            int li[KPL], lj[KPL], ll[KPL];
-            double2 Q[KPL];
-            double A[KPL], sA[KPL];
-            bool valid[KPL];
-#pragma unroll
-            for (int kk = 0; kk < KPL; ++kk) {
-                const int kl = pass0 + lane + 32 * kk;
-                valid[kk] = kl < len;
-                li[kk] = lj[kk] = ll[kk] = 0;
-                Q[kk] = make_double2(0, 0);
-                A[kk] = 0.0;
-                sA[kk] = 0.0;
-                if (valid[kk]) {
-                    const int4 nn = st.kn[kl];
-                    li[kk] = nn.x & 3;
-                    lj[kk] = (nn.y + geo.ncc) & 3;
-                    ll[kk] = (nn.z + geo.ncc) & 3;
-                    Q[kk] = st.Q[kl];
-                    A[kk] = st.A[kl];
-                    sA[kk] = st.sA[kl];
-                }
-            }
-            if (ncommit > 0) {
-#pragma unroll
-                for (int kk = 0; kk < KPL; ++kk) {
-                    double2 dq = make_double2(0, 0);
-                    if (valid[kk]) {
-                        for (int a = warp; a < ncommit; a += NW) {
-                            const double2 en = cellPhase(st.tab_com[2 * a], li[kk], lj[kk], ll[kk]);
-                            const double2 eo = cellPhase(st.tab_com[2 * a + 1], li[kk], lj[kk], ll[kk]);
-                            dq.x += s_cqn[a] * en.x - s_cqo[a] * eo.x;
-                            dq.y += s_cqn[a] * en.y - s_cqo[a] * eo.y;
-                        }
-                    }
-                    s_dq[warp][lane + 32 * kk] = dq;
-                }
-                __syncthreads();
-#pragma unroll
-                for (int kk = 0; kk < KPL; ++kk) {
-                    if (valid[kk]) { // every warp adds the shares in the same order → the same Q(k) everywhere
-#pragma unroll
-                        for (int w = 0; w < NW; ++w) {
-                            Q[kk].x += s_dq[w][lane + 32 * kk].x;
-                            Q[kk].y += s_dq[w][lane + 32 * kk].y;
-                        }
-                        if (warp == 0) {
-                            E.Q[p0 + pass0 + lane + 32 * kk] = Q[kk]; // only this block touches the cell's k-vectors
-                        }
-                    }
-                }
-            }
-            if (warp == 0) {
-#pragma unroll
-                for (int kk = 0; kk < KPL; ++kk) {
-                    eacc += A[kk] * (Q[kk].x * Q[kk].x + Q[kk].y * Q[kk].y);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < MPW; ++i) {
-                const int m = warp * MPW + i;
-#pragma unroll
-                for (int kk = 0; kk < KPL; ++kk) {
-                    double2 d = make_double2(0, 0);
-                    if (valid[kk] && m < n) {
-                        const double2 en = cellPhase(st.tab_new[2 * m], li[kk], lj[kk], ll[kk]);
-                        const double2 eo = cellPhase(st.tab_new[2 * m + 1], li[kk], lj[kk], ll[kk]);
-                        d.x = qn[i] * en.x - qo[i] * eo.x;
-                        d.y = qn[i] * en.y - qo[i] * eo.y;
-                        racc[i] += A[kk] * (2.0 * (Q[kk].x * d.x + Q[kk].y * d.y) + (d.x * d.x + d.y * d.y));
-                    }
-                    s_delta[m * LD + lane + 32 * kk] = make_double2(sA[kk] * d.x, sA[kk] * d.y);
-                }
-            }
-            __syncthreads();
-            // rank update of G: A[a][kk] = B[kk][m] = √A_k δ (re, im of two k-vectors per step of 4)
-            const int ksteps = (min(KH, len - pass0) + 1) / 2;
-            const double* sd = reinterpret_cast<const double*>(s_delta);
-            for (int step = kgroup; step < ksteps; step += KGW) {
-                const int col = 4 * step + frag_t; // double index inside a row: 2·k + (re | im)
-#pragma unroll
-                for (int q = 0; q < MAXT; ++q) {
-                    if (tile_a[q] >= 0) {
-                        const double fa = sd[(tile_a[q] * 8 + frag_g) * (2 * LD) + col];
-                        const double fb = sd[(tile_m[q] * 8 + frag_g) * (2 * LD) + col];
-                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                                     : "+d"(gacc[q][0]), "+d"(gacc[q][1])
-                                     : "d"(fa), "d"(fb));
-                    }
-                }
-            }
-            __syncthreads(); // s_delta and s_dq are free again
-        }
-        if (NBUF == 1 && c + 1 < my_cells) {
-            issue(c + 1, 0); // single buffer: after the cell is done (waited for at the top of the loop)
-        }
-    }
-
-    if (warp == 0) {
-        const double es = warpSum(eacc);
-        if (lane == 0) {
-            e_partials[blockIdx.x] = es;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < MPW; ++i) {
-        const double rs = warpSum(racc[i]);
-        if (lane == 0) {
-            r_partials[static_cast<size_t>(blockIdx.x) * STRIDE + warp * MPW + i] = rs;
-        }
-    }
-    // G: add the k-groups in fixed order through shared memory; lane (g, t) of a tile holds G[8ta + g][8tm + 2t + {0, 1}]
-    __syncthreads();
-    double* s_g = reinterpret_cast<double*>(s_delta); // [KGW][STRIDE²] doubles (≤ 32 KB)
-#pragma unroll
-    for (int q = 0; q < MAXT; ++q) {
-        if (tile_a[q] >= 0) {
-            const int a = tile_a[q] * 8 + frag_g;
-            const int m = tile_m[q] * 8 + 2 * frag_t;
-            s_g[kgroup * STRIDE * STRIDE + a * STRIDE + m] = gacc[q][0];
-            s_g[kgroup * STRIDE * STRIDE + a * STRIDE + m + 1] = gacc[q][1];
-        }
-    }
-    __syncthreads();
-    for (int o = threadIdx.x; o < STRIDE * STRIDE; o += kBlock) {
-        const int a = o / STRIDE;
-        const int m = o % STRIDE;
-        double sum = 0.0;
-        if (a / 8 <= m / 8) { // a tile on or above the diagonal was computed
-            for (int g = 0; g < KGW; ++g) {
-                sum += s_g[g * STRIDE * STRIDE + o];
-            }
-        }
-        g_partials[static_cast<size_t>(blockIdx.x) * (STRIDE * STRIDE) + o] = sum;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // final ordered sums + the pair cross terms
@@ -1102,18 +789,16 @@ __global__ void __launch_bounds__(kBlock)
     }
 }
 
-/** pair side, one warp per output: 2S pair sums and the S² cross entries (4 pair energies each, a < m) */
+/** pair side, one warp (number `w`) per output: 2S pair sums and the S² cross entries (4 pair energies each, a < m) */
 template <int KIND>
-__global__ void __launch_bounds__(kBlock)
-    batchPairFinishKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, int n_pair_blocks,
-                          const double* __restrict__ pair_partials, int sums_done, const int* __restrict__ cell_overflow,
-                          double* __restrict__ result, const double* __restrict__ fix = nullptr,
-                          const int* __restrict__ redo = nullptr)
+__device__ __forceinline__ void pairFinishWarp(const SlotView& M0, const PotParams& P, const BatchBuffers& cur, int stride,
+                                               int n_pair_blocks, const double* __restrict__ pair_partials, int sums_done,
+                                               const int* __restrict__ cell_overflow, double* __restrict__ result,
+                                               const double* __restrict__ fix, const int* __restrict__ redo, int w)
 {
     const int n = cur.in->n;
     const int S = stride;
     const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     double* u = result + 8;
     double* cross = result + 8 + 3 * S;
     if (w == 0 && lane == 0) { // the cell list ran out of bucket space: the caller re-runs the window brute force
@@ -1169,6 +854,17 @@ __global__ void __launch_bounds__(kBlock)
     }
 }
 
+template <int KIND>
+__global__ void __launch_bounds__(kBlock)
+    batchPairFinishKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, int n_pair_blocks,
+                          const double* __restrict__ pair_partials, int sums_done, const int* __restrict__ cell_overflow,
+                          double* __restrict__ result, const double* __restrict__ fix = nullptr,
+                          const int* __restrict__ redo = nullptr)
+{
+    pairFinishWarp<KIND>(M0, P, cur, stride, n_pair_blocks, pair_partials, sums_done, cell_overflow, result, fix, redo,
+                         static_cast<int>((blockIdx.x * kBlock + threadIdx.x) >> 5));
+}
+
 /**
  * k-space side: ordered sums of the per-block partials R[rows][S], G[rows][S²], E[rows] → the result block.
  * Coalesced: a block takes 32 adjacent columns (lane ↔ column), its 32 warps take the rows w, w + 32, … (all loads
@@ -1178,12 +874,13 @@ __global__ void __launch_bounds__(kBlock)
  */
 constexpr int kFinishThreads = 1024;
 
-inline int kspaceFinishGrid(int stride) { return stride * stride / 32 + (stride + 31) / 32 + 1; }
+__host__ __device__ inline int kspaceFinishGrid(int stride) { return stride * stride / 32 + (stride + 31) / 32 + 1; }
 
-__global__ void __launch_bounds__(kFinishThreads)
-    batchKspaceFinishKernel(BatchBuffers cur, int stride, int with_ewald, int n_rows, const double* __restrict__ r_partials,
-                            const double* __restrict__ g_partials, const double* __restrict__ e_partials,
-                            double* __restrict__ result)
+__device__ __forceinline__ void kspaceFinishBlock(const BatchBuffers& cur, int stride, int with_ewald, int n_rows, int n_e_rows,
+                                                  const double* __restrict__ r_partials,
+                                                  const double* __restrict__ g_partials,
+                                                  const double* __restrict__ e_partials, double* __restrict__ result,
+                                                  int block)
 {
     __shared__ double s_part[kFinishThreads / 32][33];
     const int n = cur.in->n;
@@ -1192,7 +889,6 @@ __global__ void __launch_bounds__(kFinishThreads)
     const int warp = threadIdx.x >> 5;
     const int g_blocks = S * S / 32;
     const int r_blocks = (S + 31) / 32;
-    const int block = blockIdx.x;
     const double* src;
     size_t ld;
     int col;
@@ -1214,10 +910,18 @@ __global__ void __launch_bounds__(kFinishThreads)
         col = 0;
         src = e_partials;
         ld = 1;
-        wanted = lane == 0;
+        wanted = true;
     }
     double s = 0.0;
-    if (with_ewald && wanted) {
+    if (block >= g_blocks + r_blocks) {
+        // Σ A_k|Q_k|²: one partial per unit (thousands of rows, one column): thread ↔ rows t, t + 1024, …
+        if (with_ewald) {
+            for (int row = threadIdx.x; row < n_e_rows; row += kFinishThreads) {
+                s += __ldcg(src + row);
+            }
+        }
+    }
+    else if (with_ewald && wanted) {
 #pragma unroll 10
         for (int row = warp; row < n_rows; row += kFinishThreads / 32) {
             s += __ldcg(src + static_cast<size_t>(row) * ld + col);
@@ -1244,9 +948,46 @@ __global__ void __launch_bounds__(kFinishThreads)
             u[2 * S + col] = wanted ? total : 0.0;
         }
     }
-    else if (lane == 0) {
-        result[0] = (with_ewald && n_rows > 0) ? total : 0.0;
-        result[1] = static_cast<double>(n);
+    else {
+        total = warpSum(total); // the 32 lane sums in the fixed order of the shuffle tree
+        if (lane == 0) {
+            result[0] = (with_ewald && n_e_rows > 0) ? total : 0.0;
+            result[1] = static_cast<double>(n);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFinishThreads)
+    batchKspaceFinishKernel(BatchBuffers cur, int stride, int with_ewald, int n_rows, int n_e_rows,
+                            const double* __restrict__ r_partials, const double* __restrict__ g_partials,
+                            const double* __restrict__ e_partials, double* __restrict__ result)
+{
+    kspaceFinishBlock(cur, stride, with_ewald, n_rows, n_e_rows, r_partials, g_partials, e_partials, result, blockIdx.x);
+}
+
+inline int pairFinishBlocks(int stride) { return (2 * stride + stride * stride + kFinishThreads / 32 - 1) / (kFinishThreads / 32); }
+
+/**
+ * Everything between the evaluation of a window and its walk in ONE launch: blocks [0, F) the ordered sums of the
+ * k-space partials, the others one warp per pair output (pair sums, cross terms). As two kernels on two streams the
+ * pair side could not start before the persistent k-space kernel had drained (it owns every register file): 11 µs
+ * in series.
+ */
+template <int KIND>
+__global__ void __launch_bounds__(kFinishThreads)
+    windowFinishKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, int with_ewald, int n_rows, int n_e_rows,
+                       const double* __restrict__ r_partials, const double* __restrict__ g_partials,
+                       const double* __restrict__ e_partials, int n_pair_blocks, const double* __restrict__ pair_partials,
+                       int sums_done, const int* __restrict__ cell_overflow, double* __restrict__ result,
+                       const double* __restrict__ fix, const int* __restrict__ redo)
+{
+    const int k_blocks = kspaceFinishGrid(stride);
+    if (static_cast<int>(blockIdx.x) < k_blocks) {
+        kspaceFinishBlock(cur, stride, with_ewald, n_rows, n_e_rows, r_partials, g_partials, e_partials, result, blockIdx.x);
+    }
+    else {
+        pairFinishWarp<KIND>(M0, P, cur, stride, n_pair_blocks, pair_partials, sums_done, cell_overflow, result, fix, redo,
+                             static_cast<int>(((blockIdx.x - k_blocks) * kFinishThreads + threadIdx.x) >> 5));
     }
 }
 

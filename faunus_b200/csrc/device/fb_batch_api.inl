@@ -156,18 +156,24 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
         CUDA_CHECK(cudaStreamWaitEvent(ps, b.ev_fork, 0));
     }
     const bool pair_ahead = ahead != nullptr;
-    if (commit.n > 0 || commit_moves.n > 0 || device_commit) {
+    // ---- pair side
+    const int n_pair_blocks = (c->n_slots + kPairChunk - 1) / kPairChunk;
+    const int pair_finish_grid = (2 * stride + stride * stride + kBlock / 32 - 1) / (kBlock / 32); // one warp per output
+    CellGrid grid{};
+    b.cells_used = n_groups == 0 && cellGridFor(c, grid);
+    // brute-force windows of single atoms: the pair kernel itself puts the previous window's accepted moves into the
+    // mirrors (each block those of its own particle range) and the sums / cross terms are taken by the finish kernel
+    // behind the k-space kernel: no prep launch in front of the pair kernel, no third kernel on the pair stream
+    // (mass centres of accepted rigid groups — commit_moves — still go through the prep kernel)
+    const bool lean = n_groups == 0 && !b.cells_used && !pair_ahead && commit_moves.n == 0;
+    const bool have_commit = commit.n > 0 || commit_moves.n > 0 || device_commit;
+    if (have_commit && !lean) {
         batchPrepKernel<<<1, kBatchMax, 0, ps>>>(M0, makeView(c, 1), cur, prev, pair_ahead ? b.d_pair_redo.ptr : nullptr);
         launched(c, "batchPrepKernel");
     }
     if (timing) {
         CUDA_CHECK(cudaEventRecord(b.ev[1], c->stream));
     }
-    // ---- pair side
-    const int n_pair_blocks = (c->n_slots + kPairChunk - 1) / kPairChunk;
-    const int pair_finish_grid = (2 * stride + stride * stride + kBlock / 32 - 1) / (kBlock / 32); // one warp per output
-    CellGrid grid{};
-    b.cells_used = false;
     if (n_groups > 0) { // rigid-molecule moves: one block per (move, new | old), threads over the other groups
         batchPairGroupKernel<KIND><<<2 * n_groups, kBlock, 0, ps>>>(M0, c->P, cur, stride, b.d_result.ptr);
         launched(c, "batchPairGroupKernel");
@@ -175,7 +181,6 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
         launched(c, "batchPairGroupFinishKernel");
     }
     else {
-        b.cells_used = cellGridFor(c, grid);
         if (b.cells_used) { // large N: 27 neighbour cells per position instead of all particles
             if (!b.cells_valid) {
                 buildCellList(c, grid, ps);
@@ -197,22 +202,27 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
                     M0, c->P, cur, prev, fix_limit, b.d_pair_fix.ptr, b.d_pair_redo.ptr);
                 launched(c, "batchPairFixKernel");
             }
+            const int apply_commit = (lean && have_commit) ? 1 : 0;
             if (std::isinf(c->pair_cut2)) {
                 batchPairKernel<KIND, true><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
-                                                                               b.d_pair_partials.ptr, redo);
+                                                                               b.d_pair_partials.ptr, redo, makeView(c, 1),
+                                                                               prev, apply_commit);
             }
             else {
                 batchPairKernel<KIND, false><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
-                                                                                b.d_pair_partials.ptr, redo);
+                                                                                b.d_pair_partials.ptr, redo, makeView(c, 1),
+                                                                                prev, apply_commit);
             }
             launched(c, "batchPairKernel");
         }
-        const bool fixed = pair_ahead && !b.cells_used;
-        batchPairFinishKernel<KIND><<<pair_finish_grid, kBlock, 0, ps>>>(
-            M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, b.cells_used ? 1 : 0,
-            b.cells_used ? b.d_cell_overflow.ptr : nullptr, b.d_result.ptr, fixed ? b.d_pair_fix.ptr : nullptr,
-            fixed ? b.d_pair_redo.ptr : nullptr);
-        launched(c, "batchPairFinishKernel");
+        if (!lean) {
+            const bool fixed = pair_ahead && !b.cells_used;
+            batchPairFinishKernel<KIND><<<pair_finish_grid, kBlock, 0, ps>>>(
+                M0, c->P, cur, stride, n_pair_blocks, b.d_pair_partials.ptr, b.cells_used ? 1 : 0,
+                b.cells_used ? b.d_cell_overflow.ptr : nullptr, b.d_result.ptr, fixed ? b.d_pair_fix.ptr : nullptr,
+                fixed ? b.d_pair_redo.ptr : nullptr);
+            launched(c, "batchPairFinishKernel");
+        }
     }
     if (fork) {
         CUDA_CHECK(cudaEventRecord(b.ev_join, ps));
@@ -234,70 +244,53 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
     if (timing) {
         CUDA_CHECK(cudaEventRecord(b.ev[2], c->stream));
     }
-    // ---- k-space side
-    int n_rows = 0;
+    // ---- k-space side: phase tables + commit of the previous window (windowFrontKernel), then the persistent kernel
+    int n_rows = 0, n_e_rows = 0;
     if (with_ewald) {
-        const int phase_grid = std::max(1, (2 * n_moves * b.geo.table_stride + kBlock - 1) / kBlock);
-        batchPhaseKernel<<<phase_grid, kBlock, 0, c->stream>>>(cur, b.geo);
-        launched(c, "batchPhaseKernel");
+        const Slot& sl = c->slot[0];
         const EwaldView E = makeEwaldView(c, 0);
-        const int4* kn = c->slot[0].kn.ptr;
-        const int n_cells = c->slot[0].n_cells;
-        const int* cell_start = c->slot[0].cell_start.ptr;
-        const double* ksq = c->slot[0].ksq.ptr;
-        n_rows = std::max(1, std::min(n_cells, 2 * c->n_sm));
-        b.d_e_partials.ensure(static_cast<size_t>(2 * c->n_sm));
+        const int n_phase_blocks = frontPhaseBlocks(b.geo);
+        const int n_front_blocks = std::max(1, (sl.n_units + kKsWarps - 1) / kKsWarps); // one warp per unit
+        n_e_rows = n_front_blocks;
+        n_rows = std::max(1, std::min(sl.n_units, 2 * c->n_sm));
+        b.d_kq.ensure(static_cast<size_t>(sl.n_units) * kUnitSlots);
+        b.d_e_partials.ensure(static_cast<size_t>(n_front_blocks));
         b.d_r_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax);
         b.d_g_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax * kBatchMax);
-        static const bool old_kernel = std::getenv("FAUNUS_B200_OLD_KSPACE") != nullptr; // A/B switch while the new kernel is validated
-        if (!old_kernel) {
-            const Slot& sl = c->slot[0];
-            n_rows = std::max(1, std::min(sl.n_units, 2 * c->n_sm));
-            if (!b.kspace_unit_configured) {
-                CUDA_CHECK(cudaFuncSetAttribute(windowKspaceKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                static_cast<int>(sizeof(KspaceUnitSmem))));
-                b.kspace_unit_configured = true;
-            }
-            windowKspaceKernel<<<n_rows, kKsThreads, sizeof(KspaceUnitSmem), c->stream>>>(
-                E, sl.aks.ptr, sl.unit_info.ptr, sl.unit_map.ptr, sl.n_units, cur, prev, b.geo, stride,
-                b.d_r_partials.ptr, b.d_g_partials.ptr, b.d_e_partials.ptr);
+        windowFrontKernel<<<n_phase_blocks + n_front_blocks, kKsThreads, 0, c->stream>>>(
+            E, sl.aks.ptr, sl.unit_info.ptr, sl.unit_map.ptr, sl.n_units, n_phase_blocks, cur, prev, b.geo, b.d_kq.ptr,
+            b.d_e_partials.ptr);
+        launched(c, "windowFrontKernel");
+        if (!b.kspace_unit_configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(windowKspaceKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(sizeof(KspaceSmem))));
+            b.kspace_unit_configured = true;
         }
-        else {
-#define FB_KSPACE(BT)                                                                                         \
-    {                                                                                                         \
-        bool& configured = b.kspace_configured[BT == 4 ? 0 : (BT == 8 ? 1 : 2)];                              \
-        if (!configured) { /* per device: a context lives on one device */                                   \
-            CUDA_CHECK(cudaFuncSetAttribute(batchKspaceKernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            static_cast<int>(KspaceSmem<BT>::bytes())));                      \
-            configured = true;                                                                                \
-        }                                                                                                     \
-        batchKspaceKernel<BT><<<n_rows, kBlock, KspaceSmem<BT>::bytes(), c->stream>>>(                        \
-            E, kn, ksq, cell_start, n_cells, cur, prev, b.geo, b.d_r_partials.ptr, b.d_g_partials.ptr,       \
-            b.d_e_partials.ptr);                                                                              \
-    }
-        switch (stride) {
-        case 16:
-            FB_KSPACE(4)
-            break;
-        case 32:
-            FB_KSPACE(8)
-            break;
-        default:
-            FB_KSPACE(16)
-        }
-#undef FB_KSPACE
-        }
-        launched(c, "batchKspaceKernel");
+        windowKspaceKernel<<<n_rows, kKsThreads, sizeof(KspaceSmem), c->stream>>>(
+            sl.unit_info.ptr, sl.unit_sa.ptr, b.d_kq.ptr, sl.n_units, cur, b.geo, stride, b.d_r_partials.ptr,
+            b.d_g_partials.ptr);
+        launched(c, "windowKspaceKernel");
     }
     if (timing) {
         CUDA_CHECK(cudaEventRecord(b.ev[3], c->stream));
     }
-    batchKspaceFinishKernel<<<kspaceFinishGrid(stride), kFinishThreads, 0, c->stream>>>(
-        cur, stride, with_ewald ? 1 : 0, n_rows, b.d_r_partials.ptr, b.d_g_partials.ptr, b.d_e_partials.ptr,
-        b.d_result.ptr);
-    launched(c, "batchKspaceFinishKernel");
-    if (fork) {
-        CUDA_CHECK(cudaStreamWaitEvent(c->stream, b.ev_join, 0));
+    if (lean) { // k-space sums, pair sums and cross terms in one launch, behind both the k-space and the pair kernel
+        if (fork) {
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, b.ev_join, 0));
+        }
+        windowFinishKernel<KIND><<<kspaceFinishGrid(stride) + pairFinishBlocks(stride), kFinishThreads, 0, c->stream>>>(
+            M0, c->P, cur, stride, with_ewald ? 1 : 0, n_rows, n_e_rows, b.d_r_partials.ptr, b.d_g_partials.ptr,
+            b.d_e_partials.ptr, n_pair_blocks, b.d_pair_partials.ptr, 0, nullptr, b.d_result.ptr, nullptr, nullptr);
+        launched(c, "windowFinishKernel");
+    }
+    else {
+        batchKspaceFinishKernel<<<kspaceFinishGrid(stride), kFinishThreads, 0, c->stream>>>(
+            cur, stride, with_ewald ? 1 : 0, n_rows, n_e_rows, b.d_r_partials.ptr, b.d_g_partials.ptr, b.d_e_partials.ptr,
+            b.d_result.ptr);
+        launched(c, "batchKspaceFinishKernel");
+        if (fork) {
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, b.ev_join, 0));
+        }
     }
     b.last_rec_fresh = with_ewald;
 }

@@ -1,23 +1,29 @@
 // k-space part of a window (sm_100a): R[m], G[a][m], Σ_k A_k |Q_k|² and the commit of the previous window's
-// accepted moves into Q(k) — the quantities defined at the top of fb_batch.cuh — in ONE persistent kernel.
+// accepted moves into Q(k) — the quantities defined at the top of fb_batch.cuh.
 //
-// Work unit = HALF of a 4×4×4 cell of integer triplets (the two y-rows ly ∈ {2h, 2h+1}): 32 k-slots that need only
-// 10 phase-table entries per position (4 x, 2 y, 4 z). Block b walks the units b, b + grid, …
+// Work unit = HALF of a 4×4×4 cell of integer triplets (the two y-rows ly ∈ {2h, 2h+1}): 32 k-slots
+// ks = 8·i + 4·jj + l that need only 10 phase-table entries per position (4 x, 2 y, 4 z). Per-unit data is kept in
+// SLOT layout ([unit][32], zero where the sphere cut leaves no k-vector), so nothing below tests for validity.
 //
-// Thread ↔ (move m = tid / 4, x-index i = tid % 4); warp w owns the moves 8w … 8w+7. A thread forms the 8 phases
-// e^{ik·r} of its x-index from registers — xy_j = X_i·Y_j (once per y), then xy_j·Z_l — for the trial and the old
-// position of ITS move: 14 FP64 instructions per (k, move) against 28 with lane ↔ k and six LDS.128 table reads.
-// The 16 doubles √A_k·δ_m,k it ends up with ARE the m8n8k4 fragments of the Gram update: with lane = 4·(m % 8) + i
-// the lane (g, t) of warp w holds D[8w + g][column (t, s)], which is both the A fragment A[g][t] of row block w and
-// the B fragment B[t][g] of column block w for reduction step s (the order of the reduction columns is free). The
-// diagonal tile of a warp needs no memory at all; for an off-diagonal tile the partner warp's fragments come from
-// shared memory, stored lane by lane (conflict-free LDS.128, two steps per load). Tiles are dealt as a circulant:
-// warp w takes (w, w) and (w, w+d mod 8) for d = 1, 2, 3 (and d = 4 for w < 4) — 4.5 DMMA per fragment load.
-// Σ_k A_k |δ_m,k|² is the diagonal of G and is taken from there; R keeps only the 2 Re(conj(Q) δ) part.
-//
-// Commit of the previous window: thread ↔ (x-index, y-index, group of accepted moves); partial ΔQ per group through
-// shared memory, summed in fixed order (results do not depend on scheduling), Q(k) updated in place by the unit's
-// block, which is the only one that touches those k-vectors.
+// windowFrontKernel   blocks [0, P): the per-axis phase tables of the 2n positions of the window (sincos; the x
+//                     entries carry the charge); the other blocks: ΔQ of the accepted moves of the previous window
+//                     as a small complex matrix product on the FP64 tensor path, one warp per unit, lane ↔ slot;
+//                     Q(k) updated in place, √A_k·Q_k in slot layout for the kernel below, Σ A_k |Q_k|².
+// windowKspaceKernel  persistent, block b walks the units b, b + grid, …  Thread ↔ (move m = tid / 4, x-index
+//                     i = tid % 4); warp w owns the moves 8w … 8w+7. A thread forms the 8 phases e^{ik·r} of its
+//                     x-index from registers — xy_j = X_i·Y_j once per y, then xy_j·Z_l — for the trial and the old
+//                     position of ITS move: 14 FP64 instructions per (k, move) (lane ↔ k needed 28 and six LDS.128).
+//                     The 16 doubles √A_k·δ_m,k it ends up with ARE the m8n8k4 fragments of the Gram update: with
+//                     lane = 4·(m % 8) + i, lane (g, t) of warp w holds D[8w + g][column (t, s)] — the A fragment
+//                     A[g][t] of row block w and the B fragment B[t][g] of column block w for reduction step s (the
+//                     order of the reduction columns is free). The diagonal tile of a warp needs no memory at all;
+//                     for an off-diagonal tile the partner warp's fragments come from shared memory, stored lane by
+//                     lane (conflict-free LDS.128, two steps per load). Tiles are dealt as a circulant: warp w takes
+//                     (w, w) and (w, w+d mod 8), d = 1, 2, 3 (and d = 4 for w < 4): 4.5 DMMA per fragment load.
+//                     Σ_k A_k |δ_m,k|² is the diagonal of G; R keeps only the 2 Re(conj(Q) δ) part.
+//                     Pipeline: every WARP stages its own tables (cp.async, no block barrier), the fragments are
+//                     double-buffered, so there is ONE block barrier per unit and a warp that is through with its
+//                     tiles starts on the phases of the next unit while the others still feed the tensor pipe.
 #pragma once
 #include "fb_batch.cuh"
 
@@ -27,29 +33,19 @@ constexpr int kUnitSlots = 32;    //!< k-slots of a unit: ks = 8·i + 4·jj + l
 constexpr int kUnitEntries = 10;  //!< phase-table entries per position: X0..3, Y0..1, Z0..3
 constexpr int kKsThreads = 256;
 constexpr int kKsWarps = kKsThreads / 32;
-constexpr int kCommitGroups = 32; //!< partial ΔQ sums per k-slot
-constexpr int kDqStride = 38;     //!< double2 per row: 608 B ≡ 96 (mod 128): the fixed-order sum reads conflict-free
 
 /** skewed slot index: the four x-indices of a warp land in different bank groups */
 __device__ __forceinline__ int unitSlotIndex(int i, int s) { return 9 * i + s; }
 
-struct KspaceUnitSmem
+/** table index of entry t (X0..3, Y0..1, Z0..3) of a unit; info = {first k of the cell, x, y, z index of the first slot} */
+__device__ __forceinline__ int unitTableOffset(const int4& info, int t, int ncc)
 {
-    double2 tab_new[kBatchMax][2][kUnitEntries]; //!< [move][trial | old]; 320 B per move ≡ 64 (mod 128)
-    double2 tab_com[kBatchMax][2][kUnitEntries]; //!< accepted moves of the previous window
-    union
-    {
-        double2 frag[kKsWarps][8][32];           //!< [warp][step pair][lane] = √A_k δ (re, im) of one k-slot
-        double2 dq[kCommitGroups][kDqStride];    //!< partial ΔQ of the commit groups
-    };
-    double2 Q[kUnitSlots];   //!< staged Q(k) and {A_k, √A_k} of the unit's slots (absent slots: see map)
-    double2 aks[kUnitSlots];
-    double2 kq[36];          //!< √A_k · Q_k at the skewed index
-    double sa[36];           //!< √A_k (0 for absent slots)
-    int map[kUnitSlots];     //!< index of the slot's k-vector inside its cell's storage range, −1: none
-    double cqn[kBatchMax], cqo[kBatchMax];
-    int ctable[kBatchMax];   //!< first table entry (trial position) of the accepted move in the previous window's tables
-};
+    const int base = t < 4 ? 0 : (t < 6 ? ncc + 1 : (ncc + 1) + (2 * ncc + 1));
+    const int first = t < 4 ? info.y : (t < 6 ? info.z : info.w);
+    const int local = t < 4 ? t : (t < 6 ? t - 4 : t - 6);
+    const int limit = t < 4 ? ncc : 2 * ncc;
+    return base + min(first + local, limit); // entries beyond the table belong to slots without a k-vector
+}
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
 {
@@ -58,197 +54,282 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// ------------------------------------------------------------------------------------------------
+// front kernel: phase tables of this window + commit of the previous one
+// ------------------------------------------------------------------------------------------------
+inline int frontPhaseBlocks(const PhaseGeometry& geo) { return (2 * kBatchMax * geo.table_stride + kKsThreads - 1) / kKsThreads; }
+
 /**
+ * Blocks [0, P): phase tables. Blocks [P, …): the commit of the previous window, ONE WARP PER UNIT, as a small complex
+ * matrix product on the FP64 tensor path. With the accepted positions p (trial: +, old: −; the x entries carry the
+ * charges) and the unit's slots ks = 8 xi + 4 jj + l,
+ *
+ *     ΔQ[xi, jj, l] = Σ_p  ± X_p[xi] Y_p[jj] · Z_p[l]
+ *
+ * is C = A·B with A[row = 2 xi + jj][p] = ± X_p[xi] Y_p[jj] (one complex product per lane and step) and
+ * B[p][l] = Z_p[l]. m8n8k4 takes 4 positions per step: lane (g, t) supplies A[g][p = 4 step + t] and, as column
+ * g = 2 l + c of the real 4 × 8 matrices B' = [Z_re | Z_im] and B'' = [−Z_im | Z_re], the two B fragments, so that
+ * Re(A)·B' + Im(A)·B'' leaves (Re, Im) of ΔQ[row g][l = t] in the two accumulator registers of lane (g, t) —
+ * i.e. lane ↔ slot ks = lane, no shared memory, no barrier, no reduction between threads, and the order of the sum
+ * over p is the fixed order of the tensor instruction. 2 DMMA + one complex product per 4 positions and unit instead
+ * of 88 FP64 instructions per thread of a 256-thread block (20 µs → the arithmetic of 1.8 µs).
+ *
  * @param aks        [K] {A_k, √A_k}, storage order
- * @param unit_info  [n_units] {first k of the unit's cell, x table index of slot i = 0, y table index of jj = 0, z of l = 0}
+ * @param unit_info  [n_units] {first k of the unit's cell, x, y, z table index of the first slot}
  * @param unit_map   [n_units][32] index of each slot's k-vector inside the cell's storage range, 255: none
+ * @param kq         [n_units][32] out: √A_k · Q_k of the state this window starts from (0 for empty slots)
+ * @param e_partials [blocks] out: Σ A_k |Q_k|² over the block's 8 units
+ */
+__global__ void __launch_bounds__(kKsThreads)
+    windowFrontKernel(EwaldView E, const double2* __restrict__ aks, const int4* __restrict__ unit_info,
+                      const unsigned char* __restrict__ unit_map, int n_units, int n_phase_blocks, BatchBuffers cur,
+                      BatchBuffers prev, PhaseGeometry geo, double2* __restrict__ kq, double* __restrict__ e_partials)
+{
+    __shared__ int s_table[2 * kBatchMax]; //!< first table entry of every accepted position (trial, old, trial, …)
+    __shared__ double s_e[kKsWarps];
+    __shared__ double2 s_stage[kKsWarps][32][kUnitEntries]; //!< per warp: the unit's table entries of 32 positions
+    const int tid = threadIdx.x;
+    if (static_cast<int>(blockIdx.x) < n_phase_blocks) {
+        const int total = 2 * cur.in->n * geo.table_stride;
+        const int t = blockIdx.x * kKsThreads + tid;
+        if (t < total) {
+            phaseTableEntry(cur.in, cur.table, geo, t);
+        }
+        return;
+    }
+    const int block = blockIdx.x - n_phase_blocks;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int y_last = (geo.ncc + 1) + 2 * geo.ncc, z_last = (geo.ncc + 1) + (2 * geo.ncc + 1) + 2 * geo.ncc;
+    const int u = block * kKsWarps + warp;
+    const bool unit_on = u < n_units;
+    // requested first: nothing below depends on it until the very end
+    int slot_k = -1;
+    double2 slot_q = make_double2(0.0, 0.0), slot_a = make_double2(0.0, 0.0);
+    int4 info = make_int4(0, 0, 0, 0);
+    if (unit_on) {
+        info = __ldg(unit_info + u);
+        const int t = __ldg(unit_map + static_cast<size_t>(u) * kUnitSlots + lane);
+        if (t != 255) {
+            slot_k = info.x + t;
+            slot_q = E.Q[slot_k];
+            slot_a = __ldg(aks + slot_k);
+        }
+    }
+    const CommitList& commit = cur.in->commit;
+    const int ncommit = min(commit.n, kBatchMax);
+    if (tid < 2 * ncommit) {
+        s_table[tid] = (2 * commit.index[tid >> 1] + (tid & 1)) * geo.table_stride;
+    }
+    __syncthreads();
+    double dq_re = 0.0, dq_im = 0.0;
+    if (unit_on && ncommit > 0) {
+        const int g = lane >> 2; // row of A = 2 xi + jj; column of B', B'' = 2 l + c
+        const int t = lane & 3;  // position inside the step; column pair of C = l
+        const int off_x = unitTableOffset(info, 0, geo.ncc); // the 4 x, 2 y, 4 z entries are contiguous unless clamped
+        const int off_y = unitTableOffset(info, 4, geo.ncc);
+        const int off_z = unitTableOffset(info, 6, geo.ncc);
+        const int ex = g >> 1, ey = 4 + (g & 1), ez = 6 + (g >> 1); // entries this lane multiplies
+        const bool imag = g & 1;
+        const int n_pos = 2 * ncommit;
+        const double2* __restrict__ table = prev.table;
+        double2(*stage)[kUnitEntries] = s_stage[warp];
+        // batches of 32 positions (8 steps): lane ↔ position copies its 10 table entries (cp.async: all copies of the
+        // warp in flight together — with plain loads ptxas sinks every load to its first use, one L2 round trip per
+        // step), then lane (g, t) multiplies
+        for (int p0 = 0; p0 < n_pos; p0 += 32) {
+            const int p = p0 + lane;
+            if (p < n_pos) {
+                const double2* row = table + s_table[p];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    cpAsync16(&stage[lane][i], row + min(off_x + i, geo.ncc));
+                    cpAsync16(&stage[lane][6 + i], row + min(off_z + i, z_last));
+                }
+                cpAsync16(&stage[lane][4], row + off_y);
+                cpAsync16(&stage[lane][5], row + min(off_y + 1, y_last));
+            }
+            cpAsyncCommit();
+            cpAsyncWaitAll();
+            __syncwarp();
+            const int steps = min(8, (n_pos - p0 + 3) >> 2);
+            for (int r = 0; r < steps; ++r) {
+                const int q = 4 * r + t;
+                double2 a = make_double2(0.0, 0.0), z = a;
+                if (p0 + q < n_pos) {
+                    a = cmul(stage[q][ex], stage[q][ey]);
+                    z = stage[q][ez];
+                    if (q & 1) { // old position: subtracted (p0 is even)
+                        a.x = -a.x;
+                        a.y = -a.y;
+                    }
+                }
+                const double b1 = imag ? z.y : z.x;  // B'  = [Z_re | Z_im]
+                const double b2 = imag ? z.x : -z.y; // B'' = [−Z_im | Z_re]
+                dmma884(dq_re, dq_im, a.x, b1);
+                dmma884(dq_re, dq_im, a.y, b2);
+            }
+            __syncwarp(); // the staging area is free again
+        }
+    }
+    double e = 0.0;
+    if (unit_on) {
+        double2 out = make_double2(0.0, 0.0);
+        if (slot_k >= 0) {
+            double2 Q = slot_q;
+            if (ncommit > 0) {
+                Q.x += dq_re;
+                Q.y += dq_im;
+                E.Q[slot_k] = Q; // only this warp touches the unit's k-vectors
+            }
+            out = make_double2(slot_a.y * Q.x, slot_a.y * Q.y);
+            e = slot_a.x * (Q.x * Q.x + Q.y * Q.y);
+        }
+        kq[static_cast<size_t>(u) * kUnitSlots + lane] = out;
+    }
+    e = warpSum(e); // fixed shuffle tree
+    if (lane == 0) {
+        s_e[warp] = e;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < kKsWarps; ++w) {
+            sum += s_e[w];
+        }
+        e_partials[block] = sum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the persistent k-space kernel
+// ------------------------------------------------------------------------------------------------
+/** what ONE warp stages for a unit: the tables of its 8 moves and the unit's √A_k·Q_k, √A_k */
+struct KspaceWarpStage
+{
+    double2 tab[8][2][kUnitEntries]; //!< [move of the warp][trial | old]; 320 B per move ≡ 64 (mod 128)
+    double2 kq[36];                  //!< √A_k · Q_k at the skewed slot index
+    double sa[36];                   //!< √A_k
+};
+
+struct KspaceSmem
+{
+    double2 frag[2][kKsWarps][8][32]; //!< [unit parity][warp][step pair][lane] = √A_k δ (re, im) of one k-slot
+    KspaceWarpStage stage[kKsWarps];
+};
+
+/**
+ * @param unit_info  [n_units] {first k of the unit's cell, x, y, z table index of the first slot}
+ * @param unit_sa    [n_units][32] √A_k in slot layout (0 for empty slots)
+ * @param kq         [n_units][32] √A_k · Q_k in slot layout (windowFrontKernel)
  * @param r_partials [grid][stride]   2 Σ_k A_k Re(conj(Q_k) δ_m,k) + Σ_k A_k |δ_m,k|² over the block's units
  * @param g_partials [grid][stride²]  entries [a][m], a < m: Σ_k A_k Re(conj(δ_a,k) δ_m,k)
  */
 __global__ void __launch_bounds__(kKsThreads, 2)
-    windowKspaceKernel(EwaldView E, const double2* __restrict__ aks, const int4* __restrict__ unit_info,
-                       const unsigned char* __restrict__ unit_map, int n_units, BatchBuffers cur, BatchBuffers prev,
-                       PhaseGeometry geo, int stride, double* __restrict__ r_partials, double* __restrict__ g_partials,
-                       double* __restrict__ e_partials)
+    windowKspaceKernel(const int4* __restrict__ unit_info, const double* __restrict__ unit_sa, const double2* __restrict__ kq,
+                       int n_units, BatchBuffers cur, PhaseGeometry geo, int stride, double* __restrict__ r_partials,
+                       double* __restrict__ g_partials)
 {
     extern __shared__ __align__(16) unsigned char ks_smem_raw[];
-    KspaceUnitSmem& sm = *reinterpret_cast<KspaceUnitSmem*>(ks_smem_raw);
+    KspaceSmem& sm = *reinterpret_cast<KspaceSmem*>(ks_smem_raw);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const int block = blockIdx.x;
+    const int grid = gridDim.x;
     const int n = cur.in->n;
-    const CommitList& commit = cur.in->commit;
-    const int ncommit = min(commit.n, kBatchMax);
     const int n_active_warps = (n + 7) >> 3;
+    const bool warp_active = warp < n_active_warps;
+    const int my_units = (n_units - block + grid - 1) / grid;
+    KspaceWarpStage& st = sm.stage[warp];
 
-    if (tid < ncommit) {
-        const int m = commit.index[tid];
-        sm.cqn[tid] = prev.in->pnew[m].w;
-        sm.cqo[tid] = prev.pold[m].w;
-        sm.ctable[tid] = 2 * m * geo.table_stride;
-    }
-    __syncthreads();
+    // this thread's move and x-index (the x entries of the tables carry the charges)
+    const int m = tid >> 2;
+    const int xi = tid & 3;
+    const int mg = lane >> 2; // move inside the warp = fragment row
+    const bool move_active = m < n;
 
-    const int my_units = (n_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    const int x_base = 0, y_base = geo.ncc + 1, z_base = (geo.ncc + 1) + (2 * geo.ncc + 1);
-
-    // asynchronous staging of unit number `c` of this block: tables of the 2n positions of the window and of the
-    // accepted moves of the previous one, Q(k) and {A_k, √A_k} of the unit's slots
+    // staging plan of this lane: lane = t + 10 j takes table entry t (X0..3, Y0..1, Z0..3) of the warp's positions
+    // j, j + 3, …, 15 (lanes 30, 31 only carry √A_k·Q_k and √A_k), so the table offset is one min() per unit
+    const int st_t = lane % kUnitEntries;
+    const int st_j = lane / kUnitEntries;
+    const int st_kind = st_t < 4 ? 0 : (st_t < 6 ? 1 : 2);
+    const int st_base = st_kind == 0 ? 0 : (st_kind == 1 ? geo.ncc + 1 : (geo.ncc + 1) + (2 * geo.ncc + 1));
+    const int st_local = st_t - (st_kind == 0 ? 0 : (st_kind == 1 ? 4 : 6));
+    const int st_limit = st_kind == 0 ? geo.ncc : 2 * geo.ncc;
+    const int st_positions = max(0, min(16, 2 * (n - 8 * warp))); // positions of the warp that belong to moves < n
+    const double2* __restrict__ table = cur.table + static_cast<size_t>(16 * warp) * geo.table_stride;
+    const unsigned st_dst = static_cast<unsigned>(__cvta_generic_to_shared(&st.tab[0][0][st_t]));
+    const unsigned st_kq = static_cast<unsigned>(__cvta_generic_to_shared(&st.kq[lane + (lane >> 3)]));
+    const unsigned st_sa = static_cast<unsigned>(__cvta_generic_to_shared(&st.sa[lane + (lane >> 3)]));
     auto issue = [&](int c) {
-        const int u = blockIdx.x + c * gridDim.x;
+        const int u = block + c * grid;
         const int4 info = __ldg(unit_info + u);
-        auto offset_of = [&](int t) {
-            if (t < 4) {
-                return x_base + min(info.y + t, geo.ncc);
-            }
-            if (t < 6) {
-                return y_base + min(info.z + (t - 4), 2 * geo.ncc);
-            }
-            return z_base + min(info.w + (t - 6), 2 * geo.ncc);
-        };
-        const int n_new = 2 * n * kUnitEntries;
-        for (int e = tid; e < n_new; e += kKsThreads) {
-            const int v = e / kUnitEntries;
-            const int t = e - v * kUnitEntries;
-            cpAsync16(&sm.tab_new[v >> 1][v & 1][t], cur.table + v * geo.table_stride + offset_of(t));
-        }
-        const int n_com = 2 * ncommit * kUnitEntries;
-        for (int e = tid; e < n_com; e += kKsThreads) {
-            const int v = e / kUnitEntries;
-            const int t = e - v * kUnitEntries;
-            cpAsync16(&sm.tab_com[v >> 1][v & 1][t], prev.table + sm.ctable[v >> 1] + (v & 1) * geo.table_stride + offset_of(t));
-        }
-        if (tid < kUnitSlots) {
-            const int t = __ldg(unit_map + static_cast<size_t>(u) * kUnitSlots + tid);
-            sm.map[tid] = t == 255 ? -1 : t;
-            if (t != 255) {
-                cpAsync16(&sm.Q[tid], E.Q + info.x + t);
-                cpAsync16(&sm.aks[tid], aks + info.x + t);
+        const int first = st_kind == 0 ? info.y : (st_kind == 1 ? info.z : info.w);
+        const double2* src = table + st_base + min(first + st_local, st_limit); // beyond the table: slots without k-vector
+        if (st_j < 3) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const int v = st_j + 3 * r; // position of the warp: 2·(move in warp) + (trial | old)
+                if (v < st_positions) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(st_dst + v * (kUnitEntries * 16u)),
+                                 "l"(src + v * geo.table_stride));
+                }
             }
         }
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(st_kq), "l"(kq + static_cast<size_t>(u) * kUnitSlots + lane));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(st_sa), "l"(unit_sa + static_cast<size_t>(u) * kUnitSlots + lane));
         cpAsyncCommit();
     };
 
-    // this thread's move and x-index; charges of the trial / old position
-    const int m = tid >> 2;
-    const int xi = tid & 3;
-    const bool move_active = m < n;
-    const double qn = move_active ? cur.in->pnew[m].w : 0.0;
-    const double qo = move_active ? cur.pold[m].w : 0.0;
-    const bool warp_active = warp < n_active_warps;
-
-    // Gram tiles of this warp: (w, w) and the partners (w + d) mod 8
-    int partner[4];
-    bool partner_on[4];
+    // Gram tiles of this warp: (w, w) and the partner warps (w + d) mod 8, d = 1, 2, 3 (4 for w < 4), that hold moves;
+    // the list is compacted so that the tile loop below runs without predicates (a predicated mma.sync costs a
+    // WARPSYNC each: 17 % of the samples of the first version)
+    int p0 = 0, p1 = 0, p2 = 0, p3 = 0; // (scalars: an array indexed by the running count would live in local memory)
+    int n_partners = 0;
+    if (warp_active) {
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-        partner[d] = (warp + d + 1) & 7;
-        partner_on[d] = warp_active && partner[d] < n_active_warps && (d < 3 || warp < 4);
+        for (int d = 0; d < 4; ++d) {
+            const int p = (warp + d + 1) & 7;
+            if (p < n_active_warps && (d < 3 || warp < 4)) {
+                p0 = n_partners == 0 ? p : p0;
+                p1 = n_partners == 1 ? p : p1;
+                p2 = n_partners == 2 ? p : p2;
+                p3 = n_partners == 3 ? p : p3;
+                ++n_partners;
+            }
+        }
     }
+    const int partner[4] = {p0, p1, p2, p3};
     double g_diag[2] = {0.0, 0.0};
     double g_off[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
     double racc = 0.0;
-    double eacc = 0.0;
 
-    if (my_units > 0) {
+    if (my_units > 0 && warp_active) {
         issue(0);
     }
     for (int c = 0; c < my_units; ++c) {
-        const int u = blockIdx.x + c * gridDim.x;
-        const int p0 = __ldg(unit_info + u).x;
-        cpAsyncWaitAll();
-        __syncthreads(); // unit c is staged for everybody; everybody is done with the fragments of unit c − 1
-
-        // ---- ΔQ of the accepted moves of the previous window
-        if (ncommit > 0) {
-            const int ci = tid & 3;
-            const int cj = (tid >> 2) & 1;
-            const int cg = tid >> 3;
-            double2 acc[4];
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                acc[l] = make_double2(0.0, 0.0);
-            }
-            for (int a = cg; a < ncommit; a += kCommitGroups) {
-#pragma unroll
-                for (int pos = 0; pos < 2; ++pos) {
-                    const double q = pos ? -sm.cqo[a] : sm.cqn[a];
-                    double2 xy = cmul(sm.tab_com[a][pos][ci], sm.tab_com[a][pos][4 + cj]);
-                    xy.x *= q;
-                    xy.y *= q;
-#pragma unroll
-                    for (int l = 0; l < 4; ++l) {
-                        const double2 z = sm.tab_com[a][pos][6 + l];
-                        acc[l].x = fma(xy.x, z.x, fma(-xy.y, z.y, acc[l].x));
-                        acc[l].y = fma(xy.x, z.y, fma(xy.y, z.x, acc[l].y));
-                    }
-                }
-            }
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                sm.dq[cg][unitSlotIndex(ci, 4 * cj + l)] = acc[l];
-            }
-            __syncthreads();
-        }
-        if (tid < 4 * kUnitSlots) { // four threads per slot: fixed-order sum of the 32 group shares
-            const int ks = tid >> 2;
-            const int part = tid & 3;
-            const int idx = unitSlotIndex(ks >> 3, ks & 7);
-            double2 dq = make_double2(0.0, 0.0);
-            if (ncommit > 0) {
-#pragma unroll
-                for (int r = 0; r < kCommitGroups / 4; ++r) {
-                    const double2 v = sm.dq[part + 4 * r][idx];
-                    dq.x += v.x;
-                    dq.y += v.y;
-                }
-                dq.x += __shfl_xor_sync(0xffffffffu, dq.x, 1);
-                dq.y += __shfl_xor_sync(0xffffffffu, dq.y, 1);
-                dq.x += __shfl_xor_sync(0xffffffffu, dq.x, 2);
-                dq.y += __shfl_xor_sync(0xffffffffu, dq.y, 2);
-            }
-            if (part == 0) {
-                const int t = sm.map[ks];
-                double2 Q = make_double2(0.0, 0.0);
-                double A = 0.0, sA = 0.0;
-                if (t >= 0) {
-                    Q = sm.Q[ks];
-                    A = sm.aks[ks].x;
-                    sA = sm.aks[ks].y;
-                    if (ncommit > 0) {
-                        Q.x += dq.x;
-                        Q.y += dq.y;
-                        E.Q[p0 + t] = Q; // only this block touches the unit's k-vectors
-                    }
-                }
-                sm.kq[idx] = make_double2(sA * Q.x, sA * Q.y);
-                sm.sa[idx] = sA;
-                eacc += A * (Q.x * Q.x + Q.y * Q.y);
-            }
-        }
-        __syncthreads(); // kq / sa are ready; dq (= frag) is free
-
-        // ---- δ of this thread's move for the 8 slots of its x-index, scaled by √A_k: the Gram fragments
+        const int buf = c & 1;
         double dreg[16];
         if (warp_active) {
+            cpAsyncWaitAll();
+            __syncwarp(); // the warp's tables and the unit's √A_k·Q_k are in place
+            // ---- δ of this thread's move for the 8 slots of its x-index, scaled by √A_k: the Gram fragments
             if (move_active) {
-                double2 xn = sm.tab_new[m][0][xi];
-                double2 xo = sm.tab_new[m][1][xi];
-                xn.x *= qn;
-                xn.y *= qn;
-                xo.x *= qo;
-                xo.y *= qo;
+                const double2 xn = st.tab[mg][0][xi];
+                const double2 xo = st.tab[mg][1][xi];
                 double2 zn[4], zo[4];
 #pragma unroll
                 for (int l = 0; l < 4; ++l) {
-                    zn[l] = sm.tab_new[m][0][6 + l];
-                    zo[l] = sm.tab_new[m][1][6 + l];
+                    zn[l] = st.tab[mg][0][6 + l];
+                    zo[l] = st.tab[mg][1][6 + l];
                 }
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    const double2 xyn = cmul(xn, sm.tab_new[m][0][4 + jj]);
-                    const double2 xyo = cmul(xo, sm.tab_new[m][1][4 + jj]);
+                    const double2 xyn = cmul(xn, st.tab[mg][0][4 + jj]);
+                    const double2 xyo = cmul(xo, st.tab[mg][1][4 + jj]);
 #pragma unroll
                     for (int l = 0; l < 4; ++l) {
                         const int s = 4 * jj + l;
@@ -256,11 +337,11 @@ __global__ void __launch_bounds__(kKsThreads, 2)
                         double2 d = cmul(xyn, zn[l]);
                         d.x = fma(-xyo.x, zo[l].x, fma(xyo.y, zo[l].y, d.x));
                         d.y = fma(-xyo.x, zo[l].y, fma(-xyo.y, zo[l].x, d.y));
-                        const double sa = sm.sa[idx];
-                        const double2 kq = sm.kq[idx];
+                        const double sa = st.sa[idx];
+                        const double2 q = st.kq[idx];
                         d.x *= sa;
                         d.y *= sa;
-                        racc = fma(kq.x, d.x, fma(kq.y, d.y, racc));
+                        racc = fma(q.x, d.x, fma(q.y, d.y, racc));
                         dreg[2 * s] = d.x;
                         dreg[2 * s + 1] = d.y;
                     }
@@ -272,56 +353,57 @@ __global__ void __launch_bounds__(kKsThreads, 2)
                     dreg[s] = 0.0;
                 }
             }
+            __syncwarp(); // every lane is done with the staging area
+            if (c + 1 < my_units) {
+                issue(c + 1); // lands while the Gram update runs
+            }
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
-                sm.frag[warp][s][lane] = make_double2(dreg[2 * s], dreg[2 * s + 1]);
+                sm.frag[buf][warp][s][lane] = make_double2(dreg[2 * s], dreg[2 * s + 1]);
             }
         }
-        __syncthreads(); // fragments of all warps are in place; the tables are free
-        if (c + 1 < my_units) {
-            issue(c + 1); // lands while the Gram update runs
-        }
-
-        // ---- Gram update on the FP64 tensor path
-        if (warp_active) {
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                double2 f[4];
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    if (partner_on[d]) {
-                        f[d] = sm.frag[partner[d]][s][lane];
-                    }
-                }
-                dmma884(g_diag[0], g_diag[1], dreg[2 * s], dreg[2 * s]);
-                dmma884(g_diag[0], g_diag[1], dreg[2 * s + 1], dreg[2 * s + 1]);
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    if (partner_on[d]) {
-                        dmma884(g_off[d][0], g_off[d][1], dreg[2 * s], f[d].x);
-                        dmma884(g_off[d][0], g_off[d][1], dreg[2 * s + 1], f[d].y);
-                    }
-                }
+        // the fragments of unit c of all warps are in place; every warp is through with the Gram update of unit
+        // c − 1, so the other fragment buffer may be overwritten after this barrier
+        __syncthreads();
+        if (warp_active) { // ---- Gram update on the FP64 tensor path
+            const double2* fr = &sm.frag[buf][0][0][lane];
+#define FB_GRAM(NP)                                                                                        \
+    _Pragma("unroll") for (int s = 0; s < 8; ++s)                                                          \
+    {                                                                                                      \
+        double2 f[NP > 0 ? NP : 1];                                                                        \
+        _Pragma("unroll") for (int d = 0; d < NP; ++d) { f[d] = fr[(partner[d] * 8 + s) * 32]; }           \
+        dmma884(g_diag[0], g_diag[1], dreg[2 * s], dreg[2 * s]);                                           \
+        dmma884(g_diag[0], g_diag[1], dreg[2 * s + 1], dreg[2 * s + 1]);                                   \
+        _Pragma("unroll") for (int d = 0; d < NP; ++d)                                                     \
+        {                                                                                                  \
+            dmma884(g_off[d][0], g_off[d][1], dreg[2 * s], f[d].x);                                        \
+            dmma884(g_off[d][0], g_off[d][1], dreg[2 * s + 1], f[d].y);                                    \
+        }                                                                                                  \
+    }
+            switch (n_partners) {
+            case 4:
+                FB_GRAM(4)
+                break;
+            case 3:
+                FB_GRAM(3)
+                break;
+            case 2:
+                FB_GRAM(2)
+                break;
+            case 1:
+                FB_GRAM(1)
+                break;
+            default:
+                FB_GRAM(0)
             }
+#undef FB_GRAM
         }
     }
 
     // ---- partial sums of this block
-    {
-        double es = warpSum(eacc); // the slot threads live in warps 0 … 3
-        __syncthreads();
-        double* scratch = reinterpret_cast<double*>(&sm.Q[0]);
-        if (lane == 0 && warp < 4) {
-            scratch[warp] = es;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            e_partials[blockIdx.x] = ((scratch[0] + scratch[1]) + scratch[2]) + scratch[3];
-        }
-    }
     const int frag_g = lane >> 2;
     const int frag_t = lane & 3;
-    const size_t row = static_cast<size_t>(blockIdx.x);
+    const size_t row = static_cast<size_t>(block);
     if (warp_active) {
         // R[m]: the four x-indices of a move sit in adjacent lanes; the diagonal of G carries Σ A_k |δ|²
         double rs = racc;
@@ -336,29 +418,20 @@ __global__ void __launch_bounds__(kKsThreads, 2)
         for (int e = 0; e < 2; ++e) {
             const int a = 8 * warp + frag_g;
             const int b = 8 * warp + 2 * frag_t + e;
-            if (a < b && b < stride) {
+            if (a < b) {
                 G[a * stride + b] = g_diag[e];
             }
         }
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-            if (partner_on[d]) {
+            if (d < n_partners) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int a = 8 * warp + frag_g;
                     const int b = 8 * partner[d] + 2 * frag_t + e;
-                    const int lo = min(a, b), hi = max(a, b);
-                    if (hi < stride) {
-                        G[lo * stride + hi] = g_off[d][e];
-                    }
+                    G[min(a, b) * stride + max(a, b)] = g_off[d][e];
                 }
             }
-        }
-    }
-    else {
-        // moves beyond the window: R = 0 (the sums kernel reads only m < n, but the row is defined)
-        if (m < stride && xi == 0) {
-            r_partials[row * stride + m] = 0.0;
         }
     }
 }
