@@ -122,6 +122,10 @@ struct Slot
     DeviceBuffer<unsigned char> unit_map; //!< [n_units][32] slot → index inside the cell's storage range, 255: none
     DeviceBuffer<double> unit_sa;         //!< [n_units][32] √A_k in slot layout, 0 for empty slots
     int n_units = 0;
+    // work items of the commit (windowFrontKernel): two z-adjacent cells = up to four units that share table entries
+    DeviceBuffer<int4> item_units; //!< [n_items] unit of (cell 0, h 0), (cell 0, h 1), (cell 1, h 0), (cell 1, h 1); −1: none
+    DeviceBuffer<int4> item_base;  //!< [n_items] table index of x, y (h = 0), z of cell 0, z of cell 1
+    int n_items = 0;
     std::vector<int> perm; //!< storage index → index in the reference's k-vector order
     DeviceBuffer<double2> Q;
     int K = 0;
@@ -1789,6 +1793,8 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
             std::vector<unsigned char> unit_map;
             std::vector<double> unit_sa;
             std::vector<int> cell_start_host;
+            std::vector<int4> cell_units; // per cell: unit of h = 0, of h = 1 (−1: none), table index of x, y (the z one: bz)
+            std::vector<int4> cell_key;   // per cell: cell coordinates and the z table index
             for (size_t i = 0; i < kn.size(); ++i) {
                 if (i == 0 || (kn[i].x >> 2) != (kn[i - 1].x >> 2) || ((kn[i].y + ncc) >> 2) != ((kn[i - 1].y + ncc) >> 2) ||
                     ((kn[i].z + ncc) >> 2) != ((kn[i - 1].z + ncc) >> 2)) {
@@ -1802,6 +1808,7 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
                 const int bx = kn[p0].x & ~3;
                 const int by = (kn[p0].y + ncc) & ~3; // table indices (offset by ncc)
                 const int bz = (kn[p0].z + ncc) & ~3;
+                int unit_of_half[2] = {-1, -1};
                 for (int h = 0; h < 2; ++h) {
                     unsigned char map[32];
                     double sa[32] = {};
@@ -1817,11 +1824,39 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
                         }
                     }
                     if (any) {
+                        unit_of_half[h] = static_cast<int>(unit_info.size());
                         unit_info.push_back(make_int4(p0, bx, by + 2 * h, bz));
                         unit_map.insert(unit_map.end(), map, map + 32);
                         unit_sa.insert(unit_sa.end(), sa, sa + 32);
                     }
                 }
+                cell_units.push_back(make_int4(unit_of_half[0], unit_of_half[1], bx, by));
+                cell_key.push_back(make_int4(bx >> 2, by >> 2, bz >> 2, bz));
+            }
+            // commit items: pairs of cells that follow each other in z (the cells are stored z fastest)
+            std::vector<int4> item_units, item_base;
+            for (size_t cell = 0; cell < cell_units.size();) {
+                const int4 u0 = cell_units[cell];
+                const int4 k0 = cell_key[cell];
+                int4 u1 = make_int4(-1, -1, 0, 0);
+                int z1 = k0.w;
+                size_t used = 1;
+                if (cell + 1 < cell_units.size()) {
+                    const int4 k1 = cell_key[cell + 1];
+                    if (k1.x == k0.x && k1.y == k0.y && k1.z == k0.z + 1) {
+                        u1 = cell_units[cell + 1];
+                        z1 = k1.w;
+                        used = 2;
+                    }
+                }
+                item_units.push_back(make_int4(u0.x, u0.y, u1.x, u1.y));
+                item_base.push_back(make_int4(u0.z, u0.w, k0.w, z1));
+                cell += used;
+            }
+            sl.n_items = static_cast<int>(item_units.size());
+            if (sl.n_items > 0) {
+                sl.item_units.upload(item_units.data(), item_units.size(), c->stream);
+                sl.item_base.upload(item_base.data(), item_base.size(), c->stream);
             }
             sl.n_units = static_cast<int>(unit_info.size());
             sl.aks.upload(aks.data(), aks.size(), c->stream);
@@ -1985,6 +2020,13 @@ FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
                                            cudaMemcpyDeviceToDevice, c->stream));
                 d.unit_map.ensure(static_cast<size_t>(s.n_units) * 32);
                 CUDA_CHECK(cudaMemcpyAsync(d.unit_map.ptr, s.unit_map.ptr, static_cast<size_t>(s.n_units) * 32,
+                                           cudaMemcpyDeviceToDevice, c->stream));
+                d.n_items = s.n_items;
+                d.item_units.ensure(s.n_items);
+                CUDA_CHECK(cudaMemcpyAsync(d.item_units.ptr, s.item_units.ptr, s.n_items * sizeof(int4),
+                                           cudaMemcpyDeviceToDevice, c->stream));
+                d.item_base.ensure(s.n_items);
+                CUDA_CHECK(cudaMemcpyAsync(d.item_base.ptr, s.item_base.ptr, s.n_items * sizeof(int4),
                                            cudaMemcpyDeviceToDevice, c->stream));
                 d.unit_sa.ensure(static_cast<size_t>(s.n_units) * 32);
                 CUDA_CHECK(cudaMemcpyAsync(d.unit_sa.ptr, s.unit_sa.ptr, static_cast<size_t>(s.n_units) * 32 * sizeof(double),

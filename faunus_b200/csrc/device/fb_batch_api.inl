@@ -250,16 +250,16 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
         const Slot& sl = c->slot[0];
         const EwaldView E = makeEwaldView(c, 0);
         const int n_phase_blocks = frontPhaseBlocks(b.geo);
-        const int n_front_blocks = std::max(1, (sl.n_units + kKsWarps - 1) / kKsWarps); // one warp per unit
+        const int n_front_blocks = sl.n_items; // one block per item
         n_e_rows = n_front_blocks;
         n_rows = std::max(1, std::min(sl.n_units, 2 * c->n_sm));
         b.d_kq.ensure(static_cast<size_t>(sl.n_units) * kUnitSlots);
-        b.d_e_partials.ensure(static_cast<size_t>(n_front_blocks));
+        b.d_e_partials.ensure(static_cast<size_t>(std::max(1, n_front_blocks)));
         b.d_r_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax);
         b.d_g_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax * kBatchMax);
-        windowFrontKernel<<<n_phase_blocks + n_front_blocks, kKsThreads, 0, c->stream>>>(
-            E, sl.aks.ptr, sl.unit_info.ptr, sl.unit_map.ptr, sl.n_units, n_phase_blocks, cur, prev, b.geo, b.d_kq.ptr,
-            b.d_e_partials.ptr);
+        windowFrontKernel<<<n_phase_blocks + n_front_blocks, kFrontThreads, 0, c->stream>>>(
+            E, sl.aks.ptr, sl.unit_info.ptr, sl.unit_map.ptr, sl.item_units.ptr, sl.item_base.ptr, n_phase_blocks, cur,
+            prev, b.geo, b.d_kq.ptr, b.d_e_partials.ptr);
         launched(c, "windowFrontKernel");
         if (!b.kspace_unit_configured) {
             CUDA_CHECK(cudaFuncSetAttribute(windowKspaceKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -7,8 +7,9 @@
 //
 // windowFrontKernel   blocks [0, P): the per-axis phase tables of the 2n positions of the window (sincos; the x
 //                     entries carry the charge); the other blocks: ΔQ of the accepted moves of the previous window
-//                     as a small complex matrix product on the FP64 tensor path, one warp per unit, lane ↔ slot;
-//                     Q(k) updated in place, √A_k·Q_k in slot layout for the kernel below, Σ A_k |Q_k|².
+//                     as a small complex matrix product on the FP64 tensor path, one block per item (two z-adjacent
+//                     cells = four units; a warp per 32 positions), lane ↔ slot; Q(k) updated in place, √A_k·Q_k in slot layout for the
+//                     kernel below, Σ A_k |Q_k|².
 // windowKspaceKernel  persistent, block b walks the units b, b + grid, …  Thread ↔ (move m = tid / 4, x-index
 //                     i = tid % 4); warp w owns the moves 8w … 8w+7. A thread forms the 8 phases e^{ik·r} of its
 //                     x-index from registers — xy_j = X_i·Y_j once per y, then xy_j·Z_l — for the trial and the old
@@ -57,12 +58,24 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // ------------------------------------------------------------------------------------------------
 // front kernel: phase tables of this window + commit of the previous one
 // ------------------------------------------------------------------------------------------------
-inline int frontPhaseBlocks(const PhaseGeometry& geo) { return (2 * kBatchMax * geo.table_stride + kKsThreads - 1) / kKsThreads; }
+constexpr int kFrontThreads = 128;
+constexpr int kFrontWarps = kFrontThreads / 32;
+constexpr int kItemEntries = 16; //!< table entries per position and item: X0..3, Y0..3, Z0..3 of cell 0, Z0..3 of cell 1
+constexpr int kItemStride = 17;  //!< … stored with a stride of 272 B: the four positions of a step in different banks
+
+inline int frontPhaseBlocks(const PhaseGeometry& geo) { return (2 * kBatchMax * geo.table_stride + kFrontThreads - 1) / kFrontThreads; }
+
+struct FrontSmem
+{
+    double2 stage[kFrontWarps][32][kItemStride]; //!< [warp][position of the warp's batch][entry]
+    double2 part[kFrontWarps][4][32];             //!< [warp][unit of the item][slot]: ΔQ share of the warp's positions
+};
 
 /**
- * Blocks [0, P): phase tables. Blocks [P, …): the commit of the previous window, ONE WARP PER UNIT, as a small complex
- * matrix product on the FP64 tensor path. With the accepted positions p (trial: +, old: −; the x entries carry the
- * charges) and the unit's slots ks = 8 xi + 4 jj + l,
+ * Blocks [0, P): phase tables. Blocks [P, …): the commit of the previous window as a small complex matrix product on
+ * the FP64 tensor path, ONE BLOCK PER ITEM = two z-adjacent cells = up to four units (two y-halves × two cells).
+ * With the accepted positions p (trial: +, old: −; the x entries carry the charges) and a unit's slots
+ * ks = 8 xi + 4 jj + l,
  *
  *     ΔQ[xi, jj, l] = Σ_p  ± X_p[xi] Y_p[jj] · Z_p[l]
  *
@@ -70,50 +83,62 @@ inline int frontPhaseBlocks(const PhaseGeometry& geo) { return (2 * kBatchMax * 
  * B[p][l] = Z_p[l]. m8n8k4 takes 4 positions per step: lane (g, t) supplies A[g][p = 4 step + t] and, as column
  * g = 2 l + c of the real 4 × 8 matrices B' = [Z_re | Z_im] and B'' = [−Z_im | Z_re], the two B fragments, so that
  * Re(A)·B' + Im(A)·B'' leaves (Re, Im) of ΔQ[row g][l = t] in the two accumulator registers of lane (g, t) —
- * i.e. lane ↔ slot ks = lane, no shared memory, no barrier, no reduction between threads, and the order of the sum
- * over p is the fixed order of the tensor instruction. 2 DMMA + one complex product per 4 positions and unit instead
- * of 88 FP64 instructions per thread of a 256-thread block (20 µs → the arithmetic of 1.8 µs).
+ * lane ↔ slot ks = lane: no reduction between lanes, and the order of the sum over p is fixed by the instruction.
+ * The two y-halves of a cell share X and Z, the two cells share X and Y: 16 table entries per position serve 128
+ * slots (a unit alone needs 10 for 32; the L2 sector rate set the time of the first versions). Warp w takes the
+ * positions 32 w … 32 w + 31 (its own cp.async batch, 8 steps; Re(A)·B' and Im(A)·B'' in separate accumulators: a
+ * dependent chain of 8 tensor instructions instead of 58), the four shares are added in warp order.
  *
  * @param aks        [K] {A_k, √A_k}, storage order
- * @param unit_info  [n_units] {first k of the unit's cell, x, y, z table index of the first slot}
+ * @param unit_info  [n_units] {first k of the unit's cell, …}
  * @param unit_map   [n_units][32] index of each slot's k-vector inside the cell's storage range, 255: none
+ * @param item_units [n_items] unit of (cell 0, h 0), (cell 0, h 1), (cell 1, h 0), (cell 1, h 1); −1: none
+ * @param item_base  [n_items] table index of x, y (h = 0), z of cell 0, z of cell 1
  * @param kq         [n_units][32] out: √A_k · Q_k of the state this window starts from (0 for empty slots)
- * @param e_partials [blocks] out: Σ A_k |Q_k|² over the block's 8 units
+ * @param e_partials [n_items] out: Σ A_k |Q_k|² over the item
  */
-__global__ void __launch_bounds__(kKsThreads)
+__global__ void __launch_bounds__(kFrontThreads)
     windowFrontKernel(EwaldView E, const double2* __restrict__ aks, const int4* __restrict__ unit_info,
-                      const unsigned char* __restrict__ unit_map, int n_units, int n_phase_blocks, BatchBuffers cur,
-                      BatchBuffers prev, PhaseGeometry geo, double2* __restrict__ kq, double* __restrict__ e_partials)
+                      const unsigned char* __restrict__ unit_map, const int4* __restrict__ item_units,
+                      const int4* __restrict__ item_base, int n_phase_blocks, BatchBuffers cur, BatchBuffers prev,
+                      PhaseGeometry geo, double2* __restrict__ kq, double* __restrict__ e_partials)
 {
+    __shared__ FrontSmem sm;
     __shared__ int s_table[2 * kBatchMax]; //!< first table entry of every accepted position (trial, old, trial, …)
-    __shared__ double s_e[kKsWarps];
-    __shared__ double2 s_stage[kKsWarps][32][kUnitEntries]; //!< per warp: the unit's table entries of 32 positions
     const int tid = threadIdx.x;
     if (static_cast<int>(blockIdx.x) < n_phase_blocks) {
         const int total = 2 * cur.in->n * geo.table_stride;
-        const int t = blockIdx.x * kKsThreads + tid;
+        const int t = blockIdx.x * kFrontThreads + tid;
         if (t < total) {
             phaseTableEntry(cur.in, cur.table, geo, t);
         }
         return;
     }
-    const int block = blockIdx.x - n_phase_blocks;
+    const int item = blockIdx.x - n_phase_blocks;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int y_last = (geo.ncc + 1) + 2 * geo.ncc, z_last = (geo.ncc + 1) + (2 * geo.ncc + 1) + 2 * geo.ncc;
-    const int u = block * kKsWarps + warp;
-    const bool unit_on = u < n_units;
-    // requested first: nothing below depends on it until the very end
-    int slot_k = -1;
-    double2 slot_q = make_double2(0.0, 0.0), slot_a = make_double2(0.0, 0.0);
-    int4 info = make_int4(0, 0, 0, 0);
-    if (unit_on) {
-        info = __ldg(unit_info + u);
-        const int t = __ldg(unit_map + static_cast<size_t>(u) * kUnitSlots + lane);
-        if (t != 255) {
-            slot_k = info.x + t;
-            slot_q = E.Q[slot_k];
-            slot_a = __ldg(aks + slot_k);
+    const int4 units = __ldg(item_units + item);
+    const int4 base = __ldg(item_base + item);
+    // requested first (warp 0 finishes the item): slot ks = lane of the item's four units
+    int slot_k[4] = {-1, -1, -1, -1};
+    double2 slot_q[4], slot_a[4];
+    if (warp == 0) {
+        const int uu[4] = {units.x, units.y, units.z, units.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (uu[i] >= 0) {
+                const int t = __ldg(unit_map + static_cast<size_t>(uu[i]) * kUnitSlots + lane);
+                if (t != 255) {
+                    slot_k[i] = __ldg(unit_info + uu[i]).x + t;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (slot_k[i] >= 0) {
+                slot_q[i] = E.Q[slot_k[i]];
+                slot_a[i] = __ldg(aks + slot_k[i]);
+            }
         }
     }
     const CommitList& commit = cur.in->commit;
@@ -122,83 +147,100 @@ __global__ void __launch_bounds__(kKsThreads)
         s_table[tid] = (2 * commit.index[tid >> 1] + (tid & 1)) * geo.table_stride;
     }
     __syncthreads();
-    double dq_re = 0.0, dq_im = 0.0;
-    if (unit_on && ncommit > 0) {
+    const int n_pos = 2 * ncommit;
+    const int left = n_pos - 32 * warp; // positions of this warp's batch
+    double re[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}}; // Re(A)·B' of the four units
+    double im[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}}; // Im(A)·B''
+    if (left > 0) {
         const int g = lane >> 2; // row of A = 2 xi + jj; column of B', B'' = 2 l + c
         const int t = lane & 3;  // position inside the step; column pair of C = l
-        const int off_x = unitTableOffset(info, 0, geo.ncc); // the 4 x, 2 y, 4 z entries are contiguous unless clamped
-        const int off_y = unitTableOffset(info, 4, geo.ncc);
-        const int off_z = unitTableOffset(info, 6, geo.ncc);
-        const int ex = g >> 1, ey = 4 + (g & 1), ez = 6 + (g >> 1); // entries this lane multiplies
+        const int ex = g >> 1, ey = 4 + (g & 1), ez = 8 + (g >> 1); // entries this lane multiplies (second half / cell: + 2, + 4)
         const bool imag = g & 1;
-        const int n_pos = 2 * ncommit;
-        const double2* __restrict__ table = prev.table;
-        double2(*stage)[kUnitEntries] = s_stage[warp];
-        // batches of 32 positions (8 steps): lane ↔ position copies its 10 table entries (cp.async: all copies of the
-        // warp in flight together — with plain loads ptxas sinks every load to its first use, one L2 round trip per
-        // step), then lane (g, t) multiplies
-        for (int p0 = 0; p0 < n_pos; p0 += 32) {
-            const int p = p0 + lane;
-            if (p < n_pos) {
-                const double2* row = table + s_table[p];
+        const int y_base = geo.ncc + 1, z_base = (geo.ncc + 1) + (2 * geo.ncc + 1);
+        // the batch's 32 × 16 table entries: half a warp per position, lane ↔ entry, so that every 64-byte run of four
+        // entries is fetched as two whole sectors (one lane per position asked for every sector twice, and the L2
+        // sector rate — 1.2 M requests per window — was the kernel time)
+        {
+            const int e = lane & 15;
+            const int kind = e >> 2, i = e & 3; // X, Y, Z of cell 0, Z of cell 1
+            const int first = kind == 0 ? base.x : (kind == 1 ? base.y : (kind == 2 ? base.z : base.w));
+            const int offset = (kind == 0 ? 0 : (kind == 1 ? y_base : z_base)) + min(first + i, kind == 0 ? geo.ncc : 2 * geo.ncc);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    cpAsync16(&stage[lane][i], row + min(off_x + i, geo.ncc));
-                    cpAsync16(&stage[lane][6 + i], row + min(off_z + i, z_last));
+            for (int j = 0; j < 16; ++j) {
+                const int q = 2 * j + (lane >> 4);
+                if (q < left) {
+                    cpAsync16(&sm.stage[warp][q][e], prev.table + s_table[32 * warp + q] + offset);
                 }
-                cpAsync16(&stage[lane][4], row + off_y);
-                cpAsync16(&stage[lane][5], row + min(off_y + 1, y_last));
             }
-            cpAsyncCommit();
-            cpAsyncWaitAll();
-            __syncwarp();
-            const int steps = min(8, (n_pos - p0 + 3) >> 2);
-            for (int r = 0; r < steps; ++r) {
-                const int q = 4 * r + t;
-                double2 a = make_double2(0.0, 0.0), z = a;
-                if (p0 + q < n_pos) {
-                    a = cmul(stage[q][ex], stage[q][ey]);
-                    z = stage[q][ez];
-                    if (q & 1) { // old position: subtracted (p0 is even)
-                        a.x = -a.x;
-                        a.y = -a.y;
-                    }
+        }
+        cpAsyncCommit();
+        cpAsyncWaitAll();
+        __syncwarp();
+        const double2(*st)[kItemStride] = sm.stage[warp];
+        const int steps = min(8, (left + 3) >> 2);
+        for (int r = 0; r < steps; ++r) {
+            const int q = 4 * r + t;
+            double2 a0 = make_double2(0.0, 0.0), a1 = a0, z0 = a0, z1 = a0;
+            if (q < left) {
+                double2 x = st[q][ex];
+                if (q & 1) { // old position: subtracted (batches start at even positions)
+                    x.x = -x.x;
+                    x.y = -x.y;
                 }
-                const double b1 = imag ? z.y : z.x;  // B'  = [Z_re | Z_im]
-                const double b2 = imag ? z.x : -z.y; // B'' = [−Z_im | Z_re]
-                dmma884(dq_re, dq_im, a.x, b1);
-                dmma884(dq_re, dq_im, a.y, b2);
+                a0 = cmul(x, st[q][ey]);
+                a1 = cmul(x, st[q][ey + 2]);
+                z0 = st[q][ez];
+                z1 = st[q][ez + 4];
             }
-            __syncwarp(); // the staging area is free again
+            // B' = [Z_re | Z_im], B'' = [−Z_im | Z_re]
+            const double b1 = imag ? z0.y : z0.x, b2 = imag ? z0.x : -z0.y;
+            const double c1 = imag ? z1.y : z1.x, c2 = imag ? z1.x : -z1.y;
+            dmma884(re[0][0], re[0][1], a0.x, b1);
+            dmma884(re[1][0], re[1][1], a1.x, b1);
+            dmma884(re[2][0], re[2][1], a0.x, c1);
+            dmma884(re[3][0], re[3][1], a1.x, c1);
+            dmma884(im[0][0], im[0][1], a0.y, b2);
+            dmma884(im[1][0], im[1][1], a1.y, b2);
+            dmma884(im[2][0], im[2][1], a0.y, c2);
+            dmma884(im[3][0], im[3][1], a1.y, c2);
         }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sm.part[warp][i][lane] = make_double2(re[i][0] + im[i][0], re[i][1] + im[i][1]);
+    }
+    __syncthreads();
+    if (warp != 0) {
+        return;
+    }
     double e = 0.0;
-    if (unit_on) {
-        double2 out = make_double2(0.0, 0.0);
-        if (slot_k >= 0) {
-            double2 Q = slot_q;
-            if (ncommit > 0) {
-                Q.x += dq_re;
-                Q.y += dq_im;
-                E.Q[slot_k] = Q; // only this warp touches the unit's k-vectors
+    const int uu[4] = {units.x, units.y, units.z, units.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (uu[i] >= 0) {
+            double2 out = make_double2(0.0, 0.0);
+            if (slot_k[i] >= 0) {
+                double2 Q = slot_q[i];
+                if (ncommit > 0) {
+                    double2 dq = sm.part[0][i][lane];
+#pragma unroll
+                    for (int w = 1; w < kFrontWarps; ++w) { // the shares of the four batches, in order
+                        dq.x += sm.part[w][i][lane].x;
+                        dq.y += sm.part[w][i][lane].y;
+                    }
+                    Q.x += dq.x;
+                    Q.y += dq.y;
+                    E.Q[slot_k[i]] = Q; // only this block touches the item's k-vectors
+                }
+                out = make_double2(slot_a[i].y * Q.x, slot_a[i].y * Q.y);
+                e += slot_a[i].x * (Q.x * Q.x + Q.y * Q.y);
             }
-            out = make_double2(slot_a.y * Q.x, slot_a.y * Q.y);
-            e = slot_a.x * (Q.x * Q.x + Q.y * Q.y);
+            kq[static_cast<size_t>(uu[i]) * kUnitSlots + lane] = out;
         }
-        kq[static_cast<size_t>(u) * kUnitSlots + lane] = out;
     }
     e = warpSum(e); // fixed shuffle tree
     if (lane == 0) {
-        s_e[warp] = e;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double sum = 0.0;
-#pragma unroll
-        for (int w = 0; w < kKsWarps; ++w) {
-            sum += s_e[w];
-        }
-        e_partials[block] = sum;
+        e_partials[item] = e;
     }
 }
 
