@@ -215,6 +215,7 @@ struct fb_ctx
         PinnedBuffer<BatchInput> h_in;
         DeviceBuffer<double> d_pair_partials, d_r_partials, d_g_partials, d_e_partials, d_result;
         DeviceBuffer<double2> d_kq; //!< [n_units][32] √A_k·Q_k of the window-start state (windowFrontKernel)
+        DeviceBuffer<unsigned> d_tail_ticket; //!< windowTailKernel: blocks done (the last one walks the window)
         PinnedBuffer<double> h_result;
         int parity = 0;
         int last_n = 0;            //!< moves of the most recent window (0: none evaluated)

@@ -516,6 +516,222 @@ __global__ void __launch_bounds__(kPairThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// pair part with a finite cutoff: FP32 screening, FP64 evaluation.
+// At S1 99.9 % of the 2·B·N pairs of a window lie beyond the cutoff and contribute exactly zero; all the FP64 pipe did
+// for them was to find that out (7 of its instructions per pair, and the pipe is what the k-space kernel lives on).
+// Here the distance test runs in FP32 on the FMA pipes against a cutoff enlarged by a rigorous bound of the FP32
+// rounding error (`cut2_screen`, set by the host): every pair inside the true cutoff passes, a few just outside pass
+// too. Candidates are queued per warp in ballot order and evaluated in FP64 from the double-precision positions with
+// the reference's minimum-image arithmetic and the exact test r² < cut² — so the energies, and the order in which
+// they are added, are those of the FP64 kernel bit for bit. Four particles per lane in registers (12 floats).
+// ------------------------------------------------------------------------------------------------
+constexpr int kScreenPerThread = 4;
+constexpr int kScreenChunk = kPairThreads * kScreenPerThread; //!< particles per block
+constexpr int kScreenQueue = 384;                             //!< candidates a warp collects before it evaluates them
+
+template <int KIND>
+__global__ void __launch_bounds__(kPairThreads)
+    batchPairScreenKernel(SlotView M0, PotParams P, BatchBuffers cur, double cut2, float cut2_screen, int stride,
+                          double* __restrict__ partials /*[gridDim.x][2·stride]*/, SlotView M1, BatchBuffers prev,
+                          int apply_commit)
+{
+    __shared__ double s_qr[kPairThreads / 32][kScreenQueue];
+    __shared__ unsigned short s_qe[kPairThreads / 32][kScreenQueue]; //!< variant | particle of the block << 7
+    __shared__ double4 s_var[2 * kBatchMax];
+    __shared__ float4 s_varf[2 * kBatchMax]; //!< x, y, z in FP32, w: fold flags (bit pattern)
+    __shared__ int s_vid[2 * kBatchMax];
+    __shared__ int s_vslot[2 * kBatchMax];
+    __shared__ double s_acc[kPairThreads / 32][2 * kBatchMax];
+
+    // the accepted moves of the previous window that fall into this block's particle range → both mirrors
+    if (apply_commit) {
+        const CommitList& commit = cur.in->commit;
+        if (static_cast<int>(threadIdx.x) < commit.n) {
+            const int m = commit.index[threadIdx.x];
+            const int s = prev.in->slot[m];
+            if (s >= static_cast<int>(blockIdx.x) * kScreenChunk && s < static_cast<int>(blockIdx.x + 1) * kScreenChunk) {
+                const double4 p = prev.in->pnew[m];
+                const int id = prev.in->id[m];
+                M0.posq[s] = p;
+                M0.atom_id[s] = id;
+                M1.posq[s] = p;
+                M1.atom_id[s] = id;
+            }
+        }
+        __syncthreads();
+    }
+    const int n = cur.in->n;
+    const int nv = 2 * n;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const float hx = static_cast<float>(M0.half[0]), hy = static_cast<float>(M0.half[1]), hz = static_cast<float>(M0.half[2]);
+    const float lx = static_cast<float>(M0.len_or_zero[0]), ly = static_cast<float>(M0.len_or_zero[1]),
+                lz = static_cast<float>(M0.len_or_zero[2]);
+    const float nanf_ = __int_as_float(0x7fc00000);
+
+    for (int v = threadIdx.x; v < nv; v += kPairThreads) {
+        const int m = v >> 1;
+        double4 a;
+        int id;
+        if (v & 1) {
+            a = cur.pold[m];
+            id = cur.idold[m];
+        }
+        else {
+            a = cur.in->pnew[m];
+            id = cur.in->id[m];
+        }
+        s_var[v] = a;
+        s_vid[v] = id;
+        s_vslot[v] = cur.in->slot[m];
+        // fold needed on an axis unless the variant keeps the (screening) cutoff distance from both faces
+        const float rc = sqrtf(cut2_screen) * 1.0001f;
+        int fold = 0;
+        fold |= (lx > 0.0f && !(fabsf(static_cast<float>(a.x)) + rc < hx)) ? 1 : 0;
+        fold |= (ly > 0.0f && !(fabsf(static_cast<float>(a.y)) + rc < hy)) ? 2 : 0;
+        fold |= (lz > 0.0f && !(fabsf(static_cast<float>(a.z)) + rc < hz)) ? 4 : 0;
+        s_varf[v] = make_float4(static_cast<float>(a.x), static_cast<float>(a.y), static_cast<float>(a.z), __int_as_float(fold));
+    }
+    for (int v = threadIdx.x; v < (kPairThreads / 32) * 2 * kBatchMax; v += kPairThreads) {
+        (&s_acc[0][0])[v] = 0.0;
+    }
+    // this thread's particles: j = base + t·128 + tid (coalesced); inactive ones are NaN and never in range
+    const int base = blockIdx.x * kScreenChunk;
+    float px[kScreenPerThread], py[kScreenPerThread], pz[kScreenPerThread];
+#pragma unroll
+    for (int t = 0; t < kScreenPerThread; ++t) {
+        const int jl = t * kPairThreads + threadIdx.x;
+        const int j = base + jl;
+        double4 p = make_double4(0, 0, 0, 0);
+        bool active = false;
+        if (j < M0.n_slots) {
+            p = M0.posq[j];
+            active = M0.gid[j] >= 0;
+        }
+        px[t] = active ? static_cast<float>(p.x) : nanf_;
+        py[t] = static_cast<float>(p.y);
+        pz[t] = static_cast<float>(p.z);
+    }
+    __syncthreads();
+
+    int queued = 0; // warp-uniform
+    // evaluate the queued candidates of this warp in FP64: lane ↔ entry, then lane ↔ variant for the ordered sums
+    auto flush = [&]() {
+        for (int e = lane; e < queued; e += 32) {
+            const unsigned ent = s_qe[warp][e];
+            const int v = ent & 0x7fu;
+            const int jl = ent >> 7;
+            const double4 a = s_var[v];
+            const double4 b = M0.posq[base + jl]; // the candidates are few: double-precision positions from L2
+            const double r2 = minImageR2(M0, a.x, a.y, a.z, b.x, b.y, b.z);
+            double u = 0.0;
+            if (r2 < cut2 && base + jl != s_vslot[v]) {
+                u = pairEnergy<KIND>(P, s_vid[v], M0.atom_id[base + jl], a.w, b.w, r2);
+            }
+            s_qr[warp][e] = u;
+        }
+        __syncwarp();
+        const int myv = blockIdx.y * kPairVariantsPerBlock + lane;
+        double acc = s_acc[warp][myv]; // one running sum per variant: independent of when the queue is flushed
+        for (int e = 0; e < queued; ++e) {
+            if (static_cast<int>(s_qe[warp][e] & 0x7fu) == myv) {
+                acc += s_qr[warp][e];
+            }
+        }
+        s_acc[warp][myv] = acc;
+        __syncwarp();
+        queued = 0;
+    };
+
+    const int v_begin = blockIdx.y * kPairVariantsPerBlock;
+    const int v_end = min(nv, v_begin + kPairVariantsPerBlock);
+    for (int v0 = v_begin; v0 < v_end; v0 += 2) {
+        float r2[2][kScreenPerThread];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const float4 a = s_varf[min(v0 + u, v_end - 1)];
+            const int fold = __float_as_int(a.w);
+            float dx[kScreenPerThread], dy[kScreenPerThread], dz[kScreenPerThread];
+#pragma unroll
+            for (int t = 0; t < kScreenPerThread; ++t) {
+                dx[t] = a.x - px[t];
+                dy[t] = a.y - py[t];
+                dz[t] = a.z - pz[t];
+            }
+            if (fold & 1) {
+#pragma unroll
+                for (int t = 0; t < kScreenPerThread; ++t) {
+                    const float ad = fabsf(dx[t]);
+                    dx[t] = (ad > hx) ? ad - lx : dx[t];
+                }
+            }
+            if (fold & 2) {
+#pragma unroll
+                for (int t = 0; t < kScreenPerThread; ++t) {
+                    const float ad = fabsf(dy[t]);
+                    dy[t] = (ad > hy) ? ad - ly : dy[t];
+                }
+            }
+            if (fold & 4) {
+#pragma unroll
+                for (int t = 0; t < kScreenPerThread; ++t) {
+                    const float ad = fabsf(dz[t]);
+                    dz[t] = (ad > hz) ? ad - lz : dz[t];
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < kScreenPerThread; ++t) {
+                r2[u][t] = fmaf(dz[t], dz[t], fmaf(dy[t], dy[t], dx[t] * dx[t]));
+            }
+        }
+        bool any_in = false;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int t = 0; t < kScreenPerThread; ++t) {
+                any_in = any_in || (r2[u][t] < cut2_screen);
+            }
+        }
+        if (__any_sync(0xffffffffu, any_in)) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int v = v0 + u;
+                if (v >= v_end) {
+                    continue;
+                }
+#pragma unroll
+                for (int t = 0; t < kScreenPerThread; ++t) {
+                    const bool in = r2[u][t] < cut2_screen;
+                    const unsigned mask = __ballot_sync(0xffffffffu, in);
+                    if (in) {
+                        const int at = queued + __popc(mask & ((1u << lane) - 1u));
+                        s_qe[warp][at] = static_cast<unsigned short>(v | ((t * kPairThreads + threadIdx.x) << 7));
+                    }
+                    queued += __popc(mask);
+                }
+            }
+            __syncwarp();
+            if (queued > kScreenQueue - 2 * kScreenPerThread * 32) {
+                flush();
+            }
+        }
+    }
+    flush();
+    __syncthreads();
+    const int v_store_end = (blockIdx.y + 1 == gridDim.y) ? 2 * stride : v_begin + kPairVariantsPerBlock;
+    for (int v = v_begin + threadIdx.x; v < v_store_end; v += kPairThreads) {
+        double s = 0.0;
+        if (v < nv) {
+#pragma unroll
+            for (int w = 0; w < kPairThreads / 32; ++w) {
+                s += s_acc[w][v];
+            }
+        }
+        partials[static_cast<size_t>(blockIdx.x) * (2 * stride) + v] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // group mode: rigid-molecule moves (TranslateRotate, src/move.cpp:1670-1689: Change {group, all, internal =
 // false}). Energy of the moved group with every other group (group2all → group2group with the mass-centre
 // cutoff, src/energy.h:1155-1163, 979-989, 761-768). One block per (move, new | old); threads ↔ other groups.

@@ -142,8 +142,11 @@ void buildCellList(fb_ctx* c, const CellGrid& g, cudaStream_t stream)
 template <int KIND>
 void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, const CommitList& commit,
                   const CommitList& commit_moves, int n_moves, int n_groups, int stride, bool with_ewald, bool timing,
-                  bool device_commit = false, const BatchBuffers* ahead = nullptr, double fix_limit = 0.0)
+                  bool device_commit = false, const BatchBuffers* ahead = nullptr, double fix_limit = 0.0,
+                  const RunTail* tail = nullptr, bool* walked = nullptr)
 {
+    // tail != nullptr (runs): the window is walked on the device; *walked tells the caller whether the finish kernel
+    // did that itself (windowTailKernel) or a runDecideKernel has to follow
     // ahead != nullptr (runs): the pair sums of `cur` may have been taken a window ahead, and those of `ahead` are
     // taken now, behind this window's own pair work
     // device_commit: the commit list is written on the device (a run), the host does not know whether it is empty
@@ -157,7 +160,20 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
     }
     const bool pair_ahead = ahead != nullptr;
     // ---- pair side
-    const int n_pair_blocks = (c->n_slots + kPairChunk - 1) / kPairChunk;
+    // FP32 screening of the distance test (batchPairScreenKernel): cutoff² enlarged by a bound of the FP32 rounding
+    // error of a minimum-image r² — coordinates and box lengths to 2⁻²⁴ relative, two subtractions per component
+    // (≤ 8·2⁻²⁴·L each component), three products and two sums — so that no pair inside the true cutoff is lost
+    const bool screened = !pair_ahead && std::isfinite(c->pair_cut2) && c->pair_cut2 > 0 && n_groups == 0;
+    float cut2_screen = 0.0f;
+    if (screened) {
+        const double eps = 5.9604644775390625e-08; // 2⁻²⁴
+        const double lmax = std::max(c->slot[0].box[0], std::max(c->slot[0].box[1], c->slot[0].box[2]));
+        const double rc = std::sqrt(c->pair_cut2);
+        const double ec = 8.0 * eps * lmax;
+        const double widened = (c->pair_cut2 + 2.0 * std::sqrt(3.0) * rc * ec + 3.0 * ec * ec + 8.0 * eps * c->pair_cut2) * (1.0 + 1e-6);
+        cut2_screen = std::nextafter(static_cast<float>(widened), std::numeric_limits<float>::infinity());
+    }
+    const int n_pair_blocks = (c->n_slots + (screened ? kScreenChunk : kPairChunk) - 1) / (screened ? kScreenChunk : kPairChunk);
     const int pair_finish_grid = (2 * stride + stride * stride + kBlock / 32 - 1) / (kBlock / 32); // one warp per output
     CellGrid grid{};
     b.cells_used = n_groups == 0 && cellGridFor(c, grid);
@@ -203,7 +219,12 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
                 launched(c, "batchPairFixKernel");
             }
             const int apply_commit = (lean && have_commit) ? 1 : 0;
-            if (std::isinf(c->pair_cut2)) {
+            if (screened) { // finite cutoff: FP32 screening, FP64 evaluation of the candidates
+                batchPairScreenKernel<KIND><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, cut2_screen, stride,
+                                                                               b.d_pair_partials.ptr, makeView(c, 1), prev,
+                                                                               apply_commit);
+            }
+            else if (std::isinf(c->pair_cut2)) {
                 batchPairKernel<KIND, true><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, stride,
                                                                                b.d_pair_partials.ptr, redo, makeView(c, 1),
                                                                                prev, apply_commit);
@@ -278,10 +299,33 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
         if (fork) {
             CUDA_CHECK(cudaStreamWaitEvent(c->stream, b.ev_join, 0));
         }
-        windowFinishKernel<KIND><<<kspaceFinishGrid(stride) + pairFinishBlocks(stride), kFinishThreads, 0, c->stream>>>(
-            M0, c->P, cur, stride, with_ewald ? 1 : 0, n_rows, n_e_rows, b.d_r_partials.ptr, b.d_g_partials.ptr,
-            b.d_e_partials.ptr, n_pair_blocks, b.d_pair_partials.ptr, 0, nullptr, b.d_result.ptr, nullptr, nullptr);
-        launched(c, "windowFinishKernel");
+        if (tail != nullptr) { // sums, cross terms and — by the block that finishes last — the walk
+            static bool configured[6] = {false, false, false, false, false, false};
+            if (!configured[KIND]) {
+                CUDA_CHECK(cudaFuncSetAttribute(windowTailKernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                static_cast<int>(runDecideSmemBytes(kBatchMax))));
+                configured[KIND] = true;
+            }
+            if (b.d_tail_ticket.ptr == nullptr) {
+                b.d_tail_ticket.ensure(1);
+                CUDA_CHECK(cudaMemsetAsync(b.d_tail_ticket.ptr, 0, sizeof(unsigned), c->stream));
+            }
+            windowTailKernel<KIND><<<kspaceFinishGrid(stride) + pairFinishBlocks(stride), kFinishThreads,
+                                     runDecideSmemBytes(stride), c->stream>>>(
+                M0, c->P, cur, stride, with_ewald ? 1 : 0, n_rows, n_e_rows, b.d_r_partials.ptr, b.d_g_partials.ptr,
+                b.d_e_partials.ptr, n_pair_blocks, b.d_pair_partials.ptr, b.d_result.ptr, b.d_tail_ticket.ptr, tail->hdr,
+                tail->moves, tail->st, tail->next, tail->out, tail->prev_out, tail->predicted, tail->ahead);
+            launched(c, "windowTailKernel");
+            if (walked) {
+                *walked = true;
+            }
+        }
+        else {
+            windowFinishKernel<KIND><<<kspaceFinishGrid(stride) + pairFinishBlocks(stride), kFinishThreads, 0, c->stream>>>(
+                M0, c->P, cur, stride, with_ewald ? 1 : 0, n_rows, n_e_rows, b.d_r_partials.ptr, b.d_g_partials.ptr,
+                b.d_e_partials.ptr, n_pair_blocks, b.d_pair_partials.ptr, 0, nullptr, b.d_result.ptr, nullptr, nullptr);
+            launched(c, "windowFinishKernel");
+        }
     }
     else {
         batchKspaceFinishKernel<<<kspaceFinishGrid(stride), kFinishThreads, 0, c->stream>>>(
@@ -573,10 +617,20 @@ void launchRunStep(fb_ctx* c, fb_ctx::Batch::RunSlot& r, bool timing, bool setup
                                                        ahead_next);
         launched(c, "runSetupKernel");
     }
+    RunTail tail{};
+    tail.hdr = hdr;
+    tail.moves = moves;
+    tail.st = st;
+    tail.next = next.in;
+    tail.out = r.d_back.ptr->out;
+    tail.prev_out = prev_out;
+    tail.predicted = ahead_next;
+    tail.ahead = ahead_after;
+    bool walked = false;
 #define FB_CASE(K)                                                                                             \
     case K:                                                                                                    \
         launchWindow<K>(c, cur, prev, CommitList{}, CommitList{}, stride, 0, stride, with_ewald, timing, true,   \
-                        prepair ? &ahead : nullptr, r.h_run.ptr->header.cancellation_limit);                  \
+                        prepair ? &ahead : nullptr, r.h_run.ptr->header.cancellation_limit, &tail, &walked);  \
         break;
     switch (c->P.kind) {
         FB_CASE(POT_COULOMB_LJ)
@@ -589,18 +643,20 @@ void launchRunStep(fb_ctx* c, fb_ctx::Batch::RunSlot& r, bool timing, bool setup
         throw CudaError{"unknown potential kind"};
     }
 #undef FB_CASE
-    const size_t smem = runDecideSmemBytes(stride);
-    if (!b.run_decide_configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(runDecideKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(runDecideSmemBytes(kBatchMax))));
-        b.run_decide_configured = true;
+    if (!walked) {
+        const size_t smem = runDecideSmemBytes(stride);
+        if (!b.run_decide_configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(runDecideKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(runDecideSmemBytes(kBatchMax))));
+            b.run_decide_configured = true;
+        }
+        // the walk reads the window it decides (cur) and writes the description of the next one (next == prev's
+        // buffer: the window kernels of this step, the last readers of prev, are done by then)
+        runDecideKernel<<<1, kDecideThreads, smem, c->stream>>>(hdr, moves, st, cur, next.in, stride, b.cells_used ? 1 : 0,
+                                                               b.d_result.ptr, r.d_back.ptr->out, prev_out, ahead_next,
+                                                               ahead_after);
+        launched(c, "runDecideKernel");
     }
-    // the walk reads the window it decides (cur) and writes the description of the next one (next == prev's
-    // buffer: the window kernels of this step, the last readers of prev, are done by then)
-    runDecideKernel<<<1, kDecideThreads, smem, c->stream>>>(hdr, moves, st, cur, next.in, stride, b.cells_used ? 1 : 0,
-                                                           b.d_result.ptr, r.d_back.ptr->out, prev_out, ahead_next,
-                                                           ahead_after);
-    launched(c, "runDecideKernel");
     r.steps_launched += 1;
     r.last_parity = b.parity;
 }

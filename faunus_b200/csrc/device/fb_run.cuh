@@ -262,41 +262,56 @@ __global__ void __launch_bounds__(kBatchMax)
     runSetupWindow(hdr, moves, st->cursor, st->commit, in, stride, threadIdx.x, out, prev_out, nullptr, ahead);
 }
 
-constexpr int kDecideThreads = 1024; //!< staging is latency bound: every thread has all its 16 loads in flight at once
+constexpr int kDecideThreads = 1024; //!< 16 threads per move of the window
+static_assert(kDecideThreads == kFinishThreads, "the last block of the finish kernel walks the window");
+static_assert(kDecideThreads == 16 * kBatchMax, "16 threads per move");
 
-/** dynamic shared memory of runDecideKernel: four S × (S + 1) matrices, TRANSPOSED ([a][m], padded rows) */
-inline size_t runDecideSmemBytes(int stride) { return sizeof(double) * 4 * static_cast<size_t>(stride) * (stride + 1); }
+/** dynamic shared memory of the walk: three S × (S + 1) matrices, TRANSPOSED ([a][m], padded rows) */
+inline size_t runDecideSmemBytes(int stride) { return sizeof(double) * 3 * static_cast<size_t>(stride) * (stride + 1); }
+
+/** Σ over the 16 lanes of a move (half a warp), fixed tree */
+__device__ __forceinline__ double sumOverMoveLanes(double v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 8, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 4, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 2, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 1, 16);
+    return v;
+}
 
 /**
- * The in-order walk of a window as a fixed-point iteration. One block; all threads stage the correction
- * matrices in shared memory (transposed: thread m reads column m of row a, conflict-free), then thread m < n
- * owns move m. Given a GUESS of which moves are accepted (a 64-bit mask, initially none), every thread
- * evaluates its move exactly as the host walk would — corrections of the accepted a < m added in the order
- * a = 0, 1, …, Hamiltonian sum in term order with the early exit, getEnergyChange, Metropolis — all moves in
- * parallel. The decision of move m only depends on the bits below m, so everything up to and including the
- * first move whose decision contradicts the guess is FINAL; the guess is replaced by the new decisions and the
- * iteration repeats from there. It ends after (1 + number of decisions that the corrections overturned)
- * rounds — a handful — instead of n dependent steps, with bit-identical results. A move whose correction
- * meets a huge pair energy (cancellation) ends the window: it is re-evaluated at the head of the next one.
- * At the end the next window of the run is set up (`next`).
+ * The in-order walk of a window as a fixed-point iteration, by ONE block of 1024 threads. All threads stage the
+ * correction matrices in shared memory (transposed: the lanes of a move read column m of the rows a, conflict-free),
+ * then 16 threads own each move m. Given a GUESS of which moves are accepted (a 64-bit mask, initially none), the
+ * energies of every move are evaluated as the host walk would — corrections of the accepted a < m (each of the 16
+ * lanes adds its a ≡ lane (mod 16) in ascending order, the lanes are added in a fixed tree), Hamiltonian sum in term
+ * order with the early exit, getEnergyChange, Metropolis — all moves in parallel. The decision of move m only depends
+ * on the bits below m, so everything up to and including the first move whose decision contradicts the guess is
+ * FINAL; the guess is replaced by the new decisions and the iteration repeats from there. It ends after (1 + number
+ * of decisions that the corrections overturned) rounds — a handful — instead of n dependent steps. (With one thread
+ * per move the two in-order sums over the ≈ 57 accepted earlier moves of an S1 window were 2 × 57 dependent
+ * shared-memory round trips per round: a third of the kernel.) A move whose correction meets a huge pair energy
+ * (cancellation) ends the window: it is re-evaluated at the head of the next one. At the end the next window of the
+ * run is set up (`next`).
  */
-__global__ void __launch_bounds__(kDecideThreads)
-    runDecideKernel(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves, RunState* __restrict__ st,
-                    BatchBuffers cur, BatchInput* __restrict__ next, int stride, int cell_list,
-                    const double* __restrict__ result, RunOutput* __restrict__ out,
-                    const RunOutput* __restrict__ prev_out, const BatchInput* predicted, BatchInput* __restrict__ ahead)
+__device__ __forceinline__ void runDecideBlock(unsigned char* run_smem, const RunHeader* __restrict__ hdr,
+                                               const RunMove* __restrict__ moves, RunState* __restrict__ st,
+                                               BatchBuffers cur, BatchInput* __restrict__ next, int stride, int cell_list,
+                                               const double* __restrict__ result, RunOutput* __restrict__ out,
+                                               const RunOutput* __restrict__ prev_out, const BatchInput* predicted,
+                                               BatchInput* __restrict__ ahead)
 {
-    extern __shared__ __align__(16) unsigned char run_smem[];
     __shared__ CommitList s_commit;
     __shared__ double s_rec[kBatchMax];
-    __shared__ unsigned s_ballot[3][2]; // per warp: accepted, mismatch with the guess, stop
+    __shared__ unsigned long long s_cancel[kBatchMax]; // bit a of row m: the correction (a, m) meets a huge pair energy
+    __shared__ unsigned s_bits[3][kDecideThreads / 32]; // per warp (two moves): accepted, mismatch with the guess, stop
+    __shared__ unsigned long long s_mask[3];
 
     const int S = stride;
     const int LD = S + 1;
     double* s_cn = reinterpret_cast<double*>(run_smem); // [a][m]
     double* s_co = s_cn + S * LD;
-    double* s_cmax = s_co + S * LD;
-    double* s_g = s_cmax + S * LD;
+    double* s_g = s_co + S * LD;
     const int halted = st->halted;
     const int n = cur.in->n;
     const int cursor = st->cursor;
@@ -304,17 +319,25 @@ __global__ void __launch_bounds__(kDecideThreads)
     const double* u = result + 8;
     const double* cross = result + 8 + 3 * S;
     const int shift = S == 64 ? 6 : (S == 32 ? 5 : 4);
+    const double cancellation_limit = hdr->cancellation_limit;
+    if (threadIdx.x < kBatchMax) {
+        s_cancel[threadIdx.x] = 0ull;
+    }
+    __syncthreads();
     // all S rows (rows ≥ n are zero padding): the staging does not wait for n, and it has no branch, so that the
     // loads of all rounds are in flight together
 #pragma unroll 4
     for (int t = threadIdx.x; t < S * S; t += kDecideThreads) {
         const int m = t >> shift;
         const int a = t & (S - 1);
-        const double v0 = cross[t], v1 = cross[S * S + t], v2 = cross[2 * S * S + t], v3 = cross[3 * S * S + t];
+        const double v0 = __ldcg(cross + t), v1 = __ldcg(cross + S * S + t), v2 = __ldcg(cross + 2 * S * S + t),
+                     v3 = __ldcg(cross + 3 * S * S + t);
         s_cn[a * LD + m] = v0;
         s_co[a * LD + m] = v1;
-        s_cmax[a * LD + m] = v2;
         s_g[a * LD + m] = v3;
+        if (!(v2 < cancellation_limit)) {
+            atomicOr(&s_cancel[m], 1ull << a);
+        }
     }
     if (halted) { // behind an unfinished run: nothing was evaluated, nothing is decided, nothing follows
         if (threadIdx.x == 0) {
@@ -331,21 +354,22 @@ __global__ void __launch_bounds__(kDecideThreads)
     }
     if (threadIdx.x < kBatchMax && cursor + n + static_cast<int>(threadIdx.x) < hdr->n_moves) {
         // the proposals the next window most likely starts with (this window decided completely)
-        const char* ahead = reinterpret_cast<const char*>(moves + cursor + n + threadIdx.x);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead + 128));
+        const char* ahead_moves = reinterpret_cast<const char*>(moves + cursor + n + threadIdx.x);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead_moves));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead_moves + 128));
     }
-    const int m = threadIdx.x;
+    const int m = threadIdx.x >> 4;  // the move of this thread
+    const int part = threadIdx.x & 15;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const bool mine = m < n;
     const bool with_ewald = hdr->with_ewald != 0;
     double u_new0 = 0.0, u_old0 = 0.0, rec0 = 0.0, uniform = 0.0, host_new = 0.0, host_old = 0.0;
     int flags = 0;
-    if (mine && m < kBatchMax) {
-        u_new0 = u[m];
-        u_old0 = u[S + m];
-        rec0 = with_ewald ? u[2 * S + m] : 0.0;
+    if (mine) {
+        u_new0 = __ldcg(u + m);
+        u_old0 = __ldcg(u + S + m);
+        rec0 = with_ewald ? __ldcg(u + 2 * S + m) : 0.0;
         const RunMove& mv = moves[cursor + m];
         const bool alt = mv.dep >= 0 && !runDependencyAccepted(mv, out, prev_out); // as the window set-up chose
         uniform = mv.uniform;
@@ -353,16 +377,12 @@ __global__ void __launch_bounds__(kDecideThreads)
         host_old = alt ? mv.host_old_alt : mv.host_old;
         flags = alt ? (mv.flags >> 2) : mv.flags;
     }
-    const double rec_start = result[0]; // Σ_k A_k |Q_k|² of the window-start state (0 without Ewald)
-    const bool overflow = cell_list && result[2] != 0.0; // a cell bucket ran full: nothing of this window counts
+    const double rec_start = __ldcg(result); // Σ_k A_k |Q_k|² of the window-start state (0 without Ewald)
+    const bool overflow = cell_list && __ldcg(result + 2) != 0.0; // a cell bucket ran full: nothing of this window counts
     const double limit = hdr->max_energy;
-    const double cancellation_limit = hdr->cancellation_limit;
     const double pref = hdr->rec_prefactor;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     __syncthreads();
-    if (threadIdx.x >= kBatchMax) {
-        return; // the walk is the business of the first two warps (named barrier)
-    }
 
     unsigned long long guess = 0ull; // bit a: move a taken as accepted
     int fixed = 0;                   // decisions [0, fixed) are final
@@ -374,30 +394,46 @@ __global__ void __launch_bounds__(kDecideThreads)
         n_decided = 0;
         fixed = n;
     }
-    while (fixed < n) {
+    while (fixed < n) { // uniform over the block
         rounds++;
         const bool active = mine && m >= fixed;
-        double nb_new = u_new0, nb_old = u_old0, rec = rec0;
-        bool cancelled = false;
         const unsigned long long below = guess & ((1ull << m) - 1ull);
-        if (active) { // corrections for the accepted earlier moves, in the order of the host walk
-            for (unsigned long long bits = below; bits != 0ull; bits &= bits - 1ull) {
-                const int t = (__ffsll(static_cast<long long>(bits)) - 1) * LD + m;
-                cancelled = cancelled || !(s_cmax[t] < cancellation_limit);
-                nb_new = __dadd_rn(nb_new, s_cn[t]);
-                nb_old = __dadd_rn(nb_old, s_co[t]);
-                rec = __dadd_rn(rec, __dmul_rn(2.0, s_g[t]));
-            }
-            s_rec[m] = rec;
-        }
-        barrier64();
+        // corrections for the accepted earlier moves: this lane's share a = part, part + 16, …
+        double pn = 0.0, po = 0.0, pg = 0.0;
         if (active) {
-            double rec_running = rec_start;
-            if (with_ewald) {
-                for (unsigned long long bits = below; bits != 0ull; bits &= bits - 1ull) {
-                    rec_running = __dadd_rn(rec_running, s_rec[__ffsll(static_cast<long long>(bits)) - 1]);
+#pragma unroll
+            for (int j = 0; j < kBatchMax / 16; ++j) {
+                const int a = part + 16 * j;
+                if ((below >> a) & 1ull) {
+                    const int t = a * LD + m;
+                    pn += s_cn[t];
+                    po += s_co[t];
+                    pg += s_g[t];
                 }
             }
+        }
+        pn = sumOverMoveLanes(pn);
+        po = sumOverMoveLanes(po);
+        pg = sumOverMoveLanes(pg);
+        const bool cancelled = active && (s_cancel[m] & below) != 0ull;
+        const double nb_new = u_new0 + pn, nb_old = u_old0 + po, rec = rec0 + 2.0 * pg;
+        if (active && part == 0) {
+            s_rec[m] = rec;
+        }
+        __syncthreads();
+        double pr = 0.0;
+        if (active && with_ewald) { // reciprocal sum of the state move m starts from: the accepted earlier moves' changes
+#pragma unroll
+            for (int j = 0; j < kBatchMax / 16; ++j) {
+                const int a = part + 16 * j;
+                if ((below >> a) & 1ull) {
+                    pr += s_rec[a];
+                }
+            }
+        }
+        pr = sumOverMoveLanes(pr);
+        if (active) {
+            const double rec_running = rec_start + pr;
             // Hamiltonian::energy on the trial and on the accepted state: the caller's terms, the non-bonded term,
             // the Ewald term; the sum stops after a term ≥ limit or NaN (no FMA contraction: the host adds the same
             // numbers one by one)
@@ -445,19 +481,30 @@ __global__ void __launch_bounds__(kDecideThreads)
             }
             decision = cancelled ? 2 : (accept ? 1 : 0);
         }
+        // the decisions of the two moves of a warp sit in lanes 0 and 16
         const bool taken = ((guess >> m) & 1ull) != 0ull;
-        const unsigned b_acc = __ballot_sync(0xffffffffu, mine && decision == 1);
-        const unsigned b_mis = __ballot_sync(0xffffffffu, active && ((decision == 1) != taken));
-        const unsigned b_stop = __ballot_sync(0xffffffffu, active && decision == 2);
+        const bool speaker = part == 0;
+        const unsigned b_acc = __ballot_sync(0xffffffffu, speaker && mine && decision == 1);
+        const unsigned b_mis = __ballot_sync(0xffffffffu, speaker && active && ((decision == 1) != taken));
+        const unsigned b_stop = __ballot_sync(0xffffffffu, speaker && active && decision == 2);
         if (lane == 0) {
-            s_ballot[0][warp] = b_acc;
-            s_ballot[1][warp] = b_mis;
-            s_ballot[2][warp] = b_stop;
+            s_bits[0][warp] = (b_acc & 1u) | ((b_acc >> 15) & 2u);
+            s_bits[1][warp] = (b_mis & 1u) | ((b_mis >> 15) & 2u);
+            s_bits[2][warp] = (b_stop & 1u) | ((b_stop >> 15) & 2u);
         }
-        barrier64();
-        const unsigned long long accepted = s_ballot[0][0] | (static_cast<unsigned long long>(s_ballot[0][1]) << 32);
-        const unsigned long long mismatch = s_ballot[1][0] | (static_cast<unsigned long long>(s_ballot[1][1]) << 32);
-        const unsigned long long stops = s_ballot[2][0] | (static_cast<unsigned long long>(s_ballot[2][1]) << 32);
+        __syncthreads();
+        if (warp < 3) { // warp k assembles mask k: warp w of the block holds the moves 2w, 2w + 1
+            const unsigned v = s_bits[warp][lane];
+            const unsigned lo = __reduce_or_sync(0xffffffffu, lane < 16 ? v << (2 * lane) : 0u);
+            const unsigned hi = __reduce_or_sync(0xffffffffu, lane >= 16 ? v << (2 * (lane - 16)) : 0u);
+            if (lane == 0) {
+                s_mask[warp] = static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
+            }
+        }
+        __syncthreads();
+        const unsigned long long accepted = s_mask[0];
+        const unsigned long long mismatch = s_mask[1];
+        const unsigned long long stops = s_mask[2];
         const int first_mismatch = mismatch ? __ffsll(static_cast<long long>(mismatch)) - 1 : n;
         const int first_stop = stops ? __ffsll(static_cast<long long>(stops)) - 1 : n;
         guess = accepted; // final below `fixed` (those threads kept their decision), the new guess above
@@ -468,11 +515,10 @@ __global__ void __launch_bounds__(kDecideThreads)
         else {
             fixed = min(n, first_mismatch + 1);
         }
-        barrier64(); // s_ballot / s_rec are rewritten in the next round
     }
     const unsigned long long decided_mask = n_decided >= 64 ? ~0ull : ((1ull << n_decided) - 1ull);
     const unsigned long long accepted = guess & decided_mask;
-    if (mine && m < n_decided) {
+    if (mine && part == 0 && m < n_decided) {
         RunOutput o;
         o.u_new = total_new;
         o.u_old = total_old;
@@ -485,7 +531,7 @@ __global__ void __launch_bounds__(kDecideThreads)
             st->commit.index[k] = m;
         }
     }
-    if (m == 0) {
+    if (threadIdx.x == 0) {
         const int k = __popcll(accepted);
         s_commit.n = k;
         st->commit.n = k;
@@ -495,8 +541,75 @@ __global__ void __launch_bounds__(kDecideThreads)
         st->steps = step + 1;
         st->rounds += rounds;
     }
-    barrier64();
-    runSetupWindow(hdr, moves, cursor + n_decided, s_commit, next, stride, m, out, prev_out, predicted, ahead);
+    __threadfence_block(); // the set-up below reads out[] entries written by other threads of this block
+    __syncthreads();
+    if (threadIdx.x >= kBatchMax) {
+        return; // the set-up of the next window is the business of the first two warps (named barrier)
+    }
+    runSetupWindow(hdr, moves, cursor + n_decided, s_commit, next, stride, threadIdx.x, out, prev_out, predicted, ahead);
 }
+
+__global__ void __launch_bounds__(kDecideThreads)
+    runDecideKernel(const RunHeader* __restrict__ hdr, const RunMove* __restrict__ moves, RunState* __restrict__ st,
+                    BatchBuffers cur, BatchInput* __restrict__ next, int stride, int cell_list,
+                    const double* __restrict__ result, RunOutput* __restrict__ out,
+                    const RunOutput* __restrict__ prev_out, const BatchInput* predicted, BatchInput* __restrict__ ahead)
+{
+    extern __shared__ __align__(16) unsigned char run_smem[];
+    runDecideBlock(run_smem, hdr, moves, st, cur, next, stride, cell_list, result, out, prev_out, predicted, ahead);
+}
+
+/**
+ * The tail of a window of a run in ONE launch: the sums of windowFinishKernel and, by whichever block finishes last
+ * (ticket), the walk and the set-up of the next window. The result block stays in L2 between the two.
+ */
+template <int KIND>
+__global__ void __launch_bounds__(kFinishThreads)
+    windowTailKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, int with_ewald, int n_rows, int n_e_rows,
+                     const double* __restrict__ r_partials, const double* __restrict__ g_partials,
+                     const double* __restrict__ e_partials, int n_pair_blocks, const double* __restrict__ pair_partials,
+                     double* __restrict__ result, unsigned* __restrict__ ticket, const RunHeader* __restrict__ hdr,
+                     const RunMove* __restrict__ moves, RunState* __restrict__ st, BatchInput* __restrict__ next,
+                     RunOutput* __restrict__ out, const RunOutput* __restrict__ prev_out, const BatchInput* predicted,
+                     BatchInput* __restrict__ ahead)
+{
+    extern __shared__ __align__(16) unsigned char run_smem[];
+    __shared__ unsigned s_last;
+    const int k_blocks = kspaceFinishGrid(stride);
+    if (static_cast<int>(blockIdx.x) < k_blocks) {
+        kspaceFinishBlock(cur, stride, with_ewald, n_rows, n_e_rows, r_partials, g_partials, e_partials, result, blockIdx.x);
+    }
+    else {
+        pairFinishWarp<KIND>(M0, P, cur, stride, n_pair_blocks, pair_partials, 0, nullptr, result, nullptr, nullptr,
+                             static_cast<int>(((blockIdx.x - k_blocks) * kFinishThreads + threadIdx.x) >> 5));
+    }
+    __threadfence(); // this thread's part of the result block is visible device-wide before the ticket is drawn
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) {
+        return;
+    }
+    if (threadIdx.x == 0) {
+        *ticket = 0u; // for the next window
+    }
+    __threadfence();
+    runDecideBlock(run_smem, hdr, moves, st, cur, next, stride, 0, result, out, prev_out, predicted, ahead);
+}
+
+/** what the walk of a window of a run needs (launchWindow → windowTailKernel / runDecideKernel) */
+struct RunTail
+{
+    const RunHeader* hdr;
+    const RunMove* moves;
+    RunState* st;
+    BatchInput* next;
+    RunOutput* out;
+    const RunOutput* prev_out;
+    const BatchInput* predicted;
+    BatchInput* ahead;
+};
 
 } // namespace fbdev
