@@ -44,6 +44,7 @@ class SimLibrary:
         f("sim_trial_set", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, C.c_int,
                                      c_double_p, c_double_p, c_double_p])
         f("sim_trial_commit", C.c_int, [C.c_void_p, C.c_int])
+        f("sim_seed_global", C.c_int, [C.c_void_p, C.c_uint])
         f("sim_drift", C.c_double, [C.c_void_p])
         f("sim_initial_energy", C.c_double, [C.c_void_p])
         f("sim_sum_energy_changes", C.c_double, [C.c_void_p])
@@ -237,6 +238,27 @@ class Simulation:
             raise RuntimeError("all_gather returned the wrong number of insertion energies")
         self._check(self.api.widom_collect(self.handle, wid, _dp(everyone), n), "widom_collect")
         return n
+
+    def seed_global(self, seed: int):
+        """Re-seed the global generator (`Faunus::random`: molecule insertion, Widom ghosts) — per-rank streams of
+        :meth:`widom_sample_fast`."""
+        self._check(self.api.sim_seed_global(self.handle, int(seed) & 0xFFFFFFFF), "sim_seed_global")
+
+    def widom_sample_fast(self, wid: int, nsamples: int = 1, all_reduce=None):
+        """Scalable Widom sampling over the ranks of a process group (SURVEY §8e "fast mode"): the analysis `wid` of
+        every rank holds this rank's SHARE of the insertions per sample event (create it with ``ninsert = total //
+        size``) and draws its own ghosts from its own generator (:meth:`seed_global` with a per-rank seed) — no
+        serial ghost generation that every rank repeats, no gather of insertion energies. The per-rank averages
+        combine as the reference's ``Average::operator+`` does (src/average.h:61-76: value sums and sample counts
+        add): ``all_reduce(np.array([sum_exp, count])) -> np.ndarray`` sums two doubles over the ranks. Returns
+        (sum_exp, count, mu_excess) of the combined average."""
+        self.widom_sample(wid, nsamples)
+        res = self.widom_result(wid, max_du=1)
+        both = np.array([res["sum_exp"], float(res["count"])])
+        if all_reduce is not None:
+            both = np.asarray(all_reduce(both), dtype=np.float64)
+        mu = -np.log(both[0] / both[1]) if both[1] > 0 and both[0] > 0 else float("nan")
+        return float(both[0]), int(both[1]), float(mu)
 
     # -- virtual volume move (excess pressure) --------------------------------------------------------
     def virtualvolume_create(self, config: dict) -> int:

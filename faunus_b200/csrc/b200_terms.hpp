@@ -12,6 +12,7 @@
 // the changed particles. Callers that skip updateState/sync (Widom, SystemEnergy) are served by
 // re-uploading the changed group from the Space the term is bound to.
 #pragma once
+#include <array>
 #include "../../include/faunus_b200.h"
 #include "host/energyterm.hpp"
 #include "host/analysis_rdf.hpp"
@@ -118,6 +119,12 @@ class DeviceContext
      */
     bool unsynchronised[2] = {false, false};
     std::vector<size_t> unsynchronised_groups[2]; //!< … the same for single groups (VirtualTranslate, :2847-2860)
+    /**
+     * The particles of the slot's mirror already ARE those of its Space (a replica exchange imported the partner's
+     * state on the device, fb_nccl_exchange_state, and the Space followed): the next full upload only sends the box
+     * and the group records.
+     */
+    bool particles_current[2] = {false, false};
 
     /** cheap identity of a single-group Change (group, flags, indices) */
     static uint64_t changeKey(const Change& c)
@@ -206,6 +213,19 @@ class DeviceContext
     /** full upload of a Space into a slot */
     void uploadSpace(int slot, const Space& spc)
     {
+        if (particles_current[slot]) {
+            particles_current[slot] = false;
+            std::vector<fb_group> records;
+            for (const auto& g : spc.groups) {
+                records.push_back(groupRecord(g));
+            }
+            const auto& len = spc.geometry.getLength();
+            const double lengths[3] = {len.x, len.y, len.z};
+            fbCheck(fb_set_box(ctx, slot, lengths), ctx, "fb_set_box");
+            fbCheck(fb_upload_groups(ctx, slot, records.data(), static_cast<int>(records.size())), ctx, "fb_upload_groups");
+            cache_valid = false;
+            return;
+        }
         const size_t n = spc.particles.size();
         std::vector<double> xyzq(4 * n);
         std::vector<int> ids(n);
@@ -1293,6 +1313,100 @@ class AtomRDFB200 : public AtomRDF
             throw std::runtime_error("atomrdf on the device needs exactly one B200 non-bonded term");
         }
         nonbonded = nb.front();
+    }
+};
+
+/**
+ * Replica communicator on the device library's own NCCL communicator (fb_nccl_*, one context per GPU / process):
+ * the messages of the Temper move (src/move.cpp:844-968) without the launcher in the loop — the packed mirror of the
+ * trial state goes GPU to GPU and is imported on the device, the 8-byte messages go through pinned staging. The
+ * communicator is created when the first message is due (collective: every replica tempers in the same sweep).
+ */
+class NcclReplicaComm : public ReplicaComm
+{
+    std::array<char, 128> id{};
+    int my_rank, n_ranks;
+    std::shared_ptr<DeviceContext> dev;
+    int trial_slot = 1;
+    bool ready = false;
+
+    fb_ctx* ctx()
+    {
+        if (!dev) {
+            throw std::runtime_error("NCCL replica communicator: no device context bound");
+        }
+        if (!ready) {
+            fbCheck(fb_nccl_init(dev->ctx, id.data(), my_rank, n_ranks), dev->ctx, "fb_nccl_init");
+            ready = true;
+        }
+        return dev->ctx;
+    }
+
+  public:
+    unsigned long exchanges = 0;
+
+    NcclReplicaComm(const char unique_id[128], int rank, int size)
+        : my_rank(rank)
+        , n_ranks(size)
+    {
+        std::copy(unique_id, unique_id + 128, id.begin());
+        if (size < 2 || rank < 0 || rank >= size) {
+            throw std::runtime_error("NCCL replica communicator: bad rank / size");
+        }
+    }
+    /** the device context of the simulation's non-bonded term and the slot of its TRIAL state */
+    void bind(std::shared_ptr<DeviceContext> device, int slot_of_trial_state)
+    {
+        dev = std::move(device);
+        trial_slot = slot_of_trial_state;
+    }
+    int rank() const override { return my_rank; }
+    int size() const override { return n_ranks; }
+    void barrier() override { (void)gather(0.0); }
+    void sendrecvReplace(double* data, size_t n, int partner) override
+    {
+        fbCheck(fb_nccl_sendrecv_host(ctx(), data, n, partner), dev->ctx, "fb_nccl_sendrecv_host");
+        exchanges++;
+    }
+    std::vector<double> gather(double value) override
+    {
+        std::vector<double> out(static_cast<size_t>(n_ranks), value);
+        fbCheck(fb_nccl_allgather_host(ctx(), value, out.data()), dev->ctx, "fb_nccl_allgather_host");
+        return out;
+    }
+    bool exchangeState(Space& spc, int partner, VolumeMethod method, Change& change) override
+    {
+        fb_ctx* c = ctx();
+        dev->resynchronise();
+        std::vector<double> state(fb_state_doubles(c));
+        fbCheck(fb_nccl_exchange_state(c, trial_slot, partner, state.data()), c, "fb_nccl_exchange_state");
+        exchanges++;
+        // the Space follows the mirror: volume (exchangeVolume, src/mpicontroller.cpp:231-246), group sizes
+        // (src/move.cpp:860-867), all particles incl. inactive ones (ExchangeParticles::replace, :208-219)
+        const double old_volume = spc.geometry.getVolume();
+        const double new_volume = state[0] * state[1] * state[2];
+        if (new_volume <= pc::epsilon_dbl) {
+            throw std::runtime_error("tempering: invalid partner volume");
+        }
+        if (std::fabs(new_volume - old_volume) > pc::epsilon_dbl) {
+            spc.geometry.setVolume(new_volume, method);
+            change.volume_change = true;
+        }
+        const size_t n_groups = spc.groups.size();
+        for (size_t g = 0; g < n_groups; ++g) {
+            spc.groups[g].resize(static_cast<size_t>(state[3 + g]));
+        }
+        const double* p = state.data() + 3 + n_groups;
+        for (auto& particle : spc.particles) {
+            particle.pos = {p[0], p[1], p[2]};
+            particle.charge = p[3];
+            particle.id = static_cast<int>(p[4]);
+            p += 5;
+        }
+        spc.updateMassCenters();
+        change.everything = true;
+        dev->particles_current[trial_slot] = true; // updateState(everything) sends box + group records only
+        return true;
     }
 };
 

@@ -176,8 +176,12 @@ struct fb_ctx
     DeviceBuffer<double> d_widom_partial, d_widom_du;
     PinnedBuffer<double> h_widom_du;
     PinnedBuffer<double4> h_ghost;
-    DeviceBuffer<double> d_state;
-    PinnedBuffer<double> h_state;
+    DeviceBuffer<double> d_state, d_state_recv, d_xchg;
+    PinnedBuffer<double> h_state, h_xchg;
+    // replica exchange over NCCL (fb_nccl.inl)
+    void* nccl_comm = nullptr;
+    int nccl_rank = 0, nccl_size = 0;
+    unsigned long long bytes_exchanged = 0;
 
     // Ewald
     bool ewald_configured = false;
@@ -334,6 +338,23 @@ EwaldView makeEwaldView(fb_ctx* c, int s)
 }
 
 void launched(fb_ctx* c, const char* what);
+
+/**
+ * Cutoff² for the FP32 screening of the distance test (batchPairScreenKernel, widomScreenKernel, …): the true
+ * cutoff² enlarged by a bound of the FP32 rounding error of a minimum-image r² — coordinates and box lengths to
+ * 2⁻²⁴ relative, two subtractions per component (≤ 8·2⁻²⁴·L per component), three products and two sums — so that no
+ * pair inside the true cutoff is lost
+ */
+float screeningCutoff(const fb_ctx* c, int s)
+{
+    const double eps = 5.9604644775390625e-08; // 2⁻²⁴
+    const double* box = c->slot[s].box;
+    const double lmax = std::max(box[0], std::max(box[1], box[2]));
+    const double rc = std::sqrt(c->pair_cut2);
+    const double ec = 8.0 * eps * lmax;
+    const double widened = (c->pair_cut2 + 2.0 * std::sqrt(3.0) * rc * ec + 3.0 * ec * ec + 8.0 * eps * c->pair_cut2) * (1.0 + 1e-6);
+    return std::nextafter(static_cast<float>(widened), std::numeric_limits<float>::infinity());
+}
 
 /** Write a lazily accepted fast-path move into both mirrors before any other kind of access */
 void flushBatch(fb_ctx* c);
@@ -952,6 +973,7 @@ FB_API void fb_destroy(fb_ctx* c)
     if (c->stream) {
         cudaStreamSynchronize(c->stream);
     }
+    fb_nccl_finalize(c);
     if (c->h_result) {
         cudaFreeHost(c->h_result);
     }
@@ -1126,6 +1148,37 @@ FB_API int fb_upload_space(fb_ctx* c, int s, const double* xyzq, const int* atom
         launched(c, "buildGidKernel");
         CUDA_CHECK(cudaStreamSynchronize(c->stream)); // host vectors above go out of scope
         sl.rec_valid = false;
+    });
+}
+
+FB_API int fb_upload_groups(fb_ctx* c, int s, const fb_group* groups, int n_groups)
+{
+    return guarded(c, [&] {
+        flushPending(c);
+        checkSlot(c, s);
+        if (!groups || n_groups != c->n_groups) {
+            throw CudaError{"group count differs from the uploaded space"};
+        }
+        Slot& sl = c->slot[s];
+        std::vector<int> gsize(n_groups);
+        std::vector<double4> gcm(n_groups);
+        for (int g = 0; g < n_groups; ++g) {
+            if (groups[g].begin != sl.groups[g].begin || groups[g].capacity != sl.groups[g].capacity ||
+                groups[g].molid != sl.groups[g].molid || groups[g].size < 0 || groups[g].size > groups[g].capacity) {
+                throw CudaError{"group records must keep the layout of the uploaded space"};
+            }
+            gsize[g] = groups[g].size;
+            gcm[g] = make_double4(groups[g].cm[0], groups[g].cm[1], groups[g].cm[2], 0.0);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        sl.groups.assign(groups, groups + n_groups);
+        sl.gsize.uploadVector(gsize, c->stream);
+        sl.gcm.uploadVector(gcm, c->stream);
+        buildGidKernel<<<n_groups, 128, 0, c->stream>>>(makeView(c, s));
+        launched(c, "buildGidKernel");
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        sl.rec_valid = false;
+        c->batch.cells_valid = false;
     });
 }
 
@@ -2122,12 +2175,15 @@ FB_API int fb_widom_batch(fb_ctx* c, int s, int ghost_group, int n_ghost_atoms, 
         }
         if (!molecular) { // atomic ghosts: the streaming kernel (fb_stream.cuh)
             const int n_variants = n_insertions * n_ghost_atoms;
-            c->d_widom_partial.ensure(static_cast<size_t>(n_variants));
+            const bool dense = std::isinf(c->pair_cut2);
+            // finite cutoff: FP32 screening, particle ranges of kWidomSplit as the second grid dimension
+            const int n_split = dense ? 1 : std::max(1, (c->n_slots + kWidomSplit - 1) / kWidomSplit);
+            c->d_widom_partial.ensure(static_cast<size_t>(n_variants) * n_split);
             c->d_widom_du.ensure(n_insertions);
             c->h_widom_du.ensure(n_insertions);
             const SlotView V = makeView(c, s);
             const int grid = (n_variants + kStreamVariants - 1) / kStreamVariants;
-            const bool dense = std::isinf(c->pair_cut2);
+            const float cut2_screen = dense ? 0.0f : screeningCutoff(c, s);
             beginTiming(c, TIME_WIDOM);
 #define FB_CASE(K)                                                                                            \
     case K:                                                                                                   \
@@ -2135,16 +2191,17 @@ FB_API int fb_widom_batch(fb_ctx* c, int s, int ghost_group, int n_ghost_atoms, 
             widomStreamKernel<K, true><<<grid, kStreamThreads, 0, c->stream>>>(                               \
                 V, c->P, ghost_group, n_ghost_atoms, n_variants, c->d_ghost.ptr, c->d_ghost_id.ptr, c->pair_cut2, \
                 c->d_widom_partial.ptr);                                                                      \
+            launched(c, "widomStreamKernel");                                                                 \
         }                                                                                                     \
         else {                                                                                                \
-            widomStreamKernel<K, false><<<grid, kStreamThreads, 0, c->stream>>>(                              \
+            widomScreenKernel<K><<<dim3(grid, n_split), kStreamThreads, 0, c->stream>>>(                      \
                 V, c->P, ghost_group, n_ghost_atoms, n_variants, c->d_ghost.ptr, c->d_ghost_id.ptr, c->pair_cut2, \
-                c->d_widom_partial.ptr);                                                                      \
+                cut2_screen, c->d_widom_partial.ptr);                                                         \
+            launched(c, "widomScreenKernel");                                                                 \
         }                                                                                                     \
-        launched(c, "widomStreamKernel");                                                                     \
         widomStreamFinishKernel<K><<<(n_insertions + 127) / 128, 128, 0, c->stream>>>(                        \
             V, c->P, n_ghost_atoms, n_insertions, c->d_ghost.ptr, c->d_ghost_id.ptr, internal,                \
-            c->d_widom_partial.ptr, c->d_widom_du.ptr);                                                       \
+            c->d_widom_partial.ptr, n_split, c->d_widom_du.ptr);                                              \
         launched(c, "widomStreamFinishKernel");                                                               \
         break;
             switch (c->P.kind) {
@@ -2227,6 +2284,54 @@ FB_API int fb_export_state(fb_ctx* c, int s, double* device_buffer)
     });
 }
 
+namespace {
+/**
+ * Packed state (fb_export_state layout) in device memory → slot `s`: particles, group sizes, box. `host_copy`:
+ * pinned memory that already receives the same buffer on the context's stream (saves the read-back of the header),
+ * or nullptr. The mass centres of molecular groups are NOT part of the packed state (they need the atom masses and
+ * the reference's minimum-image rule, src/geometry.h:504-527): the caller follows up with fb_upload_groups. A box that
+ * differs from the slot's drops the slot's k-vector tables (fb_ewald_update_box rebuilds them). Synchronises the
+ * stream.
+ */
+void importPackedState(fb_ctx* c, int s, const double* device_buffer, const double* host_copy)
+{
+    Slot& sl = c->slot[s];
+    std::vector<double> head(3 + c->n_groups);
+    if (host_copy == nullptr) {
+        CUDA_CHECK(cudaMemcpyAsync(head.data(), device_buffer, head.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                                   c->stream));
+    }
+    unpackStateKernel<<<gridFor(c, c->n_slots, 256), 256, 0, c->stream>>>(makeView(c, s), device_buffer);
+    launched(c, "unpackStateKernel");
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (host_copy != nullptr) {
+        std::copy(host_copy, host_copy + head.size(), head.begin());
+    }
+    bool box_changed = false;
+    for (int i = 0; i < 3; ++i) {
+        box_changed = box_changed || sl.box[i] != head[i];
+    }
+    if (box_changed) {
+        const int rc = fb_set_box(c, s, head.data());
+        if (rc != FB_OK) {
+            throw CudaError{c->last_error};
+        }
+        sl.K = 0; // k-vectors and A_k belong to the old box: fb_ewald_update_box has to follow
+    }
+    std::vector<int> gsize(c->n_groups);
+    for (int g = 0; g < c->n_groups; ++g) {
+        sl.groups[g].size = static_cast<int>(head[3 + g]);
+        gsize[g] = sl.groups[g].size;
+    }
+    sl.gsize.uploadVector(gsize, c->stream);
+    buildGidKernel<<<c->n_groups, 128, 0, c->stream>>>(makeView(c, s));
+    launched(c, "buildGidKernel");
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    sl.rec_valid = false;
+    c->batch.cells_valid = false;
+}
+} // namespace
+
 FB_API int fb_import_state(fb_ctx* c, int s, const double* device_buffer)
 {
     return guarded(c, [&] {
@@ -2235,22 +2340,7 @@ FB_API int fb_import_state(fb_ctx* c, int s, const double* device_buffer)
         if (!device_buffer) {
             throw CudaError{"null buffer"};
         }
-        Slot& sl = c->slot[s];
-        std::vector<double> head(3 + c->n_groups);
-        CUDA_CHECK(cudaMemcpyAsync(head.data(), device_buffer, head.size() * sizeof(double), cudaMemcpyDeviceToHost,
-                                   c->stream));
-        unpackStateKernel<<<gridFor(c, c->n_slots, 256), 256, 0, c->stream>>>(makeView(c, s), device_buffer);
-        launched(c, "unpackStateKernel");
-        CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        for (int i = 0; i < 3; ++i) {
-            sl.box[i] = head[i];
-        }
-        for (int g = 0; g < c->n_groups; ++g) {
-            sl.groups[g].size = static_cast<int>(head[3 + g]);
-        }
-        buildGidKernel<<<c->n_groups, 128, 0, c->stream>>>(makeView(c, s));
-        launched(c, "buildGidKernel");
-        sl.rec_valid = false;
+        importPackedState(c, s, device_buffer, nullptr);
     });
 }
 
@@ -2281,3 +2371,4 @@ FB_API int fb_import_state_host(fb_ctx* c, int s, const double* host_buffer)
 }
 
 #include "fb_batch_api.inl"
+#include "fb_nccl.inl"

@@ -160,19 +160,9 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
     }
     const bool pair_ahead = ahead != nullptr;
     // ---- pair side
-    // FP32 screening of the distance test (batchPairScreenKernel): cutoff² enlarged by a bound of the FP32 rounding
-    // error of a minimum-image r² — coordinates and box lengths to 2⁻²⁴ relative, two subtractions per component
-    // (≤ 8·2⁻²⁴·L each component), three products and two sums — so that no pair inside the true cutoff is lost
+    // FP32 screening of the distance test (batchPairScreenKernel) against the widened cutoff of screeningCutoff()
     const bool screened = !pair_ahead && std::isfinite(c->pair_cut2) && c->pair_cut2 > 0 && n_groups == 0;
-    float cut2_screen = 0.0f;
-    if (screened) {
-        const double eps = 5.9604644775390625e-08; // 2⁻²⁴
-        const double lmax = std::max(c->slot[0].box[0], std::max(c->slot[0].box[1], c->slot[0].box[2]));
-        const double rc = std::sqrt(c->pair_cut2);
-        const double ec = 8.0 * eps * lmax;
-        const double widened = (c->pair_cut2 + 2.0 * std::sqrt(3.0) * rc * ec + 3.0 * ec * ec + 8.0 * eps * c->pair_cut2) * (1.0 + 1e-6);
-        cut2_screen = std::nextafter(static_cast<float>(widened), std::numeric_limits<float>::infinity());
-    }
+    const float cut2_screen = screened ? screeningCutoff(c, 0) : 0.0f;
     const int n_pair_blocks = (c->n_slots + (screened ? kScreenChunk : kPairChunk) - 1) / (screened ? kScreenChunk : kPairChunk);
     const int pair_finish_grid = (2 * stride + stride * stride + kBlock / 32 - 1) / (kBlock / 32); // one warp per output
     CellGrid grid{};

@@ -227,19 +227,216 @@ __global__ void __launch_bounds__(kStreamThreads)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Widom with a finite cutoff: FP32 screening of the distance test, FP64 evaluation of the candidates (the scheme
+// of batchPairScreenKernel, fb_batch.cuh — 99.9 % of the ghost–particle pairs of S1 lie beyond the cutoff and
+// contribute exactly zero). Grid (blocks of 64 variants) × (splits of kWidomSplit particles): a slice of a few
+// thousand insertions — the share of one of 8 GPUs — still fills the machine. The split size is a constant, so the
+// partial sums out[split][variant], and their sum in split order, are the same numbers however the insertions are
+// sliced over launches or ranks.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWidomSplit = 8192;
+constexpr int kWidomScreenPerThread = 4;
+constexpr int kWidomScreenChunk = kStreamThreads * kWidomScreenPerThread;
+
+template <int KIND>
+__global__ void __launch_bounds__(kStreamThreads)
+    widomScreenKernel(SlotView V, PotParams P, int ghost_group, int n_ghost_atoms, int n_variants,
+                      const double4* __restrict__ ghost_posq, const int* __restrict__ ghost_id, double cut2,
+                      float cut2_screen, double* __restrict__ out /*[gridDim.y][n_variants]*/)
+{
+    constexpr int NW = kStreamThreads / 32;
+    __shared__ double4 s_var[kStreamVariants];
+    __shared__ float4 s_varf[kStreamVariants];
+    __shared__ int s_vid[kStreamVariants];
+    __shared__ double s_acc[NW][kStreamVariants];
+    __shared__ double s_qr[NW][kStreamQueue];
+    __shared__ unsigned s_qe[NW][kStreamQueue]; //!< variant of the block | particle << 6
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int v0 = blockIdx.x * kStreamVariants;
+    const int nv = min(kStreamVariants, n_variants - v0);
+    const float hx = static_cast<float>(V.half[0]), hy = static_cast<float>(V.half[1]), hz = static_cast<float>(V.half[2]);
+    const float lx = static_cast<float>(V.len_or_zero[0]), ly = static_cast<float>(V.len_or_zero[1]),
+                lz = static_cast<float>(V.len_or_zero[2]);
+    const float nanf_ = __int_as_float(0x7fc00000);
+
+    for (int v = threadIdx.x; v < kStreamVariants; v += kStreamThreads) {
+        double4 a = make_double4(0, 0, 0, 0);
+        int id = 0;
+        float4 af = make_float4(nanf_, 0.0f, 0.0f, 0.0f);
+        if (v < nv) {
+            a = ghost_posq[v0 + v];
+            id = ghost_id[(v0 + v) % n_ghost_atoms];
+            const float rc = sqrtf(cut2_screen) * 1.0001f;
+            int fold = 0;
+            fold |= (lx > 0.0f && !(fabsf(static_cast<float>(a.x)) + rc < hx)) ? 1 : 0;
+            fold |= (ly > 0.0f && !(fabsf(static_cast<float>(a.y)) + rc < hy)) ? 2 : 0;
+            fold |= (lz > 0.0f && !(fabsf(static_cast<float>(a.z)) + rc < hz)) ? 4 : 0;
+            af = make_float4(static_cast<float>(a.x), static_cast<float>(a.y), static_cast<float>(a.z), __int_as_float(fold));
+        }
+        s_var[v] = a;
+        s_varf[v] = af;
+        s_vid[v] = id;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            s_acc[w][v] = 0.0;
+        }
+    }
+    __syncthreads();
+
+    int queued = 0; // warp-uniform
+    auto flush = [&]() {
+        for (int e = lane; e < queued; e += 32) {
+            const unsigned ent = s_qe[warp][e];
+            const int v = ent & 0x3fu;
+            const int j = ent >> 6;
+            const double4 a = s_var[v];
+            const double4 b = V.posq[j]; // the candidates are few: double-precision positions from L2
+            const double r2 = minImageR2(V, a.x, a.y, a.z, b.x, b.y, b.z);
+            s_qr[warp][e] = r2 < cut2 ? pairEnergy<KIND>(P, s_vid[v], V.atom_id[j], a.w, b.w, r2) : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < kStreamVariants / 32; ++h) {
+            const int myv = lane + 32 * h;
+            double acc = s_acc[warp][myv]; // one running sum per variant: independent of when the queue is flushed
+            for (int e = 0; e < queued; ++e) {
+                if (static_cast<int>(s_qe[warp][e] & 0x3fu) == myv) {
+                    acc += s_qr[warp][e];
+                }
+            }
+            s_acc[warp][myv] = acc;
+        }
+        __syncwarp();
+        queued = 0;
+    };
+
+    const int j_begin = blockIdx.y * kWidomSplit;
+    const int j_end = min(V.n_slots, j_begin + kWidomSplit);
+    for (int base = j_begin; base < j_end; base += kWidomScreenChunk) {
+        float px[kWidomScreenPerThread], py[kWidomScreenPerThread], pz[kWidomScreenPerThread];
+#pragma unroll
+        for (int t = 0; t < kWidomScreenPerThread; ++t) {
+            const int j = base + t * kStreamThreads + threadIdx.x;
+            px[t] = nanf_; // inactive particles and the ghost group itself: never in range
+            py[t] = pz[t] = 0.0f;
+            if (j < j_end) {
+                const int g = V.gid[j];
+                if (g >= 0 && g != ghost_group) {
+                    const double4 p = V.posq[j];
+                    px[t] = static_cast<float>(p.x);
+                    py[t] = static_cast<float>(p.y);
+                    pz[t] = static_cast<float>(p.z);
+                }
+            }
+        }
+        for (int vv = 0; vv < nv; vv += 2) {
+            float r2[2][kWidomScreenPerThread];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float4 a = s_varf[min(vv + u, nv - 1)];
+                const int fold = __float_as_int(a.w);
+                float dx[kWidomScreenPerThread], dy[kWidomScreenPerThread], dz[kWidomScreenPerThread];
+#pragma unroll
+                for (int t = 0; t < kWidomScreenPerThread; ++t) {
+                    dx[t] = a.x - px[t];
+                    dy[t] = a.y - py[t];
+                    dz[t] = a.z - pz[t];
+                }
+                if (fold & 1) {
+#pragma unroll
+                    for (int t = 0; t < kWidomScreenPerThread; ++t) {
+                        const float ad = fabsf(dx[t]);
+                        dx[t] = (ad > hx) ? ad - lx : dx[t];
+                    }
+                }
+                if (fold & 2) {
+#pragma unroll
+                    for (int t = 0; t < kWidomScreenPerThread; ++t) {
+                        const float ad = fabsf(dy[t]);
+                        dy[t] = (ad > hy) ? ad - ly : dy[t];
+                    }
+                }
+                if (fold & 4) {
+#pragma unroll
+                    for (int t = 0; t < kWidomScreenPerThread; ++t) {
+                        const float ad = fabsf(dz[t]);
+                        dz[t] = (ad > hz) ? ad - lz : dz[t];
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < kWidomScreenPerThread; ++t) {
+                    r2[u][t] = fmaf(dz[t], dz[t], fmaf(dy[t], dy[t], dx[t] * dx[t]));
+                }
+            }
+            bool any_in = false;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                for (int t = 0; t < kWidomScreenPerThread; ++t) {
+                    any_in = any_in || (r2[u][t] < cut2_screen);
+                }
+            }
+            if (!__any_sync(0xffffffffu, any_in)) {
+                continue;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int v = vv + u;
+                if (v >= nv) {
+                    continue;
+                }
+#pragma unroll
+                for (int t = 0; t < kWidomScreenPerThread; ++t) {
+                    const bool in = r2[u][t] < cut2_screen;
+                    const unsigned mask = __ballot_sync(0xffffffffu, in);
+                    if (in) {
+                        const int at = queued + __popc(mask & ((1u << lane) - 1u));
+                        s_qe[warp][at] = static_cast<unsigned>(v) |
+                                         (static_cast<unsigned>(base + t * kStreamThreads + threadIdx.x) << 6);
+                    }
+                    queued += __popc(mask);
+                }
+            }
+            __syncwarp();
+            if (queued > kStreamQueue - 2 * kWidomScreenPerThread * 32) {
+                flush();
+            }
+        }
+    }
+    flush();
+    __syncthreads();
+    for (int v = threadIdx.x; v < nv; v += kStreamThreads) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            s += s_acc[w][v];
+        }
+        out[static_cast<size_t>(blockIdx.y) * n_variants + v0 + v] = s;
+    }
+}
+
 /** du[b] = Σ_a out[b·n_g + a] + ghost-internal pairs (atomic ghosts with the internal flag) */
 template <int KIND>
 __global__ void widomStreamFinishKernel(SlotView V, PotParams P, int n_ghost_atoms, int n_insertions,
                                         const double4* __restrict__ ghost_posq, const int* __restrict__ ghost_id,
-                                        int internal, const double* __restrict__ per_variant, double* __restrict__ du)
+                                        int internal, const double* __restrict__ per_variant /*[n_split][variants]*/,
+                                        int n_split, double* __restrict__ du)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_insertions) {
         return;
     }
+    const size_t n_variants = static_cast<size_t>(n_insertions) * n_ghost_atoms;
     double e = 0.0;
     for (int a = 0; a < n_ghost_atoms; ++a) {
-        e += per_variant[static_cast<size_t>(b) * n_ghost_atoms + a];
+        double atom = 0.0;
+        for (int split = 0; split < n_split; ++split) { // particle ranges in order
+            atom += per_variant[split * n_variants + static_cast<size_t>(b) * n_ghost_atoms + a];
+        }
+        e += atom;
     }
     if (internal) {
         const double4* g = ghost_posq + static_cast<size_t>(b) * n_ghost_atoms;

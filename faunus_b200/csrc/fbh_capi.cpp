@@ -28,6 +28,52 @@ FB_DEFINE_RDF_CAPI(fbh, [](const fb::Json& j, fb::capi::Sim& s) -> std::unique_p
     return std::make_unique<fb::AtomRDFB200>(j, *s.mc);
 })
 
+/**
+ * One replica of a parallel-tempering run whose Temper move talks over the device library's NCCL communicator
+ * (fb_nccl_*): `unique_id` = the 128 bytes of fb_nccl_unique_id made by one rank and handed to all by the launcher.
+ */
+extern "C" __attribute__((visibility("default"))) void* fbh_sim_create_replica_nccl(const char* json_text,
+                                                                                    const char* unique_id, int rank,
+                                                                                    int size)
+{
+    std::unique_ptr<fb::NcclReplicaComm> comm;
+    if (fb::capi::guarded([&] { comm = std::make_unique<fb::NcclReplicaComm>(unique_id, rank, size); }) != 0) {
+        return nullptr;
+    }
+    fb::NcclReplicaComm* raw = comm.get();
+    void* handle = fb::capi::create(json_text, b200_factory, std::move(comm));
+    if (handle != nullptr) {
+        auto* s = static_cast<fb::capi::Sim*>(handle);
+        const int rc = fb::capi::guarded([&] {
+            const auto terms = s->mc->trial_state.pot->find<fb::NonbondedB200>();
+            if (terms.size() != 1) {
+                throw std::runtime_error("tempering over NCCL needs exactly one B200 non-bonded term");
+            }
+            raw->bind(terms.front()->device(), terms.front()->deviceSlot());
+        });
+        if (rc != 0) {
+            delete s;
+            return nullptr;
+        }
+    }
+    return handle;
+}
+
+/** messages and bytes the replica has exchanged over NCCL so far */
+extern "C" __attribute__((visibility("default"))) int fbh_sim_exchange_stats(void* h, double out[2])
+{
+    auto* s = static_cast<fb::capi::Sim*>(h);
+    out[0] = out[1] = 0;
+    if (auto* comm = dynamic_cast<fb::NcclReplicaComm*>(s->comm.get())) {
+        out[0] = static_cast<double>(comm->exchanges);
+        const auto terms = s->mc->state.pot->find<fb::NonbondedB200>();
+        if (!terms.empty()) {
+            out[1] = static_cast<double>(fb_nccl_bytes_exchanged(terms.front()->device()->ctx));
+        }
+    }
+    return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) void fbh_set_device(int device)
 {
     fb::defaultDevice() = device;

@@ -438,6 +438,13 @@ class ReplicaComm
     virtual void sendrecvReplace(double* data, size_t n, int partner) = 0;
     /** all ranks contribute one double; rank 0 receives all (others may receive garbage) */
     virtual std::vector<double> gather(double value) = 0;
+    /**
+     * Replace volume, group sizes and ALL particles of `spc` (the trial Space) by the partner's in one exchange and
+     * return true — or return false, and the move sends the reference's three messages through sendrecvReplace
+     * (exchangeVolume, exchangeGroupSizes, ExchangeParticles; src/mpicontroller.cpp:192-246, src/move.cpp:860-881).
+     * A communicator that owns the device mirror of the Space ships the mirror itself, GPU to GPU.
+     */
+    virtual bool exchangeState(Space& /*spc*/, int /*partner*/, VolumeMethod /*method*/, Change& /*change*/) { return false; }
 };
 
 /** Replica exchange ("temper"); src/move.cpp:844-968 */
@@ -488,6 +495,9 @@ class ParallelTempering : public Move
 
     void exchangeState(Change& change)
     {
+        if (comm.exchangeState(spc, *partner, volume_scaling_method, change)) {
+            return; // volume, group sizes and particles went mirror to mirror; the Space has followed
+        }
         // exchangeVolume, src/mpicontroller.cpp:231-246
         const double old_volume = spc.geometry.getVolume();
         double new_volume = old_volume;

@@ -302,6 +302,13 @@ inline State& pick(Sim& s, int which)
             }                                                                                                \
         });                                                                                                  \
     }                                                                                                         \
+    /* per-rank generators of a sharded analysis (every rank draws its OWN ghosts): the reference seeds the ranks  \
+       of an MPI run individually (`random: {seed: hardware}`); here the seed is explicit and reproducible */    \
+    __attribute__((visibility("default"))) int P##_sim_seed_global(void* h, unsigned seed)                   \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] { s->mc->rng.global.engine.seed(seed); });                              \
+    }                                                                                                         \
     __attribute__((visibility("default"))) double P##_sim_drift(void* h)                                     \
     {                                                                                                         \
         auto* s = static_cast<fb::capi::Sim*>(h);                                                            \

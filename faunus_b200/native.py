@@ -118,7 +118,9 @@ C_ABI_SYMBOLS = [
     "fb_system_energy_shard", "fb_atom_rdf", "fb_molecule_rdf", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_submit_groups", "fb_batch_wait", "fb_run_submit", "fb_run_wait", "fb_configure_runs", "fb_get_run_stats", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing",
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
     "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
-    "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_launch_count",
+    "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_upload_groups",
+    "fb_nccl_unique_id", "fb_nccl_init", "fb_nccl_finalize", "fb_nccl_exchange_state", "fb_nccl_sendrecv_host",
+    "fb_nccl_allgather_host", "fb_nccl_bytes_exchanged", "fb_launch_count",
     "fb_stream", "fb_enable_timing", "fb_last_kernel_ms", "fb_get_timing", "fb_measure_fp64_peak",
 ]
 
@@ -178,6 +180,14 @@ def load() -> C.CDLL:
         "fb_import_state": (C.c_int, [vp, C.c_int, vp]),
         "fb_export_state_host": (C.c_int, [vp, C.c_int, c_double_p]),
         "fb_import_state_host": (C.c_int, [vp, C.c_int, c_double_p]),
+        "fb_upload_groups": (C.c_int, [vp, C.c_int, C.POINTER(FbGroup), C.c_int]),
+        "fb_nccl_unique_id": (C.c_int, [C.c_char_p]),
+        "fb_nccl_init": (C.c_int, [vp, C.c_char_p, C.c_int, C.c_int]),
+        "fb_nccl_finalize": (C.c_int, [vp]),
+        "fb_nccl_exchange_state": (C.c_int, [vp, C.c_int, C.c_int, c_double_p]),
+        "fb_nccl_sendrecv_host": (C.c_int, [vp, c_double_p, C.c_size_t, C.c_int]),
+        "fb_nccl_allgather_host": (C.c_int, [vp, C.c_double, c_double_p]),
+        "fb_nccl_bytes_exchanged": (C.c_ulonglong, [vp]),
         "fb_launch_count": (C.c_ulonglong, [vp]),
         "fb_stream": (vp, [vp]),
         "fb_enable_timing": (C.c_int, [vp, C.c_int]),

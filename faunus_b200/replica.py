@@ -86,6 +86,43 @@ class ReplicaSimulation(Simulation):
             raise RuntimeError(f"{api.prefix}_sim_create_replica: {api.error()}")
 
 
+class NcclReplicaSimulation(Simulation):
+    """A replica whose ``temper`` move exchanges over the device library's OWN NCCL communicator (``fb_nccl_*``):
+    the packed mirror of the trial state goes GPU to GPU (ncclSend/ncclRecv on device buffers, imported on the
+    device), nothing of the exchange passes through Python. ``torch.distributed`` is only used once, to hand the
+    128-byte NCCL id of rank 0 to the other ranks."""
+
+    def __init__(self, config, device: int):
+        import torch
+        import torch.distributed as dist
+        from . import native
+        lib = native.load()
+        native.require_device()
+        lib.fbh_set_device(device)
+        rank, size = dist.get_rank(), dist.get_world_size()
+        uid = C.create_string_buffer(128)
+        if rank == 0 and lib.fb_nccl_unique_id(uid) != 0:
+            raise RuntimeError("fb_nccl_unique_id: " + lib.fb_last_error(None).decode())
+        box = [uid.raw if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        fn = lib.fbh_sim_create_replica_nccl
+        fn.restype = C.c_void_p
+        fn.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+        self.api = native.sim_library()
+        text = config if isinstance(config, str) else json.dumps(config)
+        self.handle = fn(text.encode(), box[0], rank, size)
+        if not self.handle:
+            raise RuntimeError(f"fbh_sim_create_replica_nccl: {self.api.error()}")
+        lib.fbh_sim_exchange_stats.restype = C.c_int
+        lib.fbh_sim_exchange_stats.argtypes = [C.c_void_p, c_double_p]
+        self._lib = lib
+
+    def exchange_stats(self) -> dict:
+        out = (C.c_double * 2)()
+        self._lib.fbh_sim_exchange_stats(self.handle, out)
+        return {"messages": int(out[0]), "bytes": int(out[1])}
+
+
 def run_local_replicas(api: SimLibrary, configs, sweeps: int):
     """All replicas in this process, one thread each (``<prefix>_temper_run_local``)."""
     fn = getattr(api.lib, f"{api.prefix}_temper_run_local")
@@ -124,18 +161,28 @@ def torch_all_gather(device=None):
 
 
 def reduce_in_rank_order(values, device=None):
-    """Sum of per-rank partial energies in rank order on every rank (deterministic)."""
+    """Sum of per-rank partial energies in rank order on every rank (deterministic): one gather into
+    one device tensor, one copy to the host, the ranks added in order."""
     import torch
     import torch.distributed as dist
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     mine = torch.tensor(list(values), dtype=torch.float64, device=device)
-    everyone = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
-    dist.all_gather(everyone, mine)
+    everyone = torch.empty(dist.get_world_size() * len(mine), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(everyone, mine)
+    rows = everyone.cpu().numpy().reshape(dist.get_world_size(), len(mine))
     total = np.zeros(len(mine))
-    for t in everyone:
-        total += t.cpu().numpy()
+    for row in rows:
+        total += row
     return total
+
+
+def all_reduce_sum(device=None):
+    """``all_reduce(values) -> np.ndarray``: sum of a few doubles over the default process group (the two numbers of
+    :meth:`Simulation.widom_sample_fast`); the ranks are added in rank order, so every rank holds the same bits."""
+    def reduce(values):
+        return reduce_in_rank_order(values, device)
+    return reduce
 
 
 def all_reduce_pair_counts(counts, device=None):

@@ -26,6 +26,7 @@
  *                                    (updateState + energy(trial) + energy(accepted) + sync each)     src/montecarlo.cpp:139-187
  *   fb_widom_batch ................. WidomInsertion::_sample insertion loop            src/analysis.cpp:1243-1265
  *   fb_export_state/fb_import_state  MPI::ExchangeParticles / exchangeGroupSizes       src/mpicontroller.cpp:192-219, src/move.cpp:860-881
+ *   fb_nccl_* ...................... the MPI messages of move::ParallelTempering        src/move.cpp:844-968, src/mpicontroller.cpp:69-259
  */
 #ifndef FAUNUS_B200_H
 #define FAUNUS_B200_H
@@ -415,6 +416,27 @@ int fb_import_state(fb_ctx* ctx, int slot, const double* device_buffer);
 /* host-side view of the same packing (tests, gloo) */
 int fb_export_state_host(fb_ctx* ctx, int slot, double* host_buffer);
 int fb_import_state_host(fb_ctx* ctx, int slot, const double* host_buffer);
+/* group records (sizes, mass centres) of a slot whose particles are already in place (after fb_import_state: the
+ * mass centres of molecular groups follow the reference's minimum-image rule, src/geometry.h:504-527, and are
+ * computed by the caller's Space); begin / capacity / molid must be those of the uploaded space */
+int fb_upload_groups(fb_ctx* ctx, int slot, const fb_group* groups, int n_groups);
+
+/* NCCL between the contexts of the replicas (one context per GPU / process), replacing the reference's MPI
+ * point-to-point messages of the Temper move (src/move.cpp:860-923, src/mpicontroller.cpp:192-259). libnccl is
+ * opened at run time. fb_nccl_unique_id: 128 bytes made by ONE rank and distributed by the launcher (any channel);
+ * fb_nccl_init: collective over the `size` contexts. */
+int fb_nccl_unique_id(char out[128]);
+int fb_nccl_init(fb_ctx* ctx, const char id[128], int rank, int size);
+int fb_nccl_finalize(fb_ctx* ctx);
+/* packed state of `slot` → partner's `slot`, partner's → this one's (ncclSend/ncclRecv on the device buffers, import
+ * on the device); host_received (fb_state_doubles doubles, may be NULL) gets a copy of what arrived so that the
+ * caller's Space can follow. Both partners call it with each other's rank. */
+int fb_nccl_exchange_state(fb_ctx* ctx, int slot, int partner, double* host_received);
+/* n doubles in place with `partner` (MPI_Sendrecv_replace of the 8-byte energy change, src/move.cpp:905-923) */
+int fb_nccl_sendrecv_host(fb_ctx* ctx, double* data, size_t n, int partner);
+/* one double per rank to every rank, out[size] (checkRandomEngineState, src/mpicontroller.cpp:253-259; a barrier too) */
+int fb_nccl_allgather_host(fb_ctx* ctx, double value, double* out);
+unsigned long long fb_nccl_bytes_exchanged(const fb_ctx* ctx);
 
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* number of kernels this context has launched so far */

@@ -796,3 +796,48 @@ def test_restore_on_the_device(water_input):
         assert np.abs(ref["u_new"] - got["u_new"]).max() <= 1e-10 * scale
         assert np.array_equal(o.particles()[0], g.particles()[0])
         assert abs(g.drift()) < 1e-9
+
+
+def test_packed_state_round_trip(water_input):
+    """fb_export_state / fb_import_state (+ fb_upload_groups): the packed mirror of one simulation imported into the
+    mirror of another gives the energy of the original (src/mpicontroller.cpp:192-219: what a replica exchange
+    ships). Molecular groups (mass centres follow by fb_upload_groups) and a box that changed (NPT)."""
+    import ctypes as C
+    from conftest import water_with_salt
+    from faunus_b200.native import FbGroup, load, make_change
+    lib = load()
+    dp = C.POINTER(C.c_double)
+    cfg = water_with_salt(water_input, n_pairs=6, volume_move=True)
+    a, b = b200_sim(cfg, 0), b200_sim(cfg, 0)
+    a.sweep(3)  # a has moved on (its box too), b still holds the start configuration
+    n_groups = a.api.sim_num_groups(a.handle)
+    n = lib.fb_state_doubles(a.ctx)
+    assert n == 3 + n_groups + 5 * a.num_particles
+    buf = np.zeros(n)
+    assert lib.fb_export_state_host(a.ctx, 0, buf.ctypes.data_as(dp)) == 0, lib.fb_last_error(a.ctx)
+    xyzq, ids = a.particles()
+    packed = buf[3 + n_groups:].reshape(-1, 5)
+    assert np.array_equal(packed[:, :4], xyzq) and np.array_equal(packed[:, 4], ids)
+    rec, cm = a.groups()
+    assert np.array_equal(buf[3:3 + n_groups], rec[:, 1])
+    groups = (FbGroup * n_groups)()
+    for g in range(n_groups):
+        groups[g].begin, groups[g].size, groups[g].capacity, groups[g].molid = (int(v) for v in rec[g])
+        for k in range(3):
+            groups[g].cm[k] = cm[g, k]
+    everything = make_change(everything=True)
+    want = C.c_double()
+    assert lib.fb_nonbonded_energy(a.ctx, 0, C.byref(everything), C.byref(want)) == 0, lib.fb_last_error(a.ctx)
+    before = C.c_double()
+    assert lib.fb_nonbonded_energy(b.ctx, 0, C.byref(everything), C.byref(before)) == 0
+    assert abs(before.value - want.value) > 1e-6 * abs(want.value)  # b really is somewhere else
+    for slot in (0, 1):
+        assert lib.fb_import_state_host(b.ctx, slot, buf.ctypes.data_as(dp)) == 0, lib.fb_last_error(b.ctx)
+        assert lib.fb_upload_groups(b.ctx, slot, groups, n_groups) == 0, lib.fb_last_error(b.ctx)
+        got = C.c_double()
+        assert lib.fb_nonbonded_energy(b.ctx, slot, C.byref(everything), C.byref(got)) == 0, lib.fb_last_error(b.ctx)
+        assert abs(got.value - want.value) <= 1e-12 * abs(want.value)
+    # and back out again: the packed state of b is that of a, bit for bit
+    again = np.zeros(n)
+    assert lib.fb_export_state_host(b.ctx, 1, again.ctypes.data_as(dp)) == 0
+    assert np.array_equal(again, buf)

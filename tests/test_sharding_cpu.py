@@ -118,3 +118,44 @@ def test_widom_sharded_gloo_world2(tmp_path):
         padded = lambda a: np.pad(np.asarray(a, dtype=np.int64), (0, n - len(a)))
         assert np.array_equal(padded(got["rdf"]), padded(want_rdf.astype(np.int64)))
         assert 0 < got["rdf_local_pairs"] < int(want_rdf.sum())
+
+
+def _gloo_fast_worker(rank, world, port, out_dir):
+    import ctypes as C
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from faunus_b200._simapi import SimLibrary, Simulation
+    from faunus_b200.replica import all_reduce_sum
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sim = Simulation(SimLibrary(C.CDLL(ORACLE_SO), "fo"), widom_config())
+    w = sim.widom_create({"molecule": "ghost", "ninsert": 600 // world})  # this rank's share of the insertions
+    sim.seed_global(1000 + rank)                                          # … drawn from its own generator
+    combined = sim.widom_sample_fast(w, 4, all_reduce_sum())
+    local = sim.widom_result(w, max_du=1)
+    json.dump({"combined": combined, "local_sum": local["sum_exp"], "local_count": local["count"]},
+              open(os.path.join(out_dir, f"fast{rank}.json"), "w"))
+    sim.close()
+    dist.destroy_process_group()
+
+
+def test_widom_fast_mode_gloo_world2(tmp_path):
+    """fast mode: per-rank ghosts from per-rank generators, the averages combined as
+    Average::operator+ (src/average.h:61-76) — value sums and sample counts add. Every rank ends with the same
+    combined numbers; they equal the sums of the per-rank averages; the excess chemical potential agrees with a
+    single-process run of the same total number of insertions within the statistical error."""
+    import torch.multiprocessing as mp
+    mp.spawn(_gloo_fast_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got = [json.load(open(tmp_path / f"fast{rank}.json")) for rank in range(2)]
+    assert got[0]["combined"] == got[1]["combined"]
+    sum_exp, count, mu = got[0]["combined"]
+    assert count == got[0]["local_count"] + got[1]["local_count"] == 4 * 600
+    assert sum_exp == got[0]["local_sum"] + got[1]["local_sum"]
+    assert got[0]["local_sum"] != got[1]["local_sum"]  # different ghosts on the two ranks
+    ref = oracle_sim(widom_config())
+    wr = ref.widom_create({"molecule": "ghost", "ninsert": 600})
+    ref.widom_sample(wr, 4)
+    r = ref.widom_result(wr, max_du=1)
+    mu_ref = -np.log(r["sum_exp"] / r["count"])
+    assert abs(mu - mu_ref) < 0.15  # two independent estimates from 2400 insertions each
