@@ -1317,6 +1317,59 @@ class AtomRDFB200 : public AtomRDF
 };
 
 /**
+ * The Space follows a packed mirror state (fb_export_state layout: box, group sizes, x y z q id of every particle):
+ * volume (exchangeVolume, src/mpicontroller.cpp:231-246), group sizes (src/move.cpp:860-867), all particles incl.
+ * inactive ones (ExchangeParticles::replace, src/mpicontroller.cpp:208-219), mass centres (src/move.cpp:879).
+ */
+inline void applyPackedState(Space& spc, const std::vector<double>& state, VolumeMethod method, Change& change)
+{
+    const double old_volume = spc.geometry.getVolume();
+    const double new_volume = state[0] * state[1] * state[2];
+    if (new_volume <= pc::epsilon_dbl) {
+        throw std::runtime_error("tempering: invalid partner volume");
+    }
+    if (std::fabs(new_volume - old_volume) > pc::epsilon_dbl) {
+        spc.geometry.setVolume(new_volume, method);
+        change.volume_change = true;
+    }
+    const size_t n_groups = spc.groups.size();
+    if (state.size() != 3 + n_groups + 5 * spc.particles.size()) {
+        throw std::runtime_error("tempering: the partner's state has a different layout");
+    }
+    for (size_t g = 0; g < n_groups; ++g) {
+        spc.groups[g].resize(static_cast<size_t>(state[3 + g]));
+    }
+    const double* p = state.data() + 3 + n_groups;
+    for (auto& particle : spc.particles) {
+        particle.pos = {p[0], p[1], p[2]};
+        particle.charge = p[3];
+        particle.id = static_cast<int>(p[4]);
+        p += 5;
+    }
+    spc.updateMassCenters();
+    change.everything = true;
+}
+
+/**
+ * Replica exchange of the packed mirror through a communicator that only moves doubles between host buffers
+ * (in-process replicas, tests): export → sendrecv → import on the device, the Space follows. The same steps as
+ * NcclReplicaComm::exchangeState with the NVLink hop replaced by the communicator.
+ */
+inline bool exchangePackedStateThroughHost(DeviceContext& dev, int trial_slot, ReplicaComm& comm, Space& spc, int partner,
+                                           VolumeMethod method, Change& change)
+{
+    dev.resynchronise();
+    std::vector<double> state(fb_state_doubles(dev.ctx));
+    // the ACCEPTED mirror is the authoritative copy of the state the two Spaces share at this point
+    fbCheck(fb_export_state_host(dev.ctx, 1 - trial_slot, state.data()), dev.ctx, "fb_export_state_host");
+    comm.sendrecvReplace(state.data(), state.size(), partner);
+    fbCheck(fb_import_state_host(dev.ctx, trial_slot, state.data()), dev.ctx, "fb_import_state_host");
+    applyPackedState(spc, state, method, change);
+    dev.particles_current[trial_slot] = true; // updateState(everything) sends box + group records only
+    return true;
+}
+
+/**
  * Replica communicator on the device library's own NCCL communicator (fb_nccl_*, one context per GPU / process):
  * the messages of the Temper move (src/move.cpp:844-968) without the launcher in the loop — the packed mirror of the
  * trial state goes GPU to GPU and is imported on the device, the 8-byte messages go through pinned staging. The
@@ -1379,32 +1432,11 @@ class NcclReplicaComm : public ReplicaComm
         fb_ctx* c = ctx();
         dev->resynchronise();
         std::vector<double> state(fb_state_doubles(c));
-        fbCheck(fb_nccl_exchange_state(c, trial_slot, partner, state.data()), c, "fb_nccl_exchange_state");
+        // the ACCEPTED mirror is the authoritative copy of the state the two Spaces share at this point (the one-move
+        // fast path never writes trial positions into the trial mirror); the partner's state lands in the trial slot
+        fbCheck(fb_nccl_exchange_state(c, 1 - trial_slot, trial_slot, partner, state.data()), c, "fb_nccl_exchange_state");
         exchanges++;
-        // the Space follows the mirror: volume (exchangeVolume, src/mpicontroller.cpp:231-246), group sizes
-        // (src/move.cpp:860-867), all particles incl. inactive ones (ExchangeParticles::replace, :208-219)
-        const double old_volume = spc.geometry.getVolume();
-        const double new_volume = state[0] * state[1] * state[2];
-        if (new_volume <= pc::epsilon_dbl) {
-            throw std::runtime_error("tempering: invalid partner volume");
-        }
-        if (std::fabs(new_volume - old_volume) > pc::epsilon_dbl) {
-            spc.geometry.setVolume(new_volume, method);
-            change.volume_change = true;
-        }
-        const size_t n_groups = spc.groups.size();
-        for (size_t g = 0; g < n_groups; ++g) {
-            spc.groups[g].resize(static_cast<size_t>(state[3 + g]));
-        }
-        const double* p = state.data() + 3 + n_groups;
-        for (auto& particle : spc.particles) {
-            particle.pos = {p[0], p[1], p[2]};
-            particle.charge = p[3];
-            particle.id = static_cast<int>(p[4]);
-            p += 5;
-        }
-        spc.updateMassCenters();
-        change.everything = true;
+        applyPackedState(spc, state, method, change);
         dev->particles_current[trial_slot] = true; // updateState(everything) sends box + group records only
         return true;
     }

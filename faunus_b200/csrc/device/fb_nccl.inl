@@ -1,7 +1,7 @@
 // Replica exchange between GPUs without leaving C++ (parallel tempering): an NCCL communicator
 // owned by the context, point-to-point ncclSend/ncclRecv on DEVICE buffers over NVLink / NVSwitch on the context's
 // stream. Replaces the reference's MPI messages (src/move.cpp:860-923, src/mpicontroller.cpp:192-259):
-//   fb_nccl_exchange_state   the packed state of a slot (box, group sizes, x y z q id of every particle — the
+//   fb_nccl_exchange_state   the packed state of the accepted slot (box, group sizes, x y z q id of every particle — the
 //                            `ExchangeParticles` buffer, the group sizes and `exchangeVolume` in one message) goes
 //                            mirror → partner's mirror; the host only receives a copy to keep its Space in step
 //   fb_nccl_sendrecv_host    a few doubles (the 8-byte energy change), host ↔ host through pinned + device staging
@@ -140,16 +140,17 @@ FB_API int fb_nccl_finalize(fb_ctx* c)
     });
 }
 
-FB_API int fb_nccl_exchange_state(fb_ctx* c, int s, int partner, double* host_received)
+FB_API int fb_nccl_exchange_state(fb_ctx* c, int send_slot, int s, int partner, double* host_received)
 {
     return guarded(c, [&] {
         flushPending(c);
+        checkSlot(c, send_slot);
         checkSlot(c, s);
         const size_t n = fb_state_doubles(c);
         c->d_state.ensure(n);
         c->d_state_recv.ensure(n);
         c->h_state.ensure(n);
-        packStateKernel<<<gridFor(c, c->n_slots, 256), 256, 0, c->stream>>>(makeView(c, s), c->d_state.ptr);
+        packStateKernel<<<gridFor(c, c->n_slots, 256), 256, 0, c->stream>>>(makeView(c, send_slot), c->d_state.ptr);
         launched(c, "packStateKernel");
         ncclExchange(c, c->d_state.ptr, c->d_state_recv.ptr, n, partner);
         // the partner's state: into the mirror on the device, and a copy for the host's Space

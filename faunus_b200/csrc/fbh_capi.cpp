@@ -59,6 +59,45 @@ extern "C" __attribute__((visibility("default"))) void* fbh_sim_create_replica_n
     return handle;
 }
 
+/**
+ * In-process tempering (one thread and one device context per replica) with the state exchange on the packed
+ * device mirrors: fb_export_state → in-process hand-over → fb_import_state, the Spaces follow. The same host logic as
+ * the NCCL communicator, testable on one GPU. Result format as fbh_temper_run_local.
+ */
+extern "C" __attribute__((visibility("default"))) int fbh_temper_run_local_packed(const char* configs_json, int sweeps,
+                                                                                  char* buf, int len)
+{
+    int n = -1;
+    fb::capi::guarded([&] {
+        const auto configs = fb::Json::parse(configs_json);
+        const auto results = fb::capi::runLocalReplicas(
+            configs, sweeps, b200_factory, fbh_replica_setup, [](fb::MetropolisMonteCarlo& mc, fb::LocalComm& comm) {
+                const auto terms = mc.trial_state.pot->find<fb::NonbondedB200>();
+                if (terms.size() != 1) {
+                    throw std::runtime_error("packed exchange needs exactly one B200 non-bonded term");
+                }
+                auto dev = terms.front()->device();
+                const int slot = terms.front()->deviceSlot();
+                comm.state_exchanger = [dev, slot, &comm](fb::Space& spc, int partner, fb::VolumeMethod method,
+                                                          fb::Change& change) {
+                    return fb::exchangePackedStateThroughHost(*dev, slot, comm, spc, partner, method, change);
+                };
+            });
+        fb::Json out = fb::Json::array();
+        for (const auto& r : results) {
+            fb::Json j = fb::Json::object();
+            j["energy"] = r.energy;
+            j["drift"] = r.drift;
+            j["xyzq"] = fb::Json::fromVector(r.xyzq);
+            j["moves"] = r.info.empty() ? fb::Json() : fb::Json::parse(r.info);
+            j["error"] = r.error;
+            out.push_back(j);
+        }
+        n = fb::capi::copyOut(out.dump(), buf, len);
+    });
+    return n;
+}
+
 /** messages and bytes the replica has exchanged over NCCL so far */
 extern "C" __attribute__((visibility("default"))) int fbh_sim_exchange_stats(void* h, double out[2])
 {

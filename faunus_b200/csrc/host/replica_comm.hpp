@@ -76,6 +76,16 @@ class LocalComm : public ReplicaComm
     std::shared_ptr<LocalExchange> ex;
     int my_rank;
 
+  public:
+    /** optional: exchange the whole state in one go (the B200 build ships the packed device mirror) */
+    std::function<bool(Space&, int, VolumeMethod, Change&)> state_exchanger;
+    bool exchangeState(Space& spc, int partner, VolumeMethod method, Change& change) override
+    {
+        return state_exchanger ? state_exchanger(spc, partner, method, change) : false;
+    }
+
+  private:
+
     void wait(std::unique_lock<std::mutex>& lock, const std::function<bool()>& pred)
     {
         ex->cv.wait(lock, [&] { return ex->failed || pred(); });

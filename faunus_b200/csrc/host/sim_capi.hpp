@@ -79,8 +79,9 @@ struct LocalReplicaResult
  * `configs` is a JSON array of per-replica input documents; `setup(rank)` runs in the replica's thread
  * before its simulation is created (e.g. selects the CUDA device).
  */
-inline std::vector<LocalReplicaResult> runLocalReplicas(const Json& configs, int sweeps, const TermFactory& factory,
-                                                        const std::function<void(int)>& setup)
+inline std::vector<LocalReplicaResult> runLocalReplicas(
+    const Json& configs, int sweeps, const TermFactory& factory, const std::function<void(int)>& setup,
+    const std::function<void(MetropolisMonteCarlo&, LocalComm&)>& after_create = nullptr)
 {
     const int size = static_cast<int>(configs.size());
     auto exchange = std::make_shared<LocalExchange>(size);
@@ -103,6 +104,9 @@ inline std::vector<LocalReplicaResult> runLocalReplicas(const Json& configs, int
                     owner = std::make_unique<MetropolisMonteCarlo>(configs.at(r), factory, raw);
                 }
                 MetropolisMonteCarlo& mc = *owner;
+                if (after_create) {
+                    after_create(mc, *raw);
+                }
                 for (int i = 0; i < sweeps; ++i) {
                     mc.sweep();
                 }

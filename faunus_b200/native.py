@@ -184,7 +184,7 @@ def load() -> C.CDLL:
         "fb_nccl_unique_id": (C.c_int, [C.c_char_p]),
         "fb_nccl_init": (C.c_int, [vp, C.c_char_p, C.c_int, C.c_int]),
         "fb_nccl_finalize": (C.c_int, [vp]),
-        "fb_nccl_exchange_state": (C.c_int, [vp, C.c_int, C.c_int, c_double_p]),
+        "fb_nccl_exchange_state": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_double_p]),
         "fb_nccl_sendrecv_host": (C.c_int, [vp, c_double_p, C.c_size_t, C.c_int]),
         "fb_nccl_allgather_host": (C.c_int, [vp, C.c_double, c_double_p]),
         "fb_nccl_bytes_exchanged": (C.c_ulonglong, [vp]),

@@ -123,9 +123,10 @@ class NcclReplicaSimulation(Simulation):
         return {"messages": int(out[0]), "bytes": int(out[1])}
 
 
-def run_local_replicas(api: SimLibrary, configs, sweeps: int):
-    """All replicas in this process, one thread each (``<prefix>_temper_run_local``)."""
-    fn = getattr(api.lib, f"{api.prefix}_temper_run_local")
+def run_local_replicas(api: SimLibrary, configs, sweeps: int, packed: bool = False):
+    """All replicas in this process, one thread each (``<prefix>_temper_run_local``). ``packed`` (B200 library only):
+    the state exchange ships the packed device mirrors (fb_export_state → fb_import_state), the Spaces follow."""
+    fn = getattr(api.lib, f"{api.prefix}_temper_run_local" + ("_packed" if packed else ""))
     fn.restype = C.c_int
     fn.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     text = json.dumps(list(configs)).encode()

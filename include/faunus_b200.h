@@ -428,10 +428,11 @@ int fb_upload_groups(fb_ctx* ctx, int slot, const fb_group* groups, int n_groups
 int fb_nccl_unique_id(char out[128]);
 int fb_nccl_init(fb_ctx* ctx, const char id[128], int rank, int size);
 int fb_nccl_finalize(fb_ctx* ctx);
-/* packed state of `slot` → partner's `slot`, partner's → this one's (ncclSend/ncclRecv on the device buffers, import
- * on the device); host_received (fb_state_doubles doubles, may be NULL) gets a copy of what arrived so that the
- * caller's Space can follow. Both partners call it with each other's rank. */
-int fb_nccl_exchange_state(fb_ctx* ctx, int slot, int partner, double* host_received);
+/* packed state of `send_slot` (the accepted state: the authoritative mirror) → partner, the partner's → `recv_slot`
+ * (the trial state): ncclSend/ncclRecv on the device buffers, import on the device; host_received (fb_state_doubles
+ * doubles, may be NULL) gets a copy of what arrived so that the caller's Space can follow. Both partners call it
+ * with each other's rank. */
+int fb_nccl_exchange_state(fb_ctx* ctx, int send_slot, int recv_slot, int partner, double* host_received);
 /* n doubles in place with `partner` (MPI_Sendrecv_replace of the 8-byte energy change, src/move.cpp:905-923) */
 int fb_nccl_sendrecv_host(fb_ctx* ctx, double* data, size_t n, int partner);
 /* one double per rank to every rank, out[size] (checkRandomEngineState, src/mpicontroller.cpp:253-259; a barrier too) */

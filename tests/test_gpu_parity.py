@@ -841,3 +841,35 @@ def test_packed_state_round_trip(water_input):
     again = np.zeros(n)
     assert lib.fb_export_state_host(b.ctx, 1, again.ctypes.data_as(dp)) == 0
     assert np.array_equal(again, buf)
+
+
+def test_tempering_packed_exchange_equals_message_exchange():
+    """In-process replicas on the device: the exchange of the packed mirrors (fb_export_state → fb_import_state, the
+    Spaces follow; the host logic of the NCCL communicator) reproduces the exchange of the reference's three
+    messages bit for bit, and both reproduce the oracle's in-process run."""
+    from faunus_b200.config import primitive_model
+    from faunus_b200.native import sim_library
+    from faunus_b200.replica import run_local_replicas
+    from _oraclelib import oracle_api
+    cfgs = []
+    for r in range(3):
+        cfg = primitive_model(n=300, seed=11, moves_per_sweep=30,
+                              coulomb={"type": "ewald", "epsr": 60.0 + 12.0 * r, "cutoff": 10.0, "alpha": 0.3, "ncutoff": 5})
+        cfg["moves"].append({"temper": {"format": "xyzqi"}})
+        cfgs.append(cfg)
+    sweeps = 25
+    plain = run_local_replicas(sim_library(), cfgs, sweeps)
+    packed = run_local_replicas(sim_library(), cfgs, sweeps, packed=True)
+    oracle = run_local_replicas(oracle_api(), cfgs, sweeps)
+    accepted = 0.0
+    for a, b, o in zip(plain, packed, oracle):
+        assert a["error"] == b["error"] == o["error"] == ""
+        ta = [m["temper"] for m in a["moves"] if "temper" in m][0]["exchange"]
+        tb = [m["temper"] for m in b["moves"] if "temper" in m][0]["exchange"]
+        to = [m["temper"] for m in o["moves"] if "temper" in m][0]["exchange"]
+        assert ta == tb == to
+        assert a["xyzq"] == b["xyzq"] == o["xyzq"]
+        assert a["energy"] == b["energy"]
+        assert abs(b["drift"]) < 1e-9
+        accepted += sum(s["acceptance"] * s["attempts"] for s in tb.values())
+    assert accepted > 0
