@@ -45,6 +45,7 @@ class SimLibrary:
                                      c_double_p, c_double_p, c_double_p])
         f("sim_trial_commit", C.c_int, [C.c_void_p, C.c_int])
         f("sim_seed_global", C.c_int, [C.c_void_p, C.c_uint])
+        f("sim_matter_change", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, c_double_p])
         f("sim_drift", C.c_double, [C.c_void_p])
         f("sim_initial_energy", C.c_double, [C.c_void_p])
         f("sim_sum_energy_changes", C.c_double, [C.c_void_p])
@@ -238,6 +239,17 @@ class Simulation:
             raise RuntimeError("all_gather returned the wrong number of insertion energies")
         self._check(self.api.widom_collect(self.handle, wid, _dp(everyone), n), "widom_collect")
         return n
+
+    def matter_change(self, groups: Sequence[dict], mode: int = 2) -> dict:
+        """A change of the number of active particles made by the caller — ``groups`` = [{"index": group, "size": new
+        size, "atoms": [relative indices of the particles that appear / disappear], "all", "internal", "dNatomic"}] —
+        carried through the MC protocol (updateState, energy on both states, translational-entropy bias, sync);
+        mode 0 reject, 1 accept, 2 Metropolis. What a speciation / grand-canonical move asks of the Hamiltonian
+        (src/energy.h:1390-1435, src/montecarlo.cpp:271-374)."""
+        out = np.zeros(4)
+        self._check(self.api.sim_matter_change(self.handle, json.dumps({"groups": list(groups)}).encode(), int(mode),
+                                               _dp(out)), "sim_matter_change")
+        return {"u_new": out[0], "u_old": out[1], "bias": out[2], "accepted": bool(out[3])}
 
     def seed_global(self, seed: int):
         """Re-seed the global generator (`Faunus::random`: molecule insertion, Widom ghosts) — per-rank streams of

@@ -40,6 +40,7 @@ struct FlatChange
     {
         change.everything = c.everything;
         change.volume_change = c.volume_change;
+        change.matter_change = c.matter_change;
         indices.resize(c.groups.size());
         for (size_t i = 0; i < c.groups.size(); ++i) {
             const auto& g = c.groups[i];
@@ -58,7 +59,8 @@ struct FlatChange
     /** content signature used to pair trial.energy with the following accepted.energy */
     std::string signature() const
     {
-        std::string s = std::to_string(change.everything) + ":" + std::to_string(change.volume_change);
+        std::string s = std::to_string(change.everything) + ":" + std::to_string(change.volume_change) + ":" +
+                        std::to_string(change.matter_change);
         for (size_t i = 0; i < groups.size(); ++i) {
             s += "|" + std::to_string(groups[i].group_index) + "," + std::to_string(groups[i].all) + "," +
                  std::to_string(groups[i].internal);
@@ -445,9 +447,6 @@ class NonbondedB200 : public EnergyTerm
     {
         if (!change) {
             return 0.0;
-        }
-        if (change.matter_change) {
-            throw std::runtime_error("matter_change (speciation) is outside the B200 hot-path scope");
         }
         if (change.everything || change.volume_change) {
             dev->unsynchronised[slot] = false; // refreshed below (or by updateState just now) anyway

@@ -519,6 +519,79 @@ MovedDesc lowerChange(fb_ctx* c, int slot_a, int slot_b, const fb_change* change
     return md;
 }
 
+/**
+ * Change::matter_change on ONE slot (the two states differ in the number of active particles, so they are
+ * evaluated separately): the ACTIVE listed atoms of every changed group — flagged kMovedCross — and, for a group
+ * changed as a whole (`all`), its other active atoms, which only take part in the pairs inside the group
+ * (accumulateSpeciation, src/energy.h:1390-1435: group2groups with the static groups, group2group between changed
+ * groups, groupInternal(group) / groupInternal(group, index)). A group without an active listed atom adds nothing.
+ */
+MovedDesc lowerMatterChange(fb_ctx* c, int s, const fb_change* change)
+{
+    if (change->n_groups <= 0 || change->n_groups > kMaxMovedGroups) {
+        throw CudaError{"a matter change lists 1..16 groups"};
+    }
+    MovedDesc md{};
+    md.n_groups = change->n_groups;
+    md.matter = 1;
+    md.internal = 1;
+    md.all_moved = 0;
+    std::vector<int> slots, gpos;
+    const auto& groups = c->slot[s].groups;
+    for (int t = 0; t < change->n_groups; ++t) {
+        const fb_group_change& gc = change->groups[t];
+        if (gc.group_index < 0 || gc.group_index >= c->n_groups) {
+            throw CudaError{"group index out of range"};
+        }
+        if (t > 0 && gc.group_index <= change->groups[t - 1].group_index) {
+            throw CudaError{"the groups of a Change must be sorted and distinct"};
+        }
+        md.groups[t] = gc.group_index;
+        const fb_group& g = groups[gc.group_index];
+        std::vector<char> listed(static_cast<size_t>(std::max(g.size, 0)), 0);
+        bool any = false;
+        for (int i = 0; i < gc.n_atoms; ++i) {
+            if (gc.atoms[i] < 0 || gc.atoms[i] >= g.capacity) {
+                throw CudaError{"relative atom index out of range"};
+            }
+            if (gc.atoms[i] < g.size && !listed[gc.atoms[i]]) { // active particles only
+                listed[gc.atoms[i]] = 1;
+                any = true;
+            }
+        }
+        if (!any) {
+            continue;
+        }
+        for (int i = 0; i < g.size; ++i) {
+            if (listed[i]) {
+                slots.push_back(g.begin + i);
+                gpos.push_back(t | kMovedCross);
+            }
+            else if (gc.all) {
+                slots.push_back(g.begin + i);
+                gpos.push_back(t);
+            }
+        }
+    }
+    md.n_moved = static_cast<int>(slots.size());
+    if (md.n_moved <= kInlineMoved) {
+        md.list = nullptr;
+        for (int i = 0; i < md.n_moved; ++i) {
+            md.inline_slot[i] = slots[i];
+            md.inline_gpos[i] = gpos[i];
+        }
+    }
+    else {
+        CUDA_CHECK(cudaStreamSynchronize(c->stream)); // staging buffer reuse
+        c->h_list.ensure(2 * slots.size());
+        std::copy(slots.begin(), slots.end(), c->h_list.ptr);
+        std::copy(gpos.begin(), gpos.end(), c->h_list.ptr + slots.size());
+        c->d_list.upload(c->h_list.ptr, 2 * slots.size(), c->stream);
+        md.list = c->d_list.ptr;
+    }
+    return md;
+}
+
 int gridFor(fb_ctx* c, int n, int block)
 {
     return std::max(1, std::min((n + block - 1) / block, c->max_blocks));
@@ -1386,7 +1459,7 @@ FB_API int fb_nonbonded_energy(fb_ctx* c, int s, const fb_change* change, double
                 *energy = 0.0;
                 return;
             }
-            const MovedDesc md = lowerChange(c, s, s, change, false);
+            const MovedDesc md = change->matter_change ? lowerMatterChange(c, s, change) : lowerChange(c, s, s, change, false);
             if (md.n_moved == 0) {
                 *energy = 0.0;
                 return;
@@ -1424,6 +1497,22 @@ FB_API int fb_nonbonded_delta(fb_ctx* c, int s_new, int s_old, const fb_change* 
         }
         if (change->n_groups == 0) {
             *u_new = *u_old = 0.0;
+            return;
+        }
+        if (change->matter_change) { // the active sets of the two states differ: one pass per state
+            double* out[2] = {u_new, u_old};
+            const int slots[2] = {s_new, s_old};
+            for (int k = 0; k < 2; ++k) {
+                const MovedDesc one = lowerMatterChange(c, slots[k], change);
+                *out[k] = 0.0;
+                if (one.n_moved > 0) {
+                    const SlotView V = makeView(c, slots[k]);
+                    beginTiming(c, TIME_PAIR);
+                    launchMoved<false>(c, V, V, one);
+                    finish(c);
+                    *out[k] = c->h_result[0];
+                }
+            }
             return;
         }
         const MovedDesc md = lowerChange(c, s_new, s_old, change, false);

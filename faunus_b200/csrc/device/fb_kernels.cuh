@@ -103,6 +103,8 @@ struct PotParams
     int any_molecular;         //!< 0 if every group is atomic (skips cutoff / exclusion logic)
 };
 
+constexpr int kMovedCross = 0x100; //!< matter changes: the atom is listed (pairs with other groups count)
+
 struct MovedDesc
 {
     int n_moved;
@@ -110,6 +112,13 @@ struct MovedDesc
     int groups[kMaxMovedGroups];
     int internal;  //!< single moved group only
     int all_moved; //!< every active atom of the moved group(s) is in the list
+    /**
+     * Change::matter_change (GroupPairing::accumulateSpeciation, src/energy.h:1390-1435): the list holds the ACTIVE
+     * listed atoms of the changed groups (group position | kMovedCross) — plus, for a group changed as a whole,
+     * its other active atoms (no flag: they only take part in the pairs INSIDE the group). A pair of atoms of two
+     * changed groups counts if at least one of them is listed; pairs inside a group count unless it is rigid.
+     */
+    int matter;
     const int* list; //!< [2*n_moved] slots then group positions; nullptr → inline arrays
     int inline_slot[kInlineMoved];
     int inline_gpos[kInlineMoved];
@@ -375,7 +384,7 @@ __global__ void __launch_bounds__(kBlock)
             const int slot = md.list ? md.list[m] : md.inline_slot[m];
             const int gpos = md.list ? md.list[md.n_moved + m] : md.inline_gpos[m];
             s_slot[threadIdx.x] = slot;
-            s_gpos[threadIdx.x] = gpos;
+            s_gpos[threadIdx.x] = gpos; // matter changes: | kMovedCross
             s_posA[threadIdx.x] = A.posq[slot];
             s_idA[threadIdx.x] = A.atom_id[slot];
             if (FUSED) {
@@ -428,8 +437,9 @@ __global__ void __launch_bounds__(kBlock)
             }
 
             bool j_moved = false;
+            bool j_cross = false; // matter changes: j itself is a listed atom
             if (mg >= 0) {
-                if (md.all_moved || multi) {
+                if (!md.matter && (md.all_moved || multi)) {
                     j_moved = true;
                 }
                 else {
@@ -438,6 +448,7 @@ __global__ void __launch_bounds__(kBlock)
                         const int slot = md.list ? md.list[m] : md.inline_slot[m];
                         if (slot == j) {
                             j_moved = true;
+                            j_cross = ((md.list ? md.list[md.n_moved + m] : md.inline_gpos[m]) & kMovedCross) != 0;
                         }
                     }
                 }
@@ -446,9 +457,10 @@ __global__ void __launch_bounds__(kBlock)
 #pragma unroll 1
             for (int m = 0; m < nm; ++m) {
                 const int si = s_slot[m];
-                const int gp = s_gpos[m];
+                const int gp = s_gpos[m] & (kMovedCross - 1);
+                const bool i_cross = (s_gpos[m] & kMovedCross) != 0;
                 if (mg == gp) { // same group: internal pairs
-                    if (!md.internal || multi || j == si) {
+                    if (j == si || (!md.matter && (!md.internal || multi))) {
                         continue;
                     }
                     if (j_moved && j < si) {
@@ -462,6 +474,11 @@ __global__ void __launch_bounds__(kBlock)
                         if (pairExcluded(P, info_j >> 8, si - b, j - b)) {
                             continue;
                         }
+                    }
+                }
+                else if (md.matter) {
+                    if (!i_cross || (j_cross && mg < gp)) {
+                        continue; // only listed atoms pair with other groups; two listed ones: from the earlier group
                     }
                 }
                 else if (mg >= 0 && mg < gp) {

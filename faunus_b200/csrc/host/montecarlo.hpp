@@ -117,6 +117,80 @@ class WindowEvaluator
     virtual void commit(const std::vector<unsigned char>& accepted) = 0;
 };
 
+/**
+ * Ideal (translational entropy) contribution of a change of the number of atoms / molecules to the trial energy;
+ * src/montecarlo.cpp:271-374. Atom swaps (`dNswap`) are not restated.
+ */
+class TranslationalEntropy
+{
+    const Space& trial_spc;
+    const Space& spc;
+
+    /** src/montecarlo.cpp:282-299 */
+    double bias(int trial_count, int count) const
+    {
+        double energy = 0.0;
+        if (const int dN = trial_count - count; dN > 0) { // atoms or molecules were added
+            const double V_trial = trial_spc.geometry.getVolume();
+            for (int n = 0; n < dN; n++) {
+                energy += std::log((count + 1 + n) / (V_trial * units::molar));
+            }
+        }
+        else if (dN < 0) { // atoms or molecules were removed
+            const double V = spc.geometry.getVolume();
+            for (int n = 0; n < (-dN); n++) {
+                energy -= std::log((count - n) / (V * units::molar));
+            }
+        }
+        return energy;
+    }
+    double atomChangeEnergy(int molid) const // :320-333
+    {
+        const auto mollist_new = trial_spc.findMolecules(molid, Space::Selection::ALL);
+        const auto mollist_old = spc.findMolecules(molid, Space::Selection::ALL);
+        if (mollist_new.size() > 1 || mollist_old.size() > 1) {
+            throw std::runtime_error("multiple atomic groups of the same type is not allowed");
+        }
+        return bias(static_cast<int>(trial_spc.groups.at(mollist_new.front()).size()),
+                    static_cast<int>(spc.groups.at(mollist_old.front()).size()));
+    }
+    double moleculeChangeEnergy(int molid) const // :335-342
+    {
+        return bias(static_cast<int>(trial_spc.findMolecules(molid, Space::Selection::ACTIVE).size()),
+                    static_cast<int>(spc.findMolecules(molid, Space::Selection::ACTIVE).size()));
+    }
+
+  public:
+    TranslationalEntropy(const Space& trial_space, const Space& space)
+        : trial_spc(trial_space)
+        , spc(space)
+    {
+    }
+    /** logarithm of the bias for the Metropolis criterion (kT); src/montecarlo.cpp:348-374 */
+    double energy(const Change& change) const
+    {
+        double energy_change = 0.0;
+        if (!change.matter_change || change.disable_translational_entropy) {
+            return energy_change;
+        }
+        std::vector<int> already_processed;
+        for (const auto& data : change.groups) {
+            if (data.dNswap) {
+                throw std::runtime_error("atom swap moves are outside the hot-path scope");
+            }
+            const int molid = trial_spc.groups.at(data.group_index).id;
+            if (data.dNatomic && trial_spc.topology->molecules.at(molid).atomic) {
+                energy_change += atomChangeEnergy(molid);
+            }
+            else if (std::find(already_processed.begin(), already_processed.end(), molid) == already_processed.end()) {
+                energy_change += moleculeChangeEnergy(molid);
+                already_processed.push_back(molid);
+            }
+        }
+        return energy_change;
+    }
+};
+
 class MetropolisMonteCarlo
 {
   public:
@@ -284,7 +358,8 @@ class MetropolisMonteCarlo
             const double new_energy = trial_state.pot->energy(change);
             const double old_energy = state.pot->energy(change);
             double energy_change = getEnergyChange(new_energy, old_energy);
-            const double energy_bias = move.bias(change, old_energy, new_energy);
+            const double energy_bias = move.bias(change, old_energy, new_energy) +
+                                       TranslationalEntropy(*trial_state.spc, *state.spc).energy(change);
             const double total_trial_energy = energy_change + energy_bias;
             TraceRecord rec;
             rec.du = energy_change;
@@ -309,6 +384,41 @@ class MetropolisMonteCarlo
         else {
             rng.slump(); // keep the generator in sync, src/montecarlo.cpp:182-186
         }
+    }
+
+    /**
+     * One trial "move" whose Change is made by the CALLER (a matter change: group sizes set on the trial Space,
+     * the particles to be activated already in place), carried through the reference's protocol
+     * (src/montecarlo.cpp:139-187): trial.updateState → trial.energy → accepted.energy → bias (translational
+     * entropy) → accept (mode 1), reject (0) or Metropolis (2) → sync one way. What a SpeciationMove / GCMC move
+     * asks of the Hamiltonian, without the move itself.
+     */
+    struct ExternalMoveResult
+    {
+        double new_energy = 0, old_energy = 0, bias = 0;
+        bool accepted = false;
+    };
+    ExternalMoveResult performExternalChange(Change& change, int mode)
+    {
+        if (!window.empty()) {
+            throw std::runtime_error("proposals are still in flight");
+        }
+        ExternalMoveResult r;
+        trial_state.pot->updateState(change);
+        r.new_energy = trial_state.pot->energy(change);
+        r.old_energy = state.pot->energy(change);
+        double energy_change = getEnergyChange(r.new_energy, r.old_energy);
+        r.bias = TranslationalEntropy(*trial_state.spc, *state.spc).energy(change);
+        r.accepted = mode == 1 || (mode == 2 && metropolisCriterion(energy_change + r.bias));
+        if (r.accepted) {
+            state.sync(trial_state, change);
+        }
+        else {
+            trial_state.sync(state, change);
+            energy_change = 0.0;
+        }
+        sum_of_energy_changes += energy_change;
+        return r;
     }
 
     /** metropolisCriterion with the uniform drawn earlier (same rule, src/montecarlo.cpp:17-34) */

@@ -306,6 +306,52 @@ inline State& pick(Sim& s, int which)
             }                                                                                                \
         });                                                                                                  \
     }                                                                                                         \
+    /* A matter change made by the caller, carried through the MC protocol (MetropolisMonteCarlo::                \
+       performExternalChange): `change_json` = {"groups": [{"index": g, "size": new number of active particles,   \
+       "atoms": [relative indices], "pos": [[x, y, z] of each listed atom] (optional), "all", "internal", "dNatomic"}]};\
+       mode 0 reject, 1 accept,                                                                                   \
+       2 Metropolis. out = {u_new, u_old, bias, accepted}. */                                                     \
+    __attribute__((visibility("default"))) int P##_sim_matter_change(void* h, const char* change_json, int mode, \
+                                                                     double* out)                                \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] {                                                                       \
+            const auto j = fb::Json::parse(change_json);                                                     \
+            fb::Change change;                                                                               \
+            change.matter_change = true;                                                                     \
+            for (const auto& g : j.at("groups").items()) {                                                   \
+                auto& gc = change.groups.emplace_back();                                                     \
+                gc.group_index = static_cast<size_t>(g.at("index").integer());                               \
+                gc.all = g.value("all", false);                                                              \
+                gc.internal = g.value("internal", false);                                                    \
+                gc.dNatomic = g.value("dNatomic", false);                                                    \
+                for (const auto& a : g.at("atoms").items()) {                                                \
+                    gc.relative_atom_indices.push_back(static_cast<size_t>(a.integer()));                    \
+                }                                                                                            \
+                auto& group = s->mc->trial_state.spc->groups.at(gc.group_index);                             \
+                if (const auto* pos = g.find("pos")) { /* where the listed particles appear */               \
+                    size_t k = 0;                                                                            \
+                    for (const auto& p : pos->items()) {                                                     \
+                        auto& particle = s->mc->trial_state.spc->particles.at(                               \
+                            group.begin + gc.relative_atom_indices.at(k++));                                 \
+                        particle.pos = fb::pointFromJson(p);                                                 \
+                        s->mc->trial_state.spc->geometry.boundary(particle.pos);                             \
+                    }                                                                                        \
+                }                                                                                            \
+                group.resize(static_cast<size_t>(g.at("size").integer()));                                   \
+                if (group.isMolecular() && !group.empty()) {                                                 \
+                    group.mass_center = s->mc->trial_state.spc->massCenter(                                  \
+                        group, -s->mc->trial_state.spc->at(group, 0).pos);                                   \
+                }                                                                                            \
+            }                                                                                                \
+            std::sort(change.groups.begin(), change.groups.end());                                           \
+            const auto r = s->mc->performExternalChange(change, mode);                                       \
+            out[0] = r.new_energy;                                                                           \
+            out[1] = r.old_energy;                                                                           \
+            out[2] = r.bias;                                                                                 \
+            out[3] = r.accepted ? 1.0 : 0.0;                                                                 \
+        });                                                                                                  \
+    }                                                                                                         \
     /* per-rank generators of a sharded analysis (every rank draws its OWN ghosts): the reference seeds the ranks  \
        of an MPI run individually (`random: {seed: hardware}`); here the seed is explicit and reproducible */    \
     __attribute__((visibility("default"))) int P##_sim_seed_global(void* h, unsigned seed)                   \

@@ -41,7 +41,7 @@ class FbGroupChange(C.Structure):
 
 class FbChange(C.Structure):
     _fields_ = [("everything", C.c_int), ("volume_change", C.c_int), ("n_groups", C.c_int),
-                ("groups", C.POINTER(FbGroupChange))]
+                ("groups", C.POINTER(FbGroupChange)), ("matter_change", C.c_int)]
 
 
 class FbEwaldConfig(C.Structure):
@@ -313,7 +313,7 @@ class B200Simulation(Simulation):
                 "full_ms": out[4], "full_launches": int(out[5]), "widom_ms": out[6], "widom_launches": int(out[7])}
 
 
-def make_change(everything=False, volume_change=False, groups: Sequence[dict] = ()):
+def make_change(everything=False, volume_change=False, groups: Sequence[dict] = (), matter_change=False):
     """Build an :class:`FbChange` (keeps the backing arrays alive on the returned object)."""
     arr = (FbGroupChange * max(1, len(groups)))()
     keep = []
@@ -325,6 +325,6 @@ def make_change(everything=False, volume_change=False, groups: Sequence[dict] = 
         arr[i].internal = int(bool(g.get("internal", False)))
         arr[i].n_atoms = len(idx)
         arr[i].atoms = idx.ctypes.data_as(c_int_p)
-    ch = FbChange(int(everything), int(volume_change), len(groups), arr)
+    ch = FbChange(int(everything), int(volume_change), len(groups), arr, int(matter_change))
     ch._keep = (arr, keep)
     return ch

@@ -150,6 +150,10 @@ typedef struct
     int volume_change;
     int n_groups;
     const fb_group_change* groups;
+    /* Change::matter_change (src/space.h:29-75): the number of active particles of the listed groups differs
+     * between the two states; the energy is that of the pairs with a listed ACTIVE particle
+     * (GroupPairing::accumulateSpeciation, src/energy.h:1390-1435) */
+    int matter_change;
 } fb_change;
 
 /* Ewald reciprocal space parameters (EwaldData, src/energy.cpp:28-59) */

@@ -307,6 +307,83 @@ template <class TAccumulator> class GroupPairingPolicy
         }
     }
 
+    /** (group1 × ⊕group2) + (⊕group1 × ∁⊕group2): pairs with at least one indexed particle; :1055-1082 */
+    void group2group(TAccumulator& acc, const Group& g1, const Group& g2, const std::vector<size_t>& index1,
+                     const std::vector<size_t>& index2)
+    {
+        if (!cut.cut(g1, g2)) {
+            if (!index2.empty()) {
+                group2group(acc, g2, g1, index2);
+                const auto index2_complement = indexComplement(g2.size(), index2);
+                for (auto i : index1) {
+                    for (auto j : index2_complement) {
+                        acc.add(spc.at(g2, j), spc.at(g1, i));
+                    }
+                }
+            }
+            else if (!index1.empty()) {
+                group2group(acc, g1, g2, index1);
+            }
+        }
+    }
+
+    /** ⊕group × (∪ groups given by index); :1131-1141 */
+    void group2groups(TAccumulator& acc, const Group& group, const std::vector<size_t>& group_index,
+                      const std::vector<size_t>& index)
+    {
+        for (auto other_index : group_index) {
+            const auto& other = spc.groups[other_index];
+            if (&other != &group) {
+                group2group(acc, group, other, index);
+            }
+        }
+    }
+
+    /**
+     * The number of particles has changed: pairs that involve a listed, ACTIVE particle of a changed group —
+     * with the static groups, with the other changed groups, inside its own group; src/energy.h:1390-1435.
+     * Removed particles need no care: they are present in the other Space.
+     */
+    void accumulateSpeciation(TAccumulator& acc, const Change& change)
+    {
+        std::vector<size_t> moved;
+        for (const auto& g : change.groups) {
+            moved.push_back(g.group_index);
+        }
+        const auto fixed = indexComplement(spc.groups.size(), moved);
+        auto active = [](const std::vector<size_t>& listed, size_t size) {
+            std::vector<size_t> out;
+            for (auto i : listed) {
+                if (i < size) {
+                    out.push_back(i);
+                }
+            }
+            return out;
+        };
+        for (auto it1 = change.groups.begin(); it1 < change.groups.end(); ++it1) {
+            const auto& group1 = spc.groups.at(it1->group_index);
+            const auto index1 = active(it1->relative_atom_indices, group1.size());
+            if (!index1.empty()) {
+                group2groups(acc, group1, fixed, index1);
+            }
+            for (auto it2 = std::next(it1); it2 < change.groups.end(); ++it2) {
+                const auto& group2 = spc.groups.at(it2->group_index);
+                const auto index2 = active(it2->relative_atom_indices, group2.size());
+                if (!index1.empty() || !index2.empty()) {
+                    group2group(acc, group1, group2, index1, index2);
+                }
+            }
+            if (!index1.empty() && !spc.traits(group1).rigid) {
+                if (it1->all) {
+                    groupInternal(acc, group1);
+                }
+                else {
+                    groupInternal(acc, group1, index1);
+                }
+            }
+        }
+    }
+
     void group2all(TAccumulator& acc, const Group& group) // :1155-1163
     {
         for (const auto& other : spc.groups) {
@@ -448,7 +525,7 @@ template <class TPairPotential> class Nonbonded : public EnergyTerm
             }
         }
         else {
-            throw std::runtime_error("matter_change (speciation) is outside the hot-path scope");
+            pairing.accumulateSpeciation(accumulator, change);
         }
         return accumulator.result();
     }

@@ -873,3 +873,64 @@ def test_tempering_packed_exchange_equals_message_exchange():
         assert abs(b["drift"]) < 1e-9
         accepted += sum(s["acceptance"] * s["attempts"] for s in tb.values())
     assert accepted > 0
+
+
+@pytest.mark.parametrize("coulomb", [{"type": "fanourgakis", "epsr": 78.7, "cutoff": 10.0},
+                                     {"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 5}])
+@pytest.mark.parametrize("window", [0, 64])
+def test_matter_change_atomic(coulomb, window):
+    """Change::matter_change on the device (GroupPairing::accumulateSpeciation, src/energy.h:1390-1435; Ewald partial
+    update with particles that appear / disappear, src/energy.cpp:219-247; translational-entropy bias,
+    src/montecarlo.cpp:271-374): ions of an atomic group are activated and deactivated between sweeps of ordinary
+    moves; energies of both states equal the oracle's, and so do the traces of the sweeps in between."""
+    cfg = small_electrolyte(n=150, ghost_pairs=3, moves_per_sweep=60, coulomb=coulomb)
+    o, g = pair_of_sims(cfg, window)
+    rec, _ = o.groups()
+    ghost = int(np.argmax(rec[:, 2] - rec[:, 1]))
+    pos = [[3.0, -7.0, 11.0], [-9.0, 2.5, -4.0], [12.0, 12.0, -12.0], [1.0, 1.0, 1.5]]
+    steps = [
+        ([{"index": ghost, "size": 2, "atoms": [0, 1], "pos": pos[:2], "dNatomic": True}], 1),
+        ([{"index": ghost, "size": 4, "atoms": [2, 3], "pos": pos[2:], "dNatomic": True}], 0),   # rejected
+        ([{"index": ghost, "size": 3, "atoms": [2], "pos": pos[2:3], "dNatomic": True}], 1),
+        ([{"index": ghost, "size": 1, "atoms": [1, 2], "dNatomic": True}], 1),                   # two removed
+        ([{"index": ghost, "size": 0, "atoms": [0], "dNatomic": True}], 2),                       # Metropolis
+    ]
+    for s in (o, g):
+        s.trace_enable()
+    scale = np.abs(o.system_energy()[1]).max()
+    for groups, mode in steps:
+        ro, rg = o.matter_change(groups, mode), g.matter_change(groups, mode)
+        assert ro["accepted"] == rg["accepted"]
+        assert abs(ro["u_new"] - rg["u_new"]) <= 1e-10 * scale and abs(ro["u_old"] - rg["u_old"]) <= 1e-10 * scale
+        assert ro["bias"] == rg["bias"]
+        assert_close(o.system_energy()[1], g.system_energy()[1], scale=scale)
+        for s in (o, g):
+            s.sweep(1)
+        assert np.array_equal(o.trace()["accepted"], g.trace()["accepted"])
+    assert_close(o.trace()["du"], g.trace()["du"], scale=scale)
+    assert np.array_equal(o.particles()[0], g.particles()[0])
+    assert abs(g.drift()) < 1e-9
+
+
+def test_matter_change_molecule(water_input):
+    """a whole rigid molecule disappears and comes back (`all`, every atom listed), next to an atomic salt group:
+    group-group pairs with the mass-centre cutoff, no internal energy for rigid bodies, k-space follows"""
+    from conftest import water_with_salt
+    cfg = water_with_salt(water_input, n_pairs=6)
+    o, g = pair_of_sims(cfg, 64)
+    for s in (o, g):
+        s.trace_enable()
+        s.sweep(1)
+    scale = np.abs(o.system_energy()[1]).max()
+    molecule = 17
+    for size, mode in ((0, 1), (3, 1), (0, 0)):
+        groups = [{"index": molecule, "size": size, "atoms": [0, 1, 2], "all": True}]
+        ro, rg = o.matter_change(groups, mode), g.matter_change(groups, mode)
+        assert ro["accepted"] == rg["accepted"]
+        assert abs(ro["u_new"] - rg["u_new"]) <= 1e-10 * scale and abs(ro["u_old"] - rg["u_old"]) <= 1e-10 * scale
+        assert ro["bias"] == rg["bias"]
+        assert_close(o.system_energy()[1], g.system_energy()[1], scale=scale)
+        for s in (o, g):
+            s.sweep(1)
+        assert np.array_equal(o.trace()["accepted"], g.trace()["accepted"])
+    assert np.array_equal(o.particles()[0], g.particles()[0])
