@@ -531,6 +531,28 @@ class NonbondedB200 : public EnergyTerm
         state_pushed = false;
     }
 
+    /** NonbondedBase::particleParticleEnergy, src/energy.h:1500, 1531-1534 */
+    double particleParticleEnergy(const Particle& particle1, const Particle& particle2)
+    {
+        const double a[4] = {particle1.pos.x, particle1.pos.y, particle1.pos.z, particle1.charge};
+        const double b[4] = {particle2.pos.x, particle2.pos.y, particle2.pos.z, particle2.charge};
+        const int ida = particle1.id, idb = particle2.id;
+        double u = 0.0;
+        dev->resynchronise();
+        fbCheck(fb_particle_pair_energy(dev->ctx, slot, 1, a, &ida, b, &idb, &u), dev->ctx, "fb_particle_pair_energy");
+        return u;
+    }
+
+    /** NonbondedBase::groupGroupEnergy, src/energy.h:1501, 1536-1545 (groups of this term's Space, by index) */
+    double groupGroupEnergy(size_t group1, size_t group2)
+    {
+        double u = 0.0;
+        dev->resynchronise();
+        fbCheck(fb_group_group_energy(dev->ctx, slot, static_cast<int>(group1), static_cast<int>(group2), &u), dev->ctx,
+                "fb_group_group_energy");
+        return u;
+    }
+
     void to_json(Json& j) const override
     {
         j["device"] = "B200 sm_100a";

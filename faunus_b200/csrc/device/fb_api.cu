@@ -1528,6 +1528,84 @@ FB_API int fb_nonbonded_delta(fb_ctx* c, int s_new, int s_old, const fb_change* 
     });
 }
 
+FB_API int fb_particle_pair_energy(fb_ctx* c, int s, int n, const double* a_xyzq, const int* a_id, const double* b_xyzq,
+                                   const int* b_id, double* energy)
+{
+    return guarded(c, [&] {
+        flushPending(c);
+        checkSlot(c, s);
+        if (n <= 0 || !a_xyzq || !a_id || !b_xyzq || !b_id || !energy) {
+            throw CudaError{"bad arguments"};
+        }
+        for (int i = 0; i < n; ++i) {
+            if (a_id[i] < 0 || a_id[i] >= c->P.n_types || b_id[i] < 0 || b_id[i] >= c->P.n_types) {
+                throw CudaError{"atom id out of range"};
+            }
+        }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->d_ghost.ensure(2 * static_cast<size_t>(n));
+        c->d_ghost_id.ensure(2 * static_cast<size_t>(n));
+        c->d_widom_du.ensure(static_cast<size_t>(n));
+        c->h_widom_du.ensure(static_cast<size_t>(n));
+        CUDA_CHECK(cudaMemcpyAsync(c->d_ghost.ptr, a_xyzq, n * sizeof(double4), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(c->d_ghost.ptr + n, b_xyzq, n * sizeof(double4), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(c->d_ghost_id.ptr, a_id, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(c->d_ghost_id.ptr + n, b_id, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        const SlotView V = makeView(c, s);
+#define FB_CASE(K)                                                                                              \
+    case K:                                                                                                     \
+        particlePairKernel<K><<<gridFor(c, n, 128), 128, 0, c->stream>>>(V, c->P, n, c->d_ghost.ptr, c->d_ghost_id.ptr, \
+                                                                         c->d_ghost.ptr + n, c->d_ghost_id.ptr + n,     \
+                                                                         c->d_widom_du.ptr);                            \
+        break;
+        switch (c->P.kind) {
+            FB_CASE(POT_COULOMB_LJ)
+            FB_CASE(POT_COULOMB_WCA)
+            FB_CASE(POT_PM)
+            FB_CASE(POT_PMWCA)
+            FB_CASE(POT_FUNCTOR)
+            FB_CASE(POT_SPLINED)
+        default:
+            throw CudaError{"unknown potential kind"};
+        }
+#undef FB_CASE
+        launched(c, "particlePairKernel");
+        CUDA_CHECK(cudaMemcpyAsync(c->h_widom_du.ptr, c->d_widom_du.ptr, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        finish(c);
+        std::memcpy(energy, c->h_widom_du.ptr, n * sizeof(double));
+    });
+}
+
+FB_API int fb_group_group_energy(fb_ctx* c, int s, int group1, int group2, double* energy)
+{
+    return guarded(c, [&] {
+        flushPending(c);
+        checkSlot(c, s);
+        if (group1 < 0 || group1 >= c->n_groups || group2 < 0 || group2 >= c->n_groups || group1 == group2 || !energy) {
+            throw CudaError{"two different groups of the uploaded space expected"};
+        }
+        const SlotView V = makeView(c, s);
+#define FB_CASE(K)                                                                             \
+    case K:                                                                                    \
+        groupPairKernel<K><<<1, kBlock, 0, c->stream>>>(V, c->P, group1, group2, c->d_result); \
+        break;
+        switch (c->P.kind) {
+            FB_CASE(POT_COULOMB_LJ)
+            FB_CASE(POT_COULOMB_WCA)
+            FB_CASE(POT_PM)
+            FB_CASE(POT_PMWCA)
+            FB_CASE(POT_FUNCTOR)
+            FB_CASE(POT_SPLINED)
+        default:
+            throw CudaError{"unknown potential kind"};
+        }
+#undef FB_CASE
+        launched(c, "groupPairKernel");
+        finish(c);
+        *energy = c->h_result[0];
+    });
+}
+
 /** share `shard` of `n_shards` of the full-system non-bonded and reciprocal energies (multi-GPU system energy) */
 namespace {
 

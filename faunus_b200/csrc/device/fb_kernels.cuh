@@ -507,6 +507,44 @@ __global__ void __launch_bounds__(kBlock)
 }
 
 // ------------------------------------------------------------------------------------------------
+// NonbondedBase::particleParticleEnergy / groupGroupEnergy (src/energy.h:1498-1503, 1536-1545): the secondary
+// interface other callers use (angular scans, src/actions.cpp). One block.
+// ------------------------------------------------------------------------------------------------
+/** out[p] = pair energy of the explicit particles a[p], b[p] (minimum image of the slot's cell) */
+template <int KIND>
+__global__ void particlePairKernel(SlotView V, PotParams P, int n, const double4* __restrict__ a, const int* __restrict__ ida,
+                                   const double4* __restrict__ b, const int* __restrict__ idb, double* __restrict__ out)
+{
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const double r2 = minImageR2(V, a[p].x, a[p].y, a[p].z, b[p].x, b[p].y, b[p].z);
+        out[p] = pairEnergy<KIND>(P, ida[p], idb[p], a[p].w, b[p].w, r2);
+    }
+}
+
+/** out[0] = Σ over the active particles of group g1 × group g2 unless the mass-centre cutoff applies (group2group) */
+template <int KIND>
+__global__ void __launch_bounds__(kBlock) groupPairKernel(SlotView V, PotParams P, int g1, int g2, double* __restrict__ out)
+{
+    __shared__ double scratch[kBlock / 32];
+    double e = 0.0;
+    const int info1 = V.ginfo[g1], info2 = V.ginfo[g2];
+    if (!groupCut(V, P, g1, info1, g2, info2)) {
+        const int n1 = V.gsize[g1], n2 = V.gsize[g2];
+        const int b1 = V.gbegin[g1], b2 = V.gbegin[g2];
+        for (int t = threadIdx.x; t < n1 * n2; t += kBlock) {
+            const int i = b1 + t / n2, j = b2 + t % n2;
+            const double4 pi = V.posq[i], pj = V.posq[j];
+            e += pairEnergy<KIND>(P, V.atom_id[i], V.atom_id[j], pi.w, pj.w,
+                                  minImageR2(V, pi.x, pi.y, pi.z, pj.x, pj.y, pj.z));
+        }
+    }
+    const double sum = blockSum<kBlock>(e, scratch);
+    if (threadIdx.x == 0) {
+        out[0] = sum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: full energy Σ_{i<j} (GroupPairingPolicy::all); one block per (i-tile, j-tile ≥ i-tile)
 // ------------------------------------------------------------------------------------------------
 template <int KIND>

@@ -628,7 +628,7 @@ inline bool isNonbondedName(const std::string& name)
 {
     return name == "nonbonded_coulomblj" || name == "nonbonded_newcoulomblj" || name == "nonbonded_coulombwca" ||
            name == "nonbonded_pm" || name == "nonbonded_coulombhs" || name == "nonbonded_pmwca" ||
-           name == "nonbonded" || name == "nonbonded_exact" || name == "nonbonded_splined";
+           name == "nonbonded" || name == "nonbonded_exact" || name == "nonbonded_splined" || name == "nonbonded_cached";
 }
 
 inline PairTables buildPairTables(const std::string& name, const Json& cfg, const Topology& topo)
@@ -660,8 +660,11 @@ inline PairTables buildPairTables(const std::string& name, const Json& cfg, cons
         detail::addLennardJones(t, topo, cfg, true);
         t.flags.assign(n2, term::COULOMB_PLAIN | term::WCA);
     }
-    else if (name == "nonbonded" || name == "nonbonded_exact" || name == "nonbonded_splined") {
-        t.kind = (name == "nonbonded_splined") ? potkind::SPLINED : potkind::FUNCTOR;
+    else if (name == "nonbonded" || name == "nonbonded_exact" || name == "nonbonded_splined" || name == "nonbonded_cached") {
+        // `nonbonded_cached` = NonbondedCached<PairEnergy<SplinedPotential>> (src/energy.cpp:1311-1315): the splined
+        // potential behind a cache of group-group energies (src/energy.h:1614-1758) — the same energies as
+        // `nonbonded_splined`; the cache is a CPU device to avoid pair loops and has no counterpart here
+        t.kind = (name == "nonbonded_splined" || name == "nonbonded_cached") ? potkind::SPLINED : potkind::FUNCTOR;
         std::vector<uint32_t> order;
         t.flags.assign(n2, detail::lowerPotentialArray(t, topo, cfg.at("default"), order));
         t.term_order.assign(n2, order);

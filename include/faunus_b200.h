@@ -194,6 +194,13 @@ int fb_nonbonded_energy(fb_ctx* ctx, int slot, const fb_change* change, double* 
 int fb_nonbonded_delta(fb_ctx* ctx, int slot_new, int slot_old, const fb_change* change, double* u_new,
                        double* u_old);
 
+/* NonbondedBase::particleParticleEnergy (src/energy.h:1500, 1531-1534): pair energies of n explicit particle pairs
+ * (x, y, z, q and atom id each) in the cell of `slot`; NonbondedBase::groupGroupEnergy (:1501, 1536-1545): all active
+ * particles of two different groups, zero beyond the mass-centre cutoff of two molecular groups */
+int fb_particle_pair_energy(fb_ctx* ctx, int slot, int n_pairs, const double* a_xyzq, const int* a_id,
+                            const double* b_xyzq, const int* b_id, double* energy);
+int fb_group_group_energy(fb_ctx* ctx, int slot, int group1, int group2, double* energy);
+
 /* share `shard` of `n_shards` of the full-system energy of a slot, for one evaluation spread over several
  * GPUs that hold the same Space (GroupPairingPolicy::all, src/energy.h:1290-1326: tile rows are dealt
  * round robin; PolicyIonIon::updateComplex + reciprocalEnergy, src/energy.cpp:191-206, 524-531: a slab of

@@ -62,7 +62,9 @@ inline bool termFactory(Hamiltonian& h, Space& spc, const std::string& name, con
     else if (name == "nonbonded" || name == "nonbonded_exact") {
         ok = addNonbonded<FunctorPotential>(h, spc, cfg);
     }
-    else if (name == "nonbonded_splined") {
+    else if (name == "nonbonded_splined" || name == "nonbonded_cached") {
+        // NonbondedCached (src/energy.h:1614-1758) returns the energies of Nonbonded<SplinedPotential>; its
+        // group-group cache changes how often pairs are summed, not what the sums are
         ok = addNonbonded<SplinedPotential>(h, spc, cfg);
     }
     if (ok) {
@@ -206,7 +208,7 @@ FO_API int fo_pair_energy(const char* input_json, const char* nonbonded_name, in
         else if (name == "nonbonded") {
             run(oracle::FunctorPotential());
         }
-        else if (name == "nonbonded_splined") {
+        else if (name == "nonbonded_splined" || name == "nonbonded_cached") {
             run(oracle::SplinedPotential());
         }
         else {

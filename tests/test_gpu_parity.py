@@ -60,7 +60,9 @@ def functor_variants():
     splined = dict(base)
     splined["energy"] = [{"nonbonded_splined": {
         "default": [{"lennardjones": {"mixing": "LB"}}, {"coulomb": {"type": "fanourgakis", "epsr": 78.7, "cutoff": 12}}]}}]
-    return {"functor": functor, "splined": splined}
+    cached = dict(base)  # NonbondedCached<SplinedPotential> (src/energy.cpp:1311-1315): the energies of `nonbonded_splined`
+    cached["energy"] = [{"nonbonded_cached": splined["energy"][0]["nonbonded_splined"]}]
+    return {"functor": functor, "splined": splined, "cached": cached}
 
 
 ALL_VARIANTS = {**electrolyte_variants(), **functor_variants()}
@@ -934,3 +936,51 @@ def test_matter_change_molecule(water_input):
             s.sweep(1)
         assert np.array_equal(o.trace()["accepted"], g.trace()["accepted"])
     assert np.array_equal(o.particles()[0], g.particles()[0])
+
+
+def test_particle_and_group_pair_energies(water_input):
+    """NonbondedBase::particleParticleEnergy / groupGroupEnergy (src/energy.h:1498-1503) through the C ABI against the
+    oracle's pair functor: explicit particle pairs, and pairs of rigid molecules with the mass-centre cutoff."""
+    import ctypes as C
+    from _oraclelib import pair_energy
+    from faunus_b200.native import load
+    lib = load()
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    g = b200_sim(water_input, 0)
+    xyzq, ids = g.particles()
+    rec, cm = g.groups()
+    box = np.array(water_input["geometry"]["length"], dtype=float)
+    name = [k for e in water_input["energy"] for k in e if k.startswith("nonbonded")][0]
+
+    def r_min(a, b):
+        d = np.abs(a - b)
+        d -= box * (d > box / 2)
+        return np.sqrt((d * d).sum())
+
+    # explicit pairs: the first 40 atoms against atoms further down the list
+    n = 40
+    a, b = np.ascontiguousarray(xyzq[:n]), np.ascontiguousarray(xyzq[100:100 + n])
+    ia, ib = np.ascontiguousarray(ids[:n]), np.ascontiguousarray(ids[100:100 + n])
+    out = np.zeros(n)
+    assert lib.fb_particle_pair_energy(g.ctx, 0, n, a.ctypes.data_as(dp), ia.ctypes.data_as(ip), b.ctypes.data_as(dp),
+                                       ib.ctypes.data_as(ip), out.ctypes.data_as(dp)) == 0, lib.fb_last_error(g.ctx)
+    want = np.array([pair_energy(water_input, name, int(ia[k]), int(ib[k]), [r_min(a[k, :3], b[k, :3])])[0] for k in range(n)])
+    assert np.abs(out - want).max() <= 1e-10 * np.abs(want).max()
+    # molecule pairs: inside and outside the mass-centre cutoff
+    cut = 10.0
+    seen = set()
+    for g1 in range(0, 12):
+        for g2 in range(g1 + 1, 40):
+            beyond = r_min(cm[g1], cm[g2]) >= cut
+            if (beyond in seen) and len(seen) == 2 and g2 > g1 + 3:
+                continue
+            seen.add(beyond)
+            u = C.c_double()
+            assert lib.fb_group_group_energy(g.ctx, 0, g1, g2, C.byref(u)) == 0, lib.fb_last_error(g.ctx)
+            expected = 0.0
+            if not beyond:
+                for i in range(rec[g1][0], rec[g1][0] + rec[g1][1]):
+                    for j in range(rec[g2][0], rec[g2][0] + rec[g2][1]):
+                        expected += pair_energy(water_input, name, int(ids[i]), int(ids[j]), [r_min(xyzq[i, :3], xyzq[j, :3])])[0]
+            assert abs(u.value - expected) <= 1e-10 * max(1.0, abs(expected))
+    assert seen == {True, False}
