@@ -41,6 +41,7 @@ class SimLibrary:
         f("sim_system_energy", C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, c_int_p])
         f("sim_energy", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   c_int_p, C.c_int, c_double_p])
+        f("sim_forces", C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p])
         f("sim_trial_set", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, C.c_int,
                                      c_double_p, c_double_p, c_double_p])
         f("sim_trial_commit", C.c_int, [C.c_void_p, C.c_int])
@@ -164,6 +165,12 @@ class Simulation:
                                         int(all), int(internal), _ip(idx), len(idx), C.byref(out)),
                     "sim_energy")
         return out.value
+
+    def forces(self, term: int = -1, which: int = 0) -> np.ndarray:
+        """Hamiltonian::force on a zeroed vector (term < 0) or the force of one term; [n_particles, 3], kT/Å"""
+        out = np.zeros((self.num_particles, 3))
+        self._check(self.api.sim_forces(self.handle, which, term, _dp(out)), "sim_forces")
+        return out
 
     def trial_set(self, group: int, indices: Sequence[int], xyz, all: bool = False,
                   internal: bool = True):

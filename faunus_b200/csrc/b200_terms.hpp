@@ -207,6 +207,12 @@ class DeviceContext
         if (rc != FB_OK) {
             throw std::runtime_error(std::string("fb_create: ") + fb_last_error(nullptr));
         }
+        if (tables.has_coulomb && (tables.kind == potkind::COULOMB_LJ || tables.kind == potkind::COULOMB_WCA)) {
+            // the two kinds with pair forces (fb_nonbonded_force): S'(q) next to S(q)
+            fbCheck(fb_set_force_table(ctx, static_cast<int>(tables.coulomb.dS.knots.size()), tables.coulomb.dS.knots.data(),
+                                       tables.coulomb.dS.coeffs.data()),
+                    ctx, "fb_set_force_table");
+        }
     }
     ~DeviceContext() { fb_destroy(ctx); }
     DeviceContext(const DeviceContext&) = delete;
@@ -365,6 +371,20 @@ class NonbondedB200 : public EnergyTerm
     int deviceSlot() const { return slot; }
 
     void init() override { dev->uploadSpace(slot, spc); }
+
+    /**
+     * Nonbonded::force (src/energy.h:1584-1597): adds the pair forces of the whole particle vector. Forces are asked
+     * for outside the updateState / sync protocol (src/forcemove.cpp:124-125), so the mirror is refreshed first.
+     */
+    void force(std::vector<Point>& forces) override
+    {
+        static_assert(sizeof(Point) == 3 * sizeof(double), "forces travel as [n][3] doubles");
+        if (forces.size() != spc.particles.size()) {
+            throw std::runtime_error("the forces size must match the particle size");
+        }
+        dev->uploadSpace(slot, spc);
+        fbCheck(fb_nonbonded_force(dev->ctx, slot, &forces[0].x), dev->ctx, "fb_nonbonded_force");
+    }
 
     /**
      * Small move of one group (≤ 8 atoms, no size change) on the trial instance: nothing is pushed;
@@ -616,6 +636,19 @@ class EwaldB200 : public EnergyTerm
 
     /** the mirror was uploaded by the sibling's init(); rebuild k-vectors and Q(k) */
     void init() override { fullUpdate(); }
+
+    /**
+     * Ewald::force (src/energy.cpp:596-629): surface + reciprocal-space force from the CURRENT positions and the Q(k)
+     * this instance holds (the reference does not rebuild Q there either); overwrites `forces`, as the reference does.
+     */
+    void force(std::vector<Point>& forces) override
+    {
+        if (forces.size() != spc.particles.size()) {
+            throw std::runtime_error("the forces size must match the particle size");
+        }
+        dev->uploadSpace(slot, spc);
+        fbCheck(fb_ewald_force(dev->ctx, slot, &forces[0].x), dev->ctx, "fb_ewald_force");
+    }
 
     void updateState(const Change& change) override
     {

@@ -9,6 +9,7 @@
 #include "fb_cells.cuh"
 #include "fb_run.cuh"
 #include "fb_rdf.cuh"
+#include "fb_force.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -299,6 +300,11 @@ struct fb_ctx
     DeviceBuffer<double4> rdf_list[2];
     DeviceBuffer<int> rdf_n;
     bool rdf_configured = false;
+    // forces (fb_force.cuh)
+    DeviceBuffer<double> d_force_knots, d_force_coef; //!< Andrea table of S'(q) (fb_set_force_table)
+    int force_nk = 0;
+    DeviceBuffer<double> d_forces; //!< [n_slots][3]
+    PinnedBuffer<double> h_forces;
 };
 
 namespace {
@@ -1603,6 +1609,98 @@ FB_API int fb_group_group_energy(fb_ctx* c, int s, int group1, int group2, doubl
         launched(c, "groupPairKernel");
         finish(c);
         *energy = c->h_result[0];
+    });
+}
+
+// =================================================================================================
+// Forces (fb_force.cuh)
+// =================================================================================================
+FB_API int fb_set_force_table(fb_ctx* c, int n_knots, const double* knots, const double* coeffs)
+{
+    return guarded(c, [&] {
+        flushPending(c);
+        if (n_knots < 2 || !knots || !coeffs) {
+            throw CudaError{"an Andrea table of S'(q) with at least two knots expected"};
+        }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->d_force_knots.upload(knots, static_cast<size_t>(n_knots), c->stream);
+        c->d_force_coef.upload(coeffs, 6 * static_cast<size_t>(n_knots - 1), c->stream);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->force_nk = n_knots;
+    });
+}
+
+FB_API int fb_nonbonded_force(fb_ctx* c, int s, double* forces)
+{
+    return guarded(c, [&] {
+        flushPending(c);
+        checkSlot(c, s);
+        if (!forces) {
+            throw CudaError{"null argument"};
+        }
+        if (c->P.kind != POT_COULOMB_LJ && c->P.kind != POT_COULOMB_WCA) {
+            // PairPotential::force, src/potentials.cpp:246-251
+            throw CudaError{"Force computation not implemented for this setup!"};
+        }
+        if (c->force_nk < 2) {
+            throw CudaError{"fb_set_force_table has not been called"};
+        }
+        const int n = c->n_slots;
+        c->d_forces.ensure(3 * static_cast<size_t>(n));
+        c->h_forces.ensure(3 * static_cast<size_t>(n));
+        const SlotView V = makeView(c, s);
+        ForceTable T{c->force_nk, c->d_force_knots.ptr, c->d_force_coef.ptr};
+        const int grid = (n + kForceBlock - 1) / kForceBlock;
+        if (c->P.kind == POT_COULOMB_LJ) {
+            nonbondedForceKernel<POT_COULOMB_LJ><<<grid, kForceBlock, 0, c->stream>>>(V, c->P, T, c->d_forces.ptr);
+        }
+        else {
+            nonbondedForceKernel<POT_COULOMB_WCA><<<grid, kForceBlock, 0, c->stream>>>(V, c->P, T, c->d_forces.ptr);
+        }
+        launched(c, "nonbondedForceKernel");
+        CUDA_CHECK(cudaMemcpyAsync(c->h_forces.ptr, c->d_forces.ptr, 3 * static_cast<size_t>(n) * sizeof(double),
+                                   cudaMemcpyDeviceToHost, c->stream));
+        finish(c);
+        for (size_t i = 0; i < 3 * static_cast<size_t>(n); ++i) {
+            forces[i] += c->h_forces.ptr[i]; // forces[i] += f, src/energy.h:1593
+        }
+    });
+}
+
+FB_API int fb_ewald_force(fb_ctx* c, int s, double* forces)
+{
+    return guarded(c, [&] {
+        flushPending(c);
+        checkSlot(c, s);
+        if (!forces) {
+            throw CudaError{"null argument"};
+        }
+        Slot& sl = c->slot[s];
+        if (sl.K <= 0) {
+            throw CudaError{"no k-vectors"};
+        }
+        const int n = c->n_slots;
+        c->d_forces.ensure(3 * static_cast<size_t>(n));
+        c->h_forces.ensure(3 * static_cast<size_t>(n));
+        const SlotView V = makeView(c, s);
+        {
+            const int grid = gridFor(c, n, kBlock);
+            c->partials.ensure(3 * static_cast<size_t>(grid));
+            dipoleAllKernel<<<grid, kBlock, 0, c->stream>>>(V, c->partials.ptr, c->ticket.ptr, c->d_result + 5);
+            launched(c, "dipoleAllKernel");
+        }
+        const double pi = 3.141592653589793238462643383279502884;
+        const double volume = sl.ewald_box[0] * sl.ewald_box[1] * sl.ewald_box[2];
+        const double surface = 1.0 / (2.0 * c->ewald.surface_dielectric_constant + 1.0);
+        const double scale = -4.0 * pi / volume * c->ewald.bjerrum_length;
+        const int grid = (n + kEwaldForceParticles - 1) / kEwaldForceParticles;
+        ewaldForceKernel<<<grid, kEwaldForceParticles * kEwaldForceLanes, 0, c->stream>>>(V, makeEwaldView(c, s), c->d_result + 5,
+                                                                                          surface, scale, c->d_forces.ptr);
+        launched(c, "ewaldForceKernel");
+        CUDA_CHECK(cudaMemcpyAsync(c->h_forces.ptr, c->d_forces.ptr, 3 * static_cast<size_t>(n) * sizeof(double),
+                                   cudaMemcpyDeviceToHost, c->stream));
+        finish(c);
+        std::memcpy(forces, c->h_forces.ptr, 3 * static_cast<size_t>(n) * sizeof(double)); // (*force) = …, src/energy.cpp:610
     });
 }
 

@@ -155,6 +155,25 @@ extern "C" __attribute__((visibility("default"))) int fbh_coulomb_table(const ch
     return n;
 }
 
+/** the same for S'(q), the table behind fb_nonbonded_force */
+extern "C" __attribute__((visibility("default"))) int fbh_coulomb_force_table(const char* coulomb_json, double temperature,
+                                                                              double* knots, double* coeffs, int max_knots)
+{
+    int n = -1;
+    fb::capi::guarded([&] {
+        fb::pc::temperature = temperature;
+        const auto t = fb::makeCoulombTable(fb::Json::parse(coulomb_json));
+        n = static_cast<int>(t.dS.knots.size());
+        for (int i = 0; i < n && i < max_knots; ++i) {
+            knots[i] = t.dS.knots[i];
+        }
+        for (int i = 0; i < 6 * (n - 1) && i < 6 * (max_knots - 1); ++i) {
+            coeffs[i] = t.dS.coeffs[i];
+        }
+    });
+    return n;
+}
+
 /** Host-side pair tables of one `energy` entry as JSON (mixing matrices, flags, spline ranges) */
 extern "C" __attribute__((visibility("default"))) int fbh_pair_tables_json(const char* input_json,
                                                                            const char* nonbonded_name, char* buf,

@@ -32,10 +32,7 @@ class EnergyTerm
     virtual void sync(EnergyTerm*, const Change&) {}
     virtual void init() {}
     virtual void updateState(const Change&) {}
-    virtual void force(std::vector<Point>&)
-    {
-        throw std::logic_error("force computation not implemented for " + name);
-    }
+    virtual void force(std::vector<Point>&) {} //!< no-op unless a term has forces (src/externalpotential.cpp:30)
     virtual ~EnergyTerm() = default;
 };
 
@@ -259,6 +256,13 @@ class Hamiltonian : public EnergyTerm
     {
         for (auto& t : energy_terms) {
             t->init();
+        }
+    }
+    /** every term in turn on the same vector; src/energy.cpp:1162-1166 */
+    void force(std::vector<Point>& forces) override
+    {
+        for (auto& t : energy_terms) {
+            t->force(forces);
         }
     }
     void updateState(const Change& change) override

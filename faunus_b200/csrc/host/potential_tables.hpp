@@ -164,6 +164,7 @@ struct CoulombTable
     double kappa = 0;
     double self_prefactor = 0; //!< self energy per particle = lB · prefactor · q² / cutoff
     SplineTable S;
+    SplineTable dS; //!< S'(q), tabulated like S: the force is lB zz/r³ [S(1 + κr) − q S'] e^{−κr} (fb_force.cuh)
 };
 
 inline double binomialCoefficient(int n, int k)
@@ -188,12 +189,30 @@ inline CoulombTable makeCoulombTable(const Json& j)
     const double inv_debye = salt ? 1.0 / salt->debyeLength(t.bjerrum_length) : 0.0;
     const double sqrt_pi = std::sqrt(pc::pi);
     std::function<double(double)> S;
+    std::function<double(double)> dS = [](double) { return 0.0; }; // S ≡ 1 unless a type says otherwise
     auto cutoff = [&] { return j.at("cutoff").number(); };
     auto poisson = [&](int C, int D, double kappa) {
         t.cutoff = cutoff();
         t.kappa = kappa;
         const double kRc = kappa * t.cutoff;
         const bool screened = kRc > 1e-10;
+        dS = [=](double q) { // chain rule through q' (q), product rule on (1 − q')^{D+1} · Σ
+            double qp = q, dqp = 1.0;
+            if (screened) {
+                const double denominator = 1.0 - std::exp(2.0 * kRc);
+                qp = (1.0 - std::exp(2.0 * kRc * q)) / denominator;
+                dqp = -2.0 * kRc * std::exp(2.0 * kRc * q) / denominator;
+            }
+            double sum = 0, dsum = 0;
+            for (int c = 0; c < C; ++c) {
+                const double a = static_cast<double>(C - c) / C * binomialCoefficient(D - 1 + c, c);
+                sum += a * std::pow(qp, c);
+                if (c > 0) {
+                    dsum += a * c * std::pow(qp, c - 1);
+                }
+            }
+            return (-(D + 1) * std::pow(1.0 - qp, D) * sum + std::pow(1.0 - qp, D + 1) * dsum) * dqp;
+        };
         S = [=](double q) {
             double qp = q;
             if (screened) {
@@ -244,6 +263,11 @@ inline CoulombTable makeCoulombTable(const Json& j)
             const double q5 = q2 * q2 * q;
             return 1.0 - 1.75 * q + 5.25 * q5 - 7.0 * q5 * q + 2.5 * q5 * q2;
         };
+        dS = [](double q) {
+            const double q2 = q * q;
+            const double q4 = q2 * q2;
+            return -1.75 + 26.25 * q4 - 42.0 * q4 * q + 17.5 * q4 * q2;
+        };
         t.self_prefactor = -0.875;
     }
     else if (type == "qpotential") {
@@ -257,6 +281,19 @@ inline CoulombTable makeCoulombTable(const Json& j)
             }
             return product;
         };
+        dS = [order](double q) { // Σ_n −n q^{n−1} Π_{m≠n} (1 − q^m)
+            double sum = 0;
+            for (int n = 1; n <= order; ++n) {
+                double rest = 1;
+                for (int m = 1; m <= order; ++m) {
+                    if (m != n) {
+                        rest *= 1.0 - std::pow(q, m);
+                    }
+                }
+                sum -= n * std::pow(q, n - 1) * rest;
+            }
+            return sum;
+        };
         t.self_prefactor = -0.5;
     }
     else if (type == "ewald") {
@@ -266,12 +303,19 @@ inline CoulombTable makeCoulombTable(const Json& j)
         const double zeta = t.kappa * t.cutoff;
         if (zeta < 1e-12) {
             S = [eta](double q) { return std::erfc(eta * q); };
+            dS = [eta, sqrt_pi](double q) { return -2 * eta / sqrt_pi * std::exp(-eta * eta * q * q); };
             t.self_prefactor = -eta / sqrt_pi;
         }
         else {
             S = [eta, zeta](double q) {
                 return 0.5 * std::erfc(eta * q + zeta / (2 * eta)) * std::exp(2 * zeta * q) +
                        0.5 * std::erfc(eta * q - zeta / (2 * eta));
+            };
+            dS = [eta, zeta, sqrt_pi](double q) {
+                const double up = eta * q + zeta / (2 * eta);
+                const double down = eta * q - zeta / (2 * eta);
+                return zeta * std::erfc(up) * std::exp(2 * zeta * q) -
+                       eta / sqrt_pi * (std::exp(-up * up + 2 * zeta * q) + std::exp(-down * down));
             };
             t.self_prefactor = -eta / sqrt_pi * (std::exp(-zeta * zeta / (4 * eta * eta)) -
                                                  sqrt_pi * zeta / (2 * eta) * std::erfc(zeta / (2 * eta)));
@@ -282,20 +326,25 @@ inline CoulombTable makeCoulombTable(const Json& j)
         const double eta = j.at("alpha").number() * t.cutoff;
         const double e1 = std::erfc(eta);
         const double e2 = e1 + 2 * eta / sqrt_pi * std::exp(-eta * eta);
+        auto d_erfc = [eta, sqrt_pi](double q) { return -2 * eta / sqrt_pi * std::exp(-eta * eta * q * q); };
         if (type == "wolf") {
             S = [=](double q) { return std::erfc(eta * q) - e1 * q; };
+            dS = [=](double q) { return d_erfc(q) - e1; };
             t.self_prefactor = 0.5 * (-2 * eta / sqrt_pi - e1);
         }
         else if (type == "zahn") {
             S = [=](double q) { return std::erfc(eta * q) - (q - 1) * q * e2; };
+            dS = [=](double q) { return d_erfc(q) - (2 * q - 1) * e2; };
             t.self_prefactor = 0.5 * (-2 * eta / sqrt_pi + e2);
         }
         else if (type == "fennell") {
             S = [=](double q) { return std::erfc(eta * q) - q * e1 + (q - 1) * q * e2; };
+            dS = [=](double q) { return d_erfc(q) - e1 + (2 * q - 1) * e2; };
             t.self_prefactor = 0.5 * (-2 * eta / sqrt_pi - e1 - e2);
         }
         else {
             S = [=](double q) { return std::erfc(eta * q) - q * e1 + 0.5 * (q * q - 1) * q * e2; };
+            dS = [=](double q) { return d_erfc(q) - e1 + 0.5 * (3 * q * q - 1) * e2; };
             t.self_prefactor = 0.5 * (-2 * eta / sqrt_pi - e1 - 0.5 * e2);
         }
     }
@@ -306,6 +355,7 @@ inline CoulombTable makeCoulombTable(const Json& j)
         const double a = (epsrf - epsr) / (2 * epsrf + epsr);
         const double b = 3 * epsrf / (2 * epsrf + epsr);
         S = [=](double q) { return 1 + a * q * q * q - b * q; };
+        dS = [=](double q) { return 3 * a * q * q - b; };
         t.self_prefactor = -0.5 * b;
     }
     else {
@@ -314,6 +364,7 @@ inline CoulombTable makeCoulombTable(const Json& j)
     SplineOptions opt;
     opt.utol = j.value("utol", 0.005 / t.bjerrum_length); // src/potentials.cpp:1634
     t.S = tabulateAndrea(S, 0.0, 1.0, opt);
+    t.dS = tabulateAndrea(dS, 0.0, 1.0, opt);
     return t;
 }
 

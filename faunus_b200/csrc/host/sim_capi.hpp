@@ -269,6 +269,27 @@ inline State& pick(Sim& s, int which)
             *energy = fb::capi::pick(*s, which).pot->energy(c);                                              \
         });                                                                                                  \
     }                                                                                                         \
+    /* Hamiltonian::force (src/energy.cpp:1162-1166) on a zeroed vector (src/forcemove.cpp:124-125) for      \
+       term < 0, else EnergyTerm::force of that term alone; out[3 * n_particles], kT/Angstrom */            \
+    __attribute__((visibility("default"))) int P##_sim_forces(void* h, int which, int term, double* out)     \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] {                                                                       \
+            auto& st = fb::capi::pick(*s, which);                                                            \
+            std::vector<fb::Point> forces(st.spc->particles.size());                                         \
+            if (term < 0) {                                                                                  \
+                st.pot->force(forces);                                                                       \
+            }                                                                                                \
+            else {                                                                                           \
+                st.pot->terms().at(static_cast<size_t>(term))->force(forces);                                \
+            }                                                                                                \
+            for (size_t i = 0; i < forces.size(); ++i) {                                                     \
+                out[3 * i] = forces[i].x;                                                                    \
+                out[3 * i + 1] = forces[i].y;                                                                \
+                out[3 * i + 2] = forces[i].z;                                                                \
+            }                                                                                                \
+        });                                                                                                  \
+    }                                                                                                         \
     /* manual trial move: displace atoms of one group in the TRIAL space, then the reference's call          \
        protocol updateState → trial.energy → accepted.energy (montecarlo.cpp:151-155) */                     \
     __attribute__((visibility("default"))) int P##_sim_trial_set(void* h, int group_index, int all,          \

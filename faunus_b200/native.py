@@ -115,7 +115,7 @@ class FbConfig(C.Structure):
 C_ABI_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_last_error", "fb_device_count", "fb_upload_space", "fb_update_group",
     "fb_set_box", "fb_sync", "fb_download_space", "fb_nonbonded_energy", "fb_nonbonded_delta",
-    "fb_system_energy_shard", "fb_particle_pair_energy", "fb_group_group_energy", "fb_atom_rdf", "fb_molecule_rdf", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_submit_groups", "fb_batch_wait", "fb_run_submit", "fb_run_wait", "fb_configure_runs", "fb_get_run_stats", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing",
+    "fb_system_energy_shard", "fb_particle_pair_energy", "fb_group_group_energy", "fb_set_force_table", "fb_nonbonded_force", "fb_ewald_force", "fb_atom_rdf", "fb_molecule_rdf", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_submit_groups", "fb_batch_wait", "fb_run_submit", "fb_run_wait", "fb_configure_runs", "fb_get_run_stats", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing",
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
     "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
     "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_upload_groups",
@@ -154,6 +154,9 @@ def load() -> C.CDLL:
         "fb_trial_energy": (C.c_int, [vp, C.POINTER(FbTrialMove), c_double_p, c_double_p, c_double_p, c_double_p]),
         "fb_trial_commit": (C.c_int, [vp, C.c_int]),
         "fb_system_energy_shard": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p]),
+        "fb_set_force_table": (C.c_int, [vp, C.c_int, c_double_p, c_double_p]),
+        "fb_nonbonded_force": (C.c_int, [vp, C.c_int, c_double_p]),
+        "fb_ewald_force": (C.c_int, [vp, C.c_int, c_double_p]),
         "fb_particle_pair_energy": (C.c_int, [vp, C.c_int, C.c_int, c_double_p, c_int_p, c_double_p, c_int_p, c_double_p]),
         "fb_group_group_energy": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, c_double_p]),
         "fb_batch_trial": (C.c_int, [vp, C.c_int, C.POINTER(FbBatchMove), C.c_int, C.POINTER(FbBatchResult)]),

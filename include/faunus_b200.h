@@ -26,6 +26,8 @@
  *                                    (updateState + energy(trial) + energy(accepted) + sync each)     src/montecarlo.cpp:139-187
  *   fb_widom_batch ................. WidomInsertion::_sample insertion loop            src/analysis.cpp:1243-1265
  *   fb_export_state/fb_import_state  MPI::ExchangeParticles / exchangeGroupSizes       src/mpicontroller.cpp:192-219, src/move.cpp:860-881
+ *   fb_nonbonded_force ............. Nonbonded::force                                   src/energy.h:1584-1597
+ *   fb_ewald_force ................. Ewald::force                                       src/energy.cpp:596-629
  *   fb_nccl_* ...................... the MPI messages of move::ParallelTempering        src/move.cpp:844-968, src/mpicontroller.cpp:69-259
  */
 #ifndef FAUNUS_B200_H
@@ -200,6 +202,21 @@ int fb_nonbonded_delta(fb_ctx* ctx, int slot_new, int slot_old, const fb_change*
 int fb_particle_pair_energy(fb_ctx* ctx, int slot, int n_pairs, const double* a_xyzq, const int* a_id,
                             const double* b_xyzq, const int* b_id, double* energy);
 int fb_group_group_energy(fb_ctx* ctx, int slot, int group1, int group2, double* energy);
+
+/* ---- forces (EnergyTerm::force, src/externalpotential.h:40; Hamiltonian::force, src/energy.cpp:1162-1166) ------
+ * forces[3 * n_particles] in kT/Angstrom, one vector per particle slot of the uploaded space (the reference sizes the
+ * vector by spc.particles, src/energy.h:1588).
+ * fb_set_force_table: Andrea table of S'(q), q in [0,1] — the derivative of the CoulombGalore short-range function
+ *   whose own table went into fb_config (coulomb_knots / coulomb_coeffs); knots[n_knots], coeffs[6 (n_knots - 1)].
+ * fb_nonbonded_force: Nonbonded::force (src/energy.h:1584-1597) — ADDS, to every particle, the pair forces of all
+ *   other particles of the vector (active or not, no group rules: the reference's stub, reproduced). Pair forces
+ *   exist for FB_POT_COULOMB_LJ and FB_POT_COULOMB_WCA (src/potentials.h:32-40, 173-184, 600-606); every other kind
+ *   returns FB_ERR_INVALID with the message of PairPotential::force (src/potentials.cpp:246-251).
+ * fb_ewald_force: Ewald::force (src/energy.cpp:596-629) — OVERWRITES forces with the surface + reciprocal-space
+ *   force from the Q(k) of `slot` (as the reference does: `(*force) = ...`). */
+int fb_set_force_table(fb_ctx* ctx, int n_knots, const double* knots, const double* coeffs);
+int fb_nonbonded_force(fb_ctx* ctx, int slot, double* forces);
+int fb_ewald_force(fb_ctx* ctx, int slot, double* forces);
 
 /* share `shard` of `n_shards` of the full-system energy of a slot, for one evaluation spread over several
  * GPUs that hold the same Space (GroupPairingPolicy::all, src/energy.h:1290-1326: tile rows are dealt

@@ -374,6 +374,36 @@ class Ewald : public EnergyTerm
         }
         return 0.0;
     }
+    /**
+     * src/energy.cpp:596-629, as it stands there: the force of every particle of the vector is ASSIGNED the surface
+     * term (whatever earlier terms left is lost; no tinfoil test), the k-space sum is added and the lot is scaled by
+     * −4π lB / V. Dipole moments (Q_dipole, mu) are outside the scope: zero.
+     */
+    void force(std::vector<Point>& forces) override
+    {
+        if (forces.size() != spc.particles.size()) {
+            throw std::runtime_error("the forces size must match the particle size");
+        }
+        const double volume = spc.geometry.getVolume();
+        Point total_dipole_moment(0.0, 0.0, 0.0);
+        for (const auto& particle : spc.particles) {
+            total_dipole_moment = total_dipole_moment + particle.pos * particle.charge;
+        }
+        auto force = forces.begin();
+        for (const auto& particle : spc.particles) {
+            (*force) = total_dipole_moment * (particle.charge / (2.0 * data.surface_dielectric_constant + 1.0));
+            const std::complex<double> qmu(0.0, particle.charge);
+            for (size_t i = 0; i < data.k_vectors.size(); i++) {
+                const std::complex<double> Q = data.Q_ion[i];
+                const double k_dot_r = data.k_vectors[i].dot(particle.pos);
+                const std::complex<double> expKri(std::cos(k_dot_r), std::sin(k_dot_r));
+                const std::complex<double> repart = expKri * qmu * std::conj(Q);
+                (*force) = (*force) + data.k_vectors[i] * (std::real(repart) * data.Aks[i]);
+            }
+            (*force) = (*force) * (-4.0 * pc::pi / volume * data.bjerrum_length);
+            force++;
+        }
+    }
     void sync(EnergyTerm* energybase, const Change& change) override
     {
         if (auto* other = dynamic_cast<const Ewald*>(energybase)) {

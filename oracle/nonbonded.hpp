@@ -32,6 +32,12 @@ template <class TPairPotential> class PairEnergy
     {
         return pair_potential(a, b, geometry.sqdist(a.pos, b.pos));
     }
+    /** force on a due to b from the minimum-image vector b → a; src/energy.h:441-447 */
+    inline Point force(const Particle& a, const Particle& b) const
+    {
+        const Point b_towards_a = geometry.vdist(a.pos, b.pos);
+        return pair_potential.force(a, b, b_towards_a.squaredNorm(), b_towards_a);
+    }
 };
 
 /**
@@ -482,6 +488,26 @@ template <class TPairPotential> class Nonbonded : public EnergyTerm
     double particleParticleEnergy(const Particle& a, const Particle& b) const
     {
         return pair_energy.potential(a, b);
+    }
+
+    /** every pair of the particle vector, active or not (`@todo A stub`); src/energy.h:1584-1597 */
+    void force(std::vector<Point>& forces) override
+    {
+        if (forces.size() != spc.particles.size()) {
+            throw std::runtime_error("the forces size must match the particle size");
+        }
+        if constexpr (requires(const TPairPotential& pot, const Particle& p, const Point& r) { pot.force(p, p, 1.0, r); }) {
+            for (size_t i = 0; i + 1 < spc.particles.size(); ++i) {
+                for (size_t j = i + 1; j < spc.particles.size(); ++j) {
+                    const Point f = pair_energy.force(spc.particles[i], spc.particles[j]);
+                    forces[i] = forces[i] + f;
+                    forces[j] = forces[j] - f;
+                }
+            }
+        }
+        else { // FunctorPotential, SplinedPotential: PairPotential::force, src/potentials.cpp:246-251
+            throw std::logic_error("Force computation not implemented for this setup!");
+        }
     }
 
     double energy(const Change& change) override

@@ -164,6 +164,26 @@ FO_API int fo_coulomb_table(const char* coulomb_json, double temperature, double
     return n;
 }
 
+/** the same for S'(q), the table behind the pair force; returns #knots */
+FO_API int fo_coulomb_force_table(const char* coulomb_json, double temperature, double* knots, double* coeffs, int max_knots)
+{
+    int n = -1;
+    fb::capi::guarded([&] {
+        fb::pc::temperature = temperature;
+        oracle::NewCoulombGalore pot;
+        fb::Topology topo;
+        pot.from_json(fb::Json::parse(coulomb_json), topo);
+        n = static_cast<int>(pot.slope_table.r2.size());
+        for (int i = 0; i < n && i < max_knots; ++i) {
+            knots[i] = pot.slope_table.r2[i];
+        }
+        for (int i = 0; i < 6 * (n - 1) && i < 6 * (max_knots - 1); ++i) {
+            coeffs[i] = pot.slope_table.c[i];
+        }
+    });
+    return n;
+}
+
 /** Pair energy u(a,b,r) of an `energy`-entry style potential for two atom types (functor tests) */
 FO_API int fo_pair_energy(const char* input_json, const char* nonbonded_name, int id_a, int id_b, const double* r,
                           int n, double* u)
@@ -213,6 +233,58 @@ FO_API int fo_pair_energy(const char* input_json, const char* nonbonded_name, in
         }
         else {
             throw std::runtime_error("unknown nonbonded name");
+        }
+    });
+}
+
+/**
+ * Pair force on a due to b (kT/Å) for n distance vectors b → a (xyz[3n]) of an `energy`-entry style potential; the
+ * known-answer values of src/potentials.cpp:399, 661, 777-778, 1612-1626 go through here. Returns −1 with the
+ * reference's message for a potential without forces (PairPotential::force, src/potentials.cpp:246-251).
+ */
+FO_API int fo_pair_force(const char* input_json, const char* nonbonded_name, int id_a, int id_b, const double* xyz, int n,
+                         double* f)
+{
+    return fb::capi::guarded([&] {
+        const auto j = fb::Json::parse(input_json);
+        fb::pc::temperature = j.at("temperature").number();
+        auto topo = fb::topologyFromJson(j);
+        fb::Particle a = topo->makeParticle(id_a);
+        fb::Particle b = topo->makeParticle(id_b);
+        const fb::Json* cfg = nullptr;
+        for (const auto& e : j.at("energy").items()) {
+            if (e.single().first == nonbonded_name) {
+                cfg = &e.single().second;
+            }
+        }
+        if (!cfg) {
+            throw std::runtime_error("energy entry not found");
+        }
+        const std::string name = nonbonded_name;
+        auto run = [&](auto pot) {
+            pot.from_json(*cfg, *topo);
+            for (int i = 0; i < n; ++i) {
+                const fb::Point r(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+                const fb::Point force = pot.force(a, b, r.squaredNorm(), r);
+                f[3 * i] = force.x;
+                f[3 * i + 1] = force.y;
+                f[3 * i + 2] = force.z;
+            }
+        };
+        if (name == "nonbonded_coulomblj") {
+            run(oracle::CoulombLJ());
+        }
+        else if (name == "nonbonded_coulombwca") {
+            run(oracle::CoulombWCA());
+        }
+        else if (name == "nonbonded_pm") {
+            run(oracle::PrimitiveModel());
+        }
+        else if (name == "nonbonded_pmwca") {
+            run(oracle::PrimitiveModelWCA());
+        }
+        else {
+            throw std::logic_error("Force computation not implemented for this setup!");
         }
     });
 }

@@ -403,6 +403,15 @@ class LennardJones
         x = x * x * x;
         return epsilon_quadruple(a.id, b.id) * (x * x - x);
     }
+    /** force on a: 6·4ε σ⁶ (2σ⁶ − r⁶) / r¹⁴ · (b → a); src/potentials.h:32-40 */
+    inline Point force(const Particle& a, const Particle& b, double r2, const Point& b_towards_a) const
+    {
+        const double s2 = sigma_squared(a.id, b.id);
+        const double s6 = s2 * s2 * s2;
+        const double r6 = r2 * r2 * r2;
+        const double r14 = r6 * r6 * r2;
+        return b_towards_a * (6.0 * epsilon_quadruple(a.id, b.id) * s6 * (2.0 * s6 - r6) / r14);
+    }
     const PairMatrix& sigma2() const { return sigma_squared; }
     const PairMatrix& eps4() const { return epsilon_quadruple; }
 };
@@ -423,6 +432,17 @@ class WeeksChandlerAndersen : public LennardJones
         x = x / r2;
         x = x * x * x;
         return epsilon_quadruple(a.id, b.id) * (x * x - x + onefourth);
+    }
+    /** src/potentials.h:173-184 */
+    inline Point force(const Particle& a, const Particle& b, double r2, const Point& b_towards_a) const
+    {
+        double x = sigma_squared(a.id, b.id);
+        if (r2 > x * twototwosixth) {
+            return {0.0, 0.0, 0.0};
+        }
+        x = x / r2;
+        x = x * x * x;
+        return b_towards_a * (epsilon_quadruple(a.id, b.id) * 6.0 * (2.0 * x * x - x) / r2);
     }
 };
 
@@ -451,6 +471,11 @@ class HardSphere
     {
         return r2 < sigma_squared(a.id, b.id) ? pc::infty : 0.0;
     }
+    /** no force of its own: PairPotential::force throws, src/potentials.cpp:246-251 */
+    inline Point force(const Particle&, const Particle&, double, const Point&) const
+    {
+        throw std::logic_error("Force computation not implemented for this setup!");
+    }
     const PairMatrix& sigma2() const { return sigma_squared; }
 };
 
@@ -474,6 +499,11 @@ class Coulomb
     {
         return bjerrum_length * a.charge * b.charge / std::sqrt(r2);
     }
+    /** no force of its own: PairPotential::force throws, src/potentials.cpp:246-251 */
+    inline Point force(const Particle&, const Particle&, double, const Point&) const
+    {
+        throw std::logic_error("Force computation not implemented for this setup!");
+    }
     std::function<double(const Particle&)> selfEnergy() const { return nullptr; }
 };
 
@@ -487,6 +517,7 @@ struct CoulombScheme
     double kappa = 0;                         //!< inverse Debye length
     double self_prefactor = 0;                //!< self energy = lB · prefactor · q² / cutoff
     std::function<double(double)> S;          //!< short-range function S(q)
+    std::function<double(double)> dS = [](double) { return 0.0; }; //!< S'(q) (CoulombGalore short_range_function_derivative)
 };
 
 inline double binomial(int n, int k)
@@ -528,6 +559,20 @@ inline CoulombScheme makeCoulombScheme(const Json& j, double bjerrum_length)
             }
             return std::pow(1.0 - qp, D + 1) * sum;
         };
+        s.dS = [=](double q) {
+            double qp = q, slope = 1.0;
+            if (screened) {
+                qp = (1.0 - std::exp(2.0 * kRc * q)) / (1.0 - std::exp(2.0 * kRc));
+                slope = -2.0 * kRc * std::exp(2.0 * kRc * q) / (1.0 - std::exp(2.0 * kRc));
+            }
+            double sum = 0, dsum = 0;
+            for (int c = 0; c < C; ++c) {
+                const double a = static_cast<double>(C - c) / C * binomial(D - 1 + c, c);
+                sum += a * std::pow(qp, c);
+                dsum += c > 0 ? a * c * std::pow(qp, c - 1) : 0.0;
+            }
+            return slope * (std::pow(1.0 - qp, D + 1) * dsum - (D + 1) * std::pow(1.0 - qp, D) * sum);
+        };
         double dqp = 1.0;
         if (screened) {
             dqp = 2.0 * kRc / (std::exp(2.0 * kRc) - 1.0);
@@ -565,6 +610,11 @@ inline CoulombScheme makeCoulombScheme(const Json& j, double bjerrum_length)
             const double q5 = q2 * q2 * q;
             return 1.0 - 1.75 * q + 5.25 * q5 - 7.0 * q5 * q + 2.5 * q5 * q2;
         };
+        s.dS = [](double q) {
+            const double q2 = q * q;
+            const double q4 = q2 * q2;
+            return -1.75 + 26.25 * q4 - 42.0 * q4 * q + 17.5 * q4 * q2;
+        };
         s.self_prefactor = -0.875;
     }
     else if (s.type == "qpotential") {
@@ -578,6 +628,19 @@ inline CoulombScheme makeCoulombScheme(const Json& j, double bjerrum_length)
             }
             return prod;
         };
+        s.dS = [order](double q) { // product rule, one factor at a time
+            double total = 0;
+            for (int n = 1; n <= order; ++n) {
+                double others = 1;
+                for (int m = 1; m <= order; ++m) {
+                    if (m != n) {
+                        others *= 1.0 - std::pow(q, m);
+                    }
+                }
+                total -= n * std::pow(q, n - 1) * others;
+            }
+            return total;
+        };
         s.self_prefactor = -0.5;
     }
     else if (s.type == "poisson") {
@@ -590,12 +653,19 @@ inline CoulombScheme makeCoulombScheme(const Json& j, double bjerrum_length)
         const double zeta = s.kappa * s.cutoff;
         if (zeta < 1e-12) {
             s.S = [eta](double q) { return std::erfc(eta * q); };
+            s.dS = [eta, sqrt_pi](double q) { return -2 * eta / sqrt_pi * std::exp(-eta * eta * q * q); };
             s.self_prefactor = -eta / sqrt_pi;
         }
         else {
             s.S = [eta, zeta](double q) {
                 return 0.5 * std::erfc(eta * q + zeta / (2 * eta)) * std::exp(2 * zeta * q) +
                        0.5 * std::erfc(eta * q - zeta / (2 * eta));
+            };
+            s.dS = [eta, zeta, sqrt_pi](double q) {
+                const double a = eta * q + zeta / (2 * eta);
+                const double b = eta * q - zeta / (2 * eta);
+                return zeta * std::erfc(a) * std::exp(2 * zeta * q) -
+                       eta / sqrt_pi * (std::exp(-a * a + 2 * zeta * q) + std::exp(-b * b));
             };
             s.self_prefactor = -eta / sqrt_pi * (std::exp(-zeta * zeta / (4 * eta * eta)) -
                                                  sqrt_pi * zeta / (2 * eta) * std::erfc(zeta / (2 * eta)));
@@ -606,20 +676,25 @@ inline CoulombScheme makeCoulombScheme(const Json& j, double bjerrum_length)
         const double eta = j.at("alpha").number() * s.cutoff;
         const double erfc_eta = std::erfc(eta);
         const double gauss = erfc_eta + 2 * eta / sqrt_pi * std::exp(-eta * eta);
+        const auto gaussian_slope = [eta, sqrt_pi](double q) { return -2 * eta / sqrt_pi * std::exp(-eta * eta * q * q); };
         if (s.type == "wolf") {
             s.S = [=](double q) { return std::erfc(eta * q) - erfc_eta * q; };
+            s.dS = [=](double q) { return gaussian_slope(q) - erfc_eta; };
             s.self_prefactor = 0.5 * (-2 * eta / sqrt_pi - erfc_eta);
         }
         else if (s.type == "zahn") {
             s.S = [=](double q) { return std::erfc(eta * q) - (q - 1) * q * gauss; };
+            s.dS = [=](double q) { return gaussian_slope(q) - (2 * q - 1) * gauss; };
             s.self_prefactor = 0.5 * (-2 * eta / sqrt_pi + gauss);
         }
         else if (s.type == "fennell") {
             s.S = [=](double q) { return std::erfc(eta * q) - q * erfc_eta + (q - 1) * q * gauss; };
+            s.dS = [=](double q) { return gaussian_slope(q) - erfc_eta + (2 * q - 1) * gauss; };
             s.self_prefactor = 0.5 * (-2 * eta / sqrt_pi - erfc_eta - gauss);
         }
         else {
             s.S = [=](double q) { return std::erfc(eta * q) - q * erfc_eta + 0.5 * (q * q - 1) * q * gauss; };
+            s.dS = [=](double q) { return gaussian_slope(q) - erfc_eta + 0.5 * (3 * q * q - 1) * gauss; };
             s.self_prefactor = 0.5 * (-2 * eta / sqrt_pi - erfc_eta - 0.5 * gauss);
         }
     }
@@ -630,6 +705,7 @@ inline CoulombScheme makeCoulombScheme(const Json& j, double bjerrum_length)
         const double a = (epsrf - epsr) / (2 * epsrf + epsr);
         const double b = 3 * epsrf / (2 * epsrf + epsr);
         s.S = [=](double q) { return 1 + a * q * q * q - b * q; };
+        s.dS = [=](double q) { return 3 * a * q * q - b; };
         s.self_prefactor = -0.5 * b;
     }
     else {
@@ -646,6 +722,7 @@ class NewCoulombGalore
     double bjerrum_length = 0;
     CoulombScheme scheme;
     SplineData table; //!< Andrea spline of S(q) on [0,1]
+    SplineData slope_table; //!< … and of S'(q) (CoulombGalore::Splined tabulates the derivatives too)
     double inverse_cutoff = 0;
 
     void from_json(const Json& jin, const Topology&)
@@ -656,6 +733,7 @@ class NewCoulombGalore
         Andrea spline;
         spline.setTolerance(j.value("utol", 0.005 / bjerrum_length));
         table = spline.generate(scheme.S, 0.0, 1.0);
+        slope_table = spline.generate(scheme.dS, 0.0, 1.0);
         inverse_cutoff = 1.0 / scheme.cutoff;
     }
     inline double operator()(const Particle& a, const Particle& b, double r2) const
@@ -669,6 +747,26 @@ class NewCoulombGalore
             return bjerrum_length * u;
         }
         return 0.0;
+    }
+    /**
+     * src/potentials.h:600-606: lB · ion_ion_force(qa, qb, b → a). CoulombGalore (absent, PARITY UNPINNED beyond
+     * `plain`): the field of an ion, z r / r³ · [S(q)(1 + κr) − q S'(q)] e^{−κr} for r² < Rc², is minus the gradient
+     * of the energy above. Pinned for `plain` by src/potentials.cpp:1612-1626 (0.1429734149 at r = 7, ε_r = 80).
+     */
+    inline Point force(const Particle& a, const Particle& b, double r2, const Point& b_towards_a) const
+    {
+        if (r2 < scheme.cutoff * scheme.cutoff) {
+            const double r = std::sqrt(r2);
+            const double q = r * inverse_cutoff;
+            const double kr = scheme.kappa * r;
+            double f = a.charge * b.charge / (r2 * r) *
+                       (Andrea::eval(table, q) * (1.0 + kr) - q * Andrea::eval(slope_table, q));
+            if (scheme.kappa > 0) {
+                f *= std::exp(-kr);
+            }
+            return b_towards_a * (bjerrum_length * f);
+        }
+        return {0.0, 0.0, 0.0};
     }
     /** src/potentials.cpp:1599-1604 */
     std::function<double(const Particle&)> selfEnergy() const
@@ -691,6 +789,11 @@ template <class T1, class T2> class CombinedPairPotential
     inline double operator()(const Particle& a, const Particle& b, double r2) const
     {
         return first(a, b, r2) + second(a, b, r2);
+    }
+    /** src/potentials_base.h:250-256 */
+    inline Point force(const Particle& a, const Particle& b, double r2, const Point& b_towards_a) const
+    {
+        return first.force(a, b, r2, b_towards_a) + second.force(a, b, r2, b_towards_a);
     }
     std::function<double(const Particle&)> selfEnergy() const { return first.selfEnergy(); }
 };

@@ -43,6 +43,8 @@ def oracle_lib() -> C.CDLL:
                                           c_double_p, c_double_p, c_double_p]
         _lib.fo_pair_energy.restype = C.c_int
         _lib.fo_pair_energy.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p]
+        _lib.fo_pair_force.restype = C.c_int
+        _lib.fo_pair_force.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p]
         _lib.fo_ewald_kat.restype = C.c_int
         _lib.fo_ewald_kat.argtypes = [C.c_char_p, C.c_double, C.c_double, c_double_p, C.c_int, c_double_p,
                                       c_double_p]
@@ -61,6 +63,18 @@ def oracle_api() -> SimLibrary:
 
 def oracle_sim(config) -> Simulation:
     return Simulation(oracle_api(), config)
+
+
+def pair_force(config: dict, nonbonded_name: str, id_a: int, id_b: int, r_vectors) -> np.ndarray:
+    """force on a due to b (kT/Å) for distance vectors b → a, [n, 3]"""
+    import json
+    r = np.ascontiguousarray(r_vectors, dtype=np.float64).reshape(-1, 3)
+    f = np.zeros_like(r)
+    rc = oracle_lib().fo_pair_force(json.dumps(config).encode(), nonbonded_name.encode(), id_a, id_b,
+                                    r.ctypes.data_as(c_double_p), len(r), f.ctypes.data_as(c_double_p))
+    if rc != 0:
+        raise RuntimeError(oracle_api().error())
+    return f
 
 
 def pair_energy(config: dict, nonbonded_name: str, id_a: int, id_b: int, r) -> np.ndarray:

@@ -984,3 +984,57 @@ def test_particle_and_group_pair_energies(water_input):
                         expected += pair_energy(water_input, name, int(ids[i]), int(ids[j]), [r_min(xyzq[i, :3], xyzq[j, :3])])[0]
             assert abs(u.value - expected) <= 1e-10 * max(1.0, abs(expected))
     assert seen == {True, False}
+
+
+FORCE_VARIANTS = ["coulombwca_ewald_surface", "coulombwca_ewald", "coulomblj_fanourgakis", "coulombwca_yukawa", "coulombwca_qpot",
+                  "coulombwca_wolf", "coulombwca_zerodipole", "coulombwca_reactionfield", "coulombwca_poisson"]
+
+
+@pytest.mark.parametrize("name", FORCE_VARIANTS)
+def test_forces_match_oracle(name):
+    """Nonbonded::force (src/energy.h:1584-1597), Ewald::force (src/energy.cpp:596-629) and Hamiltonian::force
+    (src/energy.cpp:1162-1166) on the device against the oracle, term by term, before and after moves; 1e-10 of the
+    largest force component of the term."""
+    o, g = pair_of_sims(electrolyte_variants()[name], 64)
+    n_terms = len(o.system_energy()[1])
+    for sweep in range(2):
+        for term in range(n_terms):
+            want, got = o.forces(term=term), g.forces(term=term)
+            assert_close(want, got, scale=max(np.abs(want).max(), 1e-300))
+        want, got = o.forces(), g.forces()
+        assert np.abs(want).max() > 0
+        assert_close(want, got, scale=np.abs(want).max())
+        for s in (o, g):
+            s.sweep(1)
+        assert np.array_equal(o.trace()["accepted"], g.trace()["accepted"])
+    # the trial state's terms see the trial Space
+    assert_close(o.forces(which=1), g.forces(which=1), scale=np.abs(o.forces(which=1)).max())
+
+
+def test_forces_of_the_bulk_example(bulk_input):
+    """examples/bulk (N = 2304, fanourgakis + Lennard-Jones, no Ewald term): the pair forces of all 2.65e6 pairs"""
+    o, g = pair_of_sims(bulk_input, 64)
+    want, got = o.forces(), g.forces()
+    assert np.abs(want.sum(axis=0)).max() <= 1e-9 * np.abs(want).max()  # Newton's third law
+    assert_close(want, got, scale=np.abs(want).max())
+
+
+@pytest.mark.parametrize("name", ["pm", "pmwca", "functor", "splined"])
+def test_no_forces_where_the_reference_has_none(name):
+    """PairPotential::force throws for plain Coulomb, hard spheres and the functor potentials
+    (src/potentials.cpp:246-251): same message from the oracle and from the device library"""
+    o, g = pair_of_sims(ALL_VARIANTS[name], 0)
+    for s in (o, g):
+        with pytest.raises(RuntimeError, match="Force computation not implemented"):
+            s.forces()
+
+
+def test_forces_include_inactive_particles():
+    """the reference's stub sums over the whole particle vector, inactive ghosts included (src/energy.h:1590-1596)"""
+    cfg = small_electrolyte(n=60, coulomb={"type": "fanourgakis", "epsr": 78.7, "cutoff": 9.0}, ghost_pairs=1)
+    cfg["particles"][-2]["pos"] = [1.0, 2.0, 3.0]  # the inactive pair: somewhere, apart from each other
+    cfg["particles"][-1]["pos"] = [-4.0, 2.5, 0.5]
+    o, g = pair_of_sims(cfg, 0)
+    want, got = o.forces(), g.forces()
+    assert want.shape[0] == 62 and np.abs(want[-2:]).max() > 0 and np.all(np.isfinite(want))
+    assert_close(want, got, scale=np.abs(want).max())
