@@ -36,6 +36,10 @@ class SimLibrary:
         f("sim_create", C.c_void_p, [C.c_char_p])
         f("sim_destroy", None, [C.c_void_p])
         f("sim_restore", C.c_int, [C.c_void_p, C.c_char_p])
+        f("sim_save_state", C.c_int, [C.c_void_p, C.c_char_p, C.c_int])
+        f("sim_load_state", C.c_int, [C.c_void_p, C.c_char_p])
+        f("json_to_ubjson", C.c_int, [C.c_char_p, C.c_char_p, C.c_int])
+        f("ubjson_to_json", C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.c_int])
         f("sim_sweep", C.c_int, [C.c_void_p, C.c_int])
         f("sim_moves_per_sweep", C.c_int, [C.c_void_p])
         f("sim_system_energy", C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, c_int_p])
@@ -86,6 +90,24 @@ class SimLibrary:
     def error(self) -> str:
         return self.last_error().decode("utf-8", "replace")
 
+    def to_ubjson(self, value) -> bytes:
+        """Universal Binary JSON of a JSON value as the library's writer encodes it"""
+        text = json.dumps(value).encode()
+        n = self.json_to_ubjson(text, None, 0)
+        if n < 0:
+            raise RuntimeError(self.error())
+        buf = C.create_string_buffer(max(n, 1))
+        self.json_to_ubjson(text, buf, n)
+        return buf.raw[:n]
+
+    def from_ubjson(self, data: bytes):
+        n = self.ubjson_to_json(data, len(data), None, 0)
+        if n < 0:
+            raise RuntimeError(self.error())
+        buf = C.create_string_buffer(n)
+        self.ubjson_to_json(data, len(data), buf, n)
+        return json.loads(buf.value.decode())
+
 
 class Simulation:
     """One Metropolis MC simulation (accepted + trial state) driven through the C ABI."""
@@ -116,6 +138,14 @@ class Simulation:
     def restore(self, state: dict | str):
         text = state if isinstance(state, str) else json.dumps(state)
         self._check(self.api.sim_restore(self.handle, text.encode()), "sim_restore")
+
+    def save_state(self, filename: str, save_random: bool = True):
+        """`savestate` to a `.json` or `.ubj` file (src/analysis.cpp:640-682)"""
+        self._check(self.api.sim_save_state(self.handle, filename.encode(), int(save_random)), "sim_save_state")
+
+    def load_state(self, filename: str):
+        """`--state <file>` (.json / .ubj), then restore (src/faunus.cpp:430-455)"""
+        self._check(self.api.sim_load_state(self.handle, filename.encode()), "sim_load_state")
 
     @property
     def num_particles(self) -> int:

@@ -285,7 +285,256 @@ class Json
         return j;
     }
 
+    // --- Universal Binary JSON (the reference's `.ubj` state files: nlohmann `json::to_ubjson` with its defaults —
+    // no container size / type optimisation — src/analysis.cpp:656-668; read back by `json::from_ubjson`,
+    // src/faunus.cpp:435-449). Integers take the smallest of i, U, I, l, L that holds them, every other number is a
+    // big-endian 'D'; strings and keys carry their length as such an integer; the reader also accepts the optimised
+    // containers ('$' type, '#' count) and 'd', 'C' that other writers produce. ---
+    std::string toUbjson() const
+    {
+        std::string out;
+        writeUbjson(out);
+        return out;
+    }
+
+    static Json fromUbjson(const std::string& bytes)
+    {
+        UbjsonReader r{reinterpret_cast<const unsigned char*>(bytes.data()),
+                       reinterpret_cast<const unsigned char*>(bytes.data()) + bytes.size()};
+        Json j = r.value(r.marker());
+        if (r.cur != r.end) {
+            throw std::runtime_error("ubjson: trailing bytes");
+        }
+        return j;
+    }
+
   private:
+    static void ubjsonBigEndian(std::string& out, unsigned long long bits, int n_bytes)
+    {
+        for (int b = n_bytes - 1; b >= 0; --b) {
+            out.push_back(static_cast<char>((bits >> (8 * b)) & 0xffu));
+        }
+    }
+    static void ubjsonInteger(std::string& out, long long v)
+    {
+        if (v >= -128 && v <= 127) {
+            out.push_back('i');
+            ubjsonBigEndian(out, static_cast<unsigned long long>(v), 1);
+        }
+        else if (v >= 0 && v <= 255) {
+            out.push_back('U');
+            ubjsonBigEndian(out, static_cast<unsigned long long>(v), 1);
+        }
+        else if (v >= -32768 && v <= 32767) {
+            out.push_back('I');
+            ubjsonBigEndian(out, static_cast<unsigned long long>(v), 2);
+        }
+        else if (v >= -2147483648LL && v <= 2147483647LL) {
+            out.push_back('l');
+            ubjsonBigEndian(out, static_cast<unsigned long long>(v), 4);
+        }
+        else {
+            out.push_back('L');
+            ubjsonBigEndian(out, static_cast<unsigned long long>(v), 8);
+        }
+    }
+    void writeUbjson(std::string& out) const
+    {
+        switch (type_) {
+        case Type::Null:
+            out.push_back('Z');
+            break;
+        case Type::Bool:
+            out.push_back(bool_ ? 'T' : 'F');
+            break;
+        case Type::Number:
+            if (is_int_ && std::fabs(num_) < 9.0e18) {
+                ubjsonInteger(out, static_cast<long long>(num_));
+            }
+            else {
+                unsigned long long bits;
+                static_assert(sizeof(bits) == sizeof(num_));
+                std::memcpy(&bits, &num_, sizeof(bits));
+                out.push_back('D');
+                ubjsonBigEndian(out, bits, 8);
+            }
+            break;
+        case Type::String:
+            out.push_back('S');
+            ubjsonInteger(out, static_cast<long long>(str_.size()));
+            out += str_;
+            break;
+        case Type::Array:
+            out.push_back('[');
+            for (const auto& x : arr_) {
+                x.writeUbjson(out);
+            }
+            out.push_back(']');
+            break;
+        case Type::Object:
+            out.push_back('{');
+            for (const auto& [key, x] : obj_) {
+                ubjsonInteger(out, static_cast<long long>(key.size()));
+                out += key;
+                x.writeUbjson(out);
+            }
+            out.push_back('}');
+            break;
+        }
+    }
+
+    struct UbjsonReader
+    {
+        const unsigned char* cur;
+        const unsigned char* end;
+        [[noreturn]] void fail(const char* what) const { throw std::runtime_error(std::string("ubjson: ") + what); }
+        unsigned char marker()
+        {
+            if (cur >= end) {
+                fail("unexpected end of input");
+            }
+            return *cur++;
+        }
+        unsigned long long bigEndian(int n_bytes)
+        {
+            if (end - cur < n_bytes) {
+                fail("unexpected end of input");
+            }
+            unsigned long long bits = 0;
+            for (int b = 0; b < n_bytes; ++b) {
+                bits = (bits << 8) | *cur++;
+            }
+            return bits;
+        }
+        bool integerOf(unsigned char m, long long& v)
+        {
+            switch (m) {
+            case 'i':
+                v = static_cast<signed char>(bigEndian(1));
+                return true;
+            case 'U':
+                v = static_cast<long long>(bigEndian(1));
+                return true;
+            case 'I':
+                v = static_cast<short>(bigEndian(2));
+                return true;
+            case 'l':
+                v = static_cast<int>(bigEndian(4));
+                return true;
+            case 'L':
+                v = static_cast<long long>(bigEndian(8));
+                return true;
+            default:
+                return false;
+            }
+        }
+        size_t length()
+        {
+            long long n = 0;
+            if (!integerOf(marker(), n) || n < 0) {
+                fail("length expected");
+            }
+            if (n > static_cast<long long>(end - cur)) {
+                fail("length beyond the input");
+            }
+            return static_cast<size_t>(n);
+        }
+        std::string text()
+        {
+            const size_t n = length();
+            if (static_cast<size_t>(end - cur) < n) {
+                fail("unexpected end of input");
+            }
+            std::string s(reinterpret_cast<const char*>(cur), n);
+            cur += n;
+            return s;
+        }
+        /** optional "$ type" and "# count" after '[' or '{' */
+        void containerHeader(unsigned char& type, long long& count)
+        {
+            type = 0;
+            count = -1;
+            if (cur < end && *cur == '$') {
+                ++cur;
+                type = marker();
+                if (cur >= end || *cur != '#') {
+                    fail("a typed container needs a count");
+                }
+            }
+            if (cur < end && *cur == '#') {
+                ++cur;
+                count = static_cast<long long>(length());
+            }
+        }
+        Json value(unsigned char m)
+        {
+            long long v = 0;
+            if (integerOf(m, v)) {
+                Json j(static_cast<double>(v));
+                j.is_int_ = true;
+                return j;
+            }
+            switch (m) {
+            case 'Z':
+                return Json();
+            case 'T':
+                return Json(true);
+            case 'F':
+                return Json(false);
+            case 'D': {
+                const unsigned long long bits = bigEndian(8);
+                double d;
+                std::memcpy(&d, &bits, sizeof(d));
+                return Json(d);
+            }
+            case 'd': {
+                const unsigned bits = static_cast<unsigned>(bigEndian(4));
+                float f;
+                std::memcpy(&f, &bits, sizeof(f));
+                return Json(static_cast<double>(f));
+            }
+            case 'C':
+                return Json(std::string(1, static_cast<char>(bigEndian(1))));
+            case 'S':
+                return Json(text());
+            case '[': {
+                Json j = Json::array();
+                unsigned char type;
+                long long count;
+                containerHeader(type, count);
+                if (count >= 0) {
+                    for (long long i = 0; i < count; ++i) {
+                        j.arr_.push_back(value(type ? type : marker()));
+                    }
+                }
+                else {
+                    for (unsigned char e = marker(); e != ']'; e = marker()) {
+                        j.arr_.push_back(value(e));
+                    }
+                }
+                return j;
+            }
+            case '{': {
+                Json j = Json::object();
+                unsigned char type;
+                long long count;
+                containerHeader(type, count);
+                for (long long i = 0; count < 0 || i < count; ++i) {
+                    if (count < 0 && cur < end && *cur == '}') {
+                        ++cur;
+                        break;
+                    }
+                    std::string key = text();
+                    j.obj_.emplace_back(std::move(key), value(type ? type : marker()));
+                }
+                return j;
+            }
+            default:
+                fail("unknown type marker");
+            }
+        }
+    };
+
     static void writeString(std::string& out, const std::string& s)
     {
         out.push_back('"');

@@ -4,6 +4,8 @@
 // :139-187 (performMove), :193-209 (getEnergyChange), :220-227 (sweep), :244-254 (State),
 // src/analysis.cpp:807-823 + 1227-1312 (Widom insertion, sequential reference order).
 #pragma once
+#include <fstream>
+#include <iterator>
 #include "moves.hpp"
 #include <chrono>
 #include <algorithm>
@@ -329,6 +331,38 @@ class MetropolisMonteCarlo
         j["random-move"] = generator(rng.slump);
         j["random-global"] = generator(rng.global);
         return j;
+    }
+
+    /**
+     * `savestate` to a file: `.json` (text) or `.ubj` (Universal Binary JSON, `json::to_ubjson`), with the two generators
+     * when `save_random` (`saverandom`); any other suffix is a configuration error. src/analysis.cpp:640-682
+     */
+    void saveStateFile(const std::string& filename, bool save_random) const
+    {
+        const auto suffix = filename.substr(filename.find_last_of('.') + 1);
+        if (suffix != "json" && suffix != "ubj") {
+            throw std::runtime_error("unknown file extension for '" + filename + "'");
+        }
+        Json j = save_random ? saveState() : state.spc->toJson();
+        std::ofstream f(filename, suffix == "ubj" ? std::ios::binary : std::ios::out);
+        if (!f) {
+            throw std::runtime_error("state file error -> " + filename);
+        }
+        const std::string bytes = suffix == "ubj" ? j.toUbjson() : j.dump();
+        f.write(bytes.data(), static_cast<std::streamsize>(bytes.size()));
+    }
+
+    /** `--state <file>` (.json / .ubj): read, then restore(); src/faunus.cpp:430-455 */
+    void restoreFile(const std::string& filename)
+    {
+        const auto suffix = filename.substr(filename.find_last_of('.') + 1);
+        const bool binary = suffix == "ubj";
+        std::ifstream f(filename, binary ? std::ios::binary : std::ios::in);
+        if (!f) {
+            throw std::runtime_error("state file error -> " + filename);
+        }
+        const std::string bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        restore(binary ? Json::fromUbjson(bytes) : Json::parse(bytes));
     }
 
     /** src/montecarlo.cpp:85-99 */

@@ -229,6 +229,42 @@ inline State& pick(Sim& s, int which)
         auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
         return fb::capi::guarded([&] { s->mc->restore(fb::Json::parse(state_json)); });                      \
     }                                                                                                         \
+    /* state files as the reference writes and reads them: .json or .ubj by suffix                           \
+       (SaveState, src/analysis.cpp:640-682; --state, src/faunus.cpp:430-455) */                            \
+    __attribute__((visibility("default"))) int P##_sim_save_state(void* h, const char* filename,             \
+                                                                  int save_random)                           \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] { s->mc->saveStateFile(filename, save_random != 0); });                 \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_sim_load_state(void* h, const char* filename)             \
+    {                                                                                                         \
+        auto* s = static_cast<fb::capi::Sim*>(h);                                                            \
+        return fb::capi::guarded([&] { s->mc->restoreFile(filename); });                                     \
+    }                                                                                                         \
+    /* JSON text -> UBJSON bytes and back (known-answer tests of the encoding); return the size needed */    \
+    __attribute__((visibility("default"))) int P##_json_to_ubjson(const char* text, char* buf, int len)      \
+    {                                                                                                         \
+        int n = -1;                                                                                          \
+        fb::capi::guarded([&] {                                                                              \
+            const std::string bytes = fb::Json::parse(text).toUbjson();                                      \
+            n = static_cast<int>(bytes.size());                                                              \
+            if (buf != nullptr && len >= n) {                                                                \
+                std::memcpy(buf, bytes.data(), bytes.size());                                                \
+            }                                                                                                \
+        });                                                                                                  \
+        return n;                                                                                            \
+    }                                                                                                         \
+    __attribute__((visibility("default"))) int P##_ubjson_to_json(const char* bytes, int n_bytes, char* buf, \
+                                                                  int len)                                   \
+    {                                                                                                         \
+        int n = -1;                                                                                          \
+        fb::capi::guarded([&] {                                                                              \
+            n = fb::capi::copyOut(fb::Json::fromUbjson(std::string(bytes, bytes + n_bytes)).dump(), buf,     \
+                                  len);                                                                      \
+        });                                                                                                  \
+        return n;                                                                                            \
+    }                                                                                                         \
     __attribute__((visibility("default"))) int P##_sim_sweep(void* h, int n)                                 \
     {                                                                                                         \
         auto* s = static_cast<fb::capi::Sim*>(h);                                                            \

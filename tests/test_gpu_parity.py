@@ -800,6 +800,33 @@ def test_restore_on_the_device(water_input):
         assert abs(g.drift()) < 1e-9
 
 
+def test_restore_on_the_device_from_a_binary_state_file(water_input, tmp_path):
+    """the same through files: the oracle writes `state.ubj` (Universal Binary JSON, src/analysis.cpp:656-668), the device
+    simulation starts from it (`--state state.ubj`, src/faunus.cpp:430-455) and writes one itself that the oracle reads"""
+    from conftest import water_with_salt
+    cfg = water_with_salt(water_input, n_pairs=6)
+    o = oracle_sim(cfg)
+    o.sweep(2)
+    first = str(tmp_path / "oracle.ubj")
+    o.save_state(first)
+    g = b200_sim(cfg, 64)
+    g.load_state(first)
+    for s in (o, g):
+        s.trace_enable()
+        s.sweep(1)
+    assert np.array_equal(o.trace()["accepted"], g.trace()["accepted"])
+    second = str(tmp_path / "device.ubj")
+    g.save_state(second)
+    o2 = oracle_sim(cfg)
+    o2.load_state(second)
+    for s in (o2, g):
+        s.trace_enable()
+        s.sweep(1)
+    assert np.array_equal(o2.trace()["accepted"][-len(g.trace()["accepted"]):], g.trace()["accepted"]) or \
+        np.array_equal(o2.trace()["accepted"], g.trace()["accepted"][-len(o2.trace()["accepted"]):])
+    assert np.array_equal(o2.particles()[0], g.particles()[0])
+
+
 def test_packed_state_round_trip(water_input):
     """fb_export_state / fb_import_state (+ fb_upload_groups): the packed mirror of one simulation imported into the
     mirror of another gives the energy of the original (src/mpicontroller.cpp:192-219: what a replica exchange
