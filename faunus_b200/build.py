@@ -38,19 +38,27 @@ def _run(cmd):
     subprocess.check_call(cmd)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OUT, exist_ok=True)
-    if not force and not _stale(LIB):
-        return LIB
-    dev_o = os.path.join(OUT, "fb_api.o")
-    host_o = os.path.join(OUT, "fbh_capi.o")
+def build(force: bool = False, verbose: bool = False, variant: str | None = None, defines: tuple = ()) -> str:
+    """``variant`` + ``defines`` (-D switches of the kernels, e.g. ("FB_KS_GROUPS=2",)) build an experimental copy under
+    _build/variants/<variant>/ that ``FAUNUS_B200_LIB`` selects at load time; the product is the default build."""
+    out = OUT if variant is None else os.path.join(OUT, "variants", variant)
+    lib = os.path.join(out, "libfaunus_b200.so")
+    os.makedirs(out, exist_ok=True)
+    if not force and not _stale(lib):
+        return lib
+    dev_o = os.path.join(out, "fb_api.o")
+    host_o = os.path.join(out, "fbh_capi.o")
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += [f"-D{d}" for d in defines]
     _run([NVCC, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, "device", "fb_api.cu"), "-o", dev_o])
     _run([GXX, *GXX_FLAGS, "-c", os.path.join(CSRC, "fbh_capi.cpp"), "-o", host_o])
-    _run([NVCC, "-shared", "-o", LIB, dev_o, host_o, "-cudart", "static", "-ccbin", GXX,
+    _run([NVCC, "-shared", "-o", lib, dev_o, host_o, "-cudart", "static", "-ccbin", GXX,
           "-Wno-deprecated-gpu-targets"])
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    # python -m faunus_b200.build [--force] [--verbose] [--variant NAME -DSWITCH=VALUE …]
+    name = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=name,
+                defines=tuple(a[2:] for a in sys.argv if a.startswith("-D"))))

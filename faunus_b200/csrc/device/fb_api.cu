@@ -2,6 +2,8 @@
 // (two slots), lowering of `Change` records to launch descriptors, kernel launches.
 // One CUDA stream per context; results come back through mapped pinned memory.
 #include "../../../include/faunus_b200.h"
+#include <map>
+#include <queue>
 #include "fb_kernels.cuh"
 #include "fb_batch.cuh"
 #include "fb_kspace.cuh"
@@ -123,6 +125,12 @@ struct Slot
     DeviceBuffer<unsigned char> unit_map; //!< [n_units][32] slot → index inside the cell's storage range, 255: none
     DeviceBuffer<double> unit_sa;         //!< [n_units][32] √A_k in slot layout, 0 for empty slots
     int n_units = 0;
+    // static schedule of the units over the blocks of windowKspaceKernel (balanced by cost on the host: a result never
+    // depends on which block happens to run first)
+    DeviceBuffer<unsigned char> unit_steps; //!< [n_units] bit s: slot column s = 4·jj + l holds a k-vector for some x-index
+    DeviceBuffer<int> sched_first;          //!< [n_sched_blocks + 1]
+    DeviceBuffer<int> sched_units;          //!< [n_units] units of block b: sched_units[sched_first[b] … sched_first[b + 1])
+    int n_sched_blocks = 0;
     // work items of the commit (windowFrontKernel): two z-adjacent cells = up to four units that share table entries
     DeviceBuffer<int4> item_units; //!< [n_items] unit of (cell 0, h 0), (cell 0, h 1), (cell 1, h 0), (cell 1, h 1); −1: none
     DeviceBuffer<int4> item_base;  //!< [n_items] table index of x, y (h = 0), z of cell 0, z of cell 1
@@ -280,6 +288,17 @@ struct fb_ctx
         std::vector<int> run_last;  //!< … and its latest move there
         int run_id = 0;
         bool run_decide_configured = false;
+        // CUDA graphs of the window launches of a run (launchRunGraph): the 4 kernels × steps windows on two streams
+        // are captured the second time the same launch sequence comes up and replayed from then on
+        struct RunGraph
+        {
+            int seen = 0;
+            cudaGraphExec_t exec = nullptr;
+            long launches = 0;
+        };
+        std::map<unsigned long long, RunGraph> run_graphs;
+        bool run_graphs_enabled = true;
+        long run_graph_replays = 0;
         std::vector<unsigned char> run_accepted;
         std::vector<double> run_u_new, run_u_old;
         double run_steps = 0, run_count = 0, run_rounds = 0, run_moves = 0;
@@ -1082,6 +1101,11 @@ FB_API void fb_destroy(fb_ctx* c)
     }
     if (c->batch.pair_stream) {
         cudaStreamSynchronize(c->batch.pair_stream);
+        for (auto& [key, g] : c->batch.run_graphs) {
+            if (g.exec) {
+                cudaGraphExecDestroy(g.exec);
+            }
+        }
         cudaStreamDestroy(c->batch.pair_stream);
     }
     cudaStream_t s = c->stream;
@@ -2179,10 +2203,58 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
             }
             sl.n_units = static_cast<int>(unit_info.size());
             sl.aks.upload(aks.data(), aks.size(), c->stream);
+            // Schedule of the units over the 2·SM blocks of the persistent kernel. A unit costs its phases (fixed) plus
+            // one Gram step per slot column (jj, l) that holds a k-vector for some x-index — units cut by the sphere
+            // have fewer (8.7 % of all steps at K = 57 950). Longest processing time first onto the least loaded block
+            // (ties: lowest block), then every block walks its units in index order: 2134 units over 296 blocks are
+            // 7 or 8 units each dealt round robin (the kernel takes as long as 8 full ones), ≈ 7.2 units' worth so.
+            std::vector<unsigned char> unit_steps(unit_info.size(), 0);
+            std::vector<int> sched_first, sched_units;
+            {
+                const int n_units = static_cast<int>(unit_info.size());
+                std::vector<int> cost(n_units);
+                for (int u = 0; u < n_units; ++u) {
+                    unsigned mask = 0;
+                    for (int slot = 0; slot < 32; ++slot) {
+                        if (unit_map[static_cast<size_t>(u) * 32 + slot] != 255) {
+                            mask |= 1u << (slot & 7); // slot = 8 xi + 4 jj + l
+                        }
+                    }
+                    unit_steps[u] = static_cast<unsigned char>(mask);
+                    cost[u] = 5 + 2 * __builtin_popcount(mask);
+                }
+                const int n_blocks = std::max(1, std::min(n_units, 2 * c->n_sm));
+                std::vector<int> order(n_units);
+                for (int u = 0; u < n_units; ++u) {
+                    order[u] = u;
+                }
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+                std::vector<std::vector<int>> of_block(n_blocks);
+                std::priority_queue<std::pair<long, int>, std::vector<std::pair<long, int>>, std::greater<>> least;
+                for (int b = 0; b < n_blocks; ++b) {
+                    least.emplace(0L, b);
+                }
+                for (int u : order) {
+                    auto [load, b] = least.top();
+                    least.pop();
+                    of_block[b].push_back(u);
+                    least.emplace(load + cost[u], b);
+                }
+                sched_first.push_back(0);
+                for (auto& units : of_block) {
+                    std::sort(units.begin(), units.end());
+                    sched_units.insert(sched_units.end(), units.begin(), units.end());
+                    sched_first.push_back(static_cast<int>(sched_units.size()));
+                }
+                sl.n_sched_blocks = n_units > 0 ? n_blocks : 0;
+            }
             if (sl.n_units > 0) {
                 sl.unit_info.upload(unit_info.data(), unit_info.size(), c->stream);
                 sl.unit_map.upload(unit_map.data(), unit_map.size(), c->stream);
                 sl.unit_sa.upload(unit_sa.data(), unit_sa.size(), c->stream);
+                sl.unit_steps.upload(unit_steps.data(), unit_steps.size(), c->stream);
+                sl.sched_first.upload(sched_first.data(), sched_first.size(), c->stream);
+                sl.sched_units.upload(sched_units.data(), sched_units.size(), c->stream);
             }
             CUDA_CHECK(cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
         }
@@ -2349,6 +2421,16 @@ FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
                                            cudaMemcpyDeviceToDevice, c->stream));
                 d.unit_sa.ensure(static_cast<size_t>(s.n_units) * 32);
                 CUDA_CHECK(cudaMemcpyAsync(d.unit_sa.ptr, s.unit_sa.ptr, static_cast<size_t>(s.n_units) * 32 * sizeof(double),
+                                           cudaMemcpyDeviceToDevice, c->stream));
+                d.unit_steps.ensure(static_cast<size_t>(s.n_units));
+                CUDA_CHECK(cudaMemcpyAsync(d.unit_steps.ptr, s.unit_steps.ptr, static_cast<size_t>(s.n_units),
+                                           cudaMemcpyDeviceToDevice, c->stream));
+                d.n_sched_blocks = s.n_sched_blocks;
+                d.sched_first.ensure(static_cast<size_t>(s.n_sched_blocks) + 1);
+                CUDA_CHECK(cudaMemcpyAsync(d.sched_first.ptr, s.sched_first.ptr, (static_cast<size_t>(s.n_sched_blocks) + 1) * sizeof(int),
+                                           cudaMemcpyDeviceToDevice, c->stream));
+                d.sched_units.ensure(static_cast<size_t>(s.n_units));
+                CUDA_CHECK(cudaMemcpyAsync(d.sched_units.ptr, s.sched_units.ptr, static_cast<size_t>(s.n_units) * sizeof(int),
                                            cudaMemcpyDeviceToDevice, c->stream));
             }
             d.perm = s.perm;

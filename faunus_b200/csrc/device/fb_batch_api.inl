@@ -263,7 +263,7 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
         const int n_phase_blocks = frontPhaseBlocks(b.geo);
         const int n_front_blocks = sl.n_items; // one block per item
         n_e_rows = n_front_blocks;
-        n_rows = std::max(1, std::min(sl.n_units, 2 * c->n_sm));
+        n_rows = std::max(1, (sl.n_sched_blocks + kKsGroups - 1) / kKsGroups); // one row of partials per block
         b.d_kq.ensure(static_cast<size_t>(sl.n_units) * kUnitSlots);
         b.d_e_partials.ensure(static_cast<size_t>(std::max(1, n_front_blocks)));
         b.d_r_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax);
@@ -274,12 +274,12 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
         launched(c, "windowFrontKernel");
         if (!b.kspace_unit_configured) {
             CUDA_CHECK(cudaFuncSetAttribute(windowKspaceKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(sizeof(KspaceSmem))));
+                                            static_cast<int>(kKsGroups * sizeof(KspaceSmem))));
             b.kspace_unit_configured = true;
         }
-        windowKspaceKernel<<<n_rows, kKsThreads, sizeof(KspaceSmem), c->stream>>>(
-            sl.unit_info.ptr, sl.unit_sa.ptr, b.d_kq.ptr, sl.n_units, cur, b.geo, stride, b.d_r_partials.ptr,
-            b.d_g_partials.ptr);
+        windowKspaceKernel<<<n_rows, kKsThreads, kKsGroups * sizeof(KspaceSmem), c->stream>>>(
+            sl.unit_info.ptr, sl.unit_sa.ptr, b.d_kq.ptr, sl.unit_steps.ptr, sl.sched_first.ptr, sl.sched_units.ptr,
+            sl.n_sched_blocks, cur, b.geo, stride, b.d_r_partials.ptr, b.d_g_partials.ptr);
         launched(c, "windowKspaceKernel");
     }
     if (timing) {
@@ -300,8 +300,12 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
                 b.d_tail_ticket.ensure(1);
                 CUDA_CHECK(cudaMemsetAsync(b.d_tail_ticket.ptr, 0, sizeof(unsigned), c->stream));
             }
-            windowTailKernel<KIND><<<kspaceFinishGrid(stride) + pairFinishBlocks(stride), kFinishThreads,
-                                     runDecideSmemBytes(stride), c->stream>>>(
+#if FB_TAIL_ONE_WAVE
+            const int tail_grid = std::min(c->n_sm, kspaceFinishGrid(stride) + pairFinishBlocks(stride));
+#else
+            const int tail_grid = kspaceFinishGrid(stride) + pairFinishBlocks(stride);
+#endif
+            windowTailKernel<KIND><<<tail_grid, kFinishThreads, runDecideSmemBytes(stride), c->stream>>>(
                 M0, c->P, cur, stride, with_ewald ? 1 : 0, n_rows, n_e_rows, b.d_r_partials.ptr, b.d_g_partials.ptr,
                 b.d_e_partials.ptr, n_pair_blocks, b.d_pair_partials.ptr, b.d_result.ptr, b.d_tail_ticket.ptr, tail->hdr,
                 tail->moves, tail->st, tail->next, tail->out, tail->prev_out, tail->predicted, tail->ahead);
@@ -651,6 +655,108 @@ void launchRunStep(fb_ctx* c, fb_ctx::Batch::RunSlot& r, bool timing, bool setup
     r.last_parity = b.parity;
 }
 
+/** everything the launches of a run's windows take their arguments from, folded into one number */
+unsigned long long runGraphSignature(fb_ctx* c, const fb_ctx::Batch::RunSlot& r, int steps)
+{
+    auto& b = c->batch;
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](const void* data, size_t bytes) {
+        const unsigned char* p = static_cast<const unsigned char*>(data);
+        for (size_t i = 0; i < bytes; ++i) {
+            h = (h ^ p[i]) * 1099511628211ull;
+        }
+    };
+    auto value = [&](auto v) { mix(&v, sizeof(v)); };
+    const SlotView v0 = makeView(c, 0), v1 = makeView(c, 1);
+    mix(&v0, sizeof(v0));
+    mix(&v1, sizeof(v1));
+    const EwaldView e = makeEwaldView(c, 0);
+    mix(&e, sizeof(e));
+    mix(&c->P, sizeof(c->P));
+    mix(&b.geo, sizeof(b.geo));
+    const Slot& sl = c->slot[0];
+    const auto& other = b.run[&r == &b.run[0] ? 1 : 0];
+    const void* pointers[] = {b.d_in[0].ptr,       b.d_in[1].ptr,       b.d_ahead[0].ptr,    b.d_ahead[1].ptr,   b.d_table[0].ptr,
+                              b.d_table[1].ptr,    b.d_pair_partials.ptr, b.d_r_partials.ptr, b.d_g_partials.ptr, b.d_e_partials.ptr,
+                              b.d_result.ptr,      b.d_kq.ptr,          b.d_tail_ticket.ptr, r.d_run.ptr,        r.d_back.ptr,
+                              other.d_back.ptr,    sl.aks.ptr,          sl.unit_info.ptr,    sl.unit_map.ptr,    sl.unit_sa.ptr,
+                              sl.unit_steps.ptr,   sl.sched_first.ptr,  sl.sched_units.ptr,  sl.item_units.ptr,  sl.item_base.ptr,
+                              b.d_pair_fix.ptr,    b.d_pair_redo.ptr};
+    mix(pointers, sizeof(pointers));
+    value(sl.n_units);
+    value(sl.n_items);
+    value(sl.n_sched_blocks);
+    value(c->n_slots);
+    value(c->n_sm);
+    value(c->pair_cut2);
+    value(screeningCutoff(c, 0));
+    value(b.parity);
+    value(steps);
+    value(r.stride);
+    value(r.with_ewald);
+    value(r.h_run.ptr->header.cancellation_limit);
+    return h;
+}
+
+/**
+ * The windows of a run as ONE graph launch. A run is 4 kernels per window on two streams (fork / join events), 8
+ * windows at S1: between dependent kernels the stream scheduler leaves ≈ 3.7 µs (11 µs per 76 µs window). The same
+ * sequence — same buffers, same parity, same number of windows — comes up again and again, so the second time it is
+ * captured (the first time went through plain launches: allocations and function attributes are settled) and from
+ * then on replayed. Everything the kernels read that changes from run to run lives in device memory. Returns false
+ * when the plain path has to run (first sight, cell list, pair sums ahead, a run continued after the host looked).
+ */
+bool launchRunGraph(fb_ctx* c, fb_ctx::Batch::RunSlot& r, int steps, bool continuation)
+{
+    auto& b = c->batch;
+    static const bool switched_off = std::getenv("FAUNUS_B200_NO_GRAPHS") != nullptr; // experiments: plain launches
+    if (switched_off || !b.run_graphs_enabled || continuation || steps < 1 || r.h_run.ptr->header.prepair != 0 || r.with_ewald == 0) {
+        return false;
+    }
+    CellGrid grid{};
+    if (cellGridFor(c, grid)) {
+        return false;
+    }
+    auto& entry = b.run_graphs[runGraphSignature(c, r, steps)];
+    if (entry.exec == nullptr) {
+        if (entry.seen++ == 0) {
+            return false;
+        }
+        const long launches_before = c->launches;
+        CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+        cudaGraph_t graph = nullptr;
+        try {
+            for (int s = 0; s < steps; ++s) {
+                launchRunStep(c, r, false, false);
+            }
+        }
+        catch (...) {
+            cudaStreamEndCapture(c->stream, &graph);
+            if (graph) {
+                cudaGraphDestroy(graph);
+            }
+            throw;
+        }
+        CUDA_CHECK(cudaStreamEndCapture(c->stream, &graph));
+        CUDA_CHECK(cudaGraphInstantiate(&entry.exec, graph, 0));
+        CUDA_CHECK(cudaGraphDestroy(graph));
+        entry.launches = c->launches - launches_before;
+        CUDA_CHECK(cudaGraphLaunch(entry.exec, c->stream)); // the capture pass already advanced the host-side state
+        b.run_graph_replays += 1;
+        return true;
+    }
+    CUDA_CHECK(cudaGraphLaunch(entry.exec, c->stream));
+    // what launchRunStep / launchWindow leave behind on the host
+    b.parity ^= (steps & 1);
+    b.cells_used = false;
+    b.last_rec_fresh = r.with_ewald != 0;
+    r.steps_launched += steps;
+    r.last_parity = b.parity;
+    c->launches += entry.launches;
+    b.run_graph_replays += 1;
+    return true;
+}
+
 /** queue `steps` windows of the run and the read-back of where it stands */
 void launchRunSteps(fb_ctx* c, fb_ctx::Batch::RunSlot& r, int steps, bool continuation)
 {
@@ -666,8 +772,10 @@ void launchRunSteps(fb_ctx* c, fb_ctx::Batch::RunSlot& r, int steps, bool contin
     }
     else {
         CUDA_CHECK(cudaEventRecord(r.ev_begin, c->stream));
-        for (int s = 0; s < steps; ++s) {
-            launchRunStep(c, r, false, continuation && s == 0);
+        if (!launchRunGraph(c, r, steps, continuation)) {
+            for (int s = 0; s < steps; ++s) {
+                launchRunStep(c, r, false, continuation && s == 0);
+            }
         }
         CUDA_CHECK(cudaEventRecord(r.ev_end, c->stream));
     }
@@ -1071,7 +1179,8 @@ FB_API int fb_configure_runs(fb_ctx* c, int pair_sums_ahead)
     if (!c) {
         return FB_ERR_INVALID;
     }
-    c->batch.prepair = pair_sums_ahead != 0;
+    c->batch.prepair = (pair_sums_ahead & 1) != 0;
+    c->batch.run_graphs_enabled = (pair_sums_ahead & 2) == 0;
     return FB_OK;
 }
 

@@ -32,8 +32,15 @@ namespace fbdev {
 
 constexpr int kUnitSlots = 32;    //!< k-slots of a unit: ks = 8·i + 4·jj + l
 constexpr int kUnitEntries = 10;  //!< phase-table entries per position: X0..3, Y0..1, Z0..3
-constexpr int kKsThreads = 256;
-constexpr int kKsWarps = kKsThreads / 32;
+constexpr int kKsGroupThreads = 256;           //!< one work group: 64 moves × 4 x-indices
+#ifndef FB_KS_GROUPS
+#define FB_KS_GROUPS 1
+#endif
+constexpr int kKsGroups = FB_KS_GROUPS;        //!< 1: two blocks per SM; 2: one block of two groups per SM whose sums are added
+                                               //!< before they leave (half the partial rows; measured: k-space kernel
+                                               //!< +1.4 µs, tail −0.9 µs per window at S1 — kept as a switch, off)
+constexpr int kKsThreads = kKsGroups * kKsGroupThreads;
+constexpr int kKsWarps = kKsGroupThreads / 32; //!< warps of a group
 
 /** skewed slot index: the four x-indices of a warp land in different bank groups */
 __device__ __forceinline__ int unitSlotIndex(int i, int s) { return 9 * i + s; }
@@ -268,23 +275,29 @@ struct KspaceSmem
  * @param r_partials [grid][stride]   2 Σ_k A_k Re(conj(Q_k) δ_m,k) + Σ_k A_k |δ_m,k|² over the block's units
  * @param g_partials [grid][stride²]  entries [a][m], a < m: Σ_k A_k Re(conj(δ_a,k) δ_m,k)
  */
-__global__ void __launch_bounds__(kKsThreads, 2)
+__global__ void __launch_bounds__(kKsThreads, 2 / kKsGroups)
     windowKspaceKernel(const int4* __restrict__ unit_info, const double* __restrict__ unit_sa, const double2* __restrict__ kq,
-                       int n_units, BatchBuffers cur, PhaseGeometry geo, int stride, double* __restrict__ r_partials,
-                       double* __restrict__ g_partials)
+                       const unsigned char* __restrict__ unit_steps, const int* __restrict__ sched_first,
+                       const int* __restrict__ sched_units, int n_sched_blocks, BatchBuffers cur, PhaseGeometry geo, int stride,
+                       double* __restrict__ r_partials, double* __restrict__ g_partials)
 {
     extern __shared__ __align__(16) unsigned char ks_smem_raw[];
-    KspaceSmem& sm = *reinterpret_cast<KspaceSmem*>(ks_smem_raw);
+    // Two independent work groups of 256 threads per block (named barriers, own shared memory), each with its own
+    // list of units — "virtual block" 2·blockIdx + group of the schedule. Their sums are added (group 0 + group 1) before
+    // they leave the block: one row of partials per SM instead of two, half the bytes the tail kernel reads back.
+    const int group = kKsGroups == 1 ? 0 : threadIdx.x >> 8;
+    KspaceSmem& sm = reinterpret_cast<KspaceSmem*>(ks_smem_raw)[group];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x & (kKsGroupThreads - 1);
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int block = blockIdx.x;
-    const int grid = gridDim.x;
+    const int block = kKsGroups * blockIdx.x + group;
     const int n = cur.in->n;
     const int n_active_warps = (n + 7) >> 3;
     const bool warp_active = warp < n_active_warps;
-    const int my_units = (n_units - block + grid - 1) / grid;
+    const bool block_active = block < n_sched_blocks;
+    const int my_first = block_active ? __ldg(sched_first + block) : 0; // the units of this group: a static, cost-balanced schedule
+    const int my_units = block_active ? __ldg(sched_first + block + 1) - my_first : 0;
     KspaceWarpStage& st = sm.stage[warp];
 
     // this thread's move and x-index (the x entries of the tables carry the charges)
@@ -306,8 +319,14 @@ __global__ void __launch_bounds__(kKsThreads, 2)
     const unsigned st_dst = static_cast<unsigned>(__cvta_generic_to_shared(&st.tab[0][0][st_t]));
     const unsigned st_kq = static_cast<unsigned>(__cvta_generic_to_shared(&st.kq[lane + (lane >> 3)]));
     const unsigned st_sa = static_cast<unsigned>(__cvta_generic_to_shared(&st.sa[lane + (lane >> 3)]));
+    unsigned steps_next = 0; // slot columns (jj, l) of the unit being staged that hold a k-vector
+    int u_next = my_units > 0 ? __ldg(sched_units + my_first) : 0; // read one unit ahead: off the staging chain
     auto issue = [&](int c) {
-        const int u = block + c * grid;
+        const int u = u_next;
+        if (c + 1 < my_units) {
+            u_next = __ldg(sched_units + my_first + c + 1);
+        }
+        steps_next = __ldg(unit_steps + u);
         const int4 info = __ldg(unit_info + u);
         const int first = st_kind == 0 ? info.y : (st_kind == 1 ? info.z : info.w);
         const double2* src = table + st_base + min(first + st_local, st_limit); // beyond the table: slots without k-vector
@@ -354,6 +373,7 @@ __global__ void __launch_bounds__(kKsThreads, 2)
     }
     for (int c = 0; c < my_units; ++c) {
         const int buf = c & 1;
+        const unsigned steps = steps_next; // of unit c (issue(c + 1) below replaces steps_next)
         double dreg[16];
         if (warp_active) {
             cpAsyncWaitAll();
@@ -404,14 +424,43 @@ __global__ void __launch_bounds__(kKsThreads, 2)
                 sm.frag[buf][warp][s][lane] = make_double2(dreg[2 * s], dreg[2 * s + 1]);
             }
         }
-        // the fragments of unit c of all warps are in place; every warp is through with the Gram update of unit
-        // c − 1, so the other fragment buffer may be overwritten after this barrier
-        __syncthreads();
+        // the fragments of unit c of all warps of the GROUP are in place; every warp is through with the Gram update
+        // of unit c − 1, so the other fragment buffer may be overwritten after this barrier (named: the other group
+        // of the block runs its own units at its own pace)
+        if constexpr (kKsGroups == 1) {
+            __syncthreads();
+        }
+        else {
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kKsGroupThreads) : "memory");
+        }
         if (warp_active) { // ---- Gram update on the FP64 tensor path
             const double2* fr = &sm.frag[buf][0][0][lane];
+#ifndef FB_KS_INTERLEAVE
+#define FB_KS_INTERLEAVE 1
+#endif
+#if FB_KS_INTERLEAVE
+// the re step of every tile, then the im step of every tile: two tensor instructions on the same accumulator are
+// 1 + NP apart instead of back to back (DMMA: 16 cycles between issues of a sub-partition, ≈ 26 until the result)
 #define FB_GRAM(NP)                                                                                        \
     _Pragma("unroll") for (int s = 0; s < 8; ++s)                                                          \
     {                                                                                                      \
+        if (!((steps >> s) & 1u)) { /* block-uniform: no k-vector in this column, every δ is zero */      \
+            continue;                                                                                      \
+        }                                                                                                  \
+        double2 f[NP > 0 ? NP : 1];                                                                        \
+        _Pragma("unroll") for (int d = 0; d < NP; ++d) { f[d] = fr[(partner[d] * 8 + s) * 32]; }           \
+        dmma884(g_diag[0], g_diag[1], dreg[2 * s], dreg[2 * s]);                                           \
+        _Pragma("unroll") for (int d = 0; d < NP; ++d) { dmma884(g_off[d][0], g_off[d][1], dreg[2 * s], f[d].x); }         \
+        dmma884(g_diag[0], g_diag[1], dreg[2 * s + 1], dreg[2 * s + 1]);                                   \
+        _Pragma("unroll") for (int d = 0; d < NP; ++d) { dmma884(g_off[d][0], g_off[d][1], dreg[2 * s + 1], f[d].y); }     \
+    }
+#else
+#define FB_GRAM(NP)                                                                                        \
+    _Pragma("unroll") for (int s = 0; s < 8; ++s)                                                          \
+    {                                                                                                      \
+        if (!((steps >> s) & 1u)) { /* block-uniform: no k-vector in this column, every δ is zero */      \
+            continue;                                                                                      \
+        }                                                                                                  \
         double2 f[NP > 0 ? NP : 1];                                                                        \
         _Pragma("unroll") for (int d = 0; d < NP; ++d) { f[d] = fr[(partner[d] * 8 + s) * 32]; }           \
         dmma884(g_diag[0], g_diag[1], dreg[2 * s], dreg[2 * s]);                                           \
@@ -422,6 +471,7 @@ __global__ void __launch_bounds__(kKsThreads, 2)
             dmma884(g_off[d][0], g_off[d][1], dreg[2 * s + 1], f[d].y);                                    \
         }                                                                                                  \
     }
+#endif
             switch (n_partners) {
             case 4:
                 FB_GRAM(4)
@@ -442,15 +492,41 @@ __global__ void __launch_bounds__(kKsThreads, 2)
         }
     }
 
-    // ---- partial sums of this block
+    // ---- partial sums of this block: group 1 hands its sums over through its (now idle) staging area, group 0 adds
+    // them to its own — always own + other — and stores the row
     const int frag_g = lane >> 2;
     const int frag_t = lane & 3;
-    const size_t row = static_cast<size_t>(block);
-    if (warp_active) {
-        // R[m]: the four x-indices of a move sit in adjacent lanes; the diagonal of G carries Σ A_k |δ|²
-        double rs = racc;
-        rs += __shfl_xor_sync(0xffffffffu, rs, 1);
-        rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+    const size_t row = static_cast<size_t>(blockIdx.x);
+    // R[m]: the four x-indices of a move sit in adjacent lanes; the diagonal of G carries Σ A_k |δ|²
+    double rs = racc;
+    rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+    rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+    static_assert(sizeof(KspaceWarpStage) >= 11 * 32 * sizeof(double), "hand-over area of a warp");
+    double* hand = reinterpret_cast<double*>(&reinterpret_cast<KspaceSmem*>(ks_smem_raw)[kKsGroups - 1].stage[warp]);
+    if (kKsGroups == 2 && group == 1 && warp_active) {
+        hand[0 * 32 + lane] = rs;
+        hand[1 * 32 + lane] = g_diag[0];
+        hand[2 * 32 + lane] = g_diag[1];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            hand[(3 + 2 * d) * 32 + lane] = g_off[d][0];
+            hand[(4 + 2 * d) * 32 + lane] = g_off[d][1];
+        }
+    }
+    if constexpr (kKsGroups == 2) {
+        __syncthreads();
+    }
+    if (group == 0 && warp_active) {
+        if constexpr (kKsGroups == 2) {
+            rs += hand[0 * 32 + lane];
+            g_diag[0] += hand[1 * 32 + lane];
+            g_diag[1] += hand[2 * 32 + lane];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                g_off[d][0] += hand[(3 + 2 * d) * 32 + lane];
+                g_off[d][1] += hand[(4 + 2 * d) * 32 + lane];
+            }
+        }
         if ((frag_g >> 1) == frag_t && move_active) {
             r_partials[row * stride + m] = 2.0 * rs + g_diag[frag_g & 1];
         }

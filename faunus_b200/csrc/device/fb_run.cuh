@@ -575,7 +575,32 @@ __global__ void __launch_bounds__(kFinishThreads)
 {
     extern __shared__ __align__(16) unsigned char run_smem[];
     __shared__ unsigned s_last;
+#ifndef FB_TAIL_ONE_WAVE
+#define FB_TAIL_ONE_WAVE 0
+#endif
     const int k_blocks = kspaceFinishGrid(stride);
+#if FB_TAIL_ONE_WAVE
+    // One wave: a block of 1024 threads at 64 registers owns an SM, and the walk's shared memory is reserved for every
+    // block, so a grid of (column blocks + pair blocks) = 263 ran as two waves on 148 SMs, each paying the full latency
+    // of its loads. The grid is now at most one block per SM; a block takes the column blocks b, b + grid, … and
+    // then the pair outputs of its warps.
+    for (int kb = blockIdx.x; kb < k_blocks; kb += gridDim.x) {
+        kspaceFinishBlock(cur, stride, with_ewald, n_rows, n_e_rows, r_partials, g_partials, e_partials, result, kb);
+        __syncthreads(); // kspaceFinishBlock's staging area is free again
+    }
+    const int n_outputs = 2 * stride + stride * stride;
+    for (int w = static_cast<int>((blockIdx.x * kFinishThreads + threadIdx.x) >> 5); w < n_outputs;
+         w += static_cast<int>(gridDim.x) * (kFinishThreads / 32)) {
+        pairFinishWarp<KIND>(M0, P, cur, stride, n_pair_blocks, pair_partials, 0, nullptr, result, nullptr, nullptr, w);
+    }
+    // the writes of all threads of the block → (barrier) → thread 0 → (fence, cumulative) → device-wide before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+#else
     if (static_cast<int>(blockIdx.x) < k_blocks) {
         kspaceFinishBlock(cur, stride, with_ewald, n_rows, n_e_rows, r_partials, g_partials, e_partials, result, blockIdx.x);
     }
@@ -583,12 +608,24 @@ __global__ void __launch_bounds__(kFinishThreads)
         pairFinishWarp<KIND>(M0, P, cur, stride, n_pair_blocks, pair_partials, 0, nullptr, result, nullptr, nullptr,
                              static_cast<int>(((blockIdx.x - k_blocks) * kFinishThreads + threadIdx.x) >> 5));
     }
+#ifndef FB_TAIL_LIGHT_FENCE
+#define FB_TAIL_LIGHT_FENCE 1
+#endif
+#if FB_TAIL_LIGHT_FENCE
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence(); // cumulative: orders the writes of the whole block (seen through the barrier) before the ticket
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+#else
     __threadfence(); // this thread's part of the result block is visible device-wide before the ticket is drawn
     __syncthreads();
     if (threadIdx.x == 0) {
         s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
     }
+#endif
     __syncthreads();
+#endif
     if (!s_last) {
         return;
     }

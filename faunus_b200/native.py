@@ -133,10 +133,11 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("FAUNUS_B200_LIB", LIB_PATH)  # an experimental build (faunus_b200.build --variant)
+    if path == LIB_PATH and not os.path.exists(LIB_PATH):
         from .build import build
         build()
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp = C.c_void_p
     sig = {
         "fb_create": (C.c_int, [C.POINTER(FbConfig), C.POINTER(vp)]),
