@@ -322,7 +322,9 @@ struct fb_ctx
     // forces (fb_force.cuh)
     DeviceBuffer<double> d_force_knots, d_force_coef; //!< Andrea table of S'(q) (fb_set_force_table)
     int force_nk = 0;
+    DeviceBuffer<double2> q_partials; //!< sharded reciprocal energy: [cells of the slab][particle splits][64] shares of Q(k)
     DeviceBuffer<double> d_forces; //!< [n_slots][3]
+    DeviceBuffer<double> d_force_shares; //!< [j ranges][n_slots][3]
     PinnedBuffer<double> h_forces;
 };
 
@@ -725,7 +727,23 @@ void launchFullQ(fb_ctx* c, int s, int cell_begin, int cell_end, bool store_q, d
                                         static_cast<int>(sizeof(FullQSmem))));
         configured_device = c->device;
     }
-    ewaldFullCellKernel<<<cell_end - cell_begin, kBlock, sizeof(FullQSmem), c->stream>>>(
+    // a slab of few cells (one of several GPUs): also split the particles, so that the slab still fills the machine.
+    // 8192 particles per share whatever the number of GPUs: the same shares, added in the same order, everywhere.
+    constexpr int kSplitSize = 8192;
+    const int n_cells = cell_end - cell_begin;
+    const int n_splits = (c->n_slots + kSplitSize - 1) / kSplitSize;
+    if (!store_q && e_partials != nullptr && n_splits > 1 && n_cells < 4 * c->n_sm) {
+        c->q_partials.ensure(static_cast<size_t>(n_cells) * n_splits * kTileK);
+        ewaldFullCellKernel<<<dim3(n_cells, n_splits), kBlock, sizeof(FullQSmem), c->stream>>>(
+            makeView(c, s), makeEwaldView(c, s), sl.kn.ptr, sl.cell_start.ptr, cell_begin, geo, 0, e_partials, kSplitSize,
+            c->q_partials.ptr);
+        launched(c, "ewaldFullCellKernel");
+        ewaldCellEnergyKernel<<<n_cells, kTileK, 0, c->stream>>>(makeEwaldView(c, s), sl.cell_start.ptr, cell_begin, n_splits,
+                                                                c->q_partials.ptr, e_partials);
+        launched(c, "ewaldCellEnergyKernel");
+        return;
+    }
+    ewaldFullCellKernel<<<n_cells, kBlock, sizeof(FullQSmem), c->stream>>>(
         makeView(c, s), makeEwaldView(c, s), sl.kn.ptr, sl.cell_start.ptr, cell_begin, geo, store_q ? 1 : 0, e_partials);
     launched(c, "ewaldFullCellKernel");
 }
@@ -1674,13 +1692,17 @@ FB_API int fb_nonbonded_force(fb_ctx* c, int s, double* forces)
         c->h_forces.ensure(3 * static_cast<size_t>(n));
         const SlotView V = makeView(c, s);
         ForceTable T{c->force_nk, c->d_force_knots.ptr, c->d_force_coef.ptr};
-        const int grid = (n + kForceBlock - 1) / kForceBlock;
+        constexpr int kForceChunk = 2048; // particles j per share: a constant, so the sums do not depend on the grid
+        const int n_ranges = (n + kForceChunk - 1) / kForceChunk;
+        c->d_force_shares.ensure(3 * static_cast<size_t>(n) * n_ranges);
+        const dim3 grid((n + kForceBlock - 1) / kForceBlock, n_ranges);
         if (c->P.kind == POT_COULOMB_LJ) {
-            nonbondedForceKernel<POT_COULOMB_LJ><<<grid, kForceBlock, 0, c->stream>>>(V, c->P, T, c->d_forces.ptr);
+            nonbondedForceKernel<POT_COULOMB_LJ><<<grid, kForceBlock, 0, c->stream>>>(V, c->P, T, kForceChunk, c->d_force_shares.ptr);
         }
         else {
-            nonbondedForceKernel<POT_COULOMB_WCA><<<grid, kForceBlock, 0, c->stream>>>(V, c->P, T, c->d_forces.ptr);
+            nonbondedForceKernel<POT_COULOMB_WCA><<<grid, kForceBlock, 0, c->stream>>>(V, c->P, T, kForceChunk, c->d_force_shares.ptr);
         }
+        forceSumKernel<<<(3 * n + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->d_force_shares.ptr, 3 * n, n_ranges, c->d_forces.ptr);
         launched(c, "nonbondedForceKernel");
         CUDA_CHECK(cudaMemcpyAsync(c->h_forces.ptr, c->d_forces.ptr, 3 * static_cast<size_t>(n) * sizeof(double),
                                    cudaMemcpyDeviceToHost, c->stream));

@@ -14,9 +14,10 @@
 //     −4π lB / V — whatever the terms before it left in the vector is overwritten, and the surface term is there for
 //     any `epss` (no tinfoil test). Reproduced.
 //
-// A thread owns particle i and adds the forces of all j ≠ i in index order: F_i = Σ_j f(i, j). The reference adds
-// f(i, j) to i and subtracts it from j for i < j; vdist and the force laws are odd in the distance vector, so the two
-// differ by the order of the sums only.
+// A thread owns particle i and adds the forces of the j ≠ i of a fixed range of 2048 particles in index order; the
+// shares of the ranges are added in range order: F_i = Σ_j f(i, j). The reference adds f(i, j) to i and subtracts it
+// from j for i < j; vdist and the force laws are odd in the distance vector, so the two differ by the order of the
+// sums only.
 #pragma once
 #include "fb_kernels.cuh"
 
@@ -90,11 +91,14 @@ __device__ __forceinline__ double wcaForceFactor(const double* s2, const double*
 }
 
 /**
- * F_i = Σ_{j ≠ i} f(i, j) over every particle slot. grid = ⌈n/128⌉, thread ↔ i, the j run through shared memory in
- * tiles of 128 (index order, so the sum of a thread does not depend on the grid).
+ * F_i = Σ_{j ≠ i} f(i, j) over every particle slot. grid = ⌈n/128⌉ × j-ranges, thread ↔ i; the j of the block's range
+ * [y·j_chunk, (y+1)·j_chunk) run through shared memory in tiles of 128, in index order; the share of the range goes to
+ * out[y][i][3] and forceSumKernel adds the shares in range order. The chunk is a constant of the caller, so the sums do not
+ * depend on the grid. (One range only — 157 blocks of 4 warps at N = 20 000 — left 93 % of the warp slots empty.)
  */
 template <int KIND>
-__global__ void __launch_bounds__(kForceBlock) nonbondedForceKernel(SlotView V, PotParams P, ForceTable T, double* __restrict__ out)
+__global__ void __launch_bounds__(kForceBlock)
+    nonbondedForceKernel(SlotView V, PotParams P, ForceTable T, int j_chunk, double* __restrict__ out)
 {
     static_assert(KIND == POT_COULOMB_LJ || KIND == POT_COULOMB_WCA, "the reference has forces for these two only");
     __shared__ double4 s_pos[kForceBlock];
@@ -103,16 +107,18 @@ __global__ void __launch_bounds__(kForceBlock) nonbondedForceKernel(SlotView V, 
     const bool mine = i < V.n_slots;
     const double4 a = mine ? V.posq[i] : make_double4(0.0, 0.0, 0.0, 0.0);
     const int ida = mine ? V.atom_id[i] : 0;
+    const int j_begin = static_cast<int>(blockIdx.y) * j_chunk;
+    const int j_end = min(V.n_slots, j_begin + j_chunk);
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    for (int j0 = 0; j0 < V.n_slots; j0 += kForceBlock) {
+    for (int j0 = j_begin; j0 < j_end; j0 += kForceBlock) {
         const int j = j0 + threadIdx.x;
         __syncthreads();
-        if (j < V.n_slots) {
+        if (j < j_end) {
             s_pos[threadIdx.x] = V.posq[j];
             s_id[threadIdx.x] = V.atom_id[j];
         }
         __syncthreads();
-        const int count = min(kForceBlock, V.n_slots - j0);
+        const int count = min(kForceBlock, j_end - j0);
         if (!mine) {
             continue;
         }
@@ -139,9 +145,23 @@ __global__ void __launch_bounds__(kForceBlock) nonbondedForceKernel(SlotView V, 
         }
     }
     if (mine) {
-        out[3 * i] = fx;
-        out[3 * i + 1] = fy;
-        out[3 * i + 2] = fz;
+        double* share = out + 3 * (static_cast<size_t>(blockIdx.y) * V.n_slots + i);
+        share[0] = fx;
+        share[1] = fy;
+        share[2] = fz;
+    }
+}
+
+/** out[t] = Σ_y shares[y][t] in range order, t over the 3n force components */
+__global__ void __launch_bounds__(kBlock) forceSumKernel(const double* __restrict__ shares, int n3, int n_ranges, double* __restrict__ out)
+{
+    const int t = blockIdx.x * kBlock + threadIdx.x;
+    if (t < n3) {
+        double s = 0.0;
+        for (int y = 0; y < n_ranges; ++y) {
+            s += shares[static_cast<size_t>(y) * n3 + t];
+        }
+        out[t] = s;
     }
 }
 

@@ -622,8 +622,14 @@ struct FullQSmem
 
 __global__ void __launch_bounds__(kBlock, 2)
     ewaldFullCellKernel(SlotView V, EwaldView E, const int4* __restrict__ kn, const int* __restrict__ cell_start,
-                        int cell_begin, PhaseGeometry geo, int store_q, double* __restrict__ e_partials)
+                        int cell_begin, PhaseGeometry geo, int store_q, double* __restrict__ e_partials, int split_size = 0,
+                        double2* __restrict__ q_partials = nullptr)
 {
+    // split_size > 0 (a slab of few cells on one of several GPUs): blockIdx.y takes the particles
+    // [y·split_size, (y+1)·split_size) and leaves its share of Q(k) in q_partials[cell][y][64]; ewaldCellEnergyKernel adds
+    // the shares in y order. The split size is a constant of the caller: the sums do not depend on the number of GPUs.
+    const int j_begin = split_size > 0 ? static_cast<int>(blockIdx.y) * split_size : 0;
+    const int j_end = split_size > 0 ? min(V.n_slots, j_begin + split_size) : V.n_slots;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FullQSmem& sm = *reinterpret_cast<FullQSmem*>(smem_raw);
     const int cell = cell_begin + blockIdx.x;
@@ -648,13 +654,13 @@ __global__ void __launch_bounds__(kBlock, 2)
     const int ixy = li * 4 + lj;
     double qre = 0.0, qim = 0.0;
 
-    for (int c0 = 0; c0 < V.n_slots; c0 += kFullQChunk) {
+    for (int c0 = j_begin; c0 < j_end; c0 += kFullQChunk) {
         __syncthreads(); // previous chunk consumed
         {
             const int j = c0 + threadIdx.x;
             double4 p = make_double4(0, 0, 0, 0);
             bool active = false;
-            if (j < V.n_slots) {
+            if (j < j_end) {
                 p = V.posq[j];
                 active = V.gid[j] >= 0;
             }
@@ -685,7 +691,7 @@ __global__ void __launch_bounds__(kBlock, 2)
         }
         __syncthreads();
         if (kvalid) {
-            const int n = min(kFullQChunk, V.n_slots - c0);
+            const int n = min(kFullQChunk, j_end - c0);
 #pragma unroll 4
             for (int t = quarter; t < n; t += 4) {
                 const double2 ph = cmul(sm.exy[t][ixy], sm.ez[t][ll]);
@@ -708,10 +714,13 @@ __global__ void __launch_bounds__(kBlock, 2)
         if (store_q) {
             E.Q[p0 + kl] = Q;
         }
+        if (q_partials != nullptr) {
+            q_partials[(static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * kTileK + kl] = Q;
+        }
         e = E.kA[p0 + kl].w * (Q.x * Q.x + Q.y * Q.y);
     }
     __syncthreads();
-    if (e_partials != nullptr) {
+    if (e_partials != nullptr && q_partials == nullptr) {
         __shared__ double s_e[2];
         if (threadIdx.x < 64) {
             const double s = warpSum(e);
@@ -723,6 +732,36 @@ __global__ void __launch_bounds__(kBlock, 2)
         if (threadIdx.x == 0) {
             e_partials[blockIdx.x] = s_e[0] + s_e[1];
         }
+    }
+}
+
+/** Σ_k A_k |Σ_y Q_y(k)|² of one k-cell from the particle-range shares ewaldFullCellKernel left (y order) */
+__global__ void __launch_bounds__(kTileK)
+    ewaldCellEnergyKernel(EwaldView E, const int* __restrict__ cell_start, int cell_begin, int n_splits,
+                          const double2* __restrict__ q_partials, double* __restrict__ e_partials)
+{
+    __shared__ double s_e[kTileK / 32];
+    const int cell = cell_begin + blockIdx.x;
+    const int p0 = cell_start[cell];
+    const int len = cell_start[cell + 1] - p0;
+    const int kl = threadIdx.x;
+    double e = 0.0;
+    if (kl < len) {
+        double2 Q = make_double2(0.0, 0.0);
+        for (int y = 0; y < n_splits; ++y) {
+            const double2 q = q_partials[(static_cast<size_t>(blockIdx.x) * n_splits + y) * kTileK + kl];
+            Q.x += q.x;
+            Q.y += q.y;
+        }
+        e = E.kA[p0 + kl].w * (Q.x * Q.x + Q.y * Q.y);
+    }
+    const double s = warpSum(e);
+    if ((threadIdx.x & 31) == 0) {
+        s_e[threadIdx.x >> 5] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        e_partials[blockIdx.x] = s_e[0] + s_e[1];
     }
 }
 

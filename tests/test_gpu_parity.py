@@ -544,6 +544,23 @@ def test_system_energy_shards_add_up():
     assert abs(g.system_energy_shard(1, 3)[0]) > 0
 
 
+def test_system_energy_shards_with_particle_splits():
+    """a slab of few k-cells also splits the particles (shares of 8192, ewaldFullCellKernel + ewaldCellEnergyKernel):
+    N = 20 000 over 1, 2 and 8 'GPUs' against the oracle"""
+    cfg = small_electrolyte(n=20000, coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 9})
+    from _oraclelib import oracle_lib
+    oracle_lib().fo_set_parallel_ewald_init(1)
+    try:
+        o, g = pair_of_sims(cfg)
+        _, terms = o.system_energy()
+    finally:
+        oracle_lib().fo_set_parallel_ewald_init(0)
+    for size in (1, 2, 8):
+        parts = np.array([g.system_energy_shard(r, size) for r in range(size)])
+        assert_close([parts[:, 0].sum()], [terms[1]], scale=np.abs(terms).max())
+        assert_close([parts[:, 1].sum()], [terms[2]], scale=np.abs(terms).max())
+
+
 def test_widom_sharded_matches_unsharded():
     """Widom insertions split over two 'ranks' (two contexts on this GPU) == the unsharded batched run"""
     import ctypes as C
