@@ -306,10 +306,11 @@ struct fb_ctx
         bool force_brute = false;
         double rec_sum = 0;
         PhaseGeometry geo{};
-        cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; //!< [5]: between the front and the k-space kernel
         cudaStream_t pair_stream = nullptr; //!< the pair kernel runs beside the k-space kernels
         cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
         double acc_ms[3] = {0, 0, 0}; //!< pair, ewald, other (commit + phase + finish)
+        double acc_front_ms = 0;      //!< the windowFrontKernel part of acc_ms[1]
         double acc_total_ms = 0;      //!< first to last kernel of every window (all modes)
         double windows = 0, moves = 0;
     } batch;

@@ -272,6 +272,9 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
             E, sl.aks.ptr, sl.unit_info.ptr, sl.unit_map.ptr, sl.item_units.ptr, sl.item_base.ptr, n_phase_blocks, cur,
             prev, b.geo, b.d_kq.ptr, b.d_e_partials.ptr);
         launched(c, "windowFrontKernel");
+        if (timing) {
+            CUDA_CHECK(cudaEventRecord(b.ev[5], c->stream));
+        }
         if (!b.kspace_unit_configured) {
             CUDA_CHECK(cudaFuncSetAttribute(windowKspaceKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(kKsGroups * sizeof(KspaceSmem))));
@@ -381,6 +384,15 @@ void accumulateWindowTiming(fb_ctx* c, bool timing, cudaEvent_t begin = nullptr,
         b.acc_ms[0] += t12;
         b.acc_ms[1] += t23;
         b.acc_ms[2] += t01 + t34;
+        if (b.last_rec_fresh && cudaEventQuery(b.ev[5]) == cudaSuccess) { // a window with a k-space part
+            float t25 = 0;
+            if (cudaEventElapsedTime(&t25, b.ev[2], b.ev[5]) == cudaSuccess && t25 >= 0 && t25 <= t23) {
+                b.acc_front_ms += t25;
+            }
+            else {
+                cudaGetLastError();
+            }
+        }
     }
 }
 
@@ -1193,6 +1205,16 @@ FB_API int fb_get_run_stats(const fb_ctx* c, double out[4])
     out[1] = c->batch.run_steps;
     out[2] = c->batch.run_rounds;
     out[3] = c->batch.run_moves;
+    return FB_OK;
+}
+
+FB_API int fb_get_kspace_timing(const fb_ctx* c, double out[2])
+{
+    if (!c || !out) {
+        return FB_ERR_INVALID;
+    }
+    out[0] = c->batch.acc_front_ms;
+    out[1] = c->batch.acc_ms[1] - c->batch.acc_front_ms;
     return FB_OK;
 }
 

@@ -563,8 +563,11 @@ __global__ void __launch_bounds__(kDecideThreads)
  * The tail of a window of a run in ONE launch: the sums of windowFinishKernel and, by whichever block finishes last
  * (ticket), the walk and the set-up of the next window. The result block stays in L2 between the two.
  */
+#ifndef FB_TAIL_BLOCKS_PER_SM
+#define FB_TAIL_BLOCKS_PER_SM 1
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(kFinishThreads)
+__global__ void __launch_bounds__(kFinishThreads, FB_TAIL_BLOCKS_PER_SM)
     windowTailKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, int with_ewald, int n_rows, int n_e_rows,
                      const double* __restrict__ r_partials, const double* __restrict__ g_partials,
                      const double* __restrict__ e_partials, int n_pair_blocks, const double* __restrict__ pair_partials,

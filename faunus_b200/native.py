@@ -115,7 +115,7 @@ class FbConfig(C.Structure):
 C_ABI_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_last_error", "fb_device_count", "fb_upload_space", "fb_update_group",
     "fb_set_box", "fb_sync", "fb_download_space", "fb_nonbonded_energy", "fb_nonbonded_delta",
-    "fb_system_energy_shard", "fb_particle_pair_energy", "fb_group_group_energy", "fb_set_force_table", "fb_nonbonded_force", "fb_ewald_force", "fb_atom_rdf", "fb_molecule_rdf", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_submit_groups", "fb_batch_wait", "fb_run_submit", "fb_run_wait", "fb_configure_runs", "fb_get_run_stats", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing",
+    "fb_system_energy_shard", "fb_particle_pair_energy", "fb_group_group_energy", "fb_set_force_table", "fb_nonbonded_force", "fb_ewald_force", "fb_atom_rdf", "fb_molecule_rdf", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_submit_groups", "fb_batch_wait", "fb_run_submit", "fb_run_wait", "fb_configure_runs", "fb_get_run_stats", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing", "fb_get_kspace_timing",
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
     "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
     "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_upload_groups",
@@ -167,6 +167,7 @@ def load() -> C.CDLL:
         "fb_run_wait": (C.c_int, [vp, C.POINTER(FbRunResult)]),
         "fb_get_run_stats": (C.c_int, [vp, c_double_p]),
         "fb_configure_runs": (C.c_int, [vp, C.c_int]),
+        "fb_get_kspace_timing": (C.c_int, [vp, c_double_p]),
         "fb_batch_wait": (C.c_int, [vp, C.POINTER(FbBatchResult)]),
         "fb_batch_commit": (C.c_int, [vp, C.c_int, c_ubyte_p]),
         "fb_configure_cells": (C.c_int, [vp, C.c_int]),
@@ -288,6 +289,12 @@ class B200Simulation(Simulation):
         return {"pair_ms": out[0], "ewald_ms": out[1], "other_ms": out[2], "windows": int(out[3]),
                 "moves": int(out[4]), "total_ms": out[5], "host_evaluate_ms": out[6], "host_sweep_ms": out[7],
                 "round_trips": int(out[8]), "runs": int(out[9])}
+
+    def kspace_time_ms(self) -> dict:
+        """timing enabled: the k-space share of window_time_ms split into the front and the persistent kernel"""
+        out = np.zeros(2)
+        self._check(load().fb_get_kspace_timing(self.ctx, out.ctypes.data_as(c_double_p)), "fb_get_kspace_timing")
+        return {"front_ms": out[0], "kspace_ms": out[1]}
 
     def configure_runs(self, pair_sums_ahead: bool):
         """Runs: evaluate the pair sums of a window one window ahead (default on)."""

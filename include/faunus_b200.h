@@ -397,6 +397,9 @@ int fb_debug_set_cell_capacity(fb_ctx* ctx, int capacity);
  * out[5] = ms from the first to the last kernel of every window (always accumulated), out[6] = host round trips
  * (fb_batch_wait + fb_run_wait), out[7] = runs */
 int fb_get_batch_timing(const fb_ctx* ctx, double out[8]);
+/* timing enabled: the k-space share out[1] of fb_get_batch_timing split into out[0] = ms in windowFrontKernel (phase
+ * tables, commit of the previous window) and out[1] = ms in windowKspaceKernel */
+int fb_get_kspace_timing(const fb_ctx* ctx, double out[2]);
 
 /* ---- pair distance histogram ------------------------------------------------------------------ */
 /* One sample of AtomRDF (src/analysis.cpp:1556-1600) on the slot's mirror: all pairs of active atoms of the types
