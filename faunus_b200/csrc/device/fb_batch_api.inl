@@ -718,7 +718,7 @@ unsigned long long runGraphSignature(fb_ctx* c, const fb_ctx::Batch::RunSlot& r,
  * then on replayed. Everything the kernels read that changes from run to run lives in device memory. Returns false
  * when the plain path has to run (first sight, cell list, pair sums ahead, a run continued after the host looked).
  */
-bool launchRunGraph(fb_ctx* c, fb_ctx::Batch::RunSlot& r, int steps, bool continuation)
+bool launchRunGraph(fb_ctx* c, fb_ctx::Batch::RunSlot& r, int steps, bool continuation, int min_seen = 1)
 {
     auto& b = c->batch;
     static const bool switched_off = std::getenv("FAUNUS_B200_NO_GRAPHS") != nullptr; // experiments: plain launches
@@ -731,7 +731,7 @@ bool launchRunGraph(fb_ctx* c, fb_ctx::Batch::RunSlot& r, int steps, bool contin
     }
     auto& entry = b.run_graphs[runGraphSignature(c, r, steps)];
     if (entry.exec == nullptr) {
-        if (entry.seen++ == 0) {
+        if (entry.seen++ < min_seen) {
             return false;
         }
         const long launches_before = c->launches;
@@ -784,9 +784,17 @@ void launchRunSteps(fb_ctx* c, fb_ctx::Batch::RunSlot& r, int steps, bool contin
     }
     else {
         CUDA_CHECK(cudaEventRecord(r.ev_begin, c->stream));
-        if (!launchRunGraph(c, r, steps, continuation)) {
+        // Two granularities. One graph per WINDOW: four keys (run slot × buffer parity), all captured within the first few
+        // runs. One graph per RUN: a few µs better per window (measured 8.7–8.9e5 against 8.46e5 moves/s at S1), but the
+        // number of windows of a run varies (7 … 11 at S1) and every capture + instantiation costs ≈ 3 ms — so a run's
+        // sequence is only captured once it has come up kRunGraphMinSeen times; the rare ones go window by window.
+        constexpr int kRunGraphMinSeen = 4;
+        if (steps < 2 || !launchRunGraph(c, r, steps, continuation, kRunGraphMinSeen)) {
             for (int s = 0; s < steps; ++s) {
-                launchRunStep(c, r, false, continuation && s == 0);
+                const bool setup = continuation && s == 0;
+                if (!launchRunGraph(c, r, 1, setup)) {
+                    launchRunStep(c, r, false, setup);
+                }
             }
         }
         CUDA_CHECK(cudaEventRecord(r.ev_end, c->stream));

@@ -6,7 +6,7 @@ timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py
 tail -3 gpurun_out/r_pytest.log
 for v in default "$@"; do
     if [ "$v" = default ]; then unset FAUNUS_B200_LIB; else export FAUNUS_B200_LIB=$PWD/faunus_b200/_build/variants/$v/libfaunus_b200.so; fi
-    for rep in 1 2; do
+    for rep in 1 2 3; do
         python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r_bench_${v}_${rep}.log 2>&1
         python - "$v" gpurun_out/r_bench_${v}_${rep}.log <<'PY'
 import json, sys
