@@ -1070,6 +1070,26 @@ __device__ __forceinline__ void pairFinishWarp(const SlotView& M0, const PotPara
     }
 }
 
+#ifndef FB_CROSS_EARLY
+#define FB_CROSS_EARLY 0
+#endif
+/**
+ * The cross terms of a window (S² entries, four pair energies each) need nothing but the window's own trial and old
+ * positions — not the pair sums, not the mirror. In runs they are taken at the START of the window on the pair stream,
+ * beside the front kernel, instead of by 128 more blocks of the tail kernel behind the k-space kernel: the tail is left
+ * with 131 + 4 blocks, one wave (it was 263 blocks of 1024 threads on 148 SMs). MEASURED AND SWITCHED OFF (FB_CROSS_EARLY 0):
+ * 8.71e5 against 8.98e5 moves/s at S1 — the extra kernel competes with the front kernel, which is on the critical path,
+ * for the start of the window, and the tail's second wave was not what bounds it.
+ */
+template <int KIND>
+__global__ void __launch_bounds__(kBlock) windowCrossKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, double* __restrict__ result)
+{
+    const int task = static_cast<int>((blockIdx.x * kBlock + threadIdx.x) >> 5);
+    if (task < stride * stride) {
+        pairFinishWarp<KIND>(M0, P, cur, stride, 0, nullptr, 0, nullptr, result, nullptr, nullptr, 2 * stride + task);
+    }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kBlock)
     batchPairFinishKernel(SlotView M0, PotParams P, BatchBuffers cur, int stride, int n_pair_blocks,

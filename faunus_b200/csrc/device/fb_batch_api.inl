@@ -209,6 +209,11 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
                 launched(c, "batchPairFixKernel");
             }
             const int apply_commit = (lean && have_commit) ? 1 : 0;
+            if (FB_CROSS_EARLY && lean && tail != nullptr && !timing) { // runs: the cross terms first, beside the front kernel
+                windowCrossKernel<KIND><<<(stride * stride * 32 + kBlock - 1) / kBlock, kBlock, 0, ps>>>(M0, c->P, cur, stride,
+                                                                                                  b.d_result.ptr);
+                launched(c, "windowCrossKernel");
+            }
             if (screened) { // finite cutoff: FP32 screening, FP64 evaluation of the candidates
                 batchPairScreenKernel<KIND><<<pair_grid, kPairThreads, 0, ps>>>(M0, c->P, cur, c->pair_cut2, cut2_screen, stride,
                                                                                b.d_pair_partials.ptr, makeView(c, 1), prev,
@@ -303,15 +308,19 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
                 b.d_tail_ticket.ensure(1);
                 CUDA_CHECK(cudaMemsetAsync(b.d_tail_ticket.ptr, 0, sizeof(unsigned), c->stream));
             }
+            const int cross_done = (FB_CROSS_EARLY && !timing) ? 1 : 0; // (timing: the kernels of a window are serialised and
+                                                                        // attributed to pair / k-space / other as before)
+            const int tail_pair_blocks = cross_done ? (2 * stride + kFinishThreads / 32 - 1) / (kFinishThreads / 32)
+                                                    : pairFinishBlocks(stride);
 #if FB_TAIL_ONE_WAVE
-            const int tail_grid = std::min(c->n_sm, kspaceFinishGrid(stride) + pairFinishBlocks(stride));
+            const int tail_grid = std::min(c->n_sm, kspaceFinishGrid(stride) + tail_pair_blocks);
 #else
-            const int tail_grid = kspaceFinishGrid(stride) + pairFinishBlocks(stride);
+            const int tail_grid = kspaceFinishGrid(stride) + tail_pair_blocks;
 #endif
             windowTailKernel<KIND><<<tail_grid, kFinishThreads, runDecideSmemBytes(stride), c->stream>>>(
                 M0, c->P, cur, stride, with_ewald ? 1 : 0, n_rows, n_e_rows, b.d_r_partials.ptr, b.d_g_partials.ptr,
                 b.d_e_partials.ptr, n_pair_blocks, b.d_pair_partials.ptr, b.d_result.ptr, b.d_tail_ticket.ptr, tail->hdr,
-                tail->moves, tail->st, tail->next, tail->out, tail->prev_out, tail->predicted, tail->ahead);
+                tail->moves, tail->st, tail->next, tail->out, tail->prev_out, tail->predicted, tail->ahead, cross_done);
             launched(c, "windowTailKernel");
             if (walked) {
                 *walked = true;

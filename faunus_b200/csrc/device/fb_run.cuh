@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(kFinishThreads, FB_TAIL_BLOCKS_PER_SM)
                      double* __restrict__ result, unsigned* __restrict__ ticket, const RunHeader* __restrict__ hdr,
                      const RunMove* __restrict__ moves, RunState* __restrict__ st, BatchInput* __restrict__ next,
                      RunOutput* __restrict__ out, const RunOutput* __restrict__ prev_out, const BatchInput* predicted,
-                     BatchInput* __restrict__ ahead)
+                     BatchInput* __restrict__ ahead, int cross_done)
 {
     extern __shared__ __align__(16) unsigned char run_smem[];
     __shared__ unsigned s_last;
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(kFinishThreads, FB_TAIL_BLOCKS_PER_SM)
         kspaceFinishBlock(cur, stride, with_ewald, n_rows, n_e_rows, r_partials, g_partials, e_partials, result, kb);
         __syncthreads(); // kspaceFinishBlock's staging area is free again
     }
-    const int n_outputs = 2 * stride + stride * stride;
+    const int n_outputs = cross_done ? 2 * stride : 2 * stride + stride * stride;
     for (int w = static_cast<int>((blockIdx.x * kFinishThreads + threadIdx.x) >> 5); w < n_outputs;
          w += static_cast<int>(gridDim.x) * (kFinishThreads / 32)) {
         pairFinishWarp<KIND>(M0, P, cur, stride, n_pair_blocks, pair_partials, 0, nullptr, result, nullptr, nullptr, w);
@@ -608,8 +608,10 @@ __global__ void __launch_bounds__(kFinishThreads, FB_TAIL_BLOCKS_PER_SM)
         kspaceFinishBlock(cur, stride, with_ewald, n_rows, n_e_rows, r_partials, g_partials, e_partials, result, blockIdx.x);
     }
     else {
-        pairFinishWarp<KIND>(M0, P, cur, stride, n_pair_blocks, pair_partials, 0, nullptr, result, nullptr, nullptr,
-                             static_cast<int>(((blockIdx.x - k_blocks) * kFinishThreads + threadIdx.x) >> 5));
+        const int w = static_cast<int>(((blockIdx.x - k_blocks) * kFinishThreads + threadIdx.x) >> 5);
+        if (!cross_done || w < 2 * stride) { // cross_done: windowCrossKernel took the cross terms at the start of the window
+            pairFinishWarp<KIND>(M0, P, cur, stride, n_pair_blocks, pair_partials, 0, nullptr, result, nullptr, nullptr, w);
+        }
     }
 #ifndef FB_TAIL_LIGHT_FENCE
 #define FB_TAIL_LIGHT_FENCE 1
