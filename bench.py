@@ -200,7 +200,9 @@ def reference_arm(args):
     moves = 25  # bounded sample per step: ~4 ms/move → 0.1 s/step
     res = cpu_reference_run(args.steps, min(args.warmup, 3), moves, "openmp")
     sample = f"{res['moves']} single-ion trial moves of the N=1e5 workload ({moves}/step), -march={res['arch']}, " \
-             f"summation_policy=openmp (pair sum over {res['threads']} threads; Ewald k-loops serial as in the reference)"
+             f"summation_policy=openmp (pair sum over {res['threads']} threads; Ewald k-loops serial as in the reference); " \
+             "ewaldscheme PBC, the reference's default: PBCEigen only vectorises the full rebuild of Q(k) and the energy sum " \
+             "(src/energy.cpp:208-217, src/energy.h:220-235), the per-move partial update is the same serial loop"
     line = {
         "impl": "reference", "metric": "MC trial moves/s", "value": res["moves_per_s"], "unit": "moves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
