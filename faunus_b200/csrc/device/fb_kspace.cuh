@@ -72,10 +72,15 @@ constexpr int kItemStride = 17;  //!< … stored with a stride of 272 B: the fou
 
 inline int frontPhaseBlocks(const PhaseGeometry& geo) { return (2 * kBatchMax * geo.table_stride + kFrontThreads - 1) / kFrontThreads; }
 
+#ifndef FB_FRONT_BLOCKS_PER_SM
+#define FB_FRONT_BLOCKS_PER_SM 4
+#endif
 struct FrontSmem
 {
     double2 stage[kFrontWarps][32][kItemStride]; //!< [warp][position of the warp's batch][entry]
+#if FB_FRONT_BLOCKS_PER_SM <= 4
     double2 part[kFrontWarps][4][32];             //!< [warp][unit of the item][slot]: ΔQ share of the warp's positions
+#endif
 };
 
 /**
@@ -104,7 +109,7 @@ struct FrontSmem
  * @param kq         [n_units][32] out: √A_k · Q_k of the state this window starts from (0 for empty slots)
  * @param e_partials [n_items] out: Σ A_k |Q_k|² over the item
  */
-__global__ void __launch_bounds__(kFrontThreads)
+__global__ void __launch_bounds__(kFrontThreads, FB_FRONT_BLOCKS_PER_SM)
     windowFrontKernel(EwaldView E, const double2* __restrict__ aks, const int4* __restrict__ unit_info,
                       const unsigned char* __restrict__ unit_map, const int4* __restrict__ item_units,
                       const int4* __restrict__ item_base, int n_phase_blocks, BatchBuffers cur, BatchBuffers prev,
@@ -212,9 +217,17 @@ __global__ void __launch_bounds__(kFrontThreads)
             dmma884(im[3][0], im[3][1], a1.y, c2);
         }
     }
+#if FB_FRONT_BLOCKS_PER_SM <= 4
+    double2(*part)[4][32] = sm.part;
+#else
+    // more blocks per SM: the shares go where the warp's own staged tables were (34.8 kB per block instead of 43 kB)
+    __syncwarp();
+    double2(*part)[4][32] = reinterpret_cast<double2(*)[4][32]>(&sm.stage[0][0][0]);
+    __syncthreads(); // every warp is through with its tables
+#endif
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        sm.part[warp][i][lane] = make_double2(re[i][0] + im[i][0], re[i][1] + im[i][1]);
+        part[warp][i][lane] = make_double2(re[i][0] + im[i][0], re[i][1] + im[i][1]);
     }
     __syncthreads();
     if (warp != 0) {
@@ -229,11 +242,11 @@ __global__ void __launch_bounds__(kFrontThreads)
             if (slot_k[i] >= 0) {
                 double2 Q = slot_q[i];
                 if (ncommit > 0) {
-                    double2 dq = sm.part[0][i][lane];
+                    double2 dq = part[0][i][lane];
 #pragma unroll
                     for (int w = 1; w < kFrontWarps; ++w) { // the shares of the four batches, in order
-                        dq.x += sm.part[w][i][lane].x;
-                        dq.y += sm.part[w][i][lane].y;
+                        dq.x += part[w][i][lane].x;
+                        dq.y += part[w][i][lane].y;
                     }
                     Q.x += dq.x;
                     Q.y += dq.y;
