@@ -288,6 +288,7 @@ struct fb_ctx
         std::vector<int> run_last;  //!< … and its latest move there
         int run_id = 0;
         bool run_decide_configured = false;
+        bool tail_configured[6] = {false, false, false, false, false, false};
         // CUDA graphs of the window launches of a run (launchRunGraph): the 4 kernels × steps windows on two streams
         // are captured the second time the same launch sequence comes up and replayed from then on
         struct RunGraph
@@ -725,7 +726,7 @@ void launchFullQ(fb_ctx* c, int s, int cell_begin, int cell_end, bool store_q, d
     for (int i = 0; i < 3; ++i) {
         geo.len[i] = sl.ewald_box[i];
     }
-    static thread_local int configured_device = -1;
+    static thread_local int configured_device = -1; // (a thread drives one context at a time)
     if (configured_device != c->device) {
         CUDA_CHECK(cudaFuncSetAttribute(ewaldFullCellKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(sizeof(FullQSmem))));

@@ -298,7 +298,7 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
             CUDA_CHECK(cudaStreamWaitEvent(c->stream, b.ev_join, 0));
         }
         if (tail != nullptr) { // sums, cross terms and — by the block that finishes last — the walk
-            static bool configured[6] = {false, false, false, false, false, false};
+            bool* configured = b.tail_configured; // per context: function attributes belong to the device the context is on
             if (!configured[KIND]) {
                 CUDA_CHECK(cudaFuncSetAttribute(windowTailKernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 static_cast<int>(runDecideSmemBytes(kBatchMax))));

@@ -1082,3 +1082,16 @@ def test_forces_include_inactive_particles():
     want, got = o.forces(), g.forces()
     assert want.shape[0] == 62 and np.abs(want[-2:]).max() > 0 and np.all(np.isfinite(want))
     assert_close(want, got, scale=np.abs(want).max())
+
+
+@pytest.mark.parametrize("geometry", [{"type": "sphere", "radius": 60.0}, {"type": "slit", "length": [63.0, 63.0, 80.0]}])
+def test_forces_without_full_periodicity(geometry):
+    """`Chameleon::vdist` folds periodic axes only (src/geometry.h:429-458): a sphere (no fold) and a slit (x, y)"""
+    cfg = small_electrolyte(n=300, energy_name="nonbonded_coulomblj", coulomb={"type": "yukawa", "epsr": 78.7, "debyelength": 12.0})
+    cfg["geometry"] = geometry
+    o, g = pair_of_sims(cfg, 0)
+    terms = len(o.system_energy()[1])
+    nonbonded = [t for t in range(terms) if np.abs(o.forces(term=t)).max() > 0]
+    assert len(nonbonded) == 1
+    want, got = o.forces(term=nonbonded[0]), g.forces(term=nonbonded[0])
+    assert_close(want, got, scale=np.abs(want).max())
