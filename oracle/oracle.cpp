@@ -184,6 +184,29 @@ FO_API int fo_coulomb_force_table(const char* coulomb_json, double temperature, 
     return n;
 }
 
+/** Mass-centre cutoffs² [n_mol²] parsed from a non-bonded block (`cutoff_g2g`); src/energy.cpp:1897-1933, doctest :1955-2002 */
+FO_API int fo_group_cutoffs(const char* input_json, const char* nonbonded_json, double* cutoff_squared, int max_values)
+{
+    int n = -1;
+    fb::capi::guarded([&] {
+        const auto j = fb::Json::parse(input_json);
+        auto topo = fb::topologyFromJson(j);
+        fb::Geometry geometry = fb::Geometry::fromJson(fb::Json::parse(R"({"type":"cuboid","length":100})"));
+        oracle::GroupCutoff cutoff(geometry);
+        cutoff.from_json(fb::Json::parse(nonbonded_json), *topo);
+        const int n_mol = static_cast<int>(topo->molecules.size());
+        n = n_mol * n_mol;
+        for (int a = 0; a < n_mol; ++a) {
+            for (int b = 0; b < n_mol; ++b) {
+                if (a * n_mol + b < max_values) {
+                    cutoff_squared[a * n_mol + b] = cutoff.cutoffSquared(a, b);
+                }
+            }
+        }
+    });
+    return n;
+}
+
 /** Pair energy u(a,b,r) of an `energy`-entry style potential for two atom types (functor tests) */
 FO_API int fo_pair_energy(const char* input_json, const char* nonbonded_name, int id_a, int id_b, const double* r,
                           int n, double* u)

@@ -118,3 +118,32 @@ def test_splined_pair_tables_reproduce_exact():
         val = dz * (val + c[6 * pos + i])
     val = val + c[6 * pos]
     np.testing.assert_allclose(val, u_spline, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("block,expect", [
+    ({"cutoff_g2g": 12.0}, [[12.0, 12.0], [12.0, 12.0]]),                                   # old style default
+    ({"cutoff_g2g": {"default": 13.0}}, [[13.0, 13.0], [13.0, 13.0]]),                       # new style default
+    ({"cutoff_g2g": {"default": 13.0, "M Q": 14.0}}, [[13.0, 14.0], [14.0, 13.0]]),          # custom
+    ({"cutoff_g2g": {"M Q": 11.0}}, [[None, 11.0], [11.0, None]]),                           # custom, no default: none
+])
+def test_group_cutoff_doctest(block, expect):
+    """src/energy.cpp:1955-2002 (`[Faunus] GroupCutoff`): the four ways to write `cutoff_g2g`, in the oracle's parser and
+    in the product's table (the mass-centre cutoffs² that go into fb_config.g2g_cutoff_squared)"""
+    cfg = {"temperature": 298.15,
+           "atomlist": [{"A": {"sigma": 4.0}}, {"B": {"sigma": 2.4}}],
+           "moleculelist": [{"M": {"structure": [{"A": [0.0, 0.0, 0.0]}, {"B": [1.0, 0.0, 0.0]}]}},
+                            {"Q": {"structure": [{"A": [0.0, 0.0, 0.0]}, {"B": [1.0, 0.0, 0.0]}]}}],
+           "geometry": {"type": "cuboid", "length": 100}, "groups": [], "particles": [], "moves": [],
+           "energy": [{"nonbonded": dict({"default": [{"lennardjones": {"mixing": "LB"}}]}, **block)}]}
+    none = 1.7976931348623157e308  # pc::max_value: "no cutoff" (the reference stores sqrt(max)² the same way)
+    want = np.array([[none if v is None else v * v for v in row] for row in expect])
+    lib = oracle_lib()
+    lib.fo_group_cutoffs.restype = C.c_int
+    lib.fo_group_cutoffs.argtypes = [C.c_char_p, C.c_char_p, c_double_p, C.c_int]
+    got = np.zeros(4)
+    n = lib.fo_group_cutoffs(json.dumps(cfg).encode(), json.dumps(cfg["energy"][0]["nonbonded"]).encode(),
+                             got.ctypes.data_as(c_double_p), 4)
+    assert n == 4
+    np.testing.assert_allclose(got.reshape(2, 2), want, rtol=1e-15)
+    product = np.array(_pair_tables(cfg, "nonbonded")["g2g_cutoff_squared"]).reshape(2, 2)
+    np.testing.assert_allclose(product, want, rtol=1e-15)

@@ -298,3 +298,37 @@ def test_displacement_draw_order_is_the_gcc_order():
 
     assert np.allclose(moved, displacement(scalar_first=True), rtol=0, atol=1e-12)
     assert not np.allclose(moved, displacement(scalar_first=False), rtol=0, atol=1e-6)
+
+
+def test_space_update_particles_mass_centres_doctest():
+    """src/space.cpp:627-682 (`[Faunus] Space::updateParticles`, "Group update"): two SPC/E-like waters of
+    `SpaceFactory::makeWater` (:720-742; mw 15.999 / 1.007), positions (0,0,0), (3,3,3), (6,6,6) written over one group,
+    the other, and across both: mass centres 0.5031366235, 0.1677122078, 5.8322877922"""
+    atoms = [{"OW": {"sigma": 3.166, "eps": 0.65, "q": -0.8476, "mw": 15.999}},
+             {"HW": {"sigma": 2.0, "eps": 0.0, "q": 0.4238, "mw": 1.007}}]
+    structure = [{"OW": [2.3, 6.28, 1.13]}, {"HW": [1.37, 6.26, 1.5]}, {"HW": [2.31, 5.89, 0.21]}]
+    # (the periodic mass centre is taken relative to the old one — the doctest sets it to x = −1 first — so the waters
+    # start near x = −1: a molecule that jumps by more than half a cell is outside what the algorithm is meant for)
+    start = [[-1.0, 3.0, 7.0], [-1.9, 3.0, 7.0], [-0.7, 3.9, 7.0], [-1.0, 3.0, 3.0], [-1.9, 3.0, 3.0], [-0.7, 3.9, 3.0]]
+    cfg = {"temperature": 298.15, "random": {"seed": "fixed"}, "geometry": {"type": "cuboid", "length": 20},
+           "atomlist": atoms, "moleculelist": [{"water": {"structure": structure}}],
+           "groups": [{"id": 0, "size": 3, "cm": [-1.03, 3.05, 7.0], "atomic": False, "compressible": False},
+                      {"id": 0, "size": 3, "cm": [-1.03, 3.05, 3.0], "atomic": False, "compressible": False}],
+           "particles": [{"id": 0 if i % 3 == 0 else 1, "pos": p, "q": -0.8476 if i % 3 == 0 else 0.4238} for i, p in enumerate(start)],
+           "energy": [{"nonbonded_coulomblj": {"coulomb": {"type": "plain", "epsr": 80}, "lennardjones": {"mixing": "LB"}}}],
+           "moves": [{"moltransrot": {"molecule": "water", "dp": 0.1, "dprot": 0.1, "repeat": 1}}]}
+    sim = oracle_sim(cfg)
+    positions = [[0.0, 0.0, 0.0], [3.0, 3.0, 3.0], [6.0, 6.0, 6.0]]
+    sim.trial_set(1, [0, 1, 2], positions, all=True)
+    sim.trial_commit(True)
+    assert sim.groups()[1][1][0] == pytest.approx(0.5031366235, rel=1e-9)
+    sim.trial_set(0, [0, 1, 2], positions, all=True)
+    sim.trial_commit(True)
+    assert sim.groups()[1][0][0] == pytest.approx(0.5031366235, rel=1e-9)
+    # "both groups affected": the three positions land on the atoms 1, 2 (first water) and 3 (oxygen of the second)
+    sim.trial_set(0, [1, 2], positions[:2], all=False)
+    sim.trial_commit(True)
+    sim.trial_set(1, [0], positions[2:], all=False)
+    sim.trial_commit(True)
+    cm = sim.groups()[1]
+    assert cm[0][0] == pytest.approx(0.1677122078, rel=1e-9) and cm[1][0] == pytest.approx(5.8322877922, rel=1e-9)
