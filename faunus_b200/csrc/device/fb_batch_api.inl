@@ -738,6 +738,15 @@ bool launchRunGraph(fb_ctx* c, fb_ctx::Batch::RunSlot& r, int steps, bool contin
     if (cellGridFor(c, grid)) {
         return false;
     }
+    if (b.run_graphs.size() > 64) { // a box that keeps changing (NPT) leaves keys behind that never come back
+        CUDA_CHECK(cudaStreamSynchronize(c->stream)); // (rare) nothing of them is in flight when they go
+        for (auto& [key, g] : b.run_graphs) {
+            if (g.exec) {
+                cudaGraphExecDestroy(g.exec);
+            }
+        }
+        b.run_graphs.clear();
+    }
     auto& entry = b.run_graphs[runGraphSignature(c, r, steps)];
     if (entry.exec == nullptr) {
         if (entry.seen++ < min_seen) {

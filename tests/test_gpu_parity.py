@@ -639,9 +639,12 @@ def test_window_cell_list(capacity, window):
 
 
 @pytest.mark.parametrize("window", [16, 64])
-def test_window_with_volume_moves(window):
+@pytest.mark.parametrize("cells", [0, -1])
+def test_window_with_volume_moves(window, cells):
     """NPT electrolyte: runs of windowed `transrot` moves interleaved with `volume` moves (everything changes:
-    box, k-vectors, Q(k), cell list) — the queue is drained, the other move runs one at a time, windows resume"""
+    box, k-vectors, Q(k), cell list) — the queue is drained, the other move runs one at a time, windows resume.
+    cells = −1: brute-force windows, whose launches are replayed as CUDA graphs — every accepted volume move changes
+    the launch arguments (box lengths), so the graphs have to be captured anew"""
     cfg = small_electrolyte(n=300, moves_per_sweep=60,
                             coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 5})
     cfg["energy"] = [{"isobaric": {"P/mM": 2000.0}}] + cfg["energy"]
@@ -649,7 +652,7 @@ def test_window_with_volume_moves(window):
     o = oracle_sim(cfg)
     g = b200_sim(cfg, window)
     assert g.window == window   # the isobaric term is a per-atom host term: windows stay eligible
-    g.configure_cells(0)
+    g.configure_cells(cells)
     for s in (o, g):
         s.trace_enable()
         s.sweep(6)
