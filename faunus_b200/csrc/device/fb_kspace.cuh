@@ -454,10 +454,10 @@ __global__ void __launch_bounds__(kKsThreads, 2 / kKsGroups)
 #if FB_KS_INTERLEAVE
 // the re step of every tile, then the im step of every tile: two tensor instructions on the same accumulator are
 // 1 + NP apart instead of back to back (DMMA: 16 cycles between issues of a sub-partition, ≈ 26 until the result)
-#define FB_GRAM(NP)                                                                                        \
+#define FB_GRAM(NP, CHECK)                                                                                 \
     _Pragma("unroll") for (int s = 0; s < 8; ++s)                                                          \
     {                                                                                                      \
-        if (!((steps >> s) & 1u)) { /* block-uniform: no k-vector in this column, every δ is zero */      \
+        if (CHECK && !((steps >> s) & 1u)) { /* block-uniform: no k-vector in this column, every δ is zero */ \
             continue;                                                                                      \
         }                                                                                                  \
         double2 f[NP > 0 ? NP : 1];                                                                        \
@@ -468,10 +468,10 @@ __global__ void __launch_bounds__(kKsThreads, 2 / kKsGroups)
         _Pragma("unroll") for (int d = 0; d < NP; ++d) { dmma884(g_off[d][0], g_off[d][1], dreg[2 * s + 1], f[d].y); }     \
     }
 #else
-#define FB_GRAM(NP)                                                                                        \
+#define FB_GRAM(NP, CHECK)                                                                                 \
     _Pragma("unroll") for (int s = 0; s < 8; ++s)                                                          \
     {                                                                                                      \
-        if (!((steps >> s) & 1u)) { /* block-uniform: no k-vector in this column, every δ is zero */      \
+        if (CHECK && !((steps >> s) & 1u)) { /* block-uniform: no k-vector in this column, every δ is zero */ \
             continue;                                                                                      \
         }                                                                                                  \
         double2 f[NP > 0 ? NP : 1];                                                                        \
@@ -485,21 +485,48 @@ __global__ void __launch_bounds__(kKsThreads, 2 / kKsGroups)
         }                                                                                                  \
     }
 #endif
-            switch (n_partners) {
-            case 4:
-                FB_GRAM(4)
-                break;
-            case 3:
-                FB_GRAM(3)
-                break;
-            case 2:
-                FB_GRAM(2)
-                break;
-            case 1:
-                FB_GRAM(1)
-                break;
-            default:
-                FB_GRAM(0)
+            // (switch FB_KS_SKIP = 2: a unit whose eight slot columns all hold k-vectors — 71 % of the units at S1 — takes
+            // a copy of the loop without the per-step tests, which cost a WARPSYNC each: 47 instead of 12 in the SASS)
+#ifndef FB_KS_SKIP
+#define FB_KS_SKIP 1 // 0: no step is skipped; 1: every step tests its bit; 2: full units take the test-free loop
+                     // measured at S1: 8.79e5 / 8.97e5 / 8.90e5 moves/s — the tests (a WARPSYNC each) cost less than the
+                     // second copy of the loop does
+#endif
+            if (FB_KS_SKIP == 0 || (FB_KS_SKIP == 2 && steps == 0xffu)) {
+                switch (n_partners) {
+                case 4:
+                    FB_GRAM(4, false)
+                    break;
+                case 3:
+                    FB_GRAM(3, false)
+                    break;
+                case 2:
+                    FB_GRAM(2, false)
+                    break;
+                case 1:
+                    FB_GRAM(1, false)
+                    break;
+                default:
+                    FB_GRAM(0, false)
+                }
+            }
+            else {
+                switch (n_partners) {
+                case 4:
+                    FB_GRAM(4, true)
+                    break;
+                case 3:
+                    FB_GRAM(3, true)
+                    break;
+                case 2:
+                    FB_GRAM(2, true)
+                    break;
+                case 1:
+                    FB_GRAM(1, true)
+                    break;
+                default:
+                    FB_GRAM(0, true)
+                }
             }
 #undef FB_GRAM
         }
