@@ -1697,7 +1697,9 @@ FB_API int fb_nonbonded_force(fb_ctx* c, int s, double* forces)
         c->h_forces.ensure(3 * static_cast<size_t>(n));
         const SlotView V = makeView(c, s);
         ForceTable T{c->force_nk, c->d_force_knots.ptr, c->d_force_coef.ptr};
-        constexpr int kForceChunk = 2048; // particles j per share: a constant, so the sums do not depend on the grid
+        // particles j per share: 2048, or N/64 rounded up to whole tiles if that is more (at most 64 shares) — a function of
+        // N alone, so the sums do not depend on the machine
+        const int kForceChunk = std::max(2048, ((n + 63) / 64 + kForceBlock - 1) / kForceBlock * kForceBlock);
         const int n_ranges = (n + kForceChunk - 1) / kForceChunk;
         c->d_force_shares.ensure(3 * static_cast<size_t>(n) * n_ranges);
         const dim3 grid((n + kForceBlock - 1) / kForceBlock, n_ranges);

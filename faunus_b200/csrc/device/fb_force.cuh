@@ -14,7 +14,7 @@
 //     −4π lB / V — whatever the terms before it left in the vector is overwritten, and the surface term is there for
 //     any `epss` (no tinfoil test). Reproduced.
 //
-// A thread owns particle i and adds the forces of the j ≠ i of a fixed range of 2048 particles in index order; the
+// A thread owns particle i and adds the forces of the j ≠ i of a fixed range of particles (2048, at most 64 ranges) in index order; the
 // shares of the ranges are added in range order: F_i = Σ_j f(i, j). The reference adds f(i, j) to i and subtracts it
 // from j for i < j; vdist and the force laws are odd in the distance vector, so the two differ by the order of the
 // sums only.
