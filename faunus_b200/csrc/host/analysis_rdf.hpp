@@ -105,14 +105,22 @@ class AtomRDF
     double resolution() const { return dr; }
 
     /** g(r) as PairFunction::_to_disk prints it: N ⟨V⟩ / (4π r² dr · Σ N); 0 where the volume element vanishes */
-    double g(size_t i) const
+    double g(size_t i) const { return g(i, total()); }
+
+    /** Σ N over the bins (callers that want every g(r) take it once: the sum inside g(i) made a table of n bins O(n²)) */
+    double total() const
+    {
+        double sum = 0.0;
+        for (const auto c : histogram) {
+            sum += static_cast<double>(c);
+        }
+        return sum;
+    }
+
+    double g(size_t i, double total) const
     {
         const double r = distance(i);
         const double volume_at_r = 4.0 * pc::pi * r * r * dr;
-        double total = 0.0;
-        for (const auto c : histogram) {
-            total += static_cast<double>(c);
-        }
         if (!(volume_at_r > 0.0) || total == 0.0 || volume_count == 0) {
             return 0.0;
         }

@@ -681,6 +681,7 @@ inline State& pick(Sim& s, int which)
         fb::capi::guarded([&] {                                                                              \
             const auto& f = *s->rdfs.at(id);                                                                 \
             n = static_cast<int>(f.size());                                                                  \
+            const double total = f.total();                                                                  \
             for (int i = 0; i < n && i < max; ++i) {                                                         \
                 if (r) {                                                                                     \
                     r[i] = f.distance(i);                                                                    \
@@ -689,7 +690,7 @@ inline State& pick(Sim& s, int which)
                     pairs[i] = f.pairs(i);                                                                   \
                 }                                                                                            \
                 if (g) {                                                                                     \
-                    g[i] = f.g(i);                                                                           \
+                    g[i] = f.g(i, total);                                                                    \
                 }                                                                                            \
             }                                                                                                \
         });                                                                                                  \
