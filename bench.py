@@ -424,6 +424,8 @@ def b200_arm(args):
     sampler.start()
     cfg = workload(seed=5489 + rank)
     sim = native.B200Simulation(cfg, device=local, window=args.window)
+    if os.environ.get("FAUNUS_B200_RUN_FLAGS"):  # experiments: fb_configure_runs flags (1: pair sums ahead, 2: no graphs)
+        sim.configure_runs(int(os.environ["FAUNUS_B200_RUN_FLAGS"]))
     n = sim.num_particles
     info0 = sim.info()
     kvectors = None
