@@ -23,6 +23,24 @@
 #pragma once
 #include "fb_kernels.cuh"
 
+// Programmatic dependent launch between the kernels of the front → k-space → tail → front chain (switch FB_PDL): a
+// kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be scheduled as soon as every block of
+// the kernel before it has passed FB_LAUNCH_DEPENDENTS (or exited), and must not touch that kernel's results before
+// FB_GRID_DEPENDENCY_WAIT, which returns when the kernel before it has completed and its writes are visible. Both are
+// no-ops for a kernel launched the ordinary way. MEASURED AND LEFT OFF: parity holds (76 run / window tests), but S1 drops from
+// 8.98e5 to 8.56e5 moves/s — the blocks launched early sit on registers and shared memory while they wait, and the pair
+// kernel on the other stream, which the k-space chain overlaps with, is what they take them from.
+#ifndef FB_PDL
+#define FB_PDL 0
+#endif
+#if FB_PDL
+#define FB_GRID_DEPENDENCY_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define FB_LAUNCH_DEPENDENTS() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#else
+#define FB_GRID_DEPENDENCY_WAIT()
+#define FB_LAUNCH_DEPENDENTS()
+#endif
+
 namespace fbdev {
 
 constexpr int kBatchMax = 64;    //!< moves per window

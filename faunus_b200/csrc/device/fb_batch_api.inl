@@ -134,6 +134,23 @@ void buildCellList(fb_ctx* c, const CellGrid& g, cudaStream_t stream)
     c->batch.cells_valid = true;
 }
 
+/** kernel launch that may carry the programmatic-dependent-launch attribute (FB_PDL; see fb_batch.cuh) */
+template <class... KArgs, class... Args>
+void launchChained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool chained, Args&&... args)
+{
+    cudaLaunchConfig_t config = {};
+    config.gridDim = grid;
+    config.blockDim = block;
+    config.dynamicSmemBytes = smem;
+    config.stream = stream;
+    cudaLaunchAttribute attribute[1];
+    attribute[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attribute[0].val.programmaticStreamSerializationAllowed = 1;
+    config.attrs = attribute;
+    config.numAttrs = (FB_PDL && chained) ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&config, kernel, static_cast<KArgs>(args)...));
+}
+
 /**
  * Launches of one window. Main stream: prep → phase tables → k-space → k-space sums; pair stream (forked
  * after prep, joined before the copy-out): pair kernel → pair sums + cross terms. Serialised on the
@@ -273,9 +290,10 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
         b.d_e_partials.ensure(static_cast<size_t>(std::max(1, n_front_blocks)));
         b.d_r_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax);
         b.d_g_partials.ensure(static_cast<size_t>(2 * c->n_sm) * kBatchMax * kBatchMax);
-        windowFrontKernel<<<n_phase_blocks + n_front_blocks, kFrontThreads, 0, c->stream>>>(
-            E, sl.aks.ptr, sl.unit_info.ptr, sl.unit_map.ptr, sl.item_units.ptr, sl.item_base.ptr, n_phase_blocks, cur,
-            prev, b.geo, b.d_kq.ptr, b.d_e_partials.ptr);
+        const bool chained = tail != nullptr && !timing; // runs: front → k-space → tail → front of the next window
+        launchChained(windowFrontKernel, dim3(n_phase_blocks + n_front_blocks), dim3(kFrontThreads), 0, c->stream, chained, E,
+                      sl.aks.ptr, sl.unit_info.ptr, sl.unit_map.ptr, sl.item_units.ptr, sl.item_base.ptr, n_phase_blocks, cur, prev,
+                      b.geo, b.d_kq.ptr, b.d_e_partials.ptr);
         launched(c, "windowFrontKernel");
         if (timing) {
             CUDA_CHECK(cudaEventRecord(b.ev[5], c->stream));
@@ -285,9 +303,9 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
                                             static_cast<int>(kKsGroups * sizeof(KspaceSmem))));
             b.kspace_unit_configured = true;
         }
-        windowKspaceKernel<<<n_rows, kKsThreads, kKsGroups * sizeof(KspaceSmem), c->stream>>>(
-            sl.unit_info.ptr, sl.unit_sa.ptr, b.d_kq.ptr, sl.unit_steps.ptr, sl.sched_first.ptr, sl.sched_units.ptr,
-            sl.n_sched_blocks, cur, b.geo, stride, b.d_r_partials.ptr, b.d_g_partials.ptr);
+        launchChained(windowKspaceKernel, dim3(n_rows), dim3(kKsThreads), kKsGroups * sizeof(KspaceSmem), c->stream, chained,
+                      sl.unit_info.ptr, sl.unit_sa.ptr, b.d_kq.ptr, sl.unit_steps.ptr, sl.sched_first.ptr, sl.sched_units.ptr,
+                      sl.n_sched_blocks, cur, b.geo, stride, b.d_r_partials.ptr, b.d_g_partials.ptr);
         launched(c, "windowKspaceKernel");
     }
     if (timing) {
@@ -317,10 +335,11 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
 #else
             const int tail_grid = kspaceFinishGrid(stride) + tail_pair_blocks;
 #endif
-            windowTailKernel<KIND><<<tail_grid, kFinishThreads, runDecideSmemBytes(stride), c->stream>>>(
-                M0, c->P, cur, stride, with_ewald ? 1 : 0, n_rows, n_e_rows, b.d_r_partials.ptr, b.d_g_partials.ptr,
-                b.d_e_partials.ptr, n_pair_blocks, b.d_pair_partials.ptr, b.d_result.ptr, b.d_tail_ticket.ptr, tail->hdr,
-                tail->moves, tail->st, tail->next, tail->out, tail->prev_out, tail->predicted, tail->ahead, cross_done);
+            launchChained(windowTailKernel<KIND>, dim3(tail_grid), dim3(kFinishThreads), runDecideSmemBytes(stride), c->stream,
+                          with_ewald && !timing, M0, c->P, cur, stride, with_ewald ? 1 : 0, n_rows, n_e_rows, b.d_r_partials.ptr,
+                          b.d_g_partials.ptr, b.d_e_partials.ptr, n_pair_blocks, b.d_pair_partials.ptr, b.d_result.ptr,
+                          b.d_tail_ticket.ptr, tail->hdr, tail->moves, tail->st, tail->next, tail->out, tail->prev_out,
+                          tail->predicted, tail->ahead, cross_done);
             launched(c, "windowTailKernel");
             if (walked) {
                 *walked = true;

@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(kFrontThreads, FB_FRONT_BLOCKS_PER_SM)
     __shared__ FrontSmem sm;
     __shared__ int s_table[2 * kBatchMax]; //!< first table entry of every accepted position (trial, old, trial, …)
     const int tid = threadIdx.x;
+    FB_GRID_DEPENDENCY_WAIT(); // the window description and the commit list are the tail kernel's
+    FB_LAUNCH_DEPENDENTS();
     if (static_cast<int>(blockIdx.x) < n_phase_blocks) {
         const int total = 2 * cur.in->n * geo.table_stride;
         const int t = blockIdx.x * kFrontThreads + tid;
@@ -305,6 +307,8 @@ __global__ void __launch_bounds__(kKsThreads, 2 / kKsGroups)
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int block = kKsGroups * blockIdx.x + group;
+    FB_GRID_DEPENDENCY_WAIT(); // phase tables and √A_k·Q_k are the front kernel's
+    FB_LAUNCH_DEPENDENTS();
     const int n = cur.in->n;
     const int n_active_warps = (n + 7) >> 3;
     const bool warp_active = warp < n_active_warps;

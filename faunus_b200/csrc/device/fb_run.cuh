@@ -578,6 +578,8 @@ __global__ void __launch_bounds__(kFinishThreads, FB_TAIL_BLOCKS_PER_SM)
 {
     extern __shared__ __align__(16) unsigned char run_smem[];
     __shared__ unsigned s_last;
+    FB_GRID_DEPENDENCY_WAIT(); // the partial sums are the k-space kernel's
+    FB_LAUNCH_DEPENDENTS();
 #ifndef FB_TAIL_ONE_WAVE
 #define FB_TAIL_ONE_WAVE 0
 #endif
