@@ -1088,6 +1088,60 @@ __device__ __forceinline__ void pairFinishWarp(const SlotView& M0, const PotPara
     }
 }
 
+#ifndef FB_CROSS_PACKED
+#define FB_CROSS_PACKED 1
+#endif
+/**
+ * Cross terms, 16 per warp: the lane pair (2p, 2p + 1) of warp `wc` takes the pair of moves t = 16 wc + p = a S + m; the even
+ * lane evaluates move m at its TRIAL position against the trial and the old position of move a, the odd lane move m at its
+ * OLD position — the same four pair energies, the same two differences and the same maximum as pairFinishWarp (which used 4
+ * of the 32 lanes of a warp per pair: 4096 warps, 128 blocks of the tail kernel, a second wave; now 256 warps, 8 blocks).
+ */
+template <int KIND>
+__device__ __forceinline__ void pairCrossPacked(const SlotView& M0, const PotParams& P, const BatchBuffers& cur, int stride,
+                                                double* __restrict__ result, int wc)
+{
+    const int n = cur.in->n;
+    const int S = stride;
+    const int lane = threadIdx.x & 31;
+    double* cross = result + 8 + 3 * S;
+    const int t = 16 * wc + (lane >> 1);
+    if (t >= S * S) {
+        return; // (whole lane pairs leave together; S² is a multiple of 16)
+    }
+    const int a = t / S;
+    const int m = t % S;
+    const bool m_new = (lane & 1) == 0;
+    double diff = 0.0, largest = 0.0;
+    bool invalid = false;
+    const bool wanted = a < m && m < n;
+    if (wanted) {
+        const double4 pm = m_new ? cur.in->pnew[m] : cur.pold[m];
+        const int idm = m_new ? cur.in->id[m] : cur.idold[m];
+        const double4 pn = cur.in->pnew[a];
+        const double4 po = cur.pold[a];
+        const double with_new = pairEnergy<KIND>(P, idm, cur.in->id[a], pm.w, pn.w, minImageR2(M0, pm.x, pm.y, pm.z, pn.x, pn.y, pn.z));
+        const double with_old = pairEnergy<KIND>(P, idm, cur.idold[a], pm.w, po.w, minImageR2(M0, pm.x, pm.y, pm.z, po.x, po.y, po.z));
+        diff = with_new - with_old;
+        largest = fmax(fabs(with_new), fabs(with_old));
+        invalid = with_new != with_new || with_old != with_old;
+    }
+    const double other_largest = __shfl_xor_sync(0xffffffffu, largest, 1);
+    const bool other_invalid = __shfl_xor_sync(0xffffffffu, invalid ? 1 : 0, 1) != 0;
+    double cmax = fmax(largest, other_largest);
+    if (invalid || other_invalid) {
+        cmax = __longlong_as_double(0x7ff0000000000000LL);
+    }
+    const int tt = m * S + a; // stored [m][a]: the caller reads one row per move
+    if (m_new) {
+        cross[tt] = diff;
+        cross[2 * S * S + tt] = wanted ? cmax : 0.0;
+    }
+    else {
+        cross[S * S + tt] = diff;
+    }
+}
+
 #ifndef FB_CROSS_EARLY
 #define FB_CROSS_EARLY 0
 #endif

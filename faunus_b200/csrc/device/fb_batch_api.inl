@@ -328,8 +328,13 @@ void launchWindow(fb_ctx* c, const BatchBuffers& cur, const BatchBuffers& prev, 
             }
             const int cross_done = (FB_CROSS_EARLY && !timing) ? 1 : 0; // (timing: the kernels of a window are serialised and
                                                                         // attributed to pair / k-space / other as before)
+#if FB_CROSS_PACKED
+            const int tail_pair_warps = 2 * stride + (cross_done ? 0 : (stride * stride + 15) / 16); // sums; 16 cross terms per warp
+            const int tail_pair_blocks = (tail_pair_warps + kFinishThreads / 32 - 1) / (kFinishThreads / 32);
+#else
             const int tail_pair_blocks = cross_done ? (2 * stride + kFinishThreads / 32 - 1) / (kFinishThreads / 32)
                                                     : pairFinishBlocks(stride);
+#endif
 #if FB_TAIL_ONE_WAVE
             const int tail_grid = std::min(c->n_sm, kspaceFinishGrid(stride) + tail_pair_blocks);
 #else

@@ -584,6 +584,9 @@ __global__ void __launch_bounds__(kFinishThreads, FB_TAIL_BLOCKS_PER_SM)
 #define FB_TAIL_ONE_WAVE 0
 #endif
     const int k_blocks = kspaceFinishGrid(stride);
+#if FB_TAIL_ONE_WAVE && FB_CROSS_PACKED
+#error "FB_TAIL_ONE_WAVE walks the pair outputs with pairFinishWarp: build it with -DFB_CROSS_PACKED=0"
+#endif
 #if FB_TAIL_ONE_WAVE
     // One wave: a block of 1024 threads at 64 registers owns an SM, and the walk's shared memory is reserved for every
     // block, so a grid of (column blocks + pair blocks) = 263 ran as two waves on 148 SMs, each paying the full latency
@@ -611,9 +614,18 @@ __global__ void __launch_bounds__(kFinishThreads, FB_TAIL_BLOCKS_PER_SM)
     }
     else {
         const int w = static_cast<int>(((blockIdx.x - k_blocks) * kFinishThreads + threadIdx.x) >> 5);
+#if FB_CROSS_PACKED
+        if (w < 2 * stride) { // the 2S pair sums, one warp each; then the S² cross terms, 16 per warp
+            pairFinishWarp<KIND>(M0, P, cur, stride, n_pair_blocks, pair_partials, 0, nullptr, result, nullptr, nullptr, w);
+        }
+        else if (!cross_done) {
+            pairCrossPacked<KIND>(M0, P, cur, stride, result, w - 2 * stride);
+        }
+#else
         if (!cross_done || w < 2 * stride) { // cross_done: windowCrossKernel took the cross terms at the start of the window
             pairFinishWarp<KIND>(M0, P, cur, stride, n_pair_blocks, pair_partials, 0, nullptr, result, nullptr, nullptr, w);
         }
+#endif
     }
 #ifndef FB_TAIL_LIGHT_FENCE
 #define FB_TAIL_LIGHT_FENCE 1
