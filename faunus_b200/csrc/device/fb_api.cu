@@ -3,11 +3,13 @@
 // One CUDA stream per context; results come back through mapped pinned memory.
 #include "../../../include/faunus_b200.h"
 #include <map>
+#include <tuple>
 #include <queue>
 #include "fb_kernels.cuh"
 #include "fb_batch.cuh"
 #include "fb_kspace.cuh"
 #include "fb_stream.cuh"
+#include "fb_fullq.cuh"
 #include "fb_cells.cuh"
 #include "fb_run.cuh"
 #include "fb_rdf.cuh"
@@ -119,6 +121,10 @@ struct Slot
     DeviceBuffer<double> ksq; //!< sqrt(A_k)
     DeviceBuffer<int> cell_start; //!< [n_cells + 1] first k of each 4×4×4 cell of integer triplets (storage order)
     int n_cells = 0;
+    // tiles of the full rebuild of Q(k) (fb_fullq.cuh)
+    DeviceBuffer<int4> gemm_tiles; //!< [n_gemm_tiles] {nx, y table index, first column group, column groups}, heaviest first
+    DeviceBuffer<int> gemm_index;  //!< [K] tile · 2048 + row · 64 + column of every k-vector
+    int n_gemm_tiles = 0;
     // work units of the window k-space kernel (fb_kspace.cuh): halves of the cells, 32 k-slots each
     DeviceBuffer<double2> aks;            //!< [K] {A_k, √A_k}
     DeviceBuffer<int4> unit_info;         //!< [n_units] {first k of the cell, x, y, z table index of the first slot}
@@ -324,6 +330,8 @@ struct fb_ctx
     // forces (fb_force.cuh)
     DeviceBuffer<double> d_force_knots, d_force_coef; //!< Andrea table of S'(q) (fb_set_force_table)
     int force_nk = 0;
+    int full_q_path = 0; //!< 0: matrix product (fb_fullq.cuh), 1: one block per k-cell (FAUNUS_B200_FULLQ=cells; comparisons)
+    DeviceBuffer<double> fullq_partials; //!< full rebuild of Q(k): [tiles][particle ranges][2][32][64] shares
     DeviceBuffer<double2> q_partials; //!< sharded reciprocal energy: [cells of the slab][particle splits][64] shares of Q(k)
     DeviceBuffer<double> d_forces; //!< [n_slots][3]
     DeviceBuffer<double> d_force_shares; //!< [j ranges][n_slots][3]
@@ -753,6 +761,99 @@ void launchFullQ(fb_ctx* c, int s, int cell_begin, int cell_end, bool store_q, d
     launched(c, "ewaldFullCellKernel");
 }
 
+/**
+ * Tiles of ewaldFullGemmKernel for the k-vectors `kn` (any order): 4 nx × 8 ny rows, windows of at most 8 column groups of
+ * 8 nz between the first and the last group that holds a k-vector of the tile; heaviest tiles first (they start first).
+ */
+void buildGemmTiles(fb_ctx* c, Slot& sl, const std::vector<int4>& kn)
+{
+    sl.n_gemm_tiles = 0;
+    if (c->ewald.policy == 2 || kn.empty()) {
+        return;
+    }
+    const int ncc = static_cast<int>(std::ceil(c->ewald.n_cutoff));
+    struct Extent
+    {
+        int lo = std::numeric_limits<int>::max(), hi = -1;
+    };
+    std::map<std::pair<int, int>, Extent> extent; // (nx / 4, y index / 8) → column groups
+    for (const int4& n : kn) {
+        Extent& e = extent[{n.x >> 2, (n.y + ncc) >> 3}];
+        const int g = (n.z + ncc) >> 3;
+        e.lo = std::min(e.lo, g);
+        e.hi = std::max(e.hi, g);
+    }
+    std::vector<int4> tiles;
+    for (const auto& [key, e] : extent) {
+        for (int g = e.lo; g <= e.hi; g += 8) {
+            tiles.push_back(make_int4(4 * key.first, 8 * key.second, g, std::min(8, e.hi - g + 1)));
+        }
+    }
+    std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return a.w > b.w; });
+    std::map<std::tuple<int, int, int>, int> tile_of; // (nx / 4, y index / 8, window) → tile
+    for (size_t t = 0; t < tiles.size(); ++t) {
+        const auto& e = extent[{tiles[t].x >> 2, tiles[t].y >> 3}];
+        tile_of[{tiles[t].x >> 2, tiles[t].y >> 3, (tiles[t].z - e.lo) >> 3}] = static_cast<int>(t);
+    }
+    std::vector<int> index(kn.size());
+    for (size_t i = 0; i < kn.size(); ++i) {
+        const int4 n = kn[i];
+        const int iy = n.y + ncc, g = (n.z + ncc) >> 3;
+        const auto& e = extent[{n.x >> 2, iy >> 3}];
+        const int t = tile_of.at({n.x >> 2, iy >> 3, (g - e.lo) >> 3});
+        const int row = 8 * (n.x & 3) + (iy & 7);
+        const int col = (n.z + ncc) - 8 * tiles[t].z;
+        index[i] = t * (kGemmRows * kGemmCols) + row * kGemmCols + col;
+    }
+    sl.n_gemm_tiles = static_cast<int>(tiles.size());
+    sl.gemm_tiles.upload(tiles.data(), tiles.size(), c->stream);
+    sl.gemm_index.upload(index.data(), index.size(), c->stream);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
+}
+
+/**
+ * Q(k) of a slot from its positions: the complex matrix product of fb_fullq.cuh. The particle ranges depend on the number
+ * of particles and tiles only (≈ 6 blocks per SM of a 148-SM part, at least 256 particles each), not on the device.
+ */
+void launchFullQGemm(fb_ctx* c, int s)
+{
+    Slot& sl = c->slot[s];
+    PhaseGeometry geo{};
+    geo.ncc = static_cast<int>(std::ceil(c->ewald.n_cutoff));
+    geo.table_stride = 0;
+    for (int i = 0; i < 3; ++i) {
+        geo.len[i] = sl.ewald_box[i];
+    }
+    const int n = std::max(1, c->n_slots);
+    int n_ranges = std::max(1, (6 * 148 + sl.n_gemm_tiles - 1) / sl.n_gemm_tiles);
+    n_ranges = std::min(n_ranges, std::max(1, n / 256));
+    int range_size = (n + n_ranges - 1) / n_ranges;
+    range_size = (range_size + kGemmChunk - 1) / kGemmChunk * kGemmChunk;
+    n_ranges = (n + range_size - 1) / range_size;
+    c->fullq_partials.ensure(static_cast<size_t>(sl.n_gemm_tiles) * n_ranges * kGemmShare);
+    static thread_local int configured_device = -1; // (a thread drives one context at a time)
+    if (configured_device != c->device) {
+        CUDA_CHECK(cudaFuncSetAttribute(ewaldFullGemmKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(sizeof(FullGemmSmem))));
+        CUDA_CHECK(cudaFuncSetAttribute(ewaldFullGemmKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(sizeof(FullGemmSmem))));
+        configured_device = c->device;
+    }
+    const dim3 grid(sl.n_gemm_tiles, n_ranges);
+    if (c->ewald.policy == 1) {
+        ewaldFullGemmKernel<true><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
+            makeView(c, s), sl.gemm_tiles.ptr, geo, range_size, c->fullq_partials.ptr);
+    }
+    else {
+        ewaldFullGemmKernel<false><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
+            makeView(c, s), sl.gemm_tiles.ptr, geo, range_size, c->fullq_partials.ptr);
+    }
+    launched(c, "ewaldFullGemmKernel");
+    ewaldFullGatherKernel<<<(sl.K + 255) / 256, 256, 0, c->stream>>>(makeEwaldView(c, s), sl.gemm_index.ptr, n_ranges,
+                                                                    c->fullq_partials.ptr);
+    launched(c, "ewaldFullGatherKernel");
+}
+
 /** PolicyIonIon::updateBox / PolicyIonIonIPBC::updateBox, src/energy.cpp:133-186, 356-412 */
 void generateKVectors(const fb_ewald_config& cfg, const double box[3], std::vector<double4>& kA,
                       std::vector<int4>& kn)
@@ -862,6 +963,9 @@ FB_API int fb_create(const fb_config* cfg, fb_ctx** out)
         }
         c = new fb_ctx();
         c->device = cfg->device;
+        if (const char* v = std::getenv("FAUNUS_B200_FULLQ")) {
+            c->full_q_path = std::strcmp(v, "cells") == 0 ? 1 : 0;
+        }
         CUDA_CHECK(cudaSetDevice(c->device));
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreate(&c->ev0));
@@ -2150,6 +2254,7 @@ FB_API int fb_ewald_update_box(fb_ctx* c, int s, int* n_kvectors)
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         sl.kA.upload(kA.data(), kA.size(), c->stream);
         sl.kn.upload(kn.data(), kn.size(), c->stream);
+        buildGemmTiles(c, sl, kn);
         std::vector<double> ksq(kA.size());
         for (size_t i = 0; i < kA.size(); ++i) {
             ksq[i] = std::sqrt(kA[i].w);
@@ -2309,13 +2414,20 @@ FB_API int fb_ewald_update_full(fb_ctx* c, int s)
         if (sl.K <= 0) {
             throw CudaError{"no k-vectors (call fb_ewald_update_box first)"};
         }
-        if (c->ewald.policy != 2 && sl.n_cells > 0) { // PBC / PBCEigen: factorised phases, one block per k-cell
+        beginTiming(c);
+        if (c->ewald.policy != 2 && sl.n_gemm_tiles > 0 && c->full_q_path == 0) { // PBC / PBCEigen: matrix product
+            launchFullQGemm(c, s);
+        }
+        else if (c->ewald.policy != 2 && sl.n_cells > 0) { // factorised phases, one block per k-cell
             launchFullQ(c, s, 0, sl.n_cells, true, nullptr);
         }
         else {
             const int grid = (sl.K + kEwaldBlock - 1) / kEwaldBlock;
             ewaldFullKernel<<<grid, kEwaldBlock, 0, c->stream>>>(makeView(c, s), makeEwaldView(c, s));
             launched(c, "ewaldFullKernel");
+        }
+        if (c->timing) {
+            finish(c); // fb_last_kernel_ms: the rebuild alone
         }
         sl.rec_valid = false;
     });
@@ -2431,6 +2543,15 @@ FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
             CUDA_CHECK(cudaMemcpyAsync(d.cell_start.ptr, s.cell_start.ptr, (s.n_cells + 1) * sizeof(int),
                                        cudaMemcpyDeviceToDevice, c->stream));
             d.n_cells = s.n_cells;
+            d.n_gemm_tiles = s.n_gemm_tiles;
+            if (s.n_gemm_tiles > 0) {
+                d.gemm_tiles.ensure(s.n_gemm_tiles);
+                CUDA_CHECK(cudaMemcpyAsync(d.gemm_tiles.ptr, s.gemm_tiles.ptr, s.n_gemm_tiles * sizeof(int4),
+                                           cudaMemcpyDeviceToDevice, c->stream));
+                d.gemm_index.ensure(s.K);
+                CUDA_CHECK(cudaMemcpyAsync(d.gemm_index.ptr, s.gemm_index.ptr, s.K * sizeof(int), cudaMemcpyDeviceToDevice,
+                                           c->stream));
+            }
             d.aks.ensure(s.K);
             CUDA_CHECK(cudaMemcpyAsync(d.aks.ptr, s.aks.ptr, s.K * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
             d.n_units = s.n_units;

@@ -1,0 +1,218 @@
+// Full rebuild of Q(k) as a complex matrix product on the FP64 tensor path.
+//
+// PolicyIonIon::updateComplex (src/energy.cpp:191-206; the PBCEigen quirk :208-217) is
+//     Q(nx, ny, nz) = Σ_j w_j · X_j(nx) · Y_j(ny) · Z_j(nz),     X_j(n) = e^{i 2π n x_j / Lx}, …
+// i.e. C = A · B with A[(nx, ny), j] = w_j X_j(nx) Y_j(ny) and B[j, nz] = Z_j(nz), the particles as the inner dimension.
+// ewaldFullCellKernel (fb_stream.cuh) evaluates the same sum with one block per 4×4×4 cell on the DFMA pipe from shared-memory
+// operands and redoes the six sincos of every particle in every cell; here a block owns a TILE of 4 nx × 8 ny rows and up to
+// 64 nz columns (8 column groups of 8, only the groups the cutoff sphere touches) for a range of particles:
+//
+//   phase A  per chunk of 64 particles: the per-axis tables of the tile (4 + 8 + 8·groups entries per particle, each group of
+//            eight from its own sincos) → shared memory; the x entries carry the weight (charge; PBCEigen: the imaginary
+//            part is summed WITHOUT the charge, which needs a second copy of the x entries)
+//   phase B  warp ↔ (nx of the tile, half of the chunk's k-steps): a k-step is 4 particles; the lane forms its A element
+//            X·Y (one complex product) in registers, the B elements are one LDS.128 per column group, and
+//            C_re += A_re·B_re − A_im·B_im, C_im += A_re·B_im + A_im·B_re are 4 mma.sync.m8n8k4.f64 per group
+//
+// The two halves of a block are added in shared memory (half 0 + half 1), the particle ranges (blockIdx.y) leave their shares
+// in `partials`, and ewaldFullGatherKernel adds them in range order into Q(k) — every sum has a fixed order.
+#pragma once
+
+#include "fb_kspace.cuh"
+
+namespace fbdev {
+
+constexpr int kGemmThreads = 256;
+constexpr int kGemmChunk = 64;     //!< particles per chunk (16 k-steps)
+constexpr int kGemmRows = 32;      //!< rows of a tile: 4 nx × 8 ny
+constexpr int kGemmCols = 64;      //!< columns of a tile: up to 8 groups of 8 nz
+constexpr int kGemmZStride = 66;   //!< z entries per particle, padded: the 4 particles of a k-step in different banks
+constexpr int kGemmYStride = 68;   //!< particles per y row, padded: two y rows of a quarter warp in different banks
+constexpr int kGemmShare = 2 * kGemmRows * kGemmCols; //!< doubles per (tile, particle range): re[32][64], im[32][64]
+
+struct FullGemmSmem
+{
+    double2 x[4][kGemmChunk];       //!< w_re · X(bx + i)
+    double2 xi[4][kGemmChunk];      //!< w_im · X(bx + i) (used by the PBCEigen quirk only)
+    double2 y[8][kGemmYStride];     //!< Y(by + i)
+    double2 z[kGemmChunk][kGemmZStride]; //!< Z(8·gz0 − ncc + i); after the particle loop: the sums of the block's second half
+};
+
+/** one k-step for a warp: NG column groups */
+template <int NG, bool QUIRK>
+__device__ __forceinline__ void gemmStep(const FullGemmSmem& sm, int ix, int row, int j, double (&cre)[8][2], double (&cim)[8][2])
+{
+    const double2 yv = sm.y[row][j];
+    const double2 a = cmul(sm.x[ix][j], yv);
+    double2 b = a;
+    if (QUIRK) {
+        b = cmul(sm.xi[ix][j], yv);
+    }
+    const double na = -a.y;
+    const double2* zrow = &sm.z[j][row];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const double2 zv = zrow[8 * g];
+        dmma884(cre[g][0], cre[g][1], a.x, zv.x);
+        dmma884(cim[g][0], cim[g][1], b.x, zv.y);
+        dmma884(cre[g][0], cre[g][1], na, zv.y);
+        dmma884(cim[g][0], cim[g][1], b.y, zv.x);
+    }
+}
+
+template <int NG, bool QUIRK>
+__device__ __forceinline__ void gemmChunk(const FullGemmSmem& sm, int ix, int half, int lane, double (&cre)[8][2],
+                                          double (&cim)[8][2])
+{
+    const int row = lane >> 2;
+#pragma unroll 2
+    for (int step = half; step < kGemmChunk / 4; step += 2) {
+        gemmStep<NG, QUIRK>(sm, ix, row, 4 * step + (lane & 3), cre, cim);
+    }
+}
+
+/**
+ * @param tiles    [n_tiles] {nx of the first row, y table index of the first row (ny + ncc), first column group
+ *                 (nz = 8·group − ncc), number of column groups}, heaviest tiles first
+ * @param partials [n_tiles][gridDim.y][2][32][64]
+ */
+template <bool QUIRK>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+    ewaldFullGemmKernel(SlotView V, const int4* __restrict__ tiles, PhaseGeometry geo, int range_size,
+                        double* __restrict__ partials)
+{
+    extern __shared__ __align__(16) unsigned char gemm_smem_raw[];
+    FullGemmSmem& sm = *reinterpret_cast<FullGemmSmem*>(gemm_smem_raw);
+    const int4 tile = __ldg(tiles + blockIdx.x);
+    const int ng = tile.w;
+    const int j_begin = static_cast<int>(blockIdx.y) * range_size;
+    const int j_end = min(V.n_slots, j_begin + range_size);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int ix = warp & 3;
+    const int half = warp >> 2;
+    const double two_pi = 2.0 * 3.141592653589793238462643383279502884;
+    const double k1[3] = {two_pi / geo.len[0], two_pi / geo.len[1], two_pi / geo.len[2]};
+
+    double cre[8][2], cim[8][2];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        cre[g][0] = cre[g][1] = cim[g][0] = cim[g][1] = 0.0;
+    }
+
+    const int pj = threadIdx.x & (kGemmChunk - 1);
+    const int part = threadIdx.x / kGemmChunk; // warp-uniform: 0 = x and y entries, 1..3 = column groups part − 1, part + 2, …
+    for (int c0 = j_begin; c0 < j_end; c0 += kGemmChunk) {
+        __syncthreads(); // the previous chunk is consumed
+        {
+            const int j = c0 + pj;
+            double4 p = make_double4(0.0, 0.0, 0.0, 0.0);
+            bool active = false;
+            if (j < j_end && V.gid[j] >= 0) {
+                p = V.posq[j];
+                active = true;
+            }
+            double s, c;
+            if (part == 0) {
+                const double wre = active ? p.w : 0.0;
+                const double wim = active ? (QUIRK ? 1.0 : p.w) : 0.0;
+                sincos(k1[0] * p.x, &s, &c);
+                const double2 sx = make_double2(c, s);
+                sincos(k1[0] * static_cast<double>(tile.x) * p.x, &s, &c);
+                double2 e = make_double2(c, s);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    sm.x[i][pj] = make_double2(wre * e.x, wre * e.y);
+                    if (QUIRK) {
+                        sm.xi[i][pj] = make_double2(wim * e.x, wim * e.y);
+                    }
+                    e = cmul(e, sx);
+                }
+                sincos(k1[1] * p.y, &s, &c);
+                const double2 sy = make_double2(c, s);
+                sincos(k1[1] * static_cast<double>(tile.y - geo.ncc) * p.y, &s, &c);
+                e = make_double2(c, s);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    sm.y[i][pj] = e;
+                    e = cmul(e, sy);
+                }
+            }
+            else if (part - 1 < ng) {
+                sincos(k1[2] * p.z, &s, &c);
+                const double2 sz = make_double2(c, s);
+                for (int g = part - 1; g < ng; g += 3) {
+                    sincos(k1[2] * static_cast<double>(8 * (tile.z + g) - geo.ncc) * p.z, &s, &c);
+                    double2 e = make_double2(c, s);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        sm.z[pj][8 * g + i] = e;
+                        e = cmul(e, sz);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        switch (ng) { // (a predicated mma.sync costs a WARPSYNC each: the group count is a template argument)
+        case 1: gemmChunk<1, QUIRK>(sm, ix, half, lane, cre, cim); break;
+        case 2: gemmChunk<2, QUIRK>(sm, ix, half, lane, cre, cim); break;
+        case 3: gemmChunk<3, QUIRK>(sm, ix, half, lane, cre, cim); break;
+        case 4: gemmChunk<4, QUIRK>(sm, ix, half, lane, cre, cim); break;
+        case 5: gemmChunk<5, QUIRK>(sm, ix, half, lane, cre, cim); break;
+        case 6: gemmChunk<6, QUIRK>(sm, ix, half, lane, cre, cim); break;
+        case 7: gemmChunk<7, QUIRK>(sm, ix, half, lane, cre, cim); break;
+        default: gemmChunk<8, QUIRK>(sm, ix, half, lane, cre, cim); break;
+        }
+    }
+    // half 0 + half 1, then the block's share: row = 8·ix + lane/4, columns 8·g + 2·(lane%4) + {0, 1}
+    __syncthreads();
+    double2* other = reinterpret_cast<double2*>(&sm.z[0][0]); // [4 warps][16 values][32 lanes]
+    if (half == 1) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            other[(ix * 16 + 2 * g) * 32 + lane] = make_double2(cre[g][0], cre[g][1]);
+            other[(ix * 16 + 2 * g + 1) * 32 + lane] = make_double2(cim[g][0], cim[g][1]);
+        }
+    }
+    __syncthreads();
+    if (half == 0) {
+        double* share = partials + (static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * kGemmShare;
+        const int row = 8 * ix + (lane >> 2);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            if (g < ng) {
+                const double2 ore = other[(ix * 16 + 2 * g) * 32 + lane];
+                const double2 oim = other[(ix * 16 + 2 * g + 1) * 32 + lane];
+                const int col = 8 * g + 2 * (lane & 3);
+                *reinterpret_cast<double2*>(share + row * kGemmCols + col) = make_double2(cre[g][0] + ore.x, cre[g][1] + ore.y);
+                *reinterpret_cast<double2*>(share + kGemmRows * kGemmCols + row * kGemmCols + col) =
+                    make_double2(cim[g][0] + oim.x, cim[g][1] + oim.y);
+            }
+        }
+    }
+}
+
+/**
+ * Q(k) = Σ over the particle ranges, in range order, of the tile shares.
+ * @param index [K] (tile · 2048 + row · 64 + column) of every k-vector
+ */
+__global__ void __launch_bounds__(256)
+    ewaldFullGatherKernel(EwaldView E, const int* __restrict__ index, int n_ranges, const double* __restrict__ partials)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= E.K) {
+        return;
+    }
+    const int at = __ldg(index + k);
+    const int tile = at / (kGemmRows * kGemmCols);
+    const int inside = at % (kGemmRows * kGemmCols);
+    const double* share = partials + static_cast<size_t>(tile) * n_ranges * kGemmShare + inside;
+    double2 Q = make_double2(0.0, 0.0);
+    for (int r = 0; r < n_ranges; ++r) {
+        Q.x += share[static_cast<size_t>(r) * kGemmShare];
+        Q.y += share[static_cast<size_t>(r) * kGemmShare + kGemmRows * kGemmCols];
+    }
+    E.Q[k] = Q;
+}
+
+} // namespace fbdev

@@ -220,6 +220,34 @@ def test_ewald_doctest_values(reference_values):
     assert g.system_energy()[1][2] == pytest.approx(o.system_energy()[1][2], rel=1e-10)
 
 
+@pytest.mark.parametrize("scheme,ncutoff,n,alpha", [("PBC", 6, 400, 0.35), ("PBCEigen", 6, 400, 0.35), ("PBC", 11, 700, 0.5),
+                                                    ("PBCEigen", 13.5, 70, 0.5), ("PBC", 34, 130, 1.2)])
+def test_full_q_matrix_product(scheme, ncutoff, n, alpha):
+    """fb_ewald_update_full (ewaldFullGemmKernel, fb_fullq.cuh: Q = [X·Y]·[Z] on the FP64 tensor path) against
+    numpy's Σ_j q_j e^{ik·r_j} over the downloaded k-vectors (src/energy.cpp:191-206; PBCEigen sums the imaginary part
+    WITHOUT the charges, :208-217), tiles of 1 … 8 column groups, two z windows at ncutoff 34, ragged particle ranges"""
+    from faunus_b200 import native
+    lib = native.load()
+    cfg = small_electrolyte(n=n, coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": alpha, "ncutoff": ncutoff,
+                                          "ewaldscheme": scheme})
+    g = b200_sim(cfg)
+    xyzq, _ = g.particles()
+    assert lib.fb_ewald_update_full(g.ctx, 0) == 0
+    kmax = (int(np.ceil(ncutoff)) + 1) * (2 * int(np.ceil(ncutoff)) + 1) ** 2
+    q, kv = np.zeros(2 * kmax), np.zeros(3 * kmax)
+    assert lib.fb_ewald_download(g.ctx, 0, q.ctypes.data_as(native.c_double_p), kv.ctypes.data_as(native.c_double_p), None) == 0
+    kv = kv.reshape(-1, 3)
+    K = int(np.flatnonzero(np.abs(kv).sum(axis=1) > 0).max()) + 1
+    assert K > 100
+    Q = q[:2 * K:2] + 1j * q[1:2 * K:2]
+    ref = np.zeros(K, dtype=complex)
+    for j0 in range(0, len(xyzq), 64):
+        ph = kv[:K] @ xyzq[j0:j0 + 64, :3].T
+        w = xyzq[j0:j0 + 64, 3]
+        ref += np.cos(ph) @ w + 1j * (np.sin(ph).sum(axis=1) if scheme == "PBCEigen" else np.sin(ph) @ w)
+    assert np.abs(Q - ref).max() <= 1e-12 * n
+
+
 def test_reject_restores_state():
     """trial → reject → the next evaluation sees the accepted state again (sync direction)"""
     cfg = small_electrolyte(coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 6})
