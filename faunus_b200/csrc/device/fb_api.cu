@@ -122,9 +122,12 @@ struct Slot
     DeviceBuffer<int> cell_start; //!< [n_cells + 1] first k of each 4×4×4 cell of integer triplets (storage order)
     int n_cells = 0;
     // tiles of the full rebuild of Q(k) (fb_fullq.cuh)
-    DeviceBuffer<int4> gemm_tiles; //!< [n_gemm_tiles] {nx, y table index, first column group, column groups}, heaviest first
+    DeviceBuffer<int4> gemm_tiles; //!< [n_gemm_tiles] {nx, y table index, first column group, column groups}, storage order
+    DeviceBuffer<int> gemm_order;  //!< [n_gemm_tiles] the tiles heaviest first
     DeviceBuffer<int> gemm_index;  //!< [K] tile · 2048 + row · 64 + column of every k-vector
     int n_gemm_tiles = 0;
+    std::vector<int> gemm_tile_first_k;      //!< [n_gemm_tiles + 1] first k-vector of the tile's column of cells
+    std::vector<int> gemm_column_first_tile; //!< [columns + 1] slabs of the sharded energy are ranges of columns
     // work units of the window k-space kernel (fb_kspace.cuh): halves of the cells, 32 k-slots each
     DeviceBuffer<double2> aks;            //!< [K] {A_k, √A_k}
     DeviceBuffer<int4> unit_info;         //!< [n_units] {first k of the cell, x, y, z table index of the first slot}
@@ -762,62 +765,85 @@ void launchFullQ(fb_ctx* c, int s, int cell_begin, int cell_end, bool store_q, d
 }
 
 /**
- * Tiles of ewaldFullGemmKernel for the k-vectors `kn` (any order): 4 nx × 8 ny rows, windows of at most 8 column groups of
- * 8 nz between the first and the last group that holds a k-vector of the tile; heaviest tiles first (they start first).
+ * Tiles of ewaldFullGemmKernel for the k-vectors `kn` (cell by cell, as stored): 4 nx × 8 ny rows — two y-adjacent columns of
+ * cells, a contiguous range of k-vectors — and windows of at most 8 column groups of 8 nz between the first and the last
+ * group that holds a k-vector of the tile. Tiles are numbered in storage order of their k-vectors, so a range of tiles is a
+ * range of k-vectors (the slabs of the sharded energy); `gemm_order` lists them heaviest first (they start first).
  */
 void buildGemmTiles(fb_ctx* c, Slot& sl, const std::vector<int4>& kn)
 {
     sl.n_gemm_tiles = 0;
+    sl.gemm_tile_first_k.clear();
     if (c->ewald.policy == 2 || kn.empty()) {
         return;
     }
     const int ncc = static_cast<int>(std::ceil(c->ewald.n_cutoff));
-    struct Extent
+    struct Column
     {
-        int lo = std::numeric_limits<int>::max(), hi = -1;
+        int lo = std::numeric_limits<int>::max(), hi = -1; // column groups
+        int first_k = 0, end_k = 0, first_tile = 0;
     };
-    std::map<std::pair<int, int>, Extent> extent; // (nx / 4, y index / 8) → column groups
-    for (const int4& n : kn) {
-        Extent& e = extent[{n.x >> 2, (n.y + ncc) >> 3}];
-        const int g = (n.z + ncc) >> 3;
-        e.lo = std::min(e.lo, g);
-        e.hi = std::max(e.hi, g);
+    std::vector<Column> columns; // (nx / 4, y index / 8), in storage order
+    auto key = [&](const int4& n) { return std::make_pair(n.x >> 2, (n.y + ncc) >> 3); };
+    for (size_t i = 0; i < kn.size(); ++i) {
+        if (i == 0 || key(kn[i]) != key(kn[i - 1])) {
+            columns.emplace_back();
+            columns.back().first_k = static_cast<int>(i);
+        }
+        Column& col = columns.back();
+        const int g = (kn[i].z + ncc) >> 3;
+        col.lo = std::min(col.lo, g);
+        col.hi = std::max(col.hi, g);
+        col.end_k = static_cast<int>(i) + 1;
     }
     std::vector<int4> tiles;
-    for (const auto& [key, e] : extent) {
-        for (int g = e.lo; g <= e.hi; g += 8) {
-            tiles.push_back(make_int4(4 * key.first, 8 * key.second, g, std::min(8, e.hi - g + 1)));
+    std::vector<int> index(kn.size());
+    for (Column& col : columns) {
+        col.first_tile = static_cast<int>(tiles.size());
+        const int4 n0 = kn[col.first_k];
+        for (int g = col.lo; g <= col.hi; g += 8) {
+            // (the k-vectors of ONE tile are contiguous only if the column has a single window; a slab is a range of
+            // columns, which always is)
+            sl.gemm_tile_first_k.push_back(col.first_k);
+            tiles.push_back(make_int4(n0.x & ~3, (n0.y + ncc) & ~7, g, std::min(8, col.hi - g + 1)));
+        }
+        for (int i = col.first_k; i < col.end_k; ++i) {
+            const int4 n = kn[i];
+            const int iy = n.y + ncc, g = (n.z + ncc) >> 3;
+            const int t = col.first_tile + ((g - col.lo) >> 3);
+            index[i] = t * (kGemmRows * kGemmCols) + (8 * (n.x & 3) + (iy & 7)) * kGemmCols + ((n.z + ncc) - 8 * tiles[t].z);
         }
     }
-    std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return a.w > b.w; });
-    std::map<std::tuple<int, int, int>, int> tile_of; // (nx / 4, y index / 8, window) → tile
-    for (size_t t = 0; t < tiles.size(); ++t) {
-        const auto& e = extent[{tiles[t].x >> 2, tiles[t].y >> 3}];
-        tile_of[{tiles[t].x >> 2, tiles[t].y >> 3, (tiles[t].z - e.lo) >> 3}] = static_cast<int>(t);
+    sl.gemm_tile_first_k.push_back(static_cast<int>(kn.size()));
+    // a slab boundary must not fall between the windows of one column: boundaries are moved to the column's first tile
+    sl.gemm_column_first_tile.clear();
+    for (const Column& col : columns) {
+        sl.gemm_column_first_tile.push_back(col.first_tile);
     }
-    std::vector<int> index(kn.size());
-    for (size_t i = 0; i < kn.size(); ++i) {
-        const int4 n = kn[i];
-        const int iy = n.y + ncc, g = (n.z + ncc) >> 3;
-        const auto& e = extent[{n.x >> 2, iy >> 3}];
-        const int t = tile_of.at({n.x >> 2, iy >> 3, (g - e.lo) >> 3});
-        const int row = 8 * (n.x & 3) + (iy & 7);
-        const int col = (n.z + ncc) - 8 * tiles[t].z;
-        index[i] = t * (kGemmRows * kGemmCols) + row * kGemmCols + col;
+    sl.gemm_column_first_tile.push_back(static_cast<int>(tiles.size()));
+    std::vector<int> order(tiles.size());
+    for (size_t t = 0; t < order.size(); ++t) {
+        order[t] = static_cast<int>(t);
     }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tiles[a].w > tiles[b].w; });
     sl.n_gemm_tiles = static_cast<int>(tiles.size());
     sl.gemm_tiles.upload(tiles.data(), tiles.size(), c->stream);
+    sl.gemm_order.upload(order.data(), order.size(), c->stream);
     sl.gemm_index.upload(index.data(), index.size(), c->stream);
     CUDA_CHECK(cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
 }
 
 /**
- * Q(k) of a slot from its positions: the complex matrix product of fb_fullq.cuh. The particle ranges depend on the number
- * of particles and tiles only (≈ 6 blocks per SM of a 148-SM part, at least 256 particles each), not on the device.
+ * Q(k) of a slot from its positions as the complex matrix product of fb_fullq.cuh: all tiles → Q(k) (e_partials null), or
+ * the tiles [tile_begin, tile_end) of a slab → partial sums of Σ A_k |Q_k|² over its k-vectors, Q not stored; returns the
+ * number of partial sums. The particle ranges depend on the number of particles and of ALL tiles only — not on the device,
+ * not on the number of slabs: ≈ 6 blocks per SM of a 148-SM part for the full rebuild, of 8 such parts for the slabs.
  */
-void launchFullQGemm(fb_ctx* c, int s)
+int launchFullQGemm(fb_ctx* c, int s, int tile_begin = 0, int tile_end = -1, double* e_partials = nullptr)
 {
     Slot& sl = c->slot[s];
+    const bool slab = e_partials != nullptr;
+    tile_end = tile_end < 0 ? sl.n_gemm_tiles : tile_end;
     PhaseGeometry geo{};
     geo.ncc = static_cast<int>(std::ceil(c->ewald.n_cutoff));
     geo.table_stride = 0;
@@ -825,12 +851,12 @@ void launchFullQGemm(fb_ctx* c, int s)
         geo.len[i] = sl.ewald_box[i];
     }
     const int n = std::max(1, c->n_slots);
-    int n_ranges = std::max(1, (6 * 148 + sl.n_gemm_tiles - 1) / sl.n_gemm_tiles);
+    int n_ranges = std::max(1, ((slab ? 8 : 1) * 6 * 148 + sl.n_gemm_tiles - 1) / sl.n_gemm_tiles);
     n_ranges = std::min(n_ranges, std::max(1, n / 256));
     int range_size = (n + n_ranges - 1) / n_ranges;
     range_size = (range_size + kGemmChunk - 1) / kGemmChunk * kGemmChunk;
     n_ranges = (n + range_size - 1) / range_size;
-    c->fullq_partials.ensure(static_cast<size_t>(sl.n_gemm_tiles) * n_ranges * kGemmShare);
+    c->fullq_partials.ensure(static_cast<size_t>(tile_end - tile_begin) * n_ranges * kGemmShare);
     static thread_local int configured_device = -1; // (a thread drives one context at a time)
     if (configured_device != c->device) {
         CUDA_CHECK(cudaFuncSetAttribute(ewaldFullGemmKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -839,19 +865,29 @@ void launchFullQGemm(fb_ctx* c, int s)
                                         static_cast<int>(sizeof(FullGemmSmem))));
         configured_device = c->device;
     }
-    const dim3 grid(sl.n_gemm_tiles, n_ranges);
+    const dim3 grid(tile_end - tile_begin, n_ranges);
+    const int* order = slab ? nullptr : sl.gemm_order.ptr;
     if (c->ewald.policy == 1) {
         ewaldFullGemmKernel<true><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
-            makeView(c, s), sl.gemm_tiles.ptr, geo, range_size, c->fullq_partials.ptr);
+            makeView(c, s), sl.gemm_tiles.ptr, order, tile_begin, geo, range_size, c->fullq_partials.ptr);
     }
     else {
         ewaldFullGemmKernel<false><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
-            makeView(c, s), sl.gemm_tiles.ptr, geo, range_size, c->fullq_partials.ptr);
+            makeView(c, s), sl.gemm_tiles.ptr, order, tile_begin, geo, range_size, c->fullq_partials.ptr);
     }
     launched(c, "ewaldFullGemmKernel");
-    ewaldFullGatherKernel<<<(sl.K + 255) / 256, 256, 0, c->stream>>>(makeEwaldView(c, s), sl.gemm_index.ptr, n_ranges,
-                                                                    c->fullq_partials.ptr);
-    launched(c, "ewaldFullGatherKernel");
+    if (!slab) {
+        ewaldFullGatherKernel<<<(sl.K + 255) / 256, 256, 0, c->stream>>>(makeEwaldView(c, s), sl.gemm_index.ptr, n_ranges,
+                                                                        c->fullq_partials.ptr);
+        launched(c, "ewaldFullGatherKernel");
+        return 0;
+    }
+    const int k_begin = sl.gemm_tile_first_k[tile_begin], k_end = sl.gemm_tile_first_k[tile_end];
+    const int blocks = (k_end - k_begin + 255) / 256;
+    ewaldFullGatherEnergyKernel<<<blocks, 256, 0, c->stream>>>(makeEwaldView(c, s), sl.gemm_index.ptr, tile_begin, n_ranges,
+                                                              c->fullq_partials.ptr, k_begin, k_end, e_partials);
+    launched(c, "ewaldFullGatherEnergyKernel");
+    return blocks;
 }
 
 /** PolicyIonIon::updateBox / PolicyIonIonIPBC::updateBox, src/energy.cpp:133-186, 356-412 */
@@ -1964,7 +2000,29 @@ FB_API int fb_system_energy_shard(fb_ctx* c, int s, int shard, int n_shards, dou
         Slot& sl = c->slot[s];
         if (c->ewald_configured && sl.K > 0) {
             double sum = 0.0;
-            if (c->ewald.policy != 2 && sl.n_cells > 0) { // a slab of k-cells
+            if (c->ewald.policy != 2 && sl.n_gemm_tiles > 0 && c->full_q_path == 0) { // a slab of tile columns
+                const int n_columns = static_cast<int>(sl.gemm_column_first_tile.size()) - 1;
+                // boundaries where the k-vectors divide evenly: the first column that starts at or after K·r / n
+                auto boundary = [&](int r) {
+                    const long long want = static_cast<long long>(sl.K) * r / n_shards;
+                    int col = 0;
+                    while (col < n_columns && sl.gemm_tile_first_k[sl.gemm_column_first_tile[col]] < want) {
+                        ++col;
+                    }
+                    return r >= n_shards ? sl.n_gemm_tiles : sl.gemm_column_first_tile[col];
+                };
+                const int tile_begin = boundary(shard), tile_end = boundary(shard + 1);
+                if (tile_end > tile_begin) {
+                    const int k_blocks = (sl.gemm_tile_first_k[tile_end] - sl.gemm_tile_first_k[tile_begin] + 255) / 256;
+                    c->partials.ensure(static_cast<size_t>(k_blocks));
+                    const int grid = launchFullQGemm(c, s, tile_begin, tile_end, c->partials.ptr);
+                    orderedSumKernel<<<1, 1024, 0, c->stream>>>(c->partials.ptr, static_cast<size_t>(grid), 1, c->d_result);
+                    launched(c, "orderedSumKernel");
+                    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                    sum = c->h_result[0];
+                }
+            }
+            else if (c->ewald.policy != 2 && sl.n_cells > 0) { // a slab of k-cells
                 const int cell_begin = static_cast<int>(static_cast<long long>(sl.n_cells) * shard / n_shards);
                 const int cell_end = static_cast<int>(static_cast<long long>(sl.n_cells) * (shard + 1) / n_shards);
                 if (cell_end > cell_begin) {
@@ -2548,6 +2606,11 @@ FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
                 d.gemm_tiles.ensure(s.n_gemm_tiles);
                 CUDA_CHECK(cudaMemcpyAsync(d.gemm_tiles.ptr, s.gemm_tiles.ptr, s.n_gemm_tiles * sizeof(int4),
                                            cudaMemcpyDeviceToDevice, c->stream));
+                d.gemm_order.ensure(s.n_gemm_tiles);
+                CUDA_CHECK(cudaMemcpyAsync(d.gemm_order.ptr, s.gemm_order.ptr, s.n_gemm_tiles * sizeof(int),
+                                           cudaMemcpyDeviceToDevice, c->stream));
+                d.gemm_tile_first_k = s.gemm_tile_first_k;
+                d.gemm_column_first_tile = s.gemm_column_first_tile;
                 d.gemm_index.ensure(s.K);
                 CUDA_CHECK(cudaMemcpyAsync(d.gemm_index.ptr, s.gemm_index.ptr, s.K * sizeof(int), cudaMemcpyDeviceToDevice,
                                            c->stream));

@@ -73,17 +73,19 @@ __device__ __forceinline__ void gemmChunk(const FullGemmSmem& sm, int ix, int ha
 
 /**
  * @param tiles    [n_tiles] {nx of the first row, y table index of the first row (ny + ncc), first column group
- *                 (nz = 8·group − ncc), number of column groups}, heaviest tiles first
- * @param partials [n_tiles][gridDim.y][2][32][64]
+ *                 (nz = 8·group − ncc), number of column groups} in storage order of the k-vectors
+ * @param order    block → tile, heaviest tiles first (all tiles), or nullptr: block b takes tile tile_begin + b (a slab)
+ * @param partials [tile − tile_begin][gridDim.y][2][32][64]
  */
 template <bool QUIRK>
 __global__ void __launch_bounds__(kGemmThreads, 2)
-    ewaldFullGemmKernel(SlotView V, const int4* __restrict__ tiles, PhaseGeometry geo, int range_size,
-                        double* __restrict__ partials)
+    ewaldFullGemmKernel(SlotView V, const int4* __restrict__ tiles, const int* __restrict__ order, int tile_begin,
+                        PhaseGeometry geo, int range_size, double* __restrict__ partials)
 {
     extern __shared__ __align__(16) unsigned char gemm_smem_raw[];
     FullGemmSmem& sm = *reinterpret_cast<FullGemmSmem*>(gemm_smem_raw);
-    const int4 tile = __ldg(tiles + blockIdx.x);
+    const int tile_index = order != nullptr ? __ldg(order + blockIdx.x) : tile_begin + static_cast<int>(blockIdx.x);
+    const int4 tile = __ldg(tiles + tile_index);
     const int ng = tile.w;
     const int j_begin = static_cast<int>(blockIdx.y) * range_size;
     const int j_end = min(V.n_slots, j_begin + range_size);
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     }
     __syncthreads();
     if (half == 0) {
-        double* share = partials + (static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y) * kGemmShare;
+        double* share = partials + (static_cast<size_t>(tile_index - tile_begin) * gridDim.y + blockIdx.y) * kGemmShare;
         const int row = 8 * ix + (lane >> 2);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -192,19 +194,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     }
 }
 
-/**
- * Q(k) = Σ over the particle ranges, in range order, of the tile shares.
- * @param index [K] (tile · 2048 + row · 64 + column) of every k-vector
- */
-__global__ void __launch_bounds__(256)
-    ewaldFullGatherKernel(EwaldView E, const int* __restrict__ index, int n_ranges, const double* __restrict__ partials)
+/** Σ over the particle ranges, in range order, of the tile shares of k-vector k */
+__device__ __forceinline__ double2 gatherShares(int at, int tile_begin, int n_ranges, const double* __restrict__ partials)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= E.K) {
-        return;
-    }
-    const int at = __ldg(index + k);
-    const int tile = at / (kGemmRows * kGemmCols);
+    const int tile = at / (kGemmRows * kGemmCols) - tile_begin;
     const int inside = at % (kGemmRows * kGemmCols);
     const double* share = partials + static_cast<size_t>(tile) * n_ranges * kGemmShare + inside;
     double2 Q = make_double2(0.0, 0.0);
@@ -212,7 +205,50 @@ __global__ void __launch_bounds__(256)
         Q.x += share[static_cast<size_t>(r) * kGemmShare];
         Q.y += share[static_cast<size_t>(r) * kGemmShare + kGemmRows * kGemmCols];
     }
-    E.Q[k] = Q;
+    return Q;
+}
+
+/**
+ * Q(k) of all k-vectors from the shares.
+ * @param index [K] (tile · 2048 + row · 64 + column) of every k-vector
+ */
+__global__ void __launch_bounds__(256)
+    ewaldFullGatherKernel(EwaldView E, const int* __restrict__ index, int n_ranges, const double* __restrict__ partials)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < E.K) {
+        E.Q[k] = gatherShares(__ldg(index + k), 0, n_ranges, partials);
+    }
+}
+
+/**
+ * Sharded reciprocal energy: Σ_k A_k |Q_k|² over the k-vectors [k_begin, k_end) of a slab of tiles, one partial sum per
+ * block of 256 k-vectors (fixed shuffle tree, warps in order); Q(k) is not stored.
+ */
+__global__ void __launch_bounds__(256)
+    ewaldFullGatherEnergyKernel(EwaldView E, const int* __restrict__ index, int tile_begin, int n_ranges,
+                                const double* __restrict__ partials, int k_begin, int k_end, double* __restrict__ e_partials)
+{
+    __shared__ double s_e[8];
+    const int k = k_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (k < k_end) {
+        const double2 Q = gatherShares(__ldg(index + k), tile_begin, n_ranges, partials);
+        e = E.kA[k].w * (Q.x * Q.x + Q.y * Q.y);
+    }
+    e = warpSum(e);
+    if ((threadIdx.x & 31) == 0) {
+        s_e[threadIdx.x >> 5] = e;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            s += s_e[w];
+        }
+        e_partials[blockIdx.x] = s;
+    }
 }
 
 } // namespace fbdev

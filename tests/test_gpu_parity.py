@@ -246,6 +246,20 @@ def test_full_q_matrix_product(scheme, ncutoff, n, alpha):
         w = xyzq[j0:j0 + 64, 3]
         ref += np.cos(ph) @ w + 1j * (np.sin(ph).sum(axis=1) if scheme == "PBCEigen" else np.sin(ph) @ w)
     assert np.abs(Q - ref).max() <= 1e-12 * n
+    # slabs of tile columns (fb_system_energy_shard: the same product over a range of tiles, Q not stored) add up to the
+    # reciprocal energy of the numpy sum, whatever the number of slabs
+    if scheme == "PBC":
+        aks = np.zeros(kmax)
+        assert lib.fb_ewald_download(g.ctx, 0, None, None, aks.ctypes.data_as(native.c_double_p)) == 0
+        box = np.array(cfg["geometry"]["length"], dtype=float) * np.ones(3)
+        full = g.system_energy_shard(0, 1)[1]
+        expect = (aks[:K] * np.abs(ref) ** 2).sum()
+        for size in (2, 5):
+            parts = [g.system_energy_shard(r, size)[1] for r in range(size)]
+            assert abs(sum(parts) - full) <= 1e-11 * abs(full)
+            assert sum(1 for x in parts if x != 0.0) >= 2
+        prefactor = full / expect          # 2π lB / V
+        assert prefactor == pytest.approx(2 * np.pi * 7.1 / box.prod(), rel=0.05)   # (lB ≈ 7.1 Å at 78.7, 298 K)
 
 
 def test_reject_restores_state():
