@@ -334,6 +334,7 @@ struct fb_ctx
     DeviceBuffer<double> d_force_knots, d_force_coef; //!< Andrea table of S'(q) (fb_set_force_table)
     int force_nk = 0;
     int full_q_path = 0; //!< 0: matrix product (fb_fullq.cuh), 1: one block per k-cell (FAUNUS_B200_FULLQ=cells; comparisons)
+    DeviceBuffer<double2> fullq_steps;   //!< full rebuild of Q(k): [3 N] weights and x, y unit phases, [N] z unit phases
     DeviceBuffer<double> fullq_partials; //!< full rebuild of Q(k): [tiles][particle ranges][2][32][64] shares
     DeviceBuffer<double2> q_partials; //!< sharded reciprocal energy: [cells of the slab][particle splits][64] shares of Q(k)
     DeviceBuffer<double> d_forces; //!< [n_slots][3]
@@ -766,8 +767,8 @@ void launchFullQ(fb_ctx* c, int s, int cell_begin, int cell_end, bool store_q, d
 
 /**
  * Tiles of ewaldFullGemmKernel for the k-vectors `kn` (cell by cell, as stored): 4 nx × 8 ny rows — two y-adjacent columns of
- * cells, a contiguous range of k-vectors — and windows of at most 8 column groups of 8 nz between the first and the last
- * group that holds a k-vector of the tile. Tiles are numbered in storage order of their k-vectors, so a range of tiles is a
+ * cells, a contiguous range of k-vectors — and windows of at most 8 column groups of 8 nz from the first to the last nz
+ * that holds a k-vector of the tile. Tiles are numbered in storage order of their k-vectors, so a range of tiles is a
  * range of k-vectors (the slabs of the sharded energy); `gemm_order` lists them heaviest first (they start first).
  */
 void buildGemmTiles(fb_ctx* c, Slot& sl, const std::vector<int4>& kn)
@@ -780,7 +781,7 @@ void buildGemmTiles(fb_ctx* c, Slot& sl, const std::vector<int4>& kn)
     const int ncc = static_cast<int>(std::ceil(c->ewald.n_cutoff));
     struct Column
     {
-        int lo = std::numeric_limits<int>::max(), hi = -1; // column groups
+        int lo = std::numeric_limits<int>::max(), hi = -1; // z table indices (nz + ncc)
         int first_k = 0, end_k = 0, first_tile = 0;
     };
     std::vector<Column> columns; // (nx / 4, y index / 8), in storage order
@@ -791,9 +792,8 @@ void buildGemmTiles(fb_ctx* c, Slot& sl, const std::vector<int4>& kn)
             columns.back().first_k = static_cast<int>(i);
         }
         Column& col = columns.back();
-        const int g = (kn[i].z + ncc) >> 3;
-        col.lo = std::min(col.lo, g);
-        col.hi = std::max(col.hi, g);
+        col.lo = std::min(col.lo, kn[i].z + ncc);
+        col.hi = std::max(col.hi, kn[i].z + ncc);
         col.end_k = static_cast<int>(i) + 1;
     }
     std::vector<int4> tiles;
@@ -801,17 +801,17 @@ void buildGemmTiles(fb_ctx* c, Slot& sl, const std::vector<int4>& kn)
     for (Column& col : columns) {
         col.first_tile = static_cast<int>(tiles.size());
         const int4 n0 = kn[col.first_k];
-        for (int g = col.lo; g <= col.hi; g += 8) {
+        for (int z0 = col.lo; z0 <= col.hi; z0 += kGemmCols) { // (the windows start at the column's first nz, not on a grid)
             // (the k-vectors of ONE tile are contiguous only if the column has a single window; a slab is a range of
             // columns, which always is)
             sl.gemm_tile_first_k.push_back(col.first_k);
-            tiles.push_back(make_int4(n0.x & ~3, (n0.y + ncc) & ~7, g, std::min(8, col.hi - g + 1)));
+            tiles.push_back(make_int4(n0.x & ~3, (n0.y + ncc) & ~7, z0, std::min(8, (col.hi - z0 + 8) / 8)));
         }
         for (int i = col.first_k; i < col.end_k; ++i) {
             const int4 n = kn[i];
-            const int iy = n.y + ncc, g = (n.z + ncc) >> 3;
-            const int t = col.first_tile + ((g - col.lo) >> 3);
-            index[i] = t * (kGemmRows * kGemmCols) + (8 * (n.x & 3) + (iy & 7)) * kGemmCols + ((n.z + ncc) - 8 * tiles[t].z);
+            const int iy = n.y + ncc, iz = n.z + ncc;
+            const int t = col.first_tile + (iz - col.lo) / kGemmCols;
+            index[i] = t * (kGemmRows * kGemmCols) + (8 * (n.x & 3) + (iy & 7)) * kGemmCols + (iz - tiles[t].z);
         }
     }
     sl.gemm_tile_first_k.push_back(static_cast<int>(kn.size()));
@@ -837,7 +837,8 @@ void buildGemmTiles(fb_ctx* c, Slot& sl, const std::vector<int4>& kn)
  * Q(k) of a slot from its positions as the complex matrix product of fb_fullq.cuh: all tiles → Q(k) (e_partials null), or
  * the tiles [tile_begin, tile_end) of a slab → partial sums of Σ A_k |Q_k|² over its k-vectors, Q not stored; returns the
  * number of partial sums. The particle ranges depend on the number of particles and of ALL tiles only — not on the device,
- * not on the number of slabs: ≈ 6 blocks per SM of a 148-SM part for the full rebuild, of 8 such parts for the slabs.
+ * not on the number of slabs: ≈ 16 blocks per SM of a 148-SM part for the full rebuild (measured: 6 → 2.47 ms, 12 → 2.30, 24 → 2.28 at S1), of 8 such
+ * parts for the slabs.
  */
 int launchFullQGemm(fb_ctx* c, int s, int tile_begin = 0, int tile_end = -1, double* e_partials = nullptr)
 {
@@ -851,7 +852,11 @@ int launchFullQGemm(fb_ctx* c, int s, int tile_begin = 0, int tile_end = -1, dou
         geo.len[i] = sl.ewald_box[i];
     }
     const int n = std::max(1, c->n_slots);
-    int n_ranges = std::max(1, ((slab ? 8 : 1) * 6 * 148 + sl.n_gemm_tiles - 1) / sl.n_gemm_tiles);
+    static const int blocks_per_sm = [] { // (experiments: FAUNUS_B200_FULLQ_BLOCKS)
+        const char* v = std::getenv("FAUNUS_B200_FULLQ_BLOCKS");
+        return v != nullptr && std::atoi(v) > 0 ? std::atoi(v) : 16;
+    }();
+    int n_ranges = std::max(1, ((slab ? 8 : 1) * blocks_per_sm * 148 + sl.n_gemm_tiles - 1) / sl.n_gemm_tiles);
     n_ranges = std::min(n_ranges, std::max(1, n / 256));
     int range_size = (n + n_ranges - 1) / n_ranges;
     range_size = (range_size + kGemmChunk - 1) / kGemmChunk * kGemmChunk;
@@ -867,13 +872,18 @@ int launchFullQGemm(fb_ctx* c, int s, int tile_begin = 0, int tile_end = -1, dou
     }
     const dim3 grid(tile_end - tile_begin, n_ranges);
     const int* order = slab ? nullptr : sl.gemm_order.ptr;
+    c->fullq_steps.ensure(4 * static_cast<size_t>(n));
+    double2* steps = c->fullq_steps.ptr;
+    double2* zsteps = steps + 3 * static_cast<size_t>(n);
+    ewaldStepPhaseKernel<<<(n + 255) / 256, 256, 0, c->stream>>>(makeView(c, s), geo, c->ewald.policy == 1 ? 1 : 0, steps, zsteps);
+    launched(c, "ewaldStepPhaseKernel");
     if (c->ewald.policy == 1) {
         ewaldFullGemmKernel<true><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
-            makeView(c, s), sl.gemm_tiles.ptr, order, tile_begin, geo, range_size, c->fullq_partials.ptr);
+            c->n_slots, steps, zsteps, sl.gemm_tiles.ptr, order, tile_begin, geo, range_size, c->fullq_partials.ptr);
     }
     else {
         ewaldFullGemmKernel<false><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
-            makeView(c, s), sl.gemm_tiles.ptr, order, tile_begin, geo, range_size, c->fullq_partials.ptr);
+            c->n_slots, steps, zsteps, sl.gemm_tiles.ptr, order, tile_begin, geo, range_size, c->fullq_partials.ptr);
     }
     launched(c, "ewaldFullGemmKernel");
     if (!slab) {

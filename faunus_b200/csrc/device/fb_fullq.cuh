@@ -7,9 +7,10 @@
 // operands and redoes the six sincos of every particle in every cell; here a block owns a TILE of 4 nx × 8 ny rows and up to
 // 64 nz columns (8 column groups of 8, only the groups the cutoff sphere touches) for a range of particles:
 //
-//   phase A  per chunk of 64 particles: the per-axis tables of the tile (4 + 8 + 8·groups entries per particle, each group of
-//            eight from its own sincos) → shared memory; the x entries carry the weight (charge; PBCEigen: the imaginary
-//            part is summed WITHOUT the charge, which needs a second copy of the x entries)
+//   phase A  per chunk of 64 particles: the per-axis tables of the tile (4 + 8 + 8·groups entries per particle) → shared memory,
+//            every entry an integer power of the particle's three unit phases e^{i 2π x / L} (ewaldStepPhaseKernel: the only
+//            sincos of the rebuild), by repeated squaring and running products; the x entries carry the weight (charge;
+//            PBCEigen: the imaginary part is summed WITHOUT the charge, which needs a second copy of the x entries)
 //   phase B  warp ↔ (nx of the tile, half of the chunk's k-steps): a k-step is 4 particles; the lane forms its A element
 //            X·Y (one complex product) in registers, the B elements are one LDS.128 per column group, and
 //            C_re += A_re·B_re − A_im·B_im, C_im += A_re·B_im + A_im·B_re are 4 mma.sync.m8n8k4.f64 per group
@@ -35,7 +36,7 @@ struct FullGemmSmem
     double2 x[4][kGemmChunk];       //!< w_re · X(bx + i)
     double2 xi[4][kGemmChunk];      //!< w_im · X(bx + i) (used by the PBCEigen quirk only)
     double2 y[8][kGemmYStride];     //!< Y(by + i)
-    double2 z[kGemmChunk][kGemmZStride]; //!< Z(8·gz0 − ncc + i); after the particle loop: the sums of the block's second half
+    double2 z[kGemmChunk][kGemmZStride]; //!< Z(z0 − ncc + i); after the particle loop: the sums of the block's second half
 };
 
 /** one k-step for a warp: NG column groups */
@@ -71,16 +72,61 @@ __device__ __forceinline__ void gemmChunk(const FullGemmSmem& sm, int ix, int ha
     }
 }
 
+/** b^n of a unit complex number by repeated squaring (n is the same for the whole block) */
+__device__ __forceinline__ double2 cpowi(double2 b, int n)
+{
+    const bool negative = n < 0;
+    n = negative ? -n : n;
+    double2 r = make_double2(1.0, 0.0);
+    while (n != 0) {
+        if (n & 1) {
+            r = cmul(r, b);
+        }
+        b = cmul(b, b);
+        n >>= 1;
+    }
+    return negative ? make_double2(r.x, -r.y) : r;
+}
+
 /**
- * @param tiles    [n_tiles] {nx of the first row, y table index of the first row (ny + ncc), first column group
- *                 (nz = 8·group − ncc), number of column groups} in storage order of the k-vectors
+ * The three sincos of a particle, once per rebuild (every block of the product would otherwise redo them for its tile):
+ * steps[3 j] = {w_re, w_im} (charge, or 0 for an inactive slot; PBCEigen: w_im = 1), steps[3 j + 1] = e^{i 2π x / Lx},
+ * steps[3 j + 2] = e^{i 2π y / Ly}; zsteps[j] = e^{i 2π z / Lz}. Every table entry of the product is an integer power of these.
+ */
+__global__ void __launch_bounds__(256)
+    ewaldStepPhaseKernel(SlotView V, PhaseGeometry geo, int quirk, double2* __restrict__ steps, double2* __restrict__ zsteps)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= V.n_slots) {
+        return;
+    }
+    const double two_pi = 2.0 * 3.141592653589793238462643383279502884;
+    double4 p = make_double4(0.0, 0.0, 0.0, 0.0);
+    const bool active = V.gid[j] >= 0;
+    if (active) {
+        p = V.posq[j];
+    }
+    double s, c;
+    steps[3 * static_cast<size_t>(j)] = make_double2(active ? p.w : 0.0, active ? (quirk ? 1.0 : p.w) : 0.0);
+    sincos(two_pi / geo.len[0] * p.x, &s, &c);
+    steps[3 * static_cast<size_t>(j) + 1] = make_double2(c, s);
+    sincos(two_pi / geo.len[1] * p.y, &s, &c);
+    steps[3 * static_cast<size_t>(j) + 2] = make_double2(c, s);
+    sincos(two_pi / geo.len[2] * p.z, &s, &c);
+    zsteps[j] = make_double2(c, s);
+}
+
+/**
+ * @param tiles    [n_tiles] {nx of the first row, y table index of the first row (ny + ncc), z table index of the first
+ *                 column (nz + ncc; any integer), number of column groups} in storage order of the k-vectors
  * @param order    block → tile, heaviest tiles first (all tiles), or nullptr: block b takes tile tile_begin + b (a slab)
  * @param partials [tile − tile_begin][gridDim.y][2][32][64]
  */
 template <bool QUIRK>
 __global__ void __launch_bounds__(kGemmThreads, 2)
-    ewaldFullGemmKernel(SlotView V, const int4* __restrict__ tiles, const int* __restrict__ order, int tile_begin,
-                        PhaseGeometry geo, int range_size, double* __restrict__ partials)
+    ewaldFullGemmKernel(int n_slots, const double2* __restrict__ steps, const double2* __restrict__ zsteps,
+                        const int4* __restrict__ tiles, const int* __restrict__ order, int tile_begin, PhaseGeometry geo,
+                        int range_size, double* __restrict__ partials)
 {
     extern __shared__ __align__(16) unsigned char gemm_smem_raw[];
     FullGemmSmem& sm = *reinterpret_cast<FullGemmSmem*>(gemm_smem_raw);
@@ -88,13 +134,11 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     const int4 tile = __ldg(tiles + tile_index);
     const int ng = tile.w;
     const int j_begin = static_cast<int>(blockIdx.y) * range_size;
-    const int j_end = min(V.n_slots, j_begin + range_size);
+    const int j_end = min(n_slots, j_begin + range_size);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int ix = warp & 3;
     const int half = warp >> 2;
-    const double two_pi = 2.0 * 3.141592653589793238462643383279502884;
-    const double k1[3] = {two_pi / geo.len[0], two_pi / geo.len[1], two_pi / geo.len[2]};
 
     double cre[8][2], cim[8][2];
 #pragma unroll
@@ -108,20 +152,18 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         __syncthreads(); // the previous chunk is consumed
         {
             const int j = c0 + pj;
-            double4 p = make_double4(0.0, 0.0, 0.0, 0.0);
-            bool active = false;
-            if (j < j_end && V.gid[j] >= 0) {
-                p = V.posq[j];
-                active = true;
-            }
-            double s, c;
+            const bool in_range = j < j_end;
             if (part == 0) {
-                const double wre = active ? p.w : 0.0;
-                const double wim = active ? (QUIRK ? 1.0 : p.w) : 0.0;
-                sincos(k1[0] * p.x, &s, &c);
-                const double2 sx = make_double2(c, s);
-                sincos(k1[0] * static_cast<double>(tile.x) * p.x, &s, &c);
-                double2 e = make_double2(c, s);
+                double wre = 0.0, wim = 0.0;
+                double2 sx = make_double2(1.0, 0.0), sy = sx;
+                if (in_range) {
+                    const double2 w = steps[3 * static_cast<size_t>(j)]; // (see ewaldStepPhaseKernel)
+                    sx = steps[3 * static_cast<size_t>(j) + 1];
+                    sy = steps[3 * static_cast<size_t>(j) + 2];
+                    wre = w.x;
+                    wim = w.y;
+                }
+                double2 e = cpowi(sx, tile.x);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     sm.x[i][pj] = make_double2(wre * e.x, wre * e.y);
@@ -130,10 +172,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
                     }
                     e = cmul(e, sx);
                 }
-                sincos(k1[1] * p.y, &s, &c);
-                const double2 sy = make_double2(c, s);
-                sincos(k1[1] * static_cast<double>(tile.y - geo.ncc) * p.y, &s, &c);
-                e = make_double2(c, s);
+                e = cpowi(sy, tile.y - geo.ncc);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     sm.y[i][pj] = e;
@@ -141,16 +180,20 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
                 }
             }
             else if (part - 1 < ng) {
-                sincos(k1[2] * p.z, &s, &c);
-                const double2 sz = make_double2(c, s);
+                const double2 sz = in_range ? zsteps[j] : make_double2(1.0, 0.0);
+                double2 e = cpowi(sz, tile.z + 8 * (part - 1) - geo.ncc);
+                double2 s24 = cmul(sz, sz);
+                s24 = cmul(s24, s24);
+                s24 = cmul(s24, s24);            // 8 steps
+                s24 = cmul(cmul(s24, s24), s24); // 24 steps: this thread's next group
                 for (int g = part - 1; g < ng; g += 3) {
-                    sincos(k1[2] * static_cast<double>(8 * (tile.z + g) - geo.ncc) * p.z, &s, &c);
-                    double2 e = make_double2(c, s);
+                    double2 f = e;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        sm.z[pj][8 * g + i] = e;
-                        e = cmul(e, sz);
+                        sm.z[pj][8 * g + i] = f;
+                        f = cmul(f, sz);
                     }
+                    e = cmul(e, s24);
                 }
             }
         }
