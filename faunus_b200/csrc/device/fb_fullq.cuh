@@ -11,12 +11,12 @@
 //            every entry an integer power of the particle's three unit phases e^{i 2π x / L} (ewaldStepPhaseKernel: the only
 //            sincos of the rebuild), by repeated squaring and running products; the x entries carry the weight (charge;
 //            PBCEigen: the imaginary part is summed WITHOUT the charge, which needs a second copy of the x entries)
-//   phase B  warp ↔ (nx of the tile, half of the chunk's k-steps): a k-step is 4 particles; the lane forms its A element
-//            X·Y (one complex product) in registers, the B elements are one LDS.128 per column group, and
-//            C_re += A_re·B_re − A_im·B_im, C_im += A_re·B_im + A_im·B_re are 4 mma.sync.m8n8k4.f64 per group
+//   phase B  warp ↔ (nx of the tile, half of the column groups): a k-step is 4 particles; the lane forms its A element
+//            X·Y (one complex product) in registers, the B elements are one LDS.128 per column group, and the complex
+//            product of the fragments is three mma.sync.m8n8k4.f64 per group (Gauss's three-multiplication form, gemmStep)
 //
-// The two halves of a block are added in shared memory (half 0 + half 1), the particle ranges (blockIdx.y) leave their shares
-// in `partials`, and ewaldFullGatherKernel adds them in range order into Q(k) — every sum has a fixed order.
+// The particle ranges (blockIdx.y) leave their shares in `partials`, and ewaldFullGatherKernel adds them in range order into
+// Q(k) — every sum has a fixed order.
 #pragma once
 
 #include "fb_kspace.cuh"
@@ -36,39 +36,53 @@ struct FullGemmSmem
     double2 x[4][kGemmChunk];       //!< w_re · X(bx + i)
     double2 xi[4][kGemmChunk];      //!< w_im · X(bx + i) (used by the PBCEigen quirk only)
     double2 y[8][kGemmYStride];     //!< Y(by + i)
-    double2 z[kGemmChunk][kGemmZStride]; //!< Z(z0 − ncc + i); after the particle loop: the sums of the block's second half
+    double2 z[kGemmChunk][kGemmZStride]; //!< Z(z0 − ncc + i)
 };
 
-/** one k-step for a warp: NG column groups */
+/**
+ * One k-step (4 particles) of a warp over NG column groups. A complex product costs THREE real ones (Gauss):
+ *   P1 = (A_re + A_im)·B_re,  P2 = A_re·(B_im − B_re),  P3 = A_im·(B_re + B_im)   →   C_re = P1 − P3,  C_im = P1 + P2
+ * so a group is 3 mma.sync.m8n8k4.f64 and two additions on the B element instead of 4 mma; acc[g] = {P1, P2, P3}. With the
+ * PBCEigen quirk the real and the imaginary part carry different weights, P1 cannot be shared: acc[g] = {C_re, C_im, –},
+ * four products.
+ */
 template <int NG, bool QUIRK>
-__device__ __forceinline__ void gemmStep(const FullGemmSmem& sm, int ix, int row, int j, double (&cre)[8][2], double (&cim)[8][2])
+__device__ __forceinline__ void gemmStep(const FullGemmSmem& sm, int ix, int row, int g0, int j, double (&acc)[4][3][2])
 {
     const double2 yv = sm.y[row][j];
     const double2 a = cmul(sm.x[ix][j], yv);
-    double2 b = a;
+    const double2* zrow = &sm.z[j][8 * g0 + row];
     if (QUIRK) {
-        b = cmul(sm.xi[ix][j], yv);
-    }
-    const double na = -a.y;
-    const double2* zrow = &sm.z[j][row];
+        const double2 b = cmul(sm.xi[ix][j], yv);
+        const double na = -a.y;
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        const double2 zv = zrow[8 * g];
-        dmma884(cre[g][0], cre[g][1], a.x, zv.x);
-        dmma884(cim[g][0], cim[g][1], b.x, zv.y);
-        dmma884(cre[g][0], cre[g][1], na, zv.y);
-        dmma884(cim[g][0], cim[g][1], b.y, zv.x);
+        for (int g = 0; g < NG; ++g) {
+            const double2 zv = zrow[8 * g];
+            dmma884(acc[g][0][0], acc[g][0][1], a.x, zv.x);
+            dmma884(acc[g][1][0], acc[g][1][1], b.x, zv.y);
+            dmma884(acc[g][0][0], acc[g][0][1], na, zv.y);
+            dmma884(acc[g][1][0], acc[g][1][1], b.y, zv.x);
+        }
+    }
+    else {
+        const double sa = a.x + a.y;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const double2 zv = zrow[8 * g];
+            dmma884(acc[g][0][0], acc[g][0][1], sa, zv.x);
+            dmma884(acc[g][1][0], acc[g][1][1], a.x, zv.y - zv.x);
+            dmma884(acc[g][2][0], acc[g][2][1], a.y, zv.x + zv.y);
+        }
     }
 }
 
 template <int NG, bool QUIRK>
-__device__ __forceinline__ void gemmChunk(const FullGemmSmem& sm, int ix, int half, int lane, double (&cre)[8][2],
-                                          double (&cim)[8][2])
+__device__ __forceinline__ void gemmChunk(const FullGemmSmem& sm, int ix, int g0, int lane, double (&acc)[4][3][2])
 {
     const int row = lane >> 2;
 #pragma unroll 2
-    for (int step = half; step < kGemmChunk / 4; step += 2) {
-        gemmStep<NG, QUIRK>(sm, ix, row, 4 * step + (lane & 3), cre, cim);
+    for (int step = 0; step < kGemmChunk / 4; ++step) {
+        gemmStep<NG, QUIRK>(sm, ix, row, g0, 4 * step + (lane & 3), acc);
     }
 }
 
@@ -140,10 +154,16 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     const int ix = warp & 3;
     const int half = warp >> 2;
 
-    double cre[8][2], cim[8][2];
+    // the two warps of an nx share the column groups (the first ⌈ng / 2⌉ and the rest: both on the same SM sub-partition)
+    const int g0 = half == 0 ? 0 : (ng + 1) / 2;
+    const int my_ng = half == 0 ? (ng + 1) / 2 : ng / 2;
+    double acc[4][3][2];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        cre[g][0] = cre[g][1] = cim[g][0] = cim[g][1] = 0.0;
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            acc[g][t][0] = acc[g][t][1] = 0.0;
+        }
     }
 
     const int pj = threadIdx.x & (kGemmChunk - 1);
@@ -198,41 +218,32 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
             }
         }
         __syncthreads();
-        switch (ng) { // (a predicated mma.sync costs a WARPSYNC each: the group count is a template argument)
-        case 1: gemmChunk<1, QUIRK>(sm, ix, half, lane, cre, cim); break;
-        case 2: gemmChunk<2, QUIRK>(sm, ix, half, lane, cre, cim); break;
-        case 3: gemmChunk<3, QUIRK>(sm, ix, half, lane, cre, cim); break;
-        case 4: gemmChunk<4, QUIRK>(sm, ix, half, lane, cre, cim); break;
-        case 5: gemmChunk<5, QUIRK>(sm, ix, half, lane, cre, cim); break;
-        case 6: gemmChunk<6, QUIRK>(sm, ix, half, lane, cre, cim); break;
-        case 7: gemmChunk<7, QUIRK>(sm, ix, half, lane, cre, cim); break;
-        default: gemmChunk<8, QUIRK>(sm, ix, half, lane, cre, cim); break;
+        switch (my_ng) { // (a predicated mma.sync costs a WARPSYNC each: the group count is a template argument)
+        case 1: gemmChunk<1, QUIRK>(sm, ix, g0, lane, acc); break;
+        case 2: gemmChunk<2, QUIRK>(sm, ix, g0, lane, acc); break;
+        case 3: gemmChunk<3, QUIRK>(sm, ix, g0, lane, acc); break;
+        case 4: gemmChunk<4, QUIRK>(sm, ix, g0, lane, acc); break;
+        default: break;
         }
     }
-    // half 0 + half 1, then the block's share: row = 8·ix + lane/4, columns 8·g + 2·(lane%4) + {0, 1}
-    __syncthreads();
-    double2* other = reinterpret_cast<double2*>(&sm.z[0][0]); // [4 warps][16 values][32 lanes]
-    if (half == 1) {
+    // the block's share: row = 8·ix + lane/4, columns 8·g + 2·(lane%4) + {0, 1}
+    double* share = partials + (static_cast<size_t>(tile_index - tile_begin) * gridDim.y + blockIdx.y) * kGemmShare;
+    const int row = 8 * ix + (lane >> 2);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            other[(ix * 16 + 2 * g) * 32 + lane] = make_double2(cre[g][0], cre[g][1]);
-            other[(ix * 16 + 2 * g + 1) * 32 + lane] = make_double2(cim[g][0], cim[g][1]);
-        }
-    }
-    __syncthreads();
-    if (half == 0) {
-        double* share = partials + (static_cast<size_t>(tile_index - tile_begin) * gridDim.y + blockIdx.y) * kGemmShare;
-        const int row = 8 * ix + (lane >> 2);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            if (g < ng) {
-                const double2 ore = other[(ix * 16 + 2 * g) * 32 + lane];
-                const double2 oim = other[(ix * 16 + 2 * g + 1) * 32 + lane];
-                const int col = 8 * g + 2 * (lane & 3);
-                *reinterpret_cast<double2*>(share + row * kGemmCols + col) = make_double2(cre[g][0] + ore.x, cre[g][1] + ore.y);
-                *reinterpret_cast<double2*>(share + kGemmRows * kGemmCols + row * kGemmCols + col) =
-                    make_double2(cim[g][0] + oim.x, cim[g][1] + oim.y);
+    for (int g = 0; g < 4; ++g) {
+        if (g < my_ng) {
+            const int col = 8 * (g0 + g) + 2 * (lane & 3);
+            double2 re, im;
+            if (QUIRK) {
+                re = make_double2(acc[g][0][0], acc[g][0][1]);
+                im = make_double2(acc[g][1][0], acc[g][1][1]);
             }
+            else {
+                re = make_double2(acc[g][0][0] - acc[g][2][0], acc[g][0][1] - acc[g][2][1]);
+                im = make_double2(acc[g][0][0] + acc[g][1][0], acc[g][0][1] + acc[g][1][1]);
+            }
+            *reinterpret_cast<double2*>(share + row * kGemmCols + col) = re;
+            *reinterpret_cast<double2*>(share + kGemmRows * kGemmCols + row * kGemmCols + col) = im;
         }
     }
 }
