@@ -318,6 +318,17 @@ def sharded_extras(args, native, torch, dist, rank, world, local):
         shares["nonbonded"], shares["reciprocal"] = float(tot[0]), float(tot[1])
 
     dt_energy = timed(energy, 2)
+    # full rebuild of Q(k) from the positions (every volume move, tempering exchange, restart): the matrix-product kernel
+    # of fb_fullq.cuh, device time of step phases + product + gather (CUDA events on the context's stream)
+    lib = native.load()
+    lib.fb_enable_timing(sim.ctx, 1)
+    full_q_ms = []
+    for _ in range(4):
+        if lib.fb_ewald_update_full(sim.ctx, 0) != 0:
+            raise RuntimeError("fb_ewald_update_full failed")
+        full_q_ms.append(lib.fb_last_kernel_ms(sim.ctx))
+    lib.fb_enable_timing(sim.ctx, 0)
+    full_q_ms = min(full_q_ms[1:])
     # atomrdf (the dominant non-energy cost of examples/bulk): every Na-Cl pair of the configuration into a
     # distance histogram; tile rows dealt to the ranks, integer all-reduce of the histograms
     rdf = sim.rdf_create({"name1": "Na", "name2": "Cl", "dr": 0.1, "file": "rdf.dat"})
@@ -347,6 +358,10 @@ def sharded_extras(args, native, torch, dist, rank, world, local):
         "system_energy": {"ms": 1e3 * dt_energy, "nonbonded_kT": shares.get("nonbonded"),
                           "reciprocal_kT": shares.get("reciprocal"),
                           "pairs": N_IONS * (N_IONS - 1) // 2, "n_times_k": N_IONS * 57950},
+        "full_q": {"ms": full_q_ms, "kernel": "ewaldStepPhaseKernel + ewaldFullGemmKernel + ewaldFullGatherKernel",
+                   "algorithmic_tflops": 8.0 * N_IONS * 57950 / (full_q_ms / 1e3) / 1e12,
+                   "flop_model": "8 per particle and k-vector (one complex multiply-add); not sharded: every rank rebuilds "
+                                 "its own Q(k)"},
         "atom_rdf": {"ms_per_sample_e2e": 1e3 * dt_rdf, "pairs_per_sample": (N_IONS // 2) ** 2,
                      "pair_distances_per_s": (N_IONS // 2) ** 2 / dt_rdf,
                      "pairs_counted_after_3_samples": rdf_total.get("pairs"),
@@ -406,6 +421,8 @@ def sharded_summary(extras, world):
     out = {"n_gpus": world, "widom_fast_ins_per_s": round(w["fast_mode"]["insertions_per_s"]),
            "widom_parity_ins_per_s": round(w["insertions_per_s"]), "widom_kernel_ms_rank": round(w["kernel_ms_this_rank"], 3),
            "energy_ms": round(extras["system_energy"]["ms"], 3), "rdf_ms": round(extras["atom_rdf"]["ms_per_sample_e2e"], 3)}
+    if "full_q" in extras:
+        out["full_q_ms"] = round(extras["full_q"]["ms"], 3)
     if "temper" in extras:
         out["temper_sweeps_per_s"] = round(extras["temper"]["sweeps_per_s"], 1)
         out["temper_moves_per_s_all"] = round(extras["temper"]["moves_per_s_all_replicas"])
@@ -601,6 +618,12 @@ def b200_arm(args):
                                         "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
                                         "pairs_per_s": pairs / (w["kernel_ms_this_rank"] / 1e3),
                                         "ms_per_launch": w["kernel_ms_this_rank"]}
+        if extras and extras.get("full_q", {}).get("ms"):
+            f = extras["full_q"]
+            roofline["full_q_kernel"] = {"kernel": "ewaldFullGemmKernel (Q = [X.Y].[Z] on the FP64 tensor path, + step phases "
+                                                   "and gather)", "bound": "fp64", "achieved": f["algorithmic_tflops"],
+                                         "peak": peak, "unit": "TFLOP/s", "frac": f["algorithmic_tflops"] / peak,
+                                         "ms_per_launch": f["ms"], "flop_model": f["flop_model"]}
     cpu = None
     parity = None
     if not args.no_cpu_baseline:
