@@ -421,7 +421,10 @@ int fb_molecule_rdf(fb_ctx* ctx, int slot, int molid1, int molid2, double dr, in
 int fb_ewald_configure(fb_ctx* ctx, const fb_ewald_config* config);
 /* k-vectors and A_k for the slot's current box (PolicyIonIon::updateBox); returns K in *n_kvectors */
 int fb_ewald_update_box(fb_ctx* ctx, int slot, int* n_kvectors);
-/* Q(k) = sum_j q_j exp(i k.r_j) over all active particles (updateComplex, full) */
+/* Q(k) = sum_j q_j exp(i k.r_j) over all active particles (updateComplex, full; src/energy.cpp:191-217). PBC / PBCEigen:
+ * a complex matrix product [X.Y] x [Z] on the FP64 tensor path (ewaldFullGemmKernel, fb_fullq.cuh), sums in a fixed order;
+ * with timing enabled fb_last_kernel_ms() is the device time of the rebuild. FAUNUS_B200_FULLQ=cells (at fb_create)
+ * selects the older one-block-per-k-cell kernel for comparisons. */
 int fb_ewald_update_full(fb_ctx* ctx, int slot);
 /* Q_new(k) = Q_old(k) + sum_moved [q e^{ik.r}]_new - [q e^{ik.r}]_old (updateComplex, partial) */
 int fb_ewald_update_partial(fb_ctx* ctx, int slot_new, int slot_old, const fb_change* change);
