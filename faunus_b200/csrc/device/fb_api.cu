@@ -333,6 +333,7 @@ struct fb_ctx
     // forces (fb_force.cuh)
     DeviceBuffer<double> d_force_knots, d_force_coef; //!< Andrea table of S'(q) (fb_set_force_table)
     int force_nk = 0;
+    int full_pair_path = 0; //!< 0: FP32-screened full pair sum (fullScreenKernel), 1: all-FP64 fullStreamKernel (FAUNUS_B200_FULLPAIR=fp64)
     int full_q_path = 0; //!< 0: matrix product (fb_fullq.cuh), 1: one block per k-cell (FAUNUS_B200_FULLQ=cells; comparisons)
     DeviceBuffer<double2> fullq_steps;   //!< full rebuild of Q(k): [3 N] weights and x, y unit phases, [N] z unit phases
     DeviceBuffer<double> fullq_partials; //!< full rebuild of Q(k): [tiles][particle ranges][2][32][64] shares
@@ -386,15 +387,19 @@ void launched(fb_ctx* c, const char* what);
  * 2⁻²⁴ relative, two subtractions per component (≤ 8·2⁻²⁴·L per component), three products and two sums — so that no
  * pair inside the true cutoff is lost
  */
-float screeningCutoff(const fb_ctx* c, int s)
+float screeningCutoffFor(const fb_ctx* c, double lmax)
 {
     const double eps = 5.9604644775390625e-08; // 2⁻²⁴
-    const double* box = c->slot[s].box;
-    const double lmax = std::max(box[0], std::max(box[1], box[2]));
     const double rc = std::sqrt(c->pair_cut2);
     const double ec = 8.0 * eps * lmax;
     const double widened = (c->pair_cut2 + 2.0 * std::sqrt(3.0) * rc * ec + 3.0 * ec * ec + 8.0 * eps * c->pair_cut2) * (1.0 + 1e-6);
     return std::nextafter(static_cast<float>(widened), std::numeric_limits<float>::infinity());
+}
+
+float screeningCutoff(const fb_ctx* c, int s)
+{
+    const double* box = c->slot[s].box;
+    return screeningCutoffFor(c, std::max(box[0], std::max(box[1], box[2])));
 }
 
 /** Write a lazily accepted fast-path move into both mirrors before any other kind of access */
@@ -666,6 +671,11 @@ template <int KIND> void launchFullStream(fb_ctx* c, const SlotView& V, dim3 gri
         fullStreamKernel<KIND, true><<<grid, kStreamThreads, 0, c->stream>>>(V, c->P, c->pair_cut2, 0, shard, n_shards,
                                                                              c->partials.ptr);
     }
+    else if (c->full_pair_path == 0 && c->n_slots < (1 << 26)) { // finite cutoff: FP32 screening, FP64 candidates
+        const double lmax = std::max(V.len[0], std::max(V.len[1], V.len[2]));
+        fullScreenKernel<KIND><<<grid, kStreamThreads, 0, c->stream>>>(V, c->P, c->pair_cut2, screeningCutoffFor(c, lmax), shard,
+                                                                      n_shards, c->partials.ptr);
+    }
     else {
         fullStreamKernel<KIND, false><<<grid, kStreamThreads, 0, c->stream>>>(V, c->P, c->pair_cut2, 0, shard,
                                                                               n_shards, c->partials.ptr);
@@ -678,8 +688,15 @@ void launchFull(fb_ctx* c, const SlotView& V, int volume_predicate, int shard = 
         const int n_itiles = (c->n_slots + kStreamVariants - 1) / kStreamVariants;
         // rows of 64 particles × every gy-th chunk of the particles j: enough blocks to fill the machine, and — when the
         // rows are dealt over several GPUs — short enough ones (row r streams N − 64 r particles: with one block per row the
-        // first rows of a rank alone took 1–1.6 ms of the 0.54 ms an eighth of the pairs should)
-        const int gy = std::max(1, std::min(16, (8 * c->n_sm * n_shards + n_itiles - 1) / std::max(1, n_itiles)));
+        // first rows of a rank alone took 1–1.6 ms of the 0.54 ms an eighth of the pairs should). ≈ 64 blocks per SM: the
+        // rows are a triangle, short blocks even it out (S1, one GPU, measured: gy 1 → 2.95 ms, 4 → 2.59, 8 → 2.53)
+        static const int gy_forced = [] { // (experiments: FAUNUS_B200_FULL_GY)
+            const char* v = std::getenv("FAUNUS_B200_FULL_GY");
+            return v != nullptr ? std::atoi(v) : 0;
+        }();
+        const int gy = gy_forced > 0
+                           ? gy_forced
+                           : std::max(1, std::min(16, (64 * c->n_sm * n_shards + n_itiles - 1) / std::max(1, n_itiles)));
         const dim3 grid(n_itiles, gy);
         const size_t npart = static_cast<size_t>(n_itiles) * gy;
         c->partials.ensure(std::max<size_t>(npart, 4 * kMaxPartialBlocks));
@@ -1009,6 +1026,9 @@ FB_API int fb_create(const fb_config* cfg, fb_ctx** out)
         }
         c = new fb_ctx();
         c->device = cfg->device;
+        if (const char* v = std::getenv("FAUNUS_B200_FULLPAIR")) {
+            c->full_pair_path = std::strcmp(v, "fp64") == 0 ? 1 : 0;
+        }
         if (const char* v = std::getenv("FAUNUS_B200_FULLQ")) {
             c->full_q_path = std::strcmp(v, "cells") == 0 ? 1 : 0;
         }

@@ -601,6 +601,189 @@ __global__ void __launch_bounds__(kStreamThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Full energy of an all-atomic system with a finite cutoff: the rows and chunks of fullStreamKernel with the FP32 screening of
+// widomScreenKernel — lane ↔ 4 particles j in registers as FP32, the distance test on the FMA pipes against the cutoff widened
+// by the bound of the FP32 rounding error (screeningCutoff, fb_api.cu), the candidates (0.1 % of the pairs at S1) queued per
+// warp in ballot order and evaluated in FP64 from the FP64 positions with the reference's minimum-image arithmetic and the
+// exact test r² < cut². partials[blockIdx.y · gridDim.x + blockIdx.x] = Σ over the block's pairs (lane sums in queue order,
+// fixed shuffle tree, warps in order).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFullScreenPerThread = 4;
+constexpr int kFullScreenChunk = kStreamThreads * kFullScreenPerThread;
+
+template <int KIND>
+__global__ void __launch_bounds__(kStreamThreads)
+    fullScreenKernel(SlotView V, PotParams P, double cut2, float cut2_screen, int shard, int n_shards,
+                     double* __restrict__ partials /*[gridDim.x · gridDim.y]*/)
+{
+    constexpr int NW = kStreamThreads / 32;
+    constexpr int PT = kFullScreenPerThread;
+    __shared__ double4 s_var[kStreamVariants];
+    __shared__ float4 s_varf[kStreamVariants];
+    __shared__ int s_vid[kStreamVariants];
+    __shared__ unsigned s_qe[NW][kStreamQueue]; //!< variant of the block | particle << 6
+    __shared__ double s_sum[NW];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int i0 = blockIdx.x * kStreamVariants;
+    const size_t out_index = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
+    if (static_cast<int>(blockIdx.x) % n_shards != shard) {
+        if (threadIdx.x == 0) {
+            partials[out_index] = 0.0;
+        }
+        return;
+    }
+    const float hx = static_cast<float>(V.half[0]), hy = static_cast<float>(V.half[1]), hz = static_cast<float>(V.half[2]);
+    const float lx = static_cast<float>(V.len_or_zero[0]), ly = static_cast<float>(V.len_or_zero[1]),
+                lz = static_cast<float>(V.len_or_zero[2]);
+    const float nanf_ = __int_as_float(0x7fc00000);
+    for (int v = threadIdx.x; v < kStreamVariants; v += kStreamThreads) {
+        const int i = i0 + v;
+        double4 a = make_double4(0, 0, 0, 0);
+        int id = 0;
+        float4 af = make_float4(nanf_, 0.0f, 0.0f, 0.0f); // inactive: never in range
+        if (i < V.n_slots && V.gid[i] >= 0) {
+            a = V.posq[i];
+            id = V.atom_id[i];
+            const float rc = sqrtf(cut2_screen) * 1.0001f;
+            int fold = 0;
+            fold |= (lx > 0.0f && !(fabsf(static_cast<float>(a.x)) + rc < hx)) ? 1 : 0;
+            fold |= (ly > 0.0f && !(fabsf(static_cast<float>(a.y)) + rc < hy)) ? 2 : 0;
+            fold |= (lz > 0.0f && !(fabsf(static_cast<float>(a.z)) + rc < hz)) ? 4 : 0;
+            af = make_float4(static_cast<float>(a.x), static_cast<float>(a.y), static_cast<float>(a.z), __int_as_float(fold));
+        }
+        s_var[v] = a;
+        s_varf[v] = af;
+        s_vid[v] = id;
+    }
+    __syncthreads();
+
+    double esum = 0.0;
+    int queued = 0; // warp-uniform
+    auto flush = [&]() {
+        for (int e = lane; e < queued; e += 32) {
+            const unsigned ent = s_qe[warp][e];
+            const int v = ent & 0x3fu;
+            const int j = ent >> 6;
+            const double4 a = s_var[v];
+            const double4 b = V.posq[j]; // the candidates are few: double-precision positions from L2
+            const double r2 = minImageR2(V, a.x, a.y, a.z, b.x, b.y, b.z);
+            if (r2 < cut2) {
+                esum += pairEnergy<KIND>(P, s_vid[v], V.atom_id[j], a.w, b.w, r2);
+            }
+        }
+        __syncwarp();
+        queued = 0;
+    };
+
+    // j-chunks from the one containing i0 on; blockIdx.y takes every gridDim.y-th chunk
+    const int first_chunk = i0 / kFullScreenChunk;
+    const int n_chunks = (V.n_slots + kFullScreenChunk - 1) / kFullScreenChunk;
+    for (int chunk = first_chunk + blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
+        const int base = chunk * kFullScreenChunk;
+        float px[PT], py[PT], pz[PT];
+        int pj[PT];
+#pragma unroll
+        for (int t = 0; t < PT; ++t) {
+            const int j = base + t * kStreamThreads + threadIdx.x;
+            pj[t] = j;
+            px[t] = nanf_;
+            py[t] = pz[t] = 0.0f;
+            if (j < V.n_slots && V.gid[j] >= 0) {
+                const double4 p = V.posq[j];
+                px[t] = static_cast<float>(p.x);
+                py[t] = static_cast<float>(p.y);
+                pz[t] = static_cast<float>(p.z);
+            }
+        }
+        const bool diagonal = base < i0 + kStreamVariants; // some j of this chunk are ≤ some i of the tile
+        for (int vv = 0; vv < kStreamVariants; vv += 2) {
+            float r2[2][PT];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float4 a = s_varf[vv + u];
+                const int fold = __float_as_int(a.w);
+                float dx[PT], dy[PT], dz[PT];
+#pragma unroll
+                for (int t = 0; t < PT; ++t) {
+                    dx[t] = a.x - px[t];
+                    dy[t] = a.y - py[t];
+                    dz[t] = a.z - pz[t];
+                }
+                if (fold & 1) {
+#pragma unroll
+                    for (int t = 0; t < PT; ++t) {
+                        const float ad = fabsf(dx[t]);
+                        dx[t] = (ad > hx) ? ad - lx : dx[t];
+                    }
+                }
+                if (fold & 2) {
+#pragma unroll
+                    for (int t = 0; t < PT; ++t) {
+                        const float ad = fabsf(dy[t]);
+                        dy[t] = (ad > hy) ? ad - ly : dy[t];
+                    }
+                }
+                if (fold & 4) {
+#pragma unroll
+                    for (int t = 0; t < PT; ++t) {
+                        const float ad = fabsf(dz[t]);
+                        dz[t] = (ad > hz) ? ad - lz : dz[t];
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < PT; ++t) {
+                    r2[u][t] = fmaf(dz[t], dz[t], fmaf(dy[t], dy[t], dx[t] * dx[t]));
+                }
+            }
+            bool any_in = false;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                for (int t = 0; t < PT; ++t) {
+                    any_in = any_in || (r2[u][t] < cut2_screen);
+                }
+            }
+            if (!__any_sync(0xffffffffu, any_in)) {
+                continue;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                for (int t = 0; t < PT; ++t) {
+                    const bool in = r2[u][t] < cut2_screen && (!diagonal || pj[t] > i0 + vv + u);
+                    const unsigned mask = __ballot_sync(0xffffffffu, in);
+                    if (in) {
+                        const int at = queued + __popc(mask & ((1u << lane) - 1u));
+                        s_qe[warp][at] = static_cast<unsigned>(vv + u) | (static_cast<unsigned>(pj[t]) << 6);
+                    }
+                    queued += __popc(mask);
+                }
+            }
+            __syncwarp();
+            if (queued > kStreamQueue - 2 * PT * 32) {
+                flush();
+            }
+        }
+    }
+    flush();
+    esum = warpSum(esum);
+    if (lane == 0) {
+        s_sum[warp] = esum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            s += s_sum[w];
+        }
+        partials[out_index] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Full rebuild of Q(k) (PolicyIonIon::updateComplex, src/energy.cpp:191-206; PBCEigen quirk :208-217) with
 // factorised phases: one block per 4×4×4 cell of k-vectors, particles in chunks of 256.
 //   phase A  thread ↔ particle: 2 sincos per axis (cell base 2π b x/L and step 2π x/L), the other three
