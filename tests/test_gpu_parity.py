@@ -262,6 +262,36 @@ def test_full_q_matrix_product(scheme, ncutoff, n, alpha):
         assert prefactor == pytest.approx(2 * np.pi * 7.1 / box.prod(), rel=0.05)   # (lB ≈ 7.1 Å at 78.7, 298 K)
 
 
+def test_full_q_matrix_product_cuboid_and_inactive():
+    """The same product in a box with three different side lengths (non-spherical sum: every |n| ≤ n_cutoff) and with
+    inactive slots (a ghost group of capacity 4, empty): inactive particles carry no weight in either part"""
+    from faunus_b200 import native
+    lib = native.load()
+    for scheme in ("PBC", "PBCEigen"):
+        cfg = small_electrolyte(n=300, ghost_pairs=2,
+                                coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.4, "ncutoff": 7,
+                                         "spherical_sum": False, "ewaldscheme": scheme})
+        scale = np.array([1.3, 0.8, 1.0])
+        cfg["geometry"]["length"] = (np.array(cfg["geometry"]["length"]) * scale).tolist()
+        for p in cfg["particles"]:
+            p["pos"] = (np.array(p["pos"]) * scale).tolist()
+        g = b200_sim(cfg)
+        xyzq, _ = g.particles()
+        assert len(xyzq) == 304
+        assert lib.fb_ewald_update_full(g.ctx, 0) == 0
+        kmax = 8 * 15 * 15
+        q, kv = np.zeros(2 * kmax), np.zeros(3 * kmax)
+        assert lib.fb_ewald_download(g.ctx, 0, q.ctypes.data_as(native.c_double_p), kv.ctypes.data_as(native.c_double_p), None) == 0
+        kv = kv.reshape(-1, 3)
+        K = int(np.flatnonzero(np.abs(kv).sum(axis=1) > 0).max()) + 1
+        assert K == 8 * 15 * 15 - 1       # nx = 0 … 7, ny, nz = −7 … 7, without k = 0
+        Q = q[:2 * K:2] + 1j * q[1:2 * K:2]
+        ph = kv[:K] @ xyzq[:300, :3].T    # the four inactive slots are left out
+        w = xyzq[:300, 3]
+        ref = np.cos(ph) @ w + 1j * (np.sin(ph).sum(axis=1) if scheme == "PBCEigen" else np.sin(ph) @ w)
+        assert np.abs(Q - ref).max() <= 1e-12 * 300
+
+
 def test_reject_restores_state():
     """trial → reject → the next evaluation sees the accepted state again (sync direction)"""
     cfg = small_electrolyte(coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 6})
