@@ -10,7 +10,14 @@ import bench
 
 which = sys.argv[1] if len(sys.argv) > 1 else "s1"
 repeats = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-cfg = bench.workload(which=which)
+if which.startswith("n="):  # e.g. n=2304,ncutoff=11,alpha=0.3: a small electrolyte (the crossover with the cell kernel)
+    from faunus_b200.config import primitive_model
+    kv = dict(item.split("=") for item in which.split(","))
+    cfg = primitive_model(n=int(kv["n"]), molarity=1.0, seed=7, placement="lattice",
+                          coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": float(kv.get("alpha", 0.35)),
+                                   "ncutoff": float(kv.get("ncutoff", 7))})
+else:
+    cfg = bench.workload(which=which)
 lib = native.load()
 out = {}
 for path in ("gemm", "cells"):
