@@ -34,7 +34,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-MOVES_PER_STEP = 20000  # a fifth of the reference's own sweep for this system (`repeat: N`)
+# moves per step (sweep): a fifth of the reference's own sweep for this system (`repeat: N`); FAUNUS_B200_MOVES_PER_STEP
+# for side-by-side runs (the queue of proposals drains at the end of every sweep)
+MOVES_PER_STEP = int(os.environ.get("FAUNUS_B200_MOVES_PER_STEP", "20000"))
 N_IONS = 100_000
 FLOP_PER_PAIR = 49          # splined Coulomb + WCA, pair within the cutoffs, SURVEY §8(d)
 FLOP_PER_FAR_PAIR = 25      # pair beyond both cutoffs: min-image r² (20) + sqrt, +eps, r<Rc test (3) + WCA cut test (2)
