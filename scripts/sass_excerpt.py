@@ -29,7 +29,8 @@ def pick(fragment):
 print("# cuobjdump -sass faunus_b200/_build/libfaunus_b200.so (nvcc 12.9, -gencode arch=compute_100a,code=sm_100a), excerpts")
 print("# instruction counts per kernel: DMMA (FP64 tensor path, mma.sync.m8n8k4.f64), LDGSTS (cp.async), WARPSYNC")
 for kernel in ("windowKspaceKernel", "windowFrontKernel", "batchPairScreenKernelILi1", "windowTailKernelILi1",
-               "widomScreenKernelILi1", "nonbondedForceKernelILi1", "ewaldForceKernel", "ewaldFullCellKernel"):
+               "widomScreenKernelILi1", "fullScreenKernelILi1", "nonbondedForceKernelILi1", "ewaldForceKernel",
+               "ewaldFullCellKernel", "ewaldFullGemmKernelILb0", "ewaldFullGemmKernelILb1", "ewaldStepPhaseKernel"):
     body = pick(kernel)
     count = lambda op: sum(1 for l in body if re.search(r"\b" + op, l))
     print(f"{kernel}: DMMA {count('DMMA')}  LDGSTS {count('LDGSTS')}  DFMA {count('DFMA')}  FFMA {count('FFMA')}  "
