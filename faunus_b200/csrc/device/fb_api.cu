@@ -792,7 +792,7 @@ void buildGemmTiles(fb_ctx* c, Slot& sl, const std::vector<int4>& kn)
 {
     sl.n_gemm_tiles = 0;
     sl.gemm_tile_first_k.clear();
-    if (c->ewald.policy == 2 || kn.empty()) {
+    if (kn.empty()) {
         return;
     }
     const int ncc = static_cast<int>(std::ceil(c->ewald.n_cutoff));
@@ -881,9 +881,11 @@ int launchFullQGemm(fb_ctx* c, int s, int tile_begin = 0, int tile_end = -1, dou
     c->fullq_partials.ensure(static_cast<size_t>(tile_end - tile_begin) * n_ranges * kGemmShare);
     static thread_local int configured_device = -1; // (a thread drives one context at a time)
     if (configured_device != c->device) {
-        CUDA_CHECK(cudaFuncSetAttribute(ewaldFullGemmKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_CHECK(cudaFuncSetAttribute(ewaldFullGemmKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(sizeof(FullGemmSmem))));
-        CUDA_CHECK(cudaFuncSetAttribute(ewaldFullGemmKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_CHECK(cudaFuncSetAttribute(ewaldFullGemmKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(sizeof(FullGemmSmem))));
+        CUDA_CHECK(cudaFuncSetAttribute(ewaldFullGemmKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(sizeof(FullGemmSmem))));
         configured_device = c->device;
     }
@@ -894,12 +896,16 @@ int launchFullQGemm(fb_ctx* c, int s, int tile_begin = 0, int tile_end = -1, dou
     double2* zsteps = steps + 3 * static_cast<size_t>(n);
     ewaldStepPhaseKernel<<<(n + 255) / 256, 256, 0, c->stream>>>(makeView(c, s), geo, c->ewald.policy == 1 ? 1 : 0, steps, zsteps);
     launched(c, "ewaldStepPhaseKernel");
-    if (c->ewald.policy == 1) {
-        ewaldFullGemmKernel<true><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
+    if (c->ewald.policy == 2) { // IPBC: the real product of the cosines
+        ewaldFullGemmKernel<2><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
+            c->n_slots, steps, zsteps, sl.gemm_tiles.ptr, order, tile_begin, geo, range_size, c->fullq_partials.ptr);
+    }
+    else if (c->ewald.policy == 1) {
+        ewaldFullGemmKernel<1><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
             c->n_slots, steps, zsteps, sl.gemm_tiles.ptr, order, tile_begin, geo, range_size, c->fullq_partials.ptr);
     }
     else {
-        ewaldFullGemmKernel<false><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
+        ewaldFullGemmKernel<0><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
             c->n_slots, steps, zsteps, sl.gemm_tiles.ptr, order, tile_begin, geo, range_size, c->fullq_partials.ptr);
     }
     launched(c, "ewaldFullGemmKernel");
@@ -2030,7 +2036,7 @@ FB_API int fb_system_energy_shard(fb_ctx* c, int s, int shard, int n_shards, dou
         Slot& sl = c->slot[s];
         if (c->ewald_configured && sl.K > 0) {
             double sum = 0.0;
-            if (c->ewald.policy != 2 && sl.n_gemm_tiles > 0 && c->full_q_path == 0) { // a slab of tile columns
+            if (sl.n_gemm_tiles > 0 && c->full_q_path == 0) { // a slab of tile columns (all three policies)
                 const int n_columns = static_cast<int>(sl.gemm_column_first_tile.size()) - 1;
                 // boundaries where the k-vectors divide evenly: the first column that starts at or after K·r / n
                 auto boundary = [&](int r) {
@@ -2503,7 +2509,7 @@ FB_API int fb_ewald_update_full(fb_ctx* c, int s)
             throw CudaError{"no k-vectors (call fb_ewald_update_box first)"};
         }
         beginTiming(c);
-        if (c->ewald.policy != 2 && sl.n_gemm_tiles > 0 && c->full_q_path == 0) { // PBC / PBCEigen: matrix product
+        if (sl.n_gemm_tiles > 0 && c->full_q_path == 0) { // PBC / PBCEigen: complex matrix product; IPBC: the real one
             launchFullQGemm(c, s);
         }
         else if (c->ewald.policy != 2 && sl.n_cells > 0) { // factorised phases, one block per k-cell

@@ -43,16 +43,25 @@ struct FullGemmSmem
  * One k-step (4 particles) of a warp over NG column groups. A complex product costs THREE real ones (Gauss):
  *   P1 = (A_re + A_im)·B_re,  P2 = A_re·(B_im − B_re),  P3 = A_im·(B_re + B_im)   →   C_re = P1 − P3,  C_im = P1 + P2
  * so a group is 3 mma.sync.m8n8k4.f64 and two additions on the B element instead of 4 mma; acc[g] = {P1, P2, P3}. With the
- * PBCEigen quirk the real and the imaginary part carry different weights, P1 cannot be shared: acc[g] = {C_re, C_im, –},
- * four products.
+ * PBCEigen quirk (MODE 1) the real and the imaginary part carry different weights, P1 cannot be shared: acc[g] = {C_re, C_im, –},
+ * four products. IPBC (MODE 2; PolicyIonIonIPBC::updateComplex, src/energy.cpp:414-430) is the real product of the cosines — the
+ * real parts of the same tables —, one mma per group.
  */
-template <int NG, bool QUIRK>
+template <int NG, int MODE>
 __device__ __forceinline__ void gemmStep(const FullGemmSmem& sm, int ix, int row, int g0, int j, double (&acc)[4][3][2])
 {
     const double2 yv = sm.y[row][j];
-    const double2 a = cmul(sm.x[ix][j], yv);
     const double2* zrow = &sm.z[j][8 * g0 + row];
-    if (QUIRK) {
+    if (MODE == 2) { // IPBC: q cos(kx x) cos(ky y) cos(kz z), a real product
+        const double ar = sm.x[ix][j].x * yv.x;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            dmma884(acc[g][0][0], acc[g][0][1], ar, zrow[8 * g].x);
+        }
+        return;
+    }
+    const double2 a = cmul(sm.x[ix][j], yv);
+    if (MODE == 1) {
         const double2 b = cmul(sm.xi[ix][j], yv);
         const double na = -a.y;
 #pragma unroll
@@ -76,13 +85,13 @@ __device__ __forceinline__ void gemmStep(const FullGemmSmem& sm, int ix, int row
     }
 }
 
-template <int NG, bool QUIRK>
+template <int NG, int MODE>
 __device__ __forceinline__ void gemmChunk(const FullGemmSmem& sm, int ix, int g0, int lane, double (&acc)[4][3][2])
 {
     const int row = lane >> 2;
 #pragma unroll 2
     for (int step = 0; step < kGemmChunk / 4; ++step) {
-        gemmStep<NG, QUIRK>(sm, ix, row, g0, 4 * step + (lane & 3), acc);
+        gemmStep<NG, MODE>(sm, ix, row, g0, 4 * step + (lane & 3), acc);
     }
 }
 
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(256)
  * @param order    block → tile, heaviest tiles first (all tiles), or nullptr: block b takes tile tile_begin + b (a slab)
  * @param partials [tile − tile_begin][gridDim.y][2][32][64]
  */
-template <bool QUIRK>
+template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 2)
     ewaldFullGemmKernel(int n_slots, const double2* __restrict__ steps, const double2* __restrict__ zsteps,
                         const int4* __restrict__ tiles, const int* __restrict__ order, int tile_begin, PhaseGeometry geo,
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     sm.x[i][pj] = make_double2(wre * e.x, wre * e.y);
-                    if (QUIRK) {
+                    if (MODE == 1) {
                         sm.xi[i][pj] = make_double2(wim * e.x, wim * e.y);
                     }
                     e = cmul(e, sx);
@@ -219,10 +228,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         }
         __syncthreads();
         switch (my_ng) { // (a predicated mma.sync costs a WARPSYNC each: the group count is a template argument)
-        case 1: gemmChunk<1, QUIRK>(sm, ix, g0, lane, acc); break;
-        case 2: gemmChunk<2, QUIRK>(sm, ix, g0, lane, acc); break;
-        case 3: gemmChunk<3, QUIRK>(sm, ix, g0, lane, acc); break;
-        case 4: gemmChunk<4, QUIRK>(sm, ix, g0, lane, acc); break;
+        case 1: gemmChunk<1, MODE>(sm, ix, g0, lane, acc); break;
+        case 2: gemmChunk<2, MODE>(sm, ix, g0, lane, acc); break;
+        case 3: gemmChunk<3, MODE>(sm, ix, g0, lane, acc); break;
+        case 4: gemmChunk<4, MODE>(sm, ix, g0, lane, acc); break;
         default: break;
         }
     }
@@ -234,7 +243,11 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         if (g < my_ng) {
             const int col = 8 * (g0 + g) + 2 * (lane & 3);
             double2 re, im;
-            if (QUIRK) {
+            if (MODE == 2) {
+                re = make_double2(acc[g][0][0], acc[g][0][1]);
+                im = make_double2(0.0, 0.0);
+            }
+            else if (MODE == 1) {
                 re = make_double2(acc[g][0][0], acc[g][0][1]);
                 im = make_double2(acc[g][1][0], acc[g][1][1]);
             }

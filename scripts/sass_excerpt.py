@@ -30,7 +30,8 @@ print("# cuobjdump -sass faunus_b200/_build/libfaunus_b200.so (nvcc 12.9, -genco
 print("# instruction counts per kernel: DMMA (FP64 tensor path, mma.sync.m8n8k4.f64), LDGSTS (cp.async), WARPSYNC")
 for kernel in ("windowKspaceKernel", "windowFrontKernel", "batchPairScreenKernelILi1", "windowTailKernelILi1",
                "widomScreenKernelILi1", "fullScreenKernelILi1", "nonbondedForceKernelILi1", "ewaldForceKernel",
-               "ewaldFullCellKernel", "ewaldFullGemmKernelILb0", "ewaldFullGemmKernelILb1", "ewaldStepPhaseKernel"):
+               "ewaldFullCellKernel", "ewaldFullGemmKernelILi0", "ewaldFullGemmKernelILi1", "ewaldFullGemmKernelILi2",
+               "ewaldStepPhaseKernel"):
     body = pick(kernel)
     count = lambda op: sum(1 for l in body if re.search(r"\b" + op, l))
     print(f"{kernel}: DMMA {count('DMMA')}  LDGSTS {count('LDGSTS')}  DFMA {count('DFMA')}  FFMA {count('FFMA')}  "

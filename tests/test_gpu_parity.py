@@ -221,11 +221,13 @@ def test_ewald_doctest_values(reference_values):
 
 
 @pytest.mark.parametrize("scheme,ncutoff,n,alpha", [("PBC", 6, 400, 0.35), ("PBCEigen", 6, 400, 0.35), ("PBC", 11, 700, 0.5),
-                                                    ("PBCEigen", 13.5, 70, 0.5), ("PBC", 34, 130, 1.2)])
+                                                    ("PBCEigen", 13.5, 70, 0.5), ("PBC", 34, 130, 1.2),
+                                                    ("IPBC", 6, 400, 0.35), ("IPBC", 19, 90, 0.8)])
 def test_full_q_matrix_product(scheme, ncutoff, n, alpha):
     """fb_ewald_update_full (ewaldFullGemmKernel, fb_fullq.cuh: Q = [X·Y]·[Z] on the FP64 tensor path) against
     numpy's Σ_j q_j e^{ik·r_j} over the downloaded k-vectors (src/energy.cpp:191-206; PBCEigen sums the imaginary part
-    WITHOUT the charges, :208-217), tiles of 1 … 8 column groups, two z windows at ncutoff 34, ragged particle ranges"""
+    WITHOUT the charges, :208-217; IPBC is the real product of the cosines), tiles of 1 … 8 column groups, two z windows at
+    ncutoff 34, ragged particle ranges"""
     from faunus_b200 import native
     lib = native.load()
     cfg = small_electrolyte(n=n, coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": alpha, "ncutoff": ncutoff,
@@ -244,11 +246,14 @@ def test_full_q_matrix_product(scheme, ncutoff, n, alpha):
     for j0 in range(0, len(xyzq), 64):
         ph = kv[:K] @ xyzq[j0:j0 + 64, :3].T
         w = xyzq[j0:j0 + 64, 3]
+        if scheme == "IPBC":  # q cos(kx x) cos(ky y) cos(kz z), src/energy.cpp:414-430: the real product of the same kernel
+            ref += np.cos(kv[:K, None, :] * xyzq[None, j0:j0 + 64, :3]).prod(axis=2) @ w
+            continue
         ref += np.cos(ph) @ w + 1j * (np.sin(ph).sum(axis=1) if scheme == "PBCEigen" else np.sin(ph) @ w)
     assert np.abs(Q - ref).max() <= 1e-12 * n
     # slabs of tile columns (fb_system_energy_shard: the same product over a range of tiles, Q not stored) add up to the
     # reciprocal energy of the numpy sum, whatever the number of slabs
-    if scheme == "PBC":
+    if scheme != "PBCEigen":
         aks = np.zeros(kmax)
         assert lib.fb_ewald_download(g.ctx, 0, None, None, aks.ctypes.data_as(native.c_double_p)) == 0
         box = np.array(cfg["geometry"]["length"], dtype=float) * np.ones(3)
