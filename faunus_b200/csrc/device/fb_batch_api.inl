@@ -375,6 +375,8 @@ void flushBatch(fb_ctx* c)
     auto& b = c->batch;
     if (b.in_flight || b.runs_in_flight > 0) { // submitted work nobody waited for: drop its results
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(b.run_in_stream));
+        CUDA_CHECK(cudaStreamSynchronize(b.run_out_stream));
         b.in_flight = false;
         b.runs_in_flight = 0;
     }
@@ -842,11 +844,17 @@ void launchRunSteps(fb_ctx* c, fb_ctx::Batch::RunSlot& r, int steps, bool contin
         CUDA_CHECK(cudaEventRecord(r.ev_end, c->stream));
     }
     // state + overflow flag + the decisions
-    CUDA_CHECK(cudaMemcpyAsync(&r.d_back.ptr->overflow, b.d_result.ptr + 2, sizeof(double), cudaMemcpyDeviceToDevice,
-                               c->stream));
+    if (b.cells_used) { // (read by fb_run_wait with the cell list only; a copy node costs a few µs between two runs)
+        CUDA_CHECK(cudaMemcpyAsync(&r.d_back.ptr->overflow, b.d_result.ptr + 2, sizeof(double), cudaMemcpyDeviceToDevice,
+                                   c->stream));
+    }
+    // … on the read-back stream: the next run's kernels need not wait for the copy (they only READ this run's state and
+    // decisions; its slot is written again by the run after the next, which the host submits after this wait)
     const size_t bytes = offsetof(fb_ctx::Batch::RunBack, out) + sizeof(RunOutput) * static_cast<size_t>(r.n);
-    CUDA_CHECK(cudaMemcpyAsync(r.h_back.ptr, r.d_back.ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaEventRecord(r.ev_done, c->stream));
+    CUDA_CHECK(cudaEventRecord(r.ev_tail, c->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(b.run_out_stream, r.ev_tail, 0));
+    CUDA_CHECK(cudaMemcpyAsync(r.h_back.ptr, r.d_back.ptr, bytes, cudaMemcpyDeviceToHost, b.run_out_stream));
+    CUDA_CHECK(cudaEventRecord(r.ev_done, b.run_out_stream));
 }
 
 /** first launches of a run: its start state (from the host's pending list, or chained to the run before it) */
@@ -870,6 +878,7 @@ void launchRun(fb_ctx* c, fb_ctx::Batch::RunSlot& r, const fb_ctx::Batch::RunSlo
                                                       b.d_ahead[b.parity].ptr);
         launched(c, "runInitKernel");
     }
+    CUDA_CHECK(cudaEventRecord(r.ev_started, c->stream));
     r.chained = behind != nullptr;
     r.steps_launched = 0;
     // windows the run needs (barring cancellations): a window ends before a proposal that depends on one of its moves
@@ -1008,8 +1017,15 @@ FB_API int fb_run_submit(fb_ctx* c, int n_moves, const fb_run_move* moves, int w
         b.has_pending = false;
         b.d_result.ensure(batchResultDoubles(kBatchMax));
         b.h_result.ensure(batchResultDoubles(kBatchMax));
+        // the input goes up beside the kernels of the run in flight. That run's chain kernel read the header of the run
+        // that had this slot before: the upload waits for it (long through in practice)
         const size_t bytes = offsetof(fb_ctx::Batch::RunBlock, moves) + sizeof(RunMove) * static_cast<size_t>(n_moves);
-        CUDA_CHECK(cudaMemcpyAsync(r.d_run.ptr, r.h_run.ptr, bytes, cudaMemcpyHostToDevice, c->stream));
+        if (behind != nullptr) {
+            CUDA_CHECK(cudaStreamWaitEvent(b.run_in_stream, behind->ev_started, 0));
+        }
+        CUDA_CHECK(cudaMemcpyAsync(r.d_run.ptr, r.h_run.ptr, bytes, cudaMemcpyHostToDevice, b.run_in_stream));
+        CUDA_CHECK(cudaEventRecord(r.ev_in, b.run_in_stream));
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream, r.ev_in, 0));
         b.runs_in_flight += 1;
         launchRun(c, r, behind, pending);
     });
