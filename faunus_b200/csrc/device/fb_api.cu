@@ -788,20 +788,29 @@ void launchFullQ(fb_ctx* c, int s, int cell_begin, int cell_end, bool store_q, d
     launched(c, "ewaldFullCellKernel");
 }
 
+/** what buildGemmLayout makes of a list of k-vectors (host side of fb_fullq.cuh) */
+struct GemmLayout
+{
+    std::vector<int4> tiles;            //!< {nx, y table index, z table index of the first column, column groups}
+    std::vector<int> order;             //!< the tiles heaviest first
+    std::vector<int> index;             //!< [K] tile · 2048 + row · 64 + column of every k-vector
+    std::vector<int> tile_first_k;      //!< [tiles + 1] first k-vector of the tile's column of cells
+    std::vector<int> column_first_tile; //!< [columns + 1]
+};
+
 /**
  * Tiles of ewaldFullGemmKernel for the k-vectors `kn` (cell by cell, as stored): 4 nx × 8 ny rows — two y-adjacent columns of
  * cells, a contiguous range of k-vectors — and windows of at most 8 column groups of 8 nz from the first to the last nz
  * that holds a k-vector of the tile. Tiles are numbered in storage order of their k-vectors, so a range of tiles is a
- * range of k-vectors (the slabs of the sharded energy); `gemm_order` lists them heaviest first (they start first).
+ * range of k-vectors (the slabs of the sharded energy); `order` lists them heaviest first (they start first).
+ * Pure host code: fb_debug_fullq_layout hands it to the CPU tests.
  */
-void buildGemmTiles(fb_ctx* c, Slot& sl, const std::vector<int4>& kn)
+GemmLayout buildGemmLayout(const std::vector<int4>& kn, int ncc)
 {
-    sl.n_gemm_tiles = 0;
-    sl.gemm_tile_first_k.clear();
+    GemmLayout out;
     if (kn.empty()) {
-        return;
+        return out;
     }
-    const int ncc = static_cast<int>(std::ceil(c->ewald.n_cutoff));
     struct Column
     {
         int lo = std::numeric_limits<int>::max(), hi = -1; // z table indices (nz + ncc)
@@ -819,40 +828,49 @@ void buildGemmTiles(fb_ctx* c, Slot& sl, const std::vector<int4>& kn)
         col.hi = std::max(col.hi, kn[i].z + ncc);
         col.end_k = static_cast<int>(i) + 1;
     }
-    std::vector<int4> tiles;
-    std::vector<int> index(kn.size());
+    out.index.resize(kn.size());
     for (Column& col : columns) {
-        col.first_tile = static_cast<int>(tiles.size());
+        col.first_tile = static_cast<int>(out.tiles.size());
         const int4 n0 = kn[col.first_k];
         for (int z0 = col.lo; z0 <= col.hi; z0 += kGemmCols) { // (the windows start at the column's first nz, not on a grid)
             // (the k-vectors of ONE tile are contiguous only if the column has a single window; a slab is a range of
             // columns, which always is)
-            sl.gemm_tile_first_k.push_back(col.first_k);
-            tiles.push_back(make_int4(n0.x & ~3, (n0.y + ncc) & ~7, z0, std::min(8, (col.hi - z0 + 8) / 8)));
+            out.tile_first_k.push_back(col.first_k);
+            out.tiles.push_back(make_int4(n0.x & ~3, (n0.y + ncc) & ~7, z0, std::min(8, (col.hi - z0 + 8) / 8)));
         }
         for (int i = col.first_k; i < col.end_k; ++i) {
             const int4 n = kn[i];
             const int iy = n.y + ncc, iz = n.z + ncc;
             const int t = col.first_tile + (iz - col.lo) / kGemmCols;
-            index[i] = t * (kGemmRows * kGemmCols) + (8 * (n.x & 3) + (iy & 7)) * kGemmCols + (iz - tiles[t].z);
+            out.index[i] = t * (kGemmRows * kGemmCols) + (8 * (n.x & 3) + (iy & 7)) * kGemmCols + (iz - out.tiles[t].z);
         }
     }
-    sl.gemm_tile_first_k.push_back(static_cast<int>(kn.size()));
+    out.tile_first_k.push_back(static_cast<int>(kn.size()));
     // a slab boundary must not fall between the windows of one column: boundaries are moved to the column's first tile
-    sl.gemm_column_first_tile.clear();
     for (const Column& col : columns) {
-        sl.gemm_column_first_tile.push_back(col.first_tile);
+        out.column_first_tile.push_back(col.first_tile);
     }
-    sl.gemm_column_first_tile.push_back(static_cast<int>(tiles.size()));
-    std::vector<int> order(tiles.size());
-    for (size_t t = 0; t < order.size(); ++t) {
-        order[t] = static_cast<int>(t);
+    out.column_first_tile.push_back(static_cast<int>(out.tiles.size()));
+    out.order.resize(out.tiles.size());
+    for (size_t t = 0; t < out.order.size(); ++t) {
+        out.order[t] = static_cast<int>(t);
     }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tiles[a].w > tiles[b].w; });
-    sl.n_gemm_tiles = static_cast<int>(tiles.size());
-    sl.gemm_tiles.upload(tiles.data(), tiles.size(), c->stream);
-    sl.gemm_order.upload(order.data(), order.size(), c->stream);
-    sl.gemm_index.upload(index.data(), index.size(), c->stream);
+    std::stable_sort(out.order.begin(), out.order.end(), [&](int a, int b) { return out.tiles[a].w > out.tiles[b].w; });
+    return out;
+}
+
+void buildGemmTiles(fb_ctx* c, Slot& sl, const std::vector<int4>& kn)
+{
+    GemmLayout layout = buildGemmLayout(kn, static_cast<int>(std::ceil(c->ewald.n_cutoff)));
+    sl.n_gemm_tiles = static_cast<int>(layout.tiles.size());
+    sl.gemm_tile_first_k.swap(layout.tile_first_k);
+    sl.gemm_column_first_tile.swap(layout.column_first_tile);
+    if (sl.n_gemm_tiles == 0) {
+        return;
+    }
+    sl.gemm_tiles.upload(layout.tiles.data(), layout.tiles.size(), c->stream);
+    sl.gemm_order.upload(layout.order.data(), layout.order.size(), c->stream);
+    sl.gemm_index.upload(layout.index.data(), layout.index.size(), c->stream);
     CUDA_CHECK(cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
 }
 
@@ -2717,6 +2735,63 @@ FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
         d.rec_valid = s.rec_valid;
         d.rec_sum = s.rec_sum;
     });
+}
+
+FB_API int fb_debug_fullq_layout(const fb_ewald_config* cfg, const double box[3], int max_k, int max_tiles, int* nxyz,
+                                 int* index, int* tiles, int* order, int* column_first_tile, int* n_k, int* n_tiles,
+                                 int* n_columns)
+{
+    if (!cfg || !box || !n_k || !n_tiles || !n_columns) {
+        return FB_ERR_INVALID;
+    }
+    try {
+        std::vector<double4> kA;
+        std::vector<int4> kn;
+        generateKVectors(*cfg, box, kA, kn);
+        const int ncc = static_cast<int>(std::ceil(cfg->n_cutoff));
+        const long nc = (2 * ncc) / 4 + 1; // the storage order of fb_ewald_update_box: cell by cell, stable
+        auto cell_of = [&](const int4& n) {
+            return (static_cast<long>(n.x >> 2) * nc + ((n.y + ncc) >> 2)) * nc + ((n.z + ncc) >> 2);
+        };
+        std::stable_sort(kn.begin(), kn.end(), [&](const int4& a, const int4& b) { return cell_of(a) < cell_of(b); });
+        const GemmLayout layout = buildGemmLayout(kn, ncc);
+        *n_k = static_cast<int>(kn.size());
+        *n_tiles = static_cast<int>(layout.tiles.size());
+        *n_columns = static_cast<int>(layout.column_first_tile.size()) - 1;
+        if (*n_k > max_k || *n_tiles > max_tiles) {
+            return FB_ERR_INVALID;
+        }
+        for (int i = 0; i < *n_k; ++i) {
+            if (nxyz) {
+                nxyz[3 * i] = kn[i].x;
+                nxyz[3 * i + 1] = kn[i].y;
+                nxyz[3 * i + 2] = kn[i].z;
+            }
+            if (index) {
+                index[i] = layout.index[i];
+            }
+        }
+        for (int t = 0; t < *n_tiles; ++t) {
+            if (tiles) {
+                tiles[4 * t] = layout.tiles[t].x;
+                tiles[4 * t + 1] = layout.tiles[t].y;
+                tiles[4 * t + 2] = layout.tiles[t].z;
+                tiles[4 * t + 3] = layout.tiles[t].w;
+            }
+            if (order) {
+                order[t] = layout.order[t];
+            }
+        }
+        if (column_first_tile) {
+            for (int col = 0; col <= *n_columns; ++col) {
+                column_first_tile[col] = layout.column_first_tile[col];
+            }
+        }
+        return FB_OK;
+    }
+    catch (const std::exception&) {
+        return FB_ERR_INVALID;
+    }
 }
 
 FB_API int fb_ewald_download(fb_ctx* c, int s, double* q_re_im, double* kvectors, double* aks)

@@ -117,7 +117,7 @@ C_ABI_SYMBOLS = [
     "fb_set_box", "fb_sync", "fb_download_space", "fb_nonbonded_energy", "fb_nonbonded_delta",
     "fb_system_energy_shard", "fb_particle_pair_energy", "fb_group_group_energy", "fb_set_force_table", "fb_nonbonded_force", "fb_ewald_force", "fb_atom_rdf", "fb_molecule_rdf", "fb_trial_energy", "fb_trial_commit", "fb_batch_trial", "fb_batch_submit", "fb_batch_submit_groups", "fb_batch_wait", "fb_run_submit", "fb_run_wait", "fb_configure_runs", "fb_get_run_stats", "fb_batch_commit", "fb_configure_cells", "fb_debug_set_cell_capacity", "fb_get_batch_timing", "fb_get_kspace_timing",
     "fb_ewald_configure", "fb_ewald_update_box", "fb_ewald_update_full", "fb_ewald_update_partial",
-    "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_widom_batch", "fb_state_doubles",
+    "fb_ewald_energy", "fb_ewald_sync", "fb_ewald_download", "fb_debug_fullq_layout", "fb_widom_batch", "fb_state_doubles",
     "fb_export_state", "fb_import_state", "fb_export_state_host", "fb_import_state_host", "fb_upload_groups",
     "fb_nccl_unique_id", "fb_nccl_init", "fb_nccl_finalize", "fb_nccl_exchange_state", "fb_nccl_sendrecv_host",
     "fb_nccl_allgather_host", "fb_nccl_bytes_exchanged", "fb_launch_count",
@@ -180,6 +180,8 @@ def load() -> C.CDLL:
         "fb_ewald_energy": (C.c_int, [vp, C.c_int, C.POINTER(FbChange), c_double_p]),
         "fb_ewald_sync": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(FbChange)]),
         "fb_ewald_download": (C.c_int, [vp, C.c_int, c_double_p, c_double_p, c_double_p]),
+        "fb_debug_fullq_layout": (C.c_int, [C.POINTER(FbEwaldConfig), c_double_p, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p,
+                                            c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
         "fb_widom_batch": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_int_p, c_double_p,
                                      C.c_int, c_double_p]),
         "fb_state_doubles": (C.c_size_t, [vp]),

@@ -432,6 +432,13 @@ int fb_ewald_update_partial(fb_ctx* ctx, int slot_new, int slot_old, const fb_ch
 int fb_ewald_energy(fb_ctx* ctx, int slot, const fb_change* change, double* energy);
 /* Ewald::sync: Q (and, for everything/volume changes, k-vectors and A_k) dst := src */
 int fb_ewald_sync(fb_ctx* ctx, int dst_slot, int src_slot, const fb_change* change);
+/* debug/tests, no device needed: the k-vectors of `config` in `box` in the storage order of fb_ewald_update_box (integer
+ * triplets nxyz[3K]) and the tile layout of the full-Q matrix product (fb_fullq.cuh): index[K] = tile * 2048 + row * 64 +
+ * column, tiles[4 T] = {nx of the first row, ny + ceil(n_cutoff) of the first row, nz + ceil(n_cutoff) of the first column,
+ * column groups of 8}, order[T] (heaviest tiles first), column_first_tile[columns + 1] (slab boundaries). NULL skips;
+ * FB_ERR_INVALID if max_k / max_tiles are too small (n_k, n_tiles are set). */
+int fb_debug_fullq_layout(const fb_ewald_config* config, const double box[3], int max_k, int max_tiles, int* nxyz, int* index,
+                          int* tiles, int* order, int* column_first_tile, int* n_k, int* n_tiles, int* n_columns);
 /* debug/tests: copy out K complex numbers (re,im interleaved), k-vectors [3K], A_k [K] (NULL skips) */
 int fb_ewald_download(fb_ctx* ctx, int slot, double* q_re_im, double* kvectors, double* aks);
 
