@@ -294,6 +294,9 @@ struct fb_ctx
             bool chained = false;  //!< queued while its predecessor was still in flight (started by runChainKernel)
         };
         RunSlot run[2];
+        bool gap_stats = false; //!< FAUNUS_B200_GAP_STATS: measure the device time between chained runs, report at fb_destroy
+        double gap_ms_total = 0.0;
+        long gap_count = 0;
         int run_head = 0;      //!< slot of the oldest run in flight
         int runs_in_flight = 0;
         std::vector<int> run_stamp; //!< per particle slot: the run that last touched it (distinctness check) …
@@ -1056,6 +1059,7 @@ FB_API int fb_create(const fb_config* cfg, fb_ctx** out)
         }
         c = new fb_ctx();
         c->device = cfg->device;
+        c->batch.gap_stats = std::getenv("FAUNUS_B200_GAP_STATS") != nullptr;
         if (const char* v = std::getenv("FAUNUS_B200_FULLPAIR")) {
             c->full_pair_path = std::strcmp(v, "fp64") == 0 ? 1 : 0;
         }
@@ -1326,6 +1330,10 @@ FB_API void fb_destroy(fb_ctx* c)
                 cudaEventDestroy(e);
             }
         }
+    }
+    if (c->batch.gap_stats && c->batch.gap_count > 0) {
+        std::fprintf(stderr, "faunus_b200: %ld chained runs, %.2f us between the last window of a run and the first of the next\n",
+                     c->batch.gap_count, 1e3 * c->batch.gap_ms_total / static_cast<double>(c->batch.gap_count));
     }
     for (cudaStream_t extra : {c->batch.run_in_stream, c->batch.run_out_stream}) {
         if (extra) {

@@ -1066,6 +1066,17 @@ FB_API int fb_run_wait(fb_ctx* c, fb_run_result* out)
             const int left = r.n - st.cursor;
             launchRunSteps(c, r, (left + r.stride - 1) / r.stride, true);
         }
+        if (b.gap_stats && successor != nullptr && !continued && !c->timing) {
+            // experiments (FAUNUS_B200_GAP_STATS): device time between the last window of this run and the first window
+            // of the run queued behind it (chain kernel, event records, launch latency)
+            float gap_ms = 0.0f;
+            if (cudaEventSynchronize(successor->ev_begin) == cudaSuccess &&
+                cudaEventElapsedTime(&gap_ms, r.ev_end, successor->ev_begin) == cudaSuccess) {
+                b.gap_ms_total += gap_ms;
+                b.gap_count += 1;
+            }
+            cudaGetLastError();
+        }
         const RunState& st = r.h_back.ptr->state;
         if (successor != nullptr && continued) { // launch the halted run again, from the state this one leaves
             launchRun(c, *successor, nullptr, st.commit);
