@@ -297,6 +297,28 @@ def test_full_q_matrix_product_cuboid_and_inactive():
         assert np.abs(Q - ref).max() <= 1e-12 * 300
 
 
+def test_full_q_and_full_pair_paths_agree(monkeypatch):
+    """The kernels the product and the screened pair sum replaced stay selectable for comparisons (FAUNUS_B200_FULLQ=cells:
+    one block per k-cell; FAUNUS_B200_FULLPAIR=fp64: all-FP64 pair sum; read at fb_create): same Q(k), same energies, same
+    slabs"""
+    from faunus_b200 import native
+    lib = native.load()
+    cfg = small_electrolyte(n=1200, coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 9})
+    results = []
+    for fullq, fullpair in (("gemm", "screen"), ("cells", "fp64")):
+        monkeypatch.setenv("FAUNUS_B200_FULLQ", fullq)
+        monkeypatch.setenv("FAUNUS_B200_FULLPAIR", fullpair)
+        g = b200_sim(cfg)
+        assert lib.fb_ewald_update_full(g.ctx, 0) == 0
+        q = np.zeros(2 * 10 * 19 * 19)
+        assert lib.fb_ewald_download(g.ctx, 0, q.ctypes.data_as(native.c_double_p), None, None) == 0
+        results.append((q, np.array(g.system_energy()[1]), np.array([g.system_energy_shard(r, 3) for r in range(3)])))
+    (qa, ea, sa), (qb, eb, sb) = results
+    assert np.abs(qa).max() > 1 and np.abs(qa - qb).max() <= 1e-12 * np.abs(qb).max()
+    assert_close(ea, eb, scale=np.abs(eb).max())
+    assert_close(sa.sum(axis=0), sb.sum(axis=0), scale=np.abs(eb).max())
+
+
 def test_reject_restores_state():
     """trial → reject → the next evaluation sees the accepted state again (sync direction)"""
     cfg = small_electrolyte(coulomb={"type": "ewald", "epsr": 78.7, "cutoff": 9.0, "alpha": 0.35, "ncutoff": 6})
