@@ -124,6 +124,7 @@ struct Slot
     // tiles of the full rebuild of Q(k) (fb_fullq.cuh)
     DeviceBuffer<int4> gemm_tiles; //!< [n_gemm_tiles] {nx, y table index, first column group, column groups}, storage order
     DeviceBuffer<int> gemm_order;  //!< [n_gemm_tiles] the tiles heaviest first
+    DeviceBuffer<int> gemm_row_groups; //!< [n_gemm_tiles] column groups per nx of the tile (8 bits each: first | (last + 1) << 4)
     DeviceBuffer<int> gemm_index;  //!< [K] tile · 2048 + row · 64 + column of every k-vector
     int n_gemm_tiles = 0;
     std::vector<int> gemm_tile_first_k;      //!< [n_gemm_tiles + 1] first k-vector of the tile's column of cells
@@ -795,6 +796,7 @@ void launchFullQ(fb_ctx* c, int s, int cell_begin, int cell_end, bool store_q, d
 struct GemmLayout
 {
     std::vector<int4> tiles;            //!< {nx, y table index, z table index of the first column, column groups}
+    std::vector<int> row_groups;        //!< per tile, 8 bits per nx: first column group with a k-vector | (last + 1) << 4
     std::vector<int> order;             //!< the tiles heaviest first
     std::vector<int> index;             //!< [K] tile · 2048 + row · 64 + column of every k-vector
     std::vector<int> tile_first_k;      //!< [tiles + 1] first k-vector of the tile's column of cells
@@ -849,6 +851,22 @@ GemmLayout buildGemmLayout(const std::vector<int4>& kn, int ncc)
         }
     }
     out.tile_first_k.push_back(static_cast<int>(kn.size()));
+    { // column groups every nx of a tile needs (the warps of ewaldFullGemmKernel skip the others)
+        std::vector<int> lo(4 * out.tiles.size(), 16), hi(4 * out.tiles.size(), 0);
+        for (size_t i = 0; i < kn.size(); ++i) {
+            const int t = out.index[i] / (kGemmRows * kGemmCols);
+            const int row = 4 * t + (kn[i].x & 3);
+            const int g = (out.index[i] % kGemmCols) / 8;
+            lo[row] = std::min(lo[row], g);
+            hi[row] = std::max(hi[row], g + 1);
+        }
+        out.row_groups.assign(out.tiles.size(), 0);
+        for (size_t row = 0; row < lo.size(); ++row) {
+            if (hi[row] > 0) {
+                out.row_groups[row / 4] |= (lo[row] | (hi[row] << 4)) << (8 * (row & 3));
+            }
+        }
+    }
     // a slab boundary must not fall between the windows of one column: boundaries are moved to the column's first tile
     for (const Column& col : columns) {
         out.column_first_tile.push_back(col.first_tile);
@@ -873,6 +891,7 @@ void buildGemmTiles(fb_ctx* c, Slot& sl, const std::vector<int4>& kn)
     }
     sl.gemm_tiles.upload(layout.tiles.data(), layout.tiles.size(), c->stream);
     sl.gemm_order.upload(layout.order.data(), layout.order.size(), c->stream);
+    sl.gemm_row_groups.upload(layout.row_groups.data(), layout.row_groups.size(), c->stream);
     sl.gemm_index.upload(layout.index.data(), layout.index.size(), c->stream);
     CUDA_CHECK(cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
 }
@@ -925,15 +944,18 @@ int launchFullQGemm(fb_ctx* c, int s, int tile_begin = 0, int tile_end = -1, dou
     launched(c, "ewaldStepPhaseKernel");
     if (c->ewald.policy == 2) { // IPBC: the real product of the cosines
         ewaldFullGemmKernel<2><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
-            c->n_slots, steps, zsteps, sl.gemm_tiles.ptr, order, tile_begin, geo, range_size, c->fullq_partials.ptr);
+            c->n_slots, steps, zsteps, sl.gemm_tiles.ptr, sl.gemm_row_groups.ptr, order, tile_begin, geo, range_size,
+            c->fullq_partials.ptr);
     }
     else if (c->ewald.policy == 1) {
         ewaldFullGemmKernel<1><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
-            c->n_slots, steps, zsteps, sl.gemm_tiles.ptr, order, tile_begin, geo, range_size, c->fullq_partials.ptr);
+            c->n_slots, steps, zsteps, sl.gemm_tiles.ptr, sl.gemm_row_groups.ptr, order, tile_begin, geo, range_size,
+            c->fullq_partials.ptr);
     }
     else {
         ewaldFullGemmKernel<0><<<grid, kGemmThreads, sizeof(FullGemmSmem), c->stream>>>(
-            c->n_slots, steps, zsteps, sl.gemm_tiles.ptr, order, tile_begin, geo, range_size, c->fullq_partials.ptr);
+            c->n_slots, steps, zsteps, sl.gemm_tiles.ptr, sl.gemm_row_groups.ptr, order, tile_begin, geo, range_size,
+            c->fullq_partials.ptr);
     }
     launched(c, "ewaldFullGemmKernel");
     if (!slab) {
@@ -2694,6 +2716,9 @@ FB_API int fb_ewald_sync(fb_ctx* c, int dst, int src, const fb_change* change)
                                            cudaMemcpyDeviceToDevice, c->stream));
                 d.gemm_order.ensure(s.n_gemm_tiles);
                 CUDA_CHECK(cudaMemcpyAsync(d.gemm_order.ptr, s.gemm_order.ptr, s.n_gemm_tiles * sizeof(int),
+                                           cudaMemcpyDeviceToDevice, c->stream));
+                d.gemm_row_groups.ensure(s.n_gemm_tiles);
+                CUDA_CHECK(cudaMemcpyAsync(d.gemm_row_groups.ptr, s.gemm_row_groups.ptr, s.n_gemm_tiles * sizeof(int),
                                            cudaMemcpyDeviceToDevice, c->stream));
                 d.gemm_tile_first_k = s.gemm_tile_first_k;
                 d.gemm_column_first_tile = s.gemm_column_first_tile;

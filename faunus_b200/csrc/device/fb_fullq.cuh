@@ -142,14 +142,15 @@ __global__ void __launch_bounds__(256)
 /**
  * @param tiles    [n_tiles] {nx of the first row, y table index of the first row (ny + ncc), z table index of the first
  *                 column (nz + ncc; any integer), number of column groups} in storage order of the k-vectors
+ * @param row_groups [n_tiles] per nx of the tile (8 bits each): first column group that holds one of its k-vectors | (last + 1) << 4
  * @param order    block → tile, heaviest tiles first (all tiles), or nullptr: block b takes tile tile_begin + b (a slab)
  * @param partials [tile − tile_begin][gridDim.y][2][32][64]
  */
 template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 2)
     ewaldFullGemmKernel(int n_slots, const double2* __restrict__ steps, const double2* __restrict__ zsteps,
-                        const int4* __restrict__ tiles, const int* __restrict__ order, int tile_begin, PhaseGeometry geo,
-                        int range_size, double* __restrict__ partials)
+                        const int4* __restrict__ tiles, const int* __restrict__ row_groups, const int* __restrict__ order,
+                        int tile_begin, PhaseGeometry geo, int range_size, double* __restrict__ partials)
 {
     extern __shared__ __align__(16) unsigned char gemm_smem_raw[];
     FullGemmSmem& sm = *reinterpret_cast<FullGemmSmem*>(gemm_smem_raw);
@@ -160,12 +161,18 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     const int j_end = min(n_slots, j_begin + range_size);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int ix = warp & 3;
+    // which nx of the tile a warp takes rotates with the block: the rows of a tile need different numbers of column groups
+    // (the sphere), a warp's sub-partition is warp % 4, and the blocks that share an SM should not all have their short rows
+    // on the same one
+    const int ix = (warp + static_cast<int>(blockIdx.x + blockIdx.y)) & 3;
     const int half = warp >> 2;
+    const int row_range = __ldg(row_groups + tile_index) >> (8 * ix); // groups [lo, hi) that hold a k-vector of this nx
+    const int row_lo = row_range & 15;
+    const int row_n = ((row_range >> 4) & 15) - row_lo;
 
     // the two warps of an nx share the column groups (the first ⌈ng / 2⌉ and the rest: both on the same SM sub-partition)
-    const int g0 = half == 0 ? 0 : (ng + 1) / 2;
-    const int my_ng = half == 0 ? (ng + 1) / 2 : ng / 2;
+    const int g0 = row_lo + (half == 0 ? 0 : (row_n + 1) / 2);
+    const int my_ng = half == 0 ? (row_n + 1) / 2 : row_n / 2;
     double acc[4][3][2];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
